@@ -1,0 +1,212 @@
+/*
+ * b200hist.h -- C ABI of libb200hist.so, the Blackwell-native (sm_100a) `gpu_hist` tree updater.
+ *
+ * This is the drop-in boundary of the hot path.  Plain pointers and sizes only: no C++ types, no
+ * torch types, no exceptions cross it.  Every function returns 0 on success and non-zero on error;
+ * the message is then available from b200hist_last_error() (thread-local), mirroring the
+ * reference's `XGB_DLL int fn(...)` + `XGBGetLastError()` contract
+ * (/root/reference/include/xgboost/c_api.h:90, src/c_api/c_api_error.h:27-42).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to /root/reference).
+ * INTEGRATION.md shows the `xgboost::TreeUpdater` shim (registered as "grow_gpu_hist") that a
+ * maintainer links against these symbols.
+ *
+ * Pointers suffixed `_dev` are CUDA device pointers on the updater's device; `_host` are host
+ * pointers.  `stream` is a `cudaStream_t` passed as `void*` (0 = default stream).  All work is
+ * enqueued on that stream; functions that return host results synchronise it before returning.
+ */
+#ifndef B200HIST_H_
+#define B200HIST_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200HIST_API __attribute__((visibility("default")))
+#define B200HIST_VERSION 100
+
+/* ---------------------------------------------------------------------------------------------
+ * Plain-old-data types
+ * ------------------------------------------------------------------------------------------- */
+
+/* Subset of TrainParam the updater consumes (src/tree/param.h:25-185) plus GPUTrainingParam
+ * (src/tree/updater_gpu_common.cuh:20-40).  Field meanings and defaults are the reference's. */
+typedef struct b200hist_train_param {
+  int32_t max_depth;        /* default 6; 0 = unlimited (requires max_leaves > 0) */
+  int32_t max_leaves;       /* default 0 = unlimited */
+  int32_t grow_policy;      /* 0 = depthwise (default), 1 = lossguide */
+  float learning_rate;      /* eta, default 0.3 */
+  float reg_lambda;         /* default 1 */
+  float reg_alpha;          /* default 0 */
+  float min_child_weight;   /* default 1 */
+  float max_delta_step;     /* default 0 */
+  float min_split_loss;     /* gamma, default 0 */
+  int32_t reserved[7];
+} b200hist_train_param;
+
+/* GradientPairInt64 (include/xgboost/base.h:253-304): 64-bit fixed-point gradient statistics. */
+typedef struct b200hist_gpair64 {
+  int64_t grad;
+  int64_t hess;
+} b200hist_gpair64;
+
+/* GradientQuantiser state (src/tree/gpu_hist/quantiser.cuh:52-81). */
+typedef struct b200hist_quantiser {
+  double to_fixed_grad, to_fixed_hess;
+  double to_float_grad, to_float_hess;
+} b200hist_quantiser;
+
+/* One split decision: DeviceSplitCandidate + the weights of GPUExpandEntry
+ * (src/tree/updater_gpu_common.cuh:52-83, src/tree/gpu_hist/expand_entry.cuh:15-34). */
+typedef struct b200hist_candidate {
+  float loss_chg;
+  int32_t dir;              /* 0 = kLeftDir (missing goes left), 1 = kRightDir */
+  int32_t findex;           /* -1 = no valid split */
+  float fvalue;             /* split condition (a cut value, or -inf) */
+  b200hist_gpair64 left_sum;
+  b200hist_gpair64 right_sum;
+  float base_weight, left_weight, right_weight;
+  int32_t split_gbin;       /* global bin whose exclusive scan is the left sum; -1 if none */
+} b200hist_candidate;
+
+/* One tree node, carrying exactly what the reference records through RegTree::ExpandNode and
+ * RegTree::Stat (src/tree/tree_model.cc:805-830, src/tree/updater_gpu_hist.cu:610-655,680-684). */
+typedef struct b200hist_tree_node {
+  int32_t parent, left, right;  /* -1 when absent */
+  int32_t findex;               /* split feature; -1 for a leaf */
+  float fvalue;                 /* split condition; for a leaf: the leaf value */
+  int32_t default_left;
+  int32_t is_leaf;
+  float leaf_value;             /* learning_rate * weight (valid for leaves) */
+  float loss_chg, sum_hess, base_weight; /* RTreeNodeStat */
+  int32_t depth;
+} b200hist_tree_node;
+
+typedef struct b200hist_ellpack_s* b200hist_ellpack_t;  /* quantised feature matrix (EllpackPage) */
+typedef struct b200hist_updater_s* b200hist_updater_t;  /* tree updater (GPUHistMaker) */
+
+/* ---------------------------------------------------------------------------------------------
+ * Errors / info
+ * ------------------------------------------------------------------------------------------- */
+/* replaces XGBGetLastError (include/xgboost/c_api.h:90) for this library */
+B200HIST_API const char* b200hist_last_error(void);
+B200HIST_API int b200hist_version(void);
+/* Number of kernels this library has launched since load (bench.py's `gpu_launches` evidence). */
+B200HIST_API uint64_t b200hist_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ellpack page: HistogramCuts + quantised bin matrix
+ *   replaces EllpackPageImpl (src/data/ellpack_page.cuh:181-391) and HistogramCuts
+ *   (src/common/hist_util.h:38-190) as seen by the updater through
+ *   DMatrix::GetBatches<EllpackPage> (src/tree/updater_gpu_hist.cu:735-756).
+ * HBM layout (ours): row-major bins[n_rows][row_bytes]; one symbol per feature holding the
+ * FEATURE-LOCAL bin (uint8 when every feature has <= 256 symbols incl. the null symbol, else
+ * uint16); row_bytes is rounded up to 16 so every row is a legal TMA bulk-copy source.
+ * ------------------------------------------------------------------------------------------- */
+/* cut_ptrs_host: n_features+1 uint32 (HistogramCuts::cut_ptrs_), cut_values_host: total_bins f32.
+ * has_missing: reserve a null symbol (dense-with-missing layout, ellpack_page.cu:140-183). */
+B200HIST_API int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features,
+                                         const uint32_t* cut_ptrs_host, const float* cut_values_host,
+                                         int has_missing, b200hist_ellpack_t* out);
+B200HIST_API int b200hist_ellpack_destroy(b200hist_ellpack_t ell);
+/* Bin a dense row-major f32 batch resident on the device into rows [row_begin, row_begin+n).
+ * NaN = missing.  replaces CompressBinEllpackKernel / WriteCompressedEllpackFunctor
+ * (src/data/ellpack_page.cu:56-134,240-298) + HistogramCuts::SearchBin (hist_util.h:112-121). */
+B200HIST_API int b200hist_ellpack_push_dense(b200hist_ellpack_t ell, uint64_t row_begin,
+                                             const float* x_dev, uint64_t n, uint64_t ld, void* stream);
+/* Import a reference EllpackPage: decode its big-endian bit-packed gidx_buffer
+ * (src/common/compressed_iterator.h:110-152,228-268) into our layout.  Dense layouts only
+ * (row_stride == n_features); null_value as EllpackAccessor::NullValue (ellpack_page.cuh:85-87). */
+B200HIST_API int b200hist_ellpack_import_reference(b200hist_ellpack_t ell, const uint8_t* gidx_buffer_dev,
+                                                   uint32_t row_stride, uint32_t n_symbols, int is_dense,
+                                                   void* stream);
+/* Accessors (EllpackPageImpl::{Size, info.row_stride, NumSymbols}, ellpack_page.cuh:250-300). */
+B200HIST_API int b200hist_ellpack_info(b200hist_ellpack_t ell, uint64_t* n_rows, uint32_t* n_features,
+                                       uint32_t* total_bins, uint32_t* row_bytes, uint32_t* bin_bytes,
+                                       uint32_t* null_symbol, const void** bins_dev);
+
+/* Copy the bin matrix (n_rows * row_bytes bytes) to host memory; tests / debugging only. */
+B200HIST_API int b200hist_ellpack_copy_bins_to_host(b200hist_ellpack_t ell, void* out_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Updater: replaces GPUHistMaker / GPUHistMakerDevice (src/tree/updater_gpu_hist.cu:104-891)
+ * ------------------------------------------------------------------------------------------- */
+/* TreeUpdater::Configure + InitDataOnce (updater_gpu_hist.cu:764-771,803-827).  The ellpack is
+ * borrowed and must outlive the updater. */
+B200HIST_API int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* param,
+                                         b200hist_updater_t* out);
+B200HIST_API int b200hist_updater_destroy(b200hist_updater_t u);
+/* Upper bound on nodes a tree can have under the configured param (sizes out_nodes). */
+B200HIST_API int b200hist_updater_max_nodes(b200hist_updater_t u, int32_t* out);
+
+/* TreeUpdater::Update for one tree (updater_gpu_hist.cu:785-801 -> UpdateTree :693-732).
+ * gpair_dev: n_rows x {grad, hess} float32 (GradientPair).  out_position_dev (nullable): n_rows
+ * int32, leaf id per row, bitwise-NOT when the row's quantised hessian is 0
+ * (updater_gpu_hist.cuh:48-56).  out_nodes_host: capacity >= max_nodes. */
+B200HIST_API int b200hist_updater_update_tree(b200hist_updater_t u, const float* gpair_dev, void* stream,
+                                              b200hist_tree_node* out_nodes_host, int32_t* out_n_nodes,
+                                              int32_t* out_position_dev);
+/* Same, with the gradient in HOST memory (XGBoosterTrainOneIter with host arrays,
+ * include/xgboost/c_api.h:1080): H2D of the gradient and D2H of the tree happen inside. */
+B200HIST_API int b200hist_updater_update_tree_host(b200hist_updater_t u, const float* gpair_host,
+                                                   void* stream, b200hist_tree_node* out_nodes_host,
+                                                   int32_t* out_n_nodes, int32_t* out_position_dev);
+/* TreeUpdater::UpdatePredictionCache (updater_gpu_hist.cu:582-608,848-869):
+ * preds_dev[i] += leaf_value[decode(position[i])] for the last tree built. */
+B200HIST_API int b200hist_updater_update_prediction_cache(b200hist_updater_t u, float* preds_dev,
+                                                          void* stream);
+/* Introspection of the last update (parity tests): quantiser, per-node histogram, per-node
+ * candidate, per-node row counts. */
+B200HIST_API int b200hist_updater_last_quantiser(b200hist_updater_t u, b200hist_quantiser* out_host);
+B200HIST_API int b200hist_updater_node_histogram(b200hist_updater_t u, int32_t nidx,
+                                                 b200hist_gpair64* out_host /* total_bins */);
+B200HIST_API int b200hist_updater_node_candidate(b200hist_updater_t u, int32_t nidx,
+                                                 b200hist_candidate* out_host);
+/* Per-phase device time (ms) of the last update_tree when profiling is on: quantise, hist,
+ * subtract, evaluate, apply, partition, finalise (7 floats) and row-visits V of the hist phase. */
+B200HIST_API int b200hist_updater_set_profiling(b200hist_updater_t u, int on);
+B200HIST_API int b200hist_updater_last_profile(b200hist_updater_t u, float* out_ms7, uint64_t* out_row_visits);
+
+/* ---------------------------------------------------------------------------------------------
+ * Component entry points (each a row of SURVEY.md 8(a)); used by the parity tests.
+ * ------------------------------------------------------------------------------------------- */
+/* G1+G2+G3: GradientQuantiserGroup + CalcQuantizedGpairs + root sum
+ * (src/tree/gpu_hist/quantiser.cu:55-149, updater_gpu_hist.cu:661-664). */
+B200HIST_API int b200hist_quantise(int device, const float* gpair_dev, uint64_t n,
+                                   b200hist_quantiser* out_host, b200hist_gpair64* gq_dev,
+                                   b200hist_gpair64* root_sum_host, void* stream);
+/* H2: DeviceHistogramBuilder::BuildHistogram (src/tree/gpu_hist/histogram.cu:570-582) for a batch
+ * of nodes in one launch.  Node k owns rows ridx_dev[seg_begin[k] .. +seg_count[k]); its histogram
+ * is hist_dev + k*total_bins (cleared by the call). */
+B200HIST_API int b200hist_build_hist(b200hist_ellpack_t ell, const b200hist_gpair64* gq_dev,
+                                     const uint32_t* ridx_dev, const uint64_t* seg_begin_host,
+                                     const uint64_t* seg_count_host, int32_t n_nodes,
+                                     b200hist_gpair64* hist_dev, void* stream);
+/* H4: SubtractionTrick (src/tree/gpu_hist/histogram.cuh:208-221): out = parent - built. */
+B200HIST_API int b200hist_subtract(int device, const b200hist_gpair64* parent_dev,
+                                   const b200hist_gpair64* built_dev, b200hist_gpair64* out_dev,
+                                   uint64_t n_bins, void* stream);
+/* E1-E4: GPUHistEvaluator::EvaluateSplits (src/tree/gpu_hist/evaluate_splits.cu:400-470).
+ * hist_dev: n_nodes x total_bins; parent_sums_host: n_nodes; feature_set_host (nullable): the
+ * sampled feature ids, shared by all nodes. */
+B200HIST_API int b200hist_evaluate_splits(b200hist_ellpack_t ell, const b200hist_gpair64* hist_dev,
+                                          const b200hist_gpair64* parent_sums_host, int32_t n_nodes,
+                                          const int32_t* feature_set_host, int32_t n_feature_set,
+                                          const b200hist_train_param* param,
+                                          const b200hist_quantiser* quantiser,
+                                          b200hist_candidate* out_host, void* stream);
+/* P2: RowPartitioner::UpdatePositionBatch (src/tree/gpu_hist/row_partitioner.cuh:343-418) with the
+ * numerical GoLeftOp (updater_gpu_hist.cu:398-419).  Segment k of ridx_in_dev is split stably into
+ * ridx_out_dev (left rows first); left_count_host[k] receives the number of left rows. */
+B200HIST_API int b200hist_partition(b200hist_ellpack_t ell, const uint32_t* ridx_in_dev,
+                                    uint32_t* ridx_out_dev, const uint64_t* seg_begin_host,
+                                    const uint64_t* seg_count_host, const int32_t* findex_host,
+                                    const float* split_cond_host, const int32_t* default_left_host,
+                                    int32_t n_nodes, uint64_t* left_count_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200HIST_H_ */

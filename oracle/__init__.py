@@ -1,0 +1,202 @@
+"""ctypes wrapper of oracle/hist_oracle.c -- the CPU restatement of the reference `gpu_hist`
+algorithm.  TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs, never by xgboost_b200/.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, Structure, byref, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "hist_oracle.c")
+_LIB = os.path.join(_HERE, "liboracle.so")
+
+
+class Param(Structure):
+    _fields_ = [("max_depth", c_int32), ("max_leaves", c_int32), ("grow_policy", c_int32),
+                ("learning_rate", c_float), ("reg_lambda", c_float), ("reg_alpha", c_float),
+                ("min_child_weight", c_float), ("max_delta_step", c_float), ("min_split_loss", c_float)]
+
+    @classmethod
+    def make(cls, **kw):
+        p = cls(6, 0, 0, 0.3, 1.0, 0.0, 1.0, 0.0, 0.0)
+        alias = {"eta": "learning_rate", "lambda": "reg_lambda", "alpha": "reg_alpha", "gamma": "min_split_loss"}
+        for k, v in kw.items():
+            k = alias.get(k, k)
+            if k == "grow_policy" and isinstance(v, str):
+                v = {"depthwise": 0, "lossguide": 1}[v]
+            setattr(p, k, v)
+        return p
+
+
+class GPair64(Structure):
+    _fields_ = [("g", c_int64), ("h", c_int64)]
+
+
+class Candidate(Structure):
+    _fields_ = [("loss_chg", c_float), ("dir", c_int32), ("findex", c_int32), ("fvalue", c_float),
+                ("left_sum", GPair64), ("right_sum", GPair64),
+                ("base_weight", c_float), ("left_weight", c_float), ("right_weight", c_float),
+                ("split_gbin", c_int32)]
+
+
+class Node(Structure):
+    _fields_ = [("parent", c_int32), ("left", c_int32), ("right", c_int32), ("findex", c_int32),
+                ("fvalue", c_float), ("default_left", c_int32), ("is_leaf", c_int32), ("leaf_value", c_float),
+                ("loss_chg", c_float), ("sum_hess", c_float), ("base_weight", c_float), ("depth", c_int32)]
+
+
+_lib = None
+
+
+def build() -> str:
+    if (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < os.path.getmtime(_SRC):
+        subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-o", _LIB, _SRC,
+                        "-lm"], check=True)
+    return _LIB
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB)
+        _lib.orc_search_bin.restype = c_int32
+        _lib.orc_search_bin.argtypes = [c_float, c_void_p, c_uint32, c_uint32]
+        _lib.orc_symbol_bits.restype = c_uint32
+        _lib.orc_symbol_bits.argtypes = [c_uint64]
+        _lib.orc_ellpack_buffer_size.restype = c_uint64
+        _lib.orc_ellpack_buffer_size.argtypes = [c_uint64, c_uint64]
+        _lib.orc_ellpack_read.restype = c_uint32
+        _lib.orc_ellpack_read.argtypes = [c_void_p, c_uint64, c_uint64]
+        _lib.orc_add64_as32.restype = c_int64
+        _lib.orc_add64_as32.argtypes = [c_int64, c_int64]
+        _lib.orc_partition.restype = c_uint64
+        _lib.orc_update_tree.restype = c_int32
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return c_void_p(a.ctypes.data)
+
+
+def bin_dense(x: np.ndarray, cut_ptrs: np.ndarray, cut_values: np.ndarray) -> np.ndarray:
+    """Global bin index per entry, -1 for NaN (orc_bin_dense)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, f = x.shape
+    cp = np.ascontiguousarray(cut_ptrs, dtype=np.uint32)
+    cv = np.ascontiguousarray(cut_values, dtype=np.float32)
+    out = np.empty((n, f), dtype=np.int32)
+    lib().orc_bin_dense(_p(x), c_uint64(n), c_uint32(f), _p(cp), _p(cv), _p(out))
+    return out
+
+
+def ellpack_pack(symbols: np.ndarray, n_symbols: int) -> np.ndarray:
+    s = np.ascontiguousarray(symbols, dtype=np.uint32).ravel()
+    size = lib().orc_ellpack_buffer_size(s.size, n_symbols)
+    buf = np.zeros(size, dtype=np.uint8)
+    lib().orc_ellpack_pack(_p(s), c_uint64(s.size), c_uint64(n_symbols), _p(buf))
+    return buf
+
+
+def ellpack_read(buf: np.ndarray, n_symbols: int, n_elements: int) -> np.ndarray:
+    l = lib()
+    return np.array([l.orc_ellpack_read(_p(buf), n_symbols, i) for i in range(n_elements)], dtype=np.uint32)
+
+
+def quantiser(gpair: np.ndarray):
+    """returns (scale[4] = to_fixed_g, to_fixed_h, to_float_g, to_float_h; sums[4])"""
+    g = np.ascontiguousarray(gpair, dtype=np.float32)
+    scale = (c_double * 4)()
+    sums = (c_double * 4)()
+    lib().orc_quantiser(_p(g), c_uint64(g.shape[0]), scale, sums)
+    return np.array(scale[:], dtype=np.float64), np.array(sums[:], dtype=np.float64)
+
+
+def quantise(gpair: np.ndarray, scale: np.ndarray) -> np.ndarray:
+    g = np.ascontiguousarray(gpair, dtype=np.float32)
+    sc = (c_double * 4)(*[float(v) for v in scale])
+    out = np.empty((g.shape[0], 2), dtype=np.int64)
+    lib().orc_quantise(_p(g), c_uint64(g.shape[0]), sc, _p(out))
+    return out
+
+
+def build_hist(gbins: np.ndarray, gq: np.ndarray, ridx, total_bins: int) -> np.ndarray:
+    gb = np.ascontiguousarray(gbins, dtype=np.int32)
+    q = np.ascontiguousarray(gq, dtype=np.int64)
+    hist = np.zeros((total_bins, 2), dtype=np.int64)
+    if ridx is None:
+        lib().orc_build_hist(_p(gb), c_uint32(gb.shape[1]), _p(q), c_void_p(), c_uint64(gb.shape[0]), _p(hist))
+    else:
+        r = np.ascontiguousarray(ridx, dtype=np.uint32)
+        lib().orc_build_hist(_p(gb), c_uint32(gb.shape[1]), _p(q), _p(r), c_uint64(r.size), _p(hist))
+    return hist
+
+
+def eval_node(hist: np.ndarray, parent_sum, cut_ptrs, cut_values, param: Param, scale, feature_set=None,
+              want_gains: bool = False):
+    h = np.ascontiguousarray(hist, dtype=np.int64)
+    cp = np.ascontiguousarray(cut_ptrs, dtype=np.uint32)
+    cv = np.ascontiguousarray(cut_values, dtype=np.float32)
+    sc = (c_double * 4)(*[float(v) for v in scale])
+    out = Candidate()
+    gains = np.full((cv.size, 2), -np.inf, dtype=np.float32) if want_gains else None
+    if feature_set is not None:
+        fs = np.ascontiguousarray(feature_set, dtype=np.int32)
+        fsp, nfs = _p(fs), fs.size
+    else:
+        fsp, nfs = c_void_p(), 0
+    lib().orc_eval_node(_p(h), GPair64(int(parent_sum[0]), int(parent_sum[1])), _p(cp), _p(cv),
+                        c_uint32(cp.size - 1), fsp, c_int32(nfs), byref(param), sc, byref(out),
+                        _p(gains) if want_gains else c_void_p())
+    return (out, gains) if want_gains else out
+
+
+def partition(gbins, cut_ptrs, cut_values, ridx, findex, split_cond, default_left, is_dense_layout=True):
+    gb = np.ascontiguousarray(gbins, dtype=np.int32)
+    cp = np.ascontiguousarray(cut_ptrs, dtype=np.uint32)
+    cv = np.ascontiguousarray(cut_values, dtype=np.float32)
+    r = np.ascontiguousarray(ridx, dtype=np.uint32)
+    out = np.empty_like(r)
+    nl = lib().orc_partition(_p(gb), c_uint32(gb.shape[1]), c_int(1 if is_dense_layout else 0), _p(cp), _p(cv),
+                             _p(r), c_uint64(r.size), c_int32(findex), c_float(split_cond),
+                             c_int(1 if default_left else 0), _p(out))
+    return out, int(nl)
+
+
+def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override=None, max_nodes=None,
+                is_dense_layout=True, want_hist=False):
+    """Whole tree.  Returns dict(nodes=[Node...], position, scale, hist (optional), cands)."""
+    gb = np.ascontiguousarray(gbins, dtype=np.int32)
+    n, stride = gb.shape
+    cp = np.ascontiguousarray(cut_ptrs, dtype=np.uint32)
+    cv = np.ascontiguousarray(cut_values, dtype=np.float32)
+    g = np.ascontiguousarray(gpair, dtype=np.float32)
+    nf = cp.size - 1
+    if max_nodes is None:
+        by_d = (1 << (param.max_depth + 1)) - 1 if param.max_depth > 0 else 1 << 30
+        by_l = 2 * param.max_leaves - 1 if param.max_leaves > 0 else 1 << 30
+        max_nodes = min(by_d, by_l)
+    nodes = (Node * max_nodes)()
+    cands = (Candidate * max_nodes)()
+    pos = np.empty(n, dtype=np.int32)
+    scale_out = (c_double * 4)()
+    so = (c_double * 4)(*[float(v) for v in scale_override]) if scale_override is not None else None
+    hist = np.zeros((max_nodes, cv.size, 2), dtype=np.int64) if want_hist else None
+    nn = lib().orc_update_tree(_p(gb), c_uint64(n), c_uint32(stride), c_int(1 if is_dense_layout else 0),
+                               c_uint32(nf), _p(cp), _p(cv), _p(g), byref(param), so, nodes, c_int32(max_nodes),
+                               _p(pos), _p(hist) if want_hist else c_void_p(), cands, scale_out)
+    return dict(nodes=list(nodes[:nn]), cands=list(cands[:nn]), position=pos,
+                scale=np.array(scale_out[:], dtype=np.float64), hist=hist[:nn] if want_hist else None)
+
+
+def update_prediction_cache(nodes, position: np.ndarray, preds: np.ndarray) -> np.ndarray:
+    arr = (Node * len(nodes))(*nodes)
+    p = np.ascontiguousarray(preds, dtype=np.float32).copy()
+    pos = np.ascontiguousarray(position, dtype=np.int32)
+    lib().orc_update_prediction_cache(arr, _p(pos), c_uint64(pos.size), _p(p))
+    return p

@@ -1,0 +1,606 @@
+/*
+ * hist_oracle.c -- CPU restatement of the reference `gpu_hist` tree-updater algorithm.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (xgboost_b200/, include/) may link,
+ * import or call this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs use it, and only as the checker.
+ *
+ * Parity status: PINNED against (a) the reference's own known-answer tests restated as data in
+ * tests/golden/eval_known_answers.json (tests/cpp/tree/gpu_hist/test_evaluate_splits.cu:292-472,
+ * tests/cpp/data/test_ellpack_page.cu, test_histogram.cu:286-355) and (b) tree dumps produced by
+ * the unmodified reference built from /root/reference (tools/make_golden.py -> tests/golden/).
+ * The only step a CPU cannot reproduce bit-for-bit is `__fdividef` (device approximate
+ * division, src/tree/split_evaluator.h:122-128); this file uses IEEE division and the tests
+ * treat |delta gain| <= 4 ulp as a tie needing confirmation.
+ *
+ * Every function cites the reference file:line (relative to /root/reference) it follows.
+ * The structure is deliberately plain sequential C: it states WHAT the reference computes,
+ * not how its CUDA kernels are organised.
+ *
+ * Build: gcc -O2 -fPIC -shared -ffp-contract=off -fno-fast-math -o liboracle.so hist_oracle.c -lm
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------
+ * Parameters (src/tree/param.h:25-185 TrainParam; src/tree/updater_gpu_common.cuh:20-40)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t max_depth;       /* 0 = no limit */
+  int32_t max_leaves;      /* 0 = no limit */
+  int32_t grow_policy;     /* 0 depthwise, 1 lossguide */
+  float learning_rate;
+  float reg_lambda;
+  float reg_alpha;
+  float min_child_weight;
+  float max_delta_step;
+  float min_split_loss;
+} orc_param;
+
+/* int64 fixed-point gradient pair: include/xgboost/base.h:253-304 */
+typedef struct {
+  int64_t g, h;
+} orc_gpair64;
+
+/* split candidate: src/tree/updater_gpu_common.cuh:52-83 + expand entry expand_entry.cuh:15-34 */
+typedef struct {
+  float loss_chg;
+  int32_t dir; /* 0 = left (missing goes left), 1 = right */
+  int32_t findex;
+  float fvalue;
+  orc_gpair64 left_sum, right_sum;
+  float base_weight, left_weight, right_weight;
+  int32_t split_gbin; /* global bin index b whose scan produced the split (left = bins < b) */
+} orc_candidate;
+
+/* tree node in the layout the updater writes through RegTree::ExpandNode
+ * (src/tree/tree_model.cc:805-830, updater_gpu_hist.cu:610-655,680-684) */
+typedef struct {
+  int32_t parent, left, right; /* -1 when absent */
+  int32_t findex;
+  float fvalue; /* split condition; leaf: leaf value */
+  int32_t default_left;
+  int32_t is_leaf;
+  float leaf_value;
+  float loss_chg, sum_hess, base_weight;
+  int32_t depth;
+} orc_node;
+
+/* ------------------------------------------------------------------------------------------
+ * Q1  HistogramCuts::SearchBin  (src/common/hist_util.h:112-121; device twin
+ *     src/data/ellpack_page.cu:103-120): upper_bound over the feature's cuts, clamped to last.
+ * ---------------------------------------------------------------------------------------- */
+ORC_API int32_t orc_search_bin(float v, const float* cut_values, uint32_t beg, uint32_t end) {
+  uint32_t lo = beg, hi = end;
+  while (lo < hi) { /* first index with cut > v */
+    uint32_t mid = lo + (hi - lo) / 2;
+    if (!(v < cut_values[mid])) lo = mid + 1; else hi = mid;
+  }
+  if (lo == end) lo = end - 1;
+  return (int32_t)lo;
+}
+
+/* Dense binning: X is row-major n x F float32, NaN = missing.  out[r*F+f] = GLOBAL bin index or
+ * -1 when missing.  (ellpack_page.cu:56-134: bin = upper_bound; clamp; dense layouts then store
+ * the feature-local bin `gbin - cut_ptrs[f]`, sparse layouts the global one.) */
+ORC_API void orc_bin_dense(const float* X, uint64_t n, uint32_t F, const uint32_t* cut_ptrs,
+                           const float* cut_values, int32_t* out) {
+  for (uint64_t r = 0; r < n; ++r)
+    for (uint32_t f = 0; f < F; ++f) {
+      float v = X[r * F + f];
+      out[r * F + f] = isnan(v) ? -1 : orc_search_bin(v, cut_values, cut_ptrs[f], cut_ptrs[f + 1]);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Q3/Q4  Reference Ellpack bit packing (src/common/compressed_iterator.h:37-40,110-152,228-268).
+ * symbol_bits = max(1, ceil(log2(n_symbols))); symbols are written big-endian bit-packed
+ * starting at byte kPadding=8; buffer size rounded up to 4 bytes (min kPadding+1).
+ * ---------------------------------------------------------------------------------------- */
+ORC_API uint32_t orc_symbol_bits(uint64_t n_symbols) {
+  uint32_t bits = (uint32_t)ceil(log2((double)n_symbols));
+  return bits < 1 ? 1 : bits;
+}
+ORC_API uint64_t orc_ellpack_buffer_size(uint64_t n_elements, uint64_t n_symbols) {
+  uint64_t compressed = (uint64_t)ceil((double)(orc_symbol_bits(n_symbols) * n_elements) / 8.0);
+  uint64_t ret = (uint64_t)(ceil((double)(compressed + 8) / 4.0) * 4.0);
+  return ret < 9 ? 9 : ret;
+}
+/* AtomicWriteSymbol semantics: OR the symbol's bits MSB-first into the stream at bit offset
+ * i*symbol_bits after the padding.  buffer must be zero-initialised. */
+ORC_API void orc_ellpack_pack(const uint32_t* symbols, uint64_t n_elements, uint64_t n_symbols,
+                              uint8_t* buffer) {
+  uint32_t bits = orc_symbol_bits(n_symbols);
+  for (uint64_t i = 0; i < n_elements; ++i) {
+    uint64_t ibit_start = i * bits, ibit_end = (i + 1) * bits - 1;
+    int64_t ibyte_start = (int64_t)(ibit_start / 8), ibyte_end = (int64_t)(ibit_end / 8);
+    uint64_t sym = (uint64_t)symbols[i] << (7 - ibit_end % 8);
+    for (int64_t ib = ibyte_end; ib >= ibyte_start; --ib) {
+      buffer[8 + ib] |= (uint8_t)(sym & 0xff);
+      sym >>= 8;
+    }
+  }
+}
+/* CompressedIterator::operator[] (compressed_iterator.h:228-268): read symbol i. */
+ORC_API uint32_t orc_ellpack_read(const uint8_t* buffer, uint64_t n_symbols, uint64_t i) {
+  uint32_t bits = orc_symbol_bits(n_symbols);
+  uint64_t ibit_start = i * bits;
+  uint64_t v = 0;
+  for (uint32_t k = 0; k < bits; ++k) {
+    uint64_t b = ibit_start + k;
+    uint32_t bit = (buffer[8 + b / 8] >> (7 - b % 8)) & 1u;
+    v = (v << 1) | bit;
+  }
+  return (uint32_t)v;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * G1  Quantiser scale (src/tree/gpu_hist/quantiser.cu:30-85, src/common/deterministic.cuh:24-38)
+ * scale[0..3] = to_fixed_g, to_fixed_h, to_float_g, to_float_h.  Sums are sequential doubles
+ * here; the reference uses a device tree reduction -- results differ only if the sum lands
+ * within an ulp of a power-of-two boundary (SURVEY 7 "Quantiser scale parity").
+ * ---------------------------------------------------------------------------------------- */
+static double rounding_factor(double max_abs, uint64_t n) {
+  double delta = max_abs / (1.0 - 2.0 * (double)n * DBL_EPSILON);
+  int e;
+  (void)frexp(delta, &e);
+  return ldexp(1.0, e);
+}
+ORC_API void orc_quantiser_from_sums(const double sums[4] /* +g,+h,-g,-h */, uint64_t n,
+                                     double scale[4]) {
+  double mg = sums[0] > sums[2] ? sums[0] : sums[2];
+  double mh = sums[1] > sums[3] ? sums[1] : sums[3];
+  double rg = rounding_factor(mg, n), rh = rounding_factor(mh, n);
+  double div = (double)((int64_t)1 << 62);
+  scale[2] = rg / div;
+  scale[3] = rh / div;
+  scale[0] = 1.0 / scale[2];
+  scale[1] = 1.0 / scale[3];
+}
+ORC_API void orc_quantiser(const float* gpair, uint64_t n, double scale[4], double sums_out[4]) {
+  double s[4] = {0, 0, 0, 0};
+  for (uint64_t i = 0; i < n; ++i) { /* Clip (quantiser.cu:30-44): float clip, double sum */
+    float g = gpair[2 * i], h = gpair[2 * i + 1];
+    s[0] += (double)(g > 0 ? g : 0.0f);
+    s[1] += (double)(h > 0 ? h : 0.0f);
+    s[2] += (double)(g < 0 ? fabsf(g) : 0.0f);
+    s[3] += (double)(h < 0 ? fabsf(h) : 0.0f);
+  }
+  if (sums_out) memcpy(sums_out, s, sizeof(s));
+  orc_quantiser_from_sums(s, n, scale);
+}
+/* G2  ToFixedPoint (quantiser.cuh:65-69): (int64)((double)v * to_fixed), truncation toward 0. */
+ORC_API void orc_quantise(const float* gpair, uint64_t n, const double scale[4], orc_gpair64* out) {
+  for (uint64_t i = 0; i < n; ++i) {
+    out[i].g = (int64_t)((double)gpair[2 * i] * scale[0]);
+    out[i].h = (int64_t)((double)gpair[2 * i + 1] * scale[1]);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * H2  Histogram semantics (src/tree/gpu_hist/histogram.cu:160-183): for every row of the node and
+ * every stored entry that is not null, hist[global_bin] += gq[row].  `gbins` is n_total x stride
+ * GLOBAL bin indices, -1 = null.  hist is NOT cleared (accumulates).
+ * ---------------------------------------------------------------------------------------- */
+ORC_API void orc_build_hist(const int32_t* gbins, uint32_t stride, const orc_gpair64* gq,
+                            const uint32_t* ridx, uint64_t n_rows, orc_gpair64* hist) {
+  for (uint64_t i = 0; i < n_rows; ++i) {
+    uint32_t r = ridx ? ridx[i] : (uint32_t)i;
+    const int32_t* row = gbins + (uint64_t)r * stride;
+    for (uint32_t k = 0; k < stride; ++k) {
+      int32_t b = row[k];
+      if (b >= 0) {
+        hist[b].g += gq[r].g;
+        hist[b].h += gq[r].h;
+      }
+    }
+  }
+}
+/* H4  SubtractionTrick (src/tree/gpu_hist/histogram.cuh:208-221) */
+ORC_API void orc_subtract(const orc_gpair64* parent, const orc_gpair64* built, uint32_t n_bins,
+                          orc_gpair64* out) {
+  for (uint32_t b = 0; b < n_bins; ++b) {
+    out[b].g = parent[b].g - built[b].g;
+    out[b].h = parent[b].h - built[b].h;
+  }
+}
+/* AtomicAdd64As32 (src/tree/gpu_hist/histogram.cuh:46-59): 64-bit add decomposed into two
+ * 32-bit adds with carry -- restated for the known-answer test (test_histogram.cu:286-340). */
+ORC_API int64_t orc_add64_as32(int64_t acc, int64_t val) {
+  uint32_t lo = (uint32_t)((uint64_t)acc & 0xffffffffu), hi = (uint32_t)((uint64_t)acc >> 32);
+  uint32_t vlo = (uint32_t)((uint64_t)val & 0xffffffffu), vhi = (uint32_t)((uint64_t)val >> 32);
+  uint32_t old = lo;
+  lo += vlo;
+  uint32_t carry = (lo < old) ? 1u : 0u; /* old + vlo overflowed */
+  hi += vhi + carry;
+  return (int64_t)(((uint64_t)hi << 32) | lo);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * E3  Gain / weight arithmetic (src/tree/split_evaluator.h:73-148, src/tree/param.h:215-267)
+ * ---------------------------------------------------------------------------------------- */
+static double threshold_l1(double w, float alpha) { /* param.h:215-224, T1=double T2=float */
+  if (w > +alpha) return w - alpha;
+  if (w < -alpha) return w + alpha;
+  return 0.0;
+}
+static double calc_weight_d(const orc_param* p, double g, double h) { /* param.h:233-244 */
+  if (h < p->min_child_weight || h <= 0.0) return 0.0;
+  double dw = -threshold_l1(g, p->reg_alpha) / (h + p->reg_lambda);
+  if (p->max_delta_step != 0.0f && fabs(dw) > p->max_delta_step) dw = copysign(p->max_delta_step, dw);
+  return dw;
+}
+static double calc_gain_d(const orc_param* p, double g, double h) { /* param.h:247-267 */
+  if (h < p->min_child_weight || h <= 0.0) return 0.0;
+  if (p->max_delta_step == 0.0f) {
+    if (p->reg_alpha == 0.0f) return (g * g) / (h + p->reg_lambda);
+    double t = threshold_l1(g, p->reg_alpha);
+    return (t * t) / (h + p->reg_lambda);
+  } else {
+    double w = calc_weight_d(p, g, h);
+    double ret = -(2.0 * g * w + (h + p->reg_lambda) * (w * w));
+    if (p->reg_alpha == 0.0f) return ret;
+    return ret + p->reg_alpha * fabs(w);
+  }
+}
+/* SplitEvaluator::CalcGainGivenWeight (split_evaluator.h:130-143), no monotone constraints.
+ * Device uses __fdividef; IEEE division here (see header). */
+static float gain_given_stats(const orc_param* p, double g, double h) {
+  if (h <= 0) return 0.0f;
+  if (p->max_delta_step == 0.0f) {
+    double t = threshold_l1(g, p->reg_alpha);
+    float num = (float)(t * t);
+    float den = (float)(h + p->reg_lambda);
+    return num / den;
+  }
+  /* tree::CalcGainGivenWeight<ParamT,float>(p, (float)g, (float)h, w), param.h:227-230 */
+  float w = (float)calc_weight_d(p, g, h);
+  float fg = (float)g, fh = (float)h;
+  return -(2.0f * fg * w + (fh + p->reg_lambda) * (w * w));
+}
+static float split_gain(const orc_param* p, const double scale[4], orc_gpair64 l, orc_gpair64 r) {
+  /* CalcSplitGain (split_evaluator.h:73-92): gain(left) + gain(right) in fp32 */
+  float gl = gain_given_stats(p, (double)l.g * scale[2], (double)l.h * scale[3]);
+  float gr = gain_given_stats(p, (double)r.g * scale[2], (double)r.h * scale[3]);
+  return gl + gr;
+}
+static orc_gpair64 gp_add(orc_gpair64 a, orc_gpair64 b) { orc_gpair64 c = {a.g + b.g, a.h + b.h}; return c; }
+static orc_gpair64 gp_sub(orc_gpair64 a, orc_gpair64 b) { orc_gpair64 c = {a.g - b.g, a.h - b.h}; return c; }
+
+static void cand_init(orc_candidate* c) {
+  memset(c, 0, sizeof(*c));
+  c->loss_chg = -FLT_MAX; /* DeviceSplitCandidate default (updater_gpu_common.cuh:53-57) */
+  c->dir = 0;
+  c->findex = -1;
+  c->fvalue = 0;
+  c->split_gbin = -1;
+  c->base_weight = c->left_weight = c->right_weight = NAN;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * E1/E2/E4  Best split of one node (src/tree/gpu_hist/evaluate_splits.cu:17-32,90-146,255-311,
+ * 441-467; DeviceSplitCandidate::Update updater_gpu_common.cuh:68-83).
+ * feature_set: list of feature ids to evaluate in order (NULL = all 0..F-1).
+ * `gain_out` (optional, size total_bins*2): gain of every (bin, missing-left?0:1) for tie checks.
+ * ---------------------------------------------------------------------------------------- */
+ORC_API void orc_eval_node(const orc_gpair64* hist, orc_gpair64 parent_sum, const uint32_t* cut_ptrs,
+                           const float* cut_values, uint32_t n_features, const int32_t* feature_set,
+                           int32_t n_feature_set, const orc_param* p, const double scale[4],
+                           orc_candidate* out, float* gain_out) {
+  orc_candidate best;
+  cand_init(&best);
+  int32_t nf = feature_set ? n_feature_set : (int32_t)n_features;
+  for (int32_t fi = 0; fi < nf; ++fi) {
+    int32_t f = feature_set ? feature_set[fi] : fi;
+    uint32_t beg = cut_ptrs[f], end = cut_ptrs[f + 1];
+    orc_candidate fbest;
+    cand_init(&fbest);
+    /* ReduceFeature: missing = parent - sum(bins of f)   (evaluate_splits.cu:90-101) */
+    orc_gpair64 fsum = {0, 0};
+    for (uint32_t b = beg; b < end; ++b) fsum = gp_add(fsum, hist[b]);
+    orc_gpair64 missing = gp_sub(parent_sum, fsum);
+    orc_gpair64 running = {0, 0}; /* exclusive prefix carried across 32-bin chunks */
+    for (uint32_t cb = beg; cb < end; cb += 32) {
+      float best_gain = -INFINITY;
+      int best_t = 0; /* cub::ArgMax over 32 lanes: max value, ties -> lowest lane; all -inf -> 0 */
+      int best_ml = 1;
+      orc_gpair64 best_scan = {0, 0};
+      int any = 0;
+      for (int t = 0; t < 32; ++t) {
+        uint32_t b = cb + t;
+        int active = b < end;
+        float gain = -INFINITY;
+        int ml = 1;
+        orc_gpair64 scan = running;
+        if (active) {
+          /* LossChangeMissing (evaluate_splits.cu:17-32) */
+          orc_gpair64 left = gp_add(scan, missing);
+          float g_ml = split_gain(p, scale, left, gp_sub(parent_sum, left));
+          float g_mr = split_gain(p, scale, scan, gp_sub(parent_sum, scan));
+          ml = g_ml > g_mr;
+          gain = ml ? g_ml : g_mr;
+          if (gain_out) {
+            gain_out[2 * b] = g_ml;
+            gain_out[2 * b + 1] = g_mr;
+          }
+          running = gp_add(running, hist[b]);
+        }
+        if (!any || gain > best_gain) {
+          if (!any || gain > best_gain) {
+            best_gain = gain; best_t = t; best_ml = ml; best_scan = scan;
+          }
+          any = 1;
+        }
+      }
+      /* Only the chunk winner calls Update (evaluate_splits.cu:126-142): a winner rejected by the
+       * min_child_weight test means the whole chunk contributes nothing. */
+      uint32_t b = cb + best_t;
+      if (b < end) {
+        int32_t split_gidx = (int32_t)b - 1;
+        float fvalue = split_gidx < (int32_t)beg ? -INFINITY : cut_values[split_gidx];
+        orc_gpair64 left = best_ml ? gp_add(best_scan, missing) : best_scan;
+        orc_gpair64 right = gp_sub(parent_sum, left);
+        double lh = (double)left.h * scale[3], rh = (double)right.h * scale[3];
+        if (best_gain > fbest.loss_chg && lh >= p->min_child_weight && rh >= p->min_child_weight) {
+          fbest.loss_chg = best_gain;
+          fbest.dir = best_ml ? 0 : 1;
+          fbest.fvalue = fvalue;
+          fbest.findex = f;
+          fbest.left_sum = left;
+          fbest.right_sum = right;
+          fbest.split_gbin = (int32_t)b;
+        }
+      }
+    }
+    /* operator+ (evaluate_splits.cu:308-311): later feature wins only if strictly greater */
+    if (fbest.loss_chg > best.loss_chg) best = fbest;
+  }
+  /* post-pass (evaluate_splits.cu:441-467) */
+  double pg = (double)parent_sum.g * scale[2], ph = (double)parent_sum.h * scale[3];
+  float parent_gain = (float)calc_gain_d(p, pg, ph);
+  best.loss_chg -= parent_gain;
+  orc_gpair64 tot = gp_add(best.left_sum, best.right_sum);
+  best.base_weight = (float)calc_weight_d(p, (double)tot.g * scale[2], (double)tot.h * scale[3]);
+  best.left_weight = (float)calc_weight_d(p, (double)best.left_sum.g * scale[2], (double)best.left_sum.h * scale[3]);
+  best.right_weight = (float)calc_weight_d(p, (double)best.right_sum.g * scale[2], (double)best.right_sum.h * scale[3]);
+  *out = best;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * P2  go-left predicate (src/tree/updater_gpu_hist.cu:398-419, ellpack GetFvalue
+ * src/data/ellpack_page.cuh:147-153): fvalue = cut_values[bin]; missing -> default direction;
+ * else fvalue <= split_cond.
+ * ---------------------------------------------------------------------------------------- */
+static int32_t row_feature_gbin(const int32_t* gbins, uint32_t stride, int is_dense_layout,
+                                const uint32_t* cut_ptrs, uint64_t r, int32_t f) {
+  const int32_t* row = gbins + r * stride;
+  if (is_dense_layout) return row[f];
+  for (uint32_t k = 0; k < stride; ++k) { /* sparse ELL: BinarySearchBin over the row */
+    int32_t b = row[k];
+    if (b >= (int32_t)cut_ptrs[f] && b < (int32_t)cut_ptrs[f + 1]) return b;
+  }
+  return -1;
+}
+static int go_left(const int32_t* gbins, uint32_t stride, int is_dense_layout, const uint32_t* cut_ptrs,
+                   const float* cut_values, uint64_t r, int32_t findex, float split_cond,
+                   int default_left) {
+  int32_t b = row_feature_gbin(gbins, stride, is_dense_layout, cut_ptrs, r, findex);
+  if (b < 0) return default_left;
+  return cut_values[b] <= split_cond;
+}
+
+/* Stable partition of one node's row segment: left rows first (row order inside a node does not
+ * affect any result; the reference writes right rows reversed, row_partitioner.cuh:111-140). */
+ORC_API uint64_t orc_partition(const int32_t* gbins, uint32_t stride, int is_dense_layout,
+                               const uint32_t* cut_ptrs, const float* cut_values, const uint32_t* ridx_in,
+                               uint64_t n, int32_t findex, float split_cond, int default_left,
+                               uint32_t* ridx_out) {
+  uint64_t nl = 0;
+  for (uint64_t i = 0; i < n; ++i)
+    if (go_left(gbins, stride, is_dense_layout, cut_ptrs, cut_values, ridx_in[i], findex, split_cond, default_left)) nl++;
+  uint64_t l = 0, r = nl;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (go_left(gbins, stride, is_dense_layout, cut_ptrs, cut_values, ridx_in[i], findex, split_cond, default_left))
+      ridx_out[l++] = ridx_in[i];
+    else
+      ridx_out[r++] = ridx_in[i];
+  }
+  return nl;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * T1  Whole tree: GPUHistMakerDevice::UpdateTree (src/tree/updater_gpu_hist.cu:693-732) with
+ * InitRoot :657-691, ApplySplit :610-655, PartitionAndBuildHist :440-506, Driver driver.h:29-107,
+ * GPUExpandEntry::IsValid expand_entry.cuh:33-50, FinalisePosition :529-580.
+ *
+ * Outputs: nodes[max_nodes] (returns number of nodes), position[n_rows] (leaf id, bitwise-NOT
+ * when the row's quantised hessian is 0: updater_gpu_hist.cuh:48-56), optional per-node
+ * histograms dump (hist_dump: max_nodes x total_bins, zero where not computed) and per-node
+ * candidates (cand_dump[max_nodes]).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t nidx, depth;
+  orc_candidate c;
+  int open;
+} entry_t;
+
+static int entry_valid(const entry_t* e, const orc_param* p, int32_t num_leaves) {
+  /* GPUExpandEntry::IsValid (expand_entry.cuh:33-50); kRtEps = 1e-6f (base.h) */
+  if (e->c.loss_chg <= 1e-6f) return 0;
+  if (e->c.left_sum.h == 0 || e->c.right_sum.h == 0) return 0;
+  if (e->c.loss_chg < p->min_split_loss) return 0;
+  if (p->max_depth > 0 && e->depth == p->max_depth) return 0;
+  if (p->max_leaves > 0 && num_leaves == p->max_leaves) return 0;
+  return 1;
+}
+
+ORC_API int32_t orc_update_tree(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
+                                uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
+                                const float* gpair, const orc_param* p, const double* scale_override,
+                                orc_node* nodes, int32_t max_nodes, int32_t* position,
+                                orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4]) {
+  uint32_t total_bins = cut_ptrs[n_features];
+  double scale[4];
+  if (scale_override) memcpy(scale, scale_override, sizeof(scale));
+  else orc_quantiser(gpair, n_rows, scale, NULL);
+  if (scale_out) memcpy(scale_out, scale, sizeof(scale));
+  orc_gpair64* gq = (orc_gpair64*)malloc(sizeof(orc_gpair64) * (n_rows ? n_rows : 1));
+  orc_quantise(gpair, n_rows, scale, gq);
+
+  /* per-node state */
+  orc_gpair64** hist = (orc_gpair64**)calloc((size_t)max_nodes, sizeof(orc_gpair64*));
+  uint64_t* seg_beg = (uint64_t*)calloc((size_t)max_nodes, sizeof(uint64_t));
+  uint64_t* seg_cnt = (uint64_t*)calloc((size_t)max_nodes, sizeof(uint64_t));
+  orc_gpair64* node_sum = (orc_gpair64*)calloc((size_t)max_nodes, sizeof(orc_gpair64));
+  uint32_t* ridx = (uint32_t*)malloc(sizeof(uint32_t) * (n_rows ? n_rows : 1));
+  uint32_t* tmp = (uint32_t*)malloc(sizeof(uint32_t) * (n_rows ? n_rows : 1));
+  entry_t* queue = (entry_t*)calloc((size_t)max_nodes, sizeof(entry_t)); /* open entries by nidx */
+  for (uint64_t i = 0; i < n_rows; ++i) ridx[i] = (uint32_t)i;
+
+  int32_t n_nodes = 1, num_leaves = 1;
+  memset(&nodes[0], 0, sizeof(orc_node));
+  nodes[0].parent = nodes[0].left = nodes[0].right = -1;
+  nodes[0].is_leaf = 1;
+  nodes[0].findex = -1;
+
+  /* InitRoot */
+  orc_gpair64 root = {0, 0};
+  for (uint64_t i = 0; i < n_rows; ++i) root = gp_add(root, gq[i]);
+  node_sum[0] = root;
+  seg_beg[0] = 0;
+  seg_cnt[0] = n_rows;
+  hist[0] = (orc_gpair64*)calloc(total_bins, sizeof(orc_gpair64));
+  orc_build_hist(gbins, stride, gq, ridx, n_rows, hist[0]);
+  {
+    double rg = (double)root.g * scale[2], rh = (double)root.h * scale[3];
+    float w = (float)calc_weight_d(p, rg, rh);
+    nodes[0].sum_hess = (float)rh;
+    nodes[0].base_weight = w;
+    nodes[0].leaf_value = p->learning_rate * w;
+    nodes[0].fvalue = nodes[0].leaf_value;
+  }
+  entry_t root_e;
+  root_e.nidx = 0; root_e.depth = 0; root_e.open = 1;
+  orc_eval_node(hist[0], root, cut_ptrs, cut_values, n_features, NULL, 0, p, scale, &root_e.c, NULL);
+  if (cand_dump) cand_dump[0] = root_e.c;
+  /* driver.Push(vector) filters loss_chg > kRtEps (driver.h:42-50) */
+  int n_open = 0;
+  if (root_e.c.loss_chg > 1e-6f) { queue[0] = root_e; n_open = 1; }
+
+  while (n_open > 0) {
+    /* ---- Driver::Pop (driver.h:72-100) ---- */
+    int32_t expand[4096];
+    int n_expand = 0;
+    if (p->grow_policy == 1) { /* loss guide: single best entry; ties -> smaller nidx */
+      int32_t bi = -1;
+      for (int32_t i = 0; i < n_nodes; ++i)
+        if (queue[i].open && (bi < 0 || queue[i].c.loss_chg > queue[bi].c.loss_chg)) bi = i;
+      queue[bi].open = 0; n_open--;
+      if (entry_valid(&queue[bi], p, num_leaves)) { num_leaves++; expand[n_expand++] = bi; }
+      else break; /* Pop returned {} -> UpdateTree loop ends */
+    } else { /* depth wise: all entries of the smallest-nidx entry's depth, ascending nidx */
+      int32_t level = -1;
+      for (int32_t i = 0; i < n_nodes && n_expand < 1024; ++i) {
+        if (!queue[i].open) continue;
+        if (level < 0) level = queue[i].depth;
+        if (queue[i].depth != level) break;
+        queue[i].open = 0; n_open--;
+        if (entry_valid(&queue[i], p, num_leaves)) { num_leaves++; expand[n_expand++] = i; }
+      }
+      if (n_expand == 0) break;
+    }
+    /* ---- ApplySplit (updater_gpu_hist.cu:610-655) ---- */
+    for (int k = 0; k < n_expand; ++k) {
+      int32_t nidx = expand[k];
+      orc_candidate* c = &queue[nidx].c;
+      if (n_nodes + 2 > max_nodes) { n_open = 0; break; }
+      int32_t l = n_nodes, r = n_nodes + 1;
+      n_nodes += 2;
+      orc_gpair64 tot = gp_add(c->left_sum, c->right_sum);
+      nodes[nidx].left = l; nodes[nidx].right = r;
+      nodes[nidx].findex = c->findex;
+      nodes[nidx].fvalue = c->fvalue;
+      nodes[nidx].default_left = (c->dir == 0);
+      nodes[nidx].is_leaf = 0;
+      nodes[nidx].loss_chg = c->loss_chg;
+      nodes[nidx].sum_hess = (float)((double)tot.h * scale[3]);
+      nodes[nidx].base_weight = c->base_weight;
+      float lw = c->left_weight * p->learning_rate, rw = c->right_weight * p->learning_rate;
+      orc_node ln, rn;
+      memset(&ln, 0, sizeof(ln));
+      ln.parent = nidx; ln.left = ln.right = -1; ln.findex = -1; ln.is_leaf = 1;
+      ln.depth = queue[nidx].depth + 1;
+      rn = ln;
+      ln.leaf_value = ln.fvalue = lw; ln.base_weight = lw;
+      ln.sum_hess = (float)((double)c->left_sum.h * scale[3]);
+      rn.leaf_value = rn.fvalue = rw; rn.base_weight = rw;
+      rn.sum_hess = (float)((double)c->right_sum.h * scale[3]);
+      nodes[l] = ln; nodes[r] = rn;
+      node_sum[l] = c->left_sum; node_sum[r] = c->right_sum;
+    }
+    if (n_open == 0 && n_nodes + 2 > max_nodes) break;
+    /* ---- PartitionAndBuildHist + EvaluateSplits for the valid candidates ---- */
+    for (int k = 0; k < n_expand; ++k) {
+      int32_t nidx = expand[k];
+      int32_t depth = queue[nidx].depth;
+      /* Driver::IsChildValid (driver.h:62-66) */
+      if (p->max_depth > 0 && depth + 1 >= p->max_depth) continue;
+      if (p->max_leaves > 0 && num_leaves >= p->max_leaves) continue;
+      int32_t l = nodes[nidx].left, r = nodes[nidx].right;
+      uint64_t nl = orc_partition(gbins, stride, is_dense_layout, cut_ptrs, cut_values, ridx + seg_beg[nidx],
+                                  seg_cnt[nidx], nodes[nidx].findex, nodes[nidx].fvalue,
+                                  nodes[nidx].default_left, tmp + seg_beg[nidx]);
+      memcpy(ridx + seg_beg[nidx], tmp + seg_beg[nidx], sizeof(uint32_t) * seg_cnt[nidx]);
+      seg_beg[l] = seg_beg[nidx]; seg_cnt[l] = nl;
+      seg_beg[r] = seg_beg[nidx] + nl; seg_cnt[r] = seg_cnt[nidx] - nl;
+      /* build the child with fewer rows, subtract the other (any choice gives identical integers;
+       * the reference compares hessian sums, updater_gpu_hist.cu:461-467) */
+      int32_t build = seg_cnt[r] < seg_cnt[l] ? r : l, sub = build == l ? r : l;
+      hist[build] = (orc_gpair64*)calloc(total_bins, sizeof(orc_gpair64));
+      hist[sub] = (orc_gpair64*)calloc(total_bins, sizeof(orc_gpair64));
+      orc_build_hist(gbins, stride, gq, ridx + seg_beg[build], seg_cnt[build], hist[build]);
+      orc_subtract(hist[nidx], hist[build], total_bins, hist[sub]);
+      int32_t ch[2] = {l, r};
+      for (int s = 0; s < 2; ++s) {
+        entry_t e;
+        e.nidx = ch[s]; e.depth = depth + 1; e.open = 1;
+        orc_eval_node(hist[ch[s]], node_sum[ch[s]], cut_ptrs, cut_values, n_features, NULL, 0, p, scale, &e.c, NULL);
+        if (cand_dump) cand_dump[ch[s]] = e.c;
+        if (e.c.loss_chg > 1e-6f) { queue[ch[s]] = e; n_open++; }
+      }
+    }
+  }
+
+  /* ---- FinalisePosition: walk every row from the root to its leaf ---- */
+  if (position) {
+    for (uint64_t r = 0; r < n_rows; ++r) {
+      int32_t nidx = 0;
+      while (!nodes[nidx].is_leaf) {
+        int gl = go_left(gbins, stride, is_dense_layout, cut_ptrs, cut_values, r, nodes[nidx].findex,
+                         nodes[nidx].fvalue, nodes[nidx].default_left);
+        nidx = gl ? nodes[nidx].left : nodes[nidx].right;
+      }
+      position[r] = gq[r].h != 0 ? nidx : ~nidx;
+    }
+  }
+  if (hist_dump) {
+    for (int32_t i = 0; i < n_nodes; ++i)
+      if (hist[i]) memcpy(hist_dump + (uint64_t)i * total_bins, hist[i], sizeof(orc_gpair64) * total_bins);
+  }
+  for (int32_t i = 0; i < max_nodes; ++i) free(hist[i]);
+  free(hist); free(seg_beg); free(seg_cnt); free(node_sum); free(ridx); free(tmp); free(queue); free(gq);
+  return n_nodes;
+}
+
+/* A3  UpdatePredictionCache (updater_gpu_hist.cu:582-608): pred[i] += leaf_value[decode(pos[i])] */
+ORC_API void orc_update_prediction_cache(const orc_node* nodes, const int32_t* position, uint64_t n, float* preds) {
+  for (uint64_t i = 0; i < n; ++i) {
+    int32_t nidx = position[i] < 0 ? ~position[i] : position[i];
+    preds[i] += nodes[nidx].leaf_value;
+  }
+}

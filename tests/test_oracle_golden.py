@@ -1,0 +1,195 @@
+"""CPU tests: pin the oracle (oracle/hist_oracle.c) against the reference's own known answers.
+These run without a GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+
+
+def _dummy_scale():
+    # DummyRoundingFactor (test_evaluate_splits.cu:21-27): quantiser built from one pair {1000, 1000}
+    scale, _ = orc.quantiser(np.array([[1000.0, 1000.0]], dtype=np.float32))
+    return scale
+
+
+def _to_fixed(pairs, scale, as_float32=True):
+    a = np.array(pairs, dtype=np.float64).reshape(-1, 2)
+    if as_float32:  # ConvertToInteger goes through GradientPair (float)
+        return orc.quantise(a.astype(np.float32), scale)
+    out = np.empty((a.shape[0], 2), dtype=np.int64)
+    out[:, 0] = (a[:, 0] * scale[0]).astype(np.int64)
+    out[:, 1] = (a[:, 1] * scale[1]).astype(np.int64)
+    return out
+
+
+def test_dummy_quantiser_scale():
+    scale = _dummy_scale()
+    # max=1000 -> delta just above 1000 -> M = 1024; to_float = 1024 / 2^62 = 2^-52
+    assert scale[2] == 2.0 ** -52 and scale[3] == 2.0 ** -52
+    assert scale[0] == 2.0 ** 52
+
+
+def test_quantiser_round_trip():
+    # test_histogram.cu:341-355: 16 samples of {1, 1} survive the round trip exactly
+    g = np.ones((16, 2), dtype=np.float32)
+    scale, sums = orc.quantiser(g)
+    assert sums[0] == 16.0 and sums[2] == 0.0
+    q = orc.quantise(g, scale)
+    assert np.all(q[:, 0] * scale[2] == 1.0) and np.all(q[:, 1] * scale[3] == 1.0)
+
+
+def test_rounding_factor_power_of_two_edge():
+    # frexp semantics: an exact power of two is bumped to the next one (deterministic.cuh:24-38)
+    scale, _ = orc.quantiser(np.array([[1024.0, 0.5]], dtype=np.float32))
+    assert scale[2] * 2.0 ** 62 == 2048.0
+    scale0, _ = orc.quantiser(np.zeros((4, 2), dtype=np.float32))
+    assert scale0[2] * 2.0 ** 62 == 1.0  # frexp(0) -> exp 0
+
+
+def test_evaluate_known_answers(golden_dir):
+    spec = json.load(open(os.path.join(golden_dir, "eval_known_answers.json")))
+    scale = _dummy_scale()
+    p = orc.Param.make(**spec["param"])
+    for case in spec["cases"]:
+        hist = _to_fixed(case["hist"], scale)
+        parent = _to_fixed([case["parent"]], scale, as_float32=False)[0]
+        c = orc.eval_node(hist, parent, case["cut_ptrs"], case["cut_values"], p, scale,
+                          feature_set=case["feature_set"])
+        e = case["expect"]
+        assert c.findex == e["findex"], case["name"]
+        if "fvalue" in e:
+            assert c.fvalue == e["fvalue"], case["name"]
+        if "dir" in e:
+            assert c.dir == e["dir"], case["name"]
+        if e.get("sum_is_parent"):
+            assert (c.left_sum.g + c.right_sum.g, c.left_sum.h + c.right_sum.h) == tuple(parent)
+        if "left_sum" in e:
+            ls = _to_fixed([e["left_sum"]], scale, as_float32=False)[0]
+            rs = _to_fixed([e["right_sum"]], scale, as_float32=False)[0]
+            assert (c.left_sum.g, c.left_sum.h) == tuple(ls), case["name"]
+            assert (c.right_sum.g, c.right_sum.h) == tuple(rs), case["name"]
+        if e.get("loss_chg_negative"):
+            assert c.loss_chg < 0.0
+
+
+def test_add64_as32_known_answers():
+    # test_histogram.cu:286-340: mixed signs, values beyond 32 bits in both directions
+    acc = 0
+    for i in range(1024):
+        acc = orc.lib().orc_add64_as32(acc, i if i % 2 == 0 else -i)
+    assert acc == sum(i if i % 2 == 0 else -i for i in range(1024))
+    acc = 0
+    for _ in range(1024):
+        acc = orc.lib().orc_add64_as32(acc, (2 ** 32 - 1) // 2)
+    assert acc == 1024 * ((2 ** 32 - 1) // 2) and acc > 2 ** 32 - 1
+    acc = 0
+    for _ in range(1024):
+        acc = orc.lib().orc_add64_as32(acc, -(2 ** 31) // 2)
+    assert acc == 1024 * (-(2 ** 31) // 2) and acc < -(2 ** 31)
+
+
+# ---- RandomDataGenerator(rows, cols, sparsity).Seed(seed) restated (tests/cpp/helpers.cc:221-224,354-397)
+class _LCG:
+    def __init__(self, seed):
+        self.mod = (1 << 32) - 1
+        self.state = seed % self.mod
+
+    def __call__(self):
+        self.state = (61 * self.state + (3 if self.state == 0 else 0)) % self.mod
+        return self.state
+
+
+def _uniform(lcg):
+    # SimpleRealUniformDistribution<float>(0, 1): one draw, float(draw) / float(2^32)
+    return max(np.float32(np.float32(lcg()) / np.float32(4294967296.0)), np.float32(0.0))
+
+
+def _generate_csr(rows, cols, sparsity, seed):
+    lcg = _LCG(seed)
+    out = np.full((rows, cols), np.nan, dtype=np.float32)
+    for i in range(rows):
+        for j in range(cols):
+            g = _uniform(lcg)
+            if g >= np.float32(sparsity):
+                out[i, j] = _uniform(lcg)
+    return out
+
+
+def test_ellpack_dense_known_answer(golden_dir):
+    spec = json.load(open(os.path.join(golden_dir, "ellpack_known_answers.json")))
+    x = _generate_csr(spec["n_rows"], spec["n_cols"], 0.0, spec["seed"])
+    assert not np.isnan(x).any()
+    gb = orc.bin_dense(x, spec["cut_ptrs"], spec["cut_values"])
+    want = np.array(spec["dense_global_bins"], dtype=np.int32).reshape(spec["n_rows"], spec["n_cols"])
+    assert np.array_equal(gb, want)
+    # symbols are feature-local; NumSymbols == 3; pack / read round trip through the reference bit layout
+    local = gb - np.array(spec["cut_ptrs"][:-1], dtype=np.int32)[None, :]
+    assert local.max() + 1 == spec["dense_n_symbols"]
+    buf = orc.ellpack_pack(local.astype(np.uint32), spec["dense_n_symbols"])
+    assert orc.lib().orc_symbol_bits(3) == 2
+    assert np.array_equal(orc.ellpack_read(buf, 3, local.size), local.ravel().astype(np.uint32))
+    # big-endian bit order: first four 2-bit symbols of row 0 live in byte 8
+    assert buf[8] == (local[0, 0] << 6 | local[0, 1] << 4 | local[0, 2] << 2 | local[0, 3])
+
+
+def test_ellpack_sparse_known_answer(golden_dir):
+    spec = json.load(open(os.path.join(golden_dir, "ellpack_known_answers.json")))
+    x = _generate_csr(spec["n_rows"], spec["n_cols"], spec["sparse_sparsity"], spec["seed"])
+    gb = orc.bin_dense(x, spec["cut_ptrs"], spec["cut_values"])
+    stride, null = spec["sparse_row_stride"], spec["sparse_null"]
+    ell = np.full((spec["n_rows"], stride), null, dtype=np.int64)
+    for i in range(spec["n_rows"]):
+        present = gb[i][gb[i] >= 0]
+        assert present.size <= stride
+        ell[i, : present.size] = present
+    assert (np.sum(gb >= 0, axis=1).max()) == stride
+    assert np.array_equal(ell.ravel(), np.array(spec["sparse_symbols"]))
+    assert orc.lib().orc_symbol_bits(25) == 5
+    assert orc.lib().orc_ellpack_buffer_size(0, 1) == 9  # empty page: kPadding + 1 (test_ellpack_page.cu:30-34)
+
+
+def test_partition_semantics():
+    # test_row_partitioner.cu:60-108: left rows first, counts right
+    cut_ptrs = np.array([0, 2], dtype=np.uint32)
+    cut_values = np.array([0.5, 2.0], dtype=np.float32)
+    x = np.array([[0.0], [1.0], [0.0], [1.0], [0.0], [1.0]], dtype=np.float32)
+    gb = orc.bin_dense(x, cut_ptrs, cut_values)
+    out, nl = orc.partition(gb, cut_ptrs, cut_values, np.arange(6), 0, 0.5, True)
+    assert nl == 3 and list(out) == [0, 2, 4, 1, 3, 5]
+    out, nl = orc.partition(gb, cut_ptrs, cut_values, np.array([3, 4, 5]), 0, -np.inf, True)
+    assert nl == 0 and list(out) == [3, 4, 5]
+
+
+def test_tree_basic_invariants():
+    from tests.helpers import make_cuts, make_regression, squared_error_gpair
+    x, y = make_regression(2000, 6, seed=1)
+    cp, cv = make_cuts(x, 16)
+    gb = orc.bin_dense(x, cp, cv)
+    gpair = squared_error_gpair(np.zeros_like(y), y)
+    p = orc.Param.make(max_depth=4)
+    t = orc.update_tree(gb, cp, cv, gpair, p, want_hist=True)
+    nodes = t["nodes"]
+    assert nodes[0].parent == -1 and len(nodes) % 2 == 1
+    gq = orc.quantise(gpair, t["scale"])
+    pos = t["position"]
+    assert pos.min() >= 0  # hessian is 1 everywhere
+    for i, nd in enumerate(nodes):
+        if nd.is_leaf:
+            continue
+        # children hessians add up; histogram of a node sums to its gradient sum per feature
+        assert abs(nodes[nd.left].sum_hess + nodes[nd.right].sum_hess - nd.sum_hess) <= 1e-3 * nd.sum_hess
+        assert nd.depth < 4 and nd.loss_chg > 1e-6
+    # every leaf's rows agree with a manual traversal
+    for r in range(0, 2000, 97):
+        n = 0
+        while not nodes[n].is_leaf:
+            b = gb[r, nodes[n].findex]
+            n = nodes[n].left if cv[b] <= nodes[n].fvalue else nodes[n].right
+        assert pos[r] == n
+    # root histogram: every feature's bins sum to the root sum
+    h0 = t["hist"][0]
+    for f in range(6):
+        assert tuple(h0[cp[f]:cp[f + 1]].sum(axis=0)) == tuple(gq.sum(axis=0))

@@ -1,0 +1,18 @@
+"""xgboost_b200 -- Blackwell-native (sm_100a) `hist` tree updater behind the reference's
+TreeUpdater / EllpackPage interface.  Only the hot path lives here:
+
+  csrc/          hand-written CUDA kernels + the C ABI (include/b200hist.h) -> lib/libb200hist.so
+  lib.py         ctypes binding of the C ABI
+  updater.py     host-side mirror of the reference interface (HistogramCuts, EllpackPage,
+                 GPUHistMaker, RegTree)
+  components.py  per-stage entry points used by the parity tests
+  training.py    a minimal boosting loop (objective + prediction cache) to drive the updater
+
+There is no CPU fallback: without the built library or without a CUDA device every compute call
+raises B200HistError.
+"""
+from .lib import B200HistError, TrainParam, launch_count  # noqa: F401
+from .updater import EllpackPage, GPUHistMaker, HistogramCuts, RegTree  # noqa: F401
+
+__all__ = ["B200HistError", "TrainParam", "EllpackPage", "GPUHistMaker", "HistogramCuts", "RegTree",
+           "launch_count"]

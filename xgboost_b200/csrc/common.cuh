@@ -1,0 +1,249 @@
+// Internal shared declarations for libb200hist.so (sm_100a only).
+// Nothing here crosses the C ABI (include/b200hist.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "b200hist.h"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// Errors: C++ exceptions inside, converted to status + thread-local message at the ABI.
+// Mirrors API_BEGIN/API_END of the reference (src/c_api/c_api_error.h:27-42).
+// ---------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+void SetLastError(const std::string& msg);
+
+#define B200_CHECK(cond, msg)                                                              \
+  do {                                                                                     \
+    if (!(cond)) throw ::b200::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + \
+                                     ": check failed: " #cond ": " + (msg));               \
+  } while (0)
+
+#define B200_CUDA(expr)                                                                      \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      throw ::b200::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": CUDA " + \
+                          cudaGetErrorName(e__) + ": " + cudaGetErrorString(e__) + " in " #expr); \
+  } while (0)
+
+#define B200_API_BEGIN() try {
+#define B200_API_END()                       \
+  }                                          \
+  catch (std::exception const& e__) {        \
+    ::b200::SetLastError(e__.what());        \
+    return -1;                               \
+  }                                          \
+  return 0;
+
+extern std::atomic<uint64_t> g_launch_count;
+// Count + check every kernel launch.
+#define B200_LAUNCHED()                          \
+  do {                                           \
+    ::b200::g_launch_count.fetch_add(1);         \
+    B200_CUDA(cudaGetLastError());               \
+  } while (0)
+
+struct DeviceGuard {
+  int prev{-1};
+  explicit DeviceGuard(int dev) {
+    B200_CUDA(cudaGetDevice(&prev));
+    if (prev != dev) B200_CUDA(cudaSetDevice(dev));
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+template <typename T>
+T* DevAlloc(size_t n) {
+  void* p = nullptr;
+  B200_CUDA(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+  return static_cast<T*>(p);
+}
+
+int NumSMs(int device);
+
+// ---------------------------------------------------------------------------------------------
+// Ellpack page (ours).  bins[n_rows][row_bytes], feature-local symbols, see include/b200hist.h.
+// ---------------------------------------------------------------------------------------------
+struct EllView {
+  const uint8_t* bins;
+  const uint32_t* cut_ptrs;  // device, n_features+1
+  const float* cut_values;   // device, total_bins
+  uint64_t n_rows;
+  uint32_t n_features;
+  uint32_t total_bins;
+  uint32_t row_bytes;    // multiple of 16
+  uint32_t bin_bytes;    // 1 or 2
+  uint32_t null_symbol;  // symbol meaning "missing"; 0xFFFFFFFF when the page has no missing
+};
+
+}  // namespace b200
+
+struct b200hist_ellpack_s {
+  int device{0};
+  uint64_t n_rows{0};
+  uint32_t n_features{0};
+  uint32_t total_bins{0};
+  uint32_t row_bytes{0};
+  uint32_t bin_bytes{1};
+  uint32_t null_symbol{0xFFFFFFFFu};
+  uint32_t max_feature_bins{0};
+  bool has_missing{false};
+  std::vector<uint32_t> cut_ptrs;
+  std::vector<float> cut_values;
+  uint32_t* d_cut_ptrs{nullptr};
+  float* d_cut_values{nullptr};
+  uint8_t* d_bins{nullptr};
+  b200::EllView View() const {
+    return b200::EllView{d_bins, d_cut_ptrs, d_cut_values, n_rows, n_features, total_bins,
+                         row_bytes, bin_bytes, null_symbol};
+  }
+};
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// Tree-building state shared by the kernels.  All of it lives in device memory so a whole tree
+// is built without the host reading anything back (no per-level sync).
+// ---------------------------------------------------------------------------------------------
+constexpr int kPartTile = 2048;       // rows per partition tile (64 flag words)
+constexpr int kHistTile = 512;        // rows per histogram tile
+constexpr int kMaxLevelNodes = 4096;  // nodes expanded in one step
+
+struct NodeDev {
+  int32_t parent, left, right, depth;
+  int32_t findex;
+  float fvalue;
+  int32_t default_left;
+  int32_t is_leaf;
+  float leaf_value, loss_chg, sum_hess, base_weight;
+  int64_t sum_g, sum_h;  // quantised gradient sum of the node's rows
+  uint32_t seg_begin, seg_count;
+  int32_t seg_buf;       // which ridx buffer holds the node's row segment
+  int32_t partitioned;   // rows have been handed to the children
+  int32_t split_lbin;    // go left iff feature-local bin < split_lbin
+  int32_t cand_open;     // has a queued expand entry (driver.h Push filter passed)
+};
+
+struct PartEntry {
+  int32_t nidx, left, right;
+  int32_t findex;
+  int32_t split_lbin;
+  int32_t default_left;
+  uint32_t begin, count;
+  uint32_t tile_begin;
+  int32_t src_buf;
+  uint32_t n_left;  // filled by the scan kernel
+  uint32_t pad;
+};
+
+struct BuildEntry {
+  int32_t nidx;
+  int32_t buf;
+  uint32_t begin, count;
+  uint32_t tile_begin;
+  uint32_t pad;
+};
+
+struct SubEntry {
+  int32_t parent, built, sub;
+};
+
+struct TreeState {
+  int32_t n_nodes;
+  int32_t num_leaves;
+  int32_t level_begin, level_end;  // node-id range of the open level (depth-wise)
+  int32_t n_part;
+  int32_t n_build;
+  int32_t n_sub;
+  int32_t n_eval;
+  uint32_t part_tiles;
+  uint32_t build_tiles;
+  uint32_t final_tiles;
+  int32_t n_final;
+  unsigned long long row_visits;
+  int32_t stopped;  // lossguide: Pop() returned an invalid top -> growth ended
+  int32_t pad;
+};
+
+struct QuantDev {
+  double to_fixed_g, to_fixed_h, to_float_g, to_float_h;
+  double sums[4];
+  long long root_g, root_h;
+};
+
+struct ParamDev {
+  int32_t max_depth, max_leaves, grow_policy;
+  float learning_rate, reg_lambda, reg_alpha, min_child_weight, max_delta_step, min_split_loss;
+};
+
+inline ParamDev ToParamDev(const b200hist_train_param& p) {
+  return ParamDev{p.max_depth, p.max_leaves, p.grow_policy, p.learning_rate, p.reg_lambda,
+                  p.reg_alpha, p.min_child_weight, p.max_delta_step, p.min_split_loss};
+}
+
+// Feature group: a contiguous feature range whose bins fit the shared-memory histogram.
+struct GroupDesc {
+  uint32_t f_begin, f_end;      // features
+  uint32_t bin_begin, bin_end;  // global bins
+  uint32_t byte_begin;          // byte offset of f_begin inside a row (multiple of 4)
+  uint32_t n_words;             // 32-bit words per row covering the group
+};
+
+// Per-(node, feature) best split produced by the feature scan.
+struct FeatCand {
+  float loss_chg;
+  int32_t dir;
+  int32_t gbin;  // -1 = none
+  int32_t pad;
+  long long left_g, left_h;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Kernel launchers (one per SURVEY.md 8(a) row)
+// ---------------------------------------------------------------------------------------------
+// quantise.cu
+void LaunchQuantise(const float* gpair, uint64_t n, QuantDev* q, b200hist_gpair64* gq, uint32_t* ridx_init,
+                    double* partials /* >= 4*kQuantBlocks */, unsigned int* counter, int num_sms, cudaStream_t s);
+constexpr int kQuantBlocksPerSM = 4;
+
+// histogram.cu
+size_t HistSmemBytesFor(uint32_t group_bins);
+uint32_t HistMaxGroupBins(int device);
+void PrepareHistKernels(int device);
+void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint32_t* ridx0, const uint32_t* ridx1,
+                     const BuildEntry* build, const uint32_t* tile_seg, const TreeState* ts,
+                     const GroupDesc* groups_dev, const std::vector<GroupDesc>& groups_host,
+                     b200hist_gpair64* hist, int num_sms, cudaStream_t s);
+void LaunchSubtract(const SubEntry* sub, const TreeState* ts, b200hist_gpair64* hist, uint32_t total_bins,
+                    int num_sms, cudaStream_t s);
+void LaunchSubtractFlat(const b200hist_gpair64* parent, const b200hist_gpair64* built, b200hist_gpair64* out,
+                        uint64_t n_bins, cudaStream_t s);
+std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, uint32_t max_group_bins);
+
+// evaluate.cu
+void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = node id */,
+                    const int32_t* eval_nodes, const TreeState* ts /* n_eval */, int32_t max_eval,
+                    const NodeDev* nodes, const int32_t* feature_set, int32_t n_feature_set,
+                    const ParamDev& p, const QuantDev* q, FeatCand* scratch, b200hist_candidate* cand,
+                    NodeDev* nodes_mut, int num_sms, cudaStream_t s);
+
+// partition.cu
+void LaunchPartitionCount(const EllView& ell, const uint32_t* ridx0, const uint32_t* ridx1, const PartEntry* part,
+                          const uint32_t* tile_seg, const TreeState* ts, uint32_t* flags, uint32_t* tile_left,
+                          int num_sms, cudaStream_t s);
+void LaunchPartitionScatter(const uint32_t* ridx0, const uint32_t* ridx1, uint32_t* out0, uint32_t* out1,
+                            const PartEntry* part, const uint32_t* tile_seg, const TreeState* ts,
+                            const uint32_t* flags, const uint32_t* tile_left_off, int num_sms, cudaStream_t s);
+
+}  // namespace b200

@@ -1,0 +1,223 @@
+// Ellpack page: quantile binning of raw feature values into the HBM-resident bin matrix.
+//
+// Replaces (reference paths relative to /root/reference):
+//   HistogramCuts::SearchBin                     src/common/hist_util.h:112-121
+//   CompressBinEllpackKernel / WriteCompressed.. src/data/ellpack_page.cu:56-134,240-298
+//   CalcNumSymbols                               src/data/ellpack_page.cu:140-183
+//   CompressedIterator (import only)             src/common/compressed_iterator.h:228-268
+//
+// Layout: bins[n_rows][row_bytes], one feature-local symbol per feature, uint8 when every feature
+// needs <= 256 symbols (incl. the null symbol when the page may hold missing values) else uint16.
+// row_bytes is padded to 16 so that every row is 16-byte aligned: a row (or a 16-byte aligned
+// slice of it) is a legal source for cp.async.bulk (TMA 1-D bulk copy) and for 128-bit loads.
+// The reference's own 8-bit layout starts at byte 8 (kPadding) and is therefore only 8-byte
+// aligned -- which is why we keep our own copy instead of reading the reference buffer in place.
+#include "common.cuh"
+
+namespace b200 {
+
+std::atomic<uint64_t> g_launch_count{0};
+static thread_local std::string g_last_error;
+void SetLastError(const std::string& msg) { g_last_error = msg; }
+
+int NumSMs(int device) {
+  int n = 0;
+  B200_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+  return n;
+}
+
+// One thread per (row, 4-feature word): four upper_bound searches, one 32-bit store (uint8 bins).
+// Reads of X are coalesced along the feature dimension; cut values are L1/L2 resident (<= 256 KiB
+// for the headline 256x256 configuration).
+template <typename BinT>
+__global__ void __launch_bounds__(256) BinDenseKernel(const float* __restrict__ x, uint64_t n, uint64_t ld,
+                                                       uint32_t n_features, const uint32_t* __restrict__ cut_ptrs,
+                                                       const float* __restrict__ cut_values, uint8_t* __restrict__ bins,
+                                                       uint64_t row_begin, uint32_t row_bytes, uint32_t null_symbol) {
+  constexpr int kPerWord = 4 / sizeof(BinT);
+  const uint32_t words_per_row = row_bytes / 4;
+  const uint64_t total = n * words_per_row;
+  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = idx / words_per_row;
+    uint32_t w = (uint32_t)(idx - r * words_per_row);
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < kPerWord; ++k) {
+      uint32_t f = w * kPerWord + k;
+      uint32_t sym = 0;
+      if (f < n_features) {
+        float v = x[r * ld + f];
+        if (isnan(v)) {
+          sym = null_symbol;
+        } else {
+          uint32_t beg = cut_ptrs[f], end = cut_ptrs[f + 1];
+          uint32_t lo = beg, hi = end;  // first cut strictly greater than v
+          while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (!(v < cut_values[mid])) lo = mid + 1; else hi = mid;
+          }
+          if (lo == end) lo = end - 1;
+          sym = lo - beg;
+        }
+      }
+      packed |= (sym & ((1u << (8 * sizeof(BinT))) - 1u)) << (8 * sizeof(BinT) * k);
+    }
+    *reinterpret_cast<uint32_t*>(bins + (row_begin + r) * row_bytes + 4ull * w) = packed;
+  }
+}
+
+// Decode the reference's big-endian bit-packed symbol stream into our layout.
+template <typename BinT>
+__global__ void __launch_bounds__(256) ImportReferenceKernel(const uint8_t* __restrict__ buf, uint64_t n_rows,
+                                                              uint32_t n_features, uint32_t symbol_bits,
+                                                              uint32_t ref_null, uint8_t* __restrict__ bins,
+                                                              uint32_t row_bytes, uint32_t null_symbol) {
+  const uint64_t total = n_rows * n_features;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t bit0 = i * symbol_bits;
+    uint64_t v = 0;
+    uint64_t byte0 = bit0 >> 3;
+    uint32_t shift = (uint32_t)(bit0 & 7);
+    uint32_t nbytes = (shift + symbol_bits + 7) >> 3;                 // bytes that hold the symbol
+    for (uint32_t k = 0; k < nbytes; ++k) v = (v << 8) | buf[8 + byte0 + k];  // kPadding = 8
+    uint32_t sym = (uint32_t)((v >> (8 * nbytes - shift - symbol_bits)) & ((1ull << symbol_bits) - 1ull));
+    uint64_t r = i / n_features;
+    uint32_t f = (uint32_t)(i - r * n_features);
+    if (sym == ref_null) sym = null_symbol;
+    reinterpret_cast<BinT*>(bins + r * row_bytes)[f] = (BinT)sym;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char* b200hist_last_error(void) { return g_last_error.c_str(); }
+int b200hist_version(void) { return B200HIST_VERSION; }
+uint64_t b200hist_launch_count(void) { return g_launch_count.load(); }
+
+int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features, const uint32_t* cut_ptrs_host,
+                            const float* cut_values_host, int has_missing, b200hist_ellpack_t* out) {
+  B200_API_BEGIN();
+  B200_CHECK(out != nullptr && cut_ptrs_host != nullptr && cut_values_host != nullptr, "null argument");
+  B200_CHECK(n_features > 0, "n_features must be positive");
+  B200_CHECK(n_rows < (1ull << 32), "RowIndexT is uint32 (row_partitioner.cuh:22): n_rows must be < 2^32");
+  DeviceGuard guard(device);
+  auto* e = new b200hist_ellpack_s();
+  e->device = device;
+  e->n_rows = n_rows;
+  e->n_features = n_features;
+  e->cut_ptrs.assign(cut_ptrs_host, cut_ptrs_host + n_features + 1);
+  e->total_bins = e->cut_ptrs[n_features];
+  B200_CHECK(e->cut_ptrs[0] == 0, "cut_ptrs[0] must be 0");
+  e->cut_values.assign(cut_values_host, cut_values_host + e->total_bins);
+  uint32_t mx = 0;
+  for (uint32_t f = 0; f < n_features; ++f) {
+    B200_CHECK(e->cut_ptrs[f + 1] > e->cut_ptrs[f], "every feature needs at least one bin");
+    mx = std::max(mx, e->cut_ptrs[f + 1] - e->cut_ptrs[f]);
+  }
+  e->max_feature_bins = mx;
+  e->has_missing = has_missing != 0;
+  uint32_t n_symbols = mx + (e->has_missing ? 1 : 0);  // CalcNumSymbols (ellpack_page.cu:140-183)
+  B200_CHECK(n_symbols <= 65536, "more than 65536 symbols per feature is not supported");
+  e->bin_bytes = n_symbols <= 256 ? 1 : 2;
+  e->null_symbol = e->has_missing ? (e->bin_bytes == 1 ? 0xFFu : 0xFFFFu) : 0xFFFFFFFFu;
+  if (e->has_missing && e->null_symbol < mx) e->null_symbol = mx;  // unreachable; keeps the invariant explicit
+  e->row_bytes = (n_features * e->bin_bytes + 15u) & ~15u;
+  e->d_cut_ptrs = DevAlloc<uint32_t>(n_features + 1);
+  e->d_cut_values = DevAlloc<float>(e->total_bins);
+  B200_CUDA(cudaMemcpy(e->d_cut_ptrs, e->cut_ptrs.data(), sizeof(uint32_t) * (n_features + 1), cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(e->d_cut_values, e->cut_values.data(), sizeof(float) * e->total_bins, cudaMemcpyHostToDevice));
+  e->d_bins = DevAlloc<uint8_t>(n_rows * (uint64_t)e->row_bytes + 16);
+  B200_CUDA(cudaMemset(e->d_bins, 0, n_rows * (uint64_t)e->row_bytes + 16));
+  *out = e;
+  B200_API_END();
+}
+
+int b200hist_ellpack_destroy(b200hist_ellpack_t e) {
+  B200_API_BEGIN();
+  if (e) {
+    DeviceGuard guard(e->device);
+    cudaFree(e->d_cut_ptrs);
+    cudaFree(e->d_cut_values);
+    cudaFree(e->d_bins);
+    delete e;
+  }
+  B200_API_END();
+}
+
+int b200hist_ellpack_push_dense(b200hist_ellpack_t e, uint64_t row_begin, const float* x_dev, uint64_t n,
+                                uint64_t ld, void* stream) {
+  B200_API_BEGIN();
+  B200_CHECK(e != nullptr && x_dev != nullptr, "null argument");
+  B200_CHECK(row_begin + n <= e->n_rows, "batch exceeds the page");
+  B200_CHECK(ld >= e->n_features, "leading dimension smaller than n_features");
+  if (n == 0) return 0;
+  DeviceGuard guard(e->device);
+  auto s = static_cast<cudaStream_t>(stream);
+  uint64_t total = n * (e->row_bytes / 4);
+  int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
+  if (e->bin_bytes == 1) {
+    BinDenseKernel<uint8_t><<<blocks, 256, 0, s>>>(x_dev, n, ld, e->n_features, e->d_cut_ptrs, e->d_cut_values,
+                                                  e->d_bins, row_begin, e->row_bytes, e->null_symbol);
+  } else {
+    BinDenseKernel<uint16_t><<<blocks, 256, 0, s>>>(x_dev, n, ld, e->n_features, e->d_cut_ptrs, e->d_cut_values,
+                                                   e->d_bins, row_begin, e->row_bytes, e->null_symbol);
+  }
+  B200_LAUNCHED();
+  B200_API_END();
+}
+
+int b200hist_ellpack_import_reference(b200hist_ellpack_t e, const uint8_t* gidx_buffer_dev, uint32_t row_stride,
+                                      uint32_t n_symbols, int is_dense, void* stream) {
+  B200_API_BEGIN();
+  B200_CHECK(e != nullptr && gidx_buffer_dev != nullptr, "null argument");
+  B200_CHECK(row_stride == e->n_features, "only dense-layout reference pages (row_stride == n_features) can be imported");
+  uint32_t bits = 1;
+  while ((1ull << bits) < n_symbols) ++bits;  // SymbolBits (compressed_iterator.h:37-40)
+  // dense & no missing: n_symbols = max bins/feature; relatively dense: +1 with null = n_symbols-1
+  uint32_t ref_null = is_dense ? 0xFFFFFFFFu : n_symbols - 1;
+  B200_CHECK(is_dense || e->has_missing, "page with missing values needs an ellpack created with has_missing=1");
+  DeviceGuard guard(e->device);
+  auto s = static_cast<cudaStream_t>(stream);
+  uint64_t total = e->n_rows * (uint64_t)e->n_features;
+  if (total == 0) return 0;
+  int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
+  if (e->bin_bytes == 1) {
+    ImportReferenceKernel<uint8_t><<<blocks, 256, 0, s>>>(gidx_buffer_dev, e->n_rows, e->n_features, bits, ref_null,
+                                                         e->d_bins, e->row_bytes, e->null_symbol);
+  } else {
+    ImportReferenceKernel<uint16_t><<<blocks, 256, 0, s>>>(gidx_buffer_dev, e->n_rows, e->n_features, bits, ref_null,
+                                                          e->d_bins, e->row_bytes, e->null_symbol);
+  }
+  B200_LAUNCHED();
+  B200_API_END();
+}
+
+int b200hist_ellpack_info(b200hist_ellpack_t e, uint64_t* n_rows, uint32_t* n_features, uint32_t* total_bins,
+                          uint32_t* row_bytes, uint32_t* bin_bytes, uint32_t* null_symbol, const void** bins_dev) {
+  B200_API_BEGIN();
+  B200_CHECK(e != nullptr, "null ellpack");
+  if (n_rows) *n_rows = e->n_rows;
+  if (n_features) *n_features = e->n_features;
+  if (total_bins) *total_bins = e->total_bins;
+  if (row_bytes) *row_bytes = e->row_bytes;
+  if (bin_bytes) *bin_bytes = e->bin_bytes;
+  if (null_symbol) *null_symbol = e->null_symbol;
+  if (bins_dev) *bins_dev = e->d_bins;
+  B200_API_END();
+}
+
+int b200hist_ellpack_copy_bins_to_host(b200hist_ellpack_t e, void* out_host) {
+  B200_API_BEGIN();
+  B200_CHECK(e != nullptr && out_host != nullptr, "null argument");
+  DeviceGuard guard(e->device);
+  B200_CUDA(cudaMemcpy(out_host, e->d_bins, e->n_rows * (uint64_t)e->row_bytes, cudaMemcpyDeviceToHost));
+  B200_API_END();
+}
+
+}  // extern "C"

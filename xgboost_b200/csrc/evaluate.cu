@@ -1,0 +1,251 @@
+// Split evaluation: best (feature, bin, missing direction) for every child node of a tree level.
+//
+// Replaces (reference paths relative to /root/reference):
+//   EvaluateSplitAgent::{ReduceFeature, Numerical}, LossChangeMissing   src/tree/gpu_hist/evaluate_splits.cu:17-32,90-146
+//   EvaluateSplitsKernel + cub segmented reduce + entry lambda          evaluate_splits.cu:255-311,350-384,441-467
+//   DeviceSplitCandidate::Update                                        src/tree/updater_gpu_common.cuh:68-83
+//   SplitEvaluator::{CalcSplitGain, CalcGainGivenWeight, Divide}        src/tree/split_evaluator.h:73-148
+//   CalcWeight / CalcGain / ThresholdL1                                 src/tree/param.h:215-267
+//
+// The arithmetic follows the reference operation for operation (fp64 ToFloatingPoint, fp32 gain via
+// __fdividef == div.approx.ftz.f32, fp32 adds, tie-breaks) because split decisions must be
+// bit-identical.  What differs is the organisation:
+//   * FeatureScanKernel: one WARP per (node, feature) packed 8 warps to a CTA and grid-strided, instead
+//     of one 32-thread CTA per pair; prefix sums are warp shuffles over int64 (exact), the arg-max is a
+//     shuffle reduction with the same "max gain, lowest lane" rule as cub::ArgMax.
+//   * NodeReduceKernel: one warp per node folds the per-feature winners ("later feature wins only if
+//     strictly greater") and applies the parent-gain / weight post-pass -- two launches per level in
+//     total instead of kernel + CUB segmented reduce + transform.
+// Histograms are read straight from L2 (they were just written by the build/subtract kernels).
+#include "common.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ double ThresholdL1(double w, float alpha) {
+  if (w > +alpha) return w - alpha;
+  if (w < -alpha) return w + alpha;
+  return 0.0;
+}
+
+__device__ __forceinline__ double CalcWeightD(const ParamDev& p, double g, double h) {
+  if (h < p.min_child_weight || h <= 0.0) return 0.0;
+  double dw = -ThresholdL1(g, p.reg_alpha) / (h + p.reg_lambda);
+  if (p.max_delta_step != 0.0f && fabs(dw) > p.max_delta_step) dw = copysign((double)p.max_delta_step, dw);
+  return dw;
+}
+
+__device__ __forceinline__ double CalcGainD(const ParamDev& p, double g, double h) {
+  if (h < p.min_child_weight || h <= 0.0) return 0.0;
+  if (p.max_delta_step == 0.0f) {
+    if (p.reg_alpha == 0.0f) return (g * g) / (h + p.reg_lambda);
+    double t = ThresholdL1(g, p.reg_alpha);
+    return (t * t) / (h + p.reg_lambda);
+  }
+  double w = CalcWeightD(p, g, h);
+  double ret = -(2.0 * g * w + (h + p.reg_lambda) * (w * w));
+  if (p.reg_alpha == 0.0f) return ret;
+  return ret + p.reg_alpha * fabs(w);
+}
+
+// SplitEvaluator::CalcGainGivenWeight without monotone constraints (split_evaluator.h:130-143)
+__device__ __forceinline__ float GainOfStats(const ParamDev& p, double g, double h) {
+  if (h <= 0) return 0.0f;
+  if (p.max_delta_step == 0.0f) {
+    double t = ThresholdL1(g, p.reg_alpha);
+    return __fdividef((float)(t * t), (float)(h + p.reg_lambda));
+  }
+  float w = (float)CalcWeightD(p, g, h);
+  float fg = (float)g, fh = (float)h;
+  return -(2.0f * fg * w + (fh + p.reg_lambda) * (w * w));
+}
+
+__device__ __forceinline__ float SplitGain(const ParamDev& p, double tfg, double tfh, long long lg, long long lh,
+                                           long long rg, long long rh) {
+  float gl = GainOfStats(p, (double)lg * tfg, (double)lh * tfh);
+  float gr = GainOfStats(p, (double)rg * tfg, (double)rh * tfh);
+  return gl + gr;
+}
+
+constexpr int kEvalWarps = 8;
+
+// One warp per (node slot, feature position).
+__global__ void __launch_bounds__(kEvalWarps * 32)
+FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t* __restrict__ eval_nodes,
+                  const TreeState* __restrict__ ts, const NodeDev* __restrict__ nodes,
+                  const int32_t* __restrict__ feature_set, int32_t n_fs, ParamDev p,
+                  const QuantDev* __restrict__ q, FeatCand* __restrict__ scratch) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kEvalWarps + (threadIdx.x >> 5);
+  const int n_warps = gridDim.x * kEvalWarps;
+  const int n_eval = ts->n_eval;
+  const long long total = (long long)n_eval * n_fs;
+  const double tfg = q->to_float_g, tfh = q->to_float_h;
+  for (long long item = warp_global; item < total; item += n_warps) {
+    const int slot = (int)(item / n_fs);
+    const int fpos = (int)(item - (long long)slot * n_fs);
+    const int f = feature_set ? feature_set[fpos] : fpos;
+    const int nidx = eval_nodes[slot];
+    const longlong2* h = hist + (size_t)nidx * ell.total_bins;
+    const long long pg = nodes[nidx].sum_g, ph = nodes[nidx].sum_h;
+    const uint32_t beg = ell.cut_ptrs[f], end = ell.cut_ptrs[f + 1];
+
+    // ReduceFeature: missing = parent - sum(bins)
+    long long sg = 0, sh = 0;
+    for (uint32_t b = beg + lane; b < end; b += 32) {
+      longlong2 v = h[b];
+      sg += v.x;
+      sh += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sh += __shfl_xor_sync(0xffffffffu, sh, o);
+    }
+    const long long mg = pg - sg, mh = ph - sh;
+
+    float best_loss = -3.402823466e+38f;  // -FLT_MAX, DeviceSplitCandidate default
+    int best_dir = 0, best_bin = -1;
+    long long best_lg = 0, best_lh = 0;
+    long long run_g = 0, run_h = 0;  // exclusive prefix carried across chunks
+    for (uint32_t cb = beg; cb < end; cb += 32) {
+      const uint32_t b = cb + lane;
+      const bool active = b < end;
+      longlong2 v = active ? h[b] : make_longlong2(0, 0);
+      long long ig = v.x, ih = v.y;  // inclusive warp scan
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        long long tg = __shfl_up_sync(0xffffffffu, ig, o);
+        long long th = __shfl_up_sync(0xffffffffu, ih, o);
+        if (lane >= o) { ig += tg; ih += th; }
+      }
+      const long long scan_g = run_g + ig - v.x, scan_h = run_h + ih - v.y;
+      run_g += __shfl_sync(0xffffffffu, ig, 31);
+      run_h += __shfl_sync(0xffffffffu, ih, 31);
+
+      float gain = -INFINITY;
+      bool missing_left = true;
+      if (active) {  // LossChangeMissing
+        const long long lg = scan_g + mg, lh = scan_h + mh;
+        float g_ml = SplitGain(p, tfg, tfh, lg, lh, pg - lg, ph - lh);
+        float g_mr = SplitGain(p, tfg, tfh, scan_g, scan_h, pg - scan_g, ph - scan_h);
+        missing_left = g_ml > g_mr;
+        gain = missing_left ? g_ml : g_mr;
+      }
+      // cub::ArgMax: larger value wins, equal values -> lower lane
+      float bg = gain;
+      int bl = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float og = __shfl_xor_sync(0xffffffffu, bg, o);
+        int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+        if (og > bg || (og == bg && ol < bl)) { bg = og; bl = ol; }
+      }
+      // the winning lane proposes; DeviceSplitCandidate::Update accepts or rejects
+      const long long lg = missing_left ? scan_g + mg : scan_g;
+      const long long lh = missing_left ? scan_h + mh : scan_h;
+      const long long rh = ph - lh;
+      bool accept = (lane == bl) && active && (gain > best_loss) &&
+                    ((double)lh * tfh >= p.min_child_weight) && ((double)rh * tfh >= p.min_child_weight);
+      unsigned m = __ballot_sync(0xffffffffu, accept);
+      if (m) {
+        int src = __ffs(m) - 1;
+        best_loss = __shfl_sync(0xffffffffu, gain, src);
+        best_dir = __shfl_sync(0xffffffffu, missing_left ? 0 : 1, src);
+        best_bin = (int)cb + src;
+        best_lg = __shfl_sync(0xffffffffu, lg, src);
+        best_lh = __shfl_sync(0xffffffffu, lh, src);
+      }
+    }
+    if (lane == 0) {
+      FeatCand c;
+      c.loss_chg = best_loss;
+      c.dir = best_dir;
+      c.gbin = best_bin;
+      c.pad = 0;
+      c.left_g = best_lg;
+      c.left_h = best_lh;
+      scratch[item] = c;
+    }
+  }
+}
+
+// One warp per node slot: fold per-feature winners in feature order, then the post-pass.
+__global__ void __launch_bounds__(kEvalWarps * 32)
+NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const TreeState* __restrict__ ts,
+                 NodeDev* __restrict__ nodes, const int32_t* __restrict__ feature_set, int32_t n_fs, ParamDev p,
+                 const QuantDev* __restrict__ q, const FeatCand* __restrict__ scratch,
+                 b200hist_candidate* __restrict__ cand) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kEvalWarps + (threadIdx.x >> 5);
+  const int n_warps = gridDim.x * kEvalWarps;
+  const int n_eval = ts->n_eval;
+  const double tfg = q->to_float_g, tfh = q->to_float_h;
+  for (int slot = warp_global; slot < n_eval; slot += n_warps) {
+    const int nidx = eval_nodes[slot];
+    const FeatCand* sc = scratch + (size_t)slot * n_fs;
+    float bl = -3.402823466e+38f;
+    int bpos = 0x7fffffff;
+    for (int fpos = lane; fpos < n_fs; fpos += 32) {
+      float l = sc[fpos].loss_chg;
+      if (l > bl) { bl = l; bpos = fpos; }  // strict: the earliest position with the maximum wins
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+      if (ol > bl || (ol == bl && op < bpos)) { bl = ol; bpos = op; }
+    }
+    if (lane == 0) {
+      const long long pg = nodes[nidx].sum_g, ph = nodes[nidx].sum_h;
+      b200hist_candidate c;
+      c.loss_chg = -3.402823466e+38f;
+      c.dir = 0;
+      c.findex = -1;
+      c.fvalue = 0.0f;
+      c.left_sum = b200hist_gpair64{0, 0};
+      c.right_sum = b200hist_gpair64{0, 0};
+      c.split_gbin = -1;
+      if (bpos != 0x7fffffff && sc[bpos].gbin >= 0) {
+        FeatCand w = sc[bpos];
+        int f = feature_set ? feature_set[bpos] : bpos;
+        c.loss_chg = w.loss_chg;
+        c.dir = w.dir;
+        c.findex = f;
+        c.split_gbin = w.gbin;
+        int split_gidx = w.gbin - 1;
+        c.fvalue = split_gidx < (int)ell.cut_ptrs[f] ? -INFINITY : ell.cut_values[split_gidx];
+        c.left_sum = b200hist_gpair64{w.left_g, w.left_h};
+        c.right_sum = b200hist_gpair64{pg - w.left_g, ph - w.left_h};
+      }
+      // post-pass (evaluate_splits.cu:441-467)
+      float parent_gain = (float)CalcGainD(p, (double)pg * tfg, (double)ph * tfh);
+      c.loss_chg -= parent_gain;
+      long long tg = c.left_sum.grad + c.right_sum.grad, th = c.left_sum.hess + c.right_sum.hess;
+      c.base_weight = (float)CalcWeightD(p, (double)tg * tfg, (double)th * tfh);
+      c.left_weight = (float)CalcWeightD(p, (double)c.left_sum.grad * tfg, (double)c.left_sum.hess * tfh);
+      c.right_weight = (float)CalcWeightD(p, (double)c.right_sum.grad * tfg, (double)c.right_sum.hess * tfh);
+      cand[nidx] = c;
+      // Driver::Push filter (driver.h:42-50): kRtEps = 1e-6f
+      nodes[nidx].cand_open = c.loss_chg > 1e-6f ? 1 : 0;
+    }
+  }
+}
+
+void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist, const int32_t* eval_nodes, const TreeState* ts,
+                    int32_t max_eval, const NodeDev* nodes, const int32_t* feature_set, int32_t n_feature_set,
+                    const ParamDev& p, const QuantDev* q, FeatCand* scratch, b200hist_candidate* cand,
+                    NodeDev* nodes_mut, int num_sms, cudaStream_t s) {
+  const int32_t n_fs = feature_set ? n_feature_set : (int32_t)ell.n_features;
+  long long max_items = (long long)max_eval * n_fs;
+  if (max_items == 0) return;
+  int blocks = (int)std::min<long long>((max_items + kEvalWarps - 1) / kEvalWarps, (long long)num_sms * 8);
+  FeatureScanKernel<<<blocks, kEvalWarps * 32, 0, s>>>(ell, reinterpret_cast<const longlong2*>(hist), eval_nodes, ts,
+                                                       nodes, feature_set, n_fs, p, q, scratch);
+  B200_LAUNCHED();
+  int blocks2 = (int)std::min<long long>(((long long)max_eval + kEvalWarps - 1) / kEvalWarps, (long long)num_sms * 4);
+  NodeReduceKernel<<<blocks2, kEvalWarps * 32, 0, s>>>(ell, eval_nodes, ts, nodes_mut, feature_set, n_fs, p, q, scratch,
+                                                       cand);
+  B200_LAUNCHED();
+}
+
+}  // namespace b200

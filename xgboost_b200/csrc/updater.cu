@@ -1,0 +1,808 @@
+// Tree-level driver of the B200 hist updater and the updater part of the C ABI.
+//
+// Replaces (reference paths relative to /root/reference):
+//   GPUHistMakerDevice::{Reset, InitRoot, UpdateTree, ApplySplit, PartitionAndBuildHist,
+//     EvaluateSplits, FinalisePosition, UpdatePredictionCache}   src/tree/updater_gpu_hist.cu:172-732
+//   Driver<GPUExpandEntry> (Push/Pop/IsChildValid)                src/tree/driver.h:29-107
+//   GPUExpandEntry::IsValid                                       src/tree/gpu_hist/expand_entry.cuh:33-50
+//   AssignNodes                                                   src/tree/updater_gpu_hist.cuh:59-81
+//   RegTree::ExpandNode bookkeeping                               src/tree/tree_model.cc:805-830
+//
+// B200-first organisation: the reference keeps the tree, the expand queue and the row segments on
+// the HOST and synchronises the stream twice per level.  Here the whole growth state (nodes,
+// candidates, row segments, work lists, tile tables) lives in device memory and is advanced by small
+// single-CTA "control" kernels (ApplyKernel, ScanKernel), so one tree is a fixed, data-independent
+// sequence of launches with no host read-back until the finished tree is copied out once.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kCtlThreads = 1024;
+
+// ---------------------------------------------------------------------------------------------
+// Block-wide exclusive scan for the control kernels (kCtlThreads threads).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t BlockExclusiveScan(uint32_t v, uint32_t* s_warp /* 33 words */, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // protect s_warp reuse
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = s_warp[lane];
+    uint32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    s_warp[lane] = winc - w;
+    if (lane == 31) s_warp[32] = winc;
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[warp] + inc - v;
+}
+
+// Segment lookup: largest k with tile_begin[k] <= t (tile_begin ascending, n >= 1)
+__device__ __forceinline__ uint32_t FindSegment(const uint32_t* tile_begin, uint32_t n, uint32_t t) {
+  uint32_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (tile_begin[mid] <= t) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ double CalcWeightDev(const ParamDev& p, double g, double h) {
+  if (h < p.min_child_weight || h <= 0.0) return 0.0;
+  double t = g > +p.reg_alpha ? g - p.reg_alpha : (g < -p.reg_alpha ? g + p.reg_alpha : 0.0);
+  double dw = -t / (h + p.reg_lambda);
+  if (p.max_delta_step != 0.0f && fabs(dw) > p.max_delta_step) dw = copysign((double)p.max_delta_step, dw);
+  return dw;
+}
+
+__device__ __forceinline__ void InitLeaf(NodeDev* n, int parent, int depth, float leaf, float sum_hess, long long g,
+                                         long long h) {
+  n->parent = parent; n->left = -1; n->right = -1; n->depth = depth;
+  n->findex = -1; n->fvalue = leaf; n->default_left = 0; n->is_leaf = 1;
+  n->leaf_value = leaf; n->loss_chg = 0.0f; n->sum_hess = sum_hess; n->base_weight = leaf;
+  n->sum_g = g; n->sum_h = h;
+  n->seg_begin = 0; n->seg_count = 0; n->seg_buf = -1; n->partitioned = 0; n->split_lbin = 0; n->cand_open = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// InitRoot (updater_gpu_hist.cu:657-691) minus the histogram build / evaluation launches.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCtlThreads) InitRootKernel(ParamDev p, uint32_t n_rows, const QuantDev* q,
+                                                               TreeState* ts, NodeDev* nodes, BuildEntry* build,
+                                                               uint32_t* build_tile_seg, int32_t* eval_nodes) {
+  const uint32_t tiles = (n_rows + kHistTile - 1) / kHistTile;
+  for (uint32_t t = threadIdx.x; t < tiles; t += kCtlThreads) build_tile_seg[t] = 0;
+  if (threadIdx.x == 0) {
+    double rg = (double)q->root_g * q->to_float_g, rh = (double)q->root_h * q->to_float_h;
+    float w = (float)CalcWeightDev(p, rg, rh);
+    NodeDev* r = &nodes[0];
+    InitLeaf(r, -1, 0, p.learning_rate * w, (float)rh, q->root_g, q->root_h);
+    r->base_weight = w;
+    r->seg_begin = 0; r->seg_count = n_rows; r->seg_buf = 0;
+    build[0] = BuildEntry{0, 0, 0u, n_rows, 0u, 0u};
+    eval_nodes[0] = 0;
+    ts->n_nodes = 1; ts->num_leaves = 1; ts->level_begin = 0; ts->level_end = 1;
+    ts->n_part = 0; ts->n_build = 1; ts->n_sub = 0; ts->n_eval = 1;
+    ts->part_tiles = 0; ts->build_tiles = tiles; ts->final_tiles = 0; ts->n_final = 0;
+    ts->row_visits = n_rows; ts->stopped = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Driver::Pop + IsValid + ApplySplit + IsChildValid + partition work list for one growth step.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool EntryValidNoLeafLimit(const ParamDev& p, const b200hist_candidate& c, int depth) {
+  if (c.loss_chg <= 1e-6f) return false;                          // kRtEps
+  if (c.left_sum.hess == 0 || c.right_sum.hess == 0) return false;
+  if (c.loss_chg < p.min_split_loss) return false;
+  if (p.max_depth > 0 && depth == p.max_depth) return false;
+  return true;
+}
+
+__device__ void ApplyOne(const EllView& ell, const ParamDev& p, const QuantDev* q, NodeDev* nodes,
+                         const b200hist_candidate& c, int nidx, int left, PartEntry* part_slot) {
+  NodeDev* n = &nodes[nidx];
+  const int right = left + 1;
+  const double tfh = q->to_float_h;
+  n->left = left; n->right = right;
+  n->findex = c.findex; n->fvalue = c.fvalue; n->default_left = (c.dir == 0); n->is_leaf = 0;
+  n->loss_chg = c.loss_chg;
+  n->sum_hess = (float)((double)(c.left_sum.hess + c.right_sum.hess) * tfh);
+  n->base_weight = c.base_weight;
+  const float lw = c.left_weight * p.learning_rate, rw = c.right_weight * p.learning_rate;
+  InitLeaf(&nodes[left], nidx, n->depth + 1, lw, (float)((double)c.left_sum.hess * tfh), c.left_sum.grad, c.left_sum.hess);
+  InitLeaf(&nodes[right], nidx, n->depth + 1, rw, (float)((double)c.right_sum.hess * tfh), c.right_sum.grad, c.right_sum.hess);
+  // go left iff cut_values[bin] <= fvalue  <=>  feature-local bin < (number of cuts <= fvalue)
+  const uint32_t beg = ell.cut_ptrs[c.findex], end = ell.cut_ptrs[c.findex + 1];
+  uint32_t lo = beg, hi = end;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (ell.cut_values[mid] <= c.fvalue) lo = mid + 1; else hi = mid;
+  }
+  n->split_lbin = (int32_t)(lo - beg);
+  PartEntry e;
+  e.nidx = nidx; e.left = left; e.right = right; e.findex = c.findex; e.split_lbin = n->split_lbin;
+  e.default_left = n->default_left; e.begin = n->seg_begin; e.count = n->seg_count; e.tile_begin = 0;
+  e.src_buf = n->seg_buf; e.n_left = 0; e.pad = 0;
+  *part_slot = e;
+}
+
+__global__ void __launch_bounds__(kCtlThreads) ApplyKernel(EllView ell, ParamDev p, const QuantDev* q, TreeState* ts,
+                                                            NodeDev* nodes, const b200hist_candidate* cand,
+                                                            PartEntry* part, uint32_t* part_tile_seg,
+                                                            int32_t max_nodes) {
+  __shared__ uint32_t s_warp[33];
+  __shared__ uint32_t s_tile_begin[kMaxLevelNodes + 1];
+  __shared__ int s_n_expand, s_child_valid;
+  __shared__ float s_best_loss[kCtlThreads / 32];
+  __shared__ int s_best_idx[kCtlThreads / 32];
+  const int n_nodes0 = ts->n_nodes, leaves0 = ts->num_leaves;
+  const int allow = p.max_leaves > 0 ? max(0, p.max_leaves - leaves0) : 0x7fffffff;
+  int n_expand = 0;
+  int level_depth = 0;
+
+  if (ts->stopped) {
+    if (threadIdx.x == 0) { ts->n_part = 0; ts->n_build = 0; ts->n_sub = 0; ts->n_eval = 0; ts->part_tiles = 0; ts->build_tiles = 0; }
+    return;
+  }
+
+  if (p.grow_policy == 1) {
+    // loss guide: pop the single best open entry (ties -> smaller nidx); an invalid top ends growth
+    float bl = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n_nodes0; i += kCtlThreads)
+      if (nodes[i].cand_open) {
+        float l = cand[i].loss_chg;
+        if (l > bl || (l == bl && i < bi)) { bl = l; bi = i; }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ol > bl || (ol == bl && oi < bi))) { bl = ol; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_best_loss[threadIdx.x >> 5] = bl; s_best_idx[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kCtlThreads / 32; ++w) {
+        float ol = s_best_loss[w];
+        int oi = s_best_idx[w];
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ol > bl || (ol == bl && oi < bi))) { bl = ol; bi = oi; }
+      }
+      int ne = 0;
+      if (bi == 0x7fffffff) {
+        ts->stopped = 1;
+      } else {
+        nodes[bi].cand_open = 0;
+        b200hist_candidate c = cand[bi];
+        bool ok = EntryValidNoLeafLimit(p, c, nodes[bi].depth) && !(p.max_leaves > 0 && leaves0 == p.max_leaves) &&
+                  n_nodes0 + 2 <= max_nodes;
+        if (ok) {
+          ApplyOne(ell, p, q, nodes, c, bi, n_nodes0, &part[0]);
+          ne = 1;
+        } else {
+          ts->stopped = 1;
+        }
+      }
+      s_n_expand = ne;
+      level_depth = ne ? nodes[bi].depth : 0;
+      int leaves_new = leaves0 + ne;
+      s_child_valid = ne && (p.max_depth == 0 || level_depth + 1 < p.max_depth) &&
+                      (p.max_leaves == 0 || leaves_new < p.max_leaves);
+    }
+    __syncthreads();
+    n_expand = s_n_expand;
+  } else {
+    // depth wise: every open entry of the level, ascending nidx
+    const int lb = ts->level_begin, le = ts->level_end;
+    level_depth = lb < le ? nodes[lb].depth : 0;
+    uint32_t running = 0;
+    for (int base = lb; base < le; base += kCtlThreads) {
+      const int i = base + threadIdx.x;
+      bool valid = false;
+      b200hist_candidate c;
+      if (i < le && nodes[i].cand_open) {
+        c = cand[i];
+        valid = EntryValidNoLeafLimit(p, c, nodes[i].depth);
+        nodes[i].cand_open = 0;
+      }
+      uint32_t total;
+      uint32_t rank = running + BlockExclusiveScan(valid ? 1u : 0u, s_warp, &total);
+      bool accepted = valid && (int)rank < allow && n_nodes0 + 2 * ((int)rank + 1) <= max_nodes &&
+                      (int)rank < kMaxLevelNodes;
+      if (accepted) ApplyOne(ell, p, q, nodes, c, i, n_nodes0 + 2 * (int)rank, &part[rank]);
+      running += total;
+    }
+    n_expand = min((int)running, allow);
+    n_expand = min(n_expand, (max_nodes - n_nodes0) / 2);
+    n_expand = min(n_expand, kMaxLevelNodes);
+    if (threadIdx.x == 0) {
+      int leaves_new = leaves0 + n_expand;
+      s_child_valid = n_expand > 0 && (p.max_depth == 0 || level_depth + 1 < p.max_depth) &&
+                      (p.max_leaves == 0 || leaves_new < p.max_leaves);
+    }
+    __syncthreads();
+  }
+
+  const int n_part = s_child_valid ? n_expand : 0;
+  // partition tile table
+  uint32_t running_tiles = 0;
+  for (int base = 0; base < n_part; base += kCtlThreads) {
+    const int k = base + threadIdx.x;
+    uint32_t tiles = 0;
+    if (k < n_part) {
+      tiles = (part[k].count + kPartTile - 1) / kPartTile;
+      nodes[part[k].nidx].partitioned = 1;
+    }
+    uint32_t total;
+    uint32_t ex = running_tiles + BlockExclusiveScan(tiles, s_warp, &total);
+    if (k < n_part) {
+      part[k].tile_begin = ex;
+      s_tile_begin[k] = ex;
+    }
+    running_tiles += total;
+  }
+  __syncthreads();
+  if (n_part > 0)
+    for (uint32_t t = threadIdx.x; t < running_tiles; t += kCtlThreads)
+      part_tile_seg[t] = FindSegment(s_tile_begin, (uint32_t)n_part, t);
+  if (threadIdx.x == 0) {
+    ts->n_nodes = n_nodes0 + 2 * n_expand;
+    ts->num_leaves = leaves0 + n_expand;
+    ts->level_begin = n_nodes0;
+    ts->level_end = n_nodes0 + 2 * n_expand;
+    ts->n_part = n_part;
+    ts->part_tiles = running_tiles;
+    ts->n_build = 0; ts->n_sub = 0; ts->n_eval = 0; ts->build_tiles = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// After the count pass: per-tile offsets, children's row segments, AssignNodes (build the child
+// with fewer rows, subtract the other), evaluation list and the histogram tile table.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCtlThreads) ScanKernel(TreeState* ts, NodeDev* nodes, PartEntry* part,
+                                                           const uint32_t* part_tile_seg, const uint32_t* tile_left,
+                                                           uint32_t* tile_excl /* scratch, part_tiles+1 */,
+                                                           uint32_t* tile_left_off, BuildEntry* build, SubEntry* sub,
+                                                           int32_t* eval_nodes, uint32_t* build_tile_seg) {
+  __shared__ uint32_t s_warp[33];
+  __shared__ uint32_t s_tile_begin[kMaxLevelNodes + 1];
+  const int n_part = ts->n_part;
+  const uint32_t T = ts->part_tiles;
+  if (n_part == 0) return;
+  // 1. exclusive scan of the tile left-counts over the whole level
+  uint32_t running = 0;
+  for (uint32_t base = 0; base < T; base += kCtlThreads) {
+    const uint32_t t = base + threadIdx.x;
+    uint32_t v = t < T ? tile_left[t] : 0u;
+    uint32_t total;
+    uint32_t ex = running + BlockExclusiveScan(v, s_warp, &total);
+    if (t < T) tile_excl[t] = ex;
+    running += total;
+  }
+  if (threadIdx.x == 0) tile_excl[T] = running;
+  __syncthreads();
+  // 2. per segment: left count, children segments, build/subtract assignment
+  unsigned long long visits = 0;
+  for (int k = threadIdx.x; k < n_part; k += kCtlThreads) {
+    PartEntry e = part[k];
+    const uint32_t tb = e.tile_begin;
+    const uint32_t te = (k + 1 < n_part) ? part[k + 1].tile_begin : T;
+    const uint32_t n_left = tile_excl[te] - tile_excl[tb];
+    part[k].n_left = n_left;
+    NodeDev* l = &nodes[e.left];
+    NodeDev* r = &nodes[e.right];
+    const int dst_buf = 1 - e.src_buf;
+    l->seg_begin = e.begin; l->seg_count = n_left; l->seg_buf = dst_buf;
+    r->seg_begin = e.begin + n_left; r->seg_count = e.count - n_left; r->seg_buf = dst_buf;
+    const bool build_right = r->seg_count < l->seg_count;
+    const NodeDev* b = build_right ? r : l;
+    const int b_idx = build_right ? e.right : e.left;
+    const int s_idx = build_right ? e.left : e.right;
+    build[k] = BuildEntry{b_idx, dst_buf, b->seg_begin, b->seg_count, 0u, 0u};
+    sub[k] = SubEntry{e.nidx, b_idx, s_idx};
+    eval_nodes[2 * k] = e.left;
+    eval_nodes[2 * k + 1] = e.right;
+    visits += b->seg_count;
+  }
+  __syncthreads();
+  // 3. segment-relative tile offsets for the scatter pass
+  for (uint32_t t = threadIdx.x; t < T; t += kCtlThreads)
+    tile_left_off[t] = tile_excl[t] - tile_excl[part[part_tile_seg[t]].tile_begin];
+  // 4. histogram tile table
+  uint32_t running_tiles = 0;
+  for (int base = 0; base < n_part; base += kCtlThreads) {
+    const int k = base + threadIdx.x;
+    uint32_t tiles = k < n_part ? (build[k].count + kHistTile - 1) / kHistTile : 0u;
+    uint32_t total;
+    uint32_t ex = running_tiles + BlockExclusiveScan(tiles, s_warp, &total);
+    if (k < n_part) {
+      build[k].tile_begin = ex;
+      s_tile_begin[k] = ex;
+    }
+    running_tiles += total;
+  }
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < running_tiles; t += kCtlThreads)
+    build_tile_seg[t] = FindSegment(s_tile_begin, (uint32_t)n_part, t);
+  if (visits) atomicAdd(&ts->row_visits, visits);
+  if (threadIdx.x == 0) {
+    ts->n_build = n_part;
+    ts->n_sub = n_part;
+    ts->n_eval = 2 * n_part;
+    ts->build_tiles = running_tiles;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FinalisePosition (updater_gpu_hist.cu:529-580): list the nodes that still own a row segment,
+// then walk each row from that node to its leaf (at most the splits applied after the last
+// partition) and write position[row] = leaf, bitwise-NOT when the row's hessian is 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCtlThreads) FinalListKernel(TreeState* ts, const NodeDev* nodes, BuildEntry* fin,
+                                                                uint32_t* fin_tile_seg, uint32_t* fin_tile_begin) {
+  __shared__ uint32_t s_warp[33];
+  const int n_nodes = ts->n_nodes;
+  uint32_t running_n = 0, running_tiles = 0;
+  for (int base = 0; base < n_nodes; base += kCtlThreads) {
+    const int i = base + threadIdx.x;
+    bool term = i < n_nodes && nodes[i].seg_buf >= 0 && !nodes[i].partitioned;
+    uint32_t tiles = term ? (nodes[i].seg_count + kPartTile - 1) / kPartTile : 0u;
+    uint32_t total_n, total_t;
+    uint32_t slot = running_n + BlockExclusiveScan(term ? 1u : 0u, s_warp, &total_n);
+    uint32_t tb = running_tiles + BlockExclusiveScan(tiles, s_warp, &total_t);
+    if (term) {
+      fin[slot] = BuildEntry{i, nodes[i].seg_buf, nodes[i].seg_begin, nodes[i].seg_count, tb, 0u};
+      fin_tile_begin[slot] = tb;
+    }
+    running_n += total_n;
+    running_tiles += total_t;
+  }
+  __syncthreads();
+  __threadfence_block();
+  for (uint32_t t = threadIdx.x; t < running_tiles; t += kCtlThreads)
+    fin_tile_seg[t] = FindSegment(fin_tile_begin, running_n, t);
+  if (threadIdx.x == 0) {
+    ts->n_final = (int32_t)running_n;
+    ts->final_tiles = running_tiles;
+  }
+}
+
+template <typename BinT>
+__global__ void __launch_bounds__(256) FinaliseKernel(EllView ell, const uint32_t* __restrict__ ridx0,
+                                                       const uint32_t* __restrict__ ridx1,
+                                                       const longlong2* __restrict__ gq,
+                                                       const NodeDev* __restrict__ nodes,
+                                                       const BuildEntry* __restrict__ fin,
+                                                       const uint32_t* __restrict__ fin_tile_seg,
+                                                       const TreeState* __restrict__ ts, int32_t* __restrict__ position) {
+  const uint32_t n_tiles = ts->final_tiles;
+  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const BuildEntry e = fin[fin_tile_seg[t]];
+    const uint32_t off = (t - e.tile_begin) * kPartTile;
+    const uint32_t n = min((uint32_t)kPartTile, e.count - off);
+    const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin + off;
+    for (uint32_t j = threadIdx.x; j < n; j += 256) {
+      const uint32_t r = ridx[j];
+      int nidx = e.nidx;
+      while (!nodes[nidx].is_leaf) {
+        const NodeDev& nd = nodes[nidx];
+        const uint32_t sym = reinterpret_cast<const BinT*>(ell.bins + (size_t)r * ell.row_bytes)[nd.findex];
+        const bool left = (sym == ell.null_symbol) ? (nd.default_left != 0) : ((int32_t)sym < nd.split_lbin);
+        nidx = left ? nd.left : nd.right;
+      }
+      const long long hq = gq[r].y;
+      position[r] = hq != 0 ? nidx : ~nidx;
+    }
+  }
+}
+
+// UpdatePredictionCache (updater_gpu_hist.cu:582-608)
+__global__ void __launch_bounds__(256) PredCacheKernel(const int32_t* __restrict__ position,
+                                                        const NodeDev* __restrict__ nodes, uint64_t n,
+                                                        float* __restrict__ preds) {
+  for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256ull) {
+    int32_t p = position[i];
+    p = p < 0 ? ~p : p;  // SamplePosition::Decode
+    preds[i] += nodes[p].leaf_value;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// =============================================================================================
+// Updater object
+// =============================================================================================
+struct b200hist_updater_s {
+  b200hist_ellpack_t ell{nullptr};
+  int device{0};
+  int num_sms{0};
+  b200hist_train_param param{};
+  ParamDev pdev{};
+  int32_t max_nodes{0};
+  int32_t n_steps{0};  // growth steps (levels for depth-wise)
+  std::vector<GroupDesc> groups;
+  // device state
+  GroupDesc* d_groups{nullptr};
+  QuantDev* d_quant{nullptr};
+  double* d_partials{nullptr};
+  unsigned int* d_counter{nullptr};
+  b200hist_gpair64* d_gq{nullptr};
+  uint32_t* d_ridx[2]{nullptr, nullptr};
+  int32_t* d_position{nullptr};
+  float* d_gpair_staging{nullptr};
+  TreeState* d_ts{nullptr};
+  NodeDev* d_nodes{nullptr};
+  b200hist_candidate* d_cand{nullptr};
+  PartEntry* d_part{nullptr};
+  BuildEntry* d_build{nullptr};
+  SubEntry* d_sub{nullptr};
+  int32_t* d_eval_nodes{nullptr};
+  uint32_t* d_part_tile_seg{nullptr};
+  uint32_t* d_build_tile_seg{nullptr};
+  uint32_t* d_tile_left{nullptr};
+  uint32_t* d_tile_excl{nullptr};
+  uint32_t* d_tile_left_off{nullptr};
+  uint32_t* d_flags{nullptr};
+  BuildEntry* d_fin{nullptr};
+  uint32_t* d_fin_tile_seg{nullptr};
+  uint32_t* d_fin_tile_begin{nullptr};
+  FeatCand* d_scratch{nullptr};
+  b200hist_gpair64* d_hist{nullptr};
+  size_t hist_bytes{0};
+  // host staging
+  NodeDev* h_nodes{nullptr};  // pinned
+  TreeState* h_ts{nullptr};   // pinned
+  int32_t* last_position{nullptr};
+  int32_t last_n_nodes{0};
+  // profiling
+  bool profiling{false};
+  std::vector<cudaEvent_t> events;
+  float last_ms[7]{0, 0, 0, 0, 0, 0, 0};
+  uint64_t last_row_visits{0};
+};
+
+namespace {
+
+enum Phase { kQuant = 0, kHist = 1, kSub = 2, kEval = 3, kApply = 4, kPart = 5, kFinal = 6 };
+
+struct PhaseTimer {
+  b200hist_updater_s* u;
+  cudaStream_t s;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+  size_t next{0};
+  cudaEvent_t Get() {
+    if (next == u->events.size()) {
+      cudaEvent_t e;
+      B200_CUDA(cudaEventCreate(&e));
+      u->events.push_back(e);
+    }
+    return u->events[next++];
+  }
+  cudaEvent_t Begin() {
+    if (!u->profiling) return nullptr;
+    cudaEvent_t e = Get();
+    B200_CUDA(cudaEventRecord(e, s));
+    return e;
+  }
+  void End(int phase, cudaEvent_t b) {
+    if (!u->profiling) return;
+    cudaEvent_t e = Get();
+    B200_CUDA(cudaEventRecord(e, s));
+    spans.push_back({phase, {b, e}});
+  }
+  void Collect() {
+    if (!u->profiling) return;
+    for (auto& m : u->last_ms) m = 0;
+    for (auto& sp : spans) {
+      float ms = 0;
+      B200_CUDA(cudaEventElapsedTime(&ms, sp.second.first, sp.second.second));
+      u->last_ms[sp.first] += ms;
+    }
+  }
+};
+
+int32_t MaxNodesFor(const b200hist_train_param& p) {
+  long long by_depth = p.max_depth > 0 ? ((1ll << (p.max_depth + 1)) - 1) : (1ll << 40);
+  long long by_leaves = p.max_leaves > 0 ? (2ll * p.max_leaves - 1) : (1ll << 40);
+  long long n = std::min(by_depth, by_leaves);
+  return (int32_t)n;
+}
+
+void ToAbiNodes(const NodeDev* src, int32_t n, b200hist_tree_node* dst) {
+  for (int32_t i = 0; i < n; ++i) {
+    const NodeDev& s = src[i];
+    b200hist_tree_node d;
+    d.parent = s.parent; d.left = s.left; d.right = s.right; d.findex = s.findex;
+    d.fvalue = s.is_leaf ? s.leaf_value : s.fvalue;
+    d.default_left = s.default_left; d.is_leaf = s.is_leaf; d.leaf_value = s.leaf_value;
+    d.loss_chg = s.loss_chg; d.sum_hess = s.sum_hess; d.base_weight = s.base_weight; d.depth = s.depth;
+    dst[i] = d;
+  }
+}
+
+void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t s, b200hist_tree_node* out_nodes,
+                    int32_t* out_n_nodes, int32_t* out_position) {
+  auto* ell = u->ell;
+  const EllView view = ell->View();
+  const uint64_t n = ell->n_rows;
+  PhaseTimer timer{u, s};
+  int32_t* position = out_position ? out_position : u->d_position;
+
+  // Reset (updater_gpu_hist.cu:172-211): quantiser, quantised gpairs, row indices, histograms
+  auto t0 = timer.Begin();
+  B200_CUDA(cudaMemsetAsync(u->d_hist, 0, u->hist_bytes, s));
+  LaunchQuantise(gpair_dev, n, u->d_quant, u->d_gq, u->d_ridx[0], u->d_partials, u->d_counter, u->num_sms, s);
+  timer.End(kQuant, t0);
+
+  // InitRoot
+  auto t1 = timer.Begin();
+  InitRootKernel<<<1, kCtlThreads, 0, s>>>(u->pdev, (uint32_t)n, u->d_quant, u->d_ts, u->d_nodes, u->d_build,
+                                           u->d_build_tile_seg, u->d_eval_nodes);
+  B200_LAUNCHED();
+  timer.End(kApply, t1);
+  auto t2 = timer.Begin();
+  LaunchBuildHist(view, u->d_gq, u->d_ridx[0], u->d_ridx[1], u->d_build, u->d_build_tile_seg, u->d_ts, u->d_groups,
+                  u->groups, u->d_hist, u->num_sms, s);
+  timer.End(kHist, t2);
+  auto t3 = timer.Begin();
+  LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, nullptr, 0, u->pdev, u->d_quant,
+                 u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s);
+  timer.End(kEval, t3);
+
+  const bool depthwise = u->param.grow_policy == 0;
+  for (int step = 0; step < u->n_steps; ++step) {
+    // upper bound on nodes expanded in this step (host-known, data independent)
+    long long cap = depthwise ? std::min<long long>(1ll << std::min(step, 30), kMaxLevelNodes) : 1;
+    auto ta = timer.Begin();
+    ApplyKernel<<<1, kCtlThreads, 0, s>>>(view, u->pdev, u->d_quant, u->d_ts, u->d_nodes, u->d_cand, u->d_part,
+                                          u->d_part_tile_seg, u->max_nodes);
+    B200_LAUNCHED();
+    timer.End(kApply, ta);
+    const bool children_possible = u->param.max_depth == 0 || !depthwise || step + 1 < u->param.max_depth;
+    if (!children_possible) continue;
+    auto tp = timer.Begin();
+    LaunchPartitionCount(view, u->d_ridx[0], u->d_ridx[1], u->d_part, u->d_part_tile_seg, u->d_ts, u->d_flags,
+                         u->d_tile_left, u->num_sms, s);
+    ScanKernel<<<1, kCtlThreads, 0, s>>>(u->d_ts, u->d_nodes, u->d_part, u->d_part_tile_seg, u->d_tile_left,
+                                         u->d_tile_excl, u->d_tile_left_off, u->d_build, u->d_sub, u->d_eval_nodes,
+                                         u->d_build_tile_seg);
+    B200_LAUNCHED();
+    LaunchPartitionScatter(u->d_ridx[0], u->d_ridx[1], u->d_ridx[0], u->d_ridx[1], u->d_part, u->d_part_tile_seg,
+                           u->d_ts, u->d_flags, u->d_tile_left_off, u->num_sms, s);
+    timer.End(kPart, tp);
+    auto th = timer.Begin();
+    LaunchBuildHist(view, u->d_gq, u->d_ridx[0], u->d_ridx[1], u->d_build, u->d_build_tile_seg, u->d_ts, u->d_groups,
+                    u->groups, u->d_hist, u->num_sms, s);
+    timer.End(kHist, th);
+    auto tsb = timer.Begin();
+    LaunchSubtract(u->d_sub, u->d_ts, u->d_hist, ell->total_bins, u->num_sms, s);
+    timer.End(kSub, tsb);
+    auto te = timer.Begin();
+    LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, (int32_t)(2 * cap), u->d_nodes, nullptr, 0, u->pdev,
+                   u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s);
+    timer.End(kEval, te);
+  }
+
+  auto tf = timer.Begin();
+  FinalListKernel<<<1, kCtlThreads, 0, s>>>(u->d_ts, u->d_nodes, u->d_fin, u->d_fin_tile_seg, u->d_fin_tile_begin);
+  B200_LAUNCHED();
+  if (ell->bin_bytes == 1) {
+    FinaliseKernel<uint8_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1],
+                                                          reinterpret_cast<const longlong2*>(u->d_gq), u->d_nodes,
+                                                          u->d_fin, u->d_fin_tile_seg, u->d_ts, position);
+  } else {
+    FinaliseKernel<uint16_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1],
+                                                           reinterpret_cast<const longlong2*>(u->d_gq), u->d_nodes,
+                                                           u->d_fin, u->d_fin_tile_seg, u->d_ts, position);
+  }
+  B200_LAUNCHED();
+  timer.End(kFinal, tf);
+
+  // the one read-back of the tree
+  B200_CUDA(cudaMemcpyAsync(u->h_ts, u->d_ts, sizeof(TreeState), cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaMemcpyAsync(u->h_nodes, u->d_nodes, sizeof(NodeDev) * u->max_nodes, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  timer.Collect();
+  u->last_row_visits = u->h_ts->row_visits;
+  u->last_n_nodes = u->h_ts->n_nodes;
+  u->last_position = position;
+  if (out_nodes) ToAbiNodes(u->h_nodes, u->last_n_nodes, out_nodes);
+  if (out_n_nodes) *out_n_nodes = u->last_n_nodes;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* param, b200hist_updater_t* out) {
+  B200_API_BEGIN();
+  B200_CHECK(ell != nullptr && param != nullptr && out != nullptr, "null argument");
+  B200_CHECK(param->max_depth >= 0 && param->max_leaves >= 0, "negative max_depth / max_leaves");
+  B200_CHECK(param->max_depth > 0 || param->max_leaves > 0, "max_depth = 0 requires max_leaves > 0");
+  B200_CHECK(param->grow_policy == 0 || param->grow_policy == 1, "grow_policy must be 0 (depthwise) or 1 (lossguide)");
+  B200_CHECK(param->max_depth <= 24, "max_depth > 24 is not supported");
+  DeviceGuard guard(ell->device);
+  auto* u = new b200hist_updater_s();
+  u->ell = ell;
+  u->device = ell->device;
+  u->num_sms = NumSMs(ell->device);
+  u->param = *param;
+  u->pdev = ToParamDev(*param);
+  long long mn = MaxNodesFor(*param);
+  B200_CHECK(mn < (1ll << 26), "tree too large: bound max_depth or max_leaves");
+  u->max_nodes = (int32_t)mn;
+  if (param->grow_policy == 0) {
+    // depth-wise: one step per level; with only max_leaves the deepest chain has max_leaves-1 levels
+    u->n_steps = param->max_depth > 0 ? param->max_depth : param->max_leaves - 1;
+  } else {
+    u->n_steps = (u->max_nodes - 1) / 2;  // one split per step
+  }
+  PrepareHistKernels(u->device);
+  u->groups = MakeFeatureGroups(*ell, HistMaxGroupBins(u->device));
+  const uint64_t n = ell->n_rows;
+  const size_t part_tiles = n / kPartTile + kMaxLevelNodes + 2;
+  const size_t hist_tiles = n / kHistTile + kMaxLevelNodes + 2;
+  const size_t fin_tiles = n / kPartTile + (size_t)u->max_nodes + 2;
+  u->d_groups = DevAlloc<GroupDesc>(u->groups.size());
+  B200_CUDA(cudaMemcpy(u->d_groups, u->groups.data(), sizeof(GroupDesc) * u->groups.size(), cudaMemcpyHostToDevice));
+  u->d_quant = DevAlloc<QuantDev>(1);
+  u->d_partials = DevAlloc<double>((size_t)4 * u->num_sms * kQuantBlocksPerSM);
+  u->d_counter = DevAlloc<unsigned int>(1);
+  B200_CUDA(cudaMemset(u->d_counter, 0, sizeof(unsigned int)));
+  u->d_gq = DevAlloc<b200hist_gpair64>(n);
+  u->d_ridx[0] = DevAlloc<uint32_t>(n);
+  u->d_ridx[1] = DevAlloc<uint32_t>(n);
+  u->d_position = DevAlloc<int32_t>(n);
+  u->d_ts = DevAlloc<TreeState>(1);
+  u->d_nodes = DevAlloc<NodeDev>(u->max_nodes);
+  u->d_cand = DevAlloc<b200hist_candidate>(u->max_nodes);
+  u->d_part = DevAlloc<PartEntry>(kMaxLevelNodes);
+  u->d_build = DevAlloc<BuildEntry>(kMaxLevelNodes);
+  u->d_sub = DevAlloc<SubEntry>(kMaxLevelNodes);
+  u->d_eval_nodes = DevAlloc<int32_t>(2 * kMaxLevelNodes);
+  u->d_part_tile_seg = DevAlloc<uint32_t>(part_tiles);
+  u->d_build_tile_seg = DevAlloc<uint32_t>(hist_tiles);
+  u->d_tile_left = DevAlloc<uint32_t>(part_tiles);
+  u->d_tile_excl = DevAlloc<uint32_t>(part_tiles + 1);
+  u->d_tile_left_off = DevAlloc<uint32_t>(part_tiles);
+  u->d_flags = DevAlloc<uint32_t>(part_tiles * (kPartTile / 32));
+  u->d_fin = DevAlloc<BuildEntry>(u->max_nodes);
+  u->d_fin_tile_seg = DevAlloc<uint32_t>(fin_tiles);
+  u->d_fin_tile_begin = DevAlloc<uint32_t>((size_t)u->max_nodes + 1);
+  u->d_scratch = DevAlloc<FeatCand>((size_t)2 * kMaxLevelNodes * ell->n_features);
+  u->hist_bytes = (size_t)u->max_nodes * ell->total_bins * sizeof(b200hist_gpair64);
+  size_t free_b = 0, total_b = 0;
+  B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  B200_CHECK(u->hist_bytes < free_b, "histogram cache (" + std::to_string(u->hist_bytes >> 20) +
+                                         " MiB) does not fit in free device memory; lower max_depth/max_leaves");
+  u->d_hist = DevAlloc<b200hist_gpair64>((size_t)u->max_nodes * ell->total_bins);
+  B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&u->h_nodes), sizeof(NodeDev) * u->max_nodes));
+  B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&u->h_ts), sizeof(TreeState)));
+  *out = u;
+  B200_API_END();
+}
+
+int b200hist_updater_destroy(b200hist_updater_t u) {
+  B200_API_BEGIN();
+  if (u) {
+    DeviceGuard guard(u->device);
+    void* ptrs[] = {u->d_groups, u->d_quant, u->d_partials, u->d_counter, u->d_gq, u->d_ridx[0], u->d_ridx[1],
+                    u->d_position, u->d_gpair_staging, u->d_ts, u->d_nodes, u->d_cand, u->d_part, u->d_build,
+                    u->d_sub, u->d_eval_nodes, u->d_part_tile_seg, u->d_build_tile_seg, u->d_tile_left,
+                    u->d_tile_excl, u->d_tile_left_off, u->d_flags, u->d_fin, u->d_fin_tile_seg,
+                    u->d_fin_tile_begin, u->d_scratch, u->d_hist};
+    for (void* p : ptrs) cudaFree(p);
+    cudaFreeHost(u->h_nodes);
+    cudaFreeHost(u->h_ts);
+    for (auto e : u->events) cudaEventDestroy(e);
+    delete u;
+  }
+  B200_API_END();
+}
+
+int b200hist_updater_max_nodes(b200hist_updater_t u, int32_t* out) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && out != nullptr, "null argument");
+  *out = u->max_nodes;
+  B200_API_END();
+}
+
+int b200hist_updater_update_tree(b200hist_updater_t u, const float* gpair_dev, void* stream,
+                                 b200hist_tree_node* out_nodes_host, int32_t* out_n_nodes, int32_t* out_position_dev) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && gpair_dev != nullptr, "null argument");
+  DeviceGuard guard(u->device);
+  UpdateTreeImpl(u, gpair_dev, static_cast<cudaStream_t>(stream), out_nodes_host, out_n_nodes, out_position_dev);
+  B200_API_END();
+}
+
+int b200hist_updater_update_tree_host(b200hist_updater_t u, const float* gpair_host, void* stream,
+                                      b200hist_tree_node* out_nodes_host, int32_t* out_n_nodes,
+                                      int32_t* out_position_dev) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && gpair_host != nullptr, "null argument");
+  DeviceGuard guard(u->device);
+  auto s = static_cast<cudaStream_t>(stream);
+  const size_t bytes = sizeof(float) * 2 * u->ell->n_rows;
+  if (u->d_gpair_staging == nullptr) u->d_gpair_staging = DevAlloc<float>(2 * u->ell->n_rows);
+  B200_CUDA(cudaMemcpyAsync(u->d_gpair_staging, gpair_host, bytes, cudaMemcpyHostToDevice, s));
+  UpdateTreeImpl(u, u->d_gpair_staging, s, out_nodes_host, out_n_nodes, out_position_dev);
+  B200_API_END();
+}
+
+int b200hist_updater_update_prediction_cache(b200hist_updater_t u, float* preds_dev, void* stream) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && preds_dev != nullptr, "null argument");
+  B200_CHECK(u->last_position != nullptr, "UpdatePredictionCache called before Update (updater_gpu_hist.cu:851)");
+  DeviceGuard guard(u->device);
+  auto s = static_cast<cudaStream_t>(stream);
+  PredCacheKernel<<<u->num_sms * 8, 256, 0, s>>>(u->last_position, u->d_nodes, u->ell->n_rows, preds_dev);
+  B200_LAUNCHED();
+  B200_API_END();
+}
+
+int b200hist_updater_last_quantiser(b200hist_updater_t u, b200hist_quantiser* out_host) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && out_host != nullptr, "null argument");
+  DeviceGuard guard(u->device);
+  QuantDev h;
+  B200_CUDA(cudaMemcpy(&h, u->d_quant, sizeof(h), cudaMemcpyDeviceToHost));
+  *out_host = b200hist_quantiser{h.to_fixed_g, h.to_fixed_h, h.to_float_g, h.to_float_h};
+  B200_API_END();
+}
+
+int b200hist_updater_node_histogram(b200hist_updater_t u, int32_t nidx, b200hist_gpair64* out_host) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && out_host != nullptr, "null argument");
+  B200_CHECK(nidx >= 0 && nidx < u->last_n_nodes, "node index out of range");
+  DeviceGuard guard(u->device);
+  B200_CUDA(cudaMemcpy(out_host, u->d_hist + (size_t)nidx * u->ell->total_bins,
+                       sizeof(b200hist_gpair64) * u->ell->total_bins, cudaMemcpyDeviceToHost));
+  B200_API_END();
+}
+
+int b200hist_updater_node_candidate(b200hist_updater_t u, int32_t nidx, b200hist_candidate* out_host) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && out_host != nullptr, "null argument");
+  B200_CHECK(nidx >= 0 && nidx < u->last_n_nodes, "node index out of range");
+  DeviceGuard guard(u->device);
+  B200_CUDA(cudaMemcpy(out_host, u->d_cand + nidx, sizeof(b200hist_candidate), cudaMemcpyDeviceToHost));
+  B200_API_END();
+}
+
+int b200hist_updater_set_profiling(b200hist_updater_t u, int on) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  u->profiling = on != 0;
+  B200_API_END();
+}
+
+int b200hist_updater_last_profile(b200hist_updater_t u, float* out_ms7, uint64_t* out_row_visits) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  if (out_ms7) std::memcpy(out_ms7, u->last_ms, sizeof(u->last_ms));
+  if (out_row_visits) *out_row_visits = u->last_row_visits;
+  B200_API_END();
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+"""Host-side mirror of the reference interface for the hist tree-updater path.
+
+Names follow the reference (paths relative to /root/reference):
+  HistogramCuts   src/common/hist_util.h:38-190
+  EllpackPage     src/data/ellpack_page.cuh:181-391
+  GPUHistMaker    src/tree/updater_gpu_hist.cu:758-891  (TreeUpdater: Configure / Update /
+                  UpdatePredictionCache / Name / HasNodePosition, include/xgboost/tree_updater.h:37-108)
+  RegTree         include/xgboost/tree_model.h (only what ExpandNode records)
+
+PyTorch is used only to own device memory and streams; all compute goes through the C ABI
+(include/b200hist.h) into hand-written sm_100a kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import math
+from ctypes import POINTER, byref, c_float, c_int32, c_uint32, c_uint64, c_void_p
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib as _l
+
+
+def _stream_ptr(device: torch.device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise _l.B200HistError("%s must be a CUDA tensor (there is no CPU fallback)" % name)
+
+
+class HistogramCuts:
+    """cut_ptrs (uint32[F+1]) + cut_values (float32[total_bins]); bin b of feature f covers values
+    below cut_values[cut_ptrs[f] + b] (its upper bound)."""
+
+    def __init__(self, cut_ptrs: Sequence[int], cut_values: Sequence[float]):
+        self.cut_ptrs = np.ascontiguousarray(cut_ptrs, dtype=np.uint32)
+        self.cut_values = np.ascontiguousarray(cut_values, dtype=np.float32)
+        if self.cut_ptrs.ndim != 1 or self.cut_ptrs.size < 2 or self.cut_ptrs[0] != 0:
+            raise ValueError("cut_ptrs must be a 1-D array starting at 0")
+        if int(self.cut_ptrs[-1]) != self.cut_values.size:
+            raise ValueError("cut_ptrs[-1] must equal len(cut_values)")
+
+    @property
+    def n_features(self) -> int:
+        return int(self.cut_ptrs.size - 1)
+
+    @property
+    def total_bins(self) -> int:
+        return int(self.cut_values.size)
+
+    def search_bin(self, value: float, fidx: int) -> int:
+        """HistogramCuts::SearchBin (hist_util.h:112-121), host helper for tests."""
+        beg, end = int(self.cut_ptrs[fidx]), int(self.cut_ptrs[fidx + 1])
+        idx = beg + int(np.searchsorted(self.cut_values[beg:end], np.float32(value), side="right"))
+        return idx - 1 if idx == end else idx
+
+
+class EllpackPage:
+    """Quantised feature matrix resident in HBM (our layout, see include/b200hist.h)."""
+
+    def __init__(self, cuts: HistogramCuts, n_rows: int, device: int = 0, has_missing: bool = False):
+        lib = _l.load()
+        self.cuts = cuts
+        self.device = int(device)
+        self.n_rows = int(n_rows)
+        self._h = c_void_p()
+        _l.check(lib.b200hist_ellpack_create(
+            self.device, self.n_rows, cuts.n_features,
+            cuts.cut_ptrs.ctypes.data_as(POINTER(c_uint32)), cuts.cut_values.ctypes.data_as(POINTER(c_float)),
+            1 if has_missing else 0, byref(self._h)))
+
+    @property
+    def handle(self) -> c_void_p:
+        return self._h
+
+    def push_dense(self, x: torch.Tensor, row_begin: int) -> None:
+        """Bin a dense float32 CUDA batch into rows [row_begin, row_begin + len(x))."""
+        _require_cuda(x, "x")
+        if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+            raise ValueError("x must be a row-major float32 matrix")
+        _l.check(_l.load().b200hist_ellpack_push_dense(self._h, int(row_begin), c_void_p(x.data_ptr()),
+                                                     x.shape[0], x.stride(0), _stream_ptr(x.device)))
+
+    @classmethod
+    def from_dense(cls, x: torch.Tensor, cuts: HistogramCuts, has_missing: Optional[bool] = None) -> "EllpackPage":
+        _require_cuda(x, "x")
+        if has_missing is None:
+            has_missing = bool(torch.isnan(x).any().item())
+        page = cls(cuts, x.shape[0], x.device.index or 0, has_missing)
+        page.push_dense(x.contiguous(), 0)
+        return page
+
+    @classmethod
+    def from_batches(cls, batches: Iterable[torch.Tensor], n_rows: int, cuts: HistogramCuts, device: int = 0,
+                     has_missing: bool = False) -> "EllpackPage":
+        """QuantileDMatrix-style construction from a device batch iterator
+        (src/data/iterative_dmatrix.cu:20-97 pass 2)."""
+        page = cls(cuts, n_rows, device, has_missing)
+        at = 0
+        for b in batches:
+            page.push_dense(b, at)
+            at += b.shape[0]
+        if at != n_rows:
+            raise ValueError("batches hold %d rows, expected %d" % (at, n_rows))
+        return page
+
+    def import_reference(self, gidx_buffer: torch.Tensor, row_stride: int, n_symbols: int, is_dense: bool) -> None:
+        _require_cuda(gidx_buffer, "gidx_buffer")
+        _l.check(_l.load().b200hist_ellpack_import_reference(self._h, c_void_p(gidx_buffer.data_ptr()), row_stride,
+                                                           n_symbols, 1 if is_dense else 0,
+                                                           _stream_ptr(gidx_buffer.device)))
+
+    def info(self) -> Dict[str, int]:
+        n_rows, nf, tb, rb, bb, ns = c_uint64(), c_uint32(), c_uint32(), c_uint32(), c_uint32(), c_uint32()
+        ptr = c_void_p()
+        _l.check(_l.load().b200hist_ellpack_info(self._h, byref(n_rows), byref(nf), byref(tb), byref(rb), byref(bb),
+                                               byref(ns), byref(ptr)))
+        return dict(n_rows=n_rows.value, n_features=nf.value, total_bins=tb.value, row_bytes=rb.value,
+                    bin_bytes=bb.value, null_symbol=ns.value, bins_ptr=ptr.value)
+
+    def symbols(self) -> np.ndarray:
+        """Feature-local symbols as an int64 host matrix [n_rows, n_features] (null -> -1); tests only."""
+        i = self.info()
+        raw = np.zeros((i["n_rows"], i["row_bytes"]), dtype=np.uint8)
+        _l.check(_l.load().b200hist_ellpack_copy_bins_to_host(self._h, c_void_p(raw.ctypes.data)))
+        if i["bin_bytes"] == 1:
+            sym = raw[:, : i["n_features"]].astype(np.int64)
+        else:
+            sym = raw.view(np.uint16)[:, : i["n_features"]].astype(np.int64)
+        if i["null_symbol"] != 0xFFFFFFFF:
+            sym[sym == i["null_symbol"]] = -1
+        return sym
+
+    def __del__(self):
+        try:
+            if self._h:
+                _l.load().b200hist_ellpack_destroy(self._h)
+                self._h = c_void_p()
+        except Exception:
+            pass
+
+
+class RegTree:
+    """The tree as the updater leaves it (node arrays in ExpandNode order)."""
+
+    def __init__(self, nodes: Sequence[_l.TreeNode]):
+        self.nodes = [
+            dict(nodeid=i, parent=n.parent, left=n.left, right=n.right, findex=n.findex, fvalue=n.fvalue,
+                 default_left=bool(n.default_left), is_leaf=bool(n.is_leaf), leaf_value=n.leaf_value,
+                 loss_chg=n.loss_chg, sum_hess=n.sum_hess, base_weight=n.base_weight, depth=n.depth)
+            for i, n in enumerate(nodes)]
+
+    @property
+    def num_nodes(self) -> int:
+        return len(self.nodes)
+
+    def max_depth(self) -> int:
+        return max(n["depth"] for n in self.nodes)
+
+    def dump_json(self) -> dict:
+        """Same shape as Booster.get_dump(dump_format='json', with_stats=True) of the reference."""
+        def rec(i: int) -> dict:
+            n = self.nodes[i]
+            if n["is_leaf"]:
+                return {"nodeid": i, "leaf": n["leaf_value"], "cover": n["sum_hess"]}
+            return {"nodeid": i, "depth": n["depth"], "split": "f%d" % n["findex"], "split_condition": n["fvalue"],
+                    "yes": n["left"], "no": n["right"], "missing": n["left"] if n["default_left"] else n["right"],
+                    "gain": n["loss_chg"], "cover": n["sum_hess"], "children": [rec(n["left"]), rec(n["right"])]}
+        return rec(0)
+
+    def structure(self) -> List[tuple]:
+        """(nodeid, findex, fvalue bits, default_left, left, right) per node: the bit-parity signature."""
+        out = []
+        for n in self.nodes:
+            fv = np.float32(n["fvalue"]).view(np.uint32).item() if not n["is_leaf"] else 0
+            out.append((n["nodeid"], n["findex"], fv, n["default_left"], n["left"], n["right"]))
+        return out
+
+
+class GPUHistMaker:
+    """TreeUpdater "grow_gpu_hist" served by libb200hist.so."""
+
+    def __init__(self, page: EllpackPage):
+        self._page = page
+        self._h = c_void_p()
+        self._param = _l.TrainParam.make()
+        self._max_nodes = 0
+        self._nodes_buf = None
+        self.device = torch.device("cuda:%d" % page.device)
+
+    # TreeUpdater::Configure(Args) -- unknown keys pass through like UpdateAllowUnknown
+    def configure(self, args: Dict[str, object]) -> None:
+        known = {f[0] for f in _l.TrainParam._fields_} | {"eta", "lambda", "alpha", "gamma"}
+        kw = {k: v for k, v in args.items() if k in known}
+        self._param = _l.TrainParam.make(**kw)
+        self._destroy()
+        lib = _l.load()
+        _l.check(lib.b200hist_updater_create(self._page.handle, byref(self._param), byref(self._h)))
+        mn = c_int32()
+        _l.check(lib.b200hist_updater_max_nodes(self._h, byref(mn)))
+        self._max_nodes = mn.value
+        self._nodes_buf = (_l.TreeNode * self._max_nodes)()
+
+    def name(self) -> str:
+        return "grow_gpu_hist"
+
+    def has_node_position(self) -> bool:
+        return True
+
+    def set_profiling(self, on: bool) -> None:
+        _l.check(_l.load().b200hist_updater_set_profiling(self._h, 1 if on else 0))
+
+    def last_profile(self) -> Dict[str, float]:
+        ms = (c_float * 7)()
+        rv = c_uint64()
+        _l.check(_l.load().b200hist_updater_last_profile(self._h, ms, byref(rv)))
+        names = ["quantise", "hist", "subtract", "evaluate", "apply", "partition", "finalise"]
+        d = {k: float(v) for k, v in zip(names, ms)}
+        d["row_visits"] = int(rv.value)
+        return d
+
+    # TreeUpdater::Update for one tree
+    def update(self, gpair: torch.Tensor, out_position: Optional[torch.Tensor] = None) -> RegTree:
+        if not self._h:
+            raise _l.B200HistError("configure() must be called before update()")
+        n_nodes = c_int32()
+        pos_ptr = c_void_p(out_position.data_ptr()) if out_position is not None else c_void_p()
+        if out_position is not None:
+            _require_cuda(out_position, "out_position")
+            if out_position.dtype != torch.int32 or out_position.numel() != self._page.n_rows:
+                raise ValueError("out_position must be int32[n_rows]")
+        if gpair.dtype != torch.float32 or gpair.numel() != 2 * self._page.n_rows or not gpair.is_contiguous():
+            raise ValueError("gpair must be contiguous float32[n_rows, 2]")
+        if gpair.is_cuda:
+            _l.check(_l.load().b200hist_updater_update_tree(self._h, c_void_p(gpair.data_ptr()),
+                                                          _stream_ptr(self.device), self._nodes_buf, byref(n_nodes),
+                                                          pos_ptr))
+        else:  # host gradient: the end-to-end entry (H2D of gpair + D2H of the tree inside)
+            _l.check(_l.load().b200hist_updater_update_tree_host(self._h, c_void_p(gpair.data_ptr()),
+                                                               _stream_ptr(self.device), self._nodes_buf,
+                                                               byref(n_nodes), pos_ptr))
+        return RegTree(self._nodes_buf[: n_nodes.value])
+
+    # TreeUpdater::UpdatePredictionCache
+    def update_prediction_cache(self, preds: torch.Tensor) -> bool:
+        _require_cuda(preds, "preds")
+        if preds.dtype != torch.float32 or preds.numel() != self._page.n_rows:
+            raise ValueError("preds must be float32[n_rows]")
+        _l.check(_l.load().b200hist_updater_update_prediction_cache(self._h, c_void_p(preds.data_ptr()),
+                                                                  _stream_ptr(self.device)))
+        return True
+
+    # introspection for parity tests
+    def last_quantiser(self) -> _l.Quantiser:
+        q = _l.Quantiser()
+        _l.check(_l.load().b200hist_updater_last_quantiser(self._h, byref(q)))
+        return q
+
+    def node_histogram(self, nidx: int) -> np.ndarray:
+        out = np.zeros((self._page.cuts.total_bins, 2), dtype=np.int64)
+        _l.check(_l.load().b200hist_updater_node_histogram(self._h, nidx, c_void_p(out.ctypes.data)))
+        return out
+
+    def node_candidate(self, nidx: int) -> _l.Candidate:
+        c = _l.Candidate()
+        _l.check(_l.load().b200hist_updater_node_candidate(self._h, nidx, byref(c)))
+        return c
+
+    def _destroy(self):
+        if self._h:
+            _l.load().b200hist_updater_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
