@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- boosting iterations/second of the B200 hist tree updater on the reference's headline
+workload (BASELINE.json: 100M x 256 dense f32, 256 bins, depth 8), synthetic data.
+
+  python bench.py --gpus N --steps K --warmup W            our arm
+  python bench.py --impl reference --gpus N ...            the reference's CPU `hist` path on the host cores
+
+One "step" = one boosting iteration on the resident quantised matrix: objective gradient (reg:squarederror)
+-> TreeUpdater::Update (quantise, histograms, split evaluation, row partition, finalise) ->
+UpdatePredictionCache.  `value` times it with every input resident in HBM; `e2e` times the same iteration
+through the C-ABI entry that takes the gradient from (pinned) HOST memory and returns the tree to the host.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "boosting iters/sec, 100Mx256 dense f32, 256 bins, depth 8"
+UNIT = "iters/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=int(os.environ.get("B200_BENCH_ROWS", 100_000_000)))
+    ap.add_argument("--features", type=int, default=int(os.environ.get("B200_BENCH_FEATURES", 256)))
+    ap.add_argument("--max-bin", type=int, default=256)
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("B200_BENCH_DEPTH", 8)))
+    ap.add_argument("--cpu-sample-rows", type=int, default=int(os.environ.get("B200_BENCH_CPU_ROWS", 1_000_000)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic workload: X ~ N(0,1) per 1M-row batch generated ON DEVICE, y = X.w + 0.1 eps
+# --------------------------------------------------------------------------------------------------
+def make_cuts_device(torch, n_features, max_bin, device, seed):
+    """Cuts from exact quantiles of a 200k-row sample of the same distribution (bench plumbing: the product's
+    cut finding is a `next` row of SURVEY 8(f); parity runs take cuts from the reference)."""
+    import numpy as np
+    gen = torch.Generator(device=device).manual_seed(seed)
+    sample = torch.randn((200_000, n_features), generator=gen, device=device)
+    qs = torch.linspace(0, 1, max_bin + 1, device=device)[1:-1]
+    vals = torch.quantile(sample, qs, dim=0).T.contiguous().cpu().numpy().astype(np.float32)
+    ptrs, out = [0], []
+    for j in range(n_features):
+        c = np.unique(vals[j])
+        c = np.concatenate([c, [np.float32(3.0e38)]]).astype(np.float32)
+        out.append(c)
+        ptrs.append(ptrs[-1] + c.size)
+    return np.array(ptrs, dtype=np.uint32), np.concatenate(out)
+
+
+def build_workload(torch, xb, args, device, feat_lo=0, feat_hi=None):
+    n, f = args.rows, args.features
+    cp, cv = make_cuts_device(torch, f, args.max_bin, device, seed=2024)
+    cuts = xb.HistogramCuts(cp, cv)
+    page = xb.EllpackPage(cuts, n, device.index, has_missing=False)
+    gen = torch.Generator(device=device).manual_seed(7)
+    w = torch.randn(f, generator=gen, device=device)
+    y = torch.empty(n, dtype=torch.float32, device=device)
+    batch = 1_000_000
+    for b0 in range(0, n, batch):
+        m = min(batch, n - b0)
+        g = torch.Generator(device=device).manual_seed(2024 + b0 // batch)
+        x = torch.randn((m, f), generator=g, device=device)
+        page.push_dense(x, b0)
+        y[b0:b0 + m] = x @ w + 0.1 * torch.randn(m, generator=g, device=device)
+        del x
+    torch.cuda.synchronize(device)
+    return page, y
+
+
+def algorithmic_bytes(n, f, bin_bytes, depth, row_visits):
+    """bytes each stage must move once (dense page)."""
+    hist = row_visits * (f * bin_bytes + 16 + 4)
+    part = (depth - 1) * n * (4 + bin_bytes + 4)
+    quant = n * (8 + 8 + 16)
+    final = n * (4 + 4) + n * (4 + 4 + 4)
+    return dict(hist=hist, partition=part, quantise=quant, finalise=final, total=hist + part + quant + final)
+
+
+# --------------------------------------------------------------------------------------------------
+# reference CPU arm (the unmodified reference's tree_method=hist on the host cores)
+# --------------------------------------------------------------------------------------------------
+def reference_cpu_iters_per_s(args, steps, warmup, sample_rows):
+    """Times XGBoosterUpdateOneIter of the reference CPU library on a bounded sample of the workload
+    (same generator, same params) and scales to the full row count (hist cost is linear in rows)."""
+    import numpy as np
+    from oracle import ref_capi as rc
+    if not rc.available("cpu"):
+        return None
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(2024)
+    n, f = sample_rows, args.features
+    x = rng.standard_normal((n, f), dtype=np.float32)
+    w = np.random.default_rng(7).standard_normal(f).astype(np.float32)
+    y = (x @ w + 0.1 * rng.standard_normal(n, dtype=np.float32)).astype(np.float32)
+    dm = rc.DMatrix.quantile_from_batches([x], max_bin=args.max_bin, kind="cpu", nthread=cores)
+    dm.set_label(y)
+    bst = rc.Booster({"tree_method": "hist", "device": "cpu", "max_depth": args.depth, "max_bin": args.max_bin,
+                      "objective": "reg:squarederror", "eta": 0.3, "lambda": 1, "min_child_weight": 1,
+                      "nthread": cores}, dm)
+    for i in range(warmup):
+        bst.update(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        bst.update(warmup + i)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    scaled = (1.0 / dt) * (n / float(args.rows))
+    return dict(value=scaled, unit=UNIT, cores=cores, kind="reference",
+                sample="reference CPU hist (oracle/_ref/libxgboost.so, nthread=%d) on %d x %d rows: %.3f s/iter, "
+                       "scaled linearly in rows to %d" % (cores, n, f, dt, args.rows),
+                sample_ms_per_iter=dt * 1e3)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = reference_cpu_iters_per_s(args, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)), args.cpu_sample_rows)
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libxgboost.so not built"}))
+        return
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "synthetic %dx%d dense f32, %d bins, depth %d" % (args.rows, args.features, args.max_bin, args.depth),
+                       "l2": "inputs exceed L2"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import xgboost_b200 as xb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    page, y = build_workload(torch, xb, args, device)
+    info = page.info()
+    n, f = args.rows, args.features
+    up = xb.GPUHistMaker(page)
+    up.configure(dict(max_depth=args.depth, eta=0.3, reg_lambda=1.0, min_child_weight=1.0))
+    preds = torch.zeros(n, dtype=torch.float32, device=device)
+    gpair = torch.empty((n, 2), dtype=torch.float32, device=device)
+    gpair[:, 1] = 1.0
+    pos = torch.empty(n, dtype=torch.int32, device=device)
+
+    def step_resident():
+        torch.sub(preds, y, out=gpair[:, 0])  # reg:squarederror gradient; hessian stays 1
+        tree = up.update(gpair, pos)
+        up.update_prediction_cache(preds)
+        return tree
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = xb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        tree = step_resident()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = xb.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = 1e3 / ms_per_step
+
+    # per-phase device times + row visits from profiled iterations (events inside the library, same stream)
+    up.set_profiling(True)
+    prof = []
+    for _ in range(3):
+        step_resident()
+        prof.append(up.last_profile())
+    up.set_profiling(False)
+    torch.cuda.synchronize(device)
+    phase = {k: float(np.median([p[k] for p in prof])) for k in prof[0] if k != "row_visits"}
+    row_visits = prof[-1]["row_visits"]
+    ab = algorithmic_bytes(n, f, info["bin_bytes"], args.depth, row_visits)
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    hist_launches = args.depth
+    hist_gbs = ab["hist"] / (phase["hist"] * 1e-3) / 1e9 if phase["hist"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "HistKernel", "achieved": hist_gbs, "peak": peak, "unit": "GB/s",
+                "frac": hist_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "launches_per_step": hist_launches, "avg_launch_ms": phase["hist"] / hist_launches,
+                "algorithmic_bytes_per_launch": ab["hist"] / hist_launches, "row_visits_per_step": row_visits,
+                "whole_step_frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak}
+
+    # end-to-end: gradient arrives in pinned HOST memory, tree returns to the host (C-ABI host entry)
+    e2e = None
+    if not args.no_e2e:
+        g_host = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+        g_host.copy_(gpair)
+        loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            tree_ = up.update(g_host, pos)            # H2D of the gradient + D2H of the tree inside
+            up.update_prediction_cache(preds)
+            loss_host.copy_(((preds - y) ** 2).mean().reshape(1), non_blocking=False)  # D2H of the metric
+            return tree_
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        barrier()
+        k2 = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k2):
+            tr = step_e2e()
+        barrier()
+        dt = (time.perf_counter() - t0) / k2
+        tt = torch.tensor([dt], device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": 1.0 / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(n) * 8,
+               "d2h_bytes_per_step": int(tr.num_nodes) * 48 + 4}
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_baseline = reference_cpu_iters_per_s(args, 3, 1, args.cpu_sample_rows)
+        if cpu_baseline is not None:
+            cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                "config": {"workload": "synthetic %dx%d dense f32, %d bins, depth %d, reg:squarederror" % (n, f, args.max_bin, args.depth),
+                           "parallelism": "single GPU" if world == 1 else "feature-block shard x%d" % world,
+                           "l2": "inputs (%.1f GB bin matrix) exceed the 126 MB L2" % (n * info["row_bytes"] / 1e9),
+                           "tree_nodes": tree.num_nodes},
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "phase_ms": phase, "algorithmic_gb_per_step": {k: v / 1e9 for k, v in ab.items()}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
