@@ -198,6 +198,8 @@ struct GroupDesc {
   uint32_t bin_begin, bin_end;  // global bins
   uint32_t byte_begin;          // byte offset of f_begin inside a row (multiple of 4)
   uint32_t n_words;             // 32-bit words per row covering the group
+  uint32_t n_blocks;            // bank-mapped layout: 32-feature blocks in the group (0 = generic layout)
+  uint32_t max_sym;             // bank-mapped layout: symbols per feature slot (max bins of the group)
 };
 
 // Per-(node, feature) best split produced by the feature scan.
@@ -218,8 +220,6 @@ void LaunchQuantise(const float* gpair, uint64_t n, QuantDev* q, b200hist_gpair6
 constexpr int kQuantBlocksPerSM = 4;
 
 // histogram.cu
-size_t HistSmemBytesFor(uint32_t group_bins);
-uint32_t HistMaxGroupBins(int device);
 void PrepareHistKernels(int device);
 void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint32_t* ridx0, const uint32_t* ridx1,
                      const BuildEntry* build, const uint32_t* tile_seg, const TreeState* ts,
@@ -229,7 +229,7 @@ void LaunchSubtract(const SubEntry* sub, const TreeState* ts, b200hist_gpair64* 
                     int num_sms, cudaStream_t s);
 void LaunchSubtractFlat(const b200hist_gpair64* parent, const b200hist_gpair64* built, b200hist_gpair64* out,
                         uint64_t n_bins, cudaStream_t s);
-std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, uint32_t max_group_bins);
+std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, int device);
 
 // evaluate.cu
 void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = node id */,

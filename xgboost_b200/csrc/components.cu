@@ -33,7 +33,7 @@ int b200hist_build_hist(b200hist_ellpack_t ell, const b200hist_gpair64* gq_dev, 
   B200_CUDA(cudaMemsetAsync(hist_dev, 0, sizeof(b200hist_gpair64) * (size_t)n_nodes * ell->total_bins, s));
   if (n_nodes == 0) return 0;
   PrepareHistKernels(ell->device);
-  auto groups = MakeFeatureGroups(*ell, HistMaxGroupBins(ell->device));
+  auto groups = MakeFeatureGroups(*ell, ell->device);
   std::vector<BuildEntry> build(n_nodes);
   std::vector<uint32_t> tile_seg;
   for (int32_t k = 0; k < n_nodes; ++k) {

@@ -15,12 +15,18 @@
 //     per node).  Work = row tiles of all build nodes (tile table written on the device by the
 //     partition scan, no host sync); each persistent CTA owns a CONTIGUOUS range of tiles for one
 //     feature group, so its shared-memory histogram is flushed only when the node changes.
-//   * feature groups are sized for the 227 KB of shared memory of an sm_100 SM: 5 groups for
-//     256 features x 256 bins instead of the reference's 11 (96 KiB cap), so gpair/ridx are
-//     re-read 5x instead of 11x.
-//   * the shared histogram is int64 stored as two 32-bit words; accumulation is a 32-bit shared
-//     atomic on the low word whose returned old value yields the carry into the high word.
+//   * BANK-MAPPED shared histogram (uint8 pages, HistKernelBanked): the privatised histogram is stored
+//     as four planes {g.lo, g.hi, h.lo, h.hi} of [block][symbol][32 lanes] 32-bit words, i.e. feature
+//     (f mod 32) lives entirely in shared-memory bank (f mod 32).  A warp processes 4 rows x 32
+//     features per pass: lane (q, w) loads one 32-bit word (4 symbols) of row q and in step k uses
+//     byte (k + q) mod 4, so in every step the 32 lanes touch 32 DIFFERENT features = 32 different
+//     banks.  Every shared atomic of the inner loop is therefore bank-conflict free by construction
+//     (the reference's layout, and our first version, alias random bins onto few banks; the first
+//     version measured 0.71 updates/clk/SM on B200 because of it).
+//   * int64 accumulation = 32-bit shared atomic on the low word whose returned old value yields the
+//     carry into the high word (two ATOMS per 64-bit add, exact).
 //   * flush to global memory uses 64-bit reductions (RED.64) on non-zero bins only.
+//   * pages with more than 256 symbols per feature (uint16) use the generic kernel (HistKernelGeneric).
 #include "common.cuh"
 
 namespace b200 {
@@ -30,22 +36,56 @@ constexpr uint32_t kMaxGroupFeatures = 512;
 
 static inline size_t Round16(size_t x) { return (x + 15) & ~size_t(15); }
 
-size_t HistSmemBytesFor(uint32_t group_bins) {
+static size_t GenericSmemBytes(uint32_t group_bins) {
   return Round16((size_t)group_bins * 16) + (size_t)kHistTile * 16 + (size_t)kHistTile * 4 + kMaxGroupFeatures * 4;
 }
+static size_t BankedSmemBytes(const GroupDesc& g) { return (size_t)4 * g.n_blocks * g.max_sym * 32 * 4; }
 
-uint32_t HistMaxGroupBins(int device) {
+static int SmemOptin(int device) {
   int optin = 0;
   B200_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  size_t fixed = (size_t)kHistTile * 20 + kMaxGroupFeatures * 4 + 256;
-  B200_CHECK((size_t)optin > fixed + 4096, "device has too little shared memory");
-  return (uint32_t)(((size_t)optin - fixed) / 16);
+  return optin;
 }
 
-// Greedy split of the feature range into groups whose bins fit the shared histogram and whose first
-// feature sits on a 32-bit word boundary of the row (4 uint8 / 2 uint16 symbols per word).
-std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, uint32_t max_group_bins) {
+// Feature groups.
+//  uint8 pages : groups of 32-feature blocks for the bank-mapped kernel; a group holds as many blocks as
+//                fit (4 planes x blocks x max_sym x 32 words).
+//  uint16 pages: greedy contiguous ranges whose bins fit a linear shared histogram (generic kernel).
+std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, int device) {
   std::vector<GroupDesc> groups;
+  const size_t optin = (size_t)SmemOptin(device);
+  if (ell.bin_bytes == 1) {
+    const size_t budget = optin - 1024;
+    uint32_t f = 0;
+    while (f < ell.n_features) {
+      GroupDesc g{};
+      g.f_begin = f;
+      uint32_t blocks = 0, max_sym = 0, f_end = f;
+      while (f_end < ell.n_features) {
+        uint32_t b_end = std::min(ell.n_features, f_end + 32);
+        uint32_t ms = max_sym;
+        for (uint32_t k = f_end; k < b_end; ++k) ms = std::max(ms, ell.cut_ptrs[k + 1] - ell.cut_ptrs[k]);
+        if ((size_t)4 * (blocks + 1) * ms * 32 * 4 > budget) break;
+        max_sym = ms;
+        ++blocks;
+        f_end = b_end;
+      }
+      B200_CHECK(blocks > 0, "a 32-feature block does not fit in shared memory");
+      g.f_end = f_end;
+      g.bin_begin = ell.cut_ptrs[f];
+      g.bin_end = ell.cut_ptrs[f_end];
+      g.byte_begin = f;
+      g.n_words = (f_end - f + 3) / 4;
+      g.n_blocks = blocks;
+      g.max_sym = max_sym;
+      groups.push_back(g);
+      f = f_end;
+    }
+    return groups;
+  }
+  const size_t fixed = (size_t)kHistTile * 20 + kMaxGroupFeatures * 4 + 256;
+  B200_CHECK(optin > fixed + 4096, "device has too little shared memory");
+  const uint32_t max_group_bins = (uint32_t)((optin - fixed) / 16);
   const uint32_t per_word = 4 / ell.bin_bytes;
   uint32_t f = 0;
   while (f < ell.n_features) {
@@ -62,34 +102,141 @@ std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, uint32_t
       B200_CHECK(aligned > f, "cannot form a word-aligned feature group");
       f_end = aligned;
     }
-    GroupDesc g;
+    GroupDesc g{};
     g.f_begin = f;
     g.f_end = f_end;
     g.bin_begin = ell.cut_ptrs[f];
     g.bin_end = ell.cut_ptrs[f_end];
     g.byte_begin = f * ell.bin_bytes;
     g.n_words = (f_end - f + per_word - 1) / per_word;
+    g.n_blocks = 0;
+    g.max_sym = 0;
     groups.push_back(g);
     f = f_end;
   }
   return groups;
 }
 
-// 64-bit add into a shared-memory accumulator held as {lo, hi} 32-bit words.
-__device__ __forceinline__ void SmemAdd64(uint32_t* acc, long long v) {
+// 64-bit add into a shared accumulator whose low / high 32-bit words are `stride` words apart.
+__device__ __forceinline__ void SmemAdd64(uint32_t* lo, uint32_t* hi, long long v) {
   const uint32_t vlo = (uint32_t)(unsigned long long)v;
   const uint32_t vhi = (uint32_t)((unsigned long long)v >> 32);
-  const uint32_t old = atomicAdd(acc, vlo);
+  const uint32_t old = atomicAdd(lo, vlo);
   const uint32_t hi_add = vhi + ((uint32_t)(old + vlo) < old ? 1u : 0u);
-  if (hi_add != 0u) atomicAdd(acc + 1, hi_add);
+  if (hi_add != 0u) atomicAdd(hi, hi_add);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bank-mapped kernel (uint8 symbols)
+// ---------------------------------------------------------------------------------------------
+constexpr int kRowsPerPass = 8;  // rows a warp handles per pass: 2 quads of 4 rows (software unroll)
+
+__global__ void __launch_bounds__(kHistThreads, 1)
+HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
+                 const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
+                 const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
+                 const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist) {
+  extern __shared__ __align__(16) uint32_t sh[];
+  const GroupDesc g = groups[blockIdx.y];
+  const uint32_t S = g.max_sym, B = g.n_blocks;
+  const uint32_t plane = B * S * 32;  // words per plane
+  const uint32_t nf = g.f_end - g.f_begin;
+
+  const uint32_t n_tiles = ts->build_tiles;
+  if (n_tiles == 0) return;
+  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
+  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+  if (t0 >= t1) return;
+
+  for (uint32_t i = threadIdx.x; i < 4 * plane; i += kHistThreads) sh[i] = 0u;
+  __syncthreads();
+
+  auto flush = [&](int32_t nidx) {
+    __syncthreads();
+    longlong2* dst = hist + (size_t)nidx * ell.total_bins;
+    for (uint32_t i = threadIdx.x; i < plane; i += kHistThreads) {
+      const uint32_t lane = i & 31u;
+      const uint32_t sym = (i >> 5) % S;
+      const uint32_t blk = (i >> 5) / S;
+      const uint32_t glo = sh[i], ghi = sh[plane + i], hlo = sh[2 * plane + i], hhi = sh[3 * plane + i];
+      if (glo | ghi | hlo | hhi) {
+        const uint32_t f = g.f_begin + blk * 32 + lane;  // non-zero implies a valid (feature, bin)
+        longlong2* d = dst + ell.cut_ptrs[f] + sym;
+        if (glo | ghi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->x), ((unsigned long long)ghi << 32) | glo);
+        if (hlo | hhi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->y), ((unsigned long long)hhi << 32) | hlo);
+        sh[i] = 0u; sh[plane + i] = 0u; sh[2 * plane + i] = 0u; sh[3 * plane + i] = 0u;
+      }
+    }
+    __syncthreads();
+  };
+
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t q = lane >> 3, w = lane & 7u;  // row of the quad, 32-bit word of the block
+  constexpr uint32_t kWarps = kHistThreads / 32;
+  int32_t cur_seg = -1, cur_nidx = -1;
+  for (uint32_t t = t0; t < t1; ++t) {
+    const uint32_t seg = tile_seg[t];
+    const BuildEntry e = build[seg];
+    if ((int32_t)seg != cur_seg) {
+      if (cur_seg >= 0) flush(cur_nidx);
+      cur_seg = (int32_t)seg;
+      cur_nidx = e.nidx;
+    }
+    const uint32_t off = (t - e.tile_begin) * kHistTile;
+    const uint32_t n = min((uint32_t)kHistTile, e.count - off);
+    const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin + off;
+    for (uint32_t j0 = warp * kRowsPerPass; j0 < n; j0 += kWarps * kRowsPerPass) {
+      uint32_t r[2];
+      bool valid[2];
+      longlong2 gp[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t j = j0 + u * 4 + q;
+        valid[u] = j < n;
+        r[u] = valid[u] ? __ldg(ridx + j) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) gp[u] = valid[u] ? __ldg(gq + r[u]) : make_longlong2(0, 0);
+      for (uint32_t blk = 0; blk < B; ++blk) {
+        uint32_t word[2];
+#pragma unroll
+        const bool in_row = g.byte_begin + blk * 32 + 4 * w < ell.row_bytes;  // last block may be partial
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          word[u] = (valid[u] && in_row)
+                        ? __ldg(reinterpret_cast<const uint32_t*>(ell.bins + (size_t)r[u] * ell.row_bytes +
+                                                                  g.byte_begin + blk * 32) + w)
+                        : 0u;
+        uint32_t* base = sh + blk * S * 32;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) {
+            const uint32_t jj = (k + q) & 3u;
+            const uint32_t fl = blk * 32 + 4 * w + jj;
+            const uint32_t sym = (word[u] >> (8 * jj)) & 0xffu;
+            if (valid[u] && fl < nf && sym < S) {
+              uint32_t* a = base + sym * 32 + 4 * w + jj;
+              SmemAdd64(a, a + plane, gp[u].x);
+              SmemAdd64(a + 2 * plane, a + 3 * plane, gp[u].y);
+            }
+          }
+        }
+      }
+    }
+  }
+  flush(cur_nidx);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic kernel (uint16 symbols): linear {g.lo, g.hi, h.lo, h.hi} per bin, tile staged through smem
+// ---------------------------------------------------------------------------------------------
 template <typename BinT>
 __global__ void __launch_bounds__(kHistThreads, 1)
-HistKernel(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
-           const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
-           const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
-           const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist) {
+HistKernelGeneric(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
+                  const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
+                  const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
+                  const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int kPerWord = 4 / sizeof(BinT);
   constexpr uint32_t kSymMask = (1u << (8 * sizeof(BinT))) - 1u;
@@ -139,7 +286,6 @@ HistKernel(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __rest
     const uint32_t off = (t - e.tile_begin) * kHistTile;
     const uint32_t n = min((uint32_t)kHistTile, e.count - off);
     const uint32_t* __restrict__ ridx = e.buf ? ridx1 : ridx0;
-    // stage the tile's row ids and quantised gradient pairs once; every feature word reuses them
     for (uint32_t j = threadIdx.x; j < n; j += kHistThreads) {
       uint32_t r = ridx[e.begin + off + j];
       s_ridx[j] = r;
@@ -155,13 +301,13 @@ HistKernel(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __rest
       const longlong2 gp = s_gq[j];
 #pragma unroll
       for (int k = 0; k < kPerWord; ++k) {
-        const uint32_t fl = w * kPerWord + k;  // feature index inside the group
+        const uint32_t fl = w * kPerWord + k;
         if (fl < nf) {
           const uint32_t sym = (word >> (8 * sizeof(BinT) * k)) & kSymMask;
           if (sym != ell.null_symbol) {
             uint32_t* acc = sh_hist + 4u * (s_binoff[fl] + sym);
-            SmemAdd64(acc, gp.x);
-            SmemAdd64(acc + 2, gp.y);
+            SmemAdd64(acc, acc + 1, gp.x);
+            SmemAdd64(acc + 2, acc + 3, gp.y);
           }
         }
       }
@@ -172,30 +318,29 @@ HistKernel(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __rest
 }
 
 void PrepareHistKernels(int device) {
-  int optin = 0;
-  B200_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  B200_CUDA(cudaFuncSetAttribute(HistKernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  B200_CUDA(cudaFuncSetAttribute(HistKernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  int optin = SmemOptin(device);
+  B200_CUDA(cudaFuncSetAttribute(HistKernelBanked, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelGeneric<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
 }
 
 void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint32_t* ridx0, const uint32_t* ridx1,
                      const BuildEntry* build, const uint32_t* tile_seg, const TreeState* ts,
                      const GroupDesc* groups_dev, const std::vector<GroupDesc>& groups_host,
                      b200hist_gpair64* hist, int num_sms, cudaStream_t s) {
-  uint32_t max_bins = 0;
-  for (auto const& g : groups_host) max_bins = std::max(max_bins, g.bin_end - g.bin_begin);
-  size_t smem = HistSmemBytesFor(max_bins);
-  int n_groups = (int)groups_host.size();
-  int workers = std::max(1, num_sms / n_groups);
+  const int n_groups = (int)groups_host.size();
+  const int workers = std::max(1, num_sms / n_groups);
   dim3 grid(workers, n_groups);
   if (ell.bin_bytes == 1) {
-    HistKernel<uint8_t><<<grid, kHistThreads, smem, s>>>(ell, reinterpret_cast<const longlong2*>(gq), ridx0, ridx1,
-                                                        build, tile_seg, ts, groups_dev,
-                                                        reinterpret_cast<longlong2*>(hist));
+    size_t smem = 0;
+    for (auto const& g : groups_host) smem = std::max(smem, BankedSmemBytes(g));
+    HistKernelBanked<<<grid, kHistThreads, smem, s>>>(ell, reinterpret_cast<const longlong2*>(gq), ridx0, ridx1, build,
+                                                     tile_seg, ts, groups_dev, reinterpret_cast<longlong2*>(hist));
   } else {
-    HistKernel<uint16_t><<<grid, kHistThreads, smem, s>>>(ell, reinterpret_cast<const longlong2*>(gq), ridx0, ridx1,
-                                                         build, tile_seg, ts, groups_dev,
-                                                         reinterpret_cast<longlong2*>(hist));
+    uint32_t max_bins = 0;
+    for (auto const& g : groups_host) max_bins = std::max(max_bins, g.bin_end - g.bin_begin);
+    HistKernelGeneric<uint16_t><<<grid, kHistThreads, GenericSmemBytes(max_bins), s>>>(
+        ell, reinterpret_cast<const longlong2*>(gq), ridx0, ridx1, build, tile_seg, ts, groups_dev,
+        reinterpret_cast<longlong2*>(hist));
   }
   B200_LAUNCHED();
 }

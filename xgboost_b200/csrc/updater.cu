@@ -658,7 +658,7 @@ int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* 
     u->n_steps = (u->max_nodes - 1) / 2;  // one split per step
   }
   PrepareHistKernels(u->device);
-  u->groups = MakeFeatureGroups(*ell, HistMaxGroupBins(u->device));
+  u->groups = MakeFeatureGroups(*ell, u->device);
   const uint64_t n = ell->n_rows;
   const size_t part_tiles = n / kPartTile + kMaxLevelNodes + 2;
   const size_t hist_tiles = n / kHistTile + kMaxLevelNodes + 2;

@@ -81,8 +81,10 @@ class EllpackPage:
     def push_dense(self, x: torch.Tensor, row_begin: int) -> None:
         """Bin a dense float32 CUDA batch into rows [row_begin, row_begin + len(x))."""
         _require_cuda(x, "x")
-        if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        if x.dtype != torch.float32 or x.dim() != 2 or (x.shape[1] > 1 and x.stride(1) != 1):
             raise ValueError("x must be a row-major float32 matrix")
+        if x.shape[1] == 1:
+            x = x.reshape(-1).contiguous().reshape(-1, 1)  # normalise the stride of the unit dimension
         _l.check(_l.load().b200hist_ellpack_push_dense(self._h, int(row_begin), c_void_p(x.data_ptr()),
                                                      x.shape[0], x.stride(0), _stream_ptr(x.device)))
 
