@@ -128,9 +128,43 @@ __device__ __forceinline__ void SmemAdd64(uint32_t* lo, uint32_t* hi, long long 
 
 // ---------------------------------------------------------------------------------------------
 // Bank-mapped kernel (uint8 symbols)
+//
+// Shared layout: word index = ((blk * S + sym) * 4 + c) * 32 + lane, c in {g.lo, g.hi, h.lo, h.hi}.
+// Bank = lane = (feature mod 32); the four words of one accumulator sit at +0/+128/+256/+384 bytes, so
+// they are immediate offsets of one address register.
 // ---------------------------------------------------------------------------------------------
-constexpr int kRowsPerPass = 8;  // rows a warp handles per pass: 2 quads of 4 rows (software unroll)
+constexpr uint32_t kRowsPerPass = 8;  // rows a warp handles per pass: 2 quads of 4 rows
 
+struct PassData {       // what one lane holds for one pass (2 rows)
+  uint32_t word[2];     // 4 symbols of the lane's 32-bit column word, per row
+  uint32_t glo[2], ghi[2], hlo[2], hhi[2];
+};
+
+__device__ __forceinline__ uint32_t AtomAddShared(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t AtomAddShared256(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1+256], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+// hi += vhi + carry(old + vlo), no return value needed
+__device__ __forceinline__ void RedAddHi128(uint32_t addr, uint32_t old, uint32_t vlo, uint32_t vhi) {
+  uint32_t hi;
+  asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(hi) : "r"(old), "r"(vlo), "r"(vhi));
+  asm volatile("red.shared.add.u32 [%0+128], %1;" ::"r"(addr), "r"(hi) : "memory");
+}
+__device__ __forceinline__ void RedAddHi384(uint32_t addr, uint32_t old, uint32_t vlo, uint32_t vhi) {
+  uint32_t hi;
+  asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(hi) : "r"(old), "r"(vlo), "r"(vhi));
+  asm volatile("red.shared.add.u32 [%0+384], %1;" ::"r"(addr), "r"(hi) : "memory");
+}
+
+// kChecked = false: every block of the group is a full 32 features and the page has no null symbol, so
+// the inner loop carries no predicate at all.
+template <bool kChecked>
 __global__ void __launch_bounds__(kHistThreads, 1)
 HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
                  const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
@@ -139,7 +173,7 @@ HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
   extern __shared__ __align__(16) uint32_t sh[];
   const GroupDesc g = groups[blockIdx.y];
   const uint32_t S = g.max_sym, B = g.n_blocks;
-  const uint32_t plane = B * S * 32;  // words per plane
+  const uint32_t slots = B * S * 32;  // (block, symbol, lane) accumulators
   const uint32_t nf = g.f_end - g.f_begin;
 
   const uint32_t n_tiles = ts->build_tiles;
@@ -147,24 +181,24 @@ HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
   const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
   const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
   if (t0 >= t1) return;
+  const uint32_t n_build = (uint32_t)ts->n_build;
 
-  for (uint32_t i = threadIdx.x; i < 4 * plane; i += kHistThreads) sh[i] = 0u;
+  for (uint32_t i = threadIdx.x; i < 4 * slots; i += kHistThreads) sh[i] = 0u;
   __syncthreads();
 
   auto flush = [&](int32_t nidx) {
     __syncthreads();
     longlong2* dst = hist + (size_t)nidx * ell.total_bins;
-    for (uint32_t i = threadIdx.x; i < plane; i += kHistThreads) {
-      const uint32_t lane = i & 31u;
-      const uint32_t sym = (i >> 5) % S;
-      const uint32_t blk = (i >> 5) / S;
-      const uint32_t glo = sh[i], ghi = sh[plane + i], hlo = sh[2 * plane + i], hhi = sh[3 * plane + i];
+    for (uint32_t p = threadIdx.x; p < slots; p += kHistThreads) {
+      const uint32_t ln = p & 31u, rest = p >> 5;  // rest = blk * S + sym
+      uint32_t* a = sh + rest * 128 + ln;
+      const uint32_t glo = a[0], ghi = a[32], hlo = a[64], hhi = a[96];
       if (glo | ghi | hlo | hhi) {
-        const uint32_t f = g.f_begin + blk * 32 + lane;  // non-zero implies a valid (feature, bin)
-        longlong2* d = dst + ell.cut_ptrs[f] + sym;
+        const uint32_t f = g.f_begin + (rest / S) * 32 + ln;  // non-zero implies a valid (feature, bin)
+        longlong2* d = dst + ell.cut_ptrs[f] + (rest % S);
         if (glo | ghi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->x), ((unsigned long long)ghi << 32) | glo);
         if (hlo | hhi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->y), ((unsigned long long)hhi << 32) | hlo);
-        sh[i] = 0u; sh[plane + i] = 0u; sh[2 * plane + i] = 0u; sh[3 * plane + i] = 0u;
+        a[0] = 0u; a[32] = 0u; a[64] = 0u; a[96] = 0u;
       }
     }
     __syncthreads();
@@ -173,59 +207,116 @@ HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t q = lane >> 3, w = lane & 7u;  // row of the quad, 32-bit word of the block
   constexpr uint32_t kWarps = kHistThreads / 32;
-  int32_t cur_seg = -1, cur_nidx = -1;
-  for (uint32_t t = t0; t < t1; ++t) {
+  constexpr uint32_t kStride = kWarps * kRowsPerPass;
+  const uint32_t sh_base = (uint32_t)__cvta_generic_to_shared(sh);
+  // step k of a lane uses byte (k + q) mod 4 of its word: 32 lanes -> 32 distinct features -> 32 banks
+  uint32_t sel[4], lane_off[4];
+#pragma unroll
+  for (uint32_t k = 0; k < 4; ++k) {
+    const uint32_t jj = (k + q) & 3u;
+    sel[k] = 0x4440u | jj;               // PRMT selector: byte jj -> byte 0, zeros elsewhere
+    lane_off[k] = (4u * w + jj) * 4u;    // byte offset of the lane slot
+  }
+
+  uint32_t t = t0;
+  while (t < t1) {
     const uint32_t seg = tile_seg[t];
     const BuildEntry e = build[seg];
-    if ((int32_t)seg != cur_seg) {
-      if (cur_seg >= 0) flush(cur_nidx);
-      cur_seg = (int32_t)seg;
-      cur_nidx = e.nidx;
-    }
-    const uint32_t off = (t - e.tile_begin) * kHistTile;
-    const uint32_t n = min((uint32_t)kHistTile, e.count - off);
-    const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin + off;
-    for (uint32_t j0 = warp * kRowsPerPass; j0 < n; j0 += kWarps * kRowsPerPass) {
-      uint32_t r[2];
-      bool valid[2];
-      longlong2 gp[2];
+    const uint32_t seg_tile_end = (seg + 1 < n_build) ? build[seg + 1].tile_begin : n_tiles;
+    const uint32_t te = min(t1, seg_tile_end);
+    const uint32_t lo = (t - e.tile_begin) * kHistTile;
+    const uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
+    const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin;
+
+    for (uint32_t blk = 0; blk < B; ++blk) {
+      const uint32_t blk_base = sh_base + blk * S * 512u;
+      const uint8_t* __restrict__ col = ell.bins + g.byte_begin + blk * 32u + 4u * w;
+      const bool in_row = g.byte_begin + blk * 32u + 4u * w < ell.row_bytes;  // partial last block
+      bool fok[4];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const uint32_t j = j0 + u * 4 + q;
-        valid[u] = j < n;
-        r[u] = valid[u] ? __ldg(ridx + j) : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) gp[u] = valid[u] ? __ldg(gq + r[u]) : make_longlong2(0, 0);
-      for (uint32_t blk = 0; blk < B; ++blk) {
-        uint32_t word[2];
-#pragma unroll
-        const bool in_row = g.byte_begin + blk * 32 + 4 * w < ell.row_bytes;  // last block may be partial
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-          word[u] = (valid[u] && in_row)
-                        ? __ldg(reinterpret_cast<const uint32_t*>(ell.bins + (size_t)r[u] * ell.row_bytes +
-                                                                  g.byte_begin + blk * 32) + w)
-                        : 0u;
-        uint32_t* base = sh + blk * S * 32;
+      for (uint32_t k = 0; k < 4; ++k) fok[k] = blk * 32u + 4u * w + ((k + q) & 3u) < nf;
+
+      auto load_r = [&](uint32_t jb, uint32_t (&r)[2], bool (&v)[2]) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
+          const uint32_t j = jb + u * 4 + q;
+          v[u] = j < hi;
+          r[u] = __ldg(ridx + (v[u] ? j : lo));  // rows past the end re-read a valid row and add zero
+        }
+      };
+      auto load_d = [&](const uint32_t (&r)[2], const bool (&v)[2], PassData& d) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const longlong2 gp = __ldg(gq + r[u]);
+          const uint32_t wd = (!kChecked || in_row)
+                                  ? __ldg(reinterpret_cast<const uint32_t*>(col + (size_t)r[u] * ell.row_bytes))
+                                  : 0u;
+          d.word[u] = wd;
+          d.glo[u] = v[u] ? (uint32_t)(unsigned long long)gp.x : 0u;
+          d.ghi[u] = v[u] ? (uint32_t)((unsigned long long)gp.x >> 32) : 0u;
+          d.hlo[u] = v[u] ? (uint32_t)(unsigned long long)gp.y : 0u;
+          d.hhi[u] = v[u] ? (uint32_t)((unsigned long long)gp.y >> 32) : 0u;
+        }
+      };
+      auto process = [&](const PassData& d) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          uint32_t addr[4], og[4], oh[4], vgl[4], vgh[4], vhl[4], vhh[4];
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k) {
-            const uint32_t jj = (k + q) & 3u;
-            const uint32_t fl = blk * 32 + 4 * w + jj;
-            const uint32_t sym = (word[u] >> (8 * jj)) & 0xffu;
-            if (valid[u] && fl < nf && sym < S) {
-              uint32_t* a = base + sym * 32 + 4 * w + jj;
-              SmemAdd64(a, a + plane, gp[u].x);
-              SmemAdd64(a + 2 * plane, a + 3 * plane, gp[u].y);
+            const uint32_t sym = __byte_perm(d.word[u], 0u, sel[k]);
+            vgl[k] = d.glo[u]; vgh[k] = d.ghi[u]; vhl[k] = d.hlo[u]; vhh[k] = d.hhi[u];
+            if (kChecked) {
+              const bool ok = fok[k] && sym < S;  // partial block / null symbol: add zero to slot 0
+              addr[k] = blk_base + (ok ? sym : 0u) * 512u + lane_off[k];
+              if (!ok) { vgl[k] = 0u; vgh[k] = 0u; vhl[k] = 0u; vhh[k] = 0u; }
+            } else {
+              addr[k] = blk_base + sym * 512u + lane_off[k];
             }
           }
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) {
+            og[k] = AtomAddShared(addr[k], vgl[k]);
+            oh[k] = AtomAddShared256(addr[k], vhl[k]);
+          }
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) {
+            RedAddHi128(addr[k], og[k], vgl[k], vgh[k]);
+            RedAddHi384(addr[k], oh[k], vhl[k], vhh[k]);
+          }
+        }
+      };
+
+      // software pipeline: data of pass i+1 and row ids of pass i+2 are in flight while pass i accumulates
+      uint32_t jb = lo + warp * kRowsPerPass;
+      if (jb < hi) {
+        uint32_t r1[2], r2[2] = {0u, 0u};
+        bool v1[2], v2[2] = {false, false};
+        PassData d1, d2;
+        load_r(jb, r1, v1);
+        uint32_t jb2 = jb + kStride;
+        bool have2 = jb2 < hi;
+        if (have2) load_r(jb2, r2, v2);
+        load_d(r1, v1, d1);
+        while (true) {
+          const uint32_t jb3 = jb2 + kStride;
+          const bool have3 = have2 && jb3 < hi;
+          uint32_t r3[2] = {0u, 0u};
+          bool v3[2] = {false, false};
+          if (have2) load_d(r2, v2, d2);
+          if (have3) load_r(jb3, r3, v3);
+          process(d1);
+          if (!have2) break;
+          d1 = d2;
+          r2[0] = r3[0]; r2[1] = r3[1]; v2[0] = v3[0]; v2[1] = v3[1];
+          jb2 = jb3;
+          have2 = have3;
         }
       }
     }
+    flush(e.nidx);
+    t = te;
   }
-  flush(cur_nidx);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -319,7 +410,8 @@ HistKernelGeneric(EllView ell, const longlong2* __restrict__ gq, const uint32_t*
 
 void PrepareHistKernels(int device) {
   int optin = SmemOptin(device);
-  B200_CUDA(cudaFuncSetAttribute(HistKernelBanked, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelGeneric<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
 }
 
@@ -333,8 +425,11 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
   if (ell.bin_bytes == 1) {
     size_t smem = 0;
     for (auto const& g : groups_host) smem = std::max(smem, BankedSmemBytes(g));
-    HistKernelBanked<<<grid, kHistThreads, smem, s>>>(ell, reinterpret_cast<const longlong2*>(gq), ridx0, ridx1, build,
-                                                     tile_seg, ts, groups_dev, reinterpret_cast<longlong2*>(hist));
+    bool checked = ell.null_symbol != 0xFFFFFFFFu;
+    for (auto const& g : groups_host) checked = checked || ((g.f_end - g.f_begin) % 32u != 0u);
+    auto kernel = checked ? HistKernelBanked<true> : HistKernelBanked<false>;
+    kernel<<<grid, kHistThreads, smem, s>>>(ell, reinterpret_cast<const longlong2*>(gq), ridx0, ridx1, build, tile_seg,
+                                           ts, groups_dev, reinterpret_cast<longlong2*>(hist));
   } else {
     uint32_t max_bins = 0;
     for (auto const& g : groups_host) max_bins = std::max(max_bins, g.bin_end - g.bin_begin);
