@@ -216,6 +216,10 @@ def run_b200(args):
     n, f = args.rows, args.features
     up = xb.GPUHistMaker(page)
     up.configure(dict(max_depth=args.depth, eta=0.3, reg_lambda=1.0, min_child_weight=1.0))
+    comm = None
+    if world > 1:  # feature-block sharded histograms + one NCCL allreduce per tree level
+        comm = xb.Communicator.from_torch_distributed(device)
+        up.set_comm(comm)
     preds = torch.zeros(n, dtype=torch.float32, device=device)
     gpair = torch.empty((n, 2), dtype=torch.float32, device=device)
     gpair[:, 1] = 1.0

@@ -86,6 +86,7 @@ typedef struct b200hist_tree_node {
 
 typedef struct b200hist_ellpack_s* b200hist_ellpack_t;  /* quantised feature matrix (EllpackPage) */
 typedef struct b200hist_updater_s* b200hist_updater_t;  /* tree updater (GPUHistMaker) */
+typedef struct b200hist_comm_s* b200hist_comm_t;        /* NCCL communicator of the histogram allreduce */
 
 /* ---------------------------------------------------------------------------------------------
  * Errors / info
@@ -157,6 +158,26 @@ B200HIST_API int b200hist_updater_update_tree_host(b200hist_updater_t u, const f
  * preds_dev[i] += leaf_value[decode(position[i])] for the last tree built. */
 B200HIST_API int b200hist_updater_update_prediction_cache(b200hist_updater_t u, float* preds_dev,
                                                           void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU): feature-block sharded histogram + ONE int64 allreduce per tree level.
+ *   replaces DeviceHistogramBuilder::AllReduceHist (src/tree/gpu_hist/histogram.cu:598-609) ->
+ *   collective::Allreduce/NCCLColl (src/collective/aggregator.h:138-160, src/collective/coll.cu:251-277)
+ *   and the communicator bootstrap (src/collective/comm.cu:45-101).
+ * Every rank holds the full page and the full row state; rank r builds only the histogram slices of its
+ * feature groups, the allreduce (a sum over disjoint slices, hence exact) completes them, and all ranks then
+ * evaluate and partition identically.  Results are bit-identical to a single GPU.
+ * ------------------------------------------------------------------------------------------- */
+/* 128-byte NCCL unique id, created on one rank and distributed by the caller's control plane. */
+B200HIST_API int b200hist_comm_unique_id(uint8_t* out_id128);
+B200HIST_API int b200hist_comm_create(int device, int world, int rank, const uint8_t* id128, b200hist_comm_t* out);
+B200HIST_API int b200hist_comm_destroy(b200hist_comm_t comm);
+/* Rank `rank` of `world` owns feature groups [g_begin, g_end) out of n_groups (host logic only). */
+B200HIST_API int b200hist_shard_groups(uint32_t n_groups, int world, int rank, uint32_t* g_begin, uint32_t* g_end);
+/* Attach a communicator: the updater builds only its shard and allreduces once per level.  The
+ * communicator is borrowed.  Passing NULL returns to single-GPU mode. */
+B200HIST_API int b200hist_updater_set_comm(b200hist_updater_t u, b200hist_comm_t comm);
+B200HIST_API int b200hist_updater_num_feature_groups(b200hist_updater_t u, uint32_t* out);
+
 /* Introspection of the last update (parity tests): quantiser, per-node histogram, per-node
  * candidate, per-node row counts. */
 B200HIST_API int b200hist_updater_last_quantiser(b200hist_updater_t u, b200hist_quantiser* out_host);

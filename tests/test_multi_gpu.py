@@ -1,0 +1,107 @@
+"""Multi-GPU path (feature-block sharded histogram + one allreduce per level).
+
+CPU part (no GPU): the host logic of the sharding under a real world_size=2 torch.distributed (gloo)
+job -- group ownership must tile the group range exactly and the unique-id hand-off must deliver the same
+128 bytes to every rank.
+GPU part (needs >= 2 GPUs, run with `gpurun --gpus 2`): a 2-rank NCCL job must produce trees that are
+bit-identical to the single-GPU trees.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests.conftest import ROOT
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+dist.init_process_group("gloo")
+import xgboost_b200 as xb
+rank, world = dist.get_rank(), dist.get_world_size()
+ok = True
+for n_groups in (1, 2, 3, 7, 8, 11, 64):
+    b, e = xb.shard_groups(n_groups, world, rank)
+    t = torch.tensor([b, e], dtype=torch.int64)
+    out = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(out, t)
+    spans = [tuple(o.tolist()) for o in out]
+    # contiguous, ordered, exact cover, balanced within one group
+    ok &= spans[0][0] == 0 and spans[-1][1] == n_groups
+    ok &= all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    sizes = [s[1] - s[0] for s in spans]
+    ok &= max(sizes) - min(sizes) <= 1
+# control-plane hand-off of the 128-byte id (content is arbitrary here: NCCL itself needs a GPU)
+ident = torch.arange(128, dtype=torch.uint8) if rank == 0 else torch.zeros(128, dtype=torch.uint8)
+dist.broadcast(ident, src=0)
+ok &= ident.tolist() == list(range(128))
+flag = torch.tensor([1 if ok else 0])
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)
+'''
+
+
+def test_feature_shard_host_logic_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_shard_groups_single_process():
+    import xgboost_b200 as xb
+    assert xb.shard_groups(8, 1, 0) == (0, 8)
+    assert [xb.shard_groups(8, 8, r) for r in range(8)] == [(r, r + 1) for r in range(8)]
+    assert [xb.shard_groups(3, 4, r) for r in range(4)] == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    with pytest.raises(xb.B200HistError):
+        xb.shard_groups(8, 2, 2)
+
+
+_GPU_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+import xgboost_b200 as xb
+from tests.helpers import make_cuts, make_regression, squared_error_gpair
+x, y = make_regression(60000, 96, seed=17)
+cp, cv = make_cuts(x, 256)
+page = xb.EllpackPage.from_dense(torch.from_numpy(x).to(dev), xb.HistogramCuts(cp, cv))
+gp = torch.from_numpy(squared_error_gpair(np.zeros_like(y), y)).to(dev)
+up = xb.GPUHistMaker(page); up.configure(dict(max_depth=6))
+single = up.update(gp)
+h_single = [up.node_histogram(i) for i in (0, 1, 2)]
+comm = xb.Communicator.from_torch_distributed(dev)
+up.set_comm(comm)
+assert up.num_feature_groups() == 3
+sharded = up.update(gp)
+ok = single.structure() == sharded.structure()
+ok &= all(np.array_equal(up.node_histogram(i), h) for i, h in zip((0, 1, 2), h_single))
+ok &= [n["leaf_value"] for n in single.nodes] == [n["leaf_value"] for n in sharded.nodes]
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)
+'''
+
+
+@pytest.mark.gpu
+def test_two_rank_nccl_matches_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    script = tmp_path / "gpu_worker.py"
+    script.write_text(_GPU_WORKER % {"root": ROOT})
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29614", str(script)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     "-I", CSRC,
 ]
 SOURCES = ["ellpack.cu", "quantise.cu", "histogram.cu", "evaluate.cu", "partition.cu", "updater.cu",
-           "components.cu"]
+           "components.cu", "comm.cu"]
 
 
 def _digest(paths):

@@ -89,6 +89,13 @@ struct EllView {
 
 }  // namespace b200
 
+struct b200hist_comm_s {
+  int device{0};
+  int world{1};
+  int rank{0};
+  void* comm{nullptr};  // ncclComm_t
+};
+
 struct b200hist_ellpack_s {
   int device{0};
   uint64_t n_rows{0};
@@ -133,6 +140,8 @@ struct NodeDev {
   int32_t partitioned;   // rows have been handed to the children
   int32_t split_lbin;    // go left iff feature-local bin < split_lbin
   int32_t cand_open;     // has a queued expand entry (driver.h Push filter passed)
+  int32_t hist_slot;     // slot of the node's histogram in the histogram cache (-1 = none)
+  int32_t pad;
 };
 
 struct PartEntry {
@@ -152,11 +161,11 @@ struct BuildEntry {
   int32_t buf;
   uint32_t begin, count;
   uint32_t tile_begin;
-  uint32_t pad;
+  uint32_t slot;  // histogram slot the rows accumulate into
 };
 
 struct SubEntry {
-  int32_t parent, built, sub;
+  int32_t parent, built, sub;  // histogram SLOTS
 };
 
 struct TreeState {
@@ -180,6 +189,8 @@ struct QuantDev {
   double to_fixed_g, to_fixed_h, to_float_g, to_float_h;
   double sums[4];
   long long root_g, root_h;
+  unsigned int h_lo_or;  // OR of the low 32 bits of every quantised hessian (0 => histogram skips h.lo)
+  unsigned int pad;
 };
 
 struct ParamDev {
@@ -224,12 +235,16 @@ void PrepareHistKernels(int device);
 void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint32_t* ridx0, const uint32_t* ridx1,
                      const BuildEntry* build, const uint32_t* tile_seg, const TreeState* ts,
                      const GroupDesc* groups_dev, const std::vector<GroupDesc>& groups_host,
-                     b200hist_gpair64* hist, int num_sms, cudaStream_t s);
+                     b200hist_gpair64* hist, const QuantDev* quant /* nullable */, int num_sms, cudaStream_t s);
 void LaunchSubtract(const SubEntry* sub, const TreeState* ts, b200hist_gpair64* hist, uint32_t total_bins,
                     int num_sms, cudaStream_t s);
 void LaunchSubtractFlat(const b200hist_gpair64* parent, const b200hist_gpair64* built, b200hist_gpair64* out,
                         uint64_t n_bins, cudaStream_t s);
 std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, int device);
+
+// comm.cu
+void CommAllReduceInt64(b200hist_comm_s* c, void* buf, size_t count, cudaStream_t s);
+void ShardGroups(uint32_t n_groups, int world, int rank, uint32_t* g0, uint32_t* g1);
 
 // evaluate.cu
 void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = node id */,

@@ -39,7 +39,7 @@ int b200hist_build_hist(b200hist_ellpack_t ell, const b200hist_gpair64* gq_dev, 
   for (int32_t k = 0; k < n_nodes; ++k) {
     B200_CHECK(seg_begin_host[k] + seg_count_host[k] <= (1ull << 32), "segment out of range");
     uint32_t tiles = (uint32_t)((seg_count_host[k] + kHistTile - 1) / kHistTile);
-    build[k] = BuildEntry{k, 0, (uint32_t)seg_begin_host[k], (uint32_t)seg_count_host[k], (uint32_t)tile_seg.size(), 0u};
+    build[k] = BuildEntry{k, 0, (uint32_t)seg_begin_host[k], (uint32_t)seg_count_host[k], (uint32_t)tile_seg.size(), (uint32_t)k};
     tile_seg.insert(tile_seg.end(), tiles, (uint32_t)k);
   }
   TreeState ts{};
@@ -55,7 +55,7 @@ int b200hist_build_hist(b200hist_ellpack_t ell, const b200hist_gpair64* gq_dev, 
   B200_CUDA(cudaMemcpyAsync(d_ts.p, &ts, sizeof(ts), cudaMemcpyHostToDevice, s));
   B200_CUDA(cudaMemcpyAsync(d_groups.p, groups.data(), sizeof(GroupDesc) * groups.size(), cudaMemcpyHostToDevice, s));
   LaunchBuildHist(ell->View(), gq_dev, ridx_dev, ridx_dev, d_build.p, d_tile_seg.p, d_ts.p, d_groups.p, groups,
-                  hist_dev, NumSMs(ell->device), s);
+                  hist_dev, nullptr, NumSMs(ell->device), s);
   B200_CUDA(cudaStreamSynchronize(s));
   B200_API_END();
 }
@@ -90,6 +90,7 @@ int b200hist_evaluate_splits(b200hist_ellpack_t ell, const b200hist_gpair64* his
     nd.parent = -1; nd.left = -1; nd.right = -1; nd.is_leaf = 1; nd.findex = -1; nd.seg_buf = -1;
     nd.sum_g = parent_sums_host[k].grad;
     nd.sum_h = parent_sums_host[k].hess;
+    nd.hist_slot = k;
     nodes[k] = nd;
     eval_nodes[k] = k;
   }

@@ -85,7 +85,7 @@ FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t
     const int fpos = (int)(item - (long long)slot * n_fs);
     const int f = feature_set ? feature_set[fpos] : fpos;
     const int nidx = eval_nodes[slot];
-    const longlong2* h = hist + (size_t)nidx * ell.total_bins;
+    const longlong2* h = hist + (size_t)nodes[nidx].hist_slot * ell.total_bins;
     const long long pg = nodes[nidx].sum_g, ph = nodes[nidx].sum_h;
     const uint32_t beg = ell.cut_ptrs[f], end = ell.cut_ptrs[f + 1];
 

@@ -27,6 +27,9 @@
 //     carry into the high word (two ATOMS per 64-bit add, exact).
 //   * flush to global memory uses 64-bit reductions (RED.64) on non-zero bins only.
 //   * pages with more than 256 symbols per feature (uint16) use the generic kernel (HistKernelGeneric).
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -47,6 +50,22 @@ static int SmemOptin(int device) {
   return optin;
 }
 
+// Histogram kernel selection (B200HIST_HIST_IMPL):
+//   0 = direct global loads, software pipelined in registers (HistKernelBanked)  [default: fastest, see DESIGN.md]
+//   1 = per-warp TMA bulk-copy ring (HistKernelStaged<.., true>)
+//   2 = per-warp cp.async ring      (HistKernelStaged<.., false>)
+static int HistImpl() {
+  static int impl = [] {
+    const char* e = std::getenv("B200HIST_HIST_IMPL");
+    return e ? std::atoi(e) : 0;
+  }();
+  return impl;
+}
+constexpr uint32_t kRingStages = 4;
+static size_t RingSmemBytes(uint32_t blocks) {
+  return HistImpl() == 0 ? 0 : (size_t)(kHistThreads / 32) * kRingStages * (8 * (32 * blocks + 16) + 8);
+}
+
 // Feature groups.
 //  uint8 pages : groups of 32-feature blocks for the bank-mapped kernel; a group holds as many blocks as
 //                fit (4 planes x blocks x max_sym x 32 words).
@@ -65,7 +84,7 @@ std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, int devi
         uint32_t b_end = std::min(ell.n_features, f_end + 32);
         uint32_t ms = max_sym;
         for (uint32_t k = f_end; k < b_end; ++k) ms = std::max(ms, ell.cut_ptrs[k + 1] - ell.cut_ptrs[k]);
-        if ((size_t)4 * (blocks + 1) * ms * 32 * 4 > budget) break;
+        if ((size_t)4 * (blocks + 1) * ms * 32 * 4 + RingSmemBytes(blocks + 1) > budget) break;
         max_sym = ms;
         ++blocks;
         f_end = b_end;
@@ -156,6 +175,9 @@ __device__ __forceinline__ void RedAddHi128(uint32_t addr, uint32_t old, uint32_
   asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(hi) : "r"(old), "r"(vlo), "r"(vhi));
   asm volatile("red.shared.add.u32 [%0+128], %1;" ::"r"(addr), "r"(hi) : "memory");
 }
+__device__ __forceinline__ void RedAdd384(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0+384], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void RedAddHi384(uint32_t addr, uint32_t old, uint32_t vlo, uint32_t vhi) {
   uint32_t hi;
   asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(hi) : "r"(old), "r"(vlo), "r"(vhi));
@@ -169,7 +191,8 @@ __global__ void __launch_bounds__(kHistThreads, 1)
 HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
                  const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
                  const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
-                 const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist) {
+                 const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist,
+                 const QuantDev* __restrict__ qd) {
   extern __shared__ __align__(16) uint32_t sh[];
   const GroupDesc g = groups[blockIdx.y];
   const uint32_t S = g.max_sym, B = g.n_blocks;
@@ -182,6 +205,7 @@ HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
   const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
   if (t0 >= t1) return;
   const uint32_t n_build = (uint32_t)ts->n_build;
+  const bool h_lo_zero = qd != nullptr && qd->h_lo_or == 0u;  // uniform over the grid
 
   for (uint32_t i = threadIdx.x; i < 4 * slots; i += kHistThreads) sh[i] = 0u;
   __syncthreads();
@@ -258,7 +282,8 @@ HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
           d.hhi[u] = v[u] ? (uint32_t)((unsigned long long)gp.y >> 32) : 0u;
         }
       };
-      auto process = [&](const PassData& d) {
+      auto process = [&](const PassData& d, auto hz) {
+        constexpr bool kHLoZero = decltype(hz)::value;  // every hq has a zero low word: no h.lo atomic
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           uint32_t addr[4], og[4], oh[4], vgl[4], vgh[4], vhl[4], vhh[4];
@@ -277,6 +302,252 @@ HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k) {
             og[k] = AtomAddShared(addr[k], vgl[k]);
+            if (!kHLoZero) oh[k] = AtomAddShared256(addr[k], vhl[k]);
+          }
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) {
+            RedAddHi128(addr[k], og[k], vgl[k], vgh[k]);
+            if (kHLoZero) RedAdd384(addr[k], vhh[k]);
+            else RedAddHi384(addr[k], oh[k], vhl[k], vhh[k]);
+          }
+        }
+      };
+
+      auto run = [&](auto hz) {
+        // software pipeline: data of pass i+1 and row ids of pass i+2 are in flight while pass i accumulates
+        uint32_t jb = lo + warp * kRowsPerPass;
+        if (jb < hi) {
+          uint32_t r1[2], r2[2] = {0u, 0u};
+          bool v1[2], v2[2] = {false, false};
+          PassData d1, d2;
+          load_r(jb, r1, v1);
+          uint32_t jb2 = jb + kStride;
+          bool have2 = jb2 < hi;
+          if (have2) load_r(jb2, r2, v2);
+          load_d(r1, v1, d1);
+          while (true) {
+            const uint32_t jb3 = jb2 + kStride;
+            const bool have3 = have2 && jb3 < hi;
+            uint32_t r3[2] = {0u, 0u};
+            bool v3[2] = {false, false};
+            if (have2) load_d(r2, v2, d2);
+            if (have3) load_r(jb3, r3, v3);
+            process(d1, hz);
+            if (!have2) break;
+            d1 = d2;
+            r2[0] = r3[0]; r2[1] = r3[1]; v2[0] = v3[0]; v2[1] = v3[1];
+            jb2 = jb3;
+            have2 = have3;
+          }
+        }
+      };
+      if (h_lo_zero) run(std::true_type{}); else run(std::false_type{});
+    }
+    flush((int32_t)e.slot);
+    t = te;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Staged bank-mapped kernel: the same accumulation, but every warp feeds itself through a private ring of
+// kStages shared-memory stages filled by asynchronous copies, so the accumulating instruction stream
+// contains no global loads or 64-bit address arithmetic -- only LDS, PRMT/IMAD and the atomics.
+//
+//   kBulk = true : one TMA 1-D bulk copy (cp.async.bulk.shared::cluster.global, SASS UBLKCP) per gathered
+//                  row slice (32*B bytes of symbols, 16-byte aligned by construction of the page layout) and
+//                  one per quantised gradient pair, completion counted on a per-(warp, stage) mbarrier.
+//   kBulk = false: 16-byte cp.async (LDGSTS) per chunk, completion by commit/wait groups.
+// A stage holds the 8 rows of one pass: [8][32*B] symbol bytes then [8] x 16-byte gradient pairs.
+// Row ids for the copies are fetched two passes ahead, copies are issued kStages-1 passes ahead.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kStages = kRingStages;
+
+__device__ __forceinline__ void MbarInit(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void MbarExpectTx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void MbarWait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void BulkCopyG2S(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void CpAsync16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void CpAsyncWait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint32_t LdsU32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 LdsV4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+template <bool kChecked, bool kBulk>
+__global__ void __launch_bounds__(kHistThreads, 1)
+HistKernelStaged(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
+                 const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
+                 const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
+                 const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist,
+                 const QuantDev* __restrict__ /*qd*/) {
+  extern __shared__ __align__(16) uint32_t sh[];
+  const GroupDesc g = groups[blockIdx.y];
+  const uint32_t S = g.max_sym, B = g.n_blocks;
+  const uint32_t slots = B * S * 32;
+  const uint32_t nf = g.f_end - g.f_begin;
+  constexpr uint32_t kWarps = kHistThreads / 32;
+  const uint32_t row_b = 32u * B;                   // symbol bytes of one staged row
+  const uint32_t stage_bytes = 8u * (row_b + 16u);  // 8 rows + 8 gradient pairs
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t sh_base = (uint32_t)__cvta_generic_to_shared(sh);
+  const uint32_t ring_base = sh_base + slots * 16u + warp * kStages * stage_bytes;
+  const uint32_t bar_base = sh_base + slots * 16u + kWarps * kStages * stage_bytes + warp * kStages * 8u;
+
+  const uint32_t n_tiles = ts->build_tiles;
+  if (n_tiles == 0) return;
+  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
+  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+  if (t0 >= t1) return;
+  const uint32_t n_build = (uint32_t)ts->n_build;
+
+  for (uint32_t i = threadIdx.x; i < 4 * slots; i += kHistThreads) sh[i] = 0u;
+  if (kBulk && lane == 0) {
+#pragma unroll
+    for (uint32_t s = 0; s < kStages; ++s) MbarInit(bar_base + 8u * s, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto flush = [&](int32_t nidx) {
+    __syncthreads();
+    longlong2* dst = hist + (size_t)nidx * ell.total_bins;
+    for (uint32_t p = threadIdx.x; p < slots; p += kHistThreads) {
+      const uint32_t ln = p & 31u, rest = p >> 5;
+      uint32_t* a = sh + rest * 128 + ln;
+      const uint32_t glo = a[0], ghi = a[32], hlo = a[64], hhi = a[96];
+      if (glo | ghi | hlo | hhi) {
+        const uint32_t f = g.f_begin + (rest / S) * 32 + ln;
+        longlong2* d = dst + ell.cut_ptrs[f] + (rest % S);
+        if (glo | ghi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->x), ((unsigned long long)ghi << 32) | glo);
+        if (hlo | hhi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->y), ((unsigned long long)hhi << 32) | hlo);
+        a[0] = 0u; a[32] = 0u; a[64] = 0u; a[96] = 0u;
+      }
+    }
+    __syncthreads();
+  };
+
+  const uint32_t q = lane >> 3, w = lane & 7u;
+  uint32_t sel[4], lane_off[4];
+#pragma unroll
+  for (uint32_t k = 0; k < 4; ++k) {
+    const uint32_t jj = (k + q) & 3u;
+    sel[k] = 0x4440u | jj;
+    lane_off[k] = (4u * w + jj) * 4u;
+  }
+  // copy roles of this lane inside a pass (chunk = 16 bytes): chunks [0, 16B) are symbol chunks
+  // (row = c / 2B, part = c % 2B), chunks [16B, 16B+8) the gradient pairs of rows 0..7
+  const uint32_t n_chunks = 16u * B + 8u;
+  uint32_t mbar_phase = 0;  // bit s = parity to wait for on stage s
+
+  uint32_t t = t0;
+  while (t < t1) {
+    const uint32_t seg = tile_seg[t];
+    const BuildEntry e = build[seg];
+    const uint32_t seg_tile_end = (seg + 1 < n_build) ? build[seg + 1].tile_begin : n_tiles;
+    const uint32_t te = min(t1, seg_tile_end);
+    const uint32_t lo = (t - e.tile_begin) * kHistTile;
+    const uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
+    const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin;
+
+    // passes of this warp: rows [jb, jb+8), jb = lo + (warp + i * kWarps) * 8
+    const uint32_t first = lo + warp * kRowsPerPass;
+    const uint32_t n_pass = first < hi ? (hi - first + kWarps * kRowsPerPass - 1) / (kWarps * kRowsPerPass) : 0u;
+
+    // row this lane copies in every pass (its first chunk); its row id is prefetched two passes early
+    auto copy_row_of = [&](uint32_t c) -> uint32_t { return c < 16u * B ? c / (2u * B) : c - 16u * B; };
+    const uint32_t my_row = kBulk ? (lane & 7u) : copy_row_of(lane < n_chunks ? lane : 0u);
+    auto fetch_rid_row = [&](uint32_t i, uint32_t row) -> uint32_t {
+      const uint32_t j = first + i * kWarps * kRowsPerPass + row;
+      return __ldg(ridx + (j < hi ? j : lo));  // rows past the end re-read a valid row (zeroed by the consumer)
+    };
+    auto issue_copies = [&](uint32_t i, uint32_t rid) {
+      const uint32_t s = i % kStages;
+      const uint32_t stage = ring_base + s * stage_bytes;
+      if (kBulk) {
+        const uint32_t bar = bar_base + 8u * s;
+        if (lane == 0) MbarExpectTx(bar, stage_bytes);
+        // lanes 0..7: symbol slice of row `lane`; lanes 8..15: gradient pair of row lane-8
+        if (lane < 8u)
+          BulkCopyG2S(stage + my_row * row_b, ell.bins + (size_t)rid * ell.row_bytes + g.byte_begin, row_b, bar);
+        else if (lane < 16u)
+          BulkCopyG2S(stage + 8u * row_b + my_row * 16u, gq + rid, 16u, bar);
+      } else {
+        for (uint32_t c = lane; c < n_chunks; c += 32u) {
+          if (c != lane) rid = fetch_rid_row(i, copy_row_of(c));
+          if (c < 16u * B) {
+            const uint32_t row = c / (2u * B), part = c % (2u * B);
+            CpAsync16(stage + row * row_b + part * 16u,
+                      ell.bins + (size_t)rid * ell.row_bytes + g.byte_begin + part * 16u);
+          } else {
+            const uint32_t row = c - 16u * B;
+            CpAsync16(stage + 8u * row_b + row * 16u, gq + rid);
+          }
+        }
+        CpAsyncCommit();
+      }
+    };
+
+    auto consume = [&](uint32_t i) {
+      const uint32_t s = i % kStages;
+      const uint32_t stage = ring_base + s * stage_bytes;
+      const uint32_t jb = first + i * kWarps * kRowsPerPass;
+      const bool tail = jb + kRowsPerPass > hi;  // warp-uniform
+      uint32_t glo[2], ghi[2], hlo[2], hhi[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint4 gp = LdsV4(stage + 8u * row_b + (u * 4 + q) * 16u);
+        glo[u] = gp.x; ghi[u] = gp.y; hlo[u] = gp.z; hhi[u] = gp.w;
+        if (tail && jb + u * 4 + q >= hi) { glo[u] = 0u; ghi[u] = 0u; hlo[u] = 0u; hhi[u] = 0u; }
+      }
+      for (uint32_t blk = 0; blk < B; ++blk) {
+        const uint32_t blk_base = sh_base + blk * S * 512u;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t word = LdsU32(stage + (u * 4 + q) * row_b + blk * 32u + 4u * w);
+          uint32_t addr[4], og[4], oh[4], vgl[4], vgh[4], vhl[4], vhh[4];
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) {
+            const uint32_t sym = __byte_perm(word, 0u, sel[k]);
+            vgl[k] = glo[u]; vgh[k] = ghi[u]; vhl[k] = hlo[u]; vhh[k] = hhi[u];
+            if (kChecked) {
+              const bool ok = (blk * 32u + 4u * w + ((k + q) & 3u) < nf) && sym < S;
+              addr[k] = blk_base + (ok ? sym : 0u) * 512u + lane_off[k];
+              if (!ok) { vgl[k] = 0u; vgh[k] = 0u; vhl[k] = 0u; vhh[k] = 0u; }
+            } else {
+              addr[k] = blk_base + sym * 512u + lane_off[k];
+            }
+          }
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) {
+            og[k] = AtomAddShared(addr[k], vgl[k]);
             oh[k] = AtomAddShared256(addr[k], vhl[k]);
           }
 #pragma unroll
@@ -285,36 +556,39 @@ HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
             RedAddHi384(addr[k], oh[k], vhl[k], vhh[k]);
           }
         }
-      };
-
-      // software pipeline: data of pass i+1 and row ids of pass i+2 are in flight while pass i accumulates
-      uint32_t jb = lo + warp * kRowsPerPass;
-      if (jb < hi) {
-        uint32_t r1[2], r2[2] = {0u, 0u};
-        bool v1[2], v2[2] = {false, false};
-        PassData d1, d2;
-        load_r(jb, r1, v1);
-        uint32_t jb2 = jb + kStride;
-        bool have2 = jb2 < hi;
-        if (have2) load_r(jb2, r2, v2);
-        load_d(r1, v1, d1);
-        while (true) {
-          const uint32_t jb3 = jb2 + kStride;
-          const bool have3 = have2 && jb3 < hi;
-          uint32_t r3[2] = {0u, 0u};
-          bool v3[2] = {false, false};
-          if (have2) load_d(r2, v2, d2);
-          if (have3) load_r(jb3, r3, v3);
-          process(d1);
-          if (!have2) break;
-          d1 = d2;
-          r2[0] = r3[0]; r2[1] = r3[1]; v2[0] = v3[0]; v2[1] = v3[1];
-          jb2 = jb3;
-          have2 = have3;
-        }
       }
+    };
+
+    if (n_pass > 0) {
+      // prologue: copies for passes 0 .. kStages-2; row ids for the next two passes are kept in flight
+      for (uint32_t i = 0; i + 1 < kStages; ++i) {
+        if (i < n_pass) issue_copies(i, fetch_rid_row(i, my_row));
+        else if (!kBulk) CpAsyncCommit();
+      }
+      uint32_t rid_a = (kStages - 1 < n_pass) ? fetch_rid_row(kStages - 1, my_row) : 0u;
+      uint32_t rid_b = (kStages < n_pass) ? fetch_rid_row(kStages, my_row) : 0u;
+      for (uint32_t i = 0; i < n_pass; ++i) {
+        const uint32_t s = i % kStages;
+        if (kBulk) {
+          MbarWait(bar_base + 8u * s, (mbar_phase >> s) & 1u);
+          mbar_phase ^= 1u << s;
+        } else {
+          CpAsyncWait<kStages - 2>();
+        }
+        __syncwarp();  // pass i is visible to every lane; every lane is done reading stage (i-1) % kStages
+        const uint32_t ahead = i + kStages - 1;
+        if (ahead < n_pass) {
+          issue_copies(ahead, rid_a);
+          rid_a = rid_b;
+          if (ahead + 2 < n_pass) rid_b = fetch_rid_row(ahead + 2, my_row);
+        } else if (!kBulk) {
+          CpAsyncCommit();  // keep the group count uniform
+        }
+        consume(i);
+      }
+      if (!kBulk) CpAsyncWait<0>();
     }
-    flush(e.nidx);
+    flush((int32_t)e.slot);
     t = te;
   }
 }
@@ -372,7 +646,7 @@ HistKernelGeneric(EllView ell, const longlong2* __restrict__ gq, const uint32_t*
     if ((int32_t)seg != cur_seg) {
       if (cur_seg >= 0) flush(cur_nidx);
       cur_seg = (int32_t)seg;
-      cur_nidx = e.nidx;
+      cur_nidx = (int32_t)e.slot;
     }
     const uint32_t off = (t - e.tile_begin) * kHistTile;
     const uint32_t n = min((uint32_t)kHistTile, e.count - off);
@@ -412,13 +686,17 @@ void PrepareHistKernels(int device) {
   int optin = SmemOptin(device);
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelGeneric<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
 }
 
 void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint32_t* ridx0, const uint32_t* ridx1,
                      const BuildEntry* build, const uint32_t* tile_seg, const TreeState* ts,
                      const GroupDesc* groups_dev, const std::vector<GroupDesc>& groups_host,
-                     b200hist_gpair64* hist, int num_sms, cudaStream_t s) {
+                     b200hist_gpair64* hist, const QuantDev* quant, int num_sms, cudaStream_t s) {
   const int n_groups = (int)groups_host.size();
   const int workers = std::max(1, num_sms / n_groups);
   dim3 grid(workers, n_groups);
@@ -426,10 +704,24 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
     size_t smem = 0;
     for (auto const& g : groups_host) smem = std::max(smem, BankedSmemBytes(g));
     bool checked = ell.null_symbol != 0xFFFFFFFFu;
-    for (auto const& g : groups_host) checked = checked || ((g.f_end - g.f_begin) % 32u != 0u);
-    auto kernel = checked ? HistKernelBanked<true> : HistKernelBanked<false>;
+    uint32_t max_blocks = 1;
+    for (auto const& g : groups_host) {
+      checked = checked || ((g.f_end - g.f_begin) % 32u != 0u);
+      max_blocks = std::max(max_blocks, g.n_blocks);
+    }
+    const int impl = HistImpl();
+    using KernelT = void (*)(EllView, const longlong2*, const uint32_t*, const uint32_t*, const BuildEntry*,
+                             const uint32_t*, const TreeState*, const GroupDesc*, longlong2*, const QuantDev*);
+    KernelT kernel;
+    if (impl == 0) {
+      kernel = checked ? HistKernelBanked<true> : HistKernelBanked<false>;
+    } else {
+      smem += RingSmemBytes(max_blocks);
+      if (impl == 1) kernel = checked ? HistKernelStaged<true, true> : HistKernelStaged<false, true>;
+      else kernel = checked ? HistKernelStaged<true, false> : HistKernelStaged<false, false>;
+    }
     kernel<<<grid, kHistThreads, smem, s>>>(ell, reinterpret_cast<const longlong2*>(gq), ridx0, ridx1, build, tile_seg,
-                                           ts, groups_dev, reinterpret_cast<longlong2*>(hist));
+                                           ts, groups_dev, reinterpret_cast<longlong2*>(hist), quant);
   } else {
     uint32_t max_bins = 0;
     for (auto const& g : groups_host) max_bins = std::max(max_bins, g.bin_end - g.bin_begin);

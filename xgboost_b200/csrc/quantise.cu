@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(kQThreads) QuantReduceKernel(const float2* __r
     for (int k = 0; k < 4; ++k) q->sums[k] = t[k];
     q->root_g = 0;
     q->root_h = 0;
+    q->h_lo_or = 0u;
     *counter = 0;  // ready for the next tree
   }
 }
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(kQThreads) QuantConvertKernel(const float2* __
                                                                  uint32_t* __restrict__ ridx) {
   const double fg = q->to_fixed_g, fh = q->to_fixed_h;
   long long sg = 0, sh_ = 0;
+  unsigned int lo_or = 0u;
   for (uint64_t i = blockIdx.x * (uint64_t)kQThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kQThreads) {
     float2 v = __ldg(gpair + i);
     // ToFixedPoint (quantiser.cuh:65-69): C cast of double -> int64 truncates toward zero
@@ -106,12 +108,18 @@ __global__ void __launch_bounds__(kQThreads) QuantConvertKernel(const float2* __
     if (ridx != nullptr) ridx[i] = (uint32_t)i;
     sg += g;
     sh_ += h;
+    lo_or |= (unsigned int)(unsigned long long)h;
   }
   __shared__ long long red[2][kQThreads / 32];
   sg = WarpSumLL(sg);
   sh_ = WarpSumLL(sh_);
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { red[0][warp] = sg; red[1][warp] = sh_; }
+  lo_or = __reduce_or_sync(0xffffffffu, lo_or);
+  if (lane == 0) {
+    red[0][warp] = sg;
+    red[1][warp] = sh_;
+    if (lo_or) atomicOr(&q->h_lo_or, lo_or);
+  }
   __syncthreads();
   if (threadIdx.x < 2) {
     long long t = 0;

@@ -78,6 +78,7 @@ __device__ __forceinline__ void InitLeaf(NodeDev* n, int parent, int depth, floa
   n->leaf_value = leaf; n->loss_chg = 0.0f; n->sum_hess = sum_hess; n->base_weight = leaf;
   n->sum_g = g; n->sum_h = h;
   n->seg_begin = 0; n->seg_count = 0; n->seg_buf = -1; n->partitioned = 0; n->split_lbin = 0; n->cand_open = 0;
+  n->hist_slot = -1; n->pad = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(kCtlThreads) InitRootKernel(ParamDev p, uint32
     InitLeaf(r, -1, 0, p.learning_rate * w, (float)rh, q->root_g, q->root_h);
     r->base_weight = w;
     r->seg_begin = 0; r->seg_count = n_rows; r->seg_buf = 0;
+    r->hist_slot = 0;
     build[0] = BuildEntry{0, 0, 0u, n_rows, 0u, 0u};
     eval_nodes[0] = 0;
     ts->n_nodes = 1; ts->num_leaves = 1; ts->level_begin = 0; ts->level_end = 1;
@@ -281,7 +283,10 @@ __global__ void __launch_bounds__(kCtlThreads) ScanKernel(TreeState* ts, NodeDev
                                                            const uint32_t* part_tile_seg, const uint32_t* tile_left,
                                                            uint32_t* tile_excl /* scratch, part_tiles+1 */,
                                                            uint32_t* tile_left_off, BuildEntry* build, SubEntry* sub,
-                                                           int32_t* eval_nodes, uint32_t* build_tile_seg) {
+                                                           int32_t* eval_nodes, uint32_t* build_tile_seg,
+                                                           uint32_t slot_base, uint32_t slot_cap) {
+  // histogram slots of this step: [slot_base, +cap) for the built children (one contiguous, host-known
+  // range = the buffer of the level's single allreduce), [slot_base+cap, +cap) for the subtracted siblings
   __shared__ uint32_t s_warp[33];
   __shared__ uint32_t s_tile_begin[kMaxLevelNodes + 1];
   const int n_part = ts->n_part;
@@ -316,8 +321,11 @@ __global__ void __launch_bounds__(kCtlThreads) ScanKernel(TreeState* ts, NodeDev
     const NodeDev* b = build_right ? r : l;
     const int b_idx = build_right ? e.right : e.left;
     const int s_idx = build_right ? e.left : e.right;
-    build[k] = BuildEntry{b_idx, dst_buf, b->seg_begin, b->seg_count, 0u, 0u};
-    sub[k] = SubEntry{e.nidx, b_idx, s_idx};
+    const uint32_t b_slot = slot_base + (uint32_t)k, s_slot = slot_base + slot_cap + (uint32_t)k;
+    nodes[b_idx].hist_slot = (int32_t)b_slot;
+    nodes[s_idx].hist_slot = (int32_t)s_slot;
+    build[k] = BuildEntry{b_idx, dst_buf, b->seg_begin, b->seg_count, 0u, b_slot};
+    sub[k] = SubEntry{nodes[e.nidx].hist_slot, (int32_t)b_slot, (int32_t)s_slot};
     eval_nodes[2 * k] = e.left;
     eval_nodes[2 * k + 1] = e.right;
     visits += b->seg_count;
@@ -469,6 +477,12 @@ struct b200hist_updater_s {
   FeatCand* d_scratch{nullptr};
   b200hist_gpair64* d_hist{nullptr};
   size_t hist_bytes{0};
+  std::vector<uint32_t> step_cap;        // max nodes expanded in step s (host-known)
+  std::vector<uint32_t> step_slot_base;  // first histogram slot of step s
+  uint32_t n_slots{1};
+  // multi-GPU: feature-group shard of this rank and the allreduce communicator (borrowed)
+  b200hist_comm_s* comm{nullptr};
+  uint32_t group_begin{0}, group_end{0};
   // host staging
   NodeDev* h_nodes{nullptr};  // pinned
   TreeState* h_ts{nullptr};   // pinned
@@ -561,8 +575,17 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   B200_LAUNCHED();
   timer.End(kApply, t1);
   auto t2 = timer.Begin();
-  LaunchBuildHist(view, u->d_gq, u->d_ridx[0], u->d_ridx[1], u->d_build, u->d_build_tile_seg, u->d_ts, u->d_groups,
-                  u->groups, u->d_hist, u->num_sms, s);
+  const std::vector<GroupDesc> my_groups(u->groups.begin() + u->group_begin, u->groups.begin() + u->group_end);
+  auto build_hist = [&](uint32_t slot_base, uint32_t slot_cap) {
+    if (!my_groups.empty())
+      LaunchBuildHist(view, u->d_gq, u->d_ridx[0], u->d_ridx[1], u->d_build, u->d_build_tile_seg, u->d_ts,
+                      u->d_groups + u->group_begin, my_groups, u->d_hist, u->d_quant, u->num_sms, s);
+    // AllReduceHist: one collective per level over the level's contiguous built slots
+    if (u->comm != nullptr)
+      CommAllReduceInt64(u->comm, u->d_hist + (size_t)slot_base * ell->total_bins,
+                         (size_t)slot_cap * ell->total_bins * 2, s);
+  };
+  build_hist(0, 1);
   timer.End(kHist, t2);
   auto t3 = timer.Begin();
   LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, nullptr, 0, u->pdev, u->d_quant,
@@ -572,7 +595,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   const bool depthwise = u->param.grow_policy == 0;
   for (int step = 0; step < u->n_steps; ++step) {
     // upper bound on nodes expanded in this step (host-known, data independent)
-    long long cap = depthwise ? std::min<long long>(1ll << std::min(step, 30), kMaxLevelNodes) : 1;
+    const long long cap = u->step_cap[step];
     auto ta = timer.Begin();
     ApplyKernel<<<1, kCtlThreads, 0, s>>>(view, u->pdev, u->d_quant, u->d_ts, u->d_nodes, u->d_cand, u->d_part,
                                           u->d_part_tile_seg, u->max_nodes);
@@ -585,14 +608,13 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
                          u->d_tile_left, u->num_sms, s);
     ScanKernel<<<1, kCtlThreads, 0, s>>>(u->d_ts, u->d_nodes, u->d_part, u->d_part_tile_seg, u->d_tile_left,
                                          u->d_tile_excl, u->d_tile_left_off, u->d_build, u->d_sub, u->d_eval_nodes,
-                                         u->d_build_tile_seg);
+                                         u->d_build_tile_seg, u->step_slot_base[step], u->step_cap[step]);
     B200_LAUNCHED();
     LaunchPartitionScatter(u->d_ridx[0], u->d_ridx[1], u->d_ridx[0], u->d_ridx[1], u->d_part, u->d_part_tile_seg,
                            u->d_ts, u->d_flags, u->d_tile_left_off, u->num_sms, s);
     timer.End(kPart, tp);
     auto th = timer.Begin();
-    LaunchBuildHist(view, u->d_gq, u->d_ridx[0], u->d_ridx[1], u->d_build, u->d_build_tile_seg, u->d_ts, u->d_groups,
-                    u->groups, u->d_hist, u->num_sms, s);
+    build_hist(u->step_slot_base[step], u->step_cap[step]);
     timer.End(kHist, th);
     auto tsb = timer.Begin();
     LaunchSubtract(u->d_sub, u->d_ts, u->d_hist, ell->total_bins, u->num_sms, s);
@@ -659,6 +681,30 @@ int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* 
   }
   PrepareHistKernels(u->device);
   u->groups = MakeFeatureGroups(*ell, u->device);
+  u->group_begin = 0;
+  u->group_end = (uint32_t)u->groups.size();
+  {  // histogram slots: slot 0 = root; step s owns [base, base+cap) built + [base+cap, base+2cap) subtracted
+    const bool dw = param->grow_policy == 0;
+    uint32_t base = 1;
+    for (int st = 0; st < u->n_steps; ++st) {
+      uint32_t cap = dw ? (uint32_t)std::min<long long>(1ll << std::min(st, 30), kMaxLevelNodes) : 1u;
+      if (param->max_leaves > 0) cap = std::min<uint32_t>(cap, (uint32_t)param->max_leaves);
+      u->step_cap.push_back(cap);
+      u->step_slot_base.push_back(base);
+      const bool children = param->max_depth == 0 || !dw || st + 1 < param->max_depth;
+      if (children) base += 2 * cap;
+    }
+    u->n_slots = base;
+    if (dw) {
+      long long widest = 1;
+      for (auto c : u->step_cap) widest = std::max<long long>(widest, c);
+      long long need = param->max_depth > 0 ? (1ll << std::min(param->max_depth - 1, 40)) : (long long)param->max_leaves;
+      if (param->max_leaves > 0) need = std::min<long long>(need, param->max_leaves);
+      B200_CHECK(need <= kMaxLevelNodes, "a tree level may hold more than " + std::to_string(kMaxLevelNodes) +
+                                             " nodes to expand; bound max_depth (<= 13) or max_leaves");
+      (void)widest;
+    }
+  }
   const uint64_t n = ell->n_rows;
   const size_t part_tiles = n / kPartTile + kMaxLevelNodes + 2;
   const size_t hist_tiles = n / kHistTile + kMaxLevelNodes + 2;
@@ -690,12 +736,12 @@ int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* 
   u->d_fin_tile_seg = DevAlloc<uint32_t>(fin_tiles);
   u->d_fin_tile_begin = DevAlloc<uint32_t>((size_t)u->max_nodes + 1);
   u->d_scratch = DevAlloc<FeatCand>((size_t)2 * kMaxLevelNodes * ell->n_features);
-  u->hist_bytes = (size_t)u->max_nodes * ell->total_bins * sizeof(b200hist_gpair64);
+  u->hist_bytes = (size_t)u->n_slots * ell->total_bins * sizeof(b200hist_gpair64);
   size_t free_b = 0, total_b = 0;
   B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
   B200_CHECK(u->hist_bytes < free_b, "histogram cache (" + std::to_string(u->hist_bytes >> 20) +
                                          " MiB) does not fit in free device memory; lower max_depth/max_leaves");
-  u->d_hist = DevAlloc<b200hist_gpair64>((size_t)u->max_nodes * ell->total_bins);
+  u->d_hist = DevAlloc<b200hist_gpair64>((size_t)u->n_slots * ell->total_bins);
   B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&u->h_nodes), sizeof(NodeDev) * u->max_nodes));
   B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&u->h_ts), sizeof(TreeState)));
   *out = u;
@@ -776,7 +822,9 @@ int b200hist_updater_node_histogram(b200hist_updater_t u, int32_t nidx, b200hist
   B200_CHECK(u != nullptr && out_host != nullptr, "null argument");
   B200_CHECK(nidx >= 0 && nidx < u->last_n_nodes, "node index out of range");
   DeviceGuard guard(u->device);
-  B200_CUDA(cudaMemcpy(out_host, u->d_hist + (size_t)nidx * u->ell->total_bins,
+  const int32_t slot = u->h_nodes[nidx].hist_slot;
+  B200_CHECK(slot >= 0, "node " + std::to_string(nidx) + " has no histogram");
+  B200_CUDA(cudaMemcpy(out_host, u->d_hist + (size_t)slot * u->ell->total_bins,
                        sizeof(b200hist_gpair64) * u->ell->total_bins, cudaMemcpyDeviceToHost));
   B200_API_END();
 }
@@ -787,6 +835,28 @@ int b200hist_updater_node_candidate(b200hist_updater_t u, int32_t nidx, b200hist
   B200_CHECK(nidx >= 0 && nidx < u->last_n_nodes, "node index out of range");
   DeviceGuard guard(u->device);
   B200_CUDA(cudaMemcpy(out_host, u->d_cand + nidx, sizeof(b200hist_candidate), cudaMemcpyDeviceToHost));
+  B200_API_END();
+}
+
+int b200hist_updater_set_comm(b200hist_updater_t u, b200hist_comm_t comm) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  if (comm == nullptr) {
+    u->comm = nullptr;
+    u->group_begin = 0;
+    u->group_end = (uint32_t)u->groups.size();
+  } else {
+    B200_CHECK(comm->device == u->device, "communicator lives on a different device");
+    u->comm = comm;
+    ShardGroups((uint32_t)u->groups.size(), comm->world, comm->rank, &u->group_begin, &u->group_end);
+  }
+  B200_API_END();
+}
+
+int b200hist_updater_num_feature_groups(b200hist_updater_t u, uint32_t* out) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && out != nullptr, "null argument");
+  *out = (uint32_t)u->groups.size();
   B200_API_END();
 }
 

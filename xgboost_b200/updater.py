@@ -147,6 +147,57 @@ class EllpackPage:
             pass
 
 
+class Communicator:
+    """NCCL communicator of the per-level histogram allreduce (one process per GPU).
+
+    The 128-byte unique id is created on rank 0 and handed to the other ranks by the caller's control plane
+    (`from_torch_distributed` uses a torch.distributed broadcast -- plumbing only; the allreduce itself is
+    issued by the C++ tree driver on the kernels' stream)."""
+
+    def __init__(self, device: int, world: int, rank: int, unique_id: bytes):
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be 128 bytes")
+        self.world, self.rank, self.device = int(world), int(rank), int(device)
+        self._h = c_void_p()
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        _l.check(_l.load().b200hist_comm_create(self.device, self.world, self.rank, buf, byref(self._h)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (ctypes.c_uint8 * 128)()
+        _l.check(_l.load().b200hist_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch_distributed(cls, device: torch.device) -> "Communicator":
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        t = torch.zeros(128, dtype=torch.uint8, device=device if dist.get_backend() == "nccl" else "cpu")
+        if rank == 0:
+            t.copy_(torch.tensor(list(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        return cls(device.index or 0, world, rank, bytes(t.cpu().tolist()))
+
+    @property
+    def handle(self) -> c_void_p:
+        return self._h
+
+    def __del__(self):
+        try:
+            if self._h:
+                _l.load().b200hist_comm_destroy(self._h)
+                self._h = c_void_p()
+        except Exception:
+            pass
+
+
+def shard_groups(n_groups: int, world: int, rank: int):
+    """Feature groups [begin, end) owned by `rank` (host logic of the feature-block sharding)."""
+    b, e = c_uint32(), c_uint32()
+    _l.check(_l.load().b200hist_shard_groups(n_groups, world, rank, byref(b), byref(e)))
+    return b.value, e.value
+
+
 class RegTree:
     """The tree as the updater leaves it (node arrays in ExpandNode order)."""
 
@@ -213,6 +264,17 @@ class GPUHistMaker:
 
     def has_node_position(self) -> bool:
         return True
+
+    def set_comm(self, comm: Optional["Communicator"]) -> None:
+        """Attach (or detach with None) the allreduce communicator: this rank then builds only its
+        feature-group shard of every histogram (collective::Allreduce in the reference)."""
+        self._comm = comm  # keep it alive
+        _l.check(_l.load().b200hist_updater_set_comm(self._h, comm.handle if comm is not None else c_void_p()))
+
+    def num_feature_groups(self) -> int:
+        n = c_uint32()
+        _l.check(_l.load().b200hist_updater_num_feature_groups(self._h, byref(n)))
+        return n.value
 
     def set_profiling(self, on: bool) -> None:
         _l.check(_l.load().b200hist_updater_set_profiling(self._h, 1 if on else 0))
