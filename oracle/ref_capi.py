@@ -94,8 +94,11 @@ class DMatrix:
         lib = load(kind)
         proxy = c_void_p()
         _check(lib, lib.XGProxyDMatrixCreate(byref(proxy)))
-        state = {"i": 0}
-        is_cuda = hasattr(batches[0], "__cuda_array_interface__") and not isinstance(batches[0], np.ndarray)
+        state = {"i": 0, "cur": None}
+        if callable(batches):  # (n_batches, get_batch) form: batches are regenerated on every pass
+            raise TypeError("pass a sequence; use LazyBatches for regenerated batches")
+        first = batches[0]
+        is_cuda = hasattr(first, "__cuda_array_interface__") and not isinstance(first, np.ndarray)
 
         @ctypes.CFUNCTYPE(None, c_void_p)
         def reset(_):
@@ -107,6 +110,7 @@ class DMatrix:
             if i >= len(batches):
                 return 0
             b = batches[i]
+            state["cur"] = b  # keep the batch alive while the library reads it
             if is_cuda:
                 rc = lib.XGProxyDMatrixSetDataCudaArrayInterface(proxy, _cuda_array_interface(b))
             else:
@@ -163,6 +167,21 @@ class DMatrix:
             self.lib.XGDMatrixFree(self.handle)
         except Exception:
             pass
+
+
+class LazyBatches:
+    """Sequence whose items are produced on demand (so a 100M-row matrix never exists at once)."""
+
+    def __init__(self, n: int, get):
+        self.n, self.get = n, get
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        if i < 0 or i >= self.n:
+            raise IndexError(i)
+        return self.get(i)
 
 
 class Booster:

@@ -1,0 +1,133 @@
+"""Parity against the UNMODIFIED reference gpu_hist.
+
+tests/golden/ref_gpu_trees.json holds trees produced by the reference's own CUDA `gpu_hist` updater (built
+from /root/reference for sm_100, run on a B200 by tools/make_golden_gpu.py) together with the cuts it
+sketched.  Inputs regenerate from recorded seeds.
+
+ * CPU test: the oracle (oracle/hist_oracle.c), given the reference's cuts and the same gradients, rebuilds the
+   reference's trees -- this is what PINS the oracle.  The oracle divides in IEEE arithmetic where the device
+   uses div.approx, so a split may legitimately differ only when the oracle's own gain table shows a <= 4 ulp tie.
+ * GPU test: our CUDA updater reproduces the reference trees BIT FOR BIT (same arithmetic, same device
+   instructions): split feature, split condition bits, default direction, node numbering, base weights,
+   hessian sums, leaf values; loss_chg is compared bit-exactly as well.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from tests.helpers import make_regression
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_gpu_trees.json")
+
+
+def _cases():
+    return json.load(open(GOLD))["cases"]
+
+
+def _f32(bits):
+    return np.array(bits, dtype=np.uint32).view(np.float32)
+
+
+def _gradients(obj, margin, y):
+    if obj == "sq":
+        g = (margin - y).astype(np.float32)
+        h = np.ones_like(g)
+    else:
+        p = (1.0 / (1.0 + np.exp(-margin.astype(np.float64))))
+        g = (p - y).astype(np.float32)
+        h = np.maximum(p * (1.0 - p), 1e-16).astype(np.float32)
+    return np.stack([g, h], axis=1).astype(np.float32)
+
+
+def _inputs(case):
+    x, y = make_regression(case["n"], case["f"], seed=case["seed"], missing=case.get("missing", 0.0))
+    if case["obj"] == "logistic":
+        y = (y > 0).astype(np.float32)
+    cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+    cv = _f32(case["cut_values_bits"])
+    return x, y, cp, cv
+
+
+def _params(case):
+    p = dict(case["params"])
+    p.setdefault("lambda", 1.0)
+    p.setdefault("min_child_weight", 1.0)
+    return p
+
+
+def _leaf_margin(tree_nodes_leaf_value, position):
+    pos = np.where(position < 0, ~position, position)
+    return tree_nodes_leaf_value[pos]
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c["name"])
+def test_oracle_reproduces_reference_gpu_hist(case):
+    x, y, cp, cv = _inputs(case)
+    gb = orc.bin_dense(x, cp, cv)
+    p = orc.Param.make(**_params(case))
+    margin = np.zeros(case["n"], dtype=np.float32)
+    for t, ref in enumerate(case["trees"]):
+        gp = _gradients(case["obj"], margin, y)
+        o = orc.update_tree(gb, cp, cv, gp, p, want_hist=True)
+        nodes = o["nodes"]
+        assert len(nodes) == len(ref["left"]), "tree %d node count" % t
+        cond = _f32(ref["cond_bits"])
+        for i, nd in enumerate(nodes):
+            same = (nd.left == ref["left"][i] and nd.right == ref["right"][i])
+            if not nd.is_leaf:
+                same = same and nd.findex == ref["findex"][i] and \
+                    np.float32(nd.fvalue).view(np.uint32) == ref["cond_bits"][i] and \
+                    int(nd.default_left) == ref["default_left"][i]
+            if not same:
+                # only a <= 4 ulp tie in the oracle's own gain table excuses a difference
+                _, gains = orc.eval_node(o["hist"][i], (o["cands"][i].left_sum.g + o["cands"][i].right_sum.g,
+                                                       o["cands"][i].left_sum.h + o["cands"][i].right_sum.h),
+                                         cp, cv, p, o["scale"], want_gains=True)
+                pytest.fail("tree %d node %d differs from the reference (oracle f=%d cond=%r, ref f=%d cond=%r)" %
+                            (t, i, nd.findex, nd.fvalue, ref["findex"][i], cond[i]))
+            assert np.float32(nd.sum_hess).view(np.uint32) == ref["sum_hess_bits"][i], (t, i)
+            # weights: fp64 on both sides, but host and device fp64 code generation differ (contraction);
+            # observed: 1 node in 511 off by one float ulp on the CPU side.  The GPU test below is bit-exact.
+            assert abs(int(np.float32(nd.base_weight).view(np.int32)) -
+                       int(np.array(ref["base_weight_bits"][i], dtype=np.uint32).view(np.int32))) <= 1, (t, i)
+            if not nd.is_leaf:  # IEEE vs approximate division: tolerance scales with the gains involved
+                ref_l = float(_f32([ref["loss_chg_bits"][i]])[0])
+                c = o["cands"][i]
+                pg = float(c.left_sum.g + c.right_sum.g) * o["scale"][2]
+                ph = float(c.left_sum.h + c.right_sum.h) * o["scale"][3]
+                assert abs(nd.loss_chg - ref_l) <= 1e-5 * (abs(ref_l) + pg * pg / max(ph, 1e-30)) + 1e-6, (t, i)
+        leaf = np.array([n.leaf_value for n in nodes], dtype=np.float32)
+        margin = (margin + _leaf_margin(leaf, o["position"])).astype(np.float32)
+        assert abs(float(np.float64(margin).sum()) - case["margin_sums"][t]) <= 1e-3 * max(1.0, abs(case["margin_sums"][t]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c["name"])
+def test_cuda_matches_reference_gpu_hist_bit_for_bit(case, cuda_device):
+    import torch
+    import xgboost_b200 as xb
+    x, y, cp, cv = _inputs(case)
+    page = xb.EllpackPage.from_dense(torch.from_numpy(x).cuda(), xb.HistogramCuts(cp, cv))
+    up = xb.GPUHistMaker(page)
+    up.configure(_params(case))
+    margin = torch.zeros(case["n"], dtype=torch.float32, device="cuda")
+    for t, ref in enumerate(case["trees"]):
+        gp = torch.from_numpy(_gradients(case["obj"], margin.cpu().numpy(), y)).cuda()
+        tree = up.update(gp)
+        assert tree.num_nodes == len(ref["left"]), "tree %d node count" % t
+        for i, nd in enumerate(tree.nodes):
+            assert (nd["left"], nd["right"]) == (ref["left"][i], ref["right"][i]), (t, i)
+            if not nd["is_leaf"]:
+                assert nd["findex"] == ref["findex"][i], (t, i)
+                assert np.float32(nd["fvalue"]).view(np.uint32) == ref["cond_bits"][i], (t, i)
+                assert int(nd["default_left"]) == ref["default_left"][i], (t, i)
+                assert np.float32(nd["loss_chg"]).view(np.uint32) == ref["loss_chg_bits"][i], (t, i)
+            else:  # RegTree stores the leaf value in split_conditions
+                assert np.float32(nd["leaf_value"]).view(np.uint32) == ref["cond_bits"][i], (t, i)
+            assert np.float32(nd["sum_hess"]).view(np.uint32) == ref["sum_hess_bits"][i], (t, i)
+            assert np.float32(nd["base_weight"]).view(np.uint32) == ref["base_weight_bits"][i], (t, i)
+        up.update_prediction_cache(margin)
+        assert abs(float(margin.double().sum().item()) - case["margin_sums"][t]) <= 1e-3 * max(1.0, abs(case["margin_sums"][t]))
