@@ -33,7 +33,12 @@ def make_regression(n, f, seed, missing=0.0, dtype=np.float32):
     rng = np.random.default_rng(seed)
     x = rng.standard_normal((n, f)).astype(dtype)
     w = rng.standard_normal(f).astype(dtype)
-    y = (x @ w + 0.1 * rng.standard_normal(n)).astype(dtype)
+    # NOT `x @ w`: BLAS float32 matmul rounds differently on different CPUs, and the golden fixtures must
+    # regenerate bit-identically everywhere.  Element-wise IEEE ops in a fixed order are reproducible.
+    acc = np.zeros(n, dtype=np.float64)
+    for j in range(f):
+        acc += x[:, j].astype(np.float64) * np.float64(w[j])
+    y = (acc + 0.1 * rng.standard_normal(n)).astype(dtype)
     if missing > 0:
         mask = rng.random((n, f)) < missing
         x = x.copy()
