@@ -1,0 +1,209 @@
+// Reference-side binding: xgboost::TreeUpdater served by libb200hist.so.
+//
+// This translation unit is the ONLY file compiled against the reference's headers.  It subclasses
+// xgboost::TreeUpdater (/root/reference/include/xgboost/tree_updater.h:37-108) and registers itself in the
+// reference's dmlc registry as "grow_gpu_hist" -- the name GBTree::Configure resolves for
+// tree_method="hist" on CUDA (src/gbm/gbtree.cc:45-66,129-139) -- and as "grow_b200_hist" so both
+// implementations can be A/B-ed inside one process (param updater="grow_b200_hist").
+// dmlc::Registry::__REGISTER__ returns the existing entry for a duplicate name
+// (dmlc-core/include/dmlc/registry.h:77-86) and set_body() overwrites its factory, so loading this shared
+// object AFTER libxgboost.so replaces the factory without touching the reference.
+//
+// Everything it does is marshalling: raw device pointers and scalars out of the reference's objects into
+// the C ABI (include/b200hist.h), and the returned node array back into RegTree::ExpandNode calls.
+//
+// Build (tools/build_shim.sh): nvcc -shared against /root/reference/{include,src,dmlc-core/include} and
+// linked with oracle/_ref_cuda/libxgboost.so + xgboost_b200/lib/libb200hist.so.
+#include <dmlc/registry.h>
+#include <xgboost/base.h>
+#include <xgboost/context.h>
+#include <xgboost/data.h>
+#include <xgboost/gradient.h>
+#include <xgboost/host_device_vector.h>
+#include <xgboost/json.h>
+#include <xgboost/linalg.h>
+#include <xgboost/logging.h>
+#include <xgboost/tree_model.h>
+#include <xgboost/tree_updater.h>
+
+#include <algorithm>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../include/b200hist.h"
+#include "src/common/cuda_context.cuh"      // CUDAContext::Stream
+#include "src/data/ellpack_page.cuh"        // EllpackPageImpl
+#include "src/tree/hist/hist_param.h"       // HistMakerTrainParam
+#include "src/tree/param.h"                 // TrainParam
+#include "src/tree/updater_gpu_common.cuh"  // HistBatch
+
+namespace xgboost::tree {
+
+#define B200_SHIM_CHECK(call)                                          \
+  do {                                                                 \
+    if ((call) != 0) LOG(FATAL) << "[b200hist] " << b200hist_last_error(); \
+  } while (0)
+
+class B200HistMaker : public TreeUpdater {
+ public:
+  explicit B200HistMaker(Context const* ctx, ObjInfo const* task) : TreeUpdater(ctx), task_{task} {}
+  ~B200HistMaker() override { this->Release(); }
+
+  void Configure(Args const& args) override {
+    hist_maker_param_.UpdateAllowUnknown(args);  // unknown keys pass through like the reference
+    this->Release();                              // caches are invalidated by Configure (updater_gpu_hist.cu:764-771)
+  }
+  void LoadConfig(Json const& in) override {
+    auto const& config = get<Object const>(in);
+    FromJson(config.at("hist_train_param"), &this->hist_maker_param_);
+    this->Release();
+  }
+  void SaveConfig(Json* p_out) const override { (*p_out)["hist_train_param"] = ToJson(hist_maker_param_); }
+
+  [[nodiscard]] char const* Name() const override { return "grow_gpu_hist"; }
+  [[nodiscard]] bool HasNodePosition() const override { return true; }
+
+  void Update(TrainParam const* param, GradientContainer* in_gpair, DMatrix* p_fmat,
+              common::Span<HostDeviceVector<bst_node_t>> out_position,
+              std::vector<RegTree*> const& trees) override {
+    CHECK_EQ(in_gpair->gpair.Shape(1), 1) << "[b200hist] single-target trees only";
+    in_gpair->gpair.SetDevice(ctx_->Device());
+    this->InitDataOnce(param, p_fmat);
+    auto stream = static_cast<void*>(ctx_->CUDACtx()->Stream());
+    std::size_t t_idx{0};
+    for (RegTree* p_tree : trees) {
+      auto& pos = out_position[t_idx];
+      pos.SetDevice(ctx_->Device());
+      pos.Resize(p_fmat->Info().num_row_);
+      // GradientPair = {float grad, float hess}: exactly the n_rows x 2 float32 layout of the ABI
+      auto const* gpair = reinterpret_cast<float const*>(in_gpair->gpair.Data()->ConstDevicePointer());
+      std::int32_t n_nodes{0};
+      B200_SHIM_CHECK(b200hist_updater_update_tree(updater_, gpair, stream, nodes_.data(), &n_nodes,
+                                                   pos.DevicePointer()));
+      this->ReplayInto(p_tree, n_nodes);
+      hist_maker_param_.CheckTreesSynchronized(ctx_, p_tree);
+      ++t_idx;
+    }
+    p_last_fmat_ = p_fmat;
+  }
+
+  bool UpdatePredictionCache(DMatrix const* p_fmat, common::Span<HostDeviceVector<bst_node_t>> out_position,
+                             linalg::MatrixView<float> p_out_preds) override {
+    if (updater_ == nullptr || p_last_fmat_ == nullptr || p_last_fmat_ != p_fmat) return false;
+    if (out_position.size() > 1) return false;
+    CHECK(p_out_preds.Device().IsCUDA());
+    CHECK_EQ(p_out_preds.Shape(1), 1);
+    B200_SHIM_CHECK(b200hist_updater_update_prediction_cache(updater_, p_out_preds.Values().data(),
+                                                             static_cast<void*>(ctx_->CUDACtx()->Stream())));
+    return true;
+  }
+
+ private:
+  // InitDataOnce (updater_gpu_hist.cu:803-827): borrow the reference's EllpackPage and cuts.
+  void InitDataOnce(TrainParam const* param, DMatrix* p_fmat) {
+    if (updater_ != nullptr && p_last_fmat_ == p_fmat) return;
+    this->Release();
+    CHECK(p_fmat->SingleColBlock()) << "[b200hist] external-memory DMatrix is not supported yet";
+    for (auto const& page : p_fmat->GetBatches<EllpackPage>(ctx_, cuda_impl::HistBatch(*param))) {
+      auto const* impl = page.Impl();
+      auto cuts = impl->CutsShared();
+      auto const& ptrs = cuts->cut_ptrs_.ConstHostVector();
+      auto const& vals = cuts->cut_values_.ConstHostVector();
+      CHECK(impl->IsDenseCompressed()) << "[b200hist] sparse ELLPACK layout is not supported yet";
+      int const has_missing = impl->IsDense() ? 0 : 1;
+      B200_SHIM_CHECK(b200hist_ellpack_create(ctx_->Ordinal(), impl->n_rows, static_cast<std::uint32_t>(ptrs.size() - 1),
+                                              ptrs.data(), vals.data(), has_missing, &ellpack_));
+      B200_SHIM_CHECK(b200hist_ellpack_import_reference(ellpack_, impl->gidx_buffer.data(),
+                                                        static_cast<std::uint32_t>(impl->info.row_stride),
+                                                        static_cast<std::uint32_t>(impl->NumSymbols()),
+                                                        impl->IsDense() ? 1 : 0,
+                                                        static_cast<void*>(ctx_->CUDACtx()->Stream())));
+      break;  // in-core: exactly one page
+    }
+    b200hist_train_param p{};
+    p.max_depth = param->max_depth;
+    p.max_leaves = param->max_leaves;
+    p.grow_policy = param->grow_policy == TrainParam::kDepthWise ? 0 : 1;
+    p.learning_rate = param->learning_rate;
+    p.reg_lambda = param->reg_lambda;
+    p.reg_alpha = param->reg_alpha;
+    p.min_child_weight = param->min_child_weight;
+    p.max_delta_step = param->max_delta_step;
+    p.min_split_loss = param->min_split_loss;
+    CHECK(param->monotone_constraints.empty() && param->interaction_constraints.empty())
+        << "[b200hist] constraints are not supported yet";
+    CHECK_EQ(param->subsample, 1.0f) << "[b200hist] row sampling is not supported yet";
+    B200_SHIM_CHECK(b200hist_updater_create(ellpack_, &p, &updater_));
+    std::int32_t max_nodes{0};
+    B200_SHIM_CHECK(b200hist_updater_max_nodes(updater_, &max_nodes));
+    nodes_.resize(static_cast<std::size_t>(max_nodes));
+  }
+
+  // ApplySplit (updater_gpu_hist.cu:610-655): our nodes are numbered in the reference's expansion order,
+  // so replaying the internal nodes by ascending left-child id reproduces RegTree's AllocNode sequence.
+  void ReplayInto(RegTree* p_tree, std::int32_t n_nodes) {
+    auto& tree = *p_tree;
+    auto const& root = nodes_[0];
+    tree.Stat(RegTree::kRoot).sum_hess = root.sum_hess;
+    tree.Stat(RegTree::kRoot).base_weight = root.base_weight;
+    tree[RegTree::kRoot].SetLeaf(root.leaf_value);
+    std::vector<std::int32_t> internal;
+    for (std::int32_t i = 0; i < n_nodes; ++i) {
+      if (!nodes_[i].is_leaf) internal.push_back(i);
+    }
+    std::sort(internal.begin(), internal.end(),
+              [&](std::int32_t a, std::int32_t b) { return nodes_[a].left < nodes_[b].left; });
+    for (auto nidx : internal) {
+      auto const& n = nodes_[nidx];
+      auto const& l = nodes_[n.left];
+      auto const& r = nodes_[n.right];
+      // children are created as leaves holding learning_rate * weight; expanded later if they split
+      float const lw = l.is_leaf ? l.leaf_value : LeafOf(n.left);
+      float const rw = r.is_leaf ? r.leaf_value : LeafOf(n.right);
+      tree.ExpandNode(nidx, static_cast<bst_feature_t>(n.findex), n.fvalue, n.default_left != 0, n.base_weight, lw, rw,
+                      n.loss_chg, n.sum_hess, l.sum_hess, r.sum_hess);
+      CHECK_EQ(tree[nidx].LeftChild(), n.left);
+      CHECK_EQ(tree[nidx].RightChild(), n.right);
+    }
+  }
+  // leaf value a node had before it was expanded = learning_rate * its weight (kept by the library)
+  [[nodiscard]] float LeafOf(std::int32_t nidx) const { return nodes_[nidx].leaf_value; }
+
+  void Release() {
+    if (updater_ != nullptr) b200hist_updater_destroy(updater_);
+    if (ellpack_ != nullptr) b200hist_ellpack_destroy(ellpack_);
+    updater_ = nullptr;
+    ellpack_ = nullptr;
+    p_last_fmat_ = nullptr;
+  }
+
+  ObjInfo const* task_{nullptr};
+  HistMakerTrainParam hist_maker_param_;
+  b200hist_ellpack_t ellpack_{nullptr};
+  b200hist_updater_t updater_{nullptr};
+  std::vector<b200hist_tree_node> nodes_;
+  DMatrix* p_last_fmat_{nullptr};
+};
+
+// Replaces the factory of the reference's own "grow_gpu_hist" entry (keeping the original reachable as
+// "grow_gpu_hist_reference" for A/B runs in one process) and adds the distinct name "grow_b200_hist".
+struct B200Registrar {
+  B200Registrar() {
+    auto* reg = ::dmlc::Registry<::xgboost::TreeUpdaterReg>::Get();
+    auto make = [](Context const* ctx, ObjInfo const* task) -> TreeUpdater* { return new B200HistMaker(ctx, task); };
+    if (auto const* orig = reg->Find("grow_gpu_hist")) {
+      auto body = orig->body;  // copy before it is overwritten
+      reg->__REGISTER__("grow_gpu_hist_reference").describe("The reference's own GPU hist updater.").set_body(body);
+    }
+    reg->__REGISTER__("grow_gpu_hist")
+        .describe("Grow tree with the Blackwell-native hist updater (libb200hist.so).")
+        .set_body(make);
+    reg->__REGISTER__("grow_b200_hist")
+        .describe("Grow tree with the Blackwell-native hist updater (libb200hist.so).")
+        .set_body(make);
+  }
+};
+static B200Registrar b200_registrar__;
+
+}  // namespace xgboost::tree
