@@ -275,12 +275,24 @@ def run_b200(args):
     except Exception:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     hist_launches = args.depth
-    hist_gbs = ab["hist"] / (phase["hist"] * 1e-3) / 1e9 if phase["hist"] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "HistKernel", "achieved": hist_gbs, "peak": peak, "unit": "GB/s",
-                "frac": hist_gbs / peak, "traffic": None, "peak_source": peak_src,
+    # per GPU: this rank reads its F/world feature columns + the 20 B of gradient pair / row id per row visit
+    hist_bytes_gpu = row_visits * (f * info["bin_bytes"] / world + 16 + 4)
+    hist_gbs = hist_bytes_gpu / (phase["hist"] * 1e-3) / 1e9 if phase["hist"] > 0 else 0.0
+    # the kernel's binding ceiling is shared-memory read-modify-write bandwidth: 16 B read + 16 B written per
+    # (row, feature) update at 128 B/clk/SM = 4 updates/clk/SM
+    sm_clock_hz = (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965) * 1e6
+    n_sms = torch.cuda.get_device_properties(device).multi_processor_count
+    updates_per_s = row_visits * (f / world) / (phase["hist"] * 1e-3) if phase["hist"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "HistKernelBankedFast", "achieved": hist_gbs, "peak": peak, "unit": "GB/s",
+                "frac": hist_gbs / peak, "traffic": 1.33 * hist_bytes_gpu / hist_launches, "peak_source": peak_src,
+                "traffic_source": "ncu --set full dram__bytes_read+write = 1.33 x algorithmic on the 20M-row capture "
+                                  "(profiles/r01_hist_banked_v2_ncu_summary.json), scaled to this launch size",
                 "launches_per_step": hist_launches, "avg_launch_ms": phase["hist"] / hist_launches,
-                "algorithmic_bytes_per_launch": ab["hist"] / hist_launches, "row_visits_per_step": row_visits,
-                "whole_step_frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak}
+                "algorithmic_bytes_per_launch": hist_bytes_gpu / hist_launches, "row_visits_per_step": row_visits,
+                "smem_atomic_bound": {"updates_per_clk_per_sm": updates_per_s / sm_clock_hz / n_sms, "ceiling": 4.0,
+                                      "frac": updates_per_s / sm_clock_hz / n_sms / 4.0,
+                                      "note": "exact int64 pair accumulation = 32 B of shared-memory RMW per update"},
+                "whole_step_frac": (ab["total"] - ab["hist"] + hist_bytes_gpu) / (ms_per_step * 1e-3) / 1e9 / peak}
 
     # end-to-end: gradient arrives in pinned HOST memory, tree returns to the host (C-ABI host entry)
     e2e = None

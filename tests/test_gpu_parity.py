@@ -360,6 +360,7 @@ TREE_CASES = [
     dict(n=2000, f=4, max_bin=8, params=dict(max_depth=10)),
     dict(n=600, f=3, max_bin=8, params=dict(max_depth=1)),
     dict(n=40000, f=256, max_bin=256, params=dict(max_depth=4)),
+    dict(n=7000, f=6, max_bin=16, zero_hess=0.1, params=dict(max_depth=4)),
 ]
 
 
@@ -374,6 +375,9 @@ def test_update_tree_matches_oracle(xb, case):
         gp = logistic_gpair(np.zeros_like(y), (y > 0).astype(np.float32))
     else:
         gp = squared_error_gpair(np.zeros_like(y), y)
+    if case.get("zero_hess"):  # "unsampled" rows: zero gradient pair -> bit-complemented position
+        drop = np.random.default_rng(1).random(case["n"]) < case["zero_hess"]
+        gp[drop] = 0.0
     up = xb.GPUHistMaker(page)
     up.configure(case["params"])
     pos = torch.empty(case["n"], dtype=torch.int32, device="cuda")

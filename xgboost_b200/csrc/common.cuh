@@ -85,6 +85,10 @@ struct EllView {
   uint32_t row_bytes;    // multiple of 16
   uint32_t bin_bytes;    // 1 or 2
   uint32_t null_symbol;  // symbol meaning "missing"; 0xFFFFFFFF when the page has no missing
+  // column-major copy bins_t[f][col_stride] (uint8 pages only, may be null): one byte per (feature, row),
+  // used by the single-feature gathers of the row partitioner (32 consecutive rows share a sector)
+  const uint8_t* bins_t;
+  uint64_t col_stride;
 };
 
 }  // namespace b200
@@ -111,9 +115,11 @@ struct b200hist_ellpack_s {
   uint32_t* d_cut_ptrs{nullptr};
   float* d_cut_values{nullptr};
   uint8_t* d_bins{nullptr};
+  uint8_t* d_bins_t{nullptr};  // column-major copy (uint8 pages)
+  uint64_t col_stride{0};
   b200::EllView View() const {
     return b200::EllView{d_bins, d_cut_ptrs, d_cut_values, n_rows, n_features, total_bins,
-                         row_bytes, bin_bytes, null_symbol};
+                         row_bytes, bin_bytes, null_symbol, d_bins_t, col_stride};
   }
 };
 
@@ -189,6 +195,8 @@ struct QuantDev {
   double to_fixed_g, to_fixed_h, to_float_g, to_float_h;
   double sums[4];
   long long root_g, root_h;
+  unsigned int h_zero_any;  // some quantised hessian is 0 (position must be bit-complemented for those rows)
+  unsigned int pad0;
   unsigned int h_lo_or;  // OR of the low 32 bits of every quantised hessian (0 => histogram skips h.lo)
   unsigned int pad;
 };

@@ -12,6 +12,8 @@
 // slice of it) is a legal source for cp.async.bulk (TMA 1-D bulk copy) and for 128-bit loads.
 // The reference's own 8-bit layout starts at byte 8 (kPadding) and is therefore only 8-byte
 // aligned -- which is why we keep our own copy instead of reading the reference buffer in place.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -65,6 +67,50 @@ __global__ void __launch_bounds__(256) BinDenseKernel(const float* __restrict__ 
     }
     *reinterpret_cast<uint32_t*>(bins + (row_begin + r) * row_bytes + 4ull * w) = packed;
   }
+}
+
+// Column-major copy of rows [row_begin, row_begin + n): bins_t[f][r].  128 rows x 64 features per CTA through
+// shared memory; reads are 32-bit row-major words, writes are 128 contiguous bytes per feature.
+__global__ void __launch_bounds__(256) TransposeKernel(const uint8_t* __restrict__ bins, uint32_t row_bytes,
+                                                        uint32_t n_features, uint64_t row_begin, uint64_t n,
+                                                        uint8_t* __restrict__ bins_t, uint64_t col_stride) {
+  __shared__ uint8_t tile[64][128 + 4];
+  const uint64_t r0 = row_begin + (uint64_t)blockIdx.x * 128;
+  const uint32_t f0 = blockIdx.y * 64;
+  const uint64_t r_end = row_begin + n;
+  // load: 128 rows x 16 words
+  for (uint32_t i = threadIdx.x; i < 128 * 16; i += 256) {
+    const uint32_t r = i >> 4, w = i & 15u;
+    uint32_t word = 0;
+    if (r0 + r < r_end && f0 + 4 * w < row_bytes)
+      word = *reinterpret_cast<const uint32_t*>(bins + (r0 + r) * row_bytes + f0 + 4 * w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tile[4 * w + k][r] = (uint8_t)(word >> (8 * k));
+  }
+  __syncthreads();
+  // store: 64 features x 32 words of 4 rows
+  for (uint32_t i = threadIdx.x; i < 64 * 32; i += 256) {
+    const uint32_t f = i >> 5, w = i & 31u;
+    if (f0 + f < n_features && r0 + 4 * w < r_end) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(&tile[f][4 * w]);
+      uint8_t* dst = bins_t + (uint64_t)(f0 + f) * col_stride + r0 + 4 * w;
+      if (r0 + 4 * w + 4 <= r_end) {
+        *reinterpret_cast<uint32_t*>(dst) = v;
+      } else {
+        for (uint32_t k = 0; r0 + 4 * w + k < r_end; ++k) dst[k] = (uint8_t)(v >> (8 * k));
+      }
+    }
+  }
+}
+
+static void LaunchTranspose(b200hist_ellpack_s* e, uint64_t row_begin, uint64_t n, cudaStream_t s) {
+  if (e->d_bins_t == nullptr || n == 0) return;
+  // tiles are aligned to 128 rows of the page so that 32-bit stores stay aligned
+  const uint64_t a0 = row_begin & ~uint64_t(127);
+  const uint64_t span = row_begin + n - a0;
+  dim3 grid((unsigned)((span + 127) / 128), (e->n_features + 63) / 64);
+  TransposeKernel<<<grid, 256, 0, s>>>(e->d_bins, e->row_bytes, e->n_features, a0, span, e->d_bins_t, e->col_stride);
+  B200_LAUNCHED();
 }
 
 // Decode the reference's big-endian bit-packed symbol stream into our layout.
@@ -134,6 +180,11 @@ int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features, co
   B200_CUDA(cudaMemcpy(e->d_cut_values, e->cut_values.data(), sizeof(float) * e->total_bins, cudaMemcpyHostToDevice));
   e->d_bins = DevAlloc<uint8_t>(n_rows * (uint64_t)e->row_bytes + 16);
   B200_CUDA(cudaMemset(e->d_bins, 0, n_rows * (uint64_t)e->row_bytes + 16));
+  const char* no_t = std::getenv("B200HIST_NO_COLMAJOR");
+  if (e->bin_bytes == 1 && !(no_t && no_t[0] == '1')) {
+    e->col_stride = (n_rows + 127) & ~uint64_t(127);
+    e->d_bins_t = DevAlloc<uint8_t>((uint64_t)n_features * e->col_stride + 16);
+  }
   *out = e;
   B200_API_END();
 }
@@ -145,6 +196,7 @@ int b200hist_ellpack_destroy(b200hist_ellpack_t e) {
     cudaFree(e->d_cut_ptrs);
     cudaFree(e->d_cut_values);
     cudaFree(e->d_bins);
+    cudaFree(e->d_bins_t);
     delete e;
   }
   B200_API_END();
@@ -169,6 +221,7 @@ int b200hist_ellpack_push_dense(b200hist_ellpack_t e, uint64_t row_begin, const 
                                                    e->d_bins, row_begin, e->row_bytes, e->null_symbol);
   }
   B200_LAUNCHED();
+  LaunchTranspose(e, row_begin, n, s);
   B200_API_END();
 }
 
@@ -195,6 +248,7 @@ int b200hist_ellpack_import_reference(b200hist_ellpack_t e, const uint8_t* gidx_
                                                           e->d_bins, e->row_bytes, e->null_symbol);
   }
   B200_LAUNCHED();
+  LaunchTranspose(e, 0, e->n_rows, s);
   B200_API_END();
 }
 

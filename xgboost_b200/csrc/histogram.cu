@@ -63,7 +63,7 @@ static int HistImpl() {
 }
 constexpr uint32_t kRingStages = 4;
 static size_t RingSmemBytes(uint32_t blocks) {
-  return HistImpl() == 0 ? 0 : (size_t)(kHistThreads / 32) * kRingStages * (8 * (32 * blocks + 16) + 8);
+  return (HistImpl() == 0 || HistImpl() == 3) ? 0 : (size_t)(kHistThreads / 32) * kRingStages * (8 * (32 * blocks + 16) + 8);
 }
 
 // Feature groups.
@@ -344,6 +344,173 @@ HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
       if (h_lo_zero) run(std::true_type{}); else run(std::false_type{});
     }
     flush((int32_t)e.slot);
+    t = te;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast bank-mapped kernel for the common case (every block is a full 32 features, no null symbol):
+// the same accumulation as HistKernelBanked<false>, hand-scheduled to keep the instruction stream lean --
+// full passes only in the main loop (no validity selects), ping-pong register buffers (no copies),
+// pointer-increment addressing, block base folded into the lane offsets.  A warp's last partial pass goes
+// through a small checked tail.
+// ---------------------------------------------------------------------------------------------
+struct FastData {
+  uint32_t word[2], glo[2], ghi[2], hlo[2], hhi[2];
+};
+
+template <bool kHLoZero>
+__device__ __forceinline__ void FastProcess(const FastData& d, const uint32_t (&sel)[4], const uint32_t (&off)[4]) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    uint32_t addr[4], og[4], oh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) addr[k] = __byte_perm(d.word[u], 0u, sel[k]) * 512u + off[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      og[k] = AtomAddShared(addr[k], d.glo[u]);
+      if (!kHLoZero) oh[k] = AtomAddShared256(addr[k], d.hlo[u]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      RedAddHi128(addr[k], og[k], d.glo[u], d.ghi[u]);
+      if (kHLoZero) RedAdd384(addr[k], d.hhi[u]);
+      else RedAddHi384(addr[k], oh[k], d.hlo[u], d.hhi[u]);
+    }
+  }
+}
+
+__device__ __forceinline__ void FastLoad(FastData& d, const uint32_t (&r)[2], const longlong2* __restrict__ gq,
+                                         const uint8_t* __restrict__ col, uint32_t row_bytes) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const longlong2 gp = __ldg(gq + r[u]);
+    d.word[u] = __ldg(reinterpret_cast<const uint32_t*>(col + (size_t)r[u] * row_bytes));
+    d.glo[u] = (uint32_t)(unsigned long long)gp.x;
+    d.ghi[u] = (uint32_t)((unsigned long long)gp.x >> 32);
+    d.hlo[u] = (uint32_t)(unsigned long long)gp.y;
+    d.hhi[u] = (uint32_t)((unsigned long long)gp.y >> 32);
+  }
+}
+
+template <bool kHLoZero>
+__device__ __forceinline__ void FastRows(const uint32_t* __restrict__ ridx, uint32_t lo, uint32_t hi,
+                                         const longlong2* __restrict__ gq, const uint8_t* __restrict__ col,
+                                         uint32_t row_bytes, uint32_t warp, uint32_t q,
+                                         const uint32_t (&sel)[4], const uint32_t (&off)[4]) {
+  constexpr uint32_t kWarps = kHistThreads / 32;
+  constexpr uint32_t kStride = kWarps * kRowsPerPass;
+  const uint32_t first = lo + warp * kRowsPerPass;
+  if (first >= hi) return;
+  // passes of this warp whose 8 rows all exist
+  const uint32_t n_full = (hi >= first + kRowsPerPass) ? (hi - first - kRowsPerPass) / kStride + 1u : 0u;
+  const uint32_t* __restrict__ rp = ridx + first + q;  // row id of (u = 0); u = 1 is +4
+  if (n_full > 0) {
+    // clamp so that prefetches past the end re-read the last full pass (discarded) instead of branching
+    const uint32_t last = n_full - 1;
+    auto rid = [&](uint32_t i, uint32_t (&r)[2]) {
+      const uint32_t* p = rp + (size_t)min(i, last) * kStride;
+      r[0] = __ldg(p);
+      r[1] = __ldg(p + 4);
+    };
+    uint32_t ra[2], rb[2];
+    FastData da, db;
+    rid(0, ra);
+    rid(1, rb);
+    FastLoad(da, ra, gq, col, row_bytes);
+    rid(2, ra);
+    uint32_t i = 0;
+    for (; i + 1 < n_full; i += 2) {
+      FastLoad(db, rb, gq, col, row_bytes);  // pass i+1
+      rid(i + 3, rb);
+      FastProcess<kHLoZero>(da, sel, off);   // pass i
+      FastLoad(da, ra, gq, col, row_bytes);  // pass i+2
+      rid(i + 4, ra);
+      FastProcess<kHLoZero>(db, sel, off);   // pass i+1
+    }
+    if (i < n_full) FastProcess<kHLoZero>(da, sel, off);  // odd count: pass n_full-1 is in da
+  }
+  // partial last pass (fewer than 8 rows): zero the gradients of the missing rows
+  const uint32_t jb = first + n_full * kStride;
+  if (jb < hi) {
+    uint32_t r[2];
+    FastData d;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) r[u] = __ldg(ridx + min(jb + u * 4 + q, hi - 1));
+    FastLoad(d, r, gq, col, row_bytes);
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (jb + u * 4 + q >= hi) { d.glo[u] = 0u; d.ghi[u] = 0u; d.hlo[u] = 0u; d.hhi[u] = 0u; }
+    FastProcess<false>(d, sel, off);
+  }
+}
+
+__global__ void __launch_bounds__(kHistThreads, 1)
+HistKernelBankedFast(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
+                     const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
+                     const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
+                     const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist,
+                     const QuantDev* __restrict__ qd) {
+  extern __shared__ __align__(16) uint32_t sh[];
+  const GroupDesc g = groups[blockIdx.y];
+  const uint32_t S = g.max_sym, B = g.n_blocks;
+  const uint32_t slots = B * S * 32;
+
+  const uint32_t n_tiles = ts->build_tiles;
+  if (n_tiles == 0) return;
+  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
+  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+  if (t0 >= t1) return;
+  const uint32_t n_build = (uint32_t)ts->n_build;
+  const bool h_lo_zero = qd != nullptr && qd->h_lo_or == 0u;
+
+  for (uint32_t i = threadIdx.x; i < 4 * slots; i += kHistThreads) sh[i] = 0u;
+  __syncthreads();
+
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t q = lane >> 3, w = lane & 7u;
+  const uint32_t sh_base = (uint32_t)__cvta_generic_to_shared(sh);
+  uint32_t sel[4], lane_off[4];
+#pragma unroll
+  for (uint32_t k = 0; k < 4; ++k) {
+    const uint32_t jj = (k + q) & 3u;
+    sel[k] = 0x4440u | jj;
+    lane_off[k] = (4u * w + jj) * 4u;
+  }
+
+  uint32_t t = t0;
+  while (t < t1) {
+    const uint32_t seg = tile_seg[t];
+    const BuildEntry e = build[seg];
+    const uint32_t seg_tile_end = (seg + 1 < n_build) ? build[seg + 1].tile_begin : n_tiles;
+    const uint32_t te = min(t1, seg_tile_end);
+    const uint32_t lo = (t - e.tile_begin) * kHistTile;
+    const uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
+    const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin;
+    for (uint32_t blk = 0; blk < B; ++blk) {
+      uint32_t off[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) off[k] = sh_base + blk * S * 512u + lane_off[k];
+      const uint8_t* __restrict__ col = ell.bins + g.byte_begin + blk * 32u + 4u * w;
+      if (h_lo_zero) FastRows<true>(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
+      else FastRows<false>(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
+    }
+    // flush this CTA's share of the node (RED.64 on non-zero accumulators) and clear
+    __syncthreads();
+    longlong2* dst = hist + (size_t)e.slot * ell.total_bins;
+    for (uint32_t p = threadIdx.x; p < slots; p += kHistThreads) {
+      const uint32_t ln = p & 31u, rest = p >> 5;
+      uint32_t* a = sh + rest * 128 + ln;
+      const uint32_t glo = a[0], ghi = a[32], hlo = a[64], hhi = a[96];
+      if (glo | ghi | hlo | hhi) {
+        const uint32_t f = g.f_begin + (rest / S) * 32 + ln;
+        longlong2* d = dst + ell.cut_ptrs[f] + (rest % S);
+        if (glo | ghi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->x), ((unsigned long long)ghi << 32) | glo);
+        if (hlo | hhi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->y), ((unsigned long long)hhi << 32) | hlo);
+        a[0] = 0u; a[32] = 0u; a[64] = 0u; a[96] = 0u;
+      }
+    }
+    __syncthreads();
     t = te;
   }
 }
@@ -685,6 +852,7 @@ HistKernelGeneric(EllView ell, const longlong2* __restrict__ gq, const uint32_t*
 void PrepareHistKernels(int device) {
   int optin = SmemOptin(device);
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelBankedFast, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -713,8 +881,8 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
     using KernelT = void (*)(EllView, const longlong2*, const uint32_t*, const uint32_t*, const BuildEntry*,
                              const uint32_t*, const TreeState*, const GroupDesc*, longlong2*, const QuantDev*);
     KernelT kernel;
-    if (impl == 0) {
-      kernel = checked ? HistKernelBanked<true> : HistKernelBanked<false>;
+    if (impl == 0 || impl == 3) {  // 3 = the unscheduled direct-load kernel (for comparison)
+      kernel = checked ? HistKernelBanked<true> : (impl == 0 ? HistKernelBankedFast : HistKernelBanked<false>);
     } else {
       smem += RingSmemBytes(max_blocks);
       if (impl == 1) kernel = checked ? HistKernelStaged<true, true> : HistKernelStaged<false, true>;

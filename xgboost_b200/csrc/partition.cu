@@ -41,6 +41,7 @@ PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint
     const uint32_t n = min((uint32_t)kPartTile, e.count - off);
     const uint32_t* __restrict__ ridx = (e.src_buf ? ridx1 : ridx0) + e.begin + off;
     const uint8_t* __restrict__ col = ell.bins + (size_t)e.findex * sizeof(BinT);
+    const uint8_t* __restrict__ colt = ell.bins_t ? ell.bins_t + (uint64_t)e.findex * ell.col_stride : nullptr;
     uint32_t cnt = 0;
 #pragma unroll
     for (int k = 0; k < kRowsPerThread; ++k) {
@@ -48,7 +49,9 @@ PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint
       bool left = false;
       if (j < n) {
         const uint32_t r = ridx[j];
-        const uint32_t sym = *reinterpret_cast<const BinT*>(col + (size_t)r * ell.row_bytes);
+        const uint32_t sym = (sizeof(BinT) == 1 && colt != nullptr)
+                                 ? (uint32_t)colt[r]
+                                 : (uint32_t)*reinterpret_cast<const BinT*>(col + (size_t)r * ell.row_bytes);
         left = (sym == ell.null_symbol) ? (e.default_left != 0) : ((int32_t)sym < e.split_lbin);
       }
       const uint32_t m = __ballot_sync(0xffffffffu, left);

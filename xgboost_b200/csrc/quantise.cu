@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kQThreads) QuantReduceKernel(const float2* __r
     q->root_g = 0;
     q->root_h = 0;
     q->h_lo_or = 0u;
+    q->h_zero_any = 0u;
     *counter = 0;  // ready for the next tree
   }
 }
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(kQThreads) QuantConvertKernel(const float2* __
   const double fg = q->to_fixed_g, fh = q->to_fixed_h;
   long long sg = 0, sh_ = 0;
   unsigned int lo_or = 0u;
+  bool h_zero = false;
   for (uint64_t i = blockIdx.x * (uint64_t)kQThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kQThreads) {
     float2 v = __ldg(gpair + i);
     // ToFixedPoint (quantiser.cuh:65-69): C cast of double -> int64 truncates toward zero
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(kQThreads) QuantConvertKernel(const float2* __
     sg += g;
     sh_ += h;
     lo_or |= (unsigned int)(unsigned long long)h;
+    h_zero |= (h == 0);
   }
   __shared__ long long red[2][kQThreads / 32];
   sg = WarpSumLL(sg);
@@ -119,6 +122,9 @@ __global__ void __launch_bounds__(kQThreads) QuantConvertKernel(const float2* __
     red[0][warp] = sg;
     red[1][warp] = sh_;
     if (lo_or) atomicOr(&q->h_lo_or, lo_or);
+  }
+  if (__any_sync(0xffffffffu, h_zero) && lane == 0) {
+    atomicOr(&q->h_zero_any, 1u);
   }
   __syncthreads();
   if (threadIdx.x < 2) {

@@ -400,8 +400,10 @@ __global__ void __launch_bounds__(256) FinaliseKernel(EllView ell, const uint32_
                                                        const NodeDev* __restrict__ nodes,
                                                        const BuildEntry* __restrict__ fin,
                                                        const uint32_t* __restrict__ fin_tile_seg,
-                                                       const TreeState* __restrict__ ts, int32_t* __restrict__ position) {
+                                                       const TreeState* __restrict__ ts, int32_t* __restrict__ position,
+                                                       const QuantDev* __restrict__ qd) {
   const uint32_t n_tiles = ts->final_tiles;
+  const bool any_h_zero = qd->h_zero_any != 0u;
   for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const BuildEntry e = fin[fin_tile_seg[t]];
     const uint32_t off = (t - e.tile_begin) * kPartTile;
@@ -412,12 +414,15 @@ __global__ void __launch_bounds__(256) FinaliseKernel(EllView ell, const uint32_
       int nidx = e.nidx;
       while (!nodes[nidx].is_leaf) {
         const NodeDev& nd = nodes[nidx];
-        const uint32_t sym = reinterpret_cast<const BinT*>(ell.bins + (size_t)r * ell.row_bytes)[nd.findex];
+        const uint32_t sym = (sizeof(BinT) == 1 && ell.bins_t != nullptr)
+                                 ? (uint32_t)ell.bins_t[(uint64_t)nd.findex * ell.col_stride + r]
+                                 : (uint32_t)reinterpret_cast<const BinT*>(ell.bins + (size_t)r * ell.row_bytes)[nd.findex];
         const bool left = (sym == ell.null_symbol) ? (nd.default_left != 0) : ((int32_t)sym < nd.split_lbin);
         nidx = left ? nd.left : nd.right;
       }
-      const long long hq = gq[r].y;
-      position[r] = hq != 0 ? nidx : ~nidx;
+      // EncodeOp (updater_gpu_hist.cuh:48-56): rows whose hessian is 0 get the bit-complemented id; the
+      // quantiser tells us when no such row exists so the gradient gather can be skipped
+      position[r] = (any_h_zero && gq[r].y == 0) ? ~nidx : nidx;
     }
   }
 }
@@ -631,11 +636,11 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   if (ell->bin_bytes == 1) {
     FinaliseKernel<uint8_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1],
                                                           reinterpret_cast<const longlong2*>(u->d_gq), u->d_nodes,
-                                                          u->d_fin, u->d_fin_tile_seg, u->d_ts, position);
+                                                          u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);
   } else {
     FinaliseKernel<uint16_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1],
                                                            reinterpret_cast<const longlong2*>(u->d_gq), u->d_nodes,
-                                                           u->d_fin, u->d_fin_tile_seg, u->d_ts, position);
+                                                           u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);
   }
   B200_LAUNCHED();
   timer.End(kFinal, tf);
