@@ -111,6 +111,18 @@ B200HIST_API uint64_t b200hist_launch_count(void);
 B200HIST_API int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features,
                                          const uint32_t* cut_ptrs_host, const float* cut_values_host,
                                          int has_missing, b200hist_ellpack_t* out);
+/* Sparse ELLPACK page (the reference's layout when row_stride < n_features, ellpack_page.cu:140-183):
+ * uint32 symbols[n_rows][row_stride] holding GLOBAL bin indices in feature order, null = total_bins.
+ * row_stride = the longest row (entries); the caller computes it like GetRowStride (ellpack_page.cuh:393+). */
+B200HIST_API int b200hist_ellpack_create_sparse(int device, uint64_t n_rows, uint32_t n_features,
+                                                const uint32_t* cut_ptrs_host, const float* cut_values_host,
+                                                uint32_t row_stride, b200hist_ellpack_t* out);
+/* Bin a CSR batch resident on the device into rows [row_begin, row_begin + n): indptr int64[n+1] (batch
+ * relative), indices int32[nnz] ascending per row, values float32[nnz]; NaN values are skipped.
+ * replaces CompressBinEllpackKernel<.., kDenseCompressed=false> (src/data/ellpack_page.cu:56-134). */
+B200HIST_API int b200hist_ellpack_push_csr(b200hist_ellpack_t ell, uint64_t row_begin, const int64_t* indptr_dev,
+                                           const int32_t* indices_dev, const float* values_dev, uint64_t n,
+                                           void* stream);
 B200HIST_API int b200hist_ellpack_destroy(b200hist_ellpack_t ell);
 /* Bin a dense row-major f32 batch resident on the device into rows [row_begin, row_begin+n).
  * NaN = missing.  replaces CompressBinEllpackKernel / WriteCompressedEllpackFunctor

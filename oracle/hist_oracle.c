@@ -294,6 +294,7 @@ ORC_API void orc_eval_node(const orc_gpair64* hist, orc_gpair64 parent_sum, cons
                            orc_candidate* out, float* gain_out) {
   orc_candidate best;
   cand_init(&best);
+  int32_t best_pos = -1;
   int32_t nf = feature_set ? n_feature_set : (int32_t)n_features;
   for (int32_t fi = 0; fi < nf; ++fi) {
     int32_t f = feature_set ? feature_set[fi] : fi;
@@ -357,8 +358,22 @@ ORC_API void orc_eval_node(const orc_gpair64* hist, orc_gpair64 parent_sum, cons
         }
       }
     }
-    /* operator+ (evaluate_splits.cu:308-311): later feature wins only if strictly greater */
-    if (fbest.loss_chg > best.loss_chg) best = fbest;
+    /* Cross-feature fold: operator+ "b.loss_chg > a.loss_chg ? b : a" (evaluate_splits.cu:308-311) applied by
+     * cub::DeviceSegmentedReduce::Sum (:371-383).  The operator is not commutative and CUB (CCCL 2.8 Policy600
+     * scaled to the 56-byte candidate: 256 threads x 1 item, agent_reduce.cuh ConsumeRange) folds a segment
+     * STRIPED: thread t takes positions t, t+256, ... in order, threads are then folded in thread order.  So
+     * among equal gains the smallest (position mod 256), then the smallest position, wins.  Up to 256 features
+     * this is "lowest feature wins" (test_evaluate_splits.cu:411-434). */
+    {
+      int take = 0;
+      if (best_pos < 0) take = 1; /* first item of the fold (the init value is the default candidate) */
+      else if (fbest.loss_chg > best.loss_chg) take = 1;
+      else if (fbest.loss_chg == best.loss_chg) {
+        int a = fi & 255, b = best_pos & 255;
+        take = (a < b) || (a == b && fi < best_pos);
+      }
+      if (take) { best = fbest; best_pos = fi; }
+    }
   }
   /* post-pass (evaluate_splits.cu:441-467) */
   double pg = (double)parent_sum.g * scale[2], ph = (double)parent_sum.h * scale[3];

@@ -76,6 +76,22 @@ class DMatrix:
         return dm
 
     @classmethod
+    def from_csr(cls, indptr, indices, values, n_cols, label=None, kind="cpu", nthread=0):
+        """XGDMatrixCreateFromCSR (c_api.h): host CSR arrays."""
+        lib = load(kind)
+        ip = np.ascontiguousarray(indptr, dtype=np.uint64)
+        ix = np.ascontiguousarray(indices, dtype=np.uint32)
+        va = np.ascontiguousarray(values, dtype=np.float32)
+        h = c_void_p()
+        cfg = json.dumps({"missing": float("nan"), "nthread": int(nthread)}).encode()
+        _check(lib, lib.XGDMatrixCreateFromCSR(_array_interface(ip), _array_interface(ix), _array_interface(va),
+                                               c_uint64(n_cols), cfg, byref(h)))
+        dm = cls(lib, h, keep=(ip, ix, va))
+        if label is not None:
+            dm.set_label(label)
+        return dm
+
+    @classmethod
     def from_cuda(cls, x_cuda, label=None, kind="cuda"):
         """x_cuda: torch CUDA float32 matrix (in-core SimpleDMatrix on the device)."""
         lib = load(kind)

@@ -46,6 +46,23 @@ def make_regression(n, f, seed, missing=0.0, dtype=np.float32):
     return x, y
 
 
+def make_sparse_regression(n, f, density, seed):
+    """Deterministic sparse problem: (dense-with-NaN matrix, y, CSR indptr/indices/values)."""
+    rng = np.random.default_rng(seed)
+    mask = rng.random((n, f)) < density
+    vals_full = rng.standard_normal((n, f)).astype(np.float32)
+    x = np.where(mask, vals_full, np.float32(np.nan)).astype(np.float32)
+    w = rng.standard_normal(f).astype(np.float32)
+    acc = np.zeros(n, dtype=np.float64)
+    for j in range(f):
+        acc += np.where(mask[:, j], vals_full[:, j], np.float32(0)).astype(np.float64) * np.float64(w[j])
+    y = (acc + 0.1 * rng.standard_normal(n)).astype(np.float32)
+    indptr = np.concatenate([[0], np.cumsum(mask.sum(axis=1))]).astype(np.int64)
+    indices = np.nonzero(mask)[1].astype(np.int32)
+    values = x[mask].astype(np.float32)
+    return x, y, indptr, indices, values
+
+
 def squared_error_gpair(pred, y):
     g = (pred - y).astype(np.float32)
     h = np.ones_like(g)

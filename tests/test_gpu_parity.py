@@ -503,3 +503,53 @@ def test_properties_at_config2_size(xb):
     t2 = up.update(gp, pos)
     assert t1.structure() == t2.structure()
     assert np.array_equal(up.node_histogram(0), h0)
+
+
+# ------------------------------------------------------------------------------------------------
+# Sparse ELLPACK layout (global-bin symbols, row_stride < n_features)
+# ------------------------------------------------------------------------------------------------
+def _sparse_problem(n, f, density, seed, max_bin):
+    rng = np.random.default_rng(seed)
+    mask = rng.random((n, f)) < density
+    mask[0, : min(f, 9)] = True  # one long row fixes row_stride > typical
+    x = np.where(mask, rng.standard_normal((n, f)), np.nan).astype(np.float32)
+    w = rng.standard_normal(f)
+    y = (np.nan_to_num(x).astype(np.float64) @ w + 0.1 * rng.standard_normal(n)).astype(np.float32)
+    cp, cv = make_cuts(x, max_bin)
+    indptr = np.concatenate([[0], np.cumsum(mask.sum(axis=1))]).astype(np.int64)
+    cols = np.nonzero(mask)[1].astype(np.int32)
+    vals = x[mask].astype(np.float32)
+    return x, y, cp, cv, indptr, cols, vals
+
+
+def _ell_from_dense_bins(gb, stride):
+    n = gb.shape[0]
+    out = np.full((n, stride), -1, dtype=np.int32)
+    for i in range(n):
+        p = gb[i][gb[i] >= 0]
+        out[i, : p.size] = p
+    return out
+
+
+@pytest.mark.parametrize("n,f,density,max_bin,params", [
+    (4000, 40, 0.08, 16, dict(max_depth=4)), (9000, 200, 0.03, 64, dict(max_depth=6)),
+    (3000, 64, 0.1, 256, dict(max_depth=5, min_child_weight=5.0)),
+    (5000, 90, 0.05, 32, dict(max_depth=0, max_leaves=10, grow_policy="lossguide"))])
+def test_sparse_page_tree_matches_oracle(xb, n, f, density, max_bin, params):
+    import torch
+    x, y, cp, cv, indptr, cols, vals = _sparse_problem(n, f, density, seed=n + f, max_bin=max_bin)
+    page = xb.EllpackPage.from_csr(indptr, cols, vals, xb.HistogramCuts(cp, cv))
+    info = page.info()
+    assert info["bin_bytes"] == 4 and info["null_symbol"] == cv.size
+    gb = orc.bin_dense(x, cp, cv)
+    stride = info["row_bytes"] // 4
+    ell = _ell_from_dense_bins(gb, stride)
+    assert np.array_equal(page.symbols(), ell.astype(np.int64))
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    pos = torch.empty(n, dtype=torch.int32, device="cuda")
+    tree = up.update(torch.from_numpy(gp).cuda(), pos)
+    o = orc.update_tree(ell, cp, cv, gp, orc.Param.make(**params), is_dense_layout=False, want_hist=True)
+    _compare_tree(xb, up, tree, o, cp, cv)
+    assert np.array_equal(pos.cpu().numpy(), o["position"])

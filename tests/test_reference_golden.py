@@ -18,7 +18,7 @@ import numpy as np
 import pytest
 
 import oracle as orc
-from tests.helpers import make_regression
+from tests.helpers import make_regression, make_sparse_regression
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_gpu_trees.json")
 
@@ -43,6 +43,9 @@ def _gradients(obj, margin, y):
 
 
 def _inputs(case):
+    if case.get("sparse"):
+        x, y, _, _, _ = make_sparse_regression(case["n"], case["f"], case["sparse"], case["seed"])
+        return x, y, np.array(case["cut_ptrs"], dtype=np.uint32), _f32(case["cut_values_bits"])
     x, y = make_regression(case["n"], case["f"], seed=case["seed"], missing=case.get("missing", 0.0))
     if case["obj"] == "logistic":
         y = (y > 0).astype(np.float32)
@@ -66,7 +69,7 @@ def _leaf_margin(tree_nodes_leaf_value, position):
 @pytest.mark.parametrize("case", _cases(), ids=lambda c: c["name"])
 def test_oracle_reproduces_reference_gpu_hist(case):
     x, y, cp, cv = _inputs(case)
-    gb = orc.bin_dense(x, cp, cv)
+    gb = orc.bin_dense(x, cp, cv)  # semantics do not depend on the storage layout (dense-with-NaN here)
     p = orc.Param.make(**_params(case))
     margin = np.zeros(case["n"], dtype=np.float32)
     for t, ref in enumerate(case["trees"]):
@@ -107,7 +110,12 @@ def test_cuda_matches_reference_gpu_hist_bit_for_bit(case, cuda_device):
     import torch
     import xgboost_b200 as xb
     x, y, cp, cv = _inputs(case)
-    page = xb.EllpackPage.from_dense(torch.from_numpy(x).cuda(), xb.HistogramCuts(cp, cv))
+    if case.get("sparse"):  # the reference stores this one as a sparse ELLPACK page; so do we
+        _, _, indptr, indices, values = make_sparse_regression(case["n"], case["f"], case["sparse"], case["seed"])
+        page = xb.EllpackPage.from_csr(indptr, indices, values, xb.HistogramCuts(cp, cv))
+        assert page.info()["bin_bytes"] == 4
+    else:
+        page = xb.EllpackPage.from_dense(torch.from_numpy(x).cuda(), xb.HistogramCuts(cp, cv))
     up = xb.GPUHistMaker(page)
     up.configure(_params(case))
     margin = torch.zeros(case["n"], dtype=torch.float32, device="cuda")

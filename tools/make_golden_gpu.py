@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_capi as rc  # noqa: E402
-from tests.helpers import make_regression  # noqa: E402
+from tests.helpers import make_regression, make_sparse_regression  # noqa: E402
 
 CASES = [
     dict(name="sq_d6_b64", n=20000, f=12, seed=101, max_bin=64, obj="sq", rounds=3,
@@ -35,6 +35,8 @@ CASES = [
          params=dict(max_depth=0, max_leaves=14, grow_policy="lossguide", eta=0.3)),
     dict(name="sq_wide_256f", n=30000, f=256, seed=107, max_bin=256, obj="sq", rounds=1,
          params=dict(max_depth=5, eta=0.3)),
+    dict(name="sparse_csr_d6", n=20000, f=300, seed=108, max_bin=64, obj="sq", rounds=2, sparse=0.03,
+         params=dict(max_depth=6, eta=0.3)),
 ]
 
 
@@ -51,11 +53,14 @@ def gradients(obj, margin, y):
 
 def run_case(case):
     import torch
-    x, y = make_regression(case["n"], case["f"], seed=case["seed"], missing=case.get("missing", 0.0))
-    if case["obj"] == "logistic":
-        y = (y > 0).astype(np.float32)
-    xd = torch.from_numpy(x).cuda()
-    dm = rc.DMatrix.from_cuda(xd, kind="cuda")
+    if case.get("sparse"):
+        x, y, indptr, indices, values = make_sparse_regression(case["n"], case["f"], case["sparse"], case["seed"])
+        dm = rc.DMatrix.from_csr(indptr, indices, values, case["f"], kind="cuda")
+    else:
+        x, y = make_regression(case["n"], case["f"], seed=case["seed"], missing=case.get("missing", 0.0))
+        if case["obj"] == "logistic":
+            y = (y > 0).astype(np.float32)
+        dm = rc.DMatrix.from_cuda(torch.from_numpy(x).cuda(), kind="cuda")
     dm.set_label(y)
     params = {"tree_method": "hist", "device": "cuda:0", "max_bin": case["max_bin"], "base_score": 0.0,
               "objective": "reg:squarederror", "lambda": 1.0, "min_child_weight": 1.0}

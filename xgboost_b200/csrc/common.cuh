@@ -89,6 +89,10 @@ struct EllView {
   // used by the single-feature gathers of the row partitioner (32 consecutive rows share a sector)
   const uint8_t* bins_t;
   uint64_t col_stride;
+  // sparse ELLPACK layout (ellpack_page.cu:140-183 "Ellpack is sparse"): bins = uint32[n_rows][row_stride]
+  // holding GLOBAL bin indices in feature order, padded with the null symbol total_bins
+  uint32_t is_sparse;
+  uint32_t row_stride;
 };
 
 }  // namespace b200
@@ -117,9 +121,12 @@ struct b200hist_ellpack_s {
   uint8_t* d_bins{nullptr};
   uint8_t* d_bins_t{nullptr};  // column-major copy (uint8 pages)
   uint64_t col_stride{0};
+  bool is_sparse{false};
+  uint32_t row_stride{0};  // entries per row (sparse layout)
   b200::EllView View() const {
     return b200::EllView{d_bins, d_cut_ptrs, d_cut_values, n_rows, n_features, total_bins,
-                         row_bytes, bin_bytes, null_symbol, d_bins_t, col_stride};
+                         row_bytes, bin_bytes, null_symbol, d_bins_t, col_stride,
+                         is_sparse ? 1u : 0u, row_stride};
   }
 };
 
@@ -210,6 +217,25 @@ inline ParamDev ToParamDev(const b200hist_train_param& p) {
   return ParamDev{p.max_depth, p.max_leaves, p.grow_policy, p.learning_rate, p.reg_lambda,
                   p.reg_alpha, p.min_child_weight, p.max_delta_step, p.min_split_loss};
 }
+
+#ifdef __CUDACC__
+// Sparse page: global bin of feature [fb, fe) in row r, or 0xFFFFFFFF.  Entries are in feature order, so the
+// row (<= row_stride symbols, null-padded with values >= total_bins) is binary-searched
+// (EllpackAccessor::GetBinIndex / BinarySearchBin, src/data/ellpack_page.cuh:101-122).
+__device__ __forceinline__ uint32_t SparseRowBin(const EllView& ell, uint32_t r, uint32_t fb, uint32_t fe) {
+  const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(ell.bins) + (size_t)r * ell.row_stride;
+  uint32_t lo = 0, hi = ell.row_stride;
+  while (lo < hi) {  // first entry with symbol >= fb
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(row + mid) < fb) lo = mid + 1; else hi = mid;
+  }
+  if (lo < ell.row_stride) {
+    const uint32_t s = __ldg(row + lo);
+    if (s < fe) return s;
+  }
+  return 0xFFFFFFFFu;
+}
+#endif
 
 // Feature group: a contiguous feature range whose bins fit the shared-memory histogram.
 struct GroupDesc {

@@ -113,6 +113,70 @@ static void LaunchTranspose(b200hist_ellpack_s* e, uint64_t row_begin, uint64_t 
   B200_LAUNCHED();
 }
 
+// Sparse layout: one warp per CSR row; entry k -> global bin of (feature, value), compacted over NaNs, padded
+// with the null symbol.  Entries stay in feature order, so a row can be binary-searched by feature.
+__global__ void __launch_bounds__(256) BinCsrKernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                     const float* __restrict__ values, uint64_t n,
+                                                     const uint32_t* __restrict__ cut_ptrs,
+                                                     const float* __restrict__ cut_values, uint32_t* __restrict__ ell,
+                                                     uint64_t row_begin, uint32_t row_stride, uint32_t null_symbol,
+                                                     uint32_t n_features, int* __restrict__ error_flag) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t r = warp; r < n; r += n_warps) {
+    const int64_t beg = indptr[r], end = indptr[r + 1];
+    uint32_t* out = ell + (row_begin + r) * row_stride;
+    uint32_t written = 0;
+    for (int64_t base = beg; base < end; base += 32) {
+      const int64_t i = base + lane;
+      uint32_t sym = null_symbol;
+      bool keep = false;
+      if (i < end) {
+        const float v = values[i];
+        const uint32_t f = (uint32_t)indices[i];
+        if (f >= n_features) {
+          *error_flag = 1;
+        } else if (!isnan(v)) {
+          const uint32_t cb = cut_ptrs[f], ce = cut_ptrs[f + 1];
+          uint32_t lo = cb, hi = ce;
+          while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (!(v < cut_values[mid])) lo = mid + 1; else hi = mid;
+          }
+          if (lo == ce) lo = ce - 1;
+          sym = lo;
+          keep = true;
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, keep);
+      const uint32_t pos = written + __popc(m & ((1u << lane) - 1u));
+      if (keep) {
+        if (pos < row_stride) out[pos] = sym; else *error_flag = 2;
+      }
+      written += __popc(m);
+    }
+    for (uint32_t k = written + lane; k < row_stride; k += 32) out[k] = null_symbol;
+  }
+}
+
+// Reference sparse page (global-bin symbols, null = total_bins) -> uint32 ELL.
+__global__ void __launch_bounds__(256) ImportReferenceSparseKernel(const uint8_t* __restrict__ buf, uint64_t total,
+                                                                    uint32_t symbol_bits, uint32_t ref_stride,
+                                                                    uint32_t our_stride, uint32_t* __restrict__ ell) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t bit0 = i * symbol_bits;
+    uint64_t v = 0;
+    uint64_t byte0 = bit0 >> 3;
+    uint32_t shift = (uint32_t)(bit0 & 7);
+    uint32_t nbytes = (shift + symbol_bits + 7) >> 3;
+    for (uint32_t k = 0; k < nbytes; ++k) v = (v << 8) | buf[8 + byte0 + k];
+    const uint64_t row = i / ref_stride;
+    ell[row * our_stride + (i - row * ref_stride)] =
+        (uint32_t)((v >> (8 * nbytes - shift - symbol_bits)) & ((1ull << symbol_bits) - 1ull));
+  }
+}
+
 // Decode the reference's big-endian bit-packed symbol stream into our layout.
 template <typename BinT>
 __global__ void __launch_bounds__(256) ImportReferenceKernel(const uint8_t* __restrict__ buf, uint64_t n_rows,
@@ -189,6 +253,68 @@ int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features, co
   B200_API_END();
 }
 
+int b200hist_ellpack_create_sparse(int device, uint64_t n_rows, uint32_t n_features, const uint32_t* cut_ptrs_host,
+                                   const float* cut_values_host, uint32_t row_stride, b200hist_ellpack_t* out) {
+  B200_API_BEGIN();
+  B200_CHECK(out != nullptr && cut_ptrs_host != nullptr && cut_values_host != nullptr, "null argument");
+  B200_CHECK(n_features > 0, "n_features must be positive");
+  B200_CHECK(n_rows < (1ull << 32), "RowIndexT is uint32 (row_partitioner.cuh:22): n_rows must be < 2^32");
+  B200_CHECK(row_stride > 0 && row_stride <= n_features, "row_stride must be in [1, n_features]");
+  DeviceGuard guard(device);
+  auto* e = new b200hist_ellpack_s();
+  e->device = device;
+  e->n_rows = n_rows;
+  e->n_features = n_features;
+  e->cut_ptrs.assign(cut_ptrs_host, cut_ptrs_host + n_features + 1);
+  e->total_bins = e->cut_ptrs[n_features];
+  B200_CHECK(e->cut_ptrs[0] == 0, "cut_ptrs[0] must be 0");
+  e->cut_values.assign(cut_values_host, cut_values_host + e->total_bins);
+  for (uint32_t f = 0; f < n_features; ++f) {
+    B200_CHECK(e->cut_ptrs[f + 1] > e->cut_ptrs[f], "every feature needs at least one bin");
+    e->max_feature_bins = std::max(e->max_feature_bins, e->cut_ptrs[f + 1] - e->cut_ptrs[f]);
+  }
+  e->has_missing = true;
+  e->is_sparse = true;
+  e->bin_bytes = 4;
+  e->null_symbol = e->total_bins;  // NullValue of a sparse page (ellpack_page.cu:147)
+  e->row_stride = (row_stride + 3u) & ~3u;  // rows stay 16-byte aligned
+  e->row_bytes = e->row_stride * 4u;
+  e->d_cut_ptrs = DevAlloc<uint32_t>(n_features + 1);
+  e->d_cut_values = DevAlloc<float>(e->total_bins);
+  B200_CUDA(cudaMemcpy(e->d_cut_ptrs, e->cut_ptrs.data(), sizeof(uint32_t) * (n_features + 1), cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(e->d_cut_values, e->cut_values.data(), sizeof(float) * e->total_bins, cudaMemcpyHostToDevice));
+  e->d_bins = DevAlloc<uint8_t>(n_rows * (uint64_t)e->row_bytes + 16);
+  // every slot starts as 0xFFFFFFFF; kernels treat any symbol >= total_bins as null
+  B200_CUDA(cudaMemset(e->d_bins, 0xFF, n_rows * (uint64_t)e->row_bytes + 16));
+  *out = e;
+  B200_API_END();
+}
+
+int b200hist_ellpack_push_csr(b200hist_ellpack_t e, uint64_t row_begin, const int64_t* indptr_dev,
+                              const int32_t* indices_dev, const float* values_dev, uint64_t n, void* stream) {
+  B200_API_BEGIN();
+  B200_CHECK(e != nullptr && indptr_dev != nullptr, "null argument");
+  B200_CHECK(e->is_sparse, "push_csr needs a page created with b200hist_ellpack_create_sparse");
+  B200_CHECK(row_begin + n <= e->n_rows, "batch exceeds the page");
+  if (n == 0) return 0;
+  DeviceGuard guard(e->device);
+  auto s = static_cast<cudaStream_t>(stream);
+  int* d_err = DevAlloc<int>(1);
+  B200_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+  int blocks = (int)std::min<uint64_t>((n * 32 + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
+  BinCsrKernel<<<blocks, 256, 0, s>>>(indptr_dev, indices_dev, values_dev, n, e->d_cut_ptrs, e->d_cut_values,
+                                      reinterpret_cast<uint32_t*>(e->d_bins), row_begin, e->row_stride, e->null_symbol,
+                                      e->n_features, d_err);
+  B200_LAUNCHED();
+  int h_err = 0;
+  B200_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_err);
+  B200_CHECK(h_err != 1, "CSR column index out of range");
+  B200_CHECK(h_err != 2, "a CSR row holds more entries than row_stride");
+  B200_API_END();
+}
+
 int b200hist_ellpack_destroy(b200hist_ellpack_t e) {
   B200_API_BEGIN();
   if (e) {
@@ -206,6 +332,7 @@ int b200hist_ellpack_push_dense(b200hist_ellpack_t e, uint64_t row_begin, const 
                                 uint64_t ld, void* stream) {
   B200_API_BEGIN();
   B200_CHECK(e != nullptr && x_dev != nullptr, "null argument");
+  B200_CHECK(!e->is_sparse, "push_dense needs a dense-layout page");
   B200_CHECK(row_begin + n <= e->n_rows, "batch exceeds the page");
   B200_CHECK(ld >= e->n_features, "leading dimension smaller than n_features");
   if (n == 0) return 0;
@@ -229,7 +356,23 @@ int b200hist_ellpack_import_reference(b200hist_ellpack_t e, const uint8_t* gidx_
                                       uint32_t n_symbols, int is_dense, void* stream) {
   B200_API_BEGIN();
   B200_CHECK(e != nullptr && gidx_buffer_dev != nullptr, "null argument");
-  B200_CHECK(row_stride == e->n_features, "only dense-layout reference pages (row_stride == n_features) can be imported");
+  if (e->is_sparse) {  // global-bin symbols, n_symbols = total_bins + 1, null = total_bins
+    B200_CHECK(n_symbols == e->total_bins + 1, "sparse reference page: n_symbols must be total_bins + 1");
+    B200_CHECK(row_stride <= e->row_stride, "the reference page's row_stride exceeds this page's");
+    uint32_t sbits = 1;
+    while ((1ull << sbits) < n_symbols) ++sbits;
+    DeviceGuard guard_s(e->device);
+    auto ss = static_cast<cudaStream_t>(stream);
+    uint64_t tot = e->n_rows * (uint64_t)row_stride;
+    if (tot == 0) return 0;
+    int nb = (int)std::min<uint64_t>((tot + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
+    // slots beyond the reference's row_stride keep the fill value (>= total_bins == null)
+    ImportReferenceSparseKernel<<<nb, 256, 0, ss>>>(gidx_buffer_dev, tot, sbits, row_stride, e->row_stride,
+                                                    reinterpret_cast<uint32_t*>(e->d_bins));
+    B200_LAUNCHED();
+    return 0;
+  }
+  B200_CHECK(row_stride == e->n_features, "dense-layout reference pages need row_stride == n_features");
   uint32_t bits = 1;
   while ((1ull << bits) < n_symbols) ++bits;  // SymbolBits (compressed_iterator.h:37-40)
   // dense & no missing: n_symbols = max bins/feature; relatively dense: +1 with null = n_symbols-1

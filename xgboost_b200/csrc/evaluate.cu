@@ -183,17 +183,26 @@ NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const Tree
   for (int slot = warp_global; slot < n_eval; slot += n_warps) {
     const int nidx = eval_nodes[slot];
     const FeatCand* sc = scratch + (size_t)slot * n_fs;
+    // Cross-feature fold.  The reference reduces with cub::DeviceSegmentedReduce::Sum and the NON-commutative
+    // operator "b.loss_chg > a.loss_chg ? b : a" (evaluate_splits.cu:308-311,371-383).  CUB (CCCL 2.8, Policy600
+    // scaled for the 56-byte candidate: 256 threads x 1 item) loads a segment STRIPED -- thread t folds items
+    // t, t+256, t+512, ... in order, then threads are folded in thread order -- so among equal gains the winner
+    // is the one with the smallest (position mod 256), then the smallest position.  For <= 256 features that is
+    // "lowest feature wins" (test_evaluate_splits.cu:411-434); beyond 256 it is not, and bit-parity needs it.
+    auto earlier = [](int p2, int p1) {
+      return (p2 & 255) < (p1 & 255) || ((p2 & 255) == (p1 & 255) && p2 < p1);
+    };
     float bl = -3.402823466e+38f;
     int bpos = 0x7fffffff;
     for (int fpos = lane; fpos < n_fs; fpos += 32) {
       float l = sc[fpos].loss_chg;
-      if (l > bl) { bl = l; bpos = fpos; }  // strict: the earliest position with the maximum wins
+      if (bpos == 0x7fffffff || l > bl || (l == bl && earlier(fpos, bpos))) { bl = l; bpos = fpos; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       float ol = __shfl_xor_sync(0xffffffffu, bl, o);
       int op = __shfl_xor_sync(0xffffffffu, bpos, o);
-      if (ol > bl || (ol == bl && op < bpos)) { bl = ol; bpos = op; }
+      if (op != 0x7fffffff && (bpos == 0x7fffffff || ol > bl || (ol == bl && earlier(op, bpos)))) { bl = ol; bpos = op; }
     }
     if (lane == 0) {
       const long long pg = nodes[nidx].sum_g, ph = nodes[nidx].sum_h;

@@ -73,6 +73,18 @@ static size_t RingSmemBytes(uint32_t blocks) {
 std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, int device) {
   std::vector<GroupDesc> groups;
   const size_t optin = (size_t)SmemOptin(device);
+  if (ell.is_sparse) {
+    // global-memory histogram: "groups" only describe how features are sharded across ranks (64 per shard unit)
+    for (uint32_t f = 0; f < ell.n_features; f += 64) {
+      GroupDesc g{};
+      g.f_begin = f;
+      g.f_end = std::min(ell.n_features, f + 64);
+      g.bin_begin = ell.cut_ptrs[g.f_begin];
+      g.bin_end = ell.cut_ptrs[g.f_end];
+      groups.push_back(g);
+    }
+    return groups;
+  }
   if (ell.bin_bytes == 1) {
     const size_t budget = optin - 1024;
     uint32_t f = 0;
@@ -849,6 +861,41 @@ HistKernelGeneric(EllView ell, const longlong2* __restrict__ gq, const uint32_t*
   flush(cur_nidx);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sparse ELLPACK pages (global-bin symbols, ~1 % density): the histogram of a node spans every bin of every
+// feature (4 MiB at 1024 x 256 bins), far beyond shared memory, and a row contributes only its ~10 present
+// entries, so the accumulation goes straight to L2 with 64-bit reductions (RED.64) -- the same choice the
+// reference makes for sparse pages (feature_groups.cu: single group => global-memory histogram).
+// One thread per (row, entry); `bin_begin/bin_end` restrict a rank to its feature shard.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+HistKernelSparse(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
+                 const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
+                 const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
+                 longlong2* __restrict__ hist, uint32_t bin_begin, uint32_t bin_end) {
+  const uint32_t n_tiles = ts->build_tiles;
+  const uint32_t stride = ell.row_stride;
+  const uint32_t* __restrict__ sym_base = reinterpret_cast<const uint32_t*>(ell.bins);
+  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const BuildEntry e = build[tile_seg[t]];
+    const uint32_t off = (t - e.tile_begin) * kHistTile;
+    const uint32_t n = min((uint32_t)kHistTile, e.count - off);
+    const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin + off;
+    longlong2* __restrict__ dst = hist + (size_t)e.slot * ell.total_bins;
+    const uint32_t items = n * stride;
+    for (uint32_t idx = threadIdx.x; idx < items; idx += 256) {
+      const uint32_t j = idx / stride, k = idx - j * stride;
+      const uint32_t r = __ldg(ridx + j);
+      const uint32_t sym = __ldg(sym_base + (size_t)r * stride + k);
+      if (sym >= bin_begin && sym < bin_end) {  // also drops the null symbol (>= total_bins)
+        const longlong2 gp = __ldg(gq + r);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&dst[sym].x), (unsigned long long)gp.x);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&dst[sym].y), (unsigned long long)gp.y);
+      }
+    }
+  }
+}
+
 void PrepareHistKernels(int device) {
   int optin = SmemOptin(device);
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -865,6 +912,14 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
                      const BuildEntry* build, const uint32_t* tile_seg, const TreeState* ts,
                      const GroupDesc* groups_dev, const std::vector<GroupDesc>& groups_host,
                      b200hist_gpair64* hist, const QuantDev* quant, int num_sms, cudaStream_t s) {
+  if (ell.is_sparse) {
+    uint32_t b0 = 0xFFFFFFFFu, b1 = 0;
+    for (auto const& g : groups_host) { b0 = std::min(b0, g.bin_begin); b1 = std::max(b1, g.bin_end); }
+    HistKernelSparse<<<num_sms * 8, 256, 0, s>>>(ell, reinterpret_cast<const longlong2*>(gq), ridx0, ridx1, build,
+                                                 tile_seg, ts, reinterpret_cast<longlong2*>(hist), b0, b1);
+    B200_LAUNCHED();
+    return;
+  }
   const int n_groups = (int)groups_host.size();
   const int workers = std::max(1, num_sms / n_groups);
   dim3 grid(workers, n_groups);

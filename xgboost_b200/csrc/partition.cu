@@ -47,7 +47,11 @@ PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint
     for (int k = 0; k < kRowsPerThread; ++k) {
       const uint32_t j = k * kPartThreads + threadIdx.x;
       bool left = false;
-      if (j < n) {
+      if (j < n && ell.is_sparse) {
+        const uint32_t fb = ell.cut_ptrs[e.findex], fe = ell.cut_ptrs[e.findex + 1];
+        const uint32_t gb = SparseRowBin(ell, ridx[j], fb, fe);
+        left = (gb == 0xFFFFFFFFu) ? (e.default_left != 0) : ((int32_t)(gb - fb) < e.split_lbin);
+      } else if (j < n) {
         const uint32_t r = ridx[j];
         const uint32_t sym = (sizeof(BinT) == 1 && colt != nullptr)
                                  ? (uint32_t)colt[r]
@@ -128,6 +132,8 @@ void LaunchPartitionCount(const EllView& ell, const uint32_t* ridx0, const uint3
   int blocks = num_sms * 8;
   if (ell.bin_bytes == 1) {
     PartitionCountKernel<uint8_t><<<blocks, kPartThreads, 0, s>>>(ell, ridx0, ridx1, part, tile_seg, ts, flags, tile_left);
+  } else if (ell.is_sparse) {
+    PartitionCountKernel<uint32_t><<<blocks, kPartThreads, 0, s>>>(ell, ridx0, ridx1, part, tile_seg, ts, flags, tile_left);
   } else {
     PartitionCountKernel<uint16_t><<<blocks, kPartThreads, 0, s>>>(ell, ridx0, ridx1, part, tile_seg, ts, flags, tile_left);
   }

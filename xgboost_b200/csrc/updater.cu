@@ -414,6 +414,13 @@ __global__ void __launch_bounds__(256) FinaliseKernel(EllView ell, const uint32_
       int nidx = e.nidx;
       while (!nodes[nidx].is_leaf) {
         const NodeDev& nd = nodes[nidx];
+        if (ell.is_sparse) {
+          const uint32_t fb = ell.cut_ptrs[nd.findex], fe = ell.cut_ptrs[nd.findex + 1];
+          const uint32_t gb = SparseRowBin(ell, r, fb, fe);
+          const bool go_left = (gb == 0xFFFFFFFFu) ? (nd.default_left != 0) : ((int32_t)(gb - fb) < nd.split_lbin);
+          nidx = go_left ? nd.left : nd.right;
+          continue;
+        }
         const uint32_t sym = (sizeof(BinT) == 1 && ell.bins_t != nullptr)
                                  ? (uint32_t)ell.bins_t[(uint64_t)nd.findex * ell.col_stride + r]
                                  : (uint32_t)reinterpret_cast<const BinT*>(ell.bins + (size_t)r * ell.row_bytes)[nd.findex];
@@ -633,7 +640,11 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   auto tf = timer.Begin();
   FinalListKernel<<<1, kCtlThreads, 0, s>>>(u->d_ts, u->d_nodes, u->d_fin, u->d_fin_tile_seg, u->d_fin_tile_begin);
   B200_LAUNCHED();
-  if (ell->bin_bytes == 1) {
+  if (ell->is_sparse) {
+    FinaliseKernel<uint32_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1],
+                                                           reinterpret_cast<const longlong2*>(u->d_gq), u->d_nodes,
+                                                           u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);
+  } else if (ell->bin_bytes == 1) {
     FinaliseKernel<uint8_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1],
                                                           reinterpret_cast<const longlong2*>(u->d_gq), u->d_nodes,
                                                           u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);

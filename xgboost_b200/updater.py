@@ -63,16 +63,46 @@ class HistogramCuts:
 class EllpackPage:
     """Quantised feature matrix resident in HBM (our layout, see include/b200hist.h)."""
 
-    def __init__(self, cuts: HistogramCuts, n_rows: int, device: int = 0, has_missing: bool = False):
+    def __init__(self, cuts: HistogramCuts, n_rows: int, device: int = 0, has_missing: bool = False,
+                 sparse_row_stride: Optional[int] = None):
         lib = _l.load()
         self.cuts = cuts
         self.device = int(device)
         self.n_rows = int(n_rows)
         self._h = c_void_p()
-        _l.check(lib.b200hist_ellpack_create(
-            self.device, self.n_rows, cuts.n_features,
-            cuts.cut_ptrs.ctypes.data_as(POINTER(c_uint32)), cuts.cut_values.ctypes.data_as(POINTER(c_float)),
-            1 if has_missing else 0, byref(self._h)))
+        cp = cuts.cut_ptrs.ctypes.data_as(POINTER(c_uint32))
+        cv = cuts.cut_values.ctypes.data_as(POINTER(c_float))
+        if sparse_row_stride is not None:  # sparse ELLPACK layout (global-bin symbols)
+            _l.check(lib.b200hist_ellpack_create_sparse(self.device, self.n_rows, cuts.n_features, cp, cv,
+                                                        int(sparse_row_stride), byref(self._h)))
+        else:
+            _l.check(lib.b200hist_ellpack_create(self.device, self.n_rows, cuts.n_features, cp, cv,
+                                                 1 if has_missing else 0, byref(self._h)))
+
+    def push_csr(self, indptr: torch.Tensor, indices: torch.Tensor, values: torch.Tensor, row_begin: int) -> None:
+        """Bin a CSR batch (device tensors: int64 indptr relative to the batch, int32 indices, float32 values)."""
+        for t, name in ((indptr, "indptr"), (indices, "indices"), (values, "values")):
+            _require_cuda(t, name)
+        if indptr.dtype != torch.int64 or indices.dtype != torch.int32 or values.dtype != torch.float32:
+            raise ValueError("CSR batch must be int64 indptr, int32 indices, float32 values")
+        _l.check(_l.load().b200hist_ellpack_push_csr(self._h, int(row_begin), c_void_p(indptr.data_ptr()),
+                                                   c_void_p(indices.data_ptr()), c_void_p(values.data_ptr()),
+                                                   indptr.numel() - 1, _stream_ptr(values.device)))
+
+    @classmethod
+    def from_csr(cls, indptr, indices, values, cuts: HistogramCuts, device: int = 0) -> "EllpackPage":
+        """Sparse page from host CSR arrays (numpy); row_stride = the longest row (GetRowStride)."""
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        n = indptr.size - 1
+        keep = ~np.isnan(np.asarray(values, dtype=np.float32))
+        counts = np.add.reduceat(keep.astype(np.int64), indptr[:-1]) if n and keep.size else np.zeros(n, dtype=np.int64)
+        counts[np.diff(indptr) == 0] = 0
+        stride = max(1, int(counts.max()) if n else 1)
+        page = cls(cuts, n, device, sparse_row_stride=stride)
+        dev = "cuda:%d" % device
+        page.push_csr(torch.from_numpy(indptr).to(dev), torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int32)).to(dev),
+                      torch.from_numpy(np.ascontiguousarray(values, dtype=np.float32)).to(dev), 0)
+        return page
 
     @property
     def handle(self) -> c_void_p:
@@ -130,6 +160,10 @@ class EllpackPage:
         i = self.info()
         raw = np.zeros((i["n_rows"], i["row_bytes"]), dtype=np.uint8)
         _l.check(_l.load().b200hist_ellpack_copy_bins_to_host(self._h, c_void_p(raw.ctypes.data)))
+        if i["bin_bytes"] == 4:  # sparse layout: GLOBAL bins per ELL slot, null -> -1
+            sym = raw.view(np.uint32).astype(np.int64)
+            sym[sym >= i["total_bins"]] = -1
+            return sym
         if i["bin_bytes"] == 1:
             sym = raw[:, : i["n_features"]].astype(np.int64)
         else:
