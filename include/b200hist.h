@@ -111,6 +111,14 @@ B200HIST_API uint64_t b200hist_launch_count(void);
 B200HIST_API int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features,
                                          const uint32_t* cut_ptrs_host, const float* cut_values_host,
                                          int has_missing, b200hist_ellpack_t* out);
+/* Q2: quantile sketch -> HistogramCuts of a dense f32 batch resident on the device (NaN = missing), for the
+ * in-core, unweighted, single-window case.  replaces DeviceSketch / SketchContainer::{Push, ScanInput, MakeCuts}
+ * (src/common/hist_util.cu:234-397, src/common/quantile.cu:108-153,340-418,658-709, quantile.h:280-340).
+ * cut_ptrs_out_host: n_features + 1; cut_values_out_host: capacity >= n_features * max_bin.  n < 2^24 rows. */
+B200HIST_API int b200hist_sketch_dense(int device, const float* x_dev, uint64_t n, uint64_t ld, uint32_t n_features,
+                                       int32_t max_bin, uint32_t* cut_ptrs_out_host, float* cut_values_out_host,
+                                       uint64_t cut_values_capacity, void* stream);
+
 /* Sparse ELLPACK page (the reference's layout when row_stride < n_features, ellpack_page.cu:140-183):
  * uint32 symbols[n_rows][row_stride] holding GLOBAL bin indices in feature order, null = total_bins.
  * row_stride = the longest row (entries); the caller computes it like GetRowStride (ellpack_page.cuh:393+). */

@@ -136,3 +136,54 @@ def test_cuda_matches_reference_gpu_hist_bit_for_bit(case, cuda_device):
             assert np.float32(nd["base_weight"]).view(np.uint32) == ref["base_weight_bits"][i], (t, i)
         up.update_prediction_cache(margin)
         assert abs(float(margin.double().sum().item()) - case["margin_sums"][t]) <= 1e-3 * max(1.0, abs(case["margin_sums"][t]))
+
+
+# ------------------------------------------------------------------------------------------------
+# Q2: quantile sketch -> cuts.  The golden file holds the cut values the reference's GPU sketch produced.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [c for c in _cases() if c["f"] <= 64 or c["n"] <= 30000], ids=lambda c: c["name"])
+def test_oracle_sketch_reproduces_reference_cuts(case):
+    from oracle import sketch
+    x, _, cp, cv = _inputs(case)
+    p, v = sketch.device_sketch_cuts(x, case["max_bin"])
+    assert np.array_equal(p, cp)
+    assert np.array_equal(v.view(np.uint32), cv.view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c["name"])
+def test_cuda_sketch_reproduces_reference_cuts(case, cuda_device):
+    import torch
+    import xgboost_b200 as xb
+    x, _, cp, cv = _inputs(case)
+    cuts = xb.HistogramCuts.from_dense(torch.from_numpy(x).cuda(), case["max_bin"])
+    assert np.array_equal(cuts.cut_ptrs, cp)
+    assert np.array_equal(cuts.cut_values.view(np.uint32), cv.view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,f,max_bin,kind", [(5000, 7, 16, "int"), (70000, 5, 64, "int"), (3, 2, 8, "cont"),
+                                              (300, 4, 256, "cont"), (100000, 9, 256, "mixed"), (1, 1, 4, "cont")])
+def test_cuda_sketch_matches_oracle_on_duplicates(n, f, max_bin, kind, cuda_device):
+    """Discrete / duplicated values exercise the duplicate folding of ScanInput; edge sizes the small paths."""
+    import torch
+    import xgboost_b200 as xb
+    from oracle import sketch
+    rng = np.random.default_rng(n + f)
+    if kind == "int":
+        x = rng.integers(-3, 40, size=(n, f)).astype(np.float32)
+    elif kind == "cont":
+        x = rng.standard_normal((n, f)).astype(np.float32)
+    else:
+        x = rng.standard_normal((n, f)).astype(np.float32)
+        x[:, ::2] = np.round(x[:, ::2] * 4) / 4
+        x[rng.random((n, f)) < 0.1] = np.nan
+        x[:, -1] = np.nan  # an empty column
+    cuts = xb.HistogramCuts.from_dense(torch.from_numpy(x).cuda(), max_bin)
+    p, v = sketch.device_sketch_cuts(x, max_bin)
+    assert np.array_equal(cuts.cut_ptrs, p)
+    assert np.array_equal(cuts.cut_values.view(np.uint32), v.view(np.uint32))
+    # property the reference's own tests check (tests/cpp/common/test_hist_util.h:134-180): cuts strictly increase
+    for j in range(f):
+        seg = cuts.cut_values[p[j]:p[j + 1]]
+        assert np.all(np.diff(seg) > 0)

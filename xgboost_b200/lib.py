@@ -68,6 +68,8 @@ _SIGNATURES = {
     "b200hist_launch_count": (c_uint64, []),
     "b200hist_ellpack_create": (c_int, [c_int, c_uint64, c_uint32, POINTER(c_uint32), POINTER(c_float), c_int,
                                         POINTER(c_void_p)]),
+    "b200hist_sketch_dense": (c_int, [c_int, c_void_p, c_uint64, c_uint64, c_uint32, c_int32, POINTER(c_uint32),
+                                      POINTER(c_float), c_uint64, c_void_p]),
     "b200hist_ellpack_create_sparse": (c_int, [c_int, c_uint64, c_uint32, POINTER(c_uint32), POINTER(c_float), c_uint32,
                                                POINTER(c_void_p)]),
     "b200hist_ellpack_push_csr": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),

@@ -53,6 +53,22 @@ class HistogramCuts:
     def total_bins(self) -> int:
         return int(self.cut_values.size)
 
+    @classmethod
+    def from_dense(cls, x: torch.Tensor, max_bin: int = 256) -> "HistogramCuts":
+        """Quantile sketch of a dense float32 CUDA matrix (NaN = missing): the cuts the reference's GPU sketch
+        produces for an in-core, unweighted DMatrix (common::DeviceSketch)."""
+        _require_cuda(x, "x")
+        if x.dtype != torch.float32 or x.dim() != 2 or (x.shape[1] > 1 and x.stride(1) != 1):
+            raise ValueError("x must be a row-major float32 matrix")
+        n, f = x.shape
+        ptrs = np.zeros(f + 1, dtype=np.uint32)
+        vals = np.zeros(f * max_bin, dtype=np.float32)
+        _l.check(_l.load().b200hist_sketch_dense(x.device.index or 0, c_void_p(x.data_ptr()), n, x.stride(0), f, max_bin,
+                                               ptrs.ctypes.data_as(POINTER(c_uint32)),
+                                               vals.ctypes.data_as(POINTER(c_float)), vals.size,
+                                               _stream_ptr(x.device)))
+        return cls(ptrs, vals[: int(ptrs[-1])].copy())
+
     def search_bin(self, value: float, fidx: int) -> int:
         """HistogramCuts::SearchBin (hist_util.h:112-121), host helper for tests."""
         beg, end = int(self.cut_ptrs[fidx]), int(self.cut_ptrs[fidx + 1])
