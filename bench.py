@@ -92,26 +92,20 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # synthetic workload: X ~ N(0,1) per 1M-row batch generated ON DEVICE, y = X.w + 0.1 eps
 # --------------------------------------------------------------------------------------------------
-def make_cuts_device(torch, n_features, max_bin, device, seed):
-    """Cuts from exact quantiles of a 200k-row sample of the same distribution (bench plumbing: the product's
-    cut finding is a `next` row of SURVEY 8(f); parity runs take cuts from the reference)."""
-    import numpy as np
-    gen = torch.Generator(device=device).manual_seed(seed)
-    sample = torch.randn((200_000, n_features), generator=gen, device=device)
-    qs = torch.linspace(0, 1, max_bin + 1, device=device)[1:-1]
-    vals = torch.quantile(sample, qs, dim=0).T.contiguous().cpu().numpy().astype(np.float32)
-    ptrs, out = [0], []
-    for j in range(n_features):
-        c = np.unique(vals[j])
-        c = np.concatenate([c, [np.float32(3.0e38)]]).astype(np.float32)
-        out.append(c)
-        ptrs.append(ptrs[-1] + c.size)
-    return np.array(ptrs, dtype=np.uint32), np.concatenate(out)
+def make_cuts_device(torch, xb, n_features, max_bin, device, seed):
+    """Cuts from our own quantile sketch (b200hist_sketch_dense) over the first 1M-row batch of the stream.
+    (A 100M-row matrix needs the multi-window sketch + merge of QuantileDMatrix, which is not built yet;
+    a one-window sketch of a 1M-row prefix of an i.i.d. stream is what this bench uses -- stated in `config`.)"""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sample = torch.randn((1_000_000, n_features), generator=g, device=device)
+    cuts = xb.HistogramCuts.from_dense(sample, max_bin)
+    del sample
+    return cuts.cut_ptrs, cuts.cut_values
 
 
 def build_workload(torch, xb, args, device, feat_lo=0, feat_hi=None):
     n, f = args.rows, args.features
-    cp, cv = make_cuts_device(torch, f, args.max_bin, device, seed=2024)
+    cp, cv = make_cuts_device(torch, xb, f, args.max_bin, device, seed=2024)
     cuts = xb.HistogramCuts(cp, cv)
     page = xb.EllpackPage(cuts, n, device.index, has_missing=False)
     gen = torch.Generator(device=device).manual_seed(7)
@@ -218,8 +212,11 @@ def run_b200(args):
     up.configure(dict(max_depth=args.depth, eta=0.3, reg_lambda=1.0, min_child_weight=1.0))
     comm = None
     if world > 1:  # feature-block sharded histograms + one NCCL allreduce per tree level
-        comm = xb.Communicator.from_torch_distributed(device)
-        up.set_comm(comm)
+        if os.environ.get("B200HIST_COMM", "p2p") == "nccl":
+            comm = xb.Communicator.from_torch_distributed(device)
+            up.set_comm(comm)
+        else:  # default: peer-memory push + flag barrier over NVLink (no NCCL in the data path)
+            up.enable_peer_exchange()
     preds = torch.zeros(n, dtype=torch.float32, device=device)
     gpair = torch.empty((n, 2), dtype=torch.float32, device=device)
     gpair[:, 1] = 1.0

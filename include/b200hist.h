@@ -197,6 +197,13 @@ B200HIST_API int b200hist_shard_groups(uint32_t n_groups, int world, int rank, u
  * communicator is borrowed.  Passing NULL returns to single-GPU mode. */
 B200HIST_API int b200hist_updater_set_comm(b200hist_updater_t u, b200hist_comm_t comm);
 B200HIST_API int b200hist_updater_num_feature_groups(b200hist_updater_t u, uint32_t* out);
+/* Peer-memory exchange (default multi-GPU collective; NVLink P2P instead of NCCL): every rank exports the IPC
+ * handle of its histogram cache (64 bytes, cudaIpcMemHandle_t), the caller all-gathers the handles, and
+ * b200hist_updater_set_peers maps the peers' caches.  Afterwards each level's built histogram slices are pushed
+ * into every peer by one kernel that ends in a cross-GPU flag barrier; no NCCL call is made.
+ * handles_host: world x 64 bytes in rank order (the own entry is ignored). */
+B200HIST_API int b200hist_updater_ipc_handle(b200hist_updater_t u, uint8_t* out_handle64);
+B200HIST_API int b200hist_updater_set_peers(b200hist_updater_t u, int rank, int world, const uint8_t* handles_host);
 
 /* Introspection of the last update (parity tests): quantiser, per-node histogram, per-node
  * candidate, per-node row counts. */

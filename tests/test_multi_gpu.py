@@ -87,6 +87,12 @@ sharded = up.update(gp)
 ok = single.structure() == sharded.structure()
 ok &= all(np.array_equal(up.node_histogram(i), h) for i, h in zip((0, 1, 2), h_single))
 ok &= [n["leaf_value"] for n in single.nodes] == [n["leaf_value"] for n in sharded.nodes]
+# the default collective: peer-memory push over NVLink P2P (a second updater; the first keeps NCCL)
+up2 = xb.GPUHistMaker(page); up2.configure(dict(max_depth=6)); up2.enable_peer_exchange()
+for _ in range(3):  # repeated trees exercise the start-of-tree barrier
+    pushed = up2.update(gp)
+    ok &= single.structure() == pushed.structure()
+    ok &= all(np.array_equal(up2.node_histogram(i), h) for i, h in zip((0, 1, 2), h_single))
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()

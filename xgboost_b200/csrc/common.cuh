@@ -279,6 +279,11 @@ std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, int devi
 // comm.cu
 void CommAllReduceInt64(b200hist_comm_s* c, void* buf, size_t count, cudaStream_t s);
 void ShardGroups(uint32_t n_groups, int world, int rank, uint32_t* g0, uint32_t* g1);
+void LaunchHistExchange(longlong2* const* peer_hist, uint32_t* const* peer_flags, int rank, int world,
+                        const TreeState* ts, uint32_t slot_base, uint32_t slot_cap, bool use_n_build,
+                        uint32_t total_bins, uint32_t bin_begin, uint32_t bin_end, uint32_t epoch,
+                        unsigned int* done_counter, int num_sms, cudaStream_t s);
+constexpr int kMaxPeers = 16;
 
 // evaluate.cu
 void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = node id */,

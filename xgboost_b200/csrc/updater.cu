@@ -495,6 +495,15 @@ struct b200hist_updater_s {
   // multi-GPU: feature-group shard of this rank and the allreduce communicator (borrowed)
   b200hist_comm_s* comm{nullptr};
   uint32_t group_begin{0}, group_end{0};
+  // peer-memory exchange (P2P over NVLink): IPC-mapped histogram caches of all ranks
+  bool p2p{false};
+  int p2p_rank{0}, p2p_world{1};
+  size_t flags_offset{0};                  // byte offset of the flag array inside the histogram allocation
+  std::vector<void*> peer_base;            // opened IPC mappings (own entry = nullptr)
+  longlong2** d_peer_hist{nullptr};
+  uint32_t** d_peer_flags{nullptr};
+  unsigned int* d_exchange_counter{nullptr};
+  uint32_t exchange_epoch{0};
   // host staging
   NodeDev* h_nodes{nullptr};  // pinned
   TreeState* h_ts{nullptr};   // pinned
@@ -577,6 +586,9 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   // Reset (updater_gpu_hist.cu:172-211): quantiser, quantised gpairs, row indices, histograms
   auto t0 = timer.Begin();
   B200_CUDA(cudaMemsetAsync(u->d_hist, 0, u->hist_bytes, s));
+  if (u->p2p)  // nobody may push into a cache that its owner has not cleared yet: pure flag barrier
+    LaunchHistExchange(u->d_peer_hist, u->d_peer_flags, u->p2p_rank, u->p2p_world, u->d_ts, 0, 0, false,
+                       ell->total_bins, 0, 0, ++u->exchange_epoch, u->d_exchange_counter, u->num_sms, s);
   LaunchQuantise(gpair_dev, n, u->d_quant, u->d_gq, u->d_ridx[0], u->d_partials, u->d_counter, u->num_sms, s);
   timer.End(kQuant, t0);
 
@@ -593,9 +605,16 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
       LaunchBuildHist(view, u->d_gq, u->d_ridx[0], u->d_ridx[1], u->d_build, u->d_build_tile_seg, u->d_ts,
                       u->d_groups + u->group_begin, my_groups, u->d_hist, u->d_quant, u->num_sms, s);
     // AllReduceHist: one collective per level over the level's contiguous built slots
-    if (u->comm != nullptr)
+    if (u->p2p) {
+      const uint32_t b0 = my_groups.empty() ? 0u : my_groups.front().bin_begin;
+      const uint32_t b1 = my_groups.empty() ? 0u : my_groups.back().bin_end;
+      LaunchHistExchange(u->d_peer_hist, u->d_peer_flags, u->p2p_rank, u->p2p_world, u->d_ts, slot_base, slot_cap,
+                         /*use_n_build=*/true, ell->total_bins, b0, b1, ++u->exchange_epoch, u->d_exchange_counter,
+                         u->num_sms, s);
+    } else if (u->comm != nullptr) {
       CommAllReduceInt64(u->comm, u->d_hist + (size_t)slot_base * ell->total_bins,
                          (size_t)slot_cap * ell->total_bins * 2, s);
+    }
   };
   build_hist(0, 1);
   timer.End(kHist, t2);
@@ -757,7 +776,18 @@ int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* 
   B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
   B200_CHECK(u->hist_bytes < free_b, "histogram cache (" + std::to_string(u->hist_bytes >> 20) +
                                          " MiB) does not fit in free device memory; lower max_depth/max_leaves");
-  u->d_hist = DevAlloc<b200hist_gpair64>((size_t)u->n_slots * ell->total_bins);
+  // one allocation = histogram cache + flag array of the peer-memory exchange (one IPC handle covers both);
+  // at least 4 MiB so that it is a stand-alone driver allocation whose IPC mapping starts at the same address
+  u->flags_offset = (u->hist_bytes + 255) & ~size_t(255);
+  {
+    const size_t alloc = std::max<size_t>(u->flags_offset + 4096, size_t(4) << 20);
+    void* p = nullptr;
+    B200_CUDA(cudaMalloc(&p, alloc));
+    B200_CUDA(cudaMemset(p, 0, alloc));
+    u->d_hist = static_cast<b200hist_gpair64*>(p);
+  }
+  u->d_exchange_counter = DevAlloc<unsigned int>(1);
+  B200_CUDA(cudaMemset(u->d_exchange_counter, 0, sizeof(unsigned int)));
   B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&u->h_nodes), sizeof(NodeDev) * u->max_nodes));
   B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&u->h_ts), sizeof(TreeState)));
   *out = u;
@@ -774,6 +804,11 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
                     u->d_tile_excl, u->d_tile_left_off, u->d_flags, u->d_fin, u->d_fin_tile_seg,
                     u->d_fin_tile_begin, u->d_scratch, u->d_hist};
     for (void* p : ptrs) cudaFree(p);
+    for (void* p : u->peer_base)
+      if (p != nullptr) cudaIpcCloseMemHandle(p);
+    cudaFree(u->d_peer_hist);
+    cudaFree(u->d_peer_flags);
+    cudaFree(u->d_exchange_counter);
     cudaFreeHost(u->h_nodes);
     cudaFreeHost(u->h_ts);
     for (auto e : u->events) cudaEventDestroy(e);
@@ -866,6 +901,49 @@ int b200hist_updater_set_comm(b200hist_updater_t u, b200hist_comm_t comm) {
     u->comm = comm;
     ShardGroups((uint32_t)u->groups.size(), comm->world, comm->rank, &u->group_begin, &u->group_end);
   }
+  B200_API_END();
+}
+
+int b200hist_updater_ipc_handle(b200hist_updater_t u, uint8_t* out_handle64) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && out_handle64 != nullptr, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  DeviceGuard guard(u->device);
+  cudaIpcMemHandle_t h;
+  B200_CUDA(cudaIpcGetMemHandle(&h, u->d_hist));
+  std::memcpy(out_handle64, &h, 64);
+  B200_API_END();
+}
+
+int b200hist_updater_set_peers(b200hist_updater_t u, int rank, int world, const uint8_t* handles_host) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && handles_host != nullptr, "null argument");
+  B200_CHECK(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "bad world / rank");
+  DeviceGuard guard(u->device);
+  B200_CHECK(!u->p2p, "peers are already set");
+  u->peer_base.assign(world, nullptr);
+  std::vector<longlong2*> hist(world);
+  std::vector<uint32_t*> flags(world);
+  for (int p = 0; p < world; ++p) {
+    void* base = u->d_hist;
+    if (p != rank) {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, handles_host + 64 * p, 64);
+      B200_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+      u->peer_base[p] = base;
+    }
+    hist[p] = static_cast<longlong2*>(base);
+    flags[p] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(base) + u->flags_offset);
+  }
+  u->d_peer_hist = DevAlloc<longlong2*>(world);
+  u->d_peer_flags = DevAlloc<uint32_t*>(world);
+  B200_CUDA(cudaMemcpy(u->d_peer_hist, hist.data(), sizeof(void*) * world, cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(u->d_peer_flags, flags.data(), sizeof(void*) * world, cudaMemcpyHostToDevice));
+  ShardGroups((uint32_t)u->groups.size(), world, rank, &u->group_begin, &u->group_end);
+  u->p2p_rank = rank;
+  u->p2p_world = world;
+  u->p2p = true;
+  u->exchange_epoch = 0;
   B200_API_END();
 }
 

@@ -93,6 +93,8 @@ _SIGNATURES = {
     "b200hist_shard_groups": (c_int, [c_uint32, c_int, c_int, POINTER(c_uint32), POINTER(c_uint32)]),
     "b200hist_updater_set_comm": (c_int, [c_void_p, c_void_p]),
     "b200hist_updater_num_feature_groups": (c_int, [c_void_p, POINTER(c_uint32)]),
+    "b200hist_updater_ipc_handle": (c_int, [c_void_p, c_void_p]),
+    "b200hist_updater_set_peers": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "b200hist_updater_last_quantiser": (c_int, [c_void_p, POINTER(Quantiser)]),
     "b200hist_updater_node_histogram": (c_int, [c_void_p, c_int32, c_void_p]),
     "b200hist_updater_node_candidate": (c_int, [c_void_p, c_int32, POINTER(Candidate)]),

@@ -321,6 +321,21 @@ class GPUHistMaker:
         self._comm = comm  # keep it alive
         _l.check(_l.load().b200hist_updater_set_comm(self._h, comm.handle if comm is not None else c_void_p()))
 
+    def enable_peer_exchange(self) -> None:
+        """Map every rank's histogram cache over NVLink P2P (IPC handles all-gathered through
+        torch.distributed -- control plane only) and switch the per-level collective from NCCL to the
+        peer-memory push + flag barrier kernel."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        buf = (ctypes.c_uint8 * 64)()
+        _l.check(_l.load().b200hist_updater_ipc_handle(self._h, buf))
+        mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=self.device)
+        allh = [torch.zeros(64, dtype=torch.uint8, device=self.device) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        flat = (ctypes.c_uint8 * (64 * world)).from_buffer_copy(b"".join(bytes(t.cpu().tolist()) for t in allh))
+        _l.check(_l.load().b200hist_updater_set_peers(self._h, rank, world, flat))
+        dist.barrier()
+
     def num_feature_groups(self) -> int:
         n = c_uint32()
         _l.check(_l.load().b200hist_updater_num_feature_groups(self._h, byref(n)))
