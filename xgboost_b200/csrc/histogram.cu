@@ -61,7 +61,7 @@ static int HistImpl() {
   }();
   return impl;
 }
-constexpr uint32_t kRingStages = 4;
+constexpr uint32_t kRingStages = 6;
 static size_t RingSmemBytes(uint32_t blocks) {
   return (HistImpl() == 0 || HistImpl() == 3) ? 0 : (size_t)(kHistThreads / 32) * kRingStages * (8 * (32 * blocks + 16) + 8);
 }
@@ -457,6 +457,87 @@ __device__ __forceinline__ void FastRows(const uint32_t* __restrict__ ridx, uint
   }
 }
 
+// h.lo-skip variant with THREE register buffers: the data of passes i+1 and i+2 are in flight while pass i
+// accumulates (global-load latency, not issue or atomics, limits the two-buffer version: ncu shows the
+// long-scoreboard stall dominating at 46 % issue utilisation).  Only 8 registers per pass are needed here.
+struct FastDataZ {
+  uint32_t word[2], glo[2], ghi[2], hhi[2];
+};
+__device__ __forceinline__ void FastLoadZ(FastDataZ& d, const uint32_t (&r)[2], const longlong2* __restrict__ gq,
+                                          const uint8_t* __restrict__ col, uint32_t row_bytes) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const longlong2 gp = __ldg(gq + r[u]);
+    d.word[u] = __ldg(reinterpret_cast<const uint32_t*>(col + (size_t)r[u] * row_bytes));
+    d.glo[u] = (uint32_t)(unsigned long long)gp.x;
+    d.ghi[u] = (uint32_t)((unsigned long long)gp.x >> 32);
+    d.hhi[u] = (uint32_t)((unsigned long long)gp.y >> 32);
+  }
+}
+__device__ __forceinline__ void FastProcessZ(const FastDataZ& d, const uint32_t (&sel)[4], const uint32_t (&off)[4]) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    uint32_t addr[4], og[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) addr[k] = __byte_perm(d.word[u], 0u, sel[k]) * 512u + off[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) og[k] = AtomAddShared(addr[k], d.glo[u]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      RedAddHi128(addr[k], og[k], d.glo[u], d.ghi[u]);
+      RedAdd384(addr[k], d.hhi[u]);
+    }
+  }
+}
+
+__device__ __forceinline__ void FastRowsZ3(const uint32_t* __restrict__ ridx, uint32_t lo, uint32_t hi,
+                                           const longlong2* __restrict__ gq, const uint8_t* __restrict__ col,
+                                           uint32_t row_bytes, uint32_t warp, uint32_t q,
+                                           const uint32_t (&sel)[4], const uint32_t (&off)[4]) {
+  constexpr uint32_t kWarps = kHistThreads / 32;
+  constexpr uint32_t kStride = kWarps * kRowsPerPass;
+  const uint32_t first = lo + warp * kRowsPerPass;
+  if (first >= hi) return;
+  const uint32_t n_full = (hi >= first + kRowsPerPass) ? (hi - first - kRowsPerPass) / kStride + 1u : 0u;
+  const uint32_t* __restrict__ rp = ridx + first + q;
+  if (n_full > 0) {
+    const uint32_t last = n_full - 1;
+    auto rid = [&](uint32_t i, uint32_t (&r)[2]) {
+      const uint32_t* p = rp + (size_t)min(i, last) * kStride;
+      r[0] = __ldg(p);
+      r[1] = __ldg(p + 4);
+    };
+    uint32_t r0[2], r1[2], r2[2];
+    FastDataZ d0, d1, d2;
+    rid(0, r0); rid(1, r1); rid(2, r2);
+    FastLoadZ(d0, r0, gq, col, row_bytes); rid(3, r0);
+    FastLoadZ(d1, r1, gq, col, row_bytes); rid(4, r1);
+    uint32_t i = 0;
+    for (; i + 2 < n_full; i += 3) {
+      FastLoadZ(d2, r2, gq, col, row_bytes); rid(i + 5, r2);  // pass i+2
+      FastProcessZ(d0, sel, off);                             // pass i
+      FastLoadZ(d0, r0, gq, col, row_bytes); rid(i + 6, r0);  // pass i+3
+      FastProcessZ(d1, sel, off);                             // pass i+1
+      FastLoadZ(d1, r1, gq, col, row_bytes); rid(i + 7, r1);  // pass i+4
+      FastProcessZ(d2, sel, off);                             // pass i+2
+    }
+    if (i < n_full) FastProcessZ(d0, sel, off);
+    if (i + 1 < n_full) FastProcessZ(d1, sel, off);
+  }
+  const uint32_t jb = first + n_full * kStride;
+  if (jb < hi) {  // partial last pass
+    uint32_t r[2];
+    FastData d;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) r[u] = __ldg(ridx + min(jb + u * 4 + q, hi - 1));
+    FastLoad(d, r, gq, col, row_bytes);
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (jb + u * 4 + q >= hi) { d.glo[u] = 0u; d.ghi[u] = 0u; d.hlo[u] = 0u; d.hhi[u] = 0u; }
+    FastProcess<false>(d, sel, off);
+  }
+}
+
 __global__ void __launch_bounds__(kHistThreads, 1)
 HistKernelBankedFast(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
                      const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
@@ -504,7 +585,7 @@ HistKernelBankedFast(EllView ell, const longlong2* __restrict__ gq, const uint32
 #pragma unroll
       for (int k = 0; k < 4; ++k) off[k] = sh_base + blk * S * 512u + lane_off[k];
       const uint8_t* __restrict__ col = ell.bins + g.byte_begin + blk * 32u + 4u * w;
-      if (h_lo_zero) FastRows<true>(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
+      if (h_lo_zero) FastRowsZ3(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
       else FastRows<false>(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
     }
     // flush this CTA's share of the node (RED.64 on non-zero accumulators) and clear
@@ -586,7 +667,7 @@ HistKernelStaged(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
                  const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
                  const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
                  const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist,
-                 const QuantDev* __restrict__ /*qd*/) {
+                 const QuantDev* __restrict__ qd) {
   extern __shared__ __align__(16) uint32_t sh[];
   const GroupDesc g = groups[blockIdx.y];
   const uint32_t S = g.max_sym, B = g.n_blocks;
@@ -606,6 +687,7 @@ HistKernelStaged(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
   const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
   if (t0 >= t1) return;
   const uint32_t n_build = (uint32_t)ts->n_build;
+  const bool h_lo_zero = qd != nullptr && qd->h_lo_or == 0u;
 
   for (uint32_t i = threadIdx.x; i < 4 * slots; i += kHistThreads) sh[i] = 0u;
   if (kBulk && lane == 0) {
@@ -708,6 +790,20 @@ HistKernelStaged(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
       }
       for (uint32_t blk = 0; blk < B; ++blk) {
         const uint32_t blk_base = sh_base + blk * S * 512u;
+        if (!kChecked) {  // lean path: same hand-scheduled accumulation as HistKernelBankedFast
+          FastData d;
+          uint32_t off[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) off[k] = blk_base + lane_off[k];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            d.word[u] = LdsU32(stage + (u * 4 + q) * row_b + blk * 32u + 4u * w);
+            d.glo[u] = glo[u]; d.ghi[u] = ghi[u]; d.hlo[u] = hlo[u]; d.hhi[u] = hhi[u];
+          }
+          if (h_lo_zero && !tail) FastProcess<true>(d, sel, off);
+          else FastProcess<false>(d, sel, off);
+          continue;
+        }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const uint32_t word = LdsU32(stage + (u * 4 + q) * row_b + blk * 32u + 4u * w);
@@ -716,13 +812,9 @@ HistKernelStaged(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
           for (uint32_t k = 0; k < 4; ++k) {
             const uint32_t sym = __byte_perm(word, 0u, sel[k]);
             vgl[k] = glo[u]; vgh[k] = ghi[u]; vhl[k] = hlo[u]; vhh[k] = hhi[u];
-            if (kChecked) {
-              const bool ok = (blk * 32u + 4u * w + ((k + q) & 3u) < nf) && sym < S;
-              addr[k] = blk_base + (ok ? sym : 0u) * 512u + lane_off[k];
-              if (!ok) { vgl[k] = 0u; vgh[k] = 0u; vhl[k] = 0u; vhh[k] = 0u; }
-            } else {
-              addr[k] = blk_base + sym * 512u + lane_off[k];
-            }
+            const bool ok = (blk * 32u + 4u * w + ((k + q) & 3u) < nf) && sym < S;
+            addr[k] = blk_base + (ok ? sym : 0u) * 512u + lane_off[k];
+            if (!ok) { vgl[k] = 0u; vgh[k] = 0u; vhl[k] = 0u; vhh[k] = 0u; }
           }
 #pragma unroll
           for (uint32_t k = 0; k < 4; ++k) {
