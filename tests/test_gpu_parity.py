@@ -361,6 +361,11 @@ TREE_CASES = [
     dict(n=600, f=3, max_bin=8, params=dict(max_depth=1)),
     dict(n=40000, f=256, max_bin=256, params=dict(max_depth=4)),
     dict(n=7000, f=6, max_bin=16, zero_hess=0.1, params=dict(max_depth=4)),
+    dict(n=1, f=1, max_bin=4, params=dict(max_depth=3)),
+    dict(n=37, f=3, max_bin=4, params=dict(max_depth=3, min_child_weight=0.0)),
+    dict(n=513, f=33, max_bin=2, params=dict(max_depth=4)),
+    dict(n=5000, f=4, max_bin=8, params=dict(max_depth=12, min_child_weight=0.0, reg_lambda=0.0)),
+    dict(n=3000, f=5, max_bin=16, const_col=True, params=dict(max_depth=4)),
 ]
 
 
@@ -368,6 +373,8 @@ TREE_CASES = [
 def test_update_tree_matches_oracle(xb, case):
     import torch
     x, y = make_regression(case["n"], case["f"], seed=case["n"] + case["f"], missing=case.get("missing", 0.0))
+    if case.get("const_col"):
+        x[:, 1] = 2.5  # a constant feature has a single bin
     cp, cv = make_cuts(x, case["max_bin"])
     page = _page(xb, x, cp, cv)
     gb = orc.bin_dense(x, cp, cv)

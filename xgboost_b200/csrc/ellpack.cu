@@ -69,6 +69,52 @@ __global__ void __launch_bounds__(256) BinDenseKernel(const float* __restrict__ 
   }
 }
 
+// Faster binning for uint8 pages: a CTA owns a block of 32 features, stages their cut values in shared memory
+// (<= 32 KB at 256 bins) and walks the rows; the 8-step binary searches then run out of shared memory instead
+// of L2.  Thread = (row, 4-feature word); a warp reads 4 rows x 128 contiguous bytes of X.
+__global__ void __launch_bounds__(256) BinDenseSmemKernel(const float* __restrict__ x, uint64_t n, uint64_t ld,
+                                                           uint32_t n_features, const uint32_t* __restrict__ cut_ptrs,
+                                                           const float* __restrict__ cut_values,
+                                                           uint8_t* __restrict__ bins, uint64_t row_begin,
+                                                           uint32_t row_bytes, uint32_t null_symbol) {
+  extern __shared__ float s_cuts[];
+  __shared__ uint32_t s_ptr[33];
+  const uint32_t f0 = blockIdx.y * 32;
+  const uint32_t nf = min(32u, n_features - f0);
+  if (threadIdx.x <= nf) s_ptr[threadIdx.x] = cut_ptrs[f0 + threadIdx.x] - cut_ptrs[f0];
+  __syncthreads();
+  const uint32_t n_cuts = s_ptr[nf];
+  for (uint32_t i = threadIdx.x; i < n_cuts; i += 256) s_cuts[i] = cut_values[cut_ptrs[f0] + i];
+  __syncthreads();
+  const uint32_t w = threadIdx.x & 7u;  // word inside the feature block
+  for (uint64_t r = (uint64_t)blockIdx.x * 32 + (threadIdx.x >> 3); r < n; r += (uint64_t)gridDim.x * 32) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t fl = 4 * w + k;
+      uint32_t sym = 0;
+      if (fl < nf) {
+        const float v = x[r * ld + f0 + fl];
+        if (isnan(v)) {
+          sym = null_symbol;
+        } else {
+          const uint32_t beg = s_ptr[fl], end = s_ptr[fl + 1];
+          uint32_t lo = beg, hi = end;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (!(v < s_cuts[mid])) lo = mid + 1; else hi = mid;
+          }
+          if (lo == end) lo = end - 1;
+          sym = lo - beg;
+        }
+      }
+      packed |= (sym & 0xffu) << (8 * k);
+    }
+    if (f0 + 4 * w < row_bytes)
+      *reinterpret_cast<uint32_t*>(bins + (row_begin + r) * row_bytes + f0 + 4ull * w) = packed;
+  }
+}
+
 // Column-major copy of rows [row_begin, row_begin + n): bins_t[f][r].  128 rows x 64 features per CTA through
 // shared memory; reads are 32-bit row-major words, writes are 128 contiguous bytes per feature.
 __global__ void __launch_bounds__(256) TransposeKernel(const uint8_t* __restrict__ bins, uint32_t row_bytes,
@@ -340,7 +386,15 @@ int b200hist_ellpack_push_dense(b200hist_ellpack_t e, uint64_t row_begin, const 
   auto s = static_cast<cudaStream_t>(stream);
   uint64_t total = n * (e->row_bytes / 4);
   int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
-  if (e->bin_bytes == 1) {
+  uint32_t max_block_cuts = 0;  // cut values of the widest 32-feature block
+  for (uint32_t f0 = 0; f0 < e->n_features; f0 += 32)
+    max_block_cuts = std::max(max_block_cuts, e->cut_ptrs[std::min(e->n_features, f0 + 32)] - e->cut_ptrs[f0]);
+  if (e->bin_bytes == 1 && max_block_cuts * sizeof(float) <= 40 * 1024) {
+    dim3 grid((unsigned)std::min<uint64_t>((n + 31) / 32, (uint64_t)NumSMs(e->device) * 8), (e->n_features + 31) / 32);
+    BinDenseSmemKernel<<<grid, 256, max_block_cuts * sizeof(float), s>>>(x_dev, n, ld, e->n_features, e->d_cut_ptrs,
+                                                                        e->d_cut_values, e->d_bins, row_begin,
+                                                                        e->row_bytes, e->null_symbol);
+  } else if (e->bin_bytes == 1) {
     BinDenseKernel<uint8_t><<<blocks, 256, 0, s>>>(x_dev, n, ld, e->n_features, e->d_cut_ptrs, e->d_cut_values,
                                                   e->d_bins, row_begin, e->row_bytes, e->null_symbol);
   } else {
