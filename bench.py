@@ -92,35 +92,42 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # synthetic workload: X ~ N(0,1) per 1M-row batch generated ON DEVICE, y = X.w + 0.1 eps
 # --------------------------------------------------------------------------------------------------
-def make_cuts_device(torch, xb, n_features, max_bin, device, seed):
-    """Cuts from our own quantile sketch (b200hist_sketch_dense) over the first 1M-row batch of the stream.
-    (A 100M-row matrix needs the multi-window sketch + merge of QuantileDMatrix, which is not built yet;
-    a one-window sketch of a 1M-row prefix of an i.i.d. stream is what this bench uses -- stated in `config`.)"""
-    g = torch.Generator(device=device).manual_seed(seed)
-    sample = torch.randn((1_000_000, n_features), generator=g, device=device)
-    cuts = xb.HistogramCuts.from_dense(sample, max_bin)
-    del sample
-    return cuts.cut_ptrs, cuts.cut_values
+def batch_of(torch, device, f, rows, batch, b):
+    m = min(batch, rows - b * batch)
+    g = torch.Generator(device=device).manual_seed(2024 + b)
+    return torch.randn((m, f), generator=g, device=device), g
 
 
 def build_workload(torch, xb, args, device, feat_lo=0, feat_hi=None):
+    """DMatrix build = what QuantileDMatrix(DataIter of 1M-row device batches) does in the reference
+    (quantile_dmatrix.cu:29-126): pass 1 pushes every batch through the resident quantile sketch
+    (b200hist_sketch_push_dense, one sketch window per batch), pass 2 regenerates the batches and bins them
+    into the Ellpack page.  Returns page, labels and the two pass times (seconds)."""
     n, f = args.rows, args.features
-    cp, cv = make_cuts_device(torch, xb, f, args.max_bin, device, seed=2024)
-    cuts = xb.HistogramCuts(cp, cv)
+    batch = 1_000_000
+    nb = (n + batch - 1) // batch
+    t0 = time.perf_counter()
+    sketch = xb.QuantileSketch(f, args.max_bin, device)
+    for b in range(nb):
+        x, _ = batch_of(torch, device, f, n, batch, b)
+        sketch.push(x)
+        del x
+    cuts = sketch.make_cuts()
+    sketch.close()
+    torch.cuda.synchronize(device)
+    t_sketch = time.perf_counter() - t0
+    t0 = time.perf_counter()
     page = xb.EllpackPage(cuts, n, device.index, has_missing=False)
     gen = torch.Generator(device=device).manual_seed(7)
     w = torch.randn(f, generator=gen, device=device)
     y = torch.empty(n, dtype=torch.float32, device=device)
-    batch = 1_000_000
-    for b0 in range(0, n, batch):
-        m = min(batch, n - b0)
-        g = torch.Generator(device=device).manual_seed(2024 + b0 // batch)
-        x = torch.randn((m, f), generator=g, device=device)
-        page.push_dense(x, b0)
-        y[b0:b0 + m] = x @ w + 0.1 * torch.randn(m, generator=g, device=device)
+    for b in range(nb):
+        x, g = batch_of(torch, device, f, n, batch, b)
+        page.push_dense(x, b * batch)
+        y[b * batch:b * batch + x.shape[0]] = x @ w + 0.1 * torch.randn(x.shape[0], generator=g, device=device)
         del x
     torch.cuda.synchronize(device)
-    return page, y
+    return page, y, dict(sketch_s=t_sketch, ellpack_s=time.perf_counter() - t0, sketch_windows=nb)
 
 
 def algorithmic_bytes(n, f, bin_bytes, depth, row_visits):
@@ -205,7 +212,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    page, y = build_workload(torch, xb, args, device)
+    page, y, build_s = build_workload(torch, xb, args, device)
     info = page.info()
     n, f = args.rows, args.features
     up = xb.GPUHistMaker(page)
@@ -277,6 +284,8 @@ def run_b200(args):
     hist_gbs = hist_bytes_gpu / (phase["hist"] * 1e-3) / 1e9 if phase["hist"] > 0 else 0.0
     # the kernel's binding ceiling is shared-memory read-modify-write bandwidth: 16 B read + 16 B written per
     # (row, feature) update at 128 B/clk/SM = 4 updates/clk/SM
+    from xgboost_b200 import components as xc
+    smem_peak = xc.smem_atomic_peak(True, device)
     sm_clock_hz = (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965) * 1e6
     n_sms = torch.cuda.get_device_properties(device).multi_processor_count
     updates_per_s = row_visits * (f / world) / (phase["hist"] * 1e-3) if phase["hist"] > 0 else 0.0
@@ -286,12 +295,13 @@ def run_b200(args):
                                   "(profiles/r01_hist_banked_v2_ncu_summary.json), scaled to this launch size",
                 "launches_per_step": hist_launches, "avg_launch_ms": phase["hist"] / hist_launches,
                 "algorithmic_bytes_per_launch": hist_bytes_gpu / hist_launches, "row_visits_per_step": row_visits,
-                # reg:squarederror has a constant power-of-two quantised hessian (low word 0): 3 atomics = 24 B of
-                # shared-memory RMW per update -> ceiling 128/24 = 5.33 updates/clk/SM (4.0 with all 4 words)
-                "smem_atomic_bound": {"updates_per_clk_per_sm": updates_per_s / sm_clock_hz / n_sms, "ceiling": 16.0 / 3.0,
-                                      "frac": updates_per_s / sm_clock_hz / n_sms / (16.0 / 3.0),
-                                      "note": "exact int64 accumulation: 24 B (h.lo skipped) of shared-memory RMW per update "
-                                              "at 128 B/clk/SM; this, not HBM, bounds the kernel"},
+                # the binding resource is the shared-memory atomic pipe, not HBM: the ceiling is MEASURED on this GPU by
+                # b200hist_smem_atomic_peak (the kernel's own accumulation sequence -- 3 conflict-free 32-bit atomics
+                # per update for reg:squarederror, whose quantised hessian has a zero low word -- with no global loads)
+                "smem_atomic_bound": {"updates_per_clk_per_sm": updates_per_s / sm_clock_hz / n_sms,
+                                      "ceiling": smem_peak, "frac": updates_per_s / sm_clock_hz / n_sms / smem_peak,
+                                      "ceiling_source": "measured: b200hist_smem_atomic_peak(h_lo_zero=1), clock64 based",
+                                      "note": "exact int64 accumulation in shared memory bounds the kernel, not HBM"},
                 "whole_step_frac": (ab["total"] - ab["hist"] + hist_bytes_gpu) / (ms_per_step * 1e-3) / 1e9 / peak}
 
     # end-to-end: gradient arrives in pinned HOST memory, tree returns to the host (C-ABI host entry)
@@ -335,7 +345,10 @@ def run_b200(args):
                 "config": {"workload": "synthetic %dx%d dense f32, %d bins, depth %d, reg:squarederror" % (n, f, args.max_bin, args.depth),
                            "parallelism": "single GPU" if world == 1 else "feature-block shard x%d" % world,
                            "l2": "inputs (%.1f GB bin matrix) exceed the 126 MB L2" % (n * info["row_bytes"] / 1e9),
-                           "tree_nodes": tree.num_nodes},
+                           "tree_nodes": tree.num_nodes,
+                           "cuts": "own quantile sketch, %d windows of <= 1M rows merged (QuantileDMatrix semantics)"
+                                   % build_s["sketch_windows"]},
+                "dmatrix_build_s": {"sketch": round(build_s["sketch_s"], 3), "ellpack": round(build_s["ellpack_s"], 3)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "phase_ms": phase, "algorithmic_gb_per_step": {k: v / 1e9 for k, v in ab.items()}}
         print(json.dumps(line))

@@ -119,6 +119,26 @@ B200HIST_API int b200hist_sketch_dense(int device, const float* x_dev, uint64_t 
                                        int32_t max_bin, uint32_t* cut_ptrs_out_host, float* cut_values_out_host,
                                        uint64_t cut_values_capacity, void* stream);
 
+/* Q2, batch by batch: the resident sketch behind QuantileDMatrix(DataIter).  replaces common::SketchContainer
+ * (src/common/quantile.cuh:38-200) as driven by cuda_impl::MakeSketches (src/data/quantile_dmatrix.cu:29-126):
+ *   create     = SketchContainer ctor (quantile.cuh:95-112), numerical features only;
+ *   push_dense = one DataIter batch: AdapterDeviceSketch (src/common/hist_util.cuh:399-443; the batch is ONE sketch
+ *                window, so n < 2^24 rows and n * n_features < 2^31) -> SketchContainer::Push = PruneImpl + ScanInput
+ *                + Merge (MergeImpl, SegmentedUnique, FixError) + Prune(IntermediateNumCuts)
+ *                (src/common/quantile.cu:340-378,491-566), then MakeSketches' Prune to
+ *                RequiredSampleCutsPerColumn(max_bin, rows pushed so far) (quantile_dmatrix.cu:73-90);
+ *   make_cuts  = SketchContainer::MakeCuts on one worker (quantile.cu:658-709).  fix_error_changes_out (optional)
+ *                receives how many entries FixError had to repair over the sketch's life: the reference repairs in
+ *                place from concurrent threads, so cut values are reproducible only while this stays 0. */
+typedef struct b200hist_sketch_s* b200hist_sketch_t;
+B200HIST_API int b200hist_sketch_create(int device, uint32_t n_features, int32_t max_bin, b200hist_sketch_t* out);
+B200HIST_API int b200hist_sketch_push_dense(b200hist_sketch_t sketch, const float* x_dev, uint64_t n, uint64_t ld,
+                                            void* stream);
+B200HIST_API int b200hist_sketch_make_cuts(b200hist_sketch_t sketch, uint32_t* cut_ptrs_out_host,
+                                           float* cut_values_out_host, uint64_t cut_values_capacity,
+                                           uint32_t* fix_error_changes_out, void* stream);
+B200HIST_API int b200hist_sketch_destroy(b200hist_sketch_t sketch);
+
 /* Sparse ELLPACK page (the reference's layout when row_stride < n_features, ellpack_page.cu:140-183):
  * uint32 symbols[n_rows][row_stride] holding GLOBAL bin indices in feature order, null = total_bins.
  * row_stride = the longest row (entries); the caller computes it like GetRowStride (ellpack_page.cuh:393+). */
@@ -212,6 +232,12 @@ B200HIST_API int b200hist_updater_node_histogram(b200hist_updater_t u, int32_t n
                                                  b200hist_gpair64* out_host /* total_bins */);
 B200HIST_API int b200hist_updater_node_candidate(b200hist_updater_t u, int32_t nidx,
                                                  b200hist_candidate* out_host);
+/* (d) measurement: the shared-memory atomic ceiling the histogram kernel (H2) is judged against, MEASURED on this
+ * device: the kernel's own accumulation sequence (conflict-free 32-bit shared atomics with carry) on
+ * register-generated symbols, no global loads, same CTA shape; returns (row, feature) updates per clock per SM.
+ * h_lo_zero != 0 measures the variant that skips the hessian's low word.  No reference counterpart. */
+B200HIST_API int b200hist_smem_atomic_peak(int device, int h_lo_zero, double* updates_per_clk_per_sm, void* stream);
+
 /* Per-phase device time (ms) of the last update_tree when profiling is on: quantise, hist,
  * subtract, evaluate, apply, partition, finalise (7 floats) and row-visits V of the hist phase. */
 B200HIST_API int b200hist_updater_set_profiling(b200hist_updater_t u, int on);

@@ -78,3 +78,37 @@ def logistic_gpair(margin, y):
 
 def f32_bits(v):
     return int(np.float32(v).view(np.uint32))
+
+
+# Batch streams for the QuantileDMatrix sketch (multi-window) parity cases; regenerated from the seed everywhere.
+SKETCH_CASES = [
+    dict(name="qdm_8x5000_b16", seed=201, f=6, max_bin=16, batch_rows=[5000] * 8),
+    dict(name="qdm_uneven_b64", seed=202, f=5, max_bin=64, batch_rows=[1000, 20000, 7, 15000, 13993], missing=0.1,
+         discrete_col=2, const_col=4),
+    dict(name="qdm_10x20000_b256", seed=203, f=4, max_bin=256, batch_rows=[20000] * 10),
+    dict(name="qdm_single_col_b32", seed=204, f=1, max_bin=32, batch_rows=[3000] * 12),
+    dict(name="qdm_holes_b32", seed=205, f=3, max_bin=32, batch_rows=[4000, 500, 4000, 6000], nan_batches=[1],
+         nan_cols={0: [1], 2: [1, 2]}),
+    dict(name="qdm_6x50000_b256_wide", seed=206, f=12, max_bin=256, batch_rows=[50000] * 6, discrete_col=3),
+]
+
+
+def make_sketch_batches(case):
+    """List of float32 matrices (NaN = missing) for a SKETCH_CASES entry."""
+    rng = np.random.default_rng(case["seed"])
+    out = []
+    for b, rows in enumerate(case["batch_rows"]):
+        x = rng.standard_normal((rows, case["f"]), dtype=np.float32)
+        x = (x * np.float32(1.0 + 0.25 * b) + np.float32(0.1 * b)).astype(np.float32)   # drifting batches
+        if case.get("discrete_col") is not None:
+            x[:, case["discrete_col"]] = np.round(x[:, case["discrete_col"]] * 4.0)
+        if case.get("const_col") is not None:
+            x[:, case["const_col"]] = np.float32(2.5)
+        if case.get("missing"):
+            x[rng.random(x.shape) < case["missing"]] = np.nan
+        if b in case.get("nan_batches", []):
+            x[:] = np.nan
+        for col in case.get("nan_cols", {}).get(b, []):
+            x[:, col] = np.nan
+        out.append(np.ascontiguousarray(x))
+    return out

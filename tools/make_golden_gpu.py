@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_capi as rc  # noqa: E402
-from tests.helpers import make_regression, make_sparse_regression  # noqa: E402
+from tests.helpers import SKETCH_CASES, make_regression, make_sparse_regression, make_sketch_batches  # noqa: E402
 
 CASES = [
     dict(name="sq_d6_b64", n=20000, f=12, seed=101, max_bin=64, obj="sq", rounds=3,
@@ -123,12 +123,40 @@ def time_reference(rows, features, depth, max_bin=256, steps=5, warmup=2):
                 dmatrix_build_s=t_build)
 
 
+def run_sketch_case(case):
+    """Cuts of the reference's QuantileDMatrix over a stream of device batches (one sketch window per batch)."""
+    import torch
+    batches = [torch.from_numpy(b).cuda() for b in make_sketch_batches(case)]
+    dm = rc.DMatrix.quantile_from_batches(batches, max_bin=case["max_bin"], kind="cuda")
+    cp, cv = dm.histogram_cuts()
+    out = {k: v for k, v in case.items() if k != "nan_cols"}
+    if "nan_cols" in case:
+        out["nan_cols"] = {str(k): v for k, v in case["nan_cols"].items()}
+    out["cut_ptrs"] = [int(v) for v in cp]
+    out["cut_values_bits"] = [int(v) for v in np.asarray(cv, dtype=np.float32).view(np.uint32)]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/ref_gpu_trees.json")
+    ap.add_argument("--sketch-out", default=None,
+                    help="write the QuantileDMatrix cut fixtures (tests/golden/ref_quantile_dmatrix_cuts.json) and exit")
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--time-headline", action="store_true")
     args = ap.parse_args()
+    if args.sketch_out:
+        os.makedirs(os.path.dirname(args.sketch_out) or ".", exist_ok=True)
+        res = {"_source": "cut values of the reference's QuantileDMatrix (device DataIter batches, "
+                          "oracle/_ref_cuda/libxgboost.so = /root/reference built unmodified for sm_100) produced by "
+                          "tools/make_golden_gpu.py --sketch-out on a B200; inputs regenerate from the seeds via "
+                          "tests/helpers.make_sketch_batches", "cases": []}
+        for c in SKETCH_CASES:
+            res["cases"].append(run_sketch_case(c))
+            print("sketch case", c["name"], res["cases"][-1]["cut_ptrs"][-1], "cuts", flush=True)
+        json.dump(res, open(args.sketch_out, "w"))
+        print("wrote", args.sketch_out)
+        return
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     res = {"_source": "reference gpu_hist (oracle/_ref_cuda/libxgboost.so = /root/reference built unmodified for sm_100) "
                       "run by tools/make_golden_gpu.py on a B200; inputs regenerate from the seeds via "

@@ -12,7 +12,7 @@ There is no CPU fallback: without the built library or without a CUDA device eve
 raises B200HistError.
 """
 from .lib import B200HistError, TrainParam, launch_count  # noqa: F401
-from .updater import Communicator, EllpackPage, GPUHistMaker, HistogramCuts, RegTree, shard_groups  # noqa: F401
+from .updater import Communicator, EllpackPage, GPUHistMaker, HistogramCuts, QuantileSketch, RegTree, shard_groups  # noqa: F401
 
-__all__ = ["B200HistError", "TrainParam", "EllpackPage", "GPUHistMaker", "HistogramCuts", "RegTree",
+__all__ = ["B200HistError", "TrainParam", "EllpackPage", "GPUHistMaker", "HistogramCuts", "QuantileSketch", "RegTree",
            "Communicator", "shard_groups", "launch_count"]

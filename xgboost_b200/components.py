@@ -90,3 +90,14 @@ def partition(page: EllpackPage, ridx: torch.Tensor, seg_begin: Sequence[int], s
                                         dl.ctypes.data_as(POINTER(c_int32)), n_nodes,
                                         left.ctypes.data_as(POINTER(c_uint64)), _stream_ptr(ridx.device)))
     return out, [int(x) for x in left]
+
+
+def smem_atomic_peak(h_lo_zero: bool = True, device: Optional[torch.device] = None) -> float:
+    """Measured ceiling of the histogram kernel's shared-memory accumulation on this device, in (row, feature)
+    updates per clock per SM (b200hist_smem_atomic_peak)."""
+    from ctypes import c_double
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = c_double(0.0)
+    _l.check(_l.load().b200hist_smem_atomic_peak(device.index or 0, 1 if h_lo_zero else 0, byref(out),
+                                               _stream_ptr(device)))
+    return float(out.value)

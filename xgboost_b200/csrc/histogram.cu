@@ -1085,4 +1085,81 @@ void LaunchSubtractFlat(const b200hist_gpair64* parent, const b200hist_gpair64* 
   B200_LAUNCHED();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Measurement helper: the shared-memory atomic ceiling of the histogram kernel, measured rather than modelled.
+// Runs the exact accumulation sequence of HistKernelBankedFast (FastProcess: conflict-free ATOMS with return,
+// carry, two reductions per int64 component) on register-generated symbols -- no global loads, same 1024-thread
+// CTA, same shared-memory footprint, one CTA per SM -- and reports updates per clock per SM from clock64().
+// ---------------------------------------------------------------------------------------------
+template <bool kHLoZero>
+__global__ void __launch_bounds__(kHistThreads, 1) SmemAtomicPeakKernel(uint32_t iters, uint32_t words,
+                                                                         unsigned long long* __restrict__ clocks,
+                                                                         uint32_t* __restrict__ sink) {
+  extern __shared__ __align__(16) uint32_t sh[];
+  __shared__ unsigned long long clk_s;
+  for (uint32_t i = threadIdx.x; i < words; i += kHistThreads) sh[i] = 0u;
+  if (threadIdx.x == 0) clk_s = 0ull;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t q = lane >> 3, w = lane & 7u;
+  const uint32_t sh_base = (uint32_t)__cvta_generic_to_shared(sh);
+  uint32_t sel[4], off[4];
+#pragma unroll
+  for (uint32_t k = 0; k < 4; ++k) {
+    const uint32_t jj = (k + q) & 3u;
+    sel[k] = 0x4440u | jj;
+    off[k] = sh_base + (4u * w + jj) * 4u;
+  }
+  FastData d;
+  uint32_t x = 0x9E3779B9u * (threadIdx.x + 1u) + blockIdx.x;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) { d.glo[u] = 0xFFFFFFF0u + u; d.ghi[u] = 3u; d.hlo[u] = kHLoZero ? 0u : 0xFFFFFF00u; d.hhi[u] = 1u; }
+  const long long t0 = clock64();
+  for (uint32_t it = 0; it < iters; ++it) {
+    x = x * 1664525u + 1013904223u;
+    d.word[0] = x;
+    d.word[1] = x ^ (x >> 11) ^ 0x5bd1e995u;
+    FastProcess<kHLoZero>(d, sel, off);
+  }
+  const long long t1 = clock64();
+  atomicMax(&clk_s, (unsigned long long)(t1 - t0));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    clocks[blockIdx.x] = clk_s;
+    sink[blockIdx.x] = sh[x % words];
+  }
+}
+
+double MeasureSmemAtomicPeak(int device, bool h_lo_zero, cudaStream_t s) {
+  const uint32_t words = 256u * 32u * 4u;  // one block of 32 features x 256 symbols x int64 pair = 128 KiB
+  const size_t smem = words * sizeof(uint32_t);
+  const int n_sms = NumSMs(device);
+  const uint32_t iters = 20000;
+  auto kernel = h_lo_zero ? SmemAtomicPeakKernel<true> : SmemAtomicPeakKernel<false>;
+  B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  unsigned long long* clocks = DevAlloc<unsigned long long>(n_sms);
+  uint32_t* sink = DevAlloc<uint32_t>(n_sms);
+  for (int rep = 0; rep < 2; ++rep) {  // first launch warms up
+    kernel<<<n_sms, kHistThreads, smem, s>>>(iters, words, clocks, sink);
+    B200_LAUNCHED();
+  }
+  std::vector<unsigned long long> h(n_sms);
+  B200_CUDA(cudaMemcpyAsync(h.data(), clocks, sizeof(unsigned long long) * n_sms, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  cudaFree(clocks);
+  cudaFree(sink);
+  double sum = 0;
+  for (auto c : h) sum += (double)c;
+  const double avg_clocks = sum / n_sms;
+  return (double)kHistThreads * 8.0 * iters / avg_clocks;
+}
+
 }  // namespace b200
+
+extern "C" int b200hist_smem_atomic_peak(int device, int h_lo_zero, double* updates_per_clk_per_sm, void* stream) {
+  B200_API_BEGIN();
+  B200_CHECK(updates_per_clk_per_sm != nullptr, "null argument");
+  b200::DeviceGuard guard(device);
+  *updates_per_clk_per_sm = b200::MeasureSmemAtomicPeak(device, h_lo_zero != 0, static_cast<cudaStream_t>(stream));
+  B200_API_END();
+}

@@ -69,11 +69,66 @@ class HistogramCuts:
                                                _stream_ptr(x.device)))
         return cls(ptrs, vals[: int(ptrs[-1])].copy())
 
+    @classmethod
+    def from_batches(cls, batches, max_bin: int = 256) -> "HistogramCuts":
+        """Cuts of QuantileDMatrix(DataIter over `batches`): every batch (dense float32 CUDA matrix, NaN =
+        missing) is one sketch window merged into a resident summary (quantile_dmatrix.cu:29-126)."""
+        sketch = None
+        for x in batches:
+            if sketch is None:
+                sketch = QuantileSketch(x.shape[1], max_bin, x.device)
+            sketch.push(x)
+        if sketch is None:
+            raise ValueError("no batches")
+        return sketch.make_cuts()
+
     def search_bin(self, value: float, fidx: int) -> int:
         """HistogramCuts::SearchBin (hist_util.h:112-121), host helper for tests."""
         beg, end = int(self.cut_ptrs[fidx]), int(self.cut_ptrs[fidx + 1])
         idx = beg + int(np.searchsorted(self.cut_values[beg:end], np.float32(value), side="right"))
         return idx - 1 if idx == end else idx
+
+
+class QuantileSketch:
+    """Resident per-feature quantile summaries on the device: common::SketchContainer (quantile.cuh:38-200) as
+    QuantileDMatrix drives it -- push one DataIter batch at a time, then make_cuts()."""
+
+    def __init__(self, n_features: int, max_bin: int = 256, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_features, self.max_bin = int(n_features), int(max_bin)
+        self._h = c_void_p()
+        self.fix_error_changes = 0
+        _l.check(_l.load().b200hist_sketch_create(self.device.index or 0, self.n_features, self.max_bin, byref(self._h)))
+
+    def push(self, x: torch.Tensor) -> None:
+        _require_cuda(x, "x")
+        if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != self.n_features or \
+                (x.shape[1] > 1 and x.stride(1) != 1):
+            raise ValueError("x must be a row-major float32 matrix with n_features columns")
+        ld = x.stride(0) if x.shape[0] > 1 else max(x.shape[1], 1)
+        _l.check(_l.load().b200hist_sketch_push_dense(self._h, c_void_p(x.data_ptr()), x.shape[0], ld,
+                                                    _stream_ptr(x.device)))
+
+    def make_cuts(self) -> "HistogramCuts":
+        ptrs = np.zeros(self.n_features + 1, dtype=np.uint32)
+        vals = np.zeros(self.n_features * self.max_bin, dtype=np.float32)
+        fixes = c_uint32(0)
+        _l.check(_l.load().b200hist_sketch_make_cuts(self._h, ptrs.ctypes.data_as(POINTER(c_uint32)),
+                                                   vals.ctypes.data_as(POINTER(c_float)), vals.size, byref(fixes),
+                                                   _stream_ptr(self.device)))
+        self.fix_error_changes = int(fixes.value)
+        return HistogramCuts(ptrs, vals[: int(ptrs[-1])].copy())
+
+    def close(self) -> None:
+        if self._h:
+            _l.load().b200hist_sketch_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class EllpackPage:
