@@ -428,6 +428,32 @@ def test_boosting_rounds_match_oracle(xb):
     assert float(np.mean((pred_cpu - y) ** 2)) < float(np.mean(y ** 2)) * 0.5
 
 
+@pytest.mark.parametrize("n,f,obj,depth", [(40000, 96, "sq", 6), (30000, 256, "sq", 5), (20000, 64, "logistic", 5),
+                                         (9000, 128, "sq_then_logistic", 4)])
+def test_pair_kernel_rounds_match_oracle(xb, n, f, obj, depth):
+    """From the second tree on the updater launches the 64-feature pair kernel when the previous tree's hessians
+    had zero low words (reg:squarederror).  Every node histogram and every tree must stay bit-exact: 96 features
+    = one pair + an odd block; logistic hessians have low words, so the pair launch must fall back by itself;
+    an objective that changes between trees makes the launch hint wrong in both directions."""
+    import torch
+    x, y = make_regression(n, f, seed=n + f)
+    yb = (y > 0).astype(np.float32)
+    cp, cv = make_cuts(x, 256)
+    page = _page(xb, x, cp, cv)
+    gb = orc.bin_dense(x, cp, cv)
+    params = dict(max_depth=depth, eta=0.5)
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    pred = np.zeros(n, dtype=np.float32)
+    for it in range(4):
+        kind = obj if obj != "sq_then_logistic" else ("sq" if it in (0, 1, 3) else "logistic")
+        gp = squared_error_gpair(pred, y) if kind == "sq" else logistic_gpair(pred, yb)
+        tree = up.update(torch.from_numpy(gp).cuda())
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params))
+        _compare_tree(xb, up, tree, o, cp, cv, hists=True)
+        pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+
+
 def test_host_gradient_entry_matches_device_entry(xb):
     import torch
     n, f = 5000, 6

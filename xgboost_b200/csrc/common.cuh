@@ -269,7 +269,8 @@ void PrepareHistKernels(int device);
 void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint32_t* ridx0, const uint32_t* ridx1,
                      const BuildEntry* build, const uint32_t* tile_seg, const TreeState* ts,
                      const GroupDesc* groups_dev, const std::vector<GroupDesc>& groups_host,
-                     b200hist_gpair64* hist, const QuantDev* quant /* nullable */, int num_sms, cudaStream_t s);
+                     b200hist_gpair64* hist, const QuantDev* quant /* nullable */, int num_sms, cudaStream_t s,
+                     bool pair_hint = false /* expect hessians without low words: 64-feature pair kernel */);
 void LaunchSubtract(const SubEntry* sub, const TreeState* ts, b200hist_gpair64* hist, uint32_t total_bins,
                     int num_sms, cudaStream_t s);
 void LaunchSubtractFlat(const b200hist_gpair64* parent, const b200hist_gpair64* built, b200hist_gpair64* out,

@@ -538,24 +538,15 @@ __device__ __forceinline__ void FastRowsZ3(const uint32_t* __restrict__ ridx, ui
   }
 }
 
-__global__ void __launch_bounds__(kHistThreads, 1)
-HistKernelBankedFast(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
-                     const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
-                     const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
-                     const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist,
-                     const QuantDev* __restrict__ qd) {
-  extern __shared__ __align__(16) uint32_t sh[];
-  const GroupDesc g = groups[blockIdx.y];
+// One group (B blocks of 32 features, 16-byte accumulators) over the CTA's tile range [t0, t1).
+__device__ __forceinline__ void BankedFastGroup(const EllView& ell, const longlong2* __restrict__ gq,
+                                                const uint32_t* __restrict__ ridx0, const uint32_t* __restrict__ ridx1,
+                                                const BuildEntry* __restrict__ build,
+                                                const uint32_t* __restrict__ tile_seg, uint32_t n_tiles,
+                                                uint32_t n_build, const GroupDesc& g, longlong2* __restrict__ hist,
+                                                bool h_lo_zero, uint32_t* sh, uint32_t t0, uint32_t t1) {
   const uint32_t S = g.max_sym, B = g.n_blocks;
   const uint32_t slots = B * S * 32;
-
-  const uint32_t n_tiles = ts->build_tiles;
-  if (n_tiles == 0) return;
-  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
-  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
-  if (t0 >= t1) return;
-  const uint32_t n_build = (uint32_t)ts->n_build;
-  const bool h_lo_zero = qd != nullptr && qd->h_lo_or == 0u;
 
   for (uint32_t i = threadIdx.x; i < 4 * slots; i += kHistThreads) sh[i] = 0u;
   __syncthreads();
@@ -601,6 +592,213 @@ HistKernelBankedFast(EllView ell, const longlong2* __restrict__ gq, const uint32
         if (glo | ghi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->x), ((unsigned long long)ghi << 32) | glo);
         if (hlo | hhi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->y), ((unsigned long long)hhi << 32) | hlo);
         a[0] = 0u; a[32] = 0u; a[64] = 0u; a[96] = 0u;
+      }
+    }
+    __syncthreads();
+    t = te;
+  }
+}
+
+__global__ void __launch_bounds__(kHistThreads, 1)
+HistKernelBankedFast(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
+                     const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
+                     const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
+                     const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist,
+                     const QuantDev* __restrict__ qd) {
+  extern __shared__ __align__(16) uint32_t sh[];
+  const uint32_t n_tiles = ts->build_tiles;
+  if (n_tiles == 0) return;
+  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
+  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+  if (t0 >= t1) return;
+  const GroupDesc g = groups[blockIdx.y];
+  BankedFastGroup(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, (uint32_t)ts->n_build, g, hist,
+                  qd != nullptr && qd->h_lo_or == 0u, sh, t0, t1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pair kernel: TWO adjacent 32-feature blocks (64 features) per CTA pass, 12-byte accumulators.
+//
+// ncu on HistKernelBankedFast shows the L1TEX data pipe (l1tex__data_pipe_lsu_wavefronts) at 83-86 % of peak:
+// 57 % of its wavefronts are the shared atomics, 43 % are global-load wavefronts -- one per gathered row for the
+// symbols, one per row for the gradient pair, per 32-feature block.  When every quantised hessian has a zero
+// low word (h.lo is never accumulated, e.g. reg:squarederror) an accumulator is 12 bytes, so 64 features x 256
+// symbols fit one CTA (192 KiB): a lane loads 8 symbols of a row with ONE 64-bit load and the row's gradient
+// pair serves 64 features, which halves the global-load wavefronts per update.
+//
+// Shared layout: byte address = sym * 768 + half * 384 + c * 128 + bank * 4, c in {g.lo, g.hi, h.hi};
+// lane (q, w) holds the row's bytes 8w .. 8w+7: word `half` carries features 8w + 4*half + b, accumulated in
+// bank 4w + b -- for a fixed step the 32 lanes hit 32 different banks, as in the 32-feature kernel.
+// If the hessians turn out NOT to have zero low words (the launch is chosen from the previous tree's flag), the
+// CTA falls back to the 16-byte layout and runs its two blocks one after the other.
+// ---------------------------------------------------------------------------------------------
+template <int kOff>
+__device__ __forceinline__ uint32_t AtomAddSharedOff(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1+%3], %2;" : "=r"(old) : "r"(addr), "r"(v), "n"(kOff) : "memory");
+  return old;
+}
+template <int kOff>
+__device__ __forceinline__ void RedAddOff(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(kOff) : "memory");
+}
+template <int kOff>
+__device__ __forceinline__ void RedAddHiOff(uint32_t addr, uint32_t old, uint32_t vlo, uint32_t vhi) {
+  uint32_t hi;
+  asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(hi) : "r"(old), "r"(vlo), "r"(vhi));
+  asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(hi), "n"(kOff) : "memory");
+}
+
+struct FastDataP {
+  uint2 word[2];
+  uint32_t glo[2], ghi[2], hhi[2];
+};
+__device__ __forceinline__ void FastLoadP(FastDataP& d, const uint32_t (&r)[2], const longlong2* __restrict__ gq,
+                                          const uint8_t* __restrict__ col, uint32_t row_bytes) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const longlong2 gp = __ldg(gq + r[u]);
+    d.word[u] = __ldg(reinterpret_cast<const uint2*>(col + (size_t)r[u] * row_bytes));
+    d.glo[u] = (uint32_t)(unsigned long long)gp.x;
+    d.ghi[u] = (uint32_t)((unsigned long long)gp.x >> 32);
+    d.hhi[u] = (uint32_t)((unsigned long long)gp.y >> 32);
+  }
+}
+template <int kHalf>
+__device__ __forceinline__ void FastProcessPHalf(uint32_t word, uint32_t glo, uint32_t ghi, uint32_t hhi,
+                                                 const uint32_t (&sel)[4], const uint32_t (&off)[4]) {
+  uint32_t addr[4], og[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) addr[k] = __byte_perm(word, 0u, sel[k]) * 768u + off[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) og[k] = AtomAddSharedOff<kHalf * 384>(addr[k], glo);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    RedAddHiOff<kHalf * 384 + 128>(addr[k], og[k], glo, ghi);
+    RedAddOff<kHalf * 384 + 256>(addr[k], hhi);
+  }
+}
+__device__ __forceinline__ void FastProcessP(const FastDataP& d, const uint32_t (&sel)[4], const uint32_t (&off)[4]) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    FastProcessPHalf<0>(d.word[u].x, d.glo[u], d.ghi[u], d.hhi[u], sel, off);
+    FastProcessPHalf<1>(d.word[u].y, d.glo[u], d.ghi[u], d.hhi[u], sel, off);
+  }
+}
+
+__device__ __forceinline__ void FastRowsP(const uint32_t* __restrict__ ridx, uint32_t lo, uint32_t hi,
+                                          const longlong2* __restrict__ gq, const uint8_t* __restrict__ col,
+                                          uint32_t row_bytes, uint32_t warp, uint32_t q,
+                                          const uint32_t (&sel)[4], const uint32_t (&off)[4]) {
+  constexpr uint32_t kWarps = kHistThreads / 32;
+  constexpr uint32_t kStride = kWarps * kRowsPerPass;
+  const uint32_t first = lo + warp * kRowsPerPass;
+  if (first >= hi) return;
+  const uint32_t n_full = (hi >= first + kRowsPerPass) ? (hi - first - kRowsPerPass) / kStride + 1u : 0u;
+  const uint32_t* __restrict__ rp = ridx + first + q;
+  if (n_full > 0) {
+    const uint32_t last = n_full - 1;
+    auto rid = [&](uint32_t i, uint32_t (&r)[2]) {
+      const uint32_t* p = rp + (size_t)min(i, last) * kStride;
+      r[0] = __ldg(p);
+      r[1] = __ldg(p + 4);
+    };
+    uint32_t r0[2], r1[2], r2[2];
+    FastDataP d0, d1, d2;
+    rid(0, r0); rid(1, r1); rid(2, r2);
+    FastLoadP(d0, r0, gq, col, row_bytes); rid(3, r0);
+    FastLoadP(d1, r1, gq, col, row_bytes); rid(4, r1);
+    uint32_t i = 0;
+    for (; i + 2 < n_full; i += 3) {
+      FastLoadP(d2, r2, gq, col, row_bytes); rid(i + 5, r2);  // pass i+2
+      FastProcessP(d0, sel, off);                             // pass i
+      FastLoadP(d0, r0, gq, col, row_bytes); rid(i + 6, r0);  // pass i+3
+      FastProcessP(d1, sel, off);                             // pass i+1
+      FastLoadP(d1, r1, gq, col, row_bytes); rid(i + 7, r1);  // pass i+4
+      FastProcessP(d2, sel, off);                             // pass i+2
+    }
+    if (i < n_full) FastProcessP(d0, sel, off);
+    if (i + 1 < n_full) FastProcessP(d1, sel, off);
+  }
+  const uint32_t jb = first + n_full * kStride;
+  if (jb < hi) {  // partial last pass: rows past the end add zero
+    uint32_t r[2];
+    FastDataP d;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) r[u] = __ldg(ridx + min(jb + u * 4 + q, hi - 1));
+    FastLoadP(d, r, gq, col, row_bytes);
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (jb + u * 4 + q >= hi) { d.glo[u] = 0u; d.ghi[u] = 0u; d.hhi[u] = 0u; }
+    FastProcessP(d, sel, off);
+  }
+}
+
+__global__ void __launch_bounds__(kHistThreads, 1)
+HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
+               const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
+               const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
+               const GroupDesc* __restrict__ groups, uint32_t n_groups, longlong2* __restrict__ hist,
+               const QuantDev* __restrict__ qd) {
+  extern __shared__ __align__(16) uint32_t sh[];
+  const uint32_t n_tiles = ts->build_tiles;
+  if (n_tiles == 0) return;
+  const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
+  const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
+  if (t0 >= t1) return;
+  const uint32_t n_build = (uint32_t)ts->n_build;
+  const bool h_lo_zero = qd != nullptr && qd->h_lo_or == 0u;
+  const uint32_t gi = blockIdx.y * 2u;
+  const bool two = gi + 1u < n_groups;
+  const GroupDesc g0 = groups[gi];
+  if (!two || !h_lo_zero) {  // odd block out, or hessians with low words: 16-byte layout, block after block
+    BankedFastGroup(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, n_build, g0, hist, h_lo_zero, sh, t0, t1);
+    if (two) {
+      const GroupDesc g1 = groups[gi + 1u];
+      BankedFastGroup(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, n_build, g1, hist, h_lo_zero, sh, t0, t1);
+    }
+    return;
+  }
+  const uint32_t S = max(g0.max_sym, groups[gi + 1u].max_sym);
+  const uint32_t words = S * 192u;  // 2 halves x 3 components x 32 banks per symbol
+  for (uint32_t i = threadIdx.x; i < words; i += kHistThreads) sh[i] = 0u;
+  __syncthreads();
+
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t q = lane >> 3, w = lane & 7u;
+  const uint32_t sh_base = (uint32_t)__cvta_generic_to_shared(sh);
+  uint32_t sel[4], off[4];
+#pragma unroll
+  for (uint32_t k = 0; k < 4; ++k) {
+    const uint32_t jj = (k + q) & 3u;
+    sel[k] = 0x4440u | jj;
+    off[k] = sh_base + (4u * w + jj) * 4u;
+  }
+  const uint8_t* __restrict__ col = ell.bins + g0.byte_begin + 8u * w;
+
+  uint32_t t = t0;
+  while (t < t1) {
+    const uint32_t seg = tile_seg[t];
+    const BuildEntry e = build[seg];
+    const uint32_t seg_tile_end = (seg + 1 < n_build) ? build[seg + 1].tile_begin : n_tiles;
+    const uint32_t te = min(t1, seg_tile_end);
+    const uint32_t lo = (t - e.tile_begin) * kHistTile;
+    const uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
+    const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin;
+    FastRowsP(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
+    __syncthreads();
+    // flush this CTA's share of the node (RED.64 on non-zero accumulators) and clear
+    longlong2* dst = hist + (size_t)e.slot * ell.total_bins;
+    for (uint32_t p = threadIdx.x; p < S * 64u; p += kHistThreads) {
+      const uint32_t bank = p & 31u, half = (p >> 5) & 1u, sym = p >> 6;
+      uint32_t* a = sh + sym * 192u + half * 96u + bank;
+      const uint32_t glo = a[0], ghi = a[32], hhi = a[64];
+      if (glo | ghi | hhi) {
+        const uint32_t f = g0.f_begin + 8u * (bank >> 2) + 4u * half + (bank & 3u);
+        longlong2* d = dst + ell.cut_ptrs[f] + sym;
+        if (glo | ghi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->x), ((unsigned long long)ghi << 32) | glo);
+        if (hhi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->y), (unsigned long long)hhi << 32);
+        a[0] = 0u; a[32] = 0u; a[64] = 0u;
       }
     }
     __syncthreads();
@@ -992,6 +1190,7 @@ void PrepareHistKernels(int device) {
   int optin = SmemOptin(device);
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelBankedFast, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelPair, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -1003,7 +1202,7 @@ void PrepareHistKernels(int device) {
 void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint32_t* ridx0, const uint32_t* ridx1,
                      const BuildEntry* build, const uint32_t* tile_seg, const TreeState* ts,
                      const GroupDesc* groups_dev, const std::vector<GroupDesc>& groups_host,
-                     b200hist_gpair64* hist, const QuantDev* quant, int num_sms, cudaStream_t s) {
+                     b200hist_gpair64* hist, const QuantDev* quant, int num_sms, cudaStream_t s, bool pair_hint) {
   if (ell.is_sparse) {
     uint32_t b0 = 0xFFFFFFFFu, b1 = 0;
     for (auto const& g : groups_host) { b0 = std::min(b0, g.bin_begin); b1 = std::max(b1, g.bin_end); }
@@ -1025,6 +1224,29 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
       max_blocks = std::max(max_blocks, g.n_blocks);
     }
     const int impl = HistImpl();
+    // Pair kernel (64 features per CTA pass, 12-byte accumulators): chosen when the caller expects hessians
+    // without low words and the groups are single full blocks laid out back to back; it checks the flag itself.
+    static const bool pair_off = std::getenv("B200HIST_NO_PAIR") != nullptr;
+    bool pair = pair_hint && !pair_off && impl == 0 && !checked && n_groups >= 2 && ell.row_bytes % 8u == 0u;
+    uint32_t pair_sym = 0;
+    for (int i = 0; pair && i < n_groups; ++i) {
+      const GroupDesc& g = groups_host[i];
+      pair = g.n_blocks == 1 && g.byte_begin % 8u == 0u &&
+             (i == 0 || (g.f_begin == groups_host[i - 1].f_end && g.byte_begin == groups_host[i - 1].byte_begin + 32u));
+      pair_sym = std::max(pair_sym, g.max_sym);
+    }
+    const size_t pair_smem = (size_t)pair_sym * 192 * 4;
+    int cur_dev = 0;
+    if (pair) B200_CUDA(cudaGetDevice(&cur_dev));
+    if (pair && std::max(pair_smem, smem) <= (size_t)SmemOptin(cur_dev)) {
+      const int n_pairs = (n_groups + 1) / 2;
+      dim3 pgrid(std::max(1, num_sms / n_pairs), n_pairs);
+      HistKernelPair<<<pgrid, kHistThreads, std::max(pair_smem, smem), s>>>(
+          ell, reinterpret_cast<const longlong2*>(gq), ridx0, ridx1, build, tile_seg, ts, groups_dev, (uint32_t)n_groups,
+          reinterpret_cast<longlong2*>(hist), quant);
+      B200_LAUNCHED();
+      return;
+    }
     using KernelT = void (*)(EllView, const longlong2*, const uint32_t*, const uint32_t*, const BuildEntry*,
                              const uint32_t*, const TreeState*, const GroupDesc*, longlong2*, const QuantDev*);
     KernelT kernel;

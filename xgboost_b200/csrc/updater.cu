@@ -17,6 +17,8 @@
 #include <cmath>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -434,6 +436,99 @@ __global__ void __launch_bounds__(256) FinaliseKernel(EllView ell, const uint32_
   }
 }
 
+// Windowed FinalisePosition: the tile version above scatters 4-byte position writes all over the row range (a
+// terminal segment holds every ~2^depth-th row), so each write dirties its own 32-byte sector.  Every segment
+// lists its rows in ascending order (the partition is stable), so a CTA can instead take a WINDOW of
+// kFinWindow consecutive row ids, find by binary search the slice of every terminal segment that falls inside
+// it, resolve those rows' leaves into a shared-memory image of the window, and write the window's positions
+// (and read the hessians for the bit-complement rule) fully coalesced.
+constexpr uint32_t kFinWindow = 8192;
+
+__device__ __forceinline__ uint32_t LowerBoundRow(const uint32_t* __restrict__ r, uint32_t lo, uint32_t hi, uint32_t v) {
+  while (lo < hi) {  // first index in [lo, hi) with r[idx] >= v
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(r + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <typename BinT>
+__device__ __forceinline__ int WalkToLeaf(const EllView& ell, const NodeDev* __restrict__ nodes, int nidx, uint32_t r) {
+  while (!nodes[nidx].is_leaf) {
+    const NodeDev& nd = nodes[nidx];
+    if (ell.is_sparse) {
+      const uint32_t fb = ell.cut_ptrs[nd.findex], fe = ell.cut_ptrs[nd.findex + 1];
+      const uint32_t gb = SparseRowBin(ell, r, fb, fe);
+      const bool go_left = (gb == 0xFFFFFFFFu) ? (nd.default_left != 0) : ((int32_t)(gb - fb) < nd.split_lbin);
+      nidx = go_left ? nd.left : nd.right;
+      continue;
+    }
+    const uint32_t sym = (sizeof(BinT) == 1 && ell.bins_t != nullptr)
+                             ? (uint32_t)ell.bins_t[(uint64_t)nd.findex * ell.col_stride + r]
+                             : (uint32_t)reinterpret_cast<const BinT*>(ell.bins + (size_t)r * ell.row_bytes)[nd.findex];
+    const bool left = (sym == ell.null_symbol) ? (nd.default_left != 0) : ((int32_t)sym < nd.split_lbin);
+    nidx = left ? nd.left : nd.right;
+  }
+  return nidx;
+}
+
+template <typename BinT>
+__global__ void __launch_bounds__(256) FinaliseWindowKernel(EllView ell, const uint32_t* __restrict__ ridx0,
+                                                             const uint32_t* __restrict__ ridx1,
+                                                             const longlong2* __restrict__ gq,
+                                                             const NodeDev* __restrict__ nodes,
+                                                             const BuildEntry* __restrict__ fin,
+                                                             const TreeState* __restrict__ ts,
+                                                             int32_t* __restrict__ position,
+                                                             const QuantDev* __restrict__ qd, uint32_t n_rows) {
+  __shared__ int32_t s_pos[kFinWindow];
+  __shared__ uint32_t s_lo[256], s_hi[256];
+  const uint32_t n_final = (uint32_t)ts->n_final;
+  const bool any_h_zero = qd->h_zero_any != 0u;
+  const uint32_t n_windows = (n_rows + kFinWindow - 1) / kFinWindow;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t wdx = blockIdx.x; wdx < n_windows; wdx += gridDim.x) {
+    const uint32_t r_begin = wdx * kFinWindow, r_end = min(n_rows, r_begin + kFinWindow);
+    for (uint32_t base = 0; base < n_final; base += 256) {
+      if (base + threadIdx.x < n_final) {  // one thread per terminal segment: its slice inside the window
+        const BuildEntry e = fin[base + threadIdx.x];
+        const uint32_t* __restrict__ r = (e.buf ? ridx1 : ridx0) + e.begin;
+        const uint32_t lo = LowerBoundRow(r, 0u, e.count, r_begin);
+        s_lo[threadIdx.x] = lo;
+        s_hi[threadIdx.x] = LowerBoundRow(r, lo, min(e.count, lo + kFinWindow), r_end);
+      }
+      __syncthreads();
+      const uint32_t m = min(256u, n_final - base);
+      // a warp per segment slice, two slices in flight per warp to overlap the dependent loads
+      for (uint32_t k = warp; k < m; k += 16) {
+        const BuildEntry ea = fin[base + k];
+        const bool has_b = k + 8 < m;
+        const BuildEntry eb = fin[base + (has_b ? k + 8 : k)];
+        const uint32_t* __restrict__ ra = (ea.buf ? ridx1 : ridx0) + ea.begin;
+        const uint32_t* __restrict__ rb = (eb.buf ? ridx1 : ridx0) + eb.begin;
+        const uint32_t a_lo = s_lo[k], a_hi = s_hi[k];
+        const uint32_t b_lo = has_b ? s_lo[k + 8] : 0u, b_hi = has_b ? s_hi[k + 8] : 0u;
+        const uint32_t iters = max((a_hi - a_lo + 31u) / 32u, (b_hi - b_lo + 31u) / 32u);
+        for (uint32_t it = 0; it < iters; ++it) {
+          const uint32_t ja = a_lo + it * 32u + lane, jb = b_lo + it * 32u + lane;
+          const bool va = ja < a_hi, vb = jb < b_hi;
+          const uint32_t rowa = va ? __ldg(ra + ja) : 0u, rowb = vb ? __ldg(rb + jb) : 0u;
+          if (va) s_pos[rowa - r_begin] = WalkToLeaf<BinT>(ell, nodes, ea.nidx, rowa);
+          if (vb) s_pos[rowb - r_begin] = WalkToLeaf<BinT>(ell, nodes, eb.nidx, rowb);
+        }
+      }
+      __syncthreads();
+    }
+    // EncodeOp (updater_gpu_hist.cuh:48-56): rows whose hessian is 0 get the bit-complemented id
+    for (uint32_t i = threadIdx.x; i < r_end - r_begin; i += 256) {
+      int32_t p = s_pos[i];
+      if (any_h_zero && gq[r_begin + i].y == 0) p = ~p;
+      position[r_begin + i] = p;
+    }
+    __syncthreads();
+  }
+}
+
 // UpdatePredictionCache (updater_gpu_hist.cu:582-608)
 __global__ void __launch_bounds__(256) PredCacheKernel(const int32_t* __restrict__ position,
                                                         const NodeDev* __restrict__ nodes, uint64_t n,
@@ -507,6 +602,8 @@ struct b200hist_updater_s {
   // host staging
   NodeDev* h_nodes{nullptr};  // pinned
   TreeState* h_ts{nullptr};   // pinned
+  QuantDev* h_quant{nullptr}; // pinned copy of the last tree's quantiser record
+  bool pair_hint{false};      // last tree's hessians had zero low words -> launch the 64-feature pair kernel
   int32_t* last_position{nullptr};
   int32_t last_n_nodes{0};
   // profiling
@@ -603,7 +700,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   auto build_hist = [&](uint32_t slot_base, uint32_t slot_cap) {
     if (!my_groups.empty())
       LaunchBuildHist(view, u->d_gq, u->d_ridx[0], u->d_ridx[1], u->d_build, u->d_build_tile_seg, u->d_ts,
-                      u->d_groups + u->group_begin, my_groups, u->d_hist, u->d_quant, u->num_sms, s);
+                      u->d_groups + u->group_begin, my_groups, u->d_hist, u->d_quant, u->num_sms, s, u->pair_hint);
     // AllReduceHist: one collective per level over the level's contiguous built slots
     if (u->p2p) {
       const uint32_t b0 = my_groups.empty() ? 0u : my_groups.front().bin_begin;
@@ -659,18 +756,29 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   auto tf = timer.Begin();
   FinalListKernel<<<1, kCtlThreads, 0, s>>>(u->d_ts, u->d_nodes, u->d_fin, u->d_fin_tile_seg, u->d_fin_tile_begin);
   B200_LAUNCHED();
-  if (ell->is_sparse) {
-    FinaliseKernel<uint32_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1],
-                                                           reinterpret_cast<const longlong2*>(u->d_gq), u->d_nodes,
-                                                           u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);
+  static const bool fin_tile = std::getenv("B200HIST_FINALISE_TILE") != nullptr;  // the older per-tile scatter
+  const auto* gq64 = reinterpret_cast<const longlong2*>(u->d_gq);
+  const int fin_grid = u->num_sms * 6;
+  if (fin_tile) {
+    if (ell->is_sparse) {
+      FinaliseKernel<uint32_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes,
+                                                             u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);
+    } else if (ell->bin_bytes == 1) {
+      FinaliseKernel<uint8_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes,
+                                                            u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);
+    } else {
+      FinaliseKernel<uint16_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes,
+                                                             u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);
+    }
+  } else if (ell->is_sparse) {
+    FinaliseWindowKernel<uint32_t><<<fin_grid, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes, u->d_fin,
+                                                           u->d_ts, position, u->d_quant, (uint32_t)n);
   } else if (ell->bin_bytes == 1) {
-    FinaliseKernel<uint8_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1],
-                                                          reinterpret_cast<const longlong2*>(u->d_gq), u->d_nodes,
-                                                          u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);
+    FinaliseWindowKernel<uint8_t><<<fin_grid, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes, u->d_fin,
+                                                          u->d_ts, position, u->d_quant, (uint32_t)n);
   } else {
-    FinaliseKernel<uint16_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1],
-                                                           reinterpret_cast<const longlong2*>(u->d_gq), u->d_nodes,
-                                                           u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);
+    FinaliseWindowKernel<uint16_t><<<fin_grid, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes, u->d_fin,
+                                                           u->d_ts, position, u->d_quant, (uint32_t)n);
   }
   B200_LAUNCHED();
   timer.End(kFinal, tf);
@@ -678,7 +786,9 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   // the one read-back of the tree
   B200_CUDA(cudaMemcpyAsync(u->h_ts, u->d_ts, sizeof(TreeState), cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaMemcpyAsync(u->h_nodes, u->d_nodes, sizeof(NodeDev) * u->max_nodes, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaMemcpyAsync(u->h_quant, u->d_quant, sizeof(QuantDev), cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
+  u->pair_hint = u->h_quant->h_lo_or == 0u;  // the objective decides this; it rarely changes between trees
   timer.Collect();
   u->last_row_visits = u->h_ts->row_visits;
   u->last_n_nodes = u->h_ts->n_nodes;
@@ -790,6 +900,7 @@ int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* 
   B200_CUDA(cudaMemset(u->d_exchange_counter, 0, sizeof(unsigned int)));
   B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&u->h_nodes), sizeof(NodeDev) * u->max_nodes));
   B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&u->h_ts), sizeof(TreeState)));
+  B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&u->h_quant), sizeof(QuantDev)));
   *out = u;
   B200_API_END();
 }
@@ -811,6 +922,7 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
     cudaFree(u->d_exchange_counter);
     cudaFreeHost(u->h_nodes);
     cudaFreeHost(u->h_ts);
+    cudaFreeHost(u->h_quant);
     for (auto e : u->events) cudaEventDestroy(e);
     delete u;
   }

@@ -306,16 +306,37 @@ def shard_groups(n_groups: int, world: int, rank: int):
 class RegTree:
     """The tree as the updater leaves it (node arrays in ExpandNode order)."""
 
-    def __init__(self, nodes: Sequence[_l.TreeNode]):
-        self.nodes = [
-            dict(nodeid=i, parent=n.parent, left=n.left, right=n.right, findex=n.findex, fvalue=n.fvalue,
-                 default_left=bool(n.default_left), is_leaf=bool(n.is_leaf), leaf_value=n.leaf_value,
-                 loss_chg=n.loss_chg, sum_hess=n.sum_hess, base_weight=n.base_weight, depth=n.depth)
-            for i, n in enumerate(nodes)]
+    _DTYPE = np.dtype([("parent", "<i4"), ("left", "<i4"), ("right", "<i4"), ("findex", "<i4"), ("fvalue", "<f4"),
+                       ("default_left", "<i4"), ("is_leaf", "<i4"), ("leaf_value", "<f4"), ("loss_chg", "<f4"),
+                       ("sum_hess", "<f4"), ("base_weight", "<f4"), ("depth", "<i4")])
+
+    def __init__(self, nodes, count: Optional[int] = None):
+        """nodes: a ctypes array of b200hist_tree_node (the first `count` are taken with one memcpy; the per-node
+        dicts are built only when somebody asks) or a sequence of TreeNode."""
+        assert ctypes.sizeof(_l.TreeNode) == self._DTYPE.itemsize
+        if not isinstance(nodes, ctypes.Array):
+            nodes = (_l.TreeNode * len(nodes))(*nodes)
+        n = len(nodes) if count is None else int(count)
+        raw = ctypes.string_at(ctypes.addressof(nodes), n * self._DTYPE.itemsize)
+        self.array = np.frombuffer(raw, dtype=self._DTYPE, count=n).copy()
+        self._nodes = None
+
+    @property
+    def nodes(self) -> List[dict]:
+        if self._nodes is None:
+            a = self.array
+            self._nodes = [
+                dict(nodeid=i, parent=int(a["parent"][i]), left=int(a["left"][i]), right=int(a["right"][i]),
+                     findex=int(a["findex"][i]), fvalue=float(a["fvalue"][i]), default_left=bool(a["default_left"][i]),
+                     is_leaf=bool(a["is_leaf"][i]), leaf_value=float(a["leaf_value"][i]),
+                     loss_chg=float(a["loss_chg"][i]), sum_hess=float(a["sum_hess"][i]),
+                     base_weight=float(a["base_weight"][i]), depth=int(a["depth"][i]))
+                for i in range(a.shape[0])]
+        return self._nodes
 
     @property
     def num_nodes(self) -> int:
-        return len(self.nodes)
+        return int(self.array.shape[0])
 
     def max_depth(self) -> int:
         return max(n["depth"] for n in self.nodes)
@@ -428,7 +449,7 @@ class GPUHistMaker:
             _l.check(_l.load().b200hist_updater_update_tree_host(self._h, c_void_p(gpair.data_ptr()),
                                                                _stream_ptr(self.device), self._nodes_buf,
                                                                byref(n_nodes), pos_ptr))
-        return RegTree(self._nodes_buf[: n_nodes.value])
+        return RegTree(self._nodes_buf, n_nodes.value)
 
     # TreeUpdater::UpdatePredictionCache
     def update_prediction_cache(self, preds: torch.Tensor) -> bool:
