@@ -40,6 +40,10 @@ def parse_args():
     ap.add_argument("--max-bin", type=int, default=256)
     ap.add_argument("--depth", type=int, default=int(os.environ.get("B200_BENCH_DEPTH", 8)))
     ap.add_argument("--cpu-sample-rows", type=int, default=int(os.environ.get("B200_BENCH_CPU_ROWS", 1_000_000)))
+    ap.add_argument("--split", default=os.environ.get("B200_BENCH_SPLIT", "rows"), choices=["rows", "features"],
+                    help="multi-GPU decomposition: rows = every rank owns N/P rows, full-width partial histograms summed "
+                         "per level over peer memory; features = every rank owns F/P feature blocks of all rows "
+                         "(north_star's feature-block shard), slices exchanged per level")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -98,7 +102,7 @@ def batch_of(torch, device, f, rows, batch, b):
     return torch.randn((m, f), generator=g, device=device), g
 
 
-def build_workload(torch, xb, args, device, feat_lo=0, feat_hi=None):
+def build_workload(torch, xb, args, device, batch_lo=0, batch_hi=None):
     """DMatrix build = what QuantileDMatrix(DataIter of 1M-row device batches) does in the reference
     (quantile_dmatrix.cu:29-126): pass 1 pushes every batch through the resident quantile sketch
     (b200hist_sketch_push_dense, one sketch window per batch), pass 2 regenerates the batches and bins them
@@ -106,8 +110,10 @@ def build_workload(torch, xb, args, device, feat_lo=0, feat_hi=None):
     n, f = args.rows, args.features
     batch = 1_000_000
     nb = (n + batch - 1) // batch
+    batch_hi = nb if batch_hi is None else batch_hi       # this rank's page holds batches [batch_lo, batch_hi)
+    row_lo, row_hi = batch_lo * batch, min(n, batch_hi * batch)
     t0 = time.perf_counter()
-    sketch = xb.QuantileSketch(f, args.max_bin, device)
+    sketch = xb.QuantileSketch(f, args.max_bin, device)   # cuts always come from the WHOLE stream
     for b in range(nb):
         x, _ = batch_of(torch, device, f, n, batch, b)
         sketch.push(x)
@@ -117,14 +123,15 @@ def build_workload(torch, xb, args, device, feat_lo=0, feat_hi=None):
     torch.cuda.synchronize(device)
     t_sketch = time.perf_counter() - t0
     t0 = time.perf_counter()
-    page = xb.EllpackPage(cuts, n, device.index, has_missing=False)
+    page = xb.EllpackPage(cuts, row_hi - row_lo, device.index, has_missing=False)
     gen = torch.Generator(device=device).manual_seed(7)
     w = torch.randn(f, generator=gen, device=device)
-    y = torch.empty(n, dtype=torch.float32, device=device)
-    for b in range(nb):
+    y = torch.empty(row_hi - row_lo, dtype=torch.float32, device=device)
+    for b in range(batch_lo, batch_hi):
         x, g = batch_of(torch, device, f, n, batch, b)
-        page.push_dense(x, b * batch)
-        y[b * batch:b * batch + x.shape[0]] = x @ w + 0.1 * torch.randn(x.shape[0], generator=g, device=device)
+        o = b * batch - row_lo
+        page.push_dense(x, o)
+        y[o:o + x.shape[0]] = x @ w + 0.1 * torch.randn(x.shape[0], generator=g, device=device)
         del x
     torch.cuda.synchronize(device)
     return page, y, dict(sketch_s=t_sketch, ellpack_s=time.perf_counter() - t0, sketch_windows=nb)
@@ -212,17 +219,25 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    page, y, build_s = build_workload(torch, xb, args, device)
+    row_split = world > 1 and args.split == "rows"
+    n_total, f = args.rows, args.features
+    if row_split:  # contiguous runs of 1M-row batches per rank
+        nb = (n_total + 999_999) // 1_000_000
+        page, y, build_s = build_workload(torch, xb, args, device, nb * rank // world, nb * (rank + 1) // world)
+    else:
+        page, y, build_s = build_workload(torch, xb, args, device)
     info = page.info()
-    n, f = args.rows, args.features
+    n = int(info["n_rows"])      # rows resident on THIS rank
     up = xb.GPUHistMaker(page)
     up.configure(dict(max_depth=args.depth, eta=0.3, reg_lambda=1.0, min_child_weight=1.0))
     comm = None
-    if world > 1:  # feature-block sharded histograms + one NCCL allreduce per tree level
-        if os.environ.get("B200HIST_COMM", "p2p") == "nccl":
+    if world > 1:
+        if row_split:  # full-width partial histograms, one summing peer-memory kernel per tree level
+            up.enable_peer_exchange(row_split=True)
+        elif os.environ.get("B200HIST_COMM", "p2p") == "nccl":  # feature blocks + one NCCL allreduce per level
             comm = xb.Communicator.from_torch_distributed(device)
             up.set_comm(comm)
-        else:  # default: peer-memory push + flag barrier over NVLink (no NCCL in the data path)
+        else:  # feature blocks + peer-memory push + flag barrier over NVLink (no NCCL in the data path)
             up.enable_peer_exchange()
     preds = torch.zeros(n, dtype=torch.float32, device=device)
     gpair = torch.empty((n, 2), dtype=torch.float32, device=device)
@@ -270,6 +285,20 @@ def run_b200(args):
         prof.append(up.last_profile())
     up.set_profiling(False)
     torch.cuda.synchronize(device)
+    # where a step's time goes outside the updater's phases: gradient kernel, tree update call, prediction cache
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    parts = []
+    for _ in range(3):
+        ev[0].record()
+        torch.sub(preds, y, out=gpair[:, 0])
+        ev[1].record()
+        up.update(gpair, pos)
+        ev[2].record()
+        up.update_prediction_cache(preds)
+        ev[3].record()
+        torch.cuda.synchronize(device)
+        parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+    step_parts = dict(zip(["gradient", "update_tree", "prediction_cache"], [float(v) for v in np.median(np.array(parts), axis=0)]))
     phase = {k: float(np.median([p[k] for p in prof])) for k in prof[0] if k != "row_visits"}
     row_visits = prof[-1]["row_visits"]
     ab = algorithmic_bytes(n, f, info["bin_bytes"], args.depth, row_visits)
@@ -280,7 +309,8 @@ def run_b200(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     hist_launches = args.depth
     # per GPU: this rank reads its F/world feature columns + the 20 B of gradient pair / row id per row visit
-    hist_bytes_gpu = row_visits * (f * info["bin_bytes"] / world + 16 + 4)
+    feat_div = 1 if (world == 1 or row_split) else world   # row split: this rank's visits cover all F features
+    hist_bytes_gpu = row_visits * (f * info["bin_bytes"] / feat_div + 16 + 4)
     hist_gbs = hist_bytes_gpu / (phase["hist"] * 1e-3) / 1e9 if phase["hist"] > 0 else 0.0
     # the kernel's binding ceiling is shared-memory read-modify-write bandwidth: 16 B read + 16 B written per
     # (row, feature) update at 128 B/clk/SM = 4 updates/clk/SM
@@ -288,7 +318,7 @@ def run_b200(args):
     smem_peak = xc.smem_atomic_peak(True, device)
     sm_clock_hz = (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965) * 1e6
     n_sms = torch.cuda.get_device_properties(device).multi_processor_count
-    updates_per_s = row_visits * (f / world) / (phase["hist"] * 1e-3) if phase["hist"] > 0 else 0.0
+    updates_per_s = row_visits * (f / feat_div) / (phase["hist"] * 1e-3) if phase["hist"] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "HistKernelBankedFast", "achieved": hist_gbs, "peak": peak, "unit": "GB/s",
                 "frac": hist_gbs / peak, "traffic": 1.33 * hist_bytes_gpu / hist_launches, "peak_source": peak_src,
                 "traffic_source": "ncu --set full dram__bytes_read+write = 1.33 x algorithmic on the 20M-row capture "
@@ -329,7 +359,8 @@ def run_b200(args):
         tt = torch.tensor([dt], device=device)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": 1.0 / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(n) * 8,
+        e2e = {"value": 1.0 / float(tt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(n_total) * 8 if (world == 1 or row_split) else int(n_total) * 8 * world,
                "d2h_bytes_per_step": int(tr.num_nodes) * 48 + 4}
 
     cpu_baseline = None
@@ -342,15 +373,20 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-                "config": {"workload": "synthetic %dx%d dense f32, %d bins, depth %d, reg:squarederror" % (n, f, args.max_bin, args.depth),
-                           "parallelism": "single GPU" if world == 1 else "feature-block shard x%d" % world,
+                "config": {"workload": "synthetic %dx%d dense f32, %d bins, depth %d, reg:squarederror" % (n_total, f, args.max_bin, args.depth),
+                           "parallelism": "single GPU" if world == 1 else (
+                               "row split x%d: N/P rows per GPU, full-width partial histograms, one summing "
+                               "peer-memory exchange (reduce-scatter + all-gather over NVLink) per tree level" % world
+                               if row_split else
+                               "feature-block shard x%d: all rows on every GPU, F/P feature blocks each, one "
+                               "peer-memory slice exchange per tree level" % world),
                            "l2": "inputs (%.1f GB bin matrix) exceed the 126 MB L2" % (n * info["row_bytes"] / 1e9),
                            "tree_nodes": tree.num_nodes,
                            "cuts": "own quantile sketch, %d windows of <= 1M rows merged (QuantileDMatrix semantics)"
                                    % build_s["sketch_windows"]},
                 "dmatrix_build_s": {"sketch": round(build_s["sketch_s"], 3), "ellpack": round(build_s["ellpack_s"], 3)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "phase_ms": phase, "algorithmic_gb_per_step": {k: v / 1e9 for k, v in ab.items()}}
+                "clocks": clocks, "phase_ms": phase, "step_parts_ms": step_parts, "algorithmic_gb_per_step": {k: v / 1e9 for k, v in ab.items()}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -224,6 +224,14 @@ B200HIST_API int b200hist_updater_num_feature_groups(b200hist_updater_t u, uint3
  * handles_host: world x 64 bytes in rank order (the own entry is ignored). */
 B200HIST_API int b200hist_updater_ipc_handle(b200hist_updater_t u, uint8_t* out_handle64);
 B200HIST_API int b200hist_updater_set_peers(b200hist_updater_t u, int rank, int world, const uint8_t* handles_host);
+/* Row split (the reference's default distributed mode): every rank holds a page of ITS rows with the
+ * same cuts and builds full-width partial histograms; one peer-memory kernel per level sums them (reduce-scatter +
+ * all-gather over NVLink, integer, bit-identical to one GPU) = AllReduceHist (src/tree/gpu_hist/histogram.cu:598-609);
+ * the quantiser scale and the root sum come from rank-ordered scalar exchanges = the GlobalSum calls of
+ * GradientQuantiserGroup (src/tree/gpu_hist/quantiser.cu:88-123) and InitRoot (updater_gpu_hist.cu:661-668); the child
+ * to build is chosen by hessian sums like the reference (updater_gpu_hist.cu:461-467) so that all ranks agree.
+ * Call after b200hist_updater_set_peers; on = 0 returns to feature-block sharding. */
+B200HIST_API int b200hist_updater_set_row_split(b200hist_updater_t u, int on);
 
 /* Introspection of the last update (parity tests): quantiser, per-node histogram, per-node
  * candidate, per-node row counts. */

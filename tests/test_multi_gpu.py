@@ -1,4 +1,4 @@
-"""Multi-GPU path (feature-block sharded histogram + one allreduce per level).
+"""Multi-GPU paths (feature-block sharded histogram + one exchange per level; row split + one summing exchange per level).
 
 CPU part (no GPU): the host logic of the sharding under a real world_size=2 torch.distributed (gloo)
 job -- group ownership must tile the group range exactly and the unique-id hand-off must deliver the same
@@ -93,6 +93,29 @@ for _ in range(3):  # repeated trees exercise the start-of-tree barrier
     pushed = up2.update(gp)
     ok &= single.structure() == pushed.structure()
     ok &= all(np.array_equal(up2.node_histogram(i), h) for i, h in zip((0, 1, 2), h_single))
+# row split: every rank holds ITS rows (uneven slices), full-width partial histograms summed over peer memory
+world = dist.get_world_size()
+cutpoints = [0] + [int(60000 * (0.4 + 0.6 * (r + 1) / world)) if r + 1 < world else 60000 for r in range(world)]
+lo, hi = cutpoints[rank], cutpoints[rank + 1]
+page_r = xb.EllpackPage.from_dense(torch.from_numpy(x[lo:hi]).to(dev), xb.HistogramCuts(cp, cv))
+up3 = xb.GPUHistMaker(page_r); up3.configure(dict(max_depth=6)); up3.enable_peer_exchange(row_split=True)
+pos_single = torch.empty(60000, dtype=torch.int32, device=dev)
+single_again = up.update(gp, pos_single)  # NCCL feature-shard updater: same tree, full position vector
+for it in range(3):  # trees 2 and 3 go through the 64-feature pair kernel
+    pos_r = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+    rs = up3.update(gp[lo:hi].contiguous(), pos_r)
+    ok &= single.structure() == rs.structure()
+    ok &= [n["leaf_value"] for n in single.nodes] == [n["leaf_value"] for n in rs.nodes]
+    ok &= [n["sum_hess"] for n in single.nodes] == [n["sum_hess"] for n in rs.nodes]
+    ok &= all(np.array_equal(up3.node_histogram(i), h) for i, h in zip((0, 1, 2), h_single))
+    ok &= bool(torch.equal(pos_r, pos_single[lo:hi]))
+# logistic gradients: hessians with low words (general accumulation path), another tree shape
+p0 = torch.sigmoid(torch.from_numpy(y).to(dev) * 0.3)
+gl = torch.stack([p0 - (torch.from_numpy(y).to(dev) > 0).float(), p0 * (1 - p0)], dim=1).contiguous()
+ref_l = up.update(gl)
+rs_l = up3.update(gl[lo:hi].contiguous())
+ok &= ref_l.structure() == rs_l.structure()
+ok &= [n["leaf_value"] for n in ref_l.nodes] == [n["leaf_value"] for n in rs_l.nodes]
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()

@@ -139,6 +139,162 @@ HistExchangeKernel(longlong2* const* __restrict__ peer_hist, uint32_t* const* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row split (every rank owns a slice of the ROWS and builds full-width partial histograms): the level's
+// histograms are SUMMED across ranks by one kernel over peer memory -- a reduce-scatter and an all-gather fused:
+//   barrier A  every rank has finished building (a flag per peer, written through NVLink),
+//   reduce     rank r owns the r-th slice of the level's flat bin range: it loads that slice from every peer
+//              (P2P loads), adds in integer arithmetic (order-free, hence bit-identical to one GPU) and
+//   broadcast  stores the sum into every rank's histogram, its own included; nobody else touches that slice,
+//   barrier B  all stores have landed: the level's histograms are complete everywhere.
+// Replaces collective::Allreduce over the built nodes (src/tree/gpu_hist/histogram.cu:598-609).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void SignalPeers(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch) {
+  if (threadIdx.x < (unsigned)world && (int)threadIdx.x != rank) {
+    volatile uint32_t* f = peer_flags[threadIdx.x] + rank;  // my slot in the peer's flag array
+    *f = epoch;
+  }
+}
+__device__ __forceinline__ void WaitPeers(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch) {
+  if (threadIdx.x < (unsigned)world && (int)threadIdx.x != rank) {
+    volatile uint32_t* f = peer_flags[rank] + threadIdx.x;  // the peer's slot in my flag array
+    while ((int32_t)(*f - epoch) < 0) { /* spin: the peer's stores are ordered before its flag */ }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+HistAllReduceKernel(longlong2* const* __restrict__ peer_hist, uint32_t* const* __restrict__ peer_flags, int rank,
+                    int world, const TreeState* __restrict__ ts, uint32_t slot_base, uint32_t slot_cap,
+                    uint32_t total_bins, uint32_t epoch_a, uint32_t epoch_b, unsigned int* __restrict__ done_counter) {
+  const uint32_t n_slots = min(slot_cap, (uint32_t)ts->n_build);
+  // barrier A: my build kernel precedes this kernel in the stream, so my partial sums are visible
+  if (blockIdx.x == 0) {
+    __threadfence_system();
+    SignalPeers(peer_flags, rank, world, epoch_a);
+  }
+  WaitPeers(peer_flags, rank, world, epoch_a);
+  __syncthreads();
+  const unsigned long long total = (unsigned long long)n_slots * total_bins;
+  const unsigned long long c0 = total * (unsigned)rank / (unsigned)world, c1 = total * (unsigned)(rank + 1) / (unsigned)world;
+  const size_t base = (size_t)slot_base * total_bins;
+  for (unsigned long long i = c0 + blockIdx.x * 256ull + threadIdx.x; i < c1; i += (unsigned long long)gridDim.x * 256ull) {
+    longlong2 acc = make_longlong2(0, 0);
+    for (int p = 0; p < world; ++p) {
+      const longlong2 v = peer_hist[p][base + i];
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+    for (int p = 0; p < world; ++p) peer_hist[p][base + i] = acc;
+  }
+  // barrier B: the last CTA to finish publishes the epoch and waits for every peer's
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    SignalPeers(peer_flags, rank, world, epoch_b);
+    __threadfence_system();
+    WaitPeers(peer_flags, rank, world, epoch_b);
+    __syncthreads();
+    if (threadIdx.x == 0) *done_counter = 0;
+    __threadfence_system();
+  }
+}
+
+void LaunchHistAllReduce(longlong2* const* peer_hist, uint32_t* const* peer_flags, int rank, int world,
+                         const TreeState* ts, uint32_t slot_base, uint32_t slot_cap, uint32_t total_bins,
+                         uint32_t epoch_a, uint32_t epoch_b, unsigned int* done_counter, int num_sms, cudaStream_t s) {
+  HistAllReduceKernel<<<num_sms * 2, 256, 0, s>>>(peer_hist, peer_flags, rank, world, ts, slot_base, slot_cap,
+                                                  total_bins, epoch_a, epoch_b, done_counter);
+  B200_LAUNCHED();
+}
+
+// Row split, the two scalar exchanges of a tree: every rank posts one 64-byte record into slot `rank` of each
+// peer's mailbox (it lives behind the flag array of the shared allocation), then every rank folds the records
+// in rank order -- the same order everywhere, so all ranks derive bit-identical values.
+//   which = 0: clipped gradient sums + row count -> the GLOBAL quantiser scale   (quantiser.cu:88-123 GlobalSum)
+//   which = 1: the exact int64 root sum and the hessian flags                     (updater_gpu_hist.cu:661-668)
+struct MailRecord {
+  double d[4];
+  unsigned long long u[4];
+};
+static_assert(sizeof(MailRecord) == 64, "mailbox record is 64 bytes");
+constexpr uint32_t kMailboxOffset = 256;  // bytes after the flag array
+
+__device__ __forceinline__ double RoundingFactorD(double max_abs, unsigned long long n) {
+  double delta = max_abs / (1.0 - 2.0 * (double)n * 2.220446049250313e-16);  // deterministic.cuh:24-38
+  int e;
+  (void)frexp(delta, &e);
+  return ldexp(1.0, e);
+}
+
+__global__ void __launch_bounds__(32)
+ScalarExchangeKernel(uint32_t* const* __restrict__ peer_flags, int rank, int world, uint32_t epoch, int which,
+                     QuantDev* __restrict__ q, unsigned long long n_local) {
+  MailRecord rec;
+  if (which == 0) {
+    for (int k = 0; k < 4; ++k) { rec.d[k] = q->sums[k]; rec.u[k] = 0ull; }
+    rec.u[0] = n_local;
+  } else {
+    for (int k = 0; k < 4; ++k) rec.d[k] = 0.0;
+    rec.u[0] = (unsigned long long)q->root_g;
+    rec.u[1] = (unsigned long long)q->root_h;
+    rec.u[2] = q->h_lo_or;
+    rec.u[3] = q->h_zero_any;
+  }
+  if (threadIdx.x < (unsigned)world) {
+    auto* box = reinterpret_cast<volatile MailRecord*>(reinterpret_cast<uint8_t*>(peer_flags[threadIdx.x]) +
+                                                       kMailboxOffset + which * kMaxPeers * sizeof(MailRecord));
+    for (int k = 0; k < 4; ++k) { box[rank].d[k] = rec.d[k]; box[rank].u[k] = rec.u[k]; }
+  }
+  __threadfence_system();
+  __syncwarp();
+  SignalPeers(peer_flags, rank, world, epoch);
+  WaitPeers(peer_flags, rank, world, epoch);
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    auto* box = reinterpret_cast<volatile MailRecord*>(reinterpret_cast<uint8_t*>(peer_flags[rank]) + kMailboxOffset +
+                                                       which * kMaxPeers * sizeof(MailRecord));
+    if (which == 0) {
+      double t[4] = {0, 0, 0, 0};
+      unsigned long long n = 0;
+      for (int p = 0; p < world; ++p) {
+        for (int k = 0; k < 4; ++k) t[k] += box[p].d[k];
+        n += box[p].u[0];
+      }
+      const double mg = t[0] > t[2] ? t[0] : t[2];
+      const double mh = t[1] > t[3] ? t[1] : t[3];
+      const double rg = RoundingFactorD(mg, n), rh = RoundingFactorD(mh, n);
+      const double div = 4611686018427387904.0;  // 2^62
+      q->to_float_g = rg / div;
+      q->to_float_h = rh / div;
+      q->to_fixed_g = 1.0 / q->to_float_g;
+      q->to_fixed_h = 1.0 / q->to_float_h;
+      for (int k = 0; k < 4; ++k) q->sums[k] = t[k];
+    } else {
+      unsigned long long g = 0, h = 0, lo = 0, hz = 0;
+      for (int p = 0; p < world; ++p) {
+        g += box[p].u[0];
+        h += box[p].u[1];
+        lo |= box[p].u[2];
+        hz |= box[p].u[3];
+      }
+      q->root_g = (long long)g;
+      q->root_h = (long long)h;
+      q->h_lo_or = (unsigned int)lo;
+      q->h_zero_any = (unsigned int)hz;
+    }
+  }
+}
+
+void LaunchScalarExchange(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch, int which, QuantDev* q,
+                          uint64_t n_local, cudaStream_t s) {
+  ScalarExchangeKernel<<<1, 32, 0, s>>>(peer_flags, rank, world, epoch, which, q, (unsigned long long)n_local);
+  B200_LAUNCHED();
+}
+
 void LaunchHistExchange(longlong2* const* peer_hist, uint32_t* const* peer_flags, int rank, int world,
                         const TreeState* ts, uint32_t slot_base, uint32_t slot_cap, bool use_n_build,
                         uint32_t total_bins, uint32_t bin_begin, uint32_t bin_end, uint32_t epoch,

@@ -262,6 +262,10 @@ struct FeatCand {
 // quantise.cu
 void LaunchQuantise(const float* gpair, uint64_t n, QuantDev* q, b200hist_gpair64* gq, uint32_t* ridx_init,
                     double* partials /* >= 4*kQuantBlocks */, unsigned int* counter, int num_sms, cudaStream_t s);
+void LaunchQuantReduce(const float* gpair, uint64_t n, QuantDev* q, double* partials, unsigned int* counter,
+                       int num_sms, cudaStream_t s);
+void LaunchQuantConvert(const float* gpair, uint64_t n, QuantDev* q, b200hist_gpair64* gq, uint32_t* ridx_init,
+                        int num_sms, cudaStream_t s);
 constexpr int kQuantBlocksPerSM = 4;
 
 // histogram.cu
@@ -285,6 +289,11 @@ void LaunchHistExchange(longlong2* const* peer_hist, uint32_t* const* peer_flags
                         uint32_t total_bins, uint32_t bin_begin, uint32_t bin_end, uint32_t epoch,
                         unsigned int* done_counter, int num_sms, cudaStream_t s);
 constexpr int kMaxPeers = 16;
+void LaunchHistAllReduce(longlong2* const* peer_hist, uint32_t* const* peer_flags, int rank, int world,
+                         const TreeState* ts, uint32_t slot_base, uint32_t slot_cap, uint32_t total_bins,
+                         uint32_t epoch_a, uint32_t epoch_b, unsigned int* done_counter, int num_sms, cudaStream_t s);
+void LaunchScalarExchange(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch, int which /* 0 sums, 1 root */,
+                          QuantDev* q, uint64_t n_local, cudaStream_t s);
 
 // evaluate.cu
 void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = node id */,

@@ -136,14 +136,24 @@ __global__ void __launch_bounds__(kQThreads) QuantConvertKernel(const float2* __
   }
 }
 
+void LaunchQuantReduce(const float* gpair, uint64_t n, QuantDev* q, double* partials, unsigned int* counter,
+                       int num_sms, cudaStream_t s) {
+  QuantReduceKernel<<<num_sms * kQuantBlocksPerSM, kQThreads, 0, s>>>(reinterpret_cast<const float2*>(gpair), n,
+                                                                      partials, counter, q);
+  B200_LAUNCHED();
+}
+
+void LaunchQuantConvert(const float* gpair, uint64_t n, QuantDev* q, b200hist_gpair64* gq, uint32_t* ridx_init,
+                        int num_sms, cudaStream_t s) {
+  QuantConvertKernel<<<num_sms * kQuantBlocksPerSM, kQThreads, 0, s>>>(reinterpret_cast<const float2*>(gpair), n, q,
+                                                                       reinterpret_cast<longlong2*>(gq), ridx_init);
+  B200_LAUNCHED();
+}
+
 void LaunchQuantise(const float* gpair, uint64_t n, QuantDev* q, b200hist_gpair64* gq, uint32_t* ridx_init,
                     double* partials, unsigned int* counter, int num_sms, cudaStream_t s) {
-  int blocks = num_sms * kQuantBlocksPerSM;
-  QuantReduceKernel<<<blocks, kQThreads, 0, s>>>(reinterpret_cast<const float2*>(gpair), n, partials, counter, q);
-  B200_LAUNCHED();
-  QuantConvertKernel<<<blocks, kQThreads, 0, s>>>(reinterpret_cast<const float2*>(gpair), n, q,
-                                                  reinterpret_cast<longlong2*>(gq), ridx_init);
-  B200_LAUNCHED();
+  LaunchQuantReduce(gpair, n, q, partials, counter, num_sms, s);
+  LaunchQuantConvert(gpair, n, q, gq, ridx_init, num_sms, s);
 }
 
 }  // namespace b200

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kCtlThreads) ScanKernel(TreeState* ts, NodeDev
                                                            uint32_t* tile_excl /* scratch, part_tiles+1 */,
                                                            uint32_t* tile_left_off, BuildEntry* build, SubEntry* sub,
                                                            int32_t* eval_nodes, uint32_t* build_tile_seg,
-                                                           uint32_t slot_base, uint32_t slot_cap) {
+                                                           uint32_t slot_base, uint32_t slot_cap, int build_by_hess) {
   // histogram slots of this step: [slot_base, +cap) for the built children (one contiguous, host-known
   // range = the buffer of the level's single allreduce), [slot_base+cap, +cap) for the subtracted siblings
   __shared__ uint32_t s_warp[33];
@@ -319,7 +319,10 @@ __global__ void __launch_bounds__(kCtlThreads) ScanKernel(TreeState* ts, NodeDev
     const int dst_buf = 1 - e.src_buf;
     l->seg_begin = e.begin; l->seg_count = n_left; l->seg_buf = dst_buf;
     r->seg_begin = e.begin + n_left; r->seg_count = e.count - n_left; r->seg_buf = dst_buf;
-    const bool build_right = r->seg_count < l->seg_count;
+    // Which child gets built (the other is parent - built): the one with fewer LOCAL rows is the cheaper one;
+    // under row split every rank must pick the same child, so the hessian sums decide, as in the reference
+    // (updater_gpu_hist.cu:461-467: right iff hess_R < hess_L).  The results do not depend on the choice.
+    const bool build_right = build_by_hess ? (r->sum_h < l->sum_h) : (r->seg_count < l->seg_count);
     const NodeDev* b = build_right ? r : l;
     const int b_idx = build_right ? e.right : e.left;
     const int s_idx = build_right ? e.left : e.right;
@@ -593,6 +596,7 @@ struct b200hist_updater_s {
   // peer-memory exchange (P2P over NVLink): IPC-mapped histogram caches of all ranks
   bool p2p{false};
   int p2p_rank{0}, p2p_world{1};
+  bool row_split{false};                   // ranks own row slices (full-width partial histograms, summed) instead of feature blocks
   size_t flags_offset{0};                  // byte offset of the flag array inside the histogram allocation
   std::vector<void*> peer_base;            // opened IPC mappings (own entry = nullptr)
   longlong2** d_peer_hist{nullptr};
@@ -686,7 +690,14 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   if (u->p2p)  // nobody may push into a cache that its owner has not cleared yet: pure flag barrier
     LaunchHistExchange(u->d_peer_hist, u->d_peer_flags, u->p2p_rank, u->p2p_world, u->d_ts, 0, 0, false,
                        ell->total_bins, 0, 0, ++u->exchange_epoch, u->d_exchange_counter, u->num_sms, s);
-  LaunchQuantise(gpair_dev, n, u->d_quant, u->d_gq, u->d_ridx[0], u->d_partials, u->d_counter, u->num_sms, s);
+  if (u->p2p && u->row_split) {  // global quantiser scale and root sum (quantiser.cu:88-123 GlobalSum)
+    LaunchQuantReduce(gpair_dev, n, u->d_quant, u->d_partials, u->d_counter, u->num_sms, s);
+    LaunchScalarExchange(u->d_peer_flags, u->p2p_rank, u->p2p_world, ++u->exchange_epoch, 0, u->d_quant, n, s);
+    LaunchQuantConvert(gpair_dev, n, u->d_quant, u->d_gq, u->d_ridx[0], u->num_sms, s);
+    LaunchScalarExchange(u->d_peer_flags, u->p2p_rank, u->p2p_world, ++u->exchange_epoch, 1, u->d_quant, n, s);
+  } else {
+    LaunchQuantise(gpair_dev, n, u->d_quant, u->d_gq, u->d_ridx[0], u->d_partials, u->d_counter, u->num_sms, s);
+  }
   timer.End(kQuant, t0);
 
   // InitRoot
@@ -702,7 +713,11 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
       LaunchBuildHist(view, u->d_gq, u->d_ridx[0], u->d_ridx[1], u->d_build, u->d_build_tile_seg, u->d_ts,
                       u->d_groups + u->group_begin, my_groups, u->d_hist, u->d_quant, u->num_sms, s, u->pair_hint);
     // AllReduceHist: one collective per level over the level's contiguous built slots
-    if (u->p2p) {
+    if (u->p2p && u->row_split) {
+      const uint32_t ea = ++u->exchange_epoch, eb = ++u->exchange_epoch;
+      LaunchHistAllReduce(u->d_peer_hist, u->d_peer_flags, u->p2p_rank, u->p2p_world, u->d_ts, slot_base, slot_cap,
+                          ell->total_bins, ea, eb, u->d_exchange_counter, u->num_sms, s);
+    } else if (u->p2p) {
       const uint32_t b0 = my_groups.empty() ? 0u : my_groups.front().bin_begin;
       const uint32_t b1 = my_groups.empty() ? 0u : my_groups.back().bin_end;
       LaunchHistExchange(u->d_peer_hist, u->d_peer_flags, u->p2p_rank, u->p2p_world, u->d_ts, slot_base, slot_cap,
@@ -736,7 +751,8 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
                          u->d_tile_left, u->num_sms, s);
     ScanKernel<<<1, kCtlThreads, 0, s>>>(u->d_ts, u->d_nodes, u->d_part, u->d_part_tile_seg, u->d_tile_left,
                                          u->d_tile_excl, u->d_tile_left_off, u->d_build, u->d_sub, u->d_eval_nodes,
-                                         u->d_build_tile_seg, u->step_slot_base[step], u->step_cap[step]);
+                                         u->d_build_tile_seg, u->step_slot_base[step], u->step_cap[step],
+                                         u->row_split ? 1 : 0);
     B200_LAUNCHED();
     LaunchPartitionScatter(u->d_ridx[0], u->d_ridx[1], u->d_ridx[0], u->d_ridx[1], u->d_part, u->d_part_tile_seg,
                            u->d_ts, u->d_flags, u->d_tile_left_off, u->num_sms, s);
@@ -1056,6 +1072,20 @@ int b200hist_updater_set_peers(b200hist_updater_t u, int rank, int world, const 
   u->p2p_world = world;
   u->p2p = true;
   u->exchange_epoch = 0;
+  B200_API_END();
+}
+
+int b200hist_updater_set_row_split(b200hist_updater_t u, int on) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  B200_CHECK(u->p2p, "row split needs the peer-memory exchange: call b200hist_updater_set_peers first");
+  u->row_split = on != 0;
+  if (u->row_split) {  // every rank builds every feature group over its own rows
+    u->group_begin = 0;
+    u->group_end = (uint32_t)u->groups.size();
+  } else {
+    ShardGroups((uint32_t)u->groups.size(), u->p2p_world, u->p2p_rank, &u->group_begin, &u->group_end);
+  }
   B200_API_END();
 }
 

@@ -397,10 +397,11 @@ class GPUHistMaker:
         self._comm = comm  # keep it alive
         _l.check(_l.load().b200hist_updater_set_comm(self._h, comm.handle if comm is not None else c_void_p()))
 
-    def enable_peer_exchange(self) -> None:
+    def enable_peer_exchange(self, row_split: bool = False) -> None:
         """Map every rank's histogram cache over NVLink P2P (IPC handles all-gathered through
         torch.distributed -- control plane only) and switch the per-level collective from NCCL to the
-        peer-memory push + flag barrier kernel."""
+        peer-memory push + flag barrier kernel.  row_split=True: this rank's page holds ITS slice of the rows
+        (same cuts everywhere) and the per-level kernel sums full-width partial histograms instead."""
         import torch.distributed as dist
         world, rank = dist.get_world_size(), dist.get_rank()
         buf = (ctypes.c_uint8 * 64)()
@@ -410,6 +411,8 @@ class GPUHistMaker:
         dist.all_gather(allh, mine)
         flat = (ctypes.c_uint8 * (64 * world)).from_buffer_copy(b"".join(bytes(t.cpu().tolist()) for t in allh))
         _l.check(_l.load().b200hist_updater_set_peers(self._h, rank, world, flat))
+        if row_split:
+            _l.check(_l.load().b200hist_updater_set_row_split(self._h, 1))
         dist.barrier()
 
     def num_feature_groups(self) -> int:
