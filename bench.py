@@ -53,44 +53,78 @@ def parse_args():
 # clocks sampling during the timed region (B200_PROFILING.md recipe)
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled every 200 ms during the timed region, through NVML inside this process
+    (one library call per sample: no fork of a process that maps 100+ GB, no nvidia-smi start-up in the region).
+    Falls back to ONE long-running `nvidia-smi -lms 200` child started before the region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index: int = 0):
         self.index = index
-        self.samples = []
+        self.samples = []      # (sm_mhz, sm_max_mhz, set(reasons))
         self._stop = threading.Event()
         self._t = None
+        self._child = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._max = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
 
     def _run(self):
+        nv = self._nvml
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.samples.append((int(sm), int(self._max), {k for k, b in self.BITS.items() if mask & b}))
             except Exception:
                 pass
             self._stop.wait(0.2)
 
     def start(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self._nvml is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        else:
+            self._child = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                            "--format=csv,noheader,nounits", "-lms", "200"],
+                                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
 
     def stop(self):
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        if self._child is not None:
+            self._child.terminate()
+            try:
+                out = self._child.communicate(timeout=5)[0]
+            except Exception:
+                out = ""
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in out.splitlines():
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) >= 6 and parts[0].isdigit() and parts[1].isdigit():
+                    self.samples.append((int(parts[0]), int(parts[1]),
+                                         {n for n, v in zip(names, parts[2:6]) if v.lower().startswith("active")}))
+        sm = sorted(s[0] for s in self.samples)
+        mx = [s[1] for s in self.samples]
         reasons = set()
         for s in self.samples:
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+            reasons |= s[2]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "reasons": sorted(reasons), "samples": len(self.samples),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi -lms 200"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -286,8 +320,10 @@ def run_b200(args):
     up.set_profiling(False)
     torch.cuda.synchronize(device)
     # where a step's time goes outside the updater's phases: gradient kernel, tree update call, prediction cache
+    # (profiling stays on so that the same iterations give the phase sum: update_tree - sum(phases) = unattributed)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     parts = []
+    up.set_profiling(True)
     for _ in range(3):
         ev[0].record()
         torch.sub(preds, y, out=gpair[:, 0])
@@ -297,8 +333,11 @@ def run_b200(args):
         up.update_prediction_cache(preds)
         ev[3].record()
         torch.cuda.synchronize(device)
-        parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
-    step_parts = dict(zip(["gradient", "update_tree", "prediction_cache"], [float(v) for v in np.median(np.array(parts), axis=0)]))
+        lp = up.last_profile()
+        parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)] + [sum(v for k, v in lp.items() if k != "row_visits")])
+    up.set_profiling(False)
+    step_parts = dict(zip(["gradient", "update_tree", "prediction_cache", "update_tree_phase_sum"],
+                          [float(v) for v in np.median(np.array(parts), axis=0)]))
     phase = {k: float(np.median([p[k] for p in prof])) for k in prof[0] if k != "row_visits"}
     row_visits = prof[-1]["row_visits"]
     ab = algorithmic_bytes(n, f, info["bin_bytes"], args.depth, row_visits)
