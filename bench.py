@@ -334,7 +334,7 @@ def run_b200(args):
         ev[3].record()
         torch.cuda.synchronize(device)
         lp = up.last_profile()
-        parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)] + [sum(v for k, v in lp.items() if k != "row_visits")])
+        parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)] + [sum(v for k, v in lp.items() if k not in ("row_visits", "hist_exchange"))])
     up.set_profiling(False)
     step_parts = dict(zip(["gradient", "update_tree", "prediction_cache", "update_tree_phase_sum"],
                           [float(v) for v in np.median(np.array(parts), axis=0)]))
@@ -350,19 +350,20 @@ def run_b200(args):
     # per GPU: this rank reads its F/world feature columns + the 20 B of gradient pair / row id per row visit
     feat_div = 1 if (world == 1 or row_split) else world   # row split: this rank's visits cover all F features
     hist_bytes_gpu = row_visits * (f * info["bin_bytes"] / feat_div + 16 + 4)
-    hist_gbs = hist_bytes_gpu / (phase["hist"] * 1e-3) / 1e9 if phase["hist"] > 0 else 0.0
+    hist_ms = phase["hist"] - phase.get("hist_exchange", 0.0)   # the kernel itself, without the cross-GPU exchange
+    hist_gbs = hist_bytes_gpu / (hist_ms * 1e-3) / 1e9 if hist_ms > 0 else 0.0
     # the kernel's binding ceiling is shared-memory read-modify-write bandwidth: 16 B read + 16 B written per
     # (row, feature) update at 128 B/clk/SM = 4 updates/clk/SM
     from xgboost_b200 import components as xc
     smem_peak = xc.smem_atomic_peak(True, device)
     sm_clock_hz = (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965) * 1e6
     n_sms = torch.cuda.get_device_properties(device).multi_processor_count
-    updates_per_s = row_visits * (f / feat_div) / (phase["hist"] * 1e-3) if phase["hist"] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "HistKernelBankedFast", "achieved": hist_gbs, "peak": peak, "unit": "GB/s",
+    updates_per_s = row_visits * (f / feat_div) / (hist_ms * 1e-3) if hist_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "HistKernelPair", "achieved": hist_gbs, "peak": peak, "unit": "GB/s",
                 "frac": hist_gbs / peak, "traffic": 1.33 * hist_bytes_gpu / hist_launches, "peak_source": peak_src,
                 "traffic_source": "ncu --set full dram__bytes_read+write = 1.33 x algorithmic on the 20M-row capture "
                                   "(profiles/r01_hist_banked_v2_ncu_summary.json), scaled to this launch size",
-                "launches_per_step": hist_launches, "avg_launch_ms": phase["hist"] / hist_launches,
+                "launches_per_step": hist_launches, "avg_launch_ms": hist_ms / hist_launches,
                 "algorithmic_bytes_per_launch": hist_bytes_gpu / hist_launches, "row_visits_per_step": row_visits,
                 # the binding resource is the shared-memory atomic pipe, not HBM: the ceiling is MEASURED on this GPU by
                 # b200hist_smem_atomic_peak (the kernel's own accumulation sequence -- 3 conflict-free 32-bit atomics

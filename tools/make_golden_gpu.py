@@ -35,6 +35,8 @@ CASES = [
          params=dict(max_depth=0, max_leaves=14, grow_policy="lossguide", eta=0.3)),
     dict(name="sq_wide_256f", n=30000, f=256, seed=107, max_bin=256, obj="sq", rounds=1,
          params=dict(max_depth=5, eta=0.3)),
+    dict(name="sq_pair_128f_r3", n=25000, f=128, seed=109, max_bin=256, obj="sq", rounds=3,
+         params=dict(max_depth=6, eta=0.5)),
     dict(name="sparse_csr_d6", n=20000, f=300, seed=108, max_bin=64, obj="sq", rounds=2, sparse=0.03,
          params=dict(max_depth=6, eta=0.3)),
 ]

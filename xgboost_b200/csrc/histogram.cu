@@ -686,6 +686,7 @@ __device__ __forceinline__ void FastProcessP(const FastDataP& d, const uint32_t 
   }
 }
 
+template <int kBufs>
 __device__ __forceinline__ void FastRowsP(const uint32_t* __restrict__ ridx, uint32_t lo, uint32_t hi,
                                           const longlong2* __restrict__ gq, const uint8_t* __restrict__ col,
                                           uint32_t row_bytes, uint32_t warp, uint32_t q,
@@ -703,22 +704,39 @@ __device__ __forceinline__ void FastRowsP(const uint32_t* __restrict__ ridx, uin
       r[0] = __ldg(p);
       r[1] = __ldg(p + 4);
     };
-    uint32_t r0[2], r1[2], r2[2];
-    FastDataP d0, d1, d2;
-    rid(0, r0); rid(1, r1); rid(2, r2);
-    FastLoadP(d0, r0, gq, col, row_bytes); rid(3, r0);
-    FastLoadP(d1, r1, gq, col, row_bytes); rid(4, r1);
-    uint32_t i = 0;
-    for (; i + 2 < n_full; i += 3) {
-      FastLoadP(d2, r2, gq, col, row_bytes); rid(i + 5, r2);  // pass i+2
-      FastProcessP(d0, sel, off);                             // pass i
-      FastLoadP(d0, r0, gq, col, row_bytes); rid(i + 6, r0);  // pass i+3
-      FastProcessP(d1, sel, off);                             // pass i+1
-      FastLoadP(d1, r1, gq, col, row_bytes); rid(i + 7, r1);  // pass i+4
-      FastProcessP(d2, sel, off);                             // pass i+2
+    if (kBufs == 3) {
+      uint32_t r0[2], r1[2], r2[2];
+      FastDataP d0, d1, d2;
+      rid(0, r0); rid(1, r1); rid(2, r2);
+      FastLoadP(d0, r0, gq, col, row_bytes); rid(3, r0);
+      FastLoadP(d1, r1, gq, col, row_bytes); rid(4, r1);
+      uint32_t i = 0;
+      for (; i + 2 < n_full; i += 3) {
+        FastLoadP(d2, r2, gq, col, row_bytes); rid(i + 5, r2);  // pass i+2
+        FastProcessP(d0, sel, off);                             // pass i
+        FastLoadP(d0, r0, gq, col, row_bytes); rid(i + 6, r0);  // pass i+3
+        FastProcessP(d1, sel, off);                             // pass i+1
+        FastLoadP(d1, r1, gq, col, row_bytes); rid(i + 7, r1);  // pass i+4
+        FastProcessP(d2, sel, off);                             // pass i+2
+      }
+      if (i < n_full) FastProcessP(d0, sel, off);
+      if (i + 1 < n_full) FastProcessP(d1, sel, off);
+    } else {
+      uint32_t ra[2], rb[2];
+      FastDataP da, db;
+      rid(0, ra);
+      rid(1, rb);
+      FastLoadP(da, ra, gq, col, row_bytes);
+      rid(2, ra);
+      uint32_t i = 0;
+      for (; i + 1 < n_full; i += 2) {
+        FastLoadP(db, rb, gq, col, row_bytes); rid(i + 3, rb);  // pass i+1
+        FastProcessP(da, sel, off);                             // pass i
+        FastLoadP(da, ra, gq, col, row_bytes); rid(i + 4, ra);  // pass i+2
+        FastProcessP(db, sel, off);                             // pass i+1
+      }
+      if (i < n_full) FastProcessP(da, sel, off);
     }
-    if (i < n_full) FastProcessP(d0, sel, off);
-    if (i + 1 < n_full) FastProcessP(d1, sel, off);
   }
   const uint32_t jb = first + n_full * kStride;
   if (jb < hi) {  // partial last pass: rows past the end add zero
@@ -734,6 +752,7 @@ __device__ __forceinline__ void FastRowsP(const uint32_t* __restrict__ ridx, uin
   }
 }
 
+template <int kBufs>
 __global__ void __launch_bounds__(kHistThreads, 1)
 HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
                const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
@@ -785,7 +804,7 @@ HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __
     const uint32_t lo = (t - e.tile_begin) * kHistTile;
     const uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
     const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin;
-    FastRowsP(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
+    FastRowsP<kBufs>(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
     __syncthreads();
     // flush this CTA's share of the node (RED.64 on non-zero accumulators) and clear
     longlong2* dst = hist + (size_t)e.slot * ell.total_bins;
@@ -1190,7 +1209,8 @@ void PrepareHistKernels(int device) {
   int optin = SmemOptin(device);
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelBankedFast, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  B200_CUDA(cudaFuncSetAttribute(HistKernelPair, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelPair<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelPair<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -1241,7 +1261,12 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
     if (pair && std::max(pair_smem, smem) <= (size_t)SmemOptin(cur_dev)) {
       const int n_pairs = (n_groups + 1) / 2;
       dim3 pgrid(std::max(1, num_sms / n_pairs), n_pairs);
-      HistKernelPair<<<pgrid, kHistThreads, std::max(pair_smem, smem), s>>>(
+      static const int pair_bufs = [] {  // register buffers of prefetch in the pair kernel (2 or 3)
+        const char* e = std::getenv("B200HIST_PAIR_BUFS");
+        return e ? std::atoi(e) : 3;
+      }();
+      auto pk = pair_bufs == 2 ? HistKernelPair<2> : HistKernelPair<3>;
+      pk<<<pgrid, kHistThreads, std::max(pair_smem, smem), s>>>(
           ell, reinterpret_cast<const longlong2*>(gq), ridx0, ridx1, build, tile_seg, ts, groups_dev, (uint32_t)n_groups,
           reinterpret_cast<longlong2*>(hist), quant);
       B200_LAUNCHED();

@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -48,29 +49,40 @@ __global__ void __launch_bounds__(256) KeysTransposeKernel(const float* __restri
                                                             uint32_t n_features, uint32_t* __restrict__ keys,
                                                             uint64_t col_stride, unsigned long long* __restrict__ valid) {
   __shared__ uint32_t tile[32][33];
-  const uint64_t r0 = (uint64_t)blockIdx.x * 32;
+  __shared__ uint32_t s_valid[32];
   const uint32_t f0 = blockIdx.y * 32;
   const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (uint32_t k = ty; k < 32; k += 8) {
-    const uint64_t r = r0 + k;
-    const uint32_t f = f0 + tx;
-    uint32_t key = 0xFFFFFFFFu;
-    if (r < n && f < n_features) {
-      const float v = x[r * ld + f];
-      if (!isnan(v)) key = FloatToKey(v);
+  if (threadIdx.x < 32) s_valid[threadIdx.x] = 0u;
+  // a CTA walks kTilesPerCta row tiles so that the per-feature counts cost one global atomic per CTA, not per warp
+  constexpr uint32_t kTilesPerCta = 16;
+  for (uint32_t it = 0; it < kTilesPerCta; ++it) {
+    const uint64_t r0 = ((uint64_t)blockIdx.x * kTilesPerCta + it) * 32;
+    if (r0 >= n) break;
+    __syncthreads();
+    for (uint32_t k = ty; k < 32; k += 8) {
+      const uint64_t r = r0 + k;
+      const uint32_t f = f0 + tx;
+      uint32_t key = 0xFFFFFFFFu;
+      if (r < n && f < n_features) {
+        const float v = x[r * ld + f];
+        if (!isnan(v)) key = FloatToKey(v);
+      }
+      tile[k][tx] = key;
     }
-    tile[k][tx] = key;
+    __syncthreads();
+    for (uint32_t k = ty; k < 32; k += 8) {
+      const uint32_t f = f0 + k;
+      const uint64_t r = r0 + tx;
+      const uint32_t key = tile[tx][k];
+      const bool ok = f < n_features && r < n;
+      if (ok) keys[(uint64_t)f * col_stride + r] = key;
+      const uint32_t m = __ballot_sync(0xffffffffu, ok && key != 0xFFFFFFFFu);
+      if (tx == 0 && m) atomicAdd(&s_valid[k], (uint32_t)__popc(m));
+    }
   }
   __syncthreads();
-  for (uint32_t k = ty; k < 32; k += 8) {
-    const uint32_t f = f0 + k;
-    const uint64_t r = r0 + tx;
-    const uint32_t key = tile[tx][k];
-    const bool ok = f < n_features && r < n;
-    if (ok) keys[(uint64_t)f * col_stride + r] = key;
-    const uint32_t m = __ballot_sync(0xffffffffu, ok && key != 0xFFFFFFFFu);
-    if (tx == 0 && m && f < n_features) atomicAdd(&valid[f], (unsigned long long)__popc(m));
-  }
+  if (threadIdx.x < 32 && f0 + threadIdx.x < n_features && s_valid[threadIdx.x])
+    atomicAdd(&valid[f0 + threadIdx.x], (unsigned long long)s_valid[threadIdx.x]);
 }
 
 // pass 1/3: digit histogram of every (column, chunk)
@@ -509,8 +521,17 @@ struct b200hist_sketch_s {
   uint32_t* sel = nullptr;
   uint32_t* len = nullptr;
   uint32_t* fix_changes = nullptr;
+  // window scratch, grow-only: sort double buffer, digit counts, valid counts, selected / folded entries
+  uint32_t* keys_a = nullptr;
+  uint32_t* keys_b = nullptr;
+  uint32_t* counts = nullptr;
+  unsigned long long* valid = nullptr;
+  float4* inc = nullptr;
+  float4* inc_unique = nullptr;
+  uint64_t cap_keys = 0, cap_counts = 0, cap_inc = 0;
   ~b200hist_sketch_s() {
-    for (void* p : {(void*)res, (void*)m1, (void*)m2, (void*)sel, (void*)len, (void*)fix_changes})
+    for (void* p : {(void*)res, (void*)m1, (void*)m2, (void*)sel, (void*)len, (void*)fix_changes, (void*)keys_a,
+                    (void*)keys_b, (void*)counts, (void*)valid, (void*)inc, (void*)inc_unique})
       if (p) cudaFree(p);
   }
 };
@@ -553,14 +574,32 @@ void PushDense(b200hist_sketch_s* sk, const float* x_dev, uint64_t n, uint64_t l
   const uint32_t per_col = (uint32_t)RequiredSampleCutsPerColumn(sk->max_bin, n);
   const uint64_t col_stride = (n + 3) & ~uint64_t(3);
   const uint32_t n_chunks = (uint32_t)((n + kSortChunk - 1) / kSortChunk);
-  uint32_t* keys_a = DevAlloc<uint32_t>((uint64_t)F * col_stride);
-  uint32_t* keys_b = DevAlloc<uint32_t>((uint64_t)F * col_stride);
-  uint32_t* counts = DevAlloc<uint32_t>((uint64_t)F * n_chunks * 256);
-  unsigned long long* valid = DevAlloc<unsigned long long>(F);
-  float4* inc = DevAlloc<float4>((uint64_t)F * per_col);
-  float4* inc_unique = DevAlloc<float4>((uint64_t)F * per_col);
+  auto grow = [&](auto*& ptr, uint64_t& cap, uint64_t need) {
+    if (need <= cap) return;
+    B200_CUDA(cudaStreamSynchronize(s));
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    ptr = DevAlloc<std::remove_pointer_t<std::remove_reference_t<decltype(ptr)>>>(need);
+    cap = need;
+  };
+  {
+    uint64_t c = sk->cap_keys;
+    grow(sk->keys_a, c, (uint64_t)F * col_stride);
+    grow(sk->keys_b, sk->cap_keys, (uint64_t)F * col_stride);
+    grow(sk->counts, sk->cap_counts, (uint64_t)F * n_chunks * 256);
+    c = sk->cap_inc;
+    grow(sk->inc, c, (uint64_t)F * per_col);
+    grow(sk->inc_unique, sk->cap_inc, (uint64_t)F * per_col);
+    if (!sk->valid) sk->valid = DevAlloc<unsigned long long>(F);
+  }
+  uint32_t* keys_a = sk->keys_a;
+  uint32_t* keys_b = sk->keys_b;
+  uint32_t* counts = sk->counts;
+  unsigned long long* valid = sk->valid;
+  float4* inc = sk->inc;
+  float4* inc_unique = sk->inc_unique;
   B200_CUDA(cudaMemsetAsync(valid, 0, sizeof(unsigned long long) * F, s));
-  dim3 tgrid((unsigned)((n + 31) / 32), (F + 31) / 32);
+  dim3 tgrid((unsigned)((n + 32 * 16 - 1) / (32 * 16)), (F + 31) / 32);
   KeysTransposeKernel<<<tgrid, 256, 0, s>>>(x_dev, n, ld, F, keys_a, col_stride, valid);
   B200_LAUNCHED();
   uint32_t* src = keys_a;
@@ -589,8 +628,8 @@ void PushDense(b200hist_sketch_s* sk, const float* x_dev, uint64_t n, uint64_t l
   PruneTo(sk, LimitSizeLevel(rows, SketchEpsilon(sk->max_bin, rows)) * (size_t)F, s);
   // ... and MakeSketches prunes to the budget of the rows accumulated so far (quantile_dmatrix.cu:73-90)
   PruneTo(sk, RequiredSampleCutsPerColumn(sk->max_bin, sk->accumulated), s);
+  // the caller may free or overwrite the batch as soon as the call returns (like a DataIter does)
   B200_CUDA(cudaStreamSynchronize(s));
-  for (void* p : {(void*)keys_a, (void*)keys_b, (void*)counts, (void*)valid, (void*)inc, (void*)inc_unique}) cudaFree(p);
 }
 
 }  // namespace

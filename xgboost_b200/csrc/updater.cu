@@ -613,13 +613,13 @@ struct b200hist_updater_s {
   // profiling
   bool profiling{false};
   std::vector<cudaEvent_t> events;
-  float last_ms[7]{0, 0, 0, 0, 0, 0, 0};
+  float last_ms[8]{0, 0, 0, 0, 0, 0, 0, 0};  // [7] = the cross-GPU exchange, also contained in [1] (hist)
   uint64_t last_row_visits{0};
 };
 
 namespace {
 
-enum Phase { kQuant = 0, kHist = 1, kSub = 2, kEval = 3, kApply = 4, kPart = 5, kFinal = 6 };
+enum Phase { kQuant = 0, kHist = 1, kSub = 2, kEval = 3, kApply = 4, kPart = 5, kFinal = 6, kComm = 7 };
 
 struct PhaseTimer {
   b200hist_updater_s* u;
@@ -713,6 +713,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
       LaunchBuildHist(view, u->d_gq, u->d_ridx[0], u->d_ridx[1], u->d_build, u->d_build_tile_seg, u->d_ts,
                       u->d_groups + u->group_begin, my_groups, u->d_hist, u->d_quant, u->num_sms, s, u->pair_hint);
     // AllReduceHist: one collective per level over the level's contiguous built slots
+    auto tc = timer.Begin();
     if (u->p2p && u->row_split) {
       const uint32_t ea = ++u->exchange_epoch, eb = ++u->exchange_epoch;
       LaunchHistAllReduce(u->d_peer_hist, u->d_peer_flags, u->p2p_rank, u->p2p_world, u->d_ts, slot_base, slot_cap,
@@ -727,6 +728,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
       CommAllReduceInt64(u->comm, u->d_hist + (size_t)slot_base * ell->total_bins,
                          (size_t)slot_cap * ell->total_bins * 2, s);
     }
+    timer.End(kComm, tc);
   };
   build_hist(0, 1);
   timer.End(kHist, t2);
@@ -1103,10 +1105,17 @@ int b200hist_updater_set_profiling(b200hist_updater_t u, int on) {
   B200_API_END();
 }
 
+int b200hist_updater_last_comm_ms(b200hist_updater_t u, float* out_ms) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && out_ms != nullptr, "null argument");
+  *out_ms = u->last_ms[7];
+  B200_API_END();
+}
+
 int b200hist_updater_last_profile(b200hist_updater_t u, float* out_ms7, uint64_t* out_row_visits) {
   B200_API_BEGIN();
   B200_CHECK(u != nullptr, "null argument");
-  if (out_ms7) std::memcpy(out_ms7, u->last_ms, sizeof(u->last_ms));
+  if (out_ms7) std::memcpy(out_ms7, u->last_ms, sizeof(float) * 7);
   if (out_row_visits) *out_row_visits = u->last_row_visits;
   B200_API_END();
 }

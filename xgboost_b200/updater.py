@@ -430,6 +430,9 @@ class GPUHistMaker:
         names = ["quantise", "hist", "subtract", "evaluate", "apply", "partition", "finalise"]
         d = {k: float(v) for k, v in zip(names, ms)}
         d["row_visits"] = int(rv.value)
+        comm = c_float(0.0)
+        _l.check(_l.load().b200hist_updater_last_comm_ms(self._h, byref(comm)))
+        d["hist_exchange"] = float(comm.value)   # part of "hist"
         return d
 
     # TreeUpdater::Update for one tree
