@@ -224,6 +224,17 @@ B200HIST_API int b200hist_updater_num_feature_groups(b200hist_updater_t u, uint3
  * handles_host: world x 64 bytes in rank order (the own entry is ignored). */
 B200HIST_API int b200hist_updater_ipc_handle(b200hist_updater_t u, uint8_t* out_handle64);
 B200HIST_API int b200hist_updater_set_peers(b200hist_updater_t u, int rank, int world, const uint8_t* handles_host);
+/* Per-tree sampling, applied to every following update_tree call until changed:
+ *   feature_set_host (nullable = all features): the tree's colsample_bytree draw, strictly ascending feature ids --
+ *     what ColumnSampler::GetFeatureSet(depth) returns when only colsample_bytree < 1 (src/common/random.h:101-132,
+ *     updater_gpu_hist.cu:199-217,257-261); split evaluation visits exactly these features in this order.
+ *   subsample < 1: uniform row sampling = cuda_impl::UniformSampling::Sample (src/tree/gpu_hist/sampler.cu:160-173):
+ *     the quantised gradient pair of row i is zeroed when RandomWeight(subsample_seed)(i) > subsample
+ *     (minstd_rand + discard(i) + uniform float, sampler.cu:36-60); subsample_seed is the tree's ctx->Rng()() draw.
+ * colsample_bylevel / bynode and gradient_based sampling are not built. */
+B200HIST_API int b200hist_updater_set_tree_sampling(b200hist_updater_t u, const int32_t* feature_set_host,
+                                                    uint32_t n_feature_set, float subsample, uint32_t subsample_seed);
+
 /* Row split (the reference's default distributed mode): every rank holds a page of ITS rows with the
  * same cuts and builds full-width partial histograms; one peer-memory kernel per level sums them (reduce-scatter +
  * all-gather over NVLink, integer, bit-identical to one GPU) = AllReduceHist (src/tree/gpu_hist/histogram.cu:598-609);

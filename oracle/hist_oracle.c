@@ -454,11 +454,57 @@ static int entry_valid(const entry_t* e, const orc_param* p, int32_t num_leaves)
   return 1;
 }
 
+/* Uniform row sampling: cuda_impl::UniformSampling::Sample (src/tree/gpu_hist/sampler.cu:160-173) zeroes the
+ * QUANTISED gradient pair of row i when BernoulliTrial(seed, subsample)(i) holds, i.e. when
+ * RandomWeight(seed)(i) > subsample (sampler.cu:36-60).  RandomWeight is thrust::default_random_engine
+ * (= minstd_rand: x <- 48271 x mod 2^31-1, seeded with seed mod m, 0 -> 1), discard(i), then
+ * thrust::uniform_real_distribution<float>: float(x - 1) / (1.0f + float(max - min)) with max - min = 2^31 - 3,
+ * which rounds to 2^31 in float (thrust/random/detail/uniform_real_distribution.inl, CUDA 12.9 toolkit). */
+ORC_API float orc_random_weight(uint32_t seed, uint64_t i) {
+  const uint64_t m = 2147483647ull;
+  uint64_t x = seed % m;
+  if (x == 0) x = 1;
+  /* discard(i) then one draw = multiply by a^(i+1) */
+  uint64_t z = i + 1, mult = 48271ull, acc = 1;
+  while (z > 0) {
+    if (z & 1) acc = (acc * mult) % m;
+    z >>= 1;
+    mult = (mult * mult) % m;
+  }
+  x = (acc * x) % m;
+  float r = (float)(uint32_t)(x - 1);
+  r /= (1.0f + (float)(uint32_t)(m - 1 - 1));
+  return r * (1.0f - 0.0f) + 0.0f;
+}
+
+ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
+                                   uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
+                                   const float* gpair, const orc_param* p, const double* scale_override,
+                                   orc_node* nodes, int32_t max_nodes, int32_t* position,
+                                   orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4],
+                                   const int32_t* feature_set, int32_t n_feature_set, float subsample,
+                                   uint32_t sample_seed);
+
 ORC_API int32_t orc_update_tree(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
                                 uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
                                 const float* gpair, const orc_param* p, const double* scale_override,
                                 orc_node* nodes, int32_t max_nodes, int32_t* position,
                                 orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4]) {
+  return orc_update_tree_ex(gbins, n_rows, stride, is_dense_layout, n_features, cut_ptrs, cut_values, gpair, p,
+                            scale_override, nodes, max_nodes, position, hist_dump, cand_dump, scale_out, NULL, 0, 1.0f,
+                            0u);
+}
+
+/* feature_set (sorted ascending, NULL = all): the tree's colsample_bytree draw, evaluated in this order
+ * (column_sampler_->GetFeatureSet, updater_gpu_hist.cu:217,257-261); subsample < 1: uniform row sampling with the
+ * tree's seed (one ctx->Rng()() draw per tree, sampler.cu:165). */
+ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
+                                   uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
+                                   const float* gpair, const orc_param* p, const double* scale_override,
+                                   orc_node* nodes, int32_t max_nodes, int32_t* position,
+                                   orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4],
+                                   const int32_t* feature_set, int32_t n_feature_set, float subsample,
+                                   uint32_t sample_seed) {
   uint32_t total_bins = cut_ptrs[n_features];
   double scale[4];
   if (scale_override) memcpy(scale, scale_override, sizeof(scale));
@@ -466,6 +512,9 @@ ORC_API int32_t orc_update_tree(const int32_t* gbins, uint64_t n_rows, uint32_t 
   if (scale_out) memcpy(scale_out, scale, sizeof(scale));
   orc_gpair64* gq = (orc_gpair64*)malloc(sizeof(orc_gpair64) * (n_rows ? n_rows : 1));
   orc_quantise(gpair, n_rows, scale, gq);
+  if (subsample < 1.0f)
+    for (uint64_t i = 0; i < n_rows; ++i)
+      if (orc_random_weight(sample_seed, i) > subsample) { gq[i].g = 0; gq[i].h = 0; }
 
   /* per-node state */
   orc_gpair64** hist = (orc_gpair64**)calloc((size_t)max_nodes, sizeof(orc_gpair64*));
@@ -501,7 +550,7 @@ ORC_API int32_t orc_update_tree(const int32_t* gbins, uint64_t n_rows, uint32_t 
   }
   entry_t root_e;
   root_e.nidx = 0; root_e.depth = 0; root_e.open = 1;
-  orc_eval_node(hist[0], root, cut_ptrs, cut_values, n_features, NULL, 0, p, scale, &root_e.c, NULL);
+  orc_eval_node(hist[0], root, cut_ptrs, cut_values, n_features, feature_set, n_feature_set, p, scale, &root_e.c, NULL);
   if (cand_dump) cand_dump[0] = root_e.c;
   /* driver.Push(vector) filters loss_chg > kRtEps (driver.h:42-50) */
   int n_open = 0;
@@ -584,7 +633,7 @@ ORC_API int32_t orc_update_tree(const int32_t* gbins, uint64_t n_rows, uint32_t 
       for (int s = 0; s < 2; ++s) {
         entry_t e;
         e.nidx = ch[s]; e.depth = depth + 1; e.open = 1;
-        orc_eval_node(hist[ch[s]], node_sum[ch[s]], cut_ptrs, cut_values, n_features, NULL, 0, p, scale, &e.c, NULL);
+        orc_eval_node(hist[ch[s]], node_sum[ch[s]], cut_ptrs, cut_values, n_features, feature_set, n_feature_set, p, scale, &e.c, NULL);
         if (cand_dump) cand_dump[ch[s]] = e.c;
         if (e.c.loss_chg > 1e-6f) { queue[ch[s]] = e; n_open++; }
       }

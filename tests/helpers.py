@@ -112,3 +112,30 @@ def make_sketch_batches(case):
             x[:, col] = np.nan
         out.append(np.ascontiguousarray(x))
     return out
+
+
+class MT19937:
+    """std::mt19937 (the reference's RandomEngine, include/xgboost/context.h) seeded like `engine.seed(s)`;
+    next() returns the successive 32-bit outputs -- e.g. the per-tree seeds the GPU row sampler draws with ctx->Rng()()."""
+
+    def __init__(self, seed: int):
+        self.mt = [0] * 624
+        self.mt[0] = seed & 0xFFFFFFFF
+        for i in range(1, 624):
+            self.mt[i] = (1812433253 * (self.mt[i - 1] ^ (self.mt[i - 1] >> 30)) + i) & 0xFFFFFFFF
+        self.idx = 624
+
+    def next(self) -> int:
+        if self.idx >= 624:
+            mt = self.mt
+            for k in range(624):
+                y = (mt[k] & 0x80000000) | (mt[(k + 1) % 624] & 0x7FFFFFFF)
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ (0x9908B0DF if y & 1 else 0)
+            self.idx = 0
+        y = self.mt[self.idx]
+        self.idx += 1
+        y ^= y >> 11
+        y ^= (y << 7) & 0x9D2C5680
+        y ^= (y << 15) & 0xEFC60000
+        y ^= y >> 18
+        return y & 0xFFFFFFFF

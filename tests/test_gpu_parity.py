@@ -454,6 +454,43 @@ def test_pair_kernel_rounds_match_oracle(xb, n, f, obj, depth):
         pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
 
 
+@pytest.mark.parametrize("subsample,seed,n_fs", [(0.6, 12345, None), (1.0, 0, 9), (0.35, 4294967295, 17), (0.9, 0, 1)])
+def test_tree_sampling_matches_oracle(xb, subsample, seed, n_fs):
+    """Uniform row sampling (the quantised pair of a row that loses RandomWeight(seed)(i) <= subsample is zeroed; the
+    quantiser scale still comes from all rows) and a colsample_bytree feature set (evaluation restricted to the set,
+    ties resolved by position IN the set).  Two trees so that the pair kernel sees sampled gradients as well."""
+    import torch
+    n, f = 30000, 70
+    x, y = make_regression(n, f, seed=31)
+    cp, cv = make_cuts(x, 64)
+    page = _page(xb, x, cp, cv)
+    gb = orc.bin_dense(x, cp, cv)
+    fs = None if n_fs is None else np.sort(np.random.default_rng(n_fs).choice(f, size=n_fs, replace=False)).astype(np.int32)
+    params = dict(max_depth=5, eta=0.5)
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    pred = np.zeros(n, dtype=np.float32)
+    for it in range(2):
+        up.set_tree_sampling(fs, subsample, seed + it)
+        gp = squared_error_gpair(pred, y)
+        pos = torch.empty(n, dtype=torch.int32, device="cuda")
+        tree = up.update(torch.from_numpy(gp).cuda(), pos)
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), feature_set=fs, subsample=subsample,
+                            sample_seed=(seed + it) & 0xFFFFFFFF, want_hist=True)
+        _compare_tree(xb, up, tree, o, cp, cv, hists=True)
+        assert np.array_equal(pos.cpu().numpy(), o["position"])
+        if fs is not None:
+            assert all(nd["findex"] in set(fs.tolist()) for nd in tree.nodes if not nd["is_leaf"])
+        if subsample < 1.0:  # sampled-out rows carry the bit-complemented leaf id (their hessian is 0)
+            dropped = np.array([orc.random_weight((seed + it) & 0xFFFFFFFF, i) > np.float32(subsample) for i in range(200)])
+            assert np.array_equal(pos.cpu().numpy()[:200] < 0, dropped)
+        pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+    up.set_tree_sampling(None, 1.0, 0)   # back to no sampling: the plain tree again
+    t_plain = up.update(torch.from_numpy(squared_error_gpair(np.zeros(n, np.float32), y)).cuda())
+    o_plain = orc.update_tree(gb, cp, cv, squared_error_gpair(np.zeros(n, np.float32), y), orc.Param.make(**params))
+    _compare_tree(xb, up, t_plain, o_plain, cp, cv, hists=False)
+
+
 def test_host_gradient_entry_matches_device_entry(xb):
     import torch
     n, f = 5000, 6

@@ -193,3 +193,30 @@ def test_tree_basic_invariants():
     h0 = t["hist"][0]
     for f in range(6):
         assert tuple(h0[cp[f]:cp[f + 1]].sum(axis=0)) == tuple(gq.sum(axis=0))
+
+
+def test_random_weight_restates_thrust_minstd_discard_uniform():
+    """RandomWeight(seed)(i) (sampler.cu:36-47): minstd_rand seeded with seed, discard(i), one float draw.
+    Checked against a step-by-step big-integer evaluation and against known values of minstd_rand."""
+    import oracle as orc
+    m, a = 2147483647, 48271
+
+    def ref(seed, i):
+        x = seed % m or 1
+        for _ in range(i + 1):          # discard(i) then operator()
+            x = (a * x) % m
+        return np.float32(np.float32(x - 1) / np.float32(2147483648.0))
+
+    # the 10000th output of minstd_rand seeded with 1 is 399268537 (ISO C++ [rand.predef])
+    x = 1
+    for _ in range(10000):
+        x = (a * x) % m
+    assert x == 399268537
+    assert orc.random_weight(1, 9999) == float(np.float32(np.float32(399268537 - 1) / np.float32(2147483648.0)))
+    for seed in (0, 1, 7, 2147483647, 2147483648, 4294967295, 123456789):
+        for i in (0, 1, 2, 31, 1000, 4097):
+            assert orc.random_weight(seed, i) == float(ref(seed, i)), (seed, i)
+    # large index: fast exponentiation path
+    assert orc.random_weight(5, 10**11) == float(np.float32(np.float32((pow(a, 10**11 + 1, m) * 5) % m - 1) / np.float32(2147483648.0)))
+    u = np.array([orc.random_weight(42, i) for i in range(20000)])
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01

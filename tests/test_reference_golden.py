@@ -18,7 +18,7 @@ import numpy as np
 import pytest
 
 import oracle as orc
-from tests.helpers import make_regression, make_sparse_regression
+from tests.helpers import MT19937, make_regression, make_sparse_regression
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_gpu_trees.json")
 
@@ -55,7 +55,7 @@ def _inputs(case):
 
 
 def _params(case):
-    p = dict(case["params"])
+    p = {k: v for k, v in case["params"].items() if k not in ("subsample", "seed")}
     p.setdefault("lambda", 1.0)
     p.setdefault("min_child_weight", 1.0)
     return p
@@ -72,9 +72,11 @@ def test_oracle_reproduces_reference_gpu_hist(case):
     gb = orc.bin_dense(x, cp, cv)  # semantics do not depend on the storage layout (dense-with-NaN here)
     p = orc.Param.make(**_params(case))
     margin = np.zeros(case["n"], dtype=np.float32)
+    sub, rng = case["params"].get("subsample", 1.0), MT19937(case["params"].get("seed", 0))
     for t, ref in enumerate(case["trees"]):
         gp = _gradients(case["obj"], margin, y)
-        o = orc.update_tree(gb, cp, cv, gp, p, want_hist=True)
+        # subsample < 1: the tree's sampler seed is the next output of the Booster's mt19937 (sampler.cu:165)
+        o = orc.update_tree(gb, cp, cv, gp, p, want_hist=True, subsample=sub, sample_seed=rng.next() if sub < 1 else 0)
         nodes = o["nodes"]
         assert len(nodes) == len(ref["left"]), "tree %d node count" % t
         cond = _f32(ref["cond_bits"])
@@ -119,8 +121,11 @@ def test_cuda_matches_reference_gpu_hist_bit_for_bit(case, cuda_device):
     up = xb.GPUHistMaker(page)
     up.configure(_params(case))
     margin = torch.zeros(case["n"], dtype=torch.float32, device="cuda")
+    sub, rng = case["params"].get("subsample", 1.0), MT19937(case["params"].get("seed", 0))
     for t, ref in enumerate(case["trees"]):
         gp = torch.from_numpy(_gradients(case["obj"], margin.cpu().numpy(), y)).cuda()
+        if sub < 1:
+            up.set_tree_sampling(None, sub, rng.next())
         tree = up.update(gp)
         assert tree.num_nodes == len(ref["left"]), "tree %d node count" % t
         for i, nd in enumerate(tree.nodes):

@@ -62,3 +62,63 @@ def test_reference_booster_trains_identically_through_the_shim(cuda_device, obje
     ab_ref, _ = _train(rc, x, y, dict(params, updater="grow_gpu_hist_reference"), 2)
     ab_our, _ = _train(rc, x, y, dict(params, updater="grow_b200_hist"), 2)
     assert json.dumps(ab_ref) == json.dumps(ab_our)
+
+
+def _ensure_shim(rc):
+    rc.load("cuda")
+    f = test_reference_booster_trains_identically_through_the_shim
+    if getattr(f, "_shim", None) is None:
+        f._shim = ctypes.CDLL(SHIM, mode=ctypes.RTLD_GLOBAL)
+
+
+@pytest.mark.parametrize("extra", [{"subsample": 0.7}, {"colsample_bytree": 0.5}, {"subsample": 0.5, "colsample_bytree": 0.6},
+                                   {"subsample": 0.8, "seed": 123, "grow_policy": "lossguide", "max_leaves": 24, "max_depth": 0}],
+                         ids=lambda e: "_".join("%s%s" % kv for kv in e.items()))
+def test_sampling_through_the_shim_matches_reference(cuda_device, extra):
+    """Row sampling (uniform) and colsample_bytree: the shim draws from the Booster's RNG exactly where the reference
+    does (sampler seed, then the column sampler's shuffle seed, once per tree); the row trial itself
+    (minstd_rand + discard + uniform float) runs in our quantise kernel.  Models must match bit for bit."""
+    from oracle import ref_capi as rc
+    if not (rc.available("cuda") and os.path.exists(SHIM)):
+        pytest.skip("needs oracle/_ref_cuda/libxgboost.so and the shim")
+    _ensure_shim(rc)
+    x, y = make_regression(30000, 40, seed=78)
+    params = {"tree_method": "hist", "device": "cuda:0", "max_bin": 64, "max_depth": 5, "eta": 0.3,
+              "objective": "reg:squarederror", "base_score": 0.5}
+    params.update(extra)
+    ref_trees, ref_margin = _train(rc, x, y, dict(params, updater="grow_gpu_hist_reference"), 4)
+    our_trees, our_margin = _train(rc, x, y, dict(params, updater="grow_b200_hist"), 4)
+    assert json.dumps(our_trees) == json.dumps(ref_trees)
+    assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))
+    # sampling really happened: the unsampled model differs
+    plain, _ = _train(rc, x, y, dict({k: v for k, v in params.items() if k not in ("subsample", "colsample_bytree")},
+                                     updater="grow_b200_hist"), 4)
+    assert json.dumps(plain) != json.dumps(our_trees)
+
+
+def test_sparse_dmatrix_through_the_shim_matches_reference(cuda_device):
+    """A CSR DMatrix becomes a sparse ELLPACK page in the reference (row_stride < n_features); the shim imports it
+    into our sparse page (uint32 global-bin symbols) and must reproduce the reference's trees."""
+    from oracle import ref_capi as rc
+    from tests.helpers import make_sparse_regression
+    if not (rc.available("cuda") and os.path.exists(SHIM)):
+        pytest.skip("needs oracle/_ref_cuda/libxgboost.so and the shim")
+    _ensure_shim(rc)
+    _, y, indptr, indices, values = make_sparse_regression(20000, 200, 0.04, 79)
+
+    def train(updater):
+        dm = rc.DMatrix.from_csr(indptr, indices, values, 200, kind="cuda")
+        dm.set_label(y)
+        bst = rc.Booster({"tree_method": "hist", "device": "cuda:0", "max_bin": 64, "max_depth": 6, "eta": 0.3,
+                          "objective": "reg:squarederror", "base_score": 0.5, "updater": updater}, dm)
+        for i in range(3):
+            bst.update(i)
+        trees = bst.save_json()["learner"]["gradient_booster"]["model"]["trees"]
+        keep = ("left_children", "right_children", "split_indices", "split_conditions", "default_left",
+                "base_weights", "loss_changes", "sum_hessian")
+        return [{k: t[k] for k in keep} for t in trees], bst.predict_margin(dm)
+
+    ref_trees, ref_margin = train("grow_gpu_hist_reference")
+    our_trees, our_margin = train("grow_b200_hist")
+    assert json.dumps(our_trees) == json.dumps(ref_trees)
+    assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))

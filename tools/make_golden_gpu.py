@@ -37,6 +37,10 @@ CASES = [
          params=dict(max_depth=5, eta=0.3)),
     dict(name="sq_pair_128f_r3", n=25000, f=128, seed=109, max_bin=256, obj="sq", rounds=3,
          params=dict(max_depth=6, eta=0.5)),
+    dict(name="sq_subsample07", n=20000, f=16, seed=110, max_bin=64, obj="sq", rounds=3,
+         params=dict(max_depth=5, eta=0.3, subsample=0.7)),
+    dict(name="sq_subsample05_seed9", n=20000, f=16, seed=111, max_bin=64, obj="sq", rounds=2,
+         params=dict(max_depth=5, eta=0.3, subsample=0.5, seed=9)),
     dict(name="sparse_csr_d6", n=20000, f=300, seed=108, max_bin=64, obj="sq", rounds=2, sparse=0.03,
          params=dict(max_depth=6, eta=0.3)),
 ]

@@ -261,11 +261,12 @@ struct FeatCand {
 // ---------------------------------------------------------------------------------------------
 // quantise.cu
 void LaunchQuantise(const float* gpair, uint64_t n, QuantDev* q, b200hist_gpair64* gq, uint32_t* ridx_init,
-                    double* partials /* >= 4*kQuantBlocks */, unsigned int* counter, int num_sms, cudaStream_t s);
+                    double* partials /* >= 4*kQuantBlocks */, unsigned int* counter, int num_sms, cudaStream_t s,
+                    float subsample = 1.0f, uint32_t sample_seed = 0);
 void LaunchQuantReduce(const float* gpair, uint64_t n, QuantDev* q, double* partials, unsigned int* counter,
                        int num_sms, cudaStream_t s);
 void LaunchQuantConvert(const float* gpair, uint64_t n, QuantDev* q, b200hist_gpair64* gq, uint32_t* ridx_init,
-                        int num_sms, cudaStream_t s);
+                        int num_sms, cudaStream_t s, float subsample = 1.0f, uint32_t sample_seed = 0);
 constexpr int kQuantBlocksPerSM = 4;
 
 // histogram.cu

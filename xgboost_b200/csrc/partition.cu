@@ -43,25 +43,45 @@ PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint
     const uint8_t* __restrict__ col = ell.bins + (size_t)e.findex * sizeof(BinT);
     const uint8_t* __restrict__ colt = ell.bins_t ? ell.bins_t + (uint64_t)e.findex * ell.col_stride : nullptr;
     uint32_t cnt = 0;
+    if (ell.is_sparse) {
 #pragma unroll
-    for (int k = 0; k < kRowsPerThread; ++k) {
-      const uint32_t j = k * kPartThreads + threadIdx.x;
-      bool left = false;
-      if (j < n && ell.is_sparse) {
-        const uint32_t fb = ell.cut_ptrs[e.findex], fe = ell.cut_ptrs[e.findex + 1];
-        const uint32_t gb = SparseRowBin(ell, ridx[j], fb, fe);
-        left = (gb == 0xFFFFFFFFu) ? (e.default_left != 0) : ((int32_t)(gb - fb) < e.split_lbin);
-      } else if (j < n) {
-        const uint32_t r = ridx[j];
-        const uint32_t sym = (sizeof(BinT) == 1 && colt != nullptr)
-                                 ? (uint32_t)colt[r]
-                                 : (uint32_t)*reinterpret_cast<const BinT*>(col + (size_t)r * ell.row_bytes);
-        left = (sym == ell.null_symbol) ? (e.default_left != 0) : ((int32_t)sym < e.split_lbin);
+      for (int k = 0; k < kRowsPerThread; ++k) {
+        const uint32_t j = k * kPartThreads + threadIdx.x;
+        bool left = false;
+        if (j < n) {
+          const uint32_t fb = ell.cut_ptrs[e.findex], fe = ell.cut_ptrs[e.findex + 1];
+          const uint32_t gb = SparseRowBin(ell, ridx[j], fb, fe);
+          left = (gb == 0xFFFFFFFFu) ? (e.default_left != 0) : ((int32_t)(gb - fb) < e.split_lbin);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, left);
+        if (lane == 0) {
+          flags[(size_t)t * kWordsPerTile + (j >> 5)] = m;
+          cnt += __popc(m);
+        }
       }
-      const uint32_t m = __ballot_sync(0xffffffffu, left);
-      if (lane == 0) {
-        flags[(size_t)t * kWordsPerTile + (j >> 5)] = m;
-        cnt += __popc(m);
+    } else {
+      // all 8 row ids, then all 8 symbol gathers, then the decisions: 8 independent gathers in flight per thread
+      // (the kernel is latency bound: ncu shows long-scoreboard stalls at 20-26 per issue with the loads serialised)
+      uint32_t r[kRowsPerThread], sym[kRowsPerThread];
+#pragma unroll
+      for (int k = 0; k < kRowsPerThread; ++k) {
+        const uint32_t j = k * kPartThreads + threadIdx.x;
+        r[k] = __ldg(ridx + min(j, n - 1));
+      }
+#pragma unroll
+      for (int k = 0; k < kRowsPerThread; ++k)
+        sym[k] = (sizeof(BinT) == 1 && colt != nullptr)
+                     ? (uint32_t)__ldg(colt + r[k])
+                     : (uint32_t)__ldg(reinterpret_cast<const BinT*>(col + (size_t)r[k] * ell.row_bytes));
+#pragma unroll
+      for (int k = 0; k < kRowsPerThread; ++k) {
+        const uint32_t j = k * kPartThreads + threadIdx.x;
+        const bool left = j < n && ((sym[k] == ell.null_symbol) ? (e.default_left != 0) : ((int32_t)sym[k] < e.split_lbin));
+        const uint32_t m = __ballot_sync(0xffffffffu, left);
+        if (lane == 0) {
+          flags[(size_t)t * kWordsPerTile + (j >> 5)] = m;
+          cnt += __popc(m);
+        }
       }
     }
     if (lane == 0) s_cnt[warp] = cnt;

@@ -93,10 +93,30 @@ __global__ void __launch_bounds__(kQThreads) QuantReduceKernel(const float2* __r
   }
 }
 
+// RandomWeight(seed)(i) of the reference's row sampler (src/tree/gpu_hist/sampler.cu:36-47): minstd_rand seeded
+// with `seed`, discard(i), one uniform_real_distribution<float> draw = float(x - 1) / 2^31 (the toolkit's
+// thrust/random/detail/uniform_real_distribution.inl: 1.0f + float(max - min) rounds to 2^31).
+__device__ __forceinline__ float RandomWeight(uint32_t seed, unsigned long long i) {
+  const unsigned long long m = 2147483647ull;
+  unsigned long long x = seed % m;
+  if (x == 0) x = 1;
+  unsigned long long z = i + 1, mult = 48271ull, acc = 1;  // discard(i) + one step = multiply by a^(i+1)
+  while (z > 0) {
+    if (z & 1) acc = (acc * mult) % m;
+    z >>= 1;
+    mult = (mult * mult) % m;
+  }
+  x = (acc * x) % m;
+  float r = (float)(uint32_t)(x - 1);
+  r /= (1.0f + (float)2147483645u);
+  return r;
+}
+
 __global__ void __launch_bounds__(kQThreads) QuantConvertKernel(const float2* __restrict__ gpair, uint64_t n,
                                                                  QuantDev* __restrict__ q,
                                                                  longlong2* __restrict__ gq,
-                                                                 uint32_t* __restrict__ ridx) {
+                                                                 uint32_t* __restrict__ ridx, float subsample,
+                                                                 uint32_t sample_seed) {
   const double fg = q->to_fixed_g, fh = q->to_fixed_h;
   long long sg = 0, sh_ = 0;
   unsigned int lo_or = 0u;
@@ -106,6 +126,9 @@ __global__ void __launch_bounds__(kQThreads) QuantConvertKernel(const float2* __
     // ToFixedPoint (quantiser.cuh:65-69): C cast of double -> int64 truncates toward zero
     long long g = (long long)((double)v.x * fg);
     long long h = (long long)((double)v.y * fh);
+    // UniformSampling::Sample (sampler.cu:160-173): the quantised pair of a row that loses its Bernoulli trial
+    // becomes zero (the quantiser scale above was derived from ALL rows, as in the reference)
+    if (subsample < 1.0f && RandomWeight(sample_seed, i) > subsample) { g = 0; h = 0; }
     gq[i] = make_longlong2(g, h);
     if (ridx != nullptr) ridx[i] = (uint32_t)i;
     sg += g;
@@ -144,16 +167,18 @@ void LaunchQuantReduce(const float* gpair, uint64_t n, QuantDev* q, double* part
 }
 
 void LaunchQuantConvert(const float* gpair, uint64_t n, QuantDev* q, b200hist_gpair64* gq, uint32_t* ridx_init,
-                        int num_sms, cudaStream_t s) {
+                        int num_sms, cudaStream_t s, float subsample, uint32_t sample_seed) {
   QuantConvertKernel<<<num_sms * kQuantBlocksPerSM, kQThreads, 0, s>>>(reinterpret_cast<const float2*>(gpair), n, q,
-                                                                       reinterpret_cast<longlong2*>(gq), ridx_init);
+                                                                       reinterpret_cast<longlong2*>(gq), ridx_init,
+                                                                       subsample, sample_seed);
   B200_LAUNCHED();
 }
 
 void LaunchQuantise(const float* gpair, uint64_t n, QuantDev* q, b200hist_gpair64* gq, uint32_t* ridx_init,
-                    double* partials, unsigned int* counter, int num_sms, cudaStream_t s) {
+                    double* partials, unsigned int* counter, int num_sms, cudaStream_t s, float subsample,
+                    uint32_t sample_seed) {
   LaunchQuantReduce(gpair, n, q, partials, counter, num_sms, s);
-  LaunchQuantConvert(gpair, n, q, gq, ridx_init, num_sms, s);
+  LaunchQuantConvert(gpair, n, q, gq, ridx_init, num_sms, s, subsample, sample_seed);
 }
 
 }  // namespace b200

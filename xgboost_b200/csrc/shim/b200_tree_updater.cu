@@ -33,6 +33,7 @@
 
 #include "../../../include/b200hist.h"
 #include "src/common/cuda_context.cuh"      // CUDAContext::Stream
+#include "src/common/random.h"              // ColumnSampler (the reference's own colsample_bytree draw)
 #include "src/data/ellpack_page.cuh"        // EllpackPageImpl
 #include "src/tree/hist/hist_param.h"       // HistMakerTrainParam
 #include "src/tree/param.h"                 // TrainParam
@@ -78,6 +79,7 @@ class B200HistMaker : public TreeUpdater {
       pos.Resize(p_fmat->Info().num_row_);
       // GradientPair = {float grad, float hess}: exactly the n_rows x 2 float32 layout of the ABI
       auto const* gpair = reinterpret_cast<float const*>(in_gpair->gpair.Data()->ConstDevicePointer());
+      this->DrawSampling(param, p_fmat);
       std::int32_t n_nodes{0};
       B200_SHIM_CHECK(b200hist_updater_update_tree(updater_, gpair, stream, nodes_.data(), &n_nodes,
                                                    pos.DevicePointer()));
@@ -110,10 +112,17 @@ class B200HistMaker : public TreeUpdater {
       auto cuts = impl->CutsShared();
       auto const& ptrs = cuts->cut_ptrs_.ConstHostVector();
       auto const& vals = cuts->cut_values_.ConstHostVector();
-      CHECK(impl->IsDenseCompressed()) << "[b200hist] sparse ELLPACK layout is not supported yet";
-      int const has_missing = impl->IsDense() ? 0 : 1;
-      B200_SHIM_CHECK(b200hist_ellpack_create(ctx_->Ordinal(), impl->n_rows, static_cast<std::uint32_t>(ptrs.size() - 1),
-                                              ptrs.data(), vals.data(), has_missing, &ellpack_));
+      if (impl->IsDenseCompressed()) {
+        int const has_missing = impl->IsDense() ? 0 : 1;
+        B200_SHIM_CHECK(b200hist_ellpack_create(ctx_->Ordinal(), impl->n_rows,
+                                                static_cast<std::uint32_t>(ptrs.size() - 1), ptrs.data(), vals.data(),
+                                                has_missing, &ellpack_));
+      } else {  // sparse ELLPACK: global-bin symbols, row_stride < n_features (ellpack_page.cu:140-183)
+        B200_SHIM_CHECK(b200hist_ellpack_create_sparse(ctx_->Ordinal(), impl->n_rows,
+                                                       static_cast<std::uint32_t>(ptrs.size() - 1), ptrs.data(),
+                                                       vals.data(), static_cast<std::uint32_t>(impl->info.row_stride),
+                                                       &ellpack_));
+      }
       B200_SHIM_CHECK(b200hist_ellpack_import_reference(ellpack_, impl->gidx_buffer.data(),
                                                         static_cast<std::uint32_t>(impl->info.row_stride),
                                                         static_cast<std::uint32_t>(impl->NumSymbols()),
@@ -133,11 +142,36 @@ class B200HistMaker : public TreeUpdater {
     p.min_split_loss = param->min_split_loss;
     CHECK(param->monotone_constraints.empty() && param->interaction_constraints.empty())
         << "[b200hist] constraints are not supported yet";
-    CHECK_EQ(param->subsample, 1.0f) << "[b200hist] row sampling is not supported yet";
+    CHECK(param->subsample == 1.0f || param->sampling_method == TrainParam::kUniform)
+        << "[b200hist] gradient_based row sampling is not supported yet";
+    CHECK(param->colsample_bylevel == 1.0f && param->colsample_bynode == 1.0f)
+        << "[b200hist] colsample_bylevel / colsample_bynode are not supported yet (colsample_bytree is)";
     B200_SHIM_CHECK(b200hist_updater_create(ellpack_, &p, &updater_));
     std::int32_t max_nodes{0};
     B200_SHIM_CHECK(b200hist_updater_max_nodes(updater_, &max_nodes));
     nodes_.resize(static_cast<std::size_t>(max_nodes));
+  }
+
+  // GPUHistMakerDevice::Reset (updater_gpu_hist.cu:172-211) draws from ctx->Rng() in this order for every tree:
+  // the row sampler's seed (sampler.cu:165, only when subsample < 1), then ColumnSampler::Init's shuffle seed
+  // (random.cu:74, only when colsample_bytree < 1).  The column draw is the reference's own ColumnSampler.
+  void DrawSampling(TrainParam const* param, DMatrix* p_fmat) {
+    bool const rows = param->subsample < 1.0f;
+    bool const cols = param->colsample_bytree < 1.0f;
+    if (!rows && !cols && !sampling_set_) return;
+    std::uint32_t seed = rows ? static_cast<std::uint32_t>(ctx_->Rng()()) : 0u;
+    std::vector<std::int32_t> fs;
+    if (cols) {
+      auto const& info = p_fmat->Info();
+      column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, 1.0f, 1.0f, param->colsample_bytree);
+      auto p_set = column_sampler_.GetFeatureSet(ctx_, 0);
+      auto const& h_set = p_set->ConstHostVector();
+      fs.assign(h_set.cbegin(), h_set.cend());
+    }
+    B200_SHIM_CHECK(b200hist_updater_set_tree_sampling(updater_, cols ? fs.data() : nullptr,
+                                                       static_cast<std::uint32_t>(fs.size()),
+                                                       rows ? param->subsample : 1.0f, seed));
+    sampling_set_ = rows || cols;
   }
 
   // ApplySplit (updater_gpu_hist.cu:610-655): our nodes are numbered in the reference's expansion order,
@@ -176,6 +210,7 @@ class B200HistMaker : public TreeUpdater {
     updater_ = nullptr;
     ellpack_ = nullptr;
     p_last_fmat_ = nullptr;
+    sampling_set_ = false;
   }
 
   ObjInfo const* task_{nullptr};
@@ -184,6 +219,8 @@ class B200HistMaker : public TreeUpdater {
   b200hist_updater_t updater_{nullptr};
   std::vector<b200hist_tree_node> nodes_;
   DMatrix* p_last_fmat_{nullptr};
+  common::ColumnSampler column_sampler_;
+  bool sampling_set_{false};
 };
 
 // Replaces the factory of the reference's own "grow_gpu_hist" entry (keeping the original reachable as

@@ -596,6 +596,11 @@ struct b200hist_updater_s {
   // peer-memory exchange (P2P over NVLink): IPC-mapped histogram caches of all ranks
   bool p2p{false};
   int p2p_rank{0}, p2p_world{1};
+  // per-tree sampling state (set through b200hist_updater_set_tree_sampling, persists until changed)
+  float subsample{1.0f};
+  uint32_t sample_seed{0};
+  int32_t* d_feature_set{nullptr};  // sorted feature ids of the tree's colsample_bytree draw (nullptr = all)
+  int32_t n_feature_set{0};
   bool row_split{false};                   // ranks own row slices (full-width partial histograms, summed) instead of feature blocks
   size_t flags_offset{0};                  // byte offset of the flag array inside the histogram allocation
   std::vector<void*> peer_base;            // opened IPC mappings (own entry = nullptr)
@@ -693,10 +698,11 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   if (u->p2p && u->row_split) {  // global quantiser scale and root sum (quantiser.cu:88-123 GlobalSum)
     LaunchQuantReduce(gpair_dev, n, u->d_quant, u->d_partials, u->d_counter, u->num_sms, s);
     LaunchScalarExchange(u->d_peer_flags, u->p2p_rank, u->p2p_world, ++u->exchange_epoch, 0, u->d_quant, n, s);
-    LaunchQuantConvert(gpair_dev, n, u->d_quant, u->d_gq, u->d_ridx[0], u->num_sms, s);
+    LaunchQuantConvert(gpair_dev, n, u->d_quant, u->d_gq, u->d_ridx[0], u->num_sms, s, u->subsample, u->sample_seed);
     LaunchScalarExchange(u->d_peer_flags, u->p2p_rank, u->p2p_world, ++u->exchange_epoch, 1, u->d_quant, n, s);
   } else {
-    LaunchQuantise(gpair_dev, n, u->d_quant, u->d_gq, u->d_ridx[0], u->d_partials, u->d_counter, u->num_sms, s);
+    LaunchQuantise(gpair_dev, n, u->d_quant, u->d_gq, u->d_ridx[0], u->d_partials, u->d_counter, u->num_sms, s,
+                   u->subsample, u->sample_seed);
   }
   timer.End(kQuant, t0);
 
@@ -733,7 +739,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   build_hist(0, 1);
   timer.End(kHist, t2);
   auto t3 = timer.Begin();
-  LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, nullptr, 0, u->pdev, u->d_quant,
+  LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, u->d_feature_set, u->n_feature_set, u->pdev, u->d_quant,
                  u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s);
   timer.End(kEval, t3);
 
@@ -766,7 +772,8 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     LaunchSubtract(u->d_sub, u->d_ts, u->d_hist, ell->total_bins, u->num_sms, s);
     timer.End(kSub, tsb);
     auto te = timer.Begin();
-    LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, (int32_t)(2 * cap), u->d_nodes, nullptr, 0, u->pdev,
+    LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, (int32_t)(2 * cap), u->d_nodes, u->d_feature_set,
+                   u->n_feature_set, u->pdev,
                    u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s);
     timer.End(kEval, te);
   }
@@ -938,6 +945,7 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
     cudaFree(u->d_peer_hist);
     cudaFree(u->d_peer_flags);
     cudaFree(u->d_exchange_counter);
+    if (u->d_feature_set) cudaFree(u->d_feature_set);
     cudaFreeHost(u->h_nodes);
     cudaFreeHost(u->h_ts);
     cudaFreeHost(u->h_quant);
@@ -1074,6 +1082,33 @@ int b200hist_updater_set_peers(b200hist_updater_t u, int rank, int world, const 
   u->p2p_world = world;
   u->p2p = true;
   u->exchange_epoch = 0;
+  B200_API_END();
+}
+
+int b200hist_updater_set_tree_sampling(b200hist_updater_t u, const int32_t* feature_set_host, uint32_t n_feature_set,
+                                       float subsample, uint32_t subsample_seed) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  B200_CHECK(subsample > 0.0f && subsample <= 1.0f, "subsample must be in (0, 1]");
+  DeviceGuard guard(u->device);
+  if (u->d_feature_set) {
+    cudaFree(u->d_feature_set);
+    u->d_feature_set = nullptr;
+    u->n_feature_set = 0;
+  }
+  if (feature_set_host != nullptr) {
+    B200_CHECK(n_feature_set >= 1 && n_feature_set <= u->ell->n_features, "feature set size out of range");
+    for (uint32_t i = 0; i < n_feature_set; ++i) {
+      B200_CHECK(feature_set_host[i] >= 0 && (uint32_t)feature_set_host[i] < u->ell->n_features,
+                 "feature id out of range in feature set");
+      B200_CHECK(i == 0 || feature_set_host[i] > feature_set_host[i - 1], "feature set must be strictly ascending");
+    }
+    u->d_feature_set = DevAlloc<int32_t>(n_feature_set);
+    B200_CUDA(cudaMemcpy(u->d_feature_set, feature_set_host, sizeof(int32_t) * n_feature_set, cudaMemcpyHostToDevice));
+    u->n_feature_set = (int32_t)n_feature_set;
+  }
+  u->subsample = subsample;
+  u->sample_seed = subsample_seed;
   B200_API_END();
 }
 

@@ -415,6 +415,18 @@ class GPUHistMaker:
             _l.check(_l.load().b200hist_updater_set_row_split(self._h, 1))
         dist.barrier()
 
+    def set_tree_sampling(self, feature_set: Optional[Sequence[int]] = None, subsample: float = 1.0,
+                          seed: int = 0) -> None:
+        """Sampling of the next trees: `feature_set` = sorted feature ids of the colsample_bytree draw (None = all),
+        `subsample` + `seed` = uniform row sampling with the tree's ctx->Rng()() draw (sampler.cu:160-173)."""
+        if feature_set is not None:
+            fs = np.ascontiguousarray(feature_set, dtype=np.int32)
+            _l.check(_l.load().b200hist_updater_set_tree_sampling(self._h, fs.ctypes.data_as(POINTER(c_int32)), fs.size,
+                                                                float(subsample), int(seed) & 0xFFFFFFFF))
+        else:
+            _l.check(_l.load().b200hist_updater_set_tree_sampling(self._h, None, 0, float(subsample),
+                                                                int(seed) & 0xFFFFFFFF))
+
     def num_feature_groups(self) -> int:
         n = c_uint32()
         _l.check(_l.load().b200hist_updater_num_feature_groups(self._h, byref(n)))
