@@ -235,6 +235,14 @@ B200HIST_API int b200hist_updater_set_peers(b200hist_updater_t u, int rank, int 
 B200HIST_API int b200hist_updater_set_tree_sampling(b200hist_updater_t u, const int32_t* feature_set_host,
                                                     uint32_t n_feature_set, float subsample, uint32_t subsample_seed);
 
+/* Monotone constraints = TreeEvaluator (src/tree/split_evaluator.h:25-205): constraints_host[f] in {-1, 0, +1} for the
+ * first n features (the rest 0); n = 0 or NULL removes them.  A non-empty list switches every split gain to the
+ * weight-based form -(2 g w + (h + lambda) w^2) with child weights clamped into the bounds of the node being split
+ * (CalcSplitGain / CalcWeight :73-112), rejects splits whose child weights violate the sign, and propagates
+ * mid = (w_left + w_right) / 2 as a bound to the children (AddSplit :163-203), exactly like the reference. */
+B200HIST_API int b200hist_updater_set_monotone_constraints(b200hist_updater_t u, const int32_t* constraints_host,
+                                                           uint32_t n);
+
 /* Row split (the reference's default distributed mode): every rank holds a page of ITS rows with the
  * same cuts and builds full-width partial histograms; one peer-memory kernel per level sums them (reduce-scatter +
  * all-gather over NVLink, integer, bit-identical to one GPU) = AllReduceHist (src/tree/gpu_hist/histogram.cu:598-609);

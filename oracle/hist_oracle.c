@@ -263,11 +263,39 @@ static float gain_given_stats(const orc_param* p, double g, double h) {
   float fg = (float)g, fh = (float)h;
   return -(2.0f * fg * w + (fh + p->reg_lambda) * (w * w));
 }
+/* Monotone constraints (TreeEvaluator, split_evaluator.h:25-205): per-feature sign, per-node weight bounds. */
+typedef struct {
+  int has;            /* has_constraint_: switches EVERY gain to the weight-based formula */
+  int constraint;     /* monotone[fidx] of the feature under evaluation */
+  float lower, upper; /* bounds of the node being split */
+} orc_mono;
+static const orc_mono kNoMono = {0, 0, -FLT_MAX, FLT_MAX};
+
+/* SplitEvaluator::CalcWeight (split_evaluator.h:94-112): float weight clamped into the node's bounds */
+static float calc_weight_bounded(const orc_param* p, const orc_mono* m, double g, double h) {
+  float w = (float)calc_weight_d(p, g, h);
+  if (!m->has) return w;
+  if (w < m->lower) return m->lower;
+  if (w > m->upper) return m->upper;
+  return w;
+}
+static float split_gain_m(const orc_param* p, const double scale[4], orc_gpair64 l, orc_gpair64 r, const orc_mono* m) {
+  double lg = (double)l.g * scale[2], lh = (double)l.h * scale[3];
+  double rg = (double)r.g * scale[2], rh = (double)r.h * scale[3];
+  if (!m->has) { /* CalcSplitGain (split_evaluator.h:73-92): gain(left) + gain(right) in fp32 */
+    return gain_given_stats(p, lg, lh) + gain_given_stats(p, rg, rh);
+  }
+  /* with constraints: CalcGainGivenWeight<ParamT,float>(p, g, h, w) = -(2 g w + (h + lambda) w^2), param.h:227-230 */
+  float wl = calc_weight_bounded(p, m, lg, lh), wr = calc_weight_bounded(p, m, rg, rh);
+  float gl = lh <= 0 ? 0.0f : -(2.0f * (float)lg * wl + ((float)lh + p->reg_lambda) * (wl * wl));
+  float gr = rh <= 0 ? 0.0f : -(2.0f * (float)rg * wr + ((float)rh + p->reg_lambda) * (wr * wr));
+  float gain = gl + gr;
+  if (m->constraint == 0) return gain;
+  if (m->constraint > 0) return wl <= wr ? gain : -INFINITY;
+  return wl >= wr ? gain : -INFINITY;
+}
 static float split_gain(const orc_param* p, const double scale[4], orc_gpair64 l, orc_gpair64 r) {
-  /* CalcSplitGain (split_evaluator.h:73-92): gain(left) + gain(right) in fp32 */
-  float gl = gain_given_stats(p, (double)l.g * scale[2], (double)l.h * scale[3]);
-  float gr = gain_given_stats(p, (double)r.g * scale[2], (double)r.h * scale[3]);
-  return gl + gr;
+  return split_gain_m(p, scale, l, r, &kNoMono);
 }
 static orc_gpair64 gp_add(orc_gpair64 a, orc_gpair64 b) { orc_gpair64 c = {a.g + b.g, a.h + b.h}; return c; }
 static orc_gpair64 gp_sub(orc_gpair64 a, orc_gpair64 b) { orc_gpair64 c = {a.g - b.g, a.h - b.h}; return c; }
@@ -288,16 +316,34 @@ static void cand_init(orc_candidate* c) {
  * feature_set: list of feature ids to evaluate in order (NULL = all 0..F-1).
  * `gain_out` (optional, size total_bins*2): gain of every (bin, missing-left?0:1) for tie checks.
  * ---------------------------------------------------------------------------------------- */
+ORC_API void orc_eval_node_mono(const orc_gpair64* hist, orc_gpair64 parent_sum, const uint32_t* cut_ptrs,
+                                const float* cut_values, uint32_t n_features, const int32_t* feature_set,
+                                int32_t n_feature_set, const orc_param* p, const double scale[4],
+                                orc_candidate* out, float* gain_out, const int32_t* monotone, float lower,
+                                float upper);
+
 ORC_API void orc_eval_node(const orc_gpair64* hist, orc_gpair64 parent_sum, const uint32_t* cut_ptrs,
                            const float* cut_values, uint32_t n_features, const int32_t* feature_set,
                            int32_t n_feature_set, const orc_param* p, const double scale[4],
                            orc_candidate* out, float* gain_out) {
+  orc_eval_node_mono(hist, parent_sum, cut_ptrs, cut_values, n_features, feature_set, n_feature_set, p, scale, out,
+                     gain_out, NULL, -FLT_MAX, FLT_MAX);
+}
+
+/* monotone (NULL = no constraints): sign per feature; lower/upper: weight bounds of THIS node */
+ORC_API void orc_eval_node_mono(const orc_gpair64* hist, orc_gpair64 parent_sum, const uint32_t* cut_ptrs,
+                                const float* cut_values, uint32_t n_features, const int32_t* feature_set,
+                                int32_t n_feature_set, const orc_param* p, const double scale[4],
+                                orc_candidate* out, float* gain_out, const int32_t* monotone, float lower,
+                                float upper) {
+  orc_mono mono = {monotone != NULL, 0, lower, upper};
   orc_candidate best;
   cand_init(&best);
   int32_t best_pos = -1;
   int32_t nf = feature_set ? n_feature_set : (int32_t)n_features;
   for (int32_t fi = 0; fi < nf; ++fi) {
     int32_t f = feature_set ? feature_set[fi] : fi;
+    mono.constraint = monotone ? monotone[f] : 0;
     uint32_t beg = cut_ptrs[f], end = cut_ptrs[f + 1];
     orc_candidate fbest;
     cand_init(&fbest);
@@ -321,8 +367,8 @@ ORC_API void orc_eval_node(const orc_gpair64* hist, orc_gpair64 parent_sum, cons
         if (active) {
           /* LossChangeMissing (evaluate_splits.cu:17-32) */
           orc_gpair64 left = gp_add(scan, missing);
-          float g_ml = split_gain(p, scale, left, gp_sub(parent_sum, left));
-          float g_mr = split_gain(p, scale, scan, gp_sub(parent_sum, scan));
+          float g_ml = split_gain_m(p, scale, left, gp_sub(parent_sum, left), &mono);
+          float g_mr = split_gain_m(p, scale, scan, gp_sub(parent_sum, scan), &mono);
           ml = g_ml > g_mr;
           gain = ml ? g_ml : g_mr;
           if (gain_out) {
@@ -380,9 +426,10 @@ ORC_API void orc_eval_node(const orc_gpair64* hist, orc_gpair64 parent_sum, cons
   float parent_gain = (float)calc_gain_d(p, pg, ph);
   best.loss_chg -= parent_gain;
   orc_gpair64 tot = gp_add(best.left_sum, best.right_sum);
-  best.base_weight = (float)calc_weight_d(p, (double)tot.g * scale[2], (double)tot.h * scale[3]);
-  best.left_weight = (float)calc_weight_d(p, (double)best.left_sum.g * scale[2], (double)best.left_sum.h * scale[3]);
-  best.right_weight = (float)calc_weight_d(p, (double)best.right_sum.g * scale[2], (double)best.right_sum.h * scale[3]);
+  /* evaluator.CalcWeight(input.nidx, ...): clamped into the bounds of the node being split (:457-463) */
+  best.base_weight = calc_weight_bounded(p, &mono, (double)tot.g * scale[2], (double)tot.h * scale[3]);
+  best.left_weight = calc_weight_bounded(p, &mono, (double)best.left_sum.g * scale[2], (double)best.left_sum.h * scale[3]);
+  best.right_weight = calc_weight_bounded(p, &mono, (double)best.right_sum.g * scale[2], (double)best.right_sum.h * scale[3]);
   *out = best;
 }
 
@@ -483,7 +530,7 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
                                    orc_node* nodes, int32_t max_nodes, int32_t* position,
                                    orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4],
                                    const int32_t* feature_set, int32_t n_feature_set, float subsample,
-                                   uint32_t sample_seed);
+                                   uint32_t sample_seed, const int32_t* monotone);
 
 ORC_API int32_t orc_update_tree(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
                                 uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
@@ -492,7 +539,7 @@ ORC_API int32_t orc_update_tree(const int32_t* gbins, uint64_t n_rows, uint32_t 
                                 orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4]) {
   return orc_update_tree_ex(gbins, n_rows, stride, is_dense_layout, n_features, cut_ptrs, cut_values, gpair, p,
                             scale_override, nodes, max_nodes, position, hist_dump, cand_dump, scale_out, NULL, 0, 1.0f,
-                            0u);
+                            0u, NULL);
 }
 
 /* feature_set (sorted ascending, NULL = all): the tree's colsample_bytree draw, evaluated in this order
@@ -504,7 +551,11 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
                                    orc_node* nodes, int32_t max_nodes, int32_t* position,
                                    orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4],
                                    const int32_t* feature_set, int32_t n_feature_set, float subsample,
-                                   uint32_t sample_seed) {
+                                   uint32_t sample_seed, const int32_t* monotone) {
+  /* monotone (NULL or n_features signs): TreeEvaluator bounds per node, -/+FLT_MAX at the root */
+  float* lower = (float*)malloc(sizeof(float) * (size_t)max_nodes);
+  float* upper = (float*)malloc(sizeof(float) * (size_t)max_nodes);
+  for (int32_t i = 0; i < max_nodes; ++i) { lower[i] = -FLT_MAX; upper[i] = FLT_MAX; }
   uint32_t total_bins = cut_ptrs[n_features];
   double scale[4];
   if (scale_override) memcpy(scale, scale_override, sizeof(scale));
@@ -550,7 +601,7 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
   }
   entry_t root_e;
   root_e.nidx = 0; root_e.depth = 0; root_e.open = 1;
-  orc_eval_node(hist[0], root, cut_ptrs, cut_values, n_features, feature_set, n_feature_set, p, scale, &root_e.c, NULL);
+  orc_eval_node_mono(hist[0], root, cut_ptrs, cut_values, n_features, feature_set, n_feature_set, p, scale, &root_e.c, NULL, monotone, lower[0], upper[0]);
   if (cand_dump) cand_dump[0] = root_e.c;
   /* driver.Push(vector) filters loss_chg > kRtEps (driver.h:42-50) */
   int n_open = 0;
@@ -606,6 +657,14 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
       rn.sum_hess = (float)((double)c->right_sum.h * scale[3]);
       nodes[l] = ln; nodes[r] = rn;
       node_sum[l] = c->left_sum; node_sum[r] = c->right_sum;
+      if (monotone) { /* TreeEvaluator::AddSplit (split_evaluator.h:163-203), weights before the learning rate */
+        lower[l] = lower[r] = lower[nidx];
+        upper[l] = upper[r] = upper[nidx];
+        int32_t cst = monotone[c->findex];
+        float mid = (c->left_weight + c->right_weight) / 2;
+        if (cst < 0) { lower[l] = mid; upper[r] = mid; }
+        else if (cst > 0) { upper[l] = mid; lower[r] = mid; }
+      }
     }
     if (n_open == 0 && n_nodes + 2 > max_nodes) break;
     /* ---- PartitionAndBuildHist + EvaluateSplits for the valid candidates ---- */
@@ -633,7 +692,7 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
       for (int s = 0; s < 2; ++s) {
         entry_t e;
         e.nidx = ch[s]; e.depth = depth + 1; e.open = 1;
-        orc_eval_node(hist[ch[s]], node_sum[ch[s]], cut_ptrs, cut_values, n_features, feature_set, n_feature_set, p, scale, &e.c, NULL);
+        orc_eval_node_mono(hist[ch[s]], node_sum[ch[s]], cut_ptrs, cut_values, n_features, feature_set, n_feature_set, p, scale, &e.c, NULL, monotone, lower[ch[s]], upper[ch[s]]);
         if (cand_dump) cand_dump[ch[s]] = e.c;
         if (e.c.loss_chg > 1e-6f) { queue[ch[s]] = e; n_open++; }
       }
@@ -658,6 +717,7 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
   }
   for (int32_t i = 0; i < max_nodes; ++i) free(hist[i]);
   free(hist); free(seg_beg); free(seg_cnt); free(node_sum); free(ridx); free(tmp); free(queue); free(gq);
+  free(lower); free(upper);
   return n_nodes;
 }
 

@@ -491,6 +491,48 @@ def test_tree_sampling_matches_oracle(xb, subsample, seed, n_fs):
     _compare_tree(xb, up, t_plain, o_plain, cp, cv, hists=False)
 
 
+@pytest.mark.parametrize("mono,extra", [([1, -1, 0, 1, 0, -1], {}), ([0, 0, 0], {}), ([1] * 8, dict(reg_alpha=0.2, max_delta_step=0.5)),
+                                        ([-1, 1], dict(grow_policy="lossguide", max_leaves=20, max_depth=0))])
+def test_monotone_constraints_match_oracle(xb, mono, extra):
+    """TreeEvaluator: weight-based gains with weights clamped into the node's bounds, sign test per feature, bounds
+    handed to the children.  A list of zeros still switches the gain formula (has_constraint_), as in the reference."""
+    import torch
+    n, f = 20000, 8
+    x, y = make_regression(n, f, seed=41)
+    cp, cv = make_cuts(x, 32)
+    page = _page(xb, x, cp, cv)
+    gb = orc.bin_dense(x, cp, cv)
+    params = dict(max_depth=5, eta=0.5)
+    params.update(extra)
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    up.set_monotone_constraints(mono)
+    pred = np.zeros(n, dtype=np.float32)
+    for it in range(2):
+        gp = squared_error_gpair(pred, y)
+        tree = up.update(torch.from_numpy(gp).cuda())
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), monotone=mono, want_hist=True)
+        _compare_tree(xb, up, tree, o, cp, cv, hists=True)
+        pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+        # the property itself: along a +1 (-1) feature every left leaf is <= (>=) every right leaf
+        nodes = tree.nodes
+
+        def leaves(i):
+            nd = nodes[i]
+            return [nd["leaf_value"]] if nd["is_leaf"] else leaves(nd["left"]) + leaves(nd["right"])
+        for nd in nodes:
+            if not nd["is_leaf"] and nd["findex"] < len(mono) and mono[nd["findex"]] != 0:
+                lo, hi = leaves(nd["left"]), leaves(nd["right"])
+                if mono[nd["findex"]] > 0:
+                    assert max(lo) <= min(hi)
+                else:
+                    assert min(lo) >= max(hi)
+    up.set_monotone_constraints(None)
+    t_plain = up.update(torch.from_numpy(squared_error_gpair(np.zeros(n, np.float32), y)).cuda())
+    o_plain = orc.update_tree(gb, cp, cv, squared_error_gpair(np.zeros(n, np.float32), y), orc.Param.make(**params))
+    _compare_tree(xb, up, t_plain, o_plain, cp, cv, hists=False)
+
+
 def test_host_gradient_entry_matches_device_entry(xb):
     import torch
     n, f = 5000, 6

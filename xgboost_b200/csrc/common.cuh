@@ -208,6 +208,14 @@ struct QuantDev {
   unsigned int pad;
 };
 
+// Monotone constraints (TreeEvaluator, src/tree/split_evaluator.h:25-205): sign per feature (device, n_features
+// entries), weight bounds per node (device, max_nodes entries).  constraints == nullptr: no constraints.
+struct MonoView {
+  const int32_t* constraints;
+  float* lower;
+  float* upper;
+};
+
 struct ParamDev {
   int32_t max_depth, max_leaves, grow_policy;
   float learning_rate, reg_lambda, reg_alpha, min_child_weight, max_delta_step, min_split_loss;
@@ -301,7 +309,7 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = n
                     const int32_t* eval_nodes, const TreeState* ts /* n_eval */, int32_t max_eval,
                     const NodeDev* nodes, const int32_t* feature_set, int32_t n_feature_set,
                     const ParamDev& p, const QuantDev* q, FeatCand* scratch, b200hist_candidate* cand,
-                    NodeDev* nodes_mut, int num_sms, cudaStream_t s);
+                    NodeDev* nodes_mut, int num_sms, cudaStream_t s, MonoView mono = MonoView{nullptr, nullptr, nullptr});
 
 // partition.cu
 void LaunchPartitionCount(const EllView& ell, const uint32_t* ridx0, const uint32_t* ridx1, const PartEntry* part,

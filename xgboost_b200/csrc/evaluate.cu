@@ -66,6 +66,27 @@ __device__ __forceinline__ float SplitGain(const ParamDev& p, double tfg, double
   return gl + gr;
 }
 
+// Monotone constraints (TreeEvaluator, split_evaluator.h:25-205): sign per feature, weight bounds per node.
+// When any constraint is set EVERY gain becomes the weight-based -(2 g w + (h + lambda) w^2) with the child
+// weights clamped into the bounds of the node being split, and a split whose weights violate the sign is -inf.
+__device__ __forceinline__ float BoundedWeight(const ParamDev& p, double g, double h, float lower, float upper) {
+  float w = (float)CalcWeightD(p, g, h);
+  if (w < lower) return lower;
+  if (w > upper) return upper;
+  return w;
+}
+__device__ __forceinline__ float SplitGainMono(const ParamDev& p, double tfg, double tfh, long long lg, long long lh,
+                                               long long rg, long long rh, int constraint, float lower, float upper) {
+  const double dlg = (double)lg * tfg, dlh = (double)lh * tfh, drg = (double)rg * tfg, drh = (double)rh * tfh;
+  const float wl = BoundedWeight(p, dlg, dlh, lower, upper), wr = BoundedWeight(p, drg, drh, lower, upper);
+  const float gl = dlh <= 0 ? 0.0f : -(2.0f * (float)dlg * wl + ((float)dlh + p.reg_lambda) * (wl * wl));
+  const float gr = drh <= 0 ? 0.0f : -(2.0f * (float)drg * wr + ((float)drh + p.reg_lambda) * (wr * wr));
+  const float gain = gl + gr;
+  if (constraint == 0) return gain;
+  if (constraint > 0) return wl <= wr ? gain : -INFINITY;
+  return wl >= wr ? gain : -INFINITY;
+}
+
 constexpr int kEvalWarps = 8;
 
 // One warp per (node slot, feature position).
@@ -73,12 +94,13 @@ __global__ void __launch_bounds__(kEvalWarps * 32)
 FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t* __restrict__ eval_nodes,
                   const TreeState* __restrict__ ts, const NodeDev* __restrict__ nodes,
                   const int32_t* __restrict__ feature_set, int32_t n_fs, ParamDev p,
-                  const QuantDev* __restrict__ q, FeatCand* __restrict__ scratch) {
+                  const QuantDev* __restrict__ q, FeatCand* __restrict__ scratch, MonoView mono) {
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * kEvalWarps + (threadIdx.x >> 5);
   const int n_warps = gridDim.x * kEvalWarps;
   const int n_eval = ts->n_eval;
   const long long total = (long long)n_eval * n_fs;
+  const bool has_mono = mono.constraints != nullptr;
   const double tfg = q->to_float_g, tfh = q->to_float_h;
   for (long long item = warp_global; item < total; item += n_warps) {
     const int slot = (int)(item / n_fs);
@@ -88,6 +110,8 @@ FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t
     const longlong2* h = hist + (size_t)nodes[nidx].hist_slot * ell.total_bins;
     const long long pg = nodes[nidx].sum_g, ph = nodes[nidx].sum_h;
     const uint32_t beg = ell.cut_ptrs[f], end = ell.cut_ptrs[f + 1];
+    const int constraint = has_mono ? mono.constraints[f] : 0;
+    const float w_lo = has_mono ? mono.lower[nidx] : 0.0f, w_hi = has_mono ? mono.upper[nidx] : 0.0f;
 
     // ReduceFeature: missing = parent - sum(bins)
     long long sg = 0, sh = 0;
@@ -126,8 +150,14 @@ FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t
       bool missing_left = true;
       if (active) {  // LossChangeMissing
         const long long lg = scan_g + mg, lh = scan_h + mh;
-        float g_ml = SplitGain(p, tfg, tfh, lg, lh, pg - lg, ph - lh);
-        float g_mr = SplitGain(p, tfg, tfh, scan_g, scan_h, pg - scan_g, ph - scan_h);
+        float g_ml, g_mr;
+        if (has_mono) {
+          g_ml = SplitGainMono(p, tfg, tfh, lg, lh, pg - lg, ph - lh, constraint, w_lo, w_hi);
+          g_mr = SplitGainMono(p, tfg, tfh, scan_g, scan_h, pg - scan_g, ph - scan_h, constraint, w_lo, w_hi);
+        } else {
+          g_ml = SplitGain(p, tfg, tfh, lg, lh, pg - lg, ph - lh);
+          g_mr = SplitGain(p, tfg, tfh, scan_g, scan_h, pg - scan_g, ph - scan_h);
+        }
         missing_left = g_ml > g_mr;
         gain = missing_left ? g_ml : g_mr;
       }
@@ -174,7 +204,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32)
 NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const TreeState* __restrict__ ts,
                  NodeDev* __restrict__ nodes, const int32_t* __restrict__ feature_set, int32_t n_fs, ParamDev p,
                  const QuantDev* __restrict__ q, const FeatCand* __restrict__ scratch,
-                 b200hist_candidate* __restrict__ cand) {
+                 b200hist_candidate* __restrict__ cand, MonoView mono) {
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * kEvalWarps + (threadIdx.x >> 5);
   const int n_warps = gridDim.x * kEvalWarps;
@@ -230,9 +260,12 @@ NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const Tree
       float parent_gain = (float)CalcGainD(p, (double)pg * tfg, (double)ph * tfh);
       c.loss_chg -= parent_gain;
       long long tg = c.left_sum.grad + c.right_sum.grad, th = c.left_sum.hess + c.right_sum.hess;
-      c.base_weight = (float)CalcWeightD(p, (double)tg * tfg, (double)th * tfh);
-      c.left_weight = (float)CalcWeightD(p, (double)c.left_sum.grad * tfg, (double)c.left_sum.hess * tfh);
-      c.right_weight = (float)CalcWeightD(p, (double)c.right_sum.grad * tfg, (double)c.right_sum.hess * tfh);
+      // evaluator.CalcWeight(input.nidx, ...): clamped into the bounds of the node being split when constrained
+      const float w_lo = mono.constraints ? mono.lower[nidx] : -3.402823466e+38f;
+      const float w_hi = mono.constraints ? mono.upper[nidx] : 3.402823466e+38f;
+      c.base_weight = BoundedWeight(p, (double)tg * tfg, (double)th * tfh, w_lo, w_hi);
+      c.left_weight = BoundedWeight(p, (double)c.left_sum.grad * tfg, (double)c.left_sum.hess * tfh, w_lo, w_hi);
+      c.right_weight = BoundedWeight(p, (double)c.right_sum.grad * tfg, (double)c.right_sum.hess * tfh, w_lo, w_hi);
       cand[nidx] = c;
       // Driver::Push filter (driver.h:42-50): kRtEps = 1e-6f
       nodes[nidx].cand_open = c.loss_chg > 1e-6f ? 1 : 0;
@@ -243,17 +276,17 @@ NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const Tree
 void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist, const int32_t* eval_nodes, const TreeState* ts,
                     int32_t max_eval, const NodeDev* nodes, const int32_t* feature_set, int32_t n_feature_set,
                     const ParamDev& p, const QuantDev* q, FeatCand* scratch, b200hist_candidate* cand,
-                    NodeDev* nodes_mut, int num_sms, cudaStream_t s) {
+                    NodeDev* nodes_mut, int num_sms, cudaStream_t s, MonoView mono) {
   const int32_t n_fs = feature_set ? n_feature_set : (int32_t)ell.n_features;
   long long max_items = (long long)max_eval * n_fs;
   if (max_items == 0) return;
   int blocks = (int)std::min<long long>((max_items + kEvalWarps - 1) / kEvalWarps, (long long)num_sms * 8);
   FeatureScanKernel<<<blocks, kEvalWarps * 32, 0, s>>>(ell, reinterpret_cast<const longlong2*>(hist), eval_nodes, ts,
-                                                       nodes, feature_set, n_fs, p, q, scratch);
+                                                       nodes, feature_set, n_fs, p, q, scratch, mono);
   B200_LAUNCHED();
   int blocks2 = (int)std::min<long long>(((long long)max_eval + kEvalWarps - 1) / kEvalWarps, (long long)num_sms * 4);
   NodeReduceKernel<<<blocks2, kEvalWarps * 32, 0, s>>>(ell, eval_nodes, ts, nodes_mut, feature_set, n_fs, p, q, scratch,
-                                                       cand);
+                                                       cand, mono);
   B200_LAUNCHED();
 }
 

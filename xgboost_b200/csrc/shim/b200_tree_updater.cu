@@ -140,13 +140,19 @@ class B200HistMaker : public TreeUpdater {
     p.min_child_weight = param->min_child_weight;
     p.max_delta_step = param->max_delta_step;
     p.min_split_loss = param->min_split_loss;
-    CHECK(param->monotone_constraints.empty() && param->interaction_constraints.empty())
-        << "[b200hist] constraints are not supported yet";
+    CHECK(param->interaction_constraints.empty()) << "[b200hist] interaction constraints are not supported yet";
     CHECK(param->subsample == 1.0f || param->sampling_method == TrainParam::kUniform)
         << "[b200hist] gradient_based row sampling is not supported yet";
     CHECK(param->colsample_bylevel == 1.0f && param->colsample_bynode == 1.0f)
         << "[b200hist] colsample_bylevel / colsample_bynode are not supported yet (colsample_bytree is)";
     B200_SHIM_CHECK(b200hist_updater_create(ellpack_, &p, &updater_));
+    if (!param->monotone_constraints.empty()) {  // TreeEvaluator ctor (split_evaluator.h:37-57)
+      std::vector<std::int32_t> mono(param->monotone_constraints.cbegin(), param->monotone_constraints.cend());
+      CHECK_LE(mono.size(), p_fmat->Info().num_col_)
+          << "The size of monotone constraint should be less or equal to the number of features.";
+      B200_SHIM_CHECK(b200hist_updater_set_monotone_constraints(updater_, mono.data(),
+                                                                static_cast<std::uint32_t>(mono.size())));
+    }
     std::int32_t max_nodes{0};
     B200_SHIM_CHECK(b200hist_updater_max_nodes(updater_, &max_nodes));
     nodes_.resize(static_cast<std::size_t>(max_nodes));

@@ -88,7 +88,8 @@ __device__ __forceinline__ void InitLeaf(NodeDev* n, int parent, int depth, floa
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCtlThreads) InitRootKernel(ParamDev p, uint32_t n_rows, const QuantDev* q,
                                                                TreeState* ts, NodeDev* nodes, BuildEntry* build,
-                                                               uint32_t* build_tile_seg, int32_t* eval_nodes) {
+                                                               uint32_t* build_tile_seg, int32_t* eval_nodes,
+                                                               MonoView mono) {
   const uint32_t tiles = (n_rows + kHistTile - 1) / kHistTile;
   for (uint32_t t = threadIdx.x; t < tiles; t += kCtlThreads) build_tile_seg[t] = 0;
   if (threadIdx.x == 0) {
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(kCtlThreads) InitRootKernel(ParamDev p, uint32
     r->hist_slot = 0;
     build[0] = BuildEntry{0, 0, 0u, n_rows, 0u, 0u};
     eval_nodes[0] = 0;
+    if (mono.constraints) { mono.lower[0] = -3.402823466e+38f; mono.upper[0] = 3.402823466e+38f; }
     ts->n_nodes = 1; ts->num_leaves = 1; ts->level_begin = 0; ts->level_end = 1;
     ts->n_part = 0; ts->n_build = 1; ts->n_sub = 0; ts->n_eval = 1;
     ts->part_tiles = 0; ts->build_tiles = tiles; ts->final_tiles = 0; ts->n_final = 0;
@@ -120,7 +122,7 @@ __device__ __forceinline__ bool EntryValidNoLeafLimit(const ParamDev& p, const b
 }
 
 __device__ void ApplyOne(const EllView& ell, const ParamDev& p, const QuantDev* q, NodeDev* nodes,
-                         const b200hist_candidate& c, int nidx, int left, PartEntry* part_slot) {
+                         const b200hist_candidate& c, int nidx, int left, PartEntry* part_slot, const MonoView& mono) {
   NodeDev* n = &nodes[nidx];
   const int right = left + 1;
   const double tfh = q->to_float_h;
@@ -132,6 +134,14 @@ __device__ void ApplyOne(const EllView& ell, const ParamDev& p, const QuantDev* 
   const float lw = c.left_weight * p.learning_rate, rw = c.right_weight * p.learning_rate;
   InitLeaf(&nodes[left], nidx, n->depth + 1, lw, (float)((double)c.left_sum.hess * tfh), c.left_sum.grad, c.left_sum.hess);
   InitLeaf(&nodes[right], nidx, n->depth + 1, rw, (float)((double)c.right_sum.hess * tfh), c.right_sum.grad, c.right_sum.hess);
+  if (mono.constraints) {  // TreeEvaluator::AddSplit (split_evaluator.h:163-203): weights before the learning rate
+    mono.lower[left] = mono.lower[right] = mono.lower[nidx];
+    mono.upper[left] = mono.upper[right] = mono.upper[nidx];
+    const int32_t cst = mono.constraints[c.findex];
+    const float mid = (c.left_weight + c.right_weight) / 2;
+    if (cst < 0) { mono.lower[left] = mid; mono.upper[right] = mid; }
+    else if (cst > 0) { mono.upper[left] = mid; mono.lower[right] = mid; }
+  }
   // go left iff cut_values[bin] <= fvalue  <=>  feature-local bin < (number of cuts <= fvalue)
   const uint32_t beg = ell.cut_ptrs[c.findex], end = ell.cut_ptrs[c.findex + 1];
   uint32_t lo = beg, hi = end;
@@ -150,7 +160,7 @@ __device__ void ApplyOne(const EllView& ell, const ParamDev& p, const QuantDev* 
 __global__ void __launch_bounds__(kCtlThreads) ApplyKernel(EllView ell, ParamDev p, const QuantDev* q, TreeState* ts,
                                                             NodeDev* nodes, const b200hist_candidate* cand,
                                                             PartEntry* part, uint32_t* part_tile_seg,
-                                                            int32_t max_nodes) {
+                                                            int32_t max_nodes, MonoView mono) {
   __shared__ uint32_t s_warp[33];
   __shared__ uint32_t s_tile_begin[kMaxLevelNodes + 1];
   __shared__ int s_n_expand, s_child_valid;
@@ -198,7 +208,7 @@ __global__ void __launch_bounds__(kCtlThreads) ApplyKernel(EllView ell, ParamDev
         bool ok = EntryValidNoLeafLimit(p, c, nodes[bi].depth) && !(p.max_leaves > 0 && leaves0 == p.max_leaves) &&
                   n_nodes0 + 2 <= max_nodes;
         if (ok) {
-          ApplyOne(ell, p, q, nodes, c, bi, n_nodes0, &part[0]);
+          ApplyOne(ell, p, q, nodes, c, bi, n_nodes0, &part[0], mono);
           ne = 1;
         } else {
           ts->stopped = 1;
@@ -230,7 +240,7 @@ __global__ void __launch_bounds__(kCtlThreads) ApplyKernel(EllView ell, ParamDev
       uint32_t rank = running + BlockExclusiveScan(valid ? 1u : 0u, s_warp, &total);
       bool accepted = valid && (int)rank < allow && n_nodes0 + 2 * ((int)rank + 1) <= max_nodes &&
                       (int)rank < kMaxLevelNodes;
-      if (accepted) ApplyOne(ell, p, q, nodes, c, i, n_nodes0 + 2 * (int)rank, &part[rank]);
+      if (accepted) ApplyOne(ell, p, q, nodes, c, i, n_nodes0 + 2 * (int)rank, &part[rank], mono);
       running += total;
     }
     n_expand = min((int)running, allow);
@@ -599,6 +609,9 @@ struct b200hist_updater_s {
   // per-tree sampling state (set through b200hist_updater_set_tree_sampling, persists until changed)
   float subsample{1.0f};
   uint32_t sample_seed{0};
+  int32_t* d_monotone{nullptr};     // monotone constraint sign per feature (nullptr = none)
+  float* d_lower{nullptr};          // TreeEvaluator weight bounds per node (allocated with d_monotone)
+  float* d_upper{nullptr};
   int32_t* d_feature_set{nullptr};  // sorted feature ids of the tree's colsample_bytree draw (nullptr = all)
   int32_t n_feature_set{0};
   bool row_split{false};                   // ranks own row slices (full-width partial histograms, summed) instead of feature blocks
@@ -688,6 +701,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   const uint64_t n = ell->n_rows;
   PhaseTimer timer{u, s};
   int32_t* position = out_position ? out_position : u->d_position;
+  const MonoView mono{u->d_monotone, u->d_lower, u->d_upper};
 
   // Reset (updater_gpu_hist.cu:172-211): quantiser, quantised gpairs, row indices, histograms
   auto t0 = timer.Begin();
@@ -709,7 +723,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   // InitRoot
   auto t1 = timer.Begin();
   InitRootKernel<<<1, kCtlThreads, 0, s>>>(u->pdev, (uint32_t)n, u->d_quant, u->d_ts, u->d_nodes, u->d_build,
-                                           u->d_build_tile_seg, u->d_eval_nodes);
+                                           u->d_build_tile_seg, u->d_eval_nodes, mono);
   B200_LAUNCHED();
   timer.End(kApply, t1);
   auto t2 = timer.Begin();
@@ -740,7 +754,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   timer.End(kHist, t2);
   auto t3 = timer.Begin();
   LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, u->d_feature_set, u->n_feature_set, u->pdev, u->d_quant,
-                 u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s);
+                 u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono);
   timer.End(kEval, t3);
 
   const bool depthwise = u->param.grow_policy == 0;
@@ -749,7 +763,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     const long long cap = u->step_cap[step];
     auto ta = timer.Begin();
     ApplyKernel<<<1, kCtlThreads, 0, s>>>(view, u->pdev, u->d_quant, u->d_ts, u->d_nodes, u->d_cand, u->d_part,
-                                          u->d_part_tile_seg, u->max_nodes);
+                                          u->d_part_tile_seg, u->max_nodes, mono);
     B200_LAUNCHED();
     timer.End(kApply, ta);
     const bool children_possible = u->param.max_depth == 0 || !depthwise || step + 1 < u->param.max_depth;
@@ -774,7 +788,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     auto te = timer.Begin();
     LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, (int32_t)(2 * cap), u->d_nodes, u->d_feature_set,
                    u->n_feature_set, u->pdev,
-                   u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s);
+                   u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono);
     timer.End(kEval, te);
   }
 
@@ -946,6 +960,8 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
     cudaFree(u->d_peer_flags);
     cudaFree(u->d_exchange_counter);
     if (u->d_feature_set) cudaFree(u->d_feature_set);
+    for (void* p : {(void*)u->d_monotone, (void*)u->d_lower, (void*)u->d_upper})
+      if (p) cudaFree(p);
     cudaFreeHost(u->h_nodes);
     cudaFreeHost(u->h_ts);
     cudaFreeHost(u->h_quant);
@@ -1109,6 +1125,31 @@ int b200hist_updater_set_tree_sampling(b200hist_updater_t u, const int32_t* feat
   }
   u->subsample = subsample;
   u->sample_seed = subsample_seed;
+  B200_API_END();
+}
+
+int b200hist_updater_set_monotone_constraints(b200hist_updater_t u, const int32_t* constraints_host, uint32_t n) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  B200_CHECK(n <= u->ell->n_features, "more monotone constraints than features");
+  DeviceGuard guard(u->device);
+  for (void** p : {(void**)&u->d_monotone, (void**)&u->d_lower, (void**)&u->d_upper}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  bool any = false;
+  for (uint32_t i = 0; constraints_host != nullptr && i < n; ++i) any = any || constraints_host[i] != 0;
+  // TreeEvaluator sets has_constraint_ whenever the parameter is non-empty, even if every sign is 0
+  // (split_evaluator.h:45-57): that alone switches the gain formula, so "non-empty" is what is kept here
+  if (constraints_host != nullptr && n > 0) {
+    (void)any;
+    std::vector<int32_t> full(u->ell->n_features, 0);
+    std::copy(constraints_host, constraints_host + n, full.begin());
+    u->d_monotone = DevAlloc<int32_t>(full.size());
+    B200_CUDA(cudaMemcpy(u->d_monotone, full.data(), sizeof(int32_t) * full.size(), cudaMemcpyHostToDevice));
+    u->d_lower = DevAlloc<float>((size_t)u->max_nodes);
+    u->d_upper = DevAlloc<float>((size_t)u->max_nodes);
+  }
   B200_API_END();
 }
 

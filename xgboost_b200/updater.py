@@ -427,6 +427,14 @@ class GPUHistMaker:
             _l.check(_l.load().b200hist_updater_set_tree_sampling(self._h, None, 0, float(subsample),
                                                                 int(seed) & 0xFFFFFFFF))
 
+    def set_monotone_constraints(self, constraints: Optional[Sequence[int]]) -> None:
+        """TrainParam::monotone_constraints: sign per feature (+1 increasing, -1 decreasing, 0 free); None/[] = none."""
+        if constraints is None or len(constraints) == 0:
+            _l.check(_l.load().b200hist_updater_set_monotone_constraints(self._h, None, 0))
+        else:
+            c = np.ascontiguousarray(constraints, dtype=np.int32)
+            _l.check(_l.load().b200hist_updater_set_monotone_constraints(self._h, c.ctypes.data_as(POINTER(c_int32)), c.size))
+
     def num_feature_groups(self) -> int:
         n = c_uint32()
         _l.check(_l.load().b200hist_updater_num_feature_groups(self._h, byref(n)))
