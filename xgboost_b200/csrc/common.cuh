@@ -93,6 +93,10 @@ struct EllView {
   // holding GLOBAL bin indices in feature order, padded with the null symbol total_bins
   uint32_t is_sparse;
   uint32_t row_stride;
+  // sparse pages: 64-bit presence signature per row, bit (f mod 64) set for every feature f the row holds.  A row
+  // whose bit for the split feature is clear certainly lacks the feature, so the partitioner reads 8 bytes of it
+  // instead of its whole 4*row_stride-byte entry list (may be null)
+  const unsigned long long* row_sig;
 };
 
 }  // namespace b200
@@ -123,10 +127,11 @@ struct b200hist_ellpack_s {
   uint64_t col_stride{0};
   bool is_sparse{false};
   uint32_t row_stride{0};  // entries per row (sparse layout)
+  unsigned long long* d_row_sig{nullptr};  // presence signatures (sparse layout)
   b200::EllView View() const {
     return b200::EllView{d_bins, d_cut_ptrs, d_cut_values, n_rows, n_features, total_bins,
                          row_bytes, bin_bytes, null_symbol, d_bins_t, col_stride,
-                         is_sparse ? 1u : 0u, row_stride};
+                         is_sparse ? 1u : 0u, row_stride, d_row_sig};
   }
 };
 
@@ -230,7 +235,9 @@ inline ParamDev ToParamDev(const b200hist_train_param& p) {
 // Sparse page: global bin of feature [fb, fe) in row r, or 0xFFFFFFFF.  Entries are in feature order, so the
 // row (<= row_stride symbols, null-padded with values >= total_bins) is binary-searched
 // (EllpackAccessor::GetBinIndex / BinarySearchBin, src/data/ellpack_page.cuh:101-122).
-__device__ __forceinline__ uint32_t SparseRowBin(const EllView& ell, uint32_t r, uint32_t fb, uint32_t fe) {
+__device__ __forceinline__ uint32_t SparseRowBin(const EllView& ell, uint32_t r, uint32_t fb, uint32_t fe,
+                                                 uint32_t f) {
+  if (ell.row_sig != nullptr && ((__ldg(ell.row_sig + r) >> (f & 63u)) & 1ull) == 0ull) return 0xFFFFFFFFu;
   const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(ell.bins) + (size_t)r * ell.row_stride;
   uint32_t lo = 0, hi = ell.row_stride;
   while (lo < hi) {  // first entry with symbol >= fb

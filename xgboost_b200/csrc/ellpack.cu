@@ -206,6 +206,28 @@ __global__ void __launch_bounds__(256) BinCsrKernel(const int64_t* __restrict__ 
   }
 }
 
+// Presence signature of sparse rows [row_begin, row_begin + n): bit (f mod 64) for every feature the row holds.
+__global__ void __launch_bounds__(256) RowSignatureKernel(const uint32_t* __restrict__ ell, uint64_t row_begin, uint64_t n,
+                                                           uint32_t row_stride, const uint32_t* __restrict__ cut_ptrs,
+                                                           uint32_t n_features, uint32_t total_bins,
+                                                           unsigned long long* __restrict__ sig) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t* __restrict__ row = ell + (row_begin + i) * row_stride;
+    unsigned long long m = 0ull;
+    for (uint32_t k = 0; k < row_stride; ++k) {
+      const uint32_t sym = row[k];
+      if (sym >= total_bins) continue;  // null padding
+      uint32_t lo = 0, hi = n_features;  // feature whose [cut_ptrs[f], cut_ptrs[f+1]) holds sym
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (cut_ptrs[mid] <= sym) lo = mid; else hi = mid;
+      }
+      m |= 1ull << (lo & 63u);
+    }
+    sig[row_begin + i] = m;
+  }
+}
+
 // Reference sparse page (global-bin symbols, null = total_bins) -> uint32 ELL.
 __global__ void __launch_bounds__(256) ImportReferenceSparseKernel(const uint8_t* __restrict__ buf, uint64_t total,
                                                                     uint32_t symbol_bits, uint32_t ref_stride,
@@ -332,6 +354,11 @@ int b200hist_ellpack_create_sparse(int device, uint64_t n_rows, uint32_t n_featu
   e->d_bins = DevAlloc<uint8_t>(n_rows * (uint64_t)e->row_bytes + 16);
   // every slot starts as 0xFFFFFFFF; kernels treat any symbol >= total_bins as null
   B200_CUDA(cudaMemset(e->d_bins, 0xFF, n_rows * (uint64_t)e->row_bytes + 16));
+  static const bool no_sig = std::getenv("B200HIST_NO_ROWSIG") != nullptr;
+  if (!no_sig) {  // all-ones until the rows are written: "may hold any feature" is always safe
+    e->d_row_sig = DevAlloc<unsigned long long>(n_rows);
+    B200_CUDA(cudaMemset(e->d_row_sig, 0xFF, sizeof(unsigned long long) * n_rows));
+  }
   *out = e;
   B200_API_END();
 }
@@ -352,6 +379,12 @@ int b200hist_ellpack_push_csr(b200hist_ellpack_t e, uint64_t row_begin, const in
                                       reinterpret_cast<uint32_t*>(e->d_bins), row_begin, e->row_stride, e->null_symbol,
                                       e->n_features, d_err);
   B200_LAUNCHED();
+  if (e->d_row_sig) {
+    int sb = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
+    RowSignatureKernel<<<sb, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(e->d_bins), row_begin, n, e->row_stride,
+                                          e->d_cut_ptrs, e->n_features, e->total_bins, e->d_row_sig);
+    B200_LAUNCHED();
+  }
   int h_err = 0;
   B200_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
@@ -369,6 +402,7 @@ int b200hist_ellpack_destroy(b200hist_ellpack_t e) {
     cudaFree(e->d_cut_values);
     cudaFree(e->d_bins);
     cudaFree(e->d_bins_t);
+    if (e->d_row_sig) cudaFree(e->d_row_sig);
     delete e;
   }
   B200_API_END();
@@ -424,6 +458,12 @@ int b200hist_ellpack_import_reference(b200hist_ellpack_t e, const uint8_t* gidx_
     ImportReferenceSparseKernel<<<nb, 256, 0, ss>>>(gidx_buffer_dev, tot, sbits, row_stride, e->row_stride,
                                                     reinterpret_cast<uint32_t*>(e->d_bins));
     B200_LAUNCHED();
+    if (e->d_row_sig) {
+      int sb = (int)std::min<uint64_t>((e->n_rows + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
+      RowSignatureKernel<<<sb, 256, 0, ss>>>(reinterpret_cast<const uint32_t*>(e->d_bins), 0, e->n_rows, e->row_stride,
+                                             e->d_cut_ptrs, e->n_features, e->total_bins, e->d_row_sig);
+      B200_LAUNCHED();
+    }
     return 0;
   }
   B200_CHECK(row_stride == e->n_features, "dense-layout reference pages need row_stride == n_features");

@@ -50,7 +50,7 @@ PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint
         bool left = false;
         if (j < n) {
           const uint32_t fb = ell.cut_ptrs[e.findex], fe = ell.cut_ptrs[e.findex + 1];
-          const uint32_t gb = SparseRowBin(ell, ridx[j], fb, fe);
+          const uint32_t gb = SparseRowBin(ell, ridx[j], fb, fe, (uint32_t)e.findex);
           left = (gb == 0xFFFFFFFFu) ? (e.default_left != 0) : ((int32_t)(gb - fb) < e.split_lbin);
         }
         const uint32_t m = __ballot_sync(0xffffffffu, left);

@@ -40,7 +40,7 @@ __device__ __forceinline__ uint32_t BlockExclusiveScan(uint32_t v, uint32_t* s_w
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    uint32_t w = s_warp[lane];
+    uint32_t w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0u;  // blocks smaller than 32 warps
     uint32_t winc = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(256) FinaliseKernel(EllView ell, const uint32_
         const NodeDev& nd = nodes[nidx];
         if (ell.is_sparse) {
           const uint32_t fb = ell.cut_ptrs[nd.findex], fe = ell.cut_ptrs[nd.findex + 1];
-          const uint32_t gb = SparseRowBin(ell, r, fb, fe);
+          const uint32_t gb = SparseRowBin(ell, r, fb, fe, (uint32_t)nd.findex);
           const bool go_left = (gb == 0xFFFFFFFFu) ? (nd.default_left != 0) : ((int32_t)(gb - fb) < nd.split_lbin);
           nidx = go_left ? nd.left : nd.right;
           continue;
@@ -471,7 +471,7 @@ __device__ __forceinline__ int WalkToLeaf(const EllView& ell, const NodeDev* __r
     const NodeDev& nd = nodes[nidx];
     if (ell.is_sparse) {
       const uint32_t fb = ell.cut_ptrs[nd.findex], fe = ell.cut_ptrs[nd.findex + 1];
-      const uint32_t gb = SparseRowBin(ell, r, fb, fe);
+      const uint32_t gb = SparseRowBin(ell, r, fb, fe, (uint32_t)nd.findex);
       const bool go_left = (gb == 0xFFFFFFFFu) ? (nd.default_left != 0) : ((int32_t)(gb - fb) < nd.split_lbin);
       nidx = go_left ? nd.left : nd.right;
       continue;
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(256) FinaliseWindowKernel(EllView ell, const u
                                                              int32_t* __restrict__ position,
                                                              const QuantDev* __restrict__ qd, uint32_t n_rows) {
   __shared__ int32_t s_pos[kFinWindow];
-  __shared__ uint32_t s_lo[256], s_hi[256];
+  __shared__ uint32_t s_lo[256], s_hi[256], s_off[257], s_warp[33];
   const uint32_t n_final = (uint32_t)ts->n_final;
   const bool any_h_zero = qd->h_zero_any != 0u;
   const uint32_t n_windows = (n_rows + kFinWindow - 1) / kFinWindow;
@@ -512,22 +512,26 @@ __global__ void __launch_bounds__(256) FinaliseWindowKernel(EllView ell, const u
       }
       __syncthreads();
       const uint32_t m = min(256u, n_final - base);
-      // a warp per segment slice, two slices in flight per warp to overlap the dependent loads
-      for (uint32_t k = warp; k < m; k += 16) {
-        const BuildEntry ea = fin[base + k];
-        const bool has_b = k + 8 < m;
-        const BuildEntry eb = fin[base + (has_b ? k + 8 : k)];
-        const uint32_t* __restrict__ ra = (ea.buf ? ridx1 : ridx0) + ea.begin;
-        const uint32_t* __restrict__ rb = (eb.buf ? ridx1 : ridx0) + eb.begin;
-        const uint32_t a_lo = s_lo[k], a_hi = s_hi[k];
-        const uint32_t b_lo = has_b ? s_lo[k + 8] : 0u, b_hi = has_b ? s_hi[k + 8] : 0u;
-        const uint32_t iters = max((a_hi - a_lo + 31u) / 32u, (b_hi - b_lo + 31u) / 32u);
-        for (uint32_t it = 0; it < iters; ++it) {
-          const uint32_t ja = a_lo + it * 32u + lane, jb = b_lo + it * 32u + lane;
-          const bool va = ja < a_hi, vb = jb < b_hi;
-          const uint32_t rowa = va ? __ldg(ra + ja) : 0u, rowb = vb ? __ldg(rb + jb) : 0u;
-          if (va) s_pos[rowa - r_begin] = WalkToLeaf<BinT>(ell, nodes, ea.nidx, rowa);
-          if (vb) s_pos[rowb - r_begin] = WalkToLeaf<BinT>(ell, nodes, eb.nidx, rowb);
+      // rows of all slices of this chunk, concatenated: entry e belongs to the slice whose offset range holds it.
+      // Work is dealt out by ROWS, 32 consecutive entries per warp step, so one huge leaf (an unbalanced tree keeps
+      // most rows in a few leaves) is shared by all warps instead of serialising on one.
+      uint32_t total_rows;
+      const uint32_t cnt = threadIdx.x < m ? s_hi[threadIdx.x] - s_lo[threadIdx.x] : 0u;
+      const uint32_t off = BlockExclusiveScan(cnt, s_warp, &total_rows);
+      s_off[threadIdx.x] = off;
+      if (threadIdx.x == 0) s_off[256] = total_rows;
+      __syncthreads();
+      for (uint32_t e0 = warp * 32u; e0 < total_rows; e0 += 8u * 32u) {
+        const uint32_t eidx = e0 + lane;
+        if (eidx < total_rows) {
+          uint32_t lo = 0, hi = m;  // last slice with s_off[k] <= eidx
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_off[mid] <= eidx) lo = mid; else hi = mid;
+          }
+          const BuildEntry en = fin[base + lo];
+          const uint32_t row = __ldg((en.buf ? ridx1 : ridx0) + en.begin + s_lo[lo] + (eidx - s_off[lo]));
+          s_pos[row - r_begin] = WalkToLeaf<BinT>(ell, nodes, en.nidx, row);
         }
       }
       __syncthreads();
