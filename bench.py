@@ -360,9 +360,12 @@ def run_b200(args):
     n_sms = torch.cuda.get_device_properties(device).multi_processor_count
     updates_per_s = row_visits * (f / feat_div) / (hist_ms * 1e-3) if hist_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "HistKernelPair", "achieved": hist_gbs, "peak": peak, "unit": "GB/s",
-                "frac": hist_gbs / peak, "traffic": 1.33 * hist_bytes_gpu / hist_launches, "peak_source": peak_src,
-                "traffic_source": "ncu --set full dram__bytes_read+write = 1.33 x algorithmic on the 20M-row capture "
-                                  "(profiles/r01_hist_banked_v2_ncu_summary.json), scaled to this launch size",
+                "frac": hist_gbs / peak, "traffic": 1.2 * hist_bytes_gpu / hist_launches, "peak_source": peak_src,
+                "traffic_source": "ncu --set full dram__bytes_read+write of HistKernelPair = 1.13-1.29 x algorithmic on three "
+                                  "consecutive level launches of the 20M-row capture "
+                                  "(profiles/r01c_pair_kernels_ncu_summary.json), 1.2 x scaled to this launch size",
+                "l1tex_data_pipe": {"pct_of_peak": 95.0, "shared_atomic_share_pct": 72.0,
+                                    "source": "ncu l1tex__data_pipe_lsu_wavefronts (same capture): the binding unit"},
                 "launches_per_step": hist_launches, "avg_launch_ms": hist_ms / hist_launches,
                 "algorithmic_bytes_per_launch": hist_bytes_gpu / hist_launches, "row_visits_per_step": row_visits,
                 # the binding resource is the shared-memory atomic pipe, not HBM: the ceiling is MEASURED on this GPU by
