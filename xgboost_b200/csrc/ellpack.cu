@@ -305,7 +305,9 @@ int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features, co
   e->bin_bytes = n_symbols <= 256 ? 1 : 2;
   e->null_symbol = e->has_missing ? (e->bin_bytes == 1 ? 0xFFu : 0xFFFFu) : 0xFFFFFFFFu;
   if (e->has_missing && e->null_symbol < mx) e->null_symbol = mx;  // unreachable; keeps the invariant explicit
-  e->row_bytes = (n_features * e->bin_bytes + 15u) & ~15u;
+  // uint8 pages: rows padded to whole 32-feature blocks (zero symbols), so the histogram kernel's unpredicated
+  // 32-feature loop also serves feature counts that are not multiples of 32 (the padding is dropped at flush time)
+  e->row_bytes = e->bin_bytes == 1 ? ((n_features + 31u) & ~31u) : ((n_features * e->bin_bytes + 15u) & ~15u);
   e->d_cut_ptrs = DevAlloc<uint32_t>(n_features + 1);
   e->d_cut_values = DevAlloc<float>(e->total_bins);
   B200_CUDA(cudaMemcpy(e->d_cut_ptrs, e->cut_ptrs.data(), sizeof(uint32_t) * (n_features + 1), cudaMemcpyHostToDevice));

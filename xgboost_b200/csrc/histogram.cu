@@ -588,9 +588,11 @@ __device__ __forceinline__ void BankedFastGroup(const EllView& ell, const longlo
       const uint32_t glo = a[0], ghi = a[32], hlo = a[64], hhi = a[96];
       if (glo | ghi | hlo | hhi) {
         const uint32_t f = g.f_begin + (rest / S) * 32 + ln;
-        longlong2* d = dst + ell.cut_ptrs[f] + (rest % S);
-        if (glo | ghi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->x), ((unsigned long long)ghi << 32) | glo);
-        if (hlo | hhi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->y), ((unsigned long long)hhi << 32) | hlo);
+        if (f < ell.n_features) {  // features past the end are row padding (symbol 0): dropped
+          longlong2* d = dst + ell.cut_ptrs[f] + (rest % S);
+          if (glo | ghi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->x), ((unsigned long long)ghi << 32) | glo);
+          if (hlo | hhi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->y), ((unsigned long long)hhi << 32) | hlo);
+        }
         a[0] = 0u; a[32] = 0u; a[64] = 0u; a[96] = 0u;
       }
     }
@@ -814,9 +816,11 @@ HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __
       const uint32_t glo = a[0], ghi = a[32], hhi = a[64];
       if (glo | ghi | hhi) {
         const uint32_t f = g0.f_begin + 8u * (bank >> 2) + 4u * half + (bank & 3u);
-        longlong2* d = dst + ell.cut_ptrs[f] + sym;
-        if (glo | ghi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->x), ((unsigned long long)ghi << 32) | glo);
-        if (hhi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->y), (unsigned long long)hhi << 32);
+        if (f < ell.n_features) {  // features past the end are row padding (symbol 0): dropped
+          longlong2* d = dst + ell.cut_ptrs[f] + sym;
+          if (glo | ghi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->x), ((unsigned long long)ghi << 32) | glo);
+          if (hhi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->y), (unsigned long long)hhi << 32);
+        }
         a[0] = 0u; a[32] = 0u; a[64] = 0u;
       }
     }
@@ -1239,11 +1243,14 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
     for (auto const& g : groups_host) smem = std::max(smem, BankedSmemBytes(g));
     bool checked = ell.null_symbol != 0xFFFFFFFFu;
     uint32_t max_blocks = 1;
+    const int impl = HistImpl();
+    // a trailing partial block is fine for the default kernels when the rows are padded to whole blocks
+    const bool padded_rows = impl == 0 && ell.row_bytes >= ((ell.n_features + 31u) & ~31u);
     for (auto const& g : groups_host) {
-      checked = checked || ((g.f_end - g.f_begin) % 32u != 0u);
+      const bool partial = (g.f_end - g.f_begin) % 32u != 0u;
+      checked = checked || (partial && !(padded_rows && g.f_end == ell.n_features));
       max_blocks = std::max(max_blocks, g.n_blocks);
     }
-    const int impl = HistImpl();
     // Pair kernel (64 features per CTA pass, 12-byte accumulators): chosen when the caller expects hessians
     // without low words and the groups are single full blocks laid out back to back; it checks the flag itself.
     static const bool pair_off = std::getenv("B200HIST_NO_PAIR") != nullptr;
