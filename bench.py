@@ -44,6 +44,8 @@ def parse_args():
                     help="multi-GPU decomposition: rows = every rank owns N/P rows, full-width partial histograms summed "
                          "per level over peer memory; features = every rank owns F/P feature blocks of all rows "
                          "(north_star's feature-block shard), slices exchanged per level")
+    ap.add_argument("--missing", type=float, default=0.0,
+                    help="fraction of entries replaced by NaN (exercises the pages with a null symbol; not the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -130,10 +132,16 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # synthetic workload: X ~ N(0,1) per 1M-row batch generated ON DEVICE, y = X.w + 0.1 eps
 # --------------------------------------------------------------------------------------------------
+MISSING = 0.0
+
+
 def batch_of(torch, device, f, rows, batch, b):
     m = min(batch, rows - b * batch)
     g = torch.Generator(device=device).manual_seed(2024 + b)
-    return torch.randn((m, f), generator=g, device=device), g
+    x = torch.randn((m, f), generator=g, device=device)
+    if MISSING > 0.0:
+        x[torch.rand((m, f), generator=g, device=device) < MISSING] = float("nan")
+    return x, g
 
 
 def build_workload(torch, xb, args, device, batch_lo=0, batch_hi=None):
@@ -157,7 +165,7 @@ def build_workload(torch, xb, args, device, batch_lo=0, batch_hi=None):
     torch.cuda.synchronize(device)
     t_sketch = time.perf_counter() - t0
     t0 = time.perf_counter()
-    page = xb.EllpackPage(cuts, row_hi - row_lo, device.index, has_missing=False)
+    page = xb.EllpackPage(cuts, row_hi - row_lo, device.index, has_missing=MISSING > 0.0)
     gen = torch.Generator(device=device).manual_seed(7)
     w = torch.randn(f, generator=gen, device=device)
     y = torch.empty(row_hi - row_lo, dtype=torch.float32, device=device)
@@ -165,7 +173,7 @@ def build_workload(torch, xb, args, device, batch_lo=0, batch_hi=None):
         x, g = batch_of(torch, device, f, n, batch, b)
         o = b * batch - row_lo
         page.push_dense(x, o)
-        y[o:o + x.shape[0]] = x @ w + 0.1 * torch.randn(x.shape[0], generator=g, device=device)
+        y[o:o + x.shape[0]] = torch.nan_to_num(x) @ w + 0.1 * torch.randn(x.shape[0], generator=g, device=device)
         del x
     torch.cuda.synchronize(device)
     return page, y, dict(sketch_s=t_sketch, ellpack_s=time.perf_counter() - t0, sketch_windows=nb)
@@ -237,6 +245,8 @@ def run_reference(args):
 # our arm
 # --------------------------------------------------------------------------------------------------
 def run_b200(args):
+    global MISSING
+    MISSING = args.missing
     import numpy as np
     import torch
     import torch.distributed as dist

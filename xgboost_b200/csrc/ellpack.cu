@@ -303,8 +303,9 @@ int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features, co
   uint32_t n_symbols = mx + (e->has_missing ? 1 : 0);  // CalcNumSymbols (ellpack_page.cu:140-183)
   B200_CHECK(n_symbols <= 65536, "more than 65536 symbols per feature is not supported");
   e->bin_bytes = n_symbols <= 256 ? 1 : 2;
-  e->null_symbol = e->has_missing ? (e->bin_bytes == 1 ? 0xFFu : 0xFFFFu) : 0xFFFFFFFFu;
-  if (e->has_missing && e->null_symbol < mx) e->null_symbol = mx;  // unreachable; keeps the invariant explicit
+  // null = the first symbol no feature uses (the reference's NullValue for dense pages with missing values is
+  // n_symbols - 1 as well, ellpack_page.cu:140-183): the histogram kernels give it the accumulator slot mx
+  e->null_symbol = e->has_missing ? mx : 0xFFFFFFFFu;
   // uint8 pages: rows padded to whole 32-feature blocks (zero symbols), so the histogram kernel's unpredicated
   // 32-feature loop also serves feature counts that are not multiples of 32 (the padding is dropped at flush time)
   e->row_bytes = e->bin_bytes == 1 ? ((n_features + 31u) & ~31u) : ((n_features * e->bin_bytes + 15u) & ~15u);

@@ -96,7 +96,13 @@ std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, int devi
         uint32_t b_end = std::min(ell.n_features, f_end + 32);
         uint32_t ms = max_sym;
         for (uint32_t k = f_end; k < b_end; ++k) ms = std::max(ms, ell.cut_ptrs[k + 1] - ell.cut_ptrs[k]);
+        // pages with missing values: the null symbol (255) gets an accumulator slot of its own, so the kernels need
+        // no predicate for it; the slot is dropped at flush time (missing = parent - sum(bins) downstream anyway)
+        if (ell.null_symbol != 0xFFFFFFFFu) ms = std::max(ms, ell.null_symbol + 1u);
         if ((size_t)4 * (blocks + 1) * ms * 32 * 4 + RingSmemBytes(blocks + 1) > budget) break;
+        // default kernels: one block per group, whatever the symbol count -- equal work per grid row (a group of 6
+        // blocks next to one of 2 leaves CTAs idle) and every pair of blocks is eligible for the 64-feature kernel
+        if (HistImpl() == 0 && blocks == 1) break;
         max_sym = ms;
         ++blocks;
         f_end = b_end;
@@ -588,7 +594,8 @@ __device__ __forceinline__ void BankedFastGroup(const EllView& ell, const longlo
       const uint32_t glo = a[0], ghi = a[32], hlo = a[64], hhi = a[96];
       if (glo | ghi | hlo | hhi) {
         const uint32_t f = g.f_begin + (rest / S) * 32 + ln;
-        if (f < ell.n_features) {  // features past the end are row padding (symbol 0): dropped
+        // dropped: features past the end (row padding, symbol 0) and symbols past the feature's bins (the null slot)
+        if (f < ell.n_features && ell.cut_ptrs[f] + (rest % S) < ell.cut_ptrs[f + 1]) {
           longlong2* d = dst + ell.cut_ptrs[f] + (rest % S);
           if (glo | ghi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->x), ((unsigned long long)ghi << 32) | glo);
           if (hlo | hhi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->y), ((unsigned long long)hhi << 32) | hlo);
@@ -816,7 +823,8 @@ HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __
       const uint32_t glo = a[0], ghi = a[32], hhi = a[64];
       if (glo | ghi | hhi) {
         const uint32_t f = g0.f_begin + 8u * (bank >> 2) + 4u * half + (bank & 3u);
-        if (f < ell.n_features) {  // features past the end are row padding (symbol 0): dropped
+        // dropped: features past the end (row padding, symbol 0) and symbols past the feature's bins (the null slot)
+        if (f < ell.n_features && ell.cut_ptrs[f] + sym < ell.cut_ptrs[f + 1]) {
           longlong2* d = dst + ell.cut_ptrs[f] + sym;
           if (glo | ghi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->x), ((unsigned long long)ghi << 32) | glo);
           if (hhi) atomicAdd(reinterpret_cast<unsigned long long*>(&d->y), (unsigned long long)hhi << 32);
@@ -1241,9 +1249,10 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
   if (ell.bin_bytes == 1) {
     size_t smem = 0;
     for (auto const& g : groups_host) smem = std::max(smem, BankedSmemBytes(g));
-    bool checked = ell.null_symbol != 0xFFFFFFFFu;
-    uint32_t max_blocks = 1;
     const int impl = HistImpl();
+    // the default kernels give the null symbol its own accumulator slot (MakeFeatureGroups); the others predicate
+    bool checked = ell.null_symbol != 0xFFFFFFFFu && impl != 0;
+    uint32_t max_blocks = 1;
     // a trailing partial block is fine for the default kernels when the rows are padded to whole blocks
     const bool padded_rows = impl == 0 && ell.row_bytes >= ((ell.n_features + 31u) & ~31u);
     for (auto const& g : groups_host) {
