@@ -533,6 +533,31 @@ def test_monotone_constraints_match_oracle(xb, mono, extra):
     _compare_tree(xb, up, t_plain, o_plain, cp, cv, hists=False)
 
 
+@pytest.mark.parametrize("n,f,max_bin,missing,obj", [(30000, 96, 256, 0.1, "sq"), (20000, 40, 256, 0.3, "logistic"),
+                                                     (15000, 130, 300, 0.0, "sq"), (8000, 7, 257, 0.05, "sq")])
+def test_uint16_pages_take_the_banked_kernels(xb, n, f, max_bin, missing, obj):
+    """256 bins + missing values = 257 symbols per feature = a uint16 page: it runs the same bank-mapped kernels
+    (two registers of symbols per lane, the null symbol in its own accumulator slot) -- the 64-feature pair kernel
+    from the second squared-error tree on, the 16-byte-accumulator kernel for logistic hessians."""
+    import torch
+    x, y = make_regression(n, f, seed=n + f, missing=missing)
+    yb = (y > 0).astype(np.float32)
+    cp, cv = make_cuts(x, max_bin)
+    page = _page(xb, x, cp, cv)
+    assert page.info()["bin_bytes"] == 2
+    gb = orc.bin_dense(x, cp, cv)
+    params = dict(max_depth=5, eta=0.5)
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    pred = np.zeros(n, dtype=np.float32)
+    for it in range(3):
+        gp = squared_error_gpair(pred, y) if obj == "sq" else logistic_gpair(pred, yb)
+        tree = up.update(torch.from_numpy(gp).cuda())
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), want_hist=True)
+        _compare_tree(xb, up, tree, o, cp, cv, hists=True)
+        pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+
+
 def test_host_gradient_entry_matches_device_entry(xb):
     import torch
     n, f = 5000, 6

@@ -306,9 +306,9 @@ int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features, co
   // null = the first symbol no feature uses (the reference's NullValue for dense pages with missing values is
   // n_symbols - 1 as well, ellpack_page.cu:140-183): the histogram kernels give it the accumulator slot mx
   e->null_symbol = e->has_missing ? mx : 0xFFFFFFFFu;
-  // uint8 pages: rows padded to whole 32-feature blocks (zero symbols), so the histogram kernel's unpredicated
-  // 32-feature loop also serves feature counts that are not multiples of 32 (the padding is dropped at flush time)
-  e->row_bytes = e->bin_bytes == 1 ? ((n_features + 31u) & ~31u) : ((n_features * e->bin_bytes + 15u) & ~15u);
+  // rows padded to whole 32-feature blocks (zero symbols), so the histogram kernel's unpredicated 32-feature loop
+  // also serves feature counts that are not multiples of 32 (the padding is dropped at flush time)
+  e->row_bytes = ((n_features + 31u) & ~31u) * e->bin_bytes;
   e->d_cut_ptrs = DevAlloc<uint32_t>(n_features + 1);
   e->d_cut_values = DevAlloc<float>(e->total_bins);
   B200_CUDA(cudaMemcpy(e->d_cut_ptrs, e->cut_ptrs.data(), sizeof(uint32_t) * (n_features + 1), cudaMemcpyHostToDevice));

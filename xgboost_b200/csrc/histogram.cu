@@ -85,7 +85,12 @@ std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, int devi
     }
     return groups;
   }
-  if (ell.bin_bytes == 1) {
+  // uint16 pages take the bank-mapped kernels too while one 32-feature block of 16-byte accumulators fits
+  // (<= ~440 symbols per feature: 256 bins + the null symbol is the common case); wider ones the generic kernel
+  const bool banked16 = ell.bin_bytes == 2 && HistImpl() == 0 &&
+                        (size_t)4 * (ell.max_feature_bins + 1u) * 32 * 4 <= optin - 1024 &&
+                        ell.row_bytes >= ((ell.n_features + 31u) & ~31u) * 2u;
+  if (ell.bin_bytes == 1 || banked16) {
     const size_t budget = optin - 1024;
     uint32_t f = 0;
     while (f < ell.n_features) {
@@ -111,7 +116,7 @@ std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, int devi
       g.f_end = f_end;
       g.bin_begin = ell.cut_ptrs[f];
       g.bin_end = ell.cut_ptrs[f_end];
-      g.byte_begin = f;
+      g.byte_begin = f * ell.bin_bytes;
       g.n_words = (f_end - f + 3) / 4;
       g.n_blocks = blocks;
       g.max_sym = max_sym;
@@ -373,17 +378,39 @@ HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
 // pointer-increment addressing, block base folded into the lane offsets.  A warp's last partial pass goes
 // through a small checked tail.
 // ---------------------------------------------------------------------------------------------
-struct FastData {
-  uint32_t word[2], glo[2], ghi[2], hlo[2], hhi[2];
+// The 4 feature symbols a lane holds of one row: one register for uint8 pages, two for uint16 pages (pages with
+// 257..~440 symbols per feature, e.g. 256 bins + the null symbol of a matrix with missing values).
+template <int kSymBytes>
+struct Sym4;
+template <>
+struct Sym4<1> {
+  using T = uint32_t;
+  static __device__ __forceinline__ T Load(const uint8_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+  static __device__ __forceinline__ uint32_t Get(T w, uint32_t sel) { return __byte_perm(w, 0u, sel); }
+  static __device__ __forceinline__ uint32_t Sel(uint32_t jj) { return 0x4440u | jj; }
+};
+template <>
+struct Sym4<2> {
+  using T = uint2;
+  static __device__ __forceinline__ T Load(const uint8_t* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+  static __device__ __forceinline__ uint32_t Get(T w, uint32_t sel) { return __byte_perm(w.x, w.y, sel) & 0xFFFFu; }
+  static __device__ __forceinline__ uint32_t Sel(uint32_t jj) { return (2u * jj) | ((2u * jj + 1u) << 4); }
 };
 
-template <bool kHLoZero>
-__device__ __forceinline__ void FastProcess(const FastData& d, const uint32_t (&sel)[4], const uint32_t (&off)[4]) {
+template <int kSymBytes>
+struct FastData {
+  typename Sym4<kSymBytes>::T word[2];
+  uint32_t glo[2], ghi[2], hlo[2], hhi[2];
+};
+
+template <bool kHLoZero, int kSymBytes>
+__device__ __forceinline__ void FastProcess(const FastData<kSymBytes>& d, const uint32_t (&sel)[4],
+                                            const uint32_t (&off)[4]) {
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     uint32_t addr[4], og[4], oh[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) addr[k] = __byte_perm(d.word[u], 0u, sel[k]) * 512u + off[k];
+    for (int k = 0; k < 4; ++k) addr[k] = Sym4<kSymBytes>::Get(d.word[u], sel[k]) * 512u + off[k];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       og[k] = AtomAddShared(addr[k], d.glo[u]);
@@ -398,12 +425,14 @@ __device__ __forceinline__ void FastProcess(const FastData& d, const uint32_t (&
   }
 }
 
-__device__ __forceinline__ void FastLoad(FastData& d, const uint32_t (&r)[2], const longlong2* __restrict__ gq,
-                                         const uint8_t* __restrict__ col, uint32_t row_bytes) {
+template <int kSymBytes>
+__device__ __forceinline__ void FastLoad(FastData<kSymBytes>& d, const uint32_t (&r)[2],
+                                         const longlong2* __restrict__ gq, const uint8_t* __restrict__ col,
+                                         uint32_t row_bytes) {
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const longlong2 gp = __ldg(gq + r[u]);
-    d.word[u] = __ldg(reinterpret_cast<const uint32_t*>(col + (size_t)r[u] * row_bytes));
+    d.word[u] = Sym4<kSymBytes>::Load(col + (size_t)r[u] * row_bytes);
     d.glo[u] = (uint32_t)(unsigned long long)gp.x;
     d.ghi[u] = (uint32_t)((unsigned long long)gp.x >> 32);
     d.hlo[u] = (uint32_t)(unsigned long long)gp.y;
@@ -411,7 +440,7 @@ __device__ __forceinline__ void FastLoad(FastData& d, const uint32_t (&r)[2], co
   }
 }
 
-template <bool kHLoZero>
+template <bool kHLoZero, int kSymBytes>
 __device__ __forceinline__ void FastRows(const uint32_t* __restrict__ ridx, uint32_t lo, uint32_t hi,
                                          const longlong2* __restrict__ gq, const uint8_t* __restrict__ col,
                                          uint32_t row_bytes, uint32_t warp, uint32_t q,
@@ -432,7 +461,7 @@ __device__ __forceinline__ void FastRows(const uint32_t* __restrict__ ridx, uint
       r[1] = __ldg(p + 4);
     };
     uint32_t ra[2], rb[2];
-    FastData da, db;
+    FastData<kSymBytes> da, db;
     rid(0, ra);
     rid(1, rb);
     FastLoad(da, ra, gq, col, row_bytes);
@@ -452,7 +481,7 @@ __device__ __forceinline__ void FastRows(const uint32_t* __restrict__ ridx, uint
   const uint32_t jb = first + n_full * kStride;
   if (jb < hi) {
     uint32_t r[2];
-    FastData d;
+    FastData<kSymBytes> d;
 #pragma unroll
     for (int u = 0; u < 2; ++u) r[u] = __ldg(ridx + min(jb + u * 4 + q, hi - 1));
     FastLoad(d, r, gq, col, row_bytes);
@@ -466,26 +495,32 @@ __device__ __forceinline__ void FastRows(const uint32_t* __restrict__ ridx, uint
 // h.lo-skip variant with THREE register buffers: the data of passes i+1 and i+2 are in flight while pass i
 // accumulates (global-load latency, not issue or atomics, limits the two-buffer version: ncu shows the
 // long-scoreboard stall dominating at 46 % issue utilisation).  Only 8 registers per pass are needed here.
+template <int kSymBytes>
 struct FastDataZ {
-  uint32_t word[2], glo[2], ghi[2], hhi[2];
+  typename Sym4<kSymBytes>::T word[2];
+  uint32_t glo[2], ghi[2], hhi[2];
 };
-__device__ __forceinline__ void FastLoadZ(FastDataZ& d, const uint32_t (&r)[2], const longlong2* __restrict__ gq,
-                                          const uint8_t* __restrict__ col, uint32_t row_bytes) {
+template <int kSymBytes>
+__device__ __forceinline__ void FastLoadZ(FastDataZ<kSymBytes>& d, const uint32_t (&r)[2],
+                                          const longlong2* __restrict__ gq, const uint8_t* __restrict__ col,
+                                          uint32_t row_bytes) {
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const longlong2 gp = __ldg(gq + r[u]);
-    d.word[u] = __ldg(reinterpret_cast<const uint32_t*>(col + (size_t)r[u] * row_bytes));
+    d.word[u] = Sym4<kSymBytes>::Load(col + (size_t)r[u] * row_bytes);
     d.glo[u] = (uint32_t)(unsigned long long)gp.x;
     d.ghi[u] = (uint32_t)((unsigned long long)gp.x >> 32);
     d.hhi[u] = (uint32_t)((unsigned long long)gp.y >> 32);
   }
 }
-__device__ __forceinline__ void FastProcessZ(const FastDataZ& d, const uint32_t (&sel)[4], const uint32_t (&off)[4]) {
+template <int kSymBytes>
+__device__ __forceinline__ void FastProcessZ(const FastDataZ<kSymBytes>& d, const uint32_t (&sel)[4],
+                                             const uint32_t (&off)[4]) {
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     uint32_t addr[4], og[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) addr[k] = __byte_perm(d.word[u], 0u, sel[k]) * 512u + off[k];
+    for (int k = 0; k < 4; ++k) addr[k] = Sym4<kSymBytes>::Get(d.word[u], sel[k]) * 512u + off[k];
 #pragma unroll
     for (int k = 0; k < 4; ++k) og[k] = AtomAddShared(addr[k], d.glo[u]);
 #pragma unroll
@@ -496,6 +531,7 @@ __device__ __forceinline__ void FastProcessZ(const FastDataZ& d, const uint32_t 
   }
 }
 
+template <int kSymBytes>
 __device__ __forceinline__ void FastRowsZ3(const uint32_t* __restrict__ ridx, uint32_t lo, uint32_t hi,
                                            const longlong2* __restrict__ gq, const uint8_t* __restrict__ col,
                                            uint32_t row_bytes, uint32_t warp, uint32_t q,
@@ -514,7 +550,7 @@ __device__ __forceinline__ void FastRowsZ3(const uint32_t* __restrict__ ridx, ui
       r[1] = __ldg(p + 4);
     };
     uint32_t r0[2], r1[2], r2[2];
-    FastDataZ d0, d1, d2;
+    FastDataZ<kSymBytes> d0, d1, d2;
     rid(0, r0); rid(1, r1); rid(2, r2);
     FastLoadZ(d0, r0, gq, col, row_bytes); rid(3, r0);
     FastLoadZ(d1, r1, gq, col, row_bytes); rid(4, r1);
@@ -533,7 +569,7 @@ __device__ __forceinline__ void FastRowsZ3(const uint32_t* __restrict__ ridx, ui
   const uint32_t jb = first + n_full * kStride;
   if (jb < hi) {  // partial last pass
     uint32_t r[2];
-    FastData d;
+    FastData<kSymBytes> d;
 #pragma unroll
     for (int u = 0; u < 2; ++u) r[u] = __ldg(ridx + min(jb + u * 4 + q, hi - 1));
     FastLoad(d, r, gq, col, row_bytes);
@@ -545,6 +581,7 @@ __device__ __forceinline__ void FastRowsZ3(const uint32_t* __restrict__ ridx, ui
 }
 
 // One group (B blocks of 32 features, 16-byte accumulators) over the CTA's tile range [t0, t1).
+template <int kSymBytes>
 __device__ __forceinline__ void BankedFastGroup(const EllView& ell, const longlong2* __restrict__ gq,
                                                 const uint32_t* __restrict__ ridx0, const uint32_t* __restrict__ ridx1,
                                                 const BuildEntry* __restrict__ build,
@@ -564,7 +601,7 @@ __device__ __forceinline__ void BankedFastGroup(const EllView& ell, const longlo
 #pragma unroll
   for (uint32_t k = 0; k < 4; ++k) {
     const uint32_t jj = (k + q) & 3u;
-    sel[k] = 0x4440u | jj;
+    sel[k] = Sym4<kSymBytes>::Sel(jj);
     lane_off[k] = (4u * w + jj) * 4u;
   }
 
@@ -581,9 +618,9 @@ __device__ __forceinline__ void BankedFastGroup(const EllView& ell, const longlo
       uint32_t off[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) off[k] = sh_base + blk * S * 512u + lane_off[k];
-      const uint8_t* __restrict__ col = ell.bins + g.byte_begin + blk * 32u + 4u * w;
-      if (h_lo_zero) FastRowsZ3(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
-      else FastRows<false>(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
+      const uint8_t* __restrict__ col = ell.bins + g.byte_begin + (blk * 32u + 4u * w) * kSymBytes;
+      if (h_lo_zero) FastRowsZ3<kSymBytes>(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
+      else FastRows<false, kSymBytes>(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
     }
     // flush this CTA's share of the node (RED.64 on non-zero accumulators) and clear
     __syncthreads();
@@ -608,6 +645,7 @@ __device__ __forceinline__ void BankedFastGroup(const EllView& ell, const longlo
   }
 }
 
+template <int kSymBytes>
 __global__ void __launch_bounds__(kHistThreads, 1)
 HistKernelBankedFast(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
                      const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
@@ -621,8 +659,8 @@ HistKernelBankedFast(EllView ell, const longlong2* __restrict__ gq, const uint32
   const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
   if (t0 >= t1) return;
   const GroupDesc g = groups[blockIdx.y];
-  BankedFastGroup(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, (uint32_t)ts->n_build, g, hist,
-                  qd != nullptr && qd->h_lo_or == 0u, sh, t0, t1);
+  BankedFastGroup<kSymBytes>(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, (uint32_t)ts->n_build, g, hist,
+                             qd != nullptr && qd->h_lo_or == 0u, sh, t0, t1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -658,27 +696,40 @@ __device__ __forceinline__ void RedAddHiOff(uint32_t addr, uint32_t old, uint32_
   asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(hi), "n"(kOff) : "memory");
 }
 
+template <int kSymBytes>
 struct FastDataP {
-  uint2 word[2];
+  typename Sym4<kSymBytes>::T word[2][2];  // [row][half]: 2 x 4 symbols of a row
   uint32_t glo[2], ghi[2], hhi[2];
 };
-__device__ __forceinline__ void FastLoadP(FastDataP& d, const uint32_t (&r)[2], const longlong2* __restrict__ gq,
-                                          const uint8_t* __restrict__ col, uint32_t row_bytes) {
+__device__ __forceinline__ void LoadSym8(const uint8_t* p, uint32_t (&w)[2]) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  w[0] = v.x;
+  w[1] = v.y;
+}
+__device__ __forceinline__ void LoadSym8(const uint8_t* p, uint2 (&w)[2]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  w[0] = make_uint2(v.x, v.y);
+  w[1] = make_uint2(v.z, v.w);
+}
+template <int kSymBytes>
+__device__ __forceinline__ void FastLoadP(FastDataP<kSymBytes>& d, const uint32_t (&r)[2],
+                                          const longlong2* __restrict__ gq, const uint8_t* __restrict__ col,
+                                          uint32_t row_bytes) {
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const longlong2 gp = __ldg(gq + r[u]);
-    d.word[u] = __ldg(reinterpret_cast<const uint2*>(col + (size_t)r[u] * row_bytes));
+    LoadSym8(col + (size_t)r[u] * row_bytes, d.word[u]);
     d.glo[u] = (uint32_t)(unsigned long long)gp.x;
     d.ghi[u] = (uint32_t)((unsigned long long)gp.x >> 32);
     d.hhi[u] = (uint32_t)((unsigned long long)gp.y >> 32);
   }
 }
-template <int kHalf>
-__device__ __forceinline__ void FastProcessPHalf(uint32_t word, uint32_t glo, uint32_t ghi, uint32_t hhi,
-                                                 const uint32_t (&sel)[4], const uint32_t (&off)[4]) {
+template <int kHalf, int kSymBytes>
+__device__ __forceinline__ void FastProcessPHalf(typename Sym4<kSymBytes>::T word, uint32_t glo, uint32_t ghi,
+                                                 uint32_t hhi, const uint32_t (&sel)[4], const uint32_t (&off)[4]) {
   uint32_t addr[4], og[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) addr[k] = __byte_perm(word, 0u, sel[k]) * 768u + off[k];
+  for (int k = 0; k < 4; ++k) addr[k] = Sym4<kSymBytes>::Get(word, sel[k]) * 768u + off[k];
 #pragma unroll
   for (int k = 0; k < 4; ++k) og[k] = AtomAddSharedOff<kHalf * 384>(addr[k], glo);
 #pragma unroll
@@ -687,15 +738,17 @@ __device__ __forceinline__ void FastProcessPHalf(uint32_t word, uint32_t glo, ui
     RedAddOff<kHalf * 384 + 256>(addr[k], hhi);
   }
 }
-__device__ __forceinline__ void FastProcessP(const FastDataP& d, const uint32_t (&sel)[4], const uint32_t (&off)[4]) {
+template <int kSymBytes>
+__device__ __forceinline__ void FastProcessP(const FastDataP<kSymBytes>& d, const uint32_t (&sel)[4],
+                                             const uint32_t (&off)[4]) {
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    FastProcessPHalf<0>(d.word[u].x, d.glo[u], d.ghi[u], d.hhi[u], sel, off);
-    FastProcessPHalf<1>(d.word[u].y, d.glo[u], d.ghi[u], d.hhi[u], sel, off);
+    FastProcessPHalf<0, kSymBytes>(d.word[u][0], d.glo[u], d.ghi[u], d.hhi[u], sel, off);
+    FastProcessPHalf<1, kSymBytes>(d.word[u][1], d.glo[u], d.ghi[u], d.hhi[u], sel, off);
   }
 }
 
-template <int kBufs>
+template <int kBufs, int kSymBytes>
 __device__ __forceinline__ void FastRowsP(const uint32_t* __restrict__ ridx, uint32_t lo, uint32_t hi,
                                           const longlong2* __restrict__ gq, const uint8_t* __restrict__ col,
                                           uint32_t row_bytes, uint32_t warp, uint32_t q,
@@ -715,7 +768,7 @@ __device__ __forceinline__ void FastRowsP(const uint32_t* __restrict__ ridx, uin
     };
     if (kBufs == 3) {
       uint32_t r0[2], r1[2], r2[2];
-      FastDataP d0, d1, d2;
+      FastDataP<kSymBytes> d0, d1, d2;
       rid(0, r0); rid(1, r1); rid(2, r2);
       FastLoadP(d0, r0, gq, col, row_bytes); rid(3, r0);
       FastLoadP(d1, r1, gq, col, row_bytes); rid(4, r1);
@@ -732,7 +785,7 @@ __device__ __forceinline__ void FastRowsP(const uint32_t* __restrict__ ridx, uin
       if (i + 1 < n_full) FastProcessP(d1, sel, off);
     } else {
       uint32_t ra[2], rb[2];
-      FastDataP da, db;
+      FastDataP<kSymBytes> da, db;
       rid(0, ra);
       rid(1, rb);
       FastLoadP(da, ra, gq, col, row_bytes);
@@ -750,7 +803,7 @@ __device__ __forceinline__ void FastRowsP(const uint32_t* __restrict__ ridx, uin
   const uint32_t jb = first + n_full * kStride;
   if (jb < hi) {  // partial last pass: rows past the end add zero
     uint32_t r[2];
-    FastDataP d;
+    FastDataP<kSymBytes> d;
 #pragma unroll
     for (int u = 0; u < 2; ++u) r[u] = __ldg(ridx + min(jb + u * 4 + q, hi - 1));
     FastLoadP(d, r, gq, col, row_bytes);
@@ -761,7 +814,7 @@ __device__ __forceinline__ void FastRowsP(const uint32_t* __restrict__ ridx, uin
   }
 }
 
-template <int kBufs>
+template <int kBufs, int kSymBytes>
 __global__ void __launch_bounds__(kHistThreads, 1)
 HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
                const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
@@ -780,10 +833,11 @@ HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __
   const bool two = gi + 1u < n_groups;
   const GroupDesc g0 = groups[gi];
   if (!two || !h_lo_zero) {  // odd block out, or hessians with low words: 16-byte layout, block after block
-    BankedFastGroup(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, n_build, g0, hist, h_lo_zero, sh, t0, t1);
+    BankedFastGroup<kSymBytes>(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, n_build, g0, hist, h_lo_zero, sh, t0, t1);
     if (two) {
       const GroupDesc g1 = groups[gi + 1u];
-      BankedFastGroup(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, n_build, g1, hist, h_lo_zero, sh, t0, t1);
+      BankedFastGroup<kSymBytes>(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, n_build, g1, hist, h_lo_zero, sh, t0,
+                                 t1);
     }
     return;
   }
@@ -799,10 +853,10 @@ HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __
 #pragma unroll
   for (uint32_t k = 0; k < 4; ++k) {
     const uint32_t jj = (k + q) & 3u;
-    sel[k] = 0x4440u | jj;
+    sel[k] = Sym4<kSymBytes>::Sel(jj);
     off[k] = sh_base + (4u * w + jj) * 4u;
   }
-  const uint8_t* __restrict__ col = ell.bins + g0.byte_begin + 8u * w;
+  const uint8_t* __restrict__ col = ell.bins + g0.byte_begin + 8u * w * kSymBytes;
 
   uint32_t t = t0;
   while (t < t1) {
@@ -813,7 +867,7 @@ HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __
     const uint32_t lo = (t - e.tile_begin) * kHistTile;
     const uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
     const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin;
-    FastRowsP<kBufs>(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
+    FastRowsP<kBufs, kSymBytes>(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
     __syncthreads();
     // flush this CTA's share of the node (RED.64 on non-zero accumulators) and clear
     longlong2* dst = hist + (size_t)e.slot * ell.total_bins;
@@ -1020,7 +1074,7 @@ HistKernelStaged(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
       for (uint32_t blk = 0; blk < B; ++blk) {
         const uint32_t blk_base = sh_base + blk * S * 512u;
         if (!kChecked) {  // lean path: same hand-scheduled accumulation as HistKernelBankedFast
-          FastData d;
+          FastData<1> d;
           uint32_t off[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) off[k] = blk_base + lane_off[k];
@@ -1220,9 +1274,11 @@ HistKernelSparse(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
 void PrepareHistKernels(int device) {
   int optin = SmemOptin(device);
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  B200_CUDA(cudaFuncSetAttribute(HistKernelBankedFast, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  B200_CUDA(cudaFuncSetAttribute(HistKernelPair<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  B200_CUDA(cudaFuncSetAttribute(HistKernelPair<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelBankedFast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute(HistKernelBankedFast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute((HistKernelPair<2, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute((HistKernelPair<3, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute((HistKernelPair<2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -1246,7 +1302,9 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
   const int n_groups = (int)groups_host.size();
   const int workers = std::max(1, num_sms / n_groups);
   dim3 grid(workers, n_groups);
-  if (ell.bin_bytes == 1) {
+  const bool banked = ell.bin_bytes == 1 || (ell.bin_bytes == 2 && !groups_host.empty() && groups_host[0].n_blocks > 0);
+  if (banked) {
+    const uint32_t sym_bytes = ell.bin_bytes;
     size_t smem = 0;
     for (auto const& g : groups_host) smem = std::max(smem, BankedSmemBytes(g));
     const int impl = HistImpl();
@@ -1254,7 +1312,7 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
     bool checked = ell.null_symbol != 0xFFFFFFFFu && impl != 0;
     uint32_t max_blocks = 1;
     // a trailing partial block is fine for the default kernels when the rows are padded to whole blocks
-    const bool padded_rows = impl == 0 && ell.row_bytes >= ((ell.n_features + 31u) & ~31u);
+    const bool padded_rows = impl == 0 && ell.row_bytes >= ((ell.n_features + 31u) & ~31u) * sym_bytes;
     for (auto const& g : groups_host) {
       const bool partial = (g.f_end - g.f_begin) % 32u != 0u;
       checked = checked || (partial && !(padded_rows && g.f_end == ell.n_features));
@@ -1263,12 +1321,14 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
     // Pair kernel (64 features per CTA pass, 12-byte accumulators): chosen when the caller expects hessians
     // without low words and the groups are single full blocks laid out back to back; it checks the flag itself.
     static const bool pair_off = std::getenv("B200HIST_NO_PAIR") != nullptr;
-    bool pair = pair_hint && !pair_off && impl == 0 && !checked && n_groups >= 2 && ell.row_bytes % 8u == 0u;
+    bool pair = pair_hint && !pair_off && impl == 0 && !checked && n_groups >= 2 &&
+                ell.row_bytes % (8u * sym_bytes) == 0u;
     uint32_t pair_sym = 0;
     for (int i = 0; pair && i < n_groups; ++i) {
       const GroupDesc& g = groups_host[i];
-      pair = g.n_blocks == 1 && g.byte_begin % 8u == 0u &&
-             (i == 0 || (g.f_begin == groups_host[i - 1].f_end && g.byte_begin == groups_host[i - 1].byte_begin + 32u));
+      pair = g.n_blocks == 1 && g.byte_begin % (8u * sym_bytes) == 0u &&
+             (i == 0 || (g.f_begin == groups_host[i - 1].f_end &&
+                         g.byte_begin == groups_host[i - 1].byte_begin + 32u * sym_bytes));
       pair_sym = std::max(pair_sym, g.max_sym);
     }
     const size_t pair_smem = (size_t)pair_sym * 192 * 4;
@@ -1281,7 +1341,8 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
         const char* e = std::getenv("B200HIST_PAIR_BUFS");
         return e ? std::atoi(e) : 3;
       }();
-      auto pk = pair_bufs == 2 ? HistKernelPair<2> : HistKernelPair<3>;
+      // uint16 symbols cost two more registers per row buffer: two buffers there (measured equal on uint8)
+      auto pk = sym_bytes == 2 ? HistKernelPair<2, 2> : (pair_bufs == 2 ? HistKernelPair<2, 1> : HistKernelPair<3, 1>);
       pk<<<pgrid, kHistThreads, std::max(pair_smem, smem), s>>>(
           ell, reinterpret_cast<const longlong2*>(gq), ridx0, ridx1, build, tile_seg, ts, groups_dev, (uint32_t)n_groups,
           reinterpret_cast<longlong2*>(hist), quant);
@@ -1292,7 +1353,10 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
                              const uint32_t*, const TreeState*, const GroupDesc*, longlong2*, const QuantDev*);
     KernelT kernel;
     if (impl == 0 || impl == 3) {  // 3 = the unscheduled direct-load kernel (for comparison)
-      kernel = checked ? HistKernelBanked<true> : (impl == 0 ? HistKernelBankedFast : HistKernelBanked<false>);
+      B200_CHECK(sym_bytes == 1 || (impl == 0 && !checked), "internal: uint16 pages use the default banked kernels only");
+      kernel = checked ? HistKernelBanked<true>
+                       : (impl == 0 ? (sym_bytes == 2 ? HistKernelBankedFast<2> : HistKernelBankedFast<1>)
+                                    : HistKernelBanked<false>);
     } else {
       smem += RingSmemBytes(max_blocks);
       if (impl == 1) kernel = checked ? HistKernelStaged<true, true> : HistKernelStaged<false, true>;
@@ -1373,7 +1437,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) SmemAtomicPeakKernel(uint32_t
     sel[k] = 0x4440u | jj;
     off[k] = sh_base + (4u * w + jj) * 4u;
   }
-  FastData d;
+  FastData<1> d;
   uint32_t x = 0x9E3779B9u * (threadIdx.x + 1u) + blockIdx.x;
 #pragma unroll
   for (int u = 0; u < 2; ++u) { d.glo[u] = 0xFFFFFFF0u + u; d.ghi[u] = 3u; d.hlo[u] = kHLoZero ? 0u : 0xFFFFFF00u; d.hhi[u] = 1u; }
