@@ -149,13 +149,49 @@ __global__ void __launch_bounds__(256) TransposeKernel(const uint8_t* __restrict
   }
 }
 
+// The same for uint16 pages: bins_t is uint16[f][col_stride]; 128 rows x 32 features per CTA.
+__global__ void __launch_bounds__(256) TransposeKernel16(const uint8_t* __restrict__ bins, uint32_t row_bytes,
+                                                          uint32_t n_features, uint64_t row_begin, uint64_t n,
+                                                          uint16_t* __restrict__ bins_t, uint64_t col_stride) {
+  __shared__ uint16_t tile[32][128 + 2];
+  const uint64_t r0 = row_begin + (uint64_t)blockIdx.x * 128;
+  const uint32_t f0 = blockIdx.y * 32;
+  const uint64_t r_end = row_begin + n;
+  for (uint32_t i = threadIdx.x; i < 128 * 16; i += 256) {  // 128 rows x 16 words of 2 symbols
+    const uint32_t r = i >> 4, w = i & 15u;
+    uint32_t word = 0;
+    if (r0 + r < r_end && (f0 + 2 * w) * 2 < row_bytes)
+      word = *reinterpret_cast<const uint32_t*>(bins + (r0 + r) * row_bytes + (f0 + 2 * w) * 2);
+    tile[2 * w][r] = (uint16_t)(word & 0xFFFFu);
+    tile[2 * w + 1][r] = (uint16_t)(word >> 16);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < 32 * 64; i += 256) {  // 32 features x 64 words of 2 rows
+    const uint32_t f = i >> 6, w = i & 63u;
+    if (f0 + f < n_features && r0 + 2 * w < r_end) {
+      uint16_t* dst = bins_t + (uint64_t)(f0 + f) * col_stride + r0 + 2 * w;
+      if (r0 + 2 * w + 2 <= r_end) {
+        *reinterpret_cast<uint32_t*>(dst) = (uint32_t)tile[f][2 * w] | ((uint32_t)tile[f][2 * w + 1] << 16);
+      } else {
+        dst[0] = tile[f][2 * w];
+      }
+    }
+  }
+}
+
 static void LaunchTranspose(b200hist_ellpack_s* e, uint64_t row_begin, uint64_t n, cudaStream_t s) {
   if (e->d_bins_t == nullptr || n == 0) return;
   // tiles are aligned to 128 rows of the page so that 32-bit stores stay aligned
   const uint64_t a0 = row_begin & ~uint64_t(127);
   const uint64_t span = row_begin + n - a0;
-  dim3 grid((unsigned)((span + 127) / 128), (e->n_features + 63) / 64);
-  TransposeKernel<<<grid, 256, 0, s>>>(e->d_bins, e->row_bytes, e->n_features, a0, span, e->d_bins_t, e->col_stride);
+  if (e->bin_bytes == 2) {
+    dim3 grid((unsigned)((span + 127) / 128), (e->n_features + 31) / 32);
+    TransposeKernel16<<<grid, 256, 0, s>>>(e->d_bins, e->row_bytes, e->n_features, a0, span,
+                                           reinterpret_cast<uint16_t*>(e->d_bins_t), e->col_stride);
+  } else {
+    dim3 grid((unsigned)((span + 127) / 128), (e->n_features + 63) / 64);
+    TransposeKernel<<<grid, 256, 0, s>>>(e->d_bins, e->row_bytes, e->n_features, a0, span, e->d_bins_t, e->col_stride);
+  }
   B200_LAUNCHED();
 }
 
@@ -316,9 +352,9 @@ int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features, co
   e->d_bins = DevAlloc<uint8_t>(n_rows * (uint64_t)e->row_bytes + 16);
   B200_CUDA(cudaMemset(e->d_bins, 0, n_rows * (uint64_t)e->row_bytes + 16));
   const char* no_t = std::getenv("B200HIST_NO_COLMAJOR");
-  if (e->bin_bytes == 1 && !(no_t && no_t[0] == '1')) {
+  if (!(no_t && no_t[0] == '1')) {  // column-major copy in the page's symbol width (col_stride in symbols)
     e->col_stride = (n_rows + 127) & ~uint64_t(127);
-    e->d_bins_t = DevAlloc<uint8_t>((uint64_t)n_features * e->col_stride + 16);
+    e->d_bins_t = DevAlloc<uint8_t>((uint64_t)n_features * e->col_stride * e->bin_bytes + 16);
   }
   *out = e;
   B200_API_END();

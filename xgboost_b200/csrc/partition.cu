@@ -41,7 +41,8 @@ PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint
     const uint32_t n = min((uint32_t)kPartTile, e.count - off);
     const uint32_t* __restrict__ ridx = (e.src_buf ? ridx1 : ridx0) + e.begin + off;
     const uint8_t* __restrict__ col = ell.bins + (size_t)e.findex * sizeof(BinT);
-    const uint8_t* __restrict__ colt = ell.bins_t ? ell.bins_t + (uint64_t)e.findex * ell.col_stride : nullptr;
+    const BinT* __restrict__ colt =
+        ell.bins_t ? reinterpret_cast<const BinT*>(ell.bins_t) + (uint64_t)e.findex * ell.col_stride : nullptr;
     uint32_t cnt = 0;
     if (ell.is_sparse) {
 #pragma unroll
@@ -70,7 +71,7 @@ PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint
       }
 #pragma unroll
       for (int k = 0; k < kRowsPerThread; ++k)
-        sym[k] = (sizeof(BinT) == 1 && colt != nullptr)
+        sym[k] = (sizeof(BinT) <= 2 && colt != nullptr)
                      ? (uint32_t)__ldg(colt + r[k])
                      : (uint32_t)__ldg(reinterpret_cast<const BinT*>(col + (size_t)r[k] * ell.row_bytes));
 #pragma unroll

@@ -436,8 +436,8 @@ __global__ void __launch_bounds__(256) FinaliseKernel(EllView ell, const uint32_
           nidx = go_left ? nd.left : nd.right;
           continue;
         }
-        const uint32_t sym = (sizeof(BinT) == 1 && ell.bins_t != nullptr)
-                                 ? (uint32_t)ell.bins_t[(uint64_t)nd.findex * ell.col_stride + r]
+        const uint32_t sym = (sizeof(BinT) <= 2 && ell.bins_t != nullptr)
+                                 ? (uint32_t)reinterpret_cast<const BinT*>(ell.bins_t)[(uint64_t)nd.findex * ell.col_stride + r]
                                  : (uint32_t)reinterpret_cast<const BinT*>(ell.bins + (size_t)r * ell.row_bytes)[nd.findex];
         const bool left = (sym == ell.null_symbol) ? (nd.default_left != 0) : ((int32_t)sym < nd.split_lbin);
         nidx = left ? nd.left : nd.right;
@@ -476,8 +476,8 @@ __device__ __forceinline__ int WalkToLeaf(const EllView& ell, const NodeDev* __r
       nidx = go_left ? nd.left : nd.right;
       continue;
     }
-    const uint32_t sym = (sizeof(BinT) == 1 && ell.bins_t != nullptr)
-                             ? (uint32_t)ell.bins_t[(uint64_t)nd.findex * ell.col_stride + r]
+    const uint32_t sym = (sizeof(BinT) <= 2 && ell.bins_t != nullptr)
+                             ? (uint32_t)reinterpret_cast<const BinT*>(ell.bins_t)[(uint64_t)nd.findex * ell.col_stride + r]
                              : (uint32_t)reinterpret_cast<const BinT*>(ell.bins + (size_t)r * ell.row_bytes)[nd.findex];
     const bool left = (sym == ell.null_symbol) ? (nd.default_left != 0) : ((int32_t)sym < nd.split_lbin);
     nidx = left ? nd.left : nd.right;
