@@ -45,7 +45,23 @@ __global__ void __launch_bounds__(kQThreads) QuantReduceKernel(const float2* __r
                                                                 unsigned int* __restrict__ counter,
                                                                 QuantDev* __restrict__ q) {
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  for (uint64_t i = blockIdx.x * (uint64_t)kQThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kQThreads) {
+  // four loads in flight per thread (one 8-byte load per iteration left the kernel latency bound at ~1.1 TB/s);
+  // the per-thread summation order stays fixed, so the result is still deterministic
+  const uint64_t stride = (uint64_t)gridDim.x * kQThreads;
+  uint64_t i = blockIdx.x * (uint64_t)kQThreads + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    float2 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(gpair + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s0 += (double)(v[k].x > 0 ? v[k].x : 0.0f);
+      s1 += (double)(v[k].y > 0 ? v[k].y : 0.0f);
+      s2 += (double)(v[k].x < 0 ? fabsf(v[k].x) : 0.0f);
+      s3 += (double)(v[k].y < 0 ? fabsf(v[k].y) : 0.0f);
+    }
+  }
+  for (; i < n; i += stride) {
     float2 v = __ldg(gpair + i);
     // Clip (quantiser.cu:30-44): clip in float, accumulate in double
     s0 += (double)(v.x > 0 ? v.x : 0.0f);
