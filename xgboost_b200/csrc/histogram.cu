@@ -26,7 +26,14 @@
 //   * int64 accumulation = 32-bit shared atomic on the low word whose returned old value yields the
 //     carry into the high word (two ATOMS per 64-bit add, exact).
 //   * flush to global memory uses 64-bit reductions (RED.64) on non-zero bins only.
-//   * pages with more than 256 symbols per feature (uint16) use the generic kernel (HistKernelGeneric).
+//   * Default kernels: HistKernelBankedFast<sym bytes> (32 features x 16-byte accumulators per CTA pass) and
+//     HistKernelPair<bufs, sym bytes> (64 features x 12-byte accumulators, hessians without low words).  No
+//     predicated variant: rows are zero-padded to whole 32-feature blocks and the null symbol of a page with
+//     missing values owns an accumulator slot; both are dropped at flush time.  uint16 pages (257..~440 symbols per
+//     feature, e.g. 256 bins + missing values) run the same kernels with two registers of symbols per lane; only
+//     wider pages use the generic kernel (HistKernelGeneric).
+//   * The binding resource is the L1TEX data stage (shared atomics + global-load wavefronts): ncu shows it at
+//     94-95 % of peak for the pair kernel (profiles/r01c_pair_kernels_ncu_summary.json).
 #include <cstdlib>
 #include <type_traits>
 
