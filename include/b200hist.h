@@ -163,6 +163,12 @@ B200HIST_API int b200hist_ellpack_push_dense(b200hist_ellpack_t ell, uint64_t ro
 B200HIST_API int b200hist_ellpack_import_reference(b200hist_ellpack_t ell, const uint8_t* gidx_buffer_dev,
                                                    uint32_t row_stride, uint32_t n_symbols, int is_dense,
                                                    void* stream);
+/* The same for ONE page of a multi-page DMatrix (ExtMemQuantileDMatrix: GetBatches<EllpackPage> yields the pages one
+ * at a time, src/data/extmem_quantile_dmatrix.cu): its n_rows rows land at [row_begin, row_begin + n_rows) of this
+ * page, so that an external-memory matrix that fits HBM is trained from one resident page. */
+B200HIST_API int b200hist_ellpack_import_reference_rows(b200hist_ellpack_t e, uint64_t row_begin, uint64_t n_rows,
+                                                        const uint8_t* gidx_buffer_dev, uint32_t row_stride,
+                                                        uint32_t n_symbols, int is_dense, void* stream);
 /* Accessors (EllpackPageImpl::{Size, info.row_stride, NumSymbols}, ellpack_page.cuh:250-300). */
 B200HIST_API int b200hist_ellpack_info(b200hist_ellpack_t ell, uint64_t* n_rows, uint32_t* n_features,
                                        uint32_t* total_bins, uint32_t* row_bytes, uint32_t* bin_bytes,

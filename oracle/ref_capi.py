@@ -141,6 +141,44 @@ class DMatrix:
         _check(lib, lib.XGQuantileDMatrixCreateFromCallback(None, proxy, None, reset, nxt, cfg, byref(h)))
         return cls(lib, h, keep=(batches, reset, nxt, proxy))
 
+    @classmethod
+    def extmem_quantile_from_batches(cls, batches, max_bin=256, kind="cuda", on_host=True, nthread=0):
+        """ExtMemQuantileDMatrix over a list of batches via XGExtMemQuantileDMatrixCreateFromCallback (c_api.h:579):
+        one Ellpack page per batch (min_cache_page_bytes = 0 disables page concatenation), cached on the host."""
+        lib = load(kind)
+        proxy = c_void_p()
+        _check(lib, lib.XGProxyDMatrixCreate(byref(proxy)))
+        state = {"i": 0, "cur": None}
+        first = batches[0]
+        is_cuda = hasattr(first, "__cuda_array_interface__") and not isinstance(first, np.ndarray)
+
+        @ctypes.CFUNCTYPE(None, c_void_p)
+        def reset(_):
+            state["i"] = 0
+
+        @ctypes.CFUNCTYPE(c_int, c_void_p)
+        def nxt(_):
+            i = state["i"]
+            if i >= len(batches):
+                return 0
+            b = batches[i]
+            state["cur"] = b
+            if is_cuda:
+                rc = lib.XGProxyDMatrixSetDataCudaArrayInterface(proxy, _cuda_array_interface(b))
+            else:
+                rc = lib.XGProxyDMatrixSetDataDense(proxy, _array_interface(b))
+            if rc != 0:
+                return -1
+            state["i"] = i + 1
+            return 1
+
+        cfg = json.dumps({"missing": float("nan"), "nthread": int(nthread), "max_bin": int(max_bin),
+                          "cache_prefix": "b200hist_extmem_cache", "on_host": bool(on_host),
+                          "min_cache_page_bytes": 0}).encode()
+        h = c_void_p()
+        _check(lib, lib.XGExtMemQuantileDMatrixCreateFromCallback(None, proxy, None, reset, nxt, cfg, byref(h)))
+        return cls(lib, h, keep=(batches, reset, nxt, proxy))
+
     def set_label(self, y):
         y = np.ascontiguousarray(y, dtype=np.float32)
         _check(self.lib, self.lib.XGDMatrixSetInfoFromInterface(self.handle, b"label", _array_interface(y)))

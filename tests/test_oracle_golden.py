@@ -220,3 +220,53 @@ def test_random_weight_restates_thrust_minstd_discard_uniform():
     assert orc.random_weight(5, 10**11) == float(np.float32(np.float32((pow(a, 10**11 + 1, m) * 5) % m - 1) / np.float32(2147483648.0)))
     u = np.array([orc.random_weight(42, i) for i in range(20000)])
     assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01
+
+
+def test_oracle_monotone_constraints_hold_and_zero_list_still_switches_the_gain_formula():
+    """TreeEvaluator restated (split_evaluator.h:25-205): along a +1 (-1) feature every left leaf is <= (>=) every
+    right leaf; children inherit bounds through mid = (w_left + w_right) / 2."""
+    import oracle as orc
+    from tests.helpers import make_cuts, make_regression, squared_error_gpair
+    x, y = make_regression(6000, 6, seed=3)
+    cp, cv = make_cuts(x, 32)
+    gb = orc.bin_dense(x, cp, cv)
+    gp = squared_error_gpair(np.zeros(6000, np.float32), y)
+    p = orc.Param.make(max_depth=5)
+    mono = [1, -1, 0, 1, 0, -1]
+    o = orc.update_tree(gb, cp, cv, gp, p, monotone=mono)
+    nodes = o["nodes"]
+
+    def leaves(i):
+        n = nodes[i]
+        return [n.leaf_value] if n.is_leaf else leaves(n.left) + leaves(n.right)
+    seen = 0
+    for n in nodes:
+        if not n.is_leaf and mono[n.findex] != 0:
+            lo, hi = leaves(n.left), leaves(n.right)
+            assert (max(lo) <= min(hi)) if mono[n.findex] > 0 else (min(lo) >= max(hi))
+            seen += 1
+    assert seen > 0
+    plain = orc.update_tree(gb, cp, cv, gp, p)
+    zeros = orc.update_tree(gb, cp, cv, gp, p, monotone=[0] * 6)   # has_constraint_: weight-based gains
+    assert [n.findex for n in plain["nodes"]] == [n.findex for n in zeros["nodes"]]  # same tree here ...
+    assert any(a.loss_chg != b.loss_chg for a, b in zip(plain["nodes"], zeros["nodes"]))  # ... other gain arithmetic
+
+
+def test_oracle_feature_set_restricts_splits_and_row_sampling_zeroes_gradients():
+    import oracle as orc
+    from tests.helpers import make_cuts, make_regression, squared_error_gpair
+    x, y = make_regression(5000, 10, seed=4)
+    cp, cv = make_cuts(x, 16)
+    gb = orc.bin_dense(x, cp, cv)
+    gp = squared_error_gpair(np.zeros(5000, np.float32), y)
+    p = orc.Param.make(max_depth=4)
+    fs = [1, 4, 7]
+    o = orc.update_tree(gb, cp, cv, gp, p, feature_set=fs)
+    assert {n.findex for n in o["nodes"] if not n.is_leaf} <= set(fs)
+    s = orc.update_tree(gb, cp, cv, gp, p, subsample=0.5, sample_seed=77, want_hist=True)
+    dropped = np.array([orc.random_weight(77, i) > np.float32(0.5) for i in range(5000)])
+    assert 0.4 < dropped.mean() < 0.6
+    assert np.array_equal(s["position"] < 0, dropped)             # zero hessian -> bit-complemented leaf id
+    # the root histogram holds only the kept rows: its hessian total = kept rows * quantised 1.0
+    kept = int((~dropped).sum())
+    assert int(s["hist"][0][cp[0]:cp[1], 1].sum()) == kept * int(np.float64(1.0) / s["scale"][3])

@@ -125,3 +125,35 @@ def test_sparse_dmatrix_through_the_shim_matches_reference(cuda_device):
     our_trees, our_margin = train("grow_b200_hist")
     assert json.dumps(our_trees) == json.dumps(ref_trees)
     assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))
+
+
+def test_external_memory_dmatrix_through_the_shim_matches_reference(cuda_device):
+    """ExtMemQuantileDMatrix (four batches -> four Ellpack pages in a host cache): the reference streams the pages
+    through its updater; the shim decodes each page into its row range of one resident page.  Same trees."""
+    import torch
+    from oracle import ref_capi as rc
+    if not (rc.available("cuda") and os.path.exists(SHIM)):
+        pytest.skip("needs oracle/_ref_cuda/libxgboost.so and the shim")
+    _ensure_shim(rc)
+    x, y = make_regression(48000, 20, seed=80, missing=0.03)
+    parts = [x[:10000], x[10000:31000], x[31000:31007], x[31007:]]
+
+    def train(updater):
+        dm = rc.DMatrix.extmem_quantile_from_batches([torch.from_numpy(p).cuda() for p in parts], max_bin=64, kind="cuda")
+        dm.set_label(y)
+        bst = rc.Booster({"tree_method": "hist", "device": "cuda:0", "max_bin": 64, "max_depth": 6, "eta": 0.3,
+                          "objective": "reg:squarederror", "base_score": 0.5, "updater": updater}, dm)
+        for i in range(3):
+            bst.update(i)
+        trees = bst.save_json()["learner"]["gradient_booster"]["model"]["trees"]
+        keep = ("left_children", "right_children", "split_indices", "split_conditions", "default_left",
+                "base_weights", "loss_changes", "sum_hessian")
+        return [{k: t[k] for k in keep} for t in trees], bst.predict_margin(dm)
+
+    ref_trees, ref_margin = train("grow_gpu_hist_reference")
+    import xgboost_b200 as xb
+    before = xb.launch_count()
+    our_trees, our_margin = train("grow_b200_hist")
+    assert xb.launch_count() > before
+    assert json.dumps(our_trees) == json.dumps(ref_trees)
+    assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))

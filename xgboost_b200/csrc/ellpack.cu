@@ -479,10 +479,13 @@ int b200hist_ellpack_push_dense(b200hist_ellpack_t e, uint64_t row_begin, const 
   B200_API_END();
 }
 
-int b200hist_ellpack_import_reference(b200hist_ellpack_t e, const uint8_t* gidx_buffer_dev, uint32_t row_stride,
-                                      uint32_t n_symbols, int is_dense, void* stream) {
+int b200hist_ellpack_import_reference_rows(b200hist_ellpack_t e, uint64_t row_begin, uint64_t n_rows,
+                                           const uint8_t* gidx_buffer_dev, uint32_t row_stride, uint32_t n_symbols,
+                                           int is_dense, void* stream) {
   B200_API_BEGIN();
   B200_CHECK(e != nullptr && gidx_buffer_dev != nullptr, "null argument");
+  B200_CHECK(row_begin + n_rows <= e->n_rows, "reference page exceeds this page");
+  if (n_rows == 0) return 0;
   if (e->is_sparse) {  // global-bin symbols, n_symbols = total_bins + 1, null = total_bins
     B200_CHECK(n_symbols == e->total_bins + 1, "sparse reference page: n_symbols must be total_bins + 1");
     B200_CHECK(row_stride <= e->row_stride, "the reference page's row_stride exceeds this page's");
@@ -490,17 +493,16 @@ int b200hist_ellpack_import_reference(b200hist_ellpack_t e, const uint8_t* gidx_
     while ((1ull << sbits) < n_symbols) ++sbits;
     DeviceGuard guard_s(e->device);
     auto ss = static_cast<cudaStream_t>(stream);
-    uint64_t tot = e->n_rows * (uint64_t)row_stride;
-    if (tot == 0) return 0;
+    uint64_t tot = n_rows * (uint64_t)row_stride;
     int nb = (int)std::min<uint64_t>((tot + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
     // slots beyond the reference's row_stride keep the fill value (>= total_bins == null)
     ImportReferenceSparseKernel<<<nb, 256, 0, ss>>>(gidx_buffer_dev, tot, sbits, row_stride, e->row_stride,
-                                                    reinterpret_cast<uint32_t*>(e->d_bins));
+                                                    reinterpret_cast<uint32_t*>(e->d_bins) + row_begin * e->row_stride);
     B200_LAUNCHED();
     if (e->d_row_sig) {
-      int sb = (int)std::min<uint64_t>((e->n_rows + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
-      RowSignatureKernel<<<sb, 256, 0, ss>>>(reinterpret_cast<const uint32_t*>(e->d_bins), 0, e->n_rows, e->row_stride,
-                                             e->d_cut_ptrs, e->n_features, e->total_bins, e->d_row_sig);
+      int sb = (int)std::min<uint64_t>((n_rows + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
+      RowSignatureKernel<<<sb, 256, 0, ss>>>(reinterpret_cast<const uint32_t*>(e->d_bins), row_begin, n_rows,
+                                             e->row_stride, e->d_cut_ptrs, e->n_features, e->total_bins, e->d_row_sig);
       B200_LAUNCHED();
     }
     return 0;
@@ -513,19 +515,26 @@ int b200hist_ellpack_import_reference(b200hist_ellpack_t e, const uint8_t* gidx_
   B200_CHECK(is_dense || e->has_missing, "page with missing values needs an ellpack created with has_missing=1");
   DeviceGuard guard(e->device);
   auto s = static_cast<cudaStream_t>(stream);
-  uint64_t total = e->n_rows * (uint64_t)e->n_features;
-  if (total == 0) return 0;
+  uint64_t total = n_rows * (uint64_t)e->n_features;
   int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
+  uint8_t* dst = e->d_bins + row_begin * (uint64_t)e->row_bytes;
   if (e->bin_bytes == 1) {
-    ImportReferenceKernel<uint8_t><<<blocks, 256, 0, s>>>(gidx_buffer_dev, e->n_rows, e->n_features, bits, ref_null,
-                                                         e->d_bins, e->row_bytes, e->null_symbol);
+    ImportReferenceKernel<uint8_t><<<blocks, 256, 0, s>>>(gidx_buffer_dev, n_rows, e->n_features, bits, ref_null, dst,
+                                                         e->row_bytes, e->null_symbol);
   } else {
-    ImportReferenceKernel<uint16_t><<<blocks, 256, 0, s>>>(gidx_buffer_dev, e->n_rows, e->n_features, bits, ref_null,
-                                                          e->d_bins, e->row_bytes, e->null_symbol);
+    ImportReferenceKernel<uint16_t><<<blocks, 256, 0, s>>>(gidx_buffer_dev, n_rows, e->n_features, bits, ref_null, dst,
+                                                          e->row_bytes, e->null_symbol);
   }
   B200_LAUNCHED();
-  LaunchTranspose(e, 0, e->n_rows, s);
+  LaunchTranspose(e, row_begin, n_rows, s);
   B200_API_END();
+}
+
+int b200hist_ellpack_import_reference(b200hist_ellpack_t e, const uint8_t* gidx_buffer_dev, uint32_t row_stride,
+                                      uint32_t n_symbols, int is_dense, void* stream) {
+  if (e == nullptr) return b200hist_ellpack_import_reference_rows(e, 0, 0, gidx_buffer_dev, row_stride, n_symbols, is_dense, stream);
+  return b200hist_ellpack_import_reference_rows(e, 0, e->n_rows, gidx_buffer_dev, row_stride, n_symbols, is_dense,
+                                                stream);
 }
 
 int b200hist_ellpack_info(b200hist_ellpack_t e, uint64_t* n_rows, uint32_t* n_features, uint32_t* total_bins,

@@ -106,30 +106,37 @@ class B200HistMaker : public TreeUpdater {
   void InitDataOnce(TrainParam const* param, DMatrix* p_fmat) {
     if (updater_ != nullptr && p_last_fmat_ == p_fmat) return;
     this->Release();
-    CHECK(p_fmat->SingleColBlock()) << "[b200hist] external-memory DMatrix is not supported yet";
+    // In-core DMatrix: exactly one page.  ExtMemQuantileDMatrix: the pages come one at a time (host or disk cache);
+    // each is decoded into its row range of ONE resident page of ours -- an external-memory matrix that fits HBM
+    // trains like an in-core one (histograms are integer sums: the result does not depend on the paging).
+    std::uint64_t const n_total = p_fmat->Info().num_row_;
     for (auto const& page : p_fmat->GetBatches<EllpackPage>(ctx_, cuda_impl::HistBatch(*param))) {
       auto const* impl = page.Impl();
-      auto cuts = impl->CutsShared();
-      auto const& ptrs = cuts->cut_ptrs_.ConstHostVector();
-      auto const& vals = cuts->cut_values_.ConstHostVector();
-      if (impl->IsDenseCompressed()) {
-        int const has_missing = impl->IsDense() ? 0 : 1;
-        B200_SHIM_CHECK(b200hist_ellpack_create(ctx_->Ordinal(), impl->n_rows,
-                                                static_cast<std::uint32_t>(ptrs.size() - 1), ptrs.data(), vals.data(),
-                                                has_missing, &ellpack_));
-      } else {  // sparse ELLPACK: global-bin symbols, row_stride < n_features (ellpack_page.cu:140-183)
-        B200_SHIM_CHECK(b200hist_ellpack_create_sparse(ctx_->Ordinal(), impl->n_rows,
-                                                       static_cast<std::uint32_t>(ptrs.size() - 1), ptrs.data(),
-                                                       vals.data(), static_cast<std::uint32_t>(impl->info.row_stride),
-                                                       &ellpack_));
+      if (ellpack_ == nullptr) {
+        auto cuts = impl->CutsShared();
+        auto const& ptrs = cuts->cut_ptrs_.ConstHostVector();
+        auto const& vals = cuts->cut_values_.ConstHostVector();
+        if (impl->IsDenseCompressed()) {
+          int const has_missing = impl->IsDense() ? 0 : 1;
+          B200_SHIM_CHECK(b200hist_ellpack_create(ctx_->Ordinal(), n_total,
+                                                  static_cast<std::uint32_t>(ptrs.size() - 1), ptrs.data(), vals.data(),
+                                                  has_missing, &ellpack_));
+        } else {  // sparse ELLPACK: global-bin symbols, row_stride < n_features (ellpack_page.cu:140-183)
+          B200_SHIM_CHECK(b200hist_ellpack_create_sparse(ctx_->Ordinal(), n_total,
+                                                         static_cast<std::uint32_t>(ptrs.size() - 1), ptrs.data(),
+                                                         vals.data(), static_cast<std::uint32_t>(impl->info.row_stride),
+                                                         &ellpack_));
+        }
       }
-      B200_SHIM_CHECK(b200hist_ellpack_import_reference(ellpack_, impl->gidx_buffer.data(),
-                                                        static_cast<std::uint32_t>(impl->info.row_stride),
-                                                        static_cast<std::uint32_t>(impl->NumSymbols()),
-                                                        impl->IsDense() ? 1 : 0,
-                                                        static_cast<void*>(ctx_->CUDACtx()->Stream())));
-      break;  // in-core: exactly one page
+      B200_SHIM_CHECK(b200hist_ellpack_import_reference_rows(
+          ellpack_, static_cast<std::uint64_t>(impl->base_rowid), static_cast<std::uint64_t>(impl->n_rows),
+          impl->gidx_buffer.data(), static_cast<std::uint32_t>(impl->info.row_stride),
+          static_cast<std::uint32_t>(impl->NumSymbols()), impl->IsDense() ? 1 : 0,
+          static_cast<void*>(ctx_->CUDACtx()->Stream())));
+      // the reference may recycle the page's buffer as soon as the iterator advances
+      ctx_->CUDACtx()->Stream().Sync();
     }
+    CHECK(ellpack_ != nullptr) << "[b200hist] the DMatrix yielded no Ellpack page";
     b200hist_train_param p{};
     p.max_depth = param->max_depth;
     p.max_leaves = param->max_leaves;

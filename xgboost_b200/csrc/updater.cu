@@ -500,13 +500,18 @@ __global__ void __launch_bounds__(256) FinaliseWindowKernel(EllView ell, const u
   const bool any_h_zero = qd->h_zero_any != 0u;
   const uint32_t n_windows = (n_rows + kFinWindow - 1) / kFinWindow;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  for (uint32_t wdx = blockIdx.x; wdx < n_windows; wdx += gridDim.x) {
+  // a CTA takes CONSECUTIVE windows: a slice starts where the previous window's slice ended, so only the first
+  // window of a CTA pays the full binary search per segment (when all segments fit one 256-thread chunk)
+  const uint32_t w_first = (uint32_t)(((unsigned long long)blockIdx.x * n_windows) / gridDim.x);
+  const uint32_t w_last = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_windows) / gridDim.x);
+  const bool carry = n_final <= 256u;
+  for (uint32_t wdx = w_first; wdx < w_last; ++wdx) {
     const uint32_t r_begin = wdx * kFinWindow, r_end = min(n_rows, r_begin + kFinWindow);
     for (uint32_t base = 0; base < n_final; base += 256) {
       if (base + threadIdx.x < n_final) {  // one thread per terminal segment: its slice inside the window
         const BuildEntry e = fin[base + threadIdx.x];
         const uint32_t* __restrict__ r = (e.buf ? ridx1 : ridx0) + e.begin;
-        const uint32_t lo = LowerBoundRow(r, 0u, e.count, r_begin);
+        const uint32_t lo = (carry && wdx > w_first) ? s_hi[threadIdx.x] : LowerBoundRow(r, 0u, e.count, r_begin);
         s_lo[threadIdx.x] = lo;
         s_hi[threadIdx.x] = LowerBoundRow(r, lo, min(e.count, lo + kFinWindow), r_end);
       }
@@ -521,17 +526,57 @@ __global__ void __launch_bounds__(256) FinaliseWindowKernel(EllView ell, const u
       s_off[threadIdx.x] = off;
       if (threadIdx.x == 0) s_off[256] = total_rows;
       __syncthreads();
-      for (uint32_t e0 = warp * 32u; e0 < total_rows; e0 += 8u * 32u) {
-        const uint32_t eidx = e0 + lane;
-        if (eidx < total_rows) {
-          uint32_t lo = 0, hi = m;  // last slice with s_off[k] <= eidx
-          while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s_off[mid] <= eidx) lo = mid; else hi = mid;
+      // four entries per lane and step: their row-id loads are issued together (the chain row id -> node -> symbol
+      // is latency bound), then the walks
+      for (uint32_t e0 = warp * 128u; e0 < total_rows; e0 += 8u * 128u) {
+        uint32_t row[4];
+        int nid[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t eidx = e0 + u * 32u + lane;
+          ok[u] = eidx < total_rows;
+          row[u] = 0u;
+          nid[u] = 0;
+          if (ok[u]) {
+            uint32_t lo = 0, hi = m;  // last slice with s_off[k] <= eidx
+            while (hi - lo > 1) {
+              const uint32_t mid = (lo + hi) >> 1;
+              if (s_off[mid] <= eidx) lo = mid; else hi = mid;
+            }
+            const BuildEntry en = fin[base + lo];
+            nid[u] = en.nidx;
+            row[u] = __ldg((en.buf ? ridx1 : ridx0) + en.begin + s_lo[lo] + (eidx - s_off[lo]));
           }
-          const BuildEntry en = fin[base + lo];
-          const uint32_t row = __ldg((en.buf ? ridx1 : ridx0) + en.begin + s_lo[lo] + (eidx - s_off[lo]));
-          s_pos[row - r_begin] = WalkToLeaf<BinT>(ell, nodes, en.nidx, row);
+        }
+        if (ell.is_sparse || ell.bins_t == nullptr) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (ok[u]) s_pos[row[u] - r_begin] = WalkToLeaf<BinT>(ell, nodes, nid[u], row[u]);
+        } else {  // the four walks level by level, so that their symbol gathers overlap
+          bool live[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) live[u] = ok[u] && !nodes[nid[u]].is_leaf;
+          while (live[0] || live[1] || live[2] || live[3]) {
+            uint32_t sym[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              sym[u] = live[u] ? (uint32_t)__ldg(reinterpret_cast<const BinT*>(ell.bins_t) +
+                                                 (uint64_t)nodes[nid[u]].findex * ell.col_stride + row[u])
+                               : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (live[u]) {
+                const NodeDev& nd = nodes[nid[u]];
+                const bool left = (sym[u] == ell.null_symbol) ? (nd.default_left != 0) : ((int32_t)sym[u] < nd.split_lbin);
+                nid[u] = left ? nd.left : nd.right;
+                live[u] = !nodes[nid[u]].is_leaf;
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (ok[u]) s_pos[row[u] - r_begin] = nid[u];
         }
       }
       __syncthreads();

@@ -86,6 +86,8 @@ _SIGNATURES = {
     "b200hist_ellpack_destroy": (c_int, [c_void_p]),
     "b200hist_ellpack_push_dense": (c_int, [c_void_p, c_uint64, c_void_p, c_uint64, c_uint64, c_void_p]),
     "b200hist_ellpack_import_reference": (c_int, [c_void_p, c_void_p, c_uint32, c_uint32, c_int, c_void_p]),
+    "b200hist_ellpack_import_reference_rows": (c_int, [c_void_p, c_uint64, c_uint64, c_void_p, c_uint32, c_uint32, c_int,
+                                                       c_void_p]),
     "b200hist_ellpack_info": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint32), POINTER(c_uint32),
                                       POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32), POINTER(c_void_p)]),
     "b200hist_ellpack_copy_bins_to_host": (c_int, [c_void_p, c_void_p]),
