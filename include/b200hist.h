@@ -241,6 +241,17 @@ B200HIST_API int b200hist_updater_set_peers(b200hist_updater_t u, int rank, int 
 B200HIST_API int b200hist_updater_set_tree_sampling(b200hist_updater_t u, const int32_t* feature_set_host,
                                                     uint32_t n_feature_set, float subsample, uint32_t subsample_seed);
 
+/* colsample_bylevel: one feature list per depth, sets_host[n_levels][n_per_level], each strictly ascending -- what
+ * ColumnSampler::GetFeatureSet(depth) returns for depth = 0, 1, ... (src/common/random.h:156-175; every level draws
+ * the same number of features from the tree's set); a node at depth d is evaluated on row min(d, n_levels - 1).
+ * Replaces the tree-level set of b200hist_updater_set_tree_sampling (row sampling is kept); NULL / 0 removes it.
+ * The reference draws a level's set lazily, when the first node of that depth is evaluated:
+ * b200hist_updater_last_max_eval_depth tells the caller how many of the pre-drawn levels the last tree really used,
+ * so that it can leave its random engine exactly where the reference would (the shim does). */
+B200HIST_API int b200hist_updater_set_level_feature_sets(b200hist_updater_t u, const int32_t* sets_host,
+                                                         uint32_t n_levels, uint32_t n_per_level);
+B200HIST_API int b200hist_updater_last_max_eval_depth(b200hist_updater_t u, int32_t* out);
+
 /* Monotone constraints = TreeEvaluator (src/tree/split_evaluator.h:25-205): constraints_host[f] in {-1, 0, +1} for the
  * first n features (the rest 0); n = 0 or NULL removes them.  A non-empty list switches every split gain to the
  * weight-based form -(2 g w + (h + lambda) w^2) with child weights clamped into the bounds of the node being split

@@ -176,7 +176,7 @@ def random_weight(seed: int, i: int) -> float:
 
 def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override=None, max_nodes=None,
                 is_dense_layout=True, want_hist=False, feature_set=None, subsample=1.0, sample_seed=0,
-                monotone=None):
+                monotone=None, level_feature_sets=None):
     """Whole tree.  Returns dict(nodes=[Node...], position, scale, hist (optional), cands).
     feature_set: sorted feature ids of the tree's colsample_bytree draw; subsample/sample_seed: uniform row sampling;
     monotone: per-feature sign (+1 increasing, -1 decreasing, 0 free), padded with 0 to n_features."""
@@ -197,6 +197,10 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
     so = (c_double * 4)(*[float(v) for v in scale_override]) if scale_override is not None else None
     hist = np.zeros((max_nodes, cv.size, 2), dtype=np.int64) if want_hist else None
     fs = np.ascontiguousarray(feature_set, dtype=np.int32) if feature_set is not None else None
+    n_levels, n_fs = 0, (0 if fs is None else fs.size)
+    if level_feature_sets is not None:   # colsample_bylevel: [n_levels][n_per_level], row = node depth
+        fs = np.ascontiguousarray(level_feature_sets, dtype=np.int32)
+        n_levels, n_fs = fs.shape
     mono = None
     if monotone is not None:
         mono = np.zeros(nf, dtype=np.int32)
@@ -204,9 +208,9 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
     nn = lib().orc_update_tree_ex(_p(gb), c_uint64(n), c_uint32(stride), c_int(1 if is_dense_layout else 0),
                                   c_uint32(nf), _p(cp), _p(cv), _p(g), byref(param), so, nodes, c_int32(max_nodes),
                                   _p(pos), _p(hist) if want_hist else c_void_p(), cands, scale_out,
-                                  _p(fs) if fs is not None else c_void_p(), c_int32(0 if fs is None else fs.size),
+                                  _p(fs) if fs is not None else c_void_p(), c_int32(n_fs),
                                   c_float(subsample), c_uint32(int(sample_seed) & 0xFFFFFFFF),
-                                  _p(mono) if mono is not None else c_void_p())
+                                  _p(mono) if mono is not None else c_void_p(), c_int32(n_levels))
     return dict(nodes=list(nodes[:nn]), cands=list(cands[:nn]), position=pos,
                 scale=np.array(scale_out[:], dtype=np.float64), hist=hist[:nn] if want_hist else None)
 

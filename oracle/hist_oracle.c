@@ -530,7 +530,7 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
                                    orc_node* nodes, int32_t max_nodes, int32_t* position,
                                    orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4],
                                    const int32_t* feature_set, int32_t n_feature_set, float subsample,
-                                   uint32_t sample_seed, const int32_t* monotone);
+                                   uint32_t sample_seed, const int32_t* monotone, int32_t n_levels);
 
 ORC_API int32_t orc_update_tree(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
                                 uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
@@ -539,7 +539,7 @@ ORC_API int32_t orc_update_tree(const int32_t* gbins, uint64_t n_rows, uint32_t 
                                 orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4]) {
   return orc_update_tree_ex(gbins, n_rows, stride, is_dense_layout, n_features, cut_ptrs, cut_values, gpair, p,
                             scale_override, nodes, max_nodes, position, hist_dump, cand_dump, scale_out, NULL, 0, 1.0f,
-                            0u, NULL);
+                            0u, NULL, 0);
 }
 
 /* feature_set (sorted ascending, NULL = all): the tree's colsample_bytree draw, evaluated in this order
@@ -551,7 +551,11 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
                                    orc_node* nodes, int32_t max_nodes, int32_t* position,
                                    orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4],
                                    const int32_t* feature_set, int32_t n_feature_set, float subsample,
-                                   uint32_t sample_seed, const int32_t* monotone) {
+                                   uint32_t sample_seed, const int32_t* monotone, int32_t n_levels) {
+  /* n_levels > 0 (colsample_bylevel): feature_set is [n_levels][n_feature_set], a node at depth d is evaluated on
+   * row min(d, n_levels - 1) = ColumnSampler::GetFeatureSet(depth), src/common/random.h:156-175 */
+#define ORC_LEVEL_SET(d) \
+  ((feature_set && n_levels > 0) ? feature_set + (size_t)((d) < n_levels ? (d) : n_levels - 1) * n_feature_set : feature_set)
   /* monotone (NULL or n_features signs): TreeEvaluator bounds per node, -/+FLT_MAX at the root */
   float* lower = (float*)malloc(sizeof(float) * (size_t)max_nodes);
   float* upper = (float*)malloc(sizeof(float) * (size_t)max_nodes);
@@ -601,7 +605,7 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
   }
   entry_t root_e;
   root_e.nidx = 0; root_e.depth = 0; root_e.open = 1;
-  orc_eval_node_mono(hist[0], root, cut_ptrs, cut_values, n_features, feature_set, n_feature_set, p, scale, &root_e.c, NULL, monotone, lower[0], upper[0]);
+  orc_eval_node_mono(hist[0], root, cut_ptrs, cut_values, n_features, ORC_LEVEL_SET(0), n_feature_set, p, scale, &root_e.c, NULL, monotone, lower[0], upper[0]);
   if (cand_dump) cand_dump[0] = root_e.c;
   /* driver.Push(vector) filters loss_chg > kRtEps (driver.h:42-50) */
   int n_open = 0;
@@ -692,7 +696,7 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
       for (int s = 0; s < 2; ++s) {
         entry_t e;
         e.nidx = ch[s]; e.depth = depth + 1; e.open = 1;
-        orc_eval_node_mono(hist[ch[s]], node_sum[ch[s]], cut_ptrs, cut_values, n_features, feature_set, n_feature_set, p, scale, &e.c, NULL, monotone, lower[ch[s]], upper[ch[s]]);
+        orc_eval_node_mono(hist[ch[s]], node_sum[ch[s]], cut_ptrs, cut_values, n_features, ORC_LEVEL_SET(depth + 1), n_feature_set, p, scale, &e.c, NULL, monotone, lower[ch[s]], upper[ch[s]]);
         if (cand_dump) cand_dump[ch[s]] = e.c;
         if (e.c.loss_chg > 1e-6f) { queue[ch[s]] = e; n_open++; }
       }
@@ -718,6 +722,7 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
   for (int32_t i = 0; i < max_nodes; ++i) free(hist[i]);
   free(hist); free(seg_beg); free(seg_cnt); free(node_sum); free(ridx); free(tmp); free(queue); free(gq);
   free(lower); free(upper);
+#undef ORC_LEVEL_SET
   return n_nodes;
 }
 

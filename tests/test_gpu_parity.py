@@ -558,6 +558,40 @@ def test_uint16_pages_take_the_banked_kernels(xb, n, f, max_bin, missing, obj):
         pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
 
 
+@pytest.mark.parametrize("extra", [dict(max_depth=5), dict(max_depth=0, max_leaves=14, grow_policy="lossguide")],
+                         ids=["depthwise", "lossguide"])
+def test_level_feature_sets_match_oracle(xb, extra):
+    """colsample_bylevel: one feature list per depth; a node is evaluated on the list of its depth (the last list
+    serves deeper nodes) and the updater reports the deepest level it evaluated."""
+    import torch
+    n, f = 20000, 24
+    x, y = make_regression(n, f, seed=51)
+    cp, cv = make_cuts(x, 32)
+    page = _page(xb, x, cp, cv)
+    gb = orc.bin_dense(x, cp, cv)
+    rng = np.random.default_rng(5)
+    sets = np.stack([np.sort(rng.choice(f, size=7, replace=False)) for _ in range(6)]).astype(np.int32)
+    params = dict(eta=0.5)
+    params.update(extra)
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    up.set_level_feature_sets(sets)
+    gp = squared_error_gpair(np.zeros(n, np.float32), y)
+    tree = up.update(torch.from_numpy(gp).cuda())
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), level_feature_sets=sets, want_hist=True)
+    _compare_tree(xb, up, tree, o, cp, cv, hists=True)
+    for nd in tree.nodes:
+        if not nd["is_leaf"]:
+            assert nd["findex"] in set(sets[min(nd["depth"], 5)].tolist())
+    # deepest evaluated level: every internal node was evaluated, plus children that were allowed to be
+    assert up.last_max_eval_depth() >= max(nd["depth"] for nd in tree.nodes if not nd["is_leaf"])
+    assert up.last_max_eval_depth() <= tree.max_depth()
+    up.set_level_feature_sets(None)
+    t_plain = up.update(torch.from_numpy(gp).cuda())
+    o_plain = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params))
+    _compare_tree(xb, up, t_plain, o_plain, cp, cv, hists=False)
+
+
 def test_host_gradient_entry_matches_device_entry(xb):
     import torch
     n, f = 5000, 6

@@ -72,6 +72,9 @@ def _ensure_shim(rc):
 
 
 @pytest.mark.parametrize("extra", [{"subsample": 0.7}, {"colsample_bytree": 0.5}, {"subsample": 0.5, "colsample_bytree": 0.6},
+                                   {"colsample_bylevel": 0.5},
+                                   {"colsample_bylevel": 0.6, "colsample_bytree": 0.8, "subsample": 0.7, "max_depth": 8},
+                                   {"colsample_bylevel": 0.5, "grow_policy": "lossguide", "max_leaves": 20, "max_depth": 0},
                                    {"monotone_constraints": "(1,-1,0,1,0,0,-1)"},
                                    {"monotone_constraints": "(1,1,1,1)", "subsample": 0.8, "max_delta_step": 0.7},
                                    {"subsample": 0.8, "seed": 123, "grow_policy": "lossguide", "max_leaves": 24, "max_depth": 0}],
@@ -94,7 +97,8 @@ def test_sampling_through_the_shim_matches_reference(cuda_device, extra):
     assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))
     # sampling really happened: the unsampled model differs
     plain, _ = _train(rc, x, y, dict({k: v for k, v in params.items()
-                                      if k not in ("subsample", "colsample_bytree", "monotone_constraints")},
+                                      if k not in ("subsample", "colsample_bytree", "colsample_bylevel",
+                                                   "monotone_constraints")},
                                      updater="grow_b200_hist"), 4)
     assert json.dumps(plain) != json.dumps(our_trees)
 

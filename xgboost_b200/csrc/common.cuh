@@ -200,7 +200,7 @@ struct TreeState {
   int32_t n_final;
   unsigned long long row_visits;
   int32_t stopped;  // lossguide: Pop() returned an invalid top -> growth ended
-  int32_t pad;
+  int32_t max_eval_depth;  // deepest node that went through split evaluation
 };
 
 struct QuantDev {
@@ -316,7 +316,9 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = n
                     const int32_t* eval_nodes, const TreeState* ts /* n_eval */, int32_t max_eval,
                     const NodeDev* nodes, const int32_t* feature_set, int32_t n_feature_set,
                     const ParamDev& p, const QuantDev* q, FeatCand* scratch, b200hist_candidate* cand,
-                    NodeDev* nodes_mut, int num_sms, cudaStream_t s, MonoView mono = MonoView{nullptr, nullptr, nullptr});
+                    NodeDev* nodes_mut, int num_sms, cudaStream_t s, MonoView mono = MonoView{nullptr, nullptr, nullptr},
+                    int32_t n_levels = 0 /* > 0: feature_set is [n_levels][n_feature_set], row = node depth */,
+                    int32_t* max_eval_depth = nullptr /* device: atomicMax of the depths evaluated */);
 
 // partition.cu
 void LaunchPartitionCount(const EllView& ell, const uint32_t* ridx0, const uint32_t* ridx1, const PartEntry* part,

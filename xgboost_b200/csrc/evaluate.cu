@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32)
 FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t* __restrict__ eval_nodes,
                   const TreeState* __restrict__ ts, const NodeDev* __restrict__ nodes,
                   const int32_t* __restrict__ feature_set, int32_t n_fs, ParamDev p,
-                  const QuantDev* __restrict__ q, FeatCand* __restrict__ scratch, MonoView mono) {
+                  const QuantDev* __restrict__ q, FeatCand* __restrict__ scratch, MonoView mono, int32_t n_levels) {
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * kEvalWarps + (threadIdx.x >> 5);
   const int n_warps = gridDim.x * kEvalWarps;
@@ -105,8 +105,11 @@ FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t
   for (long long item = warp_global; item < total; item += n_warps) {
     const int slot = (int)(item / n_fs);
     const int fpos = (int)(item - (long long)slot * n_fs);
-    const int f = feature_set ? feature_set[fpos] : fpos;
     const int nidx = eval_nodes[slot];
+    // colsample_bylevel: feature_set holds one list of n_fs ids per depth (the last row serves deeper nodes)
+    const int32_t* __restrict__ fs =
+        (feature_set && n_levels > 0) ? feature_set + (size_t)min(nodes[nidx].depth, n_levels - 1) * n_fs : feature_set;
+    const int f = fs ? fs[fpos] : fpos;
     const longlong2* h = hist + (size_t)nodes[nidx].hist_slot * ell.total_bins;
     const long long pg = nodes[nidx].sum_g, ph = nodes[nidx].sum_h;
     const uint32_t beg = ell.cut_ptrs[f], end = ell.cut_ptrs[f + 1];
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32)
 NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const TreeState* __restrict__ ts,
                  NodeDev* __restrict__ nodes, const int32_t* __restrict__ feature_set, int32_t n_fs, ParamDev p,
                  const QuantDev* __restrict__ q, const FeatCand* __restrict__ scratch,
-                 b200hist_candidate* __restrict__ cand, MonoView mono) {
+                 b200hist_candidate* __restrict__ cand, MonoView mono, int32_t n_levels, int32_t* max_eval_depth) {
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * kEvalWarps + (threadIdx.x >> 5);
   const int n_warps = gridDim.x * kEvalWarps;
@@ -246,7 +249,10 @@ NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const Tree
       c.split_gbin = -1;
       if (bpos != 0x7fffffff && sc[bpos].gbin >= 0) {
         FeatCand w = sc[bpos];
-        int f = feature_set ? feature_set[bpos] : bpos;
+        const int32_t* fs = (feature_set && n_levels > 0)
+                                ? feature_set + (size_t)min(nodes[nidx].depth, n_levels - 1) * n_fs
+                                : feature_set;
+        int f = fs ? fs[bpos] : bpos;
         c.loss_chg = w.loss_chg;
         c.dir = w.dir;
         c.findex = f;
@@ -267,6 +273,7 @@ NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const Tree
       c.left_weight = BoundedWeight(p, (double)c.left_sum.grad * tfg, (double)c.left_sum.hess * tfh, w_lo, w_hi);
       c.right_weight = BoundedWeight(p, (double)c.right_sum.grad * tfg, (double)c.right_sum.hess * tfh, w_lo, w_hi);
       cand[nidx] = c;
+      if (max_eval_depth) atomicMax(max_eval_depth, nodes[nidx].depth);
       // Driver::Push filter (driver.h:42-50): kRtEps = 1e-6f
       nodes[nidx].cand_open = c.loss_chg > 1e-6f ? 1 : 0;
     }
@@ -276,17 +283,18 @@ NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const Tree
 void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist, const int32_t* eval_nodes, const TreeState* ts,
                     int32_t max_eval, const NodeDev* nodes, const int32_t* feature_set, int32_t n_feature_set,
                     const ParamDev& p, const QuantDev* q, FeatCand* scratch, b200hist_candidate* cand,
-                    NodeDev* nodes_mut, int num_sms, cudaStream_t s, MonoView mono) {
+                    NodeDev* nodes_mut, int num_sms, cudaStream_t s, MonoView mono, int32_t n_levels,
+                    int32_t* max_eval_depth) {
   const int32_t n_fs = feature_set ? n_feature_set : (int32_t)ell.n_features;
   long long max_items = (long long)max_eval * n_fs;
   if (max_items == 0) return;
   int blocks = (int)std::min<long long>((max_items + kEvalWarps - 1) / kEvalWarps, (long long)num_sms * 8);
   FeatureScanKernel<<<blocks, kEvalWarps * 32, 0, s>>>(ell, reinterpret_cast<const longlong2*>(hist), eval_nodes, ts,
-                                                       nodes, feature_set, n_fs, p, q, scratch, mono);
+                                                       nodes, feature_set, n_fs, p, q, scratch, mono, n_levels);
   B200_LAUNCHED();
   int blocks2 = (int)std::min<long long>(((long long)max_eval + kEvalWarps - 1) / kEvalWarps, (long long)num_sms * 4);
   NodeReduceKernel<<<blocks2, kEvalWarps * 32, 0, s>>>(ell, eval_nodes, ts, nodes_mut, feature_set, n_fs, p, q, scratch,
-                                                       cand, mono);
+                                                       cand, mono, n_levels, max_eval_depth);
   B200_LAUNCHED();
 }
 

@@ -28,6 +28,8 @@
 
 #include <algorithm>
 #include <memory>
+#include <type_traits>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -83,6 +85,7 @@ class B200HistMaker : public TreeUpdater {
       std::int32_t n_nodes{0};
       B200_SHIM_CHECK(b200hist_updater_update_tree(updater_, gpair, stream, nodes_.data(), &n_nodes,
                                                    pos.DevicePointer()));
+      this->FinishSampling(param, p_fmat);
       this->ReplayInto(p_tree, n_nodes);
       hist_maker_param_.CheckTreesSynchronized(ctx_, p_tree);
       ++t_idx;
@@ -150,8 +153,8 @@ class B200HistMaker : public TreeUpdater {
     CHECK(param->interaction_constraints.empty()) << "[b200hist] interaction constraints are not supported yet";
     CHECK(param->subsample == 1.0f || param->sampling_method == TrainParam::kUniform)
         << "[b200hist] gradient_based row sampling is not supported yet";
-    CHECK(param->colsample_bylevel == 1.0f && param->colsample_bynode == 1.0f)
-        << "[b200hist] colsample_bylevel / colsample_bynode are not supported yet (colsample_bytree is)";
+    CHECK(param->colsample_bynode == 1.0f)
+        << "[b200hist] colsample_bynode is not supported yet (colsample_bytree and colsample_bylevel are)";
     B200_SHIM_CHECK(b200hist_updater_create(ellpack_, &p, &updater_));
     if (!param->monotone_constraints.empty()) {  // TreeEvaluator ctor (split_evaluator.h:37-57)
       std::vector<std::int32_t> mono(param->monotone_constraints.cbegin(), param->monotone_constraints.cend());
@@ -171,20 +174,60 @@ class B200HistMaker : public TreeUpdater {
   void DrawSampling(TrainParam const* param, DMatrix* p_fmat) {
     bool const rows = param->subsample < 1.0f;
     bool const cols = param->colsample_bytree < 1.0f;
-    if (!rows && !cols && !sampling_set_) return;
+    bool const levels = param->colsample_bylevel < 1.0f;
+    if (!rows && !cols && !levels && !sampling_set_) return;
     std::uint32_t seed = rows ? static_cast<std::uint32_t>(ctx_->Rng()()) : 0u;
+    auto const& info = p_fmat->Info();
     std::vector<std::int32_t> fs;
-    if (cols) {
-      auto const& info = p_fmat->Info();
-      column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, 1.0f, 1.0f, param->colsample_bytree);
-      auto p_set = column_sampler_.GetFeatureSet(ctx_, 0);
-      auto const& h_set = p_set->ConstHostVector();
-      fs.assign(h_set.cbegin(), h_set.cend());
+    level_draws_pending_ = false;
+    if (levels) {
+      // ColumnSampler draws a level's set lazily, when the first node of that depth is evaluated
+      // (random.h:156-175).  Our tree is built without coming back to the host, so the sets of ALL possible depths
+      // are drawn up front from a COPY of the engine state; FinishSampling() then replays exactly the draws the
+      // reference would have made (the depths the tree really evaluated) on the real engine.
+      rng_before_columns_ = ctx_->Rng();
+      std::int32_t const n_levels =
+          param->max_depth > 0 ? param->max_depth : std::max<std::int32_t>(1, param->max_leaves - 1);
+      column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, 1.0f, param->colsample_bylevel,
+                           param->colsample_bytree);
+      std::size_t per_level = 0;
+      for (std::int32_t d = 0; d < n_levels; ++d) {
+        auto p_set = column_sampler_.GetFeatureSet(ctx_, d);
+        auto const& h_set = p_set->ConstHostVector();
+        if (d == 0) per_level = h_set.size();
+        CHECK_EQ(h_set.size(), per_level);
+        fs.insert(fs.end(), h_set.cbegin(), h_set.cend());
+      }
+      B200_SHIM_CHECK(b200hist_updater_set_tree_sampling(updater_, nullptr, 0, rows ? param->subsample : 1.0f, seed));
+      B200_SHIM_CHECK(b200hist_updater_set_level_feature_sets(updater_, fs.data(), static_cast<std::uint32_t>(n_levels),
+                                                              static_cast<std::uint32_t>(per_level)));
+      level_draws_pending_ = true;
+    } else {
+      if (cols) {
+        column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, 1.0f, 1.0f, param->colsample_bytree);
+        auto p_set = column_sampler_.GetFeatureSet(ctx_, 0);
+        auto const& h_set = p_set->ConstHostVector();
+        fs.assign(h_set.cbegin(), h_set.cend());
+      }
+      B200_SHIM_CHECK(b200hist_updater_set_level_feature_sets(updater_, nullptr, 0, 0));
+      B200_SHIM_CHECK(b200hist_updater_set_tree_sampling(updater_, cols ? fs.data() : nullptr,
+                                                         static_cast<std::uint32_t>(fs.size()),
+                                                         rows ? param->subsample : 1.0f, seed));
     }
-    B200_SHIM_CHECK(b200hist_updater_set_tree_sampling(updater_, cols ? fs.data() : nullptr,
-                                                       static_cast<std::uint32_t>(fs.size()),
-                                                       rows ? param->subsample : 1.0f, seed));
-    sampling_set_ = rows || cols;
+    sampling_set_ = rows || cols || levels;
+  }
+
+  // colsample_bylevel: leave ctx->Rng() where the reference would have left it after this tree.
+  void FinishSampling(TrainParam const* param, DMatrix* p_fmat) {
+    if (!level_draws_pending_) return;
+    std::int32_t deepest = 0;
+    B200_SHIM_CHECK(b200hist_updater_last_max_eval_depth(updater_, &deepest));
+    ctx_->Rng() = rng_before_columns_;
+    auto const& info = p_fmat->Info();
+    column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, 1.0f, param->colsample_bylevel,
+                         param->colsample_bytree);
+    for (std::int32_t d = 0; d <= deepest; ++d) (void)column_sampler_.GetFeatureSet(ctx_, d);
+    level_draws_pending_ = false;
   }
 
   // ApplySplit (updater_gpu_hist.cu:610-655): our nodes are numbered in the reference's expansion order,
@@ -234,6 +277,8 @@ class B200HistMaker : public TreeUpdater {
   DMatrix* p_last_fmat_{nullptr};
   common::ColumnSampler column_sampler_;
   bool sampling_set_{false};
+  bool level_draws_pending_{false};
+  std::remove_reference_t<decltype(std::declval<Context const&>().Rng())> rng_before_columns_;
 };
 
 // Replaces the factory of the reference's own "grow_gpu_hist" entry (keeping the original reachable as

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kCtlThreads) InitRootKernel(ParamDev p, uint32
     ts->n_nodes = 1; ts->num_leaves = 1; ts->level_begin = 0; ts->level_end = 1;
     ts->n_part = 0; ts->n_build = 1; ts->n_sub = 0; ts->n_eval = 1;
     ts->part_tiles = 0; ts->build_tiles = tiles; ts->final_tiles = 0; ts->n_final = 0;
-    ts->row_visits = n_rows; ts->stopped = 0;
+    ts->row_visits = n_rows; ts->stopped = 0; ts->max_eval_depth = 0;
   }
 }
 
@@ -663,6 +663,8 @@ struct b200hist_updater_s {
   float* d_upper{nullptr};
   int32_t* d_feature_set{nullptr};  // sorted feature ids of the tree's colsample_bytree draw (nullptr = all)
   int32_t n_feature_set{0};
+  int32_t n_feature_levels{0};      // > 0: d_feature_set holds one list per depth (colsample_bylevel)
+  int32_t last_max_eval_depth{0};
   bool row_split{false};                   // ranks own row slices (full-width partial histograms, summed) instead of feature blocks
   size_t flags_offset{0};                  // byte offset of the flag array inside the histogram allocation
   std::vector<void*> peer_base;            // opened IPC mappings (own entry = nullptr)
@@ -803,7 +805,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   timer.End(kHist, t2);
   auto t3 = timer.Begin();
   LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, u->d_feature_set, u->n_feature_set, u->pdev, u->d_quant,
-                 u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono);
+                 u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, u->n_feature_levels, &u->d_ts->max_eval_depth);
   timer.End(kEval, t3);
 
   const bool depthwise = u->param.grow_policy == 0;
@@ -837,7 +839,8 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     auto te = timer.Begin();
     LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, (int32_t)(2 * cap), u->d_nodes, u->d_feature_set,
                    u->n_feature_set, u->pdev,
-                   u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono);
+                   u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, u->n_feature_levels,
+                   &u->d_ts->max_eval_depth);
     timer.End(kEval, te);
   }
 
@@ -880,6 +883,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   timer.Collect();
   u->last_row_visits = u->h_ts->row_visits;
   u->last_n_nodes = u->h_ts->n_nodes;
+  u->last_max_eval_depth = u->h_ts->max_eval_depth;
   u->last_position = position;
   if (out_nodes) ToAbiNodes(u->h_nodes, u->last_n_nodes, out_nodes);
   if (out_n_nodes) *out_n_nodes = u->last_n_nodes;
@@ -1161,6 +1165,7 @@ int b200hist_updater_set_tree_sampling(b200hist_updater_t u, const int32_t* feat
     u->d_feature_set = nullptr;
     u->n_feature_set = 0;
   }
+  u->n_feature_levels = 0;
   if (feature_set_host != nullptr) {
     B200_CHECK(n_feature_set >= 1 && n_feature_set <= u->ell->n_features, "feature set size out of range");
     for (uint32_t i = 0; i < n_feature_set; ++i) {
@@ -1174,6 +1179,41 @@ int b200hist_updater_set_tree_sampling(b200hist_updater_t u, const int32_t* feat
   }
   u->subsample = subsample;
   u->sample_seed = subsample_seed;
+  B200_API_END();
+}
+
+int b200hist_updater_set_level_feature_sets(b200hist_updater_t u, const int32_t* sets_host, uint32_t n_levels,
+                                            uint32_t n_per_level) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  DeviceGuard guard(u->device);
+  if (u->d_feature_set) {
+    cudaFree(u->d_feature_set);
+    u->d_feature_set = nullptr;
+  }
+  u->n_feature_set = 0;
+  u->n_feature_levels = 0;
+  if (sets_host != nullptr && n_levels > 0) {
+    B200_CHECK(n_per_level >= 1 && n_per_level <= u->ell->n_features, "feature set size out of range");
+    for (uint32_t l = 0; l < n_levels; ++l)
+      for (uint32_t i = 0; i < n_per_level; ++i) {
+        const int32_t f = sets_host[(size_t)l * n_per_level + i];
+        B200_CHECK(f >= 0 && (uint32_t)f < u->ell->n_features, "feature id out of range in level feature set");
+        B200_CHECK(i == 0 || f > sets_host[(size_t)l * n_per_level + i - 1], "level feature sets must be strictly ascending");
+      }
+    const size_t total = (size_t)n_levels * n_per_level;
+    u->d_feature_set = DevAlloc<int32_t>(total);
+    B200_CUDA(cudaMemcpy(u->d_feature_set, sets_host, sizeof(int32_t) * total, cudaMemcpyHostToDevice));
+    u->n_feature_set = (int32_t)n_per_level;
+    u->n_feature_levels = (int32_t)n_levels;
+  }
+  B200_API_END();
+}
+
+int b200hist_updater_last_max_eval_depth(b200hist_updater_t u, int32_t* out) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && out != nullptr, "null argument");
+  *out = u->last_max_eval_depth;
   B200_API_END();
 }
 

@@ -427,6 +427,23 @@ class GPUHistMaker:
             _l.check(_l.load().b200hist_updater_set_tree_sampling(self._h, None, 0, float(subsample),
                                                                 int(seed) & 0xFFFFFFFF))
 
+    def set_level_feature_sets(self, sets) -> None:
+        """colsample_bylevel: `sets[d]` = sorted feature ids for nodes at depth d (the last row serves deeper nodes);
+        None removes them."""
+        if sets is None:
+            _l.check(_l.load().b200hist_updater_set_level_feature_sets(self._h, None, 0, 0))
+            return
+        a = np.ascontiguousarray(sets, dtype=np.int32)
+        if a.ndim != 2:
+            raise ValueError("sets must be [n_levels][n_per_level]")
+        _l.check(_l.load().b200hist_updater_set_level_feature_sets(self._h, a.ctypes.data_as(POINTER(c_int32)),
+                                                                 a.shape[0], a.shape[1]))
+
+    def last_max_eval_depth(self) -> int:
+        d = c_int32(0)
+        _l.check(_l.load().b200hist_updater_last_max_eval_depth(self._h, byref(d)))
+        return int(d.value)
+
     def set_monotone_constraints(self, constraints: Optional[Sequence[int]]) -> None:
         """TrainParam::monotone_constraints: sign per feature (+1 increasing, -1 decreasing, 0 free); None/[] = none."""
         if constraints is None or len(constraints) == 0:
