@@ -416,6 +416,43 @@ def run_b200(args):
                "h2d_bytes_per_step": int(n_total) * 8 if (world == 1 or row_split) else int(n_total) * 8 * world,
                "d2h_bytes_per_step": int(tr.num_nodes) * 48 + 4}
 
+    # north_star's decomposition measured next to the default one: all rows on every GPU, F/P feature blocks each,
+    # one peer-memory slice exchange per tree level (same matrix, same trees)
+    feature_block = None
+    if row_split and os.environ.get("B200_BENCH_ALSO_FEATURES", "1") != "0":
+        del up, page
+        torch.cuda.empty_cache()
+        page_f, y_f, _ = build_workload(torch, xb, args, device)
+        up_f = xb.GPUHistMaker(page_f)
+        up_f.configure(dict(max_depth=args.depth, eta=0.3, reg_lambda=1.0, min_child_weight=1.0))
+        up_f.enable_peer_exchange()
+        nf_rows = int(page_f.info()["n_rows"])
+        preds_f = torch.zeros(nf_rows, dtype=torch.float32, device=device)
+        gpair_f = torch.empty((nf_rows, 2), dtype=torch.float32, device=device)
+        gpair_f[:, 1] = 1.0
+
+        def step_f():
+            torch.sub(preds_f, y_f, out=gpair_f[:, 0])
+            up_f.update(gpair_f)
+            up_f.update_prediction_cache(preds_f)
+
+        for _ in range(3):
+            step_f()
+        barrier()
+        k3 = max(1, min(args.steps, 5))
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(k3):
+            step_f()
+        f1.record()
+        barrier()
+        tf = torch.tensor([f0.elapsed_time(f1) / k3], device=device)
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        feature_block = {"value": 1e3 / float(tf.item()), "unit": UNIT, "ms_per_step": float(tf.item()), "steps": k3,
+                         "parallelism": "feature-block shard x%d (north_star): all rows on every GPU, F/P feature "
+                                        "blocks each, one peer-memory slice exchange per tree level" % world}
+        del up_f, page_f, preds_f, gpair_f, y_f
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu_baseline = reference_cpu_iters_per_s(args, 3, 1, args.cpu_sample_rows)
@@ -439,7 +476,7 @@ def run_b200(args):
                                    % build_s["sketch_windows"]},
                 "dmatrix_build_s": {"sketch": round(build_s["sketch_s"], 3), "ellpack": round(build_s["ellpack_s"], 3)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "phase_ms": phase, "step_parts_ms": step_parts, "algorithmic_gb_per_step": {k: v / 1e9 for k, v in ab.items()}}
+                "clocks": clocks, "phase_ms": phase, "step_parts_ms": step_parts, "feature_block_shard": feature_block, "algorithmic_gb_per_step": {k: v / 1e9 for k, v in ab.items()}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
