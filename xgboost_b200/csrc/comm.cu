@@ -162,6 +162,7 @@ __device__ __forceinline__ void WaitPeers(uint32_t* const* peer_flags, int rank,
   }
 }
 
+template <int kWorld>  // 0 = run-time world size
 __global__ void __launch_bounds__(256)
 HistAllReduceKernel(longlong2* const* __restrict__ peer_hist, uint32_t* const* __restrict__ peer_flags, int rank,
                     int world, const TreeState* __restrict__ ts, uint32_t slot_base, uint32_t slot_cap,
@@ -177,14 +178,38 @@ HistAllReduceKernel(longlong2* const* __restrict__ peer_hist, uint32_t* const* _
   const unsigned long long total = (unsigned long long)n_slots * total_bins;
   const unsigned long long c0 = total * (unsigned)rank / (unsigned)world, c1 = total * (unsigned)(rank + 1) / (unsigned)world;
   const size_t base = (size_t)slot_base * total_bins;
-  for (unsigned long long i = c0 + blockIdx.x * 256ull + threadIdx.x; i < c1; i += (unsigned long long)gridDim.x * 256ull) {
-    longlong2 acc = make_longlong2(0, 0);
-    for (int p = 0; p < world; ++p) {
-      const longlong2 v = peer_hist[p][base + i];
-      acc.x += v.x;
-      acc.y += v.y;
+  // all peers' values of an element are requested before any is used: a remote load costs microseconds, and a
+  // load-add-load-add chain serialises them per thread.  The common world sizes are compiled with a fixed trip
+  // count so that the loads of one element (and of the next) are issued back to back.
+  if (kWorld > 0) {
+    const longlong2* src[kWorld > 0 ? kWorld : 1];
+#pragma unroll
+    for (int p = 0; p < kWorld; ++p) src[p] = peer_hist[p] + base;
+    for (unsigned long long i = c0 + blockIdx.x * 256ull + threadIdx.x; i < c1;
+         i += (unsigned long long)gridDim.x * 256ull) {
+      longlong2 v[kWorld > 0 ? kWorld : 1];
+#pragma unroll
+      for (int p = 0; p < kWorld; ++p) v[p] = src[p][i];
+      longlong2 acc = make_longlong2(0, 0);
+#pragma unroll
+      for (int p = 0; p < kWorld; ++p) {
+        acc.x += v[p].x;
+        acc.y += v[p].y;
+      }
+#pragma unroll
+      for (int p = 0; p < kWorld; ++p) peer_hist[p][base + i] = acc;
     }
-    for (int p = 0; p < world; ++p) peer_hist[p][base + i] = acc;
+  } else {
+    for (unsigned long long i = c0 + blockIdx.x * 256ull + threadIdx.x; i < c1;
+         i += (unsigned long long)gridDim.x * 256ull) {
+      longlong2 acc = make_longlong2(0, 0);
+      for (int p = 0; p < world; ++p) {
+        const longlong2 v = peer_hist[p][base + i];
+        acc.x += v.x;
+        acc.y += v.y;
+      }
+      for (int p = 0; p < world; ++p) peer_hist[p][base + i] = acc;
+    }
   }
   // barrier B: the last CTA to finish publishes the epoch and waits for every peer's
   __threadfence_system();
@@ -206,8 +231,12 @@ HistAllReduceKernel(longlong2* const* __restrict__ peer_hist, uint32_t* const* _
 void LaunchHistAllReduce(longlong2* const* peer_hist, uint32_t* const* peer_flags, int rank, int world,
                          const TreeState* ts, uint32_t slot_base, uint32_t slot_cap, uint32_t total_bins,
                          uint32_t epoch_a, uint32_t epoch_b, unsigned int* done_counter, int num_sms, cudaStream_t s) {
-  HistAllReduceKernel<<<num_sms * 2, 256, 0, s>>>(peer_hist, peer_flags, rank, world, ts, slot_base, slot_cap,
-                                                  total_bins, epoch_a, epoch_b, done_counter);
+  auto kernel = world == 2 ? HistAllReduceKernel<2>
+                : world == 4 ? HistAllReduceKernel<4>
+                : world == 8 ? HistAllReduceKernel<8>
+                             : HistAllReduceKernel<0>;
+  kernel<<<num_sms * 2, 256, 0, s>>>(peer_hist, peer_flags, rank, world, ts, slot_base, slot_cap, total_bins, epoch_a,
+                                     epoch_b, done_counter);
   B200_LAUNCHED();
 }
 
