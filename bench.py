@@ -420,6 +420,7 @@ def run_b200(args):
     # one peer-memory slice exchange per tree level (same matrix, same trees)
     feature_block = None
     if row_split and os.environ.get("B200_BENCH_ALSO_FEATURES", "1") != "0":
+        up.disable_peer_exchange()   # unmap on every rank, barrier, only then free
         del up, page
         torch.cuda.empty_cache()
         page_f, y_f, _ = build_workload(torch, xb, args, device)
@@ -451,6 +452,7 @@ def run_b200(args):
         feature_block = {"value": 1e3 / float(tf.item()), "unit": UNIT, "ms_per_step": float(tf.item()), "steps": k3,
                          "parallelism": "feature-block shard x%d (north_star): all rows on every GPU, F/P feature "
                                         "blocks each, one peer-memory slice exchange per tree level" % world}
+        up_f.disable_peer_exchange()
         del up_f, page_f, preds_f, gpair_f, y_f
 
     cpu_baseline = None

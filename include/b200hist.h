@@ -230,6 +230,11 @@ B200HIST_API int b200hist_updater_num_feature_groups(b200hist_updater_t u, uint3
  * handles_host: world x 64 bytes in rank order (the own entry is ignored). */
 B200HIST_API int b200hist_updater_ipc_handle(b200hist_updater_t u, uint8_t* out_handle64);
 B200HIST_API int b200hist_updater_set_peers(b200hist_updater_t u, int rank, int world, const uint8_t* handles_host);
+/* Unmap the peers' caches (cudaIpcCloseMemHandle) and return to single-GPU operation.  Freeing memory that another
+ * process still maps is undefined, so a job tears down in two steps: every rank calls this, the ranks meet at a
+ * barrier of the caller's control plane, then the updaters are destroyed. */
+B200HIST_API int b200hist_updater_clear_peers(b200hist_updater_t u);
+
 /* Per-tree sampling, applied to every following update_tree call until changed:
  *   feature_set_host (nullable = all features): the tree's colsample_bytree draw, strictly ascending feature ids --
  *     what ColumnSampler::GetFeatureSet(depth) returns when only colsample_bytree < 1 (src/common/random.h:101-132,

@@ -116,6 +116,11 @@ ref_l = up.update(gl)
 rs_l = up3.update(gl[lo:hi].contiguous())
 ok &= ref_l.structure() == rs_l.structure()
 ok &= [n["leaf_value"] for n in ref_l.nodes] == [n["leaf_value"] for n in rs_l.nodes]
+# teardown in two steps: unmap everywhere, barrier (inside), then the updaters may go
+up3.disable_peer_exchange()
+up2.disable_peer_exchange()
+t_after = up2.update(gp)   # back to single-GPU operation: the plain tree again
+ok &= single.structure() == t_after.structure()
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()

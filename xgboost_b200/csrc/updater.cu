@@ -1256,6 +1256,27 @@ int b200hist_updater_set_row_split(b200hist_updater_t u, int on) {
   B200_API_END();
 }
 
+int b200hist_updater_clear_peers(b200hist_updater_t u) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  DeviceGuard guard(u->device);
+  for (void*& p : u->peer_base) {
+    if (p != nullptr) cudaIpcCloseMemHandle(p);
+    p = nullptr;
+  }
+  if (u->d_peer_hist) cudaFree(u->d_peer_hist);
+  if (u->d_peer_flags) cudaFree(u->d_peer_flags);
+  u->d_peer_hist = nullptr;
+  u->d_peer_flags = nullptr;
+  u->p2p = false;
+  u->row_split = false;
+  u->p2p_world = 1;
+  u->p2p_rank = 0;
+  u->group_begin = 0;
+  u->group_end = (uint32_t)u->groups.size();
+  B200_API_END();
+}
+
 int b200hist_updater_num_feature_groups(b200hist_updater_t u, uint32_t* out) {
   B200_API_BEGIN();
   B200_CHECK(u != nullptr && out != nullptr, "null argument");

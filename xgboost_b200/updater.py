@@ -452,6 +452,14 @@ class GPUHistMaker:
             c = np.ascontiguousarray(constraints, dtype=np.int32)
             _l.check(_l.load().b200hist_updater_set_monotone_constraints(self._h, c.ctypes.data_as(POINTER(c_int32)), c.size))
 
+    def disable_peer_exchange(self) -> None:
+        """Unmap the peers' histogram caches and meet the other ranks at a barrier, so that nobody frees memory that
+        a peer still maps; call on every rank before dropping an updater that used enable_peer_exchange()."""
+        import torch.distributed as dist
+        _l.check(_l.load().b200hist_updater_clear_peers(self._h))
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+
     def num_feature_groups(self) -> int:
         n = c_uint32()
         _l.check(_l.load().b200hist_updater_num_feature_groups(self._h, byref(n)))
