@@ -1187,6 +1187,8 @@ int b200hist_updater_set_level_feature_sets(b200hist_updater_t u, const int32_t*
   B200_API_BEGIN();
   B200_CHECK(u != nullptr, "null argument");
   DeviceGuard guard(u->device);
+  if ((sets_host == nullptr || n_levels == 0) && u->n_feature_levels == 0) return 0;  // nothing to remove: a tree-level
+                                                                                       // set stays in force
   if (u->d_feature_set) {
     cudaFree(u->d_feature_set);
     u->d_feature_set = nullptr;
