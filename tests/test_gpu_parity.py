@@ -353,6 +353,8 @@ TREE_CASES = [
     dict(n=8000, f=12, max_bin=32, params=dict(max_depth=5, min_child_weight=50.0, reg_alpha=0.3)),
     dict(n=8000, f=12, max_bin=32, missing=0.2, params=dict(max_depth=5)),
     dict(n=6000, f=10, max_bin=300, params=dict(max_depth=4)),
+    dict(n=9000, f=10, max_bin=600, missing=0.1, params=dict(max_depth=4)),   # > 440 symbols: generic uint16 kernel
+    dict(n=9000, f=40, max_bin=700, params=dict(max_depth=3)),
     dict(n=9000, f=7, max_bin=32, params=dict(max_depth=6, max_leaves=9)),
     dict(n=9000, f=7, max_bin=32, params=dict(max_depth=0, max_leaves=12, grow_policy="lossguide")),
     dict(n=9000, f=7, max_bin=32, params=dict(max_depth=5, max_leaves=10, grow_policy="lossguide", min_split_loss=5.0)),
