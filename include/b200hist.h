@@ -104,7 +104,10 @@ B200HIST_API uint64_t b200hist_launch_count(void);
  *   DMatrix::GetBatches<EllpackPage> (src/tree/updater_gpu_hist.cu:735-756).
  * HBM layout (ours): row-major bins[n_rows][row_bytes]; one symbol per feature holding the
  * FEATURE-LOCAL bin (uint8 when every feature has <= 256 symbols incl. the null symbol, else
- * uint16); row_bytes is rounded up to 16 so every row is a legal TMA bulk-copy source.
+ * uint16); rows are zero-padded to whole 32-feature blocks (row_bytes = ceil32(n_features) *
+ * symbol bytes: every row 32-byte aligned); the null symbol of a page with missing values is the
+ * first symbol no feature uses (max bins per feature).  A column-major copy in the same symbol
+ * width serves the partitioner's single-feature gathers.
  * ------------------------------------------------------------------------------------------- */
 /* cut_ptrs_host: n_features+1 uint32 (HistogramCuts::cut_ptrs_), cut_values_host: total_bins f32.
  * has_missing: reserve a null symbol (dense-with-missing layout, ellpack_page.cu:140-183). */
@@ -241,7 +244,8 @@ B200HIST_API int b200hist_updater_clear_peers(b200hist_updater_t u);
  *     updater_gpu_hist.cu:199-217,257-261); split evaluation visits exactly these features in this order.
  *   subsample < 1: uniform row sampling = cuda_impl::UniformSampling::Sample (src/tree/gpu_hist/sampler.cu:160-173):
  *     the quantised gradient pair of row i is zeroed when RandomWeight(subsample_seed)(i) > subsample
- *     (minstd_rand + discard(i) + uniform float, sampler.cu:36-60); subsample_seed is the tree's ctx->Rng()() draw.
+ *     (minstd_rand + discard(i) + uniform float, sampler.cu:36-60); subsample_seed is the tree's ctx->Rng()() draw;
+ *     i is the row's index in THIS page (under row split: the rank-local index, as in the reference's workers).
  * colsample_bylevel / bynode and gradient_based sampling are not built. */
 B200HIST_API int b200hist_updater_set_tree_sampling(b200hist_updater_t u, const int32_t* feature_set_host,
                                                     uint32_t n_feature_set, float subsample, uint32_t subsample_seed);
