@@ -3,7 +3,9 @@
 //   -gencode arch=compute_100a,code=sm_100a; no public documentation in this environment, hence this probe).
 // It builds a uint8 matrix [n_rows][row_bytes] with row r filled with (r + column) mod 251, asks the TMA for 4
 // arbitrary rows x `box_cols` bytes starting at column `col0`, and prints what landed in shared memory, for a few
-// candidate tensor-map box shapes -- run it once on a B200 to learn which box shape the instruction expects:
+// candidate tensor-map box shapes.  RESULT on a B200 (driver 580, CUDA 12.9): with boxDim = {cols, 1} the four rows
+// {r0, r1, r2, r3} land back to back in shared memory (slot k = row r_k, cols bytes each) and the mbarrier completes
+// after 4 * cols bytes; boxDim = {cols, 4} raises "illegal instruction".  Build and run:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -o gather4_probe tools/gather4_probe.cu -lcuda && ./gather4_probe
 #include <cuda.h>
 #include <cuda_runtime.h>
