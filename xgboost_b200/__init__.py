@@ -3,10 +3,11 @@ TreeUpdater / EllpackPage interface.  Only the hot path lives here:
 
   csrc/          hand-written CUDA kernels + the C ABI (include/b200hist.h) -> lib/libb200hist.so
   lib.py         ctypes binding of the C ABI
-  updater.py     host-side mirror of the reference interface (HistogramCuts, EllpackPage,
-                 GPUHistMaker, RegTree)
-  components.py  per-stage entry points used by the parity tests
-  training.py    a minimal boosting loop (objective + prediction cache) to drive the updater
+  csrc/shim/     the reference-side binding (xgboost::TreeUpdater) -> lib/libb200hist_xgb_shim.so
+  lib.py         ctypes binding of the C ABI
+  updater.py     host-side mirror of the reference interface (HistogramCuts, QuantileSketch, EllpackPage,
+                 GPUHistMaker incl. sampling / constraints / peer exchange, RegTree)
+  components.py  per-stage entry points used by the parity tests, measured shared-atomic ceiling
 
 There is no CPU fallback: without the built library or without a CUDA device every compute call
 raises B200HistError.
