@@ -2,7 +2,6 @@
 TreeUpdater / EllpackPage interface.  Only the hot path lives here:
 
   csrc/          hand-written CUDA kernels + the C ABI (include/b200hist.h) -> lib/libb200hist.so
-  lib.py         ctypes binding of the C ABI
   csrc/shim/     the reference-side binding (xgboost::TreeUpdater) -> lib/libb200hist_xgb_shim.so
   lib.py         ctypes binding of the C ABI
   updater.py     host-side mirror of the reference interface (HistogramCuts, QuantileSketch, EllpackPage,
