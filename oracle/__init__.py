@@ -156,6 +156,32 @@ def eval_node(hist: np.ndarray, parent_sum, cut_ptrs, cut_values, param: Param, 
     return (out, gains) if want_gains else out
 
 
+def eval_node_cat(hist: np.ndarray, parent_sum, cut_ptrs, cut_values, param: Param, scale, feature_is_cat,
+                  max_cat_to_onehot: int, max_cat_threshold: int = 64, feature_set=None):
+    """Best split over numerical and categorical features (evaluate_splits.cu:148-348).  Returns
+    (candidate, is_cat, thresh, set of categories in the split's bit field)."""
+    h = np.ascontiguousarray(hist, dtype=np.int64)
+    cp = np.ascontiguousarray(cut_ptrs, dtype=np.uint32)
+    cv = np.ascontiguousarray(cut_values, dtype=np.float32)
+    sc = (c_double * 4)(*[float(v) for v in scale])
+    flags = np.ascontiguousarray(feature_is_cat, dtype=np.uint8)
+    out = Candidate()
+    if feature_set is not None:
+        fs = np.ascontiguousarray(feature_set, dtype=np.int32)
+        fsp, nfs = _p(fs), fs.size
+    else:
+        fsp, nfs = c_void_p(), 0
+    n_words = int(cv.max()) // 32 + 1 if cv.size else 1
+    bits = np.zeros(n_words, dtype=np.uint32)
+    is_cat, thresh = c_int32(0), c_int32(-1)
+    lib().orc_eval_node_cat(_p(h), GPair64(int(parent_sum[0]), int(parent_sum[1])), _p(cp), _p(cv),
+                            c_uint32(cp.size - 1), fsp, c_int32(nfs), byref(param), sc, _p(flags),
+                            c_int32(max_cat_to_onehot), c_int32(max_cat_threshold), byref(out), byref(is_cat),
+                            byref(thresh), _p(bits), c_uint32(n_words))
+    cats = {32 * w + (31 - b) for w in range(n_words) for b in range(32) if (int(bits[w]) >> b) & 1}
+    return out, bool(is_cat.value), int(thresh.value), cats
+
+
 def partition(gbins, cut_ptrs, cut_values, ridx, findex, split_cond, default_left, is_dense_layout=True):
     gb = np.ascontiguousarray(gbins, dtype=np.int32)
     cp = np.ascontiguousarray(cut_ptrs, dtype=np.uint32)

@@ -316,6 +316,72 @@ static void cand_init(orc_candidate* c) {
  * feature_set: list of feature ids to evaluate in order (NULL = all 0..F-1).
  * `gain_out` (optional, size total_bins*2): gain of every (bin, missing-left?0:1) for tie checks.
  * ---------------------------------------------------------------------------------------- */
+/* One numerical feature of one node: ReduceFeature + the 32-bin chunks of EvaluateSplitAgent::Numerical
+ * (evaluate_splits.cu:90-146) with DeviceSplitCandidate::Update (updater_gpu_common.cuh:68-83). */
+static void eval_feature_numerical(const orc_gpair64* hist, orc_gpair64 parent_sum, const uint32_t* cut_ptrs,
+                                   const float* cut_values, int32_t f, const orc_param* p, const double scale[4],
+                                   const orc_mono* mono, float* gain_out, orc_candidate* fbest_out) {
+  uint32_t beg = cut_ptrs[f], end = cut_ptrs[f + 1];
+  cand_init(fbest_out);
+  /* ReduceFeature: missing = parent - sum(bins of f)   (evaluate_splits.cu:90-101) */
+  orc_gpair64 fsum = {0, 0};
+  for (uint32_t b = beg; b < end; ++b) fsum = gp_add(fsum, hist[b]);
+  orc_gpair64 missing = gp_sub(parent_sum, fsum);
+  orc_gpair64 running = {0, 0}; /* exclusive prefix carried across 32-bin chunks */
+  for (uint32_t cb = beg; cb < end; cb += 32) {
+    float best_gain = -INFINITY;
+    int best_t = 0; /* cub::ArgMax over 32 lanes: max value, ties -> lowest lane; all -inf -> 0 */
+    int best_ml = 1;
+    orc_gpair64 best_scan = {0, 0};
+    int any = 0;
+    for (int t = 0; t < 32; ++t) {
+      uint32_t b = cb + t;
+      int active = b < end;
+      float gain = -INFINITY;
+      int ml = 1;
+      orc_gpair64 scan = running;
+      if (active) {
+        /* LossChangeMissing (evaluate_splits.cu:17-32) */
+        orc_gpair64 left = gp_add(scan, missing);
+        float g_ml = split_gain_m(p, scale, left, gp_sub(parent_sum, left), mono);
+        float g_mr = split_gain_m(p, scale, scan, gp_sub(parent_sum, scan), mono);
+        ml = g_ml > g_mr;
+        gain = ml ? g_ml : g_mr;
+        if (gain_out) {
+          gain_out[2 * b] = g_ml;
+          gain_out[2 * b + 1] = g_mr;
+        }
+        running = gp_add(running, hist[b]);
+      }
+      if (!any || gain > best_gain) {
+        if (!any || gain > best_gain) {
+          best_gain = gain; best_t = t; best_ml = ml; best_scan = scan;
+        }
+        any = 1;
+      }
+    }
+    /* Only the chunk winner calls Update (evaluate_splits.cu:126-142): a winner rejected by the
+     * min_child_weight test means the whole chunk contributes nothing. */
+    uint32_t b = cb + best_t;
+    if (b < end) {
+      int32_t split_gidx = (int32_t)b - 1;
+      float fvalue = split_gidx < (int32_t)beg ? -INFINITY : cut_values[split_gidx];
+      orc_gpair64 left = best_ml ? gp_add(best_scan, missing) : best_scan;
+      orc_gpair64 right = gp_sub(parent_sum, left);
+      double lh = (double)left.h * scale[3], rh = (double)right.h * scale[3];
+      if (best_gain > fbest_out->loss_chg && lh >= p->min_child_weight && rh >= p->min_child_weight) {
+        fbest_out->loss_chg = best_gain;
+        fbest_out->dir = best_ml ? 0 : 1;
+        fbest_out->fvalue = fvalue;
+        fbest_out->findex = f;
+        fbest_out->left_sum = left;
+        fbest_out->right_sum = right;
+        fbest_out->split_gbin = (int32_t)b;
+      }
+    }
+  }
+}
+
 ORC_API void orc_eval_node_mono(const orc_gpair64* hist, orc_gpair64 parent_sum, const uint32_t* cut_ptrs,
                                 const float* cut_values, uint32_t n_features, const int32_t* feature_set,
                                 int32_t n_feature_set, const orc_param* p, const double scale[4],
@@ -344,66 +410,8 @@ ORC_API void orc_eval_node_mono(const orc_gpair64* hist, orc_gpair64 parent_sum,
   for (int32_t fi = 0; fi < nf; ++fi) {
     int32_t f = feature_set ? feature_set[fi] : fi;
     mono.constraint = monotone ? monotone[f] : 0;
-    uint32_t beg = cut_ptrs[f], end = cut_ptrs[f + 1];
     orc_candidate fbest;
-    cand_init(&fbest);
-    /* ReduceFeature: missing = parent - sum(bins of f)   (evaluate_splits.cu:90-101) */
-    orc_gpair64 fsum = {0, 0};
-    for (uint32_t b = beg; b < end; ++b) fsum = gp_add(fsum, hist[b]);
-    orc_gpair64 missing = gp_sub(parent_sum, fsum);
-    orc_gpair64 running = {0, 0}; /* exclusive prefix carried across 32-bin chunks */
-    for (uint32_t cb = beg; cb < end; cb += 32) {
-      float best_gain = -INFINITY;
-      int best_t = 0; /* cub::ArgMax over 32 lanes: max value, ties -> lowest lane; all -inf -> 0 */
-      int best_ml = 1;
-      orc_gpair64 best_scan = {0, 0};
-      int any = 0;
-      for (int t = 0; t < 32; ++t) {
-        uint32_t b = cb + t;
-        int active = b < end;
-        float gain = -INFINITY;
-        int ml = 1;
-        orc_gpair64 scan = running;
-        if (active) {
-          /* LossChangeMissing (evaluate_splits.cu:17-32) */
-          orc_gpair64 left = gp_add(scan, missing);
-          float g_ml = split_gain_m(p, scale, left, gp_sub(parent_sum, left), &mono);
-          float g_mr = split_gain_m(p, scale, scan, gp_sub(parent_sum, scan), &mono);
-          ml = g_ml > g_mr;
-          gain = ml ? g_ml : g_mr;
-          if (gain_out) {
-            gain_out[2 * b] = g_ml;
-            gain_out[2 * b + 1] = g_mr;
-          }
-          running = gp_add(running, hist[b]);
-        }
-        if (!any || gain > best_gain) {
-          if (!any || gain > best_gain) {
-            best_gain = gain; best_t = t; best_ml = ml; best_scan = scan;
-          }
-          any = 1;
-        }
-      }
-      /* Only the chunk winner calls Update (evaluate_splits.cu:126-142): a winner rejected by the
-       * min_child_weight test means the whole chunk contributes nothing. */
-      uint32_t b = cb + best_t;
-      if (b < end) {
-        int32_t split_gidx = (int32_t)b - 1;
-        float fvalue = split_gidx < (int32_t)beg ? -INFINITY : cut_values[split_gidx];
-        orc_gpair64 left = best_ml ? gp_add(best_scan, missing) : best_scan;
-        orc_gpair64 right = gp_sub(parent_sum, left);
-        double lh = (double)left.h * scale[3], rh = (double)right.h * scale[3];
-        if (best_gain > fbest.loss_chg && lh >= p->min_child_weight && rh >= p->min_child_weight) {
-          fbest.loss_chg = best_gain;
-          fbest.dir = best_ml ? 0 : 1;
-          fbest.fvalue = fvalue;
-          fbest.findex = f;
-          fbest.left_sum = left;
-          fbest.right_sum = right;
-          fbest.split_gbin = (int32_t)b;
-        }
-      }
-    }
+    eval_feature_numerical(hist, parent_sum, cut_ptrs, cut_values, f, p, scale, &mono, gain_out, &fbest);
     /* Cross-feature fold: operator+ "b.loss_chg > a.loss_chg ? b : a" (evaluate_splits.cu:308-311) applied by
      * cub::DeviceSegmentedReduce::Sum (:371-383).  The operator is not commutative and CUB (CCCL 2.8 Policy600
      * scaled to the 56-byte candidate: 256 threads x 1 item, agent_reduce.cuh ConsumeRange) folds a segment
@@ -431,6 +439,215 @@ ORC_API void orc_eval_node_mono(const orc_gpair64* hist, orc_gpair64 parent_sum,
   best.left_weight = calc_weight_bounded(p, &mono, (double)best.left_sum.g * scale[2], (double)best.left_sum.h * scale[3]);
   best.right_weight = calc_weight_bounded(p, &mono, (double)best.right_sum.g * scale[2], (double)best.right_sum.h * scale[3]);
   *out = best;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Categorical features: one-hot and partition-based split evaluation
+ *   EvaluateSplitAgent::{OneHot,Partition,PartitionUpdate}     src/tree/gpu_hist/evaluate_splits.cu:148-252
+ *   kernel dispatch by feature type / UseOneHot                evaluate_splits.cu:286-299, src/common/categorical.h:86-89
+ *   GPUHistEvaluator::SortHistogram (stable sort of a feature's bins by CalcWeightCat)
+ *                                                              src/tree/gpu_hist/evaluator.cu:69-128
+ *   DeviceSplitCandidate::UpdateCat                            src/tree/updater_gpu_common.cuh:88-104
+ *   SetCategoricalSplit (category bit set of the winner)       evaluate_splits.cu:313-348
+ * Pinned by the reference's literal test vectors (tests/cpp/tree/gpu_hist/test_evaluate_splits.cu:39-335,
+ * tests/cpp/tree/test_evaluate_splits.h:56-92) in tests/golden/eval_categorical_known_answers.json.
+ * A categorical feature's bins ARE its categories (cut_values[b] = category code of bin b).
+ * ---------------------------------------------------------------------------------------- */
+static void update_cat(orc_candidate* c, int32_t* c_is_cat, int32_t* c_thresh, float gain, int dir, int32_t thresh,
+                       int32_t f, orc_gpair64 left, orc_gpair64 right, const orc_param* p, const double scale[4]) {
+  double lh = (double)left.h * scale[3], rh = (double)right.h * scale[3];
+  if (gain > c->loss_chg && lh >= p->min_child_weight && rh >= p->min_child_weight) {
+    c->loss_chg = gain;
+    c->dir = dir;
+    c->fvalue = NAN;
+    c->findex = f;
+    c->left_sum = left;
+    c->right_sum = right;
+    c->split_gbin = -1;
+    *c_is_cat = 1;
+    *c_thresh = thresh;
+  }
+}
+
+/* stable ascending order of the feature's bins by (float)CalcWeight(stats), evaluator.cu:83-126 */
+static void sort_feature_bins(const orc_gpair64* hist, uint32_t beg, uint32_t end, const orc_param* p,
+                              const double scale[4], uint32_t* order /* end - beg global bin ids */) {
+  uint32_t n = end - beg;
+  float* w = (float*)malloc(sizeof(float) * (n ? n : 1));
+  for (uint32_t i = 0; i < n; ++i) {
+    order[i] = beg + i;
+    w[i] = (float)calc_weight_d(p, (double)hist[beg + i].g * scale[2], (double)hist[beg + i].h * scale[3]);
+  }
+  for (uint32_t i = 1; i < n; ++i) { /* insertion sort: stable */
+    uint32_t oi = order[i];
+    float wi = w[i];
+    uint32_t j = i;
+    while (j > 0 && wi < w[j - 1]) { order[j] = order[j - 1]; w[j] = w[j - 1]; --j; }
+    order[j] = oi;
+    w[j] = wi;
+  }
+  free(w);
+}
+
+static void eval_feature_categorical(const orc_gpair64* hist, orc_gpair64 parent_sum, const uint32_t* cut_ptrs,
+                                     const float* cut_values, int32_t f, const orc_param* p, const double scale[4],
+                                     const orc_mono* mono, int32_t max_cat_to_onehot, int32_t max_cat_threshold,
+                                     orc_candidate* fbest, int32_t* is_cat, int32_t* thresh, uint32_t* sorted_out) {
+  uint32_t beg = cut_ptrs[f], end = cut_ptrs[f + 1];
+  uint32_t n_bins_feature = end - beg;
+  cand_init(fbest);
+  *is_cat = 0;
+  *thresh = -1;
+  if (n_bins_feature < (uint32_t)max_cat_to_onehot) { /* UseOneHot */
+    orc_gpair64 fsum = {0, 0};
+    for (uint32_t b = beg; b < end; ++b) fsum = gp_add(fsum, hist[b]);
+    orc_gpair64 missing = gp_sub(parent_sum, fsum);
+    for (uint32_t cb = beg; cb < end; cb += 32) {
+      float best_gain = -INFINITY;
+      int best_t = 0, best_ml = 1, any = 0;
+      orc_gpair64 best_bin = {0, 0};
+      for (int t = 0; t < 32; ++t) {
+        uint32_t b = cb + t;
+        float gain = -INFINITY;
+        int ml = 1;
+        orc_gpair64 bin = {0, 0};
+        if (b < end) { /* everything but this category (and the missing values) on one side */
+          bin = gp_sub(gp_sub(parent_sum, hist[b]), missing);
+          orc_gpair64 left = gp_add(bin, missing);
+          float g_ml = split_gain_m(p, scale, left, gp_sub(parent_sum, left), mono);
+          float g_mr = split_gain_m(p, scale, bin, gp_sub(parent_sum, bin), mono);
+          ml = g_ml > g_mr;
+          gain = ml ? g_ml : g_mr;
+        }
+        if (!any || gain > best_gain) { best_gain = gain; best_t = t; best_ml = ml; best_bin = bin; any = 1; }
+      }
+      uint32_t b = cb + best_t;
+      if (b < end) {
+        orc_gpair64 left = best_ml ? gp_add(best_bin, missing) : best_bin;
+        update_cat(fbest, is_cat, thresh, best_gain, best_ml ? 0 : 1, (int32_t)cut_values[b], f, left,
+                   gp_sub(parent_sum, left), p, scale);
+      }
+    }
+    return;
+  }
+  /* partition-based: scan the categories in the order of their leaf weights, from both ends */
+  sort_feature_bins(hist, beg, end, p, scale, sorted_out);
+  int32_t n_bins = (int32_t)n_bins_feature < max_cat_threshold ? (int32_t)n_bins_feature : max_cat_threshold;
+  { /* forward: the first it+1 sorted categories go right, everything else (with the missing values) left */
+    int32_t it_end = n_bins - 1;
+    orc_gpair64 prefix = {0, 0};
+    for (int32_t cb = 0; cb < it_end; cb += 32) {
+      float best_gain = -INFINITY;
+      int best_t = 0, any = 0;
+      orc_gpair64 best_l = {0, 0}, best_r = {0, 0};
+      for (int t = 0; t < 32; ++t) {
+        int32_t it = cb + t;
+        float gain = -INFINITY;
+        orc_gpair64 l = {0, 0}, r = {0, 0};
+        if (it < it_end) {
+          prefix = gp_add(prefix, hist[sorted_out[it]]);
+          r = prefix;
+          l = gp_sub(parent_sum, r);
+          gain = split_gain_m(p, scale, l, r, mono);
+        }
+        if (!any || gain > best_gain) { best_gain = gain; best_t = t; best_l = l; best_r = r; any = 1; }
+      }
+      if (cb + best_t < it_end)
+        update_cat(fbest, is_cat, thresh, best_gain, 0 /* kLeftDir */, cb + best_t, f, best_l, best_r, p, scale);
+    }
+  }
+  { /* backward: the last sorted categories go left, everything else (with the missing values) right */
+    int32_t it_begin = (int32_t)n_bins_feature - 1, it_end = it_begin - n_bins + 1;
+    orc_gpair64 prefix = {0, 0};
+    for (int32_t cb = it_begin; cb > it_end; cb -= 32) {
+      float best_gain = -INFINITY;
+      int best_t = 0, any = 0;
+      orc_gpair64 best_l = {0, 0}, best_r = {0, 0};
+      for (int t = 0; t < 32; ++t) {
+        int32_t it = cb - t;
+        float gain = -INFINITY;
+        orc_gpair64 l = {0, 0}, r = {0, 0};
+        if (it > it_end) {
+          prefix = gp_add(prefix, hist[sorted_out[it]]);
+          l = prefix;
+          r = gp_sub(parent_sum, l);
+          gain = split_gain_m(p, scale, l, r, mono);
+        }
+        if (!any || gain > best_gain) { best_gain = gain; best_t = t; best_l = l; best_r = r; any = 1; }
+      }
+      if (cb - best_t > it_end)
+        update_cat(fbest, is_cat, thresh, best_gain, 1 /* kRightDir */, cb - best_t, f, best_l, best_r, p, scale);
+    }
+  }
+}
+
+/* Best split of one node over numerical and categorical features.  feature_is_cat: n_features flags.
+ * Outputs next to the candidate: is_cat, thresh (one-hot: the category; partition: position in the sorted order) and
+ * the category bit set of SetCategoricalSplit in LBitField32 layout (category c = bit 31 - c % 32 of word c / 32). */
+ORC_API void orc_eval_node_cat(const orc_gpair64* hist, orc_gpair64 parent_sum, const uint32_t* cut_ptrs,
+                               const float* cut_values, uint32_t n_features, const int32_t* feature_set,
+                               int32_t n_feature_set, const orc_param* p, const double scale[4],
+                               const uint8_t* feature_is_cat, int32_t max_cat_to_onehot, int32_t max_cat_threshold,
+                               orc_candidate* out, int32_t* out_is_cat, int32_t* out_thresh, uint32_t* out_cat_bits,
+                               uint32_t n_cat_words) {
+  orc_mono mono = kNoMono;
+  orc_candidate best;
+  cand_init(&best);
+  int32_t best_pos = -1, best_is_cat = 0, best_thresh = -1;
+  uint32_t max_bins = 1;
+  for (uint32_t f = 0; f < n_features; ++f)
+    if (cut_ptrs[f + 1] - cut_ptrs[f] > max_bins) max_bins = cut_ptrs[f + 1] - cut_ptrs[f];
+  uint32_t* sorted = (uint32_t*)malloc(sizeof(uint32_t) * max_bins);
+  uint32_t* best_sorted = (uint32_t*)malloc(sizeof(uint32_t) * max_bins);
+  int32_t nf = feature_set ? n_feature_set : (int32_t)n_features;
+  for (int32_t fi = 0; fi < nf; ++fi) {
+    int32_t f = feature_set ? feature_set[fi] : fi;
+    orc_candidate fbest;
+    int32_t f_is_cat = 0, f_thresh = -1;
+    if (feature_is_cat && feature_is_cat[f]) {
+      eval_feature_categorical(hist, parent_sum, cut_ptrs, cut_values, f, p, scale, &mono, max_cat_to_onehot,
+                               max_cat_threshold, &fbest, &f_is_cat, &f_thresh, sorted);
+    } else {
+      eval_feature_numerical(hist, parent_sum, cut_ptrs, cut_values, f, p, scale, &mono, NULL, &fbest);
+    }
+    int take = 0; /* striped cross-feature fold, see orc_eval_node_mono */
+    if (best_pos < 0) take = 1;
+    else if (fbest.loss_chg > best.loss_chg) take = 1;
+    else if (fbest.loss_chg == best.loss_chg) {
+      int a = fi & 255, b = best_pos & 255;
+      take = (a < b) || (a == b && fi < best_pos);
+    }
+    if (take) {
+      best = fbest; best_pos = fi; best_is_cat = f_is_cat; best_thresh = f_thresh;
+      if (f_is_cat) memcpy(best_sorted, sorted, sizeof(uint32_t) * (cut_ptrs[f + 1] - cut_ptrs[f]));
+    }
+  }
+  /* post-pass (evaluate_splits.cu:441-467) */
+  double pg = (double)parent_sum.g * scale[2], ph = (double)parent_sum.h * scale[3];
+  best.loss_chg -= (float)calc_gain_d(p, pg, ph);
+  for (uint32_t w = 0; w < n_cat_words; ++w) out_cat_bits[w] = 0;
+  if (best_is_cat) { /* SetCategoricalSplit */
+    uint32_t nb = cut_ptrs[best.findex + 1] - cut_ptrs[best.findex];
+    if (nb < (uint32_t)max_cat_to_onehot) {
+      uint32_t c = (uint32_t)best_thresh;
+      if (c / 32 < n_cat_words) out_cat_bits[c / 32] |= 1u << (31 - c % 32);
+    } else if (best_thresh != -1) {
+      int32_t partition = best.dir == 0 ? best_thresh + 1 : best_thresh;
+      for (int32_t k = 0; k < partition; ++k) {
+        uint32_t c = (uint32_t)cut_values[best_sorted[k]];
+        if (c / 32 < n_cat_words) out_cat_bits[c / 32] |= 1u << (31 - c % 32);
+      }
+    }
+  }
+  orc_gpair64 tot = gp_add(best.left_sum, best.right_sum);
+  best.base_weight = calc_weight_bounded(p, &mono, (double)tot.g * scale[2], (double)tot.h * scale[3]);
+  best.left_weight = calc_weight_bounded(p, &mono, (double)best.left_sum.g * scale[2], (double)best.left_sum.h * scale[3]);
+  best.right_weight = calc_weight_bounded(p, &mono, (double)best.right_sum.g * scale[2], (double)best.right_sum.h * scale[3]);
+  *out = best;
+  *out_is_cat = best_is_cat;
+  *out_thresh = best_thresh;
+  free(sorted);
+  free(best_sorted);
 }
 
 /* ------------------------------------------------------------------------------------------

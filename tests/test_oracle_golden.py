@@ -280,3 +280,36 @@ def test_mt19937_helper_matches_the_standard_known_answers():
     v = [m.next() for _ in range(10000)]
     assert v[0] == 3499211612 and v[-1] == 4123659995
     assert MT19937(0).next() == 2357136044          # first output for seed 0 (the reference's default `seed`)
+
+
+def test_categorical_evaluation_known_answers(golden_dir):
+    """Partition-based and one-hot categorical split evaluation restated in the oracle,
+    pinned by the reference's own literal test vectors before any CUDA is written for it."""
+    spec = json.load(open(os.path.join(golden_dir, "eval_categorical_known_answers.json")))
+    scale = _dummy_scale()
+    for case in spec["cases"]:
+        p = orc.Param.make(**case["param"])
+        hist = _to_fixed(case["hist"], scale)
+        parent = _to_fixed([case["parent"]], scale, as_float32=False)[0]
+        c, is_cat, thresh, cats = orc.eval_node_cat(hist, parent, case["cut_ptrs"], case["cut_values"], p, scale,
+                                                    case["is_cat"], case["max_cat_to_onehot"])
+        e = case["expect"]
+        name = case["name"]
+        if "findex" in e:
+            assert c.findex == e["findex"], name
+        if "dir" in e:
+            assert c.dir == e["dir"], name
+        if "cats" in e:
+            assert cats == set(e["cats"]), (name, cats)
+        if "thresh" in e:
+            assert thresh == e["thresh"], name
+        if e.get("is_cat"):
+            assert is_cat, name
+        if e.get("fvalue_is_nan"):
+            assert np.isnan(c.fvalue), name
+        if e.get("sum_is_parent"):
+            assert (c.left_sum.g + c.right_sum.g, c.left_sum.h + c.right_sum.h) == tuple(parent), name
+        if "loss_chg" in e:
+            assert abs(c.loss_chg - e["loss_chg"]) <= e.get("loss_chg_tol", 1e-6), (name, c.loss_chg)
+        if "left_hess" in e:
+            assert c.left_sum.h * scale[3] == e["left_hess"] and c.right_sum.h * scale[3] == e["right_hess"], name
