@@ -313,3 +313,34 @@ def test_categorical_evaluation_known_answers(golden_dir):
             assert abs(c.loss_chg - e["loss_chg"]) <= e.get("loss_chg_tol", 1e-6), (name, c.loss_chg)
         if "left_hess" in e:
             assert c.left_sum.h * scale[3] == e["left_hess"] and c.right_sum.h * scale[3] == e["right_hess"], name
+
+
+def test_categorical_partition_finds_the_best_subset():
+    """The property behind the reference's TestPartitionBasedSplit (tests/cpp/tree/test_evaluate_splits.h:25-45,
+    test_evaluate_splits.cc SetUp: 'enumerate all possible partitions'): scanning the categories in the order of
+    their leaf weights finds the best of ALL 2^n - 2 subsets.  Checked for the oracle on random 6-category histograms
+    without missing values."""
+    import itertools
+    scale = _dummy_scale()
+    p = orc.Param.make(min_child_weight=0.0, reg_lambda=0.0)
+    rng = np.random.default_rng(7)
+    for trial in range(40):
+        g = rng.uniform(-4, 4, size=6).round(3)
+        h = rng.uniform(0.5, 3, size=6).round(3)
+        hist = _to_fixed(np.stack([g, h], axis=1).tolist(), scale)
+        parent = hist.sum(axis=0)
+        c, is_cat, thresh, cats = orc.eval_node_cat(hist, parent, [0, 6], [0.0, 1.0, 2.0, 3.0, 4.0, 5.0], p, scale, [1], 0)
+        gq, hq = hist[:, 0].astype(np.float64) * scale[2], hist[:, 1].astype(np.float64) * scale[3]
+        best = -np.inf
+        for k in range(1, 6):
+            for sub in itertools.combinations(range(6), k):
+                m = np.zeros(6, dtype=bool)
+                m[list(sub)] = True
+                gain = gq[m].sum() ** 2 / hq[m].sum() + gq[~m].sum() ** 2 / hq[~m].sum()
+                best = max(best, gain)
+        parent_gain = gq.sum() ** 2 / hq.sum()
+        assert is_cat and 0 < len(cats) < 6
+        assert abs((c.loss_chg + np.float32(parent_gain)) - best) <= 1e-4 * max(1.0, abs(best)), (trial, c.loss_chg, best)
+        # the reported category set holds the categories that go right, whichever scan direction won
+        right = sorted(cats)
+        assert c.right_sum.g == int(hist[right, 0].sum()) and c.right_sum.h == int(hist[right, 1].sum()), trial
