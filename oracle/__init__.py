@@ -200,12 +200,53 @@ def random_weight(seed: int, i: int) -> float:
     return float(lib().orc_random_weight(c_uint32(seed & 0xFFFFFFFF), c_uint64(i)))
 
 
+class _IC(Structure):
+    _fields_ = [("n_features", c_int32), ("n_sets", c_int32), ("set_ptr", c_void_p), ("set_feat", c_void_p),
+                ("shared_result_buffer", c_int32)]
+
+
+class InteractionConstraints:
+    """FeatureInteractionConstraintDevice (src/tree/constraints.cu) restated: per-node allowed-feature bit fields,
+    Split and Query.  `sets` is the parsed `interaction_constraints` parameter, e.g. [[1, 2], [3, 4, 5]]."""
+
+    def __init__(self, sets, n_features: int, max_nodes: int = 64, shared_result_buffer: bool = False):
+        self.n_features, self.max_nodes = int(n_features), int(max_nodes)
+        self._ptr = np.zeros(len(sets) + 1, dtype=np.int32)
+        self._ptr[1:] = np.cumsum([len(s) for s in sets])
+        self._feat = np.asarray([f for s in sets for f in s], dtype=np.int32)
+        if self._feat.size and (self._feat.min() < 0 or self._feat.max() >= n_features):
+            raise ValueError("interaction constraint names a feature outside the matrix")
+        self.c = _IC(self.n_features, len(sets), self._ptr.ctypes.data, self._feat.ctypes.data,
+                     1 if shared_result_buffer else 0)
+        self.words = (self.n_features + 63) // 64
+        self.bits = np.zeros((self.max_nodes, max(self.words, 1)), dtype=np.uint64)
+
+    def reset(self):
+        self.bits[:] = 0
+
+    def split(self, node: int, fid: int, left: int, right: int):
+        assert max(node, left, right) < self.max_nodes and node != left and node != right
+        lib().orc_ic_split(byref(self.c), _p(self.bits), c_int32(node), c_int32(fid), c_int32(left), c_int32(right))
+
+    def query_node(self, node: int):
+        out = np.zeros(max(self.n_features, 1), dtype=np.int32)
+        n = lib().orc_ic_query_node(byref(self.c), _p(self.bits), c_int32(node), _p(out))
+        return out[:n].tolist()
+
+    def query(self, feature_list, node: int):
+        fl = np.ascontiguousarray(feature_list, dtype=np.int32)
+        out = np.zeros(max(self.n_features, fl.size, 1), dtype=np.int32)
+        n = lib().orc_ic_query(byref(self.c), _p(self.bits), _p(fl), c_int32(fl.size), c_int32(node), _p(out))
+        return out[:n].tolist()
+
+
 def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override=None, max_nodes=None,
                 is_dense_layout=True, want_hist=False, feature_set=None, subsample=1.0, sample_seed=0,
-                monotone=None, level_feature_sets=None):
+                monotone=None, level_feature_sets=None, interaction=None, interaction_shared_buffer=False):
     """Whole tree.  Returns dict(nodes=[Node...], position, scale, hist (optional), cands).
     feature_set: sorted feature ids of the tree's colsample_bytree draw; subsample/sample_seed: uniform row sampling;
-    monotone: per-feature sign (+1 increasing, -1 decreasing, 0 free), padded with 0 to n_features."""
+    monotone: per-feature sign (+1 increasing, -1 decreasing, 0 free), padded with 0 to n_features;
+    interaction: parsed interaction_constraints ([[f, ...], ...]); interaction_shared_buffer: see orc_update_tree_ic."""
     gb = np.ascontiguousarray(gbins, dtype=np.int32)
     n, stride = gb.shape
     cp = np.ascontiguousarray(cut_ptrs, dtype=np.uint32)
@@ -231,12 +272,14 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
     if monotone is not None:
         mono = np.zeros(nf, dtype=np.int32)
         mono[:len(monotone)] = np.asarray(monotone, dtype=np.int32)
-    nn = lib().orc_update_tree_ex(_p(gb), c_uint64(n), c_uint32(stride), c_int(1 if is_dense_layout else 0),
+    ic = InteractionConstraints(interaction, nf, 1, interaction_shared_buffer) if interaction is not None else None
+    nn = lib().orc_update_tree_ic(_p(gb), c_uint64(n), c_uint32(stride), c_int(1 if is_dense_layout else 0),
                                   c_uint32(nf), _p(cp), _p(cv), _p(g), byref(param), so, nodes, c_int32(max_nodes),
                                   _p(pos), _p(hist) if want_hist else c_void_p(), cands, scale_out,
                                   _p(fs) if fs is not None else c_void_p(), c_int32(n_fs),
                                   c_float(subsample), c_uint32(int(sample_seed) & 0xFFFFFFFF),
-                                  _p(mono) if mono is not None else c_void_p(), c_int32(n_levels))
+                                  _p(mono) if mono is not None else c_void_p(), c_int32(n_levels),
+                                  byref(ic.c) if ic is not None else c_void_p())
     return dict(nodes=list(nodes[:nn]), cands=list(cands[:nn]), position=pos,
                 scale=np.array(scale_out[:], dtype=np.float64), hist=hist[:nn] if want_hist else None)
 

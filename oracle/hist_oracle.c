@@ -692,6 +692,75 @@ ORC_API uint64_t orc_partition(const int32_t* gbins, uint32_t stride, int is_den
   return nl;
 }
 
+/* ----------------------------------------------------------------------------------------
+ * Feature interaction constraints: FeatureInteractionConstraintDevice (src/tree/constraints.cu).
+ * Every node owns a bit field of allowed features (all clear at Reset, constraints.cu:134-138).
+ *   Split(node, f, left, right)  (constraints.cu:269-329): node |= union of the constraint sets that
+ *     hold f; left |= node; right |= node; then bit f is set in all three.  The PARENT's field changes too
+ *     (it has been evaluated by then).  A feature in no set adds only itself.
+ *   Query(list, nidx)  (constraints.cu:199-240): nidx == 0 returns the list untouched; otherwise the
+ *     features of `list` that the node allows, in ASCENDING feature order (copy_if over a counting
+ *     iterator), whatever the order of `list` was -- the position in this list is the tie rank of evaluation.
+ * Sets come as CSR (set_ptr[n_sets + 1], set_feat[...]), the parsed form of the JSON parameter
+ * (constraints.cu:33-44).  Bit fields here: LBitField64, bit f of word f / 64 (value 1 << (f % 64)); only
+ * membership is observable, the word layout never leaves the device in the reference.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_features, n_sets;
+  const int32_t* set_ptr;
+  const int32_t* set_feat;
+  /* 1 = model the single result buffer all Query calls of one EvaluateSplits batch share
+   * (constraints.cu:125, updater_gpu_hist.cu:251-268): see orc_update_tree_ic */
+  int32_t shared_result_buffer;
+} orc_ic;
+
+static int ic_words(int32_t n_features) { return (n_features + 63) / 64; }
+static int ic_check(const uint64_t* bits, int32_t f) { return (int)((bits[f >> 6] >> (f & 63)) & 1u); }
+static void ic_set(uint64_t* bits, int32_t f) { bits[f >> 6] |= (uint64_t)1 << (f & 63); }
+
+ORC_API void orc_ic_split(const orc_ic* ic, uint64_t* node_bits, int32_t node, int32_t fid, int32_t left,
+                          int32_t right) {
+  int w = ic_words(ic->n_features);
+  uint64_t* nb = node_bits + (size_t)node * w;
+  uint64_t* lb = node_bits + (size_t)left * w;
+  uint64_t* rb = node_bits + (size_t)right * w;
+  for (int32_t s = 0; s < ic->n_sets; ++s) { /* RestoreFeatureListFromSetsKernel */
+    int holds = 0;
+    for (int32_t k = ic->set_ptr[s]; k < ic->set_ptr[s + 1]; ++k) holds |= (ic->set_feat[k] == fid);
+    if (!holds) continue;
+    for (int32_t k = ic->set_ptr[s]; k < ic->set_ptr[s + 1]; ++k) ic_set(nb, ic->set_feat[k]);
+  }
+  for (int i = 0; i < w; ++i) { lb[i] |= nb[i]; rb[i] |= nb[i]; } /* InteractionConstraintSplitKernel */
+  ic_set(nb, fid); ic_set(lb, fid); ic_set(rb, fid);
+}
+
+/* QueryNode (constraints.cu:162-183): the node's allowed features, ascending */
+ORC_API int32_t orc_ic_query_node(const orc_ic* ic, const uint64_t* node_bits, int32_t node, int32_t* out) {
+  const uint64_t* nb = node_bits + (size_t)node * ic_words(ic->n_features);
+  int32_t n = 0;
+  for (int32_t f = 0; f < ic->n_features; ++f) if (ic_check(nb, f)) out[n++] = f;
+  return n;
+}
+
+/* Query: list == NULL means all features 0..n_features-1 */
+ORC_API int32_t orc_ic_query(const orc_ic* ic, const uint64_t* node_bits, const int32_t* list, int32_t n_list,
+                             int32_t node, int32_t* out) {
+  if (node == 0) {
+    if (!list) { for (int32_t f = 0; f < ic->n_features; ++f) out[f] = f; return ic->n_features; }
+    memcpy(out, list, sizeof(int32_t) * (size_t)n_list);
+    return n_list;
+  }
+  int w = ic_words(ic->n_features);
+  const uint64_t* nb = node_bits + (size_t)node * w;
+  uint64_t* in = (uint64_t*)calloc((size_t)w, sizeof(uint64_t));
+  if (!list) for (int32_t f = 0; f < ic->n_features; ++f) ic_set(in, f);
+  else for (int32_t k = 0; k < n_list; ++k) ic_set(in, list[k]);
+  int32_t n = 0;
+  for (int32_t f = 0; f < ic->n_features; ++f) if (ic_check(nb, f) && ic_check(in, f)) out[n++] = f;
+  free(in);
+  return n;
+}
+
 /* ------------------------------------------------------------------------------------------
  * T1  Whole tree: GPUHistMakerDevice::UpdateTree (src/tree/updater_gpu_hist.cu:693-732) with
  * InitRoot :657-691, ApplySplit :610-655, PartitionAndBuildHist :440-506, Driver driver.h:29-107,
@@ -748,6 +817,14 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
                                    orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4],
                                    const int32_t* feature_set, int32_t n_feature_set, float subsample,
                                    uint32_t sample_seed, const int32_t* monotone, int32_t n_levels);
+ORC_API int32_t orc_update_tree_ic(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
+                                   uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
+                                   const float* gpair, const orc_param* p, const double* scale_override,
+                                   orc_node* nodes, int32_t max_nodes, int32_t* position,
+                                   orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4],
+                                   const int32_t* feature_set, int32_t n_feature_set, float subsample,
+                                   uint32_t sample_seed, const int32_t* monotone, int32_t n_levels,
+                                   const orc_ic* ic);
 
 ORC_API int32_t orc_update_tree(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
                                 uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
@@ -769,6 +846,30 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
                                    orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4],
                                    const int32_t* feature_set, int32_t n_feature_set, float subsample,
                                    uint32_t sample_seed, const int32_t* monotone, int32_t n_levels) {
+  return orc_update_tree_ic(gbins, n_rows, stride, is_dense_layout, n_features, cut_ptrs, cut_values, gpair, p,
+                            scale_override, nodes, max_nodes, position, hist_dump, cand_dump, scale_out, feature_set,
+                            n_feature_set, subsample, sample_seed, monotone, n_levels, NULL);
+}
+
+/* ic (NULL = none): interaction constraints.  A node other than the root is evaluated on
+ * Query(GetFeatureSet(depth), nidx) (updater_gpu_hist.cu:217-220,257-264) and every applied split calls
+ * Split(nidx, findex, left, right) (updater_gpu_hist.cu:653-654).
+ * ic->shared_result_buffer: every Query of the reference writes its answer to the front of ONE device buffer and
+ * returns a span over it (constraints.cu:125,199-240); EvaluateSplits collects the spans of the whole batch
+ * (left0, right0, left1, ...) before the evaluation kernel runs, so a node reads the buffer as the LAST query left
+ * it, cut to its own count.  0 restates what Query returns at the moment of the call (what the unit tests of the
+ * reference pin); 1 restates what the evaluation kernel then reads.  PARITY UNPINNED for 1: needs the CUDA build
+ * of the reference on a GPU (oracle/_ref_cuda). */
+ORC_API int32_t orc_update_tree_ic(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
+                                   uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
+                                   const float* gpair, const orc_param* p, const double* scale_override,
+                                   orc_node* nodes, int32_t max_nodes, int32_t* position,
+                                   orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4],
+                                   const int32_t* feature_set, int32_t n_feature_set, float subsample,
+                                   uint32_t sample_seed, const int32_t* monotone, int32_t n_levels,
+                                   const orc_ic* ic) {
+  uint64_t* ic_bits = ic ? (uint64_t*)calloc((size_t)max_nodes * (size_t)ic_words(ic->n_features), sizeof(uint64_t)) : NULL;
+  int32_t* ic_buffer = ic ? (int32_t*)calloc((size_t)n_features + 1, sizeof(int32_t)) : NULL;
   /* n_levels > 0 (colsample_bylevel): feature_set is [n_levels][n_feature_set], a node at depth d is evaluated on
    * row min(d, n_levels - 1) = ColumnSampler::GetFeatureSet(depth), src/common/random.h:156-175 */
 #define ORC_LEVEL_SET(d) \
@@ -878,6 +979,7 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
       rn.sum_hess = (float)((double)c->right_sum.h * scale[3]);
       nodes[l] = ln; nodes[r] = rn;
       node_sum[l] = c->left_sum; node_sum[r] = c->right_sum;
+      if (ic) orc_ic_split(ic, ic_bits, nidx, c->findex, l, r);
       if (monotone) { /* TreeEvaluator::AddSplit (split_evaluator.h:163-203), weights before the learning rate */
         lower[l] = lower[r] = lower[nidx];
         upper[l] = upper[r] = upper[nidx];
@@ -888,7 +990,9 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
       }
     }
     if (n_open == 0 && n_nodes + 2 > max_nodes) break;
-    /* ---- PartitionAndBuildHist + EvaluateSplits for the valid candidates ---- */
+    /* ---- PartitionAndBuildHist for the valid candidates ---- */
+    int32_t eval_list[2 * 4096];
+    int n_eval = 0;
     for (int k = 0; k < n_expand; ++k) {
       int32_t nidx = expand[k];
       int32_t depth = queue[nidx].depth;
@@ -909,15 +1013,39 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
       hist[sub] = (orc_gpair64*)calloc(total_bins, sizeof(orc_gpair64));
       orc_build_hist(gbins, stride, gq, ridx + seg_beg[build], seg_cnt[build], hist[build]);
       orc_subtract(hist[nidx], hist[build], total_bins, hist[sub]);
-      int32_t ch[2] = {l, r};
-      for (int s = 0; s < 2; ++s) {
-        entry_t e;
-        e.nidx = ch[s]; e.depth = depth + 1; e.open = 1;
-        orc_eval_node_mono(hist[ch[s]], node_sum[ch[s]], cut_ptrs, cut_values, n_features, ORC_LEVEL_SET(depth + 1), n_feature_set, p, scale, &e.c, NULL, monotone, lower[ch[s]], upper[ch[s]]);
-        if (cand_dump) cand_dump[ch[s]] = e.c;
-        if (e.c.loss_chg > 1e-6f) { queue[ch[s]] = e; n_open++; }
+      eval_list[n_eval++] = l;
+      eval_list[n_eval++] = r;
+    }
+    /* ---- EvaluateSplits over the batch: all Query calls first, then one evaluation launch ---- */
+    int32_t* ic_lists = NULL; /* [n_eval][n_features] answers as returned */
+    int32_t* ic_count = NULL;
+    if (ic && n_eval > 0) {
+      ic_lists = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_eval * (n_features ? n_features : 1));
+      ic_count = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_eval);
+      for (int k = 0; k < n_eval; ++k) {
+        int32_t d = nodes[eval_list[k]].depth;
+        int32_t* out = ic_lists + (size_t)k * n_features;
+        const int32_t* sampled = feature_set ? ORC_LEVEL_SET(d) : NULL;
+        ic_count[k] = orc_ic_query(ic, ic_bits, sampled, sampled ? n_feature_set : 0, eval_list[k], out);
+        memcpy(ic_buffer, out, sizeof(int32_t) * (size_t)ic_count[k]);
       }
     }
+    for (int k = 0; k < n_eval; ++k) {
+      int32_t c = eval_list[k];
+      entry_t e;
+      e.nidx = c; e.depth = nodes[c].depth; e.open = 1;
+      const int32_t* fs = ORC_LEVEL_SET(e.depth);
+      int32_t nfs = n_feature_set;
+      if (ic) {
+        fs = ic->shared_result_buffer ? ic_buffer : ic_lists + (size_t)k * n_features;
+        nfs = ic_count[k];
+      }
+      /* an empty answer is a non-NULL list of length 0: nothing is scanned, the candidate stays invalid */
+      orc_eval_node_mono(hist[c], node_sum[c], cut_ptrs, cut_values, n_features, fs, nfs, p, scale, &e.c, NULL, monotone, lower[c], upper[c]);
+      if (cand_dump) cand_dump[c] = e.c;
+      if (e.c.loss_chg > 1e-6f) { queue[c] = e; n_open++; }
+    }
+    free(ic_lists); free(ic_count);
   }
 
   /* ---- FinalisePosition: walk every row from the root to its leaf ---- */
@@ -938,7 +1066,7 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
   }
   for (int32_t i = 0; i < max_nodes; ++i) free(hist[i]);
   free(hist); free(seg_beg); free(seg_cnt); free(node_sum); free(ridx); free(tmp); free(queue); free(gq);
-  free(lower); free(upper);
+  free(lower); free(upper); free(ic_bits); free(ic_buffer);
 #undef ORC_LEVEL_SET
   return n_nodes;
 }

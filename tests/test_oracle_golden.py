@@ -344,3 +344,86 @@ def test_categorical_partition_finds_the_best_subset():
         # the reported category set holds the categories that go right, whichever scan direction won
         right = sorted(cats)
         assert c.right_sum.g == int(hist[right, 0].sum()) and c.right_sum.h == int(hist[right, 1].sum()), trial
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Interaction constraints (src/tree/constraints.cu), SURVEY 8(f) rank 3: oracle first, the CUDA path comes next.
+# ---------------------------------------------------------------------------------------------------------------------
+def _ic_cases():
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "interaction_constraints_known_answers.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", _ic_cases(), ids=lambda c: c["name"])
+def test_interaction_constraints_known_answers(case):
+    """Split / QueryNode / Query of the oracle against the literal expectations of the reference's unit tests
+    (tests/cpp/tree/test_constraints.cu:127-318)."""
+    ic = orc.InteractionConstraints(case["sets"], case["n_features"], max_nodes=16)
+    for step in case["steps"]:
+        if "split" in step:
+            ic.split(*step["split"])
+        for nid, want in step.get("node_bits", {}).items():
+            assert ic.query_node(int(nid)) == want, (case["name"], nid)
+        for nid, want in step.get("query_node", {}).items():
+            assert ic.query_node(int(nid)) == want, (case["name"], nid)
+        if "query" in step:
+            for nid, want in step["query"]["answers"].items():
+                assert ic.query(step["query"]["list"], int(nid)) == want, (case["name"], nid)
+
+
+def test_interaction_query_sorts_and_intersects():
+    """Query answers in ascending feature order whatever the order of the sampled list (copy_if over a counting
+    iterator, constraints.cu:222-231) and keeps only sampled features."""
+    ic = orc.InteractionConstraints([[0, 3, 5], [1, 2]], 6, max_nodes=8)
+    ic.split(0, 5, 1, 2)
+    assert ic.query([5, 0, 4, 3], 1) == [0, 3, 5]
+    assert ic.query([4, 5], 2) == [5]
+    assert ic.query([4, 1], 1) == []
+    assert ic.query([5, 0, 4, 3], 0) == [5, 0, 4, 3]          # the root is never filtered nor reordered
+
+
+def _paths(nodes):
+    out = []
+
+    def walk(i, feats):
+        if nodes[i].is_leaf:
+            out.append(feats)
+            return
+        walk(nodes[i].left, feats + [nodes[i].findex])
+        walk(nodes[i].right, feats + [nodes[i].findex])
+    walk(0, [])
+    return out
+
+
+@pytest.mark.parametrize("shared", [False, True], ids=["per_query", "shared_result_buffer"])
+def test_tree_respects_interaction_constraints(shared):
+    """Whole-tree restatement: with per-query answers every root-to-leaf path uses features of one constraint set
+    (or a single free feature); the unconstrained tree on the same data mixes them, so the constraint is what
+    shapes the tree.  With the shared result buffer (what the reference's evaluation kernel reads) a tree is still
+    produced and its first two levels agree with the per-query tree: the root is unfiltered and a level of one batch
+    with equal answers aliases harmlessly."""
+    rng = np.random.default_rng(5)
+    n, f = 4000, 6
+    x = rng.normal(size=(n, f)).astype(np.float32)
+    y = (x[:, 0] * x[:, 3] + x[:, 1] * x[:, 4] + 0.5 * x[:, 2] * x[:, 5]).astype(np.float32)
+    from tests.helpers import make_cuts
+    cut_ptrs, cut_values = make_cuts(x, 16)
+    gbins = orc.bin_dense(x, cut_ptrs, cut_values)
+    gpair = np.stack([-y, np.ones_like(y)], axis=1).astype(np.float32)
+    p = orc.Param.make(max_depth=4, eta=0.5, min_child_weight=1.0)
+    sets = [[0, 1, 2], [3, 4, 5]]
+    free = orc.update_tree(gbins, cut_ptrs, cut_values, gpair, p)
+    mixed = [pa for pa in _paths(free["nodes"]) if any(a < 3 for a in pa) and any(a >= 3 for a in pa)]
+    assert mixed, "test data must make the unconstrained tree cross the sets"
+    t = orc.update_tree(gbins, cut_ptrs, cut_values, gpair, p, interaction=sets, interaction_shared_buffer=shared)
+    assert len(t["nodes"]) > 3
+    if not shared:
+        for pa in _paths(t["nodes"]):
+            assert all(a < 3 for a in pa) or all(a >= 3 for a in pa), pa
+    else:
+        ref = orc.update_tree(gbins, cut_ptrs, cut_values, gpair, p, interaction=sets)
+        for i in range(3):
+            assert t["nodes"][i].findex == ref["nodes"][i].findex and t["nodes"][i].fvalue == ref["nodes"][i].fvalue
+    # the root is evaluated on every feature either way
+    assert t["nodes"][0].findex == free["nodes"][0].findex and t["nodes"][0].fvalue == free["nodes"][0].fvalue
