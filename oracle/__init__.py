@@ -242,11 +242,12 @@ class InteractionConstraints:
 
 def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override=None, max_nodes=None,
                 is_dense_layout=True, want_hist=False, feature_set=None, subsample=1.0, sample_seed=0,
-                monotone=None, level_feature_sets=None, interaction=None, interaction_shared_buffer=False):
+                monotone=None, level_feature_sets=None, interaction=None, interaction_shared_buffer=True):
     """Whole tree.  Returns dict(nodes=[Node...], position, scale, hist (optional), cands).
     feature_set: sorted feature ids of the tree's colsample_bytree draw; subsample/sample_seed: uniform row sampling;
     monotone: per-feature sign (+1 increasing, -1 decreasing, 0 free), padded with 0 to n_features;
-    interaction: parsed interaction_constraints ([[f, ...], ...]); interaction_shared_buffer: see orc_update_tree_ic."""
+    interaction: parsed interaction_constraints ([[f, ...], ...]); interaction_shared_buffer (default = what the
+    reference's trees follow, tests/golden/ref_gpu_interaction_trees.json): see orc_update_tree_ic."""
     gb = np.ascontiguousarray(gbins, dtype=np.int32)
     n, stride = gb.shape
     cp = np.ascontiguousarray(cut_ptrs, dtype=np.uint32)

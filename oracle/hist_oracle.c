@@ -858,8 +858,9 @@ ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32
  * returns a span over it (constraints.cu:125,199-240); EvaluateSplits collects the spans of the whole batch
  * (left0, right0, left1, ...) before the evaluation kernel runs, so a node reads the buffer as the LAST query left
  * it, cut to its own count.  0 restates what Query returns at the moment of the call (what the unit tests of the
- * reference pin); 1 restates what the evaluation kernel then reads.  PARITY UNPINNED for 1: needs the CUDA build
- * of the reference on a GPU (oracle/_ref_cuda). */
+ * reference pin); 1 restates what the evaluation kernel then reads -- and that is what the reference's trees follow:
+ * tests/golden/ref_gpu_interaction_trees.json (oracle/_ref_cuda on a B200, overlapping sets) is rebuilt bit for bit
+ * with 1 and not with 0 (tests/test_reference_golden.py). */
 ORC_API int32_t orc_update_tree_ic(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
                                    uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
                                    const float* gpair, const orc_param* p, const double* scale_override,

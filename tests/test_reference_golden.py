@@ -196,3 +196,57 @@ def test_cuda_sketch_matches_oracle_on_duplicates(n, f, max_bin, kind, cuda_devi
     for j in range(f):
         seg = cuts.cut_values[p[j]:p[j + 1]]
         assert np.all(np.diff(seg) > 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Interaction constraints: tests/golden/ref_gpu_interaction_trees.json = the reference's gpu_hist trees under
+# OVERLAPPING constraint sets (tools/probe_interaction_reference.py on a B200).  This is the fixture that settles which
+# reading of FeatureInteractionConstraintDevice::Query the reference's trees follow (oracle orc_update_tree_ic).
+# ---------------------------------------------------------------------------------------------------------------------
+IC_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_gpu_interaction_trees.json")
+
+
+def _ic_cases():
+    return json.load(open(IC_GOLD))["cases"]
+
+
+def _ic_tree_equal(o, ref):
+    nodes = o["nodes"]
+    if len(nodes) != len(ref["left"]):
+        return False
+    for i, nd in enumerate(nodes):
+        if nd.left != ref["left"][i] or nd.right != ref["right"][i]:
+            return False
+        if not nd.is_leaf and (nd.findex != ref["findex"][i] or
+                               int(np.float32(nd.fvalue).view(np.uint32)) != ref["cond_bits"][i] or
+                               int(nd.default_left) != ref["default_left"][i]):
+            return False
+        if int(np.float32(nd.base_weight).view(np.uint32)) != ref["base_weight_bits"][i] or \
+                int(np.float32(nd.sum_hess).view(np.uint32)) != ref["sum_hess_bits"][i]:
+            return False
+    return True
+
+
+@pytest.mark.parametrize("case", _ic_cases(), ids=lambda c: c["name"])
+def test_oracle_reproduces_reference_interaction_constraints(case):
+    """The reference's evaluation kernel reads the ONE result buffer every Query of a level wrote into
+    (constraints.cu:125,199-240; updater_gpu_hist.cu:251-268): the oracle's shared_result_buffer reading rebuilds
+    every reference tree bit for bit, and on the first tree of every case the per-query reading does NOT -- so the
+    fixture discriminates."""
+    from tools.probe_interaction_reference import make_data
+    x, y = make_data(case)
+    cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+    cv = _f32(case["cut_values_bits"])
+    gb = orc.bin_dense(x, cp, cv)
+    p = orc.Param.make(**case["params"])
+    margin = np.zeros(case["n"], dtype=np.float32)
+    discriminated = False
+    for t, ref in enumerate(case["trees"]):
+        gp = np.stack([margin - y, np.ones_like(y)], axis=1).astype(np.float32)
+        o = orc.update_tree(gb, cp, cv, gp, p, interaction=case["sets"], interaction_shared_buffer=True)
+        assert _ic_tree_equal(o, ref), "tree %d differs from the reference" % t
+        per_query = orc.update_tree(gb, cp, cv, gp, p, interaction=case["sets"], interaction_shared_buffer=False)
+        discriminated = discriminated or not _ic_tree_equal(per_query, ref)
+        leaf = np.array([n.leaf_value for n in o["nodes"]], dtype=np.float32)
+        margin = (margin + _leaf_margin(leaf, o["position"])).astype(np.float32)
+    assert discriminated
