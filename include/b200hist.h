@@ -269,6 +269,21 @@ B200HIST_API int b200hist_updater_last_max_eval_depth(b200hist_updater_t u, int3
 B200HIST_API int b200hist_updater_set_monotone_constraints(b200hist_updater_t u, const int32_t* constraints_host,
                                                            uint32_t n);
 
+/* Feature interaction constraints = FeatureInteractionConstraintDevice (src/tree/constraints.cu:25-329, used at
+ * src/tree/updater_gpu_hist.cu:217-220,251-268,653-654).  The parsed `interaction_constraints` parameter as CSR:
+ * set s holds features set_feat_host[set_ptr_host[s] .. set_ptr_host[s + 1]); n_sets = 0 removes them.
+ * Every node carries the set of features it may split on: a split on f adds every set that holds f (and f itself)
+ * to the node and hands the result to both children; the root is unrestricted.  One property of the reference is
+ * reproduced on purpose because its trees depend on it (tests/golden/ref_gpu_interaction_trees.json): all Query
+ * calls of a level answer into ONE buffer before the evaluation kernel runs, so a node is evaluated on the first
+ * `its own count` entries of what the level's later answers left there.  With disjoint sets every node of a tree has
+ * the same answer and the two readings coincide.
+ * STATUS: compiled, not yet run on hardware (written after this round's GPU budget was spent); the oracle for it is
+ * pinned (tests/test_reference_golden.py), the GPU parity tests are in tests/test_gpu_parity.py behind
+ * B200HIST_RUN_UNVALIDATED=1, and the shim keeps refusing the parameter until they have passed. */
+B200HIST_API int b200hist_updater_set_interaction_constraints(b200hist_updater_t u, const int32_t* set_ptr_host,
+                                                              const int32_t* set_feat_host, uint32_t n_sets);
+
 /* Row split (the reference's default distributed mode): every rank holds a page of ITS rows with the
  * same cuts and builds full-width partial histograms; one peer-memory kernel per level sums them (reduce-scatter +
  * all-gather over NVLink, integer, bit-identical to one GPU) = AllReduceHist (src/tree/gpu_hist/histogram.cu:598-609);

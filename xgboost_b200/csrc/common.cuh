@@ -221,6 +221,17 @@ struct MonoView {
   float* upper;
 };
 
+// Feature interaction constraints (FeatureInteractionConstraintDevice, src/tree/constraints.cu) as the evaluation
+// kernels see them.  Every Query of the reference answers into the front of ONE device buffer and the spans of a
+// whole level are collected before the evaluation launch (constraints.cu:125,199-240; updater_gpu_hist.cu:251-268),
+// so the kernel reads the buffer as the level's queries left it, cut to each node's own count: `list` is that buffer
+// image, count[slot] what evaluation slot `slot` reads of it.  count == nullptr: no constraints (and always for the
+// root, which Query never filters).
+struct IcView {
+  const int32_t* list;
+  const int32_t* count;
+};
+
 struct ParamDev {
   int32_t max_depth, max_leaves, grow_policy;
   float learning_rate, reg_lambda, reg_alpha, min_child_weight, max_delta_step, min_split_loss;
@@ -318,7 +329,8 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = n
                     const ParamDev& p, const QuantDev* q, FeatCand* scratch, b200hist_candidate* cand,
                     NodeDev* nodes_mut, int num_sms, cudaStream_t s, MonoView mono = MonoView{nullptr, nullptr, nullptr},
                     int32_t n_levels = 0 /* > 0: feature_set is [n_levels][n_feature_set], row = node depth */,
-                    int32_t* max_eval_depth = nullptr /* device: atomicMax of the depths evaluated */);
+                    int32_t* max_eval_depth = nullptr /* device: atomicMax of the depths evaluated */,
+                    IcView ic = IcView{nullptr, nullptr});
 
 // partition.cu
 void LaunchPartitionCount(const EllView& ell, const uint32_t* ridx0, const uint32_t* ridx1, const PartEntry* part,

@@ -89,12 +89,16 @@ __device__ __forceinline__ float SplitGainMono(const ParamDev& p, double tfg, do
 
 constexpr int kEvalWarps = 8;
 
-// One warp per (node slot, feature position).
+// One warp per (node slot, feature position).  kIc: interaction constraints -- the feature list is the level's
+// shared Query buffer image and a slot reads only its own count of it (IcView, common.cuh); n_fs is then the
+// stride of the scratch table, not the length of a list.
+template <bool kIc>
 __global__ void __launch_bounds__(kEvalWarps * 32)
 FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t* __restrict__ eval_nodes,
                   const TreeState* __restrict__ ts, const NodeDev* __restrict__ nodes,
                   const int32_t* __restrict__ feature_set, int32_t n_fs, ParamDev p,
-                  const QuantDev* __restrict__ q, FeatCand* __restrict__ scratch, MonoView mono, int32_t n_levels) {
+                  const QuantDev* __restrict__ q, FeatCand* __restrict__ scratch, MonoView mono, int32_t n_levels,
+                  IcView ic) {
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * kEvalWarps + (threadIdx.x >> 5);
   const int n_warps = gridDim.x * kEvalWarps;
@@ -109,6 +113,10 @@ FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t
     // colsample_bylevel: feature_set holds one list of n_fs ids per depth (the last row serves deeper nodes)
     const int32_t* __restrict__ fs =
         (feature_set && n_levels > 0) ? feature_set + (size_t)min(nodes[nidx].depth, n_levels - 1) * n_fs : feature_set;
+    if constexpr (kIc) {
+      if (fpos >= ic.count[slot]) continue;  // warp-uniform: the node reads only its own count of the buffer
+      fs = ic.list;
+    }
     const int f = fs ? fs[fpos] : fpos;
     const longlong2* h = hist + (size_t)nodes[nidx].hist_slot * ell.total_bins;
     const long long pg = nodes[nidx].sum_g, ph = nodes[nidx].sum_h;
@@ -203,11 +211,13 @@ FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t
 }
 
 // One warp per node slot: fold per-feature winners in feature order, then the post-pass.
+template <bool kIc>
 __global__ void __launch_bounds__(kEvalWarps * 32)
 NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const TreeState* __restrict__ ts,
                  NodeDev* __restrict__ nodes, const int32_t* __restrict__ feature_set, int32_t n_fs, ParamDev p,
                  const QuantDev* __restrict__ q, const FeatCand* __restrict__ scratch,
-                 b200hist_candidate* __restrict__ cand, MonoView mono, int32_t n_levels, int32_t* max_eval_depth) {
+                 b200hist_candidate* __restrict__ cand, MonoView mono, int32_t n_levels, int32_t* max_eval_depth,
+                 IcView ic) {
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * kEvalWarps + (threadIdx.x >> 5);
   const int n_warps = gridDim.x * kEvalWarps;
@@ -227,7 +237,9 @@ NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const Tree
     };
     float bl = -3.402823466e+38f;
     int bpos = 0x7fffffff;
-    for (int fpos = lane; fpos < n_fs; fpos += 32) {
+    int n_here = n_fs;
+    if constexpr (kIc) n_here = ic.count[slot];
+    for (int fpos = lane; fpos < n_here; fpos += 32) {
       float l = sc[fpos].loss_chg;
       if (bpos == 0x7fffffff || l > bl || (l == bl && earlier(fpos, bpos))) { bl = l; bpos = fpos; }
     }
@@ -252,6 +264,7 @@ NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const Tree
         const int32_t* fs = (feature_set && n_levels > 0)
                                 ? feature_set + (size_t)min(nodes[nidx].depth, n_levels - 1) * n_fs
                                 : feature_set;
+        if constexpr (kIc) fs = ic.list;
         int f = fs ? fs[bpos] : bpos;
         c.loss_chg = w.loss_chg;
         c.dir = w.dir;
@@ -284,17 +297,27 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist, const int3
                     int32_t max_eval, const NodeDev* nodes, const int32_t* feature_set, int32_t n_feature_set,
                     const ParamDev& p, const QuantDev* q, FeatCand* scratch, b200hist_candidate* cand,
                     NodeDev* nodes_mut, int num_sms, cudaStream_t s, MonoView mono, int32_t n_levels,
-                    int32_t* max_eval_depth) {
+                    int32_t* max_eval_depth, IcView ic) {
   const int32_t n_fs = feature_set ? n_feature_set : (int32_t)ell.n_features;
   long long max_items = (long long)max_eval * n_fs;
   if (max_items == 0) return;
   int blocks = (int)std::min<long long>((max_items + kEvalWarps - 1) / kEvalWarps, (long long)num_sms * 8);
-  FeatureScanKernel<<<blocks, kEvalWarps * 32, 0, s>>>(ell, reinterpret_cast<const longlong2*>(hist), eval_nodes, ts,
-                                                       nodes, feature_set, n_fs, p, q, scratch, mono, n_levels);
-  B200_LAUNCHED();
   int blocks2 = (int)std::min<long long>(((long long)max_eval + kEvalWarps - 1) / kEvalWarps, (long long)num_sms * 4);
-  NodeReduceKernel<<<blocks2, kEvalWarps * 32, 0, s>>>(ell, eval_nodes, ts, nodes_mut, feature_set, n_fs, p, q, scratch,
-                                                       cand, mono, n_levels, max_eval_depth);
+  const auto* h2 = reinterpret_cast<const longlong2*>(hist);
+  if (ic.count != nullptr) {  // an answer is a subset of the sampled list, so n_fs bounds every count
+    FeatureScanKernel<true><<<blocks, kEvalWarps * 32, 0, s>>>(ell, h2, eval_nodes, ts, nodes, feature_set, n_fs, p, q,
+                                                               scratch, mono, n_levels, ic);
+    B200_LAUNCHED();
+    NodeReduceKernel<true><<<blocks2, kEvalWarps * 32, 0, s>>>(ell, eval_nodes, ts, nodes_mut, feature_set, n_fs, p, q,
+                                                               scratch, cand, mono, n_levels, max_eval_depth, ic);
+    B200_LAUNCHED();
+    return;
+  }
+  FeatureScanKernel<false><<<blocks, kEvalWarps * 32, 0, s>>>(ell, h2, eval_nodes, ts, nodes, feature_set, n_fs, p, q,
+                                                              scratch, mono, n_levels, ic);
+  B200_LAUNCHED();
+  NodeReduceKernel<false><<<blocks2, kEvalWarps * 32, 0, s>>>(ell, eval_nodes, ts, nodes_mut, feature_set, n_fs, p, q,
+                                                              scratch, cand, mono, n_levels, max_eval_depth, ic);
   B200_LAUNCHED();
 }
 

@@ -375,6 +375,97 @@ __global__ void __launch_bounds__(kCtlThreads) ScanKernel(TreeState* ts, NodeDev
 }
 
 // ---------------------------------------------------------------------------------------------
+// Feature interaction constraints (FeatureInteractionConstraintDevice, src/tree/constraints.cu).
+// One allowed-feature bit field per node (bit f of word f / 64), cleared per tree (Reset, constraints.cu:134-138).
+// After a level's ScanKernel this control kernel
+//   1. applies Split(nidx, findex, left, right) of every split whose children get evaluated (constraints.cu:269-329:
+//      node |= the sets that hold findex; left |= node; right |= node; then bit findex in all three),
+//   2. answers Query(sampled features of the depth, child) for every evaluation slot in the order of the reference's
+//      loop (left0, right0, left1, ...; updater_gpu_hist.cu:251-268): the allowed features in ASCENDING order,
+//   3. and lays those answers over each other the way the reference's single result buffer ends up
+//      (constraints.cu:125,199-240): entry i of the buffer is entry i of the LAST answer longer than i.  A node then
+//      reads the first count[slot] entries (IcView, evaluate.cu).  Pinned by tests/golden/ref_gpu_interaction_trees.json.
+// Splits whose children are not evaluated need no bit fields: nothing reads them again.
+// ---------------------------------------------------------------------------------------------
+struct IcDev {
+  int32_t n_features, words, n_sets;
+  const int32_t* set_ptr;   // CSR of the constraint sets
+  const int32_t* set_feat;
+  unsigned long long* bits;  // [max_nodes][words]
+  int32_t* list;             // [n_features] the level's buffer image
+  int32_t* count;            // [2 * kMaxLevelNodes]
+};
+
+__global__ void __launch_bounds__(kCtlThreads) IcLevelKernel(const TreeState* ts, const NodeDev* nodes,
+                                                              const PartEntry* part, const int32_t* eval_nodes,
+                                                              IcDev ic, const int32_t* feature_set, int32_t n_fs,
+                                                              int32_t n_levels) {
+  extern __shared__ unsigned long long s_mask[];  // [words] the depth's sampled features
+  const int n_part = ts->n_part;
+  if (n_part == 0) return;
+  const int W = ic.words;
+  // 1. Split: one thread per applied split; parents of a level are distinct nodes, children are fresh
+  for (int k = threadIdx.x; k < n_part; k += kCtlThreads) {
+    const PartEntry e = part[k];
+    unsigned long long* nb = ic.bits + (size_t)e.nidx * W;
+    unsigned long long* lb = ic.bits + (size_t)e.left * W;
+    unsigned long long* rb = ic.bits + (size_t)e.right * W;
+    for (int s = 0; s < ic.n_sets; ++s) {
+      bool holds = false;
+      for (int j = ic.set_ptr[s]; j < ic.set_ptr[s + 1]; ++j) holds = holds || ic.set_feat[j] == e.findex;
+      if (!holds) continue;
+      for (int j = ic.set_ptr[s]; j < ic.set_ptr[s + 1]; ++j) nb[ic.set_feat[j] >> 6] |= 1ull << (ic.set_feat[j] & 63);
+    }
+    nb[e.findex >> 6] |= 1ull << (e.findex & 63);
+    for (int w = 0; w < W; ++w) { lb[w] |= nb[w]; rb[w] |= nb[w]; }
+  }
+  // the depth's sampled features as a bit mask (all features without column sampling)
+  const int depth = nodes[eval_nodes[0]].depth;
+  for (int w = threadIdx.x; w < W; w += kCtlThreads) {
+    unsigned long long m = 0;
+    if (feature_set == nullptr) {
+      const int lo = w * 64, hi = min(ic.n_features, lo + 64);
+      m = hi - lo >= 64 ? ~0ull : ((1ull << (hi - lo)) - 1ull);
+    }
+    s_mask[w] = m;
+  }
+  __syncthreads();
+  if (feature_set != nullptr) {
+    const int32_t* fs = n_levels > 0 ? feature_set + (size_t)min(depth, n_levels - 1) * n_fs : feature_set;
+    for (int j = threadIdx.x; j < n_fs; j += kCtlThreads)
+      atomicOr(&s_mask[fs[j] >> 6], 1ull << (fs[j] & 63));
+  }
+  __syncthreads();
+  // 2. counts of the answers
+  const int n_eval = 2 * n_part;
+  for (int j = threadIdx.x; j < n_eval; j += kCtlThreads) {
+    const unsigned long long* b = ic.bits + (size_t)eval_nodes[j] * W;
+    int c = 0;
+    for (int w = 0; w < W; ++w) c += __popcll(b[w] & s_mask[w]);
+    ic.count[j] = c;
+  }
+  __syncthreads();
+  // 3. buffer image: answer j survives at positions [max count of the later answers, count_j)
+  for (int j = threadIdx.x; j < n_eval; j += kCtlThreads) {
+    const int cj = ic.count[j];
+    int later = 0;
+    for (int j2 = j + 1; j2 < n_eval; ++j2) later = max(later, ic.count[j2]);
+    if (cj <= later) continue;
+    const unsigned long long* b = ic.bits + (size_t)eval_nodes[j] * W;
+    int pos = 0;
+    for (int w = 0; w < W && pos < cj; ++w) {
+      unsigned long long v = b[w] & s_mask[w];
+      while (v) {
+        const int bit = __ffsll((long long)v) - 1;
+        v &= v - 1;
+        if (pos >= later) ic.list[pos] = w * 64 + bit;
+        ++pos;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // FinalisePosition (updater_gpu_hist.cu:529-580): list the nodes that still own a row segment,
 // then walk each row from that node to its leaf (at most the splits applied after the last
 // partition) and write position[row] = leaf, bitwise-NOT when the row's hessian is 0.
@@ -665,6 +756,14 @@ struct b200hist_updater_s {
   int32_t n_feature_set{0};
   int32_t n_feature_levels{0};      // > 0: d_feature_set holds one list per depth (colsample_bylevel)
   int32_t last_max_eval_depth{0};
+  // feature interaction constraints (nullptr = none): constraint sets as CSR, per-node allowed bit fields, the
+  // level's Query buffer image and per-slot counts (IcLevelKernel)
+  int32_t* d_ic_set_ptr{nullptr};
+  int32_t* d_ic_set_feat{nullptr};
+  unsigned long long* d_ic_bits{nullptr};
+  int32_t* d_ic_list{nullptr};
+  int32_t* d_ic_count{nullptr};
+  int32_t ic_n_sets{0}, ic_words{0};
   bool row_split{false};                   // ranks own row slices (full-width partial histograms, summed) instead of feature blocks
   size_t flags_offset{0};                  // byte offset of the flag array inside the histogram allocation
   std::vector<void*> peer_base;            // opened IPC mappings (own entry = nullptr)
@@ -770,6 +869,9 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
                    u->subsample, u->sample_seed);
   }
   timer.End(kQuant, t0);
+  const bool has_ic = u->d_ic_bits != nullptr;
+  if (has_ic)  // FeatureInteractionConstraintDevice::Reset
+    B200_CUDA(cudaMemsetAsync(u->d_ic_bits, 0, sizeof(unsigned long long) * (size_t)u->max_nodes * u->ic_words, s));
 
   // InitRoot
   auto t1 = timer.Begin();
@@ -837,10 +939,20 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     LaunchSubtract(u->d_sub, u->d_ts, u->d_hist, ell->total_bins, u->num_sms, s);
     timer.End(kSub, tsb);
     auto te = timer.Begin();
+    IcView icv{nullptr, nullptr};
+    if (has_ic) {
+      const IcDev icd{(int32_t)ell->n_features, u->ic_words, u->ic_n_sets, u->d_ic_set_ptr, u->d_ic_set_feat,
+                      u->d_ic_bits, u->d_ic_list, u->d_ic_count};
+      IcLevelKernel<<<1, kCtlThreads, sizeof(unsigned long long) * (size_t)u->ic_words, s>>>(
+          u->d_ts, u->d_nodes, u->d_part, u->d_eval_nodes, icd, u->d_feature_set, u->n_feature_set,
+          u->n_feature_levels);
+      B200_LAUNCHED();
+      icv = IcView{u->d_ic_list, u->d_ic_count};
+    }
     LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, (int32_t)(2 * cap), u->d_nodes, u->d_feature_set,
                    u->n_feature_set, u->pdev,
                    u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, u->n_feature_levels,
-                   &u->d_ts->max_eval_depth);
+                   &u->d_ts->max_eval_depth, icv);
     timer.End(kEval, te);
   }
 
@@ -1014,6 +1126,9 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
     cudaFree(u->d_exchange_counter);
     if (u->d_feature_set) cudaFree(u->d_feature_set);
     for (void* p : {(void*)u->d_monotone, (void*)u->d_lower, (void*)u->d_upper})
+      if (p) cudaFree(p);
+    for (void* p : {(void*)u->d_ic_set_ptr, (void*)u->d_ic_set_feat, (void*)u->d_ic_bits, (void*)u->d_ic_list,
+                    (void*)u->d_ic_count})
       if (p) cudaFree(p);
     cudaFreeHost(u->h_nodes);
     cudaFreeHost(u->h_ts);
@@ -1240,6 +1355,41 @@ int b200hist_updater_set_monotone_constraints(b200hist_updater_t u, const int32_
     B200_CUDA(cudaMemcpy(u->d_monotone, full.data(), sizeof(int32_t) * full.size(), cudaMemcpyHostToDevice));
     u->d_lower = DevAlloc<float>((size_t)u->max_nodes);
     u->d_upper = DevAlloc<float>((size_t)u->max_nodes);
+  }
+  B200_API_END();
+}
+
+int b200hist_updater_set_interaction_constraints(b200hist_updater_t u, const int32_t* set_ptr_host,
+                                                 const int32_t* set_feat_host, uint32_t n_sets) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  DeviceGuard guard(u->device);
+  for (void** p : {(void**)&u->d_ic_set_ptr, (void**)&u->d_ic_set_feat, (void**)&u->d_ic_bits, (void**)&u->d_ic_list,
+                   (void**)&u->d_ic_count}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  u->ic_n_sets = 0;
+  u->ic_words = 0;
+  if (n_sets > 0) {
+    B200_CHECK(set_ptr_host != nullptr && set_feat_host != nullptr, "null constraint sets");
+    B200_CHECK(set_ptr_host[0] == 0, "set_ptr must start at 0");
+    for (uint32_t i = 0; i < n_sets; ++i) B200_CHECK(set_ptr_host[i] <= set_ptr_host[i + 1], "set_ptr must not decrease");
+    const int32_t n_feat = set_ptr_host[n_sets];
+    for (int32_t i = 0; i < n_feat; ++i)
+      B200_CHECK(set_feat_host[i] >= 0 && (uint32_t)set_feat_host[i] < u->ell->n_features,
+                 "interaction constraint names a feature outside the matrix");
+    u->ic_n_sets = (int32_t)n_sets;
+    u->ic_words = (int32_t)((u->ell->n_features + 63) / 64);
+    B200_CHECK((size_t)u->ic_words * sizeof(unsigned long long) <= 40 * 1024, "too many features for the level mask");
+    u->d_ic_set_ptr = DevAlloc<int32_t>(n_sets + 1);
+    u->d_ic_set_feat = DevAlloc<int32_t>(std::max<int32_t>(n_feat, 1));
+    B200_CUDA(cudaMemcpy(u->d_ic_set_ptr, set_ptr_host, sizeof(int32_t) * (n_sets + 1), cudaMemcpyHostToDevice));
+    if (n_feat > 0)
+      B200_CUDA(cudaMemcpy(u->d_ic_set_feat, set_feat_host, sizeof(int32_t) * n_feat, cudaMemcpyHostToDevice));
+    u->d_ic_bits = DevAlloc<unsigned long long>((size_t)u->max_nodes * u->ic_words);
+    u->d_ic_list = DevAlloc<int32_t>(u->ell->n_features);
+    u->d_ic_count = DevAlloc<int32_t>(2 * (size_t)kMaxLevelNodes);
   }
   B200_API_END();
 }

@@ -452,6 +452,19 @@ class GPUHistMaker:
             c = np.ascontiguousarray(constraints, dtype=np.int32)
             _l.check(_l.load().b200hist_updater_set_monotone_constraints(self._h, c.ctypes.data_as(POINTER(c_int32)), c.size))
 
+    def set_interaction_constraints(self, sets: Optional[Sequence[Sequence[int]]]) -> None:
+        """TrainParam::interaction_constraints, parsed: e.g. [[0, 1], [2, 3, 4]]; None/[] = none.
+        (FeatureInteractionConstraintDevice, src/tree/constraints.cu; see include/b200hist.h for the reading of Query
+        that is reproduced.)  Not yet run on hardware -- see the STATUS note in include/b200hist.h."""
+        if sets is None or len(sets) == 0:
+            _l.check(_l.load().b200hist_updater_set_interaction_constraints(self._h, None, None, 0))
+            return
+        ptr = np.zeros(len(sets) + 1, dtype=np.int32)
+        ptr[1:] = np.cumsum([len(s) for s in sets])
+        feat = np.ascontiguousarray([f for s in sets for f in s] or [0], dtype=np.int32)
+        _l.check(_l.load().b200hist_updater_set_interaction_constraints(
+            self._h, ptr.ctypes.data_as(POINTER(c_int32)), feat.ctypes.data_as(POINTER(c_int32)), len(sets)))
+
     def disable_peer_exchange(self) -> None:
         """Unmap the peers' histogram caches and meet the other ranks at a barrier, so that nobody frees memory that
         a peer still maps; call on every rank before dropping an updater that used enable_peer_exchange()."""
