@@ -342,6 +342,26 @@ B200HIST_API int b200hist_evaluate_splits(b200hist_ellpack_t ell, const b200hist
                                           const b200hist_train_param* param,
                                           const b200hist_quantiser* quantiser,
                                           b200hist_candidate* out_host, void* stream);
+/* E1-E4 with categorical features: EvaluateSplitAgent::{OneHot, Partition}
+ * (src/tree/gpu_hist/evaluate_splits.cu:148-252), GPUHistEvaluator::SortHistogram (evaluator.cu:69-128),
+ * DeviceSplitCandidate::UpdateCat (updater_gpu_common.cuh:88-104), SetCategoricalSplit (evaluate_splits.cu:313-348).
+ * feature_is_cat_host[f] != 0 marks a categorical feature, whose bins are its categories (cut value = category
+ * code).  A feature with fewer than max_cat_to_onehot bins is split one category against the rest; otherwise the
+ * categories are scanned in the order of their leaf weights from both ends, max_cat_threshold deep.  Per node:
+ * out_host (fvalue = NaN, split_gbin = -1 for a categorical winner), out_is_cat_host, and the categories that go
+ * RIGHT as the reference's LBitField32 over category codes in out_cat_bits_host[node * n_cat_words ...]
+ * (category c = bit 31 - c % 32 of word c / 32).
+ * STATUS: compiled, not yet run on hardware; checker pinned (tests/golden/eval_categorical_known_answers.json),
+ * GPU tests in tests/test_gpu_next.py behind B200HIST_RUN_UNVALIDATED=1. */
+B200HIST_API int b200hist_evaluate_splits_cat(b200hist_ellpack_t ell, const b200hist_gpair64* hist_dev,
+                                              const b200hist_gpair64* parent_sums_host, int32_t n_nodes,
+                                              const int32_t* feature_set_host, int32_t n_feature_set,
+                                              const b200hist_train_param* param,
+                                              const b200hist_quantiser* quantiser,
+                                              const uint8_t* feature_is_cat_host, int32_t max_cat_to_onehot,
+                                              int32_t max_cat_threshold, b200hist_candidate* out_host,
+                                              int32_t* out_is_cat_host, uint32_t* out_cat_bits_host,
+                                              uint32_t n_cat_words, void* stream);
 /* P2: RowPartitioner::UpdatePositionBatch (src/tree/gpu_hist/row_partitioner.cuh:343-418) with the
  * numerical GoLeftOp (updater_gpu_hist.cu:398-419).  Segment k of ridx_in_dev is split stably into
  * ridx_out_dev (left rows first); left_count_host[k] receives the number of left rows. */

@@ -117,3 +117,121 @@ def test_interaction_constraints_match_oracle(xb, case):
     t_plain = up.update(torch.from_numpy(gp).cuda())
     o_plain = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params))
     _compare_tree(xb, up, t_plain, o_plain, cp, cv, hists=False)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Categorical split evaluation (b200hist_evaluate_splits_cat: CatFeatureScanKernel / CatFinishKernel, evaluate.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+def _cats_of(bits_row):
+    return {32 * w + (31 - b) for w in range(bits_row.size) for b in range(32) if (int(bits_row[w]) >> b) & 1}
+
+
+def test_categorical_evaluation_known_answers(xb):
+    """The reference's own literal vectors (tests/cpp/tree/gpu_hist/test_evaluate_splits.cu:39-335), the same twelve
+    the oracle is pinned on."""
+    import torch
+    from tests.test_oracle_golden import _dummy_scale, _to_fixed
+    spec = json.load(open(os.path.join(GOLDEN, "eval_categorical_known_answers.json")))
+    scale = _dummy_scale()
+    q = xb.lib.Quantiser(*[float(v) for v in scale])
+    for case in spec["cases"]:
+        name = case["name"]
+        cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+        cv = np.array(case["cut_values"], dtype=np.float32)
+        page = xb.EllpackPage(xb.HistogramCuts(cp, cv), 1, 0, False)
+        hist = _to_fixed(case["hist"], scale)
+        parent = _to_fixed([case["parent"]], scale, as_float32=False)[0]
+        p = xb.TrainParam.make(**case["param"])
+        cands, is_cat, bits = xb.components.evaluate_splits_cat(
+            page, torch.from_numpy(hist).cuda()[None].contiguous(), [tuple(int(v) for v in parent)], p, q,
+            case["is_cat"], max_cat_to_onehot=case["max_cat_to_onehot"], n_cat_words=max(1, int(cv.max()) // 32 + 1))
+        c, cats = cands[0], _cats_of(bits[0])
+        o, o_is_cat, _, o_cats = orc.eval_node_cat(hist, parent, cp, cv, orc.Param.make(**case["param"]), scale,
+                                                   case["is_cat"], case["max_cat_to_onehot"])
+        e = case["expect"]
+        if "findex" in e:
+            assert c.findex == e["findex"], name
+        if "dir" in e:
+            assert c.dir == e["dir"], name
+        if "cats" in e:
+            assert cats == set(e["cats"]), (name, cats)
+        if e.get("is_cat"):
+            assert is_cat[0] == 1, name
+        if e.get("fvalue_is_nan"):
+            assert np.isnan(c.fvalue), name
+        if e.get("sum_is_parent"):
+            assert (c.left_sum.grad + c.right_sum.grad, c.left_sum.hess + c.right_sum.hess) == tuple(parent), name
+        if "loss_chg" in e:
+            assert abs(c.loss_chg - e["loss_chg"]) <= e.get("loss_chg_tol", 1e-6), (name, c.loss_chg)
+        # and everything the oracle reports
+        assert (c.findex, c.dir, bool(is_cat[0]), cats) == (o.findex, o.dir, o_is_cat, o_cats), name
+        assert (c.left_sum.grad, c.left_sum.hess, c.right_sum.grad, c.right_sum.hess) == \
+            (o.left_sum.g, o.left_sum.h, o.right_sum.g, o.right_sum.h), name
+
+
+@pytest.mark.parametrize("onehot,threshold,params", [
+    (4, 64, dict()), (1, 64, dict(reg_lambda=0.0, min_child_weight=0.0)), (100, 64, dict(reg_alpha=0.3)),
+    (4, 5, dict(min_child_weight=20.0)), (4, 64, dict(max_delta_step=0.7)), (40, 33, dict(reg_lambda=3.0))])
+def test_categorical_evaluation_random_histograms(xb, onehot, threshold, params):
+    """Mixed numerical / categorical features with 2..70 categories (one-hot and sorted partition, more than one
+    32-bin chunk), several nodes of different sizes, missing values; candidate, flag and category set against the
+    oracle.  Gains are compared with the tolerance of the numerical test (approximate vs IEEE division)."""
+    import torch
+    rng = np.random.default_rng(17)
+    n = 8000
+    n_cats = [2, 3, 5, 9, 31, 33, 70]
+    cols, cut_ptrs, cut_values, is_cat = [], [0], [], []
+    for k in n_cats:  # categorical columns: codes 0..k-1, 8 % missing
+        col = rng.integers(0, k, size=n).astype(np.float32)
+        col[rng.random(n) < 0.08] = np.nan
+        cols.append(col)
+        cut_values += [float(v) for v in range(k)]
+        cut_ptrs.append(len(cut_values))
+        is_cat.append(1)
+    xnum, _ = make_regression(n, 4, seed=23, missing=0.05)
+    ncp, ncv = make_cuts(xnum, 32)
+    for j in range(4):
+        cols.append(xnum[:, j])
+        cut_values += [float(v) for v in ncv[ncp[j]:ncp[j + 1]]]
+        cut_ptrs.append(len(cut_values))
+        is_cat.append(0)
+    cp = np.array(cut_ptrs, dtype=np.uint32)
+    cv = np.array(cut_values, dtype=np.float32)
+    # global bins: a category is its own bin (SearchCatBin), numerical features through the oracle's SearchBin
+    gb = np.full((n, len(cols)), -1, dtype=np.int32)
+    for j, col in enumerate(cols):
+        ok = ~np.isnan(col)
+        if is_cat[j]:
+            gb[ok, j] = cp[j] + col[ok].astype(np.int32)
+        else:
+            gb[ok, j] = orc.bin_dense(col[:, None], np.array([0, cp[j + 1] - cp[j]], dtype=np.uint32),
+                                      cv[cp[j]:cp[j + 1]])[ok, 0] + cp[j]
+    effect = rng.normal(size=70)
+    y = (effect[np.nan_to_num(cols[6], nan=0).astype(int)] + 0.5 * effect[np.nan_to_num(cols[4], nan=0).astype(int)] +
+         np.nan_to_num(xnum[:, 0]) + 0.3 * rng.normal(size=n)).astype(np.float32)
+    gp = squared_error_gpair(np.zeros(n, np.float32), y)
+    scale, _ = orc.quantiser(gp)
+    gq = orc.quantise(gp, scale)
+    subsets = [np.arange(n), rng.choice(n, 900, replace=False), rng.choice(n, 60, replace=False)]
+    hists = np.stack([orc.build_hist(gb, gq, s.astype(np.uint32), cv.size) for s in subsets])
+    parents = [tuple(int(v) for v in gq[s].sum(axis=0)) for s in subsets]
+    q = xb.lib.Quantiser(*[float(v) for v in scale])
+    page = xb.EllpackPage(xb.HistogramCuts(cp, cv), 1, 0, False)
+    cands, flags, bits = xb.components.evaluate_splits_cat(
+        page, torch.from_numpy(hists).cuda(), parents, xb.TrainParam.make(**params), q, is_cat,
+        max_cat_to_onehot=onehot, max_cat_threshold=threshold, n_cat_words=3)
+    op = orc.Param.make(**params)
+    for k, c in enumerate(cands):
+        o, o_is_cat, _, o_cats = orc.eval_node_cat(hists[k], parents[k], cp, cv, op, scale, is_cat, onehot, threshold)
+        name = "node %d onehot %d threshold %d %r" % (k, onehot, threshold, params)
+        assert (c.findex, c.dir, bool(flags[k])) == (o.findex, o.dir, o_is_cat), name
+        assert (c.left_sum.grad, c.left_sum.hess, c.right_sum.grad, c.right_sum.hess) == \
+            (o.left_sum.g, o.left_sum.h, o.right_sum.g, o.right_sum.h), name
+        if o_is_cat:
+            assert _cats_of(bits[k]) == o_cats, name
+            assert np.isnan(c.fvalue) and c.split_gbin == -1, name
+        else:
+            assert np.float32(c.fvalue).view(np.uint32) == np.float32(o.fvalue).view(np.uint32), name
+        assert np.isclose(c.loss_chg, o.loss_chg, rtol=2e-5, atol=1e-6), name
+        for a, b in [(c.base_weight, o.base_weight), (c.left_weight, o.left_weight), (c.right_weight, o.right_weight)]:
+            assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32), name

@@ -2,7 +2,7 @@
 Used by the parity tests; each call launches the same kernels the updater launches."""
 from __future__ import annotations
 
-from ctypes import POINTER, byref, c_float, c_int32, c_uint64, c_void_p
+from ctypes import POINTER, byref, c_float, c_int32, c_uint32, c_uint64, c_void_p
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -70,6 +70,33 @@ def evaluate_splits(page: EllpackPage, hist: torch.Tensor, parent_sums: Sequence
     _l.check(_l.load().b200hist_evaluate_splits(page.handle, c_void_p(hist.data_ptr()), ps, n_nodes, fsp, nfs,
                                               byref(param), byref(quantiser), out, _stream_ptr(hist.device)))
     return list(out)
+
+
+def evaluate_splits_cat(page: EllpackPage, hist: torch.Tensor, parent_sums: Sequence[Tuple[int, int]],
+                        param: _l.TrainParam, quantiser: _l.Quantiser, feature_is_cat: Sequence[int],
+                        max_cat_to_onehot: int = 4, max_cat_threshold: int = 64, n_cat_words: int = 8,
+                        feature_set: Optional[Sequence[int]] = None):
+    """E1-E4 with categorical features (b200hist_evaluate_splits_cat): returns (candidates, is_cat flags,
+    uint32[n_nodes, n_cat_words] category sets in the reference's LBitField32 layout).  Defaults are TrainParam's
+    (max_cat_to_onehot 4, max_cat_threshold 64)."""
+    _require_cuda(hist, "hist")
+    n_nodes = len(parent_sums)
+    ps = (_l.GPair64 * n_nodes)(*[_l.GPair64(int(g), int(h)) for g, h in parent_sums])
+    out = (_l.Candidate * n_nodes)()
+    if feature_set is not None:
+        fs = np.ascontiguousarray(feature_set, dtype=np.int32)
+        fsp, nfs = fs.ctypes.data_as(POINTER(c_int32)), fs.size
+    else:
+        fsp, nfs = None, 0
+    fic = np.ascontiguousarray(feature_is_cat, dtype=np.uint8)
+    is_cat = np.zeros(n_nodes, dtype=np.int32)
+    bits = np.zeros((n_nodes, n_cat_words), dtype=np.uint32)
+    _l.check(_l.load().b200hist_evaluate_splits_cat(
+        page.handle, c_void_p(hist.data_ptr()), ps, n_nodes, fsp, nfs, byref(param), byref(quantiser),
+        c_void_p(fic.ctypes.data), int(max_cat_to_onehot), int(max_cat_threshold), out,
+        is_cat.ctypes.data_as(POINTER(c_int32)), bits.ctypes.data_as(POINTER(c_uint32)), int(n_cat_words),
+        _stream_ptr(hist.device)))
+    return list(out), is_cat, bits
 
 
 def partition(page: EllpackPage, ridx: torch.Tensor, seg_begin: Sequence[int], seg_count: Sequence[int],

@@ -144,6 +144,7 @@ namespace b200 {
 constexpr int kPartTile = 2048;       // rows per partition tile (64 flag words)
 constexpr int kHistTile = 512;        // rows per histogram tile
 constexpr int kMaxLevelNodes = 4096;  // nodes expanded in one step
+constexpr int kMaxCatBins = 1024;     // bins of one categorical feature (8 warps x 6 B x 1024 = 48 KiB of sort scratch)
 
 struct NodeDev {
   int32_t parent, left, right, depth;
@@ -230,6 +231,23 @@ struct MonoView {
 struct IcView {
   const int32_t* list;
   const int32_t* count;
+};
+
+// Categorical features (src/common/categorical.h, evaluate_splits.cu:148-252,313-348, evaluator.cu:69-128).
+// A categorical feature's bins ARE its categories: cut_values[b] is the category code of bin b.  is_cat == nullptr:
+// every feature is numerical.  Per node the winner's category set is kept twice: cat_bits = the reference's
+// LBitField32 over category codes (category c = bit 31 - c % 32 of word c / 32; what RegTree stores) and bin_bits =
+// the same set over the feature's LOCAL bins (bin b = bit b % 32 of word b / 32; what the partitioner tests).
+// A row whose category is in the set goes RIGHT (common::Decision, categorical.h:49-60).
+struct CatView {
+  const uint8_t* is_cat;       // [n_features]
+  int32_t max_cat_to_onehot;   // fewer bins than this: one-hot split (UseOneHot, categorical.h:86-89)
+  int32_t max_cat_threshold;   // sorted-partition scan looks at this many categories from either end
+  uint32_t* cat_bits;          // [max_nodes][cat_words]
+  uint32_t* bin_bits;          // [max_nodes][bin_words]
+  uint8_t* node_is_cat;        // [max_nodes] the node's candidate is a categorical split
+  int32_t cat_words, bin_words;
+  int32_t max_cat_bins;        // most bins of any categorical feature (sizes the sort scratch)
 };
 
 struct ParamDev {
@@ -330,7 +348,8 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = n
                     NodeDev* nodes_mut, int num_sms, cudaStream_t s, MonoView mono = MonoView{nullptr, nullptr, nullptr},
                     int32_t n_levels = 0 /* > 0: feature_set is [n_levels][n_feature_set], row = node depth */,
                     int32_t* max_eval_depth = nullptr /* device: atomicMax of the depths evaluated */,
-                    IcView ic = IcView{nullptr, nullptr});
+                    IcView ic = IcView{nullptr, nullptr},
+                    CatView cat = CatView{nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0, 0});
 
 // partition.cu
 void LaunchPartitionCount(const EllView& ell, const uint32_t* ridx0, const uint32_t* ridx1, const PartEntry* part,

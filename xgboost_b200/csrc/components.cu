@@ -132,6 +132,94 @@ int b200hist_evaluate_splits(b200hist_ellpack_t ell, const b200hist_gpair64* his
   B200_API_END();
 }
 
+int b200hist_evaluate_splits_cat(b200hist_ellpack_t ell, const b200hist_gpair64* hist_dev,
+                                 const b200hist_gpair64* parent_sums_host, int32_t n_nodes,
+                                 const int32_t* feature_set_host, int32_t n_feature_set,
+                                 const b200hist_train_param* param, const b200hist_quantiser* quantiser,
+                                 const uint8_t* feature_is_cat_host, int32_t max_cat_to_onehot,
+                                 int32_t max_cat_threshold, b200hist_candidate* out_host, int32_t* out_is_cat_host,
+                                 uint32_t* out_cat_bits_host, uint32_t n_cat_words, void* stream) {
+  B200_API_BEGIN();
+  B200_CHECK(ell && hist_dev && parent_sums_host && param && quantiser && out_host && feature_is_cat_host &&
+                 out_is_cat_host && out_cat_bits_host,
+             "null argument");
+  B200_CHECK(n_nodes >= 0 && n_nodes <= 2 * kMaxLevelNodes, "n_nodes out of range");
+  B200_CHECK(n_cat_words >= 1, "n_cat_words must be at least 1");
+  if (n_nodes == 0) return 0;
+  if (feature_set_host)
+    for (int32_t i = 0; i < n_feature_set; ++i)
+      B200_CHECK(feature_set_host[i] >= 0 && (uint32_t)feature_set_host[i] < ell->n_features, "feature id out of range");
+  int32_t max_cat_bins = 1;
+  for (uint32_t f = 0; f < ell->n_features; ++f)
+    if (feature_is_cat_host[f])
+      max_cat_bins = std::max<int32_t>(max_cat_bins, (int32_t)(ell->cut_ptrs[f + 1] - ell->cut_ptrs[f]));
+  B200_CHECK(max_cat_bins <= kMaxCatBins, "a categorical feature has more bins than the sort scratch holds");
+  DeviceGuard guard(ell->device);
+  auto s = static_cast<cudaStream_t>(stream);
+  std::vector<NodeDev> nodes(n_nodes);
+  std::vector<int32_t> eval_nodes(n_nodes);
+  for (int32_t k = 0; k < n_nodes; ++k) {
+    NodeDev nd{};
+    nd.parent = -1; nd.left = -1; nd.right = -1; nd.is_leaf = 1; nd.findex = -1; nd.seg_buf = -1;
+    nd.sum_g = parent_sums_host[k].grad;
+    nd.sum_h = parent_sums_host[k].hess;
+    nd.hist_slot = k;
+    nodes[k] = nd;
+    eval_nodes[k] = k;
+  }
+  TreeState ts{};
+  ts.n_eval = n_nodes;
+  QuantDev q{};
+  q.to_fixed_g = quantiser->to_fixed_grad; q.to_fixed_h = quantiser->to_fixed_hess;
+  q.to_float_g = quantiser->to_float_grad; q.to_float_h = quantiser->to_float_hess;
+  const int32_t n_fs = feature_set_host ? n_feature_set : (int32_t)ell->n_features;
+  const int32_t bin_words = (max_cat_bins + 31) / 32;
+  DevBuf<NodeDev> d_nodes(n_nodes);
+  DevBuf<int32_t> d_eval(n_nodes);
+  DevBuf<TreeState> d_ts(1);
+  DevBuf<QuantDev> d_q(1);
+  DevBuf<int32_t> d_fs(std::max(1, n_fs));
+  DevBuf<FeatCand> d_scratch((size_t)n_nodes * std::max(1, n_fs));
+  DevBuf<b200hist_candidate> d_cand(n_nodes);
+  DevBuf<uint8_t> d_is_cat(ell->n_features);
+  DevBuf<uint32_t> d_cat_bits((size_t)n_nodes * n_cat_words);
+  DevBuf<uint32_t> d_bin_bits((size_t)n_nodes * bin_words);
+  DevBuf<uint8_t> d_node_is_cat(n_nodes);
+  B200_CUDA(cudaMemcpyAsync(d_nodes.p, nodes.data(), sizeof(NodeDev) * n_nodes, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(d_eval.p, eval_nodes.data(), sizeof(int32_t) * n_nodes, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(d_ts.p, &ts, sizeof(ts), cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(d_q.p, &q, sizeof(q), cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(d_is_cat.p, feature_is_cat_host, ell->n_features, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemsetAsync(d_cat_bits.p, 0, sizeof(uint32_t) * (size_t)n_nodes * n_cat_words, s));
+  B200_CUDA(cudaMemsetAsync(d_node_is_cat.p, 0, (size_t)n_nodes, s));
+  if (feature_set_host && n_fs > 0)
+    B200_CUDA(cudaMemcpyAsync(d_fs.p, feature_set_host, sizeof(int32_t) * n_fs, cudaMemcpyHostToDevice, s));
+  std::vector<b200hist_candidate> init(n_nodes);
+  for (auto& c : init) {
+    c = b200hist_candidate{};
+    c.loss_chg = -3.402823466e+38f;
+    c.findex = -1;
+    c.split_gbin = -1;
+    c.base_weight = c.left_weight = c.right_weight = NAN;
+  }
+  B200_CUDA(cudaMemcpyAsync(d_cand.p, init.data(), sizeof(b200hist_candidate) * n_nodes, cudaMemcpyHostToDevice, s));
+  if (n_fs > 0) {
+    const CatView cat{d_is_cat.p, max_cat_to_onehot, max_cat_threshold, d_cat_bits.p, d_bin_bits.p, d_node_is_cat.p,
+                      (int32_t)n_cat_words, bin_words, max_cat_bins};
+    LaunchEvaluate(ell->View(), hist_dev, d_eval.p, d_ts.p, n_nodes, d_nodes.p, feature_set_host ? d_fs.p : nullptr,
+                   n_fs, ToParamDev(*param), d_q.p, d_scratch.p, d_cand.p, d_nodes.p, NumSMs(ell->device), s,
+                   MonoView{nullptr, nullptr, nullptr}, 0, nullptr, IcView{nullptr, nullptr}, cat);
+  }
+  std::vector<uint8_t> node_is_cat(n_nodes);
+  B200_CUDA(cudaMemcpyAsync(out_host, d_cand.p, sizeof(b200hist_candidate) * n_nodes, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaMemcpyAsync(node_is_cat.data(), d_node_is_cat.p, (size_t)n_nodes, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaMemcpyAsync(out_cat_bits_host, d_cat_bits.p, sizeof(uint32_t) * (size_t)n_nodes * n_cat_words,
+                            cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  for (int32_t k = 0; k < n_nodes; ++k) out_is_cat_host[k] = node_is_cat[k];
+  B200_API_END();
+}
+
 int b200hist_partition(b200hist_ellpack_t ell, const uint32_t* ridx_in_dev, uint32_t* ridx_out_dev,
                        const uint64_t* seg_begin_host, const uint64_t* seg_count_host, const int32_t* findex_host,
                        const float* split_cond_host, const int32_t* default_left_host, int32_t n_nodes,

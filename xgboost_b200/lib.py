@@ -123,6 +123,10 @@ _SIGNATURES = {
     "b200hist_subtract": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "b200hist_evaluate_splits": (c_int, [c_void_p, c_void_p, POINTER(GPair64), c_int32, POINTER(c_int32), c_int32,
                                          POINTER(TrainParam), POINTER(Quantiser), POINTER(Candidate), c_void_p]),
+    "b200hist_evaluate_splits_cat": (c_int, [c_void_p, c_void_p, POINTER(GPair64), c_int32, POINTER(c_int32), c_int32,
+                                             POINTER(TrainParam), POINTER(Quantiser), c_void_p, c_int32, c_int32,
+                                             POINTER(Candidate), POINTER(c_int32), POINTER(c_uint32), c_uint32,
+                                             c_void_p]),
     "b200hist_partition": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_uint64), POINTER(c_uint64),
                                    POINTER(c_int32), POINTER(c_float), POINTER(c_int32), c_int32,
                                    POINTER(c_uint64), c_void_p]),
