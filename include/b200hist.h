@@ -284,6 +284,24 @@ B200HIST_API int b200hist_updater_set_monotone_constraints(b200hist_updater_t u,
 B200HIST_API int b200hist_updater_set_interaction_constraints(b200hist_updater_t u, const int32_t* set_ptr_host,
                                                               const int32_t* set_feat_host, uint32_t n_sets);
 
+/* Categorical features in the tree updater.  feature_is_cat_host[f] != 0 for the first n
+ * features marks a categorical feature (MetaInfo::feature_types == kCategorical); its bins are its categories and
+ * its cut values the category codes, as the reference's sketch emits them (AddCategories) -- checked here.
+ * max_cat_to_onehot / max_cat_threshold are TrainParam's (src/tree/param.h; defaults 4 and 64).  All zero / NULL
+ * removes them.  Evaluation: see b200hist_evaluate_splits_cat.  An applied categorical split stores NaN as its
+ * split condition (updater_gpu_hist.cu:628-642); rows whose category is in the node's set go RIGHT, missing values
+ * follow default_left (common::Decision, src/common/categorical.h:49-60) in the partitioner and in FinalisePosition.
+ * b200hist_updater_last_tree_categories: per node of the last tree, 1 if it is a categorical split, and its
+ * category set as cat_words uint32 words in the reference's LBitField32 layout (category c = bit 31 - c % 32 of
+ * word c / 32) -- what RegTree::ExpandCategorical takes.  Buffers: n_nodes and n_nodes * cat_words entries.
+ * STATUS: compiled, not yet run on hardware; the shim keeps refusing categorical features until
+ * tests/test_gpu_next.py has passed on a B200. */
+B200HIST_API int b200hist_updater_set_categorical(b200hist_updater_t u, const uint8_t* feature_is_cat_host, uint32_t n,
+                                                  int32_t max_cat_to_onehot, int32_t max_cat_threshold);
+B200HIST_API int b200hist_updater_cat_words(b200hist_updater_t u, uint32_t* out);
+B200HIST_API int b200hist_updater_last_tree_categories(b200hist_updater_t u, int32_t* node_is_cat_host,
+                                                       uint32_t* cat_bits_host);
+
 /* Row split (the reference's default distributed mode): every rank holds a page of ITS rows with the
  * same cuts and builds full-width partial histograms; one peer-memory kernel per level sums them (reduce-scatter +
  * all-gather over NVLink, integer, bit-identical to one GPU) = AllReduceHist (src/tree/gpu_hist/histogram.cu:598-609);

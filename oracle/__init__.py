@@ -240,12 +240,21 @@ class InteractionConstraints:
         return out[:n].tolist()
 
 
+class _Cat(Structure):
+    _fields_ = [("feature_is_cat", c_void_p), ("max_cat_to_onehot", c_int32), ("max_cat_threshold", c_int32),
+                ("n_cat_words", c_uint32), ("node_is_cat", c_void_p), ("node_cat_bits", c_void_p)]
+
+
 def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override=None, max_nodes=None,
                 is_dense_layout=True, want_hist=False, feature_set=None, subsample=1.0, sample_seed=0,
-                monotone=None, level_feature_sets=None, interaction=None, interaction_shared_buffer=True):
+                monotone=None, level_feature_sets=None, interaction=None, interaction_shared_buffer=True,
+                feature_is_cat=None, max_cat_to_onehot=4, max_cat_threshold=64):
     """Whole tree.  Returns dict(nodes=[Node...], position, scale, hist (optional), cands).
     feature_set: sorted feature ids of the tree's colsample_bytree draw; subsample/sample_seed: uniform row sampling;
     monotone: per-feature sign (+1 increasing, -1 decreasing, 0 free), padded with 0 to n_features;
+    feature_is_cat: flags per feature (categorical features: bins are categories, cut values their codes), with
+    TrainParam's max_cat_to_onehot / max_cat_threshold; the result then carries is_cat[n_nodes] and cat_sets (the
+    categories that go RIGHT, per categorical split);
     interaction: parsed interaction_constraints ([[f, ...], ...]); interaction_shared_buffer (default = what the
     reference's trees follow, tests/golden/ref_gpu_interaction_trees.json): see orc_update_tree_ic."""
     gb = np.ascontiguousarray(gbins, dtype=np.int32)
@@ -274,15 +283,31 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
         mono = np.zeros(nf, dtype=np.int32)
         mono[:len(monotone)] = np.asarray(monotone, dtype=np.int32)
     ic = InteractionConstraints(interaction, nf, 1, interaction_shared_buffer) if interaction is not None else None
-    nn = lib().orc_update_tree_ic(_p(gb), c_uint64(n), c_uint32(stride), c_int(1 if is_dense_layout else 0),
+    cat = None
+    if feature_is_cat is not None and any(feature_is_cat):
+        flags = np.zeros(nf, dtype=np.uint8)
+        flags[:len(feature_is_cat)] = [1 if v else 0 for v in feature_is_cat]
+        n_words = int(cv.max()) // 32 + 1 if cv.size else 1
+        node_is_cat = np.zeros(max_nodes, dtype=np.int32)
+        node_bits = np.zeros((max_nodes, n_words), dtype=np.uint32)
+        cat = _Cat(flags.ctypes.data, int(max_cat_to_onehot), int(max_cat_threshold), n_words,
+                   node_is_cat.ctypes.data, node_bits.ctypes.data)
+    lib().orc_update_tree_full.restype = c_int32
+    nn = lib().orc_update_tree_full(_p(gb), c_uint64(n), c_uint32(stride), c_int(1 if is_dense_layout else 0),
                                   c_uint32(nf), _p(cp), _p(cv), _p(g), byref(param), so, nodes, c_int32(max_nodes),
                                   _p(pos), _p(hist) if want_hist else c_void_p(), cands, scale_out,
                                   _p(fs) if fs is not None else c_void_p(), c_int32(n_fs),
                                   c_float(subsample), c_uint32(int(sample_seed) & 0xFFFFFFFF),
                                   _p(mono) if mono is not None else c_void_p(), c_int32(n_levels),
-                                  byref(ic.c) if ic is not None else c_void_p())
-    return dict(nodes=list(nodes[:nn]), cands=list(cands[:nn]), position=pos,
-                scale=np.array(scale_out[:], dtype=np.float64), hist=hist[:nn] if want_hist else None)
+                                  byref(ic.c) if ic is not None else c_void_p(),
+                                  byref(cat) if cat is not None else c_void_p())
+    res = dict(nodes=list(nodes[:nn]), cands=list(cands[:nn]), position=pos,
+               scale=np.array(scale_out[:], dtype=np.float64), hist=hist[:nn] if want_hist else None)
+    if cat is not None:
+        res["is_cat"] = node_is_cat[:nn].copy()
+        res["cat_sets"] = [{32 * w + (31 - b) for w in range(n_words) for b in range(32) if (int(node_bits[i, w]) >> b) & 1}
+                           if node_is_cat[i] else set() for i in range(nn)]
+    return res
 
 
 def update_prediction_cache(nodes, position: np.ndarray, preds: np.ndarray) -> np.ndarray:

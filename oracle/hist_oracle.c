@@ -584,13 +584,33 @@ static void eval_feature_categorical(const orc_gpair64* hist, orc_gpair64 parent
 /* Best split of one node over numerical and categorical features.  feature_is_cat: n_features flags.
  * Outputs next to the candidate: is_cat, thresh (one-hot: the category; partition: position in the sorted order) and
  * the category bit set of SetCategoricalSplit in LBitField32 layout (category c = bit 31 - c % 32 of word c / 32). */
+static void eval_node_cat_m(const orc_gpair64* hist, orc_gpair64 parent_sum, const uint32_t* cut_ptrs,
+                            const float* cut_values, uint32_t n_features, const int32_t* feature_set,
+                            int32_t n_feature_set, const orc_param* p, const double scale[4],
+                            const uint8_t* feature_is_cat, int32_t max_cat_to_onehot, int32_t max_cat_threshold,
+                            orc_candidate* out, int32_t* out_is_cat, int32_t* out_thresh, uint32_t* out_cat_bits,
+                            uint32_t n_cat_words, const int32_t* monotone, float lower, float upper);
+
 ORC_API void orc_eval_node_cat(const orc_gpair64* hist, orc_gpair64 parent_sum, const uint32_t* cut_ptrs,
                                const float* cut_values, uint32_t n_features, const int32_t* feature_set,
                                int32_t n_feature_set, const orc_param* p, const double scale[4],
                                const uint8_t* feature_is_cat, int32_t max_cat_to_onehot, int32_t max_cat_threshold,
                                orc_candidate* out, int32_t* out_is_cat, int32_t* out_thresh, uint32_t* out_cat_bits,
                                uint32_t n_cat_words) {
-  orc_mono mono = kNoMono;
+  eval_node_cat_m(hist, parent_sum, cut_ptrs, cut_values, n_features, feature_set, n_feature_set, p, scale,
+                  feature_is_cat, max_cat_to_onehot, max_cat_threshold, out, out_is_cat, out_thresh, out_cat_bits,
+                  n_cat_words, NULL, -FLT_MAX, FLT_MAX);
+}
+
+/* monotone / lower / upper as in orc_eval_node_mono: the categorical gains go through the same evaluator
+ * (evaluate_splits.cu:160-166,203-206) */
+static void eval_node_cat_m(const orc_gpair64* hist, orc_gpair64 parent_sum, const uint32_t* cut_ptrs,
+                            const float* cut_values, uint32_t n_features, const int32_t* feature_set,
+                            int32_t n_feature_set, const orc_param* p, const double scale[4],
+                            const uint8_t* feature_is_cat, int32_t max_cat_to_onehot, int32_t max_cat_threshold,
+                            orc_candidate* out, int32_t* out_is_cat, int32_t* out_thresh, uint32_t* out_cat_bits,
+                            uint32_t n_cat_words, const int32_t* monotone, float lower, float upper) {
+  orc_mono mono = {monotone != NULL, 0, lower, upper};
   orc_candidate best;
   cand_init(&best);
   int32_t best_pos = -1, best_is_cat = 0, best_thresh = -1;
@@ -604,6 +624,7 @@ ORC_API void orc_eval_node_cat(const orc_gpair64* hist, orc_gpair64 parent_sum, 
     int32_t f = feature_set ? feature_set[fi] : fi;
     orc_candidate fbest;
     int32_t f_is_cat = 0, f_thresh = -1;
+    mono.constraint = monotone ? monotone[f] : 0;
     if (feature_is_cat && feature_is_cat[f]) {
       eval_feature_categorical(hist, parent_sum, cut_ptrs, cut_values, f, p, scale, &mono, max_cat_to_onehot,
                                max_cat_threshold, &fbest, &f_is_cat, &f_thresh, sorted);
@@ -671,6 +692,19 @@ static int go_left(const int32_t* gbins, uint32_t stride, int is_dense_layout, c
   int32_t b = row_feature_gbin(gbins, stride, is_dense_layout, cut_ptrs, r, findex);
   if (b < 0) return default_left;
   return cut_values[b] <= split_cond;
+}
+
+/* common::Decision (src/common/categorical.h:49-60) on a training row: the category of the row's bin is looked up in
+ * the split's set (LBitField32: category c = bit 31 - c % 32 of word c / 32); in the set -> RIGHT; a category beyond
+ * the set's storage or a missing value -> default direction / left as the reference does. */
+static int go_left_cat(const int32_t* gbins, uint32_t stride, int is_dense_layout, const uint32_t* cut_ptrs,
+                       const float* cut_values, uint64_t r, int32_t findex, const uint32_t* cat_bits,
+                       uint32_t n_cat_words, int default_left) {
+  int32_t b = row_feature_gbin(gbins, stride, is_dense_layout, cut_ptrs, r, findex);
+  if (b < 0) return default_left;
+  uint32_t c = (uint32_t)cut_values[b];
+  if (c / 32 >= n_cat_words) return 1;
+  return ((cat_bits[c / 32] >> (31 - c % 32)) & 1u) == 0u;
 }
 
 /* Stable partition of one node's row segment: left rows first (row order inside a node does not
@@ -825,6 +859,21 @@ ORC_API int32_t orc_update_tree_ic(const int32_t* gbins, uint64_t n_rows, uint32
                                    const int32_t* feature_set, int32_t n_feature_set, float subsample,
                                    uint32_t sample_seed, const int32_t* monotone, int32_t n_levels,
                                    const orc_ic* ic);
+typedef struct {
+  const uint8_t* feature_is_cat;
+  int32_t max_cat_to_onehot, max_cat_threshold;
+  uint32_t n_cat_words;
+  int32_t* node_is_cat;     /* out [max_nodes] */
+  uint32_t* node_cat_bits;  /* out [max_nodes][n_cat_words] */
+} orc_cat;
+ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
+                                     uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
+                                     const float* gpair, const orc_param* p, const double* scale_override,
+                                     orc_node* nodes, int32_t max_nodes, int32_t* position,
+                                     orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4],
+                                     const int32_t* feature_set, int32_t n_feature_set, float subsample,
+                                     uint32_t sample_seed, const int32_t* monotone, int32_t n_levels,
+                                     const orc_ic* ic, const orc_cat* cat);
 
 ORC_API int32_t orc_update_tree(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
                                 uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
@@ -869,6 +918,43 @@ ORC_API int32_t orc_update_tree_ic(const int32_t* gbins, uint64_t n_rows, uint32
                                    const int32_t* feature_set, int32_t n_feature_set, float subsample,
                                    uint32_t sample_seed, const int32_t* monotone, int32_t n_levels,
                                    const orc_ic* ic) {
+  return orc_update_tree_full(gbins, n_rows, stride, is_dense_layout, n_features, cut_ptrs, cut_values, gpair, p,
+                              scale_override, nodes, max_nodes, position, hist_dump, cand_dump, scale_out, feature_set,
+                              n_feature_set, subsample, sample_seed, monotone, n_levels, ic, NULL);
+}
+
+/* cat (NULL = none): categorical features.  Evaluation through eval_node_cat_m; an applied categorical split stores
+ * NaN as its condition (updater_gpu_hist.cu:628-642) and routes rows by its category set (go_left_cat) in the
+ * partitioner and in FinalisePosition.  Outputs: cat->node_is_cat[max_nodes], cat->node_cat_bits[max_nodes][n_cat_words]
+ * (set only for applied categorical splits). */
+ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
+                                     uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
+                                     const float* gpair, const orc_param* p, const double* scale_override,
+                                     orc_node* nodes, int32_t max_nodes, int32_t* position,
+                                     orc_gpair64* hist_dump, orc_candidate* cand_dump, double scale_out[4],
+                                     const int32_t* feature_set, int32_t n_feature_set, float subsample,
+                                     uint32_t sample_seed, const int32_t* monotone, int32_t n_levels,
+                                     const orc_ic* ic, const orc_cat* cat) {
+  /* candidates' category sets, kept until the candidate is applied */
+  uint32_t* cand_bits = cat ? (uint32_t*)calloc((size_t)max_nodes * cat->n_cat_words, sizeof(uint32_t)) : NULL;
+  int32_t* cand_is_cat = cat ? (int32_t*)calloc((size_t)max_nodes, sizeof(int32_t)) : NULL;
+  if (cat) {
+    memset(cat->node_is_cat, 0, sizeof(int32_t) * (size_t)max_nodes);
+    memset(cat->node_cat_bits, 0, sizeof(uint32_t) * (size_t)max_nodes * cat->n_cat_words);
+  }
+#define ORC_EVAL(nidx_, fs_, nfs_, out_)                                                                              \
+  do {                                                                                                                \
+    if (cat) {                                                                                                        \
+      int32_t th_;                                                                                                    \
+      eval_node_cat_m(hist[nidx_], node_sum[nidx_], cut_ptrs, cut_values, n_features, fs_, nfs_, p, scale,            \
+                      cat->feature_is_cat, cat->max_cat_to_onehot, cat->max_cat_threshold, out_, &cand_is_cat[nidx_], \
+                      &th_, cand_bits + (size_t)(nidx_) * cat->n_cat_words, cat->n_cat_words, monotone, lower[nidx_], \
+                      upper[nidx_]);                                                                                  \
+    } else {                                                                                                          \
+      orc_eval_node_mono(hist[nidx_], node_sum[nidx_], cut_ptrs, cut_values, n_features, fs_, nfs_, p, scale, out_,   \
+                         NULL, monotone, lower[nidx_], upper[nidx_]);                                                 \
+    }                                                                                                                 \
+  } while (0)
   uint64_t* ic_bits = ic ? (uint64_t*)calloc((size_t)max_nodes * (size_t)ic_words(ic->n_features), sizeof(uint64_t)) : NULL;
   int32_t* ic_buffer = ic ? (int32_t*)calloc((size_t)n_features + 1, sizeof(int32_t)) : NULL;
   /* n_levels > 0 (colsample_bylevel): feature_set is [n_levels][n_feature_set], a node at depth d is evaluated on
@@ -924,7 +1010,7 @@ ORC_API int32_t orc_update_tree_ic(const int32_t* gbins, uint64_t n_rows, uint32
   }
   entry_t root_e;
   root_e.nidx = 0; root_e.depth = 0; root_e.open = 1;
-  orc_eval_node_mono(hist[0], root, cut_ptrs, cut_values, n_features, ORC_LEVEL_SET(0), n_feature_set, p, scale, &root_e.c, NULL, monotone, lower[0], upper[0]);
+  ORC_EVAL(0, ORC_LEVEL_SET(0), n_feature_set, &root_e.c);
   if (cand_dump) cand_dump[0] = root_e.c;
   /* driver.Push(vector) filters loss_chg > kRtEps (driver.h:42-50) */
   int n_open = 0;
@@ -981,6 +1067,11 @@ ORC_API int32_t orc_update_tree_ic(const int32_t* gbins, uint64_t n_rows, uint32
       nodes[l] = ln; nodes[r] = rn;
       node_sum[l] = c->left_sum; node_sum[r] = c->right_sum;
       if (ic) orc_ic_split(ic, ic_bits, nidx, c->findex, l, r);
+      if (cat && cand_is_cat[nidx]) {
+        cat->node_is_cat[nidx] = 1;
+        memcpy(cat->node_cat_bits + (size_t)nidx * cat->n_cat_words, cand_bits + (size_t)nidx * cat->n_cat_words,
+               sizeof(uint32_t) * cat->n_cat_words);
+      }
       if (monotone) { /* TreeEvaluator::AddSplit (split_evaluator.h:163-203), weights before the learning rate */
         lower[l] = lower[r] = lower[nidx];
         upper[l] = upper[r] = upper[nidx];
@@ -1001,9 +1092,27 @@ ORC_API int32_t orc_update_tree_ic(const int32_t* gbins, uint64_t n_rows, uint32
       if (p->max_depth > 0 && depth + 1 >= p->max_depth) continue;
       if (p->max_leaves > 0 && num_leaves >= p->max_leaves) continue;
       int32_t l = nodes[nidx].left, r = nodes[nidx].right;
-      uint64_t nl = orc_partition(gbins, stride, is_dense_layout, cut_ptrs, cut_values, ridx + seg_beg[nidx],
-                                  seg_cnt[nidx], nodes[nidx].findex, nodes[nidx].fvalue,
-                                  nodes[nidx].default_left, tmp + seg_beg[nidx]);
+      uint64_t nl;
+      if (cat && cat->node_is_cat[nidx]) {
+        const uint32_t* bits = cat->node_cat_bits + (size_t)nidx * cat->n_cat_words;
+        const uint32_t* in = ridx + seg_beg[nidx];
+        uint32_t* outp = tmp + seg_beg[nidx];
+        uint64_t cnt = seg_cnt[nidx], li = 0, ri;
+        nl = 0;
+        for (uint64_t i = 0; i < cnt; ++i)
+          nl += go_left_cat(gbins, stride, is_dense_layout, cut_ptrs, cut_values, in[i], nodes[nidx].findex, bits,
+                            cat->n_cat_words, nodes[nidx].default_left) ? 1 : 0;
+        ri = nl;
+        for (uint64_t i = 0; i < cnt; ++i) {
+          if (go_left_cat(gbins, stride, is_dense_layout, cut_ptrs, cut_values, in[i], nodes[nidx].findex, bits,
+                          cat->n_cat_words, nodes[nidx].default_left)) outp[li++] = in[i];
+          else outp[ri++] = in[i];
+        }
+      } else {
+        nl = orc_partition(gbins, stride, is_dense_layout, cut_ptrs, cut_values, ridx + seg_beg[nidx],
+                           seg_cnt[nidx], nodes[nidx].findex, nodes[nidx].fvalue,
+                           nodes[nidx].default_left, tmp + seg_beg[nidx]);
+      }
       memcpy(ridx + seg_beg[nidx], tmp + seg_beg[nidx], sizeof(uint32_t) * seg_cnt[nidx]);
       seg_beg[l] = seg_beg[nidx]; seg_cnt[l] = nl;
       seg_beg[r] = seg_beg[nidx] + nl; seg_cnt[r] = seg_cnt[nidx] - nl;
@@ -1042,7 +1151,7 @@ ORC_API int32_t orc_update_tree_ic(const int32_t* gbins, uint64_t n_rows, uint32
         nfs = ic_count[k];
       }
       /* an empty answer is a non-NULL list of length 0: nothing is scanned, the candidate stays invalid */
-      orc_eval_node_mono(hist[c], node_sum[c], cut_ptrs, cut_values, n_features, fs, nfs, p, scale, &e.c, NULL, monotone, lower[c], upper[c]);
+      ORC_EVAL(c, fs, nfs, &e.c);
       if (cand_dump) cand_dump[c] = e.c;
       if (e.c.loss_chg > 1e-6f) { queue[c] = e; n_open++; }
     }
@@ -1054,8 +1163,12 @@ ORC_API int32_t orc_update_tree_ic(const int32_t* gbins, uint64_t n_rows, uint32
     for (uint64_t r = 0; r < n_rows; ++r) {
       int32_t nidx = 0;
       while (!nodes[nidx].is_leaf) {
-        int gl = go_left(gbins, stride, is_dense_layout, cut_ptrs, cut_values, r, nodes[nidx].findex,
-                         nodes[nidx].fvalue, nodes[nidx].default_left);
+        int gl = (cat && cat->node_is_cat[nidx])
+                     ? go_left_cat(gbins, stride, is_dense_layout, cut_ptrs, cut_values, r, nodes[nidx].findex,
+                                   cat->node_cat_bits + (size_t)nidx * cat->n_cat_words, cat->n_cat_words,
+                                   nodes[nidx].default_left)
+                     : go_left(gbins, stride, is_dense_layout, cut_ptrs, cut_values, r, nodes[nidx].findex,
+                               nodes[nidx].fvalue, nodes[nidx].default_left);
         nidx = gl ? nodes[nidx].left : nodes[nidx].right;
       }
       position[r] = gq[r].h != 0 ? nidx : ~nidx;
@@ -1067,8 +1180,9 @@ ORC_API int32_t orc_update_tree_ic(const int32_t* gbins, uint64_t n_rows, uint32
   }
   for (int32_t i = 0; i < max_nodes; ++i) free(hist[i]);
   free(hist); free(seg_beg); free(seg_cnt); free(node_sum); free(ridx); free(tmp); free(queue); free(gq);
-  free(lower); free(upper); free(ic_bits); free(ic_buffer);
+  free(lower); free(upper); free(ic_bits); free(ic_buffer); free(cand_bits); free(cand_is_cat);
 #undef ORC_LEVEL_SET
+#undef ORC_EVAL
   return n_nodes;
 }
 

@@ -183,6 +183,12 @@ class DMatrix:
         y = np.ascontiguousarray(y, dtype=np.float32)
         _check(self.lib, self.lib.XGDMatrixSetInfoFromInterface(self.handle, b"label", _array_interface(y)))
 
+    def set_feature_types(self, types):
+        """XGDMatrixSetStrFeatureInfo(handle, "feature_type", ...): "q" numerical, "c" categorical, ..."""
+        arr = (c_char_p * len(types))(*[t.encode() for t in types])
+        _check(self.lib, self.lib.XGDMatrixSetStrFeatureInfo(self.handle, b"feature_type", arr, c_uint64(len(types))))
+        self._feature_types = list(types)
+
     def quantile_cut(self):
         """(cut_ptrs uint32/64, cut_values float32) via XGDMatrixGetQuantileCut (c_api.h:972)."""
         ip, dt = c_char_p(), c_char_p()
@@ -195,8 +201,10 @@ class DMatrix:
         numerical feature's lower bound (src/c_api/c_api.cc:967-994); strip it."""
         ip, dv = self.quantile_cut()
         ptrs, vals = [0], []
+        types = getattr(self, "_feature_types", None)
         for f in range(len(ip) - 1):
-            seg = dv[int(ip[f]) + 1:int(ip[f + 1])]
+            is_cat = types is not None and types[f] == "c"   # no lower bound is prepended for a categorical feature
+            seg = dv[int(ip[f]) + (0 if is_cat else 1):int(ip[f + 1])]
             vals.append(seg)
             ptrs.append(ptrs[-1] + seg.size)
         return np.array(ptrs, dtype=np.uint32), np.concatenate(vals).astype(np.float32)

@@ -16,7 +16,7 @@ import pytest
 
 import oracle as orc
 from tests.helpers import make_cuts, make_regression, squared_error_gpair
-from tests.test_gpu_parity import _compare_tree, _page, xb  # noqa: F401  (xb is a fixture)
+from tests.test_gpu_parity import _compare_tree, _global_bins, _page, xb  # noqa: F401  (xb is a fixture)
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("B200HIST_RUN_UNVALIDATED") != "1",
@@ -235,3 +235,138 @@ def test_categorical_evaluation_random_histograms(xb, onehot, threshold, params)
         assert np.isclose(c.loss_chg, o.loss_chg, rtol=2e-5, atol=1e-6), name
         for a, b in [(c.base_weight, o.base_weight), (c.left_weight, o.left_weight), (c.right_weight, o.right_weight)]:
             assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32), name
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Categorical features through the whole updater (b200hist_updater_set_categorical: evaluation, ApplyKernel<true>,
+# PartitionCountKernel<., true>, FinaliseWindowKernel<., true>)
+# ---------------------------------------------------------------------------------------------------------------------
+def _cat_page(xb, x, cp, cv, is_cat):
+    """The page's binning kernel searches numerically (first cut greater than the value); a category code c binned
+    that way lands one bin late, c - 0.5 lands in its own bin (codes are 0..K-1 here).  Proper SearchCatBin binning at
+    page construction is not built yet: the drop-in imports pages the reference has binned."""
+    xs = x.copy()
+    for j, c in enumerate(is_cat):
+        if c:
+            xs[:, j] -= 0.5
+    return _page(xb, xs, cp, cv)
+
+
+def _compare_cat_tree(xb, up, tree, o, cp, cv):
+    """_compare_tree, but a categorical split's condition is NaN on both sides and its category set is compared."""
+    nodes = o["nodes"]
+    assert tree.num_nodes == len(nodes)
+    is_cat, sets = up.last_tree_categories(tree.num_nodes)
+    for i, (a, b) in enumerate(zip(tree.nodes, nodes)):
+        assert (a["parent"], a["left"], a["right"], a["is_leaf"], a["depth"]) == \
+            (b.parent, b.left, b.right, bool(b.is_leaf), b.depth), i
+        assert int(is_cat[i]) == int(o["is_cat"][i]), i
+        if not b.is_leaf:
+            assert (a["findex"], a["default_left"]) == (b.findex, bool(b.default_left)), i
+            if o["is_cat"][i]:
+                assert np.isnan(a["fvalue"]) and sets[i] == o["cat_sets"][i], (i, sets[i], o["cat_sets"][i])
+            else:
+                assert np.float32(a["fvalue"]).view(np.uint32) == np.float32(b.fvalue).view(np.uint32), i
+            assert np.isclose(a["loss_chg"], b.loss_chg, rtol=2e-5, atol=1e-6), i
+        else:
+            assert np.float32(a["leaf_value"]).view(np.uint32) == np.float32(b.leaf_value).view(np.uint32), i
+        assert np.float32(a["sum_hess"]).view(np.uint32) == np.float32(b.sum_hess).view(np.uint32), i
+        assert np.float32(a["base_weight"]).view(np.uint32) == np.float32(b.base_weight).view(np.uint32), i
+    for i in range(len(nodes)):
+        if o["hist"] is not None and o["hist"][i].any():
+            assert np.array_equal(up.node_histogram(i), o["hist"][i]), "hist of node %d" % i
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(GOLDEN, "ref_cpu_categorical_trees.json")))["cases"],
+                         ids=lambda c: c["name"])
+def test_categorical_trees_match_oracle_and_cpu_reference(xb, case):
+    """Data and cuts of the CPU reference fixture: our tree equals the oracle's node for node (category sets,
+    histograms, positions), and with it the discrete content of the reference's CPU tree."""
+    import torch
+    from tests.test_reference_golden import categorical_global_bins
+    from tools.make_golden_cpu_categorical import make_data
+    x, y, types = make_data(case)
+    is_cat = [1 if t == "c" else 0 for t in types]
+    cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+    cv = np.array(case["cut_values_bits"], dtype=np.uint32).view(np.float32)
+    gb = categorical_global_bins(x, cp, cv, is_cat)
+    page = _cat_page(xb, x, cp, cv, is_cat)
+    assert np.array_equal(_global_bins(page, cp), gb), "test binning recipe"
+    params = dict(case["params"])
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    up.set_categorical(is_cat, case["max_cat_to_onehot"], case["max_cat_threshold"])
+    pred = np.zeros(case["n"], dtype=np.float32)
+    pos = torch.empty(case["n"], dtype=torch.int32, device="cuda")
+    for it in range(2):
+        gp = squared_error_gpair(pred, y)
+        tree = up.update(torch.from_numpy(gp).cuda(), pos)
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), want_hist=True, feature_is_cat=is_cat,
+                            max_cat_to_onehot=case["max_cat_to_onehot"], max_cat_threshold=case["max_cat_threshold"])
+        _compare_cat_tree(xb, up, tree, o, cp, cv)
+        assert np.array_equal(pos.cpu().numpy(), o["position"])
+        if it == 0:  # the fixture's tree
+            ref = case["tree"]
+            for i, nd in enumerate(tree.nodes):
+                if not nd["is_leaf"]:
+                    assert nd["findex"] == ref["findex"][i], i
+        pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+    up.set_categorical(None)
+    gp = squared_error_gpair(np.zeros(case["n"], np.float32), y)
+    t_plain = up.update(torch.from_numpy(gp).cuda())
+    o_plain = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params))
+    _compare_tree(xb, up, t_plain, o_plain, cp, cv, hists=False)
+
+
+@pytest.mark.parametrize("extra", [dict(max_depth=6), dict(max_depth=0, max_leaves=20, grow_policy="lossguide"),
+                                   dict(max_depth=5, subsample=0.7), dict(max_depth=5, mono=True)],
+                         ids=["depthwise", "lossguide", "subsample", "monotone"])
+def test_categorical_trees_with_other_parameters(xb, extra):
+    """70 categories (more than two 32-bin chunks, uint8 page), sampling and monotone constraints next to categorical
+    features, loss-guided growth."""
+    import torch
+    rng = np.random.default_rng(91)
+    n = 15000
+    ks = [70, 5, 33]
+    cols = [rng.integers(0, k, size=n).astype(np.float32) for k in ks]
+    cols[0][rng.random(n) < 0.1] = np.nan
+    xn, _ = make_regression(n, 3, seed=92, missing=0.05)
+    x = np.column_stack(cols + [xn[:, j] for j in range(3)]).astype(np.float32)
+    is_cat = [1, 1, 1, 0, 0, 0]
+    ncp, ncv = make_cuts(xn, 32)
+    cut_values, cut_ptrs = [], [0]
+    for k in ks:
+        cut_values += [float(v) for v in range(k)]
+        cut_ptrs.append(len(cut_values))
+    for j in range(3):
+        cut_values += [float(v) for v in ncv[ncp[j]:ncp[j + 1]]]
+        cut_ptrs.append(len(cut_values))
+    cp, cv = np.array(cut_ptrs, dtype=np.uint32), np.array(cut_values, dtype=np.float32)
+    from tests.test_reference_golden import categorical_global_bins
+    gb = categorical_global_bins(x, cp, cv, is_cat)
+    eff = [rng.normal(size=k) for k in ks]
+    y = (sum(e[np.nan_to_num(c, nan=0).astype(int)] for e, c in zip(eff, cols)) + np.nan_to_num(xn[:, 0]) +
+         0.2 * rng.normal(size=n)).astype(np.float32)
+    params = {k: v for k, v in extra.items() if k not in ("subsample", "mono")}
+    params["eta"] = 0.5
+    page = _cat_page(xb, x, cp, cv, is_cat)
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    up.set_categorical(is_cat, 4, 64)
+    mono = [0, 0, 0, 1, -1, 0] if extra.get("mono") else None
+    if mono:
+        up.set_monotone_constraints(mono)
+    sub = extra.get("subsample", 1.0)
+    pred = np.zeros(n, dtype=np.float32)
+    pos = torch.empty(n, dtype=torch.int32, device="cuda")
+    for it in range(3):
+        gp = squared_error_gpair(pred, y)
+        if sub < 1:
+            up.set_tree_sampling(None, sub, 1000 + it)
+        tree = up.update(torch.from_numpy(gp).cuda(), pos)
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), want_hist=True, feature_is_cat=is_cat,
+                            subsample=sub, sample_seed=1000 + it, monotone=mono)
+        _compare_cat_tree(xb, up, tree, o, cp, cv)
+        assert np.array_equal(pos.cpu().numpy(), o["position"])
+        assert o["is_cat"].sum() >= 1
+        pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)

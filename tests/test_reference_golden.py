@@ -250,3 +250,63 @@ def test_oracle_reproduces_reference_interaction_constraints(case):
         leaf = np.array([n.leaf_value for n in o["nodes"]], dtype=np.float32)
         margin = (margin + _leaf_margin(leaf, o["position"])).astype(np.float32)
     assert discriminated
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Categorical features, whole trees: tests/golden/ref_cpu_categorical_trees.json = the reference's CPU `hist` updater
+# (tools/make_golden_cpu_categorical.py).  A STRUCTURAL pin of orc_update_tree_full until the CUDA reference has been
+# run on such data: float vs fixed-point histograms make gains differ in the last bits, everything discrete agrees.
+# ---------------------------------------------------------------------------------------------------------------------
+CAT_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cpu_categorical_trees.json")
+
+
+def categorical_global_bins(x, cp, cv, is_cat):
+    """SearchCatBin / SearchBin (src/common/hist_util.h:112-135): a category is looked up among the feature's
+    category codes, a numerical value by upper bound."""
+    gb = np.full(x.shape, -1, dtype=np.int32)
+    for j in range(x.shape[1]):
+        ok = ~np.isnan(x[:, j])
+        seg = cv[cp[j]:cp[j + 1]]
+        if is_cat[j]:
+            gb[ok, j] = cp[j] + np.searchsorted(seg, x[ok, j])
+        else:
+            gb[ok, j] = cp[j] + orc.bin_dense(x[:, j:j + 1], np.array([0, seg.size], dtype=np.uint32), seg)[ok, 0]
+    return gb
+
+
+@pytest.mark.parametrize("case", json.load(open(CAT_GOLD))["cases"], ids=lambda c: c["name"])
+def test_oracle_categorical_trees_match_cpu_reference(case):
+    from tools.make_golden_cpu_categorical import make_data
+    x, y, types = make_data(case)
+    assert types == case["feature_types"]
+    is_cat = [1 if t == "c" else 0 for t in types]
+    cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+    cv = _f32(case["cut_values_bits"])
+    gb = categorical_global_bins(x, cp, cv, is_cat)
+    gp = np.stack([-y, np.ones_like(y)], axis=1).astype(np.float32)
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**case["params"]), feature_is_cat=is_cat,
+                        max_cat_to_onehot=case["max_cat_to_onehot"], max_cat_threshold=case["max_cat_threshold"])
+    ref = case["tree"]
+    nodes = o["nodes"]
+    assert len(nodes) == len(ref["left"])
+    pos = np.where(o["position"] < 0, ~o["position"], o["position"])
+
+    def leaves(k):
+        return [k] if nodes[k].is_leaf else leaves(nodes[k].left) + leaves(nodes[k].right)
+    n_cat = 0
+    for i, nd in enumerate(nodes):
+        assert (nd.left, nd.right) == (ref["left"][i], ref["right"][i]), i
+        if nd.is_leaf:
+            continue
+        assert nd.findex == ref["findex"][i], i
+        assert int(o["is_cat"][i]) == ref["split_type"][i], i
+        if o["is_cat"][i]:
+            n_cat += 1
+            assert sorted(o["cat_sets"][i]) == ref["categories"][i], i
+            assert np.isnan(nd.fvalue), i
+        else:
+            assert int(np.float32(nd.fvalue).view(np.uint32)) == ref["cond_bits"][i], i
+        rows = np.isin(pos, leaves(i))
+        if np.isnan(x[rows, nd.findex]).any():   # otherwise both directions tie
+            assert int(nd.default_left) == ref["default_left"][i], i
+    assert n_cat >= 5

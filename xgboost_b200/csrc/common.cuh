@@ -250,6 +250,20 @@ struct CatView {
   int32_t max_cat_bins;        // most bins of any categorical feature (sizes the sort scratch)
 };
 
+// Row routing of a categorical split: NodeDev/PartEntry::split_lbin == -1 marks it, the node's set over the split
+// feature's LOCAL bins says which rows go RIGHT (CatView::bin_bits).  kCat == false compiles to the numerical test only.
+struct CatRoute {
+  const uint32_t* bin_bits;  // [max_nodes][bin_words]
+  int32_t bin_words;
+};
+template <bool kCat>
+__device__ __forceinline__ bool GoLeftBin(int32_t lbin, int32_t split_lbin, int nidx, const CatRoute& cr) {
+  if constexpr (kCat) {
+    if (split_lbin < 0) return ((__ldg(cr.bin_bits + (size_t)nidx * cr.bin_words + (lbin >> 5)) >> (lbin & 31)) & 1u) == 0u;
+  }
+  return lbin < split_lbin;
+}
+
 struct ParamDev {
   int32_t max_depth, max_leaves, grow_policy;
   float learning_rate, reg_lambda, reg_alpha, min_child_weight, max_delta_step, min_split_loss;
@@ -354,7 +368,7 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = n
 // partition.cu
 void LaunchPartitionCount(const EllView& ell, const uint32_t* ridx0, const uint32_t* ridx1, const PartEntry* part,
                           const uint32_t* tile_seg, const TreeState* ts, uint32_t* flags, uint32_t* tile_left,
-                          int num_sms, cudaStream_t s);
+                          int num_sms, cudaStream_t s, CatRoute cr = CatRoute{nullptr, 0});
 void LaunchPartitionScatter(const uint32_t* ridx0, const uint32_t* ridx1, uint32_t* out0, uint32_t* out1,
                             const PartEntry* part, const uint32_t* tile_seg, const TreeState* ts,
                             const uint32_t* flags, const uint32_t* tile_left_off, int num_sms, cudaStream_t s);

@@ -26,12 +26,12 @@ constexpr int kPartThreads = 256;
 constexpr int kRowsPerThread = kPartTile / kPartThreads;  // 8
 constexpr int kWordsPerTile = kPartTile / 32;             // 64
 
-template <typename BinT>
+template <typename BinT, bool kCat>
 __global__ void __launch_bounds__(kPartThreads)
 PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint32_t* __restrict__ ridx1,
                      const PartEntry* __restrict__ part, const uint32_t* __restrict__ tile_seg,
                      const TreeState* __restrict__ ts, uint32_t* __restrict__ flags,
-                     uint32_t* __restrict__ tile_left) {
+                     uint32_t* __restrict__ tile_left, CatRoute cr) {
   __shared__ uint32_t s_cnt[kPartThreads / 32];
   const uint32_t n_tiles = ts->part_tiles;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -52,7 +52,7 @@ PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint
         if (j < n) {
           const uint32_t fb = ell.cut_ptrs[e.findex], fe = ell.cut_ptrs[e.findex + 1];
           const uint32_t gb = SparseRowBin(ell, ridx[j], fb, fe, (uint32_t)e.findex);
-          left = (gb == 0xFFFFFFFFu) ? (e.default_left != 0) : ((int32_t)(gb - fb) < e.split_lbin);
+          left = (gb == 0xFFFFFFFFu) ? (e.default_left != 0) : GoLeftBin<kCat>((int32_t)(gb - fb), e.split_lbin, e.nidx, cr);
         }
         const uint32_t m = __ballot_sync(0xffffffffu, left);
         if (lane == 0) {
@@ -77,7 +77,8 @@ PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint
 #pragma unroll
       for (int k = 0; k < kRowsPerThread; ++k) {
         const uint32_t j = k * kPartThreads + threadIdx.x;
-        const bool left = j < n && ((sym[k] == ell.null_symbol) ? (e.default_left != 0) : ((int32_t)sym[k] < e.split_lbin));
+        const bool left = j < n && ((sym[k] == ell.null_symbol) ? (e.default_left != 0)
+                                                                : GoLeftBin<kCat>((int32_t)sym[k], e.split_lbin, e.nidx, cr));
         const uint32_t m = __ballot_sync(0xffffffffu, left);
         if (lane == 0) {
           flags[(size_t)t * kWordsPerTile + (j >> 5)] = m;
@@ -149,14 +150,25 @@ PartitionScatterKernel(const uint32_t* __restrict__ ridx0, const uint32_t* __res
 
 void LaunchPartitionCount(const EllView& ell, const uint32_t* ridx0, const uint32_t* ridx1, const PartEntry* part,
                           const uint32_t* tile_seg, const TreeState* ts, uint32_t* flags, uint32_t* tile_left,
-                          int num_sms, cudaStream_t s) {
+                          int num_sms, cudaStream_t s, CatRoute cr) {
   int blocks = num_sms * 8;
+  if (cr.bin_bits != nullptr) {  // a level may hold categorical splits
+    if (ell.bin_bytes == 1) {
+      PartitionCountKernel<uint8_t, true><<<blocks, kPartThreads, 0, s>>>(ell, ridx0, ridx1, part, tile_seg, ts, flags, tile_left, cr);
+    } else if (ell.is_sparse) {
+      PartitionCountKernel<uint32_t, true><<<blocks, kPartThreads, 0, s>>>(ell, ridx0, ridx1, part, tile_seg, ts, flags, tile_left, cr);
+    } else {
+      PartitionCountKernel<uint16_t, true><<<blocks, kPartThreads, 0, s>>>(ell, ridx0, ridx1, part, tile_seg, ts, flags, tile_left, cr);
+    }
+    B200_LAUNCHED();
+    return;
+  }
   if (ell.bin_bytes == 1) {
-    PartitionCountKernel<uint8_t><<<blocks, kPartThreads, 0, s>>>(ell, ridx0, ridx1, part, tile_seg, ts, flags, tile_left);
+    PartitionCountKernel<uint8_t, false><<<blocks, kPartThreads, 0, s>>>(ell, ridx0, ridx1, part, tile_seg, ts, flags, tile_left, cr);
   } else if (ell.is_sparse) {
-    PartitionCountKernel<uint32_t><<<blocks, kPartThreads, 0, s>>>(ell, ridx0, ridx1, part, tile_seg, ts, flags, tile_left);
+    PartitionCountKernel<uint32_t, false><<<blocks, kPartThreads, 0, s>>>(ell, ridx0, ridx1, part, tile_seg, ts, flags, tile_left, cr);
   } else {
-    PartitionCountKernel<uint16_t><<<blocks, kPartThreads, 0, s>>>(ell, ridx0, ridx1, part, tile_seg, ts, flags, tile_left);
+    PartitionCountKernel<uint16_t, false><<<blocks, kPartThreads, 0, s>>>(ell, ridx0, ridx1, part, tile_seg, ts, flags, tile_left, cr);
   }
   B200_LAUNCHED();
 }

@@ -18,6 +18,7 @@
 #include <cstring>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -121,8 +122,10 @@ __device__ __forceinline__ bool EntryValidNoLeafLimit(const ParamDev& p, const b
   return true;
 }
 
+template <bool kCat>
 __device__ void ApplyOne(const EllView& ell, const ParamDev& p, const QuantDev* q, NodeDev* nodes,
-                         const b200hist_candidate& c, int nidx, int left, PartEntry* part_slot, const MonoView& mono) {
+                         const b200hist_candidate& c, int nidx, int left, PartEntry* part_slot, const MonoView& mono,
+                         const uint8_t* node_is_cat) {
   NodeDev* n = &nodes[nidx];
   const int right = left + 1;
   const double tfh = q->to_float_h;
@@ -150,6 +153,11 @@ __device__ void ApplyOne(const EllView& ell, const ParamDev& p, const QuantDev* 
     if (ell.cut_values[mid] <= c.fvalue) lo = mid + 1; else hi = mid;
   }
   n->split_lbin = (int32_t)(lo - beg);
+  if constexpr (kCat) {
+    // categorical split (tree.ExpandCategorical, updater_gpu_hist.cu:628-642): the rows are routed by the node's
+    // category set (CatView::bin_bits, written by CatFinishKernel), -1 marks it (GoLeftBin)
+    if (node_is_cat[nidx]) n->split_lbin = -1;
+  }
   PartEntry e;
   e.nidx = nidx; e.left = left; e.right = right; e.findex = c.findex; e.split_lbin = n->split_lbin;
   e.default_left = n->default_left; e.begin = n->seg_begin; e.count = n->seg_count; e.tile_begin = 0;
@@ -157,10 +165,12 @@ __device__ void ApplyOne(const EllView& ell, const ParamDev& p, const QuantDev* 
   *part_slot = e;
 }
 
+template <bool kCat>
 __global__ void __launch_bounds__(kCtlThreads) ApplyKernel(EllView ell, ParamDev p, const QuantDev* q, TreeState* ts,
                                                             NodeDev* nodes, const b200hist_candidate* cand,
                                                             PartEntry* part, uint32_t* part_tile_seg,
-                                                            int32_t max_nodes, MonoView mono) {
+                                                            int32_t max_nodes, MonoView mono,
+                                                            const uint8_t* node_is_cat) {
   __shared__ uint32_t s_warp[33];
   __shared__ uint32_t s_tile_begin[kMaxLevelNodes + 1];
   __shared__ int s_n_expand, s_child_valid;
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(kCtlThreads) ApplyKernel(EllView ell, ParamDev
         bool ok = EntryValidNoLeafLimit(p, c, nodes[bi].depth) && !(p.max_leaves > 0 && leaves0 == p.max_leaves) &&
                   n_nodes0 + 2 <= max_nodes;
         if (ok) {
-          ApplyOne(ell, p, q, nodes, c, bi, n_nodes0, &part[0], mono);
+          ApplyOne<kCat>(ell, p, q, nodes, c, bi, n_nodes0, &part[0], mono, node_is_cat);
           ne = 1;
         } else {
           ts->stopped = 1;
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(kCtlThreads) ApplyKernel(EllView ell, ParamDev
       uint32_t rank = running + BlockExclusiveScan(valid ? 1u : 0u, s_warp, &total);
       bool accepted = valid && (int)rank < allow && n_nodes0 + 2 * ((int)rank + 1) <= max_nodes &&
                       (int)rank < kMaxLevelNodes;
-      if (accepted) ApplyOne(ell, p, q, nodes, c, i, n_nodes0 + 2 * (int)rank, &part[rank], mono);
+      if (accepted) ApplyOne<kCat>(ell, p, q, nodes, c, i, n_nodes0 + 2 * (int)rank, &part[rank], mono, node_is_cat);
       running += total;
     }
     n_expand = min((int)running, allow);
@@ -499,7 +509,7 @@ __global__ void __launch_bounds__(kCtlThreads) FinalListKernel(TreeState* ts, co
   }
 }
 
-template <typename BinT>
+template <typename BinT, bool kCat>
 __global__ void __launch_bounds__(256) FinaliseKernel(EllView ell, const uint32_t* __restrict__ ridx0,
                                                        const uint32_t* __restrict__ ridx1,
                                                        const longlong2* __restrict__ gq,
@@ -507,7 +517,7 @@ __global__ void __launch_bounds__(256) FinaliseKernel(EllView ell, const uint32_
                                                        const BuildEntry* __restrict__ fin,
                                                        const uint32_t* __restrict__ fin_tile_seg,
                                                        const TreeState* __restrict__ ts, int32_t* __restrict__ position,
-                                                       const QuantDev* __restrict__ qd) {
+                                                       const QuantDev* __restrict__ qd, CatRoute cr) {
   const uint32_t n_tiles = ts->final_tiles;
   const bool any_h_zero = qd->h_zero_any != 0u;
   for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -523,14 +533,16 @@ __global__ void __launch_bounds__(256) FinaliseKernel(EllView ell, const uint32_
         if (ell.is_sparse) {
           const uint32_t fb = ell.cut_ptrs[nd.findex], fe = ell.cut_ptrs[nd.findex + 1];
           const uint32_t gb = SparseRowBin(ell, r, fb, fe, (uint32_t)nd.findex);
-          const bool go_left = (gb == 0xFFFFFFFFu) ? (nd.default_left != 0) : ((int32_t)(gb - fb) < nd.split_lbin);
+          const bool go_left = (gb == 0xFFFFFFFFu) ? (nd.default_left != 0)
+                                                   : GoLeftBin<kCat>((int32_t)(gb - fb), nd.split_lbin, nidx, cr);
           nidx = go_left ? nd.left : nd.right;
           continue;
         }
         const uint32_t sym = (sizeof(BinT) <= 2 && ell.bins_t != nullptr)
                                  ? (uint32_t)reinterpret_cast<const BinT*>(ell.bins_t)[(uint64_t)nd.findex * ell.col_stride + r]
                                  : (uint32_t)reinterpret_cast<const BinT*>(ell.bins + (size_t)r * ell.row_bytes)[nd.findex];
-        const bool left = (sym == ell.null_symbol) ? (nd.default_left != 0) : ((int32_t)sym < nd.split_lbin);
+        const bool left = (sym == ell.null_symbol) ? (nd.default_left != 0)
+                                                   : GoLeftBin<kCat>((int32_t)sym, nd.split_lbin, nidx, cr);
         nidx = left ? nd.left : nd.right;
       }
       // EncodeOp (updater_gpu_hist.cuh:48-56): rows whose hessian is 0 get the bit-complemented id; the
@@ -556,27 +568,30 @@ __device__ __forceinline__ uint32_t LowerBoundRow(const uint32_t* __restrict__ r
   return lo;
 }
 
-template <typename BinT>
-__device__ __forceinline__ int WalkToLeaf(const EllView& ell, const NodeDev* __restrict__ nodes, int nidx, uint32_t r) {
+template <typename BinT, bool kCat>
+__device__ __forceinline__ int WalkToLeaf(const EllView& ell, const NodeDev* __restrict__ nodes, int nidx, uint32_t r,
+                                          const CatRoute& cr) {
   while (!nodes[nidx].is_leaf) {
     const NodeDev& nd = nodes[nidx];
     if (ell.is_sparse) {
       const uint32_t fb = ell.cut_ptrs[nd.findex], fe = ell.cut_ptrs[nd.findex + 1];
       const uint32_t gb = SparseRowBin(ell, r, fb, fe, (uint32_t)nd.findex);
-      const bool go_left = (gb == 0xFFFFFFFFu) ? (nd.default_left != 0) : ((int32_t)(gb - fb) < nd.split_lbin);
+      const bool go_left = (gb == 0xFFFFFFFFu) ? (nd.default_left != 0)
+                                               : GoLeftBin<kCat>((int32_t)(gb - fb), nd.split_lbin, nidx, cr);
       nidx = go_left ? nd.left : nd.right;
       continue;
     }
     const uint32_t sym = (sizeof(BinT) <= 2 && ell.bins_t != nullptr)
                              ? (uint32_t)reinterpret_cast<const BinT*>(ell.bins_t)[(uint64_t)nd.findex * ell.col_stride + r]
                              : (uint32_t)reinterpret_cast<const BinT*>(ell.bins + (size_t)r * ell.row_bytes)[nd.findex];
-    const bool left = (sym == ell.null_symbol) ? (nd.default_left != 0) : ((int32_t)sym < nd.split_lbin);
+    const bool left = (sym == ell.null_symbol) ? (nd.default_left != 0)
+                                               : GoLeftBin<kCat>((int32_t)sym, nd.split_lbin, nidx, cr);
     nidx = left ? nd.left : nd.right;
   }
   return nidx;
 }
 
-template <typename BinT>
+template <typename BinT, bool kCat>
 __global__ void __launch_bounds__(256) FinaliseWindowKernel(EllView ell, const uint32_t* __restrict__ ridx0,
                                                              const uint32_t* __restrict__ ridx1,
                                                              const longlong2* __restrict__ gq,
@@ -584,7 +599,8 @@ __global__ void __launch_bounds__(256) FinaliseWindowKernel(EllView ell, const u
                                                              const BuildEntry* __restrict__ fin,
                                                              const TreeState* __restrict__ ts,
                                                              int32_t* __restrict__ position,
-                                                             const QuantDev* __restrict__ qd, uint32_t n_rows) {
+                                                             const QuantDev* __restrict__ qd, uint32_t n_rows,
+                                                             CatRoute cr) {
   __shared__ int32_t s_pos[kFinWindow];
   __shared__ uint32_t s_lo[256], s_hi[256], s_off[257], s_warp[33];
   const uint32_t n_final = (uint32_t)ts->n_final;
@@ -643,7 +659,7 @@ __global__ void __launch_bounds__(256) FinaliseWindowKernel(EllView ell, const u
         if (ell.is_sparse || ell.bins_t == nullptr) {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (ok[u]) s_pos[row[u] - r_begin] = WalkToLeaf<BinT>(ell, nodes, nid[u], row[u]);
+            if (ok[u]) s_pos[row[u] - r_begin] = WalkToLeaf<BinT, kCat>(ell, nodes, nid[u], row[u], cr);
         } else {  // the four walks level by level, so that their symbol gathers overlap
           bool live[4];
 #pragma unroll
@@ -659,7 +675,8 @@ __global__ void __launch_bounds__(256) FinaliseWindowKernel(EllView ell, const u
             for (int u = 0; u < 4; ++u) {
               if (live[u]) {
                 const NodeDev& nd = nodes[nid[u]];
-                const bool left = (sym[u] == ell.null_symbol) ? (nd.default_left != 0) : ((int32_t)sym[u] < nd.split_lbin);
+                const bool left = (sym[u] == ell.null_symbol) ? (nd.default_left != 0)
+                                                              : GoLeftBin<kCat>((int32_t)sym[u], nd.split_lbin, nid[u], cr);
                 nid[u] = left ? nd.left : nd.right;
                 live[u] = !nodes[nid[u]].is_leaf;
               }
@@ -764,6 +781,13 @@ struct b200hist_updater_s {
   int32_t* d_ic_list{nullptr};
   int32_t* d_ic_count{nullptr};
   int32_t ic_n_sets{0}, ic_words{0};
+  // categorical features (nullptr = none): flags per feature, per-node category sets (CatView)
+  uint8_t* d_is_cat{nullptr};
+  uint32_t* d_cat_bits{nullptr};
+  uint32_t* d_bin_bits{nullptr};
+  uint8_t* d_node_is_cat{nullptr};
+  int32_t cat_words{0}, cat_bin_words{0}, max_cat_bins{0};
+  int32_t max_cat_to_onehot{4}, max_cat_threshold{64};
   bool row_split{false};                   // ranks own row slices (full-width partial histograms, summed) instead of feature blocks
   size_t flags_offset{0};                  // byte offset of the flag array inside the histogram allocation
   std::vector<void*> peer_base;            // opened IPC mappings (own entry = nullptr)
@@ -870,6 +894,10 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   }
   timer.End(kQuant, t0);
   const bool has_ic = u->d_ic_bits != nullptr;
+  const bool has_cat = u->d_is_cat != nullptr;
+  const CatView catv = has_cat ? CatView{u->d_is_cat, u->max_cat_to_onehot, u->max_cat_threshold, u->d_cat_bits,
+                                         u->d_bin_bits, u->d_node_is_cat, u->cat_words, u->cat_bin_words, u->max_cat_bins}
+                               : CatView{nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0, 0};
   if (has_ic)  // FeatureInteractionConstraintDevice::Reset
     B200_CUDA(cudaMemsetAsync(u->d_ic_bits, 0, sizeof(unsigned long long) * (size_t)u->max_nodes * u->ic_words, s));
 
@@ -907,7 +935,8 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   timer.End(kHist, t2);
   auto t3 = timer.Begin();
   LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, u->d_feature_set, u->n_feature_set, u->pdev, u->d_quant,
-                 u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, u->n_feature_levels, &u->d_ts->max_eval_depth);
+                 u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, u->n_feature_levels, &u->d_ts->max_eval_depth,
+                 IcView{nullptr, nullptr}, catv);
   timer.End(kEval, t3);
 
   const bool depthwise = u->param.grow_policy == 0;
@@ -915,15 +944,20 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     // upper bound on nodes expanded in this step (host-known, data independent)
     const long long cap = u->step_cap[step];
     auto ta = timer.Begin();
-    ApplyKernel<<<1, kCtlThreads, 0, s>>>(view, u->pdev, u->d_quant, u->d_ts, u->d_nodes, u->d_cand, u->d_part,
-                                          u->d_part_tile_seg, u->max_nodes, mono);
+    if (has_cat) {
+      ApplyKernel<true><<<1, kCtlThreads, 0, s>>>(view, u->pdev, u->d_quant, u->d_ts, u->d_nodes, u->d_cand, u->d_part,
+                                                  u->d_part_tile_seg, u->max_nodes, mono, u->d_node_is_cat);
+    } else {
+      ApplyKernel<false><<<1, kCtlThreads, 0, s>>>(view, u->pdev, u->d_quant, u->d_ts, u->d_nodes, u->d_cand, u->d_part,
+                                                   u->d_part_tile_seg, u->max_nodes, mono, nullptr);
+    }
     B200_LAUNCHED();
     timer.End(kApply, ta);
     const bool children_possible = u->param.max_depth == 0 || !depthwise || step + 1 < u->param.max_depth;
     if (!children_possible) continue;
     auto tp = timer.Begin();
     LaunchPartitionCount(view, u->d_ridx[0], u->d_ridx[1], u->d_part, u->d_part_tile_seg, u->d_ts, u->d_flags,
-                         u->d_tile_left, u->num_sms, s);
+                         u->d_tile_left, u->num_sms, s, CatRoute{u->d_bin_bits, u->cat_bin_words});
     ScanKernel<<<1, kCtlThreads, 0, s>>>(u->d_ts, u->d_nodes, u->d_part, u->d_part_tile_seg, u->d_tile_left,
                                          u->d_tile_excl, u->d_tile_left_off, u->d_build, u->d_sub, u->d_eval_nodes,
                                          u->d_build_tile_seg, u->step_slot_base[step], u->step_cap[step],
@@ -952,7 +986,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, (int32_t)(2 * cap), u->d_nodes, u->d_feature_set,
                    u->n_feature_set, u->pdev,
                    u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, u->n_feature_levels,
-                   &u->d_ts->max_eval_depth, icv);
+                   &u->d_ts->max_eval_depth, icv, catv);
     timer.End(kEval, te);
   }
 
@@ -962,27 +996,26 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   static const bool fin_tile = std::getenv("B200HIST_FINALISE_TILE") != nullptr;  // the older per-tile scatter
   const auto* gq64 = reinterpret_cast<const longlong2*>(u->d_gq);
   const int fin_grid = u->num_sms * 6;
-  if (fin_tile) {
-    if (ell->is_sparse) {
-      FinaliseKernel<uint32_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes,
-                                                             u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);
-    } else if (ell->bin_bytes == 1) {
-      FinaliseKernel<uint8_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes,
-                                                            u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);
+  const CatRoute cr{u->d_bin_bits, u->cat_bin_words};
+  auto finalise = [&](auto bin_tag, auto cat_tag) {
+    using BinT = decltype(bin_tag);
+    constexpr bool kCat = decltype(cat_tag)::value;
+    if (fin_tile) {
+      FinaliseKernel<BinT, kCat><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes,
+                                                                u->d_fin, u->d_fin_tile_seg, u->d_ts, position,
+                                                                u->d_quant, cr);
     } else {
-      FinaliseKernel<uint16_t><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes,
-                                                             u->d_fin, u->d_fin_tile_seg, u->d_ts, position, u->d_quant);
+      FinaliseWindowKernel<BinT, kCat><<<fin_grid, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes,
+                                                                u->d_fin, u->d_ts, position, u->d_quant, (uint32_t)n, cr);
     }
-  } else if (ell->is_sparse) {
-    FinaliseWindowKernel<uint32_t><<<fin_grid, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes, u->d_fin,
-                                                           u->d_ts, position, u->d_quant, (uint32_t)n);
-  } else if (ell->bin_bytes == 1) {
-    FinaliseWindowKernel<uint8_t><<<fin_grid, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes, u->d_fin,
-                                                          u->d_ts, position, u->d_quant, (uint32_t)n);
-  } else {
-    FinaliseWindowKernel<uint16_t><<<fin_grid, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes, u->d_fin,
-                                                           u->d_ts, position, u->d_quant, (uint32_t)n);
-  }
+  };
+  auto finalise_bins = [&](auto cat_tag) {
+    if (ell->is_sparse) finalise(uint32_t{}, cat_tag);
+    else if (ell->bin_bytes == 1) finalise(uint8_t{}, cat_tag);
+    else finalise(uint16_t{}, cat_tag);
+  };
+  if (has_cat) finalise_bins(std::true_type{});
+  else finalise_bins(std::false_type{});
   B200_LAUNCHED();
   timer.End(kFinal, tf);
 
@@ -1129,6 +1162,8 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
       if (p) cudaFree(p);
     for (void* p : {(void*)u->d_ic_set_ptr, (void*)u->d_ic_set_feat, (void*)u->d_ic_bits, (void*)u->d_ic_list,
                     (void*)u->d_ic_count})
+      if (p) cudaFree(p);
+    for (void* p : {(void*)u->d_is_cat, (void*)u->d_cat_bits, (void*)u->d_bin_bits, (void*)u->d_node_is_cat})
       if (p) cudaFree(p);
     cudaFreeHost(u->h_nodes);
     cudaFreeHost(u->h_ts);
@@ -1390,6 +1425,80 @@ int b200hist_updater_set_interaction_constraints(b200hist_updater_t u, const int
     u->d_ic_bits = DevAlloc<unsigned long long>((size_t)u->max_nodes * u->ic_words);
     u->d_ic_list = DevAlloc<int32_t>(u->ell->n_features);
     u->d_ic_count = DevAlloc<int32_t>(2 * (size_t)kMaxLevelNodes);
+  }
+  B200_API_END();
+}
+
+int b200hist_updater_set_categorical(b200hist_updater_t u, const uint8_t* feature_is_cat_host, uint32_t n,
+                                     int32_t max_cat_to_onehot, int32_t max_cat_threshold) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  B200_CHECK(n <= u->ell->n_features, "more feature types than features");
+  DeviceGuard guard(u->device);
+  for (void** p : {(void**)&u->d_is_cat, (void**)&u->d_cat_bits, (void**)&u->d_bin_bits, (void**)&u->d_node_is_cat}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  u->cat_words = u->cat_bin_words = u->max_cat_bins = 0;
+  bool any = false;
+  for (uint32_t f = 0; feature_is_cat_host != nullptr && f < n; ++f) any = any || feature_is_cat_host[f] != 0;
+  if (any) {
+    B200_CHECK(max_cat_to_onehot >= 1 && max_cat_threshold >= 1, "max_cat_to_onehot and max_cat_threshold must be positive");
+    std::vector<uint8_t> flags(u->ell->n_features, 0);
+    int32_t max_bins = 1;
+    float max_code = 0.0f;
+    for (uint32_t f = 0; f < n; ++f) {
+      if (!feature_is_cat_host[f]) continue;
+      flags[f] = 1;
+      const uint32_t b = u->ell->cut_ptrs[f], e = u->ell->cut_ptrs[f + 1];
+      max_bins = std::max<int32_t>(max_bins, (int32_t)(e - b));
+      for (uint32_t i = b; i < e; ++i) {
+        const float c = u->ell->cut_values[i];
+        // a categorical feature's cut values are its category codes (AddCategories, src/common/quantile.cc)
+        B200_CHECK(c >= 0.0f && c < 16777216.0f && c == std::floor(c), "categorical cut value is not a category code");
+        max_code = std::max(max_code, c);
+      }
+    }
+    B200_CHECK(max_bins <= kMaxCatBins, "a categorical feature has more bins than the sort scratch holds");
+    u->max_cat_bins = max_bins;
+    u->cat_bin_words = (max_bins + 31) / 32;
+    u->cat_words = (int32_t)max_code / 32 + 1;
+    u->max_cat_to_onehot = max_cat_to_onehot;
+    u->max_cat_threshold = max_cat_threshold;
+    u->d_is_cat = DevAlloc<uint8_t>(flags.size());
+    B200_CUDA(cudaMemcpy(u->d_is_cat, flags.data(), flags.size(), cudaMemcpyHostToDevice));
+    u->d_cat_bits = DevAlloc<uint32_t>((size_t)u->max_nodes * u->cat_words);
+    u->d_bin_bits = DevAlloc<uint32_t>((size_t)u->max_nodes * u->cat_bin_words);
+    u->d_node_is_cat = DevAlloc<uint8_t>((size_t)u->max_nodes);
+    B200_CUDA(cudaMemset(u->d_cat_bits, 0, sizeof(uint32_t) * (size_t)u->max_nodes * u->cat_words));
+    B200_CUDA(cudaMemset(u->d_bin_bits, 0, sizeof(uint32_t) * (size_t)u->max_nodes * u->cat_bin_words));
+    B200_CUDA(cudaMemset(u->d_node_is_cat, 0, (size_t)u->max_nodes));
+  }
+  B200_API_END();
+}
+
+int b200hist_updater_cat_words(b200hist_updater_t u, uint32_t* out) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && out != nullptr, "null argument");
+  *out = (uint32_t)u->cat_words;
+  B200_API_END();
+}
+
+int b200hist_updater_last_tree_categories(b200hist_updater_t u, int32_t* node_is_cat_host, uint32_t* cat_bits_host) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && node_is_cat_host != nullptr && cat_bits_host != nullptr, "null argument");
+  B200_CHECK(u->d_is_cat != nullptr, "no categorical features configured");
+  DeviceGuard guard(u->device);
+  const int32_t nn = u->last_n_nodes;
+  std::vector<uint8_t> flags((size_t)std::max(nn, 1));
+  B200_CUDA(cudaMemcpy(flags.data(), u->d_node_is_cat, (size_t)nn, cudaMemcpyDeviceToHost));
+  B200_CUDA(cudaMemcpy(cat_bits_host, u->d_cat_bits, sizeof(uint32_t) * (size_t)nn * u->cat_words, cudaMemcpyDeviceToHost));
+  for (int32_t i = 0; i < nn; ++i) {
+    // the flag belongs to the node's CANDIDATE; only an applied one is a split of the tree
+    const bool split = !u->h_nodes[i].is_leaf && flags[i] != 0;
+    node_is_cat_host[i] = split ? 1 : 0;
+    if (!split)
+      for (int32_t w = 0; w < u->cat_words; ++w) cat_bits_host[(size_t)i * u->cat_words + w] = 0u;
   }
   B200_API_END();
 }

@@ -452,6 +452,33 @@ class GPUHistMaker:
             c = np.ascontiguousarray(constraints, dtype=np.int32)
             _l.check(_l.load().b200hist_updater_set_monotone_constraints(self._h, c.ctypes.data_as(POINTER(c_int32)), c.size))
 
+    def set_categorical(self, feature_is_cat: Optional[Sequence[int]], max_cat_to_onehot: int = 4,
+                        max_cat_threshold: int = 64) -> None:
+        """MetaInfo::feature_types / TrainParam::max_cat_to_onehot, max_cat_threshold: flags per feature (non-zero =
+        categorical; its cut values must be its category codes).  None / all zero = numerical only.
+        Not yet run on hardware -- see the STATUS note in include/b200hist.h."""
+        if feature_is_cat is None or not any(feature_is_cat):
+            _l.check(_l.load().b200hist_updater_set_categorical(self._h, None, 0, 4, 64))
+            self._has_cat = False
+            return
+        flags = np.ascontiguousarray([1 if v else 0 for v in feature_is_cat], dtype=np.uint8)
+        _l.check(_l.load().b200hist_updater_set_categorical(self._h, c_void_p(flags.ctypes.data), flags.size,
+                                                          int(max_cat_to_onehot), int(max_cat_threshold)))
+        self._has_cat = True
+
+    def last_tree_categories(self, n_nodes: int):
+        """(is_cat[n_nodes], list of category sets) of the last tree: a categorical split sends the rows whose
+        category is IN the set to the right child (RegTree::ExpandCategorical's split_cat)."""
+        w = c_uint32()
+        _l.check(_l.load().b200hist_updater_cat_words(self._h, byref(w)))
+        is_cat = np.zeros(max(n_nodes, 1), dtype=np.int32)
+        bits = np.zeros((max(n_nodes, 1), max(w.value, 1)), dtype=np.uint32)
+        _l.check(_l.load().b200hist_updater_last_tree_categories(self._h, is_cat.ctypes.data_as(POINTER(c_int32)),
+                                                               bits.ctypes.data_as(POINTER(c_uint32))))
+        sets = [{32 * wi + (31 - b) for wi in range(bits.shape[1]) for b in range(32) if (int(bits[i, wi]) >> b) & 1}
+                if is_cat[i] else set() for i in range(n_nodes)]
+        return is_cat[:n_nodes], sets
+
     def set_interaction_constraints(self, sets: Optional[Sequence[Sequence[int]]]) -> None:
         """TrainParam::interaction_constraints, parsed: e.g. [[0, 1], [2, 3, 4]]; None/[] = none.
         (FeatureInteractionConstraintDevice, src/tree/constraints.cu; see include/b200hist.h for the reading of Query
