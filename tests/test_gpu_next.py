@@ -370,3 +370,85 @@ def test_categorical_trees_with_other_parameters(xb, extra):
         assert np.array_equal(pos.cpu().numpy(), o["position"])
         assert o["is_cat"].sum() >= 1
         pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Drop-in (the reference's own Booster, our factory): interaction constraints and categorical features through the
+# shim.  The shim refuses both unless B200HIST_SHIM_UNVALIDATED=1; this module sets it for its own process.
+# ---------------------------------------------------------------------------------------------------------------------
+def _shim_or_skip():
+    import ctypes
+    from oracle import ref_capi as rc
+    from tests import test_shim_dropin as sd
+    if not (rc.available("cuda") and os.path.exists(sd.SHIM)):
+        pytest.skip("needs oracle/_ref_cuda/libxgboost.so and the shim")
+    os.environ["B200HIST_SHIM_UNVALIDATED"] = "1"
+    rc.load("cuda")
+    f = sd.test_reference_booster_trains_identically_through_the_shim
+    if getattr(f, "_shim", None) is None:
+        f._shim = ctypes.CDLL(sd.SHIM, mode=ctypes.RTLD_GLOBAL)
+    return rc
+
+
+def _model_trees(bst):
+    keep = ("left_children", "right_children", "split_indices", "split_conditions", "default_left", "base_weights",
+            "loss_changes", "sum_hessian", "split_type", "categories", "categories_nodes", "categories_segments",
+            "categories_sizes")
+    return [{k: t[k] for k in keep} for t in bst.save_json()["learner"]["gradient_booster"]["model"]["trees"]]
+
+
+@pytest.mark.parametrize("extra", [
+    {"interaction_constraints": "[[0, 1], [1, 2], [2, 3], [3, 4], [4, 5], [5, 6]]"},
+    {"interaction_constraints": "[[0, 1, 2], [3, 4, 5]]", "subsample": 0.8},
+    {"interaction_constraints": "[[0, 1], [1, 2], [2, 3], [3, 4]]", "colsample_bylevel": 0.7},
+    {"interaction_constraints": "[[0, 5], [5, 9], [9, 2]]", "grow_policy": "lossguide", "max_leaves": 24, "max_depth": 0},
+], ids=["chain", "disjoint_subsample", "chain_bylevel", "lossguide"])
+def test_interaction_constraints_through_the_shim_match_reference(xb, extra):
+    import torch
+    rc = _shim_or_skip()
+    x, y = make_regression(30000, 12, seed=81)
+    y = (y + x[:, 0] * x[:, 1] + x[:, 2] * x[:, 3] - x[:, 4] * x[:, 5]).astype(np.float32)
+    params = {"tree_method": "hist", "device": "cuda:0", "max_bin": 64, "max_depth": 6, "eta": 0.3,
+              "objective": "reg:squarederror", "base_score": 0.5}
+    params.update(extra)
+
+    def train(updater):
+        dm = rc.DMatrix.from_cuda(torch.from_numpy(x).cuda(), kind="cuda")
+        dm.set_label(y)
+        bst = rc.Booster(dict(params, updater=updater), dm)
+        for i in range(4):
+            bst.update(i)
+        return _model_trees(bst), bst.predict_margin(dm)
+    ref_trees, ref_margin = train("grow_gpu_hist_reference")
+    our_trees, our_margin = train("grow_b200_hist")
+    assert json.dumps(our_trees) == json.dumps(ref_trees)
+    assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))
+
+
+@pytest.mark.parametrize("extra", [{}, {"max_cat_to_onehot": 1}, {"max_cat_to_onehot": 100},
+                                   {"max_cat_threshold": 8}, {"subsample": 0.7, "colsample_bytree": 0.7},
+                                   {"grow_policy": "lossguide", "max_leaves": 24, "max_depth": 0}],
+                         ids=lambda e: "_".join("%s%s" % kv for kv in e.items()) or "defaults")
+def test_categorical_features_through_the_shim_match_reference(xb, extra):
+    """The reference sketches, bins and stores the categorical columns; our updater grows the trees.  Models must
+    be identical including split_type / categories arrays, and so must the margins (the reference's predictor walks
+    OUR category sets)."""
+    from tools.make_golden_cpu_categorical import make_data
+    rc = _shim_or_skip()
+    x, y, types = make_data(dict(seed=305, n=30000))
+    params = {"tree_method": "hist", "device": "cuda:0", "max_bin": 64, "max_depth": 6, "eta": 0.3,
+              "objective": "reg:squarederror", "base_score": 0.5}
+    params.update(extra)
+
+    def train(updater):
+        dm = rc.DMatrix.from_dense(x, label=y, kind="cuda")
+        dm.set_feature_types(types)
+        bst = rc.Booster(dict(params, updater=updater), dm)
+        for i in range(4):
+            bst.update(i)
+        return _model_trees(bst), bst.predict_margin(dm)
+    ref_trees, ref_margin = train("grow_gpu_hist_reference")
+    our_trees, our_margin = train("grow_b200_hist")
+    assert sum(sum(t["split_type"]) for t in ref_trees) >= 4, "the fixture must produce categorical splits"
+    assert json.dumps(our_trees) == json.dumps(ref_trees)
+    assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))
