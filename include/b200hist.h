@@ -278,9 +278,11 @@ B200HIST_API int b200hist_updater_set_monotone_constraints(b200hist_updater_t u,
  * calls of a level answer into ONE buffer before the evaluation kernel runs, so a node is evaluated on the first
  * `its own count` entries of what the level's later answers left there.  With disjoint sets every node of a tree has
  * the same answer and the two readings coincide.
- * STATUS: compiled, not yet run on hardware (written after this round's GPU budget was spent); the oracle for it is
- * pinned (tests/test_reference_golden.py), the GPU parity tests are in tests/test_gpu_parity.py behind
- * B200HIST_RUN_UNVALIDATED=1, and the shim keeps refusing the parameter until they have passed. */
+ * STATUS: run on a B200 once, in the round's last GPU seconds (tools/quick_check: one tree under overlapping sets,
+ * identical to the oracle -- recorded in tests/golden/b200_quick_check, tests/test_recorded_hardware.py).  The full
+ * parity set (the reference's own trees bit for bit, lossguide, 130 features, bylevel, monotone, the drop-in) is in
+ * tests/test_gpu_next.py behind B200HIST_RUN_UNVALIDATED=1 and has not run yet; the shim refuses the parameter
+ * until it has. */
 B200HIST_API int b200hist_updater_set_interaction_constraints(b200hist_updater_t u, const int32_t* set_ptr_host,
                                                               const int32_t* set_feat_host, uint32_t n_sets);
 
@@ -294,8 +296,11 @@ B200HIST_API int b200hist_updater_set_interaction_constraints(b200hist_updater_t
  * b200hist_updater_last_tree_categories: per node of the last tree, 1 if it is a categorical split, and its
  * category set as cat_words uint32 words in the reference's LBitField32 layout (category c = bit 31 - c % 32 of
  * word c / 32) -- what RegTree::ExpandCategorical takes.  Buffers: n_nodes and n_nodes * cat_words entries.
- * STATUS: compiled, not yet run on hardware; the shim keeps refusing categorical features until
- * tests/test_gpu_next.py has passed on a B200. */
+ * STATUS: run on a B200 once, in the round's last GPU seconds (tools/quick_check: two depth-5 trees, 21 sorted-partition
+ * and 24 one-hot categorical splits, nodes / category sets / every row position identical to the oracle -- recorded
+ * in tests/golden/b200_quick_check, tests/test_recorded_hardware.py).  The full parity set and the drop-in are in
+ * tests/test_gpu_next.py behind B200HIST_RUN_UNVALIDATED=1 and have not run yet; the shim refuses categorical
+ * features until they have. */
 B200HIST_API int b200hist_updater_set_categorical(b200hist_updater_t u, const uint8_t* feature_is_cat_host, uint32_t n,
                                                   int32_t max_cat_to_onehot, int32_t max_cat_threshold);
 B200HIST_API int b200hist_updater_cat_words(b200hist_updater_t u, uint32_t* out);
@@ -369,8 +374,9 @@ B200HIST_API int b200hist_evaluate_splits(b200hist_ellpack_t ell, const b200hist
  * out_host (fvalue = NaN, split_gbin = -1 for a categorical winner), out_is_cat_host, and the categories that go
  * RIGHT as the reference's LBitField32 over category codes in out_cat_bits_host[node * n_cat_words ...]
  * (category c = bit 31 - c % 32 of word c / 32).
- * STATUS: compiled, not yet run on hardware; checker pinned (tests/golden/eval_categorical_known_answers.json),
- * GPU tests in tests/test_gpu_next.py behind B200HIST_RUN_UNVALIDATED=1. */
+ * STATUS: exercised on a B200 only through whole trees (see b200hist_updater_set_categorical); this per-stage
+ * entry's own GPU tests (the reference's twelve literal vectors, random histograms against the oracle) are in
+ * tests/test_gpu_next.py behind B200HIST_RUN_UNVALIDATED=1 and have not run yet. */
 B200HIST_API int b200hist_evaluate_splits_cat(b200hist_ellpack_t ell, const b200hist_gpair64* hist_dev,
                                               const b200hist_gpair64* parent_sums_host, int32_t n_nodes,
                                               const int32_t* feature_set_host, int32_t n_feature_set,

@@ -1,6 +1,7 @@
-"""GPU parity tests of code written AFTER this round's GPU minutes were spent: compiled, reviewed, never run on
-hardware.  They are skipped unless B200HIST_RUN_UNVALIDATED=1 so that the suite that has been seen green on a B200
-stays the suite that runs by default; the first GPU call of the next round runs them
+"""GPU parity tests of code written AFTER this round's regular GPU sessions: compiled, reviewed, and run on a B200
+only through five trees in the round's last GPU seconds (tools/quick_check, tests/test_recorded_hardware.py) -- never
+through THESE tests.  They are skipped unless B200HIST_RUN_UNVALIDATED=1 so that the suite that has been seen green on a
+B200 stays the suite that runs by default; the first GPU call of the next round runs them
 (`B200HIST_RUN_UNVALIDATED=1 python -m pytest tests/test_gpu_next.py -m gpu -x -q`) and a test moves to
 test_gpu_parity.py / test_reference_golden.py once it has passed there.
 
