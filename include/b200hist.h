@@ -261,6 +261,20 @@ B200HIST_API int b200hist_updater_set_level_feature_sets(b200hist_updater_t u, c
                                                          uint32_t n_levels, uint32_t n_per_level);
 B200HIST_API int b200hist_updater_last_max_eval_depth(b200hist_updater_t u, int32_t* out);
 
+/* colsample_bynode = ColumnSampler::GetFeatureSet's per-call draw (src/common/random.h:156-175, random.cu:62-96).
+ * gpu_hist asks for a set once for the root and then for the left and the right child of every valid candidate in
+ * Pop order (updater_gpu_hist.cu:217,257-264): the draws of a tree form one stream, independent of the data.
+ * sets_host holds the first n_sets >= max_nodes draws of that stream, n_per_set ascending feature ids each; the k-th
+ * node evaluated in the tree is evaluated on draw k (position in the list = tie rank).  b200hist_updater_last_eval_count
+ * tells the caller how many draws the last tree used, so that it can leave its random engine where the reference
+ * would.  Replaces tree- and level-wise sets while set; NULL / 0 removes it.  Not combinable with interaction
+ * constraints yet, nor with colsample_bylevel (the reference interleaves the lazy level draws with the node draws in
+ * one engine, which makes the stream data dependent).
+ * STATUS: compiled, never run on hardware; GPU tests in tests/test_gpu_next.py behind B200HIST_RUN_UNVALIDATED=1. */
+B200HIST_API int b200hist_updater_set_node_feature_sets(b200hist_updater_t u, const int32_t* sets_host, uint32_t n_sets,
+                                                        uint32_t n_per_set);
+B200HIST_API int b200hist_updater_last_eval_count(b200hist_updater_t u, int32_t* out);
+
 /* Monotone constraints = TreeEvaluator (src/tree/split_evaluator.h:25-205): constraints_host[f] in {-1, 0, +1} for the
  * first n features (the rest 0); n = 0 or NULL removes them.  A non-empty list switches every split gain to the
  * weight-based form -(2 g w + (h + lambda) w^2) with child weights clamped into the bounds of the node being split

@@ -242,19 +242,22 @@ class InteractionConstraints:
 
 class _Cat(Structure):
     _fields_ = [("feature_is_cat", c_void_p), ("max_cat_to_onehot", c_int32), ("max_cat_threshold", c_int32),
-                ("n_cat_words", c_uint32), ("node_is_cat", c_void_p), ("node_cat_bits", c_void_p)]
+                ("n_cat_words", c_uint32), ("node_is_cat", c_void_p), ("node_cat_bits", c_void_p),
+                ("node_sets", c_void_p), ("n_node_sets", c_int32), ("n_per_node", c_int32), ("eval_count", c_void_p)]
 
 
 def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override=None, max_nodes=None,
                 is_dense_layout=True, want_hist=False, feature_set=None, subsample=1.0, sample_seed=0,
                 monotone=None, level_feature_sets=None, interaction=None, interaction_shared_buffer=True,
-                feature_is_cat=None, max_cat_to_onehot=4, max_cat_threshold=64):
+                feature_is_cat=None, max_cat_to_onehot=4, max_cat_threshold=64, node_feature_sets=None):
     """Whole tree.  Returns dict(nodes=[Node...], position, scale, hist (optional), cands).
     feature_set: sorted feature ids of the tree's colsample_bytree draw; subsample/sample_seed: uniform row sampling;
     monotone: per-feature sign (+1 increasing, -1 decreasing, 0 free), padded with 0 to n_features;
     feature_is_cat: flags per feature (categorical features: bins are categories, cut values their codes), with
     TrainParam's max_cat_to_onehot / max_cat_threshold; the result then carries is_cat[n_nodes] and cat_sets (the
     categories that go RIGHT, per categorical split);
+    node_feature_sets: colsample_bynode, int32[n_draws, n_per_node]: the k-th node evaluated takes row k (the result
+    then carries eval_count, the number of draws used);
     interaction: parsed interaction_constraints ([[f, ...], ...]); interaction_shared_buffer (default = what the
     reference's trees follow, tests/golden/ref_gpu_interaction_trees.json): see orc_update_tree_ic."""
     gb = np.ascontiguousarray(gbins, dtype=np.int32)
@@ -284,14 +287,21 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
         mono[:len(monotone)] = np.asarray(monotone, dtype=np.int32)
     ic = InteractionConstraints(interaction, nf, 1, interaction_shared_buffer) if interaction is not None else None
     cat = None
-    if feature_is_cat is not None and any(feature_is_cat):
+    has_cat = feature_is_cat is not None and any(feature_is_cat)
+    eval_count = np.zeros(1, dtype=np.int32)
+    if has_cat or node_feature_sets is not None:
+        cat = _Cat(None, int(max_cat_to_onehot), int(max_cat_threshold), 1, None, None, None, 0, 0, eval_count.ctypes.data)
+    if has_cat:
         flags = np.zeros(nf, dtype=np.uint8)
         flags[:len(feature_is_cat)] = [1 if v else 0 for v in feature_is_cat]
         n_words = int(cv.max()) // 32 + 1 if cv.size else 1
         node_is_cat = np.zeros(max_nodes, dtype=np.int32)
         node_bits = np.zeros((max_nodes, n_words), dtype=np.uint32)
-        cat = _Cat(flags.ctypes.data, int(max_cat_to_onehot), int(max_cat_threshold), n_words,
-                   node_is_cat.ctypes.data, node_bits.ctypes.data)
+        cat.feature_is_cat, cat.n_cat_words = flags.ctypes.data, n_words
+        cat.node_is_cat, cat.node_cat_bits = node_is_cat.ctypes.data, node_bits.ctypes.data
+    if node_feature_sets is not None:
+        ns = np.ascontiguousarray(node_feature_sets, dtype=np.int32)
+        cat.node_sets, cat.n_node_sets, cat.n_per_node = ns.ctypes.data, ns.shape[0], ns.shape[1]
     lib().orc_update_tree_full.restype = c_int32
     nn = lib().orc_update_tree_full(_p(gb), c_uint64(n), c_uint32(stride), c_int(1 if is_dense_layout else 0),
                                   c_uint32(nf), _p(cp), _p(cv), _p(g), byref(param), so, nodes, c_int32(max_nodes),
@@ -303,7 +313,9 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
                                   byref(cat) if cat is not None else c_void_p())
     res = dict(nodes=list(nodes[:nn]), cands=list(cands[:nn]), position=pos,
                scale=np.array(scale_out[:], dtype=np.float64), hist=hist[:nn] if want_hist else None)
-    if cat is not None:
+    if node_feature_sets is not None:
+        res["eval_count"] = int(eval_count[0])
+    if has_cat:
         res["is_cat"] = node_is_cat[:nn].copy()
         res["cat_sets"] = [{32 * w + (31 - b) for w in range(n_words) for b in range(32) if (int(node_bits[i, w]) >> b) & 1}
                            if node_is_cat[i] else set() for i in range(nn)]

@@ -865,6 +865,13 @@ typedef struct {
   uint32_t n_cat_words;
   int32_t* node_is_cat;     /* out [max_nodes] */
   uint32_t* node_cat_bits;  /* out [max_nodes][n_cat_words] */
+  /* colsample_bynode (ColumnSampler::GetFeatureSet, src/common/random.h:156-175): node_sets (NULL = none) is the
+   * tree's stream of per-call draws, [n_node_sets][n_per_node] ascending feature ids; gpu_hist asks once for the root
+   * and then for the left and right child of every valid candidate in Pop order (updater_gpu_hist.cu:217,257-264),
+   * so the k-th node evaluated takes draw k.  feature_is_cat may be NULL when only this part is used. */
+  const int32_t* node_sets;
+  int32_t n_node_sets, n_per_node;
+  int32_t* eval_count; /* out: draws used */
 } orc_cat;
 ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
                                      uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
@@ -936,15 +943,25 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
                                      uint32_t sample_seed, const int32_t* monotone, int32_t n_levels,
                                      const orc_ic* ic, const orc_cat* cat) {
   /* candidates' category sets, kept until the candidate is applied */
-  uint32_t* cand_bits = cat ? (uint32_t*)calloc((size_t)max_nodes * cat->n_cat_words, sizeof(uint32_t)) : NULL;
-  int32_t* cand_is_cat = cat ? (int32_t*)calloc((size_t)max_nodes, sizeof(int32_t)) : NULL;
-  if (cat) {
+  const int has_cat = cat && cat->feature_is_cat;
+  uint32_t* cand_bits = has_cat ? (uint32_t*)calloc((size_t)max_nodes * cat->n_cat_words, sizeof(uint32_t)) : NULL;
+  int32_t* cand_is_cat = has_cat ? (int32_t*)calloc((size_t)max_nodes, sizeof(int32_t)) : NULL;
+  if (cat && cat->feature_is_cat) {
     memset(cat->node_is_cat, 0, sizeof(int32_t) * (size_t)max_nodes);
     memset(cat->node_cat_bits, 0, sizeof(uint32_t) * (size_t)max_nodes * cat->n_cat_words);
   }
-#define ORC_EVAL(nidx_, fs_, nfs_, out_)                                                                              \
+  int32_t eval_seq = 0;
+#define ORC_EVAL(nidx_, fs_in_, nfs_in_, out_)                                                                        \
   do {                                                                                                                \
-    if (cat) {                                                                                                        \
+    const int32_t* fs_ = fs_in_;                                                                                      \
+    int32_t nfs_ = nfs_in_;                                                                                           \
+    if (cat && cat->node_sets) {                                                                                      \
+      int32_t k_ = eval_seq < cat->n_node_sets ? eval_seq : cat->n_node_sets - 1;                                     \
+      fs_ = cat->node_sets + (size_t)k_ * cat->n_per_node;                                                            \
+      nfs_ = cat->n_per_node;                                                                                         \
+      eval_seq++;                                                                                                     \
+    }                                                                                                                 \
+    if (cat && cat->feature_is_cat) {                                                                                 \
       int32_t th_;                                                                                                    \
       eval_node_cat_m(hist[nidx_], node_sum[nidx_], cut_ptrs, cut_values, n_features, fs_, nfs_, p, scale,            \
                       cat->feature_is_cat, cat->max_cat_to_onehot, cat->max_cat_threshold, out_, &cand_is_cat[nidx_], \
@@ -1067,7 +1084,7 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
       nodes[l] = ln; nodes[r] = rn;
       node_sum[l] = c->left_sum; node_sum[r] = c->right_sum;
       if (ic) orc_ic_split(ic, ic_bits, nidx, c->findex, l, r);
-      if (cat && cand_is_cat[nidx]) {
+      if (has_cat && cand_is_cat[nidx]) {
         cat->node_is_cat[nidx] = 1;
         memcpy(cat->node_cat_bits + (size_t)nidx * cat->n_cat_words, cand_bits + (size_t)nidx * cat->n_cat_words,
                sizeof(uint32_t) * cat->n_cat_words);
@@ -1093,7 +1110,7 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
       if (p->max_leaves > 0 && num_leaves >= p->max_leaves) continue;
       int32_t l = nodes[nidx].left, r = nodes[nidx].right;
       uint64_t nl;
-      if (cat && cat->node_is_cat[nidx]) {
+      if (has_cat && cat->node_is_cat[nidx]) {
         const uint32_t* bits = cat->node_cat_bits + (size_t)nidx * cat->n_cat_words;
         const uint32_t* in = ridx + seg_beg[nidx];
         uint32_t* outp = tmp + seg_beg[nidx];
@@ -1163,7 +1180,7 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
     for (uint64_t r = 0; r < n_rows; ++r) {
       int32_t nidx = 0;
       while (!nodes[nidx].is_leaf) {
-        int gl = (cat && cat->node_is_cat[nidx])
+        int gl = (has_cat && cat->node_is_cat[nidx])
                      ? go_left_cat(gbins, stride, is_dense_layout, cut_ptrs, cut_values, r, nodes[nidx].findex,
                                    cat->node_cat_bits + (size_t)nidx * cat->n_cat_words, cat->n_cat_words,
                                    nodes[nidx].default_left)
@@ -1181,6 +1198,7 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
   for (int32_t i = 0; i < max_nodes; ++i) free(hist[i]);
   free(hist); free(seg_beg); free(seg_cnt); free(node_sum); free(ridx); free(tmp); free(queue); free(gq);
   free(lower); free(upper); free(ic_bits); free(ic_buffer); free(cand_bits); free(cand_is_cat);
+  if (cat && cat->eval_count) *cat->eval_count = eval_seq;
 #undef ORC_LEVEL_SET
 #undef ORC_EVAL
   return n_nodes;

@@ -453,3 +453,69 @@ def test_categorical_features_through_the_shim_match_reference(xb, extra):
     assert sum(sum(t["split_type"]) for t in ref_trees) >= 4, "the fixture must produce categorical splits"
     assert json.dumps(our_trees) == json.dumps(ref_trees)
     assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# colsample_bynode (b200hist_updater_set_node_feature_sets, NodeSetLevelKernel)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("extra", [dict(max_depth=6), dict(max_depth=0, max_leaves=20, grow_policy="lossguide"),
+                                   dict(max_depth=5, mono=True), dict(max_depth=7, max_leaves=17)],
+                         ids=["depthwise", "lossguide", "monotone", "depthwise_max_leaves"])
+def test_node_feature_sets_match_oracle(xb, extra):
+    import torch
+    n, f = 15000, 24
+    x, y = make_regression(n, f, seed=71, missing=0.05)
+    cp, cv = make_cuts(x, 32)
+    page = _page(xb, x, cp, cv)
+    gb = orc.bin_dense(x, cp, cv)
+    params = {k: v for k, v in extra.items() if k != "mono"}
+    params["eta"] = 0.5
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    mono = ([1, -1, 0] * 8) if extra.get("mono") else None
+    if mono:
+        up.set_monotone_constraints(mono)
+    rng = np.random.default_rng(72)
+    pred = np.zeros(n, dtype=np.float32)
+    for it in range(3):
+        sets = np.stack([np.sort(rng.permutation(f)[:9]) for _ in range(up.max_nodes)]).astype(np.int32)
+        up.set_node_feature_sets(sets)
+        gp = squared_error_gpair(pred, y)
+        tree = up.update(torch.from_numpy(gp).cuda())
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), want_hist=True, node_feature_sets=sets,
+                            monotone=mono)
+        _compare_tree(xb, up, tree, o, cp, cv, hists=True)
+        assert up.last_eval_count() == o["eval_count"]
+        pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+    up.set_node_feature_sets(None)
+    gp = squared_error_gpair(np.zeros(n, np.float32), y)
+    t_plain = up.update(torch.from_numpy(gp).cuda())
+    o_plain = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), monotone=mono)
+    _compare_tree(xb, up, t_plain, o_plain, cp, cv, hists=False)
+
+
+@pytest.mark.parametrize("extra", [{"colsample_bynode": 0.5}, {"colsample_bynode": 0.6, "colsample_bytree": 0.7, "subsample": 0.8},
+                                   {"colsample_bynode": 0.4, "grow_policy": "lossguide", "max_leaves": 24, "max_depth": 0}],
+                         ids=lambda e: "_".join("%s%s" % kv for kv in e.items()))
+def test_colsample_bynode_through_the_shim_matches_reference(xb, extra):
+    """The shim draws the tree's whole stream of node sets with the reference's own ColumnSampler from a copy of the
+    Booster's engine and replays the engine by the number of nodes evaluated: models and the engine state after
+    every tree (hence all later trees) must equal the reference's."""
+    import torch
+    rc = _shim_or_skip()
+    x, y = make_regression(30000, 40, seed=83)
+    params = {"tree_method": "hist", "device": "cuda:0", "max_bin": 64, "max_depth": 5, "eta": 0.3,
+              "objective": "reg:squarederror", "base_score": 0.5}
+    params.update(extra)
+
+    def train(updater):
+        dm = rc.DMatrix.from_cuda(torch.from_numpy(x).cuda(), kind="cuda")
+        dm.set_label(y)
+        bst = rc.Booster(dict(params, updater=updater), dm)
+        for i in range(4):
+            bst.update(i)
+        return _model_trees(bst), bst.predict_margin(dm)
+    ref_trees, ref_margin = train("grow_gpu_hist_reference")
+    our_trees, our_margin = train("grow_b200_hist")
+    assert json.dumps(our_trees) == json.dumps(ref_trees)
+    assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))

@@ -427,3 +427,43 @@ def test_tree_respects_interaction_constraints(shared):
             assert t["nodes"][i].findex == ref["nodes"][i].findex and t["nodes"][i].fvalue == ref["nodes"][i].fvalue
     # the root is evaluated on every feature either way
     assert t["nodes"][0].findex == free["nodes"][0].findex and t["nodes"][0].fvalue == free["nodes"][0].fvalue
+
+
+def test_oracle_node_feature_sets_follow_the_evaluation_order():
+    """colsample_bynode restated: the k-th node evaluated (root, then left and right child of every valid candidate in
+    Pop order) takes the k-th draw of the tree's stream; every split feature comes from its node's draw and the number
+    of draws used is the number of evaluated nodes."""
+    from tests.helpers import make_cuts, make_regression, squared_error_gpair
+    x, y = make_regression(8000, 10, seed=5)
+    cp, cv = make_cuts(x, 32)
+    gb = orc.bin_dense(x, cp, cv)
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    rng = np.random.default_rng(1)
+    sets = np.stack([np.sort(rng.permutation(10)[:4]) for _ in range(31)]).astype(np.int32)
+    for params in (dict(max_depth=4), dict(max_depth=0, max_leaves=8, grow_policy="lossguide")):
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), node_feature_sets=sets, max_nodes=31)
+        nodes = o["nodes"]
+        # replay the evaluation order from the finished tree
+        if params.get("grow_policy") == "lossguide":   # children are evaluated when their parent is expanded
+            order = [0]
+            for nd in sorted((n for n in nodes if not n.is_leaf), key=lambda n: n.left):
+                order += [nd.left, nd.right]
+            order = order[:o["eval_count"]]
+        else:
+            order, cur = [0], [0]
+            while cur:
+                nxt = []
+                for i in cur:
+                    if not nodes[i].is_leaf and nodes[i].depth + 1 < params["max_depth"]:
+                        nxt += [nodes[i].left, nodes[i].right]
+                order += nxt
+                cur = nxt
+        assert o["eval_count"] == len(order)
+        for k, i in enumerate(order):
+            if not nodes[i].is_leaf:
+                assert nodes[i].findex in sets[k], (params, k, i)
+    # one full-width draw per node changes nothing
+    full = np.tile(np.arange(10, dtype=np.int32), (31, 1))
+    a = orc.update_tree(gb, cp, cv, gp, orc.Param.make(max_depth=4), node_feature_sets=full)
+    b = orc.update_tree(gb, cp, cv, gp, orc.Param.make(max_depth=4))
+    assert [(n.findex, n.fvalue) for n in a["nodes"]] == [(n.findex, n.fvalue) for n in b["nodes"]]

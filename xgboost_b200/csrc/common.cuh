@@ -228,9 +228,12 @@ struct MonoView {
 // so the kernel reads the buffer as the level's queries left it, cut to each node's own count: `list` is that buffer
 // image, count[slot] what evaluation slot `slot` reads of it.  count == nullptr: no constraints (and always for the
 // root, which Query never filters).
+// The same view carries colsample_bynode: every evaluation slot then owns a list (stride > 0: slot s reads
+// list + s * stride), the next draws of the tree's stream of node feature sets (NodeSetLevelKernel, updater.cu).
 struct IcView {
   const int32_t* list;
   const int32_t* count;
+  int32_t stride;  // 0: one list shared by all slots
 };
 
 // Categorical features (src/common/categorical.h, evaluate_splits.cu:148-252,313-348, evaluator.cu:69-128).
@@ -362,7 +365,7 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = n
                     NodeDev* nodes_mut, int num_sms, cudaStream_t s, MonoView mono = MonoView{nullptr, nullptr, nullptr},
                     int32_t n_levels = 0 /* > 0: feature_set is [n_levels][n_feature_set], row = node depth */,
                     int32_t* max_eval_depth = nullptr /* device: atomicMax of the depths evaluated */,
-                    IcView ic = IcView{nullptr, nullptr},
+                    IcView ic = IcView{nullptr, nullptr, 0},
                     CatView cat = CatView{nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0, 0});
 
 // partition.cu

@@ -208,7 +208,7 @@ int b200hist_evaluate_splits_cat(b200hist_ellpack_t ell, const b200hist_gpair64*
                       (int32_t)n_cat_words, bin_words, max_cat_bins};
     LaunchEvaluate(ell->View(), hist_dev, d_eval.p, d_ts.p, n_nodes, d_nodes.p, feature_set_host ? d_fs.p : nullptr,
                    n_fs, ToParamDev(*param), d_q.p, d_scratch.p, d_cand.p, d_nodes.p, NumSMs(ell->device), s,
-                   MonoView{nullptr, nullptr, nullptr}, 0, nullptr, IcView{nullptr, nullptr}, cat);
+                   MonoView{nullptr, nullptr, nullptr}, 0, nullptr, IcView{nullptr, nullptr, 0}, cat);
   }
   std::vector<uint8_t> node_is_cat(n_nodes);
   B200_CUDA(cudaMemcpyAsync(out_host, d_cand.p, sizeof(b200hist_candidate) * n_nodes, cudaMemcpyDeviceToHost, s));

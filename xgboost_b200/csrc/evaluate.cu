@@ -115,7 +115,7 @@ FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t
         (feature_set && n_levels > 0) ? feature_set + (size_t)min(nodes[nidx].depth, n_levels - 1) * n_fs : feature_set;
     if constexpr (kIc) {
       if (fpos >= ic.count[slot]) continue;  // warp-uniform: the node reads only its own count of the buffer
-      fs = ic.list;
+      fs = ic.list + (size_t)slot * ic.stride;
     }
     const int f = fs ? fs[fpos] : fpos;
     const longlong2* h = hist + (size_t)nodes[nidx].hist_slot * ell.total_bins;
@@ -264,7 +264,7 @@ NodeReduceKernel(EllView ell, const int32_t* __restrict__ eval_nodes, const Tree
         const int32_t* fs = (feature_set && n_levels > 0)
                                 ? feature_set + (size_t)min(nodes[nidx].depth, n_levels - 1) * n_fs
                                 : feature_set;
-        if constexpr (kIc) fs = ic.list;
+        if constexpr (kIc) fs = ic.list + (size_t)slot * ic.stride;
         int f = fs ? fs[bpos] : bpos;
         c.loss_chg = w.loss_chg;
         c.dir = w.dir;
@@ -396,7 +396,7 @@ CatFeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int3
         (feature_set && n_levels > 0) ? feature_set + (size_t)min(nodes[nidx].depth, n_levels - 1) * n_fs : feature_set;
     if (ic.count != nullptr) {
       if (fpos >= ic.count[slot]) continue;
-      fs = ic.list;
+      fs = ic.list + (size_t)slot * ic.stride;
     }
     const int f = fs ? fs[fpos] : fpos;
     if (!cat.is_cat[f]) continue;  // warp-uniform

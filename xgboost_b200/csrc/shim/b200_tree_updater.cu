@@ -166,8 +166,10 @@ class B200HistMaker : public TreeUpdater {
     CHECK(!p_fmat->Info().HasCategorical() || unvalidated_ok) << "[b200hist] categorical features are not enabled yet";
     CHECK(param->subsample == 1.0f || param->sampling_method == TrainParam::kUniform)
         << "[b200hist] gradient_based row sampling is not supported yet";
-    CHECK(param->colsample_bynode == 1.0f)
-        << "[b200hist] colsample_bynode is not supported yet (colsample_bytree and colsample_bylevel are)";
+    CHECK(param->colsample_bynode == 1.0f || unvalidated_ok)
+        << "[b200hist] colsample_bynode is not enabled yet (colsample_bytree and colsample_bylevel are)";
+    CHECK(param->colsample_bynode == 1.0f || (param->colsample_bylevel == 1.0f && param->interaction_constraints.empty()))
+        << "[b200hist] colsample_bynode cannot be combined with colsample_bylevel or interaction constraints yet";
     B200_SHIM_CHECK(b200hist_updater_create(ellpack_, &p, &updater_));
     if (!param->monotone_constraints.empty()) {  // TreeEvaluator ctor (split_evaluator.h:37-57)
       std::vector<std::int32_t> mono(param->monotone_constraints.cbegin(), param->monotone_constraints.cend());
@@ -214,12 +216,37 @@ class B200HistMaker : public TreeUpdater {
     bool const rows = param->subsample < 1.0f;
     bool const cols = param->colsample_bytree < 1.0f;
     bool const levels = param->colsample_bylevel < 1.0f;
-    if (!rows && !cols && !levels && !sampling_set_) return;
+    bool const by_node = param->colsample_bynode < 1.0f;
+    if (!rows && !cols && !levels && !by_node && !sampling_set_) return;
     std::uint32_t seed = rows ? static_cast<std::uint32_t>(ctx_->Rng()()) : 0u;
     auto const& info = p_fmat->Info();
     std::vector<std::int32_t> fs;
     level_draws_pending_ = false;
-    if (levels) {
+    node_draws_pending_ = false;
+    if (by_node) {
+      // ColumnSampler::GetFeatureSet draws a fresh set per call (random.h:156-175; one ctx->Rng()() each, random.cu:67):
+      // once for the root, then for the left and right child of every valid candidate.  The stream does not depend on
+      // the data, only its length does: draw the longest possible stream from a COPY of the engine, let the updater
+      // take draw k for the k-th evaluated node, and replay the real engine by the count it reports.
+      rng_before_columns_ = ctx_->Rng();
+      column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, param->colsample_bynode, 1.0f,
+                           param->colsample_bytree);
+      std::int32_t max_nodes{0};
+      B200_SHIM_CHECK(b200hist_updater_max_nodes(updater_, &max_nodes));
+      std::size_t per_node = 0;
+      for (std::int32_t k = 0; k < max_nodes; ++k) {
+        auto p_set = column_sampler_.GetFeatureSet(ctx_, 0);
+        auto const& h_set = p_set->ConstHostVector();
+        if (k == 0) per_node = h_set.size();
+        CHECK_EQ(h_set.size(), per_node);
+        fs.insert(fs.end(), h_set.cbegin(), h_set.cend());
+      }
+      B200_SHIM_CHECK(b200hist_updater_set_level_feature_sets(updater_, nullptr, 0, 0));
+      B200_SHIM_CHECK(b200hist_updater_set_tree_sampling(updater_, nullptr, 0, rows ? param->subsample : 1.0f, seed));
+      B200_SHIM_CHECK(b200hist_updater_set_node_feature_sets(updater_, fs.data(), static_cast<std::uint32_t>(max_nodes),
+                                                             static_cast<std::uint32_t>(per_node)));
+      node_draws_pending_ = true;
+    } else if (levels) {
       // ColumnSampler draws a level's set lazily, when the first node of that depth is evaluated
       // (random.h:156-175).  Our tree is built without coming back to the host, so the sets of ALL possible depths
       // are drawn up front from a COPY of the engine state; FinishSampling() then replays exactly the draws the
@@ -253,11 +280,22 @@ class B200HistMaker : public TreeUpdater {
                                                          static_cast<std::uint32_t>(fs.size()),
                                                          rows ? param->subsample : 1.0f, seed));
     }
-    sampling_set_ = rows || cols || levels;
+    sampling_set_ = rows || cols || levels || by_node;
   }
 
   // colsample_bylevel: leave ctx->Rng() where the reference would have left it after this tree.
   void FinishSampling(TrainParam const* param, DMatrix* p_fmat) {
+    if (node_draws_pending_) {  // colsample_bynode: as many draws as nodes were evaluated
+      std::int32_t n_draws = 0;
+      B200_SHIM_CHECK(b200hist_updater_last_eval_count(updater_, &n_draws));
+      ctx_->Rng() = rng_before_columns_;
+      auto const& info = p_fmat->Info();
+      column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, param->colsample_bynode, 1.0f,
+                           param->colsample_bytree);
+      for (std::int32_t k = 0; k < n_draws; ++k) (void)column_sampler_.GetFeatureSet(ctx_, 0);
+      node_draws_pending_ = false;
+      return;
+    }
     if (!level_draws_pending_) return;
     std::int32_t deepest = 0;
     B200_SHIM_CHECK(b200hist_updater_last_max_eval_depth(updater_, &deepest));
@@ -328,6 +366,7 @@ class B200HistMaker : public TreeUpdater {
   common::ColumnSampler column_sampler_;
   bool sampling_set_{false};
   bool level_draws_pending_{false};
+  bool node_draws_pending_{false};
   bool has_categorical_{false};
   std::uint32_t cat_words_{0};
   std::vector<std::int32_t> node_is_cat_;

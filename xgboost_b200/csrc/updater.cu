@@ -475,6 +475,27 @@ __global__ void __launch_bounds__(kCtlThreads) IcLevelKernel(const TreeState* ts
   }
 }
 
+// colsample_bynode (ColumnSampler::GetFeatureSet, src/common/random.h:156-175): every call draws a fresh set from
+// the level's set, and gpu_hist calls it once for the root and then for the left and the right child of every valid
+// candidate in Pop order (updater_gpu_hist.cu:217,257-264).  The draws form ONE stream per tree, so the caller
+// hands over the stream's first max_nodes sets and evaluation slot j of the current step takes draw seq + j.
+__global__ void __launch_bounds__(kCtlThreads) NodeSetLevelKernel(const TreeState* ts, const int32_t* __restrict__ sets,
+                                                                   int32_t n_sets, int32_t n_per,
+                                                                   int32_t* __restrict__ seq,
+                                                                   int32_t* __restrict__ list,
+                                                                   int32_t* __restrict__ count) {
+  const int n_eval = ts->n_eval;
+  const int base = *seq;
+  __syncthreads();  // everybody has read the sequence number before it moves
+  for (int i = threadIdx.x; i < n_eval * n_per; i += kCtlThreads) {
+    const int j = i / n_per, k = i - j * n_per;
+    const int draw = min(base + j, n_sets - 1);  // the caller provides max_nodes draws: never short
+    list[i] = sets[(size_t)draw * n_per + k];
+  }
+  for (int j = threadIdx.x; j < n_eval; j += kCtlThreads) count[j] = n_per;
+  if (threadIdx.x == 0) *seq = base + n_eval;
+}
+
 // ---------------------------------------------------------------------------------------------
 // FinalisePosition (updater_gpu_hist.cu:529-580): list the nodes that still own a row segment,
 // then walk each row from that node to its leaf (at most the splits applied after the last
@@ -781,6 +802,13 @@ struct b200hist_updater_s {
   int32_t* d_ic_list{nullptr};
   int32_t* d_ic_count{nullptr};
   int32_t ic_n_sets{0}, ic_words{0};
+  // colsample_bynode (nullptr = none): the tree's stream of node feature sets, the per-slot lists of the current
+  // step, the stream position (device) and the position after the last tree (host)
+  int32_t* d_node_sets{nullptr};
+  int32_t* d_node_list{nullptr};
+  int32_t* d_node_count{nullptr};
+  int32_t* d_node_seq{nullptr};
+  int32_t n_node_sets{0}, n_per_node{0}, last_eval_count{0};
   // categorical features (nullptr = none): flags per feature, per-node category sets (CatView)
   uint8_t* d_is_cat{nullptr};
   uint32_t* d_cat_bits{nullptr};
@@ -895,6 +923,14 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   timer.End(kQuant, t0);
   const bool has_ic = u->d_ic_bits != nullptr;
   const bool has_cat = u->d_is_cat != nullptr;
+  const bool has_node_sets = u->d_node_sets != nullptr;
+  if (has_node_sets) B200_CUDA(cudaMemsetAsync(u->d_node_seq, 0, sizeof(int32_t), s));
+  auto node_sets_view = [&]() {  // the next n_eval draws of the stream, one list per evaluation slot
+    NodeSetLevelKernel<<<1, kCtlThreads, 0, s>>>(u->d_ts, u->d_node_sets, u->n_node_sets, u->n_per_node, u->d_node_seq,
+                                                 u->d_node_list, u->d_node_count);
+    B200_LAUNCHED();
+    return IcView{u->d_node_list, u->d_node_count, u->n_per_node};
+  };
   const CatView catv = has_cat ? CatView{u->d_is_cat, u->max_cat_to_onehot, u->max_cat_threshold, u->d_cat_bits,
                                          u->d_bin_bits, u->d_node_is_cat, u->cat_words, u->cat_bin_words, u->max_cat_bins}
                                : CatView{nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0, 0};
@@ -934,9 +970,15 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   build_hist(0, 1);
   timer.End(kHist, t2);
   auto t3 = timer.Begin();
-  LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, u->d_feature_set, u->n_feature_set, u->pdev, u->d_quant,
-                 u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, u->n_feature_levels, &u->d_ts->max_eval_depth,
-                 IcView{nullptr, nullptr}, catv);
+  if (has_node_sets) {
+    const IcView nv = node_sets_view();
+    LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, nullptr, 0, u->pdev, u->d_quant, u->d_scratch,
+                   u->d_cand, u->d_nodes, u->num_sms, s, mono, 0, &u->d_ts->max_eval_depth, nv, catv);
+  } else {
+    LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, u->d_feature_set, u->n_feature_set, u->pdev, u->d_quant,
+                   u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, u->n_feature_levels, &u->d_ts->max_eval_depth,
+                   IcView{nullptr, nullptr, 0}, catv);
+  }
   timer.End(kEval, t3);
 
   const bool depthwise = u->param.grow_policy == 0;
@@ -973,7 +1015,15 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     LaunchSubtract(u->d_sub, u->d_ts, u->d_hist, ell->total_bins, u->num_sms, s);
     timer.End(kSub, tsb);
     auto te = timer.Begin();
-    IcView icv{nullptr, nullptr};
+    IcView icv{nullptr, nullptr, 0};
+    if (has_node_sets) {
+      icv = node_sets_view();
+      LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, (int32_t)(2 * cap), u->d_nodes, nullptr, 0, u->pdev,
+                     u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, 0, &u->d_ts->max_eval_depth, icv,
+                     catv);
+      timer.End(kEval, te);
+      continue;
+    }
     if (has_ic) {
       const IcDev icd{(int32_t)ell->n_features, u->ic_words, u->ic_n_sets, u->d_ic_set_ptr, u->d_ic_set_feat,
                       u->d_ic_bits, u->d_ic_list, u->d_ic_count};
@@ -981,7 +1031,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
           u->d_ts, u->d_nodes, u->d_part, u->d_eval_nodes, icd, u->d_feature_set, u->n_feature_set,
           u->n_feature_levels);
       B200_LAUNCHED();
-      icv = IcView{u->d_ic_list, u->d_ic_count};
+      icv = IcView{u->d_ic_list, u->d_ic_count, 0};
     }
     LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, (int32_t)(2 * cap), u->d_nodes, u->d_feature_set,
                    u->n_feature_set, u->pdev,
@@ -1029,6 +1079,8 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   u->last_row_visits = u->h_ts->row_visits;
   u->last_n_nodes = u->h_ts->n_nodes;
   u->last_max_eval_depth = u->h_ts->max_eval_depth;
+  if (has_node_sets)
+    B200_CUDA(cudaMemcpy(&u->last_eval_count, u->d_node_seq, sizeof(int32_t), cudaMemcpyDeviceToHost));
   u->last_position = position;
   if (out_nodes) ToAbiNodes(u->h_nodes, u->last_n_nodes, out_nodes);
   if (out_n_nodes) *out_n_nodes = u->last_n_nodes;
@@ -1164,6 +1216,8 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
                     (void*)u->d_ic_count})
       if (p) cudaFree(p);
     for (void* p : {(void*)u->d_is_cat, (void*)u->d_cat_bits, (void*)u->d_bin_bits, (void*)u->d_node_is_cat})
+      if (p) cudaFree(p);
+    for (void* p : {(void*)u->d_node_sets, (void*)u->d_node_list, (void*)u->d_node_count, (void*)u->d_node_seq})
       if (p) cudaFree(p);
     cudaFreeHost(u->h_nodes);
     cudaFreeHost(u->h_ts);
@@ -1408,6 +1462,7 @@ int b200hist_updater_set_interaction_constraints(b200hist_updater_t u, const int
   u->ic_words = 0;
   if (n_sets > 0) {
     B200_CHECK(set_ptr_host != nullptr && set_feat_host != nullptr, "null constraint sets");
+    B200_CHECK(u->d_node_sets == nullptr, "interaction constraints and node feature sets cannot be combined yet");
     B200_CHECK(set_ptr_host[0] == 0, "set_ptr must start at 0");
     for (uint32_t i = 0; i < n_sets; ++i) B200_CHECK(set_ptr_host[i] <= set_ptr_host[i + 1], "set_ptr must not decrease");
     const int32_t n_feat = set_ptr_host[n_sets];
@@ -1426,6 +1481,41 @@ int b200hist_updater_set_interaction_constraints(b200hist_updater_t u, const int
     u->d_ic_list = DevAlloc<int32_t>(u->ell->n_features);
     u->d_ic_count = DevAlloc<int32_t>(2 * (size_t)kMaxLevelNodes);
   }
+  B200_API_END();
+}
+
+int b200hist_updater_set_node_feature_sets(b200hist_updater_t u, const int32_t* sets_host, uint32_t n_sets,
+                                           uint32_t n_per_set) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  DeviceGuard guard(u->device);
+  for (void** p : {(void**)&u->d_node_sets, (void**)&u->d_node_list, (void**)&u->d_node_count, (void**)&u->d_node_seq}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  u->n_node_sets = u->n_per_node = 0;
+  if (sets_host != nullptr && n_sets > 0) {
+    B200_CHECK(u->d_ic_bits == nullptr, "node feature sets and interaction constraints cannot be combined yet");
+    B200_CHECK(n_per_set >= 1 && n_per_set <= u->ell->n_features, "n_per_set out of range");
+    B200_CHECK((int64_t)n_sets >= (int64_t)u->max_nodes, "one draw per possible node is needed (max_nodes sets)");
+    for (size_t i = 0; i < (size_t)n_sets * n_per_set; ++i)
+      B200_CHECK(sets_host[i] >= 0 && (uint32_t)sets_host[i] < u->ell->n_features, "feature id out of range");
+    u->n_node_sets = (int32_t)n_sets;
+    u->n_per_node = (int32_t)n_per_set;
+    u->d_node_sets = DevAlloc<int32_t>((size_t)n_sets * n_per_set);
+    B200_CUDA(cudaMemcpy(u->d_node_sets, sets_host, sizeof(int32_t) * (size_t)n_sets * n_per_set, cudaMemcpyHostToDevice));
+    u->d_node_list = DevAlloc<int32_t>(2 * (size_t)kMaxLevelNodes * n_per_set);
+    u->d_node_count = DevAlloc<int32_t>(2 * (size_t)kMaxLevelNodes);
+    u->d_node_seq = DevAlloc<int32_t>(1);
+    B200_CUDA(cudaMemset(u->d_node_seq, 0, sizeof(int32_t)));
+  }
+  B200_API_END();
+}
+
+int b200hist_updater_last_eval_count(b200hist_updater_t u, int32_t* out) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && out != nullptr, "null argument");
+  *out = u->last_eval_count;
   B200_API_END();
 }
 

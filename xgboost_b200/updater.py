@@ -452,6 +452,28 @@ class GPUHistMaker:
             c = np.ascontiguousarray(constraints, dtype=np.int32)
             _l.check(_l.load().b200hist_updater_set_monotone_constraints(self._h, c.ctypes.data_as(POINTER(c_int32)), c.size))
 
+    @property
+    def max_nodes(self) -> int:
+        """Node capacity of one tree (TrainParam::MaxNodes)."""
+        return int(self._max_nodes)
+
+    def set_node_feature_sets(self, sets) -> None:
+        """colsample_bynode: int32[n_sets >= max_nodes, n_per_set], the tree's stream of per-node draws (the k-th node
+        evaluated takes row k); None removes it.  Not yet run on hardware -- see include/b200hist.h."""
+        if sets is None:
+            _l.check(_l.load().b200hist_updater_set_node_feature_sets(self._h, None, 0, 0))
+            return
+        a = np.ascontiguousarray(sets, dtype=np.int32)
+        if a.ndim != 2:
+            raise ValueError("sets must be [n_sets, n_per_set]")
+        _l.check(_l.load().b200hist_updater_set_node_feature_sets(self._h, a.ctypes.data_as(POINTER(c_int32)),
+                                                                a.shape[0], a.shape[1]))
+
+    def last_eval_count(self) -> int:
+        n = c_int32()
+        _l.check(_l.load().b200hist_updater_last_eval_count(self._h, byref(n)))
+        return int(n.value)
+
     def set_categorical(self, feature_is_cat: Optional[Sequence[int]], max_cat_to_onehot: int = 4,
                         max_cat_threshold: int = 64) -> None:
         """MetaInfo::feature_types / TrainParam::max_cat_to_onehot, max_cat_threshold: flags per feature (non-zero =
