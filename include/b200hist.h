@@ -137,6 +137,11 @@ typedef struct b200hist_sketch_s* b200hist_sketch_t;
 B200HIST_API int b200hist_sketch_create(int device, uint32_t n_features, int32_t max_bin, b200hist_sketch_t* out);
 B200HIST_API int b200hist_sketch_push_dense(b200hist_sketch_t sketch, const float* x_dev, uint64_t n, uint64_t ld,
                                             void* stream);
+/* Feature types of the sketch (SketchContainer's feature_types): a categorical column (flag != 0) gets the cut values
+ * 0, 1, .., its largest category code instead of quantiles (quantile.cu:684-696, AddCategories); a negative code or
+ * one beyond 2^24 is an error as in the reference (InvalidCat).  Host-side only: call any time before make_cuts. */
+B200HIST_API int b200hist_sketch_set_feature_types(b200hist_sketch_t sketch, const uint8_t* feature_is_cat_host,
+                                                   uint32_t n);
 B200HIST_API int b200hist_sketch_make_cuts(b200hist_sketch_t sketch, uint32_t* cut_ptrs_out_host,
                                            float* cut_values_out_host, uint64_t cut_values_capacity,
                                            uint32_t* fix_error_changes_out, void* stream);
@@ -160,6 +165,12 @@ B200HIST_API int b200hist_ellpack_destroy(b200hist_ellpack_t ell);
  * (src/data/ellpack_page.cu:56-134,240-298) + HistogramCuts::SearchBin (hist_util.h:112-121). */
 B200HIST_API int b200hist_ellpack_push_dense(b200hist_ellpack_t ell, uint64_t row_begin,
                                              const float* x_dev, uint64_t n, uint64_t ld, void* stream);
+/* Feature types of a dense-layout page: the categorical columns (flag != 0) of every later push_dense are binned by
+ * HistogramCuts::SearchCatBin (src/common/hist_util.h:132-144: lower bound of the truncated value among the feature's
+ * category codes, clamped to the last bin) instead of SearchBin.  Call before push_dense.
+ * STATUS: compiled, never run on hardware (tests/test_gpu_next.py). */
+B200HIST_API int b200hist_ellpack_set_feature_types(b200hist_ellpack_t ell, const uint8_t* feature_is_cat_host,
+                                                    uint32_t n);
 /* Import a reference EllpackPage: decode its big-endian bit-packed gidx_buffer
  * (src/common/compressed_iterator.h:110-152,228-268) into our layout.  Dense layouts only
  * (row_stride == n_features); null_value as EllpackAccessor::NullValue (ellpack_page.cuh:85-87). */

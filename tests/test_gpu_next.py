@@ -519,3 +519,56 @@ def test_colsample_bynode_through_the_shim_matches_reference(xb, extra):
     our_trees, our_margin = train("grow_b200_hist")
     assert json.dumps(our_trees) == json.dumps(ref_trees)
     assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Categorical columns at DMatrix construction: cut values (b200hist_sketch_set_feature_types) and SearchCatBin binning
+# (b200hist_ellpack_set_feature_types, RebinCategoricalKernel)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_categorical_cuts_and_binning(xb):
+    import torch
+    from tests.test_reference_golden import categorical_global_bins
+    from tools.make_golden_cpu_categorical import N_CATS, make_data
+    case = json.load(open(os.path.join(GOLDEN, "ref_cpu_categorical_trees.json")))["cases"][0]
+    x, _, types = make_data(case)
+    is_cat = [1 if t == "c" else 0 for t in types]
+    xd = torch.from_numpy(x).cuda()
+    sk = xb.QuantileSketch(x.shape[1], case["max_bin"], torch.device("cuda", 0))
+    sk.set_feature_types(is_cat)
+    for b in range(0, x.shape[0], 3000):          # several windows
+        sk.push(xd[b:b + 3000])
+    cuts = sk.make_cuts()
+    sk.close()
+    ref_cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+    ref_cv = np.array(case["cut_values_bits"], dtype=np.uint32).view(np.float32)
+    for j, k in enumerate(N_CATS):                 # the reference's categorical cuts: every code 0 .. max
+        seg = cuts.cut_values[cuts.cut_ptrs[j]:cuts.cut_ptrs[j + 1]]
+        assert np.array_equal(seg, np.arange(k, dtype=np.float32)), j
+        assert np.array_equal(seg, ref_cv[ref_cp[j]:ref_cp[j + 1]]), j
+    # numerical columns are untouched by the flags
+    plain = xb.QuantileSketch(x.shape[1], case["max_bin"], torch.device("cuda", 0))
+    for b in range(0, x.shape[0], 3000):
+        plain.push(xd[b:b + 3000])
+    pc = plain.make_cuts()
+    plain.close()
+    for j in range(len(N_CATS), x.shape[1]):
+        assert np.array_equal(cuts.cut_values[cuts.cut_ptrs[j]:cuts.cut_ptrs[j + 1]],
+                              pc.cut_values[pc.cut_ptrs[j]:pc.cut_ptrs[j + 1]]), j
+    # binning: a category lands in the bin of its code, a value between codes truncates, too large clamps
+    page = xb.EllpackPage.from_dense(xd, cuts, feature_is_cat=is_cat)
+    gb = categorical_global_bins(x, cuts.cut_ptrs, cuts.cut_values, is_cat)
+    assert np.array_equal(_global_bins(page, cuts.cut_ptrs), gb)
+    odd = x[:64].copy()
+    odd[:, 0] = np.array([0.0, 0.9, 1.2, 2.0, 2.7, 9.0, np.nan, 1.0] * 8, dtype=np.float32)
+    page2 = xb.EllpackPage.from_dense(torch.from_numpy(odd).cuda(), cuts, has_missing=True, feature_is_cat=is_cat)
+    want = np.array([0, 0, 1, 2, 2, 2, -1, 1] * 8)
+    assert np.array_equal(page2.symbols()[:, 0], want)
+    # an invalid category is an error, as in the reference
+    bad = xb.QuantileSketch(x.shape[1], case["max_bin"], torch.device("cuda", 0))
+    bad.set_feature_types(is_cat)
+    neg = x[:100].copy()
+    neg[3, 1] = -1.0
+    bad.push(torch.from_numpy(neg).cuda())
+    with pytest.raises(xb.B200HistError):
+        bad.make_cuts()
+    bad.close()

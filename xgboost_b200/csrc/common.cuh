@@ -128,6 +128,10 @@ struct b200hist_ellpack_s {
   bool is_sparse{false};
   uint32_t row_stride{0};  // entries per row (sparse layout)
   unsigned long long* d_row_sig{nullptr};  // presence signatures (sparse layout)
+  // categorical features (dense layout): ids of the categorical columns, re-binned by SearchCatBin after the
+  // numerical binning kernel has run (nullptr = none)
+  uint32_t* d_cat_features{nullptr};
+  uint32_t n_cat_features{0};
   b200::EllView View() const {
     return b200::EllView{d_bins, d_cut_ptrs, d_cut_values, n_rows, n_features, total_bins,
                          row_bytes, bin_bytes, null_symbol, d_bins_t, col_stride,

@@ -69,6 +69,39 @@ __global__ void __launch_bounds__(256) BinDenseKernel(const float* __restrict__ 
   }
 }
 
+// Categorical columns (HistogramCuts::SearchCatBin, src/common/hist_util.h:132-144): the bin of a category is its
+// position among the feature's cut values (= category codes), found by lower bound on the truncated value and
+// clamped to the last bin.  Runs after the numerical binning kernel and rewrites only the categorical columns'
+// symbols: one thread per (row, categorical column).
+template <typename BinT>
+__global__ void __launch_bounds__(256) RebinCategoricalKernel(const float* __restrict__ x, uint64_t n, uint64_t ld,
+                                                               const uint32_t* __restrict__ cat_features,
+                                                               uint32_t n_cat, const uint32_t* __restrict__ cut_ptrs,
+                                                               const float* __restrict__ cut_values,
+                                                               uint8_t* __restrict__ bins, uint64_t row_begin,
+                                                               uint32_t row_bytes, uint32_t null_symbol) {
+  const uint64_t total = n * n_cat;
+  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = idx / n_cat;
+    const uint32_t f = cat_features[idx - r * n_cat];
+    const float raw = x[r * ld + f];
+    uint32_t sym = null_symbol;
+    if (!isnan(raw)) {
+      const float v = (float)(int)raw;  // AsCat: truncation (categorical.h:25-31)
+      const uint32_t beg = cut_ptrs[f], end = cut_ptrs[f + 1];
+      uint32_t lo = beg, hi = end;  // first cut not less than v
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (cut_values[mid] < v) lo = mid + 1; else hi = mid;
+      }
+      if (lo == end) lo = end - 1;
+      sym = lo - beg;
+    }
+    reinterpret_cast<BinT*>(bins + (row_begin + r) * row_bytes)[f] = (BinT)sym;
+  }
+}
+
 // Faster binning for uint8 pages: a CTA owns a block of 32 features, stages their cut values in shared memory
 // (<= 32 KB at 256 bins) and walks the rows; the 8-step binary searches then run out of shared memory instead
 // of L2.  Thread = (row, 4-feature word); a warp reads 4 rows x 128 contiguous bytes of X.
@@ -442,6 +475,7 @@ int b200hist_ellpack_destroy(b200hist_ellpack_t e) {
     cudaFree(e->d_bins);
     cudaFree(e->d_bins_t);
     if (e->d_row_sig) cudaFree(e->d_row_sig);
+    if (e->d_cat_features) cudaFree(e->d_cat_features);
     delete e;
   }
   B200_API_END();
@@ -475,7 +509,41 @@ int b200hist_ellpack_push_dense(b200hist_ellpack_t e, uint64_t row_begin, const 
                                                    e->d_bins, row_begin, e->row_bytes, e->null_symbol);
   }
   B200_LAUNCHED();
+  if (e->d_cat_features != nullptr) {
+    const uint64_t cat_total = n * (uint64_t)e->n_cat_features;
+    const int cb = (int)std::min<uint64_t>((cat_total + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
+    if (e->bin_bytes == 1) {
+      RebinCategoricalKernel<uint8_t><<<cb, 256, 0, s>>>(x_dev, n, ld, e->d_cat_features, e->n_cat_features,
+                                                         e->d_cut_ptrs, e->d_cut_values, e->d_bins, row_begin,
+                                                         e->row_bytes, e->null_symbol);
+    } else {
+      RebinCategoricalKernel<uint16_t><<<cb, 256, 0, s>>>(x_dev, n, ld, e->d_cat_features, e->n_cat_features,
+                                                          e->d_cut_ptrs, e->d_cut_values, e->d_bins, row_begin,
+                                                          e->row_bytes, e->null_symbol);
+    }
+    B200_LAUNCHED();
+  }
   LaunchTranspose(e, row_begin, n, s);
+  B200_API_END();
+}
+
+int b200hist_ellpack_set_feature_types(b200hist_ellpack_t e, const uint8_t* feature_is_cat_host, uint32_t n) {
+  B200_API_BEGIN();
+  B200_CHECK(e != nullptr, "null argument");
+  B200_CHECK(!e->is_sparse, "feature types are supported on dense-layout pages only");
+  B200_CHECK(n <= e->n_features, "more feature types than features");
+  DeviceGuard guard(e->device);
+  if (e->d_cat_features) cudaFree(e->d_cat_features);
+  e->d_cat_features = nullptr;
+  e->n_cat_features = 0;
+  std::vector<uint32_t> ids;
+  for (uint32_t f = 0; feature_is_cat_host != nullptr && f < n; ++f)
+    if (feature_is_cat_host[f]) ids.push_back(f);
+  if (!ids.empty()) {
+    e->d_cat_features = DevAlloc<uint32_t>(ids.size());
+    B200_CUDA(cudaMemcpy(e->d_cat_features, ids.data(), sizeof(uint32_t) * ids.size(), cudaMemcpyHostToDevice));
+    e->n_cat_features = (uint32_t)ids.size();
+  }
   B200_API_END();
 }
 

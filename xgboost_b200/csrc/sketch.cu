@@ -511,6 +511,7 @@ struct b200hist_sketch_s {
   int device = 0;
   uint32_t n_features = 0;
   int32_t max_bin = 0;
+  std::vector<uint8_t> is_cat;  // feature types (empty = all numerical): a categorical column's cuts are its codes
   uint64_t rows_seen = 0;       // SketchContainer::rows_seen_
   uint64_t accumulated = 0;     // ExternalDataInfo::accumulated_rows
   uint64_t stride = 0;          // entries per column in res/m1/m2/sel
@@ -673,6 +674,20 @@ extern "C" int b200hist_sketch_push_dense(b200hist_sketch_t sk, const float* x_d
   B200_API_END();
 }
 
+extern "C" int b200hist_sketch_set_feature_types(b200hist_sketch_t sk, const uint8_t* feature_is_cat_host, uint32_t n) {
+  B200_API_BEGIN();
+  B200_CHECK(sk != nullptr, "null argument");
+  B200_CHECK(n <= sk->n_features, "more feature types than features");
+  sk->is_cat.clear();
+  bool any = false;
+  for (uint32_t f = 0; feature_is_cat_host != nullptr && f < n; ++f) any = any || feature_is_cat_host[f] != 0;
+  if (any) {
+    sk->is_cat.assign(sk->n_features, 0);
+    for (uint32_t f = 0; f < n; ++f) sk->is_cat[f] = feature_is_cat_host[f] != 0 ? 1 : 0;
+  }
+  B200_API_END();
+}
+
 extern "C" int b200hist_sketch_make_cuts(b200hist_sketch_t sk, uint32_t* cut_ptrs_out_host, float* cut_values_out_host,
                                          uint64_t cut_values_capacity, uint32_t* fix_error_changes_out, void* stream) {
   B200_API_BEGIN();
@@ -697,7 +712,19 @@ extern "C" int b200hist_sketch_make_cuts(b200hist_sketch_t sk, uint32_t* cut_ptr
   for (uint32_t f = 0; f < F; ++f) {
     B200_CHECK(h_len[f] <= width, "internal: column longer than its bound");
     cuts.clear();
-    QueryCutValues(h_entries.data() + (size_t)f * width, h_len[f], (size_t)sk->max_bin, &cuts);
+    if (!sk->is_cat.empty() && sk->is_cat[f]) {
+      // categorical column (quantile.cu:684-696): cut values = every code 0 .. max category.  The column's largest
+      // value is the last entry of its summary whatever was pruned (a summary always keeps its extremes); the
+      // reference keeps categorical columns unpruned, which changes nothing here.
+      const SummaryEntry* col = h_entries.data() + (size_t)f * width;
+      for (uint32_t i = 0; i < h_len[f]; ++i)
+        B200_CHECK(col[i].value >= 0.0f && col[i].value < 16777216.0f,  // InvalidCat (categorical.h:33-36)
+                   "invalid category: negative or not representable as an integer in float32");
+      const float feature_max = h_len[f] == 0 ? 0.0f : col[h_len[f] - 1].value;
+      for (size_t c = 0; c <= static_cast<size_t>(feature_max); ++c) cuts.push_back(static_cast<float>(c));
+    } else {
+      QueryCutValues(h_entries.data() + (size_t)f * width, h_len[f], (size_t)sk->max_bin, &cuts);
+    }
     B200_CHECK(total + cuts.size() <= cut_values_capacity, "cut_values buffer too small");
     std::memcpy(cut_values_out_host + total, cuts.data(), sizeof(float) * cuts.size());
     total += cuts.size();

@@ -86,6 +86,7 @@ _SIGNATURES = {
     "b200hist_smem_atomic_peak": (c_int, [c_int, c_int, POINTER(c_double), c_void_p]),
     "b200hist_sketch_create": (c_int, [c_int, c_uint32, c_int32, POINTER(c_void_p)]),
     "b200hist_sketch_push_dense": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p]),
+    "b200hist_sketch_set_feature_types": (c_int, [c_void_p, c_void_p, c_uint32]),
     "b200hist_sketch_make_cuts": (c_int, [c_void_p, POINTER(c_uint32), POINTER(c_float), c_uint64, POINTER(c_uint32),
                                           c_void_p]),
     "b200hist_sketch_destroy": (c_int, [c_void_p]),
@@ -93,6 +94,7 @@ _SIGNATURES = {
                                                POINTER(c_void_p)]),
     "b200hist_ellpack_push_csr": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "b200hist_ellpack_destroy": (c_int, [c_void_p]),
+    "b200hist_ellpack_set_feature_types": (c_int, [c_void_p, c_void_p, c_uint32]),
     "b200hist_ellpack_push_dense": (c_int, [c_void_p, c_uint64, c_void_p, c_uint64, c_uint64, c_void_p]),
     "b200hist_ellpack_import_reference": (c_int, [c_void_p, c_void_p, c_uint32, c_uint32, c_int, c_void_p]),
     "b200hist_ellpack_import_reference_rows": (c_int, [c_void_p, c_uint64, c_uint64, c_void_p, c_uint32, c_uint32, c_int,

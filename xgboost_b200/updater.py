@@ -100,6 +100,15 @@ class QuantileSketch:
         self.fix_error_changes = 0
         _l.check(_l.load().b200hist_sketch_create(self.device.index or 0, self.n_features, self.max_bin, byref(self._h)))
 
+    def set_feature_types(self, feature_is_cat: Optional[Sequence[int]]) -> None:
+        """Categorical columns (non-zero flag) get the cut values 0 .. largest code instead of quantiles."""
+        self._has_cat = bool(feature_is_cat is not None and any(feature_is_cat))
+        if not self._has_cat:
+            _l.check(_l.load().b200hist_sketch_set_feature_types(self._h, None, 0))
+            return
+        flags = np.ascontiguousarray([1 if v else 0 for v in feature_is_cat], dtype=np.uint8)
+        _l.check(_l.load().b200hist_sketch_set_feature_types(self._h, c_void_p(flags.ctypes.data), flags.size))
+
     def push(self, x: torch.Tensor) -> None:
         _require_cuda(x, "x")
         if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != self.n_features or \
@@ -111,7 +120,9 @@ class QuantileSketch:
 
     def make_cuts(self) -> "HistogramCuts":
         ptrs = np.zeros(self.n_features + 1, dtype=np.uint32)
-        vals = np.zeros(self.n_features * self.max_bin, dtype=np.float32)
+        # a categorical column may hold more categories than max_bin
+        vals = np.zeros(self.n_features * self.max_bin + (self.n_features * 1024 if getattr(self, "_has_cat", False) else 0),
+                        dtype=np.float32)
         fixes = c_uint32(0)
         _l.check(_l.load().b200hist_sketch_make_cuts(self._h, ptrs.ctypes.data_as(POINTER(c_uint32)),
                                                    vals.ctypes.data_as(POINTER(c_float)), vals.size, byref(fixes),
@@ -179,6 +190,15 @@ class EllpackPage:
     def handle(self) -> c_void_p:
         return self._h
 
+    def set_feature_types(self, feature_is_cat: Optional[Sequence[int]]) -> None:
+        """Categorical columns (non-zero flag) of later push_dense calls are binned by SearchCatBin: a category's
+        bin is its position among the feature's category codes.  Dense-layout pages; call before push_dense."""
+        if feature_is_cat is None or not any(feature_is_cat):
+            _l.check(_l.load().b200hist_ellpack_set_feature_types(self._h, None, 0))
+            return
+        flags = np.ascontiguousarray([1 if v else 0 for v in feature_is_cat], dtype=np.uint8)
+        _l.check(_l.load().b200hist_ellpack_set_feature_types(self._h, c_void_p(flags.ctypes.data), flags.size))
+
     def push_dense(self, x: torch.Tensor, row_begin: int) -> None:
         """Bin a dense float32 CUDA batch into rows [row_begin, row_begin + len(x))."""
         _require_cuda(x, "x")
@@ -190,11 +210,14 @@ class EllpackPage:
                                                      x.shape[0], x.stride(0), _stream_ptr(x.device)))
 
     @classmethod
-    def from_dense(cls, x: torch.Tensor, cuts: HistogramCuts, has_missing: Optional[bool] = None) -> "EllpackPage":
+    def from_dense(cls, x: torch.Tensor, cuts: HistogramCuts, has_missing: Optional[bool] = None,
+                   feature_is_cat: Optional[Sequence[int]] = None) -> "EllpackPage":
         _require_cuda(x, "x")
         if has_missing is None:
             has_missing = bool(torch.isnan(x).any().item())
         page = cls(cuts, x.shape[0], x.device.index or 0, has_missing)
+        if feature_is_cat is not None:
+            page.set_feature_types(feature_is_cat)
         page.push_dense(x.contiguous(), 0)
         return page
 
