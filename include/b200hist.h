@@ -87,6 +87,7 @@ typedef struct b200hist_tree_node {
 typedef struct b200hist_ellpack_s* b200hist_ellpack_t;  /* quantised feature matrix (EllpackPage) */
 typedef struct b200hist_updater_s* b200hist_updater_t;  /* tree updater (GPUHistMaker) */
 typedef struct b200hist_comm_s* b200hist_comm_t;        /* NCCL communicator of the histogram allreduce */
+typedef struct b200hist_forest_s* b200hist_forest_t;    /* trees resolved against a page's cuts, for prediction */
 
 /* ---------------------------------------------------------------------------------------------
  * Errors / info
@@ -419,6 +420,32 @@ B200HIST_API int b200hist_partition(b200hist_ellpack_t ell, const uint32_t* ridx
                                     const uint64_t* seg_count_host, const int32_t* findex_host,
                                     const float* split_cond_host, const int32_t* default_left_host,
                                     int32_t n_nodes, uint64_t* left_count_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Prediction on the quantised matrix
+ *   replaces GPUPredictor's PredictKernel / PredictBatch over Ellpack pages
+ *   (src/predictor/gpu_predictor.cu:180-230,316-351; EllpackLoader, ellpack_page.cuh:147-170) for trees grown on the
+ *   page's cuts: a split condition then IS a cut value and a row is routed by its bin alone.
+ * forest_create borrows `ell` for its cuts (keep it alive); add_tree takes a tree as update_tree returned it, with the
+ * categorical flags / LBitField32 sets of b200hist_updater_last_tree_categories (NULL, NULL, 0 without categorical
+ * splits).  predict_margin: for rows [row_begin, row_begin + n_rows) of `page` (any page quantised with the same
+ * cuts, e.g. a validation set), out_dev[k] += sum over trees [tree_begin, tree_end) of the leaf the row reaches, the
+ * sum taken in tree order from 0.0f like the reference (gpu_predictor.cu:221-228).  predict_leaf: out_dev[k *
+ * n_trees + t] = the leaf's node id inside tree t (:196-201).
+ * STATUS: compiled, never run on hardware; the oracle (orc_predict_leaf) reproduces the reference CPU predictor's
+ * margins bit for bit (tests/test_reference_golden.py); GPU tests in tests/test_gpu_next.py, gated. */
+B200HIST_API int b200hist_forest_create(b200hist_ellpack_t ell, b200hist_forest_t* out);
+B200HIST_API int b200hist_forest_destroy(b200hist_forest_t forest);
+B200HIST_API int b200hist_forest_num_trees(b200hist_forest_t forest, uint32_t* out);
+B200HIST_API int b200hist_forest_add_tree(b200hist_forest_t forest, const b200hist_tree_node* nodes_host,
+                                          int32_t n_nodes, const int32_t* node_is_cat_host,
+                                          const uint32_t* cat_bits_host, uint32_t cat_words);
+B200HIST_API int b200hist_forest_predict_margin(b200hist_forest_t forest, b200hist_ellpack_t page,
+                                                uint32_t tree_begin, uint32_t tree_end, uint64_t row_begin,
+                                                uint64_t n_rows, float* out_dev, void* stream);
+B200HIST_API int b200hist_forest_predict_leaf(b200hist_forest_t forest, b200hist_ellpack_t page, uint32_t tree_begin,
+                                              uint32_t tree_end, uint64_t row_begin, uint64_t n_rows,
+                                              int32_t* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -322,6 +322,45 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
     return res
 
 
+def predict_leaf(gbins, cut_ptrs, cut_values, nodes, is_cat=None, cat_sets=None, is_dense_layout=True) -> np.ndarray:
+    """Leaf every row reaches in ONE tree (nodes: list of Node, or anything with the same fields).  cat_sets: per
+    node, the set of categories that go right (for nodes flagged in is_cat)."""
+    gb = np.ascontiguousarray(gbins, dtype=np.int32)
+    cp = np.ascontiguousarray(cut_ptrs, dtype=np.uint32)
+    cv = np.ascontiguousarray(cut_values, dtype=np.float32)
+    arr = (Node * len(nodes))(*nodes)
+    out = np.empty(gb.shape[0], dtype=np.int32)
+    flags = bits = None
+    n_words = 1
+    if is_cat is not None and any(is_cat):
+        n_words = int(cv.max()) // 32 + 1
+        flags = np.ascontiguousarray(is_cat, dtype=np.int32)
+        bits = np.zeros((len(nodes), n_words), dtype=np.uint32)
+        for i, cs in enumerate(cat_sets):
+            for c in cs:
+                bits[i, c // 32] |= np.uint32(1 << (31 - c % 32))
+    lib().orc_predict_leaf(_p(gb), c_uint64(gb.shape[0]), c_uint32(gb.shape[1]), c_int(1 if is_dense_layout else 0),
+                           _p(cp), _p(cv), arr, _p(flags) if flags is not None else c_void_p(),
+                           _p(bits) if bits is not None else c_void_p(), c_uint32(n_words), _p(out))
+    return out
+
+
+def predict_margin(gbins, cut_ptrs, cut_values, trees, base=None, is_dense_layout=True) -> np.ndarray:
+    """GPUPredictor::PredictBatch on binned data (gpu_predictor.cu:221-228): per row, float sum = 0; sum += leaf of
+    every tree in order; out += sum.  trees: list of dict(nodes=[Node...], is_cat=..., cat_sets=...) as returned by
+    update_tree, or plain node lists."""
+    n = np.asarray(gbins).shape[0]
+    total = np.zeros(n, dtype=np.float32)
+    for t in trees:
+        nodes = t["nodes"] if isinstance(t, dict) else t
+        leaf = predict_leaf(gbins, cut_ptrs, cut_values, nodes, t.get("is_cat") if isinstance(t, dict) else None,
+                            t.get("cat_sets") if isinstance(t, dict) else None, is_dense_layout)
+        values = np.array([nd.leaf_value for nd in nodes], dtype=np.float32)
+        total = (total + values[leaf]).astype(np.float32)
+    out = np.zeros(n, dtype=np.float32) if base is None else np.asarray(base, dtype=np.float32).copy()
+    return (out + total).astype(np.float32)
+
+
 def update_prediction_cache(nodes, position: np.ndarray, preds: np.ndarray) -> np.ndarray:
     arr = (Node * len(nodes))(*nodes)
     p = np.ascontiguousarray(preds, dtype=np.float32).copy()

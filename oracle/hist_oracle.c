@@ -1204,6 +1204,30 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
   return n_nodes;
 }
 
+/* R4  Prediction on the quantised matrix: GPUPredictor's kernel over an EllpackPage
+ * (src/predictor/gpu_predictor.cu:180-230 PredictKernel with EllpackLoader, :316-351 PredictBatch): every row walks
+ * every tree from the root -- missing -> default child, categorical split -> common::Decision on the bin's category,
+ * else fvalue < split_cond, which on binned data is cut_values[bin] <= split_cond for a split at a cut -- and the
+ * leaf values of trees [0, n) are summed IN TREE ORDER into a float that starts at 0 and is then added to the output
+ * (:221-228).  This function does one tree: out_leaf[r] = leaf the row reaches (cat arguments may be NULL). */
+ORC_API void orc_predict_leaf(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
+                              const uint32_t* cut_ptrs, const float* cut_values, const orc_node* nodes,
+                              const int32_t* node_is_cat, const uint32_t* node_cat_bits, uint32_t n_cat_words,
+                              int32_t* out_leaf) {
+  for (uint64_t r = 0; r < n_rows; ++r) {
+    int32_t nidx = 0;
+    while (!nodes[nidx].is_leaf) {
+      int gl = (node_is_cat && node_is_cat[nidx])
+                   ? go_left_cat(gbins, stride, is_dense_layout, cut_ptrs, cut_values, r, nodes[nidx].findex,
+                                 node_cat_bits + (size_t)nidx * n_cat_words, n_cat_words, nodes[nidx].default_left)
+                   : go_left(gbins, stride, is_dense_layout, cut_ptrs, cut_values, r, nodes[nidx].findex,
+                             nodes[nidx].fvalue, nodes[nidx].default_left);
+      nidx = gl ? nodes[nidx].left : nodes[nidx].right;
+    }
+    out_leaf[r] = nidx;
+  }
+}
+
 /* A3  UpdatePredictionCache (updater_gpu_hist.cu:582-608): pred[i] += leaf_value[decode(pos[i])] */
 ORC_API void orc_update_prediction_cache(const orc_node* nodes, const int32_t* position, uint64_t n, float* preds) {
   for (uint64_t i = 0; i < n; ++i) {

@@ -572,3 +572,83 @@ def test_categorical_cuts_and_binning(xb):
     with pytest.raises(xb.B200HistError):
         bad.make_cuts()
     bad.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Prediction on quantised pages (b200hist_forest_*, csrc/predict.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("missing,max_bin", [(0.0, 64), (0.1, 256), (0.05, 600)], ids=["dense", "missing_u16", "wide_bins"])
+def test_forest_prediction_matches_oracle(xb, missing, max_bin):
+    """Train a few trees, then predict the training page and a VALIDATION page quantised with the same cuts: margins
+    bit for bit (tree-order float sum from 0, then added to the output) and leaf ids, against the oracle's walk."""
+    import torch
+    n, f = 20000, 20
+    x, y = make_regression(n, f, seed=95, missing=missing)
+    xv, _ = make_regression(7000, f, seed=96, missing=missing)
+    cp, cv = make_cuts(x, max_bin)
+    page = _page(xb, x, cp, cv, has_missing=missing > 0)
+    vpage = _page(xb, xv, cp, cv, has_missing=missing > 0)
+    gb, gbv = orc.bin_dense(x, cp, cv), orc.bin_dense(xv, cp, cv)
+    params = dict(max_depth=6, eta=0.3)
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    forest = xb.Forest(page)
+    pred = np.zeros(n, dtype=np.float32)
+    trees = []
+    for it in range(6):
+        gp = squared_error_gpair(pred, y)
+        tree = up.update(torch.from_numpy(gp).cuda())
+        forest.add_tree(tree)
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params))
+        trees.append(o["nodes"])
+        pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+    assert forest.num_trees == 6
+    for pg, bins, rows in ((page, gb, n), (vpage, gbv, 7000)):
+        base = np.full(rows, 0.5, dtype=np.float32)
+        out = forest.predict_margin(pg, torch.from_numpy(base.copy()).cuda())
+        want = orc.predict_margin(bins, cp, cv, trees, base=base)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+        leaves = forest.predict_leaf(pg).cpu().numpy()
+        for t, nodes in enumerate(trees):
+            assert np.array_equal(leaves[:, t], orc.predict_leaf(bins, cp, cv, nodes))
+        # a tree range and a row range
+        part = forest.predict_margin(pg, torch.zeros(1000, device="cuda"), tree_begin=2, tree_end=5, row_begin=123)
+        want_part = orc.predict_margin(bins[123:1123], cp, cv, trees[2:5])
+        assert np.array_equal(part.cpu().numpy().view(np.uint32), want_part.view(np.uint32))
+    # a page with other cuts is refused
+    cp2, cv2 = make_cuts(xv, max_bin)
+    other = _page(xb, xv, cp2, cv2, has_missing=missing > 0)
+    with pytest.raises(xb.B200HistError):
+        forest.predict_margin(other, torch.zeros(7000, device="cuda"))
+
+
+def test_forest_prediction_with_categorical_splits(xb):
+    import torch
+    from tests.test_reference_golden import categorical_global_bins
+    from tools.make_golden_cpu_categorical import make_data
+    case = json.load(open(os.path.join(GOLDEN, "ref_cpu_categorical_trees.json")))["cases"][0]
+    x, y, types = make_data(case)
+    is_cat = [1 if t == "c" else 0 for t in types]
+    cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+    cv = np.array(case["cut_values_bits"], dtype=np.uint32).view(np.float32)
+    gb = categorical_global_bins(x, cp, cv, is_cat)
+    page = _cat_page(xb, x, cp, cv, is_cat)
+    up = xb.GPUHistMaker(page)
+    up.configure(dict(case["params"]))
+    up.set_categorical(is_cat, case["max_cat_to_onehot"], case["max_cat_threshold"])
+    forest = xb.Forest(page)
+    pred = np.zeros(case["n"], dtype=np.float32)
+    trees = []
+    for it in range(3):
+        gp = squared_error_gpair(pred, y)
+        tree = up.update(torch.from_numpy(gp).cuda())
+        flags, sets = up.last_tree_categories(tree.num_nodes)
+        forest.add_tree(tree, flags, sets)
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**case["params"]), feature_is_cat=is_cat,
+                            max_cat_to_onehot=case["max_cat_to_onehot"], max_cat_threshold=case["max_cat_threshold"])
+        trees.append(o)
+        pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+    out = forest.predict_margin(page, torch.zeros(case["n"], device="cuda"))
+    want = orc.predict_margin(gb, cp, cv, trees)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(want.view(np.uint32), pred.view(np.uint32)) or np.allclose(want, pred, rtol=1e-5, atol=1e-6)

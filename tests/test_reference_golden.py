@@ -310,3 +310,39 @@ def test_oracle_categorical_trees_match_cpu_reference(case):
         if np.isnan(x[rows, nd.findex]).any():   # otherwise both directions tie
             assert int(nd.default_left) == ref["default_left"][i], i
     assert n_cat >= 5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Prediction on quantised data: the oracle's walk + summation order against the reference's own
+# CPU predictor, run live on oracle/_ref when it is there (build container); the GPU parity test of the CUDA kernel
+# compares with this oracle.
+# ---------------------------------------------------------------------------------------------------------------------
+def test_oracle_predictor_reproduces_reference_cpu_margins():
+    from oracle import ref_capi as rc
+    if not rc.available("cpu"):
+        pytest.skip("needs oracle/_ref/libxgboost.so (built where /root/reference exists)")
+    x, y = make_regression(20000, 12, seed=88, missing=0.05)
+    dm = rc.DMatrix.from_dense(x, label=y, kind="cpu")
+    bst = rc.Booster({"tree_method": "hist", "device": "cpu", "max_bin": 64, "base_score": 0.0,
+                      "objective": "reg:squarederror", "max_depth": 6, "eta": 0.3}, dm)
+    for i in range(8):
+        bst.update(i)
+    cp, cv = dm.histogram_cuts()
+    gb = orc.bin_dense(x, cp, cv)
+    forest = []
+    for t in rc.trees_from_model(bst.save_json()):
+        nodes = []
+        for i in range(len(t["left"])):
+            leaf = t["left"][i] == -1
+            nodes.append(orc.Node(t["parent"][i], t["left"][i], t["right"][i], -1 if leaf else t["findex"][i],
+                                  t["cond"][i], t["default_left"][i], 1 if leaf else 0, t["cond"][i] if leaf else 0.0,
+                                  0, 0, 0, 0))
+        forest.append(nodes)
+    ours = orc.predict_margin(gb, cp, cv, forest)
+    ref = bst.predict_margin(dm)
+    assert np.array_equal(ours.view(np.uint32), ref.view(np.uint32))
+    # the summation order is part of the result: per-tree accumulation into the output differs in the last bits
+    naive = np.zeros(len(y), dtype=np.float32)
+    for nodes in forest:
+        naive = orc.predict_margin(gb, cp, cv, [nodes], base=naive)
+    assert np.allclose(naive, ref, rtol=1e-5, atol=1e-6)

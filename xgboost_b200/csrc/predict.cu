@@ -1,0 +1,292 @@
+// Prediction on the quantised matrix: the step that follows the updater in every boosting
+// iteration whenever the prediction cache misses (validation sets, a fresh DMatrix bound to the training cuts).
+//
+// Replaces (reference paths relative to /root/reference):
+//   PredictKernel with EllpackLoader, PredictBatch over Ellpack pages    src/predictor/gpu_predictor.cu:180-230,316-351
+//   EllpackDeviceAccessor::GetFvalue (bin -> representative value)       src/data/ellpack_page.cuh:147-170
+//   common::Decision (categorical routing)                               src/common/categorical.h:49-60
+//
+// The reference turns a row's bin back into a feature value and compares it with the split condition.  A split
+// condition of a tree grown on these cuts IS a cut value, so the comparison is decided by the bin alone: the forest
+// is resolved against the page's cuts once, when a tree is added (split_lbin = number of the feature's cuts <= the
+// condition, as in the updater's ApplySplit), and the kernel compares small integers.  Categorical splits carry the
+// set of the feature's local bins that go right.  A row sums the leaves of trees [begin, end) in tree order into a
+// float that starts at 0 and is then added to the output (gpu_predictor.cu:221-228) -- the order is part of the
+// result.
+//
+// One thread per row, grid-strided; a row's symbols are one contiguous run of the row-major page (<= 512 B at the
+// headline width), so after the first tree they are L1/L2 hits; the forest (24 B per node) is read through the
+// read-only path.  HBM-bound on the first touch of each row: row_bytes per row + 4 B output.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+struct PredNode {
+  int32_t findex;       // -1: leaf
+  int32_t split_lbin;   // go left iff local bin < split_lbin; -1: categorical (bin set)
+  int32_t left, right;  // absolute indices into the forest's node array
+  float leaf_value;
+  int32_t default_left;
+};
+
+struct ForestView {
+  const PredNode* nodes;
+  const uint32_t* tree_root;  // [n_trees] index of every tree's root
+  const uint32_t* bin_bits;   // [n_nodes][bin_words] (categorical nodes only meaningful), may be null
+  int32_t bin_words;
+};
+
+template <typename BinT>
+__device__ __forceinline__ float WalkTree(const EllView& ell, const ForestView& fv, uint32_t root, uint64_t r) {
+  uint32_t i = root;
+  PredNode nd = fv.nodes[i];
+  while (nd.findex >= 0) {
+    int32_t lbin;
+    if (ell.is_sparse) {
+      const uint32_t fb = ell.cut_ptrs[nd.findex], fe = ell.cut_ptrs[nd.findex + 1];
+      const uint32_t gb = SparseRowBin(ell, (uint32_t)r, fb, fe, (uint32_t)nd.findex);
+      lbin = gb == 0xFFFFFFFFu ? -1 : (int32_t)(gb - fb);
+    } else {
+      const uint32_t sym = (uint32_t)__ldg(reinterpret_cast<const BinT*>(ell.bins + r * ell.row_bytes) + nd.findex);
+      lbin = sym == ell.null_symbol ? -1 : (int32_t)sym;
+    }
+    bool left;
+    if (lbin < 0) {
+      left = nd.default_left != 0;
+    } else if (nd.split_lbin < 0) {  // categorical: a bin in the set goes right
+      left = ((__ldg(fv.bin_bits + (size_t)i * fv.bin_words + (lbin >> 5)) >> (lbin & 31)) & 1u) == 0u;
+    } else {
+      left = lbin < nd.split_lbin;
+    }
+    i = (uint32_t)(left ? nd.left : nd.right);
+    nd = fv.nodes[i];
+  }
+  return nd.leaf_value;
+}
+
+template <typename BinT>
+__global__ void __launch_bounds__(256) PredictMarginKernel(EllView ell, ForestView fv, uint32_t tree_begin,
+                                                            uint32_t tree_end, uint64_t row_begin, uint64_t n_rows,
+                                                            float* __restrict__ out) {
+  for (uint64_t k = blockIdx.x * 256ull + threadIdx.x; k < n_rows; k += (uint64_t)gridDim.x * 256ull) {
+    const uint64_t r = row_begin + k;
+    float sum = 0.0f;
+    for (uint32_t t = tree_begin; t < tree_end; ++t) sum += WalkTree<BinT>(ell, fv, fv.tree_root[t], r);
+    out[k] += sum;
+  }
+}
+
+// PredictLeaf (gpu_predictor.cu:196-201): out[row * n_trees + t] = id of the leaf inside tree t
+template <typename BinT>
+__global__ void __launch_bounds__(256) PredictLeafKernel(EllView ell, ForestView fv, uint32_t tree_begin,
+                                                          uint32_t tree_end, uint64_t row_begin, uint64_t n_rows,
+                                                          int32_t* __restrict__ out) {
+  const uint32_t nt = tree_end - tree_begin;
+  for (uint64_t k = blockIdx.x * 256ull + threadIdx.x; k < n_rows * nt; k += (uint64_t)gridDim.x * 256ull) {
+    const uint64_t row = k / nt;
+    const uint32_t t = tree_begin + (uint32_t)(k - row * nt);
+    const uint64_t r = row_begin + row;
+    uint32_t i = fv.tree_root[t];
+    PredNode nd = fv.nodes[i];
+    while (nd.findex >= 0) {
+      int32_t lbin;
+      if (ell.is_sparse) {
+        const uint32_t fb = ell.cut_ptrs[nd.findex], fe = ell.cut_ptrs[nd.findex + 1];
+        const uint32_t gb = SparseRowBin(ell, (uint32_t)r, fb, fe, (uint32_t)nd.findex);
+        lbin = gb == 0xFFFFFFFFu ? -1 : (int32_t)(gb - fb);
+      } else {
+        const uint32_t sym = (uint32_t)__ldg(reinterpret_cast<const BinT*>(ell.bins + r * ell.row_bytes) + nd.findex);
+        lbin = sym == ell.null_symbol ? -1 : (int32_t)sym;
+      }
+      bool left;
+      if (lbin < 0) left = nd.default_left != 0;
+      else if (nd.split_lbin < 0)
+        left = ((__ldg(fv.bin_bits + (size_t)i * fv.bin_words + (lbin >> 5)) >> (lbin & 31)) & 1u) == 0u;
+      else left = lbin < nd.split_lbin;
+      i = (uint32_t)(left ? nd.left : nd.right);
+      nd = fv.nodes[i];
+    }
+    out[k] = (int32_t)(i - fv.tree_root[t]);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200hist_forest_s {
+  b200hist_ellpack_t ell{nullptr};  // the cuts the split conditions are resolved against (borrowed)
+  int device{0};
+  std::vector<PredNode> nodes;
+  std::vector<uint32_t> roots;
+  std::vector<uint32_t> bin_bits;  // [nodes][bin_words]
+  int32_t bin_words{0};
+  // device copy, refreshed lazily
+  PredNode* d_nodes{nullptr};
+  uint32_t* d_roots{nullptr};
+  uint32_t* d_bin_bits{nullptr};
+  bool dirty{true};
+};
+
+extern "C" {
+
+int b200hist_forest_create(b200hist_ellpack_t ell, b200hist_forest_t* out) {
+  B200_API_BEGIN();
+  B200_CHECK(ell != nullptr && out != nullptr, "null argument");
+  auto* f = new b200hist_forest_s();
+  f->ell = ell;
+  f->device = ell->device;
+  f->bin_words = (int32_t)((ell->max_feature_bins + 31) / 32);
+  if (f->bin_words < 1) f->bin_words = 1;
+  *out = f;
+  B200_API_END();
+}
+
+int b200hist_forest_destroy(b200hist_forest_t f) {
+  B200_API_BEGIN();
+  if (f) {
+    DeviceGuard guard(f->device);
+    cudaFree(f->d_nodes);
+    cudaFree(f->d_roots);
+    cudaFree(f->d_bin_bits);
+    delete f;
+  }
+  B200_API_END();
+}
+
+int b200hist_forest_num_trees(b200hist_forest_t f, uint32_t* out) {
+  B200_API_BEGIN();
+  B200_CHECK(f != nullptr && out != nullptr, "null argument");
+  *out = (uint32_t)f->roots.size();
+  B200_API_END();
+}
+
+int b200hist_forest_add_tree(b200hist_forest_t f, const b200hist_tree_node* nodes_host, int32_t n_nodes,
+                             const int32_t* node_is_cat_host, const uint32_t* cat_bits_host, uint32_t cat_words) {
+  B200_API_BEGIN();
+  B200_CHECK(f != nullptr && nodes_host != nullptr && n_nodes >= 1, "null argument");
+  const auto* ell = f->ell;
+  const uint32_t base = (uint32_t)f->nodes.size();
+  std::vector<PredNode> add((size_t)n_nodes);
+  std::vector<uint32_t> bits((size_t)n_nodes * f->bin_words, 0u);
+  for (int32_t i = 0; i < n_nodes; ++i) {
+    const b200hist_tree_node& s = nodes_host[i];
+    PredNode d{};
+    d.leaf_value = s.leaf_value;
+    d.default_left = s.default_left;
+    if (s.is_leaf) {
+      d.findex = -1; d.split_lbin = 0; d.left = d.right = (int32_t)(base + i);
+    } else {
+      B200_CHECK(s.findex >= 0 && (uint32_t)s.findex < ell->n_features, "split feature out of range");
+      B200_CHECK(s.left > i && s.left < n_nodes && s.right > i && s.right < n_nodes, "child index out of range");
+      d.findex = s.findex;
+      d.left = (int32_t)(base + s.left);
+      d.right = (int32_t)(base + s.right);
+      const uint32_t beg = ell->cut_ptrs[s.findex], end = ell->cut_ptrs[s.findex + 1];
+      if (node_is_cat_host != nullptr && node_is_cat_host[i]) {
+        B200_CHECK(cat_bits_host != nullptr && cat_words >= 1, "categorical node without a category set");
+        d.split_lbin = -1;
+        for (uint32_t b = beg; b < end; ++b) {  // the feature's bins whose category is in the set
+          const float cv = ell->cut_values[b];
+          if (!(cv >= 0.0f)) continue;
+          const uint32_t c = (uint32_t)cv;
+          if (c / 32 < cat_words && ((cat_bits_host[(size_t)i * cat_words + c / 32] >> (31 - c % 32)) & 1u))
+            bits[(size_t)i * f->bin_words + ((b - beg) >> 5)] |= 1u << ((b - beg) & 31);
+        }
+      } else {
+        B200_CHECK(!std::isnan(s.fvalue), "numerical split with a NaN condition");
+        // go left iff cut_values[bin] <= fvalue  <=>  local bin < number of the feature's cuts <= fvalue
+        const float* lo = ell->cut_values.data() + beg;
+        const float* hi = ell->cut_values.data() + end;
+        d.split_lbin = (int32_t)(std::upper_bound(lo, hi, s.fvalue) - lo);
+      }
+    }
+    add[i] = d;
+  }
+  f->roots.push_back(base);
+  f->nodes.insert(f->nodes.end(), add.begin(), add.end());
+  f->bin_bits.insert(f->bin_bits.end(), bits.begin(), bits.end());
+  f->dirty = true;
+  B200_API_END();
+}
+
+static void SyncForest(b200hist_forest_s* f, cudaStream_t s) {
+  if (!f->dirty) return;
+  cudaFree(f->d_nodes);
+  cudaFree(f->d_roots);
+  cudaFree(f->d_bin_bits);
+  f->d_nodes = DevAlloc<PredNode>(std::max<size_t>(f->nodes.size(), 1));
+  f->d_roots = DevAlloc<uint32_t>(std::max<size_t>(f->roots.size(), 1));
+  f->d_bin_bits = DevAlloc<uint32_t>(std::max<size_t>(f->bin_bits.size(), 1));
+  B200_CUDA(cudaMemcpyAsync(f->d_nodes, f->nodes.data(), sizeof(PredNode) * f->nodes.size(), cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(f->d_roots, f->roots.data(), sizeof(uint32_t) * f->roots.size(), cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(f->d_bin_bits, f->bin_bits.data(), sizeof(uint32_t) * f->bin_bits.size(),
+                            cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaStreamSynchronize(s));  // the host vectors may grow again right after this call
+  f->dirty = false;
+}
+
+static void CheckPage(const b200hist_forest_s* f, const b200hist_ellpack_s* page) {
+  B200_CHECK(page->device == f->device, "the page lives on another device than the forest");
+  B200_CHECK(page->n_features == f->ell->n_features && page->cut_ptrs == f->ell->cut_ptrs &&
+                 page->cut_values == f->ell->cut_values,
+             "the page must be quantised with the cuts the forest was resolved against");
+}
+
+int b200hist_forest_predict_margin(b200hist_forest_t f, b200hist_ellpack_t page, uint32_t tree_begin,
+                                   uint32_t tree_end, uint64_t row_begin, uint64_t n_rows, float* out_dev,
+                                   void* stream) {
+  B200_API_BEGIN();
+  B200_CHECK(f != nullptr && page != nullptr && (out_dev != nullptr || n_rows == 0), "null argument");
+  B200_CHECK(tree_begin <= tree_end && tree_end <= f->roots.size(), "tree range out of bounds");
+  B200_CHECK(row_begin + n_rows <= page->n_rows, "row range exceeds the page");
+  CheckPage(f, page);
+  if (n_rows == 0 || tree_begin == tree_end) return 0;
+  DeviceGuard guard(f->device);
+  auto s = static_cast<cudaStream_t>(stream);
+  SyncForest(f, s);
+  const ForestView fv{f->d_nodes, f->d_roots, f->d_bin_bits, f->bin_words};
+  const EllView view = page->View();
+  const int blocks = (int)std::min<uint64_t>((n_rows + 255) / 256, (uint64_t)NumSMs(f->device) * 16);
+  if (page->is_sparse) {
+    PredictMarginKernel<uint32_t><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, row_begin, n_rows, out_dev);
+  } else if (page->bin_bytes == 1) {
+    PredictMarginKernel<uint8_t><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, row_begin, n_rows, out_dev);
+  } else {
+    PredictMarginKernel<uint16_t><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, row_begin, n_rows, out_dev);
+  }
+  B200_LAUNCHED();
+  B200_API_END();
+}
+
+int b200hist_forest_predict_leaf(b200hist_forest_t f, b200hist_ellpack_t page, uint32_t tree_begin, uint32_t tree_end,
+                                 uint64_t row_begin, uint64_t n_rows, int32_t* out_dev, void* stream) {
+  B200_API_BEGIN();
+  B200_CHECK(f != nullptr && page != nullptr && (out_dev != nullptr || n_rows == 0), "null argument");
+  B200_CHECK(tree_begin <= tree_end && tree_end <= f->roots.size(), "tree range out of bounds");
+  B200_CHECK(row_begin + n_rows <= page->n_rows, "row range exceeds the page");
+  CheckPage(f, page);
+  if (n_rows == 0 || tree_begin == tree_end) return 0;
+  DeviceGuard guard(f->device);
+  auto s = static_cast<cudaStream_t>(stream);
+  SyncForest(f, s);
+  const ForestView fv{f->d_nodes, f->d_roots, f->d_bin_bits, f->bin_words};
+  const EllView view = page->View();
+  const uint64_t total = n_rows * (uint64_t)(tree_end - tree_begin);
+  const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)NumSMs(f->device) * 16);
+  if (page->is_sparse) {
+    PredictLeafKernel<uint32_t><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, row_begin, n_rows, out_dev);
+  } else if (page->bin_bytes == 1) {
+    PredictLeafKernel<uint8_t><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, row_begin, n_rows, out_dev);
+  } else {
+    PredictLeafKernel<uint16_t><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, row_begin, n_rows, out_dev);
+  }
+  B200_LAUNCHED();
+  B200_API_END();
+}
+
+}  // extern "C"

@@ -134,6 +134,14 @@ _SIGNATURES = {
                                              POINTER(TrainParam), POINTER(Quantiser), c_void_p, c_int32, c_int32,
                                              POINTER(Candidate), POINTER(c_int32), POINTER(c_uint32), c_uint32,
                                              c_void_p]),
+    "b200hist_forest_create": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "b200hist_forest_destroy": (c_int, [c_void_p]),
+    "b200hist_forest_num_trees": (c_int, [c_void_p, POINTER(c_uint32)]),
+    "b200hist_forest_add_tree": (c_int, [c_void_p, c_void_p, c_int32, POINTER(c_int32), POINTER(c_uint32), c_uint32]),
+    "b200hist_forest_predict_margin": (c_int, [c_void_p, c_void_p, c_uint32, c_uint32, c_uint64, c_uint64, c_void_p,
+                                               c_void_p]),
+    "b200hist_forest_predict_leaf": (c_int, [c_void_p, c_void_p, c_uint32, c_uint32, c_uint64, c_uint64, c_void_p,
+                                             c_void_p]),
     "b200hist_partition": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_uint64), POINTER(c_uint64),
                                    POINTER(c_int32), POINTER(c_float), POINTER(c_int32), c_int32,
                                    POINTER(c_uint64), c_void_p]),

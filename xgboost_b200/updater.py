@@ -384,6 +384,66 @@ class RegTree:
         return out
 
 
+class Forest:
+    """Trees resolved against a page's cuts, for prediction on quantised pages (include/b200hist.h, "Prediction on the
+    quantised matrix"): the GPUPredictor step for DMatrices bound to the training cuts."""
+
+    def __init__(self, page: EllpackPage):
+        self._page = page            # keeps the cuts alive
+        self._h = c_void_p()
+        _l.check(_l.load().b200hist_forest_create(page.handle, byref(self._h)))
+
+    def add_tree(self, tree: RegTree, is_cat: Optional[Sequence[int]] = None, cat_sets: Optional[Sequence[set]] = None) -> None:
+        """tree: what GPUHistMaker.update returned; is_cat / cat_sets: GPUHistMaker.last_tree_categories(...)."""
+        a = np.ascontiguousarray(tree.array)
+        flags_p, bits_p, words = None, None, 0
+        if is_cat is not None and any(is_cat):
+            flags = np.ascontiguousarray(is_cat, dtype=np.int32)
+            words = max((max(cs) if cs else 0) for cs in cat_sets) // 32 + 1
+            bits = np.zeros((a.shape[0], words), dtype=np.uint32)
+            for i, cs in enumerate(cat_sets):
+                for c in cs:
+                    bits[i, c // 32] |= np.uint32(1 << (31 - c % 32))
+            flags_p, bits_p = flags.ctypes.data_as(POINTER(c_int32)), bits.ctypes.data_as(POINTER(c_uint32))
+        _l.check(_l.load().b200hist_forest_add_tree(self._h, c_void_p(a.ctypes.data), a.shape[0], flags_p, bits_p, words))
+
+    @property
+    def num_trees(self) -> int:
+        n = c_uint32()
+        _l.check(_l.load().b200hist_forest_num_trees(self._h, byref(n)))
+        return int(n.value)
+
+    def predict_margin(self, page: EllpackPage, out: torch.Tensor, tree_begin: int = 0, tree_end: Optional[int] = None,
+                       row_begin: int = 0) -> torch.Tensor:
+        """out[k] += sum of the leaves row row_begin + k reaches in trees [tree_begin, tree_end), in tree order."""
+        _require_cuda(out, "out")
+        if out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be contiguous float32")
+        te = self.num_trees if tree_end is None else int(tree_end)
+        _l.check(_l.load().b200hist_forest_predict_margin(self._h, page.handle, int(tree_begin), te, int(row_begin),
+                                                        out.numel(), c_void_p(out.data_ptr()),
+                                                        _stream_ptr(out.device)))
+        return out
+
+    def predict_leaf(self, page: EllpackPage, tree_begin: int = 0, tree_end: Optional[int] = None) -> torch.Tensor:
+        te = self.num_trees if tree_end is None else int(tree_end)
+        out = torch.empty((page.n_rows, te - tree_begin), dtype=torch.int32, device=torch.device("cuda", page.device))
+        _l.check(_l.load().b200hist_forest_predict_leaf(self._h, page.handle, int(tree_begin), te, 0, page.n_rows,
+                                                      c_void_p(out.data_ptr()), _stream_ptr(out.device)))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            _l.load().b200hist_forest_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class GPUHistMaker:
     """TreeUpdater "grow_gpu_hist" served by libb200hist.so."""
 
