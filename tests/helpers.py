@@ -139,3 +139,34 @@ class MT19937:
         y ^= (y << 15) & 0xEFC60000
         y ^= y >> 18
         return y & 0xFFFFFFFF
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Data recipes of the fixtures generated by tools/probe_interaction_reference.py and tools/make_golden_cpu_categorical.py
+# (kept here so that the generators, the tests and tools/quick_check regenerate exactly the same inputs from a seed)
+# ---------------------------------------------------------------------------------------------------------------------
+def make_interaction_data(case):
+    """n x f standard normal features, y = sum of neighbour products + 0.3 * row sum: a chain of pairwise interactions."""
+    rng = np.random.default_rng(case["seed"])
+    x = rng.normal(size=(case["n"], case["f"])).astype(np.float32)
+    y = (x[:, 0] * x[:, 1] + x[:, 1] * x[:, 2] + x[:, 2] * x[:, 3] + x[:, 3] * x[:, 4] + x[:, 4] * x[:, 5] +
+         0.3 * x.sum(1)).astype(np.float32)
+    return x, y
+
+
+CATEGORICAL_N_CATS = [3, 6, 12, 40]
+
+
+def make_categorical_data(case):
+    """Four categorical columns (3 / 6 / 12 / 40 categories, 5 % missing) + three numerical ones; the label is the sum
+    of per-category effects, the first numerical column and noise.  Returns x, y, feature types ("c" / "q")."""
+    rng = np.random.default_rng(case["seed"])
+    n = case["n"]
+    cols = [rng.integers(0, k, size=n).astype(np.float32) for k in CATEGORICAL_N_CATS]
+    for c in cols:
+        c[rng.random(n) < 0.05] = np.nan
+    xn = rng.normal(size=(n, 3)).astype(np.float32)
+    x = np.column_stack(cols + [xn[:, 0], xn[:, 1], xn[:, 2]]).astype(np.float32)
+    eff = [rng.normal(size=k) for k in CATEGORICAL_N_CATS]
+    y = sum(e[np.nan_to_num(c, nan=0).astype(int)] for e, c in zip(eff, cols)) + xn[:, 0] + 0.2 * rng.normal(size=n)
+    return x, y.astype(np.float32), ["c"] * len(CATEGORICAL_N_CATS) + ["q"] * 3

@@ -1,13 +1,14 @@
 #!/usr/bin/env python
-"""Checks the *.bin files quick_gpu_check wrote on a B200 against the oracle.
-  python tools/quick_check/compare.py [directory]     (default gpurun_out/quick_check; the run kept from round 1 is
+"""Checks the *.bin files tools/quick_check/quick_gpu_check wrote on a B200 against the oracle (test infrastructure:
+the oracle is only ever imported from tests/).
+  python tests/quick_check_compare.py [directory]     (default gpurun_out/quick_check; the run kept from round 1 is
                                                        tests/golden/b200_quick_check)"""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import oracle as orc  # noqa: E402
 from tests.test_reference_golden import categorical_global_bins  # noqa: E402

@@ -71,3 +71,23 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src \
                     or f == "_build.py", f
+
+
+def test_only_fixture_generators_outside_tests_touch_the_oracle_directory():
+    """Outside tests/, `oracle/` may appear in bench.py (cpu_baseline / --impl reference legs), in
+    __graft_entry__.smoke() and in the FIXTURE GENERATORS under tools/ that drive the unmodified reference through
+    oracle/ref_capi.py (the scripts that wrote tests/golden/*.json).  No tool may import the CPU restatement itself
+    (`import oracle` / `oracle as orc`): checking against it is the tests' job."""
+    allowed_ref_capi = {"make_golden_gpu.py", "make_golden_cpu_categorical.py", "probe_interaction_reference.py",
+                        "bench_sparse.py"}
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tools")):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            src = open(os.path.join(dirpath, f)).read()
+            assert "import oracle" not in src and "liboracle" not in src, f
+            if "from oracle" in src:
+                assert f in allowed_ref_capi and "from oracle import ref_capi" in src, f
+    entry = open(os.path.join(ROOT, "__graft_entry__.py")).read()
+    build_body = entry[entry.index("def build()"):entry.index("def smoke()")]
+    assert "import oracle" not in build_body and "from oracle" not in build_body

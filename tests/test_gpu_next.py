@@ -35,7 +35,7 @@ def test_interaction_constraints_match_reference_gpu_hist_bit_for_bit(xb, case):
     """Overlapping constraint sets: the reference's trees depend on its shared Query buffer (include/b200hist.h);
     ours must be the same trees, bit for bit, loss_chg included."""
     import torch
-    from tools.probe_interaction_reference import make_data
+    from tests.helpers import make_interaction_data as make_data
     x, y = make_data(case)
     cp = np.array(case["cut_ptrs"], dtype=np.uint32)
     cv = np.array(case["cut_values_bits"], dtype=np.uint32).view(np.float32)
@@ -285,7 +285,7 @@ def test_categorical_trees_match_oracle_and_cpu_reference(xb, case):
     histograms, positions), and with it the discrete content of the reference's CPU tree."""
     import torch
     from tests.test_reference_golden import categorical_global_bins
-    from tools.make_golden_cpu_categorical import make_data
+    from tests.helpers import make_categorical_data as make_data
     x, y, types = make_data(case)
     is_cat = [1 if t == "c" else 0 for t in types]
     cp = np.array(case["cut_ptrs"], dtype=np.uint32)
@@ -434,7 +434,7 @@ def test_categorical_features_through_the_shim_match_reference(xb, extra):
     """The reference sketches, bins and stores the categorical columns; our updater grows the trees.  Models must
     be identical including split_type / categories arrays, and so must the margins (the reference's predictor walks
     OUR category sets)."""
-    from tools.make_golden_cpu_categorical import make_data
+    from tests.helpers import make_categorical_data as make_data
     rc = _shim_or_skip()
     x, y, types = make_data(dict(seed=305, n=30000))
     params = {"tree_method": "hist", "device": "cuda:0", "max_bin": 64, "max_depth": 6, "eta": 0.3,
@@ -528,7 +528,7 @@ def test_colsample_bynode_through_the_shim_matches_reference(xb, extra):
 def test_categorical_cuts_and_binning(xb):
     import torch
     from tests.test_reference_golden import categorical_global_bins
-    from tools.make_golden_cpu_categorical import N_CATS, make_data
+    from tests.helpers import CATEGORICAL_N_CATS as N_CATS, make_categorical_data as make_data
     case = json.load(open(os.path.join(GOLDEN, "ref_cpu_categorical_trees.json")))["cases"][0]
     x, _, types = make_data(case)
     is_cat = [1 if t == "c" else 0 for t in types]
@@ -625,7 +625,7 @@ def test_forest_prediction_matches_oracle(xb, missing, max_bin):
 def test_forest_prediction_with_categorical_splits(xb):
     import torch
     from tests.test_reference_golden import categorical_global_bins
-    from tools.make_golden_cpu_categorical import make_data
+    from tests.helpers import make_categorical_data as make_data
     case = json.load(open(os.path.join(GOLDEN, "ref_cpu_categorical_trees.json")))["cases"][0]
     x, y, types = make_data(case)
     is_cat = [1 if t == "c" else 0 for t in types]

@@ -13,7 +13,7 @@ import os
 
 import numpy as np
 
-from tools.quick_check import compare
+from tests import quick_check_compare as compare
 
 REC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "b200_quick_check")
 

@@ -233,7 +233,7 @@ def test_oracle_reproduces_reference_interaction_constraints(case):
     (constraints.cu:125,199-240; updater_gpu_hist.cu:251-268): the oracle's shared_result_buffer reading rebuilds
     every reference tree bit for bit, and on the first tree of every case the per-query reading does NOT -- so the
     fixture discriminates."""
-    from tools.probe_interaction_reference import make_data
+    from tests.helpers import make_interaction_data as make_data
     x, y = make_data(case)
     cp = np.array(case["cut_ptrs"], dtype=np.uint32)
     cv = _f32(case["cut_values_bits"])
@@ -276,7 +276,7 @@ def categorical_global_bins(x, cp, cv, is_cat):
 
 @pytest.mark.parametrize("case", json.load(open(CAT_GOLD))["cases"], ids=lambda c: c["name"])
 def test_oracle_categorical_trees_match_cpu_reference(case):
-    from tools.make_golden_cpu_categorical import make_data
+    from tests.helpers import make_categorical_data as make_data
     x, y, types = make_data(case)
     assert types == case["feature_types"]
     is_cat = [1 if t == "c" else 0 for t in types]

@@ -22,25 +22,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_capi as rc  # noqa: E402
+from tests.helpers import CATEGORICAL_N_CATS as N_CATS, make_categorical_data as make_data  # noqa: E402,F401
 
-N_CATS = [3, 6, 12, 40]
 CASES = [dict(name="s%d_onehot%d_thr%d" % (s, oh, thr), seed=s, n=8000, max_bin=64, max_cat_to_onehot=oh,
               max_cat_threshold=thr, params=dict(max_depth=4, eta=0.5))
          for s, oh, thr in [(301, 4, 64), (301, 1, 64), (301, 100, 64), (302, 4, 64), (302, 100, 64), (303, 4, 8),
                             (304, 1, 3)]]
-
-
-def make_data(case):
-    rng = np.random.default_rng(case["seed"])
-    n = case["n"]
-    cols = [rng.integers(0, k, size=n).astype(np.float32) for k in N_CATS]
-    for c in cols:
-        c[rng.random(n) < 0.05] = np.nan
-    xn = rng.normal(size=(n, 3)).astype(np.float32)
-    x = np.column_stack(cols + [xn[:, 0], xn[:, 1], xn[:, 2]]).astype(np.float32)
-    eff = [rng.normal(size=k) for k in N_CATS]
-    y = sum(e[np.nan_to_num(c, nan=0).astype(int)] for e, c in zip(eff, cols)) + xn[:, 0] + 0.2 * rng.normal(size=n)
-    return x, y.astype(np.float32), ["c"] * len(N_CATS) + ["q"] * 3
 
 
 def bits(a):

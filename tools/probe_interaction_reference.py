@@ -17,18 +17,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_capi as rc  # noqa: E402
+from tests.helpers import make_interaction_data as make_data  # noqa: E402
 
 SETS = [[0, 1], [1, 2], [2, 3], [3, 4], [4, 5]]
 CASES = [dict(name="chain_%d" % s, seed=s, n=6000, f=6, max_bin=32, rounds=2,
               params=dict(max_depth=5, eta=0.5)) for s in (201, 202, 203)]
-
-
-def make_data(case):
-    rng = np.random.default_rng(case["seed"])
-    x = rng.normal(size=(case["n"], case["f"])).astype(np.float32)
-    y = (x[:, 0] * x[:, 1] + x[:, 1] * x[:, 2] + x[:, 2] * x[:, 3] + x[:, 3] * x[:, 4] + x[:, 4] * x[:, 5] +
-         0.3 * x.sum(1)).astype(np.float32)
-    return x, y
 
 
 def bits(a):

@@ -9,9 +9,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+from tests.helpers import make_categorical_data as cat_data  # noqa: E402
 from tests.helpers import make_cuts  # noqa: E402
-from tools.make_golden_cpu_categorical import make_data as cat_data  # noqa: E402
-from tools.probe_interaction_reference import make_data as num_data  # noqa: E402
+from tests.helpers import make_interaction_data as num_data  # noqa: E402
 
 OUT = os.path.join(ROOT, "tools", "quick_check", "inputs")
 

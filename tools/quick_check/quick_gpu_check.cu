@@ -1,6 +1,6 @@
 // A seconds-long hardware check through the C ABI only (no Python start-up): reads binary inputs written by
 // tools/quick_check/make_inputs.py, grows a few trees with libb200hist.so and writes the node arrays to
-// gpurun_out/quick_check/, which tools/quick_check/compare.py then checks against the oracle on the CPU.
+// gpurun_out/quick_check/, which tests/quick_check_compare.py then checks against the oracle on the CPU.
 // Cases: plain tree, interaction constraints (overlapping sets), categorical features.
 #include <cuda_runtime.h>
 
