@@ -1,0 +1,17 @@
+#!/bin/bash
+# The first GPU call of the next round, in one piece (gpurun --timeout 1500 -- 'bash tools/first_gpu_call_next_round.sh'):
+#   1. the gated tests of the paths written late in round 1 (no -x: the log must show everything that fails),
+#   2. the default GPU suite (what the driver runs),
+#   3. a short bench line.
+# Logs land in gpurun_out/ and come back with the call.
+mkdir -p gpurun_out
+export PYTHONDONTWRITEBYTECODE=1
+B200HIST_RUN_UNVALIDATED=1 timeout 1200 python -m pytest tests/test_gpu_next.py -m gpu -q -p no:cacheprovider \
+  > gpurun_out/next_tests.log 2>&1
+echo "gated tests rc=$?" | tee -a gpurun_out/next_tests.log
+timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/gpu_suite.log 2>&1
+echo "default suite rc=$?" | tee -a gpurun_out/gpu_suite.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_line.json 2> gpurun_out/bench.err
+echo "bench rc=$?"
+tail -5 gpurun_out/next_tests.log gpurun_out/gpu_suite.log
+cat gpurun_out/bench_line.json
