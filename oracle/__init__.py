@@ -194,6 +194,20 @@ def partition(gbins, cut_ptrs, cut_values, ridx, findex, split_cond, default_lef
     return out, int(nl)
 
 
+def gradient_based_sample(gq: np.ndarray, scale, subsample: float, seed: int):
+    """GradientBasedSampling::Sample restated (PARITY UNPINNED, see orc_gradient_based_sample).  gq: int64[n, 2]
+    quantised pairs.  Returns (sampled pairs, mu, threshold index, regularised absolute gradients)."""
+    out = np.ascontiguousarray(gq, dtype=np.int64).copy()
+    n = out.shape[0]
+    sc = (c_double * 4)(*[float(v) for v in scale])
+    tidx = c_uint64(0)
+    rag = np.zeros(max(n, 1), dtype=np.float32)
+    lib().orc_gradient_based_sample.restype = c_float
+    mu = lib().orc_gradient_based_sample(_p(out), c_uint64(n), sc, c_float(subsample), c_uint32(seed & 0xFFFFFFFF),
+                                         byref(tidx), _p(rag))
+    return out, float(mu), int(tidx.value), rag[:n]
+
+
 def random_weight(seed: int, i: int) -> float:
     """RandomWeight(seed)(i) of the reference's row sampler (sampler.cu:36-47)."""
     lib().orc_random_weight.restype = c_float
@@ -243,13 +257,15 @@ class InteractionConstraints:
 class _Cat(Structure):
     _fields_ = [("feature_is_cat", c_void_p), ("max_cat_to_onehot", c_int32), ("max_cat_threshold", c_int32),
                 ("n_cat_words", c_uint32), ("node_is_cat", c_void_p), ("node_cat_bits", c_void_p),
-                ("node_sets", c_void_p), ("n_node_sets", c_int32), ("n_per_node", c_int32), ("eval_count", c_void_p)]
+                ("node_sets", c_void_p), ("n_node_sets", c_int32), ("n_per_node", c_int32), ("eval_count", c_void_p),
+                ("gradient_based", c_int32)]
 
 
 def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override=None, max_nodes=None,
                 is_dense_layout=True, want_hist=False, feature_set=None, subsample=1.0, sample_seed=0,
                 monotone=None, level_feature_sets=None, interaction=None, interaction_shared_buffer=True,
-                feature_is_cat=None, max_cat_to_onehot=4, max_cat_threshold=64, node_feature_sets=None):
+                feature_is_cat=None, max_cat_to_onehot=4, max_cat_threshold=64, node_feature_sets=None,
+                sampling_method="uniform"):
     """Whole tree.  Returns dict(nodes=[Node...], position, scale, hist (optional), cands).
     feature_set: sorted feature ids of the tree's colsample_bytree draw; subsample/sample_seed: uniform row sampling;
     monotone: per-feature sign (+1 increasing, -1 decreasing, 0 free), padded with 0 to n_features;
@@ -289,8 +305,10 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
     cat = None
     has_cat = feature_is_cat is not None and any(feature_is_cat)
     eval_count = np.zeros(1, dtype=np.int32)
-    if has_cat or node_feature_sets is not None:
-        cat = _Cat(None, int(max_cat_to_onehot), int(max_cat_threshold), 1, None, None, None, 0, 0, eval_count.ctypes.data)
+    gradient_based = sampling_method == "gradient_based" and subsample < 1.0
+    if has_cat or node_feature_sets is not None or gradient_based:
+        cat = _Cat(None, int(max_cat_to_onehot), int(max_cat_threshold), 1, None, None, None, 0, 0, eval_count.ctypes.data,
+                   1 if gradient_based else 0)
     if has_cat:
         flags = np.zeros(nf, dtype=np.uint8)
         flags[:len(feature_is_cat)] = [1 if v else 0 for v in feature_is_cat]

@@ -844,6 +844,82 @@ ORC_API float orc_random_weight(uint32_t seed, uint64_t i) {
   return r * (1.0f - 0.0f) + 0.0f;
 }
 
+/* Gradient-based row sampling: cuda_impl::GradientBasedSampling::Sample (src/tree/gpu_hist/sampler.cu:98-115,
+ * 257-312; helpers src/tree/hist/sampler.h:48-74, src/tree/gpu_hist/quantiser.cuh:22-47) on the QUANTISED pairs of one
+ * target, in place:
+ *   rag_i  = sqrtf(float(g_i^2 + 0.1 * h_i^2))   with (g, h) = the pair converted back to double (MvsGradOp)
+ *   thr    = sort(rag) ++ [FLT_MAX]
+ *   csum_i = float(ToFloatingPoint(sum_{k<=i} int64(double(thr_k) * to_fixed)))   (FloatQuantiser of sum(thr), n)
+ *   i*     = first i with denom = float(sample_rows) - float(n - i - 1) > 0 and thr_i < u = csum_i / denom <= thr_{i+1};
+ *            thr_{i*+1} := u;  mu = thr[i* + 1]   (no such i: min_element picks index 0, mu = thr[1])
+ *   row i: pair (0,0) stays; p = rag_i / mu (|mu| < 1e-6 -> 1e-6); p >= 1 keeps the pair; otherwise the pair becomes
+ *          ToFixedPoint(pair_as_double * (1.0f / p)) when RandomWeight(seed)(i) <= p and (0,0) when not.
+ * sample_rows = (uint64)(n * subsample) with the product taken in float (bst_idx_t = n_samples * subsample_).
+ * PARITY UNPINNED: no literal vector of the reference covers this (its tests are statistical,
+ * tests/cpp/tree/gpu_hist/test_sampler.cu:79-179) and the CUDA reference has not been run against it yet; the double
+ * sum behind the quantiser is taken sequentially here (device reduction order there: matters only at a power of two).
+ * Returns mu. */
+ORC_API float orc_gradient_based_sample(orc_gpair64* gq, uint64_t n, const double scale[4], float subsample,
+                                        uint32_t seed, uint64_t* threshold_index_out, float* rag_out) {
+  float* rag = (float*)malloc(sizeof(float) * (n ? n : 1));
+  float* thr = (float*)malloc(sizeof(float) * (n + 1));
+  for (uint64_t i = 0; i < n; ++i) {
+    double g = (double)gq[i].g * scale[2], h = (double)gq[i].h * scale[3];
+    float m = (float)(g * g + (double)0.1f * (h * h)); /* Sqr(g) + lambda * Sqr(h): float lambda promoted to double */
+    rag[i] = sqrtf(m);
+    thr[i] = rag[i];
+  }
+  thr[n] = FLT_MAX;
+  /* ascending sort (thrust::sort of floats: any correct sort gives this array) */
+  for (uint64_t gap = n / 2; gap > 0; gap /= 2) /* shell sort keeps the oracle dependency-free */
+    for (uint64_t i = gap; i < n; ++i) {
+      float v = thr[i];
+      uint64_t j = i;
+      while (j >= gap && thr[j - gap] > v) { thr[j] = thr[j - gap]; j -= gap; }
+      thr[j] = v;
+    }
+  double total = 0.0;
+  for (uint64_t i = 0; i < n; ++i) total += (double)thr[i];
+  double to_float = rounding_factor(total, n) / (double)((int64_t)1 << 62);
+  double to_fixed = 1.0 / to_float;
+  uint64_t sample_rows = (uint64_t)((float)n * subsample);
+  int64_t run = 0;
+  uint64_t best = 0;
+  int found = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    run += (int64_t)((double)thr[i] * to_fixed);
+    float csum = (float)((double)run * to_float);
+    if (found) continue;
+    float denom = (float)sample_rows - (float)(n - i - 1);
+    if (denom <= 0) continue;
+    float u = csum / denom;
+    if (u > thr[i] && u <= thr[i + 1]) { thr[i + 1] = u; best = i; found = 1; }
+  }
+  uint64_t tidx = (found ? best : 0) + 1;
+  float mu = n ? thr[tidx] : FLT_MAX;
+  if (threshold_index_out) *threshold_index_out = tidx;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (gq[i].g == 0 && gq[i].h == 0) continue;
+    float u = mu;
+    if (fabsf(u) < 1e-6f) u = copysignf(1e-6f, u);
+    float pr = rag[i] / u;
+    if (pr >= 1.0f) continue;
+    if (orc_random_weight(seed, i) <= pr) {
+      float inv = 1.0f / pr;
+      double g = ((double)gq[i].g * scale[2]) * (double)inv, h = ((double)gq[i].h * scale[3]) * (double)inv;
+      gq[i].g = (int64_t)(g * scale[0]);
+      gq[i].h = (int64_t)(h * scale[1]);
+    } else {
+      gq[i].g = 0;
+      gq[i].h = 0;
+    }
+  }
+  if (rag_out) memcpy(rag_out, rag, sizeof(float) * n);
+  free(rag);
+  free(thr);
+  return mu;
+}
+
 ORC_API int32_t orc_update_tree_ex(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
                                    uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
                                    const float* gpair, const orc_param* p, const double* scale_override,
@@ -872,6 +948,7 @@ typedef struct {
   const int32_t* node_sets;
   int32_t n_node_sets, n_per_node;
   int32_t* eval_count; /* out: draws used */
+  int32_t gradient_based; /* subsample < 1: TrainParam::sampling_method == kGradientBased (orc_gradient_based_sample) */
 } orc_cat;
 ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
                                      uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
@@ -989,9 +1066,12 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
   if (scale_out) memcpy(scale_out, scale, sizeof(scale));
   orc_gpair64* gq = (orc_gpair64*)malloc(sizeof(orc_gpair64) * (n_rows ? n_rows : 1));
   orc_quantise(gpair, n_rows, scale, gq);
-  if (subsample < 1.0f)
+  if (subsample < 1.0f && cat && cat->gradient_based) {
+    (void)orc_gradient_based_sample(gq, n_rows, scale, subsample, sample_seed, NULL, NULL);
+  } else if (subsample < 1.0f) {
     for (uint64_t i = 0; i < n_rows; ++i)
       if (orc_random_weight(sample_seed, i) > subsample) { gq[i].g = 0; gq[i].h = 0; }
+  }
 
   /* per-node state */
   orc_gpair64** hist = (orc_gpair64**)calloc((size_t)max_nodes, sizeof(orc_gpair64*));

@@ -467,3 +467,46 @@ def test_oracle_node_feature_sets_follow_the_evaluation_order():
     a = orc.update_tree(gb, cp, cv, gp, orc.Param.make(max_depth=4), node_feature_sets=full)
     b = orc.update_tree(gb, cp, cv, gp, orc.Param.make(max_depth=4))
     assert [(n.findex, n.fvalue) for n in a["nodes"]] == [(n.findex, n.fvalue) for n in b["nodes"]]
+
+
+def test_gradient_based_sampling_properties():
+    """GradientBasedSampling::Sample restated (parity unpinned -- the reference's own tests are statistical too,
+    tests/cpp/tree/gpu_hist/test_sampler.cu:79-179): the threshold mu makes the EXPECTED number of sampled rows equal
+    n * subsample (the CpuGpuConsistency property, :129-179), rows at or above mu are kept untouched, kept rows below
+    it are scaled by 1 / p so that the gradient sum stays unbiased, dropped rows are zero."""
+    from tests.helpers import make_regression, squared_error_gpair
+    _, y = make_regression(20000, 4, seed=9)
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    scale, _ = orc.quantiser(gp)
+    gq = orc.quantise(gp, scale)
+    for subsample in (0.1, 0.5, 0.9):
+        out, mu, tidx, rag = orc.gradient_based_sample(gq, scale, subsample, seed=1234)
+        p = np.minimum(1.0, rag / np.float32(mu))
+        assert abs(float(p.sum()) - int(np.float32(len(y)) * np.float32(subsample))) <= 1.0, (subsample, p.sum())
+        kept = (out[:, 1] != 0)
+        assert abs(kept.sum() - p.sum()) <= 4 * np.sqrt((p * (1 - p)).sum()) + 1      # Poisson sampling spread
+        sure = rag >= np.float32(mu)
+        assert np.array_equal(out[sure], gq[sure])
+        assert (out[~kept] == 0).all()
+        scaled = kept & ~sure
+        ratio = out[scaled, 1].astype(np.float64) / gq[scaled, 1].astype(np.float64)
+        assert np.allclose(ratio, 1.0 / p[scaled], rtol=1e-5)
+        # unbiased: the gradient sum is preserved up to sampling noise
+        g_before, g_after = gq[:, 0].sum() * scale[2], out[:, 0].sum() * scale[2]
+        noise = np.sqrt((((gq[:, 0] * scale[2]) ** 2) * (1 - p) / np.maximum(p, 1e-12)).sum())
+        assert abs(g_after - g_before) <= 5 * noise + 1e-6
+    # the same trial stream as uniform sampling: RandomWeight(seed)(i)
+    out1, *_ = orc.gradient_based_sample(gq, scale, 0.5, seed=7)
+    out2, *_ = orc.gradient_based_sample(gq, scale, 0.5, seed=7)
+    assert np.array_equal(out1, out2)
+    # and a whole tree grows on the sampled pairs
+    from tests.helpers import make_cuts
+    x, y2 = make_regression(6000, 5, seed=10)
+    cp, cv = make_cuts(x, 16)
+    gb = orc.bin_dense(x, cp, cv)
+    gp2 = squared_error_gpair(np.zeros_like(y2), y2)
+    t = orc.update_tree(gb, cp, cv, gp2, orc.Param.make(max_depth=4), subsample=0.3, sample_seed=5,
+                        sampling_method="gradient_based")
+    u = orc.update_tree(gb, cp, cv, gp2, orc.Param.make(max_depth=4), subsample=0.3, sample_seed=5)
+    assert len(t["nodes"]) >= 3 and (t["position"] < 0).sum() > 0
+    assert (t["position"] < 0).sum() != (u["position"] < 0).sum()
