@@ -346,3 +346,75 @@ def test_oracle_predictor_reproduces_reference_cpu_margins():
     for nodes in forest:
         naive = orc.predict_margin(gb, cp, cv, [nodes], base=naive)
     assert np.allclose(naive, ref, rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Waiting for their fixture: tests/golden/ref_gpu_next_trees.json (tools/make_golden_gpu_next.py, one short GPU call).
+# The reference's own gpu_hist trees for categorical features and gradient-based sampling pin the two oracle
+# restatements bit for bit, the way ref_gpu_trees.json pins the numerical path.
+# ---------------------------------------------------------------------------------------------------------------------
+NEXT_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_gpu_next_trees.json")
+
+
+def _next_cases(kind):
+    if not os.path.exists(NEXT_GOLD):
+        return []
+    return [c for c in json.load(open(NEXT_GOLD))["cases"] if c["kind"] == kind]
+
+
+def _assert_tree_equals_reference(o, ref, t, cats=False):
+    nodes = o["nodes"]
+    assert len(nodes) == len(ref["left"]), "tree %d node count" % t
+    for i, nd in enumerate(nodes):
+        assert (nd.left, nd.right) == (ref["left"][i], ref["right"][i]), (t, i)
+        if not nd.is_leaf:
+            assert nd.findex == ref["findex"][i] and int(nd.default_left) == ref["default_left"][i], (t, i)
+            if cats and o["is_cat"][i]:
+                assert ref["split_type"][i] == 1 and sorted(o["cat_sets"][i]) == ref["categories"][i], (t, i)
+            else:
+                assert ref["split_type"][i] == 0, (t, i)
+                assert int(np.float32(nd.fvalue).view(np.uint32)) == ref["cond_bits"][i], (t, i)
+            ref_l = float(_f32([ref["loss_chg_bits"][i]])[0])
+            assert abs(nd.loss_chg - ref_l) <= 2e-5 * (abs(ref_l) + abs(nd.loss_chg)) + 1e-5, (t, i)
+        assert int(np.float32(nd.sum_hess).view(np.uint32)) == ref["sum_hess_bits"][i], (t, i)
+        assert int(np.float32(nd.base_weight).view(np.uint32)) == ref["base_weight_bits"][i], (t, i)
+
+
+@pytest.mark.skipif(not os.path.exists(NEXT_GOLD), reason="fixture not generated yet (tools/make_golden_gpu_next.py)")
+@pytest.mark.parametrize("case", _next_cases("categorical"), ids=lambda c: c["name"])
+def test_oracle_reproduces_reference_gpu_categorical_trees(case):
+    from tests.helpers import make_categorical_data
+    x, y, types = make_categorical_data(case)
+    is_cat = [1 if t == "c" else 0 for t in types]
+    cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+    cv = _f32(case["cut_values_bits"])
+    gb = categorical_global_bins(x, cp, cv, is_cat)
+    params = {k: v for k, v in case["params"].items() if k not in ("max_cat_to_onehot", "max_cat_threshold")}
+    margin = np.zeros(case["n"], dtype=np.float32)
+    for t, ref in enumerate(case["trees"]):
+        gp = np.stack([margin - y, np.ones_like(y)], axis=1).astype(np.float32)
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), feature_is_cat=is_cat,
+                            max_cat_to_onehot=case["params"]["max_cat_to_onehot"],
+                            max_cat_threshold=case["params"]["max_cat_threshold"])
+        _assert_tree_equals_reference(o, ref, t, cats=True)
+        leaf = np.array([n.leaf_value for n in o["nodes"]], dtype=np.float32)
+        margin = (margin + _leaf_margin(leaf, o["position"])).astype(np.float32)
+
+
+@pytest.mark.skipif(not os.path.exists(NEXT_GOLD), reason="fixture not generated yet (tools/make_golden_gpu_next.py)")
+@pytest.mark.parametrize("case", _next_cases("sampling"), ids=lambda c: c["name"])
+def test_oracle_reproduces_reference_gpu_gradient_based_sampling(case):
+    x, y = make_regression(case["n"], case["f"], seed=case["seed"])
+    cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+    cv = _f32(case["cut_values_bits"])
+    gb = orc.bin_dense(x, cp, cv)
+    params = {k: v for k, v in case["params"].items() if k not in ("subsample", "sampling_method", "seed")}
+    rng = MT19937(case["params"].get("seed", 0))
+    margin = np.zeros(case["n"], dtype=np.float32)
+    for t, ref in enumerate(case["trees"]):
+        gp = np.stack([margin - y, np.ones_like(y)], axis=1).astype(np.float32)
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), subsample=case["params"]["subsample"],
+                            sample_seed=rng.next(), sampling_method="gradient_based")
+        _assert_tree_equals_reference(o, ref, t)
+        leaf = np.array([n.leaf_value for n in o["nodes"]], dtype=np.float32)
+        margin = (margin + _leaf_margin(leaf, o["position"])).astype(np.float32)

@@ -6,6 +6,10 @@
 # Logs land in gpurun_out/ and come back with the call.
 mkdir -p gpurun_out
 export PYTHONDONTWRITEBYTECODE=1
+# 0. fixtures of the unmodified reference for the oracle restatements that still wait for a GPU pin (seconds);
+#    copy gpurun_out/ref_gpu_next_trees.json to tests/golden/ afterwards: two waiting CPU tests wake up
+timeout 300 python tools/make_golden_gpu_next.py --out gpurun_out/ref_gpu_next_trees.json > gpurun_out/next_fixture.log 2>&1
+echo "fixture rc=$?"
 B200HIST_RUN_UNVALIDATED=1 timeout 1200 python -m pytest tests/test_gpu_next.py -m gpu -q -p no:cacheprovider \
   > gpurun_out/next_tests.log 2>&1
 echo "gated tests rc=$?" | tee -a gpurun_out/next_tests.log
