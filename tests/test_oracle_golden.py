@@ -510,3 +510,36 @@ def test_gradient_based_sampling_properties():
     u = orc.update_tree(gb, cp, cv, gp2, orc.Param.make(max_depth=4), subsample=0.3, sample_seed=5)
     assert len(t["nodes"]) >= 3 and (t["position"] < 0).sum() > 0
     assert (t["position"] < 0).sum() != (u["position"] < 0).sum()
+
+
+def test_interaction_constraint_oracle_against_a_set_model():
+    """orc_ic_split / orc_ic_query (bit fields, CSR sets) against the three-line set model of the reference's kernels
+    on random constraint sets, split sequences and sampled lists, incl. features beyond one 64-bit word."""
+    rng = np.random.default_rng(123)
+    for trial in range(60):
+        nf = int(rng.integers(3, 200))
+        sets = [sorted(set(int(v) for v in rng.integers(0, nf, size=rng.integers(1, 6)))) for _ in range(rng.integers(1, 7))]
+        ic = orc.InteractionConstraints(sets, nf, max_nodes=64)
+        model = [set() for _ in range(64)]
+        n_nodes = 1
+        for _ in range(int(rng.integers(1, 20))):
+            if n_nodes + 2 > 64:
+                break
+            node = int(rng.integers(0, n_nodes))
+            f = int(rng.integers(0, nf))
+            left, right = n_nodes, n_nodes + 1
+            n_nodes += 2
+            ic.split(node, f, left, right)
+            for s in sets:
+                if f in s:
+                    model[node] |= set(s)
+            model[left] |= model[node]
+            model[right] |= model[node]
+            for k in (node, left, right):
+                model[k].add(f)
+            for k in range(n_nodes):
+                assert ic.query_node(k) == sorted(model[k]), (trial, k)
+            sampled = [int(v) for v in rng.permutation(nf)[:int(rng.integers(1, nf + 1))]]
+            k = int(rng.integers(0, n_nodes))
+            want = sampled if k == 0 else sorted(model[k] & set(sampled))
+            assert ic.query(sampled, k) == want, (trial, k)
