@@ -273,6 +273,15 @@ B200HIST_API int b200hist_updater_set_level_feature_sets(b200hist_updater_t u, c
                                                          uint32_t n_levels, uint32_t n_per_level);
 B200HIST_API int b200hist_updater_last_max_eval_depth(b200hist_updater_t u, int32_t* out);
 
+/* TrainParam::sampling_method: 0 = uniform (default), 1 = gradient_based = GradientBasedSampling::Sample
+ * (src/tree/gpu_hist/sampler.cu:194-312): with subsample < 1 (b200hist_updater_set_tree_sampling; its seed is the one
+ * ctx->Rng()() draw the reference makes per tree, sampler.cu:308) rows are kept with probability min(1, rag_i / mu),
+ * rag_i = sqrt(g_i^2 + 0.1 h_i^2) on the quantised pair, mu chosen so that the expected sample size is
+ * n * subsample; kept rows below mu are scaled by 1 / p.  Single GPU.
+ * STATUS: compiled, never run on hardware; its oracle is parity-unpinned until the reference has produced a fixture
+ * (tools/make_golden_gpu_next.py); tests in tests/test_gpu_next.py, gated. */
+B200HIST_API int b200hist_updater_set_sampling_method(b200hist_updater_t u, int gradient_based);
+
 /* colsample_bynode = ColumnSampler::GetFeatureSet's per-call draw (src/common/random.h:156-175, random.cu:62-96).
  * gpu_hist asks for a set once for the root and then for the left and the right child of every valid candidate in
  * Pop order (updater_gpu_hist.cu:217,257-264): the draws of a tree form one stream, independent of the data.

@@ -78,7 +78,8 @@ def test_only_fixture_generators_outside_tests_touch_the_oracle_directory():
     __graft_entry__.smoke() and in the FIXTURE GENERATORS under tools/ that drive the unmodified reference through
     oracle/ref_capi.py (the scripts that wrote tests/golden/*.json).  No tool may import the CPU restatement itself
     (`import oracle` / `oracle as orc`): checking against it is the tests' job."""
-    allowed_ref_capi = {"make_golden_gpu.py", "make_golden_cpu_categorical.py", "probe_interaction_reference.py",
+    allowed_ref_capi = {"make_golden_gpu.py", "make_golden_gpu_next.py", "make_golden_cpu_categorical.py",
+                        "probe_interaction_reference.py",
                         "bench_sparse.py"}
     for dirpath, _, files in os.walk(os.path.join(ROOT, "tools")):
         for f in files:

@@ -652,3 +652,67 @@ def test_forest_prediction_with_categorical_splits(xb):
     want = orc.predict_margin(gb, cp, cv, trees)
     assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
     assert np.array_equal(want.view(np.uint32), pred.view(np.uint32)) or np.allclose(want, pred, rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Gradient-based row sampling (b200hist_updater_set_sampling_method, csrc/sampling.cu).  Its oracle is itself waiting
+# for a GPU-reference fixture (tests/golden/ref_gpu_next_trees.json): until then this compares two restatements.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("subsample,seed,obj", [(0.3, 12345, "sq"), (0.7, 4294967295, "sq"), (0.1, 7, "logistic"),
+                                                (0.9, 0, "sq")])
+def test_gradient_based_sampling_matches_oracle(xb, subsample, seed, obj):
+    import torch
+    from tests.helpers import logistic_gpair
+    n, f = 30000, 12
+    x, y = make_regression(n, f, seed=97)
+    if obj == "logistic":
+        y = (y > 0).astype(np.float32)
+    cp, cv = make_cuts(x, 64)
+    page = _page(xb, x, cp, cv)
+    gb = orc.bin_dense(x, cp, cv)
+    params = dict(max_depth=5, eta=0.3)
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    up.set_sampling_method("gradient_based")
+    pred = np.zeros(n, dtype=np.float32)
+    pos = torch.empty(n, dtype=torch.int32, device="cuda")
+    for it in range(3):
+        gp = squared_error_gpair(pred, y) if obj == "sq" else logistic_gpair(pred, y)
+        up.set_tree_sampling(None, subsample, seed + it)
+        tree = up.update(torch.from_numpy(gp).cuda(), pos)
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), want_hist=True, subsample=subsample,
+                            sample_seed=(seed + it) & 0xFFFFFFFF, sampling_method="gradient_based")
+        _compare_tree(xb, up, tree, o, cp, cv, hists=True)
+        assert np.array_equal(pos.cpu().numpy(), o["position"])       # ~leaf for the rows that lost their trial
+        dropped = float((o["position"] < 0).mean())
+        assert abs((1.0 - dropped) - subsample) < 0.05
+        pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+    up.set_sampling_method("uniform")
+    up.set_tree_sampling(None, subsample, seed)
+    gp = squared_error_gpair(np.zeros(n, np.float32), y)
+    t_uni = up.update(torch.from_numpy(gp).cuda())
+    o_uni = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), subsample=subsample, sample_seed=seed & 0xFFFFFFFF)
+    _compare_tree(xb, up, t_uni, o_uni, cp, cv, hists=False)
+
+
+@pytest.mark.parametrize("extra", [{"subsample": 0.3}, {"subsample": 0.6, "colsample_bytree": 0.7, "seed": 5}],
+                         ids=lambda e: "_".join("%s%s" % kv for kv in e.items()))
+def test_gradient_based_sampling_through_the_shim_matches_reference(xb, extra):
+    import torch
+    rc = _shim_or_skip()
+    x, y = make_regression(40000, 20, seed=98)
+    params = {"tree_method": "hist", "device": "cuda:0", "max_bin": 64, "max_depth": 5, "eta": 0.3,
+              "objective": "reg:squarederror", "base_score": 0.5, "sampling_method": "gradient_based"}
+    params.update(extra)
+
+    def train(updater):
+        dm = rc.DMatrix.from_cuda(torch.from_numpy(x).cuda(), kind="cuda")
+        dm.set_label(y)
+        bst = rc.Booster(dict(params, updater=updater), dm)
+        for i in range(4):
+            bst.update(i)
+        return _model_trees(bst), bst.predict_margin(dm)
+    ref_trees, ref_margin = train("grow_gpu_hist_reference")
+    our_trees, our_margin = train("grow_b200_hist")
+    assert json.dumps(our_trees) == json.dumps(ref_trees)
+    assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))

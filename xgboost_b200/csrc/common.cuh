@@ -372,6 +372,12 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = n
                     IcView ic = IcView{nullptr, nullptr, 0},
                     CatView cat = CatView{nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0, 0});
 
+// sampling.cu: gradient-based row sampling on the quantised pairs (after LaunchQuantise without uniform sampling);
+// recomputes the record's root sum and hessian flags from the sampled pairs
+size_t GradientBasedScratchBytes(uint64_t n, int num_sms);
+void LaunchGradientBasedSample(b200hist_gpair64* gq, uint64_t n, QuantDev* q, float subsample, uint32_t seed,
+                               void* scratch, size_t scratch_bytes, int num_sms, cudaStream_t s);
+
 // partition.cu
 void LaunchPartitionCount(const EllView& ell, const uint32_t* ridx0, const uint32_t* ridx1, const PartEntry* part,
                           const uint32_t* tile_seg, const TreeState* ts, uint32_t* flags, uint32_t* tile_left,

@@ -164,13 +164,16 @@ class B200HistMaker : public TreeUpdater {
     CHECK(param->interaction_constraints.empty() || unvalidated_ok)
         << "[b200hist] interaction constraints are not enabled yet";
     CHECK(!p_fmat->Info().HasCategorical() || unvalidated_ok) << "[b200hist] categorical features are not enabled yet";
-    CHECK(param->subsample == 1.0f || param->sampling_method == TrainParam::kUniform)
-        << "[b200hist] gradient_based row sampling is not supported yet";
+    CHECK(param->subsample == 1.0f || param->sampling_method == TrainParam::kUniform || unvalidated_ok)
+        << "[b200hist] gradient_based row sampling is not enabled yet";
     CHECK(param->colsample_bynode == 1.0f || unvalidated_ok)
         << "[b200hist] colsample_bynode is not enabled yet (colsample_bytree and colsample_bylevel are)";
     CHECK(param->colsample_bynode == 1.0f || (param->colsample_bylevel == 1.0f && param->interaction_constraints.empty()))
         << "[b200hist] colsample_bynode cannot be combined with colsample_bylevel or interaction constraints yet";
     B200_SHIM_CHECK(b200hist_updater_create(ellpack_, &p, &updater_));
+    // Sampler ctor (sampler.cu:343-363): the strategy follows sampling_method whenever subsample < 1
+    B200_SHIM_CHECK(b200hist_updater_set_sampling_method(
+        updater_, param->subsample < 1.0f && param->sampling_method == TrainParam::kGradientBased ? 1 : 0));
     if (!param->monotone_constraints.empty()) {  // TreeEvaluator ctor (split_evaluator.h:37-57)
       std::vector<std::int32_t> mono(param->monotone_constraints.cbegin(), param->monotone_constraints.cend());
       CHECK_LE(mono.size(), p_fmat->Info().num_col_)

@@ -787,6 +787,9 @@ struct b200hist_updater_s {
   // per-tree sampling state (set through b200hist_updater_set_tree_sampling, persists until changed)
   float subsample{1.0f};
   uint32_t sample_seed{0};
+  bool gradient_based{false};       // TrainParam::sampling_method == kGradientBased (applies when subsample < 1)
+  void* d_gbs_scratch{nullptr};
+  size_t gbs_scratch_bytes{0};
   int32_t* d_monotone{nullptr};     // monotone constraint sign per feature (nullptr = none)
   float* d_lower{nullptr};          // TreeEvaluator weight bounds per node (allocated with d_monotone)
   float* d_upper{nullptr};
@@ -911,14 +914,29 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   if (u->p2p)  // nobody may push into a cache that its owner has not cleared yet: pure flag barrier
     LaunchHistExchange(u->d_peer_hist, u->d_peer_flags, u->p2p_rank, u->p2p_world, u->d_ts, 0, 0, false,
                        ell->total_bins, 0, 0, ++u->exchange_epoch, u->d_exchange_counter, u->num_sms, s);
+  const bool gbs = u->gradient_based && u->subsample < 1.0f;
+  if (gbs) {
+    B200_CHECK(!u->p2p && u->comm == nullptr, "gradient-based sampling is single-GPU only so far (the threshold needs a global sort)");
+    const size_t need = GradientBasedScratchBytes(n, u->num_sms);
+    if (need > u->gbs_scratch_bytes) {
+      if (u->d_gbs_scratch) cudaFree(u->d_gbs_scratch);
+      u->d_gbs_scratch = nullptr;
+      B200_CUDA(cudaMalloc(&u->d_gbs_scratch, need));
+      u->gbs_scratch_bytes = need;
+    }
+  }
   if (u->p2p && u->row_split) {  // global quantiser scale and root sum (quantiser.cu:88-123 GlobalSum)
     LaunchQuantReduce(gpair_dev, n, u->d_quant, u->d_partials, u->d_counter, u->num_sms, s);
     LaunchScalarExchange(u->d_peer_flags, u->p2p_rank, u->p2p_world, ++u->exchange_epoch, 0, u->d_quant, n, s);
     LaunchQuantConvert(gpair_dev, n, u->d_quant, u->d_gq, u->d_ridx[0], u->num_sms, s, u->subsample, u->sample_seed);
     LaunchScalarExchange(u->d_peer_flags, u->p2p_rank, u->p2p_world, ++u->exchange_epoch, 1, u->d_quant, n, s);
   } else {
+    // gradient-based sampling works on the quantised pairs of ALL rows: no Bernoulli trial in the conversion
     LaunchQuantise(gpair_dev, n, u->d_quant, u->d_gq, u->d_ridx[0], u->d_partials, u->d_counter, u->num_sms, s,
-                   u->subsample, u->sample_seed);
+                   gbs ? 1.0f : u->subsample, u->sample_seed);
+    if (gbs)
+      LaunchGradientBasedSample(u->d_gq, n, u->d_quant, u->subsample, u->sample_seed, u->d_gbs_scratch,
+                                u->gbs_scratch_bytes, u->num_sms, s);
   }
   timer.End(kQuant, t0);
   const bool has_ic = u->d_ic_bits != nullptr;
@@ -1219,6 +1237,7 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
       if (p) cudaFree(p);
     for (void* p : {(void*)u->d_node_sets, (void*)u->d_node_list, (void*)u->d_node_count, (void*)u->d_node_seq})
       if (p) cudaFree(p);
+    if (u->d_gbs_scratch) cudaFree(u->d_gbs_scratch);
     cudaFreeHost(u->h_nodes);
     cudaFreeHost(u->h_ts);
     cudaFreeHost(u->h_quant);
@@ -1481,6 +1500,13 @@ int b200hist_updater_set_interaction_constraints(b200hist_updater_t u, const int
     u->d_ic_list = DevAlloc<int32_t>(u->ell->n_features);
     u->d_ic_count = DevAlloc<int32_t>(2 * (size_t)kMaxLevelNodes);
   }
+  B200_API_END();
+}
+
+int b200hist_updater_set_sampling_method(b200hist_updater_t u, int gradient_based) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  u->gradient_based = gradient_based != 0;
   B200_API_END();
 }
 

@@ -535,6 +535,13 @@ class GPUHistMaker:
             c = np.ascontiguousarray(constraints, dtype=np.int32)
             _l.check(_l.load().b200hist_updater_set_monotone_constraints(self._h, c.ctypes.data_as(POINTER(c_int32)), c.size))
 
+    def set_sampling_method(self, method: str) -> None:
+        """TrainParam::sampling_method: "uniform" or "gradient_based" (applies when subsample < 1 in
+        set_tree_sampling).  gradient_based has not run on hardware -- see include/b200hist.h."""
+        if method not in ("uniform", "gradient_based"):
+            raise ValueError("sampling_method must be 'uniform' or 'gradient_based'")
+        _l.check(_l.load().b200hist_updater_set_sampling_method(self._h, 1 if method == "gradient_based" else 0))
+
     @property
     def max_nodes(self) -> int:
         """Node capacity of one tree (TrainParam::MaxNodes)."""
