@@ -716,3 +716,36 @@ def test_gradient_based_sampling_through_the_shim_matches_reference(xb, extra):
     our_trees, our_margin = train("grow_b200_hist")
     assert json.dumps(our_trees) == json.dumps(ref_trees)
     assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# More of the reference's callers through the (already validated) default path: several trees per Update call.
+# Gated only because they have not run yet; nothing new on the device side.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("extra", [{"objective": "multi:softprob", "num_class": 3},
+                                   {"num_parallel_tree": 3, "subsample": 0.7, "colsample_bynode": 1.0},
+                                   {"objective": "multi:softmax", "num_class": 4, "colsample_bytree": 0.6, "subsample": 0.8}],
+                         ids=["multiclass", "random_forest", "multiclass_sampled"])
+def test_several_trees_per_iteration_through_the_shim(xb, extra):
+    """Multi-class boosting calls the updater once per class with that class's gradient column; num_parallel_tree
+    hands several trees to one Update call, each with its own sampling draws."""
+    import torch
+    rc = _shim_or_skip()
+    x, y = make_regression(30000, 16, seed=99)
+    if "num_class" in extra:
+        y = np.digitize(y, np.quantile(y, np.linspace(0, 1, extra["num_class"] + 1)[1:-1])).astype(np.float32)
+    params = {"tree_method": "hist", "device": "cuda:0", "max_bin": 64, "max_depth": 5, "eta": 0.3,
+              "objective": "reg:squarederror", "base_score": 0.5}
+    params.update(extra)
+
+    def train(updater):
+        dm = rc.DMatrix.from_cuda(torch.from_numpy(x).cuda(), kind="cuda")
+        dm.set_label(y)
+        bst = rc.Booster(dict(params, updater=updater), dm)
+        for i in range(3):
+            bst.update(i)
+        return _model_trees(bst)
+    ref_trees = train("grow_gpu_hist_reference")
+    our_trees = train("grow_b200_hist")
+    assert len(ref_trees) == 3 * max(extra.get("num_class", 1), extra.get("num_parallel_tree", 1))
+    assert json.dumps(our_trees) == json.dumps(ref_trees)
