@@ -194,6 +194,23 @@ def partition(gbins, cut_ptrs, cut_values, ridx, findex, split_cond, default_lef
     return out, int(nl)
 
 
+def thrust_shuffle(seed: int, n: int) -> np.ndarray:
+    """Permutation thrust::shuffle applies to n elements with default_random_engine(seed): out[i] = input index."""
+    perm = np.zeros(max(n, 1), dtype=np.uint32)
+    lib().orc_thrust_shuffle(c_uint32(seed & 0xFFFFFFFF), c_uint64(n), _p(perm))
+    return perm[:n]
+
+
+def col_sample(features, colsample: float, seed: int) -> np.ndarray:
+    """ColumnSampler::ColSample on CUDA without feature weights: shuffle with the seed, keep int(colsample * n)
+    (at least 1), sort ascending."""
+    f = np.ascontiguousarray(features, dtype=np.int32)
+    out = np.zeros(max(f.size, 1), dtype=np.int32)
+    lib().orc_col_sample.restype = c_int32
+    k = lib().orc_col_sample(_p(f), c_int32(f.size), c_float(colsample), c_uint32(seed & 0xFFFFFFFF), _p(out))
+    return out[:k].copy()
+
+
 def gradient_based_sample(gq: np.ndarray, scale, subsample: float, seed: int):
     """GradientBasedSampling::Sample restated (PARITY UNPINNED, see orc_gradient_based_sample).  gq: int64[n, 2]
     quantised pairs.  Returns (sampled pairs, mu, threshold index, regularised absolute gradients)."""

@@ -844,6 +844,56 @@ ORC_API float orc_random_weight(uint32_t seed, uint64_t i) {
   return r * (1.0f - 0.0f) + 0.0f;
 }
 
+/* thrust::shuffle as the reference's column sampler calls it (src/common/random.cu:86-91: thrust::shuffle on the device
+ * with thrust::default_random_engine seeded by one ctx->Rng()() draw): the toolkit's generic algorithm
+ * (thrust/system/detail/generic/shuffle.inl, CUDA 12.9): a 24-round Feistel bijection over [0, 2^bits), bits =
+ * max(4, ceil(log2 m)), whose round keys are the engine's next 24 outputs; out = the inputs at the images below m, in
+ * index order.  minstd_rand: x <- 48271 x mod (2^31 - 1), seeded with seed mod m (0 -> 1); a key is the uint32 state.
+ * Pinned by tests/golden/thrust_shuffle_known_answers.json (the toolkit's own host backend). */
+ORC_API void orc_thrust_shuffle(uint32_t seed, uint64_t m, uint32_t* perm /* m entries: out[i] = index of the input */) {
+  const uint64_t mod = 2147483647ull;
+  uint64_t x = seed % mod;
+  if (x == 0) x = 1;
+  uint32_t key[24];
+  for (int i = 0; i < 24; ++i) { x = (x * 48271ull) % mod; key[i] = (uint32_t)x; }
+  uint64_t bits = 4;
+  if (m > 16) { uint64_t t = m - 1; bits = 0; while (t != 0) { bits++; t >>= 1; } }
+  const uint64_t left_bits = bits / 2, right_bits = bits - left_bits;
+  const uint64_t left_mask = (1ull << left_bits) - 1, right_mask = (1ull << right_bits) - 1;
+  uint64_t count = 0;
+  for (uint64_t idx = 0; idx < (1ull << bits); ++idx) {
+    uint32_t s0 = (uint32_t)(idx >> right_bits), s1 = (uint32_t)(idx & right_mask);
+    for (int i = 0; i < 24; ++i) {
+      uint64_t product = 0xD2B74407B1CE6E93ull * (uint64_t)s0;
+      uint32_t hi = (uint32_t)(product >> 32), lo = (uint32_t)product;
+      lo = (lo << (right_bits - left_bits)) | (s1 >> left_bits);
+      s0 = ((hi ^ key[i]) ^ s1) & (uint32_t)left_mask;
+      s1 = lo & (uint32_t)right_mask;
+    }
+    uint64_t image = ((uint64_t)s0 << right_bits) | (uint64_t)s1;
+    if (image < m) perm[count++] = (uint32_t)image;
+  }
+}
+
+/* ColumnSampler::ColSample on CUDA without feature weights (src/common/random.cc:27-46, random.cu:62-96): n_sel =
+ * max(1, int(colsample * size)); shuffle a copy of the features with the seed, keep the first n_sel, sort ascending.
+ * Returns n_sel. */
+ORC_API int32_t orc_col_sample(const int32_t* features, int32_t n, float colsample, uint32_t seed, int32_t* out) {
+  if (colsample == 1.0f) { memcpy(out, features, sizeof(int32_t) * (size_t)n); return n; }
+  int32_t n_sel = (int32_t)(colsample * (float)n);
+  if (n_sel < 1) n_sel = 1;
+  uint32_t* perm = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n ? n : 1));
+  orc_thrust_shuffle(seed, (uint64_t)n, perm);
+  for (int32_t i = 0; i < n_sel; ++i) out[i] = features[perm[i]];
+  for (int32_t i = 1; i < n_sel; ++i) { /* ascending */
+    int32_t v = out[i], j = i;
+    while (j > 0 && out[j - 1] > v) { out[j] = out[j - 1]; --j; }
+    out[j] = v;
+  }
+  free(perm);
+  return n_sel;
+}
+
 /* Gradient-based row sampling: cuda_impl::GradientBasedSampling::Sample (src/tree/gpu_hist/sampler.cu:98-115,
  * 257-312; helpers src/tree/hist/sampler.h:48-74, src/tree/gpu_hist/quantiser.cuh:22-47) on the QUANTISED pairs of one
  * target, in place:

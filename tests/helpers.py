@@ -140,6 +140,11 @@ class MT19937:
         y ^= y >> 18
         return y & 0xFFFFFFFF
 
+    def copy(self) -> "MT19937":
+        c = MT19937.__new__(MT19937)
+        c.mt, c.idx = list(self.mt), self.idx
+        return c
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # Data recipes of the fixtures generated by tools/probe_interaction_reference.py and tools/make_golden_cpu_categorical.py

@@ -543,3 +543,20 @@ def test_interaction_constraint_oracle_against_a_set_model():
             k = int(rng.integers(0, n_nodes))
             want = sampled if k == 0 else sorted(model[k] & set(sampled))
             assert ic.query(sampled, k) == want, (trial, k)
+
+
+def test_thrust_shuffle_known_answers(golden_dir):
+    """orc_thrust_shuffle against permutations produced by the toolkit's own thrust::shuffle (host backend of the same
+    generic algorithm the device runs; tools/thrust_vectors/shuffle_vectors.cpp): sizes around the cipher's
+    power-of-two boundaries (<= 16 uses 4 bits), seeds 0 / 2^31-1 / 2^32-1 (the engine's seed folding)."""
+    spec = json.load(open(os.path.join(golden_dir, "thrust_shuffle_known_answers.json")))
+    assert len(spec["cases"]) >= 50
+    for c in spec["cases"]:
+        assert orc.thrust_shuffle(c["seed"], c["n"]).tolist() == c["perm"], (c["seed"], c["n"])
+    # ColSample: a sorted subset of the right size, the whole set at 1.0, never empty
+    feats = np.arange(40, dtype=np.int32) * 2
+    s = orc.col_sample(feats, 0.5, 12345)
+    perm = orc.thrust_shuffle(12345, 40)
+    assert s.tolist() == sorted(feats[perm[:20]].tolist())
+    assert orc.col_sample(feats, 1.0, 1).tolist() == feats.tolist()
+    assert orc.col_sample(feats, 0.001, 1).size == 1

@@ -418,3 +418,36 @@ def test_oracle_reproduces_reference_gpu_gradient_based_sampling(case):
         _assert_tree_equals_reference(o, ref, t)
         leaf = np.array([n.leaf_value for n in o["nodes"]], dtype=np.float32)
         margin = (margin + _leaf_margin(leaf, o["position"])).astype(np.float32)
+
+
+@pytest.mark.skipif(not os.path.exists(NEXT_GOLD), reason="fixture not generated yet (tools/make_golden_gpu_next.py)")
+@pytest.mark.parametrize("case", _next_cases("bynode"), ids=lambda c: c["name"])
+def test_oracle_reproduces_reference_gpu_colsample_bynode(case):
+    """The per-node feature sets are regenerated from the Booster's mt19937: per tree, one draw seeds the tree-level
+    shuffle (colsample_bytree < 1 only, ColumnSampler::Init), then every GetFeatureSet call -- root, then left and
+    right child of every valid candidate in Pop order -- takes one draw for a thrust::shuffle of the tree set
+    (random.cu:62-96), restated by orc.col_sample."""
+    x, y = make_regression(case["n"], case["f"], seed=case["seed"])
+    cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+    cv = _f32(case["cut_values_bits"])
+    gb = orc.bin_dense(x, cp, cv)
+    prm = case["params"]
+    params = {k: v for k, v in prm.items() if k not in ("colsample_bynode", "colsample_bytree", "seed")}
+    p = orc.Param.make(**params)
+    max_nodes = min((1 << (p.max_depth + 1)) - 1 if p.max_depth > 0 else 1 << 30,
+                    2 * p.max_leaves - 1 if p.max_leaves > 0 else 1 << 30)
+    rng = MT19937(prm.get("seed", 0))
+    margin = np.zeros(case["n"], dtype=np.float32)
+    all_features = np.arange(case["f"], dtype=np.int32)
+    for t, ref in enumerate(case["trees"]):
+        bytree = prm.get("colsample_bytree", 1.0)
+        tree_set = orc.col_sample(all_features, bytree, rng.next()) if bytree < 1.0 else all_features
+        ahead = rng.copy()            # the draws the tree MAY use; the engine itself advances by the draws it DID use
+        sets = np.stack([orc.col_sample(tree_set, prm["colsample_bynode"], ahead.next()) for _ in range(max_nodes)])
+        gp = np.stack([margin - y, np.ones_like(y)], axis=1).astype(np.float32)
+        o = orc.update_tree(gb, cp, cv, gp, p, node_feature_sets=sets)
+        _assert_tree_equals_reference(o, ref, t)
+        for _ in range(o["eval_count"]):
+            rng.next()
+        leaf = np.array([n.leaf_value for n in o["nodes"]], dtype=np.float32)
+        margin = (margin + _leaf_margin(leaf, o["position"])).astype(np.float32)

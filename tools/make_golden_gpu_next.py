@@ -3,12 +3,15 @@
 whose oracle restatements are not yet pinned bit for bit on a GPU reference:
 
   * categorical features (so far pinned structurally on the reference's CPU hist trees),
-  * gradient-based row sampling (so far property-tested only).
+  * gradient-based row sampling (so far property-tested only),
+  * colsample_bynode (the oracle regenerates the reference's per-node draws from the Booster's mt19937 through its
+    restatement of thrust::shuffle, which is pinned on the toolkit's own vectors; the tree-level order of the draws
+    is what this fixture pins).
 
     python tools/make_golden_gpu_next.py --out gpurun_out/ref_gpu_next_trees.json
     cp gpurun_out/ref_gpu_next_trees.json tests/golden/        # activates the tests that wait for it
 
-tests/test_reference_golden.py::test_oracle_reproduces_reference_gpu_{categorical_trees,gradient_based_sampling} skip
+tests/test_reference_golden.py::test_oracle_reproduces_reference_gpu_{categorical_trees,gradient_based_sampling} and ..._colsample_bynode skip
 while the fixture is absent.  Inputs regenerate from the seeds through tests/helpers.
 """
 import argparse
@@ -34,6 +37,11 @@ CASES = [
     dict(name="cat_threshold8_lossguide", kind="categorical", seed=314, n=8000, max_bin=64, rounds=2,
          params=dict(max_depth=0, max_leaves=20, grow_policy="lossguide", eta=0.5, max_cat_to_onehot=4,
                      max_cat_threshold=8)),
+    dict(name="bynode_05", kind="bynode", seed=331, n=20000, f=24, max_bin=64, rounds=3,
+         params=dict(max_depth=5, eta=0.3, colsample_bynode=0.5)),
+    dict(name="bynode_06_bytree_07_lossguide", kind="bynode", seed=332, n=20000, f=24, max_bin=64, rounds=3,
+         params=dict(max_depth=0, max_leaves=20, grow_policy="lossguide", eta=0.3, colsample_bynode=0.6,
+                     colsample_bytree=0.7, seed=3)),
     dict(name="gbs_03", kind="sampling", seed=321, n=20000, f=12, max_bin=64, rounds=3,
          params=dict(max_depth=5, eta=0.3, subsample=0.3, sampling_method="gradient_based")),
     dict(name="gbs_07_seed9", kind="sampling", seed=322, n=20000, f=12, max_bin=64, rounds=3,
