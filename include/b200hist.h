@@ -296,6 +296,16 @@ B200HIST_API int b200hist_updater_set_node_feature_sets(b200hist_updater_t u, co
                                                         uint32_t n_per_set);
 B200HIST_API int b200hist_updater_last_eval_count(b200hist_updater_t u, int32_t* out);
 
+/* Column-sampling draws, many at once: ColumnSampler::ColSample on CUDA without feature weights (src/common/random.cc:
+ * 27-46; cuda_impl::SampleFeature, random.cu:62-96 = thrust::shuffle with default_random_engine(seed), keep the first
+ * n_sel = max(1, int(colsample * n)), sort ascending).  Draw d uses seeds_host[d] -- the value the reference obtains
+ * from ctx->Rng()() for that call.  out_host: n_draws x n_sel.  One launch instead of one host call per draw; n <= 8192.
+ * STATUS: compiled, never run on hardware; the arithmetic is pinned on the CPU against the toolkit's own
+ * thrust::shuffle (tests/golden/thrust_shuffle_known_answers.json). */
+B200HIST_API int b200hist_col_sample_stream(int device, const int32_t* features_host, uint32_t n, float colsample,
+                                            const uint32_t* seeds_host, uint32_t n_draws, int32_t* out_host,
+                                            uint32_t* n_sel_out, void* stream);
+
 /* Monotone constraints = TreeEvaluator (src/tree/split_evaluator.h:25-205): constraints_host[f] in {-1, 0, +1} for the
  * first n features (the rest 0); n = 0 or NULL removes them.  A non-empty list switches every split gain to the
  * weight-based form -(2 g w + (h + lambda) w^2) with child weights clamped into the bounds of the node being split

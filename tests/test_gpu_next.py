@@ -749,3 +749,20 @@ def test_several_trees_per_iteration_through_the_shim(xb, extra):
     our_trees = train("grow_b200_hist")
     assert len(ref_trees) == 3 * max(extra.get("num_class", 1), extra.get("num_parallel_tree", 1))
     assert json.dumps(our_trees) == json.dumps(ref_trees)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Column-sampling draws on the device (b200hist_col_sample_stream, csrc/colsample.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,colsample", [(1, 0.5), (7, 0.5), (16, 0.3), (17, 0.9), (256, 0.5), (257, 0.25), (1000, 0.01),
+                                         (4096, 0.7), (8192, 0.5), (40, 1.0)])
+def test_col_sample_stream_matches_the_thrust_shuffle_restatement(xb, n, colsample):
+    """Every draw of the stream equals ColSample restated on the CPU (oracle.col_sample, itself pinned on the toolkit's
+    thrust::shuffle): sizes around the cipher's power-of-two boundaries, the engine's seed folding, a sparse id set."""
+    rng = np.random.default_rng(n)
+    features = np.sort(rng.choice(3 * n + 5, size=n, replace=False)).astype(np.int32)
+    seeds = [0, 1, 2147483647, 4294967295] + [int(v) for v in rng.integers(0, 2 ** 32, size=60)]
+    got = xb.components.col_sample_stream(features, colsample, seeds)
+    assert got.shape[0] == len(seeds)
+    for d, seed in enumerate(seeds):
+        assert np.array_equal(got[d], orc.col_sample(features, colsample, seed)), (n, colsample, seed)

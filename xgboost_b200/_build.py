@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     "-I", CSRC,
 ]
 SOURCES = ["ellpack.cu", "quantise.cu", "histogram.cu", "evaluate.cu", "partition.cu", "updater.cu",
-           "components.cu", "comm.cu", "sketch.cu", "predict.cu", "sampling.cu"]
+           "components.cu", "comm.cu", "sketch.cu", "predict.cu", "sampling.cu", "colsample.cu"]
 
 
 def _digest(paths):

@@ -99,6 +99,19 @@ def evaluate_splits_cat(page: EllpackPage, hist: torch.Tensor, parent_sums: Sequ
     return list(out), is_cat, bits
 
 
+def col_sample_stream(features: Sequence[int], colsample: float, seeds: Sequence[int], device: int = 0) -> np.ndarray:
+    """b200hist_col_sample_stream: int32[len(seeds), n_sel], draw d = the reference's ColSample with engine seed
+    seeds[d]."""
+    f = np.ascontiguousarray(features, dtype=np.int32)
+    sd = np.ascontiguousarray([int(s) & 0xFFFFFFFF for s in seeds], dtype=np.uint32)
+    n_sel = c_uint32(0)
+    out = np.zeros((max(sd.size, 1), max(f.size, 1)), dtype=np.int32).reshape(-1)
+    _l.check(_l.load().b200hist_col_sample_stream(int(device), f.ctypes.data_as(POINTER(c_int32)), f.size,
+                                                 float(colsample), sd.ctypes.data_as(POINTER(c_uint32)), sd.size,
+                                                 out.ctypes.data_as(POINTER(c_int32)), byref(n_sel), c_void_p()))
+    return out[: sd.size * n_sel.value].reshape(sd.size, n_sel.value).copy()
+
+
 def partition(page: EllpackPage, ridx: torch.Tensor, seg_begin: Sequence[int], seg_count: Sequence[int],
               findex: Sequence[int], split_cond: Sequence[float], default_left: Sequence[bool]
               ) -> Tuple[torch.Tensor, List[int]]:

@@ -232,17 +232,40 @@ class B200HistMaker : public TreeUpdater {
       // the data, only its length does: draw the longest possible stream from a COPY of the engine, let the updater
       // take draw k for the k-th evaluated node, and replay the real engine by the count it reports.
       rng_before_columns_ = ctx_->Rng();
-      column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, param->colsample_bynode, 1.0f,
-                           param->colsample_bytree);
       std::int32_t max_nodes{0};
       B200_SHIM_CHECK(b200hist_updater_max_nodes(updater_, &max_nodes));
       std::size_t per_node = 0;
-      for (std::int32_t k = 0; k < max_nodes; ++k) {
-        auto p_set = column_sampler_.GetFeatureSet(ctx_, 0);
-        auto const& h_set = p_set->ConstHostVector();
-        if (k == 0) per_node = h_set.size();
-        CHECK_EQ(h_set.size(), per_node);
-        fs.insert(fs.end(), h_set.cbegin(), h_set.cend());
+      node_draws_by_seed_ = info.feature_weights.Empty() && info.num_col_ <= 8192;
+      if (node_draws_by_seed_) {
+        // One launch for the whole stream: the tree-level set comes from the reference's sampler (Init consumes the
+        // colsample_bytree draw exactly as it would), every node draw is ColSample(tree set, bynode) seeded with the
+        // engine's next output (random.cu:67), which b200hist_col_sample_stream restates on the device.
+        column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, 1.0f, 1.0f, param->colsample_bytree);
+        auto p_tree = column_sampler_.GetFeatureSet(ctx_, 0);
+        auto const& h_tree = p_tree->ConstHostVector();
+        std::vector<std::int32_t> tree_set(h_tree.cbegin(), h_tree.cend());
+        rng_after_init_ = ctx_->Rng();
+        auto ahead = ctx_->Rng();  // a copy: the real engine moves in FinishSampling by the draws really used
+        std::vector<std::uint32_t> seeds(static_cast<std::size_t>(max_nodes));
+        for (auto& sd : seeds) sd = static_cast<std::uint32_t>(ahead());
+        std::uint32_t n_sel = 0;
+        fs.resize(static_cast<std::size_t>(max_nodes) * tree_set.size());
+        B200_SHIM_CHECK(b200hist_col_sample_stream(ctx_->Ordinal(), tree_set.data(),
+                                                   static_cast<std::uint32_t>(tree_set.size()), param->colsample_bynode,
+                                                   seeds.data(), static_cast<std::uint32_t>(max_nodes), fs.data(), &n_sel,
+                                                   static_cast<void*>(ctx_->CUDACtx()->Stream())));
+        per_node = n_sel;
+        fs.resize(static_cast<std::size_t>(max_nodes) * per_node);
+      } else {  // feature weights: weighted sampling without replacement, through the reference's own sampler
+        column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, param->colsample_bynode, 1.0f,
+                             param->colsample_bytree);
+        for (std::int32_t k = 0; k < max_nodes; ++k) {
+          auto p_set = column_sampler_.GetFeatureSet(ctx_, 0);
+          auto const& h_set = p_set->ConstHostVector();
+          if (k == 0) per_node = h_set.size();
+          CHECK_EQ(h_set.size(), per_node);
+          fs.insert(fs.end(), h_set.cbegin(), h_set.cend());
+        }
       }
       B200_SHIM_CHECK(b200hist_updater_set_level_feature_sets(updater_, nullptr, 0, 0));
       B200_SHIM_CHECK(b200hist_updater_set_tree_sampling(updater_, nullptr, 0, rows ? param->subsample : 1.0f, seed));
@@ -291,6 +314,12 @@ class B200HistMaker : public TreeUpdater {
     if (node_draws_pending_) {  // colsample_bynode: as many draws as nodes were evaluated
       std::int32_t n_draws = 0;
       B200_SHIM_CHECK(b200hist_updater_last_eval_count(updater_, &n_draws));
+      if (node_draws_by_seed_) {  // one engine output per ColSample call
+        ctx_->Rng() = rng_after_init_;
+        ctx_->Rng().discard(static_cast<unsigned long long>(n_draws));
+        node_draws_pending_ = false;
+        return;
+      }
       ctx_->Rng() = rng_before_columns_;
       auto const& info = p_fmat->Info();
       column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, param->colsample_bynode, 1.0f,
@@ -370,12 +399,14 @@ class B200HistMaker : public TreeUpdater {
   bool sampling_set_{false};
   bool level_draws_pending_{false};
   bool node_draws_pending_{false};
+  bool node_draws_by_seed_{false};
   bool has_categorical_{false};
   std::uint32_t cat_words_{0};
   std::vector<std::int32_t> node_is_cat_;
   std::vector<std::uint32_t> cat_bits_;
   std::vector<std::uint32_t> ellpack_cut_bins_;
   std::remove_reference_t<decltype(std::declval<Context const&>().Rng())> rng_before_columns_;
+  std::remove_reference_t<decltype(std::declval<Context const&>().Rng())> rng_after_init_;
 };
 
 // Replaces the factory of the reference's own "grow_gpu_hist" entry (keeping the original reachable as
