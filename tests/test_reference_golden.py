@@ -451,3 +451,38 @@ def test_oracle_reproduces_reference_gpu_colsample_bynode(case):
             rng.next()
         leaf = np.array([n.leaf_value for n in o["nodes"]], dtype=np.float32)
         margin = (margin + _leaf_margin(leaf, o["position"])).astype(np.float32)
+
+
+@pytest.mark.skipif(not os.path.exists(NEXT_GOLD), reason="fixture not generated yet (tools/make_golden_gpu_next.py)")
+@pytest.mark.parametrize("case", _next_cases("colsample"), ids=lambda c: c["name"])
+def test_oracle_reproduces_reference_gpu_colsample_bytree_bylevel(case):
+    """Engine draws per tree, in the reference's order (GPUHistMakerDevice::Reset, updater_gpu_hist.cu:172-211): the row
+    sampler's seed (subsample < 1), the tree-level shuffle seed (colsample_bytree < 1, ColumnSampler::Init), then one
+    seed per depth the first time a node of that depth is evaluated (colsample_bylevel < 1, random.h:156-175)."""
+    x, y = make_regression(case["n"], case["f"], seed=case["seed"])
+    cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+    cv = _f32(case["cut_values_bits"])
+    gb = orc.bin_dense(x, cp, cv)
+    prm = case["params"]
+    params = {k: v for k, v in prm.items() if k not in ("colsample_bylevel", "colsample_bytree", "subsample", "seed")}
+    p = orc.Param.make(**params)
+    rng = MT19937(prm.get("seed", 0))
+    margin = np.zeros(case["n"], dtype=np.float32)
+    all_features = np.arange(case["f"], dtype=np.int32)
+    sub, bytree, bylevel = prm.get("subsample", 1.0), prm.get("colsample_bytree", 1.0), prm.get("colsample_bylevel", 1.0)
+    for t, ref in enumerate(case["trees"]):
+        row_seed = rng.next() if sub < 1.0 else 0
+        tree_set = orc.col_sample(all_features, bytree, rng.next()) if bytree < 1.0 else all_features
+        gp = np.stack([margin - y, np.ones_like(y)], axis=1).astype(np.float32)
+        if bylevel < 1.0:
+            ahead = rng.copy()
+            levels = np.stack([orc.col_sample(tree_set, bylevel, ahead.next()) for _ in range(p.max_depth)])
+            o = orc.update_tree(gb, cp, cv, gp, p, subsample=sub, sample_seed=row_seed, level_feature_sets=levels)
+            deepest = max(nd.depth for nd, c in zip(o["nodes"], o["cands"]) if c.loss_chg != 0.0)   # evaluated nodes
+            for _ in range(deepest + 1):
+                rng.next()
+        else:
+            o = orc.update_tree(gb, cp, cv, gp, p, subsample=sub, sample_seed=row_seed, feature_set=tree_set)
+        _assert_tree_equals_reference(o, ref, t)
+        leaf = np.array([n.leaf_value for n in o["nodes"]], dtype=np.float32)
+        margin = (margin + _leaf_margin(leaf, o["position"])).astype(np.float32)

@@ -42,6 +42,12 @@ CASES = [
     dict(name="bynode_06_bytree_07_lossguide", kind="bynode", seed=332, n=20000, f=24, max_bin=64, rounds=3,
          params=dict(max_depth=0, max_leaves=20, grow_policy="lossguide", eta=0.3, colsample_bynode=0.6,
                      colsample_bytree=0.7, seed=3)),
+    dict(name="bytree_05", kind="colsample", seed=341, n=20000, f=24, max_bin=64, rounds=3,
+         params=dict(max_depth=5, eta=0.3, colsample_bytree=0.5)),
+    dict(name="bylevel_05", kind="colsample", seed=342, n=20000, f=24, max_bin=64, rounds=3,
+         params=dict(max_depth=6, eta=0.3, colsample_bylevel=0.5, seed=11)),
+    dict(name="bylevel_06_bytree_07_subsample", kind="colsample", seed=343, n=20000, f=24, max_bin=64, rounds=3,
+         params=dict(max_depth=5, eta=0.3, colsample_bylevel=0.6, colsample_bytree=0.7, subsample=0.8)),
     dict(name="gbs_03", kind="sampling", seed=321, n=20000, f=12, max_bin=64, rounds=3,
          params=dict(max_depth=5, eta=0.3, subsample=0.3, sampling_method="gradient_based")),
     dict(name="gbs_07_seed9", kind="sampling", seed=322, n=20000, f=12, max_bin=64, rounds=3,
