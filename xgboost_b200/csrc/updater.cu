@@ -1530,7 +1530,10 @@ int b200hist_updater_set_node_feature_sets(b200hist_updater_t u, const int32_t* 
     u->n_per_node = (int32_t)n_per_set;
     u->d_node_sets = DevAlloc<int32_t>((size_t)n_sets * n_per_set);
     B200_CUDA(cudaMemcpy(u->d_node_sets, sets_host, sizeof(int32_t) * (size_t)n_sets * n_per_set, cudaMemcpyHostToDevice));
-    u->d_node_list = DevAlloc<int32_t>(2 * (size_t)kMaxLevelNodes * n_per_set);
+    // evaluation slots of one step: twice the most nodes any step can expand (host-known, data independent)
+    size_t max_cap = 1;
+    for (uint32_t c : u->step_cap) max_cap = std::max<size_t>(max_cap, c);
+    u->d_node_list = DevAlloc<int32_t>(2 * max_cap * n_per_set);
     u->d_node_count = DevAlloc<int32_t>(2 * (size_t)kMaxLevelNodes);
     u->d_node_seq = DevAlloc<int32_t>(1);
     B200_CUDA(cudaMemset(u->d_node_seq, 0, sizeof(int32_t)));
