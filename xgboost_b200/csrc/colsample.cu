@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t BlockExclusiveScanCs(uint32_t v, uint32_t* s
 __global__ void __launch_bounds__(kCsThreads) ColSampleStreamKernel(const int32_t* __restrict__ features, int32_t n,
                                                                      int32_t n_sel, const uint32_t* __restrict__ seeds,
                                                                      int32_t* __restrict__ out) {
-  extern __shared__ int32_t s_sel[];  // n_sel selected ids, then n_sel sorted ids
+  B200_DYNAMIC_SHARED(int32_t, s_sel);  // n_sel selected ids, then n_sel sorted ids
   __shared__ uint32_t s_key[24];
   __shared__ uint32_t s_warp[33];
   int32_t* s_sorted = s_sel + n_sel;
@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(kCsThreads) ColSampleStreamKernel(const int32_
   for (int i = threadIdx.x; i < n_sel; i += kCsThreads) out[(size_t)blockIdx.x * n_sel + i] = s_sorted[i];
 }
 
+#ifndef B200_KERNELS_ONLY
 void LaunchColSampleStream(const int32_t* features_dev, int32_t n, int32_t n_sel, const uint32_t* seeds_dev,
                            int32_t n_draws, int32_t* out_dev, cudaStream_t s) {
   if (n_draws == 0) return;
@@ -121,8 +122,11 @@ void LaunchColSampleStream(const int32_t* features_dev, int32_t n, int32_t n_sel
   B200_LAUNCHED();
 }
 
+#endif  // B200_KERNELS_ONLY
+
 }  // namespace b200
 
+#ifndef B200_KERNELS_ONLY
 using namespace b200;
 
 // Stand-alone entry: out_host[n_draws][n_sel], n_sel = max(1, int(colsample * n)).
@@ -155,3 +159,4 @@ extern "C" int b200hist_col_sample_stream(int device, const int32_t* features_ho
   cudaFree(d_out);
   B200_API_END();
 }
+#endif  // B200_KERNELS_ONLY

@@ -12,6 +12,13 @@
 
 #include "b200hist.h"
 
+// Dynamic shared memory of a kernel.  The CPU emulator of the tests (tests/emu/cuda_emu.h) supplies its own definition
+// so that the kernel sources run unmodified there; B200_KERNELS_ONLY (also set by those tests) compiles the host
+// launchers out, which the emulator cannot parse (<<< >>>).
+#ifndef B200_DYNAMIC_SHARED
+#define B200_DYNAMIC_SHARED(type, name) extern __shared__ type name[]
+#endif
+
 namespace b200 {
 
 // ---------------------------------------------------------------------------------------------

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(256) PredictLeafKernel(EllView ell, ForestView
 
 }  // namespace b200
 
+#ifndef B200_KERNELS_ONLY
 using namespace b200;
 
 struct b200hist_forest_s {
@@ -290,3 +291,4 @@ int b200hist_forest_predict_leaf(b200hist_forest_t f, b200hist_ellpack_t page, u
 }
 
 }  // extern "C"
+#endif  // B200_KERNELS_ONLY
