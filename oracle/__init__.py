@@ -156,6 +156,29 @@ def eval_node(hist: np.ndarray, parent_sum, cut_ptrs, cut_values, param: Param, 
     return (out, gains) if want_gains else out
 
 
+def eval_node_mono(hist: np.ndarray, parent_sum, cut_ptrs, cut_values, param: Param, scale, feature_set=None,
+                   monotone=None, lower=-3.402823466e+38, upper=3.402823466e+38):
+    """orc_eval_node_mono: eval_node under monotone constraints (sign per feature, weight bounds of this node)."""
+    h = np.ascontiguousarray(hist, dtype=np.int64)
+    cp = np.ascontiguousarray(cut_ptrs, dtype=np.uint32)
+    cv = np.ascontiguousarray(cut_values, dtype=np.float32)
+    sc = (c_double * 4)(*[float(v) for v in scale])
+    out = Candidate()
+    if feature_set is not None:
+        fs = np.ascontiguousarray(feature_set, dtype=np.int32)
+        fsp, nfs = _p(fs), fs.size
+    else:
+        fsp, nfs = c_void_p(), 0
+    mono = None
+    if monotone is not None:
+        mono = np.zeros(cp.size - 1, dtype=np.int32)
+        mono[:len(monotone)] = np.asarray(monotone, dtype=np.int32)
+    lib().orc_eval_node_mono(_p(h), GPair64(int(parent_sum[0]), int(parent_sum[1])), _p(cp), _p(cv),
+                             c_uint32(cp.size - 1), fsp, c_int32(nfs), byref(param), sc, byref(out), c_void_p(),
+                             _p(mono) if mono is not None else c_void_p(), c_float(lower), c_float(upper))
+    return out
+
+
 def eval_node_cat(hist: np.ndarray, parent_sum, cut_ptrs, cut_values, param: Param, scale, feature_is_cat,
                   max_cat_to_onehot: int, max_cat_threshold: int = 64, feature_set=None):
     """Best split over numerical and categorical features (evaluate_splits.cu:148-348).  Returns

@@ -146,3 +146,180 @@ def test_predict_kernel_sources(tmp_path, kind):
     assert np.array_equal(margin.view(np.uint32), want.view(np.uint32))
     for t, o in enumerate(trees):
         assert np.array_equal(leaves[:, t], orc.predict_leaf(gb, cp, cv, o["nodes"], o.get("is_cat"), o.get("cat_sets")))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Split evaluation (csrc/evaluate.cu) under the emulator.  The emulator divides in IEEE arithmetic like the oracle (the
+# device uses div.approx), so everything -- loss_chg included -- must agree bit for bit.
+# ---------------------------------------------------------------------------------------------------------------------
+CAND = np.dtype([("loss_chg", "<f4"), ("dir", "<i4"), ("findex", "<i4"), ("fvalue", "<f4"), ("left_g", "<i8"),
+                 ("left_h", "<i8"), ("right_g", "<i8"), ("right_h", "<i8"), ("base_weight", "<f4"),
+                 ("left_weight", "<f4"), ("right_weight", "<f4"), ("split_gbin", "<i4")])
+
+
+def _evaluate(tmp_path, cp, cv, hists, parents, params, scale, depth=None, feature_set=None, n_levels=0, ic_list=None,
+              ic_count=None, ic_stride=0, mono=None, lower=None, upper=None, is_cat=None, onehot=4, threshold=64):
+    exe = _build("emu_evaluate")
+    n_eval, total_bins = hists.shape[0], hists.shape[1]
+    nf = cp.size - 1
+    n_fs = nf if feature_set is None else (feature_set.shape[-1])
+    cat_words = int(cv.max()) // 32 + 1
+    max_cat_bins = int(max([cp[f + 1] - cp[f] for f in range(nf) if is_cat is not None and is_cat[f]] or [1]))
+    ic_mode = 0 if ic_count is None else (2 if ic_stride > 0 else 1)
+    d = str(tmp_path)
+    np.array([nf, total_bins, n_eval, n_fs, 0 if feature_set is None else 1, n_levels, ic_mode, ic_stride,
+              0 if mono is None else 1, 0 if is_cat is None else 1, onehot, threshold, cat_words,
+              (max_cat_bins + 31) // 32, max_cat_bins], dtype=np.int32).tofile(os.path.join(d, "meta.bin"))
+    p = orc.Param.make(**params)
+    np.array([p.learning_rate, p.reg_lambda, p.reg_alpha, p.min_child_weight, p.max_delta_step, p.min_split_loss],
+             dtype=np.float32).tofile(os.path.join(d, "param_f.bin"))
+    np.array([p.max_depth, p.max_leaves, p.grow_policy], dtype=np.int32).tofile(os.path.join(d, "param_i.bin"))
+    np.asarray(scale, dtype=np.float64).tofile(os.path.join(d, "quant.bin"))
+    cp.astype(np.uint32).tofile(os.path.join(d, "cut_ptrs.bin"))
+    cv.astype(np.float32).tofile(os.path.join(d, "cut_values.bin"))
+    np.ascontiguousarray(hists, dtype=np.int64).tofile(os.path.join(d, "hist.bin"))
+    np.asarray(parents, dtype=np.int64).tofile(os.path.join(d, "parents.bin"))
+    np.asarray(depth if depth is not None else np.zeros(n_eval), dtype=np.int32).tofile(os.path.join(d, "depth.bin"))
+    for name, arr, dt in (("feature_set", feature_set, np.int32), ("ic_list", ic_list, np.int32),
+                          ("ic_count", ic_count, np.int32), ("mono", mono, np.int32), ("is_cat", is_cat, np.uint8)):
+        if arr is not None:
+            np.ascontiguousarray(arr, dtype=dt).tofile(os.path.join(d, name + ".bin"))
+    np.asarray(lower if lower is not None else np.full(n_eval, -3.402823466e+38), dtype=np.float32).tofile(os.path.join(d, "lower.bin"))
+    np.asarray(upper if upper is not None else np.full(n_eval, 3.402823466e+38), dtype=np.float32).tofile(os.path.join(d, "upper.bin"))
+    subprocess.run([exe, d], check=True, timeout=900)
+    cand = np.fromfile(os.path.join(d, "cand.bin"), dtype=CAND)
+    flags = np.fromfile(os.path.join(d, "node_is_cat.bin"), dtype=np.uint8)
+    bits = np.fromfile(os.path.join(d, "cat_bits.bin"), dtype=np.uint32).reshape(n_eval, -1)
+    return cand, flags, bits
+
+
+def _same_candidate(c, o, name, cat=False):
+    assert (int(c["findex"]), int(c["dir"])) == (o.findex, o.dir), name
+    assert (int(c["left_g"]), int(c["left_h"]), int(c["right_g"]), int(c["right_h"])) == \
+        (o.left_sum.g, o.left_sum.h, o.right_sum.g, o.right_sum.h), name
+    for a, b in ((c["loss_chg"], o.loss_chg), (c["base_weight"], o.base_weight), (c["left_weight"], o.left_weight),
+                 (c["right_weight"], o.right_weight)):
+        assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32), (name, a, b)
+    if cat:
+        assert np.isnan(c["fvalue"]) and c["split_gbin"] == -1, name
+    else:
+        assert np.float32(c["fvalue"]).view(np.uint32) == np.float32(o.fvalue).view(np.uint32), name
+        assert int(c["split_gbin"]) == o.split_gbin, name
+
+
+def _histograms(n=6000, f=14, max_bin=48, missing=0.1, seed=3):
+    from tests.helpers import logistic_gpair
+    x, y = make_regression(n, f, seed=seed, missing=missing)
+    cp, cv = make_cuts(x, max_bin)
+    gb = orc.bin_dense(x, cp, cv)
+    gp = logistic_gpair(y, (y > 0).astype(np.float32))
+    scale, _ = orc.quantiser(gp)
+    gq = orc.quantise(gp, scale)
+    rng = np.random.default_rng(seed)
+    subsets = [np.arange(n), rng.choice(n, 900, replace=False), rng.choice(n, 70, replace=False),
+               rng.choice(n, 2500, replace=False), rng.choice(n, 9, replace=False)]
+    hists = np.stack([orc.build_hist(gb, gq, s.astype(np.uint32), cv.size) for s in subsets])
+    parents = np.array([gq[s].sum(axis=0) for s in subsets], dtype=np.int64)
+    return cp, cv, hists, parents, scale
+
+
+@pytest.mark.parametrize("params", [dict(), dict(reg_alpha=0.4, min_child_weight=20.0), dict(max_delta_step=0.6, reg_lambda=0.0)],
+                         ids=["default", "alpha_mcw", "delta_step"])
+def test_evaluation_kernel_sources_plain_and_feature_lists(tmp_path, params):
+    cp, cv, hists, parents, scale = _histograms()
+    nf = cp.size - 1
+    p = orc.Param.make(**params)
+    # all features
+    cand, _, _ = _evaluate(tmp_path, cp, cv, hists, parents, params, scale)
+    for k in range(len(parents)):
+        _same_candidate(cand[k], orc.eval_node(hists[k], parents[k], cp, cv, p, scale), "all features, node %d" % k)
+    # one list per evaluation slot (colsample_bynode): IcView with a stride
+    rng = np.random.default_rng(8)
+    lists = np.stack([np.sort(rng.permutation(nf)[:5]) for _ in range(len(parents))]).astype(np.int32)
+    counts = np.full(len(parents), 5, dtype=np.int32)
+    cand, _, _ = _evaluate(tmp_path, cp, cv, hists, parents, params, scale, ic_list=lists, ic_count=counts, ic_stride=5)
+    for k in range(len(parents)):
+        _same_candidate(cand[k], orc.eval_node(hists[k], parents[k], cp, cv, p, scale, feature_set=lists[k]),
+                        "per-slot list, node %d" % k)
+    # one shared list, a count per slot (interaction constraints): duplicates and an empty answer included
+    shared = np.array([2, 3, 7, 7, 11, 12, 13, 0, 0, 0, 0, 0, 0, 0], dtype=np.int32)
+    counts = np.array([7, 4, 0, 5, 1], dtype=np.int32)
+    cand, _, _ = _evaluate(tmp_path, cp, cv, hists, parents, params, scale, ic_list=shared, ic_count=counts, ic_stride=0)
+    for k in range(len(parents)):
+        if counts[k] == 0:
+            assert cand[k]["findex"] == -1 and cand[k]["loss_chg"] < -1e30, k
+            continue
+        _same_candidate(cand[k], orc.eval_node(hists[k], parents[k], cp, cv, p, scale, feature_set=shared[:counts[k]]),
+                        "shared list, node %d" % k)
+    # colsample_bylevel: one list per depth, the last row serves deeper nodes
+    levels = np.stack([np.sort(rng.permutation(nf)[:6]) for _ in range(3)]).astype(np.int32)
+    depth = np.array([0, 1, 2, 5, 1], dtype=np.int32)
+    cand, _, _ = _evaluate(tmp_path, cp, cv, hists, parents, params, scale, depth=depth, feature_set=levels, n_levels=3)
+    for k in range(len(parents)):
+        _same_candidate(cand[k], orc.eval_node(hists[k], parents[k], cp, cv, p, scale, feature_set=levels[min(depth[k], 2)]),
+                        "level list, node %d" % k)
+
+
+def test_evaluation_kernel_sources_monotone(tmp_path):
+    cp, cv, hists, parents, scale = _histograms(seed=4)
+    nf = cp.size - 1
+    mono = np.array([1, -1, 0, 1, 0, -1, 1, 0, 0, -1, 1, 1, 0, -1], dtype=np.int32)[:nf]
+    lower = np.array([-3.402823466e+38, -0.2, -3.402823466e+38, 0.05, -1.0], dtype=np.float32)
+    upper = np.array([3.402823466e+38, 3.402823466e+38, 0.1, 0.4, 1.0], dtype=np.float32)
+    params = dict(reg_lambda=1.0)
+    cand, _, _ = _evaluate(tmp_path, cp, cv, hists, parents, params, scale, mono=mono, lower=lower, upper=upper)
+    p = orc.Param.make(**params)
+    for k in range(len(parents)):
+        o = orc.eval_node_mono(hists[k], parents[k], cp, cv, p, scale, monotone=mono, lower=float(lower[k]), upper=float(upper[k]))
+        _same_candidate(cand[k], o, "monotone, node %d" % k)
+
+
+@pytest.mark.parametrize("onehot,threshold", [(4, 64), (1, 64), (100, 64), (4, 5)])
+def test_evaluation_kernel_sources_categorical(tmp_path, onehot, threshold):
+    """CatFeatureScanKernel / CatFinishKernel incl. features with more than 32 and more than 64 categories (several
+    arg-max chunks in both scan directions), next to numerical features, on nodes of very different sizes."""
+    rng = np.random.default_rng(17)
+    n = 6000
+    n_cats = [2, 3, 5, 9, 31, 33, 70]
+    cols, cut_ptrs, cut_values, is_cat = [], [0], [], []
+    for k in n_cats:
+        col = rng.integers(0, k, size=n).astype(np.float32)
+        col[rng.random(n) < 0.08] = np.nan
+        cols.append(col)
+        cut_values += [float(v) for v in range(k)]
+        cut_ptrs.append(len(cut_values))
+        is_cat.append(1)
+    xnum, _ = make_regression(n, 3, seed=23, missing=0.05)
+    ncp, ncv = make_cuts(xnum, 32)
+    for j in range(3):
+        cols.append(xnum[:, j])
+        cut_values += [float(v) for v in ncv[ncp[j]:ncp[j + 1]]]
+        cut_ptrs.append(len(cut_values))
+        is_cat.append(0)
+    cp, cv = np.array(cut_ptrs, dtype=np.uint32), np.array(cut_values, dtype=np.float32)
+    from tests.test_reference_golden import categorical_global_bins
+    gb = categorical_global_bins(np.column_stack(cols).astype(np.float32), cp, cv, is_cat)
+    effect = rng.normal(size=70)
+    y = (effect[np.nan_to_num(cols[6], nan=0).astype(int)] + 0.5 * effect[np.nan_to_num(cols[4], nan=0).astype(int)] +
+         np.nan_to_num(xnum[:, 0]) + 0.3 * rng.normal(size=n)).astype(np.float32)
+    gp = squared_error_gpair(np.zeros(n, np.float32), y)
+    scale, _ = orc.quantiser(gp)
+    gq = orc.quantise(gp, scale)
+    subsets = [np.arange(n), rng.choice(n, 900, replace=False), rng.choice(n, 60, replace=False)]
+    hists = np.stack([orc.build_hist(gb, gq, s.astype(np.uint32), cv.size) for s in subsets])
+    parents = np.array([gq[s].sum(axis=0) for s in subsets], dtype=np.int64)
+    params = dict(min_child_weight=2.0)
+    cand, flags, bits = _evaluate(tmp_path, cp, cv, hists, parents, params, scale, is_cat=np.array(is_cat, dtype=np.uint8),
+                                  onehot=onehot, threshold=threshold)
+    p = orc.Param.make(**params)
+    n_cat_winners = 0
+    for k in range(len(parents)):
+        o, o_is_cat, _, o_cats = orc.eval_node_cat(hists[k], parents[k], cp, cv, p, scale, is_cat, onehot, threshold)
+        _same_candidate(cand[k], o, "categorical, node %d" % k, cat=o_is_cat)
+        assert bool(flags[k]) == o_is_cat, k
+        if o_is_cat:
+            n_cat_winners += 1
+            got = {32 * w + (31 - b) for w in range(bits.shape[1]) for b in range(32) if (int(bits[k, w]) >> b) & 1}
+            assert got == o_cats, (k, got, o_cats)
+    if threshold == 64 and onehot != 100:   # in the other configurations a numerical feature wins on this data
+        assert n_cat_winners >= 1

@@ -376,7 +376,7 @@ CatFeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int3
                      const int32_t* __restrict__ feature_set, int32_t n_fs, ParamDev p,
                      const QuantDev* __restrict__ q, FeatCand* __restrict__ scratch, MonoView mono, int32_t n_levels,
                      IcView ic, CatView cat) {
-  extern __shared__ unsigned char s_cat_raw[];
+  B200_DYNAMIC_SHARED(unsigned char, s_cat_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float* w_s = reinterpret_cast<float*>(s_cat_raw) + (size_t)warp * cat.max_cat_bins;
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32)
 CatFinishKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t* __restrict__ eval_nodes,
                 const TreeState* __restrict__ ts, const NodeDev* __restrict__ nodes, ParamDev p,
                 const QuantDev* __restrict__ q, b200hist_candidate* __restrict__ cand, CatView cat) {
-  extern __shared__ unsigned char s_cat_raw[];
+  B200_DYNAMIC_SHARED(unsigned char, s_cat_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float* w_s = reinterpret_cast<float*>(s_cat_raw) + (size_t)warp * cat.max_cat_bins;
@@ -567,6 +567,7 @@ CatFinishKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t* 
   }
 }
 
+#ifndef B200_KERNELS_ONLY
 void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist, const int32_t* eval_nodes, const TreeState* ts,
                     int32_t max_eval, const NodeDev* nodes, const int32_t* feature_set, int32_t n_feature_set,
                     const ParamDev& p, const QuantDev* q, FeatCand* scratch, b200hist_candidate* cand,
@@ -611,5 +612,7 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist, const int3
   B200_LAUNCHED();
   finish_cat();
 }
+
+#endif  // B200_KERNELS_ONLY
 
 }  // namespace b200
