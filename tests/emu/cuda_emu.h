@@ -60,6 +60,8 @@ inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n); return 0; }
 template <typename T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = static_cast<T*>(std::malloc(n)); return 0; }
 inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 1; return 0; }
 
 namespace emu {
 
@@ -144,6 +146,10 @@ inline unsigned __reduce_or_sync(unsigned, unsigned v) {
   return r;
 }
 
+using std::isnan;
+using std::isinf;
+inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }

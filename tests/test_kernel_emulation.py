@@ -323,3 +323,160 @@ def test_evaluation_kernel_sources_categorical(tmp_path, onehot, threshold):
             assert got == o_cats, (k, got, o_cats)
     if threshold == 64 and onehot != 100:   # in the other configurations a numerical feature wins on this data
         assert n_cat_winners >= 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Control kernels of csrc/updater.cu and the categorical re-binning kernel of csrc/ellpack.cu
+# ---------------------------------------------------------------------------------------------------------------------
+def test_node_set_level_kernel_source(tmp_path):
+    """NodeSetLevelKernel deals draw seq + j to evaluation slot j and moves the stream position, step after step."""
+    exe = _build("emu_updater")
+    rng = np.random.default_rng(3)
+    n_sets, n_per = 40, 7
+    sets = rng.integers(0, 100, size=(n_sets, n_per)).astype(np.int32)
+    steps = np.array([1, 2, 4, 0, 6, 2], dtype=np.int32)
+    d = str(tmp_path)
+    np.array([n_sets, n_per, 0], dtype=np.int32).tofile(os.path.join(d, "meta.bin"))
+    sets.tofile(os.path.join(d, "sets.bin"))
+    steps.tofile(os.path.join(d, "steps.bin"))
+    _run(exe, "nodeset", d)
+    lists = np.fromfile(os.path.join(d, "lists.bin"), dtype=np.int32).reshape(-1, n_per)
+    counts = np.fromfile(os.path.join(d, "counts.bin"), dtype=np.int32)
+    seq = int(np.fromfile(os.path.join(d, "seq.bin"), dtype=np.int32)[0])
+    assert seq == steps.sum() and lists.shape[0] == steps.sum()
+    assert np.array_equal(lists, sets[:steps.sum()]) and (counts == n_per).all()
+
+
+@pytest.mark.parametrize("with_level_set", [False, True], ids=["all_features", "level_set"])
+def test_interaction_level_kernel_source(tmp_path, with_level_set):
+    """IcLevelKernel: Split of the level's applied splits, per-slot counts and the shared Query buffer image, against
+    the oracle's bit fields and a literal replay of the reference's sequential buffer writes.  130 features = three
+    64-bit words; several levels are chained so that bit fields inherited from earlier launches are used."""
+    exe = _build("emu_updater")
+    rng = np.random.default_rng(11)
+    nf = 130
+    sets = [[0, 1, 129], [129, 64, 65], [65, 100], [2, 3], [3, 64], [100, 7, 8, 9]]
+    set_ptr = np.cumsum([0] + [len(s) for s in sets]).astype(np.int32)
+    set_feat = np.array([f for s in sets for f in s], dtype=np.int32)
+    max_nodes = 63
+    words = (nf + 63) // 64
+    bits = np.zeros((max_nodes, words), dtype=np.uint64)
+    ic = orc.InteractionConstraints(sets, nf, max_nodes=max_nodes)
+    level_sets = np.stack([np.sort(rng.permutation(nf)[:60]) for _ in range(4)]).astype(np.int32)
+    depth = np.zeros(max_nodes, dtype=np.int32)
+    level, n_nodes = [0], 1
+    pool = [0, 1, 129, 64, 65, 100, 2, 3, 7, 50, 77]      # split features: members of sets and free ones
+    for d_level in range(4):
+        parts = []
+        for nidx in level:
+            left, right = n_nodes, n_nodes + 1
+            n_nodes += 2
+            depth[left] = depth[right] = d_level + 1
+            parts.append((nidx, int(rng.choice(pool)), left, right))
+        dd = str(tmp_path)
+        n_fs = level_sets.shape[1] if with_level_set else 0
+        np.array([nf, len(sets), max_nodes, len(parts), n_fs, 4 if with_level_set else 0, 1 if with_level_set else 0],
+                 dtype=np.int32).tofile(os.path.join(dd, "meta.bin"))
+        set_ptr.tofile(os.path.join(dd, "set_ptr.bin"))
+        set_feat.tofile(os.path.join(dd, "set_feat.bin"))
+        bits.tofile(os.path.join(dd, "bits.bin"))
+        np.array(parts, dtype=np.int32).tofile(os.path.join(dd, "part.bin"))
+        depth.tofile(os.path.join(dd, "depth.bin"))
+        if with_level_set:
+            level_sets.tofile(os.path.join(dd, "feature_set.bin"))
+        _run(exe, "iclevel", dd)
+        bits = np.fromfile(os.path.join(dd, "bits_out.bin"), dtype=np.uint64).reshape(max_nodes, words)
+        got_list = np.fromfile(os.path.join(dd, "list.bin"), dtype=np.int32)
+        got_count = np.fromfile(os.path.join(dd, "count.bin"), dtype=np.int32)
+        # the oracle's fields after the same splits
+        for nidx, f, left, right in parts:
+            ic.split(nidx, f, left, right)
+        for k in range(n_nodes):
+            mine = [f for f in range(nf) if (int(bits[k, f >> 6]) >> (f & 63)) & 1]
+            assert mine == ic.query_node(k), (d_level, k)
+        # the reference's buffer: every Query writes its answer to the front, in the order left0, right0, left1, ...
+        sampled = level_sets[min(d_level + 1, 3)].tolist() if with_level_set else list(range(nf))
+        buffer = [-7] * nf
+        order = [c for _, _, left, right in parts for c in (left, right)]
+        for j, node in enumerate(order):
+            answer = ic.query(sampled, node)
+            buffer[:len(answer)] = answer
+            assert got_count[j] == len(answer), (d_level, j)
+        longest = max(got_count[:len(order)])
+        assert got_list[:longest].tolist() == buffer[:longest], d_level
+        level = order if d_level < 2 else order[:6]
+
+
+@pytest.mark.parametrize("bin_bytes", [1, 2])
+def test_rebin_categorical_kernel_source(tmp_path, bin_bytes):
+    """RebinCategoricalKernel = HistogramCuts::SearchCatBin on the categorical columns, other columns untouched."""
+    exe = _build("emu_updater")
+    rng = np.random.default_rng(5)
+    n, nf = 700, 6
+    ks = {1: 5, 4: 300 if bin_bytes == 2 else 40}       # categorical columns and their category counts
+    x = rng.normal(size=(n, nf)).astype(np.float32)
+    cut_values, cut_ptrs = [], [0]
+    for f in range(nf):
+        if f in ks:
+            x[:, f] = rng.integers(0, ks[f] + 3, size=n).astype(np.float32) + rng.choice([0.0, 0.4], size=n)  # beyond the max too
+            x[rng.random(n) < 0.1, f] = np.nan
+            cut_values += [float(v) for v in range(ks[f])]
+        else:
+            cut_values += sorted(rng.normal(size=6).tolist())
+        cut_ptrs.append(len(cut_values))
+    cp, cv = np.array(cut_ptrs, dtype=np.uint32), np.array(cut_values, dtype=np.float32)
+    row_bytes = 32 * bin_bytes
+    null_symbol = int(np.diff(cp).max())
+    dt = np.uint8 if bin_bytes == 1 else np.uint16
+    page = rng.integers(0, 5, size=(n, 32)).astype(dt)                 # whatever the numerical kernel left there
+    d = str(tmp_path)
+    np.array([n, nf, nf, row_bytes, bin_bytes, null_symbol], dtype=np.uint32).tofile(os.path.join(d, "meta.bin"))
+    x.tofile(os.path.join(d, "x.bin"))
+    np.array(sorted(ks), dtype=np.uint32).tofile(os.path.join(d, "cat_features.bin"))
+    cp.tofile(os.path.join(d, "cut_ptrs.bin"))
+    cv.tofile(os.path.join(d, "cut_values.bin"))
+    page.tofile(os.path.join(d, "bins.bin"))
+    _run(exe, "rebin", d)
+    out = np.fromfile(os.path.join(d, "bins_out.bin"), dtype=dt).reshape(n, 32)
+    want = page.copy()
+    for f, k in ks.items():
+        col = x[:, f]
+        v = np.trunc(col)
+        b = np.minimum(np.searchsorted(cv[cp[f]:cp[f + 1]], v, side="left"), k - 1)
+        want[:, f] = np.where(np.isnan(col), null_symbol, b).astype(dt)
+    assert np.array_equal(out, want)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Gradient-based row sampling (csrc/sampling.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("subsample,seed,obj", [(0.3, 12345, "sq"), (0.7, 4294967295, "sq"), (0.1, 7, "logistic"),
+                                                (0.95, 0, "sq")])
+def test_gradient_based_sampling_kernel_sources(tmp_path, subsample, seed, obj):
+    """The kernels of csrc/sampling.cu around a CPU sort / integer scan: sampled pairs, threshold, the recomputed root
+    sum and hessian flags against orc_gradient_based_sample.  Some rows carry a zero pair (they must stay untouched and
+    unsampled)."""
+    from tests.helpers import logistic_gpair
+    exe = _build("emu_sampling")
+    _, y = make_regression(5000, 4, seed=31)
+    gp = squared_error_gpair(np.zeros_like(y), y) if obj == "sq" else logistic_gpair(y, (y > 0).astype(np.float32))
+    gp[::97] = 0.0
+    scale, _ = orc.quantiser(gp)
+    gq = orc.quantise(gp, scale)
+    d = str(tmp_path)
+    gq.tofile(os.path.join(d, "gq.bin"))
+    np.asarray(scale, dtype=np.float64).tofile(os.path.join(d, "quant.bin"))
+    np.array([subsample], dtype=np.float32).tofile(os.path.join(d, "param.bin"))
+    np.array([seed], dtype=np.uint32).tofile(os.path.join(d, "seed.bin"))
+    subprocess.run([exe, d], check=True, timeout=900)
+    out = np.fromfile(os.path.join(d, "gq_out.bin"), dtype=np.int64).reshape(-1, 2)
+    mu = float(np.fromfile(os.path.join(d, "mu.bin"), dtype=np.float32)[0])
+    rag = np.fromfile(os.path.join(d, "rag.bin"), dtype=np.float32)
+    root = np.fromfile(os.path.join(d, "root.bin"), dtype=np.int64)
+    want, want_mu, want_tidx, want_rag = orc.gradient_based_sample(gq, scale, subsample, seed)
+    assert np.array_equal(rag.view(np.uint32), want_rag.view(np.uint32))
+    assert np.float32(mu).view(np.uint32) == np.float32(want_mu).view(np.uint32)
+    assert np.array_equal(out, want)
+    assert (int(root[0]), int(root[1])) == (int(want[:, 0].sum()), int(want[:, 1].sum()))
+    assert int(root[2]) == int(np.bitwise_or.reduce(want[:, 1].astype(np.uint64) & np.uint64(0xFFFFFFFF)))
+    assert int(root[3]) == int((want[:, 1] == 0).any())

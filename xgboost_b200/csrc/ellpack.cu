@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) BinDenseSmemKernel(const float* __restric
                                                            const float* __restrict__ cut_values,
                                                            uint8_t* __restrict__ bins, uint64_t row_begin,
                                                            uint32_t row_bytes, uint32_t null_symbol) {
-  extern __shared__ float s_cuts[];
+  B200_DYNAMIC_SHARED(float, s_cuts);
   __shared__ uint32_t s_ptr[33];
   const uint32_t f0 = blockIdx.y * 32;
   const uint32_t nf = min(32u, n_features - f0);
@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(256) TransposeKernel16(const uint8_t* __restri
   }
 }
 
+#ifndef B200_KERNELS_ONLY
 static void LaunchTranspose(b200hist_ellpack_s* e, uint64_t row_begin, uint64_t n, cudaStream_t s) {
   if (e->d_bins_t == nullptr || n == 0) return;
   // tiles are aligned to 128 rows of the page so that 32-bit stores stay aligned
@@ -227,6 +228,7 @@ static void LaunchTranspose(b200hist_ellpack_s* e, uint64_t row_begin, uint64_t 
   }
   B200_LAUNCHED();
 }
+#endif  // B200_KERNELS_ONLY
 
 // Sparse layout: one warp per CSR row; entry k -> global bin of (feature, value), compacted over NaNs, padded
 // with the null symbol.  Entries stay in feature order, so a row can be binary-searched by feature.
@@ -339,6 +341,7 @@ __global__ void __launch_bounds__(256) ImportReferenceKernel(const uint8_t* __re
 
 }  // namespace b200
 
+#ifndef B200_KERNELS_ONLY
 using namespace b200;
 
 extern "C" {
@@ -628,3 +631,4 @@ int b200hist_ellpack_copy_bins_to_host(b200hist_ellpack_t e, void* out_host) {
 }
 
 }  // extern "C"
+#endif  // B200_KERNELS_ONLY

@@ -20,8 +20,10 @@
 // same arrays, and this is not the hot path of a tree (one pass over n floats; the histogram visits n * F symbols).
 // STATUS: compiled, never run on hardware; its oracle (orc_gradient_based_sample) is itself parity-unpinned until
 // tests/golden/ref_gpu_next_trees.json exists.
+#ifndef B200_KERNELS_ONLY
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#endif
 
 #include <cfloat>
 
@@ -196,6 +198,7 @@ __global__ void ResetRootKernel(QuantDev* q) {
   q->h_zero_any = 0u;
 }
 
+#ifndef B200_KERNELS_ONLY
 size_t GradientBasedScratchBytes(uint64_t n, int num_sms) {
   size_t sort_bytes = 0, scan_bytes = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (const float*)nullptr, (float*)nullptr, (int64_t)n);
@@ -243,5 +246,7 @@ void LaunchGradientBasedSample(b200hist_gpair64* gq, uint64_t n, QuantDev* q, fl
   PoissonKernel<<<blocks, kSampThreads, 0, s>>>(g2, n, rag, st, q, seed);
   B200_LAUNCHED();
 }
+
+#endif  // B200_KERNELS_ONLY
 
 }  // namespace b200

@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(kCtlThreads) IcLevelKernel(const TreeState* ts
                                                               const PartEntry* part, const int32_t* eval_nodes,
                                                               IcDev ic, const int32_t* feature_set, int32_t n_fs,
                                                               int32_t n_levels) {
-  extern __shared__ unsigned long long s_mask[];  // [words] the depth's sampled features
+  B200_DYNAMIC_SHARED(unsigned long long, s_mask);  // [words] the depth's sampled features
   const int n_part = ts->n_part;
   if (n_part == 0) return;
   const int W = ic.words;
@@ -733,6 +733,7 @@ __global__ void __launch_bounds__(256) PredCacheKernel(const int32_t* __restrict
 
 }  // namespace b200
 
+#ifndef B200_KERNELS_ONLY
 using namespace b200;
 
 // =============================================================================================
@@ -1687,3 +1688,4 @@ int b200hist_updater_last_profile(b200hist_updater_t u, float* out_ms7, uint64_t
 }
 
 }  // extern "C"
+#endif  // B200_KERNELS_ONLY
