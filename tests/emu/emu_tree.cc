@@ -1,0 +1,224 @@
+// A whole tree under the CPU emulator: the launch sequence of UpdateTreeImpl (xgboost_b200/csrc/updater.cu) with the
+// real control, evaluation, partition and finalise kernels; only the histogram build / subtraction -- the
+// hardware-validated hot kernel, which uses inline PTX -- is replaced by a plain CPU accumulation over the kernels' own
+// work lists.  Checks what no single-kernel test can: the order in which nodes are evaluated (colsample_bynode draws,
+// the interaction-constraint buffer), categorical routing through partition and FinalisePosition, loss-guided growth.
+#define B200_KERNELS_ONLY 1
+#include "cuda_emu.h"
+#include "emu_io.h"
+
+#include "../../xgboost_b200/csrc/evaluate.cu"
+#include "../../xgboost_b200/csrc/partition.cu"
+#include "../../xgboost_b200/csrc/updater.cu"
+
+using namespace b200;
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 2;
+  const std::string dir = argv[1];
+  // meta: n_rows, n_features, row_bytes, bin_bytes, null_symbol, has_mono, has_cat, onehot, threshold, cat_words,
+  //       bin_words, max_cat_bins, n_ic_sets, n_node_sets, n_per_node, has_fs, n_fs, n_levels
+  auto meta = ReadAll<int64_t>(dir + "/meta.bin");
+  auto prm = ReadAll<float>(dir + "/param_f.bin");
+  auto prm_i = ReadAll<int32_t>(dir + "/param_i.bin");
+  auto quant = ReadAll<double>(dir + "/quant.bin");
+  auto root = ReadAll<long long>(dir + "/root.bin");  // root_g, root_h, h_zero_any
+  auto bins = ReadAll<uint8_t>(dir + "/bins.bin");
+  auto cut_ptrs = ReadAll<uint32_t>(dir + "/cut_ptrs.bin");
+  auto cut_values = ReadAll<float>(dir + "/cut_values.bin");
+  auto gq = ReadAll<longlong2>(dir + "/gq.bin");
+  auto mono_c = ReadAll<int32_t>(dir + "/mono.bin", true);
+  auto is_cat = ReadAll<uint8_t>(dir + "/is_cat.bin", true);
+  auto ic_set_ptr = ReadAll<int32_t>(dir + "/ic_set_ptr.bin", true);
+  auto ic_set_feat = ReadAll<int32_t>(dir + "/ic_set_feat.bin", true);
+  auto node_sets = ReadAll<int32_t>(dir + "/node_sets.bin", true);
+  auto fs = ReadAll<int32_t>(dir + "/feature_set.bin", true);
+  const uint64_t n = (uint64_t)meta[0];
+  const uint32_t nf = (uint32_t)meta[1];
+  EllView view{};
+  view.bins = bins.data();
+  view.cut_ptrs = cut_ptrs.data();
+  view.cut_values = cut_values.data();
+  view.n_rows = n;
+  view.n_features = nf;
+  view.total_bins = (uint32_t)cut_values.size();
+  view.row_bytes = (uint32_t)meta[2];
+  view.bin_bytes = (uint32_t)meta[3];
+  view.null_symbol = (uint32_t)meta[4];
+  const ParamDev p{prm_i[0], prm_i[1], prm_i[2], prm[0], prm[1], prm[2], prm[3], prm[4], prm[5]};
+  QuantDev q{};
+  q.to_fixed_g = quant[0]; q.to_fixed_h = quant[1]; q.to_float_g = quant[2]; q.to_float_h = quant[3];
+  q.root_g = root[0]; q.root_h = root[1]; q.h_zero_any = (unsigned)root[2];
+
+  // ---- what b200hist_updater_create derives on the host ----
+  long long by_depth = p.max_depth > 0 ? ((1ll << (p.max_depth + 1)) - 1) : (1ll << 40);
+  long long by_leaves = p.max_leaves > 0 ? (2ll * p.max_leaves - 1) : (1ll << 40);
+  const int32_t max_nodes = (int32_t)std::min(by_depth, by_leaves);
+  const bool dw = p.grow_policy == 0;
+  const int n_steps = dw ? (p.max_depth > 0 ? p.max_depth : p.max_leaves - 1) : (max_nodes - 1) / 2;
+  std::vector<uint32_t> step_cap, step_slot_base;
+  uint32_t base = 1;
+  for (int st = 0; st < n_steps; ++st) {
+    uint32_t cap = dw ? (uint32_t)std::min<long long>(1ll << std::min(st, 30), kMaxLevelNodes) : 1u;
+    if (p.max_leaves > 0) cap = std::min<uint32_t>(cap, (uint32_t)p.max_leaves);
+    step_cap.push_back(cap);
+    step_slot_base.push_back(base);
+    const bool children = p.max_depth == 0 || !dw || st + 1 < p.max_depth;
+    if (children) base += 2 * cap;
+  }
+  const uint32_t n_slots = base;
+  const size_t part_tiles = n / kPartTile + (size_t)max_nodes + 2, hist_tiles = n / kHistTile + (size_t)max_nodes + 2;
+  std::vector<uint32_t> ridx0(n), ridx1(n);
+  for (uint64_t i = 0; i < n; ++i) ridx0[i] = (uint32_t)i;
+  std::vector<int32_t> position(n, -12345);
+  TreeState ts{};
+  std::vector<NodeDev> nodes((size_t)max_nodes);
+  std::vector<b200hist_candidate> cand((size_t)max_nodes);
+  std::vector<PartEntry> part(kMaxLevelNodes);
+  std::vector<BuildEntry> build(kMaxLevelNodes), fin((size_t)max_nodes);
+  std::vector<SubEntry> sub(kMaxLevelNodes);
+  std::vector<int32_t> eval_nodes(2 * kMaxLevelNodes);
+  std::vector<uint32_t> part_tile_seg(part_tiles), build_tile_seg(hist_tiles), tile_left(part_tiles), tile_excl(part_tiles + 1),
+      tile_left_off(part_tiles), flags(part_tiles * (kPartTile / 32)), fin_tile_seg(part_tiles), fin_tile_begin((size_t)max_nodes + 1);
+  std::vector<FeatCand> scratch((size_t)2 * 64 * nf);  // the emulated trees expand at most 64 nodes per step
+  std::vector<longlong2> hist((size_t)n_slots * view.total_bins, make_longlong2(0, 0));
+  std::vector<float> lower((size_t)max_nodes), upper((size_t)max_nodes);
+  const MonoView mono{meta[5] ? mono_c.data() : nullptr, lower.data(), upper.data()};
+  const bool has_cat = meta[6] != 0;
+  std::vector<uint32_t> cat_bits((size_t)max_nodes * std::max<int64_t>(1, meta[9])), bin_bits((size_t)max_nodes * std::max<int64_t>(1, meta[10]));
+  std::vector<uint8_t> node_is_cat((size_t)max_nodes, 0);
+  const CatView catv = has_cat ? CatView{is_cat.data(), (int32_t)meta[7], (int32_t)meta[8], cat_bits.data(), bin_bits.data(),
+                                         node_is_cat.data(), (int32_t)meta[9], (int32_t)meta[10], (int32_t)std::max<int64_t>(1, meta[11])}
+                               : CatView{nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0, 0};
+  const CatRoute cr{has_cat ? bin_bits.data() : nullptr, (int32_t)meta[10]};
+  const bool has_ic = meta[12] > 0;
+  const int ic_words = (int)((nf + 63) / 64);
+  std::vector<unsigned long long> ic_bits((size_t)max_nodes * ic_words, 0ull);
+  std::vector<int32_t> ic_list(nf), ic_count(2 * kMaxLevelNodes);
+  const bool has_node_sets = meta[13] > 0;
+  const int32_t n_per_node = (int32_t)meta[14];
+  std::vector<int32_t> node_list((size_t)2 * 64 * std::max(1, n_per_node)), node_count(2 * 64);
+  int32_t node_seq = 0;
+  const int32_t* d_fs = meta[15] ? fs.data() : nullptr;
+  const int32_t n_fs = (int32_t)meta[16], n_levels = (int32_t)meta[17];
+  const size_t cat_smem = (size_t)kEvalWarps * (size_t)catv.max_cat_bins * (sizeof(float) + sizeof(uint16_t));
+
+  auto build_hist = [&]() {  // the CPU stand-in for LaunchBuildHist over the kernels' own work list
+    for (int k = 0; k < ts.n_build; ++k) {
+      const BuildEntry e = build[k];
+      const uint32_t* rows = (e.buf ? ridx1.data() : ridx0.data()) + e.begin;
+      longlong2* h = hist.data() + (size_t)e.slot * view.total_bins;
+      for (uint32_t j = 0; j < e.count; ++j) {
+        const uint32_t r = rows[j];
+        for (uint32_t f = 0; f < nf; ++f) {
+          const uint32_t sym = view.bin_bytes == 1 ? (uint32_t)bins[(size_t)r * view.row_bytes + f]
+                                                   : (uint32_t)reinterpret_cast<const uint16_t*>(bins.data() + (size_t)r * view.row_bytes)[f];
+          if (sym == view.null_symbol) continue;
+          h[cut_ptrs[f] + sym].x += gq[r].x;
+          h[cut_ptrs[f] + sym].y += gq[r].y;
+        }
+      }
+    }
+  };
+  auto subtract = [&]() {
+    for (int k = 0; k < ts.n_sub; ++k) {
+      const SubEntry e = sub[k];
+      for (uint32_t b = 0; b < view.total_bins; ++b) {
+        hist[(size_t)e.sub * view.total_bins + b].x = hist[(size_t)e.parent * view.total_bins + b].x - hist[(size_t)e.built * view.total_bins + b].x;
+        hist[(size_t)e.sub * view.total_bins + b].y = hist[(size_t)e.parent * view.total_bins + b].y - hist[(size_t)e.built * view.total_bins + b].y;
+      }
+    }
+  };
+  auto evaluate = [&](int32_t max_eval, IcView ic, const int32_t* feature_set, int32_t n_feature_set, int32_t levels) {
+    const int32_t stride = feature_set ? n_feature_set : (int32_t)nf;
+    const long long items = (long long)max_eval * stride;
+    if (items == 0) return;
+    const unsigned b1 = (unsigned)std::min<long long>((items + kEvalWarps - 1) / kEvalWarps, 4);
+    const unsigned b2 = (unsigned)std::min<long long>(((long long)max_eval + kEvalWarps - 1) / kEvalWarps, 2);
+    const longlong2* h2 = hist.data();
+    if (ic.count != nullptr) {
+      EMU_LAUNCH((b1), (kEvalWarps * 32), 0, FeatureScanKernel<true>(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), mono, levels, ic));
+    } else {
+      EMU_LAUNCH((b1), (kEvalWarps * 32), 0, FeatureScanKernel<false>(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), mono, levels, ic));
+    }
+    if (has_cat)
+      EMU_LAUNCH((b1), (kEvalWarps * 32), cat_smem, CatFeatureScanKernel(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), mono, levels, ic, catv));
+    if (ic.count != nullptr) {
+      EMU_LAUNCH((b2), (kEvalWarps * 32), 0, NodeReduceKernel<true>(view, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), cand.data(), mono, levels, &ts.max_eval_depth, ic));
+    } else {
+      EMU_LAUNCH((b2), (kEvalWarps * 32), 0, NodeReduceKernel<false>(view, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), cand.data(), mono, levels, &ts.max_eval_depth, ic));
+    }
+    if (has_cat)
+      EMU_LAUNCH((b2), (kEvalWarps * 32), cat_smem, CatFinishKernel(view, h2, eval_nodes.data(), &ts, nodes.data(), p, &q, cand.data(), catv));
+  };
+  auto node_sets_view = [&]() {
+    EMU_LAUNCH((1), (kCtlThreads), 0, NodeSetLevelKernel(&ts, node_sets.data(), (int32_t)meta[13], n_per_node, &node_seq, node_list.data(), node_count.data()));
+    return IcView{node_list.data(), node_count.data(), n_per_node};
+  };
+
+  // ---- UpdateTreeImpl ----
+  EMU_LAUNCH((1), (kCtlThreads), 0, InitRootKernel(p, (uint32_t)n, &q, &ts, nodes.data(), build.data(), build_tile_seg.data(), eval_nodes.data(), mono));
+  build_hist();
+  if (has_node_sets) evaluate(1, node_sets_view(), nullptr, 0, 0);
+  else evaluate(1, IcView{nullptr, nullptr, 0}, d_fs, n_fs, n_levels);
+  for (int step = 0; step < n_steps; ++step) {
+    const long long cap = step_cap[step];
+    if (has_cat) {
+      EMU_LAUNCH((1), (kCtlThreads), 0, ApplyKernel<true>(view, p, &q, &ts, nodes.data(), cand.data(), part.data(), part_tile_seg.data(), max_nodes, mono, node_is_cat.data()));
+    } else {
+      EMU_LAUNCH((1), (kCtlThreads), 0, ApplyKernel<false>(view, p, &q, &ts, nodes.data(), cand.data(), part.data(), part_tile_seg.data(), max_nodes, mono, nullptr));
+    }
+    const bool children_possible = p.max_depth == 0 || !dw || step + 1 < p.max_depth;
+    if (!children_possible) continue;
+    if (view.bin_bytes == 1) {
+      if (has_cat) { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint8_t, true>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
+      else { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint8_t, false>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
+    } else {
+      if (has_cat) { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint16_t, true>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
+      else { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint16_t, false>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
+    }
+    EMU_LAUNCH((1), (kCtlThreads), 0, ScanKernel(&ts, nodes.data(), part.data(), part_tile_seg.data(), tile_left.data(), tile_excl.data(), tile_left_off.data(), build.data(), sub.data(), eval_nodes.data(), build_tile_seg.data(), step_slot_base[step], step_cap[step], 0));
+    EMU_LAUNCH((3), (kPartThreads), 0, PartitionScatterKernel(ridx0.data(), ridx1.data(), ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left_off.data()));
+    build_hist();
+    subtract();
+    IcView icv{nullptr, nullptr, 0};
+    if (has_node_sets) {
+      icv = node_sets_view();
+      evaluate((int32_t)(2 * cap), icv, nullptr, 0, 0);
+      continue;
+    }
+    if (has_ic) {
+      const IcDev icd{(int32_t)nf, ic_words, (int32_t)meta[12], ic_set_ptr.data(), ic_set_feat.data(), ic_bits.data(), ic_list.data(), ic_count.data()};
+      EMU_LAUNCH((1), (kCtlThreads), sizeof(unsigned long long) * (size_t)ic_words, IcLevelKernel(&ts, nodes.data(), part.data(), eval_nodes.data(), icd, d_fs, n_fs, n_levels));
+      icv = IcView{ic_list.data(), ic_count.data(), 0};
+    }
+    evaluate((int32_t)(2 * cap), icv, d_fs, n_fs, n_levels);
+  }
+  EMU_LAUNCH((1), (kCtlThreads), 0, FinalListKernel(&ts, nodes.data(), fin.data(), fin_tile_seg.data(), fin_tile_begin.data()));
+  if (view.bin_bytes == 1) {
+    if (has_cat) { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint8_t, true>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
+    else { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint8_t, false>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
+  } else {
+    if (has_cat) { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint16_t, true>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
+    else { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint16_t, false>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
+  }
+  // ---- results ----
+  std::vector<b200hist_tree_node> out((size_t)ts.n_nodes);
+  for (int32_t i = 0; i < ts.n_nodes; ++i) {
+    const NodeDev& s = nodes[i];
+    b200hist_tree_node d{};
+    d.parent = s.parent; d.left = s.left; d.right = s.right; d.findex = s.findex;
+    d.fvalue = s.is_leaf ? s.leaf_value : s.fvalue;
+    d.default_left = s.default_left; d.is_leaf = s.is_leaf; d.leaf_value = s.leaf_value;
+    d.loss_chg = s.loss_chg; d.sum_hess = s.sum_hess; d.base_weight = s.base_weight; d.depth = s.depth;
+    out[i] = d;
+  }
+  WriteAll(dir + "/nodes.bin", out);
+  WriteAll(dir + "/position.bin", position);
+  std::vector<int32_t> flags_out((size_t)ts.n_nodes);
+  for (int32_t i = 0; i < ts.n_nodes; ++i) flags_out[i] = (!nodes[i].is_leaf && node_is_cat[i]) ? 1 : 0;
+  WriteAll(dir + "/is_cat.bin", flags_out);
+  WriteAll(dir + "/cat_bits.bin", cat_bits);
+  WriteAll(dir + "/eval_count.bin", std::vector<int32_t>{node_seq, ts.max_eval_depth});
+  return 0;
+}

@@ -480,3 +480,181 @@ def test_gradient_based_sampling_kernel_sources(tmp_path, subsample, seed, obj):
     assert (int(root[0]), int(root[1])) == (int(want[:, 0].sum()), int(want[:, 1].sum()))
     assert int(root[2]) == int(np.bitwise_or.reduce(want[:, 1].astype(np.uint64) & np.uint64(0xFFFFFFFF)))
     assert int(root[3]) == int((want[:, 1] == 0).any())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# A whole tree: the launch sequence of UpdateTreeImpl with the real control / evaluation / partition / finalise kernels
+# (tests/emu/emu_tree.cc); only the histogram build is a CPU loop over the kernels' own work lists.
+# ---------------------------------------------------------------------------------------------------------------------
+TREE_NODE = np.dtype([("parent", "<i4"), ("left", "<i4"), ("right", "<i4"), ("findex", "<i4"), ("fvalue", "<f4"),
+                      ("default_left", "<i4"), ("is_leaf", "<i4"), ("leaf_value", "<f4"), ("loss_chg", "<f4"),
+                      ("sum_hess", "<f4"), ("base_weight", "<f4"), ("depth", "<i4")])
+
+
+def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, onehot=4, threshold=64, ic_sets=None,
+                  node_sets=None, feature_set=None, n_levels=0):
+    exe = _build("emu_tree")
+    n, nf = gb.shape
+    max_bins = int(np.diff(cp).max())
+    has_missing = bool((gb < 0).any())
+    bin_bytes = 2 if max_bins + (1 if has_missing else 0) > 256 else 1
+    null_symbol = max_bins if has_missing else 0xFFFFFFFF
+    page = _page_bytes(gb, cp, bin_bytes, null_symbol if has_missing else 0)
+    scale, _ = orc.quantiser(gp)
+    gq = orc.quantise(gp, scale)
+    cat_words = int(cv.max()) // 32 + 1
+    max_cat_bins = int(max([cp[f + 1] - cp[f] for f in range(nf) if is_cat is not None and is_cat[f]] or [1]))
+    d = str(tmp_path)
+    p = orc.Param.make(**params)
+    fs = None if feature_set is None else np.ascontiguousarray(feature_set, dtype=np.int32)
+    np.array([n, nf, page.shape[1], bin_bytes, null_symbol, 0 if mono is None else 1, 0 if is_cat is None else 1, onehot,
+              threshold, cat_words, (max_cat_bins + 31) // 32, max_cat_bins, 0 if ic_sets is None else len(ic_sets),
+              0 if node_sets is None else node_sets.shape[0], 0 if node_sets is None else node_sets.shape[1],
+              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels], dtype=np.int64).tofile(os.path.join(d, "meta.bin"))
+    np.array([p.learning_rate, p.reg_lambda, p.reg_alpha, p.min_child_weight, p.max_delta_step, p.min_split_loss],
+             dtype=np.float32).tofile(os.path.join(d, "param_f.bin"))
+    np.array([p.max_depth, p.max_leaves, p.grow_policy], dtype=np.int32).tofile(os.path.join(d, "param_i.bin"))
+    np.asarray(scale, dtype=np.float64).tofile(os.path.join(d, "quant.bin"))
+    np.array([gq[:, 0].sum(), gq[:, 1].sum(), int((gq[:, 1] == 0).any())], dtype=np.int64).tofile(os.path.join(d, "root.bin"))
+    page.tofile(os.path.join(d, "bins.bin"))
+    cp.astype(np.uint32).tofile(os.path.join(d, "cut_ptrs.bin"))
+    cv.astype(np.float32).tofile(os.path.join(d, "cut_values.bin"))
+    gq.tofile(os.path.join(d, "gq.bin"))
+    if mono is not None:
+        m = np.zeros(nf, dtype=np.int32)
+        m[:len(mono)] = mono
+        m.tofile(os.path.join(d, "mono.bin"))
+    if is_cat is not None:
+        np.asarray(is_cat, dtype=np.uint8).tofile(os.path.join(d, "is_cat.bin"))
+    if ic_sets is not None:
+        np.cumsum([0] + [len(s) for s in ic_sets]).astype(np.int32).tofile(os.path.join(d, "ic_set_ptr.bin"))
+        np.array([f for s in ic_sets for f in s], dtype=np.int32).tofile(os.path.join(d, "ic_set_feat.bin"))
+    if node_sets is not None:
+        np.ascontiguousarray(node_sets, dtype=np.int32).tofile(os.path.join(d, "node_sets.bin"))
+    if fs is not None:
+        fs.tofile(os.path.join(d, "feature_set.bin"))
+    subprocess.run([exe, d], check=True, timeout=1800)
+    nodes = np.fromfile(os.path.join(d, "nodes.bin"), dtype=TREE_NODE)
+    pos = np.fromfile(os.path.join(d, "position.bin"), dtype=np.int32)
+    flags = np.fromfile(os.path.join(d, "is_cat.bin"), dtype=np.int32)
+    bits = np.fromfile(os.path.join(d, "cat_bits.bin"), dtype=np.uint32).reshape(-1, cat_words)
+    counts = np.fromfile(os.path.join(d, "eval_count.bin"), dtype=np.int32)
+    return nodes, pos, flags, bits, counts
+
+
+def _same_tree(nodes, pos, o, flags=None, bits=None):
+    assert len(nodes) == len(o["nodes"])
+    for i, (a, b) in enumerate(zip(nodes, o["nodes"])):
+        assert (int(a["parent"]), int(a["left"]), int(a["right"]), bool(a["is_leaf"]), int(a["depth"])) == \
+            (b.parent, b.left, b.right, bool(b.is_leaf), b.depth), i
+        if not b.is_leaf:
+            assert (int(a["findex"]), bool(a["default_left"])) == (b.findex, bool(b.default_left)), i
+            cat_node = "is_cat" in o and o["is_cat"][i]
+            if cat_node:
+                got = {32 * w + (31 - k) for w in range(bits.shape[1]) for k in range(32) if (int(bits[i, w]) >> k) & 1}
+                assert flags[i] == 1 and np.isnan(a["fvalue"]) and got == o["cat_sets"][i], i
+            else:
+                assert np.float32(a["fvalue"]).view(np.uint32) == np.float32(b.fvalue).view(np.uint32), i
+                assert flags is None or flags[i] == 0, i
+            assert np.float32(a["loss_chg"]).view(np.uint32) == np.float32(b.loss_chg).view(np.uint32), i
+        else:
+            assert np.float32(a["leaf_value"]).view(np.uint32) == np.float32(b.leaf_value).view(np.uint32), i
+        assert np.float32(a["sum_hess"]).view(np.uint32) == np.float32(b.sum_hess).view(np.uint32), i
+        assert np.float32(a["base_weight"]).view(np.uint32) == np.float32(b.base_weight).view(np.uint32), i
+    assert np.array_equal(pos, o["position"])
+
+
+def _tree_data(n=2500, f=8, max_bin=24, missing=0.0, seed=13, zero_hess=False):
+    x, y = make_regression(n, f, seed=seed, missing=missing)
+    y = (y + x[:, 0] * np.nan_to_num(x[:, 1]) - np.nan_to_num(x[:, 2]) * np.nan_to_num(x[:, 3])).astype(np.float32)
+    cp, cv = make_cuts(x, max_bin)
+    gb = orc.bin_dense(x, cp, cv)
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    if zero_hess:
+        gp[::11, 1] = 0.0
+    return gb, cp, cv, gp
+
+
+@pytest.mark.parametrize("name,params,extra", [
+    ("depthwise", dict(max_depth=5, eta=0.5), {}),
+    ("lossguide", dict(max_depth=0, max_leaves=13, grow_policy="lossguide", eta=0.5), {}),
+    ("depthwise_max_leaves", dict(max_depth=6, max_leaves=9, eta=0.5), {}),
+    ("missing_u16_zero_hess", dict(max_depth=4, eta=0.3, min_child_weight=0.0), dict(missing=0.15, max_bin=300, zero_hess=True)),
+    ("monotone", dict(max_depth=5, eta=0.5), dict(mono=[1, -1, 0, 1, 0, -1, 0, 0])),
+    ("level_sets", dict(max_depth=5, eta=0.5), dict(level_sets=True)),
+], ids=lambda v: v if isinstance(v, str) else "")
+def test_whole_tree_kernel_sources(tmp_path, name, params, extra):
+    gb, cp, cv, gp = _tree_data(missing=extra.get("missing", 0.0), max_bin=extra.get("max_bin", 24),
+                                zero_hess=extra.get("zero_hess", False))
+    kw, okw = {}, {}
+    if extra.get("mono"):
+        kw["mono"] = okw["monotone"] = extra["mono"]
+    if extra.get("level_sets"):
+        rng = np.random.default_rng(4)
+        levels = np.stack([rng.permutation(8)[:5] for _ in range(5)]).astype(np.int32)   # unsorted: position = tie rank
+        kw.update(feature_set=levels, n_levels=5)
+        okw["level_feature_sets"] = levels
+    nodes, pos, _, _, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, **kw)
+    _same_tree(nodes, pos, orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), **okw))
+
+
+@pytest.mark.parametrize("params", [dict(max_depth=5, eta=0.5), dict(max_depth=0, max_leaves=12, grow_policy="lossguide", eta=0.5)],
+                         ids=["depthwise", "lossguide"])
+def test_whole_tree_kernel_sources_colsample_bynode(tmp_path, params):
+    """The k-th node evaluated takes the k-th draw: NodeSetLevelKernel + the evaluation order of the real control
+    kernels against the oracle's evaluation order, and the number of draws used."""
+    gb, cp, cv, gp = _tree_data(seed=14)
+    p = orc.Param.make(**params)
+    max_nodes = min((1 << (p.max_depth + 1)) - 1 if p.max_depth > 0 else 1 << 30, 2 * p.max_leaves - 1 if p.max_leaves > 0 else 1 << 30)
+    rng = np.random.default_rng(15)
+    sets = np.stack([np.sort(rng.permutation(8)[:3]) for _ in range(max_nodes)]).astype(np.int32)
+    nodes, pos, _, _, counts = _emulate_tree(tmp_path, gb, cp, cv, gp, params, node_sets=sets)
+    o = orc.update_tree(gb, cp, cv, gp, p, node_feature_sets=sets)
+    _same_tree(nodes, pos, o)
+    assert int(counts[0]) == o["eval_count"]
+
+
+@pytest.mark.parametrize("with_levels", [False, True], ids=["all_features", "level_sets"])
+def test_whole_tree_kernel_sources_interaction_constraints(tmp_path, with_levels):
+    """Overlapping sets: the tree must follow the shared Query buffer (the reference's behaviour), not the per-query
+    answers -- IcLevelKernel and the constrained evaluation kernels chained over the levels of a real tree."""
+    from tests.helpers import make_interaction_data
+    x, y = make_interaction_data(dict(seed=201, n=2500, f=6))
+    cp, cv = make_cuts(x, 24)
+    gb = orc.bin_dense(x, cp, cv)
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    chain = [[0, 1], [1, 2], [2, 3], [3, 4], [4, 5]]
+    params = dict(max_depth=5, eta=0.5)
+    kw, okw = {}, {}
+    if with_levels:
+        rng = np.random.default_rng(6)
+        levels = np.stack([np.sort(rng.permutation(6)[:5]) for _ in range(5)]).astype(np.int32)
+        kw.update(feature_set=levels, n_levels=5)
+        okw["level_feature_sets"] = levels
+    nodes, pos, _, _, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, ic_sets=chain, **kw)
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), interaction=chain, **okw)
+    _same_tree(nodes, pos, o)
+    per_query = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), interaction=chain, interaction_shared_buffer=False, **okw)
+    if not with_levels:
+        assert [nd.findex for nd in per_query["nodes"]] != [int(v) for v in nodes["findex"]]
+
+
+@pytest.mark.parametrize("onehot,params", [(4, dict(max_depth=5, eta=0.5)), (100, dict(max_depth=4, eta=0.5)),
+                                           (1, dict(max_depth=0, max_leaves=10, grow_policy="lossguide", eta=0.5))],
+                         ids=["mixed_depthwise", "all_onehot", "all_partition_lossguide"])
+def test_whole_tree_kernel_sources_categorical(tmp_path, onehot, params):
+    """Categorical splits through ApplyKernel<true>, PartitionCountKernel<., true> and FinaliseWindowKernel<., true>:
+    category sets, NaN conditions and the position of every row."""
+    from tests.helpers import make_categorical_data
+    from tests.test_reference_golden import categorical_global_bins
+    case = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_cpu_categorical_trees.json")))["cases"][0]
+    x, y, types = make_categorical_data(dict(case, n=2500))
+    is_cat = [1 if t == "c" else 0 for t in types]
+    cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+    cv = np.array(case["cut_values_bits"], dtype=np.uint32).view(np.float32)
+    gb = categorical_global_bins(x, cp, cv, is_cat)
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    nodes, pos, flags, bits, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, is_cat=is_cat, onehot=onehot)
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), feature_is_cat=is_cat, max_cat_to_onehot=onehot)
+    _same_tree(nodes, pos, o, flags, bits)
+    assert int(o["is_cat"].sum()) >= 3

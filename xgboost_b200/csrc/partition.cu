@@ -148,6 +148,7 @@ PartitionScatterKernel(const uint32_t* __restrict__ ridx0, const uint32_t* __res
   }
 }
 
+#ifndef B200_KERNELS_ONLY
 void LaunchPartitionCount(const EllView& ell, const uint32_t* ridx0, const uint32_t* ridx1, const PartEntry* part,
                           const uint32_t* tile_seg, const TreeState* ts, uint32_t* flags, uint32_t* tile_left,
                           int num_sms, cudaStream_t s, CatRoute cr) {
@@ -180,5 +181,7 @@ void LaunchPartitionScatter(const uint32_t* ridx0, const uint32_t* ridx1, uint32
                                                               tile_left_off);
   B200_LAUNCHED();
 }
+
+#endif  // B200_KERNELS_ONLY
 
 }  // namespace b200
