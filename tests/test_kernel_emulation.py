@@ -658,3 +658,24 @@ def test_whole_tree_kernel_sources_categorical(tmp_path, onehot, params):
     o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), feature_is_cat=is_cat, max_cat_to_onehot=onehot)
     _same_tree(nodes, pos, o, flags, bits)
     assert int(o["is_cat"].sum()) >= 3
+
+
+def test_whole_tree_kernel_sources_combined(tmp_path):
+    """Categorical features + colsample_bynode + monotone constraints on the numerical features in one tree."""
+    from tests.helpers import make_categorical_data
+    from tests.test_reference_golden import categorical_global_bins
+    case = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_cpu_categorical_trees.json")))["cases"][0]
+    x, y, types = make_categorical_data(dict(case, n=2500, seed=77))
+    is_cat = [1 if t == "c" else 0 for t in types]
+    cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+    cv = np.array(case["cut_values_bits"], dtype=np.uint32).view(np.float32)
+    gb = categorical_global_bins(x, cp, cv, is_cat)
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    params = dict(max_depth=5, eta=0.5)
+    mono = [0, 0, 0, 0, 1, -1, 0]
+    rng = np.random.default_rng(21)
+    sets = np.stack([np.sort(rng.permutation(7)[:4]) for _ in range(63)]).astype(np.int32)
+    nodes, pos, flags, bits, counts = _emulate_tree(tmp_path, gb, cp, cv, gp, params, is_cat=is_cat, node_sets=sets, mono=mono)
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), feature_is_cat=is_cat, node_feature_sets=sets, monotone=mono)
+    _same_tree(nodes, pos, o, flags, bits)
+    assert int(counts[0]) == o["eval_count"] and int(o["is_cat"].sum()) >= 2
