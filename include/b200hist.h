@@ -296,6 +296,23 @@ B200HIST_API int b200hist_updater_set_node_feature_sets(b200hist_updater_t u, co
                                                         uint32_t n_per_set);
 B200HIST_API int b200hist_updater_last_eval_count(b200hist_updater_t u, int32_t* out);
 
+/* The whole column sampler of a tree on the device (ColumnSampler::GetFeatureSet, src/common/random.h:156-175): tree_set =
+ * what ColumnSampler::Init produced (colsample_bytree), seeds_host = the values ctx->Rng()() returns after Init, in
+ * order.  A node of depth d is evaluated on: the depth's level set, drawn from tree_set with the next output the first
+ * time a node of that depth is evaluated (colsample_bylevel < 1), and -- colsample_bynode < 1 -- a node set drawn from
+ * the level set with the next output.  Calls happen in evaluation order, so the position of a level draw in the stream
+ * depends on the data; the cursor therefore lives on the device.  n_seeds >= max_nodes + max depth + 1.
+ * b200hist_updater_last_draw_count = outputs the last tree consumed: the caller advances its engine by that many.
+ * Covers colsample_bynode with or without colsample_bylevel (and colsample_bylevel alone); replaces
+ * b200hist_updater_set_node_feature_sets / set_level_feature_sets while set; NULL / 0 removes it.
+ * STATUS: compiled; kernel sources and whole trees run under the CPU emulator against the oracle
+ * (tests/test_kernel_emulation.py); never run on hardware. */
+B200HIST_API int b200hist_updater_set_column_sampler(b200hist_updater_t u, const int32_t* tree_set_host,
+                                                     uint32_t n_tree_set, float colsample_bylevel,
+                                                     float colsample_bynode, const uint32_t* seeds_host,
+                                                     uint32_t n_seeds);
+B200HIST_API int b200hist_updater_last_draw_count(b200hist_updater_t u, int32_t* out);
+
 /* Column-sampling draws, many at once: ColumnSampler::ColSample on CUDA without feature weights (src/common/random.cc:
  * 27-46; cuda_impl::SampleFeature, random.cu:62-96 = thrust::shuffle with default_random_engine(seed), keep the first
  * n_sel = max(1, int(colsample * n)), sort ascending).  Draw d uses seeds_host[d] -- the value the reference obtains

@@ -298,20 +298,24 @@ class _Cat(Structure):
     _fields_ = [("feature_is_cat", c_void_p), ("max_cat_to_onehot", c_int32), ("max_cat_threshold", c_int32),
                 ("n_cat_words", c_uint32), ("node_is_cat", c_void_p), ("node_cat_bits", c_void_p),
                 ("node_sets", c_void_p), ("n_node_sets", c_int32), ("n_per_node", c_int32), ("eval_count", c_void_p),
-                ("gradient_based", c_int32)]
+                ("gradient_based", c_int32), ("seeds", c_void_p), ("n_seeds", c_int32), ("tree_set", c_void_p),
+                ("n_tree_set", c_int32), ("colsample_bylevel", c_float), ("colsample_bynode", c_float),
+                ("draws_used", c_void_p)]
 
 
 def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override=None, max_nodes=None,
                 is_dense_layout=True, want_hist=False, feature_set=None, subsample=1.0, sample_seed=0,
                 monotone=None, level_feature_sets=None, interaction=None, interaction_shared_buffer=True,
                 feature_is_cat=None, max_cat_to_onehot=4, max_cat_threshold=64, node_feature_sets=None,
-                sampling_method="uniform"):
+                sampling_method="uniform", column_seeds=None, tree_set=None, colsample_bylevel=1.0, colsample_bynode=1.0):
     """Whole tree.  Returns dict(nodes=[Node...], position, scale, hist (optional), cands).
     feature_set: sorted feature ids of the tree's colsample_bytree draw; subsample/sample_seed: uniform row sampling;
     monotone: per-feature sign (+1 increasing, -1 decreasing, 0 free), padded with 0 to n_features;
     feature_is_cat: flags per feature (categorical features: bins are categories, cut values their codes), with
     TrainParam's max_cat_to_onehot / max_cat_threshold; the result then carries is_cat[n_nodes] and cat_sets (the
     categories that go RIGHT, per categorical split);
+    column_seeds (+ tree_set, colsample_bylevel, colsample_bynode): the column sampler driven by the engine's outputs --
+    level sets drawn lazily per depth, a node set per evaluated node, in evaluation order (result: draws_used);
     node_feature_sets: colsample_bynode, int32[n_draws, n_per_node]: the k-th node evaluated takes row k (the result
     then carries eval_count, the number of draws used);
     interaction: parsed interaction_constraints ([[f, ...], ...]); interaction_shared_buffer (default = what the
@@ -346,9 +350,15 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
     has_cat = feature_is_cat is not None and any(feature_is_cat)
     eval_count = np.zeros(1, dtype=np.int32)
     gradient_based = sampling_method == "gradient_based" and subsample < 1.0
-    if has_cat or node_feature_sets is not None or gradient_based:
+    draws_used = np.zeros(1, dtype=np.int32)
+    if has_cat or node_feature_sets is not None or gradient_based or column_seeds is not None:
         cat = _Cat(None, int(max_cat_to_onehot), int(max_cat_threshold), 1, None, None, None, 0, 0, eval_count.ctypes.data,
-                   1 if gradient_based else 0)
+                   1 if gradient_based else 0, None, 0, None, 0, 1.0, 1.0, draws_used.ctypes.data)
+    if column_seeds is not None:
+        sd = np.ascontiguousarray([int(v) & 0xFFFFFFFF for v in column_seeds], dtype=np.uint32)
+        ts_ = np.ascontiguousarray(tree_set if tree_set is not None else np.arange(nf), dtype=np.int32)
+        cat.seeds, cat.n_seeds, cat.tree_set, cat.n_tree_set = sd.ctypes.data, sd.size, ts_.ctypes.data, ts_.size
+        cat.colsample_bylevel, cat.colsample_bynode = float(colsample_bylevel), float(colsample_bynode)
     if has_cat:
         flags = np.zeros(nf, dtype=np.uint8)
         flags[:len(feature_is_cat)] = [1 if v else 0 for v in feature_is_cat]
@@ -373,6 +383,8 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
                scale=np.array(scale_out[:], dtype=np.float64), hist=hist[:nn] if want_hist else None)
     if node_feature_sets is not None:
         res["eval_count"] = int(eval_count[0])
+    if column_seeds is not None:
+        res["draws_used"] = int(draws_used[0])
     if has_cat:
         res["is_cat"] = node_is_cat[:nn].copy()
         res["cat_sets"] = [{32 * w + (31 - b) for w in range(n_words) for b in range(32) if (int(node_bits[i, w]) >> b) & 1}

@@ -999,6 +999,17 @@ typedef struct {
   int32_t n_node_sets, n_per_node;
   int32_t* eval_count; /* out: draws used */
   int32_t gradient_based; /* subsample < 1: TrainParam::sampling_method == kGradientBased (orc_gradient_based_sample) */
+  /* The column sampler driven by the engine's outputs (ColumnSampler::GetFeatureSet, src/common/random.h:156-175, with
+   * ColSample on CUDA = orc_col_sample): seeds (NULL = off) are the values ctx->Rng()() returns AFTER ColumnSampler::Init,
+   * tree_set the tree-level set Init produced.  A call for a node of depth d first draws the level's set if the depth
+   * has none yet (colsample_bylevel < 1: one seed), then the node's set from it (colsample_bynode < 1: one seed).
+   * Calls happen in evaluation order.  draws_used (out) = seeds consumed. */
+  const uint32_t* seeds;
+  int32_t n_seeds;
+  const int32_t* tree_set;
+  int32_t n_tree_set;
+  float colsample_bylevel, colsample_bynode;
+  int32_t* draws_used;
 } orc_cat;
 ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
                                      uint32_t n_features, const uint32_t* cut_ptrs, const float* cut_values,
@@ -1078,10 +1089,37 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
     memset(cat->node_cat_bits, 0, sizeof(uint32_t) * (size_t)max_nodes * cat->n_cat_words);
   }
   int32_t eval_seq = 0;
+  /* lazily drawn level sets of the seed-driven column sampler */
+  enum { kOrcMaxLevels = 64 };
+  int32_t* lvl_sets = NULL;
+  int32_t lvl_n = 0, seed_pos = 0;
+  int32_t lvl_drawn[kOrcMaxLevels];
+  int32_t* node_draw = NULL;
+  memset(lvl_drawn, 0, sizeof(lvl_drawn));
+  if (cat && cat->seeds) {
+    lvl_sets = (int32_t*)malloc(sizeof(int32_t) * (size_t)kOrcMaxLevels * (size_t)(cat->n_tree_set ? cat->n_tree_set : 1));
+    node_draw = (int32_t*)malloc(sizeof(int32_t) * (size_t)(cat->n_tree_set ? cat->n_tree_set : 1));
+  }
 #define ORC_EVAL(nidx_, fs_in_, nfs_in_, out_)                                                                        \
   do {                                                                                                                \
     const int32_t* fs_ = fs_in_;                                                                                      \
     int32_t nfs_ = nfs_in_;                                                                                           \
+    if (cat && cat->seeds) {                                                                                          \
+      int32_t d_ = nodes[nidx_].depth < kOrcMaxLevels ? nodes[nidx_].depth : kOrcMaxLevels - 1;                       \
+      int32_t* lv_ = lvl_sets + (size_t)d_ * cat->n_tree_set;                                                         \
+      if (!lvl_drawn[d_]) {                                                                                           \
+        uint32_t sd_ = 0;                                                                                             \
+        if (cat->colsample_bylevel != 1.0f) sd_ = cat->seeds[seed_pos < cat->n_seeds ? seed_pos : cat->n_seeds - 1], seed_pos++; \
+        lvl_n = orc_col_sample(cat->tree_set, cat->n_tree_set, cat->colsample_bylevel, sd_, lv_);                      \
+        lvl_drawn[d_] = 1;                                                                                            \
+      }                                                                                                               \
+      {                                                                                                               \
+        uint32_t sd_ = 0;                                                                                             \
+        if (cat->colsample_bynode != 1.0f) sd_ = cat->seeds[seed_pos < cat->n_seeds ? seed_pos : cat->n_seeds - 1], seed_pos++; \
+        nfs_ = orc_col_sample(lv_, lvl_n, cat->colsample_bynode, sd_, node_draw);                                      \
+        fs_ = node_draw;                                                                                              \
+      }                                                                                                               \
+    }                                                                                                                 \
     if (cat && cat->node_sets) {                                                                                      \
       int32_t k_ = eval_seq < cat->n_node_sets ? eval_seq : cat->n_node_sets - 1;                                     \
       fs_ = cat->node_sets + (size_t)k_ * cat->n_per_node;                                                            \
@@ -1329,6 +1367,8 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
   free(hist); free(seg_beg); free(seg_cnt); free(node_sum); free(ridx); free(tmp); free(queue); free(gq);
   free(lower); free(upper); free(ic_bits); free(ic_buffer); free(cand_bits); free(cand_is_cat);
   if (cat && cat->eval_count) *cat->eval_count = eval_seq;
+  if (cat && cat->draws_used) *cat->draws_used = seed_pos;
+  free(lvl_sets); free(node_draw);
 #undef ORC_LEVEL_SET
 #undef ORC_EVAL
   return n_nodes;

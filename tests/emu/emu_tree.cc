@@ -7,6 +7,7 @@
 #include "cuda_emu.h"
 #include "emu_io.h"
 
+#include "../../xgboost_b200/csrc/colsample.cu"
 #include "../../xgboost_b200/csrc/evaluate.cu"
 #include "../../xgboost_b200/csrc/partition.cu"
 #include "../../xgboost_b200/csrc/updater.cu"
@@ -17,7 +18,8 @@ int main(int argc, char** argv) {
   if (argc < 2) return 2;
   const std::string dir = argv[1];
   // meta: n_rows, n_features, row_bytes, bin_bytes, null_symbol, has_mono, has_cat, onehot, threshold, cat_words,
-  //       bin_words, max_cat_bins, n_ic_sets, n_node_sets, n_per_node, has_fs, n_fs, n_levels
+  //       bin_words, max_cat_bins, n_ic_sets, n_node_sets, n_per_node, has_fs, n_fs, n_levels,
+  //       [18] n_col_seeds, [19] col_n_level, [20] col_n_node, [21] bylevel_is_one, [22] bynode_is_one
   auto meta = ReadAll<int64_t>(dir + "/meta.bin");
   auto prm = ReadAll<float>(dir + "/param_f.bin");
   auto prm_i = ReadAll<int32_t>(dir + "/param_i.bin");
@@ -33,6 +35,8 @@ int main(int argc, char** argv) {
   auto ic_set_feat = ReadAll<int32_t>(dir + "/ic_set_feat.bin", true);
   auto node_sets = ReadAll<int32_t>(dir + "/node_sets.bin", true);
   auto fs = ReadAll<int32_t>(dir + "/feature_set.bin", true);
+  auto col_seeds = ReadAll<uint32_t>(dir + "/col_seeds.bin", true);
+  auto col_tree_set = ReadAll<int32_t>(dir + "/col_tree_set.bin", true);
   const uint64_t n = (uint64_t)meta[0];
   const uint32_t nf = (uint32_t)meta[1];
   EllView view{};
@@ -102,6 +106,16 @@ int main(int argc, char** argv) {
   const int32_t* d_fs = meta[15] ? fs.data() : nullptr;
   const int32_t n_fs = (int32_t)meta[16], n_levels = (int32_t)meta[17];
   const size_t cat_smem = (size_t)kEvalWarps * (size_t)catv.max_cat_bins * (sizeof(float) + sizeof(uint16_t));
+  // seed-driven column sampler (b200hist_updater_set_column_sampler)
+  const bool has_col = meta[18] > 0;
+  const int32_t col_n_level = (int32_t)meta[19], col_n_node = (int32_t)meta[20];
+  const int32_t col_max_levels = p.max_depth > 0 ? p.max_depth + 1 : std::max(2, p.max_leaves);
+  std::vector<int32_t> col_cursor(2, 0), col_level_sets((size_t)col_max_levels * std::max(1, col_n_level), -9),
+      col_level_drawn((size_t)col_max_levels, 0), col_node_list((size_t)2 * 64 * std::max(1, col_n_node), -9),
+      col_node_count(2 * 64, -9);
+  const ColDrawDev cold{col_seeds.data(), (int32_t)meta[18], col_cursor.data(), col_tree_set.data(),
+                        (int32_t)col_tree_set.size(), col_level_sets.data(), col_n_level, col_level_drawn.data(),
+                        col_max_levels, (int32_t)meta[21]};
 
   auto build_hist = [&]() {  // the CPU stand-in for LaunchBuildHist over the kernels' own work list
     for (int k = 0; k < ts.n_build; ++k) {
@@ -156,10 +170,22 @@ int main(int argc, char** argv) {
     return IcView{node_list.data(), node_count.data(), n_per_node};
   };
 
+  auto evaluate_with_column_sampler = [&](int32_t max_eval) {
+    EMU_LAUNCH((1), (kCsThreads), sizeof(int32_t) * 2 * (size_t)col_n_level, LevelDrawKernel(&ts, nodes.data(), eval_nodes.data(), cold));
+    if (!meta[22]) {
+      EMU_LAUNCH(((unsigned)max_eval), (kCsThreads), sizeof(int32_t) * 2 * (size_t)col_n_node,
+                 NodeDrawKernel(&ts, nodes.data(), eval_nodes.data(), cold, col_n_node, col_node_list.data(), col_node_count.data()));
+      evaluate(max_eval, IcView{col_node_list.data(), col_node_count.data(), col_n_node}, nullptr, 0, 0);
+    } else {
+      evaluate(max_eval, IcView{nullptr, nullptr, 0}, col_level_sets.data(), col_n_level, col_max_levels);
+    }
+  };
+
   // ---- UpdateTreeImpl ----
   EMU_LAUNCH((1), (kCtlThreads), 0, InitRootKernel(p, (uint32_t)n, &q, &ts, nodes.data(), build.data(), build_tile_seg.data(), eval_nodes.data(), mono));
   build_hist();
-  if (has_node_sets) evaluate(1, node_sets_view(), nullptr, 0, 0);
+  if (has_col) evaluate_with_column_sampler(1);
+  else if (has_node_sets) evaluate(1, node_sets_view(), nullptr, 0, 0);
   else evaluate(1, IcView{nullptr, nullptr, 0}, d_fs, n_fs, n_levels);
   for (int step = 0; step < n_steps; ++step) {
     const long long cap = step_cap[step];
@@ -182,6 +208,10 @@ int main(int argc, char** argv) {
     build_hist();
     subtract();
     IcView icv{nullptr, nullptr, 0};
+    if (has_col) {
+      evaluate_with_column_sampler((int32_t)(2 * cap));
+      continue;
+    }
     if (has_node_sets) {
       icv = node_sets_view();
       evaluate((int32_t)(2 * cap), icv, nullptr, 0, 0);
@@ -219,6 +249,6 @@ int main(int argc, char** argv) {
   for (int32_t i = 0; i < ts.n_nodes; ++i) flags_out[i] = (!nodes[i].is_leaf && node_is_cat[i]) ? 1 : 0;
   WriteAll(dir + "/is_cat.bin", flags_out);
   WriteAll(dir + "/cat_bits.bin", cat_bits);
-  WriteAll(dir + "/eval_count.bin", std::vector<int32_t>{node_seq, ts.max_eval_depth});
+  WriteAll(dir + "/eval_count.bin", std::vector<int32_t>{node_seq, ts.max_eval_depth, col_cursor[0] + col_cursor[1]});
   return 0;
 }

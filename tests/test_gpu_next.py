@@ -766,3 +766,66 @@ def test_col_sample_stream_matches_the_thrust_shuffle_restatement(xb, n, colsamp
     assert got.shape[0] == len(seeds)
     for d, seed in enumerate(seeds):
         assert np.array_equal(got[d], orc.col_sample(features, colsample, seed)), (n, colsample, seed)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The seed-driven column sampler on the device (b200hist_updater_set_column_sampler: LevelDrawKernel / NodeDrawKernel)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bylevel,bynode,extra", [
+    (1.0, 0.5, dict(max_depth=6)), (0.6, 0.5, dict(max_depth=6)), (0.6, 1.0, dict(max_depth=5)),
+    (0.7, 0.6, dict(max_depth=0, max_leaves=20, grow_policy="lossguide")), (0.5, 0.5, dict(max_depth=7, max_leaves=17))],
+    ids=["bynode", "bylevel_bynode", "bylevel", "lossguide", "max_leaves"])
+def test_column_sampler_matches_oracle(xb, bylevel, bynode, extra):
+    import torch
+    n, f = 15000, 24
+    x, y = make_regression(n, f, seed=73, missing=0.05)
+    cp, cv = make_cuts(x, 32)
+    page = _page(xb, x, cp, cv)
+    gb = orc.bin_dense(x, cp, cv)
+    params = dict(extra, eta=0.5)
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    rng = np.random.default_rng(74)
+    pred = np.zeros(n, dtype=np.float32)
+    for it in range(3):
+        seeds = [int(v) for v in rng.integers(0, 2 ** 32, size=up.max_nodes + 300)]
+        tree_set = np.sort(rng.permutation(f)[:18]).astype(np.int32)
+        up.set_column_sampler(tree_set, bylevel, bynode, seeds)
+        gp = squared_error_gpair(pred, y)
+        tree = up.update(torch.from_numpy(gp).cuda())
+        o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), want_hist=True, column_seeds=seeds, tree_set=tree_set,
+                            colsample_bylevel=bylevel, colsample_bynode=bynode)
+        _compare_tree(xb, up, tree, o, cp, cv, hists=True)
+        assert up.last_draw_count() == o["draws_used"]
+        pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+    up.set_column_sampler(None, 1.0, 1.0, None)
+    gp = squared_error_gpair(np.zeros(n, np.float32), y)
+    t_plain = up.update(torch.from_numpy(gp).cuda())
+    _compare_tree(xb, up, t_plain, orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params)), cp, cv, hists=False)
+
+
+@pytest.mark.parametrize("extra", [{"colsample_bynode": 0.5, "colsample_bylevel": 0.6},
+                                   {"colsample_bynode": 0.7, "colsample_bylevel": 0.7, "colsample_bytree": 0.8, "subsample": 0.8,
+                                    "grow_policy": "lossguide", "max_leaves": 24, "max_depth": 0}],
+                         ids=["bylevel_bynode", "all_three_lossguide"])
+def test_colsample_bynode_with_bylevel_through_the_shim_matches_reference(xb, extra):
+    """Level and node draws interleave in one engine in the reference; the shim hands the stream of outputs to the
+    device sampler and advances the engine by the count it reports."""
+    import torch
+    rc = _shim_or_skip()
+    x, y = make_regression(30000, 40, seed=84)
+    params = {"tree_method": "hist", "device": "cuda:0", "max_bin": 64, "max_depth": 5, "eta": 0.3,
+              "objective": "reg:squarederror", "base_score": 0.5}
+    params.update(extra)
+
+    def train(updater):
+        dm = rc.DMatrix.from_cuda(torch.from_numpy(x).cuda(), kind="cuda")
+        dm.set_label(y)
+        bst = rc.Booster(dict(params, updater=updater), dm)
+        for i in range(4):
+            bst.update(i)
+        return _model_trees(bst), bst.predict_margin(dm)
+    ref_trees, ref_margin = train("grow_gpu_hist_reference")
+    our_trees, our_margin = train("grow_b200_hist")
+    assert json.dumps(our_trees) == json.dumps(ref_trees)
+    assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))

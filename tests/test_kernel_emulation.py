@@ -492,7 +492,7 @@ TREE_NODE = np.dtype([("parent", "<i4"), ("left", "<i4"), ("right", "<i4"), ("fi
 
 
 def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, onehot=4, threshold=64, ic_sets=None,
-                  node_sets=None, feature_set=None, n_levels=0):
+                  node_sets=None, feature_set=None, n_levels=0, col_seeds=None, col_tree_set=None, bylevel=1.0, bynode=1.0):
     exe = _build("emu_tree")
     n, nf = gb.shape
     max_bins = int(np.diff(cp).max())
@@ -507,10 +507,20 @@ def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, oneh
     d = str(tmp_path)
     p = orc.Param.make(**params)
     fs = None if feature_set is None else np.ascontiguousarray(feature_set, dtype=np.int32)
+    col_meta = [0, 0, 0, 1, 1]
+    if col_seeds is not None:
+        ts_ = np.ascontiguousarray(col_tree_set if col_tree_set is not None else np.arange(nf), dtype=np.int32)
+        n_level = ts_.size if bylevel == 1.0 else max(1, int(np.float32(bylevel) * np.float32(ts_.size)))
+        n_node = n_level if bynode == 1.0 else max(1, int(np.float32(bynode) * np.float32(n_level)))
+        col_meta = [len(col_seeds), n_level, n_node, 1 if bylevel == 1.0 else 0, 1 if bynode == 1.0 else 0]
+        os.makedirs(str(tmp_path), exist_ok=True)
+        np.ascontiguousarray(col_seeds, dtype=np.uint32).tofile(os.path.join(str(tmp_path), "col_seeds.bin"))
+        ts_.tofile(os.path.join(str(tmp_path), "col_tree_set.bin"))
     np.array([n, nf, page.shape[1], bin_bytes, null_symbol, 0 if mono is None else 1, 0 if is_cat is None else 1, onehot,
               threshold, cat_words, (max_cat_bins + 31) // 32, max_cat_bins, 0 if ic_sets is None else len(ic_sets),
               0 if node_sets is None else node_sets.shape[0], 0 if node_sets is None else node_sets.shape[1],
-              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels], dtype=np.int64).tofile(os.path.join(d, "meta.bin"))
+              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta,
+             dtype=np.int64).tofile(os.path.join(d, "meta.bin"))
     np.array([p.learning_rate, p.reg_lambda, p.reg_alpha, p.min_child_weight, p.max_delta_step, p.min_split_loss],
              dtype=np.float32).tofile(os.path.join(d, "param_f.bin"))
     np.array([p.max_depth, p.max_leaves, p.grow_policy], dtype=np.int32).tofile(os.path.join(d, "param_i.bin"))
@@ -679,3 +689,29 @@ def test_whole_tree_kernel_sources_combined(tmp_path):
     o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), feature_is_cat=is_cat, node_feature_sets=sets, monotone=mono)
     _same_tree(nodes, pos, o, flags, bits)
     assert int(counts[0]) == o["eval_count"] and int(o["is_cat"].sum()) >= 2
+
+
+@pytest.mark.parametrize("bylevel,bynode,params", [
+    (1.0, 0.5, dict(max_depth=5, eta=0.5)),
+    (0.6, 0.5, dict(max_depth=5, eta=0.5)),
+    (0.6, 1.0, dict(max_depth=5, eta=0.5)),
+    (0.7, 0.6, dict(max_depth=0, max_leaves=12, grow_policy="lossguide", eta=0.5)),
+], ids=["bynode", "bylevel_bynode", "bylevel", "bylevel_bynode_lossguide"])
+def test_whole_tree_kernel_sources_column_sampler(tmp_path, bylevel, bynode, params):
+    """The seed-driven column sampler (LevelDrawKernel / NodeDrawKernel, csrc/colsample.cu) inside a real tree: level
+    sets drawn the first time a depth is evaluated, node sets per evaluated node, all from one stream of engine outputs
+    whose cursor lives on the device -- incl. loss-guided growth, where depths come in data-dependent order -- against
+    the oracle's lazy restatement, and the number of outputs consumed."""
+    gb, cp, cv, gp = _tree_data(seed=16, f=10)
+    rng = np.random.default_rng(17)
+    seeds = [int(v) for v in rng.integers(0, 2 ** 32, size=200)]
+    tree_set = np.sort(rng.permutation(10)[:8]).astype(np.int32)       # a colsample_bytree draw
+    nodes, pos, _, _, counts = _emulate_tree(tmp_path, gb, cp, cv, gp, params, col_seeds=seeds, col_tree_set=tree_set,
+                                             bylevel=bylevel, bynode=bynode)
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), column_seeds=seeds, tree_set=tree_set,
+                        colsample_bylevel=bylevel, colsample_bynode=bynode)
+    _same_tree(nodes, pos, o)
+    assert int(counts[2]) == o["draws_used"]
+    for nd in o["nodes"]:
+        if not nd.is_leaf:
+            assert nd.findex in tree_set

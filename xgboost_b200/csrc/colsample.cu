@@ -51,16 +51,15 @@ __device__ __forceinline__ uint32_t BlockExclusiveScanCs(uint32_t v, uint32_t* s
   return ex;
 }
 
-__global__ void __launch_bounds__(kCsThreads) ColSampleStreamKernel(const int32_t* __restrict__ features, int32_t n,
-                                                                     int32_t n_sel, const uint32_t* __restrict__ seeds,
-                                                                     int32_t* __restrict__ out) {
-  B200_DYNAMIC_SHARED(int32_t, s_sel);  // n_sel selected ids, then n_sel sorted ids
-  __shared__ uint32_t s_key[24];
-  __shared__ uint32_t s_warp[33];
+// One draw by the whole CTA: ColSample(features[0..n), n_sel, seed) -> out[0..n_sel), ascending.  s_sel: 2 * n_sel ints.
+__device__ __forceinline__ void ColSampleBlock(const int32_t* __restrict__ features, int32_t n, int32_t n_sel,
+                                               uint32_t seed, int32_t* s_sel, uint32_t* s_key, uint32_t* s_warp,
+                                               int32_t* __restrict__ out) {
   int32_t* s_sorted = s_sel + n_sel;
+  __syncthreads();  // the caller's earlier use of the scratch is over
   if (threadIdx.x == 0) {  // minstd_rand seeded like thrust: seed mod m, 0 -> 1; a key is the next state
     const unsigned long long mod = 2147483647ull;
-    unsigned long long x = seeds[blockIdx.x] % mod;
+    unsigned long long x = seed % mod;
     if (x == 0) x = 1;
     for (int i = 0; i < 24; ++i) {
       x = (x * 48271ull) % mod;
@@ -110,10 +109,95 @@ __global__ void __launch_bounds__(kCsThreads) ColSampleStreamKernel(const int32_
     s_sorted[rank] = v;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n_sel; i += kCsThreads) out[(size_t)blockIdx.x * n_sel + i] = s_sorted[i];
+  for (int i = threadIdx.x; i < n_sel; i += kCsThreads) out[i] = s_sorted[i];
+}
+
+__global__ void __launch_bounds__(kCsThreads) ColSampleStreamKernel(const int32_t* __restrict__ features, int32_t n,
+                                                                     int32_t n_sel, const uint32_t* __restrict__ seeds,
+                                                                     int32_t* __restrict__ out) {
+  B200_DYNAMIC_SHARED(int32_t, s_sel);  // n_sel selected ids, then n_sel sorted ids
+  __shared__ uint32_t s_key[24];
+  __shared__ uint32_t s_warp[33];
+  ColSampleBlock(features, n, n_sel, seeds[blockIdx.x], s_sel, s_key, s_warp, out + (size_t)blockIdx.x * n_sel);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The column sampler of one tree, driven by the engine's outputs (ColumnSampler::GetFeatureSet, random.h:156-175).
+// A GetFeatureSet call for a node of depth d first draws the depth's level set if it has none yet
+// (colsample_bylevel < 1: one engine output), then the node's set from it (colsample_bynode < 1: one output); the calls
+// come in evaluation order: the root, then left and right child of every valid candidate in Pop order.  With both
+// fractions below 1 the position of a level draw in the stream depends on how many nodes were evaluated before the
+// level's first node -- known on the device only.  So the device holds the stream of outputs (`seeds`) and a cursor.
+// All evaluation slots of one step share a depth (a level, or the two children of one loss-guided split).
+//   LevelDrawKernel  1 CTA : cursor += draws of the previous step; draw the step's level set if it is missing
+//   NodeDrawKernel   1 CTA per evaluation slot: slot j takes output cursor + j
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCsThreads) LevelDrawKernel(const TreeState* ts, const NodeDev* __restrict__ nodes,
+                                                               const int32_t* __restrict__ eval_nodes, ColDrawDev cd) {
+  B200_DYNAMIC_SHARED(int32_t, s_sel);
+  __shared__ uint32_t s_key[24];
+  __shared__ uint32_t s_warp[33];
+  __shared__ int s_draw, s_pos;
+  if (threadIdx.x == 0) {
+    cd.cursor[0] += cd.cursor[1];
+    cd.cursor[1] = 0;
+    s_draw = 0;
+    if (ts->n_eval > 0) {
+      const int d = min(nodes[eval_nodes[0]].depth, cd.max_levels - 1);
+      if (!cd.level_drawn[d]) {
+        s_draw = 1 + d;
+        s_pos = cd.cursor[0];
+        cd.level_drawn[d] = 1;
+        if (!cd.bylevel_is_one) cd.cursor[0] += 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (s_draw == 0) return;
+  int32_t* out = cd.level_sets + (size_t)(s_draw - 1) * cd.n_level;
+  if (cd.bylevel_is_one) {
+    for (int i = threadIdx.x; i < cd.n_tree; i += kCsThreads) out[i] = cd.tree_set[i];
+    return;
+  }
+  ColSampleBlock(cd.tree_set, cd.n_tree, cd.n_level, cd.seeds[min(s_pos, cd.n_seeds - 1)], s_sel, s_key, s_warp, out);
+}
+
+__global__ void __launch_bounds__(kCsThreads) NodeDrawKernel(const TreeState* ts, const NodeDev* __restrict__ nodes,
+                                                              const int32_t* __restrict__ eval_nodes, ColDrawDev cd,
+                                                              int32_t n_node, int32_t* __restrict__ list,
+                                                              int32_t* __restrict__ count) {
+  B200_DYNAMIC_SHARED(int32_t, s_sel);
+  __shared__ uint32_t s_key[24];
+  __shared__ uint32_t s_warp[33];
+  const int n_eval = ts->n_eval;
+  const int j = blockIdx.x;
+  if (j >= n_eval) return;
+  const int d = min(nodes[eval_nodes[0]].depth, cd.max_levels - 1);
+  const int32_t* level = cd.level_sets + (size_t)d * cd.n_level;
+  const int pos = cd.cursor[0] + j;
+  ColSampleBlock(level, cd.n_level, n_node, cd.seeds[min(pos, cd.n_seeds - 1)], s_sel, s_key, s_warp,
+                 list + (size_t)j * n_node);
+  if (threadIdx.x == 0) {
+    count[j] = n_node;
+    if (j == 0) cd.cursor[1] = n_eval;  // nobody reads [1] in this launch; LevelDrawKernel folds it into the cursor
+  }
 }
 
 #ifndef B200_KERNELS_ONLY
+void LaunchLevelDraw(const TreeState* ts, const NodeDev* nodes, const int32_t* eval_nodes, const ColDrawDev& cd,
+                     cudaStream_t s) {
+  LevelDrawKernel<<<1, kCsThreads, sizeof(int32_t) * 2 * (size_t)cd.n_level, s>>>(ts, nodes, eval_nodes, cd);
+  B200_LAUNCHED();
+}
+
+void LaunchNodeDraw(const TreeState* ts, const NodeDev* nodes, const int32_t* eval_nodes, const ColDrawDev& cd,
+                    int32_t n_node, int32_t max_eval, int32_t* list, int32_t* count, cudaStream_t s) {
+  if (max_eval == 0) return;
+  NodeDrawKernel<<<max_eval, kCsThreads, sizeof(int32_t) * 2 * (size_t)n_node, s>>>(ts, nodes, eval_nodes, cd, n_node,
+                                                                                     list, count);
+  B200_LAUNCHED();
+}
+
 void LaunchColSampleStream(const int32_t* features_dev, int32_t n, int32_t n_sel, const uint32_t* seeds_dev,
                            int32_t n_draws, int32_t* out_dev, cudaStream_t s) {
   if (n_draws == 0) return;

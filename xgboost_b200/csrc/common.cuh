@@ -379,6 +379,24 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = n
                     IcView ic = IcView{nullptr, nullptr, 0},
                     CatView cat = CatView{nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0, 0});
 
+// colsample.cu: the seed-driven column sampler of one tree (see the kernels there)
+struct ColDrawDev {
+  const uint32_t* seeds;  // engine outputs after ColumnSampler::Init
+  int32_t n_seeds;
+  int32_t* cursor;        // [0] outputs consumed so far, [1] outputs the last NodeDrawKernel consumed
+  const int32_t* tree_set;
+  int32_t n_tree;
+  int32_t* level_sets;    // [max_levels][n_level], row = depth (the last row serves deeper nodes)
+  int32_t n_level;
+  int32_t* level_drawn;   // [max_levels]
+  int32_t max_levels;
+  int32_t bylevel_is_one;  // colsample_bylevel == 1: a level set is the tree set, no output consumed
+};
+void LaunchLevelDraw(const TreeState* ts, const NodeDev* nodes, const int32_t* eval_nodes, const ColDrawDev& cd,
+                     cudaStream_t s);
+void LaunchNodeDraw(const TreeState* ts, const NodeDev* nodes, const int32_t* eval_nodes, const ColDrawDev& cd,
+                    int32_t n_node, int32_t max_eval, int32_t* list, int32_t* count, cudaStream_t s);
+
 // sampling.cu: gradient-based row sampling on the quantised pairs (after LaunchQuantise without uniform sampling);
 // recomputes the record's root sum and hessian flags from the sampled pairs
 size_t GradientBasedScratchBytes(uint64_t n, int num_sms);

@@ -168,8 +168,11 @@ class B200HistMaker : public TreeUpdater {
         << "[b200hist] gradient_based row sampling is not enabled yet";
     CHECK(param->colsample_bynode == 1.0f || unvalidated_ok)
         << "[b200hist] colsample_bynode is not enabled yet (colsample_bytree and colsample_bylevel are)";
-    CHECK(param->colsample_bynode == 1.0f || (param->colsample_bylevel == 1.0f && param->interaction_constraints.empty()))
-        << "[b200hist] colsample_bynode cannot be combined with colsample_bylevel or interaction constraints yet";
+    CHECK(param->colsample_bynode == 1.0f || param->interaction_constraints.empty())
+        << "[b200hist] colsample_bynode cannot be combined with interaction constraints yet";
+    CHECK(param->colsample_bynode == 1.0f || param->colsample_bylevel == 1.0f ||
+          (p_fmat->Info().feature_weights.Empty() && p_fmat->Info().num_col_ <= 8192))
+        << "[b200hist] colsample_bynode with colsample_bylevel needs the device sampler (no feature weights, <= 8192 features)";
     B200_SHIM_CHECK(b200hist_updater_create(ellpack_, &p, &updater_));
     // Sampler ctor (sampler.cu:343-363): the strategy follows sampling_method whenever subsample < 1
     B200_SHIM_CHECK(b200hist_updater_set_sampling_method(
@@ -237,25 +240,29 @@ class B200HistMaker : public TreeUpdater {
       std::size_t per_node = 0;
       node_draws_by_seed_ = info.feature_weights.Empty() && info.num_col_ <= 8192;
       if (node_draws_by_seed_) {
-        // One launch for the whole stream: the tree-level set comes from the reference's sampler (Init consumes the
-        // colsample_bytree draw exactly as it would), every node draw is ColSample(tree set, bynode) seeded with the
-        // engine's next output (random.cu:67), which b200hist_col_sample_stream restates on the device.
+        // The whole column sampler of the tree on the device: the tree-level set comes from the reference's sampler
+        // (Init consumes the colsample_bytree draw exactly as it would); every later GetFeatureSet call -- a lazy level
+        // draw the first time a depth is evaluated, a node draw per evaluated node -- takes the engine's next output as
+        // its shuffle seed (random.cu:67).  The updater gets the stream of outputs and keeps the cursor itself.
         column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, 1.0f, 1.0f, param->colsample_bytree);
         auto p_tree = column_sampler_.GetFeatureSet(ctx_, 0);
         auto const& h_tree = p_tree->ConstHostVector();
         std::vector<std::int32_t> tree_set(h_tree.cbegin(), h_tree.cend());
         rng_after_init_ = ctx_->Rng();
-        auto ahead = ctx_->Rng();  // a copy: the real engine moves in FinishSampling by the draws really used
-        std::vector<std::uint32_t> seeds(static_cast<std::size_t>(max_nodes));
+        auto ahead = ctx_->Rng();  // a copy: the real engine moves in FinishSampling by the outputs really used
+        std::int32_t const max_levels =
+            param->max_depth > 0 ? param->max_depth + 1 : std::max<std::int32_t>(2, param->max_leaves);
+        std::vector<std::uint32_t> seeds(static_cast<std::size_t>(max_nodes + max_levels));
         for (auto& sd : seeds) sd = static_cast<std::uint32_t>(ahead());
-        std::uint32_t n_sel = 0;
-        fs.resize(static_cast<std::size_t>(max_nodes) * tree_set.size());
-        B200_SHIM_CHECK(b200hist_col_sample_stream(ctx_->Ordinal(), tree_set.data(),
-                                                   static_cast<std::uint32_t>(tree_set.size()), param->colsample_bynode,
-                                                   seeds.data(), static_cast<std::uint32_t>(max_nodes), fs.data(), &n_sel,
-                                                   static_cast<void*>(ctx_->CUDACtx()->Stream())));
-        per_node = n_sel;
-        fs.resize(static_cast<std::size_t>(max_nodes) * per_node);
+        B200_SHIM_CHECK(b200hist_updater_set_level_feature_sets(updater_, nullptr, 0, 0));
+        B200_SHIM_CHECK(b200hist_updater_set_tree_sampling(updater_, nullptr, 0, rows ? param->subsample : 1.0f, seed));
+        B200_SHIM_CHECK(b200hist_updater_set_column_sampler(updater_, tree_set.data(),
+                                                            static_cast<std::uint32_t>(tree_set.size()),
+                                                            param->colsample_bylevel, param->colsample_bynode,
+                                                            seeds.data(), static_cast<std::uint32_t>(seeds.size())));
+        node_draws_pending_ = true;
+        sampling_set_ = true;
+        return;
       } else {  // feature weights: weighted sampling without replacement, through the reference's own sampler
         column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, param->colsample_bynode, 1.0f,
                              param->colsample_bytree);
@@ -313,13 +320,14 @@ class B200HistMaker : public TreeUpdater {
   void FinishSampling(TrainParam const* param, DMatrix* p_fmat) {
     if (node_draws_pending_) {  // colsample_bynode: as many draws as nodes were evaluated
       std::int32_t n_draws = 0;
-      B200_SHIM_CHECK(b200hist_updater_last_eval_count(updater_, &n_draws));
-      if (node_draws_by_seed_) {  // one engine output per ColSample call
+      if (node_draws_by_seed_) {  // one engine output per ColSample call, level draws included
+        B200_SHIM_CHECK(b200hist_updater_last_draw_count(updater_, &n_draws));
         ctx_->Rng() = rng_after_init_;
         ctx_->Rng().discard(static_cast<unsigned long long>(n_draws));
         node_draws_pending_ = false;
         return;
       }
+      B200_SHIM_CHECK(b200hist_updater_last_eval_count(updater_, &n_draws));
       ctx_->Rng() = rng_before_columns_;
       auto const& info = p_fmat->Info();
       column_sampler_.Init(ctx_, info.num_col_, info.feature_weights, param->colsample_bynode, 1.0f,

@@ -813,6 +813,16 @@ struct b200hist_updater_s {
   int32_t* d_node_count{nullptr};
   int32_t* d_node_seq{nullptr};
   int32_t n_node_sets{0}, n_per_node{0}, last_eval_count{0};
+  // seed-driven column sampler (nullptr = none): engine outputs, cursor, tree set, lazily drawn level sets
+  uint32_t* d_col_seeds{nullptr};
+  int32_t* d_col_cursor{nullptr};
+  int32_t* d_col_tree_set{nullptr};
+  int32_t* d_col_level_sets{nullptr};
+  int32_t* d_col_level_drawn{nullptr};
+  int32_t* d_col_node_list{nullptr};
+  int32_t* d_col_node_count{nullptr};
+  int32_t col_n_seeds{0}, col_n_tree{0}, col_n_level{0}, col_n_node{0}, col_max_levels{0}, last_draw_count{0};
+  bool col_bylevel_is_one{true}, col_bynode_is_one{true};
   // categorical features (nullptr = none): flags per feature, per-node category sets (CatView)
   uint8_t* d_is_cat{nullptr};
   uint32_t* d_cat_bits{nullptr};
@@ -943,6 +953,30 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   const bool has_ic = u->d_ic_bits != nullptr;
   const bool has_cat = u->d_is_cat != nullptr;
   const bool has_node_sets = u->d_node_sets != nullptr;
+  const bool has_col = u->d_col_seeds != nullptr;
+  const ColDrawDev cold{u->d_col_seeds, u->col_n_seeds, u->d_col_cursor, u->d_col_tree_set, u->col_n_tree,
+                        u->d_col_level_sets, u->col_n_level, u->d_col_level_drawn, u->col_max_levels,
+                        u->col_bylevel_is_one ? 1 : 0};
+  if (has_col) {
+    B200_CUDA(cudaMemsetAsync(u->d_col_cursor, 0, 2 * sizeof(int32_t), s));
+    B200_CUDA(cudaMemsetAsync(u->d_col_level_drawn, 0, sizeof(int32_t) * (size_t)u->col_max_levels, s));
+  }
+  // evaluation through the seed-driven column sampler: level set of the step's depth (drawn on first use), then a
+  // node set per evaluation slot (colsample_bynode < 1) or the level set itself
+  auto evaluate_with_column_sampler = [&](int32_t max_eval, const CatView& cv) {
+    LaunchLevelDraw(u->d_ts, u->d_nodes, u->d_eval_nodes, cold, s);
+    if (!u->col_bynode_is_one) {
+      LaunchNodeDraw(u->d_ts, u->d_nodes, u->d_eval_nodes, cold, u->col_n_node, max_eval, u->d_col_node_list,
+                     u->d_col_node_count, s);
+      LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, max_eval, u->d_nodes, nullptr, 0, u->pdev, u->d_quant,
+                     u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, 0, &u->d_ts->max_eval_depth,
+                     IcView{u->d_col_node_list, u->d_col_node_count, u->col_n_node}, cv);
+    } else {
+      LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, max_eval, u->d_nodes, u->d_col_level_sets, u->col_n_level,
+                     u->pdev, u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, u->col_max_levels,
+                     &u->d_ts->max_eval_depth, IcView{nullptr, nullptr, 0}, cv);
+    }
+  };
   if (has_node_sets) B200_CUDA(cudaMemsetAsync(u->d_node_seq, 0, sizeof(int32_t), s));
   auto node_sets_view = [&]() {  // the next n_eval draws of the stream, one list per evaluation slot
     NodeSetLevelKernel<<<1, kCtlThreads, 0, s>>>(u->d_ts, u->d_node_sets, u->n_node_sets, u->n_per_node, u->d_node_seq,
@@ -989,7 +1023,9 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   build_hist(0, 1);
   timer.End(kHist, t2);
   auto t3 = timer.Begin();
-  if (has_node_sets) {
+  if (has_col) {
+    evaluate_with_column_sampler(1, catv);
+  } else if (has_node_sets) {
     const IcView nv = node_sets_view();
     LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, nullptr, 0, u->pdev, u->d_quant, u->d_scratch,
                    u->d_cand, u->d_nodes, u->num_sms, s, mono, 0, &u->d_ts->max_eval_depth, nv, catv);
@@ -1035,6 +1071,11 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     timer.End(kSub, tsb);
     auto te = timer.Begin();
     IcView icv{nullptr, nullptr, 0};
+    if (has_col) {
+      evaluate_with_column_sampler((int32_t)(2 * cap), catv);
+      timer.End(kEval, te);
+      continue;
+    }
     if (has_node_sets) {
       icv = node_sets_view();
       LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, (int32_t)(2 * cap), u->d_nodes, nullptr, 0, u->pdev,
@@ -1100,6 +1141,11 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   u->last_max_eval_depth = u->h_ts->max_eval_depth;
   if (has_node_sets)
     B200_CUDA(cudaMemcpy(&u->last_eval_count, u->d_node_seq, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (has_col) {
+    int32_t cur[2] = {0, 0};
+    B200_CUDA(cudaMemcpy(cur, u->d_col_cursor, sizeof(cur), cudaMemcpyDeviceToHost));
+    u->last_draw_count = cur[0] + cur[1];
+  }
   u->last_position = position;
   if (out_nodes) ToAbiNodes(u->h_nodes, u->last_n_nodes, out_nodes);
   if (out_n_nodes) *out_n_nodes = u->last_n_nodes;
@@ -1239,6 +1285,9 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
     for (void* p : {(void*)u->d_node_sets, (void*)u->d_node_list, (void*)u->d_node_count, (void*)u->d_node_seq})
       if (p) cudaFree(p);
     if (u->d_gbs_scratch) cudaFree(u->d_gbs_scratch);
+    for (void* p : {(void*)u->d_col_seeds, (void*)u->d_col_cursor, (void*)u->d_col_tree_set, (void*)u->d_col_level_sets,
+                    (void*)u->d_col_level_drawn, (void*)u->d_col_node_list, (void*)u->d_col_node_count})
+      if (p) cudaFree(p);
     cudaFreeHost(u->h_nodes);
     cudaFreeHost(u->h_ts);
     cudaFreeHost(u->h_quant);
@@ -1501,6 +1550,73 @@ int b200hist_updater_set_interaction_constraints(b200hist_updater_t u, const int
     u->d_ic_list = DevAlloc<int32_t>(u->ell->n_features);
     u->d_ic_count = DevAlloc<int32_t>(2 * (size_t)kMaxLevelNodes);
   }
+  B200_API_END();
+}
+
+int b200hist_updater_set_column_sampler(b200hist_updater_t u, const int32_t* tree_set_host, uint32_t n_tree_set,
+                                        float colsample_bylevel, float colsample_bynode, const uint32_t* seeds_host,
+                                        uint32_t n_seeds) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  DeviceGuard guard(u->device);
+  // the usual caller sets a fresh stream of outputs before every tree: same shapes -> only the two copies
+  if (seeds_host != nullptr && u->d_col_seeds != nullptr && (int32_t)n_seeds == u->col_n_seeds &&
+      (int32_t)n_tree_set == u->col_n_tree && tree_set_host != nullptr &&
+      u->col_bylevel_is_one == (colsample_bylevel == 1.0f) && u->col_bynode_is_one == (colsample_bynode == 1.0f) &&
+      u->col_n_level == (colsample_bylevel == 1.0f ? (int32_t)n_tree_set
+                                                    : std::max(1, (int32_t)(colsample_bylevel * (float)n_tree_set))) &&
+      u->col_n_node == (colsample_bynode == 1.0f ? u->col_n_level
+                                                  : std::max(1, (int32_t)(colsample_bynode * (float)u->col_n_level)))) {
+    for (uint32_t i = 0; i < n_tree_set; ++i)
+      B200_CHECK(tree_set_host[i] >= 0 && (uint32_t)tree_set_host[i] < u->ell->n_features, "feature id out of range");
+    B200_CUDA(cudaMemcpy(u->d_col_seeds, seeds_host, sizeof(uint32_t) * n_seeds, cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(u->d_col_tree_set, tree_set_host, sizeof(int32_t) * n_tree_set, cudaMemcpyHostToDevice));
+    return 0;
+  }
+  for (void** p : {(void**)&u->d_col_seeds, (void**)&u->d_col_cursor, (void**)&u->d_col_tree_set,
+                   (void**)&u->d_col_level_sets, (void**)&u->d_col_level_drawn, (void**)&u->d_col_node_list,
+                   (void**)&u->d_col_node_count}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  u->col_n_seeds = 0;
+  if (seeds_host != nullptr && n_seeds > 0) {
+    B200_CHECK(tree_set_host != nullptr && n_tree_set >= 1 && n_tree_set <= 8192, "tree set out of range");
+    B200_CHECK(colsample_bylevel > 0.0f && colsample_bylevel <= 1.0f && colsample_bynode > 0.0f && colsample_bynode <= 1.0f,
+               "colsample fractions must be in (0, 1]");
+    B200_CHECK(u->d_ic_bits == nullptr && u->d_node_sets == nullptr,
+               "the column sampler cannot be combined with interaction constraints or explicit node sets yet");
+    for (uint32_t i = 0; i < n_tree_set; ++i)
+      B200_CHECK(tree_set_host[i] >= 0 && (uint32_t)tree_set_host[i] < u->ell->n_features, "feature id out of range");
+    // a tree consumes at most one output per possible depth and one per node
+    const int32_t max_levels = u->param.max_depth > 0 ? u->param.max_depth + 1 : std::max(2, u->param.max_leaves);
+    B200_CHECK((int64_t)n_seeds >= (int64_t)u->max_nodes + max_levels, "need max_nodes + max depth + 1 engine outputs");
+    u->col_n_seeds = (int32_t)n_seeds;
+    u->col_n_tree = (int32_t)n_tree_set;
+    u->col_bylevel_is_one = colsample_bylevel == 1.0f;
+    u->col_bynode_is_one = colsample_bynode == 1.0f;
+    u->col_n_level = u->col_bylevel_is_one ? u->col_n_tree : std::max(1, (int32_t)(colsample_bylevel * (float)n_tree_set));
+    u->col_n_node = u->col_bynode_is_one ? u->col_n_level : std::max(1, (int32_t)(colsample_bynode * (float)u->col_n_level));
+    u->col_max_levels = max_levels;
+    u->d_col_seeds = DevAlloc<uint32_t>(n_seeds);
+    B200_CUDA(cudaMemcpy(u->d_col_seeds, seeds_host, sizeof(uint32_t) * n_seeds, cudaMemcpyHostToDevice));
+    u->d_col_cursor = DevAlloc<int32_t>(2);
+    u->d_col_tree_set = DevAlloc<int32_t>(n_tree_set);
+    B200_CUDA(cudaMemcpy(u->d_col_tree_set, tree_set_host, sizeof(int32_t) * n_tree_set, cudaMemcpyHostToDevice));
+    u->d_col_level_sets = DevAlloc<int32_t>((size_t)max_levels * u->col_n_level);
+    u->d_col_level_drawn = DevAlloc<int32_t>((size_t)max_levels);
+    size_t max_cap = 1;
+    for (uint32_t c : u->step_cap) max_cap = std::max<size_t>(max_cap, c);
+    u->d_col_node_list = DevAlloc<int32_t>(2 * max_cap * (size_t)u->col_n_node);
+    u->d_col_node_count = DevAlloc<int32_t>(2 * max_cap);
+  }
+  B200_API_END();
+}
+
+int b200hist_updater_last_draw_count(b200hist_updater_t u, int32_t* out) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && out != nullptr, "null argument");
+  *out = u->last_draw_count;
   B200_API_END();
 }
 

@@ -77,6 +77,9 @@ _SIGNATURES = {
     "b200hist_updater_set_monotone_constraints": (c_int, [c_void_p, POINTER(c_int32), c_uint32]),
     "b200hist_updater_set_interaction_constraints": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32), c_uint32]),
     "b200hist_updater_set_sampling_method": (c_int, [c_void_p, c_int]),
+    "b200hist_updater_set_column_sampler": (c_int, [c_void_p, POINTER(c_int32), c_uint32, c_float, c_float,
+                                                    POINTER(c_uint32), c_uint32]),
+    "b200hist_updater_last_draw_count": (c_int, [c_void_p, POINTER(c_int32)]),
     "b200hist_col_sample_stream": (c_int, [c_int, POINTER(c_int32), c_uint32, c_float, POINTER(c_uint32), c_uint32,
                                            POINTER(c_int32), POINTER(c_uint32), c_void_p]),
     "b200hist_updater_set_node_feature_sets": (c_int, [c_void_p, POINTER(c_int32), c_uint32, c_uint32]),

@@ -535,6 +535,23 @@ class GPUHistMaker:
             c = np.ascontiguousarray(constraints, dtype=np.int32)
             _l.check(_l.load().b200hist_updater_set_monotone_constraints(self._h, c.ctypes.data_as(POINTER(c_int32)), c.size))
 
+    def set_column_sampler(self, tree_set, colsample_bylevel: float, colsample_bynode: float, seeds) -> None:
+        """The tree's column sampler on the device: `tree_set` (colsample_bytree draw), the two fractions, and the engine
+        outputs the sampler would consume, in order (>= max_nodes + max depth + 1).  None for `seeds` removes it."""
+        if seeds is None:
+            _l.check(_l.load().b200hist_updater_set_column_sampler(self._h, None, 0, 1.0, 1.0, None, 0))
+            return
+        ts = np.ascontiguousarray(tree_set, dtype=np.int32)
+        sd = np.ascontiguousarray([int(v) & 0xFFFFFFFF for v in seeds], dtype=np.uint32)
+        _l.check(_l.load().b200hist_updater_set_column_sampler(self._h, ts.ctypes.data_as(POINTER(c_int32)), ts.size,
+                                                             float(colsample_bylevel), float(colsample_bynode),
+                                                             sd.ctypes.data_as(POINTER(c_uint32)), sd.size))
+
+    def last_draw_count(self) -> int:
+        n = c_int32()
+        _l.check(_l.load().b200hist_updater_last_draw_count(self._h, byref(n)))
+        return int(n.value)
+
     def set_sampling_method(self, method: str) -> None:
         """TrainParam::sampling_method: "uniform" or "gradient_based" (applies when subsample < 1 in
         set_tree_sampling).  gradient_based has not run on hardware -- see include/b200hist.h."""
