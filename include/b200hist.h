@@ -304,7 +304,8 @@ B200HIST_API int b200hist_updater_last_eval_count(b200hist_updater_t u, int32_t*
  * depends on the data; the cursor therefore lives on the device.  n_seeds >= max_nodes + max depth + 1.
  * b200hist_updater_last_draw_count = outputs the last tree consumed: the caller advances its engine by that many.
  * Covers colsample_bynode with or without colsample_bylevel (and colsample_bylevel alone); replaces
- * b200hist_updater_set_node_feature_sets / set_level_feature_sets while set; NULL / 0 removes it.
+ * b200hist_updater_set_node_feature_sets / set_level_feature_sets while set; NULL / 0 removes it.  With interaction
+ * constraints a node's Query runs on its OWN sampled list (updater_gpu_hist.cu:257-264).
  * STATUS: compiled; kernel sources and whole trees run under the CPU emulator against the oracle
  * (tests/test_kernel_emulation.py); never run on hardware. */
 B200HIST_API int b200hist_updater_set_column_sampler(b200hist_updater_t u, const int32_t* tree_set_host,

@@ -1092,40 +1092,43 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
   /* lazily drawn level sets of the seed-driven column sampler */
   enum { kOrcMaxLevels = 64 };
   int32_t* lvl_sets = NULL;
-  int32_t lvl_n = 0, seed_pos = 0;
-  int32_t lvl_drawn[kOrcMaxLevels];
+  int32_t seed_pos = 0;
+  int32_t lvl_drawn[kOrcMaxLevels], lvl_n[kOrcMaxLevels];
   int32_t* node_draw = NULL;
   memset(lvl_drawn, 0, sizeof(lvl_drawn));
   if (cat && cat->seeds) {
     lvl_sets = (int32_t*)malloc(sizeof(int32_t) * (size_t)kOrcMaxLevels * (size_t)(cat->n_tree_set ? cat->n_tree_set : 1));
     node_draw = (int32_t*)malloc(sizeof(int32_t) * (size_t)(cat->n_tree_set ? cat->n_tree_set : 1));
   }
-#define ORC_EVAL(nidx_, fs_in_, nfs_in_, out_)                                                                        \
+/* the column sampler's answer for node nidx_ (explicit node sets, or the seed-driven lazy sampler): overrides fs_v / nfs_v */
+#define ORC_DRAW(nidx_, fs_v, nfs_v)                                                                                  \
   do {                                                                                                                \
-    const int32_t* fs_ = fs_in_;                                                                                      \
-    int32_t nfs_ = nfs_in_;                                                                                           \
+    if (cat && cat->node_sets) {                                                                                      \
+      int32_t k_ = eval_seq < cat->n_node_sets ? eval_seq : cat->n_node_sets - 1;                                     \
+      fs_v = cat->node_sets + (size_t)k_ * cat->n_per_node;                                                           \
+      nfs_v = cat->n_per_node;                                                                                        \
+      eval_seq++;                                                                                                     \
+    }                                                                                                                 \
     if (cat && cat->seeds) {                                                                                          \
       int32_t d_ = nodes[nidx_].depth < kOrcMaxLevels ? nodes[nidx_].depth : kOrcMaxLevels - 1;                       \
       int32_t* lv_ = lvl_sets + (size_t)d_ * cat->n_tree_set;                                                         \
       if (!lvl_drawn[d_]) {                                                                                           \
         uint32_t sd_ = 0;                                                                                             \
         if (cat->colsample_bylevel != 1.0f) sd_ = cat->seeds[seed_pos < cat->n_seeds ? seed_pos : cat->n_seeds - 1], seed_pos++; \
-        lvl_n = orc_col_sample(cat->tree_set, cat->n_tree_set, cat->colsample_bylevel, sd_, lv_);                      \
+        lvl_n[d_] = orc_col_sample(cat->tree_set, cat->n_tree_set, cat->colsample_bylevel, sd_, lv_);                  \
         lvl_drawn[d_] = 1;                                                                                            \
       }                                                                                                               \
       {                                                                                                               \
         uint32_t sd_ = 0;                                                                                             \
         if (cat->colsample_bynode != 1.0f) sd_ = cat->seeds[seed_pos < cat->n_seeds ? seed_pos : cat->n_seeds - 1], seed_pos++; \
-        nfs_ = orc_col_sample(lv_, lvl_n, cat->colsample_bynode, sd_, node_draw);                                      \
-        fs_ = node_draw;                                                                                              \
+        nfs_v = orc_col_sample(lv_, lvl_n[d_], cat->colsample_bynode, sd_, node_draw);                                 \
+        fs_v = node_draw;                                                                                             \
       }                                                                                                               \
     }                                                                                                                 \
-    if (cat && cat->node_sets) {                                                                                      \
-      int32_t k_ = eval_seq < cat->n_node_sets ? eval_seq : cat->n_node_sets - 1;                                     \
-      fs_ = cat->node_sets + (size_t)k_ * cat->n_per_node;                                                            \
-      nfs_ = cat->n_per_node;                                                                                         \
-      eval_seq++;                                                                                                     \
-    }                                                                                                                 \
+  } while (0)
+/* evaluation of node nidx_ on the list fs_ / nfs_ */
+#define ORC_EVAL_ON(nidx_, fs_, nfs_, out_)                                                                           \
+  do {                                                                                                                \
     if (cat && cat->feature_is_cat) {                                                                                 \
       int32_t th_;                                                                                                    \
       eval_node_cat_m(hist[nidx_], node_sum[nidx_], cut_ptrs, cut_values, n_features, fs_, nfs_, p, scale,            \
@@ -1136,6 +1139,13 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
       orc_eval_node_mono(hist[nidx_], node_sum[nidx_], cut_ptrs, cut_values, n_features, fs_, nfs_, p, scale, out_,   \
                          NULL, monotone, lower[nidx_], upper[nidx_]);                                                 \
     }                                                                                                                 \
+  } while (0)
+#define ORC_EVAL(nidx_, fs_in_, nfs_in_, out_)                                                                        \
+  do {                                                                                                                \
+    const int32_t* fsd_ = fs_in_;                                                                                     \
+    int32_t nfsd_ = nfs_in_;                                                                                          \
+    ORC_DRAW(nidx_, fsd_, nfsd_);                                                                                     \
+    ORC_EVAL_ON(nidx_, fsd_, nfsd_, out_);                                                                            \
   } while (0)
   uint64_t* ic_bits = ic ? (uint64_t*)calloc((size_t)max_nodes * (size_t)ic_words(ic->n_features), sizeof(uint64_t)) : NULL;
   int32_t* ic_buffer = ic ? (int32_t*)calloc((size_t)n_features + 1, sizeof(int32_t)) : NULL;
@@ -1321,7 +1331,9 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
         int32_t d = nodes[eval_list[k]].depth;
         int32_t* out = ic_lists + (size_t)k * n_features;
         const int32_t* sampled = feature_set ? ORC_LEVEL_SET(d) : NULL;
-        ic_count[k] = orc_ic_query(ic, ic_bits, sampled, sampled ? n_feature_set : 0, eval_list[k], out);
+        int32_t n_sampled = sampled ? n_feature_set : 0;
+        ORC_DRAW(eval_list[k], sampled, n_sampled); /* colsample_bynode: Query(the node's own draw, nidx) */
+        ic_count[k] = orc_ic_query(ic, ic_bits, sampled, n_sampled, eval_list[k], out);
         memcpy(ic_buffer, out, sizeof(int32_t) * (size_t)ic_count[k]);
       }
     }
@@ -1336,7 +1348,8 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
         nfs = ic_count[k];
       }
       /* an empty answer is a non-NULL list of length 0: nothing is scanned, the candidate stays invalid */
-      ORC_EVAL(c, fs, nfs, &e.c);
+      if (ic) ORC_EVAL_ON(c, fs, nfs, &e.c); /* the draws were made with the queries */
+      else ORC_EVAL(c, fs, nfs, &e.c);
       if (cand_dump) cand_dump[c] = e.c;
       if (e.c.loss_chg > 1e-6f) { queue[c] = e; n_open++; }
     }
@@ -1371,6 +1384,8 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
   free(lvl_sets); free(node_draw);
 #undef ORC_LEVEL_SET
 #undef ORC_EVAL
+#undef ORC_EVAL_ON
+#undef ORC_DRAW
   return n_nodes;
 }
 

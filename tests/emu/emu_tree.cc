@@ -170,8 +170,22 @@ int main(int argc, char** argv) {
     return IcView{node_list.data(), node_count.data(), n_per_node};
   };
 
-  auto evaluate_with_column_sampler = [&](int32_t max_eval) {
+  auto evaluate_with_column_sampler = [&](int32_t max_eval, bool is_root) {
     EMU_LAUNCH((1), (kCsThreads), sizeof(int32_t) * 2 * (size_t)col_n_level, LevelDrawKernel(&ts, nodes.data(), eval_nodes.data(), cold));
+    if (has_ic && !is_root) {
+      const IcDev icd{(int32_t)nf, ic_words, (int32_t)meta[12], ic_set_ptr.data(), ic_set_feat.data(), ic_bits.data(), ic_list.data(), ic_count.data()};
+      if (!meta[22]) {
+        EMU_LAUNCH(((unsigned)max_eval), (kCsThreads), sizeof(int32_t) * 2 * (size_t)col_n_node,
+                   NodeDrawKernel(&ts, nodes.data(), eval_nodes.data(), cold, col_n_node, col_node_list.data(), col_node_count.data()));
+        EMU_LAUNCH((1), (kCtlThreads), sizeof(unsigned long long) * (size_t)ic_words,
+                   IcLevelKernel(&ts, nodes.data(), part.data(), eval_nodes.data(), icd, nullptr, 0, 0, col_node_list.data(), col_n_node));
+      } else {
+        EMU_LAUNCH((1), (kCtlThreads), sizeof(unsigned long long) * (size_t)ic_words,
+                   IcLevelKernel(&ts, nodes.data(), part.data(), eval_nodes.data(), icd, col_level_sets.data(), col_n_level, col_max_levels, nullptr, 0));
+      }
+      evaluate(max_eval, IcView{ic_list.data(), ic_count.data(), 0}, nullptr, 0, 0);
+      return;
+    }
     if (!meta[22]) {
       EMU_LAUNCH(((unsigned)max_eval), (kCsThreads), sizeof(int32_t) * 2 * (size_t)col_n_node,
                  NodeDrawKernel(&ts, nodes.data(), eval_nodes.data(), cold, col_n_node, col_node_list.data(), col_node_count.data()));
@@ -184,7 +198,7 @@ int main(int argc, char** argv) {
   // ---- UpdateTreeImpl ----
   EMU_LAUNCH((1), (kCtlThreads), 0, InitRootKernel(p, (uint32_t)n, &q, &ts, nodes.data(), build.data(), build_tile_seg.data(), eval_nodes.data(), mono));
   build_hist();
-  if (has_col) evaluate_with_column_sampler(1);
+  if (has_col) evaluate_with_column_sampler(1, true);
   else if (has_node_sets) evaluate(1, node_sets_view(), nullptr, 0, 0);
   else evaluate(1, IcView{nullptr, nullptr, 0}, d_fs, n_fs, n_levels);
   for (int step = 0; step < n_steps; ++step) {
@@ -209,7 +223,7 @@ int main(int argc, char** argv) {
     subtract();
     IcView icv{nullptr, nullptr, 0};
     if (has_col) {
-      evaluate_with_column_sampler((int32_t)(2 * cap));
+      evaluate_with_column_sampler((int32_t)(2 * cap), false);
       continue;
     }
     if (has_node_sets) {
@@ -219,7 +233,7 @@ int main(int argc, char** argv) {
     }
     if (has_ic) {
       const IcDev icd{(int32_t)nf, ic_words, (int32_t)meta[12], ic_set_ptr.data(), ic_set_feat.data(), ic_bits.data(), ic_list.data(), ic_count.data()};
-      EMU_LAUNCH((1), (kCtlThreads), sizeof(unsigned long long) * (size_t)ic_words, IcLevelKernel(&ts, nodes.data(), part.data(), eval_nodes.data(), icd, d_fs, n_fs, n_levels));
+      EMU_LAUNCH((1), (kCtlThreads), sizeof(unsigned long long) * (size_t)ic_words, IcLevelKernel(&ts, nodes.data(), part.data(), eval_nodes.data(), icd, d_fs, n_fs, n_levels, nullptr, 0));
       icv = IcView{ic_list.data(), ic_count.data(), 0};
     }
     evaluate((int32_t)(2 * cap), icv, d_fs, n_fs, n_levels);

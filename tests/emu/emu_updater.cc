@@ -60,7 +60,7 @@ int main(int argc, char** argv) {
     const b200::IcDev icd{nf, words, meta[1], set_ptr.data(), set_feat.data(), bits.data(), list.data(), count.data()};
     EMU_LAUNCH((1), (b200::kCtlThreads), sizeof(unsigned long long) * (size_t)words,
                b200::IcLevelKernel(&ts, nodes.data(), part.data(), eval_nodes.data(), icd, meta[6] ? fs.data() : nullptr,
-                                   meta[4], meta[5]));
+                                   meta[4], meta[5], nullptr, 0));
     WriteAll(dir + "/bits_out.bin", bits);
     WriteAll(dir + "/list.bin", list);
     WriteAll(dir + "/count.bin", count);

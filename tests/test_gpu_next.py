@@ -829,3 +829,26 @@ def test_colsample_bynode_with_bylevel_through_the_shim_matches_reference(xb, ex
     our_trees, our_margin = train("grow_b200_hist")
     assert json.dumps(our_trees) == json.dumps(ref_trees)
     assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))
+
+
+def test_colsample_bynode_with_interaction_constraints_through_the_shim(xb):
+    """Query(the node's own sampled list, nidx) with overlapping sets, through the device column sampler."""
+    import torch
+    rc = _shim_or_skip()
+    x, y = make_regression(30000, 12, seed=85)
+    y = (y + x[:, 0] * x[:, 1] + x[:, 2] * x[:, 3] - x[:, 4] * x[:, 5]).astype(np.float32)
+    params = {"tree_method": "hist", "device": "cuda:0", "max_bin": 64, "max_depth": 6, "eta": 0.3,
+              "objective": "reg:squarederror", "base_score": 0.5, "colsample_bynode": 0.7, "colsample_bylevel": 0.9,
+              "interaction_constraints": "[[0, 1, 2], [2, 3, 4], [4, 5, 6], [6, 7, 8, 9, 10, 11]]"}
+
+    def train(updater):
+        dm = rc.DMatrix.from_cuda(torch.from_numpy(x).cuda(), kind="cuda")
+        dm.set_label(y)
+        bst = rc.Booster(dict(params, updater=updater), dm)
+        for i in range(4):
+            bst.update(i)
+        return _model_trees(bst), bst.predict_margin(dm)
+    ref_trees, ref_margin = train("grow_gpu_hist_reference")
+    our_trees, our_margin = train("grow_b200_hist")
+    assert json.dumps(our_trees) == json.dumps(ref_trees)
+    assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))

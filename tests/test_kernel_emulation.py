@@ -715,3 +715,24 @@ def test_whole_tree_kernel_sources_column_sampler(tmp_path, bylevel, bynode, par
     for nd in o["nodes"]:
         if not nd.is_leaf:
             assert nd.findex in tree_set
+
+
+@pytest.mark.parametrize("bylevel,bynode", [(1.0, 0.6), (0.8, 0.7), (0.7, 1.0)], ids=["bynode", "bylevel_bynode", "bylevel"])
+def test_whole_tree_kernel_sources_column_sampler_with_interaction_constraints(tmp_path, bylevel, bynode):
+    """Query(the node's own sampled list, nidx): IcLevelKernel with per-slot lists from NodeDrawKernel (or the lazily
+    drawn level sets), overlapping constraint sets, the shared result buffer."""
+    from tests.helpers import make_interaction_data
+    x, y = make_interaction_data(dict(seed=202, n=2500, f=6))
+    cp, cv = make_cuts(x, 24)
+    gb = orc.bin_dense(x, cp, cv)
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    chain = [[0, 1], [1, 2], [2, 3], [3, 4], [4, 5]]
+    params = dict(max_depth=5, eta=0.5)
+    rng = np.random.default_rng(19)
+    seeds = [int(v) for v in rng.integers(0, 2 ** 32, size=200)]
+    nodes, pos, _, _, counts = _emulate_tree(tmp_path, gb, cp, cv, gp, params, ic_sets=chain, col_seeds=seeds,
+                                             bylevel=bylevel, bynode=bynode)
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), interaction=chain, column_seeds=seeds,
+                        colsample_bylevel=bylevel, colsample_bynode=bynode)
+    _same_tree(nodes, pos, o)
+    assert int(counts[2]) == o["draws_used"] and len(o["nodes"]) > 7

@@ -168,11 +168,11 @@ class B200HistMaker : public TreeUpdater {
         << "[b200hist] gradient_based row sampling is not enabled yet";
     CHECK(param->colsample_bynode == 1.0f || unvalidated_ok)
         << "[b200hist] colsample_bynode is not enabled yet (colsample_bytree and colsample_bylevel are)";
-    CHECK(param->colsample_bynode == 1.0f || param->interaction_constraints.empty())
-        << "[b200hist] colsample_bynode cannot be combined with interaction constraints yet";
-    CHECK(param->colsample_bynode == 1.0f || param->colsample_bylevel == 1.0f ||
+    CHECK(param->colsample_bynode == 1.0f ||
+          (param->colsample_bylevel == 1.0f && param->interaction_constraints.empty()) ||
           (p_fmat->Info().feature_weights.Empty() && p_fmat->Info().num_col_ <= 8192))
-        << "[b200hist] colsample_bynode with colsample_bylevel needs the device sampler (no feature weights, <= 8192 features)";
+        << "[b200hist] colsample_bynode with colsample_bylevel or interaction constraints needs the device sampler "
+           "(no feature weights, <= 8192 features)";
     B200_SHIM_CHECK(b200hist_updater_create(ellpack_, &p, &updater_));
     // Sampler ctor (sampler.cu:343-363): the strategy follows sampling_method whenever subsample < 1
     B200_SHIM_CHECK(b200hist_updater_set_sampling_method(

@@ -409,7 +409,8 @@ struct IcDev {
 __global__ void __launch_bounds__(kCtlThreads) IcLevelKernel(const TreeState* ts, const NodeDev* nodes,
                                                               const PartEntry* part, const int32_t* eval_nodes,
                                                               IcDev ic, const int32_t* feature_set, int32_t n_fs,
-                                                              int32_t n_levels) {
+                                                              int32_t n_levels, const int32_t* slot_lists,
+                                                              int32_t slot_stride) {
   B200_DYNAMIC_SHARED(unsigned long long, s_mask);  // [words] the depth's sampled features
   const int n_part = ts->n_part;
   if (n_part == 0) return;
@@ -446,12 +447,18 @@ __global__ void __launch_bounds__(kCtlThreads) IcLevelKernel(const TreeState* ts
       atomicOr(&s_mask[fs[j] >> 6], 1ull << (fs[j] & 63));
   }
   __syncthreads();
-  // 2. counts of the answers
+  // 2. counts of the answers.  slot_lists (colsample_bynode): Query(the node's OWN sampled list, nidx) -- the list is
+  //    ascending, so the answer is the list filtered by the node's bit field, in order
   const int n_eval = 2 * n_part;
   for (int j = threadIdx.x; j < n_eval; j += kCtlThreads) {
     const unsigned long long* b = ic.bits + (size_t)eval_nodes[j] * W;
     int c = 0;
-    for (int w = 0; w < W; ++w) c += __popcll(b[w] & s_mask[w]);
+    if (slot_lists != nullptr) {
+      const int32_t* mine = slot_lists + (size_t)j * slot_stride;
+      for (int k = 0; k < slot_stride; ++k) c += (int)((b[mine[k] >> 6] >> (mine[k] & 63)) & 1ull);
+    } else {
+      for (int w = 0; w < W; ++w) c += __popcll(b[w] & s_mask[w]);
+    }
     ic.count[j] = c;
   }
   __syncthreads();
@@ -463,6 +470,16 @@ __global__ void __launch_bounds__(kCtlThreads) IcLevelKernel(const TreeState* ts
     if (cj <= later) continue;
     const unsigned long long* b = ic.bits + (size_t)eval_nodes[j] * W;
     int pos = 0;
+    if (slot_lists != nullptr) {
+      const int32_t* mine = slot_lists + (size_t)j * slot_stride;
+      for (int k = 0; k < slot_stride && pos < cj; ++k) {
+        if ((b[mine[k] >> 6] >> (mine[k] & 63)) & 1ull) {
+          if (pos >= later) ic.list[pos] = mine[k];
+          ++pos;
+        }
+      }
+      continue;
+    }
     for (int w = 0; w < W && pos < cj; ++w) {
       unsigned long long v = b[w] & s_mask[w];
       while (v) {
@@ -963,8 +980,27 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   }
   // evaluation through the seed-driven column sampler: level set of the step's depth (drawn on first use), then a
   // node set per evaluation slot (colsample_bynode < 1) or the level set itself
-  auto evaluate_with_column_sampler = [&](int32_t max_eval, const CatView& cv) {
+  auto evaluate_with_column_sampler = [&](int32_t max_eval, const CatView& cv, bool root) {
     LaunchLevelDraw(u->d_ts, u->d_nodes, u->d_eval_nodes, cold, s);
+    if (has_ic && !root) {  // Query(the node's sampled list, nidx): the root is never filtered (constraints.cu:201-203)
+      const IcDev icd{(int32_t)ell->n_features, u->ic_words, u->ic_n_sets, u->d_ic_set_ptr, u->d_ic_set_feat,
+                      u->d_ic_bits, u->d_ic_list, u->d_ic_count};
+      if (!u->col_bynode_is_one) {
+        LaunchNodeDraw(u->d_ts, u->d_nodes, u->d_eval_nodes, cold, u->col_n_node, max_eval, u->d_col_node_list,
+                       u->d_col_node_count, s);
+        IcLevelKernel<<<1, kCtlThreads, sizeof(unsigned long long) * (size_t)u->ic_words, s>>>(
+            u->d_ts, u->d_nodes, u->d_part, u->d_eval_nodes, icd, nullptr, 0, 0, u->d_col_node_list, u->col_n_node);
+      } else {
+        IcLevelKernel<<<1, kCtlThreads, sizeof(unsigned long long) * (size_t)u->ic_words, s>>>(
+            u->d_ts, u->d_nodes, u->d_part, u->d_eval_nodes, icd, u->d_col_level_sets, u->col_n_level, u->col_max_levels,
+            nullptr, 0);
+      }
+      B200_LAUNCHED();
+      LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, max_eval, u->d_nodes, nullptr, 0, u->pdev, u->d_quant,
+                     u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, 0, &u->d_ts->max_eval_depth,
+                     IcView{u->d_ic_list, u->d_ic_count, 0}, cv);
+      return;
+    }
     if (!u->col_bynode_is_one) {
       LaunchNodeDraw(u->d_ts, u->d_nodes, u->d_eval_nodes, cold, u->col_n_node, max_eval, u->d_col_node_list,
                      u->d_col_node_count, s);
@@ -1024,7 +1060,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   timer.End(kHist, t2);
   auto t3 = timer.Begin();
   if (has_col) {
-    evaluate_with_column_sampler(1, catv);
+    evaluate_with_column_sampler(1, catv, true);
   } else if (has_node_sets) {
     const IcView nv = node_sets_view();
     LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, nullptr, 0, u->pdev, u->d_quant, u->d_scratch,
@@ -1072,7 +1108,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     auto te = timer.Begin();
     IcView icv{nullptr, nullptr, 0};
     if (has_col) {
-      evaluate_with_column_sampler((int32_t)(2 * cap), catv);
+      evaluate_with_column_sampler((int32_t)(2 * cap), catv, false);
       timer.End(kEval, te);
       continue;
     }
@@ -1089,7 +1125,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
                       u->d_ic_bits, u->d_ic_list, u->d_ic_count};
       IcLevelKernel<<<1, kCtlThreads, sizeof(unsigned long long) * (size_t)u->ic_words, s>>>(
           u->d_ts, u->d_nodes, u->d_part, u->d_eval_nodes, icd, u->d_feature_set, u->n_feature_set,
-          u->n_feature_levels);
+          u->n_feature_levels, nullptr, 0);
       B200_LAUNCHED();
       icv = IcView{u->d_ic_list, u->d_ic_count, 0};
     }
@@ -1584,8 +1620,7 @@ int b200hist_updater_set_column_sampler(b200hist_updater_t u, const int32_t* tre
     B200_CHECK(tree_set_host != nullptr && n_tree_set >= 1 && n_tree_set <= 8192, "tree set out of range");
     B200_CHECK(colsample_bylevel > 0.0f && colsample_bylevel <= 1.0f && colsample_bynode > 0.0f && colsample_bynode <= 1.0f,
                "colsample fractions must be in (0, 1]");
-    B200_CHECK(u->d_ic_bits == nullptr && u->d_node_sets == nullptr,
-               "the column sampler cannot be combined with interaction constraints or explicit node sets yet");
+    B200_CHECK(u->d_node_sets == nullptr, "the column sampler cannot be combined with explicit node sets");
     for (uint32_t i = 0; i < n_tree_set; ++i)
       B200_CHECK(tree_set_host[i] >= 0 && (uint32_t)tree_set_host[i] < u->ell->n_features, "feature id out of range");
     // a tree consumes at most one output per possible depth and one per node
