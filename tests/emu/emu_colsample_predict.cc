@@ -68,10 +68,17 @@ int main(int argc, char** argv) {
     ell.bins_t = nullptr;
     ell.is_sparse = 0;
     ell.row_sig = nullptr;
+    if (meta.size() > 7 && meta[7] > 0) {  // sparse ELLPACK: uint32 global bins, row_stride entries per row
+      ell.is_sparse = 1;
+      ell.row_stride = meta[7];
+    }
     const b200::ForestView fv{nodes.data(), roots.data(), bin_bits.data(), (int32_t)meta[6]};
     std::vector<float> out = base;
     std::vector<int32_t> leaves((size_t)meta[0] * meta[5]);
-    if (meta[3] == 1) {
+    if (ell.is_sparse) {
+      EMU_LAUNCH((3), (256), 0, b200::PredictMarginKernel<uint32_t>(ell, fv, 0, meta[5], 0, meta[0], out.data()));
+      EMU_LAUNCH((3), (256), 0, b200::PredictLeafKernel<uint32_t>(ell, fv, 0, meta[5], 0, meta[0], leaves.data()));
+    } else if (meta[3] == 1) {
       EMU_LAUNCH((3), (256), 0, b200::PredictMarginKernel<uint8_t>(ell, fv, 0, meta[5], 0, meta[0], out.data()));
       EMU_LAUNCH((3), (256), 0, b200::PredictLeafKernel<uint8_t>(ell, fv, 0, meta[5], 0, meta[0], leaves.data()));
     } else {

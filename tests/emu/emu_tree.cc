@@ -19,7 +19,8 @@ int main(int argc, char** argv) {
   const std::string dir = argv[1];
   // meta: n_rows, n_features, row_bytes, bin_bytes, null_symbol, has_mono, has_cat, onehot, threshold, cat_words,
   //       bin_words, max_cat_bins, n_ic_sets, n_node_sets, n_per_node, has_fs, n_fs, n_levels,
-  //       [18] n_col_seeds, [19] col_n_level, [20] col_n_node, [21] bylevel_is_one, [22] bynode_is_one
+  //       [18] n_col_seeds, [19] col_n_level, [20] col_n_node, [21] bylevel_is_one, [22] bynode_is_one,
+  //       [23] row_stride of a SPARSE page (0 = dense layout): bins = uint32[n][row_stride] global bins, null = total_bins
   auto meta = ReadAll<int64_t>(dir + "/meta.bin");
   auto prm = ReadAll<float>(dir + "/param_f.bin");
   auto prm_i = ReadAll<int32_t>(dir + "/param_i.bin");
@@ -49,6 +50,8 @@ int main(int argc, char** argv) {
   view.row_bytes = (uint32_t)meta[2];
   view.bin_bytes = (uint32_t)meta[3];
   view.null_symbol = (uint32_t)meta[4];
+  const bool sparse = meta.size() > 23 && meta[23] > 0;
+  if (sparse) { view.is_sparse = 1; view.row_stride = (uint32_t)meta[23]; }
   const ParamDev p{prm_i[0], prm_i[1], prm_i[2], prm[0], prm[1], prm[2], prm[3], prm[4], prm[5]};
   QuantDev q{};
   q.to_fixed_g = quant[0]; q.to_fixed_h = quant[1]; q.to_float_g = quant[2]; q.to_float_h = quant[3];
@@ -124,6 +127,15 @@ int main(int argc, char** argv) {
       longlong2* h = hist.data() + (size_t)e.slot * view.total_bins;
       for (uint32_t j = 0; j < e.count; ++j) {
         const uint32_t r = rows[j];
+        if (sparse) {
+          const uint32_t* row = reinterpret_cast<const uint32_t*>(bins.data()) + (size_t)r * view.row_stride;
+          for (uint32_t k = 0; k < view.row_stride; ++k) {
+            if (row[k] >= view.total_bins) continue;
+            h[row[k]].x += gq[r].x;
+            h[row[k]].y += gq[r].y;
+          }
+          continue;
+        }
         for (uint32_t f = 0; f < nf; ++f) {
           const uint32_t sym = view.bin_bytes == 1 ? (uint32_t)bins[(size_t)r * view.row_bytes + f]
                                                    : (uint32_t)reinterpret_cast<const uint16_t*>(bins.data() + (size_t)r * view.row_bytes)[f];
@@ -210,7 +222,10 @@ int main(int argc, char** argv) {
     }
     const bool children_possible = p.max_depth == 0 || !dw || step + 1 < p.max_depth;
     if (!children_possible) continue;
-    if (view.bin_bytes == 1) {
+    if (sparse) {
+      if (has_cat) { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint32_t, true>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
+      else { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint32_t, false>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
+    } else if (view.bin_bytes == 1) {
       if (has_cat) { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint8_t, true>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
       else { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint8_t, false>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
     } else {
@@ -239,7 +254,10 @@ int main(int argc, char** argv) {
     evaluate((int32_t)(2 * cap), icv, d_fs, n_fs, n_levels);
   }
   EMU_LAUNCH((1), (kCtlThreads), 0, FinalListKernel(&ts, nodes.data(), fin.data(), fin_tile_seg.data(), fin_tile_begin.data()));
-  if (view.bin_bytes == 1) {
+  if (sparse) {
+    if (has_cat) { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint32_t, true>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
+    else { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint32_t, false>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
+  } else if (view.bin_bytes == 1) {
     if (has_cat) { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint8_t, true>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
     else { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint8_t, false>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
   } else {

@@ -95,7 +95,7 @@ def _page_bytes(gb, cp, bin_bytes, null_symbol):
     return page.view(np.uint8).reshape(n, width * bin_bytes)
 
 
-@pytest.mark.parametrize("kind", ["numerical_u8", "missing_u16", "categorical"])
+@pytest.mark.parametrize("kind", ["numerical_u8", "missing_u16", "categorical", "sparse"])
 def test_predict_kernel_sources(tmp_path, kind):
     """PredictMarginKernel / PredictLeafKernel (csrc/predict.cu) against the oracle's walk and tree-order sum."""
     exe = _build("emu_colsample_predict")
@@ -111,7 +111,7 @@ def test_predict_kernel_sources(tmp_path, kind):
         gb = categorical_global_bins(x, cp, cv, is_cat)
         kw = dict(feature_is_cat=is_cat)
     else:
-        x, y = make_regression(3000, 9, seed=5, missing=0.1 if kind == "missing_u16" else 0.0)
+        x, y = make_regression(3000, 9, seed=5, missing={"missing_u16": 0.1, "sparse": 0.6}.get(kind, 0.0))
         cp, cv = make_cuts(x, 300 if kind == "missing_u16" else 32)
         gb = orc.bin_dense(x, cp, cv)
         kw = {}
@@ -128,9 +128,18 @@ def test_predict_kernel_sources(tmp_path, kind):
     bin_words = (max_bins + 31) // 32
     nodes, roots, bits = _forest_arrays(trees, cp, cv, bin_words)
     page = _page_bytes(gb, cp, bin_bytes, null_symbol if has_missing else 0)
+    row_stride = 0
+    if kind == "sparse":
+        row_stride = max(1, int((gb >= 0).sum(axis=1).max()))
+        ell = np.full((len(y), row_stride), cv.size, dtype=np.uint32)
+        for r in range(len(y)):
+            present = gb[r][gb[r] >= 0]
+            ell[r, :present.size] = present
+        page = ell.view(np.uint8).reshape(len(y), row_stride * 4)
+        bin_bytes, null_symbol = 4, cv.size
     base = np.full(len(y), 0.25, dtype=np.float32)
     d = str(tmp_path)
-    np.array([len(y), gb.shape[1], page.shape[1], bin_bytes, null_symbol, len(trees), bin_words],
+    np.array([len(y), gb.shape[1], page.shape[1], bin_bytes, null_symbol, len(trees), bin_words, row_stride],
              dtype=np.uint32).tofile(os.path.join(d, "meta.bin"))
     page.tofile(os.path.join(d, "bins.bin"))
     nodes.tofile(os.path.join(d, "nodes.bin"))
@@ -492,7 +501,8 @@ TREE_NODE = np.dtype([("parent", "<i4"), ("left", "<i4"), ("right", "<i4"), ("fi
 
 
 def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, onehot=4, threshold=64, ic_sets=None,
-                  node_sets=None, feature_set=None, n_levels=0, col_seeds=None, col_tree_set=None, bylevel=1.0, bynode=1.0):
+                  node_sets=None, feature_set=None, n_levels=0, col_seeds=None, col_tree_set=None, bylevel=1.0, bynode=1.0,
+                  sparse=False):
     exe = _build("emu_tree")
     n, nf = gb.shape
     max_bins = int(np.diff(cp).max())
@@ -500,6 +510,15 @@ def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, oneh
     bin_bytes = 2 if max_bins + (1 if has_missing else 0) > 256 else 1
     null_symbol = max_bins if has_missing else 0xFFFFFFFF
     page = _page_bytes(gb, cp, bin_bytes, null_symbol if has_missing else 0)
+    row_stride = 0
+    if sparse:   # the reference's sparse ELLPACK: a row's present global bins in feature order, padded with total_bins
+        row_stride = max(1, int((gb >= 0).sum(axis=1).max()))
+        ell = np.full((n, row_stride), cv.size, dtype=np.uint32)
+        for r in range(n):
+            present = gb[r][gb[r] >= 0]
+            ell[r, :present.size] = present
+        page = ell.view(np.uint8).reshape(n, row_stride * 4)
+        bin_bytes, null_symbol = 4, cv.size
     scale, _ = orc.quantiser(gp)
     gq = orc.quantise(gp, scale)
     cat_words = int(cv.max()) // 32 + 1
@@ -519,7 +538,7 @@ def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, oneh
     np.array([n, nf, page.shape[1], bin_bytes, null_symbol, 0 if mono is None else 1, 0 if is_cat is None else 1, onehot,
               threshold, cat_words, (max_cat_bins + 31) // 32, max_cat_bins, 0 if ic_sets is None else len(ic_sets),
               0 if node_sets is None else node_sets.shape[0], 0 if node_sets is None else node_sets.shape[1],
-              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta,
+              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta + [row_stride],
              dtype=np.int64).tofile(os.path.join(d, "meta.bin"))
     np.array([p.learning_rate, p.reg_lambda, p.reg_alpha, p.min_child_weight, p.max_delta_step, p.min_split_loss],
              dtype=np.float32).tofile(os.path.join(d, "param_f.bin"))
@@ -736,3 +755,31 @@ def test_whole_tree_kernel_sources_column_sampler_with_interaction_constraints(t
                         colsample_bylevel=bylevel, colsample_bynode=bynode)
     _same_tree(nodes, pos, o)
     assert int(counts[2]) == o["draws_used"] and len(o["nodes"]) > 7
+
+
+@pytest.mark.parametrize("categorical", [False, True], ids=["numerical", "categorical"])
+def test_whole_tree_kernel_sources_sparse_page(tmp_path, categorical):
+    """The sparse ELLPACK layout (global-bin symbols, row searched by feature) through partition and FinalisePosition,
+    with and without categorical routing."""
+    if categorical:
+        from tests.helpers import make_categorical_data
+        from tests.test_reference_golden import categorical_global_bins
+        case = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_cpu_categorical_trees.json")))["cases"][0]
+        x, y, types = make_categorical_data(dict(case, n=2000, seed=78))
+        rng = np.random.default_rng(3)
+        x[rng.random(x.shape) < 0.5] = np.nan                       # a sparse matrix
+        is_cat = [1 if t == "c" else 0 for t in types]
+        cp = np.array(case["cut_ptrs"], dtype=np.uint32)
+        cv = np.array(case["cut_values_bits"], dtype=np.uint32).view(np.float32)
+        gb = categorical_global_bins(x, cp, cv, is_cat)
+        kw, okw = dict(is_cat=is_cat), dict(feature_is_cat=is_cat)
+    else:
+        x, y = make_regression(2000, 12, seed=41, missing=0.6)
+        cp, cv = make_cuts(x, 24)
+        gb = orc.bin_dense(x, cp, cv)
+        kw, okw = {}, {}
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    params = dict(max_depth=5, eta=0.5)
+    nodes, pos, flags, bits, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, sparse=True, **kw)
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), **okw)
+    _same_tree(nodes, pos, o, flags if categorical else None, bits if categorical else None)
