@@ -46,6 +46,7 @@ inline longlong2 make_longlong2(long long a, long long b) { return longlong2{a, 
 inline float2 make_float2(float a, float b) { return float2{a, b}; }
 inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
+inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
 
 // ---- the bits of the runtime API that common.cuh names (never executed under B200_KERNELS_ONLY) ----
 typedef int cudaError_t;
@@ -61,7 +62,10 @@ inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n); return 
 template <typename T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = static_cast<T*>(std::malloc(n)); return 0; }
 inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
-inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 1; return 0; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, int attr, int) {
+  *v = attr == 97 ? 232448 : 1;  // 97 = cudaDevAttrMaxSharedMemoryPerBlockOptin: B200's 227 KiB; anything else: 1
+  return 0;
+}
 
 namespace emu {
 
@@ -71,13 +75,27 @@ class Barrier {  // reusable; a thread that returns from the kernel drops out
   void ArriveAndWait() {
     std::unique_lock<std::mutex> l(m_);
     const uint64_t g = gen_;
-    if (++waiting_ >= expected_) { waiting_ = 0; ++gen_; cv_.notify_all(); }
-    else cv_.wait(l, [&] { return gen_ != g; });
+    if (++waiting_ >= expected_) {
+      waiting_ = 0;
+      ++gen_;
+      l.unlock();
+      cv_.notify_all();
+      return;
+    }
+    if (expected_ <= 32) {  // warp-sized groups meet within microseconds: spin a little before sleeping
+      l.unlock();
+      for (int spin = 0; spin < 2000; ++spin) {
+        if (__atomic_load_n(&gen_, __ATOMIC_ACQUIRE) != g) return;
+        if ((spin & 63) == 63) std::this_thread::yield();
+      }
+      l.lock();
+    }
+    cv_.wait(l, [&] { return gen_ != g; });
   }
   void Drop() {
     std::unique_lock<std::mutex> l(m_);
     --expected_;
-    if (expected_ > 0 && waiting_ >= expected_) { waiting_ = 0; ++gen_; cv_.notify_all(); }
+    if (expected_ > 0 && waiting_ >= expected_) { waiting_ = 0; ++gen_; l.unlock(); cv_.notify_all(); }
   }
  private:
   std::mutex m_;
@@ -182,5 +200,28 @@ template <typename A, typename B> inline typename std::common_type<A, B>::type m
   return (C)a > (C)b ? (C)a : (C)b;
 }
 
+// shared-window addresses (what __cvta_generic_to_shared yields on the device) are byte offsets into the CTA's dynamic
+// shared memory here; SharedWord turns one back into a pointer
+namespace emu {
+inline uint32_t* SharedWord(uint32_t addr) { return reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(DynShared()) + addr); }
+}  // namespace emu
+inline size_t __cvta_generic_to_shared(const void* p) {
+  return (size_t)(static_cast<const unsigned char*>(p) - static_cast<const unsigned char*>(emu::DynShared()));
+}
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {  // PRMT, default mode
+  const unsigned long long v = ((unsigned long long)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) {
+    const unsigned sel = (s >> (4 * i)) & 0xF;
+    unsigned byte = (unsigned)(v >> (8 * (sel & 7))) & 0xFF;
+    if (sel & 8) byte = (byte & 0x80) ? 0xFF : 0x00;  // sign replication
+    r |= byte << (8 * i);
+  }
+  return r;
+}
+inline long long clock64() { return 0; }
+enum { cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
+
 #define B200_DYNAMIC_SHARED(type, name) type* name = reinterpret_cast<type*>(::emu::DynShared())
+#define B200_DYNAMIC_SHARED_ALIGNED(type, name, bytes) type* name = reinterpret_cast<type*>(::emu::DynShared())
 #define EMU_LAUNCH(grid, block, smem, call) ::emu::Launch(dim3 grid, dim3 block, (smem), [&]() { call; })

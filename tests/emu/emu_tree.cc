@@ -1,7 +1,8 @@
 // A whole tree under the CPU emulator: the launch sequence of UpdateTreeImpl (xgboost_b200/csrc/updater.cu) with the
-// real control, evaluation, partition and finalise kernels; only the histogram build / subtraction -- the
-// hardware-validated hot kernel, which uses inline PTX -- is replaced by a plain CPU accumulation over the kernels' own
-// work lists.  Checks what no single-kernel test can: the order in which nodes are evaluated (colsample_bynode draws,
+// real control, evaluation, partition and finalise kernels.  The histogram build is either a plain CPU accumulation
+// over the kernels' own work lists (hist_mode 0) or the REAL histogram kernels chosen like LaunchBuildHist does
+// (hist_mode 1, and 2 = with the pair-kernel hint); their inline-PTX shared atomics have emulator twins in histogram.cu
+// (B200_EMU), the async-copy ring variants are not emulated.  Checks what no single-kernel test can: the order in which nodes are evaluated (colsample_bynode draws,
 // the interaction-constraint buffer), categorical routing through partition and FinalisePosition, loss-guided growth.
 #define B200_KERNELS_ONLY 1
 #include "cuda_emu.h"
@@ -9,6 +10,7 @@
 
 #include "../../xgboost_b200/csrc/colsample.cu"
 #include "../../xgboost_b200/csrc/evaluate.cu"
+#include "../../xgboost_b200/csrc/histogram.cu"
 #include "../../xgboost_b200/csrc/partition.cu"
 #include "../../xgboost_b200/csrc/updater.cu"
 
@@ -21,6 +23,7 @@ int main(int argc, char** argv) {
   //       bin_words, max_cat_bins, n_ic_sets, n_node_sets, n_per_node, has_fs, n_fs, n_levels,
   //       [18] n_col_seeds, [19] col_n_level, [20] col_n_node, [21] bylevel_is_one, [22] bynode_is_one,
   //       [23] row_stride of a SPARSE page (0 = dense layout): bins = uint32[n][row_stride] global bins, null = total_bins
+  //       [24] hist_mode
   auto meta = ReadAll<int64_t>(dir + "/meta.bin");
   auto prm = ReadAll<float>(dir + "/param_f.bin");
   auto prm_i = ReadAll<int32_t>(dir + "/param_i.bin");
@@ -56,6 +59,7 @@ int main(int argc, char** argv) {
   QuantDev q{};
   q.to_fixed_g = quant[0]; q.to_fixed_h = quant[1]; q.to_float_g = quant[2]; q.to_float_h = quant[3];
   q.root_g = root[0]; q.root_h = root[1]; q.h_zero_any = (unsigned)root[2];
+  q.h_lo_or = root.size() > 3 ? (unsigned)root[3] : 1u;
 
   // ---- what b200hist_updater_create derives on the host ----
   long long by_depth = p.max_depth > 0 ? ((1ll << (p.max_depth + 1)) - 1) : (1ll << 40);
@@ -120,7 +124,65 @@ int main(int argc, char** argv) {
                         (int32_t)col_tree_set.size(), col_level_sets.data(), col_n_level, col_level_drawn.data(),
                         col_max_levels, (int32_t)meta[21]};
 
+  // ---- the real histogram kernels, selected like LaunchBuildHist (default implementation) ----
+  const int hist_mode = meta.size() > 24 ? (int)meta[24] : 0;
+  b200hist_ellpack_s ell_host;
+  ell_host.n_rows = n; ell_host.n_features = nf; ell_host.total_bins = view.total_bins; ell_host.row_bytes = view.row_bytes;
+  ell_host.bin_bytes = view.bin_bytes; ell_host.null_symbol = view.null_symbol;
+  ell_host.cut_ptrs = cut_ptrs; ell_host.cut_values = cut_values;
+  ell_host.is_sparse = sparse; ell_host.row_stride = view.row_stride;
+  ell_host.max_feature_bins = 0;
+  for (uint32_t f = 0; f < nf; ++f) ell_host.max_feature_bins = std::max(ell_host.max_feature_bins, cut_ptrs[f + 1] - cut_ptrs[f]);
+  const std::vector<GroupDesc> groups = hist_mode ? MakeFeatureGroups(ell_host, 0) : std::vector<GroupDesc>();
+  auto build_hist_kernels = [&]() {
+    const int n_groups = (int)groups.size();
+    if (sparse) {
+      uint32_t b0 = 0xFFFFFFFFu, b1 = 0;
+      for (auto const& g : groups) { b0 = std::min(b0, g.bin_begin); b1 = std::max(b1, g.bin_end); }
+      EMU_LAUNCH((3), (256), 0, HistKernelSparse(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, hist.data(), b0, b1));
+      return;
+    }
+    const bool banked = view.bin_bytes == 1 || (view.bin_bytes == 2 && !groups.empty() && groups[0].n_blocks > 0);
+    if (!banked) {
+      uint32_t max_bins = 0;
+      for (auto const& g : groups) max_bins = std::max(max_bins, g.bin_end - g.bin_begin);
+      EMU_LAUNCH((2, (unsigned)n_groups), (kHistThreads), GenericSmemBytes(max_bins),
+                 HistKernelGeneric<uint16_t>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist.data()));
+      return;
+    }
+    const uint32_t sym_bytes = view.bin_bytes;
+    size_t smem = 0;
+    for (auto const& g : groups) smem = std::max(smem, BankedSmemBytes(g));
+    bool pair = hist_mode == 2 && n_groups >= 2 && view.row_bytes % (8u * sym_bytes) == 0u;
+    uint32_t pair_sym = 0;
+    for (int i = 0; pair && i < n_groups; ++i) {
+      const GroupDesc& g = groups[i];
+      pair = g.n_blocks == 1 && g.byte_begin % (8u * sym_bytes) == 0u &&
+             (i == 0 || (g.f_begin == groups[i - 1].f_end && g.byte_begin == groups[i - 1].byte_begin + 32u * sym_bytes));
+      pair_sym = std::max(pair_sym, g.max_sym);
+    }
+    if (pair) {
+      const size_t pair_smem = (size_t)pair_sym * 192 * 4;
+      const int n_pairs = (n_groups + 1) / 2;
+      if (sym_bytes == 2) {
+        EMU_LAUNCH((2, (unsigned)n_pairs), (kHistThreads), std::max(pair_smem, smem),
+                   (HistKernelPair<2, 2>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist.data(), &q)));
+      } else {
+        EMU_LAUNCH((2, (unsigned)n_pairs), (kHistThreads), std::max(pair_smem, smem),
+                   (HistKernelPair<3, 1>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist.data(), &q)));
+      }
+      return;
+    }
+    if (sym_bytes == 2) {
+      EMU_LAUNCH((2, (unsigned)n_groups), (kHistThreads), smem,
+                 HistKernelBankedFast<2>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist.data(), &q));
+    } else {
+      EMU_LAUNCH((2, (unsigned)n_groups), (kHistThreads), smem,
+                 HistKernelBankedFast<1>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist.data(), &q));
+    }
+  };
   auto build_hist = [&]() {  // the CPU stand-in for LaunchBuildHist over the kernels' own work list
+    if (hist_mode) { build_hist_kernels(); return; }
     for (int k = 0; k < ts.n_build; ++k) {
       const BuildEntry e = build[k];
       const uint32_t* rows = (e.buf ? ridx1.data() : ridx0.data()) + e.begin;

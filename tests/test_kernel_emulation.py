@@ -502,7 +502,7 @@ TREE_NODE = np.dtype([("parent", "<i4"), ("left", "<i4"), ("right", "<i4"), ("fi
 
 def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, onehot=4, threshold=64, ic_sets=None,
                   node_sets=None, feature_set=None, n_levels=0, col_seeds=None, col_tree_set=None, bylevel=1.0, bynode=1.0,
-                  sparse=False):
+                  sparse=False, hist_mode=0):
     exe = _build("emu_tree")
     n, nf = gb.shape
     max_bins = int(np.diff(cp).max())
@@ -538,13 +538,15 @@ def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, oneh
     np.array([n, nf, page.shape[1], bin_bytes, null_symbol, 0 if mono is None else 1, 0 if is_cat is None else 1, onehot,
               threshold, cat_words, (max_cat_bins + 31) // 32, max_cat_bins, 0 if ic_sets is None else len(ic_sets),
               0 if node_sets is None else node_sets.shape[0], 0 if node_sets is None else node_sets.shape[1],
-              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta + [row_stride],
+              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta + [row_stride, hist_mode],
              dtype=np.int64).tofile(os.path.join(d, "meta.bin"))
     np.array([p.learning_rate, p.reg_lambda, p.reg_alpha, p.min_child_weight, p.max_delta_step, p.min_split_loss],
              dtype=np.float32).tofile(os.path.join(d, "param_f.bin"))
     np.array([p.max_depth, p.max_leaves, p.grow_policy], dtype=np.int32).tofile(os.path.join(d, "param_i.bin"))
     np.asarray(scale, dtype=np.float64).tofile(os.path.join(d, "quant.bin"))
-    np.array([gq[:, 0].sum(), gq[:, 1].sum(), int((gq[:, 1] == 0).any())], dtype=np.int64).tofile(os.path.join(d, "root.bin"))
+    np.array([gq[:, 0].sum(), gq[:, 1].sum(), int((gq[:, 1] == 0).any()),
+              int(np.bitwise_or.reduce(gq[:, 1].astype(np.uint64) & np.uint64(0xFFFFFFFF)))],
+             dtype=np.int64).tofile(os.path.join(d, "root.bin"))
     page.tofile(os.path.join(d, "bins.bin"))
     cp.astype(np.uint32).tofile(os.path.join(d, "cut_ptrs.bin"))
     cv.astype(np.float32).tofile(os.path.join(d, "cut_values.bin"))
@@ -783,3 +785,31 @@ def test_whole_tree_kernel_sources_sparse_page(tmp_path, categorical):
     nodes, pos, flags, bits, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, sparse=True, **kw)
     o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), **okw)
     _same_tree(nodes, pos, o, flags if categorical else None, bits if categorical else None)
+
+
+@pytest.mark.parametrize("name,hist_mode,kw", [
+    ("banked_u8_64f", 1, dict(f=64, max_bin=24)),
+    ("banked_u8_missing_37f", 1, dict(f=37, max_bin=24, missing=0.1)),
+    ("pair_u8_96f", 2, dict(f=96, max_bin=16)),
+    ("pair_fallback_logistic_64f", 2, dict(f=64, max_bin=16, logistic=True)),
+    ("banked_u16_300bins", 1, dict(f=9, max_bin=300, missing=0.1)),
+    ("generic_u16_600bins", 1, dict(f=6, max_bin=600)),
+    ("sparse", 1, dict(f=12, max_bin=24, missing=0.6, sparse=True)),
+], ids=lambda v: v if isinstance(v, str) else "")
+def test_whole_tree_with_the_real_histogram_kernels(tmp_path, name, hist_mode, kw):
+    """The hot kernels themselves under the emulator (their inline-PTX shared atomics replaced by emulator twins, the
+    rest of the text unchanged): bank-mapped 32-feature kernel on uint8 and uint16 symbols, the 64-feature pair kernel
+    and its fallback when hessians carry low words, the generic kernel beyond ~440 symbols, the sparse kernel --
+    chosen like LaunchBuildHist chooses them, inside a whole tree, so that every node histogram feeds evaluation."""
+    from tests.helpers import logistic_gpair
+    n = 1500
+    x, y = make_regression(n, kw["f"], seed=23, missing=kw.get("missing", 0.0))
+    cp, cv = make_cuts(x, kw["max_bin"])
+    gb = orc.bin_dense(x, cp, cv)
+    if kw.get("logistic"):
+        gp = logistic_gpair(np.zeros_like(y), (y > 0).astype(np.float32))
+    else:
+        gp = squared_error_gpair(np.zeros_like(y), y)
+    params = dict(max_depth=4, eta=0.5)
+    nodes, pos, _, _, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, sparse=kw.get("sparse", False), hist_mode=hist_mode)
+    _same_tree(nodes, pos, orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params)))

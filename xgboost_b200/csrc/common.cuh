@@ -17,6 +17,7 @@
 // launchers out, which the emulator cannot parse (<<< >>>).
 #ifndef B200_DYNAMIC_SHARED
 #define B200_DYNAMIC_SHARED(type, name) extern __shared__ type name[]
+#define B200_DYNAMIC_SHARED_ALIGNED(type, name, bytes) extern __shared__ __align__(bytes) type name[]
 #endif
 
 namespace b200 {

@@ -189,6 +189,21 @@ struct PassData {       // what one lane holds for one pass (2 rows)
   uint32_t glo[2], ghi[2], hlo[2], hhi[2];
 };
 
+#ifdef B200_EMU
+// CPU emulator (tests/emu): the same operations on the emulated shared window; `addr` is an offset into it
+__device__ __forceinline__ uint32_t AtomAddShared(uint32_t addr, uint32_t v) { return atomicAdd(emu::SharedWord(addr), v); }
+__device__ __forceinline__ uint32_t AtomAddShared256(uint32_t addr, uint32_t v) { return atomicAdd(emu::SharedWord(addr + 256), v); }
+__device__ __forceinline__ uint32_t EmuCarryHi(uint32_t old, uint32_t vlo, uint32_t vhi) {
+  return vhi + (uint32_t)(((unsigned long long)old + vlo) >> 32);
+}
+__device__ __forceinline__ void RedAddHi128(uint32_t addr, uint32_t old, uint32_t vlo, uint32_t vhi) {
+  atomicAdd(emu::SharedWord(addr + 128), EmuCarryHi(old, vlo, vhi));
+}
+__device__ __forceinline__ void RedAdd384(uint32_t addr, uint32_t v) { atomicAdd(emu::SharedWord(addr + 384), v); }
+__device__ __forceinline__ void RedAddHi384(uint32_t addr, uint32_t old, uint32_t vlo, uint32_t vhi) {
+  atomicAdd(emu::SharedWord(addr + 384), EmuCarryHi(old, vlo, vhi));
+}
+#else
 __device__ __forceinline__ uint32_t AtomAddShared(uint32_t addr, uint32_t v) {
   uint32_t old;
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
@@ -213,6 +228,7 @@ __device__ __forceinline__ void RedAddHi384(uint32_t addr, uint32_t old, uint32_
   asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(hi) : "r"(old), "r"(vlo), "r"(vhi));
   asm volatile("red.shared.add.u32 [%0+384], %1;" ::"r"(addr), "r"(hi) : "memory");
 }
+#endif  // B200_EMU
 
 // kChecked = false: every block of the group is a full 32 features and the page has no null symbol, so
 // the inner loop carries no predicate at all.
@@ -223,7 +239,7 @@ HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
                  const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
                  const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist,
                  const QuantDev* __restrict__ qd) {
-  extern __shared__ __align__(16) uint32_t sh[];
+  B200_DYNAMIC_SHARED_ALIGNED(uint32_t, sh, 16);
   const GroupDesc g = groups[blockIdx.y];
   const uint32_t S = g.max_sym, B = g.n_blocks;
   const uint32_t slots = B * S * 32;  // (block, symbol, lane) accumulators
@@ -659,7 +675,7 @@ HistKernelBankedFast(EllView ell, const longlong2* __restrict__ gq, const uint32
                      const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
                      const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist,
                      const QuantDev* __restrict__ qd) {
-  extern __shared__ __align__(16) uint32_t sh[];
+  B200_DYNAMIC_SHARED_ALIGNED(uint32_t, sh, 16);
   const uint32_t n_tiles = ts->build_tiles;
   if (n_tiles == 0) return;
   const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
@@ -686,6 +702,16 @@ HistKernelBankedFast(EllView ell, const longlong2* __restrict__ gq, const uint32
 // If the hessians turn out NOT to have zero low words (the launch is chosen from the previous tree's flag), the
 // CTA falls back to the 16-byte layout and runs its two blocks one after the other.
 // ---------------------------------------------------------------------------------------------
+#ifdef B200_EMU
+template <int kOff>
+__device__ __forceinline__ uint32_t AtomAddSharedOff(uint32_t addr, uint32_t v) { return atomicAdd(emu::SharedWord(addr + kOff), v); }
+template <int kOff>
+__device__ __forceinline__ void RedAddOff(uint32_t addr, uint32_t v) { atomicAdd(emu::SharedWord(addr + kOff), v); }
+template <int kOff>
+__device__ __forceinline__ void RedAddHiOff(uint32_t addr, uint32_t old, uint32_t vlo, uint32_t vhi) {
+  atomicAdd(emu::SharedWord(addr + kOff), EmuCarryHi(old, vlo, vhi));
+}
+#else
 template <int kOff>
 __device__ __forceinline__ uint32_t AtomAddSharedOff(uint32_t addr, uint32_t v) {
   uint32_t old;
@@ -702,6 +728,7 @@ __device__ __forceinline__ void RedAddHiOff(uint32_t addr, uint32_t old, uint32_
   asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(hi) : "r"(old), "r"(vlo), "r"(vhi));
   asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(hi), "n"(kOff) : "memory");
 }
+#endif  // B200_EMU
 
 template <int kSymBytes>
 struct FastDataP {
@@ -828,7 +855,7 @@ HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __
                const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
                const GroupDesc* __restrict__ groups, uint32_t n_groups, longlong2* __restrict__ hist,
                const QuantDev* __restrict__ qd) {
-  extern __shared__ __align__(16) uint32_t sh[];
+  B200_DYNAMIC_SHARED_ALIGNED(uint32_t, sh, 16);
   const uint32_t n_tiles = ts->build_tiles;
   if (n_tiles == 0) return;
   const uint32_t t0 = (uint32_t)(((unsigned long long)blockIdx.x * n_tiles) / gridDim.x);
@@ -898,6 +925,7 @@ HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __
   }
 }
 
+#ifndef B200_EMU  // async-copy rings (mbarrier / cp.async / TMA): not emulated
 // ---------------------------------------------------------------------------------------------
 // Staged bank-mapped kernel: the same accumulation, but every warp feeds itself through a private ring of
 // kStages shared-memory stages filled by asynchronous copies, so the accumulating instruction stream
@@ -958,7 +986,7 @@ HistKernelStaged(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
                  const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
                  const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist,
                  const QuantDev* __restrict__ qd) {
-  extern __shared__ __align__(16) uint32_t sh[];
+  B200_DYNAMIC_SHARED_ALIGNED(uint32_t, sh, 16);
   const GroupDesc g = groups[blockIdx.y];
   const uint32_t S = g.max_sym, B = g.n_blocks;
   const uint32_t slots = B * S * 32;
@@ -1154,6 +1182,7 @@ HistKernelStaged(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
   }
 }
 
+#endif  // B200_EMU
 // ---------------------------------------------------------------------------------------------
 // Generic kernel (uint16 symbols): linear {g.lo, g.hi, h.lo, h.hi} per bin, tile staged through smem
 // ---------------------------------------------------------------------------------------------
@@ -1163,7 +1192,7 @@ HistKernelGeneric(EllView ell, const longlong2* __restrict__ gq, const uint32_t*
                   const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
                   const uint32_t* __restrict__ tile_seg, const TreeState* __restrict__ ts,
                   const GroupDesc* __restrict__ groups, longlong2* __restrict__ hist) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  B200_DYNAMIC_SHARED_ALIGNED(uint8_t, smem, 16);
   constexpr int kPerWord = 4 / sizeof(BinT);
   constexpr uint32_t kSymMask = (1u << (8 * sizeof(BinT))) - 1u;
 
@@ -1278,6 +1307,7 @@ HistKernelSparse(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
   }
 }
 
+#ifndef B200_KERNELS_ONLY
 void PrepareHistKernels(int device) {
   int optin = SmemOptin(device);
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -1293,7 +1323,9 @@ void PrepareHistKernels(int device) {
   B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelGeneric<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
 }
+#endif  // B200_KERNELS_ONLY
 
+#ifndef B200_KERNELS_ONLY
 void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint32_t* ridx0, const uint32_t* ridx1,
                      const BuildEntry* build, const uint32_t* tile_seg, const TreeState* ts,
                      const GroupDesc* groups_dev, const std::vector<GroupDesc>& groups_host,
@@ -1380,6 +1412,7 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
   }
   B200_LAUNCHED();
 }
+#endif  // B200_KERNELS_ONLY
 
 // sibling = parent - built for every (parent, built, sibling) triple of the level, one launch.
 __global__ void __launch_bounds__(256) SubtractKernel(const SubEntry* __restrict__ sub, const TreeState* __restrict__ ts,
@@ -1395,11 +1428,13 @@ __global__ void __launch_bounds__(256) SubtractKernel(const SubEntry* __restrict
   }
 }
 
+#ifndef B200_KERNELS_ONLY
 void LaunchSubtract(const SubEntry* sub, const TreeState* ts, b200hist_gpair64* hist, uint32_t total_bins,
                     int num_sms, cudaStream_t s) {
   SubtractKernel<<<num_sms * 8, 256, 0, s>>>(sub, ts, reinterpret_cast<longlong2*>(hist), total_bins);
   B200_LAUNCHED();
 }
+#endif  // B200_KERNELS_ONLY
 
 __global__ void __launch_bounds__(256) SubtractFlatKernel(const longlong2* __restrict__ p, const longlong2* __restrict__ c,
                                                            longlong2* __restrict__ o, uint64_t n) {
@@ -1409,6 +1444,7 @@ __global__ void __launch_bounds__(256) SubtractFlatKernel(const longlong2* __res
   }
 }
 
+#ifndef B200_KERNELS_ONLY
 void LaunchSubtractFlat(const b200hist_gpair64* parent, const b200hist_gpair64* built, b200hist_gpair64* out,
                         uint64_t n_bins, cudaStream_t s) {
   int blocks = (int)std::min<uint64_t>((n_bins + 255) / 256, 148 * 8);
@@ -1418,6 +1454,7 @@ void LaunchSubtractFlat(const b200hist_gpair64* parent, const b200hist_gpair64* 
                                             reinterpret_cast<longlong2*>(out), n_bins);
   B200_LAUNCHED();
 }
+#endif  // B200_KERNELS_ONLY
 
 // ---------------------------------------------------------------------------------------------
 // Measurement helper: the shared-memory atomic ceiling of the histogram kernel, measured rather than modelled.
@@ -1425,11 +1462,12 @@ void LaunchSubtractFlat(const b200hist_gpair64* parent, const b200hist_gpair64* 
 // carry, two reductions per int64 component) on register-generated symbols -- no global loads, same 1024-thread
 // CTA, same shared-memory footprint, one CTA per SM -- and reports updates per clock per SM from clock64().
 // ---------------------------------------------------------------------------------------------
+#ifndef B200_EMU
 template <bool kHLoZero>
 __global__ void __launch_bounds__(kHistThreads, 1) SmemAtomicPeakKernel(uint32_t iters, uint32_t words,
                                                                          unsigned long long* __restrict__ clocks,
                                                                          uint32_t* __restrict__ sink) {
-  extern __shared__ __align__(16) uint32_t sh[];
+  B200_DYNAMIC_SHARED_ALIGNED(uint32_t, sh, 16);
   __shared__ unsigned long long clk_s;
   for (uint32_t i = threadIdx.x; i < words; i += kHistThreads) sh[i] = 0u;
   if (threadIdx.x == 0) clk_s = 0ull;
@@ -1463,7 +1501,9 @@ __global__ void __launch_bounds__(kHistThreads, 1) SmemAtomicPeakKernel(uint32_t
     sink[blockIdx.x] = sh[x % words];
   }
 }
+#endif  // B200_EMU
 
+#ifndef B200_KERNELS_ONLY
 double MeasureSmemAtomicPeak(int device, bool h_lo_zero, cudaStream_t s) {
   const uint32_t words = 256u * 32u * 4u;  // one block of 32 features x 256 symbols x int64 pair = 128 KiB
   const size_t smem = words * sizeof(uint32_t);
@@ -1487,9 +1527,11 @@ double MeasureSmemAtomicPeak(int device, bool h_lo_zero, cudaStream_t s) {
   const double avg_clocks = sum / n_sms;
   return (double)kHistThreads * 8.0 * iters / avg_clocks;
 }
+#endif  // B200_KERNELS_ONLY
 
 }  // namespace b200
 
+#ifndef B200_KERNELS_ONLY
 extern "C" int b200hist_smem_atomic_peak(int device, int h_lo_zero, double* updates_per_clk_per_sm, void* stream) {
   B200_API_BEGIN();
   B200_CHECK(updates_per_clk_per_sm != nullptr, "null argument");
@@ -1497,3 +1539,4 @@ extern "C" int b200hist_smem_atomic_peak(int device, int h_lo_zero, double* upda
   *updates_per_clk_per_sm = b200::MeasureSmemAtomicPeak(device, h_lo_zero != 0, static_cast<cudaStream_t>(stream));
   B200_API_END();
 }
+#endif  // B200_KERNELS_ONLY
