@@ -461,8 +461,12 @@ B200HIST_API int b200hist_partition(b200hist_ellpack_t ell, const uint32_t* ridx
 /* ---------------------------------------------------------------------------------------------
  * Prediction on the quantised matrix
  *   replaces GPUPredictor's PredictKernel / PredictBatch over Ellpack pages
- *   (src/predictor/gpu_predictor.cu:180-230,316-351; EllpackLoader, ellpack_page.cuh:147-170) for trees grown on the
- *   page's cuts: a split condition then IS a cut value and a row is routed by its bin alone.
+ *   (src/predictor/gpu_predictor.cu:180-230,316-351; EllpackLoader::GetElement,
+ *   src/predictor/gpu_data_accessor.cuh:95-107: a bin stands for its lower cut, -inf for a feature's first bin).
+ *   A row is routed by its bin alone: add_tree resolves every condition against the page's cuts (threshold = 1 +
+ *   number of the feature's cuts < the condition).  For trees grown on these cuts that is the updater's own
+ *   threshold; for any other forest (a loaded model, a page with its own cuts) it is still the reference's result
+ *   on that page.
  * forest_create borrows `ell` for its cuts (keep it alive); add_tree takes a tree as update_tree returned it, with the
  * categorical flags / LBitField32 sets of b200hist_updater_last_tree_categories (NULL, NULL, 0 without categorical
  * splits).  predict_margin: for rows [row_begin, row_begin + n_rows) of `page` (any page quantised with the same
@@ -470,7 +474,9 @@ B200HIST_API int b200hist_partition(b200hist_ellpack_t ell, const uint32_t* ridx
  * sum taken in tree order from 0.0f like the reference (gpu_predictor.cu:221-228).  predict_leaf: out_dev[k *
  * n_trees + t] = the leaf's node id inside tree t (:196-201).
  * STATUS: compiled, never run on hardware; the oracle (orc_predict_leaf) reproduces the reference CPU predictor's
- * margins bit for bit (tests/test_reference_golden.py); GPU tests in tests/test_gpu_next.py, gated. */
+ * margins bit for bit, on the training cuts and on a QuantileDMatrix with foreign cuts
+ * (tests/test_reference_golden.py); the kernels equal the oracle under the CPU emulator
+ * (tests/test_kernel_emulation.py); GPU tests in tests/test_gpu_next.py, gated. */
 B200HIST_API int b200hist_forest_create(b200hist_ellpack_t ell, b200hist_forest_t* out);
 B200HIST_API int b200hist_forest_destroy(b200hist_forest_t forest);
 B200HIST_API int b200hist_forest_num_trees(b200hist_forest_t forest, uint32_t* out);

@@ -694,6 +694,17 @@ static int go_left(const int32_t* gbins, uint32_t stride, int is_dense_layout, c
   return cut_values[b] <= split_cond;
 }
 
+/* EllpackLoader::GetElement + the numerical test of GetNextNode (src/predictor/gpu_data_accessor.cuh:95-107,
+ * src/predictor/predict_fn.h): value = -inf for the feature's first bin, else the cut BELOW the bin; left iff
+ * value < split_cond. */
+static int go_left_predict(const int32_t* gbins, uint32_t stride, int is_dense_layout, const uint32_t* cut_ptrs,
+                           const float* cut_values, uint64_t r, int32_t findex, float split_cond, int default_left) {
+  int32_t b = row_feature_gbin(gbins, stride, is_dense_layout, cut_ptrs, r, findex);
+  if (b < 0) return default_left;
+  float v = ((uint32_t)b == cut_ptrs[findex]) ? -INFINITY : cut_values[b - 1];
+  return v < split_cond;
+}
+
 /* common::Decision (src/common/categorical.h:49-60) on a training row: the category of the row's bin is looked up in
  * the split's set (LBitField32: category c = bit 31 - c % 32 of word c / 32); in the set -> RIGHT; a category beyond
  * the set's storage or a missing value -> default direction / left as the reference does. */
@@ -1392,7 +1403,9 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
 /* R4  Prediction on the quantised matrix: GPUPredictor's kernel over an EllpackPage
  * (src/predictor/gpu_predictor.cu:180-230 PredictKernel with EllpackLoader, :316-351 PredictBatch): every row walks
  * every tree from the root -- missing -> default child, categorical split -> common::Decision on the bin's category,
- * else fvalue < split_cond, which on binned data is cut_values[bin] <= split_cond for a split at a cut -- and the
+ * else fvalue < split_cond, where the loader (src/predictor/gpu_data_accessor.cuh:95-107) hands out the bin's LOWER
+ * cut as its value (-inf for a feature's first bin); for a condition that is one of the cuts this agrees with the
+ * updater's cut_values[bin] <= split_cond, for any other condition only this rule is the reference's -- and the
  * leaf values of trees [0, n) are summed IN TREE ORDER into a float that starts at 0 and is then added to the output
  * (:221-228).  This function does one tree: out_leaf[r] = leaf the row reaches (cat arguments may be NULL). */
 ORC_API void orc_predict_leaf(const int32_t* gbins, uint64_t n_rows, uint32_t stride, int is_dense_layout,
@@ -1405,8 +1418,8 @@ ORC_API void orc_predict_leaf(const int32_t* gbins, uint64_t n_rows, uint32_t st
       int gl = (node_is_cat && node_is_cat[nidx])
                    ? go_left_cat(gbins, stride, is_dense_layout, cut_ptrs, cut_values, r, nodes[nidx].findex,
                                  node_cat_bits + (size_t)nidx * n_cat_words, n_cat_words, nodes[nidx].default_left)
-                   : go_left(gbins, stride, is_dense_layout, cut_ptrs, cut_values, r, nodes[nidx].findex,
-                             nodes[nidx].fvalue, nodes[nidx].default_left);
+                   : go_left_predict(gbins, stride, is_dense_layout, cut_ptrs, cut_values, r, nodes[nidx].findex,
+                                     nodes[nidx].fvalue, nodes[nidx].default_left);
       nidx = gl ? nodes[nidx].left : nodes[nidx].right;
     }
     out_leaf[r] = nidx;

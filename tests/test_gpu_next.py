@@ -622,6 +622,40 @@ def test_forest_prediction_matches_oracle(xb, missing, max_bin):
         forest.predict_margin(other, torch.zeros(7000, device="cuda"))
 
 
+def _as_tree(nodes):
+    """An oracle tree (list of orc.Node) as the RegTree Forest.add_tree takes: the two structs have the same fields."""
+    from xgboost_b200 import lib as _l
+    from xgboost_b200.updater import RegTree
+    return RegTree([_l.TreeNode(*[getattr(nd, name) for name, _ in _l.TreeNode._fields_]) for nd in nodes])
+
+
+def test_forest_resolved_against_foreign_cuts_matches_oracle(xb):
+    """A forest grown elsewhere (other cuts), resolved against the cuts of the page it predicts: the conditions are
+    not cuts of that page, and the reference's loader rule (the bin's lower cut, gpu_data_accessor.cuh:95-107)
+    decides -- the oracle's walk is pinned on the reference for exactly this case
+    (tests/test_reference_golden.py::test_oracle_predictor_on_foreign_cuts_...)."""
+    import torch
+    x, y = make_regression(15000, 12, seed=97, missing=0.05)
+    cp, cv = make_cuts(x, 64)
+    gb = orc.bin_dense(x, cp, cv)
+    pred = np.zeros(len(y), dtype=np.float32)
+    trees = []
+    for _ in range(5):
+        o = orc.update_tree(gb, cp, cv, squared_error_gpair(pred, y), orc.Param.make(max_depth=5, eta=0.3))
+        trees.append(o["nodes"])
+        pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+    xv, _ = make_regression(9000, 12, seed=98, missing=0.05)
+    cp2, cv2 = make_cuts(xv, 24)
+    vpage = _page(xb, xv, cp2, cv2, has_missing=True)
+    gbv = orc.bin_dense(xv, cp2, cv2)
+    forest = xb.Forest(vpage)
+    for nodes in trees:
+        forest.add_tree(_as_tree(nodes))
+    out = forest.predict_margin(vpage, torch.zeros(9000, device="cuda"))
+    want = orc.predict_margin(gbv, cp2, cv2, trees)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
 def test_forest_prediction_with_categorical_splits(xb):
     import torch
     from tests.test_reference_golden import categorical_global_bins

@@ -79,7 +79,9 @@ def _forest_arrays(trees, cp, cv, bin_words):
                         if int(cv[b]) in t["cat_sets"][i]:
                             w[(b - beg) >> 5] |= np.uint32(1 << ((b - beg) & 31))
                 else:
-                    lbin = int(np.searchsorted(cv[beg:end], np.float32(nd.fvalue), side="right"))
+                    # 1 + number of the feature's cuts < the condition (csrc/predict.cu add_tree)
+                    lbin = (1 + int(np.searchsorted(cv[beg:end], np.float32(nd.fvalue), side="left"))
+                            if np.float32(nd.fvalue) > -np.inf else 0)
                 nodes.append((nd.findex, lbin, base + nd.left, base + nd.right, nd.leaf_value, int(nd.default_left)))
             bits.append(w)
     return np.array(nodes, dtype=PRED_NODE), np.array(roots, dtype=np.uint32), np.stack(bits)
@@ -95,7 +97,7 @@ def _page_bytes(gb, cp, bin_bytes, null_symbol):
     return page.view(np.uint8).reshape(n, width * bin_bytes)
 
 
-@pytest.mark.parametrize("kind", ["numerical_u8", "missing_u16", "categorical", "sparse"])
+@pytest.mark.parametrize("kind", ["numerical_u8", "missing_u16", "categorical", "sparse", "foreign_cuts"])
 def test_predict_kernel_sources(tmp_path, kind):
     """PredictMarginKernel / PredictLeafKernel (csrc/predict.cu) against the oracle's walk and tree-order sum."""
     exe = _build("emu_colsample_predict")
@@ -121,6 +123,13 @@ def test_predict_kernel_sources(tmp_path, kind):
         o = orc.update_tree(gb, cp, cv, squared_error_gpair(pred, y), orc.Param.make(max_depth=4, eta=0.5), **kw)
         trees.append(o)
         pred = orc.update_prediction_cache(o["nodes"], o["position"], pred)
+    if kind == "foreign_cuts":
+        # the forest meets a page quantised with other cuts: its conditions are no longer cuts of the page
+        x, y = make_regression(3000, 9, seed=6, missing=0.05)
+        cp, cv = make_cuts(x, 20)
+        gb = orc.bin_dense(x, cp, cv)
+        for o in trees:
+            o["nodes"][0].fvalue = -np.inf if o is trees[0] else o["nodes"][0].fvalue   # nothing is below -inf
     max_bins = int(np.diff(cp).max())
     has_missing = bool((gb < 0).any())
     bin_bytes = 2 if max_bins + (1 if has_missing else 0) > 256 else 1
@@ -505,6 +514,13 @@ def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, oneh
                   sparse=False, hist_mode=0):
     exe = _build("emu_tree")
     n, nf = gb.shape
+    if kind == "foreign_cuts":
+        # the forest meets a page quantised with other cuts: its conditions are no longer cuts of the page
+        x, y = make_regression(3000, 9, seed=6, missing=0.05)
+        cp, cv = make_cuts(x, 20)
+        gb = orc.bin_dense(x, cp, cv)
+        for o in trees:
+            o["nodes"][0].fvalue = -np.inf if o is trees[0] else o["nodes"][0].fvalue   # nothing is below -inf
     max_bins = int(np.diff(cp).max())
     has_missing = bool((gb < 0).any())
     bin_bytes = 2 if max_bins + (1 if has_missing else 0) > 256 else 1

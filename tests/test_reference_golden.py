@@ -348,6 +348,43 @@ def test_oracle_predictor_reproduces_reference_cpu_margins():
     assert np.allclose(naive, ref, rtol=1e-5, atol=1e-6)
 
 
+def test_oracle_predictor_on_foreign_cuts_reproduces_reference_quantised_prediction():
+    """Trees grown on one set of cuts, predicted on a matrix quantised with ANOTHER: the split conditions are no longer
+    cuts of the page, and the only rule that reproduces the reference is its loader's (the bin's lower cut, -inf for
+    a feature's first bin; src/predictor/data_accessor.h:117-126 on the CPU, gpu_data_accessor.cuh:95-107 on the
+    GPU).  The reference predicts from the QuantileDMatrix's bins, the oracle from the same bins."""
+    from oracle import ref_capi as rc
+    if not rc.available("cpu"):
+        pytest.skip("needs oracle/_ref/libxgboost.so (built where /root/reference exists)")
+    x, y = make_regression(12000, 10, seed=89, missing=0.08)
+    dm = rc.DMatrix.from_dense(x, label=y, kind="cpu")
+    bst = rc.Booster({"tree_method": "hist", "device": "cpu", "max_bin": 64, "base_score": 0.0,
+                      "objective": "reg:squarederror", "max_depth": 5, "eta": 0.3}, dm)
+    for i in range(6):
+        bst.update(i)
+    forest = []
+    for t in rc.trees_from_model(bst.save_json()):
+        nodes = []
+        for i in range(len(t["left"])):
+            leaf = t["left"][i] == -1
+            nodes.append(orc.Node(t["parent"][i], t["left"][i], t["right"][i], -1 if leaf else t["findex"][i],
+                                  t["cond"][i], t["default_left"][i], 1 if leaf else 0, t["cond"][i] if leaf else 0.0,
+                                  0, 0, 0, 0))
+        forest.append(nodes)
+    x2, y2 = make_regression(5000, 10, seed=90, missing=0.08)
+    qdm = rc.DMatrix.quantile_from_batches([x2], max_bin=24, kind="cpu")
+    cp2, cv2 = qdm.histogram_cuts()
+    train_cuts = set(np.asarray(dm.histogram_cuts()[1]).view(np.uint32).tolist())
+    assert not set(np.asarray(cv2).view(np.uint32).tolist()) <= train_cuts   # really foreign cuts
+    gb2 = orc.bin_dense(x2, cp2, cv2)
+    ours = orc.predict_margin(gb2, cp2, cv2, forest)
+    ref = bst.predict_margin(qdm)
+    assert np.array_equal(ours.view(np.uint32), ref.view(np.uint32))
+    # ... and it is NOT what predicting from the raw values gives (quantisation moved some rows across a split)
+    raw = bst.predict_margin(rc.DMatrix.from_dense(x2, kind="cpu"))
+    assert not np.array_equal(raw.view(np.uint32), ref.view(np.uint32))
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Waiting for their fixture: tests/golden/ref_gpu_next_trees.json (tools/make_golden_gpu_next.py, one short GPU call).
 # The reference's own gpu_hist trees for categorical features and gradient-based sampling pin the two oracle

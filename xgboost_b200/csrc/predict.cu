@@ -6,10 +6,11 @@
 //   EllpackDeviceAccessor::GetFvalue (bin -> representative value)       src/data/ellpack_page.cuh:147-170
 //   common::Decision (categorical routing)                               src/common/categorical.h:49-60
 //
-// The reference turns a row's bin back into a feature value and compares it with the split condition.  A split
-// condition of a tree grown on these cuts IS a cut value, so the comparison is decided by the bin alone: the forest
-// is resolved against the page's cuts once, when a tree is added (split_lbin = number of the feature's cuts <= the
-// condition, as in the updater's ApplySplit), and the kernel compares small integers.  Categorical splits carry the
+// The reference turns a row's bin back into a feature value (the bin's lower cut, gpu_data_accessor.cuh:95-107) and
+// compares it with the split condition.  That comparison is decided by the bin alone: the forest is resolved
+// against the page's cuts once, when a tree is added (split_lbin = 1 + number of the feature's cuts < the
+// condition; for a tree grown on these cuts that is the updater's ApplySplit threshold), and the kernel compares
+// small integers.  Categorical splits carry the
 // set of the feature's local bins that go right.  A row sums the leaves of trees [begin, end) in tree order into a
 // float that starts at 0 and is then added to the output (gpu_predictor.cu:221-228) -- the order is part of the
 // result.
@@ -200,10 +201,13 @@ int b200hist_forest_add_tree(b200hist_forest_t f, const b200hist_tree_node* node
         }
       } else {
         B200_CHECK(!std::isnan(s.fvalue), "numerical split with a NaN condition");
-        // go left iff cut_values[bin] <= fvalue  <=>  local bin < number of the feature's cuts <= fvalue
+        // The reference's loader hands out the bin's lower cut (-inf for the first bin) and goes left iff that value
+        // < fvalue (gpu_data_accessor.cuh:95-107): local bin b goes left iff b == 0 or cut[b-1] < fvalue, i.e. iff
+        // b < 1 + (number of the feature's cuts < fvalue).  For a condition that is one of the cuts this is the
+        // updater's cut[b] <= fvalue; it also holds for trees grown on other cuts.
         const float* lo = ell->cut_values.data() + beg;
         const float* hi = ell->cut_values.data() + end;
-        d.split_lbin = (int32_t)(std::upper_bound(lo, hi, s.fvalue) - lo);
+        d.split_lbin = s.fvalue > -INFINITY ? 1 + (int32_t)(std::lower_bound(lo, hi, s.fvalue) - lo) : 0;
       }
     }
     add[i] = d;
