@@ -656,6 +656,32 @@ def test_forest_resolved_against_foreign_cuts_matches_oracle(xb):
     assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("case", ["dense", "missing", "wide_bins"])
+def test_predictor_binding_serves_quantised_matrices_like_the_reference(xb, case, tmp_path):
+    """The reference's Booster.predict on QuantileDMatrices with the "gpu_predictor" factory served by the shim
+    (xgboost_b200/csrc/shim/b200_predictor.cu) against the same call served by the reference itself: margins bit for
+    bit, on the training matrix and on a matrix with its own cuts, and the shim's run really launched our kernels.
+    Two child processes: the shim decides at load time (B200HIST_SHIM_PREDICTOR)."""
+    import subprocess
+    import sys
+    from oracle import ref_capi as rc
+    from tests import test_shim_dropin as sd
+    from tests.conftest import ROOT
+    if not (rc.available("cuda") and os.path.exists(sd.SHIM)):
+        pytest.skip("needs oracle/_ref_cuda/libxgboost.so and the shim")
+    got = {}
+    for gate in ("0", "1"):
+        out = os.path.join(str(tmp_path), "margins_%s.npz" % gate)
+        env = dict(os.environ, B200HIST_SHIM_PREDICTOR=gate)
+        subprocess.run([sys.executable, "-m", "tests.shim_predictor_check", out, case], cwd=ROOT, env=env, check=True,
+                       timeout=600)
+        got[gate] = np.load(out)
+    assert int(got["0"]["launches"]) == 0
+    assert int(got["1"]["launches"]) >= 2          # import + predict per matrix, at least
+    for key in ("valid", "train"):
+        assert np.array_equal(got["1"][key].view(np.uint32), got["0"][key].view(np.uint32)), key
+
+
 def test_forest_prediction_with_categorical_splits(xb):
     import torch
     from tests.test_reference_golden import categorical_global_bins

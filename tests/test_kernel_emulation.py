@@ -514,13 +514,6 @@ def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, oneh
                   sparse=False, hist_mode=0):
     exe = _build("emu_tree")
     n, nf = gb.shape
-    if kind == "foreign_cuts":
-        # the forest meets a page quantised with other cuts: its conditions are no longer cuts of the page
-        x, y = make_regression(3000, 9, seed=6, missing=0.05)
-        cp, cv = make_cuts(x, 20)
-        gb = orc.bin_dense(x, cp, cv)
-        for o in trees:
-            o["nodes"][0].fvalue = -np.inf if o is trees[0] else o["nodes"][0].fvalue   # nothing is below -inf
     max_bins = int(np.diff(cp).max())
     has_missing = bool((gb < 0).any())
     bin_bytes = 2 if max_bins + (1 if has_missing else 0) > 256 else 1

@@ -1,0 +1,277 @@
+// Reference-side binding 2: xgboost::Predictor served by libb200hist.so for quantised (Ellpack-only) matrices.
+//
+// Compiled against the reference's headers, next to b200_tree_updater.cu, into the same shim library.  It subclasses
+// xgboost::Predictor (/root/reference/include/xgboost/predictor.h:63-178), keeps the reference's own "gpu_predictor"
+// alive inside itself and forwards EVERYTHING to it except the one call the hot path owns:
+//
+//   PredictBatch on a DMatrix that has no SparsePage, i.e. a QuantileDMatrix (src/predictor/gpu_predictor.cu:565-589
+//   routes exactly those through EllpackLoader), one output per row, no tree weights, no category re-coding, no
+//   column split, trees [tree_begin, tree_end) all single-target.
+//
+// That is the call GBTree::PredictBatchImpl makes for a validation set every boosting iteration
+// (src/gbm/gbtree.cc:514-560: tree_begin = the cache's version, so only the NEW trees are walked).  Anything else --
+// and any tree b200hist_forest_add_tree refuses -- goes to the reference's predictor before an output is touched.
+//
+// STATUS: compiled only.  libb200hist's forest kernels equal the oracle under the CPU emulator
+// (tests/test_kernel_emulation.py) and the oracle equals the reference's quantised prediction bit for bit
+// (tests/test_reference_golden.py), but neither this file nor those kernels have run on hardware.  The factory is
+// therefore only replaced when B200HIST_SHIM_PREDICTOR=1 is set when the shim is loaded; without it this translation
+// unit registers nothing.
+#include <dmlc/registry.h>
+#include <xgboost/base.h>
+#include <xgboost/context.h>
+#include <xgboost/data.h>
+#include <xgboost/host_device_vector.h>
+#include <xgboost/learner.h>
+#include <xgboost/logging.h>
+#include <xgboost/predictor.h>
+#include <xgboost/tree_model.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <memory>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "../../../include/b200hist.h"
+#include "src/common/cuda_context.cuh"  // CUDAContext::Stream
+#include "src/data/batch_utils.h"       // cuda_impl::StaticBatch
+#include "src/data/cat_container.h"     // CatContainer::NeedRecode
+#include "src/data/ellpack_page.cuh"    // EllpackPageImpl
+#include "src/gbm/gbtree_model.h"       // GBTreeModel
+
+namespace xgboost::predictor {
+
+class B200Predictor : public Predictor {
+ public:
+  B200Predictor(Context const* ctx, std::unique_ptr<Predictor> reference)
+      : Predictor{ctx}, ref_{std::move(reference)} {}
+  ~B200Predictor() override { this->ReleaseScratch(); }
+
+  void Configure(Args const& args) override { ref_->Configure(args); }
+  void InitOutPredictions(MetaInfo const& info, HostDeviceVector<float>* out_predt,
+                          gbm::GBTreeModel const& model) const override {
+    ref_->InitOutPredictions(info, out_predt, model);
+  }
+
+  void PredictBatch(DMatrix* dmat, PredictionCacheEntry* out_preds, gbm::GBTreeModel const& model,
+                    bst_tree_t tree_begin, bst_tree_t tree_end = 0,
+                    std::vector<float> const* tree_weights = nullptr) const override {
+    bst_tree_t const end = tree_end == 0 ? static_cast<bst_tree_t>(model.trees.size()) : tree_end;
+    if (this->Eligible(dmat, out_preds->predictions, model, tree_begin, end, tree_weights) &&
+        this->PredictQuantised(dmat, &out_preds->predictions, model, tree_begin, end)) {
+      return;
+    }
+    ref_->PredictBatch(dmat, out_preds, model, tree_begin, tree_end, tree_weights);
+  }
+
+  bool InplacePredict(std::shared_ptr<DMatrix> p_fmat, gbm::GBTreeModel const& model, float missing,
+                      PredictionCacheEntry* out_preds, bst_tree_t tree_begin = 0, bst_tree_t tree_end = 0,
+                      std::vector<float> const* tree_weights = nullptr) const override {
+    return ref_->InplacePredict(std::move(p_fmat), model, missing, out_preds, tree_begin, tree_end, tree_weights);
+  }
+  void PredictLeaf(DMatrix* dmat, HostDeviceVector<float>* out_preds, gbm::GBTreeModel const& model,
+                   bst_tree_t tree_end = 0) const override {
+    ref_->PredictLeaf(dmat, out_preds, model, tree_end);
+  }
+  void PredictContribution(DMatrix* dmat, HostDeviceVector<float>* out_contribs, gbm::GBTreeModel const& model,
+                           bst_tree_t tree_end = 0, std::vector<float> const* tree_weights = nullptr,
+                           bool approximate = false, int condition = 0,
+                           unsigned condition_feature = 0) const override {
+    ref_->PredictContribution(dmat, out_contribs, model, tree_end, tree_weights, approximate, condition,
+                              condition_feature);
+  }
+  void PredictInteractionContributions(DMatrix* dmat, HostDeviceVector<float>* out_contribs,
+                                       gbm::GBTreeModel const& model, bst_tree_t tree_end = 0,
+                                       std::vector<float> const* tree_weights = nullptr,
+                                       bool approximate = false) const override {
+    ref_->PredictInteractionContributions(dmat, out_contribs, model, tree_end, tree_weights, approximate);
+  }
+
+ private:
+  // The conditions under which GPUPredictor::PredictDMatrix (gpu_predictor.cu:627-660) reaches EllpackLoader with
+  // the no-op category accessor and unit tree weights -- the only configuration the forest kernels restate.
+  bool Eligible(DMatrix* dmat, HostDeviceVector<float> const& out, gbm::GBTreeModel const& model, bst_tree_t begin,
+                bst_tree_t end, std::vector<float> const* tree_weights) const {
+    if (!ctx_->IsCUDA() || tree_weights != nullptr || end <= begin) return false;
+    if (end > static_cast<bst_tree_t>(model.trees.size())) return false;
+    auto const& info = dmat->Info();
+    if (info.IsColumnSplit() || model.learner_model_param->OutputLength() != 1) return false;
+    if (dmat->PageExists<SparsePage>() || !dmat->PageExists<EllpackPage>() || !dmat->SingleColBlock()) return false;
+    if (dmat->Cats() != nullptr && dmat->Cats()->NeedRecode()) return false;
+    if (info.num_col_ > model.learner_model_param->num_feature) return false;  // the reference raises its own error
+    if (out.Size() != info.num_row_) return false;
+    for (bst_tree_t t = begin; t < end; ++t) {
+      if (model.trees[t]->IsMultiTarget()) return false;
+    }
+    return true;
+  }
+
+  // One scratch page of ours, reused while the incoming pages keep their shape and cuts; the rows are re-imported on
+  // every call (the reference's page may have been rebuilt behind the same address).
+  bool FitScratch(EllpackPageImpl const* impl) const {
+    auto cuts = impl->CutsShared();
+    auto const& ptrs = cuts->cut_ptrs_.ConstHostVector();
+    auto const& vals = cuts->cut_values_.ConstHostVector();
+    bool const dense_layout = impl->IsDenseCompressed();
+    int const has_missing = impl->IsDense() ? 0 : 1;
+    auto const stride = static_cast<std::uint32_t>(impl->info.row_stride);
+    if (scratch_ != nullptr && scratch_rows_ >= impl->n_rows && scratch_dense_layout_ == dense_layout &&
+        scratch_has_missing_ == has_missing && scratch_stride_ == stride && scratch_ptrs_ == ptrs &&
+        scratch_vals_ == vals) {
+      return true;
+    }
+    this->ReleaseScratch();
+    int rc;
+    if (dense_layout) {
+      rc = b200hist_ellpack_create(ctx_->Ordinal(), impl->n_rows, static_cast<std::uint32_t>(ptrs.size() - 1),
+                                   ptrs.data(), vals.data(), has_missing, &scratch_);
+    } else {
+      rc = b200hist_ellpack_create_sparse(ctx_->Ordinal(), impl->n_rows, static_cast<std::uint32_t>(ptrs.size() - 1),
+                                          ptrs.data(), vals.data(), stride, &scratch_);
+    }
+    if (rc != 0) {
+      scratch_ = nullptr;
+      return false;
+    }
+    scratch_rows_ = impl->n_rows;
+    scratch_dense_layout_ = dense_layout;
+    scratch_has_missing_ = has_missing;
+    scratch_stride_ = stride;
+    scratch_ptrs_ = ptrs;
+    scratch_vals_ = vals;
+    return true;
+  }
+
+  void ReleaseScratch() const {
+    if (scratch_ != nullptr) b200hist_ellpack_destroy(scratch_);
+    scratch_ = nullptr;
+    scratch_rows_ = 0;
+  }
+
+  // Trees [begin, end) of the model as the C ABI's node arrays, resolved against the scratch page's cuts.
+  // RegTree::GetNodes / Node accessors: include/xgboost/tree_model.h:96-190,256-261; categorical storage: :491-520 (one LBitField32
+  // segment per node, the layout b200hist_forest_add_tree takes).
+  bool BuildForest(gbm::GBTreeModel const& model, bst_tree_t begin, bst_tree_t end, b200hist_forest_t* out) const {
+    b200hist_forest_t forest{nullptr};
+    if (b200hist_forest_create(scratch_, &forest) != 0) return false;
+    std::vector<b200hist_tree_node> nodes;
+    std::vector<std::int32_t> is_cat;
+    std::vector<std::uint32_t> bits;
+    for (bst_tree_t t = begin; t < end; ++t) {
+      RegTree const& tree = *model.trees[t];
+      auto const n = static_cast<std::size_t>(tree.NumNodes());
+      auto types = tree.GetSplitTypes(DeviceOrd::CPU());
+      auto cats = tree.GetSplitCategories(DeviceOrd::CPU());
+      auto tree_nodes = tree.GetNodes(DeviceOrd::CPU());
+      auto const& segments = tree.GetSplitCategoriesPtr();
+      std::size_t words{0};
+      for (std::size_t nid = 0; nid < n; ++nid) {
+        auto const& node = tree_nodes[nid];
+        if (!node.IsDeleted() && !node.IsLeaf() && nid < types.size() && types[nid] == FeatureType::kCategorical &&
+            nid < segments.size()) {
+          words = std::max(words, segments[nid].size);
+        }
+      }
+      nodes.assign(n, b200hist_tree_node{});
+      is_cat.assign(n, 0);
+      bits.assign(n * std::max<std::size_t>(words, 1), 0u);
+      for (std::size_t nid = 0; nid < n; ++nid) {
+        auto const& node = tree_nodes[nid];
+        auto& d = nodes[nid];
+        d.parent = node.IsDeleted() || node.IsRoot() ? -1 : static_cast<std::int32_t>(node.Parent());
+        if (node.IsDeleted() || node.IsLeaf()) {  // a deleted node is unreachable
+          d.left = d.right = -1;
+          d.findex = -1;
+          d.is_leaf = 1;
+          d.leaf_value = node.IsDeleted() ? 0.0f : node.LeafValue();
+          continue;
+        }
+        d.left = node.LeftChild();
+        d.right = node.RightChild();
+        d.findex = static_cast<std::int32_t>(node.SplitIndex());
+        d.fvalue = node.SplitCond();
+        d.default_left = node.DefaultLeft() ? 1 : 0;
+        if (words > 0 && nid < types.size() && types[nid] == FeatureType::kCategorical && nid < segments.size()) {
+          is_cat[nid] = 1;
+          auto const& seg = segments[nid];
+          for (std::size_t w = 0; w < seg.size && seg.beg + w < cats.size(); ++w) {
+            bits[nid * words + w] = cats[seg.beg + w];
+          }
+        }
+      }
+      bool const any_cat = words > 0;
+      if (b200hist_forest_add_tree(forest, nodes.data(), static_cast<std::int32_t>(n),
+                                   any_cat ? is_cat.data() : nullptr, any_cat ? bits.data() : nullptr,
+                                   static_cast<std::uint32_t>(words)) != 0) {
+        b200hist_forest_destroy(forest);
+        return false;  // e.g. a pruned tree whose node ids are no longer in expansion order
+      }
+    }
+    *out = forest;
+    return true;
+  }
+
+  bool PredictQuantised(DMatrix* dmat, HostDeviceVector<float>* out_preds, gbm::GBTreeModel const& model,
+                        bst_tree_t begin, bst_tree_t end) const {
+    std::lock_guard<std::mutex> guard{mu_};
+    out_preds->SetDevice(ctx_->Device());
+    auto* stream = static_cast<void*>(ctx_->CUDACtx()->Stream());
+    b200hist_forest_t forest{nullptr};
+    bool wrote{false}, ok{true};
+    bst_idx_t offset{0};
+    for (auto const& page : dmat->GetBatches<EllpackPage>(ctx_, cuda_impl::StaticBatch(true))) {
+      auto const* impl = page.Impl();
+      ok = this->FitScratch(impl) && this->BuildForest(model, begin, end, &forest);
+      if (!ok) break;
+      ok = b200hist_ellpack_import_reference_rows(
+               scratch_, 0, static_cast<std::uint64_t>(impl->n_rows), impl->gidx_buffer.data(),
+               static_cast<std::uint32_t>(impl->info.row_stride), static_cast<std::uint32_t>(impl->NumSymbols()),
+               impl->IsDense() ? 1 : 0, stream) == 0 &&
+           b200hist_forest_predict_margin(forest, scratch_, 0, static_cast<std::uint32_t>(end - begin), 0,
+                                          static_cast<std::uint64_t>(impl->n_rows),
+                                          out_preds->DevicePointer() + offset, stream) == 0;
+      ctx_->CUDACtx()->Stream().Sync();  // the forest is freed below; the reference may recycle the page
+      b200hist_forest_destroy(forest);
+      forest = nullptr;
+      if (!ok) break;
+      wrote = true;
+      offset += impl->n_rows;
+    }
+    if (!ok && wrote) LOG(FATAL) << "[b200hist] prediction failed half way: " << b200hist_last_error();
+    return ok && wrote;
+  }
+
+  std::unique_ptr<Predictor> ref_;
+  mutable std::mutex mu_;
+  mutable b200hist_ellpack_t scratch_{nullptr};
+  mutable bst_idx_t scratch_rows_{0};
+  mutable bool scratch_dense_layout_{true};
+  mutable int scratch_has_missing_{0};
+  mutable std::uint32_t scratch_stride_{0};
+  mutable std::vector<std::uint32_t> scratch_ptrs_;
+  mutable std::vector<float> scratch_vals_;
+};
+
+// Replaces the factory of "gpu_predictor" (the name Learner/GBTree resolve on CUDA, src/gbm/gbtree.cc:566-590) --
+// only on request, see STATUS above -- and keeps the original reachable as "gpu_predictor_reference".
+struct B200PredictorRegistrar {
+  B200PredictorRegistrar() {
+    char const* e = std::getenv("B200HIST_SHIM_PREDICTOR");
+    if (e == nullptr || e[0] != '1') return;
+    auto* reg = ::dmlc::Registry<::xgboost::PredictorReg>::Get();
+    auto const* orig = reg->Find("gpu_predictor");
+    if (orig == nullptr) return;
+    auto body = orig->body;  // copy before it is overwritten
+    reg->__REGISTER__("gpu_predictor_reference").describe("The reference's own GPU predictor.").set_body(body);
+    reg->__REGISTER__("gpu_predictor")
+        .describe("GPU predictor; quantised matrices are served by libb200hist.so.")
+        .set_body([body](Context const* ctx) -> Predictor* {
+          return new B200Predictor(ctx, std::unique_ptr<Predictor>(body(ctx)));
+        });
+  }
+};
+static B200PredictorRegistrar b200_predictor_registrar__;
+
+}  // namespace xgboost::predictor
