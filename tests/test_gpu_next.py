@@ -238,6 +238,49 @@ def test_categorical_evaluation_random_histograms(xb, onehot, threshold, params)
             assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32), name
 
 
+def test_categorical_evaluation_with_a_thousand_categories(xb):
+    """One feature with 1000 categories: the categorical kernels' sort scratch (8 warps x 1000 bins x 6 B) plus their
+    static shared memory passes 48 KiB, so the launch needs the per-kernel opt-in (AllowDynamicShared); the sorted
+    partition spans 32 chunks of 32 bins."""
+    import torch
+    rng = np.random.default_rng(41)
+    n, k = 60000, 1000
+    col = rng.integers(0, k, size=n).astype(np.float32)
+    col[rng.random(n) < 0.05] = np.nan
+    xnum, _ = make_regression(n, 1, seed=29)
+    ncp, ncv = make_cuts(xnum, 32)
+    cp = np.array([0, k, k + int(ncp[1])], dtype=np.uint32)
+    cv = np.array([float(v) for v in range(k)] + [float(v) for v in ncv], dtype=np.float32)
+    is_cat = [1, 0]
+    gb = np.full((n, 2), -1, dtype=np.int32)
+    ok = ~np.isnan(col)
+    gb[ok, 0] = col[ok].astype(np.int32)
+    gb[:, 1] = orc.bin_dense(xnum, ncp, ncv)[:, 0] + k
+    effect = rng.normal(size=k)
+    y = (effect[np.nan_to_num(col, nan=0).astype(int)] + 0.2 * rng.normal(size=n)).astype(np.float32)
+    gp = squared_error_gpair(np.zeros(n, np.float32), y)
+    scale, _ = orc.quantiser(gp)
+    gq = orc.quantise(gp, scale)
+    subsets = [np.arange(n), rng.choice(n, 5000, replace=False)]
+    hists = np.stack([orc.build_hist(gb, gq, s.astype(np.uint32), cv.size) for s in subsets])
+    parents = [tuple(int(v) for v in gq[s].sum(axis=0)) for s in subsets]
+    q = xb.lib.Quantiser(*[float(v) for v in scale])
+    page = xb.EllpackPage(xb.HistogramCuts(cp, cv), 1, 0, False)
+    for threshold in (64, 1000):
+        params = dict(max_depth=6)
+        cands, flags, bits = xb.components.evaluate_splits_cat(
+            page, torch.from_numpy(hists).cuda(), parents, xb.TrainParam.make(**params), q, is_cat,
+            max_cat_to_onehot=4, max_cat_threshold=threshold, n_cat_words=(k + 31) // 32)
+        for j, c in enumerate(cands):
+            o, o_is_cat, _, o_cats = orc.eval_node_cat(hists[j], parents[j], cp, cv, orc.Param.make(**params), scale,
+                                                       is_cat, 4, threshold)
+            assert o_is_cat and bool(flags[j]), (threshold, j)
+            assert (c.findex, c.dir) == (o.findex, o.dir), (threshold, j)
+            assert _cats_of(bits[j]) == o_cats, (threshold, j)
+            assert (c.left_sum.grad, c.left_sum.hess, c.right_sum.grad, c.right_sum.hess) == \
+                (o.left_sum.g, o.left_sum.h, o.right_sum.g, o.right_sum.h), (threshold, j)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Categorical features through the whole updater (b200hist_updater_set_categorical: evaluation, ApplyKernel<true>,
 # PartitionCountKernel<., true>, FinaliseWindowKernel<., true>)
@@ -815,7 +858,7 @@ def test_several_trees_per_iteration_through_the_shim(xb, extra):
 # Column-sampling draws on the device (b200hist_col_sample_stream, csrc/colsample.cu)
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,colsample", [(1, 0.5), (7, 0.5), (16, 0.3), (17, 0.9), (256, 0.5), (257, 0.25), (1000, 0.01),
-                                         (4096, 0.7), (8192, 0.5), (40, 1.0)])
+                                         (4096, 0.7), (8192, 0.5), (8192, 0.9), (40, 1.0)])
 def test_col_sample_stream_matches_the_thrust_shuffle_restatement(xb, n, colsample):
     """Every draw of the stream equals ColSample restated on the CPU (oracle.col_sample, itself pinned on the toolkit's
     thrust::shuffle): sizes around the cipher's power-of-two boundaries, the engine's seed folding, a sparse id set."""

@@ -425,6 +425,43 @@ def test_interaction_level_kernel_source(tmp_path, with_level_set):
         level = order if d_level < 2 else order[:6]
 
 
+@pytest.mark.parametrize("threshold", [64, 1000])
+def test_evaluation_kernel_sources_with_a_thousand_categories(tmp_path, threshold):
+    """The categorical kernels at the width the driver allows (kMaxCatBins = 1024): a 1000-category feature is 32
+    arg-max chunks per scan direction and a warp sort over 1000 weights."""
+    rng = np.random.default_rng(41)
+    n, k = 30000, 1000
+    col = rng.integers(0, k, size=n).astype(np.float32)
+    col[rng.random(n) < 0.05] = np.nan
+    xnum, _ = make_regression(n, 1, seed=29)
+    ncp, ncv = make_cuts(xnum, 32)
+    cp = np.array([0, k, k + int(ncp[1])], dtype=np.uint32)
+    cv = np.array([float(v) for v in range(k)] + [float(v) for v in ncv], dtype=np.float32)
+    is_cat = [1, 0]
+    gb = np.full((n, 2), -1, dtype=np.int32)
+    ok = ~np.isnan(col)
+    gb[ok, 0] = col[ok].astype(np.int32)
+    gb[:, 1] = orc.bin_dense(xnum, ncp, ncv)[:, 0] + k
+    effect = rng.normal(size=k)
+    y = (effect[np.nan_to_num(col, nan=0).astype(int)] + 0.2 * rng.normal(size=n)).astype(np.float32)
+    gp = squared_error_gpair(np.zeros(n, np.float32), y)
+    scale, _ = orc.quantiser(gp)
+    gq = orc.quantise(gp, scale)
+    subsets = [np.arange(n), rng.choice(n, 4000, replace=False)]
+    hists = np.stack([orc.build_hist(gb, gq, s.astype(np.uint32), cv.size) for s in subsets])
+    parents = np.array([gq[s].sum(axis=0) for s in subsets], dtype=np.int64)
+    params = dict(max_depth=6)
+    cand, flags, bits = _evaluate(tmp_path, cp, cv, hists, parents, params, scale, is_cat=np.array(is_cat, dtype=np.uint8),
+                                  onehot=4, threshold=threshold)
+    p = orc.Param.make(**params)
+    for j in range(len(parents)):
+        o, o_is_cat, _, o_cats = orc.eval_node_cat(hists[j], parents[j], cp, cv, p, scale, is_cat, 4, threshold)
+        assert o_is_cat and bool(flags[j]), j
+        _same_candidate(cand[j], o, "1000 categories, node %d" % j, cat=True)
+        got = {32 * w + (31 - b) for w in range(bits.shape[1]) for b in range(32) if (int(bits[j, w]) >> b) & 1}
+        assert got == o_cats, (j, len(got), len(o_cats))
+
+
 @pytest.mark.parametrize("bin_bytes", [1, 2])
 def test_rebin_categorical_kernel_source(tmp_path, bin_bytes):
     """RebinCategoricalKernel = HistogramCuts::SearchCatBin on the categorical columns, other columns untouched."""

@@ -21,7 +21,7 @@
 namespace b200 {
 
 constexpr int kCsThreads = 256;
-constexpr int kCsMaxFeatures = 8192;  // 32 KiB of shared memory for the selected ids
+constexpr int kCsMaxFeatures = 8192;  // 2 x 32 KiB of shared memory (selected ids + sort keys): opt-in above 48 KiB
 
 __device__ __forceinline__ uint32_t BlockExclusiveScanCs(uint32_t v, uint32_t* s_warp, uint32_t* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(kCsThreads) NodeDrawKernel(const TreeState* ts
 #ifndef B200_KERNELS_ONLY
 void LaunchLevelDraw(const TreeState* ts, const NodeDev* nodes, const int32_t* eval_nodes, const ColDrawDev& cd,
                      cudaStream_t s) {
+  AllowDynamicShared(LevelDrawKernel, sizeof(int32_t) * 2 * (size_t)cd.n_level);
   LevelDrawKernel<<<1, kCsThreads, sizeof(int32_t) * 2 * (size_t)cd.n_level, s>>>(ts, nodes, eval_nodes, cd);
   B200_LAUNCHED();
 }
@@ -193,6 +194,7 @@ void LaunchLevelDraw(const TreeState* ts, const NodeDev* nodes, const int32_t* e
 void LaunchNodeDraw(const TreeState* ts, const NodeDev* nodes, const int32_t* eval_nodes, const ColDrawDev& cd,
                     int32_t n_node, int32_t max_eval, int32_t* list, int32_t* count, cudaStream_t s) {
   if (max_eval == 0) return;
+  AllowDynamicShared(NodeDrawKernel, sizeof(int32_t) * 2 * (size_t)n_node);
   NodeDrawKernel<<<max_eval, kCsThreads, sizeof(int32_t) * 2 * (size_t)n_node, s>>>(ts, nodes, eval_nodes, cd, n_node,
                                                                                      list, count);
   B200_LAUNCHED();
@@ -201,6 +203,7 @@ void LaunchNodeDraw(const TreeState* ts, const NodeDev* nodes, const int32_t* ev
 void LaunchColSampleStream(const int32_t* features_dev, int32_t n, int32_t n_sel, const uint32_t* seeds_dev,
                            int32_t n_draws, int32_t* out_dev, cudaStream_t s) {
   if (n_draws == 0) return;
+  AllowDynamicShared(ColSampleStreamKernel, sizeof(int32_t) * 2 * (size_t)n_sel);
   ColSampleStreamKernel<<<n_draws, kCsThreads, sizeof(int32_t) * 2 * (size_t)n_sel, s>>>(features_dev, n, n_sel,
                                                                                          seeds_dev, out_dev);
   B200_LAUNCHED();

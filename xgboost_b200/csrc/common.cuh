@@ -62,6 +62,18 @@ extern std::atomic<uint64_t> g_launch_count;
     B200_CUDA(cudaGetLastError());               \
   } while (0)
 
+// A launch whose static + dynamic shared memory passes 48 KiB needs the per-kernel opt-in.  Called right before such a
+// launch with exactly the dynamic bytes it asks for (the static part of every kernel here is below 18 KiB, so dynamic
+// sizes up to 16 KiB can never reach the limit and skip the call).
+#ifndef B200_KERNELS_ONLY
+template <typename Kernel>
+inline void AllowDynamicShared(Kernel kernel, size_t dynamic_bytes) {
+  if (dynamic_bytes > 16 * 1024) {
+    B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynamic_bytes));
+  }
+}
+#endif
+
 struct DeviceGuard {
   int prev{-1};
   explicit DeviceGuard(int dev) {

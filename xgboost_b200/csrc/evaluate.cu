@@ -583,12 +583,14 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist, const int3
   const size_t cat_smem = (size_t)kEvalWarps * (size_t)cat.max_cat_bins * (sizeof(float) + sizeof(uint16_t));
   auto scan_cat = [&]() {
     if (cat.is_cat == nullptr) return;
+    AllowDynamicShared(CatFeatureScanKernel, cat_smem);
     CatFeatureScanKernel<<<blocks, kEvalWarps * 32, cat_smem, s>>>(ell, h2, eval_nodes, ts, nodes, feature_set, n_fs, p,
                                                                    q, scratch, mono, n_levels, ic, cat);
     B200_LAUNCHED();
   };
   auto finish_cat = [&]() {
     if (cat.is_cat == nullptr) return;
+    AllowDynamicShared(CatFinishKernel, cat_smem);
     CatFinishKernel<<<blocks2, kEvalWarps * 32, cat_smem, s>>>(ell, h2, eval_nodes, ts, nodes, p, q, cand, cat);
     B200_LAUNCHED();
   };
