@@ -489,6 +489,23 @@ B200HIST_API int b200hist_forest_predict_margin(b200hist_forest_t forest, b200hi
 B200HIST_API int b200hist_forest_predict_leaf(b200hist_forest_t forest, b200hist_ellpack_t page, uint32_t tree_begin,
                                               uint32_t tree_end, uint64_t row_begin, uint64_t n_rows,
                                               int32_t* out_dev, void* stream);
+/* Several output groups (multi-class: tree t feeds output groups_host[t]; gbm::GBTreeModel::tree_info).  With more
+ * than one group the reference adds every leaf straight onto the output, tree after tree
+ * (gpu_predictor.cu:229-239), instead of summing from 0.0f first: out_dev[(k * n_groups) + g] is read once, the
+ * leaves of the group's trees in [tree_begin, tree_end) are added in tree order, and it is written once.
+ * set_tree_groups replaces the group of EVERY tree added so far (n_trees must equal forest_num_trees; trees added
+ * later start in group 0).  predict_leaf_f32 is predict_leaf with the id stored as a float, the layout
+ * Predictor::PredictLeaf returns (gpu_predictor.cu:793-830).
+ * STATUS: compiled, equal to the oracle under the CPU emulator, never run on hardware. */
+B200HIST_API int b200hist_forest_set_tree_groups(b200hist_forest_t forest, const uint32_t* groups_host,
+                                                 uint32_t n_trees);
+B200HIST_API int b200hist_forest_predict_margin_groups(b200hist_forest_t forest, b200hist_ellpack_t page,
+                                                       uint32_t tree_begin, uint32_t tree_end, uint32_t n_groups,
+                                                       uint64_t row_begin, uint64_t n_rows, float* out_dev,
+                                                       void* stream);
+B200HIST_API int b200hist_forest_predict_leaf_f32(b200hist_forest_t forest, b200hist_ellpack_t page,
+                                                  uint32_t tree_begin, uint32_t tree_end, uint64_t row_begin,
+                                                  uint64_t n_rows, float* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

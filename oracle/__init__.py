@@ -431,6 +431,23 @@ def predict_margin(gbins, cut_ptrs, cut_values, trees, base=None, is_dense_layou
     return (out + total).astype(np.float32)
 
 
+def predict_margin_groups(gbins, cut_ptrs, cut_values, trees, tree_groups, n_groups, base=None,
+                          is_dense_layout=True) -> np.ndarray:
+    """GPUPredictor's kernel with more than one output group (gpu_predictor.cu:229-239; the CPU predictor does the same,
+    cpu_predictor.cc PredictByAllTrees): every leaf is added STRAIGHT onto out[row, group(tree)], tree after tree --
+    no sum from 0 first.  Returns float32 [n_rows, n_groups]."""
+    n = np.asarray(gbins).shape[0]
+    out = (np.zeros((n, n_groups), dtype=np.float32) if base is None
+           else np.asarray(base, dtype=np.float32).reshape(n, n_groups).copy())
+    for t, g in zip(trees, tree_groups):
+        nodes = t["nodes"] if isinstance(t, dict) else t
+        leaf = predict_leaf(gbins, cut_ptrs, cut_values, nodes, t.get("is_cat") if isinstance(t, dict) else None,
+                            t.get("cat_sets") if isinstance(t, dict) else None, is_dense_layout)
+        values = np.array([nd.leaf_value for nd in nodes], dtype=np.float32)
+        out[:, g] = (out[:, g] + values[leaf]).astype(np.float32)
+    return out
+
+
 def update_prediction_cache(nodes, position: np.ndarray, preds: np.ndarray) -> np.ndarray:
     arr = (Node * len(nodes))(*nodes)
     p = np.ascontiguousarray(preds, dtype=np.float32).copy()

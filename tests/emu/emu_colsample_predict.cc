@@ -8,6 +8,8 @@
 #include <string>
 
 #include "../../xgboost_b200/csrc/colsample.cu"
+#include <fstream>
+
 #include "../../xgboost_b200/csrc/predict.cu"
 
 template <typename T>
@@ -87,6 +89,27 @@ int main(int argc, char** argv) {
     }
     WriteAll(dir + "/margin.bin", out);
     WriteAll(dir + "/leaves.bin", leaves);
+    // optional: several output groups (tree_groups.bin, base_groups.bin [n_rows * n_groups]) and float leaf ids
+    if (std::ifstream(dir + "/tree_groups.bin").good()) {
+      auto groups = ReadAll<uint32_t>(dir + "/tree_groups.bin");
+      auto gout = ReadAll<float>(dir + "/base_groups.bin");
+      const uint32_t n_groups = (uint32_t)(gout.size() / meta[0]);
+      b200::ForestView fg = fv;
+      fg.tree_group = groups.data();
+      std::vector<float> fleaves((size_t)meta[0] * meta[5]);
+      if (ell.is_sparse) {
+        EMU_LAUNCH((3), (256), 0, b200::PredictMarginGroupsKernel<uint32_t>(ell, fg, 0, meta[5], n_groups, 0, meta[0], gout.data()));
+        EMU_LAUNCH((3), (256), 0, (b200::PredictLeafKernel<uint32_t, float>(ell, fv, 0, meta[5], 0, meta[0], fleaves.data())));
+      } else if (meta[3] == 1) {
+        EMU_LAUNCH((3), (256), 0, b200::PredictMarginGroupsKernel<uint8_t>(ell, fg, 0, meta[5], n_groups, 0, meta[0], gout.data()));
+        EMU_LAUNCH((3), (256), 0, (b200::PredictLeafKernel<uint8_t, float>(ell, fv, 0, meta[5], 0, meta[0], fleaves.data())));
+      } else {
+        EMU_LAUNCH((3), (256), 0, b200::PredictMarginGroupsKernel<uint16_t>(ell, fg, 0, meta[5], n_groups, 0, meta[0], gout.data()));
+        EMU_LAUNCH((3), (256), 0, (b200::PredictLeafKernel<uint16_t, float>(ell, fv, 0, meta[5], 0, meta[0], fleaves.data())));
+      }
+      WriteAll(dir + "/margin_groups.bin", gout);
+      WriteAll(dir + "/leaves_f32.bin", fleaves);
+    }
     return 0;
   }
   return 2;

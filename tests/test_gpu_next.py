@@ -654,6 +654,14 @@ def test_forest_prediction_matches_oracle(xb, missing, max_bin):
         leaves = forest.predict_leaf(pg).cpu().numpy()
         for t, nodes in enumerate(trees):
             assert np.array_equal(leaves[:, t], orc.predict_leaf(bins, cp, cv, nodes))
+        assert np.array_equal(forest.predict_leaf(pg, as_float=True).cpu().numpy(), leaves.astype(np.float32))
+        # three output groups: leaves straight onto the output, tree after tree
+        groups = [1, 0, 2, 2, 0, 1]
+        forest.set_tree_groups(groups)
+        gbase = np.random.default_rng(rows).normal(size=(rows, 3)).astype(np.float32)
+        gout = forest.predict_margin_groups(pg, torch.from_numpy(gbase.copy()).cuda(), 3)
+        gwant = orc.predict_margin_groups(bins, cp, cv, trees, groups, 3, base=gbase)
+        assert np.array_equal(gout.cpu().numpy().view(np.uint32), gwant.view(np.uint32))
         # a tree range and a row range
         part = forest.predict_margin(pg, torch.zeros(1000, device="cuda"), tree_begin=2, tree_end=5, row_begin=123)
         want_part = orc.predict_margin(bins[123:1123], cp, cv, trees[2:5])
@@ -699,11 +707,12 @@ def test_forest_resolved_against_foreign_cuts_matches_oracle(xb):
     assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
 
 
-@pytest.mark.parametrize("case", ["dense", "missing", "wide_bins"])
+@pytest.mark.parametrize("case", ["dense", "missing", "wide_bins", "multiclass"])
 def test_predictor_binding_serves_quantised_matrices_like_the_reference(xb, case, tmp_path):
     """The reference's Booster.predict on QuantileDMatrices with the "gpu_predictor" factory served by the shim
     (xgboost_b200/csrc/shim/b200_predictor.cu) against the same call served by the reference itself: margins bit for
-    bit, on the training matrix and on a matrix with its own cuts, and the shim's run really launched our kernels.
+    bit (one output or one per class), on the training matrix and on a matrix with its own cuts, leaf ids too, and the
+    shim's run really launched our kernels.
     Two child processes: the shim decides at load time (B200HIST_SHIM_PREDICTOR)."""
     import subprocess
     import sys
@@ -720,8 +729,8 @@ def test_predictor_binding_serves_quantised_matrices_like_the_reference(xb, case
                        timeout=600)
         got[gate] = np.load(out)
     assert int(got["0"]["launches"]) == 0
-    assert int(got["1"]["launches"]) >= 2          # import + predict per matrix, at least
-    for key in ("valid", "train"):
+    assert int(got["1"]["launches"]) >= 3          # import + predict per matrix, at least
+    for key in ("valid", "train", "leaf"):
         assert np.array_equal(got["1"][key].view(np.uint32), got["0"][key].view(np.uint32)), key
 
 

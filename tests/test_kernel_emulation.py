@@ -157,6 +157,11 @@ def test_predict_kernel_sources(tmp_path, kind):
     cp.tofile(os.path.join(d, "cut_ptrs.bin"))
     cv.tofile(os.path.join(d, "cut_values.bin"))
     base.tofile(os.path.join(d, "base.bin"))
+    n_groups = 3
+    tree_groups = np.array([(2 * t + 1) % n_groups for t in range(len(trees))], dtype=np.uint32)   # 1, 0, 2, 1
+    base_groups = np.random.default_rng(3).normal(size=(len(y), n_groups)).astype(np.float32)
+    tree_groups.tofile(os.path.join(d, "tree_groups.bin"))
+    base_groups.tofile(os.path.join(d, "base_groups.bin"))
     _run(exe, "predict", d)
     margin = np.fromfile(os.path.join(d, "margin.bin"), dtype=np.float32)
     leaves = np.fromfile(os.path.join(d, "leaves.bin"), dtype=np.int32).reshape(len(y), len(trees))
@@ -164,6 +169,12 @@ def test_predict_kernel_sources(tmp_path, kind):
     assert np.array_equal(margin.view(np.uint32), want.view(np.uint32))
     for t, o in enumerate(trees):
         assert np.array_equal(leaves[:, t], orc.predict_leaf(gb, cp, cv, o["nodes"], o.get("is_cat"), o.get("cat_sets")))
+    # several output groups: leaves go straight onto the output, tree after tree; leaf ids as floats
+    got_groups = np.fromfile(os.path.join(d, "margin_groups.bin"), dtype=np.float32).reshape(len(y), n_groups)
+    want_groups = orc.predict_margin_groups(gb, cp, cv, trees, tree_groups, n_groups, base=base_groups)
+    assert np.array_equal(got_groups.view(np.uint32), want_groups.view(np.uint32))
+    fleaves = np.fromfile(os.path.join(d, "leaves_f32.bin"), dtype=np.float32).reshape(len(y), len(trees))
+    assert np.array_equal(fleaves, leaves.astype(np.float32))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

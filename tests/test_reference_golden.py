@@ -385,6 +385,50 @@ def test_oracle_predictor_on_foreign_cuts_reproduces_reference_quantised_predict
     assert not np.array_equal(raw.view(np.uint32), ref.view(np.uint32))
 
 
+def test_oracle_grouped_prediction_reproduces_reference_multiclass_margins():
+    """Three output groups (multi:softprob): tree t feeds group tree_info[t] and every leaf goes straight onto the
+    output, tree after tree -- with a non-zero base score that differs in the last bits from summing the trees first.
+    The reference's CPU predictor is the pin (the GPU kernel's multi-group branch has the same form,
+    gpu_predictor.cu:229-239)."""
+    from oracle import ref_capi as rc
+    if not rc.available("cpu"):
+        pytest.skip("needs oracle/_ref/libxgboost.so (built where /root/reference exists)")
+    x, y = make_regression(9000, 8, seed=91, missing=0.05)
+    label = np.digitize(y, np.quantile(y, [1 / 3, 2 / 3])).astype(np.float32)
+    dm = rc.DMatrix.from_dense(x, label=label, kind="cpu")
+    bst = rc.Booster({"tree_method": "hist", "device": "cpu", "max_bin": 32, "objective": "multi:softprob",
+                      "num_class": 3, "base_score": 0.5, "max_depth": 4, "eta": 0.5}, dm)
+    for i in range(5):
+        bst.update(i)
+    model = bst.save_json()
+    groups = [int(g) for g in model["learner"]["gradient_booster"]["model"]["tree_info"]]
+    assert groups == [0, 1, 2] * 5
+    cp, cv = dm.histogram_cuts()
+    gb = orc.bin_dense(x, cp, cv)
+    forest = []
+    for t in rc.trees_from_model(model):
+        nodes = []
+        for i in range(len(t["left"])):
+            leaf = t["left"][i] == -1
+            nodes.append(orc.Node(t["parent"][i], t["left"][i], t["right"][i], -1 if leaf else t["findex"][i],
+                                  t["cond"][i], t["default_left"][i], 1 if leaf else 0, t["cond"][i] if leaf else 0.0,
+                                  0, 0, 0, 0))
+        forest.append(nodes)
+    ref = bst.predict_margin(dm).reshape(len(y), 3)
+    # the margin of a model without trees is the base margin: recover it from the reference itself
+    bst0 = rc.Booster({"tree_method": "hist", "device": "cpu", "max_bin": 32, "objective": "multi:softprob",
+                       "num_class": 3, "base_score": 0.5}, dm)
+    base = bst0.predict_margin(dm).reshape(len(y), 3)
+    assert float(base[0, 0]) != 0.0
+    ours = orc.predict_margin_groups(gb, cp, cv, forest, groups, 3, base=base)
+    assert np.array_equal(ours.view(np.uint32), ref.view(np.uint32))
+    # summing a group's trees first and adding the sum afterwards is NOT the same float
+    summed = base.copy()
+    for g in range(3):
+        summed[:, g] = base[:, g] + orc.predict_margin(gb, cp, cv, [forest[i] for i in range(15) if groups[i] == g])
+    assert not np.array_equal(summed.view(np.uint32), ref.view(np.uint32))
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Waiting for their fixture: tests/golden/ref_gpu_next_trees.json (tools/make_golden_gpu_next.py, one short GPU call).
 # The reference's own gpu_hist trees for categorical features and gradient-based sampling pin the two oracle

@@ -39,6 +39,7 @@ struct ForestView {
   const uint32_t* tree_root;  // [n_trees] index of every tree's root
   const uint32_t* bin_bits;   // [n_nodes][bin_words] (categorical nodes only meaningful), may be null
   int32_t bin_words;
+  const uint32_t* tree_group{nullptr};  // [n_trees] output group of every tree (multi-class), null: all 0
 };
 
 template <typename BinT>
@@ -81,11 +82,32 @@ __global__ void __launch_bounds__(256) PredictMarginKernel(EllView ell, ForestVi
   }
 }
 
-// PredictLeaf (gpu_predictor.cu:196-201): out[row * n_trees + t] = id of the leaf inside tree t
+// Several output groups (multi-class: tree t feeds output tree_group[t]).  The reference's kernel then adds every
+// leaf STRAIGHT onto the output, tree after tree (gpu_predictor.cu:229-239) -- not into a sum that starts at 0 as in
+// the single-group branch -- so per output the chain is out, out + l1, (out + l1) + l2, ...  One thread per
+// (row, group): the output is read once, the group's trees of [begin, end) are walked in order, and it is written once.
 template <typename BinT>
+__global__ void __launch_bounds__(256) PredictMarginGroupsKernel(EllView ell, ForestView fv, uint32_t tree_begin,
+                                                                  uint32_t tree_end, uint32_t n_groups,
+                                                                  uint64_t row_begin, uint64_t n_rows,
+                                                                  float* __restrict__ out) {
+  for (uint64_t k = blockIdx.x * 256ull + threadIdx.x; k < n_rows * n_groups; k += (uint64_t)gridDim.x * 256ull) {
+    const uint64_t row = k / n_groups;
+    const uint32_t g = (uint32_t)(k - row * n_groups);
+    float acc = out[k];
+    for (uint32_t t = tree_begin; t < tree_end; ++t) {
+      if (__ldg(fv.tree_group + t) == g) acc += WalkTree<BinT>(ell, fv, fv.tree_root[t], row_begin + row);
+    }
+    out[k] = acc;
+  }
+}
+
+// PredictLeaf (gpu_predictor.cu:196-201): out[row * n_trees + t] = id of the leaf inside tree t
+// (OutT = float is the layout Predictor::PredictLeaf hands back: the id as a float.)
+template <typename BinT, typename OutT = int32_t>
 __global__ void __launch_bounds__(256) PredictLeafKernel(EllView ell, ForestView fv, uint32_t tree_begin,
                                                           uint32_t tree_end, uint64_t row_begin, uint64_t n_rows,
-                                                          int32_t* __restrict__ out) {
+                                                          OutT* __restrict__ out) {
   const uint32_t nt = tree_end - tree_begin;
   for (uint64_t k = blockIdx.x * 256ull + threadIdx.x; k < n_rows * nt; k += (uint64_t)gridDim.x * 256ull) {
     const uint64_t row = k / nt;
@@ -111,7 +133,7 @@ __global__ void __launch_bounds__(256) PredictLeafKernel(EllView ell, ForestView
       i = (uint32_t)(left ? nd.left : nd.right);
       nd = fv.nodes[i];
     }
-    out[k] = (int32_t)(i - fv.tree_root[t]);
+    out[k] = (OutT)(int32_t)(i - fv.tree_root[t]);
   }
 }
 
@@ -126,13 +148,19 @@ struct b200hist_forest_s {
   std::vector<PredNode> nodes;
   std::vector<uint32_t> roots;
   std::vector<uint32_t> bin_bits;  // [nodes][bin_words]
+  std::vector<uint32_t> groups;    // [trees] output group of every tree (0 unless set_tree_groups said otherwise)
   int32_t bin_words{0};
   // device copy, refreshed lazily
   PredNode* d_nodes{nullptr};
   uint32_t* d_roots{nullptr};
   uint32_t* d_bin_bits{nullptr};
+  uint32_t* d_groups{nullptr};
   bool dirty{true};
 };
+
+template <typename OutT>
+static int PredictLeafImpl(b200hist_forest_t f, b200hist_ellpack_t page, uint32_t tree_begin, uint32_t tree_end,
+                           uint64_t row_begin, uint64_t n_rows, OutT* out_dev, void* stream);
 
 extern "C" {
 
@@ -155,6 +183,7 @@ int b200hist_forest_destroy(b200hist_forest_t f) {
     cudaFree(f->d_nodes);
     cudaFree(f->d_roots);
     cudaFree(f->d_bin_bits);
+    cudaFree(f->d_groups);
     delete f;
   }
   B200_API_END();
@@ -213,6 +242,7 @@ int b200hist_forest_add_tree(b200hist_forest_t f, const b200hist_tree_node* node
     add[i] = d;
   }
   f->roots.push_back(base);
+  f->groups.push_back(0u);
   f->nodes.insert(f->nodes.end(), add.begin(), add.end());
   f->bin_bits.insert(f->bin_bits.end(), bits.begin(), bits.end());
   f->dirty = true;
@@ -224,6 +254,9 @@ static void SyncForest(b200hist_forest_s* f, cudaStream_t s) {
   cudaFree(f->d_nodes);
   cudaFree(f->d_roots);
   cudaFree(f->d_bin_bits);
+  cudaFree(f->d_groups);
+  f->d_groups = DevAlloc<uint32_t>(std::max<size_t>(f->groups.size(), 1));
+  B200_CUDA(cudaMemcpyAsync(f->d_groups, f->groups.data(), sizeof(uint32_t) * f->groups.size(), cudaMemcpyHostToDevice, s));
   f->d_nodes = DevAlloc<PredNode>(std::max<size_t>(f->nodes.size(), 1));
   f->d_roots = DevAlloc<uint32_t>(std::max<size_t>(f->roots.size(), 1));
   f->d_bin_bits = DevAlloc<uint32_t>(std::max<size_t>(f->bin_bits.size(), 1));
@@ -268,8 +301,64 @@ int b200hist_forest_predict_margin(b200hist_forest_t f, b200hist_ellpack_t page,
   B200_API_END();
 }
 
+int b200hist_forest_set_tree_groups(b200hist_forest_t f, const uint32_t* groups_host, uint32_t n_trees) {
+  B200_API_BEGIN();
+  B200_CHECK(f != nullptr && (groups_host != nullptr || n_trees == 0), "null argument");
+  B200_CHECK(n_trees == f->roots.size(), "one group per tree of the forest");
+  f->groups.assign(groups_host, groups_host + n_trees);
+  f->dirty = true;
+  B200_API_END();
+}
+
+int b200hist_forest_predict_margin_groups(b200hist_forest_t f, b200hist_ellpack_t page, uint32_t tree_begin,
+                                          uint32_t tree_end, uint32_t n_groups, uint64_t row_begin, uint64_t n_rows,
+                                          float* out_dev, void* stream) {
+  B200_API_BEGIN();
+  B200_CHECK(f != nullptr && page != nullptr && (out_dev != nullptr || n_rows == 0), "null argument");
+  B200_CHECK(n_groups >= 1, "at least one output group");
+  B200_CHECK(tree_begin <= tree_end && tree_end <= f->roots.size(), "tree range out of bounds");
+  B200_CHECK(row_begin + n_rows <= page->n_rows, "row range exceeds the page");
+  for (uint32_t t = tree_begin; t < tree_end; ++t) B200_CHECK(f->groups[t] < n_groups, "tree group out of range");
+  CheckPage(f, page);
+  if (n_rows == 0 || tree_begin == tree_end) return 0;
+  DeviceGuard guard(f->device);
+  auto s = static_cast<cudaStream_t>(stream);
+  SyncForest(f, s);
+  ForestView fv{f->d_nodes, f->d_roots, f->d_bin_bits, f->bin_words};
+  fv.tree_group = f->d_groups;
+  const EllView view = page->View();
+  const uint64_t total = n_rows * (uint64_t)n_groups;
+  const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)NumSMs(f->device) * 16);
+  if (page->is_sparse) {
+    PredictMarginGroupsKernel<uint32_t><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, n_groups, row_begin,
+                                                               n_rows, out_dev);
+  } else if (page->bin_bytes == 1) {
+    PredictMarginGroupsKernel<uint8_t><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, n_groups, row_begin,
+                                                              n_rows, out_dev);
+  } else {
+    PredictMarginGroupsKernel<uint16_t><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, n_groups, row_begin,
+                                                               n_rows, out_dev);
+  }
+  B200_LAUNCHED();
+  B200_API_END();
+}
+
 int b200hist_forest_predict_leaf(b200hist_forest_t f, b200hist_ellpack_t page, uint32_t tree_begin, uint32_t tree_end,
                                  uint64_t row_begin, uint64_t n_rows, int32_t* out_dev, void* stream) {
+  return PredictLeafImpl<int32_t>(f, page, tree_begin, tree_end, row_begin, n_rows, out_dev, stream);
+}
+
+int b200hist_forest_predict_leaf_f32(b200hist_forest_t f, b200hist_ellpack_t page, uint32_t tree_begin,
+                                     uint32_t tree_end, uint64_t row_begin, uint64_t n_rows, float* out_dev,
+                                     void* stream) {
+  return PredictLeafImpl<float>(f, page, tree_begin, tree_end, row_begin, n_rows, out_dev, stream);
+}
+
+}  // extern "C"
+
+template <typename OutT>
+static int PredictLeafImpl(b200hist_forest_t f, b200hist_ellpack_t page, uint32_t tree_begin, uint32_t tree_end,
+                           uint64_t row_begin, uint64_t n_rows, OutT* out_dev, void* stream) {
   B200_API_BEGIN();
   B200_CHECK(f != nullptr && page != nullptr && (out_dev != nullptr || n_rows == 0), "null argument");
   B200_CHECK(tree_begin <= tree_end && tree_end <= f->roots.size(), "tree range out of bounds");
@@ -284,15 +373,13 @@ int b200hist_forest_predict_leaf(b200hist_forest_t f, b200hist_ellpack_t page, u
   const uint64_t total = n_rows * (uint64_t)(tree_end - tree_begin);
   const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)NumSMs(f->device) * 16);
   if (page->is_sparse) {
-    PredictLeafKernel<uint32_t><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, row_begin, n_rows, out_dev);
+    PredictLeafKernel<uint32_t, OutT><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, row_begin, n_rows, out_dev);
   } else if (page->bin_bytes == 1) {
-    PredictLeafKernel<uint8_t><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, row_begin, n_rows, out_dev);
+    PredictLeafKernel<uint8_t, OutT><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, row_begin, n_rows, out_dev);
   } else {
-    PredictLeafKernel<uint16_t><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, row_begin, n_rows, out_dev);
+    PredictLeafKernel<uint16_t, OutT><<<blocks, 256, 0, s>>>(view, fv, tree_begin, tree_end, row_begin, n_rows, out_dev);
   }
   B200_LAUNCHED();
   B200_API_END();
 }
-
-}  // extern "C"
 #endif  // B200_KERNELS_ONLY

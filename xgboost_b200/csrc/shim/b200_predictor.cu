@@ -4,9 +4,10 @@
 // xgboost::Predictor (/root/reference/include/xgboost/predictor.h:63-178), keeps the reference's own "gpu_predictor"
 // alive inside itself and forwards EVERYTHING to it except the one call the hot path owns:
 //
-//   PredictBatch on a DMatrix that has no SparsePage, i.e. a QuantileDMatrix (src/predictor/gpu_predictor.cu:565-589
-//   routes exactly those through EllpackLoader), one output per row, no tree weights, no category re-coding, no
-//   column split, trees [tree_begin, tree_end) all single-target.
+//   PredictBatch and PredictLeaf on a DMatrix that has no SparsePage, i.e. a QuantileDMatrix
+//   (src/predictor/gpu_predictor.cu:565-589 routes exactly those through EllpackLoader), scalar leaves (one output
+//   per row, or one per class with tree_info naming each tree's output), no tree weights, no category re-coding, no
+//   column split.
 //
 // That is the call GBTree::PredictBatchImpl makes for a validation set every boosting iteration
 // (src/gbm/gbtree.cc:514-560: tree_begin = the cache's version, so only the NEW trees are walked).  Anything else --
@@ -59,8 +60,9 @@ class B200Predictor : public Predictor {
                     bst_tree_t tree_begin, bst_tree_t tree_end = 0,
                     std::vector<float> const* tree_weights = nullptr) const override {
     bst_tree_t const end = tree_end == 0 ? static_cast<bst_tree_t>(model.trees.size()) : tree_end;
-    if (this->Eligible(dmat, out_preds->predictions, model, tree_begin, end, tree_weights) &&
-        this->PredictQuantised(dmat, &out_preds->predictions, model, tree_begin, end)) {
+    if (this->Eligible(dmat, model, tree_begin, end, tree_weights) &&
+        out_preds->predictions.Size() == dmat->Info().num_row_ * model.learner_model_param->OutputLength() &&
+        this->PredictQuantised(dmat, &out_preds->predictions, model, tree_begin, end, /*leaf=*/false)) {
       return;
     }
     ref_->PredictBatch(dmat, out_preds, model, tree_begin, tree_end, tree_weights);
@@ -73,6 +75,15 @@ class B200Predictor : public Predictor {
   }
   void PredictLeaf(DMatrix* dmat, HostDeviceVector<float>* out_preds, gbm::GBTreeModel const& model,
                    bst_tree_t tree_end = 0) const override {
+    // GPUPredictor::PredictLeaf (gpu_predictor.cu:793-830): trees [0, GetTreeLimit), ids as floats, row-major
+    bst_tree_t const end = tree_end == 0 || tree_end > static_cast<bst_tree_t>(model.trees.size())
+                               ? static_cast<bst_tree_t>(model.trees.size())
+                               : tree_end;
+    if (this->Eligible(dmat, model, 0, end, nullptr)) {
+      out_preds->SetDevice(ctx_->Device());
+      out_preds->Resize(dmat->Info().num_row_ * static_cast<std::size_t>(end));
+      if (this->PredictQuantised(dmat, out_preds, model, 0, end, /*leaf=*/true)) return;
+    }
     ref_->PredictLeaf(dmat, out_preds, model, tree_end);
   }
   void PredictContribution(DMatrix* dmat, HostDeviceVector<float>* out_contribs, gbm::GBTreeModel const& model,
@@ -92,16 +103,17 @@ class B200Predictor : public Predictor {
  private:
   // The conditions under which GPUPredictor::PredictDMatrix (gpu_predictor.cu:627-660) reaches EllpackLoader with
   // the no-op category accessor and unit tree weights -- the only configuration the forest kernels restate.
-  bool Eligible(DMatrix* dmat, HostDeviceVector<float> const& out, gbm::GBTreeModel const& model, bst_tree_t begin,
-                bst_tree_t end, std::vector<float> const* tree_weights) const {
+  bool Eligible(DMatrix* dmat, gbm::GBTreeModel const& model, bst_tree_t begin, bst_tree_t end,
+                std::vector<float> const* tree_weights) const {
     if (!ctx_->IsCUDA() || tree_weights != nullptr || end <= begin) return false;
     if (end > static_cast<bst_tree_t>(model.trees.size())) return false;
     auto const& info = dmat->Info();
-    if (info.IsColumnSplit() || model.learner_model_param->OutputLength() != 1) return false;
+    if (info.IsColumnSplit() || model.learner_model_param->IsVectorLeaf()) return false;
+    if (model.learner_model_param->OutputLength() > 1 &&
+        model.tree_info.Size() < static_cast<std::size_t>(end)) return false;
     if (dmat->PageExists<SparsePage>() || !dmat->PageExists<EllpackPage>() || !dmat->SingleColBlock()) return false;
     if (dmat->Cats() != nullptr && dmat->Cats()->NeedRecode()) return false;
     if (info.num_col_ > model.learner_model_param->num_feature) return false;  // the reference raises its own error
-    if (out.Size() != info.num_row_) return false;
     for (bst_tree_t t = begin; t < end; ++t) {
       if (model.trees[t]->IsMultiTarget()) return false;
     }
@@ -209,12 +221,23 @@ class B200Predictor : public Predictor {
         return false;  // e.g. a pruned tree whose node ids are no longer in expansion order
       }
     }
+    auto const n_groups = model.learner_model_param->OutputLength();
+    if (n_groups > 1) {  // gbm::GBTreeModel::tree_info: the output every tree feeds
+      auto const& info = model.tree_info.ConstHostVector();
+      std::vector<std::uint32_t> groups(info.cbegin() + begin, info.cbegin() + end);
+      if (b200hist_forest_set_tree_groups(forest, groups.data(), static_cast<std::uint32_t>(groups.size())) != 0) {
+        b200hist_forest_destroy(forest);
+        return false;
+      }
+    }
     *out = forest;
     return true;
   }
 
+  // leaf == false: margins are ADDED to out_preds (n_rows x n_groups); leaf == true: out_preds (n_rows x n_trees) is
+  // overwritten with leaf ids.
   bool PredictQuantised(DMatrix* dmat, HostDeviceVector<float>* out_preds, gbm::GBTreeModel const& model,
-                        bst_tree_t begin, bst_tree_t end) const {
+                        bst_tree_t begin, bst_tree_t end, bool leaf) const {
     std::lock_guard<std::mutex> guard{mu_};
     out_preds->SetDevice(ctx_->Device());
     auto* stream = static_cast<void*>(ctx_->CUDACtx()->Stream());
@@ -225,13 +248,22 @@ class B200Predictor : public Predictor {
       auto const* impl = page.Impl();
       ok = this->FitScratch(impl) && this->BuildForest(model, begin, end, &forest);
       if (!ok) break;
+      auto const n_trees = static_cast<std::uint32_t>(end - begin);
+      auto const n_rows = static_cast<std::uint64_t>(impl->n_rows);
+      auto const n_groups = static_cast<std::uint32_t>(model.learner_model_param->OutputLength());
       ok = b200hist_ellpack_import_reference_rows(
-               scratch_, 0, static_cast<std::uint64_t>(impl->n_rows), impl->gidx_buffer.data(),
-               static_cast<std::uint32_t>(impl->info.row_stride), static_cast<std::uint32_t>(impl->NumSymbols()),
-               impl->IsDense() ? 1 : 0, stream) == 0 &&
-           b200hist_forest_predict_margin(forest, scratch_, 0, static_cast<std::uint32_t>(end - begin), 0,
-                                          static_cast<std::uint64_t>(impl->n_rows),
-                                          out_preds->DevicePointer() + offset, stream) == 0;
+               scratch_, 0, n_rows, impl->gidx_buffer.data(), static_cast<std::uint32_t>(impl->info.row_stride),
+               static_cast<std::uint32_t>(impl->NumSymbols()), impl->IsDense() ? 1 : 0, stream) == 0;
+      if (ok && leaf) {
+        ok = b200hist_forest_predict_leaf_f32(forest, scratch_, 0, n_trees, 0, n_rows,
+                                              out_preds->DevicePointer() + offset * n_trees, stream) == 0;
+      } else if (ok && n_groups == 1) {
+        ok = b200hist_forest_predict_margin(forest, scratch_, 0, n_trees, 0, n_rows,
+                                            out_preds->DevicePointer() + offset, stream) == 0;
+      } else if (ok) {
+        ok = b200hist_forest_predict_margin_groups(forest, scratch_, 0, n_trees, n_groups, 0, n_rows,
+                                                   out_preds->DevicePointer() + offset * n_groups, stream) == 0;
+      }
       ctx_->CUDACtx()->Stream().Sync();  // the forest is freed below; the reference may recycle the page
       b200hist_forest_destroy(forest);
       forest = nullptr;

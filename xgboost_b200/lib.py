@@ -148,6 +148,11 @@ _SIGNATURES = {
                                                c_void_p]),
     "b200hist_forest_predict_leaf": (c_int, [c_void_p, c_void_p, c_uint32, c_uint32, c_uint64, c_uint64, c_void_p,
                                              c_void_p]),
+    "b200hist_forest_predict_leaf_f32": (c_int, [c_void_p, c_void_p, c_uint32, c_uint32, c_uint64, c_uint64, c_void_p,
+                                                 c_void_p]),
+    "b200hist_forest_set_tree_groups": (c_int, [c_void_p, POINTER(c_uint32), c_uint32]),
+    "b200hist_forest_predict_margin_groups": (c_int, [c_void_p, c_void_p, c_uint32, c_uint32, c_uint32, c_uint64,
+                                                      c_uint64, c_void_p, c_void_p]),
     "b200hist_partition": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_uint64), POINTER(c_uint64),
                                    POINTER(c_int32), POINTER(c_float), POINTER(c_int32), c_int32,
                                    POINTER(c_uint64), c_void_p]),

@@ -425,11 +425,33 @@ class Forest:
                                                         _stream_ptr(out.device)))
         return out
 
-    def predict_leaf(self, page: EllpackPage, tree_begin: int = 0, tree_end: Optional[int] = None) -> torch.Tensor:
+    def predict_leaf(self, page: EllpackPage, tree_begin: int = 0, tree_end: Optional[int] = None,
+                     as_float: bool = False) -> torch.Tensor:
+        """Leaf ids [n_rows, n_trees]; as_float: stored as float32, the layout Predictor::PredictLeaf returns."""
         te = self.num_trees if tree_end is None else int(tree_end)
-        out = torch.empty((page.n_rows, te - tree_begin), dtype=torch.int32, device=torch.device("cuda", page.device))
-        _l.check(_l.load().b200hist_forest_predict_leaf(self._h, page.handle, int(tree_begin), te, 0, page.n_rows,
-                                                      c_void_p(out.data_ptr()), _stream_ptr(out.device)))
+        out = torch.empty((page.n_rows, te - tree_begin), dtype=torch.float32 if as_float else torch.int32,
+                          device=torch.device("cuda", page.device))
+        fn = _l.load().b200hist_forest_predict_leaf_f32 if as_float else _l.load().b200hist_forest_predict_leaf
+        _l.check(fn(self._h, page.handle, int(tree_begin), te, 0, page.n_rows, c_void_p(out.data_ptr()),
+                    _stream_ptr(out.device)))
+        return out
+
+    def set_tree_groups(self, groups: Sequence[int]) -> None:
+        """Output group of every tree added so far (gbm::GBTreeModel::tree_info; multi-class)."""
+        g = np.ascontiguousarray(groups, dtype=np.uint32)
+        _l.check(_l.load().b200hist_forest_set_tree_groups(self._h, g.ctypes.data_as(POINTER(c_uint32)), g.size))
+
+    def predict_margin_groups(self, page: EllpackPage, out: torch.Tensor, n_groups: int, tree_begin: int = 0,
+                              tree_end: Optional[int] = None, row_begin: int = 0) -> torch.Tensor:
+        """out[k, g] += the leaves row row_begin + k reaches in the trees of group g, one after the other in tree
+        order (the reference's multi-group rule: straight onto the output)."""
+        _require_cuda(out, "out")
+        if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() % int(n_groups) != 0:
+            raise ValueError("out must be contiguous float32 [n_rows, n_groups]")
+        te = self.num_trees if tree_end is None else int(tree_end)
+        _l.check(_l.load().b200hist_forest_predict_margin_groups(
+            self._h, page.handle, int(tree_begin), te, int(n_groups), int(row_begin), out.numel() // int(n_groups),
+            c_void_p(out.data_ptr()), _stream_ptr(out.device)))
         return out
 
     def close(self) -> None:
