@@ -503,6 +503,20 @@ B200HIST_API int b200hist_forest_predict_margin_groups(b200hist_forest_t forest,
                                                        uint32_t tree_begin, uint32_t tree_end, uint32_t n_groups,
                                                        uint64_t row_begin, uint64_t n_rows, float* out_dev,
                                                        void* stream);
+/* The same three results straight from a page of the REFERENCE, without importing it: gidx_buffer_dev is
+ * EllpackPageImpl::gidx_buffer (8 bytes of padding, then the MSB-first bit stream of ceil(log2(n_symbols))-bit
+ * symbols, src/common/compressed_iterator.h:37-40,228-268); dense_layout = EllpackPageImpl::IsDenseCompressed
+ * (feature-local symbols, row_stride == n_features), is_dense = no missing values (null = n_symbols - 1 otherwise);
+ * a sparse page holds ascending global bins and is searched per row like EllpackAccessorImpl::GetBinIndex
+ * (src/data/ellpack_page.cuh:101-122).  The page must be quantised with the cuts the forest was created on.
+ * mode 0: out_dev[n_rows] += margin (sum from 0.0f first); 1: out_dev[n_rows * n_groups], leaves straight onto the
+ * output; 2: out_dev[n_rows * n_trees] = leaf ids as floats.  This is what the Predictor binding calls.
+ * STATUS: compiled, equal to the oracle under the CPU emulator, never run on hardware. */
+B200HIST_API int b200hist_forest_predict_reference_page(b200hist_forest_t forest, const uint8_t* gidx_buffer_dev,
+                                                        uint64_t n_rows, uint32_t row_stride, uint32_t n_symbols,
+                                                        int dense_layout, int is_dense, int mode,
+                                                        uint32_t tree_begin, uint32_t tree_end, uint32_t n_groups,
+                                                        float* out_dev, void* stream);
 B200HIST_API int b200hist_forest_predict_leaf_f32(b200hist_forest_t forest, b200hist_ellpack_t page,
                                                   uint32_t tree_begin, uint32_t tree_end, uint64_t row_begin,
                                                   uint64_t n_rows, float* out_dev, void* stream);

@@ -109,6 +109,28 @@ int main(int argc, char** argv) {
       }
       WriteAll(dir + "/margin_groups.bin", gout);
       WriteAll(dir + "/leaves_f32.bin", fleaves);
+      // the same three results straight from the reference's compressed page (ref_page.bin + ref_meta.bin:
+      // row_stride, n_symbols, dense_layout, is_dense)
+      if (std::ifstream(dir + "/ref_page.bin").good()) {
+        auto ref = ReadAll<uint8_t>(dir + "/ref_page.bin");
+        auto rm = ReadAll<uint32_t>(dir + "/ref_meta.bin");
+        b200::RefPageView pg{};
+        pg.buf = ref.data();
+        pg.cut_ptrs = cut_ptrs.data();
+        pg.symbol_bits = 1;
+        while ((1ull << pg.symbol_bits) < rm[1]) ++pg.symbol_bits;
+        pg.row_stride = rm[0];
+        pg.ref_null = (rm[2] && !rm[3]) ? rm[1] - 1 : 0xFFFFFFFFu;
+        pg.total_bins = (uint32_t)cut_values.size();
+        pg.dense_layout = (int32_t)rm[2];
+        std::vector<float> r0 = base, r1 = ReadAll<float>(dir + "/base_groups.bin"), r2((size_t)meta[0] * meta[5]);
+        EMU_LAUNCH((3), (256), 0, b200::PredictRefKernel<0>(pg, fg, 0, meta[5], n_groups, meta[0], r0.data()));
+        EMU_LAUNCH((3), (256), 0, b200::PredictRefKernel<1>(pg, fg, 0, meta[5], n_groups, meta[0], r1.data()));
+        EMU_LAUNCH((3), (256), 0, b200::PredictRefKernel<2>(pg, fg, 0, meta[5], n_groups, meta[0], r2.data()));
+        WriteAll(dir + "/ref_margin.bin", r0);
+        WriteAll(dir + "/ref_margin_groups.bin", r1);
+        WriteAll(dir + "/ref_leaves.bin", r2);
+      }
     }
     return 0;
   }

@@ -175,3 +175,36 @@ def make_categorical_data(case):
     eff = [rng.normal(size=k) for k in CATEGORICAL_N_CATS]
     y = sum(e[np.nan_to_num(c, nan=0).astype(int)] for e, c in zip(eff, cols)) + xn[:, 0] + 0.2 * rng.normal(size=n)
     return x, y.astype(np.float32), ["c"] * len(CATEGORICAL_N_CATS) + ["q"] * 3
+
+
+def pack_reference_page(gbins, cut_ptrs, dense_layout: bool):
+    """A matrix of global bins (-1 = missing) as the reference's EllpackPageImpl::gidx_buffer: 8 bytes of padding, then
+    an MSB-first bit stream of ceil(log2(n_symbols))-bit symbols (src/common/compressed_iterator.h:37-40,140-152,
+    CalcNumSymbols src/data/ellpack_page.cu:140-183).  Dense layout: feature-local bins, null = n_symbols - 1 when any
+    value is missing.  Sparse layout: the row's global bins in ascending order, padded with null = total_bins to the
+    longest row.  Returns (bytes as uint8 array, row_stride, n_symbols, is_dense)."""
+    gb = np.asarray(gbins)
+    cp = np.asarray(cut_ptrs, dtype=np.int64)
+    n, f = gb.shape
+    has_missing = bool((gb < 0).any())
+    if dense_layout:
+        max_bins = int(np.diff(cp).max())
+        n_symbols = max_bins + (1 if has_missing else 0)
+        sym = np.where(gb >= 0, gb - cp[:-1][None, :], n_symbols - 1).astype(np.uint64)
+        row_stride = f
+    else:
+        total = int(cp[-1])
+        n_symbols = total + 1
+        row_stride = max(1, int((gb >= 0).sum(axis=1).max()))
+        sym = np.full((n, row_stride), total, dtype=np.uint64)
+        for r in range(n):
+            present = np.sort(gb[r][gb[r] >= 0])
+            sym[r, :present.size] = present
+    bits = 1
+    while (1 << bits) < n_symbols:
+        bits += 1
+    flat = sym.reshape(-1)
+    stream = ((flat[:, None] >> np.arange(bits - 1, -1, -1, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.uint8)
+    packed = np.packbits(stream.reshape(-1))
+    buf = np.concatenate([np.zeros(8, dtype=np.uint8), packed, np.zeros(8, dtype=np.uint8)])
+    return buf, row_stride, n_symbols, not has_missing

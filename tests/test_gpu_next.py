@@ -662,6 +662,25 @@ def test_forest_prediction_matches_oracle(xb, missing, max_bin):
         gout = forest.predict_margin_groups(pg, torch.from_numpy(gbase.copy()).cuda(), 3)
         gwant = orc.predict_margin_groups(bins, cp, cv, trees, groups, 3, base=gbase)
         assert np.array_equal(gout.cpu().numpy().view(np.uint32), gwant.view(np.uint32))
+        # the same three results straight from the page as the reference stores it (bit-packed gidx_buffer)
+        from tests.helpers import pack_reference_page
+        buf, stride, n_symbols, is_dense = pack_reference_page(bins, cp, dense_layout=True)
+        dbuf = torch.from_numpy(buf).cuda()
+        r0 = forest.predict_reference_page(dbuf, rows, stride, n_symbols, True, is_dense,
+                                           torch.from_numpy(base.copy()).cuda(), mode=0)
+        assert np.array_equal(r0.cpu().numpy().view(np.uint32), want.view(np.uint32))
+        r1 = forest.predict_reference_page(dbuf, rows, stride, n_symbols, True, is_dense,
+                                           torch.from_numpy(gbase.copy()).cuda(), mode=1, n_groups=3)
+        assert np.array_equal(r1.cpu().numpy().view(np.uint32), gwant.view(np.uint32))
+        r2 = forest.predict_reference_page(dbuf, rows, stride, n_symbols, True, is_dense,
+                                           torch.empty((rows, 6), dtype=torch.float32, device="cuda"), mode=2)
+        assert np.array_equal(r2.cpu().numpy(), leaves.astype(np.float32))
+        if missing > 0:   # and from a sparse-layout page (ascending global bins, searched per row)
+            sbuf, sstride, ssym, _ = pack_reference_page(bins, cp, dense_layout=False)
+            r3 = forest.predict_reference_page(torch.from_numpy(sbuf).cuda(), rows, sstride, ssym, False, False,
+                                               torch.from_numpy(base.copy()).cuda(), mode=0)
+            assert np.array_equal(r3.cpu().numpy().view(np.uint32), want.view(np.uint32))
+        forest.set_tree_groups([0] * 6)
         # a tree range and a row range
         part = forest.predict_margin(pg, torch.zeros(1000, device="cuda"), tree_begin=2, tree_end=5, row_begin=123)
         want_part = orc.predict_margin(bins[123:1123], cp, cv, trees[2:5])

@@ -162,6 +162,11 @@ def test_predict_kernel_sources(tmp_path, kind):
     base_groups = np.random.default_rng(3).normal(size=(len(y), n_groups)).astype(np.float32)
     tree_groups.tofile(os.path.join(d, "tree_groups.bin"))
     base_groups.tofile(os.path.join(d, "base_groups.bin"))
+    from tests.helpers import pack_reference_page
+    ref_buf, ref_stride, ref_symbols, ref_is_dense = pack_reference_page(gb, cp, dense_layout=kind != "sparse")
+    ref_buf.tofile(os.path.join(d, "ref_page.bin"))
+    np.array([ref_stride, ref_symbols, 0 if kind == "sparse" else 1, 1 if ref_is_dense else 0],
+             dtype=np.uint32).tofile(os.path.join(d, "ref_meta.bin"))
     _run(exe, "predict", d)
     margin = np.fromfile(os.path.join(d, "margin.bin"), dtype=np.float32)
     leaves = np.fromfile(os.path.join(d, "leaves.bin"), dtype=np.int32).reshape(len(y), len(trees))
@@ -175,6 +180,13 @@ def test_predict_kernel_sources(tmp_path, kind):
     assert np.array_equal(got_groups.view(np.uint32), want_groups.view(np.uint32))
     fleaves = np.fromfile(os.path.join(d, "leaves_f32.bin"), dtype=np.float32).reshape(len(y), len(trees))
     assert np.array_equal(fleaves, leaves.astype(np.float32))
+    # ... and straight from the page as the reference stores it (bit-packed, 6..10-bit symbols here)
+    ref_margin = np.fromfile(os.path.join(d, "ref_margin.bin"), dtype=np.float32)
+    ref_groups = np.fromfile(os.path.join(d, "ref_margin_groups.bin"), dtype=np.float32).reshape(len(y), n_groups)
+    ref_leaves = np.fromfile(os.path.join(d, "ref_leaves.bin"), dtype=np.float32).reshape(len(y), len(trees))
+    assert np.array_equal(ref_margin.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(ref_groups.view(np.uint32), want_groups.view(np.uint32))
+    assert np.array_equal(ref_leaves, leaves.astype(np.float32))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

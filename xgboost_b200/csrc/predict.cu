@@ -137,6 +137,99 @@ __global__ void __launch_bounds__(256) PredictLeafKernel(EllView ell, ForestView
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same walks straight on a page of the REFERENCE (EllpackPageImpl::gidx_buffer: 8 bytes of padding, then an
+// MSB-first bit stream of ceil(log2(n_symbols))-bit symbols, src/common/compressed_iterator.h:37-40,140-152,228-268),
+// so that the Predictor binding does not have to copy the page first.  Dense layout: row_stride == n_features, symbols
+// are feature-local bins, null = n_symbols - 1 when the page has missing values.  Sparse layout: global bins in
+// ascending order, null = total_bins at the end of a row; a feature is found by binary search over the row
+// (EllpackAccessorImpl::GetBinIndex, src/data/ellpack_page.cuh:101-122).
+// ---------------------------------------------------------------------------------------------------------------------
+struct RefPageView {
+  const uint8_t* buf;         // gidx_buffer, including its 8 bytes of padding
+  const uint32_t* cut_ptrs;   // the forest's cuts (device)
+  uint32_t symbol_bits;
+  uint32_t row_stride;
+  uint32_t ref_null;          // dense layout: the null symbol, 0xFFFFFFFF without missing values
+  uint32_t total_bins;
+  int32_t dense_layout;
+};
+
+__device__ __forceinline__ uint32_t RefSymbol(const uint8_t* __restrict__ buf, uint64_t i, uint32_t bits) {
+  const uint64_t bit0 = i * bits;
+  const uint64_t byte0 = bit0 >> 3;
+  const uint32_t shift = (uint32_t)(bit0 & 7);
+  const uint32_t nbytes = (shift + bits + 7) >> 3;
+  uint64_t v = 0;
+  for (uint32_t k = 0; k < nbytes; ++k) v = (v << 8) | __ldg(buf + 8 + byte0 + k);
+  return (uint32_t)((v >> (8 * nbytes - shift - bits)) & ((1ull << bits) - 1ull));
+}
+
+// local bin of (row, feature), -1 when missing
+__device__ __forceinline__ int32_t RefLocalBin(const RefPageView& pg, uint64_t r, uint32_t f) {
+  if (pg.dense_layout) {
+    const uint32_t sym = RefSymbol(pg.buf, r * pg.row_stride + f, pg.symbol_bits);
+    return sym == pg.ref_null ? -1 : (int32_t)sym;
+  }
+  const uint32_t fb = pg.cut_ptrs[f], fe = pg.cut_ptrs[f + 1];
+  uint32_t lo = 0, hi = pg.row_stride;  // first slot whose symbol >= fb
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (RefSymbol(pg.buf, r * pg.row_stride + mid, pg.symbol_bits) < fb) lo = mid + 1; else hi = mid;
+  }
+  if (lo == pg.row_stride) return -1;
+  const uint32_t sym = RefSymbol(pg.buf, r * pg.row_stride + lo, pg.symbol_bits);
+  return sym < fe ? (int32_t)(sym - fb) : -1;
+}
+
+__device__ __forceinline__ uint32_t WalkTreeRef(const RefPageView& pg, const ForestView& fv, uint32_t root, uint64_t r) {
+  uint32_t i = root;
+  PredNode nd = fv.nodes[i];
+  while (nd.findex >= 0) {
+    const int32_t lbin = RefLocalBin(pg, r, (uint32_t)nd.findex);
+    bool left;
+    if (lbin < 0) {
+      left = nd.default_left != 0;
+    } else if (nd.split_lbin < 0) {
+      left = ((__ldg(fv.bin_bits + (size_t)i * fv.bin_words + (lbin >> 5)) >> (lbin & 31)) & 1u) == 0u;
+    } else {
+      left = lbin < nd.split_lbin;
+    }
+    i = (uint32_t)(left ? nd.left : nd.right);
+    nd = fv.nodes[i];
+  }
+  return i;
+}
+
+// kMode 0: one output per row (sum from 0, then added); 1: n_groups outputs per row (leaves straight onto the output);
+// 2: leaf ids as floats, [row][tree].
+template <int kMode>
+__global__ void __launch_bounds__(256) PredictRefKernel(RefPageView pg, ForestView fv, uint32_t tree_begin,
+                                                         uint32_t tree_end, uint32_t n_groups, uint64_t n_rows,
+                                                         float* __restrict__ out) {
+  const uint32_t nt = tree_end - tree_begin;
+  const uint64_t per_row = kMode == 0 ? 1 : (kMode == 1 ? n_groups : nt);
+  for (uint64_t k = blockIdx.x * 256ull + threadIdx.x; k < n_rows * per_row; k += (uint64_t)gridDim.x * 256ull) {
+    const uint64_t row = k / per_row;
+    const uint32_t sub = (uint32_t)(k - row * per_row);
+    if (kMode == 0) {
+      float sum = 0.0f;
+      for (uint32_t t = tree_begin; t < tree_end; ++t) sum += fv.nodes[WalkTreeRef(pg, fv, fv.tree_root[t], row)].leaf_value;
+      out[k] += sum;
+    } else if (kMode == 1) {
+      float acc = out[k];
+      for (uint32_t t = tree_begin; t < tree_end; ++t) {
+        if (__ldg(fv.tree_group + t) == sub) acc += fv.nodes[WalkTreeRef(pg, fv, fv.tree_root[t], row)].leaf_value;
+      }
+      out[k] = acc;
+    } else {
+      const uint32_t t = tree_begin + sub;
+      out[k] = (float)(int32_t)(WalkTreeRef(pg, fv, fv.tree_root[t], row) - fv.tree_root[t]);
+    }
+  }
+}
+
 }  // namespace b200
 
 #ifndef B200_KERNELS_ONLY
@@ -155,6 +248,7 @@ struct b200hist_forest_s {
   uint32_t* d_roots{nullptr};
   uint32_t* d_bin_bits{nullptr};
   uint32_t* d_groups{nullptr};
+  uint32_t* d_cut_ptrs{nullptr};  // device copy of the cuts' feature segments (reference-page path)
   bool dirty{true};
 };
 
@@ -184,6 +278,7 @@ int b200hist_forest_destroy(b200hist_forest_t f) {
     cudaFree(f->d_roots);
     cudaFree(f->d_bin_bits);
     cudaFree(f->d_groups);
+    cudaFree(f->d_cut_ptrs);
     delete f;
   }
   B200_API_END();
@@ -352,6 +447,63 @@ int b200hist_forest_predict_leaf_f32(b200hist_forest_t f, b200hist_ellpack_t pag
                                      uint32_t tree_end, uint64_t row_begin, uint64_t n_rows, float* out_dev,
                                      void* stream) {
   return PredictLeafImpl<float>(f, page, tree_begin, tree_end, row_begin, n_rows, out_dev, stream);
+}
+
+int b200hist_forest_predict_reference_page(b200hist_forest_t f, const uint8_t* gidx_buffer_dev, uint64_t n_rows,
+                                           uint32_t row_stride, uint32_t n_symbols, int dense_layout_in,
+                                           int is_dense, int mode,
+                                           uint32_t tree_begin, uint32_t tree_end, uint32_t n_groups, float* out_dev,
+                                           void* stream) {
+  B200_API_BEGIN();
+  B200_CHECK(f != nullptr && (n_rows == 0 || (gidx_buffer_dev != nullptr && out_dev != nullptr)), "null argument");
+  B200_CHECK(mode >= 0 && mode <= 2, "mode: 0 margin, 1 margin per group, 2 leaf ids");
+  B200_CHECK(tree_begin <= tree_end && tree_end <= f->roots.size(), "tree range out of bounds");
+  B200_CHECK(n_symbols >= 1 && row_stride >= 1, "empty page geometry");
+  const auto* ell = f->ell;
+  const bool dense_layout = dense_layout_in != 0;
+  if (!dense_layout) {
+    B200_CHECK(n_symbols == ell->total_bins + 1, "sparse reference page: n_symbols must be total_bins + 1");
+  } else {
+    B200_CHECK(row_stride == ell->n_features, "dense-layout reference pages need row_stride == n_features");
+    B200_CHECK(n_symbols >= ell->max_feature_bins + (is_dense ? 0u : 1u),
+               "dense reference page: n_symbols below the widest feature (+1 with missing values)");
+  }
+  if (mode == 1) {
+    B200_CHECK(n_groups >= 1, "at least one output group");
+    for (uint32_t t = tree_begin; t < tree_end; ++t) B200_CHECK(f->groups[t] < n_groups, "tree group out of range");
+  }
+  if (n_rows == 0 || tree_begin == tree_end) return 0;
+  DeviceGuard guard(f->device);
+  auto s = static_cast<cudaStream_t>(stream);
+  SyncForest(f, s);
+  if (f->d_cut_ptrs == nullptr) {
+    f->d_cut_ptrs = DevAlloc<uint32_t>(ell->cut_ptrs.size());
+    B200_CUDA(cudaMemcpyAsync(f->d_cut_ptrs, ell->cut_ptrs.data(), sizeof(uint32_t) * ell->cut_ptrs.size(),
+                              cudaMemcpyHostToDevice, s));
+    B200_CUDA(cudaStreamSynchronize(s));
+  }
+  ForestView fv{f->d_nodes, f->d_roots, f->d_bin_bits, f->bin_words};
+  fv.tree_group = f->d_groups;
+  RefPageView pg{};
+  pg.buf = gidx_buffer_dev;
+  pg.cut_ptrs = f->d_cut_ptrs;
+  pg.symbol_bits = 1;
+  while ((1ull << pg.symbol_bits) < n_symbols) ++pg.symbol_bits;  // SymbolBits (compressed_iterator.h:37-40)
+  pg.row_stride = row_stride;
+  pg.ref_null = (dense_layout && !is_dense) ? n_symbols - 1 : 0xFFFFFFFFu;
+  pg.total_bins = ell->total_bins;
+  pg.dense_layout = dense_layout ? 1 : 0;
+  const uint64_t per_row = mode == 0 ? 1 : (mode == 1 ? n_groups : tree_end - tree_begin);
+  const int blocks = (int)std::min<uint64_t>((n_rows * per_row + 255) / 256, (uint64_t)NumSMs(f->device) * 16);
+  if (mode == 0) {
+    PredictRefKernel<0><<<blocks, 256, 0, s>>>(pg, fv, tree_begin, tree_end, n_groups, n_rows, out_dev);
+  } else if (mode == 1) {
+    PredictRefKernel<1><<<blocks, 256, 0, s>>>(pg, fv, tree_begin, tree_end, n_groups, n_rows, out_dev);
+  } else {
+    PredictRefKernel<2><<<blocks, 256, 0, s>>>(pg, fv, tree_begin, tree_end, n_groups, n_rows, out_dev);
+  }
+  B200_LAUNCHED();
+  B200_API_END();
 }
 
 }  // extern "C"

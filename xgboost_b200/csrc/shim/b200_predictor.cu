@@ -9,6 +9,9 @@
 //   per row, or one per class with tree_info naming each tree's output), no tree weights, no category re-coding, no
 //   column split.
 //
+// The page is read in place (b200hist_forest_predict_reference_page decodes EllpackPageImpl::gidx_buffer itself):
+// nothing is copied, and a call costs what the reference's own walk costs in memory traffic.
+//
 // That is the call GBTree::PredictBatchImpl makes for a validation set every boosting iteration
 // (src/gbm/gbtree.cc:514-560: tree_begin = the cache's version, so only the NEW trees are walked).  Anything else --
 // and any tree b200hist_forest_add_tree refuses -- goes to the reference's predictor before an output is touched.
@@ -120,37 +123,19 @@ class B200Predictor : public Predictor {
     return true;
   }
 
-  // One scratch page of ours, reused while the incoming pages keep their shape and cuts; the rows are re-imported on
-  // every call (the reference's page may have been rebuilt behind the same address).
+  // The forest resolves split conditions against a page object of ours that carries the cuts; a one-row page is all
+  // it needs (the rows are read straight from the reference's buffer).  Rebuilt when the cuts change.
   bool FitScratch(EllpackPageImpl const* impl) const {
     auto cuts = impl->CutsShared();
     auto const& ptrs = cuts->cut_ptrs_.ConstHostVector();
     auto const& vals = cuts->cut_values_.ConstHostVector();
-    bool const dense_layout = impl->IsDenseCompressed();
-    int const has_missing = impl->IsDense() ? 0 : 1;
-    auto const stride = static_cast<std::uint32_t>(impl->info.row_stride);
-    if (scratch_ != nullptr && scratch_rows_ >= impl->n_rows && scratch_dense_layout_ == dense_layout &&
-        scratch_has_missing_ == has_missing && scratch_stride_ == stride && scratch_ptrs_ == ptrs &&
-        scratch_vals_ == vals) {
-      return true;
-    }
+    if (scratch_ != nullptr && scratch_ptrs_ == ptrs && scratch_vals_ == vals) return true;
     this->ReleaseScratch();
-    int rc;
-    if (dense_layout) {
-      rc = b200hist_ellpack_create(ctx_->Ordinal(), impl->n_rows, static_cast<std::uint32_t>(ptrs.size() - 1),
-                                   ptrs.data(), vals.data(), has_missing, &scratch_);
-    } else {
-      rc = b200hist_ellpack_create_sparse(ctx_->Ordinal(), impl->n_rows, static_cast<std::uint32_t>(ptrs.size() - 1),
-                                          ptrs.data(), vals.data(), stride, &scratch_);
-    }
-    if (rc != 0) {
+    if (b200hist_ellpack_create(ctx_->Ordinal(), 1, static_cast<std::uint32_t>(ptrs.size() - 1), ptrs.data(),
+                                vals.data(), /*has_missing=*/1, &scratch_) != 0) {
       scratch_ = nullptr;
       return false;
     }
-    scratch_rows_ = impl->n_rows;
-    scratch_dense_layout_ = dense_layout;
-    scratch_has_missing_ = has_missing;
-    scratch_stride_ = stride;
     scratch_ptrs_ = ptrs;
     scratch_vals_ = vals;
     return true;
@@ -159,7 +144,6 @@ class B200Predictor : public Predictor {
   void ReleaseScratch() const {
     if (scratch_ != nullptr) b200hist_ellpack_destroy(scratch_);
     scratch_ = nullptr;
-    scratch_rows_ = 0;
   }
 
   // Trees [begin, end) of the model as the C ABI's node arrays, resolved against the scratch page's cuts.
@@ -251,19 +235,15 @@ class B200Predictor : public Predictor {
       auto const n_trees = static_cast<std::uint32_t>(end - begin);
       auto const n_rows = static_cast<std::uint64_t>(impl->n_rows);
       auto const n_groups = static_cast<std::uint32_t>(model.learner_model_param->OutputLength());
-      ok = b200hist_ellpack_import_reference_rows(
-               scratch_, 0, n_rows, impl->gidx_buffer.data(), static_cast<std::uint32_t>(impl->info.row_stride),
-               static_cast<std::uint32_t>(impl->NumSymbols()), impl->IsDense() ? 1 : 0, stream) == 0;
-      if (ok && leaf) {
-        ok = b200hist_forest_predict_leaf_f32(forest, scratch_, 0, n_trees, 0, n_rows,
-                                              out_preds->DevicePointer() + offset * n_trees, stream) == 0;
-      } else if (ok && n_groups == 1) {
-        ok = b200hist_forest_predict_margin(forest, scratch_, 0, n_trees, 0, n_rows,
-                                            out_preds->DevicePointer() + offset, stream) == 0;
-      } else if (ok) {
-        ok = b200hist_forest_predict_margin_groups(forest, scratch_, 0, n_trees, n_groups, 0, n_rows,
-                                                   out_preds->DevicePointer() + offset * n_groups, stream) == 0;
-      }
+      // EllpackPageImpl: gidx_buffer, info.row_stride, NumSymbols, IsDenseCompressed, IsDense
+      // (src/data/ellpack_page.cuh:181-391) -- read in place, nothing is copied
+      int const mode = leaf ? 2 : (n_groups == 1 ? 0 : 1);
+      std::uint64_t const width = leaf ? n_trees : n_groups;
+      ok = b200hist_forest_predict_reference_page(
+               forest, impl->gidx_buffer.data(), n_rows, static_cast<std::uint32_t>(impl->info.row_stride),
+               static_cast<std::uint32_t>(impl->NumSymbols()), impl->IsDenseCompressed() ? 1 : 0,
+               impl->IsDense() ? 1 : 0, mode, 0, n_trees, n_groups, out_preds->DevicePointer() + offset * width,
+               stream) == 0;
       ctx_->CUDACtx()->Stream().Sync();  // the forest is freed below; the reference may recycle the page
       b200hist_forest_destroy(forest);
       forest = nullptr;
@@ -278,10 +258,6 @@ class B200Predictor : public Predictor {
   std::unique_ptr<Predictor> ref_;
   mutable std::mutex mu_;
   mutable b200hist_ellpack_t scratch_{nullptr};
-  mutable bst_idx_t scratch_rows_{0};
-  mutable bool scratch_dense_layout_{true};
-  mutable int scratch_has_missing_{0};
-  mutable std::uint32_t scratch_stride_{0};
   mutable std::vector<std::uint32_t> scratch_ptrs_;
   mutable std::vector<float> scratch_vals_;
 };

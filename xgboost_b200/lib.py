@@ -150,6 +150,8 @@ _SIGNATURES = {
                                              c_void_p]),
     "b200hist_forest_predict_leaf_f32": (c_int, [c_void_p, c_void_p, c_uint32, c_uint32, c_uint64, c_uint64, c_void_p,
                                                  c_void_p]),
+    "b200hist_forest_predict_reference_page": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_int, c_int,
+                                                       c_int, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p]),
     "b200hist_forest_set_tree_groups": (c_int, [c_void_p, POINTER(c_uint32), c_uint32]),
     "b200hist_forest_predict_margin_groups": (c_int, [c_void_p, c_void_p, c_uint32, c_uint32, c_uint32, c_uint64,
                                                       c_uint64, c_void_p, c_void_p]),

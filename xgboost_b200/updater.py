@@ -436,6 +436,23 @@ class Forest:
                     _stream_ptr(out.device)))
         return out
 
+    def predict_reference_page(self, gidx_buffer: torch.Tensor, n_rows: int, row_stride: int, n_symbols: int,
+                               dense_layout: bool, is_dense: bool, out: torch.Tensor, mode: int = 0, n_groups: int = 1,
+                               tree_begin: int = 0, tree_end: Optional[int] = None) -> torch.Tensor:
+        """Predict straight from a reference EllpackPage's compressed buffer (uint8 CUDA tensor incl. its 8 bytes of
+        padding).  mode 0: out[n_rows] += margin; 1: out[n_rows, n_groups] += per class; 2: out[n_rows, n_trees] = leaf
+        ids as floats."""
+        _require_cuda(out, "out")
+        _require_cuda(gidx_buffer, "gidx_buffer")
+        if out.dtype != torch.float32 or not out.is_contiguous() or gidx_buffer.dtype != torch.uint8:
+            raise ValueError("out must be contiguous float32, gidx_buffer uint8")
+        te = self.num_trees if tree_end is None else int(tree_end)
+        _l.check(_l.load().b200hist_forest_predict_reference_page(
+            self._h, c_void_p(gidx_buffer.data_ptr()), int(n_rows), int(row_stride), int(n_symbols),
+            1 if dense_layout else 0, 1 if is_dense else 0, int(mode), int(tree_begin), te, int(n_groups),
+            c_void_p(out.data_ptr()), _stream_ptr(out.device)))
+        return out
+
     def set_tree_groups(self, groups: Sequence[int]) -> None:
         """Output group of every tree added so far (gbm::GBTreeModel::tree_info; multi-class)."""
         g = np.ascontiguousarray(groups, dtype=np.uint32)
