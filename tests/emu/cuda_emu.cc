@@ -2,6 +2,9 @@
 
 #include <atomic>
 #include <memory>
+#ifdef __SANITIZE_ADDRESS__
+#include <sanitizer/asan_interface.h>
+#endif
 
 namespace emu {
 
@@ -101,7 +104,16 @@ void Launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>&
           w->bar.Drop();
           blk.bar.Drop();
         };
+#ifdef __SANITIZE_ADDRESS__
+        // the slack behind the CTA's dynamic shared memory is off limits: an index past what the launch asked for
+        // is a report, as it would be a fault (or a neighbour's data) on the device
+        const size_t used = (dyn_smem + 7) / 8 * 8;
+        ASAN_POISON_MEMORY_REGION(blk.dyn.data() + used, blk.dyn.size() - used);
+#endif
         ThePool().Run(n_threads, job);
+#ifdef __SANITIZE_ADDRESS__
+        ASAN_UNPOISON_MEMORY_REGION(blk.dyn.data() + used, blk.dyn.size() - used);
+#endif
       }
 }
 

@@ -37,11 +37,12 @@
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
-struct longlong2 { long long x, y; };
-struct float2 { float x, y; };
-struct float4 { float x, y, z, w; };
-struct uint4 { unsigned x, y, z, w; };
-struct uint2 { unsigned x, y; };
+// aligned like the device types, so that -fsanitize=undefined reports a vector access the hardware would fault on
+struct alignas(16) longlong2 { long long x, y; };
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
 inline longlong2 make_longlong2(long long a, long long b) { return longlong2{a, b}; }
 inline float2 make_float2(float a, float b) { return float2{a, b}; }
 inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }

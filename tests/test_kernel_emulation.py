@@ -21,15 +21,24 @@ EMU = os.path.join(ROOT, "tests", "emu")
 BUILD = os.path.join(ROOT, "build", "emu")
 
 
+# B200_EMU_SANITIZE=address|thread|undefined builds the harnesses with that sanitizer into their own directory: the
+# kernels' global buffers are heap vectors and their __shared__ arrays function statics, so an out-of-bounds index in
+# kernel text is an ASan report (and a non-zero exit) instead of a silently wrong neighbour.
+SANITIZE = os.environ.get("B200_EMU_SANITIZE", "")
+
+
 def _build(name):
-    os.makedirs(BUILD, exist_ok=True)
-    exe = os.path.join(BUILD, name)
+    build = BUILD + ("_" + SANITIZE if SANITIZE else "")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, name)
     srcs = [os.path.join(EMU, name + ".cc"), os.path.join(EMU, "cuda_emu.cc")]
     csrc = os.path.join(ROOT, "xgboost_b200", "csrc")
     deps = srcs + [os.path.join(EMU, "cuda_emu.h")] + \
         [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))]
     if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
-        subprocess.run(["g++", "-std=c++17", "-O1", "-pthread", "-I" + os.path.join(EMU, "include"), "-I" + EMU,
+        extra = ["-fsanitize=" + SANITIZE, "-g", "-fno-omit-frame-pointer"] if SANITIZE else []
+        subprocess.run(["g++", "-std=c++17", "-O1", "-pthread"] + extra +
+                       ["-I" + os.path.join(EMU, "include"), "-I" + EMU,
                         "-I" + os.path.join(ROOT, "include"), "-I" + csrc, "-o", exe] + srcs, check=True)
     return exe
 
