@@ -14,6 +14,11 @@
 #include "../../xgboost_b200/csrc/partition.cu"
 #include "../../xgboost_b200/csrc/updater.cu"
 
+// The fixed-point sums wrap as the device's 64-bit atomics do (a zero hessian total quantises to INT64_MIN): the host
+// restatement adds them as unsigned so that the wrap is defined behaviour here too.
+static inline long long WrapAdd(long long a, long long b) { return (long long)((unsigned long long)a + (unsigned long long)b); }
+static inline long long WrapSub(long long a, long long b) { return (long long)((unsigned long long)a - (unsigned long long)b); }
+
 using namespace b200;
 
 int main(int argc, char** argv) {
@@ -193,8 +198,8 @@ int main(int argc, char** argv) {
           const uint32_t* row = reinterpret_cast<const uint32_t*>(bins.data()) + (size_t)r * view.row_stride;
           for (uint32_t k = 0; k < view.row_stride; ++k) {
             if (row[k] >= view.total_bins) continue;
-            h[row[k]].x += gq[r].x;
-            h[row[k]].y += gq[r].y;
+            h[row[k]].x = WrapAdd(h[row[k]].x, gq[r].x);
+            h[row[k]].y = WrapAdd(h[row[k]].y, gq[r].y);
           }
           continue;
         }
@@ -202,8 +207,8 @@ int main(int argc, char** argv) {
           const uint32_t sym = view.bin_bytes == 1 ? (uint32_t)bins[(size_t)r * view.row_bytes + f]
                                                    : (uint32_t)reinterpret_cast<const uint16_t*>(bins.data() + (size_t)r * view.row_bytes)[f];
           if (sym == view.null_symbol) continue;
-          h[cut_ptrs[f] + sym].x += gq[r].x;
-          h[cut_ptrs[f] + sym].y += gq[r].y;
+          h[cut_ptrs[f] + sym].x = WrapAdd(h[cut_ptrs[f] + sym].x, gq[r].x);
+          h[cut_ptrs[f] + sym].y = WrapAdd(h[cut_ptrs[f] + sym].y, gq[r].y);
         }
       }
     }
@@ -212,8 +217,8 @@ int main(int argc, char** argv) {
     for (int k = 0; k < ts.n_sub; ++k) {
       const SubEntry e = sub[k];
       for (uint32_t b = 0; b < view.total_bins; ++b) {
-        hist[(size_t)e.sub * view.total_bins + b].x = hist[(size_t)e.parent * view.total_bins + b].x - hist[(size_t)e.built * view.total_bins + b].x;
-        hist[(size_t)e.sub * view.total_bins + b].y = hist[(size_t)e.parent * view.total_bins + b].y - hist[(size_t)e.built * view.total_bins + b].y;
+        hist[(size_t)e.sub * view.total_bins + b].x = WrapSub(hist[(size_t)e.parent * view.total_bins + b].x, hist[(size_t)e.built * view.total_bins + b].x);
+        hist[(size_t)e.sub * view.total_bins + b].y = WrapSub(hist[(size_t)e.parent * view.total_bins + b].y, hist[(size_t)e.built * view.total_bins + b].y);
       }
     }
   };

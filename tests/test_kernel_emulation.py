@@ -36,7 +36,8 @@ def _build(name):
     deps = srcs + [os.path.join(EMU, "cuda_emu.h")] + \
         [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))]
     if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
-        extra = ["-fsanitize=" + SANITIZE, "-g", "-fno-omit-frame-pointer"] if SANITIZE else []
+        # -fno-sanitize-recover: a UBSan finding ends the harness non-zero instead of printing and carrying on
+        extra = ["-fsanitize=" + SANITIZE, "-fno-sanitize-recover=all", "-g", "-fno-omit-frame-pointer"] if SANITIZE else []
         subprocess.run(["g++", "-std=c++17", "-O1", "-pthread"] + extra +
                        ["-I" + os.path.join(EMU, "include"), "-I" + EMU,
                         "-I" + os.path.join(ROOT, "include"), "-I" + csrc, "-o", exe] + srcs, check=True)
@@ -675,7 +676,7 @@ def _same_tree(nodes, pos, o, flags=None, bits=None):
 
 def _tree_data(n=2500, f=8, max_bin=24, missing=0.0, seed=13, zero_hess=False):
     x, y = make_regression(n, f, seed=seed, missing=missing)
-    y = (y + x[:, 0] * np.nan_to_num(x[:, 1]) - np.nan_to_num(x[:, 2]) * np.nan_to_num(x[:, 3])).astype(np.float32)
+    y = (y + np.nan_to_num(x[:, 0]) * np.nan_to_num(x[:, 1]) - np.nan_to_num(x[:, 2]) * np.nan_to_num(x[:, 3])).astype(np.float32)
     cp, cv = make_cuts(x, max_bin)
     gb = orc.bin_dense(x, cp, cv)
     gp = squared_error_gpair(np.zeros_like(y), y)
