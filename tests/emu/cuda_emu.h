@@ -78,7 +78,7 @@ class Barrier {  // reusable; a thread that returns from the kernel drops out
     const uint64_t g = gen_;
     if (++waiting_ >= expected_) {
       waiting_ = 0;
-      ++gen_;
+      Advance();
       l.unlock();
       cv_.notify_all();
       return;
@@ -96,9 +96,12 @@ class Barrier {  // reusable; a thread that returns from the kernel drops out
   void Drop() {
     std::unique_lock<std::mutex> l(m_);
     --expected_;
-    if (expected_ > 0 && waiting_ >= expected_) { waiting_ = 0; ++gen_; l.unlock(); cv_.notify_all(); }
+    if (expected_ > 0 && waiting_ >= expected_) { waiting_ = 0; Advance(); l.unlock(); cv_.notify_all(); }
   }
  private:
+  // a release store: the spinning waiters leave on an acquire load without taking the mutex, and what the other
+  // threads wrote before the barrier must be ordered before what they read after it (for -fsanitize=thread as well)
+  void Advance() { __atomic_store_n(&gen_, gen_ + 1, __ATOMIC_RELEASE); }
   std::mutex m_;
   std::condition_variable cv_;
   int expected_, waiting_{0};
