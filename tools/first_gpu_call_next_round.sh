@@ -19,3 +19,10 @@ timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_line.json 2>
 echo "bench rc=$?"
 tail -5 gpurun_out/next_tests.log gpurun_out/gpu_suite.log
 cat gpurun_out/bench_line.json
+# 4. DESIGN (f) rank 1: can TMA gather4 carry the histogram kernel's row gathers?  (compiles here: the box has nvcc;
+#    cross-compiled clean in round 1, never run -- its own timeout keeps a wedged copy from costing the call)
+timeout 200 nvcc -O3 -lineinfo -std=c++17 -gencode arch=compute_100a,code=sm_100a -o /tmp/gather4_throughput \
+  tools/gather4_throughput.cu -lcuda > gpurun_out/gather4_build.log 2>&1 \
+  && timeout 120 /tmp/gather4_throughput > gpurun_out/gather4_throughput.log 2>&1
+echo "gather4 rc=$?"
+tail -30 gpurun_out/gather4_throughput.log 2>/dev/null
