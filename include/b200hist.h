@@ -219,6 +219,20 @@ B200HIST_API int b200hist_updater_update_tree_host(b200hist_updater_t u, const f
  * preds_dev[i] += leaf_value[decode(position[i])] for the last tree built. */
 B200HIST_API int b200hist_updater_update_prediction_cache(b200hist_updater_t u, float* preds_dev,
                                                           void* stream);
+/* The same with everything the reference's call can vary (updater_gpu_hist.cu:582-608):
+ *   stride            elements between consecutive rows of the output column -- GBTree::DoBoost hands class `gid` of a
+ *                     multi-class model as out.Slice(All, gid): Values() starts at column gid, Stride(0) = n_groups
+ *                     (src/gbm/gbtree.cc:224-253);
+ *   position_dev      the positions Update wrote (NULL = the buffer of the last Update call, which the caller must
+ *                     then still own);
+ *   leaf_values_host  leaf value per node id of the last tree (NULL = the values Update computed): adaptive
+ *                     objectives rewrite RegTree's leaves between Update and UpdatePredictionCache
+ *                     (ObjFunction::UpdateTreeLeaf, src/objective/adaptive.cu), the reference therefore reads
+ *                     p_tree->GetNodes() here. */
+B200HIST_API int b200hist_updater_update_prediction_cache_ex(b200hist_updater_t u, float* preds_dev, uint64_t stride,
+                                                             const int32_t* position_dev,
+                                                             const float* leaf_values_host, int32_t n_leaf_values,
+                                                             void* stream);
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU): feature-block sharded histogram + ONE int64 allreduce per tree level.
  *   replaces DeviceHistogramBuilder::AllReduceHist (src/tree/gpu_hist/histogram.cu:598-609) ->

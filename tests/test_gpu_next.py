@@ -1,11 +1,10 @@
-"""GPU parity tests of code written AFTER this round's regular GPU sessions: compiled, reviewed, and run on a B200
-only through five trees in the round's last GPU seconds (tools/quick_check, tests/test_recorded_hardware.py) -- never
-through THESE tests.  They are skipped unless B200HIST_RUN_UNVALIDATED=1 so that the suite that has been seen green on a
-B200 stays the suite that runs by default; the first GPU call of the next round runs them
-(`B200HIST_RUN_UNVALIDATED=1 python -m pytest tests/test_gpu_next.py -m gpu -x -q`) and a test moves to
-test_gpu_parity.py / test_reference_golden.py once it has passed there.
+"""GPU parity tests of the updater's remaining parameters -- interaction constraints, categorical splits, colsample_bynode,
+gradient-based sampling, prediction on quantised pages, several trees per iteration -- and their drop-in tests through
+the shim.  Written at the end of round 1 behind a gate; first run on a B200 at the start of round 2
+(gpurun_out/next_tests.log of that call: 76 of 84 green, the other 8 were two test defects, one count assumption and
+the multi-class prediction-cache stride), ungated since.
 
-Their checkers are already pinned on the CPU: the oracle functions they compare with reproduce the reference's
+Their checkers are pinned on the CPU: the oracle functions they compare with reproduce the reference's
 literal unit-test expectations and, for whole trees, trees of the unmodified reference gpu_hist
 (tests/test_oracle_golden.py, tests/test_reference_golden.py).
 """
@@ -19,9 +18,7 @@ import oracle as orc
 from tests.helpers import make_cuts, make_regression, squared_error_gpair
 from tests.test_gpu_parity import _compare_tree, _global_bins, _page, xb  # noqa: F401  (xb is a fixture)
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200HIST_RUN_UNVALIDATED") != "1",
-                                 reason="not yet run on hardware; set B200HIST_RUN_UNVALIDATED=1")]
+pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -95,8 +92,10 @@ def test_interaction_constraints_match_oracle(xb, case):
     up.configure(params)
     up.set_interaction_constraints(case["sets"])
     level_sets = None
-    if case.get("level_sets"):  # colsample_bylevel draws: 5 of 8 features per depth, ascending or not
-        level_sets = np.stack([rng.permutation(f)[:5] for _ in range(params["max_depth"] + 1)]).astype(np.int32)
+    if case.get("level_sets"):  # colsample_bylevel draws: 5 of 8 features per depth
+        # ascending, like every set the reference's ColumnSampler hands out (src/common/random.cu:98 thrust::sort,
+        # random.cc:71 std::sort); the ABI refuses anything else
+        level_sets = np.stack([np.sort(rng.permutation(f)[:5]) for _ in range(params["max_depth"] + 1)]).astype(np.int32)
         up.set_level_feature_sets(level_sets)
     if case.get("mono"):
         up.set_monotone_constraints(case["mono"])
@@ -311,7 +310,14 @@ def _compare_cat_tree(xb, up, tree, o, cp, cv):
                 assert np.isnan(a["fvalue"]) and sets[i] == o["cat_sets"][i], (i, sets[i], o["cat_sets"][i])
             else:
                 assert np.float32(a["fvalue"]).view(np.uint32) == np.float32(b.fvalue).view(np.uint32), i
-            assert np.isclose(a["loss_chg"], b.loss_chg, rtol=2e-5, atol=1e-6), i
+            # the device divides with div.approx.ftz.f32 like the reference, the oracle in IEEE arithmetic: the error
+            # of loss_chg = split gain - parent gain scales with the gains, not with their difference
+            # (same bound as tests/test_gpu_parity._compare_tree)
+            c = o["cands"][i]
+            pg = float(c.left_sum.g + c.right_sum.g) * o["scale"][2]
+            ph = float(c.left_sum.h + c.right_sum.h) * o["scale"][3]
+            gain_scale = abs(b.loss_chg) + pg * pg / max(ph, 1e-30)
+            assert abs(a["loss_chg"] - b.loss_chg) <= 2e-5 * gain_scale + 1e-6, i
         else:
             assert np.float32(a["leaf_value"]).view(np.uint32) == np.float32(b.leaf_value).view(np.uint32), i
         assert np.float32(a["sum_hess"]).view(np.uint32) == np.float32(b.sum_hess).view(np.uint32), i
@@ -418,7 +424,7 @@ def test_categorical_trees_with_other_parameters(xb, extra):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # Drop-in (the reference's own Booster, our factory): interaction constraints and categorical features through the
-# shim.  The shim refuses both unless B200HIST_SHIM_UNVALIDATED=1; this module sets it for its own process.
+# shim.
 # ---------------------------------------------------------------------------------------------------------------------
 def _shim_or_skip():
     import ctypes
@@ -426,7 +432,6 @@ def _shim_or_skip():
     from tests import test_shim_dropin as sd
     if not (rc.available("cuda") and os.path.exists(sd.SHIM)):
         pytest.skip("needs oracle/_ref_cuda/libxgboost.so and the shim")
-    os.environ["B200HIST_SHIM_UNVALIDATED"] = "1"
     rc.load("cuda")
     f = sd.test_reference_booster_trains_identically_through_the_shim
     if getattr(f, "_shim", None) is None:
@@ -748,7 +753,9 @@ def test_predictor_binding_serves_quantised_matrices_like_the_reference(xb, case
                        timeout=600)
         got[gate] = np.load(out)
     assert int(got["0"]["launches"]) == 0
-    assert int(got["1"]["launches"]) >= 3          # import + predict per matrix, at least
+    # margins of the validation matrix + leaf ids: two predict launches at least (the training matrix's margins come
+    # from the Booster's prediction cache, no predictor call)
+    assert int(got["1"]["launches"]) >= 2
     for key in ("valid", "train", "leaf"):
         assert np.array_equal(got["1"][key].view(np.uint32), got["0"][key].view(np.uint32)), key
 

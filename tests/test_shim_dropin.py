@@ -161,3 +161,25 @@ def test_external_memory_dmatrix_through_the_shim_matches_reference(cuda_device)
     assert xb.launch_count() > before
     assert json.dumps(our_trees) == json.dumps(ref_trees)
     assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))
+
+
+@pytest.mark.parametrize("extra", [{"objective": "reg:absoluteerror"},
+                                   {"objective": "reg:quantileerror", "quantile_alpha": 0.3},
+                                   {"objective": "reg:absoluteerror", "subsample": 0.7, "max_depth": 4}],
+                         ids=["absoluteerror", "quantileerror", "absoluteerror_subsample"])
+def test_adaptive_objectives_through_the_shim_match_reference(cuda_device, extra):
+    """reg:absoluteerror / reg:quantileerror rewrite the tree's leaves AFTER Update (ObjFunction::UpdateTreeLeaf,
+    gbtree.cc:205-222) from the positions the updater returned, and UpdatePredictionCache must then add the REWRITTEN
+    leaves (the reference reads p_tree->GetNodes() there, updater_gpu_hist.cu:594-598).  From the second iteration on
+    the gradients depend on that cache: three rounds, identical models and margins."""
+    from oracle import ref_capi as rc
+    if not (rc.available("cuda") and os.path.exists(SHIM)):
+        pytest.skip("needs oracle/_ref_cuda/libxgboost.so and the shim")
+    _ensure_shim(rc)
+    x, y = make_regression(30000, 16, seed=83, missing=0.02)
+    params = {"tree_method": "hist", "device": "cuda:0", "max_bin": 64, "max_depth": 5, "eta": 0.3, "base_score": 0.5}
+    params.update(extra)
+    ref_trees, ref_margin = _train(rc, x, y, dict(params, updater="grow_gpu_hist_reference"), 3)
+    our_trees, our_margin = _train(rc, x, y, dict(params, updater="grow_b200_hist"), 3)
+    assert json.dumps(our_trees) == json.dumps(ref_trees)
+    assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))

@@ -94,16 +94,33 @@ class B200HistMaker : public TreeUpdater {
       ++t_idx;
     }
     p_last_fmat_ = p_fmat;
+    p_last_tree_ = trees.empty() ? nullptr : trees.back();
   }
 
   bool UpdatePredictionCache(DMatrix const* p_fmat, common::Span<HostDeviceVector<bst_node_t>> out_position,
                              linalg::MatrixView<float> p_out_preds) override {
     if (updater_ == nullptr || p_last_fmat_ == nullptr || p_last_fmat_ != p_fmat) return false;
     if (out_position.size() > 1) return false;
+    CHECK(p_last_tree_ != nullptr);
     CHECK(p_out_preds.Device().IsCUDA());
+    CHECK_EQ(p_out_preds.Device().ordinal, ctx_->Ordinal());
+    CHECK_EQ(out_position.size(), 1);
     CHECK_EQ(p_out_preds.Shape(1), 1);
-    B200_SHIM_CHECK(b200hist_updater_update_prediction_cache(updater_, p_out_preds.Values().data(),
-                                                             static_cast<void*>(ctx_->CUDACtx()->Stream())));
+    CHECK_EQ(p_out_preds.Size(), out_position.front().Size());
+    // updater_gpu_hist.cu:582-608.  Two things the reference's call depends on and a plain `preds[i] += leaf` misses:
+    //  * the view is out.Slice(All, Range(gid, gid + 1)) of the (n_rows, n_groups) cache (gbtree.cc DoBoost): element
+    //    (i, 0) sits at Values().data() + i * Stride(0);
+    //  * the leaf values come from the RegTree, because ObjFunction::UpdateTreeLeaf (adaptive objectives such as
+    //    reg:absoluteerror) rewrites them between Update and this call.
+    auto const& tree_nodes = p_last_tree_->GetNodes(DeviceOrd::CPU());
+    leaf_values_.assign(tree_nodes.size(), 0.0f);
+    for (std::size_t i = 0; i < tree_nodes.size(); ++i) {
+      if (tree_nodes[i].IsLeaf()) leaf_values_[i] = tree_nodes[i].LeafValue();
+    }
+    B200_SHIM_CHECK(b200hist_updater_update_prediction_cache_ex(
+        updater_, p_out_preds.Values().data(), static_cast<std::uint64_t>(p_out_preds.Stride(0)),
+        out_position.front().ConstDevicePointer(), leaf_values_.data(), static_cast<std::int32_t>(leaf_values_.size()),
+        static_cast<void*>(ctx_->CUDACtx()->Stream())));
     return true;
   }
 
@@ -136,6 +153,12 @@ class B200HistMaker : public TreeUpdater {
                                                          &ellpack_));
         }
       }
+      // ExtMem "direct access" read path (ellpack_page_source.cu:349-360): the page is split between gidx_buffer (host
+      // part) and d_gidx_buffer (device part) and read through DoubleCompressedIter; decoding n_rows rows from
+      // gidx_buffer alone would run past its end.
+      CHECK(impl->d_gidx_buffer.empty())
+          << "[b200hist] Ellpack pages split between a host and a device buffer (ExtMem direct-access cache) are not "
+             "imported; build the ExtMemQuantileDMatrix with cache_host_ratio=1.0 or 0.0";
       B200_SHIM_CHECK(b200hist_ellpack_import_reference_rows(
           ellpack_, static_cast<std::uint64_t>(impl->base_rowid), static_cast<std::uint64_t>(impl->n_rows),
           impl->gidx_buffer.data(), static_cast<std::uint32_t>(impl->info.row_stride),
@@ -155,19 +178,6 @@ class B200HistMaker : public TreeUpdater {
     p.min_child_weight = param->min_child_weight;
     p.max_delta_step = param->max_delta_step;
     p.min_split_loss = param->min_split_loss;
-    // Paths of libb200hist.so that were written after the last GPU session of their round and have not been seen
-    // green on hardware stay refused here unless B200HIST_SHIM_UNVALIDATED=1 (tests/test_gpu_next.py decides).
-    bool const unvalidated_ok = [] {
-      char const* e = std::getenv("B200HIST_SHIM_UNVALIDATED");
-      return e != nullptr && e[0] == '1';
-    }();
-    CHECK(param->interaction_constraints.empty() || unvalidated_ok)
-        << "[b200hist] interaction constraints are not enabled yet";
-    CHECK(!p_fmat->Info().HasCategorical() || unvalidated_ok) << "[b200hist] categorical features are not enabled yet";
-    CHECK(param->subsample == 1.0f || param->sampling_method == TrainParam::kUniform || unvalidated_ok)
-        << "[b200hist] gradient_based row sampling is not enabled yet";
-    CHECK(param->colsample_bynode == 1.0f || unvalidated_ok)
-        << "[b200hist] colsample_bynode is not enabled yet (colsample_bytree and colsample_bylevel are)";
     CHECK(param->colsample_bynode == 1.0f ||
           (param->colsample_bylevel == 1.0f && param->interaction_constraints.empty()) ||
           (p_fmat->Info().feature_weights.Empty() && p_fmat->Info().num_col_ <= 8192))
@@ -394,6 +404,7 @@ class B200HistMaker : public TreeUpdater {
     updater_ = nullptr;
     ellpack_ = nullptr;
     p_last_fmat_ = nullptr;
+    p_last_tree_ = nullptr;
     sampling_set_ = false;
   }
 
@@ -403,6 +414,8 @@ class B200HistMaker : public TreeUpdater {
   b200hist_updater_t updater_{nullptr};
   std::vector<b200hist_tree_node> nodes_;
   DMatrix* p_last_fmat_{nullptr};
+  RegTree const* p_last_tree_{nullptr};
+  std::vector<float> leaf_values_;
   common::ColumnSampler column_sampler_;
   bool sampling_set_{false};
   bool level_draws_pending_{false};

@@ -748,6 +748,26 @@ __global__ void __launch_bounds__(256) PredCacheKernel(const int32_t* __restrict
   }
 }
 
+// The same update for a caller whose output is a strided column (multi-class: out.Slice(All, gid), stride = n_groups,
+// gbtree.cc DoBoost) and/or whose leaf values were rewritten after Update (adaptive objectives: obj->UpdateTreeLeaf
+// runs between Update and UpdatePredictionCache, which is why the reference reads p_tree->GetNodes() there,
+// updater_gpu_hist.cu:594-598).  `leaves` is indexed by node id.
+__global__ void __launch_bounds__(256) PredCacheStridedKernel(const int32_t* __restrict__ position,
+                                                               const float* __restrict__ leaves, uint64_t n,
+                                                               uint64_t stride, float* __restrict__ preds) {
+  for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256ull) {
+    int32_t p = position[i];
+    p = p < 0 ? ~p : p;  // SamplePosition::Decode
+    preds[i * stride] += leaves[p];
+  }
+}
+
+__global__ void __launch_bounds__(256) GatherLeavesKernel(const NodeDev* __restrict__ nodes, int32_t n,
+                                                           float* __restrict__ leaves) {
+  int32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) leaves[i] = nodes[i].leaf_value;
+}
+
 }  // namespace b200
 
 #ifndef B200_KERNELS_ONLY
@@ -861,6 +881,7 @@ struct b200hist_updater_s {
   bool pair_hint{false};      // last tree's hessians had zero low words -> launch the 64-feature pair kernel
   int32_t* last_position{nullptr};
   int32_t last_n_nodes{0};
+  float* d_leaf_override{nullptr};  // leaf values handed to update_prediction_cache_ex (or gathered for a strided output)
   // profiling
   bool profiling{false};
   std::vector<cudaEvent_t> events;
@@ -948,6 +969,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     const size_t need = GradientBasedScratchBytes(n, u->num_sms);
     if (need > u->gbs_scratch_bytes) {
       if (u->d_gbs_scratch) cudaFree(u->d_gbs_scratch);
+    if (u->d_leaf_override) cudaFree(u->d_leaf_override);
       u->d_gbs_scratch = nullptr;
       B200_CUDA(cudaMalloc(&u->d_gbs_scratch, need));
       u->gbs_scratch_bytes = need;
@@ -1371,6 +1393,38 @@ int b200hist_updater_update_prediction_cache(b200hist_updater_t u, float* preds_
   auto s = static_cast<cudaStream_t>(stream);
   PredCacheKernel<<<u->num_sms * 8, 256, 0, s>>>(u->last_position, u->d_nodes, u->ell->n_rows, preds_dev);
   B200_LAUNCHED();
+  B200_API_END();
+}
+
+int b200hist_updater_update_prediction_cache_ex(b200hist_updater_t u, float* preds_dev, uint64_t stride,
+                                                const int32_t* position_dev, const float* leaf_values_host,
+                                                int32_t n_leaf_values, void* stream) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && preds_dev != nullptr, "null argument");
+  B200_CHECK(stride >= 1, "stride must be >= 1");
+  const int32_t* position = position_dev != nullptr ? position_dev : u->last_position;
+  B200_CHECK(position != nullptr, "UpdatePredictionCache called before Update (updater_gpu_hist.cu:851)");
+  B200_CHECK(leaf_values_host == nullptr || (n_leaf_values >= u->last_n_nodes && n_leaf_values <= u->max_nodes),
+             "leaf_values_host must hold one value per node of the last tree");
+  DeviceGuard guard(u->device);
+  auto s = static_cast<cudaStream_t>(stream);
+  if (stride == 1 && leaf_values_host == nullptr) {
+    PredCacheKernel<<<u->num_sms * 8, 256, 0, s>>>(position, u->d_nodes, u->ell->n_rows, preds_dev);
+    B200_LAUNCHED();
+  } else {
+    if (u->d_leaf_override == nullptr) u->d_leaf_override = DevAlloc<float>((size_t)u->max_nodes);
+    if (leaf_values_host != nullptr) {
+      // pageable host memory: the copy is staged by the driver before the call returns, the caller may reuse its buffer
+      B200_CUDA(cudaMemcpyAsync(u->d_leaf_override, leaf_values_host, sizeof(float) * (size_t)n_leaf_values,
+                                cudaMemcpyHostToDevice, s));
+    } else {
+      GatherLeavesKernel<<<(u->max_nodes + 255) / 256, 256, 0, s>>>(u->d_nodes, u->max_nodes, u->d_leaf_override);
+      B200_LAUNCHED();
+    }
+    PredCacheStridedKernel<<<u->num_sms * 8, 256, 0, s>>>(position, u->d_leaf_override, u->ell->n_rows, stride,
+                                                          preds_dev);
+    B200_LAUNCHED();
+  }
   B200_API_END();
 }
 

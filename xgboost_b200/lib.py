@@ -116,6 +116,8 @@ _SIGNATURES = {
     "b200hist_updater_update_tree_host": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(TreeNode),
                                                   POINTER(c_int32), c_void_p]),
     "b200hist_updater_update_prediction_cache": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "b200hist_updater_update_prediction_cache_ex": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_int32,
+                                                            c_void_p]),
     "b200hist_comm_unique_id": (c_int, [c_void_p]),
     "b200hist_comm_create": (c_int, [c_int, c_int, c_int, c_void_p, POINTER(c_void_p)]),
     "b200hist_comm_destroy": (c_int, [c_void_p]),

@@ -492,6 +492,7 @@ class GPUHistMaker:
         self._param = _l.TrainParam.make()
         self._max_nodes = 0
         self._nodes_buf = None
+        self._last_position = None
         self.device = torch.device("cuda:%d" % page.device)
 
     # TreeUpdater::Configure(Args) -- unknown keys pass through like UpdateAllowUnknown
@@ -694,6 +695,7 @@ class GPUHistMaker:
             raise _l.B200HistError("configure() must be called before update()")
         n_nodes = c_int32()
         pos_ptr = c_void_p(out_position.data_ptr()) if out_position is not None else c_void_p()
+        self._last_position = out_position  # kept alive for update_prediction_cache (None = the updater's own buffer)
         if out_position is not None:
             _require_cuda(out_position, "out_position")
             if out_position.dtype != torch.int32 or out_position.numel() != self._page.n_rows:
@@ -711,12 +713,26 @@ class GPUHistMaker:
         return RegTree(self._nodes_buf, n_nodes.value)
 
     # TreeUpdater::UpdatePredictionCache
-    def update_prediction_cache(self, preds: torch.Tensor) -> bool:
+    def update_prediction_cache(self, preds: torch.Tensor, leaf_values=None) -> bool:
+        """preds: float32[n_rows] or one column of a float32[n_rows, n_groups] matrix (multi-class: the column of the
+        class this tree belongs to, GBTree::DoBoost's out.Slice(All, gid)).  leaf_values: leaf value per node id when
+        the objective rewrote the tree's leaves after update() (adaptive objectives); default = the updater's own."""
         _require_cuda(preds, "preds")
-        if preds.dtype != torch.float32 or preds.numel() != self._page.n_rows:
-            raise ValueError("preds must be float32[n_rows]")
-        _l.check(_l.load().b200hist_updater_update_prediction_cache(self._h, c_void_p(preds.data_ptr()),
-                                                                  _stream_ptr(self.device)))
+        if preds.dtype != torch.float32 or preds.numel() != self._page.n_rows or preds.dim() != 1:
+            raise ValueError("preds must be float32[n_rows] (a strided column view is fine)")
+        stride = preds.stride(0) if preds.numel() > 1 else 1
+        if stride < 1:
+            raise ValueError("preds must have a positive stride")
+        # the positions of the last update(): the tensor handed to update() is kept alive here, so the library never
+        # reads a buffer the caller has dropped
+        pos = self._last_position
+        lv_ptr, n_lv = c_void_p(), 0
+        if leaf_values is not None:
+            lv = np.ascontiguousarray(leaf_values, dtype=np.float32)
+            lv_ptr, n_lv = c_void_p(lv.ctypes.data), int(lv.size)
+        _l.check(_l.load().b200hist_updater_update_prediction_cache_ex(
+            self._h, c_void_p(preds.data_ptr()), stride, c_void_p(pos.data_ptr()) if pos is not None else c_void_p(),
+            lv_ptr, n_lv, _stream_ptr(self.device)))
         return True
 
     # introspection for parity tests
