@@ -39,7 +39,10 @@ def parse_args():
     ap.add_argument("--features", type=int, default=int(os.environ.get("B200_BENCH_FEATURES", 256)))
     ap.add_argument("--max-bin", type=int, default=256)
     ap.add_argument("--depth", type=int, default=int(os.environ.get("B200_BENCH_DEPTH", 8)))
-    ap.add_argument("--cpu-sample-rows", type=int, default=int(os.environ.get("B200_BENCH_CPU_ROWS", 1_000_000)))
+    ap.add_argument("--cpu-sample-rows", type=int, default=int(os.environ.get("B200_BENCH_CPU_ROWS", 4_000_000)),
+                    help="rows of the workload the cpu_baseline leg of OUR arm times (bounded sample)")
+    ap.add_argument("--ref-rows", type=int, default=int(os.environ.get("B200_BENCH_REF_ROWS", 100_000_000)),
+                    help="rows of the workload `--impl reference` times (default: all of them)")
     ap.add_argument("--split", default=os.environ.get("B200_BENCH_SPLIT", "rows"), choices=["rows", "features"],
                     help="multi-GPU decomposition: rows = every rank owns N/P rows, full-width partial histograms summed "
                          "per level over peer memory; features = every rank owns F/P feature blocks of all rows "
@@ -144,18 +147,15 @@ def batch_of(torch, device, f, rows, batch, b):
     return x, g
 
 
-def build_workload(torch, xb, args, device, batch_lo=0, batch_hi=None):
-    """DMatrix build = what QuantileDMatrix(DataIter of 1M-row device batches) does in the reference
-    (quantile_dmatrix.cu:29-126): pass 1 pushes every batch through the resident quantile sketch
-    (b200hist_sketch_push_dense, one sketch window per batch), pass 2 regenerates the batches and bins them
-    into the Ellpack page.  Returns page, labels and the two pass times (seconds)."""
+def build_cuts(torch, xb, args, device):
+    """Pass 1 of the DMatrix build = what QuantileDMatrix(DataIter of 1M-row device batches) does in the reference
+    (quantile_dmatrix.cu:29-126): every batch goes through the resident quantile sketch (b200hist_sketch_push_dense,
+    one sketch window per batch); cuts always come from the WHOLE stream.  Returns (cuts, seconds)."""
     n, f = args.rows, args.features
     batch = 1_000_000
     nb = (n + batch - 1) // batch
-    batch_hi = nb if batch_hi is None else batch_hi       # this rank's page holds batches [batch_lo, batch_hi)
-    row_lo, row_hi = batch_lo * batch, min(n, batch_hi * batch)
     t0 = time.perf_counter()
-    sketch = xb.QuantileSketch(f, args.max_bin, device)   # cuts always come from the WHOLE stream
+    sketch = xb.QuantileSketch(f, args.max_bin, device)
     for b in range(nb):
         x, _ = batch_of(torch, device, f, n, batch, b)
         sketch.push(x)
@@ -163,7 +163,15 @@ def build_workload(torch, xb, args, device, batch_lo=0, batch_hi=None):
     cuts = sketch.make_cuts()
     sketch.close()
     torch.cuda.synchronize(device)
-    t_sketch = time.perf_counter() - t0
+    return cuts, time.perf_counter() - t0
+
+
+def build_page(torch, xb, args, device, cuts, batch_lo, batch_hi):
+    """Pass 2: regenerate batches [batch_lo, batch_hi) and bin them into an Ellpack page; labels y = X.w + 0.1 eps.
+    Returns (page, y, seconds)."""
+    n, f = args.rows, args.features
+    batch = 1_000_000
+    row_lo, row_hi = batch_lo * batch, min(n, batch_hi * batch)
     t0 = time.perf_counter()
     page = xb.EllpackPage(cuts, row_hi - row_lo, device.index, has_missing=MISSING > 0.0)
     gen = torch.Generator(device=device).manual_seed(7)
@@ -176,7 +184,7 @@ def build_workload(torch, xb, args, device, batch_lo=0, batch_hi=None):
         y[o:o + x.shape[0]] = torch.nan_to_num(x) @ w + 0.1 * torch.randn(x.shape[0], generator=g, device=device)
         del x
     torch.cuda.synchronize(device)
-    return page, y, dict(sketch_s=t_sketch, ellpack_s=time.perf_counter() - t0, sketch_windows=nb)
+    return page, y, time.perf_counter() - t0
 
 
 def algorithmic_bytes(n, f, bin_bytes, depth, row_visits):
@@ -189,56 +197,184 @@ def algorithmic_bytes(n, f, bin_bytes, depth, row_visits):
 
 
 # --------------------------------------------------------------------------------------------------
+# tree signature: every bit the reference records per node (RegTree::ExpandNode + RTreeNodeStat)
+# --------------------------------------------------------------------------------------------------
+def tree_sha(tree) -> str:
+    import hashlib
+    a = tree.array
+    h = hashlib.sha256()
+    for k in ("parent", "left", "right", "findex", "fvalue", "default_left", "is_leaf", "leaf_value", "loss_chg",
+              "sum_hess", "base_weight"):
+        h.update(a[k].tobytes())
+    return h.hexdigest()[:16]
+
+
+def model_sha(trees_json) -> str:
+    import hashlib
+    keep = ("left_children", "right_children", "split_indices", "split_conditions", "default_left", "base_weights",
+            "loss_changes", "sum_hessian")
+    return hashlib.sha256(json.dumps([{k: t[k] for k in keep} for t in trees_json]).encode()).hexdigest()[:16]
+
+
+# --------------------------------------------------------------------------------------------------
 # reference CPU arm (the unmodified reference's tree_method=hist on the host cores)
 # --------------------------------------------------------------------------------------------------
-def reference_cpu_iters_per_s(args, steps, warmup, sample_rows):
-    """Times XGBoosterUpdateOneIter of the reference CPU library on a bounded sample of the workload
-    (same generator, same params) and scales to the full row count (hist cost is linear in rows)."""
+def _host_batches(args, rows):
+    """1M-row float32 batches of the workload as numpy arrays, regenerated on every pass (SURVEY 8(d) generator: torch
+    Philox on the device when there is one -- generation is not what is timed -- else numpy on the host)."""
+    import numpy as np
+    from oracle import ref_capi as rc
+    f = args.features
+    nb = (rows + 999_999) // 1_000_000
+    try:
+        import torch
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else None
+    except Exception:
+        torch, dev = None, None
+    if dev is not None:
+        def get(b):
+            x, _ = batch_of(torch, dev, f, rows, 1_000_000, b)
+            return x.cpu().numpy()
+        w = torch.randn(f, generator=torch.Generator(device=dev).manual_seed(7), device=dev)
+        y = np.empty(rows, dtype=np.float32)
+        for b in range(nb):
+            x, g = batch_of(torch, dev, f, rows, 1_000_000, b)
+            yb = torch.nan_to_num(x) @ w + 0.1 * torch.randn(x.shape[0], generator=g, device=dev)
+            y[b * 1_000_000:b * 1_000_000 + x.shape[0]] = yb.cpu().numpy()
+        gen = "torch Philox on cuda, seed 2024 + batch"
+    else:
+        def get(b):
+            m = min(1_000_000, rows - b * 1_000_000)
+            return np.random.default_rng(2024 + b).standard_normal((m, f), dtype=np.float32)
+        w = np.random.default_rng(7).standard_normal(f).astype(np.float32)
+        y = np.empty(rows, dtype=np.float32)
+        for b in range(nb):
+            x = get(b)
+            y[b * 1_000_000:b * 1_000_000 + x.shape[0]] = x @ w
+        gen = "numpy PCG64 on the host, seed 2024 + batch"
+    return rc.LazyBatches(nb, get), y, gen
+
+
+def reference_cpu(args, steps, warmup, rows):
+    """XGBoosterUpdateOneIter of the reference CPU library (oracle/_ref/libxgboost.so, tree_method=hist) on `rows` rows
+    of the workload with every host core; per-iteration wall times.  Returns None when the library is not built."""
     import numpy as np
     from oracle import ref_capi as rc
     if not rc.available("cpu"):
         return None
     cores = os.cpu_count() or 1
-    rng = np.random.default_rng(2024)
-    n, f = sample_rows, args.features
-    x = rng.standard_normal((n, f), dtype=np.float32)
-    w = np.random.default_rng(7).standard_normal(f).astype(np.float32)
-    y = (x @ w + 0.1 * rng.standard_normal(n, dtype=np.float32)).astype(np.float32)
-    dm = rc.DMatrix.quantile_from_batches([x], max_bin=args.max_bin, kind="cpu", nthread=cores)
+    t0 = time.perf_counter()
+    batches, y, gen = _host_batches(args, rows)
+    dm = rc.DMatrix.quantile_from_batches(batches, max_bin=args.max_bin, kind="cpu", nthread=cores)
     dm.set_label(y)
+    build_s = time.perf_counter() - t0
     bst = rc.Booster({"tree_method": "hist", "device": "cpu", "max_depth": args.depth, "max_bin": args.max_bin,
                       "objective": "reg:squarederror", "eta": 0.3, "lambda": 1, "min_child_weight": 1,
                       "nthread": cores}, dm)
     for i in range(warmup):
         bst.update(i)
-    t0 = time.perf_counter()
+    ts = []
+    t_all = time.perf_counter()
     for i in range(steps):
+        t1 = time.perf_counter()
         bst.update(warmup + i)
-    dt = (time.perf_counter() - t0) / max(1, steps)
-    scaled = (1.0 / dt) * (n / float(args.rows))
-    return dict(value=scaled, unit=UNIT, cores=cores, kind="reference",
-                sample="reference CPU hist (oracle/_ref/libxgboost.so, nthread=%d) on %d x %d rows: %.3f s/iter, "
-                       "scaled linearly in rows to %d" % (cores, n, f, dt, args.rows),
-                sample_ms_per_iter=dt * 1e3)
+        ts.append(time.perf_counter() - t1)
+    total = time.perf_counter() - t_all
+    return dict(rows=rows, cores=cores, s_per_iter_mean=total / max(1, steps), s_per_iter_median=float(np.median(ts)),
+                s_per_iter_min=float(min(ts)), s_per_iter_max=float(max(ts)), dmatrix_build_s=build_s, generator=gen,
+                omp=os.environ.get("OMP_NUM_THREADS"))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = reference_cpu_iters_per_s(args, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)), args.cpu_sample_rows)
+    rows = min(args.rows, args.ref_rows)
+    res = reference_cpu(args, args.steps, args.warmup, rows)
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libxgboost.so not built"}))
         return
-    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "strong",
+    scale = rows / float(args.rows)                   # 1.0 when the full matrix is timed
+    value = scale / res["s_per_iter_mean"]
+    sample = ("unmodified reference CPU hist (oracle/_ref/libxgboost.so, XGBoosterUpdateOneIter, nthread=%d, "
+              "OMP_NUM_THREADS=%s) on %d x %d rows%s: mean %.3f s/iter over %d iters (median %.3f, min %.3f, max %.3f)"
+              % (res["cores"], res["omp"], rows, args.features,
+                 "" if scale == 1.0 else " = 1/%g of the workload, scaled linearly in rows" % (1.0 / scale),
+                 res["s_per_iter_mean"], args.steps, res["s_per_iter_median"], res["s_per_iter_min"],
+                 res["s_per_iter_max"]))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "synthetic %dx%d dense f32, %d bins, depth %d" % (args.rows, args.features, args.max_bin, args.depth),
-                       "l2": "inputs exceed L2"},
-            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": {"workload": "synthetic %dx%d dense f32, %d bins, depth %d, reg:squarederror"
+                                   % (args.rows, args.features, args.max_bin, args.depth),
+                       "timed_rows": rows, "l2": "inputs exceed L2"},
+            "dmatrix_build_s": round(res["dmatrix_build_s"], 2),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference's own Booster on the GPU: e2e of our arm (shim loaded) and the reference gpu_hist beside it
+# --------------------------------------------------------------------------------------------------
+def reference_booster_section(torch, args, device, steps, warmup):
+    """One QuantileDMatrix of the UNMODIFIED reference CUDA library over the same batches; two Boosters on it:
+    updater=grow_b200_hist (our shim: XGBoosterUpdateOneIter = objective gradient + Update + UpdatePredictionCache,
+    tree replayed into RegTree on the host) and updater=grow_gpu_hist_reference (the reference's own kernels).
+    Wall time per XGBoosterUpdateOneIter call with a device synchronise on both sides."""
+    import ctypes
+    import numpy as np
+    from oracle import ref_capi as rc
+    shim = os.path.join(ROOT, "xgboost_b200", "lib", "libb200hist_xgb_shim.so")
+    if not (rc.available("cuda") and os.path.exists(shim)):
+        return None
+    rc.load("cuda")
+    ctypes.CDLL(os.path.join(ROOT, "xgboost_b200", "lib", "libb200hist.so"), mode=ctypes.RTLD_GLOBAL)
+    keep = ctypes.CDLL(shim, mode=ctypes.RTLD_GLOBAL)
+    n, f = args.rows, args.features
+    nb = (n + 999_999) // 1_000_000
+    t0 = time.perf_counter()
+    batches = rc.LazyBatches(nb, lambda b: batch_of(torch, device, f, n, 1_000_000, b)[0])
+    dm = rc.DMatrix.quantile_from_batches(batches, max_bin=args.max_bin, kind="cuda")
+    w = torch.randn(f, generator=torch.Generator(device=device).manual_seed(7), device=device)
+    y = np.empty(n, dtype=np.float32)
+    for b in range(nb):
+        x, g = batch_of(torch, device, f, n, 1_000_000, b)
+        yb = torch.nan_to_num(x) @ w + 0.1 * torch.randn(x.shape[0], generator=g, device=device)
+        y[b * 1_000_000:b * 1_000_000 + x.shape[0]] = yb.cpu().numpy()
+        del x
+    dm.set_label(y)
+    torch.cuda.synchronize(device)
+    build_s = time.perf_counter() - t0
+    torch.cuda.empty_cache()
+    params = {"tree_method": "hist", "device": "cuda:%d" % device.index, "max_depth": args.depth,
+              "max_bin": args.max_bin, "objective": "reg:squarederror", "eta": 0.3, "lambda": 1, "min_child_weight": 1,
+              "base_score": 0.5}
+    out = {"dmatrix_build_s": round(build_s, 2)}
+    models = {}
+    for name, updater in (("ours", "grow_b200_hist"), ("reference_gpu", "grow_gpu_hist_reference")):
+        bst = rc.Booster(dict(params, updater=updater), dm)
+        ts = []
+        for i in range(warmup + steps):
+            torch.cuda.synchronize(device)
+            t1 = time.perf_counter()
+            bst.update(i)
+            torch.cuda.synchronize(device)
+            ts.append(time.perf_counter() - t1)
+        timed = ts[warmup:]
+        trees = bst.save_json()["learner"]["gradient_booster"]["model"]["trees"]
+        models[name] = model_sha(trees)
+        out[name] = {"iters_per_s": len(timed) / sum(timed), "ms_per_iter_mean": 1e3 * sum(timed) / len(timed),
+                     "ms_per_iter_median": 1e3 * float(np.median(timed)), "first_iter_ms": 1e3 * ts[0],
+                     "steps": steps, "warmup": warmup, "n_trees": len(trees), "model_sha": models[name],
+                     "last_tree_nodes": len(trees[-1]["left_children"])}
+        del bst
+        torch.cuda.empty_cache()
+    out["models_identical"] = models["ours"] == models["reference_gpu"]
+    del dm, keep
+    torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -265,24 +401,78 @@ def run_b200(args):
 
     row_split = world > 1 and args.split == "rows"
     n_total, f = args.rows, args.features
+    nb = (n_total + 999_999) // 1_000_000
+    params = dict(max_depth=args.depth, eta=0.3, reg_lambda=1.0, min_child_weight=1.0)
+    cuts, sketch_s = build_cuts(torch, xb, args, device)
     if row_split:  # contiguous runs of 1M-row batches per rank
-        nb = (n_total + 999_999) // 1_000_000
-        page, y, build_s = build_workload(torch, xb, args, device, nb * rank // world, nb * (rank + 1) // world)
+        page, y, ellpack_s = build_page(torch, xb, args, device, cuts, nb * rank // world, nb * (rank + 1) // world)
     else:
-        page, y, build_s = build_workload(torch, xb, args, device)
+        page, y, ellpack_s = build_page(torch, xb, args, device, cuts, 0, nb)
+    build_s = dict(sketch_s=sketch_s, ellpack_s=ellpack_s, sketch_windows=nb)
     info = page.info()
     n = int(info["n_rows"])      # rows resident on THIS rank
-    up = xb.GPUHistMaker(page)
-    up.configure(dict(max_depth=args.depth, eta=0.3, reg_lambda=1.0, min_child_weight=1.0))
-    comm = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def make_updater(pg, mode):
+        u = xb.GPUHistMaker(pg)
+        u.configure(params)
+        if mode == "rows":
+            u.enable_peer_exchange(row_split=True)
+        elif mode == "features":
+            if os.environ.get("B200HIST_COMM", "p2p") == "nccl":   # feature blocks + one NCCL allreduce per level
+                u._bench_comm = xb.Communicator.from_torch_distributed(device)
+                u.set_comm(u._bench_comm)
+            else:   # feature blocks + peer-memory push + flag barrier over NVLink (no NCCL in the data path)
+                u.enable_peer_exchange()
+        return u
+
+    def boost(u, yy, k, keep_pos=None):
+        """k boosting iterations from a zero margin; returns the trees."""
+        m = yy.shape[0]
+        pr = torch.zeros(m, dtype=torch.float32, device=device)
+        gp = torch.empty((m, 2), dtype=torch.float32, device=device)
+        gp[:, 1] = 1.0
+        out = []
+        for _ in range(k):
+            torch.sub(pr, yy, out=gp[:, 0])
+            out.append(u.update(gp, keep_pos))
+            u.update_prediction_cache(pr)
+        return out
+
+    up = make_updater(page, "single" if world == 1 else ("rows" if row_split else "features"))
+
+    # ---- multi-GPU parity, visible in the bench line: the tree of boosting step VERIFY_STEPS-1 built by all N GPUs
+    #      together must hash to the same value as the tree one GPU builds alone from the same cuts and the same rows
+    verify = None
+    VERIFY_STEPS = 3
     if world > 1:
-        if row_split:  # full-width partial histograms, one summing peer-memory kernel per tree level
-            up.enable_peer_exchange(row_split=True)
-        elif os.environ.get("B200HIST_COMM", "p2p") == "nccl":  # feature blocks + one NCCL allreduce per level
-            comm = xb.Communicator.from_torch_distributed(device)
-            up.set_comm(comm)
-        else:  # feature blocks + peer-memory push + flag barrier over NVLink (no NCCL in the data path)
-            up.enable_peer_exchange()
+        trees_n = boost(up, y, VERIFY_STEPS)
+        sha_n = tree_sha(trees_n[-1])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, sha_n)
+        sha_1 = None
+        if rank == 0:
+            if row_split:
+                full_page, full_y, _ = build_page(torch, xb, args, device, cuts, 0, nb)
+            else:
+                full_page, full_y = page, y
+            solo = make_updater(full_page, "single")
+            sha_1 = tree_sha(boost(solo, full_y, VERIFY_STEPS)[-1])
+            del solo
+            if row_split:
+                del full_page, full_y
+            torch.cuda.empty_cache()
+        barrier()
+        verify = {"step": VERIFY_STEPS - 1, "tree_sha": sha_n, "tree_sha_1gpu": sha_1,
+                  "all_ranks_agree": len(set(gathered)) == 1, "nodes": trees_n[-1].num_nodes}
+        if rank == 0:
+            assert verify["all_ranks_agree"], "ranks built different trees: %s" % gathered
+            assert sha_n == sha_1, "the %d-GPU tree differs from the single-GPU tree (%s vs %s)" % (world, sha_n, sha_1)
+
     preds = torch.zeros(n, dtype=torch.float32, device=device)
     gpair = torch.empty((n, 2), dtype=torch.float32, device=device)
     gpair[:, 1] = 1.0
@@ -294,11 +484,9 @@ def run_b200(args):
         up.update_prediction_cache(preds)
         return tree
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(device)
-
+    # phase events inside the library stay ON in the timed region (~50 cudaEventRecord per tree, no extra sync: the
+    # per-tree read-back synchronises anyway), so that the phases, the row visits and the step time are the SAME trees
+    up.set_profiling(True)
     for _ in range(args.warmup):
         step_resident()
     barrier()
@@ -306,10 +494,12 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = xb.launch_count()
+    prof, host_gap = [], []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         tree = step_resident()
+        prof.append(up.last_profile())
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -320,20 +510,19 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = 1e3 / ms_per_step
-
-    # per-phase device times + row visits from profiled iterations (events inside the library, same stream)
-    up.set_profiling(True)
-    prof = []
-    for _ in range(3):
-        step_resident()
-        prof.append(up.last_profile())
     up.set_profiling(False)
-    torch.cuda.synchronize(device)
-    # where a step's time goes outside the updater's phases: gradient kernel, tree update call, prediction cache
-    # (profiling stays on so that the same iterations give the phase sum: update_tree - sum(phases) = unattributed)
+
+    names = [k for k in prof[0] if k not in ("row_visits", "hist_levels")]
+    phase = {k: float(np.mean([p[k] for p in prof])) for k in names}
+    row_visits_mean = float(np.mean([p["row_visits"] for p in prof]))
+    row_visits_minmax = [int(min(p["row_visits"] for p in prof)), int(max(p["row_visits"] for p in prof))]
+    hist_levels = None
+    if "hist_levels" in prof[0]:
+        hist_levels = [float(v) for v in np.mean(np.array([p["hist_levels"] for p in prof]), axis=0)]
+    phase_sum = sum(v for k, v in phase.items() if k != "hist_exchange")
+    # outside the updater's phases: the objective's gradient kernel and the prediction cache (measured apart, 3 steps)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     parts = []
-    up.set_profiling(True)
     for _ in range(3):
         ev[0].record()
         torch.sub(preds, y, out=gpair[:, 0])
@@ -343,90 +532,61 @@ def run_b200(args):
         up.update_prediction_cache(preds)
         ev[3].record()
         torch.cuda.synchronize(device)
-        lp = up.last_profile()
-        parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)] + [sum(v for k, v in lp.items() if k not in ("row_visits", "hist_exchange"))])
-    up.set_profiling(False)
-    step_parts = dict(zip(["gradient", "update_tree", "prediction_cache", "update_tree_phase_sum"],
-                          [float(v) for v in np.median(np.array(parts), axis=0)]))
-    phase = {k: float(np.median([p[k] for p in prof])) for k in prof[0] if k != "row_visits"}
-    row_visits = prof[-1]["row_visits"]
-    ab = algorithmic_bytes(n, f, info["bin_bytes"], args.depth, row_visits)
+        parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+    pm = np.median(np.array(parts), axis=0)
+    step_parts = {"gradient": float(pm[0]), "prediction_cache": float(pm[2]), "updater_phase_sum_timed_mean": phase_sum,
+                  "unattributed": ms_per_step - phase_sum - float(pm[0]) - float(pm[2]),
+                  "note": "phases and ms_per_step are means over the SAME timed trees; unattributed = launch gaps + the "
+                          "per-tree host read-back"}
+    ab = algorithmic_bytes(n, f, info["bin_bytes"], args.depth, row_visits_mean)
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     hist_launches = args.depth
-    # per GPU: this rank reads its F/world feature columns + the 20 B of gradient pair / row id per row visit
     feat_div = 1 if (world == 1 or row_split) else world   # row split: this rank's visits cover all F features
-    hist_bytes_gpu = row_visits * (f * info["bin_bytes"] / feat_div + 16 + 4)
+    hist_bytes_gpu = row_visits_mean * (f * info["bin_bytes"] / feat_div + 16 + 4)
     hist_ms = phase["hist"] - phase.get("hist_exchange", 0.0)   # the kernel itself, without the cross-GPU exchange
     hist_gbs = hist_bytes_gpu / (hist_ms * 1e-3) / 1e9 if hist_ms > 0 else 0.0
-    # the binding unit is the L1TEX data stage (shared atomics + gather wavefronts); the ceiling of the atomics alone
-    # is measured here by the library's own micro-benchmark
     from xgboost_b200 import components as xc
     smem_peak = xc.smem_atomic_peak(True, device)
     sm_clock_hz = (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965) * 1e6
     n_sms = torch.cuda.get_device_properties(device).multi_processor_count
-    updates_per_s = row_visits * (f / feat_div) / (hist_ms * 1e-3) if hist_ms > 0 else 0.0
+    updates_per_s = row_visits_mean * (f / feat_div) / (hist_ms * 1e-3) if hist_ms > 0 else 0.0
+    # DRAM traffic of the dominant kernel: only from an ncu --set full capture of THIS workload (profiles/), else null
+    traffic, traffic_src = None, "no ncu --set full capture of this workload under profiles/ (null, not a literal)"
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r02_hist_kernel_ncu_headline.json")))
+        if cap.get("rows") == n_total and cap.get("features") == f and world == 1:
+            traffic = float(cap["dram_bytes_per_launch_mean"])
+            traffic_src = cap.get("source", "profiles/r02_hist_kernel_ncu_headline.json")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "HistKernelPair", "achieved": hist_gbs, "peak": peak, "unit": "GB/s",
-                "frac": hist_gbs / peak, "traffic": 1.2 * hist_bytes_gpu / hist_launches, "peak_source": peak_src,
-                "traffic_source": "ncu --set full dram__bytes_read+write of HistKernelPair = 1.13-1.29 x algorithmic on three "
-                                  "consecutive level launches of the 20M-row capture "
-                                  "(profiles/r01c_pair_kernels_ncu_summary.json), 1.2 x scaled to this launch size",
-                "l1tex_data_pipe": {"pct_of_peak": 95.0, "shared_atomic_share_pct": 72.0,
-                                    "source": "ncu l1tex__data_pipe_lsu_wavefronts (same capture): the binding unit"},
+                "frac": hist_gbs / peak, "traffic": traffic, "peak_source": peak_src, "traffic_source": traffic_src,
                 "launches_per_step": hist_launches, "avg_launch_ms": hist_ms / hist_launches,
-                "algorithmic_bytes_per_launch": hist_bytes_gpu / hist_launches, "row_visits_per_step": row_visits,
+                "algorithmic_bytes_per_launch": hist_bytes_gpu / hist_launches,
+                "row_visits_per_step_mean": row_visits_mean, "row_visits_per_step_minmax": row_visits_minmax,
+                "per_level_ms": hist_levels,
                 # the binding resource is the shared-memory atomic pipe, not HBM: the ceiling is MEASURED on this GPU by
-                # b200hist_smem_atomic_peak (the kernel's own accumulation sequence -- 3 conflict-free 32-bit atomics
-                # per update for reg:squarederror, whose quantised hessian has a zero low word -- with no global loads)
+                # b200hist_smem_atomic_peak (the kernel's own accumulation sequence with no global loads)
                 "smem_atomic_bound": {"updates_per_clk_per_sm": updates_per_s / sm_clock_hz / n_sms,
                                       "ceiling": smem_peak, "frac": updates_per_s / sm_clock_hz / n_sms / smem_peak,
                                       "ceiling_source": "measured: b200hist_smem_atomic_peak(h_lo_zero=1), clock64 based",
                                       "note": "exact int64 accumulation in shared memory bounds the kernel, not HBM"},
                 "whole_step_frac": (ab["total"] - ab["hist"] + hist_bytes_gpu) / (ms_per_step * 1e-3) / 1e9 / peak}
 
-    # end-to-end: gradient arrives in pinned HOST memory, tree returns to the host (C-ABI host entry)
-    e2e = None
-    if not args.no_e2e:
-        g_host = torch.empty((n, 2), dtype=torch.float32).pin_memory()
-        g_host.copy_(gpair)
-        loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
-
-        def step_e2e():
-            tree_ = up.update(g_host, pos)            # H2D of the gradient + D2H of the tree inside
-            up.update_prediction_cache(preds)
-            loss_host.copy_(((preds - y) ** 2).mean().reshape(1), non_blocking=False)  # D2H of the metric
-            return tree_
-
-        for _ in range(max(1, min(args.warmup, 2))):
-            step_e2e()
-        barrier()
-        k2 = max(1, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(k2):
-            tr = step_e2e()
-        barrier()
-        dt = (time.perf_counter() - t0) / k2
-        tt = torch.tensor([dt], device=device)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": 1.0 / float(tt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(n_total) * 8 if (world == 1 or row_split) else int(n_total) * 8 * world,
-               "d2h_bytes_per_step": int(tr.num_nodes) * 48 + 4}
-
     # north_star's decomposition measured next to the default one: all rows on every GPU, F/P feature blocks each,
     # one peer-memory slice exchange per tree level (same matrix, same trees)
     feature_block = None
     if row_split and os.environ.get("B200_BENCH_ALSO_FEATURES", "1") != "0":
         up.disable_peer_exchange()   # unmap on every rank, barrier, only then free
-        del up, page
+        del up, page, preds, gpair, pos
         torch.cuda.empty_cache()
-        page_f, y_f, _ = build_workload(torch, xb, args, device)
-        up_f = xb.GPUHistMaker(page_f)
-        up_f.configure(dict(max_depth=args.depth, eta=0.3, reg_lambda=1.0, min_child_weight=1.0))
-        up_f.enable_peer_exchange()
+        page_f, y_f, _ = build_page(torch, xb, args, device, cuts, 0, nb)
+        up_f = make_updater(page_f, "features")
+        sha_f = tree_sha(boost(up_f, y_f, VERIFY_STEPS)[-1])
         nf_rows = int(page_f.info()["n_rows"])
         preds_f = torch.zeros(nf_rows, dtype=torch.float32, device=device)
         gpair_f = torch.empty((nf_rows, 2), dtype=torch.float32, device=device)
@@ -450,16 +610,48 @@ def run_b200(args):
         tf = torch.tensor([f0.elapsed_time(f1) / k3], device=device)
         dist.all_reduce(tf, op=dist.ReduceOp.MAX)
         feature_block = {"value": 1e3 / float(tf.item()), "unit": UNIT, "ms_per_step": float(tf.item()), "steps": k3,
+                         "tree_sha": sha_f, "tree_sha_1gpu": verify["tree_sha_1gpu"] if verify else None,
                          "parallelism": "feature-block shard x%d (north_star): all rows on every GPU, F/P feature "
                                         "blocks each, one peer-memory slice exchange per tree level" % world}
+        if rank == 0 and verify:
+            assert sha_f == verify["tree_sha_1gpu"], "feature-block tree differs from the single-GPU tree"
         up_f.disable_peer_exchange()
         del up_f, page_f, preds_f, gpair_f, y_f
+    else:
+        if world > 1:
+            up.disable_peer_exchange()
+        del up, page, preds, gpair, pos
+    torch.cuda.empty_cache()
+
+    # end to end through the reference's own Booster (N = 1): XGBoosterUpdateOneIter with the shim loaded, and the
+    # reference's gpu_hist on the same DMatrix.  N > 1: the shim's distributed mode is exercised by the tests; here the
+    # C-ABI host entry is timed with a gradient that is refreshed from the device every step.
+    e2e, ref_section = None, None
+    if not args.no_e2e and world == 1 and rank == 0:
+        k2 = max(1, min(args.steps, 10))
+        ref_section = reference_booster_section(torch, args, device, k2, 2)
+        if ref_section is not None:
+            nodes = ref_section["ours"]["last_tree_nodes"]
+            e2e = {"value": ref_section["ours"]["iters_per_s"], "unit": UNIT,
+                   "h2d_bytes_per_step": nodes * 4,            # the RegTree's leaf values for the prediction cache
+                   "d2h_bytes_per_step": nodes * 64 + 256,     # node records + tree state + quantiser record
+                   "path": "XGBoosterUpdateOneIter of the unmodified reference (oracle/_ref_cuda) with "
+                           "libb200hist_xgb_shim.so serving grow_gpu_hist: objective gradient, Update, host replay "
+                           "into RegTree, UpdatePredictionCache; labels resident in the DMatrix as in any xgb.train",
+                   "ms_per_iter_median": ref_section["ours"]["ms_per_iter_median"], "steps": k2,
+                   "model_identical_to_reference_gpu_hist": ref_section["models_identical"]}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu_baseline = reference_cpu_iters_per_s(args, 3, 1, args.cpu_sample_rows)
-        if cpu_baseline is not None:
-            cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        rows_c = min(args.rows, args.cpu_sample_rows)
+        res = reference_cpu(args, 3, 1, rows_c)
+        if res is not None:
+            sc = rows_c / float(args.rows)
+            cpu_baseline = {"value": sc / res["s_per_iter_mean"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
+                            "sample": "unmodified reference CPU hist (oracle/_ref/libxgboost.so, nthread=%d, "
+                                      "OMP_NUM_THREADS=%s) on %d x %d rows: %.3f s/iter over 3 iters, scaled linearly in "
+                                      "rows to %d; the full-size run is `bench.py --impl reference`"
+                                      % (res["cores"], res["omp"], rows_c, args.features, res["s_per_iter_mean"], args.rows)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -478,15 +670,37 @@ def run_b200(args):
                                    % build_s["sketch_windows"]},
                 "dmatrix_build_s": {"sketch": round(build_s["sketch_s"], 3), "ellpack": round(build_s["ellpack_s"], 3)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "phase_ms": phase, "step_parts_ms": step_parts, "feature_block_shard": feature_block, "algorithmic_gb_per_step": {k: v / 1e9 for k, v in ab.items()}}
+                "clocks": clocks, "phase_ms": phase, "step_parts_ms": step_parts,
+                "multi_gpu_parity": verify, "feature_block_shard": feature_block,
+                "reference_gpu": None if ref_section is None else dict(
+                    ref_section["reference_gpu"], unit=UNIT, value=ref_section["reference_gpu"]["iters_per_s"],
+                    what="the UNMODIFIED reference's CUDA gpu_hist (oracle/_ref_cuda, updater=grow_gpu_hist_reference) "
+                         "through XGBoosterUpdateOneIter on the same QuantileDMatrix in this process: the kernel to beat",
+                    dmatrix_build_s=ref_section["dmatrix_build_s"]),
+                "algorithmic_gb_per_step": {k: v / 1e9 for k, v in ab.items()}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _exec_with_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers and libgomp reads it once, at load: the reference's
+    OmpGetNumThreads() then clamps nthread=128 to 1 (src/common/threading_utils.cc).  The reference arm therefore
+    re-executes itself with the thread count pinned to the host's cores before any OpenMP runtime is loaded."""
+    cores = str(os.cpu_count() or 1)
+    if os.environ.get("OMP_NUM_THREADS") == cores and os.environ.get("B200_BENCH_REEXEC") == "1":
+        return
+    env = dict(os.environ, OMP_NUM_THREADS=cores, OMP_PROC_BIND="false", B200_BENCH_REEXEC="1")
+    env.pop("OMP_THREAD_LIMIT", None)
+    os.execve(sys.executable, [sys.executable] + sys.argv, env)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        _exec_with_all_cores()
         run_reference(args)
     else:
         run_b200(args)

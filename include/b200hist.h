@@ -410,6 +410,10 @@ B200HIST_API int b200hist_smem_atomic_peak(int device, int h_lo_zero, double* up
  * subtract, evaluate, apply, partition, finalise (7 floats) and row-visits V of the hist phase. */
 B200HIST_API int b200hist_updater_set_profiling(b200hist_updater_t u, int on);
 B200HIST_API int b200hist_updater_last_profile(b200hist_updater_t u, float* out_ms7, uint64_t* out_row_visits);
+/* Device time of the histogram phase of every growth step (level) of the last profiled tree, in launch order
+ * (root first); *out_n = number of steps, at most `capacity` values are written. */
+B200HIST_API int b200hist_updater_last_hist_steps(b200hist_updater_t u, float* out_ms, int32_t capacity,
+                                                  int32_t* out_n);
 /* with profiling on: device time of the last tree's cross-GPU histogram exchanges (already contained in the
  * "hist" phase of b200hist_updater_last_profile); 0 on one GPU. */
 B200HIST_API int b200hist_updater_last_comm_ms(b200hist_updater_t u, float* out_ms);

@@ -313,3 +313,46 @@ def trees_from_model(model: dict):
             loss_chg=[float(v) for v in t["loss_changes"]],
             sum_hess=[float(v) for v in t["sum_hessian"]]))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The reference's own distributed plumbing (tracker + communicator, include/xgboost/c_api.h:1669-1853), for the
+# 2-process drop-in test of the shim's distributed mode.
+# ----------------------------------------------------------------------------------------------------------------------
+class Tracker:
+    """RabitTracker through XGTrackerCreate / XGTrackerRun / XGTrackerWorkerArgs / XGTrackerWaitFor / XGTrackerFree."""
+
+    def __init__(self, n_workers: int, kind: str = "cuda", host_ip: str = "127.0.0.1", timeout: int = 300):
+        self.lib = load(kind)
+        self.h = c_void_p()
+        cfg = json.dumps({"dmlc_communicator": "rabit", "n_workers": int(n_workers), "host": host_ip, "port": 0,
+                          "sortby": 0, "timeout": int(timeout)}).encode()
+        _check(self.lib, self.lib.XGTrackerCreate(cfg, byref(self.h)))
+        _check(self.lib, self.lib.XGTrackerRun(self.h, b"{}"))
+
+    def worker_args(self) -> dict:
+        out = c_char_p()
+        _check(self.lib, self.lib.XGTrackerWorkerArgs(self.h, byref(out)))
+        return json.loads(out.value.decode())
+
+    def wait(self, timeout: int = 300):
+        _check(self.lib, self.lib.XGTrackerWaitFor(self.h, json.dumps({"timeout": int(timeout)}).encode()))
+
+    def free(self):
+        if self.h:
+            self.lib.XGTrackerFree(self.h)
+            self.h = c_void_p()
+
+
+def communicator_init(kind: str, args: dict) -> None:
+    lib = load(kind)
+    _check(lib, lib.XGCommunicatorInit(json.dumps(args).encode()))
+
+
+def communicator_finalize(kind: str) -> None:
+    lib = load(kind)
+    _check(lib, lib.XGCommunicatorFinalize())
+
+
+def communicator_rank(kind: str) -> int:
+    return int(load(kind).XGCommunicatorGetRank())

@@ -139,3 +139,47 @@ def test_two_rank_nccl_matches_single_gpu(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29614", str(script)],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [{}, {"objective": "binary:logistic", "max_depth": 5},
+                                   {"subsample": 0.7, "colsample_bytree": 0.6, "grow_policy": "lossguide",
+                                    "max_leaves": 20, "max_depth": 0}],
+                         ids=["squarederror", "logistic", "sampled_lossguide"])
+def test_two_process_reference_job_through_the_shim(tmp_path, extra):
+    """Distributed mode through the boundary: a 2-worker job of the UNMODIFIED reference (its own RabitTracker and
+    communicator, row-split data, one GPU per worker, uneven shards) with our factory serving grow_gpu_hist must give
+    the model the reference's own distributed gpu_hist gives (histogram.cu:598-609 AllReduceHist, quantiser.cu:88-123
+    GlobalSum, updater_gpu_hist.cu:661-668 root sum) -- same trees bit for bit on both workers."""
+    import json
+    import torch
+    from oracle import ref_capi as rc
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    shim = os.path.join(ROOT, "xgboost_b200", "lib", "libb200hist_xgb_shim.so")
+    if not (rc.available("cuda") and os.path.exists(shim)):
+        pytest.skip("needs oracle/_ref_cuda/libxgboost.so and the shim")
+    if "binary:logistic" in extra.values():
+        extra = dict(extra)
+    models = {}
+    for updater in ("grow_gpu_hist_reference", "grow_b200_hist"):
+        tracker = rc.Tracker(2, kind="cuda")
+        args = tracker.worker_args()
+        out = str(tmp_path / ("model_%s.json" % updater))
+        procs = [subprocess.Popen([sys.executable, "-m", "tests.dist_shim_worker", str(t), json.dumps(args), updater, out,
+                                   json.dumps(extra)], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                  text=True) for t in range(2)]
+        logs = [p.communicate(timeout=600)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), "\n".join(l[-3000:] for l in logs)
+        tracker.wait(60)
+        tracker.free()
+        got = [json.load(open("%s.rank%d" % (out, r))) for r in range(2)]
+        assert got[0]["trees"] == got[1]["trees"], "the two workers hold different models"
+        models[updater] = got
+    ref, ours = models["grow_gpu_hist_reference"], models["grow_b200_hist"]
+    assert ours[0]["launches"] > 0 and ours[1]["launches"] > 0, "the shim did not route Update() into libb200hist.so"
+    assert ref[0]["launches"] == 0
+    assert len(ref[0]["trees"]) == 4 and len(ref[0]["trees"][0]["left_children"]) > 7
+    assert json.dumps(ours[0]["trees"]) == json.dumps(ref[0]["trees"])
+    for r in range(2):
+        assert ours[r]["margin_bits"] == ref[r]["margin_bits"], "prediction cache of worker %d" % r

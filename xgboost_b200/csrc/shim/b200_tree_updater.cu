@@ -35,6 +35,9 @@
 #include <vector>
 
 #include "../../../include/b200hist.h"
+#include "src/collective/allgather.h"       // collective::Allgather (IPC handle exchange)
+#include "src/collective/allreduce.h"       // collective::Allreduce (barrier before unmapping)
+#include "src/collective/communicator-inl.h"  // IsDistributed, GetRank, GetWorldSize, GetProcessorName
 #include "src/common/bitfield.h"            // CatBitField
 #include "src/common/categorical.h"         // CatBitField alias
 #include "src/common/cuda_context.cuh"      // CUDAContext::Stream
@@ -187,6 +190,7 @@ class B200HistMaker : public TreeUpdater {
     // Sampler ctor (sampler.cu:343-363): the strategy follows sampling_method whenever subsample < 1
     B200_SHIM_CHECK(b200hist_updater_set_sampling_method(
         updater_, param->subsample < 1.0f && param->sampling_method == TrainParam::kGradientBased ? 1 : 0));
+    this->ConnectWorkers(p_fmat);
     if (!param->monotone_constraints.empty()) {  // TreeEvaluator ctor (split_evaluator.h:37-57)
       std::vector<std::int32_t> mono(param->monotone_constraints.cbegin(), param->monotone_constraints.cend());
       CHECK_LE(mono.size(), p_fmat->Info().num_col_)
@@ -223,6 +227,40 @@ class B200HistMaker : public TreeUpdater {
       node_is_cat_.resize(static_cast<std::size_t>(max_nodes));
       cat_bits_.resize(static_cast<std::size_t>(max_nodes) * cat_words_);
     }
+  }
+
+  // Distributed training (collective::IsDistributed(), data split by rows -- the reference's default): the reference
+  // sums every level's partial histograms with collective::Allreduce -> ncclAllReduce (histogram.cu:598-609), takes the
+  // quantiser's scale and the root sum from collective::GlobalSum (quantiser.cu:88-123, updater_gpu_hist.cu:661-668).
+  // Ours does the same three exchanges inside its own kernels over peer memory: every worker's histogram cache is
+  // IPC-mapped into the others (b200hist_updater_ipc_handle / set_peers; the 64-byte handles travel through the
+  // reference's OWN communicator, collective::Allgather on the CPU backend), then b200hist_updater_set_row_split.
+  // Requirements checked here, loudly: row split, one GPU per worker, all workers on one host (NVLink peer access).
+  void ConnectWorkers(DMatrix* p_fmat) {
+    if (!collective::IsDistributed()) return;
+    CHECK(p_fmat->Info().IsRowSplit())
+        << "[b200hist] distributed training is implemented for row-split data only (column split: use the "
+           "reference's updater, updater=grow_gpu_hist_reference)";
+    CHECK(!collective::IsFederated()) << "[b200hist] federated learning is not supported";
+    auto const world = collective::GetWorldSize();
+    auto const rank = collective::GetRank();
+    // same host?  compare a hash of the processor name of every worker
+    auto const name = collective::GetProcessorName();
+    std::vector<std::uint64_t> hosts(static_cast<std::size_t>(world), 0);
+    hosts[rank] = std::hash<std::string>{}(name);
+    auto rc = collective::Allgather(ctx_, linalg::MakeVec(hosts.data(), hosts.size()));
+    collective::SafeColl(rc);
+    for (auto h : hosts) {
+      CHECK_EQ(h, hosts[rank]) << "[b200hist] workers on different hosts: the peer-memory histogram exchange needs all "
+                                  "GPUs in one NVLink domain of one node";
+    }
+    std::vector<std::uint8_t> handles(static_cast<std::size_t>(world) * 64, 0);
+    B200_SHIM_CHECK(b200hist_updater_ipc_handle(updater_, handles.data() + static_cast<std::size_t>(rank) * 64));
+    rc = collective::Allgather(ctx_, linalg::MakeVec(handles.data(), handles.size()));
+    collective::SafeColl(rc);
+    B200_SHIM_CHECK(b200hist_updater_set_peers(updater_, rank, world, handles.data()));
+    B200_SHIM_CHECK(b200hist_updater_set_row_split(updater_, 1));
+    connected_ = true;
   }
 
   // GPUHistMakerDevice::Reset (updater_gpu_hist.cu:172-211) draws from ctx->Rng() in this order for every tree:
@@ -399,6 +437,19 @@ class B200HistMaker : public TreeUpdater {
   [[nodiscard]] float LeafOf(std::int32_t nidx) const { return nodes_[nidx].leaf_value; }
 
   void Release() {
+    if (updater_ != nullptr && connected_) {
+      // unmap the peers' caches; nobody frees a cache that a peer still maps: meet the other workers first (when the
+      // communicator is still up -- after XGCommunicatorFinalize every worker has finished its last exchange, whose
+      // closing barrier is the guarantee that no peer reads this cache any more)
+      ctx_->CUDACtx()->Stream().Sync();
+      b200hist_updater_clear_peers(updater_);
+      if (collective::IsDistributed()) {
+        std::int32_t one{1};
+        auto rc = collective::Allreduce(ctx_, linalg::MakeVec(&one, 1), collective::Op::kSum);
+        (void)rc;
+      }
+    }
+    connected_ = false;
     if (updater_ != nullptr) b200hist_updater_destroy(updater_);
     if (ellpack_ != nullptr) b200hist_ellpack_destroy(ellpack_);
     updater_ = nullptr;
@@ -418,6 +469,7 @@ class B200HistMaker : public TreeUpdater {
   std::vector<float> leaf_values_;
   common::ColumnSampler column_sampler_;
   bool sampling_set_{false};
+  bool connected_{false};
   bool level_draws_pending_{false};
   bool node_draws_pending_{false};
   bool node_draws_by_seed_{false};

@@ -887,6 +887,7 @@ struct b200hist_updater_s {
   std::vector<cudaEvent_t> events;
   float last_ms[8]{0, 0, 0, 0, 0, 0, 0, 0};  // [7] = the cross-GPU exchange, also contained in [1] (hist)
   uint64_t last_row_visits{0};
+  std::vector<float> last_hist_ms;  // the histogram span of every growth step of the last profiled tree
 };
 
 namespace {
@@ -921,10 +922,12 @@ struct PhaseTimer {
   void Collect() {
     if (!u->profiling) return;
     for (auto& m : u->last_ms) m = 0;
+    u->last_hist_ms.clear();
     for (auto& sp : spans) {
       float ms = 0;
       B200_CUDA(cudaEventElapsedTime(&ms, sp.second.first, sp.second.second));
       u->last_ms[sp.first] += ms;
+      if (sp.first == kHist) u->last_hist_ms.push_back(ms);  // one span per growth step (level), exchange included
     }
   }
 };
@@ -969,7 +972,6 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     const size_t need = GradientBasedScratchBytes(n, u->num_sms);
     if (need > u->gbs_scratch_bytes) {
       if (u->d_gbs_scratch) cudaFree(u->d_gbs_scratch);
-    if (u->d_leaf_override) cudaFree(u->d_leaf_override);
       u->d_gbs_scratch = nullptr;
       B200_CUDA(cudaMalloc(&u->d_gbs_scratch, need));
       u->gbs_scratch_bytes = need;
@@ -1342,6 +1344,7 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
       if (p) cudaFree(p);
     for (void* p : {(void*)u->d_node_sets, (void*)u->d_node_list, (void*)u->d_node_count, (void*)u->d_node_seq})
       if (p) cudaFree(p);
+    if (u->d_leaf_override) cudaFree(u->d_leaf_override);
     if (u->d_gbs_scratch) cudaFree(u->d_gbs_scratch);
     for (void* p : {(void*)u->d_col_seeds, (void*)u->d_col_cursor, (void*)u->d_col_tree_set, (void*)u->d_col_level_sets,
                     (void*)u->d_col_level_drawn, (void*)u->d_col_node_list, (void*)u->d_col_node_count})
@@ -1881,6 +1884,16 @@ int b200hist_updater_last_comm_ms(b200hist_updater_t u, float* out_ms) {
   B200_API_BEGIN();
   B200_CHECK(u != nullptr && out_ms != nullptr, "null argument");
   *out_ms = u->last_ms[7];
+  B200_API_END();
+}
+
+int b200hist_updater_last_hist_steps(b200hist_updater_t u, float* out_ms, int32_t capacity, int32_t* out_n) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && out_n != nullptr, "null argument");
+  const int32_t n = (int32_t)u->last_hist_ms.size();
+  *out_n = n;
+  if (out_ms)
+    for (int32_t i = 0; i < n && i < capacity; ++i) out_ms[i] = u->last_hist_ms[(size_t)i];
   B200_API_END();
 }
 

@@ -130,6 +130,7 @@ _SIGNATURES = {
     "b200hist_updater_node_histogram": (c_int, [c_void_p, c_int32, c_void_p]),
     "b200hist_updater_node_candidate": (c_int, [c_void_p, c_int32, POINTER(Candidate)]),
     "b200hist_updater_set_profiling": (c_int, [c_void_p, c_int]),
+    "b200hist_updater_last_hist_steps": (c_int, [c_void_p, c_void_p, c_int32, POINTER(c_int32)]),
     "b200hist_updater_last_profile": (c_int, [c_void_p, POINTER(c_float), POINTER(c_uint64)]),
     "b200hist_quantise": (c_int, [c_int, c_void_p, c_uint64, POINTER(Quantiser), c_void_p, POINTER(GPair64),
                                   c_void_p]),

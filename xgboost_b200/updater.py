@@ -687,6 +687,11 @@ class GPUHistMaker:
         comm = c_float(0.0)
         _l.check(_l.load().b200hist_updater_last_comm_ms(self._h, byref(comm)))
         d["hist_exchange"] = float(comm.value)   # part of "hist"
+        n = c_int32()
+        buf = (c_float * 64)()
+        _l.check(_l.load().b200hist_updater_last_hist_steps(self._h, buf, 64, byref(n)))
+        if 0 < n.value <= 64:
+            d["hist_levels"] = [float(buf[i]) for i in range(n.value)]
         return d
 
     # TreeUpdater::Update for one tree
