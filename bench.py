@@ -41,8 +41,9 @@ def parse_args():
     ap.add_argument("--depth", type=int, default=int(os.environ.get("B200_BENCH_DEPTH", 8)))
     ap.add_argument("--cpu-sample-rows", type=int, default=int(os.environ.get("B200_BENCH_CPU_ROWS", 4_000_000)),
                     help="rows of the workload the cpu_baseline leg of OUR arm times (bounded sample)")
-    ap.add_argument("--ref-rows", type=int, default=int(os.environ.get("B200_BENCH_REF_ROWS", 100_000_000)),
-                    help="rows of the workload `--impl reference` times (default: all of them)")
+    ap.add_argument("--ref-rows", type=int, default=int(os.environ.get("B200_BENCH_REF_ROWS", 25_000_000)),
+                    help="rows of the workload `--impl reference` times per step (bounded sample, default a quarter: the "
+                         "run ends within minutes; 100000000 = the whole matrix, ~13 min)")
     ap.add_argument("--split", default=os.environ.get("B200_BENCH_SPLIT", "rows"), choices=["rows", "features"],
                     help="multi-GPU decomposition: rows = every rank owns N/P rows, full-width partial histograms summed "
                          "per level over peer memory; features = every rank owns F/P feature blocks of all rows "
@@ -220,10 +221,10 @@ def model_sha(trees_json) -> str:
 # reference CPU arm (the unmodified reference's tree_method=hist on the host cores)
 # --------------------------------------------------------------------------------------------------
 def _host_batches(args, rows):
-    """1M-row float32 batches of the workload as numpy arrays, regenerated on every pass (SURVEY 8(d) generator: torch
-    Philox on the device when there is one -- generation is not what is timed -- else numpy on the host)."""
+    """The workload's 1M-row float32 batches as numpy arrays held in host RAM (rows x features x 4 bytes; the B200
+    hosts have 2 TB), generated ONCE (SURVEY 8(d) generator: torch Philox on the device when there is one -- generation
+    is not what is timed -- else numpy on the host) so that both passes of the QuantileDMatrix build read memory."""
     import numpy as np
-    from oracle import ref_capi as rc
     f = args.features
     nb = (rows + 999_999) // 1_000_000
     try:
@@ -231,28 +232,28 @@ def _host_batches(args, rows):
         dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else None
     except Exception:
         torch, dev = None, None
+    store = np.empty((rows, f), dtype=np.float32)
+    y = np.empty(rows, dtype=np.float32)
     if dev is not None:
-        def get(b):
-            x, _ = batch_of(torch, dev, f, rows, 1_000_000, b)
-            return x.cpu().numpy()
         w = torch.randn(f, generator=torch.Generator(device=dev).manual_seed(7), device=dev)
-        y = np.empty(rows, dtype=np.float32)
         for b in range(nb):
             x, g = batch_of(torch, dev, f, rows, 1_000_000, b)
-            yb = torch.nan_to_num(x) @ w + 0.1 * torch.randn(x.shape[0], generator=g, device=dev)
-            y[b * 1_000_000:b * 1_000_000 + x.shape[0]] = yb.cpu().numpy()
+            o = b * 1_000_000
+            store[o:o + x.shape[0]] = x.cpu().numpy()
+            y[o:o + x.shape[0]] = (torch.nan_to_num(x) @ w + 0.1 * torch.randn(x.shape[0], generator=g, device=dev)).cpu().numpy()
+            del x
         gen = "torch Philox on cuda, seed 2024 + batch"
     else:
-        def get(b):
-            m = min(1_000_000, rows - b * 1_000_000)
-            return np.random.default_rng(2024 + b).standard_normal((m, f), dtype=np.float32)
         w = np.random.default_rng(7).standard_normal(f).astype(np.float32)
-        y = np.empty(rows, dtype=np.float32)
         for b in range(nb):
-            x = get(b)
-            y[b * 1_000_000:b * 1_000_000 + x.shape[0]] = x @ w
+            o = b * 1_000_000
+            m = min(1_000_000, rows - o)
+            rng = np.random.default_rng(2024 + b)
+            store[o:o + m] = rng.standard_normal((m, f), dtype=np.float32)
+            y[o:o + m] = store[o:o + m] @ w + 0.1 * rng.standard_normal(m, dtype=np.float32)
         gen = "numpy PCG64 on the host, seed 2024 + batch"
-    return rc.LazyBatches(nb, get), y, gen
+    batches = [store[b * 1_000_000:min(rows, (b + 1) * 1_000_000)] for b in range(nb)]
+    return batches, y, gen
 
 
 def reference_cpu(args, steps, warmup, rows):
@@ -297,17 +298,22 @@ def run_reference(args):
     scale = rows / float(args.rows)                   # 1.0 when the full matrix is timed
     value = scale / res["s_per_iter_mean"]
     sample = ("unmodified reference CPU hist (oracle/_ref/libxgboost.so, XGBoosterUpdateOneIter, nthread=%d, "
-              "OMP_NUM_THREADS=%s) on %d x %d rows%s: mean %.3f s/iter over %d iters (median %.3f, min %.3f, max %.3f)"
-              % (res["cores"], res["omp"], rows, args.features,
-                 "" if scale == 1.0 else " = 1/%g of the workload, scaled linearly in rows" % (1.0 / scale),
-                 res["s_per_iter_mean"], args.steps, res["s_per_iter_median"], res["s_per_iter_min"],
-                 res["s_per_iter_max"]))
+              "OMP_NUM_THREADS=%s) on %d x %d rows: mean %.3f s/iter over %d iters (median %.3f, min %.3f, max %.3f)%s"
+              % (res["cores"], res["omp"], rows, args.features, res["s_per_iter_mean"], args.steps,
+                 res["s_per_iter_median"], res["s_per_iter_min"], res["s_per_iter_max"],
+                 "" if scale == 1.0 else
+                 "; a step is one iteration on this 1/%g sample, `value` = sample rate x %g (hist cost is linear in rows: the "
+                 "full 100M x 256 run, profiles/r02_reference_cpu_full_size.json, took 8.14 s/iter on the same host = "
+                 "0.123 iters/s; B200_BENCH_REF_ROWS=100000000 repeats it, ~13 min)" % (1.0 / scale, scale)))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup,
+            # the wall time of one timed step as it ran (on the sample); 1e3 / value is the full-size equivalent
+            "ms_per_step": 1e3 * res["s_per_iter_mean"], "ms_per_step_full_size_equivalent": 1e3 / value,
+            "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": {"workload": "synthetic %dx%d dense f32, %d bins, depth %d, reg:squarederror"
                                    % (args.rows, args.features, args.max_bin, args.depth),
-                       "timed_rows": rows, "l2": "inputs exceed L2"},
+                       "timed_rows": rows, "rows_scale": scale, "l2": "inputs exceed L2"},
             "dmatrix_build_s": round(res["dmatrix_build_s"], 2),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -115,6 +115,21 @@ B200HIST_API uint64_t b200hist_launch_count(void);
 B200HIST_API int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features,
                                          const uint32_t* cut_ptrs_host, const float* cut_values_host,
                                          int has_missing, b200hist_ellpack_t* out);
+/* External memory: the same dense page, but the quantised matrix lives in PINNED HOST memory and is streamed through
+ * two device staging buffers of `page_rows` rows each (double-buffered H2D on a copy stream owned by the page set) by
+ * every phase of the updater that reads it -- histogram build, partition, FinalisePosition -- once per tree level.
+ *   replaces the Ellpack page sources and caches of ExtMemQuantileDMatrix (src/data/ellpack_page_source.h:37-337,
+ *   src/data/extmem_quantile_dmatrix.cu) and the per-page loop of the updater (src/tree/updater_gpu_hist.cu:475-499,
+ *   529-580, src/tree/gpu_hist/row_partitioner.cuh:449-501).
+ * Device memory: 2 * page_rows * row_bytes for the pages + ~28 bytes per row of updater state; push_dense /
+ * import_reference_rows work as for an in-core page (any row range, in any order).  Trees are bit-identical to the
+ * in-core page's: histograms are integer sums, their value does not depend on how rows are grouped into pages. */
+B200HIST_API int b200hist_ellpack_create_paged(int device, uint64_t n_rows, uint32_t n_features,
+                                               const uint32_t* cut_ptrs_host, const float* cut_values_host,
+                                               int has_missing, uint64_t page_rows, b200hist_ellpack_t* out);
+/* n_pages = 0 for an in-core page; h2d_bytes = bytes streamed host -> device by the updater so far. */
+B200HIST_API int b200hist_ellpack_paging_info(b200hist_ellpack_t ell, uint32_t* n_pages, uint64_t* page_rows,
+                                              uint64_t* h2d_bytes);
 /* Q2: quantile sketch -> HistogramCuts of a dense f32 batch resident on the device (NaN = missing), for the
  * in-core, unweighted, single-window case.  replaces DeviceSketch / SketchContainer::{Push, ScanInput, MakeCuts}
  * (src/common/hist_util.cu:234-397, src/common/quantile.cu:108-153,340-418,658-709, quantile.h:280-340).

@@ -131,6 +131,23 @@ int main(int argc, char** argv) {
 
   // ---- the real histogram kernels, selected like LaunchBuildHist (default implementation) ----
   const int hist_mode = meta.size() > 24 ? (int)meta[24] : 0;
+  // [25] page_rows > 0: external memory -- every phase that reads the matrix runs once per page on a view of a COPY of
+  // that page alone (exact-size heap buffer: a read outside the page is an ASan report), like UpdateTreeImpl's
+  // for_each_page over the staging buffers
+  const uint64_t page_rows = meta.size() > 25 ? (uint64_t)meta[25] : 0;
+  auto for_each_page = [&](auto&& fn) {
+    if (page_rows == 0) { fn(view); return; }
+    for (uint64_t lo = 0; lo < n; lo += page_rows) {
+      const uint64_t hi = std::min<uint64_t>(n, lo + page_rows);
+      std::vector<uint8_t> stage(bins.begin() + lo * view.row_bytes, bins.begin() + hi * view.row_bytes);
+      EllView pv = view;
+      pv.bins = stage.data() - lo * (uint64_t)view.row_bytes;
+      pv.bins_t = nullptr;
+      pv.page_lo = (uint32_t)lo;
+      pv.page_hi = (uint32_t)hi;
+      fn(pv);
+    }
+  };
   b200hist_ellpack_s ell_host;
   ell_host.n_rows = n; ell_host.n_features = nf; ell_host.total_bins = view.total_bins; ell_host.row_bytes = view.row_bytes;
   ell_host.bin_bytes = view.bin_bytes; ell_host.null_symbol = view.null_symbol;
@@ -139,7 +156,8 @@ int main(int argc, char** argv) {
   ell_host.max_feature_bins = 0;
   for (uint32_t f = 0; f < nf; ++f) ell_host.max_feature_bins = std::max(ell_host.max_feature_bins, cut_ptrs[f + 1] - cut_ptrs[f]);
   const std::vector<GroupDesc> groups = hist_mode ? MakeFeatureGroups(ell_host, 0) : std::vector<GroupDesc>();
-  auto build_hist_kernels = [&]() {
+  auto build_hist_kernels = [&](const EllView& view) {
+    const bool paged = view.page_hi != 0xFFFFFFFFu;
     const int n_groups = (int)groups.size();
     if (sparse) {
       uint32_t b0 = 0xFFFFFFFFu, b1 = 0;
@@ -169,7 +187,13 @@ int main(int argc, char** argv) {
     if (pair) {
       const size_t pair_smem = (size_t)pair_sym * 192 * 4;
       const int n_pairs = (n_groups + 1) / 2;
-      if (sym_bytes == 2) {
+      if (paged && sym_bytes == 2) {
+        EMU_LAUNCH((2, (unsigned)n_pairs), (kHistThreads), std::max(pair_smem, smem),
+                   (HistKernelPair<2, 2, true>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist.data(), &q)));
+      } else if (paged) {
+        EMU_LAUNCH((2, (unsigned)n_pairs), (kHistThreads), std::max(pair_smem, smem),
+                   (HistKernelPair<3, 1, true>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist.data(), &q)));
+      } else if (sym_bytes == 2) {
         EMU_LAUNCH((2, (unsigned)n_pairs), (kHistThreads), std::max(pair_smem, smem),
                    (HistKernelPair<2, 2>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist.data(), &q)));
       } else {
@@ -178,7 +202,13 @@ int main(int argc, char** argv) {
       }
       return;
     }
-    if (sym_bytes == 2) {
+    if (paged && sym_bytes == 2) {
+      EMU_LAUNCH((2, (unsigned)n_groups), (kHistThreads), smem,
+                 (HistKernelBankedFast<2, true>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist.data(), &q)));
+    } else if (paged) {
+      EMU_LAUNCH((2, (unsigned)n_groups), (kHistThreads), smem,
+                 (HistKernelBankedFast<1, true>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist.data(), &q)));
+    } else if (sym_bytes == 2) {
       EMU_LAUNCH((2, (unsigned)n_groups), (kHistThreads), smem,
                  HistKernelBankedFast<2>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist.data(), &q));
     } else {
@@ -187,7 +217,7 @@ int main(int argc, char** argv) {
     }
   };
   auto build_hist = [&]() {  // the CPU stand-in for LaunchBuildHist over the kernels' own work list
-    if (hist_mode) { build_hist_kernels(); return; }
+    if (hist_mode) { for_each_page(build_hist_kernels); return; }
     for (int k = 0; k < ts.n_build; ++k) {
       const BuildEntry e = build[k];
       const uint32_t* rows = (e.buf ? ridx1.data() : ridx0.data()) + e.begin;
@@ -289,6 +319,11 @@ int main(int argc, char** argv) {
     }
     const bool children_possible = p.max_depth == 0 || !dw || step + 1 < p.max_depth;
     if (!children_possible) continue;
+    if (page_rows > 0) {  // the updater clears the accumulators before the first page
+      std::fill(flags.begin(), flags.end(), 0u);
+      std::fill(tile_left.begin(), tile_left.end(), 0u);
+    }
+    for_each_page([&](const EllView& view) {
     if (sparse) {
       if (has_cat) { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint32_t, true>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
       else { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint32_t, false>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
@@ -299,6 +334,7 @@ int main(int argc, char** argv) {
       if (has_cat) { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint16_t, true>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
       else { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint16_t, false>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
     }
+    });
     EMU_LAUNCH((1), (kCtlThreads), 0, ScanKernel(&ts, nodes.data(), part.data(), part_tile_seg.data(), tile_left.data(), tile_excl.data(), tile_left_off.data(), build.data(), sub.data(), eval_nodes.data(), build_tile_seg.data(), step_slot_base[step], step_cap[step], 0));
     EMU_LAUNCH((3), (kPartThreads), 0, PartitionScatterKernel(ridx0.data(), ridx1.data(), ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left_off.data()));
     build_hist();
@@ -321,16 +357,19 @@ int main(int argc, char** argv) {
     evaluate((int32_t)(2 * cap), icv, d_fs, n_fs, n_levels);
   }
   EMU_LAUNCH((1), (kCtlThreads), 0, FinalListKernel(&ts, nodes.data(), fin.data(), fin_tile_seg.data(), fin_tile_begin.data()));
+  for_each_page([&](const EllView& view) {
+  const uint32_t r_lo = page_rows ? view.page_lo : 0u, r_hi = page_rows ? view.page_hi : (uint32_t)n;
   if (sparse) {
-    if (has_cat) { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint32_t, true>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
-    else { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint32_t, false>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
+    if (has_cat) { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint32_t, true>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, r_lo, r_hi, cr))); }
+    else { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint32_t, false>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, r_lo, r_hi, cr))); }
   } else if (view.bin_bytes == 1) {
-    if (has_cat) { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint8_t, true>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
-    else { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint8_t, false>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
+    if (has_cat) { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint8_t, true>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, r_lo, r_hi, cr))); }
+    else { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint8_t, false>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, r_lo, r_hi, cr))); }
   } else {
-    if (has_cat) { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint16_t, true>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
-    else { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint16_t, false>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, (uint32_t)n, cr))); }
+    if (has_cat) { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint16_t, true>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, r_lo, r_hi, cr))); }
+    else { EMU_LAUNCH((2), (256), 0, (FinaliseWindowKernel<uint16_t, false>(view, ridx0.data(), ridx1.data(), gq.data(), nodes.data(), fin.data(), &ts, position.data(), &q, r_lo, r_hi, cr))); }
   }
+  });
   // ---- results ----
   std::vector<b200hist_tree_node> out((size_t)ts.n_nodes);
   for (int32_t i = 0; i < ts.n_nodes; ++i) {

@@ -581,7 +581,7 @@ TREE_NODE = np.dtype([("parent", "<i4"), ("left", "<i4"), ("right", "<i4"), ("fi
 
 def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, onehot=4, threshold=64, ic_sets=None,
                   node_sets=None, feature_set=None, n_levels=0, col_seeds=None, col_tree_set=None, bylevel=1.0, bynode=1.0,
-                  sparse=False, hist_mode=0):
+                  sparse=False, hist_mode=0, page_rows=0):
     exe = _build("emu_tree")
     n, nf = gb.shape
     max_bins = int(np.diff(cp).max())
@@ -617,7 +617,7 @@ def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, oneh
     np.array([n, nf, page.shape[1], bin_bytes, null_symbol, 0 if mono is None else 1, 0 if is_cat is None else 1, onehot,
               threshold, cat_words, (max_cat_bins + 31) // 32, max_cat_bins, 0 if ic_sets is None else len(ic_sets),
               0 if node_sets is None else node_sets.shape[0], 0 if node_sets is None else node_sets.shape[1],
-              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta + [row_stride, hist_mode],
+              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta + [row_stride, hist_mode, page_rows],
              dtype=np.int64).tofile(os.path.join(d, "meta.bin"))
     np.array([p.learning_rate, p.reg_lambda, p.reg_alpha, p.min_child_weight, p.max_delta_step, p.min_split_loss],
              dtype=np.float32).tofile(os.path.join(d, "param_f.bin"))
@@ -864,6 +864,35 @@ def test_whole_tree_kernel_sources_sparse_page(tmp_path, categorical):
     nodes, pos, flags, bits, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, sparse=True, **kw)
     o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), **okw)
     _same_tree(nodes, pos, o, flags if categorical else None, bits if categorical else None)
+
+
+@pytest.mark.parametrize("name,hist_mode,page_rows,kw", [
+    ("pair_u8_96f_pages_of_400", 2, 400, dict(f=96, max_bin=16)),
+    ("banked_u8_missing_37f_pages_of_311", 1, 311, dict(f=37, max_bin=24, missing=0.1)),
+    ("pair_fallback_logistic_64f_pages_of_1000", 2, 1000, dict(f=64, max_bin=16, logistic=True)),
+    ("banked_u16_300bins_pages_of_64", 1, 64, dict(f=9, max_bin=300, missing=0.1)),
+    ("generic_u16_600bins_pages_of_700", 1, 700, dict(f=6, max_bin=600)),
+    ("cpu_hist_lossguide_pages_of_512", 0, 512, dict(f=12, max_bin=24, lossguide=True)),
+], ids=lambda v: v if isinstance(v, str) else "")
+def test_whole_tree_over_external_memory_pages(tmp_path, name, hist_mode, page_rows, kw):
+    """External memory (b200hist_ellpack_create_paged, UpdateTreeImpl's for_each_page): every phase that reads the matrix
+    -- the real histogram kernels with the page clip compiled in, PartitionCountKernel accumulating decision bits over
+    the pages, FinaliseWindowKernel page by page -- sees ONE page at a time (an exact-size copy: reading a row outside it
+    is out of bounds).  The tree, every position and the row partition must be those of the in-core matrix."""
+    from tests.helpers import logistic_gpair
+    n = 1500
+    x, y = make_regression(n, kw["f"], seed=29, missing=kw.get("missing", 0.0))
+    cp, cv = make_cuts(x, kw["max_bin"])
+    gb = orc.bin_dense(x, cp, cv)
+    if kw.get("logistic"):
+        gp = logistic_gpair(np.zeros_like(y), (y > 0).astype(np.float32))
+    else:
+        gp = squared_error_gpair(np.zeros_like(y), y)
+    params = dict(max_depth=4, eta=0.5)
+    if kw.get("lossguide"):
+        params = dict(max_depth=0, max_leaves=11, grow_policy="lossguide", eta=0.5)
+    nodes, pos, _, _, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, hist_mode=hist_mode, page_rows=page_rows)
+    _same_tree(nodes, pos, orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params)))
 
 
 @pytest.mark.parametrize("name,hist_mode,kw", [

@@ -117,7 +117,33 @@ struct EllView {
   // whose bit for the split feature is clear certainly lacks the feature, so the partitioner reads 8 bytes of it
   // instead of its whole 4*row_stride-byte entry list (may be null)
   const unsigned long long* row_sig;
+  // External-memory pages (b200hist_ellpack_create_paged): `bins` addresses ONE resident page, biased so that
+  // `bins + r * row_bytes` is row r for the page's GLOBAL row ids r in [page_lo, page_hi); rows outside that range
+  // are not resident and must not be read.  In-core pages: page_lo = 0, page_hi = 0xFFFFFFFF (every row).
+  uint32_t page_lo = 0u;
+  uint32_t page_hi = 0xFFFFFFFFu;
 };
+
+#ifdef __CUDACC__
+// A node's row segment lists its rows in ascending order (the partition is stable), so the rows of one page are a
+// contiguous slice of it: [lo, hi) -> the slice whose row ids fall in [page_lo, page_hi).
+__device__ __forceinline__ void ClipToPage(const uint32_t* __restrict__ ridx, uint32_t& lo, uint32_t& hi,
+                                           uint32_t page_lo, uint32_t page_hi) {
+  uint32_t a = lo, b = hi;
+  while (a < b) {  // first index with ridx >= page_lo
+    const uint32_t mid = (a + b) >> 1;
+    if (__ldg(ridx + mid) < page_lo) a = mid + 1; else b = mid;
+  }
+  const uint32_t first = a;
+  b = hi;
+  while (a < b) {  // first index with ridx >= page_hi
+    const uint32_t mid = (a + b) >> 1;
+    if (__ldg(ridx + mid) < page_hi) a = mid + 1; else b = mid;
+  }
+  lo = first;
+  hi = a;
+}
+#endif
 
 }  // namespace b200
 
@@ -152,10 +178,37 @@ struct b200hist_ellpack_s {
   // numerical binning kernel has run (nullptr = none)
   uint32_t* d_cat_features{nullptr};
   uint32_t n_cat_features{0};
+  // External memory (b200hist_ellpack_create_paged): the quantised matrix lives in PINNED HOST memory (one
+  // allocation, row-major, our layout); page p = rows [p * page_rows, min(n_rows, (p + 1) * page_rows)).  The updater
+  // streams the pages through two device staging buffers (double-buffered H2D on `copy_stream`); incoming batches
+  // are binned / decoded into `d_import` on the device and copied out.  d_bins stays null.
+  bool paged{false};
+  uint64_t page_rows{0};
+  uint8_t* h_bins{nullptr};
+  uint8_t* d_stage[2]{nullptr, nullptr};
+  uint8_t* d_import{nullptr};
+  size_t import_bytes{0};
+  void* copy_stream{nullptr};              // cudaStream_t
+  void* ev_ready[2]{nullptr, nullptr};     // cudaEvent_t: the page has landed in stage b (recorded on copy_stream)
+  void* ev_done[2]{nullptr, nullptr};      // cudaEvent_t: the kernels reading stage b have finished (compute stream)
+  uint64_t stage_uses{0};                  // staging buffer of the next page = stage_uses & 1
+  uint64_t h2d_bytes{0};                   // bytes streamed from the host so far (bench / tests)
+  uint32_t NumPages() const { return paged ? (uint32_t)((n_rows + page_rows - 1) / page_rows) : 1u; }
   b200::EllView View() const {
     return b200::EllView{d_bins, d_cut_ptrs, d_cut_values, n_rows, n_features, total_bins,
                          row_bytes, bin_bytes, null_symbol, d_bins_t, col_stride,
-                         is_sparse ? 1u : 0u, row_stride, d_row_sig};
+                         is_sparse ? 1u : 0u, row_stride, d_row_sig, 0u, 0xFFFFFFFFu};
+  }
+  // the view of page p once it is resident in staging buffer b
+  b200::EllView PageView(uint32_t p, int b) const {
+    b200::EllView v = View();
+    const uint64_t lo = (uint64_t)p * page_rows;
+    const uint64_t hi = lo + page_rows < n_rows ? lo + page_rows : n_rows;
+    v.bins = d_stage[b] - lo * (uint64_t)row_bytes;  // biased: never dereferenced outside [lo, hi)
+    v.bins_t = nullptr;
+    v.page_lo = (uint32_t)lo;
+    v.page_hi = (uint32_t)hi;
+    return v;
   }
 };
 

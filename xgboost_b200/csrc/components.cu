@@ -54,6 +54,7 @@ int b200hist_build_hist(b200hist_ellpack_t ell, const b200hist_gpair64* gq_dev, 
     B200_CUDA(cudaMemcpyAsync(d_tile_seg.p, tile_seg.data(), sizeof(uint32_t) * tile_seg.size(), cudaMemcpyHostToDevice, s));
   B200_CUDA(cudaMemcpyAsync(d_ts.p, &ts, sizeof(ts), cudaMemcpyHostToDevice, s));
   B200_CUDA(cudaMemcpyAsync(d_groups.p, groups.data(), sizeof(GroupDesc) * groups.size(), cudaMemcpyHostToDevice, s));
+  B200_CHECK(!ell->paged, "component entry points need an in-core page");
   LaunchBuildHist(ell->View(), gq_dev, ridx_dev, ridx_dev, d_build.p, d_tile_seg.p, d_ts.p, d_groups.p, groups,
                   hist_dev, nullptr, NumSMs(ell->device), s);
   B200_CUDA(cudaStreamSynchronize(s));
@@ -261,6 +262,7 @@ int b200hist_partition(b200hist_ellpack_t ell, const uint32_t* ridx_in_dev, uint
   if (T) B200_CUDA(cudaMemcpyAsync(d_tile_seg.p, tile_seg.data(), sizeof(uint32_t) * T, cudaMemcpyHostToDevice, s));
   B200_CUDA(cudaMemcpyAsync(d_ts.p, &ts, sizeof(ts), cudaMemcpyHostToDevice, s));
   const int sms = NumSMs(ell->device);
+  B200_CHECK(!ell->paged, "component entry points need an in-core page");
   LaunchPartitionCount(ell->View(), ridx_in_dev, ridx_in_dev, d_part.p, d_tile_seg.p, d_ts.p, d_flags.p, d_tile_left.p, sms, s);
   std::vector<uint32_t> tile_left(T), tile_off(T);
   if (T) B200_CUDA(cudaMemcpyAsync(tile_left.data(), d_tile_left.p, sizeof(uint32_t) * T, cudaMemcpyDeviceToHost, s));

@@ -13,6 +13,7 @@
 // The reference's own 8-bit layout starts at byte 8 (kPadding) and is therefore only 8-byte
 // aligned -- which is why we keep our own copy instead of reading the reference buffer in place.
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -213,6 +214,23 @@ __global__ void __launch_bounds__(256) TransposeKernel16(const uint8_t* __restri
 }
 
 #ifndef B200_KERNELS_ONLY
+// External memory: scratch for one incoming batch in OUR row layout, and its copy-out into the pinned host image.
+static uint8_t* ImportScratch(b200hist_ellpack_s* e, uint64_t n) {
+  const size_t need = (size_t)n * e->row_bytes + 16;
+  if (need > e->import_bytes) {
+    if (e->d_import) cudaFree(e->d_import);
+    e->d_import = nullptr;
+    e->d_import = DevAlloc<uint8_t>(need);
+    e->import_bytes = need;
+  }
+  return e->d_import;
+}
+static void ExportImported(b200hist_ellpack_s* e, uint64_t row_begin, uint64_t n, cudaStream_t s) {
+  B200_CUDA(cudaMemcpyAsync(e->h_bins + row_begin * (uint64_t)e->row_bytes, e->d_import, n * (uint64_t)e->row_bytes,
+                            cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));  // the scratch is reused by the next batch
+}
+
 static void LaunchTranspose(b200hist_ellpack_s* e, uint64_t row_begin, uint64_t n, cudaStream_t s) {
   if (e->d_bins_t == nullptr || n == 0) return;
   // tiles are aligned to 128 rows of the page so that 32-bit stores stay aligned
@@ -350,8 +368,9 @@ const char* b200hist_last_error(void) { return g_last_error.c_str(); }
 int b200hist_version(void) { return B200HIST_VERSION; }
 uint64_t b200hist_launch_count(void) { return g_launch_count.load(); }
 
-int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features, const uint32_t* cut_ptrs_host,
-                            const float* cut_values_host, int has_missing, b200hist_ellpack_t* out) {
+static int EllpackCreateDense(int device, uint64_t n_rows, uint32_t n_features, const uint32_t* cut_ptrs_host,
+                              const float* cut_values_host, int has_missing, uint64_t page_rows,
+                              b200hist_ellpack_t* out) {
   B200_API_BEGIN();
   B200_CHECK(out != nullptr && cut_ptrs_host != nullptr && cut_values_host != nullptr, "null argument");
   B200_CHECK(n_features > 0, "n_features must be positive");
@@ -385,14 +404,76 @@ int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features, co
   e->d_cut_values = DevAlloc<float>(e->total_bins);
   B200_CUDA(cudaMemcpy(e->d_cut_ptrs, e->cut_ptrs.data(), sizeof(uint32_t) * (n_features + 1), cudaMemcpyHostToDevice));
   B200_CUDA(cudaMemcpy(e->d_cut_values, e->cut_values.data(), sizeof(float) * e->total_bins, cudaMemcpyHostToDevice));
+  if (page_rows > 0) {  // external memory: pinned host storage + two device staging buffers of one page each
+    e->paged = true;
+    e->page_rows = std::min<uint64_t>(page_rows, std::max<uint64_t>(n_rows, 1));
+    const size_t host_bytes = (size_t)n_rows * e->row_bytes + 16;
+    B200_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->h_bins), host_bytes, cudaHostAllocPortable));
+    std::memset(e->h_bins, 0, host_bytes);
+    const size_t stage_bytes = (size_t)e->page_rows * e->row_bytes + 16;
+    for (int b = 0; b < 2; ++b) {
+      e->d_stage[b] = DevAlloc<uint8_t>(stage_bytes);
+      cudaEvent_t ev;
+      B200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->ev_ready[b] = ev;
+      B200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->ev_done[b] = ev;
+    }
+    cudaStream_t cs;
+    B200_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    e->copy_stream = cs;
+    *out = e;
+    return 0;
+  }
   e->d_bins = DevAlloc<uint8_t>(n_rows * (uint64_t)e->row_bytes + 16);
   B200_CUDA(cudaMemset(e->d_bins, 0, n_rows * (uint64_t)e->row_bytes + 16));
+  // Column-major copy in the page's symbol width (col_stride in symbols): the partitioner's single-feature gathers
+  // read it (32 consecutive rows share a sector: 4.9 instead of 16 ms of partition per tree at 100M x 256).  It
+  // doubles the page, so it is an accelerator, not a requirement: kept when it fits next to the updater's state
+  // (gradient pairs, row ids, positions: ~40 B per row, plus the histogram cache) with a fifth of the device to
+  // spare, dropped otherwise -- the partition kernels then gather from the row-major page.
+  // B200HIST_NO_COLMAJOR=1 drops it always, =0 keeps it always.
   const char* no_t = std::getenv("B200HIST_NO_COLMAJOR");
-  if (!(no_t && no_t[0] == '1')) {  // column-major copy in the page's symbol width (col_stride in symbols)
-    e->col_stride = (n_rows + 127) & ~uint64_t(127);
-    e->d_bins_t = DevAlloc<uint8_t>((uint64_t)n_features * e->col_stride * e->bin_bytes + 16);
+  const uint64_t col_stride = (n_rows + 127) & ~uint64_t(127);
+  const uint64_t copy_bytes = (uint64_t)n_features * col_stride * e->bin_bytes + 16;
+  bool want_copy = true;
+  if (no_t && no_t[0] == '1') {
+    want_copy = false;
+  } else if (!(no_t && no_t[0] == '0')) {
+    size_t free_b = 0, total_b = 0;
+    B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t state_bytes = n_rows * 40ull + (1ull << 30);
+    want_copy = (uint64_t)free_b >= copy_bytes + state_bytes + (uint64_t)total_b / 5;
+  }
+  if (want_copy) {
+    e->col_stride = col_stride;
+    e->d_bins_t = DevAlloc<uint8_t>(copy_bytes);
   }
   *out = e;
+  B200_API_END();
+}
+
+int b200hist_ellpack_create(int device, uint64_t n_rows, uint32_t n_features, const uint32_t* cut_ptrs_host,
+                            const float* cut_values_host, int has_missing, b200hist_ellpack_t* out) {
+  return EllpackCreateDense(device, n_rows, n_features, cut_ptrs_host, cut_values_host, has_missing, 0, out);
+}
+
+int b200hist_ellpack_create_paged(int device, uint64_t n_rows, uint32_t n_features, const uint32_t* cut_ptrs_host,
+                                  const float* cut_values_host, int has_missing, uint64_t page_rows,
+                                  b200hist_ellpack_t* out) {
+  if (page_rows == 0) {
+    ::b200::SetLastError("b200hist_ellpack_create_paged: page_rows must be positive");
+    return -1;
+  }
+  return EllpackCreateDense(device, n_rows, n_features, cut_ptrs_host, cut_values_host, has_missing, page_rows, out);
+}
+
+int b200hist_ellpack_paging_info(b200hist_ellpack_t e, uint32_t* n_pages, uint64_t* page_rows, uint64_t* h2d_bytes) {
+  B200_API_BEGIN();
+  B200_CHECK(e != nullptr, "null ellpack");
+  if (n_pages) *n_pages = e->paged ? e->NumPages() : 0u;
+  if (page_rows) *page_rows = e->paged ? e->page_rows : 0ull;
+  if (h2d_bytes) *h2d_bytes = e->h2d_bytes;
   B200_API_END();
 }
 
@@ -477,6 +558,19 @@ int b200hist_ellpack_destroy(b200hist_ellpack_t e) {
     cudaFree(e->d_cut_values);
     cudaFree(e->d_bins);
     cudaFree(e->d_bins_t);
+    if (e->paged) {
+      if (e->copy_stream) {
+        cudaStreamSynchronize(static_cast<cudaStream_t>(e->copy_stream));
+        cudaStreamDestroy(static_cast<cudaStream_t>(e->copy_stream));
+      }
+      for (int b = 0; b < 2; ++b) {
+        cudaFree(e->d_stage[b]);
+        if (e->ev_ready[b]) cudaEventDestroy(static_cast<cudaEvent_t>(e->ev_ready[b]));
+        if (e->ev_done[b]) cudaEventDestroy(static_cast<cudaEvent_t>(e->ev_done[b]));
+      }
+      cudaFree(e->d_import);
+      cudaFreeHost(e->h_bins);
+    }
     if (e->d_row_sig) cudaFree(e->d_row_sig);
     if (e->d_cat_features) cudaFree(e->d_cat_features);
     delete e;
@@ -494,6 +588,10 @@ int b200hist_ellpack_push_dense(b200hist_ellpack_t e, uint64_t row_begin, const 
   if (n == 0) return 0;
   DeviceGuard guard(e->device);
   auto s = static_cast<cudaStream_t>(stream);
+  // external memory: the batch is binned into the import scratch (biased so that the kernels' row_begin indexing
+  // lands at its start) and copied out to the pinned host image afterwards
+  uint8_t* const dst_bins = e->paged ? ImportScratch(e, n) - row_begin * (uint64_t)e->row_bytes : e->d_bins;
+  if (e->paged) B200_CUDA(cudaMemsetAsync(e->d_import, 0, n * (uint64_t)e->row_bytes, s));
   uint64_t total = n * (e->row_bytes / 4);
   int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
   uint32_t max_block_cuts = 0;  // cut values of the widest 32-feature block
@@ -502,14 +600,14 @@ int b200hist_ellpack_push_dense(b200hist_ellpack_t e, uint64_t row_begin, const 
   if (e->bin_bytes == 1 && max_block_cuts * sizeof(float) <= 40 * 1024) {
     dim3 grid((unsigned)std::min<uint64_t>((n + 31) / 32, (uint64_t)NumSMs(e->device) * 8), (e->n_features + 31) / 32);
     BinDenseSmemKernel<<<grid, 256, max_block_cuts * sizeof(float), s>>>(x_dev, n, ld, e->n_features, e->d_cut_ptrs,
-                                                                        e->d_cut_values, e->d_bins, row_begin,
+                                                                        e->d_cut_values, dst_bins, row_begin,
                                                                         e->row_bytes, e->null_symbol);
   } else if (e->bin_bytes == 1) {
     BinDenseKernel<uint8_t><<<blocks, 256, 0, s>>>(x_dev, n, ld, e->n_features, e->d_cut_ptrs, e->d_cut_values,
-                                                  e->d_bins, row_begin, e->row_bytes, e->null_symbol);
+                                                  dst_bins, row_begin, e->row_bytes, e->null_symbol);
   } else {
     BinDenseKernel<uint16_t><<<blocks, 256, 0, s>>>(x_dev, n, ld, e->n_features, e->d_cut_ptrs, e->d_cut_values,
-                                                   e->d_bins, row_begin, e->row_bytes, e->null_symbol);
+                                                   dst_bins, row_begin, e->row_bytes, e->null_symbol);
   }
   B200_LAUNCHED();
   if (e->d_cat_features != nullptr) {
@@ -517,15 +615,16 @@ int b200hist_ellpack_push_dense(b200hist_ellpack_t e, uint64_t row_begin, const 
     const int cb = (int)std::min<uint64_t>((cat_total + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
     if (e->bin_bytes == 1) {
       RebinCategoricalKernel<uint8_t><<<cb, 256, 0, s>>>(x_dev, n, ld, e->d_cat_features, e->n_cat_features,
-                                                         e->d_cut_ptrs, e->d_cut_values, e->d_bins, row_begin,
+                                                         e->d_cut_ptrs, e->d_cut_values, dst_bins, row_begin,
                                                          e->row_bytes, e->null_symbol);
     } else {
       RebinCategoricalKernel<uint16_t><<<cb, 256, 0, s>>>(x_dev, n, ld, e->d_cat_features, e->n_cat_features,
-                                                          e->d_cut_ptrs, e->d_cut_values, e->d_bins, row_begin,
+                                                          e->d_cut_ptrs, e->d_cut_values, dst_bins, row_begin,
                                                           e->row_bytes, e->null_symbol);
     }
     B200_LAUNCHED();
   }
+  if (e->paged) ExportImported(e, row_begin, n, s);
   LaunchTranspose(e, row_begin, n, s);
   B200_API_END();
 }
@@ -588,7 +687,8 @@ int b200hist_ellpack_import_reference_rows(b200hist_ellpack_t e, uint64_t row_be
   auto s = static_cast<cudaStream_t>(stream);
   uint64_t total = n_rows * (uint64_t)e->n_features;
   int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)NumSMs(e->device) * 16);
-  uint8_t* dst = e->d_bins + row_begin * (uint64_t)e->row_bytes;
+  uint8_t* dst = e->paged ? ImportScratch(e, n_rows) : e->d_bins + row_begin * (uint64_t)e->row_bytes;
+  if (e->paged) B200_CUDA(cudaMemsetAsync(e->d_import, 0, n_rows * (uint64_t)e->row_bytes, s));
   if (e->bin_bytes == 1) {
     ImportReferenceKernel<uint8_t><<<blocks, 256, 0, s>>>(gidx_buffer_dev, n_rows, e->n_features, bits, ref_null, dst,
                                                          e->row_bytes, e->null_symbol);
@@ -597,6 +697,7 @@ int b200hist_ellpack_import_reference_rows(b200hist_ellpack_t e, uint64_t row_be
                                                           e->row_bytes, e->null_symbol);
   }
   B200_LAUNCHED();
+  if (e->paged) ExportImported(e, row_begin, n_rows, s);
   LaunchTranspose(e, row_begin, n_rows, s);
   B200_API_END();
 }
@@ -626,6 +727,10 @@ int b200hist_ellpack_copy_bins_to_host(b200hist_ellpack_t e, void* out_host) {
   B200_API_BEGIN();
   B200_CHECK(e != nullptr && out_host != nullptr, "null argument");
   DeviceGuard guard(e->device);
+  if (e->paged) {
+    std::memcpy(out_host, e->h_bins, e->n_rows * (uint64_t)e->row_bytes);
+    return 0;
+  }
   B200_CUDA(cudaMemcpy(out_host, e->d_bins, e->n_rows * (uint64_t)e->row_bytes, cudaMemcpyDeviceToHost));
   B200_API_END();
 }

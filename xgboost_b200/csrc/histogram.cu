@@ -294,8 +294,8 @@ HistKernelBanked(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
     const BuildEntry e = build[seg];
     const uint32_t seg_tile_end = (seg + 1 < n_build) ? build[seg + 1].tile_begin : n_tiles;
     const uint32_t te = min(t1, seg_tile_end);
-    const uint32_t lo = (t - e.tile_begin) * kHistTile;
-    const uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
+    uint32_t lo = (t - e.tile_begin) * kHistTile;
+    uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
     const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin;
 
     for (uint32_t blk = 0; blk < B; ++blk) {
@@ -604,7 +604,7 @@ __device__ __forceinline__ void FastRowsZ3(const uint32_t* __restrict__ ridx, ui
 }
 
 // One group (B blocks of 32 features, 16-byte accumulators) over the CTA's tile range [t0, t1).
-template <int kSymBytes>
+template <int kSymBytes, bool kPaged = false>
 __device__ __forceinline__ void BankedFastGroup(const EllView& ell, const longlong2* __restrict__ gq,
                                                 const uint32_t* __restrict__ ridx0, const uint32_t* __restrict__ ridx1,
                                                 const BuildEntry* __restrict__ build,
@@ -634,9 +634,10 @@ __device__ __forceinline__ void BankedFastGroup(const EllView& ell, const longlo
     const BuildEntry e = build[seg];
     const uint32_t seg_tile_end = (seg + 1 < n_build) ? build[seg + 1].tile_begin : n_tiles;
     const uint32_t te = min(t1, seg_tile_end);
-    const uint32_t lo = (t - e.tile_begin) * kHistTile;
-    const uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
+    uint32_t lo = (t - e.tile_begin) * kHistTile;
+    uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
     const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin;
+    if constexpr (kPaged) ClipToPage(ridx, lo, hi, ell.page_lo, ell.page_hi);  // external memory: this page's rows
     for (uint32_t blk = 0; blk < B; ++blk) {
       uint32_t off[4];
 #pragma unroll
@@ -668,7 +669,7 @@ __device__ __forceinline__ void BankedFastGroup(const EllView& ell, const longlo
   }
 }
 
-template <int kSymBytes>
+template <int kSymBytes, bool kPaged = false>
 __global__ void __launch_bounds__(kHistThreads, 1)
 HistKernelBankedFast(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
                      const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
@@ -682,8 +683,8 @@ HistKernelBankedFast(EllView ell, const longlong2* __restrict__ gq, const uint32
   const uint32_t t1 = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
   if (t0 >= t1) return;
   const GroupDesc g = groups[blockIdx.y];
-  BankedFastGroup<kSymBytes>(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, (uint32_t)ts->n_build, g, hist,
-                             qd != nullptr && qd->h_lo_or == 0u, sh, t0, t1);
+  BankedFastGroup<kSymBytes, kPaged>(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, (uint32_t)ts->n_build, g, hist,
+                                     qd != nullptr && qd->h_lo_or == 0u, sh, t0, t1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -848,7 +849,7 @@ __device__ __forceinline__ void FastRowsP(const uint32_t* __restrict__ ridx, uin
   }
 }
 
-template <int kBufs, int kSymBytes>
+template <int kBufs, int kSymBytes, bool kPaged = false>
 __global__ void __launch_bounds__(kHistThreads, 1)
 HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx0,
                const uint32_t* __restrict__ ridx1, const BuildEntry* __restrict__ build,
@@ -867,11 +868,11 @@ HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __
   const bool two = gi + 1u < n_groups;
   const GroupDesc g0 = groups[gi];
   if (!two || !h_lo_zero) {  // odd block out, or hessians with low words: 16-byte layout, block after block
-    BankedFastGroup<kSymBytes>(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, n_build, g0, hist, h_lo_zero, sh, t0, t1);
+    BankedFastGroup<kSymBytes, kPaged>(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, n_build, g0, hist, h_lo_zero, sh, t0, t1);
     if (two) {
       const GroupDesc g1 = groups[gi + 1u];
-      BankedFastGroup<kSymBytes>(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, n_build, g1, hist, h_lo_zero, sh, t0,
-                                 t1);
+      BankedFastGroup<kSymBytes, kPaged>(ell, gq, ridx0, ridx1, build, tile_seg, n_tiles, n_build, g1, hist, h_lo_zero, sh,
+                                         t0, t1);
     }
     return;
   }
@@ -898,9 +899,10 @@ HistKernelPair(EllView ell, const longlong2* __restrict__ gq, const uint32_t* __
     const BuildEntry e = build[seg];
     const uint32_t seg_tile_end = (seg + 1 < n_build) ? build[seg + 1].tile_begin : n_tiles;
     const uint32_t te = min(t1, seg_tile_end);
-    const uint32_t lo = (t - e.tile_begin) * kHistTile;
-    const uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
+    uint32_t lo = (t - e.tile_begin) * kHistTile;
+    uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
     const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin;
+    if constexpr (kPaged) ClipToPage(ridx, lo, hi, ell.page_lo, ell.page_hi);  // external memory: this page's rows
     FastRowsP<kBufs, kSymBytes>(ridx, lo, hi, gq, col, ell.row_bytes, warp, q, sel, off);
     __syncthreads();
     // flush this CTA's share of the node (RED.64 on non-zero accumulators) and clear
@@ -1052,8 +1054,8 @@ HistKernelStaged(EllView ell, const longlong2* __restrict__ gq, const uint32_t* 
     const BuildEntry e = build[seg];
     const uint32_t seg_tile_end = (seg + 1 < n_build) ? build[seg + 1].tile_begin : n_tiles;
     const uint32_t te = min(t1, seg_tile_end);
-    const uint32_t lo = (t - e.tile_begin) * kHistTile;
-    const uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
+    uint32_t lo = (t - e.tile_begin) * kHistTile;
+    uint32_t hi = min(e.count, (te - e.tile_begin) * kHistTile);
     const uint32_t* __restrict__ ridx = (e.buf ? ridx1 : ridx0) + e.begin;
 
     // passes of this warp: rows [jb, jb+8), jb = lo + (warp + i * kWarps) * 8
@@ -1252,6 +1254,7 @@ HistKernelGeneric(EllView ell, const longlong2* __restrict__ gq, const uint32_t*
       const uint32_t j = idx / W;
       const uint32_t w = idx - j * W;
       const uint32_t r = s_ridx[j];
+      if (r < ell.page_lo || r >= ell.page_hi) continue;  // external memory: only the resident page's rows
       const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(ell.bins + (size_t)r * ell.row_bytes + g.byte_begin) + w);
       const longlong2 gp = s_gq[j];
 #pragma unroll
@@ -1316,6 +1319,10 @@ void PrepareHistKernels(int device) {
   B200_CUDA(cudaFuncSetAttribute((HistKernelPair<2, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute((HistKernelPair<3, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute((HistKernelPair<2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute((HistKernelPair<3, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute((HistKernelPair<2, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute((HistKernelBankedFast<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  B200_CUDA(cudaFuncSetAttribute((HistKernelBankedFast<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelBanked<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   B200_CUDA(cudaFuncSetAttribute(HistKernelStaged<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -1346,7 +1353,8 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
     const uint32_t sym_bytes = ell.bin_bytes;
     size_t smem = 0;
     for (auto const& g : groups_host) smem = std::max(smem, BankedSmemBytes(g));
-    const int impl = HistImpl();
+    const bool paged = ell.page_hi != 0xFFFFFFFFu;
+    const int impl = paged ? 0 : HistImpl();
     // the default kernels give the null symbol its own accumulator slot (MakeFeatureGroups); the others predicate
     bool checked = ell.null_symbol != 0xFFFFFFFFu && impl != 0;
     uint32_t max_blocks = 1;
@@ -1382,6 +1390,7 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
       }();
       // uint16 symbols cost two more registers per row buffer: two buffers there (measured equal on uint8)
       auto pk = sym_bytes == 2 ? HistKernelPair<2, 2> : (pair_bufs == 2 ? HistKernelPair<2, 1> : HistKernelPair<3, 1>);
+      if (paged) pk = sym_bytes == 2 ? HistKernelPair<2, 2, true> : HistKernelPair<3, 1, true>;
       pk<<<pgrid, kHistThreads, std::max(pair_smem, smem), s>>>(
           ell, reinterpret_cast<const longlong2*>(gq), ridx0, ridx1, build, tile_seg, ts, groups_dev, (uint32_t)n_groups,
           reinterpret_cast<longlong2*>(hist), quant);
@@ -1391,7 +1400,10 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
     using KernelT = void (*)(EllView, const longlong2*, const uint32_t*, const uint32_t*, const BuildEntry*,
                              const uint32_t*, const TreeState*, const GroupDesc*, longlong2*, const QuantDev*);
     KernelT kernel;
-    if (impl == 0 || impl == 3) {  // 3 = the unscheduled direct-load kernel (for comparison)
+    if (paged) {  // external memory: the default kernels with the page clip compiled in
+      B200_CHECK(!checked, "internal: external-memory pages are padded to whole feature blocks");
+      kernel = sym_bytes == 2 ? HistKernelBankedFast<2, true> : HistKernelBankedFast<1, true>;
+    } else if (impl == 0 || impl == 3) {  // 3 = the unscheduled direct-load kernel (for comparison)
       B200_CHECK(sym_bytes == 1 || (impl == 0 && !checked), "internal: uint16 pages use the default banked kernels only");
       kernel = checked ? HistKernelBanked<true>
                        : (impl == 0 ? (sym_bytes == 2 ? HistKernelBankedFast<2> : HistKernelBankedFast<1>)

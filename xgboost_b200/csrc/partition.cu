@@ -44,6 +44,11 @@ PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint
     const BinT* __restrict__ colt =
         ell.bins_t ? reinterpret_cast<const BinT*>(ell.bins_t) + (uint64_t)e.findex * ell.col_stride : nullptr;
     uint32_t cnt = 0;
+    // External memory (one launch per resident page): only the rows of [page_lo, page_hi) are decided here; the
+    // decision bits and the tile's left count ACCUMULATE over the page launches (the updater clears them before the
+    // first page).  A tile lists ascending row ids, so one that lies entirely outside the page is skipped after two loads.
+    const bool paged = ell.page_hi != 0xFFFFFFFFu;
+    if (paged && (__ldg(ridx + n - 1) < ell.page_lo || __ldg(ridx) >= ell.page_hi)) continue;
     if (ell.is_sparse) {
 #pragma unroll
       for (int k = 0; k < kRowsPerThread; ++k) {
@@ -69,19 +74,25 @@ PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint
         const uint32_t j = k * kPartThreads + threadIdx.x;
         r[k] = __ldg(ridx + min(j, n - 1));
       }
+      bool in_page[kRowsPerThread];
 #pragma unroll
-      for (int k = 0; k < kRowsPerThread; ++k)
-        sym[k] = (sizeof(BinT) <= 2 && colt != nullptr)
+      for (int k = 0; k < kRowsPerThread; ++k) {
+        in_page[k] = r[k] >= ell.page_lo && r[k] < ell.page_hi;  // always true for an in-core page
+        sym[k] = !in_page[k] ? 0u
+                 : (sizeof(BinT) <= 2 && colt != nullptr)
                      ? (uint32_t)__ldg(colt + r[k])
                      : (uint32_t)__ldg(reinterpret_cast<const BinT*>(col + (size_t)r[k] * ell.row_bytes));
+      }
 #pragma unroll
       for (int k = 0; k < kRowsPerThread; ++k) {
         const uint32_t j = k * kPartThreads + threadIdx.x;
-        const bool left = j < n && ((sym[k] == ell.null_symbol) ? (e.default_left != 0)
-                                                                : GoLeftBin<kCat>((int32_t)sym[k], e.split_lbin, e.nidx, cr));
+        const bool left = j < n && in_page[k] &&
+                          ((sym[k] == ell.null_symbol) ? (e.default_left != 0)
+                                                       : GoLeftBin<kCat>((int32_t)sym[k], e.split_lbin, e.nidx, cr));
         const uint32_t m = __ballot_sync(0xffffffffu, left);
         if (lane == 0) {
-          flags[(size_t)t * kWordsPerTile + (j >> 5)] = m;
+          uint32_t* fw = flags + (size_t)t * kWordsPerTile + (j >> 5);
+          *fw = paged ? (*fw | m) : m;
           cnt += __popc(m);
         }
       }
@@ -92,7 +103,7 @@ PartitionCountKernel(EllView ell, const uint32_t* __restrict__ ridx0, const uint
       uint32_t c = 0;
 #pragma unroll
       for (int w = 0; w < kPartThreads / 32; ++w) c += s_cnt[w];
-      tile_left[t] = c;
+      tile_left[t] = paged ? tile_left[t] + c : c;
     }
     __syncthreads();
   }

@@ -383,6 +383,7 @@ int b200hist_forest_predict_margin(b200hist_forest_t f, b200hist_ellpack_t page,
   auto s = static_cast<cudaStream_t>(stream);
   SyncForest(f, s);
   const ForestView fv{f->d_nodes, f->d_roots, f->d_bin_bits, f->bin_words};
+  B200_CHECK(!page->paged, "prediction on external-memory page sets is not implemented: predict page by page");
   const EllView view = page->View();
   const int blocks = (int)std::min<uint64_t>((n_rows + 255) / 256, (uint64_t)NumSMs(f->device) * 16);
   if (page->is_sparse) {
@@ -421,6 +422,7 @@ int b200hist_forest_predict_margin_groups(b200hist_forest_t f, b200hist_ellpack_
   SyncForest(f, s);
   ForestView fv{f->d_nodes, f->d_roots, f->d_bin_bits, f->bin_words};
   fv.tree_group = f->d_groups;
+  B200_CHECK(!page->paged, "prediction on external-memory page sets is not implemented: predict page by page");
   const EllView view = page->View();
   const uint64_t total = n_rows * (uint64_t)n_groups;
   const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)NumSMs(f->device) * 16);
@@ -521,6 +523,7 @@ static int PredictLeafImpl(b200hist_forest_t f, b200hist_ellpack_t page, uint32_
   auto s = static_cast<cudaStream_t>(stream);
   SyncForest(f, s);
   const ForestView fv{f->d_nodes, f->d_roots, f->d_bin_bits, f->bin_words};
+  B200_CHECK(!page->paged, "prediction on external-memory page sets is not implemented: predict page by page");
   const EllView view = page->View();
   const uint64_t total = n_rows * (uint64_t)(tree_end - tree_begin);
   const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)NumSMs(f->device) * 16);

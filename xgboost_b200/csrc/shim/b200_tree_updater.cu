@@ -146,9 +146,28 @@ class B200HistMaker : public TreeUpdater {
         for (std::size_t f = 0; f + 1 < ptrs.size(); ++f) ellpack_cut_bins_.push_back(ptrs[f + 1] - ptrs[f]);
         if (impl->IsDenseCompressed()) {
           int const has_missing = impl->IsDense() ? 0 : 1;
-          B200_SHIM_CHECK(b200hist_ellpack_create(ctx_->Ordinal(), n_total,
-                                                  static_cast<std::uint32_t>(ptrs.size() - 1), ptrs.data(), vals.data(),
-                                                  has_missing, &ellpack_));
+          // External memory (ExtMemQuantileDMatrix: several pages) larger than the resident budget: our page set keeps
+          // the matrix in pinned host memory and the updater streams it (b200hist_ellpack_create_paged); within the
+          // budget the pages are decoded into ONE resident page as before.  Budget = B200HIST_RESIDENT_BUDGET_BYTES,
+          // default 60 % of the free device memory.
+          auto const n_feat = static_cast<std::uint32_t>(ptrs.size() - 1);
+          std::uint64_t const row_bytes =
+              static_cast<std::uint64_t>((n_feat + 31u) & ~31u) * (impl->NumSymbols() <= 256 ? 1u : 2u);
+          std::uint64_t budget = 0;
+          if (char const* e = std::getenv("B200HIST_RESIDENT_BUDGET_BYTES")) budget = std::strtoull(e, nullptr, 10);
+          if (budget == 0) {
+            std::size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            budget = static_cast<std::uint64_t>(free_b) * 6 / 10;
+          }
+          if (!p_fmat->SingleColBlock() && n_total * row_bytes > budget) {
+            std::uint64_t const page_rows = std::max<std::uint64_t>(4096, budget / (2 * row_bytes));
+            B200_SHIM_CHECK(b200hist_ellpack_create_paged(ctx_->Ordinal(), n_total, n_feat, ptrs.data(), vals.data(),
+                                                          has_missing, page_rows, &ellpack_));
+          } else {
+            B200_SHIM_CHECK(b200hist_ellpack_create(ctx_->Ordinal(), n_total, n_feat, ptrs.data(), vals.data(),
+                                                    has_missing, &ellpack_));
+          }
         } else {  // sparse ELLPACK: global-bin symbols, row_stride < n_features (ellpack_page.cu:140-183)
           B200_SHIM_CHECK(b200hist_ellpack_create_sparse(ctx_->Ordinal(), n_total,
                                                          static_cast<std::uint32_t>(ptrs.size() - 1), ptrs.data(),

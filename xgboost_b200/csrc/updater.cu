@@ -637,13 +637,14 @@ __global__ void __launch_bounds__(256) FinaliseWindowKernel(EllView ell, const u
                                                              const BuildEntry* __restrict__ fin,
                                                              const TreeState* __restrict__ ts,
                                                              int32_t* __restrict__ position,
-                                                             const QuantDev* __restrict__ qd, uint32_t n_rows,
-                                                             CatRoute cr) {
+                                                             const QuantDev* __restrict__ qd, uint32_t row_lo,
+                                                             uint32_t n_rows, CatRoute cr) {
+  // rows [row_lo, n_rows): the whole matrix, or the rows of the resident page (external memory: one launch per page)
   __shared__ int32_t s_pos[kFinWindow];
   __shared__ uint32_t s_lo[256], s_hi[256], s_off[257], s_warp[33];
   const uint32_t n_final = (uint32_t)ts->n_final;
   const bool any_h_zero = qd->h_zero_any != 0u;
-  const uint32_t n_windows = (n_rows + kFinWindow - 1) / kFinWindow;
+  const uint32_t n_windows = (n_rows - row_lo + kFinWindow - 1) / kFinWindow;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   // a CTA takes CONSECUTIVE windows: a slice starts where the previous window's slice ended, so only the first
   // window of a CTA pays the full binary search per segment (when all segments fit one 256-thread chunk)
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(256) FinaliseWindowKernel(EllView ell, const u
   const uint32_t w_last = (uint32_t)(((unsigned long long)(blockIdx.x + 1) * n_windows) / gridDim.x);
   const bool carry = n_final <= 256u;
   for (uint32_t wdx = w_first; wdx < w_last; ++wdx) {
-    const uint32_t r_begin = wdx * kFinWindow, r_end = min(n_rows, r_begin + kFinWindow);
+    const uint32_t r_begin = row_lo + wdx * kFinWindow, r_end = min(n_rows, r_begin + kFinWindow);
     for (uint32_t base = 0; base < n_final; base += 256) {
       if (base + threadIdx.x < n_final) {  // one thread per terminal segment: its slice inside the window
         const BuildEntry e = fin[base + threadIdx.x];
@@ -957,6 +958,44 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   const EllView view = ell->View();
   const uint64_t n = ell->n_rows;
   PhaseTimer timer{u, s};
+  // External memory (b200hist_ellpack_create_paged): every phase that reads the quantised matrix -- histogram build,
+  // partition count, FinalisePosition -- runs once per page while the NEXT page travels host -> device on the page
+  // set's copy stream (two staging buffers).  Replaces the per-page loop of GPUHistMakerDevice
+  // (updater_gpu_hist.cu:475-499, 529-580) over EllpackPageSource (ellpack_page_source.h:128-337).  The row
+  // state (gradient pairs, row ids, positions) stays resident for ALL rows; a node's segment lists its rows in ascending
+  // order, so the rows of one page are a contiguous slice of it (ClipToPage): no per-page partitioner is needed, and
+  // integer histograms make the result independent of the paging -- the trees are those of the in-core matrix.
+  const uint32_t n_pages = ell->NumPages();
+  auto for_each_page = [&](auto&& fn) {
+    if (!ell->paged) {
+      fn(view);
+      return;
+    }
+    auto cs = static_cast<cudaStream_t>(ell->copy_stream);
+    auto prefetch = [&](uint32_t p) {
+      const int b = (int)((ell->stage_uses + p) & 1u);
+      const uint64_t lo = (uint64_t)p * ell->page_rows;
+      const uint64_t rows = std::min<uint64_t>(ell->page_rows, n - lo);
+      B200_CUDA(cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(ell->ev_done[b]), 0));  // last readers of stage b
+      B200_CUDA(cudaMemcpyAsync(ell->d_stage[b], ell->h_bins + lo * (uint64_t)ell->row_bytes,
+                                rows * (uint64_t)ell->row_bytes, cudaMemcpyHostToDevice, cs));
+      B200_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ell->ev_ready[b]), cs));
+      ell->h2d_bytes += rows * (uint64_t)ell->row_bytes;
+    };
+    prefetch(0);
+    for (uint32_t p = 0; p < n_pages; ++p) {
+      const int b = (int)((ell->stage_uses + p) & 1u);
+      if (p + 1 < n_pages) prefetch(p + 1);
+      B200_CUDA(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(ell->ev_ready[b]), 0));
+      fn(ell->PageView(p, b));
+      B200_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ell->ev_done[b]), s));
+    }
+    ell->stage_uses += n_pages;
+  };
+  if (ell->paged) {
+    B200_CHECK(!u->p2p && u->comm == nullptr, "external-memory pages and multi-GPU training are not combined yet");
+    B200_CHECK(!ell->is_sparse, "external-memory pages use the dense layout");
+  }
   int32_t* position = out_position ? out_position : u->d_position;
   const MonoView mono{u->d_monotone, u->d_lower, u->d_upper};
 
@@ -1060,8 +1099,10 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   const std::vector<GroupDesc> my_groups(u->groups.begin() + u->group_begin, u->groups.begin() + u->group_end);
   auto build_hist = [&](uint32_t slot_base, uint32_t slot_cap) {
     if (!my_groups.empty())
-      LaunchBuildHist(view, u->d_gq, u->d_ridx[0], u->d_ridx[1], u->d_build, u->d_build_tile_seg, u->d_ts,
-                      u->d_groups + u->group_begin, my_groups, u->d_hist, u->d_quant, u->num_sms, s, u->pair_hint);
+      for_each_page([&](const EllView& pv) {
+        LaunchBuildHist(pv, u->d_gq, u->d_ridx[0], u->d_ridx[1], u->d_build, u->d_build_tile_seg, u->d_ts,
+                        u->d_groups + u->group_begin, my_groups, u->d_hist, u->d_quant, u->num_sms, s, u->pair_hint);
+      });
     // AllReduceHist: one collective per level over the level's contiguous built slots
     auto tc = timer.Begin();
     if (u->p2p && u->row_split) {
@@ -1113,8 +1154,15 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     const bool children_possible = u->param.max_depth == 0 || !depthwise || step + 1 < u->param.max_depth;
     if (!children_possible) continue;
     auto tp = timer.Begin();
-    LaunchPartitionCount(view, u->d_ridx[0], u->d_ridx[1], u->d_part, u->d_part_tile_seg, u->d_ts, u->d_flags,
-                         u->d_tile_left, u->num_sms, s, CatRoute{u->d_bin_bits, u->cat_bin_words});
+    if (ell->paged) {  // decision bits and tile counts accumulate over the page launches
+      const size_t pt = n / kPartTile + kMaxLevelNodes + 2;
+      B200_CUDA(cudaMemsetAsync(u->d_flags, 0, sizeof(uint32_t) * pt * (kPartTile / 32), s));
+      B200_CUDA(cudaMemsetAsync(u->d_tile_left, 0, sizeof(uint32_t) * pt, s));
+    }
+    for_each_page([&](const EllView& pv) {
+      LaunchPartitionCount(pv, u->d_ridx[0], u->d_ridx[1], u->d_part, u->d_part_tile_seg, u->d_ts, u->d_flags,
+                           u->d_tile_left, u->num_sms, s, CatRoute{u->d_bin_bits, u->cat_bin_words});
+    });
     ScanKernel<<<1, kCtlThreads, 0, s>>>(u->d_ts, u->d_nodes, u->d_part, u->d_part_tile_seg, u->d_tile_left,
                                          u->d_tile_excl, u->d_tile_left_off, u->d_build, u->d_sub, u->d_eval_nodes,
                                          u->d_build_tile_seg, u->step_slot_base[step], u->step_cap[step],
@@ -1170,13 +1218,18 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   auto finalise = [&](auto bin_tag, auto cat_tag) {
     using BinT = decltype(bin_tag);
     constexpr bool kCat = decltype(cat_tag)::value;
-    if (fin_tile) {
+    if (fin_tile && !ell->paged) {
       FinaliseKernel<BinT, kCat><<<u->num_sms * 8, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes,
                                                                 u->d_fin, u->d_fin_tile_seg, u->d_ts, position,
                                                                 u->d_quant, cr);
-    } else {
-      FinaliseWindowKernel<BinT, kCat><<<fin_grid, 256, 0, s>>>(view, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes,
-                                                                u->d_fin, u->d_ts, position, u->d_quant, (uint32_t)n, cr);
+      B200_LAUNCHED();
+    } else {  // the windows of row ids cover the whole matrix, or page after page the rows that are resident
+      for_each_page([&](const EllView& pv) {
+        const uint32_t r_lo = ell->paged ? pv.page_lo : 0u, r_hi = ell->paged ? pv.page_hi : (uint32_t)n;
+        FinaliseWindowKernel<BinT, kCat><<<fin_grid, 256, 0, s>>>(pv, u->d_ridx[0], u->d_ridx[1], gq64, u->d_nodes,
+                                                                  u->d_fin, u->d_ts, position, u->d_quant, r_lo, r_hi, cr);
+        B200_LAUNCHED();
+      });
     }
   };
   auto finalise_bins = [&](auto cat_tag) {
@@ -1186,7 +1239,6 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   };
   if (has_cat) finalise_bins(std::true_type{});
   else finalise_bins(std::false_type{});
-  B200_LAUNCHED();
   timer.End(kFinal, tf);
 
   // the one read-back of the tree

@@ -100,6 +100,9 @@ _SIGNATURES = {
                                                POINTER(c_void_p)]),
     "b200hist_ellpack_push_csr": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "b200hist_ellpack_destroy": (c_int, [c_void_p]),
+    "b200hist_ellpack_create_paged": (c_int, [c_int, c_uint64, c_uint32, POINTER(c_uint32), POINTER(c_float), c_int,
+                                              c_uint64, POINTER(c_void_p)]),
+    "b200hist_ellpack_paging_info": (c_int, [c_void_p, POINTER(c_uint32), POINTER(c_uint64), POINTER(c_uint64)]),
     "b200hist_ellpack_set_feature_types": (c_int, [c_void_p, c_void_p, c_uint32]),
     "b200hist_ellpack_push_dense": (c_int, [c_void_p, c_uint64, c_void_p, c_uint64, c_uint64, c_void_p]),
     "b200hist_ellpack_import_reference": (c_int, [c_void_p, c_void_p, c_uint32, c_uint32, c_int, c_void_p]),

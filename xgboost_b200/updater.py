@@ -146,7 +146,9 @@ class EllpackPage:
     """Quantised feature matrix resident in HBM (our layout, see include/b200hist.h)."""
 
     def __init__(self, cuts: HistogramCuts, n_rows: int, device: int = 0, has_missing: bool = False,
-                 sparse_row_stride: Optional[int] = None):
+                 sparse_row_stride: Optional[int] = None, page_rows: Optional[int] = None):
+        """page_rows: external memory -- the matrix lives in pinned host memory and the updater streams it through two
+        device staging buffers of that many rows (b200hist_ellpack_create_paged); None = resident in HBM."""
         lib = _l.load()
         self.cuts = cuts
         self.device = int(device)
@@ -157,9 +159,18 @@ class EllpackPage:
         if sparse_row_stride is not None:  # sparse ELLPACK layout (global-bin symbols)
             _l.check(lib.b200hist_ellpack_create_sparse(self.device, self.n_rows, cuts.n_features, cp, cv,
                                                         int(sparse_row_stride), byref(self._h)))
+        elif page_rows is not None:
+            _l.check(lib.b200hist_ellpack_create_paged(self.device, self.n_rows, cuts.n_features, cp, cv,
+                                                       1 if has_missing else 0, int(page_rows), byref(self._h)))
         else:
             _l.check(lib.b200hist_ellpack_create(self.device, self.n_rows, cuts.n_features, cp, cv,
                                                  1 if has_missing else 0, byref(self._h)))
+
+    def paging_info(self) -> Dict[str, int]:
+        """n_pages (0 = in-core), page_rows and the bytes the updater has streamed host -> device so far."""
+        n_pages, rows, h2d = c_uint32(), c_uint64(), c_uint64()
+        _l.check(_l.load().b200hist_ellpack_paging_info(self._h, byref(n_pages), byref(rows), byref(h2d)))
+        return {"n_pages": int(n_pages.value), "page_rows": int(rows.value), "h2d_bytes": int(h2d.value)}
 
     def push_csr(self, indptr: torch.Tensor, indices: torch.Tensor, values: torch.Tensor, row_begin: int) -> None:
         """Bin a CSR batch (device tensors: int64 indptr relative to the batch, int32 indices, float32 values)."""
@@ -211,11 +222,11 @@ class EllpackPage:
 
     @classmethod
     def from_dense(cls, x: torch.Tensor, cuts: HistogramCuts, has_missing: Optional[bool] = None,
-                   feature_is_cat: Optional[Sequence[int]] = None) -> "EllpackPage":
+                   feature_is_cat: Optional[Sequence[int]] = None, page_rows: Optional[int] = None) -> "EllpackPage":
         _require_cuda(x, "x")
         if has_missing is None:
             has_missing = bool(torch.isnan(x).any().item())
-        page = cls(cuts, x.shape[0], x.device.index or 0, has_missing)
+        page = cls(cuts, x.shape[0], x.device.index or 0, has_missing, page_rows=page_rows)
         if feature_is_cat is not None:
             page.set_feature_types(feature_is_cat)
         page.push_dense(x.contiguous(), 0)
