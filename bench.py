@@ -302,9 +302,9 @@ def run_reference(args):
               % (res["cores"], res["omp"], rows, args.features, res["s_per_iter_mean"], args.steps,
                  res["s_per_iter_median"], res["s_per_iter_min"], res["s_per_iter_max"],
                  "" if scale == 1.0 else
-                 "; a step is one iteration on this 1/%g sample, `value` = sample rate x %g (hist cost is linear in rows: the "
-                 "full 100M x 256 run, profiles/r02_reference_cpu_full_size.json, took 8.14 s/iter on the same host = "
-                 "0.123 iters/s; B200_BENCH_REF_ROWS=100000000 repeats it, ~13 min)" % (1.0 / scale, scale)))
+                 "; a step is one iteration on this 1/%g sample, `value` = sample rate x %g -- linear scaling FAVOURS the "
+                 "reference: the full 100M x 256 run (profiles/r02_reference_cpu_full_size.json) took 8.14 s/iter on the "
+                 "same host = 0.123 iters/s; B200_BENCH_REF_ROWS=100000000 repeats it, ~13 min" % (1.0 / scale, scale)))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup,
             # the wall time of one timed step as it ran (on the sample); 1e3 / value is the full-size equivalent
@@ -649,15 +649,21 @@ def run_b200(args):
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
+        # a child process: the OpenMP runtime of THIS process was initialised under whatever OMP_NUM_THREADS the
+        # launcher exported (torchrun: 1), the child re-executes itself with every host core (see _exec_with_all_cores)
         rows_c = min(args.rows, args.cpu_sample_rows)
-        res = reference_cpu(args, 3, 1, rows_c)
-        if res is not None:
-            sc = rows_c / float(args.rows)
-            cpu_baseline = {"value": sc / res["s_per_iter_mean"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
-                            "sample": "unmodified reference CPU hist (oracle/_ref/libxgboost.so, nthread=%d, "
-                                      "OMP_NUM_THREADS=%s) on %d x %d rows: %.3f s/iter over 3 iters, scaled linearly in "
-                                      "rows to %d; the full-size run is `bench.py --impl reference`"
-                                      % (res["cores"], res["omp"], rows_c, args.features, res["s_per_iter_mean"], args.rows)}
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", "1", "--steps", "3",
+                   "--warmup", "1", "--ref-rows", str(rows_c), "--rows", str(args.rows), "--features", str(args.features),
+                   "--max-bin", str(args.max_bin), "--depth", str(args.depth)]
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "B200_BENCH_REEXEC")}
+            env["LOCAL_RANK"] = str(local_rank)
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+            ref_line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+            cpu_baseline = ref_line.get("cpu_baseline")
+        except Exception as exc:  # the baseline leg must not take the measurement down with it
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                            "sample": "cpu_baseline leg failed: %r" % (exc,)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -28,6 +28,8 @@ def main(task_id: int, tracker_args: dict, updater: str, out_path: str, extra: d
         n = int(extra.pop("rows", 60000))
         x, y = make_regression(n, 24, seed=91, missing=float(extra.pop("missing", 0.03)))
         lo, hi = (n * rank) // world + (17 if rank else 0), (n * (rank + 1)) // world + (17 if rank + 1 < world else 0)
+        if extra.get("objective") == "binary:logistic":
+            y = (y > 0).astype(np.float32)
         xs, ys = x[lo:hi], y[lo:hi]                      # uneven shards
         dm = rc.DMatrix.from_cuda(torch.from_numpy(xs).to("cuda:%d" % dev), kind="cuda")
         dm.set_label(ys)

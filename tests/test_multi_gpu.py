@@ -159,8 +159,6 @@ def test_two_process_reference_job_through_the_shim(tmp_path, extra):
     shim = os.path.join(ROOT, "xgboost_b200", "lib", "libb200hist_xgb_shim.so")
     if not (rc.available("cuda") and os.path.exists(shim)):
         pytest.skip("needs oracle/_ref_cuda/libxgboost.so and the shim")
-    if "binary:logistic" in extra.values():
-        extra = dict(extra)
     models = {}
     for updater in ("grow_gpu_hist_reference", "grow_b200_hist"):
         tracker = rc.Tracker(2, kind="cuda")
