@@ -566,7 +566,9 @@ def run_b200(args):
         cap = json.load(open(os.path.join(ROOT, "profiles", "r02_hist_kernel_ncu_headline.json")))
         if cap.get("rows") == n_total and cap.get("features") == f and world == 1:
             traffic = float(cap["dram_bytes_per_launch_mean"])
-            traffic_src = cap.get("source", "profiles/r02_hist_kernel_ncu_headline.json")
+            traffic_src = (cap.get("source", "profiles/r02_hist_kernel_ncu_headline.json") +
+                           "; the captured launches move %.2f x their own algorithmic bytes"
+                           % float(cap.get("traffic_over_algorithmic_captured", float("nan"))))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "HistKernelPair", "achieved": hist_gbs, "peak": peak, "unit": "GB/s",
