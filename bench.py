@@ -324,7 +324,7 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # the reference's own Booster on the GPU: e2e of our arm (shim loaded) and the reference gpu_hist beside it
 # --------------------------------------------------------------------------------------------------
-def reference_booster_section(torch, args, device, steps, warmup):
+def reference_booster_section(torch, args, device, steps, warmup, rows=None, features=None, depth=None):
     """One QuantileDMatrix of the UNMODIFIED reference CUDA library over the same batches; two Boosters on it:
     updater=grow_b200_hist (our shim: XGBoosterUpdateOneIter = objective gradient + Update + UpdatePredictionCache,
     tree replayed into RegTree on the host) and updater=grow_gpu_hist_reference (the reference's own kernels).
@@ -338,7 +338,8 @@ def reference_booster_section(torch, args, device, steps, warmup):
     rc.load("cuda")
     ctypes.CDLL(os.path.join(ROOT, "xgboost_b200", "lib", "libb200hist.so"), mode=ctypes.RTLD_GLOBAL)
     keep = ctypes.CDLL(shim, mode=ctypes.RTLD_GLOBAL)
-    n, f = args.rows, args.features
+    n, f = rows or args.rows, features or args.features
+    depth = depth or args.depth
     nb = (n + 999_999) // 1_000_000
     t0 = time.perf_counter()
     batches = rc.LazyBatches(nb, lambda b: batch_of(torch, device, f, n, 1_000_000, b)[0])
@@ -354,7 +355,7 @@ def reference_booster_section(torch, args, device, steps, warmup):
     torch.cuda.synchronize(device)
     build_s = time.perf_counter() - t0
     torch.cuda.empty_cache()
-    params = {"tree_method": "hist", "device": "cuda:%d" % device.index, "max_depth": args.depth,
+    params = {"tree_method": "hist", "device": "cuda:%d" % device.index, "max_depth": depth,
               "max_bin": args.max_bin, "objective": "reg:squarederror", "eta": 0.3, "lambda": 1, "min_child_weight": 1,
               "base_score": 0.5}
     out = {"dmatrix_build_s": round(build_s, 2)}
@@ -649,6 +650,20 @@ def run_b200(args):
                    "ms_per_iter_median": ref_section["ours"]["ms_per_iter_median"], "steps": k2,
                    "model_identical_to_reference_gpu_hist": ref_section["models_identical"]}
 
+    # BASELINE.json config C2 (10M x 64 dense, depth 6) beside the headline: same generator, same two Boosters on one
+    # reference QuantileDMatrix.  A parity-test configuration timed for the record, not the metric.
+    other_configs = None
+    if not args.no_e2e and world == 1 and rank == 0 and args.rows == 100_000_000 and os.environ.get("B200_BENCH_OTHER", "1") != "0":
+        c2 = reference_booster_section(torch, args, device, 10, 3, rows=10_000_000, features=64, depth=6)
+        if c2 is not None:
+            other_configs = {"C2 synthetic 10Mx64 dense f32, 256 bins, depth 6, 1xB200": {
+                "ours_through_the_shim_iters_per_s": c2["ours"]["iters_per_s"],
+                "reference_gpu_hist_iters_per_s": c2["reference_gpu"]["iters_per_s"],
+                "ours_ms_per_iter_median": c2["ours"]["ms_per_iter_median"],
+                "reference_ms_per_iter_median": c2["reference_gpu"]["ms_per_iter_median"],
+                "models_identical": c2["models_identical"], "steps": 10, "warmup": 3,
+                "path": "XGBoosterUpdateOneIter, wall clock with a device synchronise on both sides"}}
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         # a child process: the OpenMP runtime of THIS process was initialised under whatever OMP_NUM_THREADS the
@@ -691,6 +706,7 @@ def run_b200(args):
                     what="the UNMODIFIED reference's CUDA gpu_hist (oracle/_ref_cuda, updater=grow_gpu_hist_reference) "
                          "through XGBoosterUpdateOneIter on the same QuantileDMatrix in this process: the kernel to beat",
                     dmatrix_build_s=ref_section["dmatrix_build_s"]),
+                "other_configs": other_configs,
                 "algorithmic_gb_per_step": {k: v / 1e9 for k, v in ab.items()}}
         print(json.dumps(line))
     if world > 1:

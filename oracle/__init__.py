@@ -307,8 +307,10 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
                 is_dense_layout=True, want_hist=False, feature_set=None, subsample=1.0, sample_seed=0,
                 monotone=None, level_feature_sets=None, interaction=None, interaction_shared_buffer=True,
                 feature_is_cat=None, max_cat_to_onehot=4, max_cat_threshold=64, node_feature_sets=None,
-                sampling_method="uniform", column_seeds=None, tree_set=None, colsample_bylevel=1.0, colsample_bynode=1.0):
+                sampling_method="uniform", column_seeds=None, tree_set=None, colsample_bylevel=1.0, colsample_bynode=1.0,
+                node_batch=None):
     """Whole tree.  Returns dict(nodes=[Node...], position, scale, hist (optional), cands).
+    node_batch: the Driver's max_node_batch_size for this call (default: the GPU updater's 1024).
     feature_set: sorted feature ids of the tree's colsample_bytree draw; subsample/sample_seed: uniform row sampling;
     monotone: per-feature sign (+1 increasing, -1 decreasing, 0 free), padded with 0 to n_features;
     feature_is_cat: flags per feature (categorical features: bins are categories, cut values their codes), with
@@ -371,6 +373,7 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
         ns = np.ascontiguousarray(node_feature_sets, dtype=np.int32)
         cat.node_sets, cat.n_node_sets, cat.n_per_node = ns.ctypes.data, ns.shape[0], ns.shape[1]
     lib().orc_update_tree_full.restype = c_int32
+    lib().orc_set_node_batch(c_int32(int(node_batch) if node_batch else 0))   # 0 restores the default (1024)
     nn = lib().orc_update_tree_full(_p(gb), c_uint64(n), c_uint32(stride), c_int(1 if is_dense_layout else 0),
                                   c_uint32(nf), _p(cp), _p(cv), _p(g), byref(param), so, nodes, c_int32(max_nodes),
                                   _p(pos), _p(hist) if want_hist else c_void_p(), cands, scale_out,
@@ -379,6 +382,7 @@ def update_tree(gbins, cut_ptrs, cut_values, gpair, param: Param, scale_override
                                   _p(mono) if mono is not None else c_void_p(), c_int32(n_levels),
                                   byref(ic.c) if ic is not None else c_void_p(),
                                   byref(cat) if cat is not None else c_void_p())
+    lib().orc_set_node_batch(c_int32(0))
     res = dict(nodes=list(nodes[:nn]), cands=list(cands[:nn]), position=pos,
                scale=np.array(scale_out[:], dtype=np.float64), hist=hist[:nn] if want_hist else None)
     if node_feature_sets is not None:

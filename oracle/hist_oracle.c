@@ -750,6 +750,11 @@ ORC_API uint64_t orc_partition(const int32_t* gbins, uint32_t stride, int is_den
  * (constraints.cu:33-44).  Bit fields here: LBitField64, bit f of word f / 64 (value 1 << (f % 64)); only
  * membership is observable, the word layout never leaves the device in the reference.
  * ---------------------------------------------------------------------------------------- */
+/* Driver's max_node_batch_size (driver.h:36-40; the GPU updater passes kMaxNodeBatchSize = 1024,
+ * updater_gpu_hist.cuh:34, updater_gpu_hist.cu:695).  Settable so that tests can batch small trees. */
+static int32_t g_node_batch = 1024;
+ORC_API void orc_set_node_batch(int32_t b) { g_node_batch = b > 0 && b <= 4096 ? b : 1024; }
+
 typedef struct {
   int32_t n_features, n_sets;
   const int32_t* set_ptr;
@@ -1235,7 +1240,7 @@ ORC_API int32_t orc_update_tree_full(const int32_t* gbins, uint64_t n_rows, uint
       else break; /* Pop returned {} -> UpdateTree loop ends */
     } else { /* depth wise: all entries of the smallest-nidx entry's depth, ascending nidx */
       int32_t level = -1;
-      for (int32_t i = 0; i < n_nodes && n_expand < 1024; ++i) {
+      for (int32_t i = 0; i < n_nodes && n_expand < g_node_batch; ++i) {
         if (!queue[i].open) continue;
         if (level < 0) level = queue[i].depth;
         if (queue[i].depth != level) break;

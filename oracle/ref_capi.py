@@ -279,9 +279,10 @@ class Booster:
         _check(self.lib, self.lib.XGBoosterSaveModelToBuffer(self.h, b'{"format": "json"}', byref(n), byref(p)))
         return json.loads(ctypes.string_at(p, n.value).decode())
 
-    def predict_margin(self, dm: DMatrix, pred_type: int = 1) -> np.ndarray:
-        """pred_type: 1 = margin, 6 = leaf ids (c_api.h XGBoosterPredictFromDMatrix); flat float32."""
-        cfg = json.dumps({"type": int(pred_type), "training": False, "iteration_begin": 0, "iteration_end": 0,
+    def predict_margin(self, dm: DMatrix, pred_type: int = 1, iteration_begin: int = 0) -> np.ndarray:
+        """pred_type: 1 = margin, 6 = leaf ids (c_api.h XGBoosterPredictFromDMatrix); flat float32.
+        iteration_begin > 0 also bypasses the Booster's prediction cache (GBTree::PredictBatchImpl resets it)."""
+        cfg = json.dumps({"type": int(pred_type), "training": False, "iteration_begin": int(iteration_begin), "iteration_end": 0,
                           "strict_shape": False}).encode()
         shape = POINTER(c_uint64)()
         dim = c_uint64()

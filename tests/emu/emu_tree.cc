@@ -71,16 +71,28 @@ int main(int argc, char** argv) {
   long long by_leaves = p.max_leaves > 0 ? (2ll * p.max_leaves - 1) : (1ll << 40);
   const int32_t max_nodes = (int32_t)std::min(by_depth, by_leaves);
   const bool dw = p.grow_policy == 0;
-  const int n_steps = dw ? (p.max_depth > 0 ? p.max_depth : p.max_leaves - 1) : (max_nodes - 1) / 2;
+  const int n_tree_levels = dw ? (p.max_depth > 0 ? p.max_depth : p.max_leaves - 1) : (max_nodes - 1) / 2;
+  // [26] level batch (0 = the library's default): valid entries one step expands at most -- node batching
+  int level_batch = p.max_leaves > 0 ? 1024 : kMaxLevelNodes;
+  if (meta.size() > 26 && meta[26] > 0) level_batch = (int)meta[26];
   std::vector<uint32_t> step_cap, step_slot_base;
+  std::vector<int> step_level, step_level_start;
   uint32_t base = 1;
-  for (int st = 0; st < n_steps; ++st) {
-    uint32_t cap = dw ? (uint32_t)std::min<long long>(1ll << std::min(st, 30), kMaxLevelNodes) : 1u;
-    if (p.max_leaves > 0) cap = std::min<uint32_t>(cap, (uint32_t)p.max_leaves);
-    step_cap.push_back(cap);
-    step_slot_base.push_back(base);
+  int n_steps = 0;
+  for (int st = 0; st < n_tree_levels; ++st) {
+    long long width = dw ? (1ll << std::min(st, 40)) : 1ll;
+    if (p.max_leaves > 0) width = std::min<long long>(width, p.max_leaves);
     const bool children = p.max_depth == 0 || !dw || st + 1 < p.max_depth;
-    if (children) base += 2 * cap;
+    const long long n_sub = dw ? (width + level_batch - 1) / level_batch : 1;
+    for (long long b = 0; b < n_sub; ++b) {
+      const uint32_t cap = (uint32_t)std::min<long long>(level_batch, width - b * level_batch);
+      step_cap.push_back(cap);
+      step_slot_base.push_back(base);
+      step_level.push_back(st);
+      step_level_start.push_back(b == 0 ? 1 : 0);
+      if (children) base += 2 * cap;
+      ++n_steps;
+    }
   }
   const uint32_t n_slots = base;
   const size_t part_tiles = n / kPartTile + (size_t)max_nodes + 2, hist_tiles = n / kHistTile + (size_t)max_nodes + 2;
@@ -313,11 +325,11 @@ int main(int argc, char** argv) {
   for (int step = 0; step < n_steps; ++step) {
     const long long cap = step_cap[step];
     if (has_cat) {
-      EMU_LAUNCH((1), (kCtlThreads), 0, ApplyKernel<true>(view, p, &q, &ts, nodes.data(), cand.data(), part.data(), part_tile_seg.data(), max_nodes, mono, node_is_cat.data()));
+      EMU_LAUNCH((1), (kCtlThreads), 0, ApplyKernel<true>(view, p, &q, &ts, nodes.data(), cand.data(), part.data(), part_tile_seg.data(), max_nodes, mono, node_is_cat.data(), step_level_start[step], level_batch));
     } else {
-      EMU_LAUNCH((1), (kCtlThreads), 0, ApplyKernel<false>(view, p, &q, &ts, nodes.data(), cand.data(), part.data(), part_tile_seg.data(), max_nodes, mono, nullptr));
+      EMU_LAUNCH((1), (kCtlThreads), 0, ApplyKernel<false>(view, p, &q, &ts, nodes.data(), cand.data(), part.data(), part_tile_seg.data(), max_nodes, mono, nullptr, step_level_start[step], level_batch));
     }
-    const bool children_possible = p.max_depth == 0 || !dw || step + 1 < p.max_depth;
+    const bool children_possible = p.max_depth == 0 || !dw || step_level[step] + 1 < p.max_depth;
     if (!children_possible) continue;
     if (page_rows > 0) {  // the updater clears the accumulators before the first page
       std::fill(flags.begin(), flags.end(), 0u);

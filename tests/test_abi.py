@@ -79,7 +79,7 @@ def test_only_fixture_generators_outside_tests_touch_the_oracle_directory():
     oracle/ref_capi.py (the scripts that wrote tests/golden/*.json).  No tool may import the CPU restatement itself
     (`import oracle` / `oracle as orc`): checking against it is the tests' job."""
     allowed_ref_capi = {"make_golden_gpu.py", "make_golden_gpu_next.py", "make_golden_cpu_categorical.py",
-                        "make_golden_agaricus.py", "probe_interaction_reference.py",
+                        "make_golden_agaricus.py", "probe_interaction_reference.py", "bench_predictor.py",
                         "bench_sparse.py"}
     for dirpath, _, files in os.walk(os.path.join(ROOT, "tools")):
         for f in files:

@@ -726,3 +726,38 @@ def test_sparse_page_tree_matches_oracle(xb, n, f, density, max_bin, params):
     o = orc.update_tree(ell, cp, cv, gp, orc.Param.make(**params), is_dense_layout=False, want_hist=True)
     _compare_tree(xb, up, tree, o, cp, cv)
     assert np.array_equal(pos.cpu().numpy(), o["position"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Node batching (H3): levels wider than one step's capacity, and the Driver's batch semantics under a leaf budget
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch,params,n", [
+    (5, dict(max_depth=6), 20000),
+    (3, dict(max_depth=7, max_leaves=40), 20000),
+    (0, dict(max_depth=14, min_child_weight=0.0), 300000),    # 8192-node levels: two steps of 4096 each
+    (0, dict(max_depth=13, max_leaves=3000, min_child_weight=0.0), 300000),   # leaf budget: the reference's 1024 batches
+], ids=["steps_of_5", "leaf_budget_steps_of_3", "depth14", "depth13_leaf_budget"])
+def test_tree_grown_in_node_batches_matches_oracle(xb, monkeypatch, batch, params, n):
+    """Driver::Pop hands out at most max_node_batch_size valid entries of a level (driver.h:84-99, kMaxNodeBatchSize
+    updater_gpu_hist.cuh:34); our steps do the same, so max_depth is no longer capped at 13.  B200HIST_LEVEL_BATCH shrinks
+    the batch so that small trees exercise it; the oracle restates the Driver with the same batch size."""
+    import torch
+    if batch:
+        monkeypatch.setenv("B200HIST_LEVEL_BATCH", str(batch))
+    else:
+        monkeypatch.delenv("B200HIST_LEVEL_BATCH", raising=False)
+    f = 6
+    x, y = make_regression(n, f, seed=211)
+    cp, cv = make_cuts(x, 16)
+    page = _page(xb, x, cp, cv)
+    gb = orc.bin_dense(x, cp, cv)
+    up = xb.GPUHistMaker(page)
+    up.configure(params)
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    pos = torch.empty(n, dtype=torch.int32, device="cuda")
+    tree = up.update(torch.from_numpy(gp).cuda(), pos)
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), node_batch=batch if batch else None)
+    _compare_tree(xb, up, tree, o, cp, cv, hists=False)
+    assert np.array_equal(pos.cpu().numpy(), o["position"])
+    if params["max_depth"] >= 13:
+        assert tree.num_nodes > 8192

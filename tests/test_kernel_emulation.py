@@ -581,7 +581,7 @@ TREE_NODE = np.dtype([("parent", "<i4"), ("left", "<i4"), ("right", "<i4"), ("fi
 
 def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, onehot=4, threshold=64, ic_sets=None,
                   node_sets=None, feature_set=None, n_levels=0, col_seeds=None, col_tree_set=None, bylevel=1.0, bynode=1.0,
-                  sparse=False, hist_mode=0, page_rows=0):
+                  sparse=False, hist_mode=0, page_rows=0, level_batch=0):
     exe = _build("emu_tree")
     n, nf = gb.shape
     max_bins = int(np.diff(cp).max())
@@ -617,7 +617,7 @@ def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, oneh
     np.array([n, nf, page.shape[1], bin_bytes, null_symbol, 0 if mono is None else 1, 0 if is_cat is None else 1, onehot,
               threshold, cat_words, (max_cat_bins + 31) // 32, max_cat_bins, 0 if ic_sets is None else len(ic_sets),
               0 if node_sets is None else node_sets.shape[0], 0 if node_sets is None else node_sets.shape[1],
-              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta + [row_stride, hist_mode, page_rows],
+              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta + [row_stride, hist_mode, page_rows, level_batch],
              dtype=np.int64).tofile(os.path.join(d, "meta.bin"))
     np.array([p.learning_rate, p.reg_lambda, p.reg_alpha, p.min_child_weight, p.max_delta_step, p.min_split_loss],
              dtype=np.float32).tofile(os.path.join(d, "param_f.bin"))
@@ -864,6 +864,30 @@ def test_whole_tree_kernel_sources_sparse_page(tmp_path, categorical):
     nodes, pos, flags, bits, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, sparse=True, **kw)
     o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), **okw)
     _same_tree(nodes, pos, o, flags if categorical else None, bits if categorical else None)
+
+
+@pytest.mark.parametrize("batch,params", [
+    (3, dict(max_depth=5, eta=0.5)),                                    # levels of 4, 8, 16 nodes in steps of 3
+    (1, dict(max_depth=4, eta=0.5)),                                    # one node per step
+    (5, dict(max_depth=6, max_leaves=19, eta=0.5)),                     # the leaf budget ends a level half way
+    (2, dict(max_depth=5, eta=0.5, min_child_weight=40.0, min_split_loss=2.0)),   # invalid entries inside a level
+    (4, dict(max_depth=0, max_leaves=13, eta=0.5)),                     # depth-wise under a leaf budget alone
+], ids=["steps_of_3", "steps_of_1", "leaf_budget", "invalid_entries", "leaves_only"])
+def test_whole_tree_with_node_batching(tmp_path, batch, params):
+    """Node batching (Driver::Pop hands out at most max_node_batch_size entries of a level, driver.h:84-99;
+    kMaxNodeBatchSize, updater_gpu_hist.cuh:34): a level is expanded by several steps of ApplyKernel / partition /
+    build / evaluate.  The oracle restates the Driver with the same batch size; without a leaf budget the tree also
+    equals the unbatched one."""
+    n, f = 2500, 9
+    x, y = make_regression(n, f, seed=41)
+    cp, cv = make_cuts(x, 24)
+    gb = orc.bin_dense(x, cp, cv)
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    nodes, pos, _, _, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, level_batch=batch)
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), node_batch=batch)
+    _same_tree(nodes, pos, o)
+    if not params.get("max_leaves"):
+        _same_tree(nodes, pos, orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params)))
 
 
 @pytest.mark.parametrize("name,hist_mode,page_rows,kw", [

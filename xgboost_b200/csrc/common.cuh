@@ -268,6 +268,11 @@ struct TreeState {
   int32_t n_nodes;
   int32_t num_leaves;
   int32_t level_begin, level_end;  // node-id range of the open level (depth-wise)
+  // Node batching (Driver::Pop returns at most max_node_batch_size entries of one level, driver.h:71-100;
+  // updater_gpu_hist.cuh:34 kMaxNodeBatchSize): a level wider than a step's capacity is expanded by several steps.
+  // level_cursor = first node of the level no step has consumed yet; next_begin = first node of the NEXT level
+  // (the children created so far by this level's steps).
+  int32_t level_cursor, next_begin;
   int32_t n_part;
   int32_t n_build;
   int32_t n_sub;

@@ -16,11 +16,12 @@
 // (src/gbm/gbtree.cc:514-560: tree_begin = the cache's version, so only the NEW trees are walked).  Anything else --
 // and any tree b200hist_forest_add_tree refuses -- goes to the reference's predictor before an output is touched.
 //
-// STATUS: compiled only.  libb200hist's forest kernels equal the oracle under the CPU emulator
-// (tests/test_kernel_emulation.py) and the oracle equals the reference's quantised prediction bit for bit
-// (tests/test_reference_golden.py), but neither this file nor those kernels have run on hardware.  The factory is
-// therefore only replaced when B200HIST_SHIM_PREDICTOR=1 is set when the shim is loaded; without it this translation
-// unit registers nothing.
+// STATUS: on since round 2.  libb200hist's forest kernels equal the oracle under the CPU emulator
+// (tests/test_kernel_emulation.py), the oracle equals the reference's quantised prediction bit for bit
+// (tests/test_reference_golden.py), and on a B200 this binding returns the reference predictor's margins and leaf ids
+// bit for bit (tests/test_gpu_next.py::test_predictor_binding_serves_quantised_matrices_like_the_reference: dense,
+// missing values, uint16 symbols, multi-class; timing: tools/bench_predictor.py, profiles/).  B200HIST_SHIM_PREDICTOR=0
+// when the shim is loaded leaves the reference's own factory in place.
 #include <dmlc/registry.h>
 #include <xgboost/base.h>
 #include <xgboost/context.h>
@@ -263,11 +264,11 @@ class B200Predictor : public Predictor {
 };
 
 // Replaces the factory of "gpu_predictor" (the name Learner/GBTree resolve on CUDA, src/gbm/gbtree.cc:566-590) --
-// only on request, see STATUS above -- and keeps the original reachable as "gpu_predictor_reference".
+// unless B200HIST_SHIM_PREDICTOR=0, see STATUS above -- and keeps the original reachable as "gpu_predictor_reference".
 struct B200PredictorRegistrar {
   B200PredictorRegistrar() {
     char const* e = std::getenv("B200HIST_SHIM_PREDICTOR");
-    if (e == nullptr || e[0] != '1') return;
+    if (e != nullptr && e[0] == '0') return;
     auto* reg = ::dmlc::Registry<::xgboost::PredictorReg>::Get();
     auto const* orig = reg->Find("gpu_predictor");
     if (orig == nullptr) return;

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(kCtlThreads) InitRootKernel(ParamDev p, uint32
     eval_nodes[0] = 0;
     if (mono.constraints) { mono.lower[0] = -3.402823466e+38f; mono.upper[0] = 3.402823466e+38f; }
     ts->n_nodes = 1; ts->num_leaves = 1; ts->level_begin = 0; ts->level_end = 1;
+    ts->level_cursor = 0; ts->next_begin = 0;  // the first step opens level [next_begin, n_nodes) = [0, 1)
     ts->n_part = 0; ts->n_build = 1; ts->n_sub = 0; ts->n_eval = 1;
     ts->part_tiles = 0; ts->build_tiles = tiles; ts->final_tiles = 0; ts->n_final = 0;
     ts->row_visits = n_rows; ts->stopped = 0; ts->max_eval_depth = 0;
@@ -170,10 +171,13 @@ __global__ void __launch_bounds__(kCtlThreads) ApplyKernel(EllView ell, ParamDev
                                                             NodeDev* nodes, const b200hist_candidate* cand,
                                                             PartEntry* part, uint32_t* part_tile_seg,
                                                             int32_t max_nodes, MonoView mono,
-                                                            const uint8_t* node_is_cat) {
+                                                            const uint8_t* node_is_cat, int level_start,
+                                                            int batch_cap) {
+  // level_start (depth-wise): this step opens the next level; otherwise it continues the open level where the
+  // previous step stopped.  batch_cap: valid entries one step pops at most (Driver's max_node_batch_size).
   __shared__ uint32_t s_warp[33];
   __shared__ uint32_t s_tile_begin[kMaxLevelNodes + 1];
-  __shared__ int s_n_expand, s_child_valid;
+  __shared__ int s_n_expand, s_child_valid, s_cutoff;
   __shared__ float s_best_loss[kCtlThreads / 32];
   __shared__ int s_best_idx[kCtlThreads / 32];
   const int n_nodes0 = ts->n_nodes, leaves0 = ts->num_leaves;
@@ -233,26 +237,44 @@ __global__ void __launch_bounds__(kCtlThreads) ApplyKernel(EllView ell, ParamDev
     __syncthreads();
     n_expand = s_n_expand;
   } else {
-    // depth wise: every open entry of the level, ascending nidx
-    const int lb = ts->level_begin, le = ts->level_end;
+    // depth wise: the open entries of the level in ascending nidx, at most batch_cap VALID ones per step
+    // (Driver::Pop, driver.h:84-99: invalid entries are popped and dropped without counting)
+    if (threadIdx.x == 0) {
+      if (level_start) {
+        ts->level_begin = ts->next_begin;
+        ts->level_end = n_nodes0;
+        ts->level_cursor = ts->next_begin;
+        ts->next_begin = n_nodes0;
+      }
+      s_cutoff = ts->level_end;
+    }
+    __syncthreads();
+    const int lb = ts->level_cursor, le = ts->level_end;
+    const int cap = min(batch_cap, kMaxLevelNodes);
     level_depth = lb < le ? nodes[lb].depth : 0;
     uint32_t running = 0;
-    for (int base = lb; base < le; base += kCtlThreads) {
+    int base = lb;
+    for (; base < le && (int)running < cap; base += kCtlThreads) {
       const int i = base + threadIdx.x;
       bool valid = false;
       b200hist_candidate c;
       if (i < le && nodes[i].cand_open) {
         c = cand[i];
         valid = EntryValidNoLeafLimit(p, c, nodes[i].depth);
-        nodes[i].cand_open = 0;
       }
       uint32_t total;
-      uint32_t rank = running + BlockExclusiveScan(valid ? 1u : 0u, s_warp, &total);
-      bool accepted = valid && (int)rank < allow && n_nodes0 + 2 * ((int)rank + 1) <= max_nodes &&
-                      (int)rank < kMaxLevelNodes;
+      const uint32_t rank = running + BlockExclusiveScan(valid ? 1u : 0u, s_warp, &total);
+      // consumed by this step: everything in front of the (cap + 1)-th valid entry
+      const bool consumed = i < le && (int)rank < cap;
+      if (i < le && !consumed) atomicMin(&s_cutoff, i);
+      if (consumed) nodes[i].cand_open = 0;
+      bool accepted = consumed && valid && (int)rank < allow && n_nodes0 + 2 * ((int)rank + 1) <= max_nodes;
       if (accepted) ApplyOne<kCat>(ell, p, q, nodes, c, i, n_nodes0 + 2 * (int)rank, &part[rank], mono, node_is_cat);
       running += total;
     }
+    // the step stopped in front of `base` (batch full at a chunk boundary) or inside the last chunk scanned
+    if (threadIdx.x == 0) atomicMin(&s_cutoff, min(le, base));
+    running = min(running, (uint32_t)cap);
     n_expand = min((int)running, allow);
     n_expand = min(n_expand, (max_nodes - n_nodes0) / 2);
     n_expand = min(n_expand, kMaxLevelNodes);
@@ -289,8 +311,7 @@ __global__ void __launch_bounds__(kCtlThreads) ApplyKernel(EllView ell, ParamDev
   if (threadIdx.x == 0) {
     ts->n_nodes = n_nodes0 + 2 * n_expand;
     ts->num_leaves = leaves0 + n_expand;
-    ts->level_begin = n_nodes0;
-    ts->level_end = n_nodes0 + 2 * n_expand;
+    if (p.grow_policy == 0) ts->level_cursor = s_cutoff;  // what is left of the level for the next step
     ts->n_part = n_part;
     ts->part_tiles = running_tiles;
     ts->n_build = 0; ts->n_sub = 0; ts->n_eval = 0; ts->build_tiles = 0;
@@ -816,6 +837,9 @@ struct b200hist_updater_s {
   size_t hist_bytes{0};
   std::vector<uint32_t> step_cap;        // max nodes expanded in step s (host-known)
   std::vector<uint32_t> step_slot_base;  // first histogram slot of step s
+  std::vector<int> step_level;           // tree level (depth-wise) / split number (loss-guide) the step belongs to
+  std::vector<int> step_level_start;     // 1: the step opens its level, 0: it continues it (node batching)
+  int level_batch{kMaxLevelNodes};       // valid entries one step expands at most
   uint32_t n_slots{1};
   // multi-GPU: feature-group shard of this rank and the allreduce communicator (borrowed)
   b200hist_comm_s* comm{nullptr};
@@ -1144,14 +1168,17 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     auto ta = timer.Begin();
     if (has_cat) {
       ApplyKernel<true><<<1, kCtlThreads, 0, s>>>(view, u->pdev, u->d_quant, u->d_ts, u->d_nodes, u->d_cand, u->d_part,
-                                                  u->d_part_tile_seg, u->max_nodes, mono, u->d_node_is_cat);
+                                                  u->d_part_tile_seg, u->max_nodes, mono, u->d_node_is_cat,
+                                                  u->step_level_start[step], u->level_batch);
     } else {
       ApplyKernel<false><<<1, kCtlThreads, 0, s>>>(view, u->pdev, u->d_quant, u->d_ts, u->d_nodes, u->d_cand, u->d_part,
-                                                   u->d_part_tile_seg, u->max_nodes, mono, nullptr);
+                                                   u->d_part_tile_seg, u->max_nodes, mono, nullptr,
+                                                   u->step_level_start[step], u->level_batch);
     }
     B200_LAUNCHED();
     timer.End(kApply, ta);
-    const bool children_possible = u->param.max_depth == 0 || !depthwise || step + 1 < u->param.max_depth;
+    const bool children_possible =
+        u->param.max_depth == 0 || !depthwise || u->step_level[step] + 1 < u->param.max_depth;
     if (!children_possible) continue;
     auto tp = timer.Begin();
     if (ell->paged) {  // decision bits and tile counts accumulate over the page launches
@@ -1295,26 +1322,33 @@ int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* 
   u->group_begin = 0;
   u->group_end = (uint32_t)u->groups.size();
   {  // histogram slots: slot 0 = root; step s owns [base, base+cap) built + [base+cap, base+2cap) subtracted
+    // Depth-wise: a level that may hold more nodes than one step expands (level_batch) takes several steps -- node
+    // batching, updater_gpu_hist.cuh:34 kMaxNodeBatchSize + Driver::Pop (driver.h:84-99).  With a leaf budget the
+    // batch size is part of the semantics (IsChildValid sees the leaf count after each batch), so it is the
+    // reference's 1024 there; without one it is only a capacity and we take 4096.
     const bool dw = param->grow_policy == 0;
+    u->level_batch = param->max_leaves > 0 ? 1024 : kMaxLevelNodes;
+    if (const char* e = std::getenv("B200HIST_LEVEL_BATCH")) u->level_batch = std::max(1, std::min(std::atoi(e), kMaxLevelNodes));
     uint32_t base = 1;
-    for (int st = 0; st < u->n_steps; ++st) {
-      uint32_t cap = dw ? (uint32_t)std::min<long long>(1ll << std::min(st, 30), kMaxLevelNodes) : 1u;
-      if (param->max_leaves > 0) cap = std::min<uint32_t>(cap, (uint32_t)param->max_leaves);
-      u->step_cap.push_back(cap);
-      u->step_slot_base.push_back(base);
+    const int n_levels = u->n_steps;
+    u->n_steps = 0;
+    for (int st = 0; st < n_levels; ++st) {
+      long long width = dw ? (1ll << std::min(st, 40)) : 1ll;
+      if (param->max_leaves > 0) width = std::min<long long>(width, param->max_leaves);
       const bool children = param->max_depth == 0 || !dw || st + 1 < param->max_depth;
-      if (children) base += 2 * cap;
+      const long long n_sub = dw ? (width + u->level_batch - 1) / u->level_batch : 1;
+      B200_CHECK(u->n_steps + n_sub < (1ll << 22), "tree too large: bound max_depth or max_leaves");
+      for (long long b = 0; b < n_sub; ++b) {
+        const uint32_t cap = (uint32_t)std::min<long long>(u->level_batch, width - b * u->level_batch);
+        u->step_cap.push_back(cap);
+        u->step_slot_base.push_back(base);
+        u->step_level.push_back(st);
+        u->step_level_start.push_back(b == 0 ? 1 : 0);
+        if (children) base += 2 * cap;
+        ++u->n_steps;
+      }
     }
     u->n_slots = base;
-    if (dw) {
-      long long widest = 1;
-      for (auto c : u->step_cap) widest = std::max<long long>(widest, c);
-      long long need = param->max_depth > 0 ? (1ll << std::min(param->max_depth - 1, 40)) : (long long)param->max_leaves;
-      if (param->max_leaves > 0) need = std::min<long long>(need, param->max_leaves);
-      B200_CHECK(need <= kMaxLevelNodes, "a tree level may hold more than " + std::to_string(kMaxLevelNodes) +
-                                             " nodes to expand; bound max_depth (<= 13) or max_leaves");
-      (void)widest;
-    }
   }
   const uint64_t n = ell->n_rows;
   const size_t part_tiles = n / kPartTile + kMaxLevelNodes + 2;
