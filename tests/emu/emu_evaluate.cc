@@ -68,11 +68,11 @@ int main(int argc, char** argv) {
   if (meta[6]) {
     EMU_LAUNCH((blocks), (b200::kEvalWarps * 32), 0,
                b200::FeatureScanKernel<true>(ell, hist.data(), eval_nodes.data(), &ts, nodes.data(), d_fs, n_fs, p, &q,
-                                             scratch.data(), mono, meta[5], ic));
+                                             scratch.data(), mono, meta[5], ic, b200::EvalShard{0, 1, (uint32_t)ell.n_features}));
   } else {
     EMU_LAUNCH((blocks), (b200::kEvalWarps * 32), 0,
                b200::FeatureScanKernel<false>(ell, hist.data(), eval_nodes.data(), &ts, nodes.data(), d_fs, n_fs, p, &q,
-                                              scratch.data(), mono, meta[5], ic));
+                                              scratch.data(), mono, meta[5], ic, b200::EvalShard{0, 1, (uint32_t)ell.n_features}));
   }
   if (meta[9])
     EMU_LAUNCH((blocks), (b200::kEvalWarps * 32), cat_smem,

@@ -272,9 +272,9 @@ int main(int argc, char** argv) {
     const unsigned b2 = (unsigned)std::min<long long>(((long long)max_eval + kEvalWarps - 1) / kEvalWarps, 2);
     const longlong2* h2 = hist.data();
     if (ic.count != nullptr) {
-      EMU_LAUNCH((b1), (kEvalWarps * 32), 0, FeatureScanKernel<true>(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), mono, levels, ic));
+      EMU_LAUNCH((b1), (kEvalWarps * 32), 0, FeatureScanKernel<true>(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), mono, levels, ic, EvalShard{0, 1, nf}));
     } else {
-      EMU_LAUNCH((b1), (kEvalWarps * 32), 0, FeatureScanKernel<false>(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), mono, levels, ic));
+      EMU_LAUNCH((b1), (kEvalWarps * 32), 0, FeatureScanKernel<false>(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), mono, levels, ic, EvalShard{0, 1, nf}));
     }
     if (has_cat)
       EMU_LAUNCH((b1), (kEvalWarps * 32), cat_smem, CatFeatureScanKernel(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), mono, levels, ic, catv));

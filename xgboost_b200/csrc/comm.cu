@@ -324,6 +324,130 @@ void LaunchScalarExchange(uint32_t* const* peer_flags, int rank, int world, uint
   B200_LAUNCHED();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row split, evaluation by feature slice (the default row-split path): a reduce-scatter WITHOUT the all-gather.
+//   HistSliceReduceKernel   barrier A (everyone has built), then rank r sums the peers' partial histograms over ITS
+//                           bin range [bin_begin, bin_end) of every built slot (P2P loads) into its own cache.  Nobody
+//                           writes into a peer: each rank ends up with the complete histograms of its features only.
+//   (local)                 SubtractKernel and FeatureScanKernel over that bin / feature range.
+//   ScratchExchangeKernel   every rank pushes the per-feature winners it owns (32 bytes per (node, feature)) into all
+//                           peers' scratch tables and meets them at barrier B; the fold over features (NodeReduceKernel)
+//                           then runs replicated on identical tables -- the reference's column-split evaluation
+//                           (evaluate_splits.cu:412-435: allgather of candidates).
+// Per level a rank reads (P-1)/P of the built histograms' bytes from its peers and writes 32 B x nodes x features / P
+// to each: half the NVLink traffic of the fused reduce-scatter + all-gather, and evaluation / subtraction shrink by P.
+// ---------------------------------------------------------------------------------------------
+template <int kWorld>
+__global__ void __launch_bounds__(256)
+HistSliceReduceKernel(longlong2* const* __restrict__ peer_hist, uint32_t* const* __restrict__ peer_flags, int rank,
+                      int world, const TreeState* __restrict__ ts, uint32_t slot_base, uint32_t slot_cap,
+                      uint32_t total_bins, uint32_t bin_begin, uint32_t bin_end, uint32_t epoch) {
+  const uint32_t n_slots = min(slot_cap, (uint32_t)ts->n_build);
+  if (blockIdx.x == 0) {  // barrier A: my build kernel precedes this kernel in the stream
+    __threadfence_system();
+    SignalPeers(peer_flags, rank, world, epoch);
+  }
+  WaitPeers(peer_flags, rank, world, epoch);
+  __syncthreads();
+  const uint32_t width = bin_end - bin_begin;
+  const unsigned long long total = (unsigned long long)n_slots * width;
+  longlong2* __restrict__ mine = peer_hist[rank];
+  if (kWorld > 0) {
+    const longlong2* src[kWorld > 0 ? kWorld : 1];
+#pragma unroll
+    for (int p = 0; p < kWorld; ++p) src[p] = peer_hist[p];
+    for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * 256ull) {
+      const uint32_t sl = (uint32_t)(i / width);
+      const size_t off = (size_t)(slot_base + sl) * total_bins + bin_begin + (uint32_t)(i - (unsigned long long)sl * width);
+      longlong2 v[kWorld > 0 ? kWorld : 1];
+#pragma unroll
+      for (int p = 0; p < kWorld; ++p) v[p] = src[p][off];
+      longlong2 acc = make_longlong2(0, 0);
+#pragma unroll
+      for (int p = 0; p < kWorld; ++p) { acc.x += v[p].x; acc.y += v[p].y; }
+      mine[off] = acc;
+    }
+  } else {
+    for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * 256ull) {
+      const uint32_t sl = (uint32_t)(i / width);
+      const size_t off = (size_t)(slot_base + sl) * total_bins + bin_begin + (uint32_t)(i - (unsigned long long)sl * width);
+      longlong2 acc = make_longlong2(0, 0);
+      for (int p = 0; p < world; ++p) {
+        const longlong2 v = peer_hist[p][off];
+        acc.x += v.x;
+        acc.y += v.y;
+      }
+      mine[off] = acc;
+    }
+  }
+}
+
+void LaunchHistSliceReduce(longlong2* const* peer_hist, uint32_t* const* peer_flags, int rank, int world,
+                           const TreeState* ts, uint32_t slot_base, uint32_t slot_cap, uint32_t total_bins,
+                           uint32_t bin_begin, uint32_t bin_end, uint32_t epoch, int num_sms, cudaStream_t s) {
+  auto kernel = world == 2 ? HistSliceReduceKernel<2>
+                : world == 4 ? HistSliceReduceKernel<4>
+                : world == 8 ? HistSliceReduceKernel<8>
+                             : HistSliceReduceKernel<0>;
+  kernel<<<num_sms * 2, 256, 0, s>>>(peer_hist, peer_flags, rank, world, ts, slot_base, slot_cap, total_bins, bin_begin,
+                                     bin_end, epoch);
+  B200_LAUNCHED();
+}
+
+// One thread per (evaluation slot, feature position): the entry travels iff this rank scanned it.  The feature of an
+// item is looked up exactly as FeatureScanKernel does (evaluate.cu).
+__global__ void __launch_bounds__(256)
+ScratchExchangeKernel(FeatCand* const* __restrict__ peer_scratch, uint32_t* const* __restrict__ peer_flags,
+                      EvalShard shard, const TreeState* __restrict__ ts, const int32_t* __restrict__ eval_nodes,
+                      const NodeDev* __restrict__ nodes, const int32_t* __restrict__ feature_set, int32_t n_fs,
+                      int32_t n_levels, IcView ic, uint32_t epoch, unsigned int* __restrict__ done_counter) {
+  const int rank = shard.rank, world = shard.world;
+  const long long total = (long long)ts->n_eval * n_fs;
+  const FeatCand* __restrict__ mine = peer_scratch[rank];
+  for (long long item = blockIdx.x * 256ll + threadIdx.x; item < total; item += (long long)gridDim.x * 256ll) {
+    const int slot = (int)(item / n_fs);
+    const int fpos = (int)(item - (long long)slot * n_fs);
+    const int nidx = eval_nodes[slot];
+    const int32_t* __restrict__ fs =
+        (feature_set && n_levels > 0) ? feature_set + (size_t)min(nodes[nidx].depth, n_levels - 1) * n_fs : feature_set;
+    if (ic.count != nullptr) {
+      if (fpos >= ic.count[slot]) continue;
+      fs = ic.list + (size_t)slot * ic.stride;
+    }
+    const int f = fs ? fs[fpos] : fpos;
+    if (!shard.Owns(f)) continue;
+    const FeatCand c = mine[item];
+    for (int p = 0; p < world; ++p)
+      if (p != rank) peer_scratch[p][item] = c;
+  }
+  // barrier B: the last CTA to finish publishes the epoch to every peer and waits for all peers
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    SignalPeers(peer_flags, rank, world, epoch);
+    __threadfence_system();
+    WaitPeers(peer_flags, rank, world, epoch);
+    __syncthreads();
+    if (threadIdx.x == 0) *done_counter = 0;
+    __threadfence_system();
+  }
+}
+
+void LaunchScratchExchange(FeatCand* const* peer_scratch, uint32_t* const* peer_flags, const EvalShard& shard,
+                           const TreeState* ts, const int32_t* eval_nodes, const NodeDev* nodes,
+                           const int32_t* feature_set, int32_t n_fs, int32_t n_levels, IcView ic, int32_t max_eval,
+                           uint32_t epoch, unsigned int* done_counter, int num_sms, cudaStream_t s) {
+  const long long items = (long long)max_eval * n_fs;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((items + 255) / 256, (long long)num_sms * 2));
+  ScratchExchangeKernel<<<blocks, 256, 0, s>>>(peer_scratch, peer_flags, shard, ts, eval_nodes, nodes, feature_set,
+                                               n_fs, n_levels, ic, epoch, done_counter);
+  B200_LAUNCHED();
+}
+
 void LaunchHistExchange(longlong2* const* peer_hist, uint32_t* const* peer_flags, int rank, int world,
                         const TreeState* ts, uint32_t slot_base, uint32_t slot_cap, bool use_n_build,
                         uint32_t total_bins, uint32_t bin_begin, uint32_t bin_end, uint32_t epoch,

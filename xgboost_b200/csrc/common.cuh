@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "b200hist.h"
@@ -390,6 +391,19 @@ struct GroupDesc {
   uint32_t max_sym;             // bank-mapped layout: symbols per feature slot (max bins of the group)
 };
 
+// Row split over several GPUs, evaluation by feature slice: rank r of `world` owns the features f with
+// f * world / n_features == r -- after the reduce step it holds the complete histograms of exactly those features'
+// bins, scans only them and pushes their per-feature winners to the peers (the reference's column-split evaluation,
+// evaluate_splits.cu:412-435, applied to the slices a reduce-scatter leaves behind).  world == 1: everything.
+struct EvalShard {
+  int32_t rank;
+  int32_t world;
+  uint32_t n_features;
+  __host__ __device__ bool Owns(int f) const {
+    return world <= 1 || (int32_t)(((unsigned long long)(uint32_t)f * (uint32_t)world) / n_features) == rank;
+  }
+};
+
 // Per-(node, feature) best split produced by the feature scan.
 struct FeatCand {
   float loss_chg;
@@ -420,7 +434,7 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
                      b200hist_gpair64* hist, const QuantDev* quant /* nullable */, int num_sms, cudaStream_t s,
                      bool pair_hint = false /* expect hessians without low words: 64-feature pair kernel */);
 void LaunchSubtract(const SubEntry* sub, const TreeState* ts, b200hist_gpair64* hist, uint32_t total_bins,
-                    int num_sms, cudaStream_t s);
+                    int num_sms, cudaStream_t s, uint32_t bin_begin = 0, uint32_t bin_end = 0xFFFFFFFFu);
 void LaunchSubtractFlat(const b200hist_gpair64* parent, const b200hist_gpair64* built, b200hist_gpair64* out,
                         uint64_t n_bins, cudaStream_t s);
 std::vector<GroupDesc> MakeFeatureGroups(const b200hist_ellpack_s& ell, int device);
@@ -438,6 +452,16 @@ void LaunchHistAllReduce(longlong2* const* peer_hist, uint32_t* const* peer_flag
                          uint32_t epoch_a, uint32_t epoch_b, unsigned int* done_counter, int num_sms, cudaStream_t s);
 void LaunchScalarExchange(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch, int which /* 0 sums, 1 root */,
                           QuantDev* q, uint64_t n_local, cudaStream_t s);
+// row split, evaluation by feature slice: sum the peers' partial histograms over this rank's bin range into its OWN
+// cache (reduce-scatter, no all-gather) ...
+void LaunchHistSliceReduce(longlong2* const* peer_hist, uint32_t* const* peer_flags, int rank, int world,
+                           const TreeState* ts, uint32_t slot_base, uint32_t slot_cap, uint32_t total_bins,
+                           uint32_t bin_begin, uint32_t bin_end, uint32_t epoch, int num_sms, cudaStream_t s);
+// ... and after the feature scan push the owned per-feature winners into every peer's scratch table, then the barrier
+void LaunchScratchExchange(FeatCand* const* peer_scratch, uint32_t* const* peer_flags, const EvalShard& shard,
+                           const TreeState* ts, const int32_t* eval_nodes, const NodeDev* nodes,
+                           const int32_t* feature_set, int32_t n_fs, int32_t n_levels, IcView ic, int32_t max_eval,
+                           uint32_t epoch, unsigned int* done_counter, int num_sms, cudaStream_t s);
 
 // evaluate.cu
 void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = node id */,
@@ -448,7 +472,9 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist /* slot = n
                     int32_t n_levels = 0 /* > 0: feature_set is [n_levels][n_feature_set], row = node depth */,
                     int32_t* max_eval_depth = nullptr /* device: atomicMax of the depths evaluated */,
                     IcView ic = IcView{nullptr, nullptr, 0},
-                    CatView cat = CatView{nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0, 0});
+                    CatView cat = CatView{nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0, 0},
+                    EvalShard shard = EvalShard{0, 1, 0} /* scan only the features this rank owns */,
+                    const std::function<void()>* between = nullptr /* runs after the feature scans, before the fold */);
 
 // colsample.cu: the seed-driven column sampler of one tree (see the kernels there)
 struct ColDrawDev {

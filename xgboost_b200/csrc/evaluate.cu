@@ -98,7 +98,7 @@ FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t
                   const TreeState* __restrict__ ts, const NodeDev* __restrict__ nodes,
                   const int32_t* __restrict__ feature_set, int32_t n_fs, ParamDev p,
                   const QuantDev* __restrict__ q, FeatCand* __restrict__ scratch, MonoView mono, int32_t n_levels,
-                  IcView ic) {
+                  IcView ic, EvalShard shard) {
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * kEvalWarps + (threadIdx.x >> 5);
   const int n_warps = gridDim.x * kEvalWarps;
@@ -118,6 +118,7 @@ FeatureScanKernel(EllView ell, const longlong2* __restrict__ hist, const int32_t
       fs = ic.list + (size_t)slot * ic.stride;
     }
     const int f = fs ? fs[fpos] : fpos;
+    if (!shard.Owns(f)) continue;  // warp-uniform: another rank holds this feature's complete histogram
     const longlong2* h = hist + (size_t)nodes[nidx].hist_slot * ell.total_bins;
     const long long pg = nodes[nidx].sum_g, ph = nodes[nidx].sum_h;
     const uint32_t beg = ell.cut_ptrs[f], end = ell.cut_ptrs[f + 1];
@@ -572,8 +573,11 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist, const int3
                     int32_t max_eval, const NodeDev* nodes, const int32_t* feature_set, int32_t n_feature_set,
                     const ParamDev& p, const QuantDev* q, FeatCand* scratch, b200hist_candidate* cand,
                     NodeDev* nodes_mut, int num_sms, cudaStream_t s, MonoView mono, int32_t n_levels,
-                    int32_t* max_eval_depth, IcView ic, CatView cat) {
+                    int32_t* max_eval_depth, IcView ic, CatView cat, EvalShard shard,
+                    const std::function<void()>* between) {
   const int32_t n_fs = feature_set ? n_feature_set : (int32_t)ell.n_features;
+  if (shard.world > 1) shard.n_features = ell.n_features;
+  B200_CHECK(shard.world <= 1 || cat.is_cat == nullptr, "internal: evaluation by feature slice has no categorical path");
   long long max_items = (long long)max_eval * n_fs;
   if (max_items == 0) return;
   int blocks = (int)std::min<long long>((max_items + kEvalWarps - 1) / kEvalWarps, (long long)num_sms * 8);
@@ -596,9 +600,10 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist, const int3
   };
   if (ic.count != nullptr) {  // an answer is a subset of the sampled list, so n_fs bounds every count
     FeatureScanKernel<true><<<blocks, kEvalWarps * 32, 0, s>>>(ell, h2, eval_nodes, ts, nodes, feature_set, n_fs, p, q,
-                                                               scratch, mono, n_levels, ic);
+                                                               scratch, mono, n_levels, ic, shard);
     B200_LAUNCHED();
     scan_cat();
+    if (between) (*between)();
     NodeReduceKernel<true><<<blocks2, kEvalWarps * 32, 0, s>>>(ell, eval_nodes, ts, nodes_mut, feature_set, n_fs, p, q,
                                                                scratch, cand, mono, n_levels, max_eval_depth, ic);
     B200_LAUNCHED();
@@ -606,9 +611,10 @@ void LaunchEvaluate(const EllView& ell, const b200hist_gpair64* hist, const int3
     return;
   }
   FeatureScanKernel<false><<<blocks, kEvalWarps * 32, 0, s>>>(ell, h2, eval_nodes, ts, nodes, feature_set, n_fs, p, q,
-                                                              scratch, mono, n_levels, ic);
+                                                              scratch, mono, n_levels, ic, shard);
   B200_LAUNCHED();
   scan_cat();
+  if (between) (*between)();
   NodeReduceKernel<false><<<blocks2, kEvalWarps * 32, 0, s>>>(ell, eval_nodes, ts, nodes_mut, feature_set, n_fs, p, q,
                                                               scratch, cand, mono, n_levels, max_eval_depth, ic);
   B200_LAUNCHED();

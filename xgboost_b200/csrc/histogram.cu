@@ -1427,12 +1427,15 @@ void LaunchBuildHist(const EllView& ell, const b200hist_gpair64* gq, const uint3
 #endif  // B200_KERNELS_ONLY
 
 // sibling = parent - built for every (parent, built, sibling) triple of the level, one launch.
+// [bin_begin, bin_end): the bins to subtract (a rank's feature slice under row split; everything otherwise)
 __global__ void __launch_bounds__(256) SubtractKernel(const SubEntry* __restrict__ sub, const TreeState* __restrict__ ts,
-                                                       longlong2* __restrict__ hist, uint32_t total_bins) {
-  const unsigned long long total = (unsigned long long)ts->n_sub * total_bins;
+                                                       longlong2* __restrict__ hist, uint32_t total_bins,
+                                                       uint32_t bin_begin, uint32_t bin_end) {
+  const uint32_t width = bin_end - bin_begin;
+  const unsigned long long total = (unsigned long long)ts->n_sub * width;
   for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * 256ull) {
-    uint32_t k = (uint32_t)(i / total_bins);
-    uint32_t b = (uint32_t)(i - (unsigned long long)k * total_bins);
+    uint32_t k = (uint32_t)(i / width);
+    uint32_t b = bin_begin + (uint32_t)(i - (unsigned long long)k * width);
     SubEntry e = sub[k];
     longlong2 p = hist[(size_t)e.parent * total_bins + b];
     longlong2 c = hist[(size_t)e.built * total_bins + b];
@@ -1442,8 +1445,9 @@ __global__ void __launch_bounds__(256) SubtractKernel(const SubEntry* __restrict
 
 #ifndef B200_KERNELS_ONLY
 void LaunchSubtract(const SubEntry* sub, const TreeState* ts, b200hist_gpair64* hist, uint32_t total_bins,
-                    int num_sms, cudaStream_t s) {
-  SubtractKernel<<<num_sms * 8, 256, 0, s>>>(sub, ts, reinterpret_cast<longlong2*>(hist), total_bins);
+                    int num_sms, cudaStream_t s, uint32_t bin_begin, uint32_t bin_end) {
+  SubtractKernel<<<num_sms * 8, 256, 0, s>>>(sub, ts, reinterpret_cast<longlong2*>(hist), total_bins, bin_begin,
+                                             std::min(bin_end, total_bins));
   B200_LAUNCHED();
 }
 #endif  // B200_KERNELS_ONLY

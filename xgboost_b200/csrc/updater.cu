@@ -897,6 +897,9 @@ struct b200hist_updater_s {
   std::vector<void*> peer_base;            // opened IPC mappings (own entry = nullptr)
   longlong2** d_peer_hist{nullptr};
   uint32_t** d_peer_flags{nullptr};
+  FeatCand** d_peer_scratch{nullptr};      // every rank's evaluation scratch table (inside the shared allocation)
+  size_t scratch_offset{0};                // byte offset of the scratch table inside the histogram allocation
+  bool last_sliced{false};                 // the last tree was evaluated by feature slice (node_histogram assembles)
   unsigned int* d_exchange_counter{nullptr};
   uint32_t exchange_epoch{0};
   // host staging
@@ -962,6 +965,17 @@ int32_t MaxNodesFor(const b200hist_train_param& p) {
   long long by_leaves = p.max_leaves > 0 ? (2ll * p.max_leaves - 1) : (1ll << 40);
   long long n = std::min(by_depth, by_leaves);
   return (int32_t)n;
+}
+
+// bins of the features rank owns under EvalShard::Owns: f * world / n_features == rank
+void SliceBins(const b200hist_ellpack_s& ell, int rank, int world, uint32_t* lo, uint32_t* hi) {
+  const EvalShard sh{rank, world, ell.n_features};
+  uint32_t f0 = ell.n_features, f1 = 0;
+  for (uint32_t f = 0; f < ell.n_features; ++f)
+    if (sh.Owns((int)f)) { f0 = std::min(f0, f); f1 = std::max(f1, f + 1); }
+  if (f0 >= f1) { *lo = 0; *hi = 0; return; }
+  *lo = ell.cut_ptrs[f0];
+  *hi = ell.cut_ptrs[f1];
 }
 
 void ToAbiNodes(const NodeDev* src, int32_t n, b200hist_tree_node* dst) {
@@ -1065,6 +1079,26 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     B200_CUDA(cudaMemsetAsync(u->d_col_cursor, 0, 2 * sizeof(int32_t), s));
     B200_CUDA(cudaMemsetAsync(u->d_col_level_drawn, 0, sizeof(int32_t) * (size_t)u->col_max_levels, s));
   }
+  // Row split: evaluation by feature slice (comm.cu, HistSliceReduceKernel / ScratchExchangeKernel).  Categorical
+  // features keep the fused reduce-scatter + all-gather (CatFinishKernel re-reads the winner's histogram, which may be
+  // another rank's slice); B200HIST_ROWSPLIT_FULL=1 forces it everywhere (A/B runs).
+  static const bool force_full_exchange = std::getenv("B200HIST_ROWSPLIT_FULL") != nullptr;
+  const bool sliced = u->p2p && u->row_split && u->d_is_cat == nullptr && !force_full_exchange &&
+                      ell->n_features >= (uint32_t)u->p2p_world;
+  u->last_sliced = sliced;
+  const EvalShard shard{sliced ? u->p2p_rank : 0, sliced ? u->p2p_world : 1, ell->n_features};
+  uint32_t slice_bin_lo = 0, slice_bin_hi = ell->total_bins;
+  if (sliced) SliceBins(*ell, u->p2p_rank, u->p2p_world, &slice_bin_lo, &slice_bin_hi);
+  auto evaluate = [&](int32_t max_eval, const int32_t* fset, int32_t n_fset, int32_t n_lv, IcView icv, const CatView& cv) {
+    const int32_t n_fs = fset ? n_fset : (int32_t)ell->n_features;
+    std::function<void()> exchange = [&]() {  // its time is part of the evaluation phase
+      LaunchScratchExchange(u->d_peer_scratch, u->d_peer_flags, shard, u->d_ts, u->d_eval_nodes, u->d_nodes, fset, n_fs,
+                            n_lv, icv, max_eval, ++u->exchange_epoch, u->d_exchange_counter, u->num_sms, s);
+    };
+    LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, max_eval, u->d_nodes, fset, n_fset, u->pdev, u->d_quant,
+                   u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, n_lv, &u->d_ts->max_eval_depth, icv, cv,
+                   shard, sliced ? &exchange : nullptr);
+  };
   // evaluation through the seed-driven column sampler: level set of the step's depth (drawn on first use), then a
   // node set per evaluation slot (colsample_bynode < 1) or the level set itself
   auto evaluate_with_column_sampler = [&](int32_t max_eval, const CatView& cv, bool root) {
@@ -1083,21 +1117,15 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
             nullptr, 0);
       }
       B200_LAUNCHED();
-      LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, max_eval, u->d_nodes, nullptr, 0, u->pdev, u->d_quant,
-                     u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, 0, &u->d_ts->max_eval_depth,
-                     IcView{u->d_ic_list, u->d_ic_count, 0}, cv);
+      evaluate(max_eval, nullptr, 0, 0, IcView{u->d_ic_list, u->d_ic_count, 0}, cv);
       return;
     }
     if (!u->col_bynode_is_one) {
       LaunchNodeDraw(u->d_ts, u->d_nodes, u->d_eval_nodes, cold, u->col_n_node, max_eval, u->d_col_node_list,
                      u->d_col_node_count, s);
-      LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, max_eval, u->d_nodes, nullptr, 0, u->pdev, u->d_quant,
-                     u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, 0, &u->d_ts->max_eval_depth,
-                     IcView{u->d_col_node_list, u->d_col_node_count, u->col_n_node}, cv);
+      evaluate(max_eval, nullptr, 0, 0, IcView{u->d_col_node_list, u->d_col_node_count, u->col_n_node}, cv);
     } else {
-      LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, max_eval, u->d_nodes, u->d_col_level_sets, u->col_n_level,
-                     u->pdev, u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, u->col_max_levels,
-                     &u->d_ts->max_eval_depth, IcView{nullptr, nullptr, 0}, cv);
+      evaluate(max_eval, u->d_col_level_sets, u->col_n_level, u->col_max_levels, IcView{nullptr, nullptr, 0}, cv);
     }
   };
   if (has_node_sets) B200_CUDA(cudaMemsetAsync(u->d_node_seq, 0, sizeof(int32_t), s));
@@ -1129,7 +1157,10 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
       });
     // AllReduceHist: one collective per level over the level's contiguous built slots
     auto tc = timer.Begin();
-    if (u->p2p && u->row_split) {
+    if (sliced) {  // reduce-scatter only: this rank's bin range of every built slot, summed into its own cache
+      LaunchHistSliceReduce(u->d_peer_hist, u->d_peer_flags, u->p2p_rank, u->p2p_world, u->d_ts, slot_base, slot_cap,
+                            ell->total_bins, slice_bin_lo, slice_bin_hi, ++u->exchange_epoch, u->num_sms, s);
+    } else if (u->p2p && u->row_split) {
       const uint32_t ea = ++u->exchange_epoch, eb = ++u->exchange_epoch;
       LaunchHistAllReduce(u->d_peer_hist, u->d_peer_flags, u->p2p_rank, u->p2p_world, u->d_ts, slot_base, slot_cap,
                           ell->total_bins, ea, eb, u->d_exchange_counter, u->num_sms, s);
@@ -1152,12 +1183,9 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     evaluate_with_column_sampler(1, catv, true);
   } else if (has_node_sets) {
     const IcView nv = node_sets_view();
-    LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, nullptr, 0, u->pdev, u->d_quant, u->d_scratch,
-                   u->d_cand, u->d_nodes, u->num_sms, s, mono, 0, &u->d_ts->max_eval_depth, nv, catv);
+    evaluate(1, nullptr, 0, 0, nv, catv);
   } else {
-    LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, 1, u->d_nodes, u->d_feature_set, u->n_feature_set, u->pdev, u->d_quant,
-                   u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, u->n_feature_levels, &u->d_ts->max_eval_depth,
-                   IcView{nullptr, nullptr, 0}, catv);
+    evaluate(1, u->d_feature_set, u->n_feature_set, u->n_feature_levels, IcView{nullptr, nullptr, 0}, catv);
   }
   timer.End(kEval, t3);
 
@@ -1202,7 +1230,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     build_hist(u->step_slot_base[step], u->step_cap[step]);
     timer.End(kHist, th);
     auto tsb = timer.Begin();
-    LaunchSubtract(u->d_sub, u->d_ts, u->d_hist, ell->total_bins, u->num_sms, s);
+    LaunchSubtract(u->d_sub, u->d_ts, u->d_hist, ell->total_bins, u->num_sms, s, slice_bin_lo, slice_bin_hi);
     timer.End(kSub, tsb);
     auto te = timer.Begin();
     IcView icv{nullptr, nullptr, 0};
@@ -1213,9 +1241,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     }
     if (has_node_sets) {
       icv = node_sets_view();
-      LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, (int32_t)(2 * cap), u->d_nodes, nullptr, 0, u->pdev,
-                     u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, 0, &u->d_ts->max_eval_depth, icv,
-                     catv);
+      evaluate((int32_t)(2 * cap), nullptr, 0, 0, icv, catv);
       timer.End(kEval, te);
       continue;
     }
@@ -1228,10 +1254,7 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
       B200_LAUNCHED();
       icv = IcView{u->d_ic_list, u->d_ic_count, 0};
     }
-    LaunchEvaluate(view, u->d_hist, u->d_eval_nodes, u->d_ts, (int32_t)(2 * cap), u->d_nodes, u->d_feature_set,
-                   u->n_feature_set, u->pdev,
-                   u->d_quant, u->d_scratch, u->d_cand, u->d_nodes, u->num_sms, s, mono, u->n_feature_levels,
-                   &u->d_ts->max_eval_depth, icv, catv);
+    evaluate((int32_t)(2 * cap), u->d_feature_set, u->n_feature_set, u->n_feature_levels, icv, catv);
     timer.End(kEval, te);
   }
 
@@ -1380,7 +1403,6 @@ int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* 
   u->d_fin = DevAlloc<BuildEntry>(u->max_nodes);
   u->d_fin_tile_seg = DevAlloc<uint32_t>(fin_tiles);
   u->d_fin_tile_begin = DevAlloc<uint32_t>((size_t)u->max_nodes + 1);
-  u->d_scratch = DevAlloc<FeatCand>((size_t)2 * kMaxLevelNodes * ell->n_features);
   u->hist_bytes = (size_t)u->n_slots * ell->total_bins * sizeof(b200hist_gpair64);
   size_t free_b = 0, total_b = 0;
   B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -1390,11 +1412,15 @@ int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* 
   // at least 4 MiB so that it is a stand-alone driver allocation whose IPC mapping starts at the same address
   u->flags_offset = (u->hist_bytes + 255) & ~size_t(255);
   {
-    const size_t alloc = std::max<size_t>(u->flags_offset + 4096, size_t(4) << 20);
+    // ... + the evaluation scratch table: under row split the ranks push per-feature winners into each other's
+    u->scratch_offset = u->flags_offset + 4096;
+    const size_t scratch_bytes = sizeof(FeatCand) * (size_t)2 * kMaxLevelNodes * ell->n_features;
+    const size_t alloc = std::max<size_t>(u->scratch_offset + scratch_bytes, size_t(4) << 20);
     void* p = nullptr;
     B200_CUDA(cudaMalloc(&p, alloc));
     B200_CUDA(cudaMemset(p, 0, alloc));
     u->d_hist = static_cast<b200hist_gpair64*>(p);
+    u->d_scratch = reinterpret_cast<FeatCand*>(static_cast<uint8_t*>(p) + u->scratch_offset);
   }
   u->d_exchange_counter = DevAlloc<unsigned int>(1);
   B200_CUDA(cudaMemset(u->d_exchange_counter, 0, sizeof(unsigned int)));
@@ -1413,12 +1439,13 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
                     u->d_position, u->d_gpair_staging, u->d_ts, u->d_nodes, u->d_cand, u->d_part, u->d_build,
                     u->d_sub, u->d_eval_nodes, u->d_part_tile_seg, u->d_build_tile_seg, u->d_tile_left,
                     u->d_tile_excl, u->d_tile_left_off, u->d_flags, u->d_fin, u->d_fin_tile_seg,
-                    u->d_fin_tile_begin, u->d_scratch, u->d_hist};
+                    u->d_fin_tile_begin, u->d_hist};
     for (void* p : ptrs) cudaFree(p);
     for (void* p : u->peer_base)
       if (p != nullptr) cudaIpcCloseMemHandle(p);
     cudaFree(u->d_peer_hist);
     cudaFree(u->d_peer_flags);
+    cudaFree(u->d_peer_scratch);
     cudaFree(u->d_exchange_counter);
     if (u->d_feature_set) cudaFree(u->d_feature_set);
     for (void* p : {(void*)u->d_monotone, (void*)u->d_lower, (void*)u->d_upper})
@@ -1534,6 +1561,19 @@ int b200hist_updater_node_histogram(b200hist_updater_t u, int32_t nidx, b200hist
   DeviceGuard guard(u->device);
   const int32_t slot = u->h_nodes[nidx].hist_slot;
   B200_CHECK(slot >= 0, "node " + std::to_string(nidx) + " has no histogram");
+  if (u->p2p && u->last_sliced) {
+    // evaluation by feature slice: rank p holds the complete sums of ITS features' bins only -- assemble the node's
+    // histogram from every rank's slice through the peer mappings
+    for (int p = 0; p < u->p2p_world; ++p) {
+      uint32_t lo = 0, hi = 0;
+      SliceBins(*u->ell, p, u->p2p_world, &lo, &hi);
+      if (hi <= lo) continue;
+      const auto* base = p == u->p2p_rank ? u->d_hist : static_cast<const b200hist_gpair64*>(u->peer_base[(size_t)p]);
+      B200_CUDA(cudaMemcpy(out_host + lo, base + (size_t)slot * u->ell->total_bins + lo,
+                           sizeof(b200hist_gpair64) * (hi - lo), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+  }
   B200_CUDA(cudaMemcpy(out_host, u->d_hist + (size_t)slot * u->ell->total_bins,
                        sizeof(b200hist_gpair64) * u->ell->total_bins, cudaMemcpyDeviceToHost));
   B200_API_END();
@@ -1594,10 +1634,15 @@ int b200hist_updater_set_peers(b200hist_updater_t u, int rank, int world, const 
     hist[p] = static_cast<longlong2*>(base);
     flags[p] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(base) + u->flags_offset);
   }
+  std::vector<FeatCand*> scratch(world);
+  for (int p = 0; p < world; ++p)
+    scratch[p] = reinterpret_cast<FeatCand*>(reinterpret_cast<uint8_t*>(hist[p]) + u->scratch_offset);
   u->d_peer_hist = DevAlloc<longlong2*>(world);
   u->d_peer_flags = DevAlloc<uint32_t*>(world);
+  u->d_peer_scratch = DevAlloc<FeatCand*>(world);
   B200_CUDA(cudaMemcpy(u->d_peer_hist, hist.data(), sizeof(void*) * world, cudaMemcpyHostToDevice));
   B200_CUDA(cudaMemcpy(u->d_peer_flags, flags.data(), sizeof(void*) * world, cudaMemcpyHostToDevice));
+  B200_CUDA(cudaMemcpy(u->d_peer_scratch, scratch.data(), sizeof(void*) * world, cudaMemcpyHostToDevice));
   ShardGroups((uint32_t)u->groups.size(), world, rank, &u->group_begin, &u->group_end);
   u->p2p_rank = rank;
   u->p2p_world = world;
@@ -1941,8 +1986,10 @@ int b200hist_updater_clear_peers(b200hist_updater_t u) {
   }
   if (u->d_peer_hist) cudaFree(u->d_peer_hist);
   if (u->d_peer_flags) cudaFree(u->d_peer_flags);
+  if (u->d_peer_scratch) cudaFree(u->d_peer_scratch);
   u->d_peer_hist = nullptr;
   u->d_peer_flags = nullptr;
+  u->d_peer_scratch = nullptr;
   u->p2p = false;
   u->row_split = false;
   u->p2p_world = 1;
