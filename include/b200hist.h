@@ -230,6 +230,15 @@ B200HIST_API int b200hist_updater_update_tree(b200hist_updater_t u, const float*
 B200HIST_API int b200hist_updater_update_tree_host(b200hist_updater_t u, const float* gpair_host,
                                                    void* stream, b200hist_tree_node* out_nodes_host,
                                                    int32_t* out_n_nodes, int32_t* out_position_dev);
+/* The same tree with a DEFERRED read-back: every kernel and the device -> host copy of the tree are enqueued on
+ * `stream` and the call returns without waiting (the reference synchronises twice per level).  The prediction cache
+ * (below) reads the device-side tree, so objective gradient -> update_tree_async -> update_prediction_cache of the
+ * next iteration can be enqueued while this tree is still being built; b200hist_updater_fetch_tree returns the trees
+ * in order (it waits for the oldest one in flight; at most two may be in flight). */
+B200HIST_API int b200hist_updater_update_tree_async(b200hist_updater_t u, const float* gpair_dev, void* stream,
+                                                    int32_t* out_position_dev);
+B200HIST_API int b200hist_updater_fetch_tree(b200hist_updater_t u, b200hist_tree_node* out_nodes_host,
+                                             int32_t* out_n_nodes);
 /* TreeUpdater::UpdatePredictionCache (updater_gpu_hist.cu:582-608,848-869):
  * preds_dev[i] += leaf_value[decode(position[i])] for the last tree built. */
 B200HIST_API int b200hist_updater_update_prediction_cache(b200hist_updater_t u, float* preds_dev,

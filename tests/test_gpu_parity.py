@@ -763,3 +763,38 @@ def test_tree_grown_in_node_batches_matches_oracle(xb, monkeypatch, batch, param
         assert tree.num_nodes > 8192        # a level wider than one step really occurred
     if params.get("max_leaves", 0) >= 3000:
         assert tree.num_nodes == 2 * params["max_leaves"] - 1
+
+
+def test_deferred_tree_readback_returns_the_same_trees_in_order(xb):
+    """update_async / fetch_tree (two trees in flight, read-back never waited for inside a step) against update():
+    identical trees, positions and margins over five boosting rounds; a third tree in flight is refused."""
+    import torch
+    n, f = 40000, 20
+    x, y = make_regression(n, f, seed=223)
+    cp, cv = make_cuts(x, 64)
+    yd = torch.from_numpy(y).cuda()
+    ups = [xb.GPUHistMaker(_page(xb, x, cp, cv)) for _ in range(2)]
+    for u in ups:
+        u.configure(dict(max_depth=6, eta=0.4))
+    m_sync, m_async = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    p_sync, p_async = (torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(2))
+    sync_trees, async_trees = [], []
+    g_async = torch.empty((n, 2), device="cuda")
+    g_async[:, 1] = 1.0
+    for it in range(5):
+        gp = torch.stack([m_sync - yd, torch.ones_like(yd)], dim=1).contiguous()
+        sync_trees.append(ups[0].update(gp, p_sync))
+        ups[0].update_prediction_cache(m_sync)
+        torch.sub(m_async, yd, out=g_async[:, 0])
+        ups[1].update_async(g_async, p_async)
+        ups[1].update_prediction_cache(m_async)
+        if it >= 1:
+            async_trees.append(ups[1].fetch_tree())
+    with pytest.raises(xb.lib.B200HistError):
+        ups[1].update_async(g_async, p_async)
+        ups[1].update_async(g_async, p_async)      # the third in flight
+    while len(async_trees) < 5:
+        async_trees.append(ups[1].fetch_tree())
+    for a, b in zip(sync_trees, async_trees[:5]):
+        assert a.array.tobytes() == b.array.tobytes()
+    assert torch.equal(m_sync, m_async)

@@ -906,6 +906,18 @@ struct b200hist_updater_s {
   NodeDev* h_nodes{nullptr};  // pinned
   TreeState* h_ts{nullptr};   // pinned
   QuantDev* h_quant{nullptr}; // pinned copy of the last tree's quantiser record
+  // deferred read-back (b200hist_updater_update_tree_async / fetch_tree): up to two trees in flight, each with its own
+  // pinned staging, "tree landed" event and phase-event pool
+  struct PendingTree {
+    NodeDev* h_nodes{nullptr};
+    TreeState* h_ts{nullptr};
+    QuantDev* h_quant{nullptr};
+    cudaEvent_t landed{nullptr};
+    std::vector<cudaEvent_t> events;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+    bool busy{false};
+  } pending[2];
+  uint64_t async_issued{0}, async_fetched{0};
   bool pair_hint{false};      // last tree's hessians had zero low words -> launch the 64-feature pair kernel
   int32_t* last_position{nullptr};
   int32_t last_n_nodes{0};
@@ -927,13 +939,15 @@ struct PhaseTimer {
   cudaStream_t s;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
   size_t next{0};
+  std::vector<cudaEvent_t>* pool{nullptr};  // nullptr: the updater's own pool (synchronous trees)
   cudaEvent_t Get() {
-    if (next == u->events.size()) {
+    auto& ev = pool ? *pool : u->events;
+    if (next == ev.size()) {
       cudaEvent_t e;
       B200_CUDA(cudaEventCreate(&e));
-      u->events.push_back(e);
+      ev.push_back(e);
     }
-    return u->events[next++];
+    return ev[next++];
   }
   cudaEvent_t Begin() {
     if (!u->profiling) return nullptr;
@@ -991,11 +1005,12 @@ void ToAbiNodes(const NodeDev* src, int32_t n, b200hist_tree_node* dst) {
 }
 
 void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t s, b200hist_tree_node* out_nodes,
-                    int32_t* out_n_nodes, int32_t* out_position) {
+                    int32_t* out_n_nodes, int32_t* out_position, b200hist_updater_s::PendingTree* defer = nullptr) {
   auto* ell = u->ell;
   const EllView view = ell->View();
   const uint64_t n = ell->n_rows;
   PhaseTimer timer{u, s};
+  if (defer) timer.pool = &defer->events;
   // External memory (b200hist_ellpack_create_paged): every phase that reads the quantised matrix -- histogram build,
   // partition count, FinalisePosition -- runs once per page while the NEXT page travels host -> device on the page
   // set's copy stream (two staging buffers).  Replaces the per-page loop of GPUHistMakerDevice
@@ -1291,6 +1306,16 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
   else finalise_bins(std::false_type{});
   timer.End(kFinal, tf);
 
+  if (defer) {  // deferred read-back: the copies are enqueued, nobody waits; b200hist_updater_fetch_tree finishes the job
+    B200_CUDA(cudaMemcpyAsync(defer->h_ts, u->d_ts, sizeof(TreeState), cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaMemcpyAsync(defer->h_nodes, u->d_nodes, sizeof(NodeDev) * u->max_nodes, cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaMemcpyAsync(defer->h_quant, u->d_quant, sizeof(QuantDev), cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaEventRecord(defer->landed, s));
+    defer->spans = std::move(timer.spans);
+    defer->busy = true;
+    u->last_position = position;
+    return;
+  }
   // the one read-back of the tree
   B200_CUDA(cudaMemcpyAsync(u->h_ts, u->d_ts, sizeof(TreeState), cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaMemcpyAsync(u->h_nodes, u->d_nodes, sizeof(NodeDev) * u->max_nodes, cudaMemcpyDeviceToHost, s));
@@ -1465,6 +1490,16 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
     cudaFreeHost(u->h_nodes);
     cudaFreeHost(u->h_ts);
     cudaFreeHost(u->h_quant);
+    for (auto& slot : u->pending) {
+      if (slot.landed) {
+        cudaEventSynchronize(slot.landed);
+        cudaEventDestroy(slot.landed);
+      }
+      if (slot.h_nodes) cudaFreeHost(slot.h_nodes);
+      if (slot.h_ts) cudaFreeHost(slot.h_ts);
+      if (slot.h_quant) cudaFreeHost(slot.h_quant);
+      for (auto e : slot.events) cudaEventDestroy(e);
+    }
     for (auto e : u->events) cudaEventDestroy(e);
     delete u;
   }
@@ -1498,6 +1533,55 @@ int b200hist_updater_update_tree_host(b200hist_updater_t u, const float* gpair_h
   if (u->d_gpair_staging == nullptr) u->d_gpair_staging = DevAlloc<float>(2 * u->ell->n_rows);
   B200_CUDA(cudaMemcpyAsync(u->d_gpair_staging, gpair_host, bytes, cudaMemcpyHostToDevice, s));
   UpdateTreeImpl(u, u->d_gpair_staging, s, out_nodes_host, out_n_nodes, out_position_dev);
+  B200_API_END();
+}
+
+int b200hist_updater_update_tree_async(b200hist_updater_t u, const float* gpair_dev, void* stream,
+                                       int32_t* out_position_dev) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr && gpair_dev != nullptr, "null argument");
+  B200_CHECK(u->async_issued - u->async_fetched < 2, "two trees are in flight already: call b200hist_updater_fetch_tree");
+  B200_CHECK(u->d_node_sets == nullptr && u->d_col_seeds == nullptr,
+             "deferred read-back is not available with colsample_bynode (the draw count is read back per tree)");
+  DeviceGuard guard(u->device);
+  auto& slot = u->pending[u->async_issued & 1u];
+  if (slot.landed == nullptr) {
+    B200_CUDA(cudaEventCreateWithFlags(&slot.landed, cudaEventDisableTiming));
+    B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&slot.h_nodes), sizeof(NodeDev) * u->max_nodes));
+    B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&slot.h_ts), sizeof(TreeState)));
+    B200_CUDA(cudaMallocHost(reinterpret_cast<void**>(&slot.h_quant), sizeof(QuantDev)));
+  }
+  UpdateTreeImpl(u, gpair_dev, static_cast<cudaStream_t>(stream), nullptr, nullptr, out_position_dev, &slot);
+  ++u->async_issued;
+  B200_API_END();
+}
+
+int b200hist_updater_fetch_tree(b200hist_updater_t u, b200hist_tree_node* out_nodes_host, int32_t* out_n_nodes) {
+  B200_API_BEGIN();
+  B200_CHECK(u != nullptr, "null argument");
+  B200_CHECK(u->async_fetched < u->async_issued, "no tree in flight");
+  DeviceGuard guard(u->device);
+  auto& slot = u->pending[u->async_fetched & 1u];
+  B200_CUDA(cudaEventSynchronize(slot.landed));
+  u->pair_hint = slot.h_quant->h_lo_or == 0u;
+  if (u->profiling) {
+    for (auto& m : u->last_ms) m = 0;
+    u->last_hist_ms.clear();
+    for (auto& sp : slot.spans) {
+      float ms = 0;
+      B200_CUDA(cudaEventElapsedTime(&ms, sp.second.first, sp.second.second));
+      u->last_ms[sp.first] += ms;
+      if (sp.first == kHist) u->last_hist_ms.push_back(ms);
+    }
+  }
+  u->last_row_visits = slot.h_ts->row_visits;
+  u->last_n_nodes = slot.h_ts->n_nodes;
+  u->last_max_eval_depth = slot.h_ts->max_eval_depth;
+  std::memcpy(u->h_nodes, slot.h_nodes, sizeof(NodeDev) * (size_t)u->last_n_nodes);  // node_histogram & co read h_nodes
+  if (out_nodes_host) ToAbiNodes(slot.h_nodes, u->last_n_nodes, out_nodes_host);
+  if (out_n_nodes) *out_n_nodes = u->last_n_nodes;
+  slot.busy = false;
+  ++u->async_fetched;
   B200_API_END();
 }
 

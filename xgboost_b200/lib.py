@@ -118,6 +118,8 @@ _SIGNATURES = {
                                              c_void_p]),
     "b200hist_updater_update_tree_host": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(TreeNode),
                                                   POINTER(c_int32), c_void_p]),
+    "b200hist_updater_update_tree_async": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200hist_updater_fetch_tree": (c_int, [c_void_p, POINTER(TreeNode), POINTER(c_int32)]),
     "b200hist_updater_update_prediction_cache": (c_int, [c_void_p, c_void_p, c_void_p]),
     "b200hist_updater_update_prediction_cache_ex": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_int32,
                                                             c_void_p]),

@@ -728,6 +728,28 @@ class GPUHistMaker:
                                                                byref(n_nodes), pos_ptr))
         return RegTree(self._nodes_buf, n_nodes.value)
 
+    def update_async(self, gpair: torch.Tensor, out_position: Optional[torch.Tensor] = None) -> None:
+        """update() without waiting for the tree: kernels and the read-back are enqueued, fetch_tree() returns the trees
+        in order (at most two in flight).  update_prediction_cache() may follow at once: it reads the device-side tree."""
+        if not self._h:
+            raise _l.B200HistError("configure() must be called before update_async()")
+        _require_cuda(gpair, "gpair")
+        if gpair.dtype != torch.float32 or gpair.numel() != 2 * self._page.n_rows or not gpair.is_contiguous():
+            raise ValueError("gpair must be contiguous float32[n_rows, 2]")
+        if out_position is not None:
+            _require_cuda(out_position, "out_position")
+            if out_position.dtype != torch.int32 or out_position.numel() != self._page.n_rows:
+                raise ValueError("out_position must be int32[n_rows]")
+        self._last_position = out_position
+        _l.check(_l.load().b200hist_updater_update_tree_async(
+            self._h, c_void_p(gpair.data_ptr()), _stream_ptr(self.device),
+            c_void_p(out_position.data_ptr()) if out_position is not None else c_void_p()))
+
+    def fetch_tree(self) -> RegTree:
+        n_nodes = c_int32()
+        _l.check(_l.load().b200hist_updater_fetch_tree(self._h, self._nodes_buf, byref(n_nodes)))
+        return RegTree(self._nodes_buf, n_nodes.value)
+
     # TreeUpdater::UpdatePredictionCache
     def update_prediction_cache(self, preds: torch.Tensor, leaf_values=None) -> bool:
         """preds: float32[n_rows] or one column of a float32[n_rows, n_groups] matrix (multi-class: the column of the
