@@ -324,7 +324,7 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # the reference's own Booster on the GPU: e2e of our arm (shim loaded) and the reference gpu_hist beside it
 # --------------------------------------------------------------------------------------------------
-def reference_booster_section(torch, args, device, steps, warmup, rows=None, features=None, depth=None):
+def reference_booster_section(torch, args, device, steps, warmup, rows=None, features=None, depth=None, missing=None):
     """One QuantileDMatrix of the UNMODIFIED reference CUDA library over the same batches; two Boosters on it:
     updater=grow_b200_hist (our shim: XGBoosterUpdateOneIter = objective gradient + Update + UpdatePredictionCache,
     tree replayed into RegTree on the host) and updater=grow_gpu_hist_reference (the reference's own kernels).
@@ -338,8 +338,12 @@ def reference_booster_section(torch, args, device, steps, warmup, rows=None, fea
     rc.load("cuda")
     ctypes.CDLL(os.path.join(ROOT, "xgboost_b200", "lib", "libb200hist.so"), mode=ctypes.RTLD_GLOBAL)
     keep = ctypes.CDLL(shim, mode=ctypes.RTLD_GLOBAL)
+    global MISSING
     n, f = rows or args.rows, features or args.features
     depth = depth or args.depth
+    saved_missing = MISSING
+    if missing is not None:
+        MISSING = missing       # batch_of replaces that fraction of the entries by NaN (a sparse ELLPACK page results)
     nb = (n + 999_999) // 1_000_000
     t0 = time.perf_counter()
     batches = rc.LazyBatches(nb, lambda b: batch_of(torch, device, f, n, 1_000_000, b)[0])
@@ -379,6 +383,7 @@ def reference_booster_section(torch, args, device, steps, warmup, rows=None, fea
         del bst
         torch.cuda.empty_cache()
     out["models_identical"] = models["ours"] == models["reference_gpu"]
+    MISSING = saved_missing
     del dm, keep
     torch.cuda.empty_cache()
     return out
@@ -684,6 +689,19 @@ def run_b200(args):
                 "reference_ms_per_iter_median": c2["reference_gpu"]["ms_per_iter_median"],
                 "models_identical": c2["models_identical"], "steps": 10, "warmup": 3,
                 "path": "XGBoosterUpdateOneIter, wall clock with a device synchronise on both sides"}}
+        # config C5: 50M x 1024, each entry present with probability 0.01 (NaN otherwise): the reference stores a sparse
+        # ELLPACK page (row_stride = longest row, 19-bit symbols), the shim imports it into our sparse page
+        if other_configs is not None and os.environ.get("B200_BENCH_C5", "1") != "0":
+            c5 = reference_booster_section(torch, args, device, 5, 2, rows=50_000_000, features=1024, depth=10, missing=0.99)
+            if c5 is not None:
+                other_configs["C5 synthetic 50Mx1024, 1 % present, 256 bins, depth 10, 1xB200 (sparse Ellpack path)"] = {
+                    "ours_through_the_shim_iters_per_s": c5["ours"]["iters_per_s"],
+                    "reference_gpu_hist_iters_per_s": c5["reference_gpu"]["iters_per_s"],
+                    "ours_ms_per_iter_median": c5["ours"]["ms_per_iter_median"],
+                    "reference_ms_per_iter_median": c5["reference_gpu"]["ms_per_iter_median"],
+                    "models_identical": c5["models_identical"], "steps": 5, "warmup": 2,
+                    "reference_dmatrix_build_s": c5["dmatrix_build_s"],
+                    "path": "XGBoosterUpdateOneIter, wall clock with a device synchronise on both sides"}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:

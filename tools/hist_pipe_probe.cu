@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #define CK(x)                                                                                   \
@@ -367,6 +368,149 @@ double RunH(const uint8_t* bins, const longlong2* gq, const uint32_t* ridx, uint
   return rows * 64.0 / (ms * 1e-3) / 1.965e9 / n_sms;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Variant I: the SYMBOLS arrive by TMA (cp.async.bulk.tensor ... tile::gather4, SASS UTMALDG.2D.GATHER4: four arbitrary
+// rows x 64 bytes per instruction, issued by lane 0 of each warp into a per-warp ring of kStagesI stages of 4 rows,
+// completion on an mbarrier per stage); the consumers read their 8 bytes with LDS.64.  Gradient pairs and row ids stay
+// on LDG as today.  Shared memory: 192 KiB histogram + 32 warps x 4 stages x 256 B + barriers = 225 KiB.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStagesI = 4;
+__device__ __forceinline__ bool BarDone(uint32_t bar_a, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar_a), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+ProbeI(const __grid_constant__ CUtensorMap tm, const longlong2* __restrict__ gq, const uint32_t* __restrict__ ridx,
+       uint32_t n_list, uint32_t* sink, int* stuck) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint32_t* sh = reinterpret_cast<uint32_t*>(smem_raw);
+  constexpr uint32_t kHistBytes = 256u * 768u;
+  constexpr uint32_t kSlot = 256u;  // 4 rows x 64 bytes
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, q = lane >> 3, w = lane & 7u;
+  uint8_t* ring = smem_raw + kHistBytes + warp * (kStagesI * kSlot);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + kHistBytes + 32u * kStagesI * kSlot) + warp * kStagesI;
+  for (uint32_t i = threadIdx.x; i < 256u * 192u; i += kThreads) sh[i] = 0u;
+  if (lane == 0) {
+    for (int s = 0; s < kStagesI; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bars[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  __syncthreads();
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(sh);
+  uint32_t shift[4], off[4];
+#pragma unroll
+  for (uint32_t k = 0; k < 4; ++k) {
+    const uint32_t jj = (k + q) & 3u;
+    shift[k] = 8u * jj;
+    off[k] = (4u * w + jj) * 4u;
+  }
+  const uint32_t per = (n_list / gridDim.x) & ~255u;   // 16-byte aligned row-id groups
+  const uint32_t lo = blockIdx.x * per;
+  constexpr uint32_t kStride = 32u * 8u;
+  const uint32_t n_pass = per / kStride;
+  // group g of this warp = 4 consecutive entries of its row list: pass i holds groups 2i (rows q) and 2i + 1 (rows q + 4)
+  const uint32_t* __restrict__ wl = ridx + lo + warp * 8u;
+  auto issue = [&](uint32_t g) {  // lane 0: group g -> stage g % kStagesI
+    const uint32_t st = g % kStagesI;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bars[st]);
+    const uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(ring + st * kSlot);
+    const uint4 r = *reinterpret_cast<const uint4*>(wl + (size_t)(g >> 1) * kStride + (g & 1u) * 4u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(256));
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(dst_a), "l"(&tm), "r"(0), "r"((int)r.x), "r"((int)r.y), "r"((int)r.z), "r"((int)r.w), "r"(bar_a)
+        : "memory");
+  };
+  const uint32_t n_groups = 2u * n_pass;
+  if (lane == 0)
+    for (uint32_t g = 0; g < (uint32_t)kStagesI && g < n_groups; ++g) issue(g);
+  // gradient pairs + row ids: two passes ahead in registers, as today
+  auto pair_of = [&](uint32_t i, uint32_t u, uint32_t& glo, uint32_t& ghi, uint32_t& hhi) {
+    const uint32_t r = __ldg(wl + (size_t)(i < n_pass ? i : n_pass - 1) * kStride + u * 4u + q);
+    const longlong2 gp = __ldg(gq + r);
+    glo = (uint32_t)(unsigned long long)gp.x; ghi = (uint32_t)((unsigned long long)gp.x >> 32);
+    hhi = (uint32_t)((unsigned long long)gp.y >> 32);
+  };
+  uint32_t parity = 0;
+  auto consume = [&](uint32_t i, const uint32_t (&pgv)[2][3]) {
+#pragma unroll
+    for (uint32_t u = 0; u < 2; ++u) {
+      const uint32_t g = 2u * i + u, st = g % kStagesI;
+      const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bars[st]);
+      int spin = 0;
+      while (!BarDone(bar_a, parity)) {
+        if (++spin > (1 << 22)) { if (lane == 0) atomicAdd(stuck, 1); return false; }
+      }
+      const uint2 v = *reinterpret_cast<const uint2*>(ring + st * kSlot + q * 64u + w * 8u);
+      __syncwarp();
+      if (lane == 0 && g + kStagesI < n_groups) issue(g + kStagesI);
+      const uint32_t words[2] = {v.x, v.y};
+      const uint32_t glo = pgv[u][0], ghi = pgv[u][1], hhi = pgv[u][2];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t addr[4], og[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) addr[k] = base + ((words[half] >> shift[k]) & 0xFFu) * 768u + half * 384u + off[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) og[k] = AtomAdd(addr[k], glo);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          RedAdd(addr[k] + 128u, CarryHi(og[k], glo, ghi));
+          RedAdd(addr[k] + 256u, hhi);
+        }
+      }
+      if (st == kStagesI - 1) parity ^= 1u;
+    }
+    return true;
+  };
+  uint32_t pa[2][3], pb[2][3];   // gradient pairs of two passes in registers
+  pair_of(0, 0, pa[0][0], pa[0][1], pa[0][2]);
+  pair_of(0, 1, pa[1][0], pa[1][1], pa[1][2]);
+  for (uint32_t i = 0; i + 1 < n_pass; i += 2) {
+    pair_of(i + 1, 0, pb[0][0], pb[0][1], pb[0][2]);
+    pair_of(i + 1, 1, pb[1][0], pb[1][1], pb[1][2]);
+    if (!consume(i, pa)) return;
+    pair_of(i + 2, 0, pa[0][0], pa[0][1], pa[0][2]);
+    pair_of(i + 2, 1, pa[1][0], pa[1][1], pa[1][2]);
+    if (!consume(i + 1, pb)) return;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) sink[blockIdx.x] = sh[(lo + n_pass) % (256u * 192u)];
+}
+
+double RunI(const CUtensorMap& tm, const longlong2* gq, const uint32_t* ridx, uint32_t n_list, int n_sms, uint32_t* sink) {
+  const size_t smem = 256u * 768u + 32u * kStagesI * 256u + 32u * kStagesI * 8u;
+  CK(cudaFuncSetAttribute(ProbeI, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int* stuck;
+  CK(cudaMalloc(&stuck, 4));
+  CK(cudaMemset(stuck, 0, 4));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  ProbeI<<<n_sms, kThreads, smem>>>(tm, gq, ridx, n_list, sink, stuck);
+  CK(cudaEventRecord(e0));
+  for (int rep = 0; rep < 3; ++rep) ProbeI<<<n_sms, kThreads, smem>>>(tm, gq, ridx, n_list, sink, stuck);
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= 3;
+  int h_stuck = 0;
+  CK(cudaMemcpy(&h_stuck, stuck, 4, cudaMemcpyDeviceToHost));
+  if (h_stuck) std::printf("  [variant I: %d warps gave up waiting]\n", h_stuck);
+  cudaFree(stuck);
+  const uint32_t per = (n_list / n_sms) & ~255u;
+  const double rows = (double)(per / 256u / 2u * 2u) * 256.0 * n_sms;
+  return rows * 64.0 / (ms * 1e-3) / 1.965e9 / n_sms;
+}
+
 template <int kMode>
 double Run(const uint8_t* bins, const longlong2* gq, const uint32_t* ridx, uint32_t n_list, int n_sms, uint32_t* sink) {
   const size_t smem = 256u * 192u * 4u;
@@ -435,6 +579,26 @@ int main(int argc, char** argv) {
               RunH<false>(bins, gq, seq, rows, n_seq, n_sms, sink), RunH<false>(bins, gq, perm, rows, n_sparse, n_sms, sink));
   std::printf("%-66s %8.2f %8.2f\n", "H2 pair AND row ids through the texture unit",
               RunH<true>(bins, gq, seq, rows, n_seq, n_sms, sink), RunH<true>(bins, gq, perm, rows, n_sparse, n_sms, sink));
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    auto encode = reinterpret_cast<CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                                 CUtensorMapFloatOOBfill)>(fn);
+    CUtensorMap tm;
+    cuuint64_t dims[2] = {kRowBytes, rows};
+    cuuint64_t strides[1] = {kRowBytes};
+    cuuint32_t box[2] = {64, 1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult rc = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, bins, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { std::printf("cuTensorMapEncodeTiled -> %d\n", (int)rc); return 1; }
+    std::printf("%-66s %8.2f %8.2f\n", "I  symbols by TMA gather4 (4-stage ring per warp) + LDS, pair/ids LDG",
+                RunI(tm, gq, seq, n_seq, n_sms, sink), RunI(tm, gq, perm, n_sparse, n_sms, sink));
+  }
   std::printf("%-66s %8.2f %8.2f\n", "G4 the same with 4 buffers",
               RunG<4>(bins, gq, seq, n_seq, n_sms, sink), RunG<4>(bins, gq, perm, n_sparse, n_sms, sink));
   return 0;
