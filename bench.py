@@ -377,6 +377,7 @@ def reference_booster_section(torch, args, device, steps, warmup, rows=None, fea
         trees = bst.save_json()["learner"]["gradient_booster"]["model"]["trees"]
         models[name] = model_sha(trees)
         out[name] = {"iters_per_s": len(timed) / sum(timed), "ms_per_iter_mean": 1e3 * sum(timed) / len(timed),
+                     "ms_per_iter_all": [round(1e3 * t, 2) for t in ts],
                      "ms_per_iter_median": 1e3 * float(np.median(timed)), "first_iter_ms": 1e3 * ts[0],
                      "steps": steps, "warmup": warmup, "n_trees": len(trees), "model_sha": models[name],
                      "last_tree_nodes": len(trees[-1]["left_children"])}
@@ -699,6 +700,8 @@ def run_b200(args):
                     "reference_gpu_hist_iters_per_s": c5["reference_gpu"]["iters_per_s"],
                     "ours_ms_per_iter_median": c5["ours"]["ms_per_iter_median"],
                     "reference_ms_per_iter_median": c5["reference_gpu"]["ms_per_iter_median"],
+                    "ours_ms_per_iter_all": c5["ours"]["ms_per_iter_all"],
+                    "reference_ms_per_iter_all": c5["reference_gpu"]["ms_per_iter_all"],
                     "models_identical": c5["models_identical"], "steps": 5, "warmup": 2,
                     "reference_dmatrix_build_s": c5["dmatrix_build_s"],
                     "path": "XGBoosterUpdateOneIter, wall clock with a device synchronise on both sides"}

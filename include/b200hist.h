@@ -43,7 +43,10 @@ typedef struct b200hist_train_param {
   float min_child_weight;   /* default 1 */
   float max_delta_step;     /* default 0 */
   float min_split_loss;     /* gamma, default 0 */
-  int32_t reserved[7];
+  int32_t reserved[7];      /* [0]: histogram cache capacity in nodes, HistMakerTrainParam::max_cached_hist_node
+                             * (src/tree/hist/hist_param.h:18-45); 0 = sized from the free device memory.  A cache
+                             * smaller than the tree is a ring: a split whose parent histogram has been overwritten
+                             * builds both children (histogram.cuh:72-168, updater_gpu_hist.cu:309-325).  [1..6]: 0 */
 } b200hist_train_param;
 
 /* GradientPairInt64 (include/xgboost/base.h:253-304): 64-bit fixed-point gradient statistics. */

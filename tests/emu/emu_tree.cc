@@ -76,9 +76,10 @@ int main(int argc, char** argv) {
   int level_batch = p.max_leaves > 0 ? 1024 : kMaxLevelNodes;
   if (meta.size() > 26 && meta[26] > 0) level_batch = (int)meta[26];
   std::vector<uint32_t> step_cap, step_slot_base;
-  std::vector<int> step_level, step_level_start;
+  std::vector<int> step_level, step_level_start, step_children, step_reuses;
   uint32_t base = 1;
   int n_steps = 0;
+  unsigned long long total_slots = 1, max_window = 0;
   for (int st = 0; st < n_tree_levels; ++st) {
     long long width = dw ? (1ll << std::min(st, 40)) : 1ll;
     if (p.max_leaves > 0) width = std::min<long long>(width, p.max_leaves);
@@ -87,15 +88,32 @@ int main(int argc, char** argv) {
     for (long long b = 0; b < n_sub; ++b) {
       const uint32_t cap = (uint32_t)std::min<long long>(level_batch, width - b * level_batch);
       step_cap.push_back(cap);
-      step_slot_base.push_back(base);
       step_level.push_back(st);
       step_level_start.push_back(b == 0 ? 1 : 0);
-      if (children) base += 2 * cap;
+      step_children.push_back(children ? 1 : 0);
+      if (children) { total_slots += 2ull * cap; max_window = std::max<unsigned long long>(max_window, 2ull * cap); }
       ++n_steps;
     }
   }
+  // [27] histogram cache capacity in slots (0 = a slot per possible node): a smaller cache is a ring whose windows wrap;
+  // splits whose parent histogram has been overwritten build both children
+  unsigned long long ring = total_slots - 1;
+  if (meta.size() > 27 && meta[27] > 0 && (unsigned long long)meta[27] < total_slots)
+    ring = std::max<unsigned long long>(max_window, (unsigned long long)meta[27] - 1);
+  {
+    unsigned long long pos = 0;
+    bool wrapped = false;
+    for (int st = 0; st < n_steps; ++st) {
+      const unsigned long long w = step_children[st] ? 2ull * step_cap[st] : 0ull;
+      if (pos + w > ring) { pos = 0; wrapped = true; }
+      step_slot_base.push_back((uint32_t)(1 + pos));
+      step_reuses.push_back(wrapped ? 1 : 0);
+      pos += w;
+    }
+  }
+  base = (uint32_t)(ring + 1);
   const uint32_t n_slots = base;
-  const size_t part_tiles = n / kPartTile + (size_t)max_nodes + 2, hist_tiles = n / kHistTile + (size_t)max_nodes + 2;
+  const size_t part_tiles = n / kPartTile + (size_t)max_nodes + 2, hist_tiles = n / kHistTile + 2 * (size_t)max_nodes + 2;
   std::vector<uint32_t> ridx0(n), ridx1(n);
   for (uint64_t i = 0; i < n; ++i) ridx0[i] = (uint32_t)i;
   std::vector<int32_t> position(n, -12345);
@@ -103,7 +121,8 @@ int main(int argc, char** argv) {
   std::vector<NodeDev> nodes((size_t)max_nodes);
   std::vector<b200hist_candidate> cand((size_t)max_nodes);
   std::vector<PartEntry> part(kMaxLevelNodes);
-  std::vector<BuildEntry> build(kMaxLevelNodes), fin((size_t)max_nodes);
+  std::vector<BuildEntry> build(2 * kMaxLevelNodes), fin((size_t)max_nodes);
+  std::vector<int32_t> slot_owner((size_t)n_slots, -1);
   std::vector<SubEntry> sub(kMaxLevelNodes);
   std::vector<int32_t> eval_nodes(2 * kMaxLevelNodes);
   std::vector<uint32_t> part_tile_seg(part_tiles), build_tile_seg(hist_tiles), tile_left(part_tiles), tile_excl(part_tiles + 1),
@@ -317,7 +336,7 @@ int main(int argc, char** argv) {
   };
 
   // ---- UpdateTreeImpl ----
-  EMU_LAUNCH((1), (kCtlThreads), 0, InitRootKernel(p, (uint32_t)n, &q, &ts, nodes.data(), build.data(), build_tile_seg.data(), eval_nodes.data(), mono));
+  EMU_LAUNCH((1), (kCtlThreads), 0, InitRootKernel(p, (uint32_t)n, &q, &ts, nodes.data(), build.data(), build_tile_seg.data(), eval_nodes.data(), mono, slot_owner.data()));
   build_hist();
   if (has_col) evaluate_with_column_sampler(1, true);
   else if (has_node_sets) evaluate(1, node_sets_view(), nullptr, 0, 0);
@@ -347,8 +366,11 @@ int main(int argc, char** argv) {
       else { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint16_t, false>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
     }
     });
-    EMU_LAUNCH((1), (kCtlThreads), 0, ScanKernel(&ts, nodes.data(), part.data(), part_tile_seg.data(), tile_left.data(), tile_excl.data(), tile_left_off.data(), build.data(), sub.data(), eval_nodes.data(), build_tile_seg.data(), step_slot_base[step], step_cap[step], 0));
+    EMU_LAUNCH((1), (kCtlThreads), 0, ScanKernel(&ts, nodes.data(), part.data(), part_tile_seg.data(), tile_left.data(), tile_excl.data(), tile_left_off.data(), build.data(), sub.data(), eval_nodes.data(), build_tile_seg.data(), step_slot_base[step], step_cap[step], 0, slot_owner.data()));
     EMU_LAUNCH((3), (kPartThreads), 0, PartitionScatterKernel(ridx0.data(), ridx1.data(), ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left_off.data()));
+    if (step_reuses[step])  // a reused window holds other nodes' sums
+      std::fill(hist.begin() + (size_t)step_slot_base[step] * view.total_bins,
+                hist.begin() + (size_t)(step_slot_base[step] + 2 * step_cap[step]) * view.total_bins, make_longlong2(0, 0));
     build_hist();
     subtract();
     IcView icv{nullptr, nullptr, 0};

@@ -798,3 +798,40 @@ def test_deferred_tree_readback_returns_the_same_trees_in_order(xb):
     for a, b in zip(sync_trees, async_trees[:5]):
         assert a.array.tobytes() == b.array.tobytes()
     assert torch.equal(m_sync, m_async)
+
+
+@pytest.mark.parametrize("slots,params", [
+    (40, dict(max_depth=7)),
+    (9, dict(max_depth=0, max_leaves=60, grow_policy="lossguide")),
+    (300, dict(max_depth=10, min_child_weight=0.0)),
+], ids=["depthwise_ring", "lossguide_ring", "depth10_ring"])
+def test_histogram_cache_smaller_than_the_tree(xb, monkeypatch, slots, params):
+    """DeviceHistogramStorage's overflow path (histogram.cuh:72-168): with room for `slots` histograms only, a split whose
+    parent's histogram has been overwritten builds both children (more row visits), and the tree is the one the full
+    cache gives."""
+    import torch
+    n, f = 60000, 10
+    x, y = make_regression(n, f, seed=227)
+    cp, cv = make_cuts(x, 32)
+    page = _page(xb, x, cp, cv)
+    gb = orc.bin_dense(x, cp, cv)
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    gd = torch.from_numpy(gp).cuda()
+    trees, visits = [], []
+    for cap in (0, slots):
+        if cap:
+            monkeypatch.setenv("B200HIST_CACHE_SLOTS", str(cap))
+        else:
+            monkeypatch.delenv("B200HIST_CACHE_SLOTS", raising=False)
+        up = xb.GPUHistMaker(page)
+        up.configure(params)
+        up.set_profiling(True)
+        pos = torch.empty(n, dtype=torch.int32, device="cuda")
+        trees.append((up.update(gd, pos), pos.cpu().numpy()))
+        visits.append(up.last_profile()["row_visits"])
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params))
+    for tree, pos in trees:
+        assert tree.num_nodes == len(o["nodes"])
+        assert np.array_equal(pos, o["position"])
+    assert trees[0][0].array.tobytes() == trees[1][0].array.tobytes()
+    assert visits[1] > visits[0], "no split had to rebuild both children: the ring never lost a parent"

@@ -581,7 +581,7 @@ TREE_NODE = np.dtype([("parent", "<i4"), ("left", "<i4"), ("right", "<i4"), ("fi
 
 def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, onehot=4, threshold=64, ic_sets=None,
                   node_sets=None, feature_set=None, n_levels=0, col_seeds=None, col_tree_set=None, bylevel=1.0, bynode=1.0,
-                  sparse=False, hist_mode=0, page_rows=0, level_batch=0):
+                  sparse=False, hist_mode=0, page_rows=0, level_batch=0, cache_slots=0):
     exe = _build("emu_tree")
     n, nf = gb.shape
     max_bins = int(np.diff(cp).max())
@@ -617,7 +617,7 @@ def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, oneh
     np.array([n, nf, page.shape[1], bin_bytes, null_symbol, 0 if mono is None else 1, 0 if is_cat is None else 1, onehot,
               threshold, cat_words, (max_cat_bins + 31) // 32, max_cat_bins, 0 if ic_sets is None else len(ic_sets),
               0 if node_sets is None else node_sets.shape[0], 0 if node_sets is None else node_sets.shape[1],
-              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta + [row_stride, hist_mode, page_rows, level_batch],
+              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta + [row_stride, hist_mode, page_rows, level_batch, cache_slots],
              dtype=np.int64).tofile(os.path.join(d, "meta.bin"))
     np.array([p.learning_rate, p.reg_lambda, p.reg_alpha, p.min_child_weight, p.max_delta_step, p.min_split_loss],
              dtype=np.float32).tofile(os.path.join(d, "param_f.bin"))
@@ -864,6 +864,25 @@ def test_whole_tree_kernel_sources_sparse_page(tmp_path, categorical):
     nodes, pos, flags, bits, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, sparse=True, **kw)
     o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), **okw)
     _same_tree(nodes, pos, o, flags if categorical else None, bits if categorical else None)
+
+
+@pytest.mark.parametrize("slots,hist_mode,params", [
+    (9, 0, dict(max_depth=6, eta=0.5)),                                          # windows of up to 32 slots: the floor
+    (40, 1, dict(max_depth=6, eta=0.5)),                                         # ring of 39: the last levels wrap
+    (7, 2, dict(max_depth=0, max_leaves=24, grow_policy="lossguide", eta=0.5)),  # loss-guide: old parents get recycled
+    (12, 0, dict(max_depth=5, max_leaves=14, eta=0.5)),
+], ids=["floor", "wrap_real_kernels", "lossguide_pair_kernel", "leaf_budget"])
+def test_whole_tree_with_a_histogram_cache_smaller_than_the_tree(tmp_path, slots, hist_mode, params):
+    """DeviceHistogramStorage's overflow (histogram.cuh:72-168, updater_gpu_hist.cu:309-325): with a cache of `slots`
+    histograms the steps' slot windows wrap around a ring, ScanKernel finds parents whose histogram has been overwritten
+    (slot ownership) and builds BOTH children there instead of subtracting.  Integer sums: the tree must not change."""
+    n, f = 2500, 64 if hist_mode == 2 else 9
+    x, y = make_regression(n, f, seed=43)
+    cp, cv = make_cuts(x, 16)
+    gb = orc.bin_dense(x, cp, cv)
+    gp = squared_error_gpair(np.zeros_like(y), y)
+    nodes, pos, _, _, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, hist_mode=hist_mode, cache_slots=slots)
+    _same_tree(nodes, pos, orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params)))
 
 
 @pytest.mark.parametrize("batch,params", [

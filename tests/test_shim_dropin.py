@@ -183,3 +183,19 @@ def test_adaptive_objectives_through_the_shim_match_reference(cuda_device, extra
     our_trees, our_margin = _train(rc, x, y, dict(params, updater="grow_b200_hist"), 3)
     assert json.dumps(our_trees) == json.dumps(ref_trees)
     assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))
+
+
+def test_small_histogram_cache_through_the_shim_matches_reference(cuda_device):
+    """max_cached_hist_node (HistMakerTrainParam) below the tree's size: the reference overflows its cache and rebuilds
+    what it cannot subtract (updater_gpu_hist.cu:309-325); ours wraps its ring and builds both children.  Same model."""
+    from oracle import ref_capi as rc
+    if not (rc.available("cuda") and os.path.exists(SHIM)):
+        pytest.skip("needs oracle/_ref_cuda/libxgboost.so and the shim")
+    _ensure_shim(rc)
+    x, y = make_regression(40000, 12, seed=229)
+    params = {"tree_method": "hist", "device": "cuda:0", "max_bin": 32, "max_depth": 8, "eta": 0.3,
+              "objective": "reg:squarederror", "base_score": 0.5, "max_cached_hist_node": 24}
+    ref_trees, ref_margin = _train(rc, x, y, dict(params, updater="grow_gpu_hist_reference"), 3)
+    our_trees, our_margin = _train(rc, x, y, dict(params, updater="grow_b200_hist"), 3)
+    assert json.dumps(our_trees) == json.dumps(ref_trees)
+    assert np.array_equal(our_margin.view(np.uint32), ref_margin.view(np.uint32))

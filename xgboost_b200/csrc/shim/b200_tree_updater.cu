@@ -61,6 +61,12 @@ class B200HistMaker : public TreeUpdater {
 
   void Configure(Args const& args) override {
     hist_maker_param_.UpdateAllowUnknown(args);  // unknown keys pass through like the reference
+    // max_cached_hist_node (hist_param.h:18-45): honoured when the user sets it; otherwise the library sizes its
+    // histogram cache from the free device memory (the reference's CUDA default of 4096 nodes would make deep trees
+    // rebuild histograms that fit comfortably)
+    for (auto const& kv : args) {
+      if (kv.first == "max_cached_hist_node") max_cached_hist_node_ = std::max<long long>(0, std::atoll(kv.second.c_str()));
+    }
     this->Release();                              // caches are invalidated by Configure (updater_gpu_hist.cu:764-771)
   }
   void LoadConfig(Json const& in) override {
@@ -200,6 +206,7 @@ class B200HistMaker : public TreeUpdater {
     p.min_child_weight = param->min_child_weight;
     p.max_delta_step = param->max_delta_step;
     p.min_split_loss = param->min_split_loss;
+    p.reserved[0] = static_cast<std::int32_t>(std::min<long long>(max_cached_hist_node_, 0x7fffffff));
     CHECK(param->colsample_bynode == 1.0f ||
           (param->colsample_bylevel == 1.0f && param->interaction_constraints.empty()) ||
           (p_fmat->Info().feature_weights.Empty() && p_fmat->Info().num_col_ <= 8192))
@@ -489,6 +496,7 @@ class B200HistMaker : public TreeUpdater {
   common::ColumnSampler column_sampler_;
   bool sampling_set_{false};
   bool connected_{false};
+  long long max_cached_hist_node_{0};  // 0 = not set by the user
   bool level_draws_pending_{false};
   bool node_draws_pending_{false};
   bool node_draws_by_seed_{false};

@@ -90,7 +90,7 @@ __device__ __forceinline__ void InitLeaf(NodeDev* n, int parent, int depth, floa
 __global__ void __launch_bounds__(kCtlThreads) InitRootKernel(ParamDev p, uint32_t n_rows, const QuantDev* q,
                                                                TreeState* ts, NodeDev* nodes, BuildEntry* build,
                                                                uint32_t* build_tile_seg, int32_t* eval_nodes,
-                                                               MonoView mono) {
+                                                               MonoView mono, int32_t* slot_owner) {
   const uint32_t tiles = (n_rows + kHistTile - 1) / kHistTile;
   for (uint32_t t = threadIdx.x; t < tiles; t += kCtlThreads) build_tile_seg[t] = 0;
   if (threadIdx.x == 0) {
@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kCtlThreads) InitRootKernel(ParamDev p, uint32
     r->base_weight = w;
     r->seg_begin = 0; r->seg_count = n_rows; r->seg_buf = 0;
     r->hist_slot = 0;
+    slot_owner[0] = 0;  // slot 0 is the root's for the whole tree (outside the ring)
     build[0] = BuildEntry{0, 0, 0u, n_rows, 0u, 0u};
     eval_nodes[0] = 0;
     if (mono.constraints) { mono.lower[0] = -3.402823466e+38f; mono.upper[0] = 3.402823466e+38f; }
@@ -321,20 +322,30 @@ __global__ void __launch_bounds__(kCtlThreads) ApplyKernel(EllView ell, ParamDev
 // ---------------------------------------------------------------------------------------------
 // After the count pass: per-tile offsets, children's row segments, AssignNodes (build the child
 // with fewer rows, subtract the other), evaluation list and the histogram tile table.
+//
+// Histogram slots (DeviceHistogramStorage, histogram.cuh:72-168).  The step owns the slot window
+// [slot_base, slot_base + 2 * slot_cap); the cache behind it may be a RING that later steps reuse (the host plans the
+// windows), so every slot has an owner: a node's histogram is usable iff slot_owner[hist_slot] still names the node.
+// The step first takes its window (whoever owned those slots loses them), then for every split:
+//   parent's histogram still cached  -> build the smaller child, sibling = parent - built (SubtractHist);
+//   parent's histogram gone          -> build BOTH children (the reference's slow path, updater_gpu_hist.cu:309-325).
+// Built histograms take the first n_build slots of the window -- one contiguous range for the level's exchange --,
+// subtracted ones follow.  With a cache that holds every node (the default) nothing is ever lost.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCtlThreads) ScanKernel(TreeState* ts, NodeDev* nodes, PartEntry* part,
                                                            const uint32_t* part_tile_seg, const uint32_t* tile_left,
                                                            uint32_t* tile_excl /* scratch, part_tiles+1 */,
                                                            uint32_t* tile_left_off, BuildEntry* build, SubEntry* sub,
                                                            int32_t* eval_nodes, uint32_t* build_tile_seg,
-                                                           uint32_t slot_base, uint32_t slot_cap, int build_by_hess) {
-  // histogram slots of this step: [slot_base, +cap) for the built children (one contiguous, host-known
-  // range = the buffer of the level's single allreduce), [slot_base+cap, +cap) for the subtracted siblings
+                                                           uint32_t slot_base, uint32_t slot_cap, int build_by_hess,
+                                                           int32_t* slot_owner) {
   __shared__ uint32_t s_warp[33];
-  __shared__ uint32_t s_tile_begin[kMaxLevelNodes + 1];
+  __shared__ uint32_t s_tile_begin[2 * kMaxLevelNodes + 1];
   const int n_part = ts->n_part;
   const uint32_t T = ts->part_tiles;
   if (n_part == 0) return;
+  // 0. take the window
+  for (uint32_t i = threadIdx.x; i < 2u * slot_cap; i += kCtlThreads) slot_owner[slot_base + i] = -1;
   // 1. exclusive scan of the tile left-counts over the whole level
   uint32_t running = 0;
   for (uint32_t base = 0; base < T; base += kCtlThreads) {
@@ -347,59 +358,95 @@ __global__ void __launch_bounds__(kCtlThreads) ScanKernel(TreeState* ts, NodeDev
   }
   if (threadIdx.x == 0) tile_excl[T] = running;
   __syncthreads();
-  // 2. per segment: left count, children segments, build/subtract assignment
+  // 2. per segment: left count, children segments, build list (1 or 2 entries per split)
   unsigned long long visits = 0;
-  for (int k = threadIdx.x; k < n_part; k += kCtlThreads) {
-    PartEntry e = part[k];
-    const uint32_t tb = e.tile_begin;
-    const uint32_t te = (k + 1 < n_part) ? part[k + 1].tile_begin : T;
-    const uint32_t n_left = tile_excl[te] - tile_excl[tb];
-    part[k].n_left = n_left;
-    NodeDev* l = &nodes[e.left];
-    NodeDev* r = &nodes[e.right];
-    const int dst_buf = 1 - e.src_buf;
-    l->seg_begin = e.begin; l->seg_count = n_left; l->seg_buf = dst_buf;
-    r->seg_begin = e.begin + n_left; r->seg_count = e.count - n_left; r->seg_buf = dst_buf;
-    // Which child gets built (the other is parent - built): the one with fewer LOCAL rows is the cheaper one;
-    // under row split every rank must pick the same child, so the hessian sums decide, as in the reference
-    // (updater_gpu_hist.cu:461-467: right iff hess_R < hess_L).  The results do not depend on the choice.
-    const bool build_right = build_by_hess ? (r->sum_h < l->sum_h) : (r->seg_count < l->seg_count);
-    const NodeDev* b = build_right ? r : l;
-    const int b_idx = build_right ? e.right : e.left;
-    const int s_idx = build_right ? e.left : e.right;
-    const uint32_t b_slot = slot_base + (uint32_t)k, s_slot = slot_base + slot_cap + (uint32_t)k;
-    nodes[b_idx].hist_slot = (int32_t)b_slot;
-    nodes[s_idx].hist_slot = (int32_t)s_slot;
-    build[k] = BuildEntry{b_idx, dst_buf, b->seg_begin, b->seg_count, 0u, b_slot};
-    sub[k] = SubEntry{nodes[e.nidx].hist_slot, (int32_t)b_slot, (int32_t)s_slot};
-    eval_nodes[2 * k] = e.left;
-    eval_nodes[2 * k + 1] = e.right;
-    visits += b->seg_count;
+  uint32_t n_build = 0;
+  for (int base = 0; base < n_part; base += kCtlThreads) {
+    const int k = base + threadIdx.x;
+    PartEntry e{};
+    bool parent_cached = true;
+    bool build_right = false;
+    if (k < n_part) {
+      e = part[k];
+      const uint32_t tb = e.tile_begin;
+      const uint32_t te = (k + 1 < n_part) ? part[k + 1].tile_begin : T;
+      const uint32_t n_left = tile_excl[te] - tile_excl[tb];
+      part[k].n_left = n_left;
+      NodeDev* l = &nodes[e.left];
+      NodeDev* r = &nodes[e.right];
+      const int dst_buf = 1 - e.src_buf;
+      l->seg_begin = e.begin; l->seg_count = n_left; l->seg_buf = dst_buf;
+      r->seg_begin = e.begin + n_left; r->seg_count = e.count - n_left; r->seg_buf = dst_buf;
+      // Which child gets built (the other is parent - built): the one with fewer LOCAL rows is the cheaper one;
+      // under row split every rank must pick the same child, so the hessian sums decide, as in the reference
+      // (updater_gpu_hist.cu:461-467: right iff hess_R < hess_L).  The results do not depend on the choice.
+      build_right = build_by_hess ? (r->sum_h < l->sum_h) : (r->seg_count < l->seg_count);
+      const int32_t ps = nodes[e.nidx].hist_slot;
+      parent_cached = ps >= 0 && slot_owner[ps] == e.nidx;
+      eval_nodes[2 * k] = e.left;
+      eval_nodes[2 * k + 1] = e.right;
+    }
+    uint32_t total;
+    const uint32_t first = n_build + BlockExclusiveScan(k < n_part ? (parent_cached ? 1u : 2u) : 0u, s_warp, &total);
+    if (k < n_part) {
+      const int dst_buf = 1 - e.src_buf;
+      const int b_idx = build_right ? e.right : e.left;
+      const int s_idx = build_right ? e.left : e.right;
+      const NodeDev* b = &nodes[b_idx];
+      build[first] = BuildEntry{b_idx, dst_buf, b->seg_begin, b->seg_count, 0u, slot_base + first};
+      nodes[b_idx].hist_slot = (int32_t)(slot_base + first);
+      slot_owner[slot_base + first] = b_idx;
+      visits += b->seg_count;
+      if (!parent_cached) {
+        const NodeDev* o = &nodes[s_idx];
+        build[first + 1] = BuildEntry{s_idx, dst_buf, o->seg_begin, o->seg_count, 0u, slot_base + first + 1};
+        nodes[s_idx].hist_slot = (int32_t)(slot_base + first + 1);
+        slot_owner[slot_base + first + 1] = s_idx;
+        visits += o->seg_count;
+      }
+      part[k].pad = first | (parent_cached ? 0x80000000u : 0u);  // for the second pass
+    }
+    n_build += total;
   }
   __syncthreads();
+  // 2b. subtracted siblings: slots behind the built ones, in split order
+  const uint32_t n_sub = 2u * (uint32_t)n_part - n_build;
+  for (int k = threadIdx.x; k < n_part; k += kCtlThreads) {
+    const uint32_t tag = part[k].pad;
+    if ((tag & 0x80000000u) == 0u) continue;
+    const uint32_t first = tag & 0x7FFFFFFFu;
+    const uint32_t rank = 2u * (uint32_t)k - first;  // cached parents in front of split k
+    const PartEntry e = part[k];
+    const int b_idx = build[first].nidx;
+    const int s_idx = b_idx == e.left ? e.right : e.left;
+    const uint32_t s_slot = slot_base + n_build + rank;
+    nodes[s_idx].hist_slot = (int32_t)s_slot;
+    slot_owner[s_slot] = s_idx;
+    sub[rank] = SubEntry{nodes[e.nidx].hist_slot, (int32_t)(slot_base + first), (int32_t)s_slot};
+  }
   // 3. segment-relative tile offsets for the scatter pass
   for (uint32_t t = threadIdx.x; t < T; t += kCtlThreads)
     tile_left_off[t] = tile_excl[t] - tile_excl[part[part_tile_seg[t]].tile_begin];
   // 4. histogram tile table
   uint32_t running_tiles = 0;
-  for (int base = 0; base < n_part; base += kCtlThreads) {
-    const int k = base + threadIdx.x;
-    uint32_t tiles = k < n_part ? (build[k].count + kHistTile - 1) / kHistTile : 0u;
+  for (uint32_t base = 0; base < n_build; base += kCtlThreads) {
+    const uint32_t j = base + threadIdx.x;
+    uint32_t tiles = j < n_build ? (build[j].count + kHistTile - 1) / kHistTile : 0u;
     uint32_t total;
     uint32_t ex = running_tiles + BlockExclusiveScan(tiles, s_warp, &total);
-    if (k < n_part) {
-      build[k].tile_begin = ex;
-      s_tile_begin[k] = ex;
+    if (j < n_build) {
+      build[j].tile_begin = ex;
+      s_tile_begin[j] = ex;
     }
     running_tiles += total;
   }
   __syncthreads();
   for (uint32_t t = threadIdx.x; t < running_tiles; t += kCtlThreads)
-    build_tile_seg[t] = FindSegment(s_tile_begin, (uint32_t)n_part, t);
+    build_tile_seg[t] = FindSegment(s_tile_begin, n_build, t);
   if (visits) atomicAdd(&ts->row_visits, visits);
   if (threadIdx.x == 0) {
-    ts->n_build = n_part;
-    ts->n_sub = n_part;
+    ts->n_build = (int32_t)n_build;
+    ts->n_sub = (int32_t)n_sub;
     ts->n_eval = 2 * n_part;
     ts->build_tiles = running_tiles;
   }
@@ -840,6 +887,9 @@ struct b200hist_updater_s {
   std::vector<int> step_level;           // tree level (depth-wise) / split number (loss-guide) the step belongs to
   std::vector<int> step_level_start;     // 1: the step opens its level, 0: it continues it (node batching)
   int level_batch{kMaxLevelNodes};       // valid entries one step expands at most
+  std::vector<int> step_reuses;          // 1: the step's slot window has held other histograms in this tree (ring wrapped)
+  int32_t* d_slot_owner{nullptr};        // [n_slots] node that owns the slot's histogram, -1 = none
+  bool ring_reuse{false};                // the cache is smaller than the tree: windows are reused, parents may get lost
   uint32_t n_slots{1};
   // multi-GPU: feature-group shard of this rank and the allreduce communicator (borrowed)
   b200hist_comm_s* comm{nullptr};
@@ -1158,8 +1208,9 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
 
   // InitRoot
   auto t1 = timer.Begin();
+  B200_CUDA(cudaMemsetAsync(u->d_slot_owner, 0xFF, sizeof(int32_t) * (size_t)u->n_slots, s));  // -1: nobody
   InitRootKernel<<<1, kCtlThreads, 0, s>>>(u->pdev, (uint32_t)n, u->d_quant, u->d_ts, u->d_nodes, u->d_build,
-                                           u->d_build_tile_seg, u->d_eval_nodes, mono);
+                                           u->d_build_tile_seg, u->d_eval_nodes, mono, u->d_slot_owner);
   B200_LAUNCHED();
   timer.End(kApply, t1);
   auto t2 = timer.Begin();
@@ -1236,13 +1287,17 @@ void UpdateTreeImpl(b200hist_updater_s* u, const float* gpair_dev, cudaStream_t 
     ScanKernel<<<1, kCtlThreads, 0, s>>>(u->d_ts, u->d_nodes, u->d_part, u->d_part_tile_seg, u->d_tile_left,
                                          u->d_tile_excl, u->d_tile_left_off, u->d_build, u->d_sub, u->d_eval_nodes,
                                          u->d_build_tile_seg, u->step_slot_base[step], u->step_cap[step],
-                                         u->row_split ? 1 : 0);
+                                         u->row_split ? 1 : 0, u->d_slot_owner);
     B200_LAUNCHED();
     LaunchPartitionScatter(u->d_ridx[0], u->d_ridx[1], u->d_ridx[0], u->d_ridx[1], u->d_part, u->d_part_tile_seg,
                            u->d_ts, u->d_flags, u->d_tile_left_off, u->num_sms, s);
     timer.End(kPart, tp);
     auto th = timer.Begin();
-    build_hist(u->step_slot_base[step], u->step_cap[step]);
+    if (u->step_reuses[step])  // a reused window holds other nodes' sums: the build accumulates into zeros
+      B200_CUDA(cudaMemsetAsync(u->d_hist + (size_t)u->step_slot_base[step] * ell->total_bins, 0,
+                                sizeof(b200hist_gpair64) * (size_t)2 * u->step_cap[step] * ell->total_bins, s));
+    // the exchange covers the built slots: at most both children of every split when parents were lost
+    build_hist(u->step_slot_base[step], u->ring_reuse ? 2 * u->step_cap[step] : u->step_cap[step]);
     timer.End(kHist, th);
     auto tsb = timer.Begin();
     LaunchSubtract(u->d_sub, u->d_ts, u->d_hist, ell->total_bins, u->num_sms, s, slice_bin_lo, slice_bin_hi);
@@ -1377,9 +1432,10 @@ int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* 
     const bool dw = param->grow_policy == 0;
     u->level_batch = param->max_leaves > 0 ? 1024 : kMaxLevelNodes;
     if (const char* e = std::getenv("B200HIST_LEVEL_BATCH")) u->level_batch = std::max(1, std::min(std::atoi(e), kMaxLevelNodes));
-    uint32_t base = 1;
     const int n_levels = u->n_steps;
     u->n_steps = 0;
+    std::vector<int> step_children;
+    unsigned long long total_slots = 1, max_window = 0;
     for (int st = 0; st < n_levels; ++st) {
       long long width = dw ? (1ll << std::min(st, 40)) : 1ll;
       if (param->max_leaves > 0) width = std::min<long long>(width, param->max_leaves);
@@ -1389,18 +1445,48 @@ int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* 
       for (long long b = 0; b < n_sub; ++b) {
         const uint32_t cap = (uint32_t)std::min<long long>(u->level_batch, width - b * u->level_batch);
         u->step_cap.push_back(cap);
-        u->step_slot_base.push_back(base);
         u->step_level.push_back(st);
         u->step_level_start.push_back(b == 0 ? 1 : 0);
-        if (children) base += 2 * cap;
+        step_children.push_back(children ? 1 : 0);
+        if (children) { total_slots += 2ull * cap; max_window = std::max<unsigned long long>(max_window, 2ull * cap); }
         ++u->n_steps;
       }
     }
-    u->n_slots = base;
+    // The cache holds a slot per possible node when that fits (nothing is ever rebuilt); otherwise it is a ring of
+    // `ring` slots behind the root's: the steps' windows wrap around it and a split whose parent histogram has been
+    // overwritten builds both children (DeviceHistogramStorage's overflow, histogram.cuh:72-168).  Capacity:
+    // train_param.reserved[0] (= HistMakerTrainParam::max_cached_hist_node) or B200HIST_CACHE_SLOTS, else half of the
+    // free device memory.
+    size_t free_b = 0, total_b = 0;
+    B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const unsigned long long slot_bytes = (unsigned long long)ell->total_bins * sizeof(b200hist_gpair64);
+    unsigned long long ring = total_slots - 1;
+    unsigned long long budget_slots = std::max<unsigned long long>(1, (unsigned long long)(free_b / 2) / slot_bytes);
+    if (param->reserved[0] > 0) budget_slots = (unsigned long long)param->reserved[0];
+    if (const char* e = std::getenv("B200HIST_CACHE_SLOTS")) budget_slots = std::strtoull(e, nullptr, 10);
+    if (ring + 1 > budget_slots) ring = std::max<unsigned long long>(max_window, budget_slots > 1 ? budget_slots - 1 : 1);
+    B200_CHECK((ring + 1) * slot_bytes < (unsigned long long)free_b,
+               "histogram cache: even one step's window (" + std::to_string(((ring + 1) * slot_bytes) >> 20) +
+                   " MiB) does not fit in free device memory; lower max_bin / max_depth");
+    u->ring_reuse = ring + 1 < total_slots;
+    unsigned long long pos = 0;
+    bool wrapped = false;
+    for (int st = 0; st < u->n_steps; ++st) {
+      const unsigned long long w = step_children[(size_t)st] ? 2ull * u->step_cap[(size_t)st] : 0ull;
+      if (pos + w > ring) { pos = 0; wrapped = true; }
+      u->step_slot_base.push_back((uint32_t)(1 + pos));
+      u->step_reuses.push_back(wrapped ? 1 : 0);
+      pos += w;
+    }
+    u->n_slots = (uint32_t)(ring + 1);
+    if (std::getenv("B200HIST_VERBOSE") != nullptr)
+      std::fprintf(stderr, "[b200hist] updater: %llu rows, %d steps, histogram cache %u of %llu slots x %llu KiB%s, free %zu MiB\n",
+                   (unsigned long long)ell->n_rows, u->n_steps, u->n_slots, total_slots, slot_bytes >> 10,
+                   u->ring_reuse ? " (ring: parents may be rebuilt)" : "", free_b >> 20);
   }
   const uint64_t n = ell->n_rows;
   const size_t part_tiles = n / kPartTile + kMaxLevelNodes + 2;
-  const size_t hist_tiles = n / kHistTile + kMaxLevelNodes + 2;
+  const size_t hist_tiles = n / kHistTile + 2 * kMaxLevelNodes + 2;  // a split may build both children
   const size_t fin_tiles = n / kPartTile + (size_t)u->max_nodes + 2;
   u->d_groups = DevAlloc<GroupDesc>(u->groups.size());
   B200_CUDA(cudaMemcpy(u->d_groups, u->groups.data(), sizeof(GroupDesc) * u->groups.size(), cudaMemcpyHostToDevice));
@@ -1416,7 +1502,7 @@ int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* 
   u->d_nodes = DevAlloc<NodeDev>(u->max_nodes);
   u->d_cand = DevAlloc<b200hist_candidate>(u->max_nodes);
   u->d_part = DevAlloc<PartEntry>(kMaxLevelNodes);
-  u->d_build = DevAlloc<BuildEntry>(kMaxLevelNodes);
+  u->d_build = DevAlloc<BuildEntry>(2 * kMaxLevelNodes);
   u->d_sub = DevAlloc<SubEntry>(kMaxLevelNodes);
   u->d_eval_nodes = DevAlloc<int32_t>(2 * kMaxLevelNodes);
   u->d_part_tile_seg = DevAlloc<uint32_t>(part_tiles);
@@ -1429,10 +1515,7 @@ int b200hist_updater_create(b200hist_ellpack_t ell, const b200hist_train_param* 
   u->d_fin_tile_seg = DevAlloc<uint32_t>(fin_tiles);
   u->d_fin_tile_begin = DevAlloc<uint32_t>((size_t)u->max_nodes + 1);
   u->hist_bytes = (size_t)u->n_slots * ell->total_bins * sizeof(b200hist_gpair64);
-  size_t free_b = 0, total_b = 0;
-  B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  B200_CHECK(u->hist_bytes < free_b, "histogram cache (" + std::to_string(u->hist_bytes >> 20) +
-                                         " MiB) does not fit in free device memory; lower max_depth/max_leaves");
+  u->d_slot_owner = DevAlloc<int32_t>(u->n_slots);
   // one allocation = histogram cache + flag array of the peer-memory exchange (one IPC handle covers both);
   // at least 4 MiB so that it is a stand-alone driver allocation whose IPC mapping starts at the same address
   u->flags_offset = (u->hist_bytes + 255) & ~size_t(255);
@@ -1464,7 +1547,7 @@ int b200hist_updater_destroy(b200hist_updater_t u) {
                     u->d_position, u->d_gpair_staging, u->d_ts, u->d_nodes, u->d_cand, u->d_part, u->d_build,
                     u->d_sub, u->d_eval_nodes, u->d_part_tile_seg, u->d_build_tile_seg, u->d_tile_left,
                     u->d_tile_excl, u->d_tile_left_off, u->d_flags, u->d_fin, u->d_fin_tile_seg,
-                    u->d_fin_tile_begin, u->d_hist};
+                    u->d_fin_tile_begin, u->d_hist, u->d_slot_owner};
     for (void* p : ptrs) cudaFree(p);
     for (void* p : u->peer_base)
       if (p != nullptr) cudaIpcCloseMemHandle(p);
