@@ -390,6 +390,83 @@ def reference_booster_section(torch, args, device, steps, warmup, rows=None, fea
     return out
 
 
+def reference_booster_distributed(torch, dist, args, device, rank, world, steps, warmup):
+    """N > 1: a distributed job of the UNMODIFIED reference -- its own tracker (on rank 0) and communicator, row-split
+    data: every rank builds a QuantileDMatrix of ITS batches (the reference's distributed sketch makes the cuts), then
+    two Boosters train on it: updater=grow_b200_hist (the shim in distributed mode: IPC handles through the
+    reference's collective::Allgather, histograms exchanged over NVLink peer memory) and
+    updater=grow_gpu_hist_reference (the reference's own NCCL allreduce).  Wall time per XGBoosterUpdateOneIter,
+    max over ranks."""
+    import ctypes
+    import numpy as np
+    from oracle import ref_capi as rc
+    shim = os.path.join(ROOT, "xgboost_b200", "lib", "libb200hist_xgb_shim.so")
+    if not (rc.available("cuda") and os.path.exists(shim)):
+        return None
+    rc.load("cuda")
+    ctypes.CDLL(os.path.join(ROOT, "xgboost_b200", "lib", "libb200hist.so"), mode=ctypes.RTLD_GLOBAL)
+    keep = ctypes.CDLL(shim, mode=ctypes.RTLD_GLOBAL)
+    tracker, box = None, [None]
+    if rank == 0:
+        tracker = rc.Tracker(world, kind="cuda")
+        box[0] = tracker.worker_args()
+    dist.broadcast_object_list(box, src=0)
+    rc.communicator_init("cuda", dict(box[0], dmlc_task_id=str(rank), dmlc_communicator="rabit"))
+    out = None
+    try:
+        n, f = args.rows, args.features
+        nb = (n + 999_999) // 1_000_000
+        b_lo, b_hi = nb * rank // world, nb * (rank + 1) // world
+        t0 = time.perf_counter()
+        batches = rc.LazyBatches(b_hi - b_lo, lambda b: batch_of(torch, device, f, n, 1_000_000, b_lo + b)[0])
+        dm = rc.DMatrix.quantile_from_batches(batches, max_bin=args.max_bin, kind="cuda")
+        w = torch.randn(f, generator=torch.Generator(device=device).manual_seed(7), device=device)
+        rows_here = min(n, b_hi * 1_000_000) - b_lo * 1_000_000
+        y = np.empty(rows_here, dtype=np.float32)
+        for b in range(b_lo, b_hi):
+            x, g = batch_of(torch, device, f, n, 1_000_000, b)
+            o = (b - b_lo) * 1_000_000
+            y[o:o + x.shape[0]] = (torch.nan_to_num(x) @ w + 0.1 * torch.randn(x.shape[0], generator=g, device=device)).cpu().numpy()
+            del x
+        dm.set_label(y)
+        torch.cuda.synchronize(device)
+        build_s = time.perf_counter() - t0
+        torch.cuda.empty_cache()
+        params = {"tree_method": "hist", "device": "cuda:%d" % device.index, "max_depth": args.depth,
+                  "max_bin": args.max_bin, "objective": "reg:squarederror", "eta": 0.3, "lambda": 1,
+                  "min_child_weight": 1, "base_score": 0.5}
+        out = {"dmatrix_build_s": round(build_s, 2)}
+        shas = {}
+        for name, updater in (("ours", "grow_b200_hist"), ("reference_gpu", "grow_gpu_hist_reference")):
+            bst = rc.Booster(dict(params, updater=updater), dm)
+            ts = []
+            for i in range(warmup + steps):
+                torch.cuda.synchronize(device)
+                t1 = time.perf_counter()
+                bst.update(i)
+                torch.cuda.synchronize(device)
+                ts.append(time.perf_counter() - t1)
+            tot = torch.tensor([sum(ts[warmup:])], device=device, dtype=torch.float64)
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+            trees = bst.save_json()["learner"]["gradient_booster"]["model"]["trees"]
+            shas[name] = model_sha(trees)
+            out[name] = {"iters_per_s": steps / float(tot.item()), "ms_per_iter_mean": 1e3 * float(tot.item()) / steps,
+                         "ms_per_iter_median_rank0": 1e3 * float(np.median(ts[warmup:])), "steps": steps, "warmup": warmup,
+                         "model_sha": shas[name], "last_tree_nodes": len(trees[-1]["left_children"])}
+            del bst
+            torch.cuda.empty_cache()
+        out["models_identical"] = shas["ours"] == shas["reference_gpu"]
+        del dm
+    finally:
+        rc.communicator_finalize("cuda")
+        if tracker is not None:
+            tracker.wait(120)
+            tracker.free()
+    del keep
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
@@ -544,7 +621,6 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = 1e3 / ms_per_step
-    up.set_profiling(False)
 
     names = [k for k in prof[0] if k not in ("row_visits", "hist_levels")]
     phase = {k: float(np.mean([p[k] for p in prof])) for k in names}
@@ -613,6 +689,47 @@ def run_b200(args):
                                       "note": "exact int64 accumulation in shared memory bounds the kernel, not HBM"},
                 "whole_step_frac": (ab["total"] - ab["hist"] + hist_bytes_gpu) / (ms_per_step * 1e-3) / 1e9 / peak}
 
+    # The same matrix under binary:logistic (labels y > 0): hessians p(1-p) have low words, so the histogram runs the
+    # general 16-byte-accumulator path (HistKernelBankedFast: 32 features per CTA pass, 4 shared atomics per update)
+    # instead of the 12-byte pair kernel.  Not the metric: a second objective on the headline matrix, for the record.
+    logistic = None
+    if world == 1 and os.environ.get("B200_BENCH_LOGISTIC", "1") != "0":
+        yb = (y > 0).to(torch.float32)
+        pl = torch.zeros(n, dtype=torch.float32, device=device)
+        gl = torch.empty((n, 2), dtype=torch.float32, device=device)
+
+        def step_logistic():
+            pr = torch.sigmoid(pl)
+            torch.sub(pr, yb, out=gl[:, 0])
+            torch.mul(pr, 1.0 - pr, out=gl[:, 1])
+            del pr
+            up.update_async(gl, pos)
+            up.update_prediction_cache(pl)
+            return up.fetch_tree()
+
+        for _ in range(3):
+            step_logistic()
+        torch.cuda.synchronize(device)
+        k4 = max(1, min(args.steps, 8))
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        lp = []
+        for _ in range(k4):
+            step_logistic()
+            lp.append(up.last_profile())
+        l1.record()
+        torch.cuda.synchronize(device)
+        lms = l0.elapsed_time(l1) / k4
+        lv = float(np.mean([q_["row_visits"] for q_ in lp]))
+        lh = float(np.mean([q_["hist"] for q_ in lp]))
+        logistic = {"value": 1e3 / lms, "unit": UNIT, "ms_per_step": lms, "steps": k4, "hist_ms": lh,
+                    "row_visits_per_step_mean": lv,
+                    "updates_per_clk_per_sm": lv * f / (lh * 1e-3) / sm_clock_hz / n_sms if lh > 0 else None,
+                    "kernel": "HistKernelBankedFast (16-byte accumulators, 4 shared atomics per update)",
+                    "objective": "binary:logistic on labels y > 0 (gradient kernels of the objective included in the step)"}
+        del yb, pl, gl
+    up.set_profiling(False)
+
     # north_star's decomposition measured next to the default one: all rows on every GPU, F/P feature blocks each,
     # one peer-memory slice exchange per tree level (same matrix, same trees)
     feature_block = None
@@ -663,6 +780,22 @@ def run_b200(args):
     # reference's gpu_hist on the same DMatrix.  N > 1: the shim's distributed mode is exercised by the tests; here the
     # C-ABI host entry is timed with a gradient that is refreshed from the device every step.
     e2e, ref_section = None, None
+    if not args.no_e2e and world > 1:
+        k2 = max(1, min(args.steps, 10))
+        try:
+            ref_section = reference_booster_distributed(torch, dist, args, device, rank, world, k2, 2)
+        except Exception as exc:   # the measurement above must survive a failure of this leg
+            ref_section = None
+            if rank == 0:
+                sys.stderr.write("distributed e2e leg failed: %r\n" % (exc,))
+        if ref_section is not None:
+            nodes = ref_section["ours"]["last_tree_nodes"]
+            e2e = {"value": ref_section["ours"]["iters_per_s"], "unit": UNIT,
+                   "h2d_bytes_per_step": nodes * 4 * world, "d2h_bytes_per_step": (nodes * 64 + 256) * world,
+                   "path": "a %d-worker job of the unmodified reference (its tracker and communicator, row-split "
+                           "QuantileDMatrix per worker, XGBoosterUpdateOneIter) with libb200hist_xgb_shim.so serving "
+                           "grow_gpu_hist in distributed mode; max over ranks" % world,
+                   "steps": k2, "model_identical_to_reference_gpu_hist": ref_section["models_identical"]}
     if not args.no_e2e and world == 1 and rank == 0:
         k2 = max(1, min(args.steps, 10))
         ref_section = reference_booster_section(torch, args, device, k2, 2)
@@ -748,9 +881,10 @@ def run_b200(args):
                 "reference_gpu": None if ref_section is None else dict(
                     ref_section["reference_gpu"], unit=UNIT, value=ref_section["reference_gpu"]["iters_per_s"],
                     what="the UNMODIFIED reference's CUDA gpu_hist (oracle/_ref_cuda, updater=grow_gpu_hist_reference) "
-                         "through XGBoosterUpdateOneIter on the same QuantileDMatrix in this process: the kernel to beat",
+                         "through XGBoosterUpdateOneIter on the same QuantileDMatrix in this process (N > 1: its own "
+                         "distributed gpu_hist, NCCL allreduce, in the same job): the kernel to beat",
                     dmatrix_build_s=ref_section["dmatrix_build_s"]),
-                "other_configs": other_configs,
+                "other_configs": other_configs, "headline_matrix_binary_logistic": logistic,
                 "algorithmic_gb_per_step": {k: v / 1e9 for k, v in ab.items()}}
         print(json.dumps(line))
     if world > 1:
