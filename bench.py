@@ -451,7 +451,8 @@ def reference_booster_distributed(torch, dist, args, device, rank, world, steps,
             trees = bst.save_json()["learner"]["gradient_booster"]["model"]["trees"]
             shas[name] = model_sha(trees)
             out[name] = {"iters_per_s": steps / float(tot.item()), "ms_per_iter_mean": 1e3 * float(tot.item()) / steps,
-                         "ms_per_iter_median_rank0": 1e3 * float(np.median(ts[warmup:])), "steps": steps, "warmup": warmup,
+                         "ms_per_iter_median_rank0": 1e3 * float(np.median(ts[warmup:])),
+                         "ms_per_iter_all_rank0": [round(1e3 * t_, 2) for t_ in ts], "steps": steps, "warmup": warmup,
                          "model_sha": shas[name], "last_tree_nodes": len(trees[-1]["left_children"])}
             del bst
             torch.cuda.empty_cache()
@@ -795,6 +796,7 @@ def run_b200(args):
                    "path": "a %d-worker job of the unmodified reference (its tracker and communicator, row-split "
                            "QuantileDMatrix per worker, XGBoosterUpdateOneIter) with libb200hist_xgb_shim.so serving "
                            "grow_gpu_hist in distributed mode; max over ranks" % world,
+                   "ms_per_iter_all_rank0": ref_section["ours"]["ms_per_iter_all_rank0"],
                    "steps": k2, "model_identical_to_reference_gpu_hist": ref_section["models_identical"]}
     if not args.no_e2e and world == 1 and rank == 0:
         k2 = max(1, min(args.steps, 10))

@@ -14,6 +14,7 @@
 // single-CTA "control" kernels (ApplyKernel, ScanKernel), so one tree is a fixed, data-independent
 // sequence of launches with no host read-back until the finished tree is copied out once.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 
@@ -1601,6 +1602,21 @@ int b200hist_updater_update_tree(b200hist_updater_t u, const float* gpair_dev, v
   B200_API_BEGIN();
   B200_CHECK(u != nullptr && gpair_dev != nullptr, "null argument");
   DeviceGuard guard(u->device);
+  static const bool verbose = std::getenv("B200HIST_VERBOSE") != nullptr;
+  if (verbose) {  // wall time of the whole call and its device phases, one line per tree (diagnostics)
+    const bool was = u->profiling;
+    u->profiling = true;
+    B200_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    const auto t0 = std::chrono::steady_clock::now();
+    UpdateTreeImpl(u, gpair_dev, static_cast<cudaStream_t>(stream), out_nodes_host, out_n_nodes, out_position_dev);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::fprintf(stderr, "[b200hist] update_tree %.2f ms wall: quant %.2f hist %.2f (exchange %.2f) sub %.2f eval %.2f apply %.2f "
+                         "part %.2f final %.2f, %llu row visits, rank %d/%d\n",
+                 ms, u->last_ms[0], u->last_ms[1], u->last_ms[7], u->last_ms[2], u->last_ms[3], u->last_ms[4], u->last_ms[5],
+                 u->last_ms[6], (unsigned long long)u->last_row_visits, u->p2p_rank, u->p2p_world);
+    u->profiling = was;
+    return 0;
+  }
   UpdateTreeImpl(u, gpair_dev, static_cast<cudaStream_t>(stream), out_nodes_host, out_n_nodes, out_position_dev);
   B200_API_END();
 }
