@@ -868,12 +868,12 @@ def run_b200(args):
         del up, page, preds, gpair, pos
     torch.cuda.empty_cache()
 
-    # end to end through the reference's own Booster (N = 1): XGBoosterUpdateOneIter with the shim loaded, and the
-    # reference's gpu_hist on the same DMatrix.  N > 1: the shim's distributed mode is exercised by the tests; here the
-    # C-ABI host entry is timed with a gradient that is refreshed from the device every step.
-    # A distributed job of the unmodified reference through the shim: validated on 2 GPUs (tests/test_multi_gpu.py and
-    # profiles/r02_bench_n2_driver_flags.json); on 8 GPUs the leg did not return within 8 minutes in round 2's last GPU
-    # call (no budget was left to find out where), so beyond N = 2 it runs only on request (B200_BENCH_DIST_E2E=1).
+    # End to end through the reference's own Booster.  N = 1: XGBoosterUpdateOneIter with the shim loaded, and the
+    # reference's gpu_hist on the same DMatrix in this process.  N = 2: a distributed job of the unmodified reference (its
+    # tracker and communicator) with the shim in distributed mode -- validated on 2 GPUs (tests/test_multi_gpu.py,
+    # profiles/r02_bench_n2_driver_flags.json).  On 8 GPUs that leg did not return within the 9.5 minutes round 2's last
+    # GPU call had left (no budget remained to find out where it waits), so beyond N = 2 it runs only on request
+    # (B200_BENCH_DIST_E2E=1) and `e2e` stays the C-ABI host-gradient measurement above.
     if not args.no_e2e and world > 1 and (world == 2 or os.environ.get("B200_BENCH_DIST_E2E") == "1"):
         k2 = max(1, min(args.steps, 10))
         try:
