@@ -25,6 +25,10 @@
 #include <thread>
 #include <vector>
 
+#include <sched.h>
+// a rank of a multi-process emulation that waits for a peer's flag gives its core to that peer
+#define B200_SPIN_PAUSE() sched_yield()
+
 #define __global__
 #define __device__
 #define __host__
@@ -172,6 +176,7 @@ using std::isnan;
 using std::isinf;
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }

@@ -8,7 +8,12 @@
 #include "cuda_emu.h"
 #include "emu_io.h"
 
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
 #include "../../xgboost_b200/csrc/colsample.cu"
+#include "../../xgboost_b200/csrc/comm.cu"
 #include "../../xgboost_b200/csrc/evaluate.cu"
 #include "../../xgboost_b200/csrc/histogram.cu"
 #include "../../xgboost_b200/csrc/partition.cu"
@@ -46,7 +51,7 @@ int main(int argc, char** argv) {
   auto fs = ReadAll<int32_t>(dir + "/feature_set.bin", true);
   auto col_seeds = ReadAll<uint32_t>(dir + "/col_seeds.bin", true);
   auto col_tree_set = ReadAll<int32_t>(dir + "/col_tree_set.bin", true);
-  const uint64_t n = (uint64_t)meta[0];
+  uint64_t n = (uint64_t)meta[0];
   const uint32_t nf = (uint32_t)meta[1];
   EllView view{};
   view.bins = bins.data();
@@ -113,6 +118,91 @@ int main(int argc, char** argv) {
   }
   base = (uint32_t)(ring + 1);
   const uint32_t n_slots = base;
+
+  // ---- [28] world > 1: row split over `world` PROCESSES (one per emulated GPU), like torchrun's ranks.  The histogram
+  // caches, flag arrays + mailboxes and evaluation scratch tables live in one shared mapping created before the fork, so
+  // that "peer memory" is what it is on the device: memory another rank's kernels load from and store to while this
+  // rank's kernels run.  Rank r keeps rows [n r / world, n (r+1) / world) (or shard_ptr.bin's) and the kernels'
+  // own flag barriers (comm.cu) order the ranks.  [29] = 1: the fused reduce-scatter + all-gather instead of the
+  // evaluation by feature slice.
+  const int world = meta.size() > 28 && meta[28] > 1 ? (int)meta[28] : 1;
+  const bool full_exchange = meta.size() > 29 && meta[29] != 0;
+  int rank = 0;
+  const size_t hist_elems = (size_t)n_slots * view.total_bins;
+  const size_t scratch_elems = (size_t)2 * 64 * nf;  // the emulated trees expand at most 64 nodes per step
+  const size_t flag_bytes = kMailboxOffset + 2 * kMaxPeers * sizeof(MailRecord);
+  auto round_up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t per_rank = round_up(hist_elems * sizeof(longlong2)) + round_up(flag_bytes) + round_up(scratch_elems * sizeof(FeatCand));
+  std::vector<longlong2> hist_local;
+  std::vector<FeatCand> scratch_local;
+  longlong2* peer_hist[kMaxPeers] = {};
+  uint32_t* peer_flags[kMaxPeers] = {};
+  FeatCand* peer_scratch[kMaxPeers] = {};
+  if (world > 1) {
+    if (world > kMaxPeers) return 3;
+    auto* shm = static_cast<uint8_t*>(mmap(nullptr, per_rank * world, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0));
+    if (shm == MAP_FAILED) return 4;
+    std::memset(shm, 0, per_rank * world);
+    for (int r = 0; r < world; ++r) {
+      uint8_t* b = shm + per_rank * r;
+      peer_hist[r] = reinterpret_cast<longlong2*>(b);
+      peer_flags[r] = reinterpret_cast<uint32_t*>(b + round_up(hist_elems * sizeof(longlong2)));
+      peer_scratch[r] = reinterpret_cast<FeatCand*>(b + round_up(hist_elems * sizeof(longlong2)) + round_up(flag_bytes));
+    }
+    auto shard_ptr = ReadAll<int64_t>(dir + "/shard_ptr.bin", true);
+    std::vector<pid_t> kids;
+    bool child = false;
+    for (int r = 0; r < world; ++r) {
+      const pid_t pid = fork();  // before the first launch: the emulator's thread pool does not exist yet
+      if (pid < 0) return 5;
+      if (pid == 0) { rank = r; child = true; break; }
+      kids.push_back(pid);
+    }
+    if (!child) {
+      int bad = 0;
+      for (pid_t k : kids) {
+        int st = 0;
+        waitpid(k, &st, 0);
+        if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) bad = 6;
+      }
+      return bad;
+    }
+    const uint64_t r0 = shard_ptr.empty() ? n * (uint64_t)rank / world : (uint64_t)shard_ptr[rank];
+    const uint64_t r1 = shard_ptr.empty() ? n * (uint64_t)(rank + 1) / world : (uint64_t)shard_ptr[rank + 1];
+    bins = std::vector<uint8_t>(bins.begin() + r0 * view.row_bytes, bins.begin() + r1 * view.row_bytes);
+    gq = std::vector<longlong2>(gq.begin() + r0, gq.begin() + r1);
+    view.bins = bins.data();
+    n = r1 - r0;
+    view.n_rows = n;
+    // what QuantConvertKernel leaves on this rank: the sums and hessian flags of ITS rows (ScalarExchangeKernel folds them)
+    unsigned long long sg = 0, sh = 0;
+    unsigned lo_or = 0, zero_any = 0;
+    for (auto const& v : gq) {
+      sg += (unsigned long long)v.x;
+      sh += (unsigned long long)v.y;
+      lo_or |= (unsigned)((unsigned long long)v.y & 0xFFFFFFFFull);
+      zero_any |= v.y == 0 ? 1u : 0u;
+    }
+    q.root_g = (long long)sg; q.root_h = (long long)sh; q.h_lo_or = lo_or; q.h_zero_any = zero_any;
+  } else {
+    hist_local.assign(hist_elems, make_longlong2(0, 0));
+    scratch_local.resize(scratch_elems);
+  }
+  longlong2* const hist_p = world > 1 ? peer_hist[rank] : hist_local.data();
+  FeatCand* const scratch_p = world > 1 ? peer_scratch[rank] : scratch_local.data();
+  const bool sliced = world > 1 && !full_exchange && meta[6] == 0 && nf >= (uint32_t)world;
+  const EvalShard shard{sliced ? rank : 0, sliced ? world : 1, nf};
+  uint32_t slice_lo = 0, slice_hi = view.total_bins;
+  if (sliced) {  // SliceBins (updater.cu): the bins of the features this rank owns
+    uint32_t f0 = nf, f1 = 0;
+    for (uint32_t f = 0; f < nf; ++f)
+      if (shard.Owns((int)f)) { f0 = std::min(f0, f); f1 = std::max(f1, f + 1); }
+    slice_lo = f0 < f1 ? cut_ptrs[f0] : 0u;
+    slice_hi = f0 < f1 ? cut_ptrs[f1] : 0u;
+  }
+  uint32_t epoch = 0;
+  unsigned int done_counter = 0;
+  const std::string out_suffix = world > 1 ? "_r" + std::to_string(rank) : "";
   const size_t part_tiles = n / kPartTile + (size_t)max_nodes + 2, hist_tiles = n / kHistTile + 2 * (size_t)max_nodes + 2;
   std::vector<uint32_t> ridx0(n), ridx1(n);
   for (uint64_t i = 0; i < n; ++i) ridx0[i] = (uint32_t)i;
@@ -127,8 +217,6 @@ int main(int argc, char** argv) {
   std::vector<int32_t> eval_nodes(2 * kMaxLevelNodes);
   std::vector<uint32_t> part_tile_seg(part_tiles), build_tile_seg(hist_tiles), tile_left(part_tiles), tile_excl(part_tiles + 1),
       tile_left_off(part_tiles), flags(part_tiles * (kPartTile / 32)), fin_tile_seg(part_tiles), fin_tile_begin((size_t)max_nodes + 1);
-  std::vector<FeatCand> scratch((size_t)2 * 64 * nf);  // the emulated trees expand at most 64 nodes per step
-  std::vector<longlong2> hist((size_t)n_slots * view.total_bins, make_longlong2(0, 0));
   std::vector<float> lower((size_t)max_nodes), upper((size_t)max_nodes);
   const MonoView mono{meta[5] ? mono_c.data() : nullptr, lower.data(), upper.data()};
   const bool has_cat = meta[6] != 0;
@@ -193,7 +281,7 @@ int main(int argc, char** argv) {
     if (sparse) {
       uint32_t b0 = 0xFFFFFFFFu, b1 = 0;
       for (auto const& g : groups) { b0 = std::min(b0, g.bin_begin); b1 = std::max(b1, g.bin_end); }
-      EMU_LAUNCH((3), (256), 0, HistKernelSparse(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, hist.data(), b0, b1));
+      EMU_LAUNCH((3), (256), 0, HistKernelSparse(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, hist_p, b0, b1));
       return;
     }
     const bool banked = view.bin_bytes == 1 || (view.bin_bytes == 2 && !groups.empty() && groups[0].n_blocks > 0);
@@ -201,7 +289,7 @@ int main(int argc, char** argv) {
       uint32_t max_bins = 0;
       for (auto const& g : groups) max_bins = std::max(max_bins, g.bin_end - g.bin_begin);
       EMU_LAUNCH((2, (unsigned)n_groups), (kHistThreads), GenericSmemBytes(max_bins),
-                 HistKernelGeneric<uint16_t>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist.data()));
+                 HistKernelGeneric<uint16_t>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist_p));
       return;
     }
     const uint32_t sym_bytes = view.bin_bytes;
@@ -220,39 +308,39 @@ int main(int argc, char** argv) {
       const int n_pairs = (n_groups + 1) / 2;
       if (paged && sym_bytes == 2) {
         EMU_LAUNCH((2, (unsigned)n_pairs), (kHistThreads), std::max(pair_smem, smem),
-                   (HistKernelPair<2, 2, true>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist.data(), &q)));
+                   (HistKernelPair<2, 2, true>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist_p, &q)));
       } else if (paged) {
         EMU_LAUNCH((2, (unsigned)n_pairs), (kHistThreads), std::max(pair_smem, smem),
-                   (HistKernelPair<3, 1, true>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist.data(), &q)));
+                   (HistKernelPair<3, 1, true>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist_p, &q)));
       } else if (sym_bytes == 2) {
         EMU_LAUNCH((2, (unsigned)n_pairs), (kHistThreads), std::max(pair_smem, smem),
-                   (HistKernelPair<2, 2>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist.data(), &q)));
+                   (HistKernelPair<2, 2>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist_p, &q)));
       } else {
         EMU_LAUNCH((2, (unsigned)n_pairs), (kHistThreads), std::max(pair_smem, smem),
-                   (HistKernelPair<3, 1>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist.data(), &q)));
+                   (HistKernelPair<3, 1>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), (uint32_t)n_groups, hist_p, &q)));
       }
       return;
     }
     if (paged && sym_bytes == 2) {
       EMU_LAUNCH((2, (unsigned)n_groups), (kHistThreads), smem,
-                 (HistKernelBankedFast<2, true>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist.data(), &q)));
+                 (HistKernelBankedFast<2, true>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist_p, &q)));
     } else if (paged) {
       EMU_LAUNCH((2, (unsigned)n_groups), (kHistThreads), smem,
-                 (HistKernelBankedFast<1, true>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist.data(), &q)));
+                 (HistKernelBankedFast<1, true>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist_p, &q)));
     } else if (sym_bytes == 2) {
       EMU_LAUNCH((2, (unsigned)n_groups), (kHistThreads), smem,
-                 HistKernelBankedFast<2>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist.data(), &q));
+                 HistKernelBankedFast<2>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist_p, &q));
     } else {
       EMU_LAUNCH((2, (unsigned)n_groups), (kHistThreads), smem,
-                 HistKernelBankedFast<1>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist.data(), &q));
+                 HistKernelBankedFast<1>(view, gq.data(), ridx0.data(), ridx1.data(), build.data(), build_tile_seg.data(), &ts, groups.data(), hist_p, &q));
     }
   };
-  auto build_hist = [&]() {  // the CPU stand-in for LaunchBuildHist over the kernels' own work list
+  auto build_local = [&]() {  // the CPU stand-in for LaunchBuildHist over the kernels' own work list
     if (hist_mode) { for_each_page(build_hist_kernels); return; }
     for (int k = 0; k < ts.n_build; ++k) {
       const BuildEntry e = build[k];
       const uint32_t* rows = (e.buf ? ridx1.data() : ridx0.data()) + e.begin;
-      longlong2* h = hist.data() + (size_t)e.slot * view.total_bins;
+      longlong2* h = hist_p + (size_t)e.slot * view.total_bins;
       for (uint32_t j = 0; j < e.count; ++j) {
         const uint32_t r = rows[j];
         if (sparse) {
@@ -274,12 +362,30 @@ int main(int argc, char** argv) {
       }
     }
   };
+  // AllReduceHist of UpdateTreeImpl's build_hist: one collective per level over the level's contiguous built slots
+  auto build_hist = [&](uint32_t slot_base, uint32_t slot_cap) {
+    build_local();
+    if (world == 1) return;
+    if (sliced) {
+      ++epoch;
+      if (world == 2) { EMU_LAUNCH((3), (256), 0, HistSliceReduceKernel<2>(peer_hist, peer_flags, rank, world, &ts, slot_base, slot_cap, view.total_bins, slice_lo, slice_hi, epoch)); }
+      else if (world == 4) { EMU_LAUNCH((3), (256), 0, HistSliceReduceKernel<4>(peer_hist, peer_flags, rank, world, &ts, slot_base, slot_cap, view.total_bins, slice_lo, slice_hi, epoch)); }
+      else if (world == 8) { EMU_LAUNCH((3), (256), 0, HistSliceReduceKernel<8>(peer_hist, peer_flags, rank, world, &ts, slot_base, slot_cap, view.total_bins, slice_lo, slice_hi, epoch)); }
+      else { EMU_LAUNCH((3), (256), 0, HistSliceReduceKernel<0>(peer_hist, peer_flags, rank, world, &ts, slot_base, slot_cap, view.total_bins, slice_lo, slice_hi, epoch)); }
+      return;
+    }
+    const uint32_t ea = ++epoch, eb = ++epoch;
+    if (world == 2) { EMU_LAUNCH((3), (256), 0, HistAllReduceKernel<2>(peer_hist, peer_flags, rank, world, &ts, slot_base, slot_cap, view.total_bins, ea, eb, &done_counter)); }
+    else if (world == 4) { EMU_LAUNCH((3), (256), 0, HistAllReduceKernel<4>(peer_hist, peer_flags, rank, world, &ts, slot_base, slot_cap, view.total_bins, ea, eb, &done_counter)); }
+    else if (world == 8) { EMU_LAUNCH((3), (256), 0, HistAllReduceKernel<8>(peer_hist, peer_flags, rank, world, &ts, slot_base, slot_cap, view.total_bins, ea, eb, &done_counter)); }
+    else { EMU_LAUNCH((3), (256), 0, HistAllReduceKernel<0>(peer_hist, peer_flags, rank, world, &ts, slot_base, slot_cap, view.total_bins, ea, eb, &done_counter)); }
+  };
   auto subtract = [&]() {
     for (int k = 0; k < ts.n_sub; ++k) {
       const SubEntry e = sub[k];
-      for (uint32_t b = 0; b < view.total_bins; ++b) {
-        hist[(size_t)e.sub * view.total_bins + b].x = WrapSub(hist[(size_t)e.parent * view.total_bins + b].x, hist[(size_t)e.built * view.total_bins + b].x);
-        hist[(size_t)e.sub * view.total_bins + b].y = WrapSub(hist[(size_t)e.parent * view.total_bins + b].y, hist[(size_t)e.built * view.total_bins + b].y);
+      for (uint32_t b = slice_lo; b < slice_hi; ++b) {  // LaunchSubtract's bin range: this rank's slice, or everything
+        hist_p[(size_t)e.sub * view.total_bins + b].x = WrapSub(hist_p[(size_t)e.parent * view.total_bins + b].x, hist_p[(size_t)e.built * view.total_bins + b].x);
+        hist_p[(size_t)e.sub * view.total_bins + b].y = WrapSub(hist_p[(size_t)e.parent * view.total_bins + b].y, hist_p[(size_t)e.built * view.total_bins + b].y);
       }
     }
   };
@@ -289,18 +395,23 @@ int main(int argc, char** argv) {
     if (items == 0) return;
     const unsigned b1 = (unsigned)std::min<long long>((items + kEvalWarps - 1) / kEvalWarps, 4);
     const unsigned b2 = (unsigned)std::min<long long>(((long long)max_eval + kEvalWarps - 1) / kEvalWarps, 2);
-    const longlong2* h2 = hist.data();
+    const longlong2* h2 = hist_p;
     if (ic.count != nullptr) {
-      EMU_LAUNCH((b1), (kEvalWarps * 32), 0, FeatureScanKernel<true>(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), mono, levels, ic, EvalShard{0, 1, nf}));
+      EMU_LAUNCH((b1), (kEvalWarps * 32), 0, FeatureScanKernel<true>(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch_p, mono, levels, ic, shard));
     } else {
-      EMU_LAUNCH((b1), (kEvalWarps * 32), 0, FeatureScanKernel<false>(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), mono, levels, ic, EvalShard{0, 1, nf}));
+      EMU_LAUNCH((b1), (kEvalWarps * 32), 0, FeatureScanKernel<false>(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch_p, mono, levels, ic, shard));
     }
     if (has_cat)
-      EMU_LAUNCH((b1), (kEvalWarps * 32), cat_smem, CatFeatureScanKernel(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), mono, levels, ic, catv));
+      EMU_LAUNCH((b1), (kEvalWarps * 32), cat_smem, CatFeatureScanKernel(view, h2, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch_p, mono, levels, ic, catv));
+    if (sliced) {  // LaunchEvaluate's `between`: the per-feature winners this rank owns travel to every peer
+      const unsigned bx = (unsigned)std::max<long long>(1, std::min<long long>((items + 255) / 256, 3));
+      ++epoch;
+      EMU_LAUNCH((bx), (256), 0, ScratchExchangeKernel(peer_scratch, peer_flags, shard, &ts, eval_nodes.data(), nodes.data(), feature_set, stride, levels, ic, epoch, &done_counter));
+    }
     if (ic.count != nullptr) {
-      EMU_LAUNCH((b2), (kEvalWarps * 32), 0, NodeReduceKernel<true>(view, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), cand.data(), mono, levels, &ts.max_eval_depth, ic));
+      EMU_LAUNCH((b2), (kEvalWarps * 32), 0, NodeReduceKernel<true>(view, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch_p, cand.data(), mono, levels, &ts.max_eval_depth, ic));
     } else {
-      EMU_LAUNCH((b2), (kEvalWarps * 32), 0, NodeReduceKernel<false>(view, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch.data(), cand.data(), mono, levels, &ts.max_eval_depth, ic));
+      EMU_LAUNCH((b2), (kEvalWarps * 32), 0, NodeReduceKernel<false>(view, eval_nodes.data(), &ts, nodes.data(), feature_set, stride, p, &q, scratch_p, cand.data(), mono, levels, &ts.max_eval_depth, ic));
     }
     if (has_cat)
       EMU_LAUNCH((b2), (kEvalWarps * 32), cat_smem, CatFinishKernel(view, h2, eval_nodes.data(), &ts, nodes.data(), p, &q, cand.data(), catv));
@@ -336,8 +447,17 @@ int main(int argc, char** argv) {
   };
 
   // ---- UpdateTreeImpl ----
+  if (world > 1) {
+    // nobody may push into a cache that its owner has not cleared yet (a pure flag barrier), then the root sum and the
+    // hessian flags of all rows (the scale was derived from all rows by the caller: ScalarExchangeKernel's which = 0
+    // is covered where the quantiser kernels are, tests/test_multi_gpu.py on hardware)
+    ++epoch;
+    EMU_LAUNCH((3), (256), 0, HistExchangeKernel(peer_hist, peer_flags, rank, world, &ts, 0, 0, 0, view.total_bins, 0, 0, epoch, &done_counter));
+    ++epoch;
+    EMU_LAUNCH((1), (32), 0, ScalarExchangeKernel(peer_flags, rank, world, epoch, 1, &q, (unsigned long long)n));
+  }
   EMU_LAUNCH((1), (kCtlThreads), 0, InitRootKernel(p, (uint32_t)n, &q, &ts, nodes.data(), build.data(), build_tile_seg.data(), eval_nodes.data(), mono, slot_owner.data()));
-  build_hist();
+  build_hist(0, 1);
   if (has_col) evaluate_with_column_sampler(1, true);
   else if (has_node_sets) evaluate(1, node_sets_view(), nullptr, 0, 0);
   else evaluate(1, IcView{nullptr, nullptr, 0}, d_fs, n_fs, n_levels);
@@ -366,12 +486,12 @@ int main(int argc, char** argv) {
       else { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint16_t, false>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
     }
     });
-    EMU_LAUNCH((1), (kCtlThreads), 0, ScanKernel(&ts, nodes.data(), part.data(), part_tile_seg.data(), tile_left.data(), tile_excl.data(), tile_left_off.data(), build.data(), sub.data(), eval_nodes.data(), build_tile_seg.data(), step_slot_base[step], step_cap[step], 0, slot_owner.data()));
+    EMU_LAUNCH((1), (kCtlThreads), 0, ScanKernel(&ts, nodes.data(), part.data(), part_tile_seg.data(), tile_left.data(), tile_excl.data(), tile_left_off.data(), build.data(), sub.data(), eval_nodes.data(), build_tile_seg.data(), step_slot_base[step], step_cap[step], world > 1 ? 1 : 0, slot_owner.data()));
     EMU_LAUNCH((3), (kPartThreads), 0, PartitionScatterKernel(ridx0.data(), ridx1.data(), ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left_off.data()));
     if (step_reuses[step])  // a reused window holds other nodes' sums
-      std::fill(hist.begin() + (size_t)step_slot_base[step] * view.total_bins,
-                hist.begin() + (size_t)(step_slot_base[step] + 2 * step_cap[step]) * view.total_bins, make_longlong2(0, 0));
-    build_hist();
+      std::fill(hist_p + (size_t)step_slot_base[step] * view.total_bins,
+                hist_p + (size_t)(step_slot_base[step] + 2 * step_cap[step]) * view.total_bins, make_longlong2(0, 0));
+    build_hist(step_slot_base[step], ring < total_slots - 1 ? 2 * step_cap[step] : step_cap[step]);
     subtract();
     IcView icv{nullptr, nullptr, 0};
     if (has_col) {
@@ -415,12 +535,12 @@ int main(int argc, char** argv) {
     d.loss_chg = s.loss_chg; d.sum_hess = s.sum_hess; d.base_weight = s.base_weight; d.depth = s.depth;
     out[i] = d;
   }
-  WriteAll(dir + "/nodes.bin", out);
-  WriteAll(dir + "/position.bin", position);
+  WriteAll(dir + "/nodes.bin" + out_suffix, out);
+  WriteAll(dir + "/position.bin" + out_suffix, position);
   std::vector<int32_t> flags_out((size_t)ts.n_nodes);
   for (int32_t i = 0; i < ts.n_nodes; ++i) flags_out[i] = (!nodes[i].is_leaf && node_is_cat[i]) ? 1 : 0;
-  WriteAll(dir + "/is_cat.bin", flags_out);
-  WriteAll(dir + "/cat_bits.bin", cat_bits);
-  WriteAll(dir + "/eval_count.bin", std::vector<int32_t>{node_seq, ts.max_eval_depth, col_cursor[0] + col_cursor[1]});
+  WriteAll(dir + "/is_cat.bin" + out_suffix, flags_out);
+  WriteAll(dir + "/cat_bits.bin" + out_suffix, cat_bits);
+  WriteAll(dir + "/eval_count.bin" + out_suffix, std::vector<int32_t>{node_seq, ts.max_eval_depth, col_cursor[0] + col_cursor[1]});
   return 0;
 }

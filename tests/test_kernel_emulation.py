@@ -581,7 +581,8 @@ TREE_NODE = np.dtype([("parent", "<i4"), ("left", "<i4"), ("right", "<i4"), ("fi
 
 def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, onehot=4, threshold=64, ic_sets=None,
                   node_sets=None, feature_set=None, n_levels=0, col_seeds=None, col_tree_set=None, bylevel=1.0, bynode=1.0,
-                  sparse=False, hist_mode=0, page_rows=0, level_batch=0, cache_slots=0):
+                  sparse=False, hist_mode=0, page_rows=0, level_batch=0, cache_slots=0, world=1, full_exchange=False,
+                  shard_ptr=None):
     exe = _build("emu_tree")
     n, nf = gb.shape
     max_bins = int(np.diff(cp).max())
@@ -617,7 +618,8 @@ def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, oneh
     np.array([n, nf, page.shape[1], bin_bytes, null_symbol, 0 if mono is None else 1, 0 if is_cat is None else 1, onehot,
               threshold, cat_words, (max_cat_bins + 31) // 32, max_cat_bins, 0 if ic_sets is None else len(ic_sets),
               0 if node_sets is None else node_sets.shape[0], 0 if node_sets is None else node_sets.shape[1],
-              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta + [row_stride, hist_mode, page_rows, level_batch, cache_slots],
+              0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta + [row_stride, hist_mode, page_rows, level_batch, cache_slots,
+                                                                                         world, 1 if full_exchange else 0],
              dtype=np.int64).tofile(os.path.join(d, "meta.bin"))
     np.array([p.learning_rate, p.reg_lambda, p.reg_alpha, p.min_child_weight, p.max_delta_step, p.min_split_loss],
              dtype=np.float32).tofile(os.path.join(d, "param_f.bin"))
@@ -643,7 +645,12 @@ def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, oneh
         np.ascontiguousarray(node_sets, dtype=np.int32).tofile(os.path.join(d, "node_sets.bin"))
     if fs is not None:
         fs.tofile(os.path.join(d, "feature_set.bin"))
+    if shard_ptr is not None:
+        np.asarray(shard_ptr, dtype=np.int64).tofile(os.path.join(d, "shard_ptr.bin"))
     subprocess.run([exe, d], check=True, timeout=1800)
+    if world > 1:   # one result set per rank (a process each, tests/emu/emu_tree.cc): rows are sharded, trees replicated
+        return [(np.fromfile(os.path.join(d, "nodes.bin_r%d" % r), dtype=TREE_NODE),
+                 np.fromfile(os.path.join(d, "position.bin_r%d" % r), dtype=np.int32)) for r in range(world)]
     nodes = np.fromfile(os.path.join(d, "nodes.bin"), dtype=TREE_NODE)
     pos = np.fromfile(os.path.join(d, "position.bin"), dtype=np.int32)
     flags = np.fromfile(os.path.join(d, "is_cat.bin"), dtype=np.int32)
@@ -964,3 +971,81 @@ def test_whole_tree_with_the_real_histogram_kernels(tmp_path, name, hist_mode, k
     params = dict(max_depth=4, eta=0.5)
     nodes, pos, _, _, _ = _emulate_tree(tmp_path, gb, cp, cv, gp, params, sparse=kw.get("sparse", False), hist_mode=hist_mode)
     _same_tree(nodes, pos, orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params)))
+
+
+# Row split over several emulated GPUs: one PROCESS per rank, the histogram caches / flag arrays / scratch tables in a
+# shared mapping (what IPC-mapped peer memory is on the device), the exchange kernels of comm.cu and their flag barriers
+# running as written.  Every rank must grow the single-GPU tree and leave the oracle's positions for its rows.
+@pytest.mark.parametrize("world,full_exchange,f,params,extra", [
+    (2, False, 8, dict(max_depth=5, eta=0.5), {}),
+    (3, False, 8, dict(max_depth=4, eta=0.5), dict(uneven=True)),
+    (4, False, 10, dict(max_depth=5, eta=0.5), dict(missing=0.1)),
+    (8, False, 8, dict(max_depth=4, eta=0.5), {}),
+    (4, False, 9, dict(max_depth=0, max_leaves=11, grow_policy="lossguide", eta=0.5), {}),
+    (4, False, 8, dict(max_depth=4, eta=0.5), dict(level_sets=True)),
+    (3, False, 8, dict(max_depth=4, eta=0.5), dict(mono=[1, -1, 0, 1, 0, -1, 0, 0])),
+    (4, False, 8, dict(max_depth=5, eta=0.5), dict(hist_mode=2)),
+    (4, True, 8, dict(max_depth=4, eta=0.5), {}),
+    (4, False, 8, dict(max_depth=6, eta=0.5), dict(cache_slots=20)),      # ring cache: lost parents -> both children built and exchanged
+    (2, True, 8, dict(max_depth=6, eta=0.5), dict(cache_slots=20)),
+    (3, False, 8, dict(max_depth=6, eta=0.5), dict(level_batch=5)),       # levels expanded in node batches
+    (5, False, 4, dict(max_depth=4, eta=0.5), {}),        # fewer features than ranks: the fused allreduce serves
+], ids=lambda v: str(v) if isinstance(v, (int, bool)) else "")
+def test_whole_tree_row_split_over_emulated_ranks(tmp_path, world, full_exchange, f, params, extra):
+    gb, cp, cv, gp = _tree_data(n=2100, f=f, missing=extra.get("missing", 0.0), seed=29)
+    n = gb.shape[0]
+    kw, okw = {}, {}
+    if extra.get("mono"):
+        kw["mono"] = okw["monotone"] = extra["mono"]
+    if extra.get("level_sets"):
+        rng = np.random.default_rng(5)
+        levels = np.stack([rng.permutation(f)[:5] for _ in range(4)]).astype(np.int32)
+        kw.update(feature_set=levels, n_levels=4)
+        okw["level_feature_sets"] = levels
+    shard_ptr = None
+    if extra.get("uneven"):
+        shard_ptr = [0, 100, 1700, n]
+    ranks = _emulate_tree(tmp_path, gb, cp, cv, gp, params, world=world, full_exchange=full_exchange, shard_ptr=shard_ptr,
+                          hist_mode=extra.get("hist_mode", 0), cache_slots=extra.get("cache_slots", 0),
+                          level_batch=extra.get("level_batch", 0), **kw)
+    if extra.get("level_batch"):
+        okw["node_batch"] = extra["level_batch"]
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params), **okw)   # which child is built does not show in exact sums
+    bounds = shard_ptr if shard_ptr is not None else [n * r // world for r in range(world + 1)]
+    for r, (nodes, pos) in enumerate(ranks):
+        _same_tree(nodes, pos, dict(o, position=o["position"][bounds[r]:bounds[r + 1]]))
+
+
+@pytest.mark.parametrize("world,what", [(4, "node_sets"), (3, "interaction"), (4, "column_sampler"),
+                                        (2, "column_sampler_with_interaction")])
+def test_row_split_over_emulated_ranks_with_per_node_feature_lists(tmp_path, world, what):
+    """Evaluation by feature slice when every evaluation slot has its OWN feature list (colsample_bynode draws, the
+    interaction-constraint query result): a rank scans the list entries whose feature it owns, and ScratchExchangeKernel
+    must move exactly those entries -- both look a slot's feature up through the same list."""
+    from tests.helpers import make_interaction_data
+    params = dict(max_depth=5, eta=0.5)
+    p = orc.Param.make(**params)
+    kw, okw = {}, {}
+    if what == "node_sets":
+        gb, cp, cv, gp = _tree_data(n=2100, seed=31)
+        rng = np.random.default_rng(15)
+        sets = np.stack([np.sort(rng.permutation(8)[:3]) for _ in range((1 << (p.max_depth + 1)) - 1)]).astype(np.int32)
+        kw["node_sets"], okw["node_feature_sets"] = sets, sets
+    else:
+        x, y = make_interaction_data(dict(seed=203, n=2100, f=6))
+        cp, cv = make_cuts(x, 24)
+        gb = orc.bin_dense(x, cp, cv)
+        gp = squared_error_gpair(np.zeros_like(y), y)
+        if "interaction" in what:
+            chain = [[0, 1], [1, 2], [2, 3], [3, 4], [4, 5]]
+            kw["ic_sets"], okw["interaction"] = chain, chain
+        if "column_sampler" in what:
+            rng = np.random.default_rng(18)
+            seeds = [int(v) for v in rng.integers(0, 2 ** 32, size=200)]
+            kw.update(col_seeds=seeds, bylevel=0.8, bynode=0.7)
+            okw.update(column_seeds=seeds, colsample_bylevel=0.8, colsample_bynode=0.7)
+    n = gb.shape[0]
+    ranks = _emulate_tree(tmp_path, gb, cp, cv, gp, params, world=world, **kw)
+    o = orc.update_tree(gb, cp, cv, gp, p, **okw)
+    for r, (nodes, pos) in enumerate(ranks):
+        _same_tree(nodes, pos, dict(o, position=o["position"][n * r // world:n * (r + 1) // world]))

@@ -13,12 +13,15 @@
 // disjoint, so the sum is exact and order-free: results are bit-identical to one GPU.  No helper thread,
 // no host synchronisation (the reference blocks the host on every collective, coll.cu:274-276).
 // NCCL is resolved with dlopen so that single-GPU use does not need it.
+#ifndef B200_KERNELS_ONLY
 #include <dlfcn.h>
+#endif
 
 #include <cstring>
 
 #include "common.cuh"
 
+#ifndef B200_KERNELS_ONLY
 namespace b200 {
 
 struct NcclUniqueId {
@@ -85,6 +88,8 @@ void ShardGroups(uint32_t n_groups, int world, int rank, uint32_t* g0, uint32_t*
 
 }  // namespace b200
 
+#endif  // B200_KERNELS_ONLY
+
 namespace b200 {
 
 // ---------------------------------------------------------------------------------------------
@@ -131,7 +136,7 @@ HistExchangeKernel(longlong2* const* __restrict__ peer_hist, uint32_t* const* __
     __threadfence_system();
     if (threadIdx.x < (unsigned)world && (int)threadIdx.x != rank) {
       volatile uint32_t* f = peer_flags[rank] + threadIdx.x;  // peer's slot in my flag array
-      while ((int32_t)(*f - epoch) < 0) { /* spin: the peer's stores are ordered before its flag */ }
+      while ((int32_t)(*f - epoch) < 0) { B200_SPIN_PAUSE(); /* the peer's stores are ordered before its flag */ }
     }
     __syncthreads();
     if (threadIdx.x == 0) *done_counter = 0;
@@ -158,7 +163,7 @@ __device__ __forceinline__ void SignalPeers(uint32_t* const* peer_flags, int ran
 __device__ __forceinline__ void WaitPeers(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch) {
   if (threadIdx.x < (unsigned)world && (int)threadIdx.x != rank) {
     volatile uint32_t* f = peer_flags[rank] + threadIdx.x;  // the peer's slot in my flag array
-    while ((int32_t)(*f - epoch) < 0) { /* spin: the peer's stores are ordered before its flag */ }
+    while ((int32_t)(*f - epoch) < 0) { B200_SPIN_PAUSE(); /* the peer's stores are ordered before its flag */ }
   }
 }
 
@@ -228,6 +233,7 @@ HistAllReduceKernel(longlong2* const* __restrict__ peer_hist, uint32_t* const* _
   }
 }
 
+#ifndef B200_KERNELS_ONLY
 void LaunchHistAllReduce(longlong2* const* peer_hist, uint32_t* const* peer_flags, int rank, int world,
                          const TreeState* ts, uint32_t slot_base, uint32_t slot_cap, uint32_t total_bins,
                          uint32_t epoch_a, uint32_t epoch_b, unsigned int* done_counter, int num_sms, cudaStream_t s) {
@@ -239,6 +245,7 @@ void LaunchHistAllReduce(longlong2* const* peer_hist, uint32_t* const* peer_flag
                                      epoch_b, done_counter);
   B200_LAUNCHED();
 }
+#endif  // B200_KERNELS_ONLY
 
 // Row split, the two scalar exchanges of a tree: every rank posts one 64-byte record into slot `rank` of each
 // peer's mailbox (it lives behind the flag array of the shared allocation), then every rank folds the records
@@ -318,11 +325,13 @@ ScalarExchangeKernel(uint32_t* const* __restrict__ peer_flags, int rank, int wor
   }
 }
 
+#ifndef B200_KERNELS_ONLY
 void LaunchScalarExchange(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch, int which, QuantDev* q,
                           uint64_t n_local, cudaStream_t s) {
   ScalarExchangeKernel<<<1, 32, 0, s>>>(peer_flags, rank, world, epoch, which, q, (unsigned long long)n_local);
   B200_LAUNCHED();
 }
+#endif  // B200_KERNELS_ONLY
 
 // ---------------------------------------------------------------------------------------------
 // Row split, evaluation by feature slice (the default row-split path): a reduce-scatter WITHOUT the all-gather.
@@ -382,6 +391,7 @@ HistSliceReduceKernel(longlong2* const* __restrict__ peer_hist, uint32_t* const*
   }
 }
 
+#ifndef B200_KERNELS_ONLY
 void LaunchHistSliceReduce(longlong2* const* peer_hist, uint32_t* const* peer_flags, int rank, int world,
                            const TreeState* ts, uint32_t slot_base, uint32_t slot_cap, uint32_t total_bins,
                            uint32_t bin_begin, uint32_t bin_end, uint32_t epoch, int num_sms, cudaStream_t s) {
@@ -393,6 +403,7 @@ void LaunchHistSliceReduce(longlong2* const* peer_hist, uint32_t* const* peer_fl
                                      bin_end, epoch);
   B200_LAUNCHED();
 }
+#endif  // B200_KERNELS_ONLY
 
 // One thread per (evaluation slot, feature position): the entry travels iff this rank scanned it.  The feature of an
 // item is looked up exactly as FeatureScanKernel does (evaluate.cu).
@@ -437,6 +448,7 @@ ScratchExchangeKernel(FeatCand* const* __restrict__ peer_scratch, uint32_t* cons
   }
 }
 
+#ifndef B200_KERNELS_ONLY
 void LaunchScratchExchange(FeatCand* const* peer_scratch, uint32_t* const* peer_flags, const EvalShard& shard,
                            const TreeState* ts, const int32_t* eval_nodes, const NodeDev* nodes,
                            const int32_t* feature_set, int32_t n_fs, int32_t n_levels, IcView ic, int32_t max_eval,
@@ -447,7 +459,9 @@ void LaunchScratchExchange(FeatCand* const* peer_scratch, uint32_t* const* peer_
                                                n_fs, n_levels, ic, epoch, done_counter);
   B200_LAUNCHED();
 }
+#endif  // B200_KERNELS_ONLY
 
+#ifndef B200_KERNELS_ONLY
 void LaunchHistExchange(longlong2* const* peer_hist, uint32_t* const* peer_flags, int rank, int world,
                         const TreeState* ts, uint32_t slot_base, uint32_t slot_cap, bool use_n_build,
                         uint32_t total_bins, uint32_t bin_begin, uint32_t bin_end, uint32_t epoch,
@@ -457,11 +471,13 @@ void LaunchHistExchange(longlong2* const* peer_hist, uint32_t* const* peer_flags
                                                  done_counter);
   B200_LAUNCHED();
 }
+#endif  // B200_KERNELS_ONLY
 
 }  // namespace b200
 
 using namespace b200;
 
+#ifndef B200_KERNELS_ONLY
 extern "C" {
 
 int b200hist_comm_unique_id(uint8_t* out_id128) {
@@ -507,3 +523,4 @@ int b200hist_shard_groups(uint32_t n_groups, int world, int rank, uint32_t* g_be
 }
 
 }  // extern "C"
+#endif  // B200_KERNELS_ONLY

@@ -16,6 +16,10 @@
 // Dynamic shared memory of a kernel.  The CPU emulator of the tests (tests/emu/cuda_emu.h) supplies its own definition
 // so that the kernel sources run unmodified there; B200_KERNELS_ONLY (also set by those tests) compiles the host
 // launchers out, which the emulator cannot parse (<<< >>>).
+// Body of a flag spin loop (comm.cu): nothing on the device; the emulator yields the core to the process it waits for.
+#ifndef B200_SPIN_PAUSE
+#define B200_SPIN_PAUSE() ((void)0)
+#endif
 #ifndef B200_DYNAMIC_SHARED
 #define B200_DYNAMIC_SHARED(type, name) extern __shared__ type name[]
 #define B200_DYNAMIC_SHARED_ALIGNED(type, name, bytes) extern __shared__ __align__(bytes) type name[]
