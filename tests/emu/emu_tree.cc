@@ -126,7 +126,12 @@ int main(int argc, char** argv) {
   // own flag barriers (comm.cu) order the ranks.  [29] = 1: the fused reduce-scatter + all-gather instead of the
   // evaluation by feature slice.
   const int world = meta.size() > 28 && meta[28] > 1 ? (int)meta[28] : 1;
-  const bool full_exchange = meta.size() > 29 && meta[29] != 0;
+  const int hist_mode_early = meta.size() > 24 ? (int)meta[24] : 0;
+  const bool full_exchange = meta.size() > 29 && meta[29] == 1;
+  // [29] = 2: feature-block shard (north_star's decomposition): ALL rows on every rank, rank r builds the histograms of
+  // its contiguous feature block only and pushes that bin range into every peer's cache (HistExchangeKernel); evaluation,
+  // partition and finalise are replicated.  hist_mode 0 only (the CPU accumulation, restricted to the block).
+  const bool feature_block = meta.size() > 29 && meta[29] == 2;
   int rank = 0;
   const size_t hist_elems = (size_t)n_slots * view.total_bins;
   const size_t scratch_elems = (size_t)2 * 64 * nf;  // the emulated trees expand at most 64 nodes per step
@@ -167,6 +172,7 @@ int main(int argc, char** argv) {
       }
       return bad;
     }
+    if (!feature_block) {
     const uint64_t r0 = shard_ptr.empty() ? n * (uint64_t)rank / world : (uint64_t)shard_ptr[rank];
     const uint64_t r1 = shard_ptr.empty() ? n * (uint64_t)(rank + 1) / world : (uint64_t)shard_ptr[rank + 1];
     bins = std::vector<uint8_t>(bins.begin() + r0 * view.row_bytes, bins.begin() + r1 * view.row_bytes);
@@ -184,13 +190,22 @@ int main(int argc, char** argv) {
       zero_any |= v.y == 0 ? 1u : 0u;
     }
     q.root_g = (long long)sg; q.root_h = (long long)sh; q.h_lo_or = lo_or; q.h_zero_any = zero_any;
+    }
   } else {
     hist_local.assign(hist_elems, make_longlong2(0, 0));
     scratch_local.resize(scratch_elems);
   }
   longlong2* const hist_p = world > 1 ? peer_hist[rank] : hist_local.data();
   FeatCand* const scratch_p = world > 1 ? peer_scratch[rank] : scratch_local.data();
-  const bool sliced = world > 1 && !full_exchange && meta[6] == 0 && nf >= (uint32_t)world;
+  const bool sliced = world > 1 && !full_exchange && !feature_block && meta[6] == 0 && nf >= (uint32_t)world;
+  // the block of rank r: ShardGroups' contiguous split (comm.cu), over features here (the product splits 32-feature groups)
+  uint32_t fb0 = 0, fb1 = nf;
+  if (feature_block && world > 1) {
+    const uint32_t bs = nf / (uint32_t)world, rem = nf % (uint32_t)world, r = (uint32_t)rank;
+    fb0 = r * bs + std::min(r, rem);
+    fb1 = fb0 + bs + (r < rem ? 1u : 0u);
+    if (hist_mode_early != 0) return 7;
+  }
   const EvalShard shard{sliced ? rank : 0, sliced ? world : 1, nf};
   uint32_t slice_lo = 0, slice_hi = view.total_bins;
   if (sliced) {  // SliceBins (updater.cu): the bins of the features this rank owns
@@ -352,7 +367,7 @@ int main(int argc, char** argv) {
           }
           continue;
         }
-        for (uint32_t f = 0; f < nf; ++f) {
+        for (uint32_t f = fb0; f < fb1; ++f) {
           const uint32_t sym = view.bin_bytes == 1 ? (uint32_t)bins[(size_t)r * view.row_bytes + f]
                                                    : (uint32_t)reinterpret_cast<const uint16_t*>(bins.data() + (size_t)r * view.row_bytes)[f];
           if (sym == view.null_symbol) continue;
@@ -366,6 +381,11 @@ int main(int argc, char** argv) {
   auto build_hist = [&](uint32_t slot_base, uint32_t slot_cap) {
     build_local();
     if (world == 1) return;
+    if (feature_block) {
+      ++epoch;
+      EMU_LAUNCH((3), (256), 0, HistExchangeKernel(peer_hist, peer_flags, rank, world, &ts, slot_base, slot_cap, 1, view.total_bins, cut_ptrs[fb0], cut_ptrs[fb1], epoch, &done_counter));
+      return;
+    }
     if (sliced) {
       ++epoch;
       if (world == 2) { EMU_LAUNCH((3), (256), 0, HistSliceReduceKernel<2>(peer_hist, peer_flags, rank, world, &ts, slot_base, slot_cap, view.total_bins, slice_lo, slice_hi, epoch)); }
@@ -453,8 +473,8 @@ int main(int argc, char** argv) {
     // is covered where the quantiser kernels are, tests/test_multi_gpu.py on hardware)
     ++epoch;
     EMU_LAUNCH((3), (256), 0, HistExchangeKernel(peer_hist, peer_flags, rank, world, &ts, 0, 0, 0, view.total_bins, 0, 0, epoch, &done_counter));
-    ++epoch;
-    EMU_LAUNCH((1), (32), 0, ScalarExchangeKernel(peer_flags, rank, world, epoch, 1, &q, (unsigned long long)n));
+    if (!feature_block) ++epoch;
+    if (!feature_block) EMU_LAUNCH((1), (32), 0, ScalarExchangeKernel(peer_flags, rank, world, epoch, 1, &q, (unsigned long long)n));
   }
   EMU_LAUNCH((1), (kCtlThreads), 0, InitRootKernel(p, (uint32_t)n, &q, &ts, nodes.data(), build.data(), build_tile_seg.data(), eval_nodes.data(), mono, slot_owner.data()));
   build_hist(0, 1);
@@ -486,7 +506,7 @@ int main(int argc, char** argv) {
       else { EMU_LAUNCH((3), (kPartThreads), 0, (PartitionCountKernel<uint16_t, false>(view, ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left.data(), cr))); }
     }
     });
-    EMU_LAUNCH((1), (kCtlThreads), 0, ScanKernel(&ts, nodes.data(), part.data(), part_tile_seg.data(), tile_left.data(), tile_excl.data(), tile_left_off.data(), build.data(), sub.data(), eval_nodes.data(), build_tile_seg.data(), step_slot_base[step], step_cap[step], world > 1 ? 1 : 0, slot_owner.data()));
+    EMU_LAUNCH((1), (kCtlThreads), 0, ScanKernel(&ts, nodes.data(), part.data(), part_tile_seg.data(), tile_left.data(), tile_excl.data(), tile_left_off.data(), build.data(), sub.data(), eval_nodes.data(), build_tile_seg.data(), step_slot_base[step], step_cap[step], world > 1 && !feature_block ? 1 : 0, slot_owner.data()));
     EMU_LAUNCH((3), (kPartThreads), 0, PartitionScatterKernel(ridx0.data(), ridx1.data(), ridx0.data(), ridx1.data(), part.data(), part_tile_seg.data(), &ts, flags.data(), tile_left_off.data()));
     if (step_reuses[step])  // a reused window holds other nodes' sums
       std::fill(hist_p + (size_t)step_slot_base[step] * view.total_bins,

@@ -619,7 +619,7 @@ def _emulate_tree(tmp_path, gb, cp, cv, gp, params, mono=None, is_cat=None, oneh
               threshold, cat_words, (max_cat_bins + 31) // 32, max_cat_bins, 0 if ic_sets is None else len(ic_sets),
               0 if node_sets is None else node_sets.shape[0], 0 if node_sets is None else node_sets.shape[1],
               0 if fs is None else 1, 0 if fs is None else fs.shape[-1], n_levels] + col_meta + [row_stride, hist_mode, page_rows, level_batch, cache_slots,
-                                                                                         world, 1 if full_exchange else 0],
+                                                                                         world, int(full_exchange)],   # [29]: 0 slices, 1 fused allreduce, 2 feature blocks
              dtype=np.int64).tofile(os.path.join(d, "meta.bin"))
     np.array([p.learning_rate, p.reg_lambda, p.reg_alpha, p.min_child_weight, p.max_delta_step, p.min_split_loss],
              dtype=np.float32).tofile(os.path.join(d, "param_f.bin"))
@@ -1049,3 +1049,16 @@ def test_row_split_over_emulated_ranks_with_per_node_feature_lists(tmp_path, wor
     o = orc.update_tree(gb, cp, cv, gp, p, **okw)
     for r, (nodes, pos) in enumerate(ranks):
         _same_tree(nodes, pos, dict(o, position=o["position"][n * r // world:n * (r + 1) // world]))
+
+
+@pytest.mark.parametrize("world,f,params", [(2, 8, dict(max_depth=5, eta=0.5)), (4, 10, dict(max_depth=4, eta=0.5)),
+                                            (3, 8, dict(max_depth=0, max_leaves=10, grow_policy="lossguide", eta=0.5)),
+                                            (8, 8, dict(max_depth=4, eta=0.5))])
+def test_feature_block_shard_over_emulated_ranks(tmp_path, world, f, params):
+    """north_star's decomposition: all rows on every rank, a contiguous feature block each; HistExchangeKernel pushes the
+    block's bin range of the level's built histograms into every peer, everything else is replicated."""
+    gb, cp, cv, gp = _tree_data(n=1500, f=f, missing=0.05, seed=37)
+    ranks = _emulate_tree(tmp_path, gb, cp, cv, gp, params, world=world, full_exchange=2)
+    o = orc.update_tree(gb, cp, cv, gp, orc.Param.make(**params))
+    for nodes, pos in ranks:
+        _same_tree(nodes, pos, o)
