@@ -187,7 +187,7 @@ B200HIST_API int b200hist_ellpack_push_dense(b200hist_ellpack_t ell, uint64_t ro
 /* Feature types of a dense-layout page: the categorical columns (flag != 0) of every later push_dense are binned by
  * HistogramCuts::SearchCatBin (src/common/hist_util.h:132-144: lower bound of the truncated value among the feature's
  * category codes, clamped to the last bin) instead of SearchBin.  Call before push_dense.
- * STATUS: compiled, never run on hardware (tests/test_gpu_next.py). */
+ * STATUS: green on a B200 since round 2 (tests/test_gpu_next.py, categorical cases; on by default). */
 B200HIST_API int b200hist_ellpack_set_feature_types(b200hist_ellpack_t ell, const uint8_t* feature_is_cat_host,
                                                     uint32_t n);
 /* Import a reference EllpackPage: decode its big-endian bit-packed gidx_buffer
@@ -319,8 +319,9 @@ B200HIST_API int b200hist_updater_last_max_eval_depth(b200hist_updater_t u, int3
  * ctx->Rng()() draw the reference makes per tree, sampler.cu:308) rows are kept with probability min(1, rag_i / mu),
  * rag_i = sqrt(g_i^2 + 0.1 h_i^2) on the quantised pair, mu chosen so that the expected sample size is
  * n * subsample; kept rows below mu are scaled by 1 / p.  Single GPU.
- * STATUS: compiled, never run on hardware; its oracle is parity-unpinned until the reference has produced a fixture
- * (tools/make_golden_gpu_next.py); tests in tests/test_gpu_next.py, gated. */
+ * STATUS: green on a B200 since round 2: the reference's own gpu_hist trees under sampling_method=gradient_based are
+ * committed as fixtures (tests/golden/ref_gpu_next_trees.json, tools/make_golden_gpu_next.py) and reproduced bit for bit
+ * by this path and by the oracle; drop-in test through the shim in tests/test_gpu_next.py. */
 B200HIST_API int b200hist_updater_set_sampling_method(b200hist_updater_t u, int gradient_based);
 
 /* colsample_bynode = ColumnSampler::GetFeatureSet's per-call draw (src/common/random.h:156-175, random.cu:62-96).
@@ -332,7 +333,7 @@ B200HIST_API int b200hist_updater_set_sampling_method(b200hist_updater_t u, int 
  * would.  Replaces tree- and level-wise sets while set; NULL / 0 removes it.  Not combinable with interaction
  * constraints yet, nor with colsample_bylevel (the reference interleaves the lazy level draws with the node draws in
  * one engine, which makes the stream data dependent).
- * STATUS: compiled, never run on hardware; GPU tests in tests/test_gpu_next.py behind B200HIST_RUN_UNVALIDATED=1. */
+ * STATUS: green on a B200 since round 2 (tests/test_gpu_next.py). */
 B200HIST_API int b200hist_updater_set_node_feature_sets(b200hist_updater_t u, const int32_t* sets_host, uint32_t n_sets,
                                                         uint32_t n_per_set);
 B200HIST_API int b200hist_updater_last_eval_count(b200hist_updater_t u, int32_t* out);
@@ -347,8 +348,8 @@ B200HIST_API int b200hist_updater_last_eval_count(b200hist_updater_t u, int32_t*
  * Covers colsample_bynode with or without colsample_bylevel (and colsample_bylevel alone); replaces
  * b200hist_updater_set_node_feature_sets / set_level_feature_sets while set; NULL / 0 removes it.  With interaction
  * constraints a node's Query runs on its OWN sampled list (updater_gpu_hist.cu:257-264).
- * STATUS: compiled; kernel sources and whole trees run under the CPU emulator against the oracle
- * (tests/test_kernel_emulation.py); never run on hardware. */
+ * STATUS: green on a B200 since round 2: colsample_bylevel / bynode through the shim equal the reference's own trees
+ * (tests/test_gpu_next.py, tests/golden/ref_gpu_next_trees.json); whole trees also under the CPU emulator. */
 B200HIST_API int b200hist_updater_set_column_sampler(b200hist_updater_t u, const int32_t* tree_set_host,
                                                      uint32_t n_tree_set, float colsample_bylevel,
                                                      float colsample_bynode, const uint32_t* seeds_host,
@@ -359,8 +360,8 @@ B200HIST_API int b200hist_updater_last_draw_count(b200hist_updater_t u, int32_t*
  * 27-46; cuda_impl::SampleFeature, random.cu:62-96 = thrust::shuffle with default_random_engine(seed), keep the first
  * n_sel = max(1, int(colsample * n)), sort ascending).  Draw d uses seeds_host[d] -- the value the reference obtains
  * from ctx->Rng()() for that call.  out_host: n_draws x n_sel.  One launch instead of one host call per draw; n <= 8192.
- * STATUS: compiled, never run on hardware; the arithmetic is pinned on the CPU against the toolkit's own
- * thrust::shuffle (tests/golden/thrust_shuffle_known_answers.json). */
+ * STATUS: green on a B200 since round 2 (tests/test_gpu_next.py); the arithmetic is also pinned on the CPU against the toolkit's
+ * own thrust::shuffle (tests/golden/thrust_shuffle_known_answers.json). */
 B200HIST_API int b200hist_col_sample_stream(int device, const int32_t* features_host, uint32_t n, float colsample,
                                             const uint32_t* seeds_host, uint32_t n_draws, int32_t* out_host,
                                             uint32_t* n_sel_out, void* stream);
@@ -382,11 +383,8 @@ B200HIST_API int b200hist_updater_set_monotone_constraints(b200hist_updater_t u,
  * calls of a level answer into ONE buffer before the evaluation kernel runs, so a node is evaluated on the first
  * `its own count` entries of what the level's later answers left there.  With disjoint sets every node of a tree has
  * the same answer and the two readings coincide.
- * STATUS: run on a B200 once, in the round's last GPU seconds (tools/quick_check: one tree under overlapping sets,
- * identical to the oracle -- recorded in tests/golden/b200_quick_check, tests/test_recorded_hardware.py).  The full
- * parity set (the reference's own trees bit for bit, lossguide, 130 features, bylevel, monotone, the drop-in) is in
- * tests/test_gpu_next.py behind B200HIST_RUN_UNVALIDATED=1 and has not run yet; the shim refuses the parameter
- * until it has. */
+ * STATUS: green on a B200 since round 2: the reference's own trees bit for bit (overlapping sets, lossguide, 130 features,
+ * with colsample_bylevel / monotone constraints) and the drop-in through the shim (tests/test_gpu_next.py); on by default. */
 B200HIST_API int b200hist_updater_set_interaction_constraints(b200hist_updater_t u, const int32_t* set_ptr_host,
                                                               const int32_t* set_feat_host, uint32_t n_sets);
 
@@ -400,11 +398,8 @@ B200HIST_API int b200hist_updater_set_interaction_constraints(b200hist_updater_t
  * b200hist_updater_last_tree_categories: per node of the last tree, 1 if it is a categorical split, and its
  * category set as cat_words uint32 words in the reference's LBitField32 layout (category c = bit 31 - c % 32 of
  * word c / 32) -- what RegTree::ExpandCategorical takes.  Buffers: n_nodes and n_nodes * cat_words entries.
- * STATUS: run on a B200 once, in the round's last GPU seconds (tools/quick_check: two depth-5 trees, 21 sorted-partition
- * and 24 one-hot categorical splits, nodes / category sets / every row position identical to the oracle -- recorded
- * in tests/golden/b200_quick_check, tests/test_recorded_hardware.py).  The full parity set and the drop-in are in
- * tests/test_gpu_next.py behind B200HIST_RUN_UNVALIDATED=1 and have not run yet; the shim refuses categorical
- * features until they have. */
+ * STATUS: green on a B200 since round 2: one-hot and sorted-partition splits, the reference's own trees bit for bit and the
+ * drop-in through the shim (tests/test_gpu_next.py); on by default. */
 B200HIST_API int b200hist_updater_set_categorical(b200hist_updater_t u, const uint8_t* feature_is_cat_host, uint32_t n,
                                                   int32_t max_cat_to_onehot, int32_t max_cat_threshold);
 B200HIST_API int b200hist_updater_cat_words(b200hist_updater_t u, uint32_t* out);
@@ -482,9 +477,8 @@ B200HIST_API int b200hist_evaluate_splits(b200hist_ellpack_t ell, const b200hist
  * out_host (fvalue = NaN, split_gbin = -1 for a categorical winner), out_is_cat_host, and the categories that go
  * RIGHT as the reference's LBitField32 over category codes in out_cat_bits_host[node * n_cat_words ...]
  * (category c = bit 31 - c % 32 of word c / 32).
- * STATUS: exercised on a B200 only through whole trees (see b200hist_updater_set_categorical); this per-stage
- * entry's own GPU tests (the reference's twelve literal vectors, random histograms against the oracle) are in
- * tests/test_gpu_next.py behind B200HIST_RUN_UNVALIDATED=1 and have not run yet. */
+ * STATUS: green on a B200 since round 2: the reference's twelve literal vectors and random histograms against the oracle
+ * (tests/test_gpu_next.py). */
 B200HIST_API int b200hist_evaluate_splits_cat(b200hist_ellpack_t ell, const b200hist_gpair64* hist_dev,
                                               const b200hist_gpair64* parent_sums_host, int32_t n_nodes,
                                               const int32_t* feature_set_host, int32_t n_feature_set,
@@ -518,10 +512,9 @@ B200HIST_API int b200hist_partition(b200hist_ellpack_t ell, const uint32_t* ridx
  * cuts, e.g. a validation set), out_dev[k] += sum over trees [tree_begin, tree_end) of the leaf the row reaches, the
  * sum taken in tree order from 0.0f like the reference (gpu_predictor.cu:221-228).  predict_leaf: out_dev[k *
  * n_trees + t] = the leaf's node id inside tree t (:196-201).
- * STATUS: compiled, never run on hardware; the oracle (orc_predict_leaf) reproduces the reference CPU predictor's
- * margins bit for bit, on the training cuts and on a QuantileDMatrix with foreign cuts
- * (tests/test_reference_golden.py); the kernels equal the oracle under the CPU emulator
- * (tests/test_kernel_emulation.py); GPU tests in tests/test_gpu_next.py, gated. */
+ * STATUS: green on a B200 since round 2 (tests/test_gpu_next.py: margins and leaf ids against the oracle, which reproduces
+ * the reference CPU predictor's margins bit for bit on the training cuts and on a QuantileDMatrix with foreign cuts,
+ * tests/test_reference_golden.py); the kernels also equal the oracle under the CPU emulator. */
 B200HIST_API int b200hist_forest_create(b200hist_ellpack_t ell, b200hist_forest_t* out);
 B200HIST_API int b200hist_forest_destroy(b200hist_forest_t forest);
 B200HIST_API int b200hist_forest_num_trees(b200hist_forest_t forest, uint32_t* out);
@@ -541,7 +534,8 @@ B200HIST_API int b200hist_forest_predict_leaf(b200hist_forest_t forest, b200hist
  * set_tree_groups replaces the group of EVERY tree added so far (n_trees must equal forest_num_trees; trees added
  * later start in group 0).  predict_leaf_f32 is predict_leaf with the id stored as a float, the layout
  * Predictor::PredictLeaf returns (gpu_predictor.cu:793-830).
- * STATUS: compiled, equal to the oracle under the CPU emulator, never run on hardware. */
+ * STATUS: green on a B200 since round 2 (multi-class margins and leaf ids through the Predictor binding,
+ * tests/test_gpu_next.py::test_predictor_binding_serves_quantised_matrices_like_the_reference). */
 B200HIST_API int b200hist_forest_set_tree_groups(b200hist_forest_t forest, const uint32_t* groups_host,
                                                  uint32_t n_trees);
 B200HIST_API int b200hist_forest_predict_margin_groups(b200hist_forest_t forest, b200hist_ellpack_t page,
@@ -556,7 +550,8 @@ B200HIST_API int b200hist_forest_predict_margin_groups(b200hist_forest_t forest,
  * (src/data/ellpack_page.cuh:101-122).  The page must be quantised with the cuts the forest was created on.
  * mode 0: out_dev[n_rows] += margin (sum from 0.0f first); 1: out_dev[n_rows * n_groups], leaves straight onto the
  * output; 2: out_dev[n_rows * n_trees] = leaf ids as floats.  This is what the Predictor binding calls.
- * STATUS: compiled, equal to the oracle under the CPU emulator, never run on hardware. */
+ * STATUS: green on a B200 since round 2: what the shim's Predictor serves by default -- bit-identical to the reference's
+ * GPUPredictor, margins 1.26x its speed on 10M x 64 x 50 trees (profiles/r02_predictor_bench.json). */
 B200HIST_API int b200hist_forest_predict_reference_page(b200hist_forest_t forest, const uint8_t* gidx_buffer_dev,
                                                         uint64_t n_rows, uint32_t row_stride, uint32_t n_symbols,
                                                         int dense_layout, int is_dense, int mode,

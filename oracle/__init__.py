@@ -235,7 +235,7 @@ def col_sample(features, colsample: float, seed: int) -> np.ndarray:
 
 
 def gradient_based_sample(gq: np.ndarray, scale, subsample: float, seed: int):
-    """GradientBasedSampling::Sample restated (PARITY UNPINNED, see orc_gradient_based_sample).  gq: int64[n, 2]
+    """GradientBasedSampling::Sample restated (pinned on the reference's own gpu_hist trees, see orc_gradient_based_sample).  gq: int64[n, 2]
     quantised pairs.  Returns (sampled pairs, mu, threshold index, regularised absolute gradients)."""
     out = np.ascontiguousarray(gq, dtype=np.int64).copy()
     n = out.shape[0]

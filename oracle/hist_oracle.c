@@ -921,9 +921,12 @@ ORC_API int32_t orc_col_sample(const int32_t* features, int32_t n, float colsamp
  *   row i: pair (0,0) stays; p = rag_i / mu (|mu| < 1e-6 -> 1e-6); p >= 1 keeps the pair; otherwise the pair becomes
  *          ToFixedPoint(pair_as_double * (1.0f / p)) when RandomWeight(seed)(i) <= p and (0,0) when not.
  * sample_rows = (uint64)(n * subsample) with the product taken in float (bst_idx_t = n_samples * subsample_).
- * PARITY UNPINNED: no literal vector of the reference covers this (its tests are statistical,
- * tests/cpp/tree/gpu_hist/test_sampler.cu:79-179) and the CUDA reference has not been run against it yet; the double
- * sum behind the quantiser is taken sequentially here (device reduction order there: matters only at a power of two).
+ * PINNED (round 2): no literal vector of the reference covers this (its tests are statistical,
+ * tests/cpp/tree/gpu_hist/test_sampler.cu:79-179), so the unmodified reference's gpu_hist was run on a B200 with
+ * sampling_method=gradient_based and its trees committed (tests/golden/ref_gpu_next_trees.json, generator
+ * tools/make_golden_gpu_next.py); tests/test_reference_golden.py::test_oracle_reproduces_reference_gpu_gradient_based_sampling
+ * rebuilds them bit for bit from this function.  The double sum behind the quantiser is taken sequentially here (device
+ * reduction order there: matters only at a power of two).
  * Returns mu. */
 ORC_API float orc_gradient_based_sample(orc_gpair64* gq, uint64_t n, const double scale[4], float subsample,
                                         uint32_t seed, uint64_t* threshold_index_out, float* rag_out) {

@@ -1,5 +1,5 @@
 // A small CPU emulator for CUDA kernels -- TEST INFRASTRUCTURE (tests/emu/): it lets the kernel sources of
-// xgboost_b200/csrc that could not be run on a GPU yet execute, unmodified, against the oracle.
+// xgboost_b200/csrc execute, unmodified, against the oracle where there is no GPU (this container; the `not gpu` suite).
 //
 // Model: every CUDA thread is an OS thread; the CTAs of a launch run one after another.  __syncthreads and the warp
 // collectives (__shfl_*_sync, __ballot_sync, __any_sync, __reduce_or_sync, __syncwarp) are barriers that tolerate

@@ -470,8 +470,9 @@ def test_oracle_node_feature_sets_follow_the_evaluation_order():
 
 
 def test_gradient_based_sampling_properties():
-    """GradientBasedSampling::Sample restated (parity unpinned -- the reference's own tests are statistical too,
-    tests/cpp/tree/gpu_hist/test_sampler.cu:79-179): the threshold mu makes the EXPECTED number of sampled rows equal
+    """GradientBasedSampling::Sample restated: the properties the reference's own (statistical) tests check,
+    tests/cpp/tree/gpu_hist/test_sampler.cu:79-179 -- the bit-level pin is tests/test_reference_golden.py, on trees of the
+    unmodified reference.  The threshold mu makes the EXPECTED number of sampled rows equal
     n * subsample (the CpuGpuConsistency property, :129-179), rows at or above mu are kept untouched, kept rows below
     it are scaled by 1 / p so that the gradient sum stays unbiased, dropped rows are zero."""
     from tests.helpers import make_regression, squared_error_gpair

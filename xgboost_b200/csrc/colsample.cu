@@ -12,7 +12,7 @@
 // gives each kept element its output position -- the same compaction thrust's inclusive scan of flags performs),
 // stops after n_sel elements and sorts them ascending (rank sort in shared memory).
 // Pinned on the CPU: the same arithmetic in oracle/hist_oracle.c (orc_thrust_shuffle) reproduces permutations of the
-// toolkit's own thrust::shuffle (tests/golden/thrust_shuffle_known_answers.json).  STATUS: compiled, never run.
+// toolkit's own thrust::shuffle (tests/golden/thrust_shuffle_known_answers.json).  STATUS: green on a B200 since round 2 (tests/test_gpu_next.py).
 #include <algorithm>
 #include <vector>
 

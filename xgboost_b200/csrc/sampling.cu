@@ -18,8 +18,9 @@
 //   6. the root sum and the two hessian flags of the quantiser record are recomputed from the sampled pairs.
 // The sort and the scan are library primitives (CUB, part of the toolkit): any correct sort / integer scan gives the
 // same arrays, and this is not the hot path of a tree (one pass over n floats; the histogram visits n * F symbols).
-// STATUS: compiled, never run on hardware; its oracle (orc_gradient_based_sample) is itself parity-unpinned until
-// tests/golden/ref_gpu_next_trees.json exists.
+// STATUS: green on a B200 since round 2; pinned on the reference's own gpu_hist trees under sampling_method=gradient_based
+// (tests/golden/ref_gpu_next_trees.json, generated on a B200 by tools/make_golden_gpu_next.py), which this path and the
+// oracle (orc_gradient_based_sample) reproduce bit for bit.
 #ifndef B200_KERNELS_ONLY
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
