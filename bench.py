@@ -782,7 +782,7 @@ def run_b200(args):
             sys.stdout.flush()
         os._exit(0)
 
-    watchdog = threading.Timer(float(os.environ.get("B200_BENCH_SIDE_DEADLINE_S", 480 if world == 1 else 360)), on_deadline)
+    watchdog = threading.Timer(float(os.environ.get("B200_BENCH_SIDE_DEADLINE_S", 360 if world == 1 else 240)), on_deadline)
     watchdog.daemon = True
     watchdog.start()
 
